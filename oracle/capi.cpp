@@ -1,0 +1,362 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY. Not part of the product path.
+// Flat C entry points over the C++ restatement, for tests/ (ctypes), __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs. Nothing in vermeer_b200/ may link or load this.
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <thread>
+#include <algorithm>
+
+#include "ldseq.h"
+#include "scene.h"
+#include "shading.h"
+
+using namespace orc;
+
+namespace {
+thread_local std::string g_err;
+struct Handle {
+  Renderer r;
+};
+template <class F>
+int guard(F f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+Vec3 v3(const float* p) { return V3(p[0], p[1], p[2]); }
+}  // namespace
+
+extern "C" {
+
+struct OrcRay { float o[3]; float d[3]; float tmax; float time; };
+struct OrcHit { float t, u, v, w; int32_t prim, geom; int32_t nodesT, trisT; };
+
+const char* orc_last_error() { return g_err.c_str(); }
+
+void* orc_create() { return new Handle(); }
+void orc_destroy(void* h) { delete (Handle*)h; }
+
+int orc_set_globals(void* h, int xres, int yres) {
+  Handle* H = (Handle*)h;
+  H->r.XRes = xres;
+  H->r.YRes = yres;
+  return 0;
+}
+
+// mask bits / p[] slots: 0 EmissionColour(p0..2) 1 EmissionStrength(p3) 2 DiffuseColour(p4..6) 3 DiffuseStrength(p7)
+// 4 DiffuseRoughness(p8) 5 Spec1Colour(p9..11) 6 Spec1Strength(p12) 7 Spec1Roughness(p13) 8 IOR(p14)
+int orc_add_shader(void* h, const char* name, uint32_t mask, const float* p) {
+  Handle* H = (Handle*)h;
+  auto s = std::make_unique<ShaderStd>();
+  s->Name = name;
+  if (mask & 1) { s->hasEmissionColour = true; s->EmissionColour = MakeRGB(p[0], p[1], p[2]); }
+  if (mask & 2) { s->hasEmissionStrength = true; s->EmissionStrength = p[3]; }
+  if (mask & 4) { s->hasDiffuseColour = true; s->DiffuseColour = MakeRGB(p[4], p[5], p[6]); }
+  if (mask & 8) { s->hasDiffuseStrength = true; s->DiffuseStrength = p[7]; }
+  if (mask & 16) { s->hasDiffuseRoughness = true; s->DiffuseRoughness = p[8]; }
+  if (mask & 32) { s->hasSpec1Colour = true; s->Spec1Colour = MakeRGB(p[9], p[10], p[11]); }
+  if (mask & 64) { s->hasSpec1Strength = true; s->Spec1Strength = p[12]; }
+  if (mask & 128) { s->hasSpec1Roughness = true; s->Spec1Roughness = p[13]; }
+  if (mask & 256) { s->hasIOR = true; s->IOR = p[14]; }
+  H->r.shaders.push_back(std::move(s));
+  return 0;
+}
+
+// verts: keys*nverts*3 floats (key-major, core/param/array.go:26). polycount/faceidx/shaderidx/normals may be null.
+// shaders: '\n'-separated shader names.
+int orc_add_polymesh(void* h, const char* name, const float* verts, int nverts, int keys, const int32_t* polycount, int npoly,
+                     const int32_t* faceidx, int nfaceidx, const char* shaders, const int32_t* shaderidx, int nshaderidx,
+                     const float* normals, int nnormals, const int32_t* normalidx, int nnormalidx, float raybias) {
+  Handle* H = (Handle*)h;
+  return guard([&] {
+    auto m = std::make_unique<PolyMesh>();
+    m->Name = name;
+    m->RayBias = raybias;
+    m->Verts.MotionKeys = keys;
+    m->Verts.ElemsPerKey = nverts;
+    m->Verts.Elems.resize((size_t)keys * nverts);
+    std::memcpy(m->Verts.Elems.data(), verts, sizeof(float) * 3 * (size_t)keys * nverts);
+    if (polycount) { m->hasPolyCount = true; m->PolyCount.assign(polycount, polycount + npoly); }
+    if (faceidx) { m->hasFaceIdx = true; m->FaceIdx.assign(faceidx, faceidx + nfaceidx); }
+    if (shaderidx) m->ShaderIdx.assign(shaderidx, shaderidx + nshaderidx);
+    if (normals) {
+      m->Normals.MotionKeys = 1;
+      m->Normals.ElemsPerKey = nnormals;
+      m->Normals.Elems.resize(nnormals);
+      std::memcpy(m->Normals.Elems.data(), normals, sizeof(float) * 3 * (size_t)nnormals);
+      if (normalidx) { m->hasNormalIdx = true; m->NormalIdx.assign(normalidx, normalidx + nnormalidx); }
+    }
+    std::string s(shaders ? shaders : "");
+    size_t pos = 0;
+    while (pos <= s.size() && !s.empty()) {
+      size_t e = s.find('\n', pos);
+      std::string nm = s.substr(pos, e == std::string::npos ? std::string::npos : e - pos);
+      ShaderStd* sh = H->r.findShader(nm);
+      if (!sh) throw std::runtime_error("Unable to find node (shader " + nm + ")");
+      m->shader.push_back(sh);
+      if (e == std::string::npos) break;
+      pos = e + 1;
+    }
+    H->r.meshes.push_back(std::move(m));
+  });
+}
+
+int orc_add_trilight(void* h, const char* name, const float* p0, const float* p1, const float* p2, const char* shader, int samples) {
+  Handle* H = (Handle*)h;
+  return guard([&] {
+    auto t = std::make_unique<Tri>();
+    t->Name = name;
+    t->P0 = v3(p0);
+    t->P1 = v3(p1);
+    t->P2 = v3(p2);
+    t->Samples = samples;
+    t->shader = H->r.findShader(shader);
+    if (!t->shader) throw std::runtime_error(std::string("Unable to find node (shader ") + shader + ")");
+    H->r.tris.push_back(std::move(t));
+  });
+}
+
+int orc_set_camera(void* h, const float* from, const float* to, const float* up, float roll, float fov, float focal, float aspect, float radius) {
+  Handle* H = (Handle*)h;
+  H->r.camera.From = v3(from);
+  H->r.camera.To = v3(to);
+  H->r.camera.Up = v3(up);
+  H->r.camera.Roll = roll;
+  H->r.camera.Fov = fov;
+  H->r.camera.Focal = focal;
+  H->r.camera.Aspect = aspect;
+  H->r.camera.Radius = radius;
+  return 0;
+}
+
+int orc_set_motion_ref_compat(void* h, int on) {
+  Handle* H = (Handle*)h;
+  for (auto& m : H->r.meshes) m->ref_compat_motion = on != 0;
+  return 0;
+}
+
+int orc_prerender(void* h) {
+  Handle* H = (Handle*)h;
+  return guard([&] { H->r.PreRender(); });
+}
+
+int orc_set_scramble(void* h, const uint64_t* table, int64_t npix) {
+  Handle* H = (Handle*)h;
+  H->r.framescramble.resize(npix);
+  std::memcpy(H->r.framescramble.data(), table, sizeof(pixelscramble) * (size_t)npix);
+  return 0;
+}
+
+int orc_clear_framebuffer(void* h) {
+  Handle* H = (Handle*)h;
+  std::fill(H->r.framebuffer.begin(), H->r.framebuffer.end(), 0.0f);
+  return 0;
+}
+
+// stats: [rays, shadow rays, nanoseconds]
+int orc_render(void* h, int iter_begin, int iter_end, int nthreads, int trace_last_level, float* fb_out, uint64_t* stats) {
+  Handle* H = (Handle*)h;
+  return guard([&] {
+    H->r.trace_last_level = trace_last_level != 0;
+    RenderStats s = H->r.Render(iter_begin, iter_end, nthreads);
+    if (fb_out) std::memcpy(fb_out, H->r.framebuffer.data(), sizeof(float) * H->r.framebuffer.size());
+    if (stats) {
+      stats[0] = s.rayCount;
+      stats[1] = s.shadowRayCount;
+      stats[2] = (uint64_t)(s.seconds * 1e9);
+    }
+  });
+}
+
+// camera rays of iteration `iter1` (1-based, as render() receives it) for the pixel rectangle
+int orc_camera_rays(void* h, int iter1, int x0, int y0, int w, int hh, OrcRay* out) {
+  Handle* H = (Handle*)h;
+  return guard([&] {
+    RenderTask task;
+    task.scene = &H->r.scene;
+    Ray ray;
+    ray.Task = &task;
+    ShaderContext sc;
+    sc.task = &task;
+    size_t n = 0;
+    for (int y = y0; y < y0 + hh; y++)
+      for (int x = x0; x < x0 + w; x++) {
+        H->r.GenerateCameraRay(iter1, x, y, &sc, &ray);
+        OrcRay& o = out[n++];
+        for (int k = 0; k < 3; k++) { o.o[k] = ray.P[k]; o.d[k] = ray.D[k]; }
+        o.tmax = ray.Tclosest;
+        o.time = ray.Time;
+      }
+  });
+}
+
+// flags: bit0 = any-hit (RayTypeShadow). bit1 = brute force over all triangles of every mesh (anchor).
+int orc_trace_batch(void* h, const OrcRay* rays, int64_t n, uint32_t flags, int nthreads, OrcHit* hits) {
+  Handle* H = (Handle*)h;
+  return guard([&] {
+    H->r.PreRender();
+    auto work = [&](int64_t b, int64_t e) {
+      RenderTask task;
+      task.scene = &H->r.scene;
+      for (int64_t i = b; i < e; i++) {
+        Ray ray;
+        ray.Task = &task;
+        ShaderContext sc;
+        sc.task = &task;
+        sc.Time = rays[i].time;
+        ray.Init((flags & 1) ? RayTypeShadow : RayTypeCamera, v3(rays[i].o), v3(rays[i].d), rays[i].tmax, 0, &sc);
+        bool hit;
+        if (flags & 2) {
+          hit = false;
+          for (Geom* g : H->r.scene.geoms) {
+            PolyMesh* pm = static_cast<PolyMesh*>(g);
+            if (pm->TraceBrute(&ray, &sc)) { hit = true; sc.geom = g; }
+          }
+        } else {
+          hit = TraceProbe(&ray, &sc);
+        }
+        OrcHit& o = hits[i];
+        o.nodesT = (int32_t)ray.NodesT;
+        o.trisT = (int32_t)ray.TrisT;
+        if (hit) {
+          o.t = ray.Tclosest; o.u = sc.Bu; o.v = sc.Bv; o.w = sc.Bw;
+          o.prim = (int32_t)sc.ElemID;
+          o.geom = sc.geom ? sc.geom->id : -1;
+        } else {
+          o.t = ray.Tclosest; o.u = o.v = o.w = 0;
+          o.prim = -1; o.geom = -1;
+        }
+      }
+    };
+    if (nthreads <= 1) work(0, n);
+    else {
+      std::vector<std::thread> th;
+      int64_t per = (n + nthreads - 1) / nthreads;
+      for (int t = 0; t < nthreads; t++) {
+        int64_t b = t * per, e = std::min<int64_t>(n, b + per);
+        if (b < e) th.emplace_back(work, b, e);
+      }
+      for (auto& t : th) t.join();
+    }
+  });
+}
+
+// ---- structure export (so tests can compare the product's host builder and upload oracle-built trees) ----
+int orc_num_geoms(void* h) { return (int)((Handle*)h)->r.scene.geoms.size(); }
+// geom id (creation order) of the i-th geom in scene leaf order
+int orc_scene_geom_id(void* h, int i) { return ((Handle*)h)->r.scene.geoms[i]->id; }
+int orc_scene_num_nodes(void* h) {
+  Scene& s = ((Handle*)h)->r.scene;
+  return s.qbvh.empty() ? (int)s.mqbvh.Nodes.size() : (int)s.qbvh.size();
+}
+int orc_scene_is_motion(void* h) { return ((Handle*)h)->r.scene.qbvh.empty() ? 1 : 0; }
+int orc_scene_keys(void* h) { return (int)((Handle*)h)->r.scene.mqbvh.Boxes.size(); }
+int orc_scene_nodes(void* h, void* out) {
+  Scene& s = ((Handle*)h)->r.scene;
+  std::memcpy(out, s.qbvh.data(), s.qbvh.size() * sizeof(Node));
+  return 0;
+}
+int orc_scene_motion_nodes(void* h, void* topo /*40 B each*/, float* boxes /*[key][node][24]*/) {
+  Scene& s = ((Handle*)h)->r.scene;
+  std::memcpy(topo, s.mqbvh.Nodes.data(), s.mqbvh.Nodes.size() * sizeof(MotionNode));
+  size_t nn = s.mqbvh.Nodes.size();
+  for (size_t k = 0; k < s.mqbvh.Boxes.size(); k++) std::memcpy(boxes + k * nn * 24, s.mqbvh.Boxes[k].data(), nn * 96);
+  return 0;
+}
+static PolyMesh* meshById(Handle* H, int id) {
+  for (auto& m : H->r.meshes) if (m->id == id) return m.get();
+  return nullptr;
+}
+int orc_mesh_info(void* h, int id, int32_t* out /* nodes, tris, keys, nverts, is_motion, has_normals */) {
+  PolyMesh* m = meshById((Handle*)h, id);
+  if (!m) return -1;
+  out[0] = m->accel.qbvh.empty() ? (int)m->accel.mqbvh.Nodes.size() : (int)m->accel.qbvh.size();
+  out[1] = m->facecount;
+  out[2] = m->Verts.MotionKeys;
+  out[3] = m->Verts.ElemsPerKey;
+  out[4] = m->accel.qbvh.empty() ? 1 : 0;
+  out[5] = m->Normals.Elems.empty() ? 0 : 1;
+  return 0;
+}
+int orc_mesh_nodes(void* h, int id, void* out) {
+  PolyMesh* m = meshById((Handle*)h, id);
+  std::memcpy(out, m->accel.qbvh.data(), m->accel.qbvh.size() * sizeof(Node));
+  return 0;
+}
+int orc_mesh_motion_nodes(void* h, int id, void* topo, float* boxes) {
+  PolyMesh* m = meshById((Handle*)h, id);
+  std::memcpy(topo, m->accel.mqbvh.Nodes.data(), m->accel.mqbvh.Nodes.size() * sizeof(MotionNode));
+  size_t nn = m->accel.mqbvh.Nodes.size();
+  for (size_t k = 0; k < m->accel.mqbvh.Boxes.size(); k++) std::memcpy(boxes + k * nn * 24, m->accel.mqbvh.Boxes[k].data(), nn * 96);
+  return 0;
+}
+int orc_mesh_idxp(void* h, int id, uint32_t* idxp, int32_t* accel_idx) {
+  PolyMesh* m = meshById((Handle*)h, id);
+  if (idxp) std::memcpy(idxp, m->idxp.data(), m->idxp.size() * 4);
+  if (accel_idx) std::memcpy(accel_idx, m->accel.idx.data(), m->accel.idx.size() * 4);
+  return 0;
+}
+int orc_mesh_bounds(void* h, int id, float* out6) {
+  PolyMesh* m = meshById((Handle*)h, id);
+  std::memcpy(out6, m->bounds.b, 24);
+  return 0;
+}
+int orc_camera_matrix(void* h, float* m16, float* tan_theta_focal, float* aspect) {
+  Handle* H = (Handle*)h;
+  std::memcpy(m16, H->r.camera.M.m, 64);
+  *tan_theta_focal = H->r.camera.TanThetaFocal;
+  *aspect = H->r.camera.Aspect;
+  return 0;
+}
+
+// ---- scalar function probes for unit tests ----
+uint64_t orc_vdc_u(uint64_t i, uint64_t s) { return vanDerCorput_u(i, s); }
+uint64_t orc_sobol_u(uint64_t i, uint64_t s) { return sobol_u(i, s); }
+double orc_vdc(uint64_t i, uint64_t s) { return VanDerCorput(i, s); }
+double orc_sobol(uint64_t i, uint64_t s) { return Sobol(i, s); }
+uint64_t orc_raster_xy(uint32_t frame, uint32_t px, uint32_t py, uint64_t sx, uint64_t sy, double* rx, double* ry) {
+  return RasterXY12(frame, px, py, sx, sy, rx, ry);
+}
+// box test probes: ray = P(3),D(3) ; boxes 24 floats (16-B aligned copy made inside)
+void orc_box_test(const float* P, const float* D, const float* boxes, int which, int32_t* hits, float* t) {
+  Ray ray;
+  ray.P = v3(P);
+  ray.D = v3(D);
+  ray.Setup();
+  alignas(16) float b[24];
+  alignas(16) float tt[4];
+  alignas(16) int32_t hh[4];
+  std::memcpy(b, boxes, 96);
+  if (which == 0) intersectBoxes(&ray, b, hh, tt);
+  else intersectBoxesSlow2(&ray, b, hh, tt);
+  std::memcpy(hits, hh, 16);
+  std::memcpy(t, tt, 16);
+}
+void orc_ray_setup(const float* P, const float* D, float* out /* Dinv3 S3 */, int32_t* k /*Kx Ky Kz*/) {
+  Ray ray;
+  ray.P = v3(P);
+  ray.D = v3(D);
+  ray.Setup();
+  for (int i = 0; i < 3; i++) { out[i] = ray.Dinv[i]; out[3 + i] = ray.S[i]; }
+  k[0] = ray.Kx; k[1] = ray.Ky; k[2] = ray.Kz;
+}
+void orc_normalize(const float* a, float* out) {
+  Vec3 r = Vec3Normalize(v3(a));
+  out[0] = r[0]; out[1] = r[1]; out[2] = r[2];
+}
+void orc_spectrum_roundtrip(const float* rgb, float lambda, float* spec4, float* rgb_out) {
+  Spectrum s;
+  s.Lambda = lambda;
+  s.FromRGB(MakeRGB(rgb[0], rgb[1], rgb[2]));
+  for (int k = 0; k < 4; k++) spec4[k] = s.C[k];
+  RGB o = s.ToRGB();
+  rgb_out[0] = o[0]; rgb_out[1] = o[1]; rgb_out[2] = o[2];
+}
+
+}  // extern "C"

@@ -1,0 +1,700 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY. See scene.h / core.h for the reference files this restates.
+#include "scene.h"
+
+#include <cmath>
+
+#include "ldseq.h"
+
+namespace orc {
+
+// ---------------------------------------------------------------------------------------------
+// core/ray.go:103-148
+void Ray::Setup() {
+  Kz = 0;
+  if (Abs(D[1]) > Abs(D[2])) {
+    if (Abs(D[1]) > Abs(D[0])) Kz = 1;
+  } else {
+    if (Abs(D[2]) > Abs(D[0])) Kz = 2;
+  }
+  Kx = Kz + 1;
+  if (Kx == 3) Kx = 0;
+  Ky = Kx + 1;
+  if (Ky == 3) Ky = 0;
+  if (D[Kz] < 0.0f) {
+    int32_t tmp = Kx;
+    Kx = Ky;
+    Ky = tmp;
+  }
+  double z = (double)D[Kz];
+  S[2] = (float)(1.0 / z);
+  S[0] = (float)((double)D[Kx] / z);
+  S[1] = (float)((double)D[Ky] / z);
+  Dinv[0] = (float)(1.0 / (double)D[0]);
+  Dinv[1] = (float)(1.0 / (double)D[1]);
+  Dinv[2] = (float)(1.0 / (double)D[2]);
+}
+
+// core/ray.go:56-93 (differentials omitted)
+void Ray::Init(uint32_t ty, Vec3 P_, Vec3 D_, float maxdist, uint8_t level, const ShaderContext* sc) {
+  P = P_;
+  D = D_;
+  Tclosest = maxdist;
+  Type = ty;
+  Setup();
+  Level = level;
+  Lambda = sc->Lambda;
+  Time = sc->Time;
+  NodesT = 0;
+  LeafsT = 0;
+  TrisT = 0;
+  Scramble[0] = sc->Scramble[0];
+  Scramble[1] = sc->Scramble[1];
+  I = sc->I;
+}
+
+// ---------------------------------------------------------------------------------------------
+// builtin/geom/polymesh/init.go:12-134
+void PolyMesh::init() {
+  const bool hasNormals = !Normals.Elems.empty();
+  if (hasPolyCount) {
+    uint32_t basei = 0;
+    for (size_t k = 0; k < PolyCount.size(); k++) {
+      uint32_t i = 0;
+      for (int j = 0; j < (int)(PolyCount[k] - 2); j++) {
+        i++;
+        idxp.push_back((uint32_t)FaceIdx[basei]);
+        idxp.push_back((uint32_t)FaceIdx[basei + i]);
+        idxp.push_back((uint32_t)FaceIdx[basei + i + 1]);
+        if (hasNormals) {
+          const std::vector<int32_t>& src = hasNormalIdx ? NormalIdx : FaceIdx;
+          normalidx.push_back((uint32_t)src[basei]);
+          normalidx.push_back((uint32_t)src[basei + i]);
+          normalidx.push_back((uint32_t)src[basei + i + 1]);
+        }
+        if (!ShaderIdx.empty()) shaderidx.push_back((uint8_t)ShaderIdx[k]);
+      }
+      basei += (uint32_t)PolyCount[k];
+    }
+  } else {
+    if (hasFaceIdx) {
+      for (size_t j = 0; j < FaceIdx.size(); j++) {
+        idxp.push_back((uint32_t)FaceIdx[j]);
+        if (hasNormals) normalidx.push_back(hasNormalIdx ? (uint32_t)NormalIdx[j] : (uint32_t)FaceIdx[j]);
+      }
+    } else {
+      for (int j = 0; j < Verts.ElemsPerKey; j++) {
+        idxp.push_back((uint32_t)j);
+        if (hasNormals) normalidx.push_back(hasNormalIdx ? (uint32_t)NormalIdx[j] : (uint32_t)j);
+      }
+    }
+    for (int32_t idx : ShaderIdx) shaderidx.push_back((uint8_t)idx);
+  }
+  FaceIdx.clear();
+  PolyCount.clear();
+  NormalIdx.clear();
+  ShaderIdx.clear();
+}
+
+// builtin/geom/polymesh/buildqbvh.go:14-144
+void PolyMesh::initAccel() {
+  std::vector<BoundingBox> boxes(facecount);
+  std::vector<Vec3> centroids(facecount);
+  std::vector<int32_t> idxs(facecount);
+
+  if (Verts.MotionKeys > 1) {
+    float k = 0.5f * (float)(Verts.MotionKeys - 1);
+    float time = k - Floor(k);
+    int key = (int)Floor(k);
+    int key2 = (int)Ceil(k);
+    for (int i = 0; i < facecount; i++) {
+      Vec3 V0 = Vec3Lerp(Verts.Elems[(int)idxp[i * 3 + 0] + Verts.ElemsPerKey * key], Verts.Elems[(int)idxp[i * 3 + 0] + Verts.ElemsPerKey * key2], time);
+      Vec3 V1 = Vec3Lerp(Verts.Elems[(int)idxp[i * 3 + 1] + Verts.ElemsPerKey * key], Verts.Elems[(int)idxp[i * 3 + 1] + Verts.ElemsPerKey * key2], time);
+      Vec3 V2 = Vec3Lerp(Verts.Elems[(int)idxp[i * 3 + 2] + Verts.ElemsPerKey * key], Verts.Elems[(int)idxp[i * 3 + 2] + Verts.ElemsPerKey * key2], time);
+      boxes[i].Reset();
+      boxes[i].GrowVec3(V0);
+      boxes[i].GrowVec3(V1);
+      boxes[i].GrowVec3(V2);
+      for (int c = 0; c < 3; c++) centroids[i][c] = (V0[c] + V1[c] + V2[c]) / 3;
+      idxs[i] = (int32_t)i;
+    }
+    accel.mqbvh.Nodes = BuildAccelMotion(boxes.data(), centroids.data(), idxs.data(), facecount, 16);
+    accel.idx = idxs;
+    initMotionBoxes();
+    return;
+  }
+
+  for (int i = 0; i < facecount; i++) {
+    Vec3 V0 = Verts.Elems[(int)idxp[i * 3 + 0]];
+    Vec3 V1 = Verts.Elems[(int)idxp[i * 3 + 1]];
+    Vec3 V2 = Verts.Elems[(int)idxp[i * 3 + 2]];
+    boxes[i].Reset();
+    boxes[i].GrowVec3(V0);
+    boxes[i].GrowVec3(V1);
+    boxes[i].GrowVec3(V2);
+    for (int c = 0; c < 3; c++) centroids[i][c] = (V0[c] + V1[c] + V2[c]) / 3;
+    idxs[i] = (int32_t)i;
+  }
+
+  accel.qbvh = BuildAccel(boxes.data(), centroids.data(), idxs.data(), facecount, 16, &bounds);
+  accel.idx = idxs;
+
+  std::vector<uint32_t> nidxp(idxp.size());
+  for (size_t i = 0; i < idxs.size(); i++) {
+    nidxp[i * 3 + 0] = idxp[idxs[i] * 3 + 0];
+    nidxp[i * 3 + 1] = idxp[idxs[i] * 3 + 1];
+    nidxp[i * 3 + 2] = idxp[idxs[i] * 3 + 2];
+  }
+  if (!shaderidx.empty()) {
+    std::vector<uint8_t> ns(shaderidx.size());
+    for (size_t i = 0; i < idxs.size(); i++) ns[i] = shaderidx[idxs[i]];
+    shaderidx = ns;
+  }
+  if (!normalidx.empty()) {
+    std::vector<uint32_t> nn(normalidx.size());
+    for (size_t i = 0; i < idxs.size(); i++) {
+      nn[i * 3 + 0] = normalidx[idxs[i] * 3 + 0];
+      nn[i * 3 + 1] = normalidx[idxs[i] * 3 + 1];
+      nn[i * 3 + 2] = normalidx[idxs[i] * 3 + 2];
+    }
+    normalidx = nn;
+  }
+  idxp = nidxp;
+}
+
+// builtin/geom/polymesh/buildqbvh.go:148-169
+void PolyMesh::initMotionBoxes() {
+  if (Verts.MotionKeys < 2) throw std::runtime_error("initMotionBoxes: can't init with < 2 motion keys");
+  accel.mqbvh.Boxes.assign(Verts.MotionKeys, {});
+  BoundingBox fullbox;
+  fullbox.Reset();
+  for (int k = 0; k < Verts.MotionKeys; k++) {
+    accel.mqbvh.Boxes[k].assign(accel.mqbvh.Nodes.size(), MotionNodeBoxes{});
+    BoundingBox box = initMotionBoxesRec(k, 0);
+    motionBounds.push_back(box);
+    fullbox.GrowBox(box);
+  }
+  bounds = fullbox;
+}
+
+// builtin/geom/polymesh/buildqbvh.go:171-212
+BoundingBox PolyMesh::initMotionBoxesRec(int key, int32_t node) {
+  BoundingBox nodebox;
+  nodebox.Reset();
+  for (int k = 0; k < 4; k++) {
+    int32_t ch = accel.mqbvh.Nodes[node].Children[k];
+    if (ch < 0) {
+      if (ch == -1) continue;
+      BoundingBox box;
+      box.Reset();
+      int leafBase = LeafBase(ch);
+      int leafCount = LeafCount(ch);
+      for (int i = leafBase; i < leafBase + leafCount; i++) {
+        int faceidx = (int)accel.idx[i];
+        box.GrowVec3(Verts.Elems[(int)idxp[faceidx * 3 + 0] + (Verts.ElemsPerKey * key)]);
+        box.GrowVec3(Verts.Elems[(int)idxp[faceidx * 3 + 1] + (Verts.ElemsPerKey * key)]);
+        box.GrowVec3(Verts.Elems[(int)idxp[faceidx * 3 + 2] + (Verts.ElemsPerKey * key)]);
+      }
+      accel.mqbvh.Boxes[key][node].SetBounds(k, box);
+      nodebox.GrowBox(box);
+    } else {
+      BoundingBox box = initMotionBoxesRec(key, ch);
+      accel.mqbvh.Boxes[key][node].SetBounds(k, box);
+      nodebox.GrowBox(box);
+    }
+  }
+  return nodebox;
+}
+
+// builtin/geom/polymesh/bounds.go:25-53
+BoundingBox PolyMesh::Bounds(float time) const {
+  if (!accel.qbvh.empty()) return bounds;
+  float k = time * (float)((int)motionBounds.size() - 1);
+  float t = k - Floor(k);
+  int key = (int)Floor(k);
+  int key2 = (int)Ceil(k);
+  return BoundingBoxLerp(motionBounds[key], motionBounds[key2], t);
+}
+
+// builtin/geom/polymesh/trace.go:15-104 (object Transform path out of scope)
+bool PolyMesh::Trace(Ray* ray, ShaderContext* sg) {
+  if (!accel.qbvh.empty()) return QTrace(accel.qbvh, this, ray, sg);
+  float k = ray->Time * (float)(Verts.MotionKeys - 1);
+  float time = k - Floor(k);
+  int key = (int)Floor(k);
+  int key2 = (int)Ceil(k);
+  return QTraceMotion(accel.mqbvh, time, key, key2, this, ray, sg);
+}
+
+// The watertight edge functions of trace.go:127-155 for one triangle; returns false if rejected.
+// Shared by the static (bias test `<`, eps+RayBias) and motion (`<=`, RayBias) variants.
+static inline bool triTest(const Ray* ray, const Vec3& P0, const Vec3& P1, const Vec3& P2, float biasTerm, bool motionBias,
+                           float* U, float* V, float* W, float* Tout) {
+  const int Kx = ray->Kx, Ky = ray->Ky, Kz = ray->Kz;
+  float AKz = P0[Kz] - ray->P[Kz];
+  float BKz = P1[Kz] - ray->P[Kz];
+  float CKz = P2[Kz] - ray->P[Kz];
+  float fU, fV, fW;
+  {
+    float Cx = (P2[Kx] - ray->P[Kx]) - ray->S[0] * CKz;
+    float By = (P1[Ky] - ray->P[Ky]) - ray->S[1] * BKz;
+    float Cy = (P2[Ky] - ray->P[Ky]) - ray->S[1] * CKz;
+    float Bx = (P1[Kx] - ray->P[Kx]) - ray->S[0] * BKz;
+    float Ax = (P0[Kx] - ray->P[Kx]) - ray->S[0] * AKz;
+    float Ay = (P0[Ky] - ray->P[Ky]) - ray->S[1] * AKz;
+    fU = Cx * By - Cy * Bx;
+    fV = Ax * Cy - Ay * Cx;
+    fW = Bx * Ay - By * Ax;
+    if (fU == 0.0f || fV == 0.0f || fW == 0.0f) {
+      double CxBy = (double)Cx * (double)By;
+      double CyBx = (double)Cy * (double)Bx;
+      fU = (float)(CxBy - CyBx);
+      double AxCy = (double)Ax * (double)Cy;
+      double AyCx = (double)Ay * (double)Cx;
+      fV = (float)(AxCy - AyCx);
+      double BxAy = (double)Bx * (double)Ay;
+      double ByAx = (double)By * (double)Ax;
+      fW = (float)(BxAy - ByAx);
+    }
+  }
+  if ((fU < 0.0f || fV < 0.0f || fW < 0.0f) && (fU > 0.0f || fV > 0.0f || fW > 0.0f)) return false;
+  float det = fU + fV + fW;
+  if (det == 0.0f) return false;
+  float T = ray->S[2] * (fU * AKz + fV * BKz + fW * CKz);
+  uint32_t detSign = SignMask(det);
+  if (!motionBias) {
+    if (Xorf(T, detSign) < biasTerm * Xorf(det, detSign) || Xorf(T, detSign) > ray->Tclosest * Xorf(det, detSign)) return false;
+  } else {
+    if (Xorf(T, detSign) <= biasTerm * Xorf(det, detSign) || Xorf(T, detSign) > ray->Tclosest * Xorf(det, detSign)) return false;
+  }
+  float rcpDet = 1.0f / det;
+  *U = fU * rcpDet;
+  *V = fV * rcpDet;
+  *W = fW * rcpDet;
+  *Tout = T * rcpDet;
+  return true;
+}
+
+// builtin/geom/polymesh/trace.go:108-194 (intersection) + :276-360, :504-515 (hit record).
+// mesh.idxp is always non-nil after init(), so the `else` branch (:195-270) is dead and not restated.
+bool PolyMesh::TraceElems(Ray* ray, ShaderContext* sg, int base, int count) {
+  int32_t idx = -1;
+  float U = 0, V = 0, W = 0;
+  ray->TrisT += count;
+  const float biasTerm = kEpsilonFloat32 + RayBias;
+  for (int i = base; i < base + count; i++) {
+    int i0 = (int)idxp[i * 3 + 0], i1 = (int)idxp[i * 3 + 1], i2 = (int)idxp[i * 3 + 2];
+    float u, v, w, t;
+    if (!triTest(ray, Verts.Elems[i0], Verts.Elems[i1], Verts.Elems[i2], biasTerm, false, &u, &v, &w, &t)) continue;
+    U = u; V = v; W = w;
+    ray->Tclosest = t;
+    idx = (int32_t)i;
+  }
+  if (idx == -1) return false;
+
+  int32_t i0 = (int32_t)idxp[idx * 3 + 0], i1 = (int32_t)idxp[idx * 3 + 1], i2 = (int32_t)idxp[idx * 3 + 2];
+  const Vec3& E0 = Verts.Elems[i0];
+  const Vec3& E1 = Verts.Elems[i1];
+  const Vec3& E2 = Verts.Elems[i2];
+
+  float xAbsSum = Abs(U * E0[0]) + Abs(V * E1[0]) + Abs(W * E2[0]);
+  float yAbsSum = Abs(U * E0[1]) + Abs(V * E1[1]) + Abs(W * E2[1]);
+  float zAbsSum = Abs(U * E0[2]) + Abs(V * E1[2]) + Abs(W * E2[2]);
+
+  uint8_t shaderIdx = 0;
+  if (!shaderidx.empty()) shaderIdx = shaderidx[idx];
+  sg->shader = shader.empty() ? nullptr : shader[shaderIdx];
+
+  float e00 = E1[0] - E0[0], e01 = E1[1] - E0[1], e02 = E1[2] - E0[2];
+  float e10 = E2[0] - E0[0], e11 = E2[1] - E0[1], e12 = E2[2] - E0[2];
+
+  sg->Ng[0] = e01 * e12 - e02 * e11;
+  sg->Ng[1] = e02 * e10 - e00 * e12;
+  sg->Ng[2] = e00 * e11 - e01 * e10;
+  sg->Ng = Vec3Normalize(sg->Ng);
+
+  if (!Normals.Elems.empty()) {
+    for (int k = 0; k < 3; k++)
+      sg->N[k] = U * Normals.Elems[normalidx[(idx * 3) + 0]][k] + V * Normals.Elems[normalidx[(idx * 3) + 1]][k] + W * Normals.Elems[normalidx[(idx * 3) + 2]][k];
+    sg->N = Vec3Normalize(sg->N);
+  } else {
+    sg->N = sg->Ng;
+  }
+
+  float d = Gamma(7) * xAbsSum * Abs(sg->Ng[0]) + Gamma(7) * yAbsSum * Abs(sg->Ng[1]) + Gamma(7) * zAbsSum * Abs(sg->Ng[2]);
+  sg->Poffset = Vec3Scale(d, sg->Ng);
+  sg->Bu = U;
+  sg->Bv = V;
+  sg->Bw = W;
+  for (int k = 0; k < 3; k++) sg->P[k] = U * E0[k] + V * E1[k] + W * E2[k];
+  sg->Po = sg->P;
+
+  // trace.go:504-511
+  Vec3 axisu = Vec3Sub(V3(1, 0, 0), Vec3Scale(Vec3Dot(V3(1, 0, 0), sg->Ng), sg->Ng));
+  if (Vec3Length2(axisu) < 0.1f || Abs(Vec3Dot(axisu, sg->Ng)) > 0.3f)
+    axisu = Vec3Sub(V3(0, 0, 1), Vec3Scale(Vec3Dot(V3(0, 0, 1), sg->Ng), sg->Ng));
+  sg->DdPdu = Vec3Normalize(axisu);
+  sg->DdPdv = Vec3Cross(sg->Ng, sg->DdPdu);
+  sg->ElemID = (uint32_t)idx;
+  return true;
+}
+
+// Brute force: every triangle in leaf order through the same routine (one "leaf" of facecount tris).
+bool PolyMesh::TraceBrute(Ray* ray, ShaderContext* sg) {
+  bool hit = false;
+  if (Verts.MotionKeys > 1) {
+    float k = ray->Time * (float)(Verts.MotionKeys - 1);
+    float time = k - Floor(k);
+    int key = (int)Floor(k), key2 = (int)Ceil(k);
+    // iterate in leaf order so that "fixed" mode visits faces accel.idx[i]
+    return TraceMotionElems(time, key, key2, ray, sg, 0, facecount);
+  }
+  for (int b = 0; b < facecount; b += 16) {
+    int c = facecount - b < 16 ? facecount - b : 16;
+    if (TraceElems(ray, sg, b, c)) hit = true;
+  }
+  return hit;
+}
+
+// builtin/geom/polymesh/trace.go:520-719
+bool PolyMesh::TraceMotionElems(float time, int key, int key2, Ray* ray, ShaderContext* sg, int base, int count) {
+  int32_t idx = -1;
+  float U = 0, V = 0, W = 0;
+  ray->TrisT += count;
+  for (int i = base; i < base + count; i++) {
+    int32_t faceidx = (int32_t)i;
+    int i0, i1, i2;
+    if (ref_compat_motion) {
+      // trace.go:532-537: idxp != nil, so face i is tested although the leaf box bounds face accel.idx[i] (quirk b)
+      i0 = (int)idxp[i * 3 + 0]; i1 = (int)idxp[i * 3 + 1]; i2 = (int)idxp[i * 3 + 2];
+    } else {
+      faceidx = accel.idx[i];
+      i0 = (int)idxp[faceidx * 3 + 0]; i1 = (int)idxp[faceidx * 3 + 1]; i2 = (int)idxp[faceidx * 3 + 2];
+    }
+    Vec3 V0 = Vec3Lerp(Verts.Elems[i0 + Verts.ElemsPerKey * key], Verts.Elems[i0 + Verts.ElemsPerKey * key2], time);
+    Vec3 V1 = Vec3Lerp(Verts.Elems[i1 + Verts.ElemsPerKey * key], Verts.Elems[i1 + Verts.ElemsPerKey * key2], time);
+    Vec3 V2 = Vec3Lerp(Verts.Elems[i2 + Verts.ElemsPerKey * key], Verts.Elems[i2 + Verts.ElemsPerKey * key2], time);
+
+    float u, v, w, t;
+    if (!triTest(ray, V0, V1, V2, RayBias, true, &u, &v, &w, &t)) continue;
+    U = u; V = v; W = w;
+    ray->Tclosest = t;
+    idx = faceidx;
+
+    for (int k = 0; k < 3; k++) sg->Po[k] = U * V0[k] + V * V1[k] + W * V2[k];
+    float xAbsSum = Abs(U * V0[0]) + Abs(V * V1[0]) + Abs(W * V2[0]);
+    float yAbsSum = Abs(U * V0[1]) + Abs(V * V1[1]) + Abs(W * V2[1]);
+    float zAbsSum = Abs(U * V0[2]) + Abs(V * V1[2]) + Abs(W * V2[2]);
+    float e00 = V1[0] - V0[0], e01 = V1[1] - V0[1], e02 = V1[2] - V0[2];
+    float e10 = V2[0] - V0[0], e11 = V2[1] - V0[1], e12 = V2[2] - V0[2];
+    sg->Ng[0] = e01 * e12 - e02 * e11;
+    sg->Ng[1] = e02 * e10 - e00 * e12;
+    sg->Ng[2] = e00 * e11 - e01 * e10;
+    sg->Ng = Vec3Normalize(sg->Ng);
+    sg->DdPdu = V3(e00, e01, e02);
+    sg->DdPdv = V3(e10, e11, e12);
+    float d = Gamma(7) * xAbsSum * Abs(sg->Ng[0]) + Gamma(7) * yAbsSum * Abs(sg->Ng[1]) + Gamma(7) * zAbsSum * Abs(sg->Ng[2]);
+    sg->Poffset = Vec3Scale(d, sg->Ng);
+    sg->Bu = U;
+    sg->Bv = V;
+    sg->Bw = W;
+  }
+  if (idx == -1) return false;
+
+  uint8_t shaderIdx = 0;
+  if (!shaderidx.empty()) shaderIdx = shaderidx[idx];
+  sg->shader = shader.empty() ? nullptr : shader[shaderIdx];
+  sg->P = sg->Po;
+
+  if (!Normals.Elems.empty() && Normals.MotionKeys == Verts.MotionKeys) {
+    Vec3 N0 = Vec3Lerp(Normals.Elems[(int)((idx * 3) + 0) + Normals.ElemsPerKey * key], Normals.Elems[(int)((idx * 3) + 0) + Normals.ElemsPerKey * key2], time);
+    Vec3 N1 = Vec3Lerp(Normals.Elems[(int)((idx * 3) + 1) + Normals.ElemsPerKey * key], Normals.Elems[(int)((idx * 3) + 1) + Normals.ElemsPerKey * key2], time);
+    Vec3 N2 = Vec3Lerp(Normals.Elems[(int)((idx * 3) + 2) + Normals.ElemsPerKey * key], Normals.Elems[(int)((idx * 3) + 2) + Normals.ElemsPerKey * key2], time);
+    for (int k = 0; k < 3; k++) sg->N[k] = U * N0[k] + V * N1[k] + W * N2[k];
+    sg->N = Vec3Normalize(sg->N);
+  } else {
+    sg->N = sg->Ng;
+  }
+  sg->ElemID = (uint32_t)idx;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// builtin/scene/scene.go:30-59
+bool Scene::Trace(Ray* ray, ShaderContext* sg) {
+  if (!qbvh.empty()) return QTrace(qbvh, this, ray, sg);
+  float k = ray->Time * (float)((int)mqbvh.Boxes.size() - 1);
+  float time = k - Floor(k);
+  int key = (int)Floor(k);
+  int key2 = (int)Ceil(k);
+  return QTraceMotion(mqbvh, time, key, key2, this, ray, sg);
+}
+
+// builtin/scene/scene.go:61-78
+bool Scene::TraceElems(Ray* ray, ShaderContext* sc, int base, int count) {
+  bool hit = false;
+  for (int i = base; i < base + count; i++) {
+    if (geoms[i]->Trace(ray, sc)) {
+      sc->geom = geoms[i];
+      hit = true;
+      if (ray->Type & RayTypeShadow) return true;
+    }
+  }
+  return hit;
+}
+bool Scene::TraceMotionElems(float, int, int, Ray* ray, ShaderContext* sc, int base, int count) {
+  return TraceElems(ray, sc, base, count);
+}
+
+// builtin/scene/scene.go:100-116
+void Scene::LightsPrepare(ShaderContext* sg) {
+  sg->Lights.clear();
+  for (Light* l : lights) {
+    if (l->GetGeom() != sg->geom) sg->Lights.push_back(l);
+  }
+}
+
+// builtin/scene/scene.go:135-203
+void Scene::initAccel() {
+  std::vector<BoundingBox> boxes;
+  std::vector<int32_t> indices;
+  std::vector<Vec3> centroids;
+  int maxKeys = 0;
+  for (Geom* g : geoms) if (g->MotionKeys() > maxKeys) maxKeys = g->MotionKeys();
+
+  if (maxKeys == 1) {
+    for (size_t i = 0; i < geoms.size(); i++) {
+      BoundingBox box = geoms[i]->Bounds(0);
+      boxes.push_back(box);
+      indices.push_back((int32_t)i);
+      centroids.push_back(box.Centroid());
+    }
+    qbvh = BuildAccel(boxes.data(), centroids.data(), indices.data(), (int)indices.size(), 1, &bounds);
+    std::vector<Geom*> ngeoms(indices.size());
+    for (size_t i = 0; i < indices.size(); i++) ngeoms[i] = geoms[indices[i]];
+    geoms = ngeoms;
+  } else {
+    for (size_t i = 0; i < geoms.size(); i++) {
+      BoundingBox box = geoms[i]->Bounds(0.5f);
+      boxes.push_back(box);
+      indices.push_back((int32_t)i);
+      centroids.push_back(box.Centroid());
+    }
+    mqbvh.Nodes = BuildAccelMotion(boxes.data(), centroids.data(), indices.data(), (int)indices.size(), 1);
+    std::vector<Geom*> ngeoms(indices.size());
+    for (size_t i = 0; i < indices.size(); i++) ngeoms[i] = geoms[indices[i]];
+    geoms = ngeoms;
+    bounds.Reset();
+    initMotionBoxes(maxKeys);
+  }
+}
+
+// builtin/scene/scene.go:207-226
+void Scene::initMotionBoxes(int keys) {
+  if (keys < 2) throw std::runtime_error("s.initMotionBoxes: can't init with < 2 motion keys");
+  mqbvh.Boxes.assign(keys, {});
+  BoundingBox fullbox;
+  fullbox.Reset();
+  for (int k = 0; k < keys; k++) {
+    mqbvh.Boxes[k].assign(mqbvh.Nodes.size(), MotionNodeBoxes{});
+    BoundingBox box = initMotionBoxesRec(k, 0);
+    fullbox.GrowBox(box);
+  }
+  bounds = fullbox;
+}
+
+// builtin/scene/scene.go:228-268
+BoundingBox Scene::initMotionBoxesRec(int key, int32_t node) {
+  BoundingBox nodebox;
+  nodebox.Reset();
+  for (int k = 0; k < 4; k++) {
+    int32_t ch = mqbvh.Nodes[node].Children[k];
+    if (ch < 0) {
+      if (ch == -1) continue;
+      BoundingBox box;
+      box.Reset();
+      int leafBase = LeafBase(ch);
+      int leafCount = LeafCount(ch);
+      for (int i = leafBase; i < leafBase + leafCount; i++) {
+        float time = (float)key / (float)((int)mqbvh.Boxes.size() - 1);
+        box.GrowBox(geoms[i]->Bounds(time));
+      }
+      mqbvh.Boxes[key][node].SetBounds(k, box);
+      nodebox.GrowBox(box);
+    } else {
+      BoundingBox box = initMotionBoxesRec(key, ch);
+      mqbvh.Boxes[key][node].SetBounds(k, box);
+      nodebox.GrowBox(box);
+    }
+  }
+  return nodebox;
+}
+
+// ---------------------------------------------------------------------------------------------
+// core/trace.go:26-35
+bool TraceProbe(Ray* ray, ShaderContext* sg) {
+  ray->Task->rayCount++;
+  if (ray->Type & RayTypeShadow) ray->Task->shadowRayCount++;
+  return ray->Task->scene->Trace(ray, sg);
+}
+
+// core/trace.go:40-83
+bool Trace(Ray* ray, TraceSample* samp) {
+  ShaderContext sg;
+  sg.Ro = ray->P;
+  sg.Rd = ray->D;
+  sg.Level = ray->Level;
+  sg.Lambda = ray->Lambda;
+  sg.I = ray->I;
+  sg.Time = ray->Time;
+  sg.task = ray->Task;
+  sg.Scramble[0] = ray->Scramble[0];
+  sg.Scramble[1] = ray->Scramble[1];
+
+  if (TraceProbe(ray, &sg)) {
+    if (sg.shader == nullptr) return false;
+    sg.ApplyTransform();
+    sg.shader->Eval(&sg);
+    if (samp != nullptr) {
+      samp->Colour = sg.OutRGB;
+      samp->Point = sg.P;
+      samp->ElemID = sg.ElemID;
+      samp->geom = sg.geom;
+    }
+    return true;
+  }
+  return false;
+}
+
+// core/shader.go:129-135 with Transform = InvTransform = identity (object transforms out of scope):
+// the matrix products are exact, the re-normalisations are kept.
+void ShaderContext::ApplyTransform() {
+  P = Po;
+  N = Vec3Normalize(N);
+  Ng = Vec3Normalize(Ng);
+  DdPdu = Vec3Normalize(DdPdu);
+  DdPdv = Vec3Normalize(DdPdv);
+}
+
+// core/shader.go:139-162
+Vec3 ShaderContext::OffsetP(int dir) const {
+  Vec3 pofs = dir < 0 ? Vec3Neg(Poffset) : Poffset;
+  Vec3 po = Vec3Add(P, pofs);
+  for (int i = 0; i < 3; i++) {
+    if (pofs[i] > 0) po[i] = NextFloatUp(po[i]);
+    else if (pofs[i] < -0.0f) po[i] = NextFloatDown(po[i]);
+  }
+  return po;
+}
+
+// core/shader.go:166-176
+void ShaderContext::LightsPrepare() {
+  task->scene->LightsPrepare(this);
+  Lidx = -1;
+  Lsamples.clear();
+}
+
+// core/shader.go:179-197
+bool ShaderContext::NextLight() {
+  Lidx++;
+  if (Lidx < (int)Lights.size()) {
+    Lp = Lights[Lidx];
+    NSamples = Lp->NumSamples(this);
+    if (Level > 0) NSamples = 1;
+    return true;
+  }
+  return false;
+}
+
+// core/shader.go:203-402
+RGB ShaderContext::EvaluateLightSamples(BSDF* bsdf) {
+  std::vector<BSDFSample> bsdfSamples;
+  RGB col;
+
+  if (NSamples > 1) {
+    for (int i = 0; i < NSamples / 2; i++) {
+      uint64_t idx = (uint64_t)(I * (NSamples / 2) + i);
+      double r0 = VanDerCorput(idx, Scramble[0]);
+      double r1 = Sobol(idx, Scramble[1]);
+      Vec3 omegaO = Vec3Normalize(bsdf->Sample(r0, r1));
+      BSDFSample s{};
+      s.D = omegaO;
+      s.Pdf = bsdf->PDF(omegaO);
+      if (s.Pdf <= 0) continue;
+      if (Lp->ValidSample(this, &s)) bsdfSamples.push_back(s);
+    }
+    Lsamples.clear();
+    Lp->SampleArea(this, NSamples / 2);
+
+    int nBSDFSamples = NSamples / 2;
+    int nLightSamples = NSamples / 2;
+    if (Lsamples.empty()) nLightSamples = 0;
+    if (bsdfSamples.empty()) nBSDFSamples = 0;
+    int totalSamples = nBSDFSamples + nLightSamples;
+    if (totalSamples == 0) return RGB{};
+
+    Ray ray;
+    ray.Task = task;
+    ShaderContext chsc;
+    chsc.task = task;
+
+    for (const LightSample& ls : Lsamples) {
+      if (Vec3Dot(ls.Ld, N) <= 0) continue;
+      if (Vec3Dot(ls.Ld, Ng) < 0)
+        ray.Init(RayTypeShadow, OffsetP(-1), Vec3Scale(ls.Ldist * (1.0f - ShadowRayEpsilon), ls.Ld), 1.0f, 0, this);
+      else
+        ray.Init(RayTypeShadow, OffsetP(1), Vec3Scale(ls.Ldist * (1.0f - ShadowRayEpsilon), ls.Ld), 1.0f, 0, this);
+      if (!TraceProbe(&ray, &chsc)) {
+        Spectrum rho = bsdf->Eval(ls.Ld);
+        rho.Mul(ls.Liu);
+        float p_hat = (float)nBSDFSamples * (float)bsdf->PDF(ls.Ld) / (float)totalSamples;
+        p_hat += (float)nLightSamples * ls.Pdf / (float)totalSamples;
+        rho.Scale(1.0f / p_hat);
+        RGB rgb = rho.ToRGB();
+        for (int k = 0; k < 3; k++) if (rgb[k] < 0) rgb[k] = 0;
+        col.Add(rgb);
+      }
+    }
+    for (const BSDFSample& bs : bsdfSamples) {
+      if (Vec3Dot(bs.Ld, N) <= 0) continue;
+      if (Vec3Dot(bs.Ld, Ng) < 0)
+        ray.Init(RayTypeShadow, OffsetP(-1), Vec3Scale(bs.Ldist * (1.0f - ShadowRayEpsilon), bs.Ld), 1.0f, 0, this);
+      else
+        ray.Init(RayTypeShadow, OffsetP(1), Vec3Scale(bs.Ldist * (1.0f - ShadowRayEpsilon), bs.Ld), 1.0f, 0, this);
+      if (!TraceProbe(&ray, &chsc)) {
+        Spectrum rho = bsdf->Eval(bs.Ld);
+        rho.Mul(bs.Liu);
+        float p_hat = (float)nBSDFSamples * (float)bs.Pdf / (float)totalSamples;
+        p_hat += (float)nLightSamples * bs.PdfLight / (float)totalSamples;
+        rho.Scale(1.0f / p_hat);
+        RGB rgb = rho.ToRGB();
+        for (int k = 0; k < 3; k++) if (rgb[k] < 0) rgb[k] = 0;
+        col.Add(rgb);
+      }
+    }
+    col.Scale(1.0f / (float)totalSamples);
+  } else {
+    Lsamples.clear();
+    Lp->SampleArea(this, NSamples);
+    for (const LightSample& ls : Lsamples) {
+      Ray ray;
+      ray.Task = task;
+      ShaderContext chsc;
+      chsc.task = task;
+      if (Vec3Dot(ls.Ld, N) <= 0) continue;
+      if (Vec3Dot(ls.Ld, Ng) < 0)
+        ray.Init(RayTypeShadow, OffsetP(-1), Vec3Scale(ls.Ldist * (1.0f - ShadowRayEpsilon), ls.Ld), 1.0f, 0, this);
+      else
+        ray.Init(RayTypeShadow, OffsetP(1), Vec3Scale(ls.Ldist * (1.0f - ShadowRayEpsilon), ls.Ld), 1.0f, 0, this);
+      if (!TraceProbe(&ray, &chsc)) {
+        Spectrum rho = bsdf->Eval(ls.Ld);
+        rho.Mul(ls.Liu);
+        rho.Scale(1.0f / ls.Pdf);
+        RGB rgb = rho.ToRGB();
+        col.Add(rgb);
+      }
+    }
+  }
+  return col;
+}
+
+}  // namespace orc

@@ -1,0 +1,581 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY. See shading.h for the reference files this restates.
+#include "shading.h"
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <stdexcept>
+#include <thread>
+
+#include "ldseq.h"
+
+namespace orc {
+
+static inline float sqr(float x) { return x * x; }
+
+// ---------------------------------------------------------------------------------------------
+// math/sample/sample.go:18-27
+static Vec3 CosineHemisphere(double u0, double u1) {
+  double r = std::sqrt(1 - u0);
+  double theta = 2 * M_PI * u1;
+  double x = r * std::cos(theta);
+  double y = r * std::sin(theta);
+  return V3((float)x, (float)y, (float)std::sqrt(u0));
+}
+
+// math/sample/sample.go:105-129
+static void UniformDisk2D(float radius, float r0, float r1, float* xo, float* yo) {
+  float x = -1 + 2 * r0;
+  float y = -1 + 2 * r1;
+  float r = 0, theta = 0;
+  if (x > -y && x > y) {
+    r = x;
+    theta = (kPi / 4) * y / x;
+  } else if (x > -y && x < y) {
+    r = y;
+    theta = (kPi / 4) * (2 - x / y);
+  } else if (x < y && x < -y) {
+    r = -x;
+    theta = (kPi / 4) * (4 + y / x);
+  } else if (x > y && x < -y) {
+    r = -y;
+    theta = (kPi / 4) * (6 - x / y);
+  }
+  *xo = radius * r * Cos(theta);
+  *yo = radius * r * Sin(theta);
+}
+
+// builtin/shader/bsdf/orennayar.go:16-73
+struct OrenNayar : BSDF {
+  float Lambda;
+  Vec3 OmegaI;
+  float Roughness;
+  Vec3 U, V, N;
+  OrenNayar(float lambda, Vec3 omegaI, float roughness, Vec3 U_, Vec3 V_, Vec3 N_)
+      : Lambda(lambda), OmegaI(Vec3BasisProject(U_, V_, N_, omegaI)), Roughness(roughness * roughness), U(U_), V(V_), N(N_) {}
+  Vec3 Sample(double r0, double r1) override { return Vec3BasisExpand(U, V, N, CosineHemisphere(r0, r1)); }
+  double PDF(Vec3 _omegaO) override {
+    Vec3 omegaO = Vec3BasisProject(U, V, N, _omegaO);
+    double ODotN = (double)Max(0, omegaO[2]);
+    return ODotN / M_PI;
+  }
+  Spectrum Eval(Vec3 _omegaO) override {
+    Vec3 omegaO = Vec3BasisProject(U, V, N, _omegaO);
+    float sigma = Roughness;
+    float A = 1 - (0.5f * (sigma * sigma) / ((sigma * sigma) + 0.57f));
+    float B = 0.45f * (sigma * sigma) / ((sigma * sigma) + 0.09f);
+    float phiI = Atan2(OmegaI[1], OmegaI[0]);
+    float phiO = Atan2(omegaO[1], omegaO[0]);
+    float thetaI = Acos(OmegaI[2]);
+    float thetaO = Acos(omegaO[2]);
+    float alpha = Max(thetaI, thetaO);
+    float beta = Min(thetaI, thetaO);
+    float C = Sin(alpha) * Tan(beta);
+    float gamma = Cos(phiO - phiI);
+    float scale = omegaO[2] * (A + (B * Max(0, gamma) * C));
+    Spectrum rho;
+    rho.Lambda = Lambda;
+    rho.FromRGB(MakeRGB(1, 1, 1));
+    rho.Scale(scale / (float)M_PI);
+    return rho;
+  }
+};
+
+// builtin/shader/fresnel/dielectric.go:34-47
+static RGB DielectricKr(float eta, float cosTheta) {
+  float c = cosTheta;
+  float g = (eta * eta) - 1 + (c * c);
+  if (g < 0.0f) return MakeRGB(1, 1, 1);
+  g = Sqrt(g);
+  float fr = 0.5f * sqr((g - c) / (g + c)) * (1 + sqr((c * (g + c) - 1) / (c * (g - c) + 1)));
+  return MakeRGB(fr, fr, fr);
+}
+
+// builtin/shader/bsdf/specular.go:13-101
+static Vec3 reflectV(Vec3 omegaR, Vec3 N) { return Vec3Sub(Vec3Scale(2.0f * Vec3Dot(N, omegaR), N), omegaR); }
+struct Specular : BSDF {
+  float Lambda;
+  Vec3 OmegaR;
+  float eta;
+  Vec3 U, V, N;
+  Specular(float lambda, Vec3 omegaI, float eta_, Vec3 U_, Vec3 V_, Vec3 N_)
+      : Lambda(lambda), OmegaR(Vec3BasisProject(U_, V_, N_, omegaI)), eta(eta_), U(U_), V(V_), N(N_) {}
+  Vec3 Sample(double, double) override {
+    Vec3 omegaO = reflectV(OmegaR, V3(0, 0, 1));
+    omegaO = Vec3Normalize(omegaO);
+    return Vec3BasisExpand(U, V, N, omegaO);
+  }
+  double PDF(Vec3 _omegaO) override {
+    Vec3 omegaO = Vec3BasisProject(U, V, N, _omegaO);
+    Vec3 omegaORefl = reflectV(OmegaR, V3(0, 0, 1));
+    if (Vec3Dot(omegaO, omegaORefl) < 0.9999f) return 0;
+    return 1;
+  }
+  Spectrum Eval(Vec3 _omegaO) override {
+    Spectrum rho;
+    Vec3 omegaO = Vec3BasisProject(U, V, N, _omegaO);
+    Vec3 omegaORefl = reflectV(OmegaR, V3(0, 0, 1));
+    if (Vec3Dot(omegaO, omegaORefl) < 0.9999f) return rho;
+    RGB fresnel = DielectricKr(eta, OmegaR[2]);
+    rho.Lambda = Lambda;
+    rho.FromRGB(fresnel);
+    rho.Scale(Vec3DotAbs(omegaO, V3(0, 0, 1)));
+    return rho;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// builtin/shader/std.go:77-296
+void ShaderStd::Eval(ShaderContext* sg) {
+  if (sg->Level > 3) return;
+
+  Vec3 V = Vec3Cross(sg->N, sg->DdPdu);
+  if (Vec3Length2(V) < 0.1f) V = Vec3Cross(sg->N, sg->DdPdv);
+  V = Vec3Normalize(V);
+  Vec3 U = Vec3Normalize(Vec3Cross(sg->N, V));
+
+  float diffRoughness = 0.5f;
+  if (hasDiffuseRoughness) diffRoughness = DiffuseRoughness;
+  OrenNayar diffBrdf(sg->Lambda, Vec3Neg(sg->Rd), diffRoughness, U, V, sg->N);
+
+  RGB diffContrib;
+  RGB diffColour;
+  if (hasDiffuseColour) diffColour = DiffuseColour;
+
+  float diffWeight = 0, spec1Weight = 0;
+  if (hasDiffuseStrength) diffWeight = DiffuseStrength;
+  if (hasSpec1Strength) spec1Weight = Spec1Strength;
+  float totalWeight = diffWeight + spec1Weight;
+  diffWeight /= totalWeight;
+  spec1Weight /= totalWeight;
+  if (totalWeight == 0.0f) throw std::runtime_error("Shader " + Name + " has no weight");
+
+  if (diffWeight > 0.0f) {
+    sg->LightsPrepare();
+    while (sg->NextLight()) {
+      if (sg->Lp->DiffuseShadeMult() > 0.0f) {
+        RGB col = sg->EvaluateLightSamples(&diffBrdf);
+        col.Mul(diffColour);
+        diffContrib.Add(col);
+      }
+    }
+    diffContrib.Scale(diffWeight);
+  }
+
+  float ior = 1.7f;
+  if (hasIOR) ior = IOR;
+
+  RGB spec1Contrib;
+  if (spec1Weight > 0.0f) {
+    float spec1Roughness = 0.5f;
+    if (hasSpec1Roughness) spec1Roughness = Spec1Roughness;
+    RGB spec1Colour;
+    if (hasSpec1Colour) spec1Colour = Spec1Colour;
+    if (spec1Roughness != 0.0f) throw std::runtime_error("oracle: GGX glossy lobe (Spec1Roughness>0) is not restated yet");
+    Specular spec1BRDF(sg->Lambda, Vec3Neg(sg->Rd), ior, U, V, sg->N);
+
+    TraceSample samp;
+    Ray ray;
+    ray.Task = sg->task;
+    int spec1Samples = 1;
+    for (int i = 0; i < spec1Samples; i++) {
+      uint64_t idx = (uint64_t)(sg->I * spec1Samples + i);
+      double r0 = VanDerCorput(idx, sg->Scramble[0]);
+      double r1 = Sobol(idx, sg->Scramble[1]);
+      Vec3 spec1OmegaO = spec1BRDF.Sample(r0, r1);
+      double pdf = spec1BRDF.PDF(spec1OmegaO);
+      if (Vec3Dot(spec1OmegaO, sg->Ng) <= 0.0f) continue;
+      ray.Init(RayTypeReflected, sg->OffsetP(1), spec1OmegaO, kInfPos, (uint8_t)(sg->Level + 1), sg);
+      bool traced;
+      if (sg->Level + 1 > 3 && !sg->task->trace_last_level) {
+        traced = false;  // optional: skip the level-4 ray whose shader returns black (std.go:95)
+      } else {
+        traced = Trace(&ray, &samp);
+      }
+      if (traced) {
+        Spectrum rho = spec1BRDF.Eval(spec1OmegaO);
+        rho.Scale(1.0f / (float)pdf);
+        RGB col = rho.ToRGB();
+        col.Mul(spec1Colour);
+        col.Mul(samp.Colour);
+        for (int k = 0; k < 3; k++)
+          if (col[k] < 0 || std::isnan((double)col[k])) col[k] = 0;
+        spec1Contrib.Add(col);
+      }
+    }
+    if (spec1Samples > 0) spec1Contrib.Scale(spec1Weight / (float)spec1Samples);
+  }
+
+  RGB contrib;
+  RGB emissContrib = EvalEmission(sg, Vec3Neg(sg->Rd));
+  contrib.Add(emissContrib);
+  contrib.Add(diffContrib);
+  contrib.Add(spec1Contrib);
+  sg->OutRGB = contrib;
+}
+
+// builtin/shader/std.go:299-316
+RGB ShaderStd::EvalEmission(ShaderContext*, Vec3) {
+  RGB emissColour;
+  float emissStrength = 0;
+  if (hasEmissionColour) emissColour = EmissionColour;
+  if (hasEmissionStrength) emissStrength = EmissionStrength;
+  else return RGB{};
+  emissColour.Scale(emissStrength);
+  return emissColour;
+}
+
+// ---------------------------------------------------------------------------------------------
+// builtin/light/triangle.go:79-134
+static bool rayTriangleIntersect(Vec3 Ro, Vec3 Rd, Vec3 P0, Vec3 P1, Vec3 P2, Vec3* pout, float* tout) {
+  Vec3 e1 = Vec3Sub(P1, P0);
+  Vec3 e2 = Vec3Sub(P2, P0);
+  Vec3 P = Vec3Cross(Rd, e2);
+  float det = Vec3Dot(e1, P);
+  if (det > -1e-6f && det < 1e-6f) return false;
+  float inv_det = 1 / det;
+  Vec3 T = Vec3Sub(Ro, P0);
+  float u = Vec3Dot(T, P) * inv_det;
+  if (u < 0 || u > 1) return false;
+  Vec3 Q = Vec3Cross(T, e1);
+  float v = Vec3Dot(Rd, Q) * inv_det;
+  if (v < 0 || u + v > 1) return false;
+  float t = Vec3Dot(e2, Q) * inv_det;
+  if (t > 1e-6f) {
+    *pout = Vec3Add3(Vec3Scale(1 - u - v, P0), Vec3Scale(u, P1), Vec3Scale(v, P2));
+    *tout = t;
+    return true;
+  }
+  return false;
+}
+
+static float triangleArea(Vec3 P0, Vec3 P1, Vec3 P2) { return 0.5f * Vec3Length(Vec3Cross(Vec3Sub(P1, P0), Vec3Sub(P2, P0))); }
+
+// builtin/light/disk.go:38-51
+static float rayPlaneIntersect(Vec3 Ro, Vec3 Rd, Vec3 P, Vec3 N) {
+  float denom = Vec3Dot(N, Rd);
+  if (Abs(denom) > 1e-6f) {
+    Vec3 p0l0 = Vec3Sub(P, Ro);
+    return Vec3Dot(p0l0, N) / denom;
+  }
+  return 0;
+}
+
+// builtin/light/triangle.go:376-417
+static void triangleSidesToAngles(float as, float bs, float cs, float* a, float* b, float* c) {
+  float ssu = (as + bs + cs) / 2;
+  float sinssuas = Sin(ssu - as);
+  float sinssubs = Sin(ssu - bs);
+  float sinssucs = Sin(ssu - cs);
+  float sinssu = Sin(ssu);
+  float tanA2 = Sqrt(sinssubs * sinssucs / (sinssu * sinssuas));
+  float tanB2 = Sqrt(sinssuas * sinssucs / (sinssu * sinssubs));
+  float tanC2 = Sqrt(sinssuas * sinssubs / (sinssu * sinssucs));
+  *a = 2 * Atan(tanA2);
+  *b = 2 * Atan(tanB2);
+  *c = 2 * Atan(tanC2);
+}
+// builtin/light/triangle.go:430-459
+static void triangleVerticesToSides(Vec3 pa, Vec3 pb, Vec3 pc, float* a, float* b, float* c) {
+  float adot = Vec3Dot(pb, pc);
+  float bdot = Vec3Dot(pc, pa);
+  float cdot = Vec3Dot(pa, pb);
+  *a = Acos(adot);
+  *b = Acos(bdot);
+  *c = Acos(cdot);
+}
+
+// builtin/light/triangle.go:474-535
+static Vec3 sampleSphericalTriangle(Vec3 p0, Vec3 p1, Vec3 p2, Vec3 p, double r0, double r1, double* pdf) {
+  Vec3 pa = Vec3Normalize(Vec3Sub(p0, p));
+  Vec3 pb = Vec3Normalize(Vec3Sub(p1, p));
+  Vec3 pc = Vec3Normalize(Vec3Sub(p2, p));
+  float a, b, c;
+  triangleVerticesToSides(pa, pb, pc, &a, &b, &c);
+  float alpha, beta, gamma;
+  triangleSidesToAngles(a, b, c, &alpha, &beta, &gamma);
+  float area = alpha + beta + gamma - kPi;
+  float areaHat = (float)r0 * area;
+  float s = Sin(areaHat - alpha), t = Cos(areaHat - alpha);  // m.Sincos
+  float sinAlpha = Sin(alpha), cosAlpha = Cos(alpha);
+  float u = t - cosAlpha;
+  float v = s + sinAlpha * Cos(c);
+  float q = ((v * t - u * s) * cosAlpha - v) / ((v * s + u * t) * sinAlpha);
+  q = Max(-1, Min(q, 1));
+  float w = Vec3Dot(pc, pa);
+  Vec3 v31;
+  for (int k = 0; k < 3; k++) v31[k] = pc[k] - w * pa[k];
+  v31 = Vec3Normalize(v31);
+  Vec3 v4;
+  for (int k = 0; k < 3; k++) v4[k] = q * pa[k] + Sqrt(1 - q * q) * v31[k];
+  float z = 1 - (float)r1 * (1 - Vec3Dot(v4, pb));
+  w = Vec3Dot(v4, pb);
+  Vec3 v42;
+  for (int k = 0; k < 3; k++) v42[k] = v4[k] - w * pb[k];
+  v42 = Vec3Normalize(v42);
+  Vec3 x = Vec3Add(Vec3Scale(z, pb), Vec3Scale(Sqrt(1 - z * z), v42));
+  *pdf = 1 / (double)area;
+  return x;
+}
+
+// builtin/light/triangle.go:537-565 (UVs omitted)
+PolyMesh* Tri::createMesh() {
+  PolyMesh* msh = new PolyMesh();
+  msh->Name = Name + ":<mesh>";
+  msh->shader.push_back(shader);
+  msh->Verts.MotionKeys = 1;
+  msh->Normals.MotionKeys = 1;
+  Vec3 N = Vec3Normalize(Vec3Cross(Vec3Sub(P1, P0), Vec3Sub(P2, P0)));
+  msh->Verts.Elems = {P0, P1, P2};
+  msh->Verts.ElemsPerKey = 3;
+  msh->Normals.Elems = {N, N, N};
+  msh->Normals.ElemsPerKey = 3;
+  return msh;
+}
+
+// builtin/light/triangle.go:136-230
+bool Tri::ValidSample(ShaderContext* sg, BSDFSample* sample) {
+  Vec3 P;
+  float tdummy;
+  if (!rayTriangleIntersect(sg->P, sample->D, P0, P1, P2, &P, &tdummy)) return false;
+
+  if (Vec3Dot(sg->Ng, Vec3Sub(P0, P)) < 0 || Vec3Dot(sg->Ng, Vec3Sub(P1, P)) < 0 || Vec3Dot(sg->Ng, Vec3Sub(P2, P)) < 0) {
+    double pdf = (double)(1 / triangleArea(P0, P1, P2));
+    Vec3 D = Vec3Sub(P, sg->P);
+    sample->Ldist = Vec3Length(D);
+    sample->Ld = Vec3Normalize(D);
+    Vec3 N = Vec3Normalize(Vec3Cross(Vec3Sub(P1, P0), Vec3Sub(P2, P0)));
+    if (Vec3Dot(sample->Ld, N) > 0 || Vec3Dot(sample->Ld, sg->Ng) < 0) return false;
+    sample->Liu.Lambda = sg->Lambda;
+    RGB E = shader->EvalEmission(nullptr, Vec3Neg(sample->Ld));
+    sample->Liu.FromRGB(E);
+    sample->PdfLight = (float)pdf * sqr(sample->Ldist) / Vec3DotAbs(sample->Ld, N);
+  } else {
+    Vec3 pa = Vec3Normalize(Vec3Sub(P0, sg->P));
+    Vec3 pb = Vec3Normalize(Vec3Sub(P1, sg->P));
+    Vec3 pc = Vec3Normalize(Vec3Sub(P2, sg->P));
+    float a, b, c;
+    triangleVerticesToSides(pa, pb, pc, &a, &b, &c);
+    float alpha, beta, gamma;
+    triangleSidesToAngles(a, b, c, &alpha, &beta, &gamma);
+    float area = alpha + beta + gamma - kPi;
+    double pdf = (double)(1 / area);
+    Vec3 D = Vec3Sub(P, sg->P);
+    sample->Ldist = Vec3Length(D);
+    sample->Ld = Vec3Normalize(D);
+    Vec3 N = Vec3Normalize(Vec3Cross(Vec3Sub(P1, P0), Vec3Sub(P2, P0)));
+    if (Vec3Dot(sample->Ld, N) > 0 || Vec3Dot(sample->Ld, sg->Ng) < 0) return false;
+    sample->Liu.Lambda = sg->Lambda;
+    RGB E = shader->EvalEmission(nullptr, Vec3Neg(sample->Ld));
+    sample->Liu.FromRGB(E);
+    sample->PdfLight = (float)pdf;
+  }
+  return true;
+}
+
+// builtin/light/triangle.go:232-282
+void Tri::sampleByArea(ShaderContext* sg, int n) {
+  double pdf = (double)(1 / triangleArea(P0, P1, P2));
+  Vec3 N = Vec3Normalize(Vec3Cross(Vec3Sub(P1, P0), Vec3Sub(P2, P0)));
+  for (int i = 0; i < n; i++) {
+    uint64_t idx = (uint64_t)(sg->I * n + i);
+    double r0 = VanDerCorput(idx, sg->Scramble[0]);
+    double r1 = Sobol(idx, sg->Scramble[1]);
+    Vec3 P = Vec3Add3(P0, Vec3Scale((float)(r1 * std::sqrt(1 - r0)), Vec3Sub(P1, P0)), Vec3Scale((float)(1 - std::sqrt(1 - r0)), Vec3Sub(P2, P0)));
+    Vec3 D = Vec3Sub(P, sg->P);
+    LightSample ls{};
+    ls.Ldist = Vec3Length(D);
+    ls.Ld = Vec3Normalize(D);
+    if (Vec3Dot(ls.Ld, N) > 0 || Vec3Dot(ls.Ld, sg->Ng) < 0) continue;
+    ls.Liu.Lambda = sg->Lambda;
+    RGB E = shader->EvalEmission(nullptr, Vec3Neg(ls.Ld));
+    ls.Liu.FromRGB(E);
+    ls.Pdf = (float)pdf * sqr(ls.Ldist) / Vec3DotAbs(ls.Ld, N);
+    ls.P = P;
+    sg->Lsamples.push_back(ls);
+  }
+}
+
+// builtin/light/triangle.go:285-343
+void Tri::SampleArea(ShaderContext* sg, int n) {
+  if (Vec3Dot(sg->Ng, Vec3Sub(P0, sg->P)) < 0 || Vec3Dot(sg->Ng, Vec3Sub(P1, sg->P)) < 0 || Vec3Dot(sg->Ng, Vec3Sub(P2, sg->P)) < 0) {
+    sampleByArea(sg, n);
+    return;
+  }
+  for (int i = 0; i < n; i++) {
+    uint64_t idx = (uint64_t)(sg->I * n + i);
+    double r0 = VanDerCorput(idx, sg->Scramble[0]);
+    double r1 = Sobol(idx, sg->Scramble[1]);
+    double pdf;
+    Vec3 x = sampleSphericalTriangle(P0, P1, P2, sg->P, r0, r1, &pdf);
+    Vec3 N = Vec3Normalize(Vec3Cross(Vec3Sub(P1, P0), Vec3Sub(P2, P0)));
+    float t = rayPlaneIntersect(sg->P, x, P0, N);
+    Vec3 P = Vec3Mad(sg->P, x, t);
+    Vec3 D = Vec3Sub(P, sg->P);
+    LightSample ls{};
+    ls.Ldist = Vec3Length(D);
+    ls.Ld = Vec3Normalize(D);
+    if (Vec3Dot(ls.Ld, N) > 0 || Vec3Dot(ls.Ld, sg->Ng) < 0) continue;
+    ls.Liu.Lambda = sg->Lambda;
+    RGB E = shader->EvalEmission(nullptr, Vec3Neg(ls.Ld));
+    ls.Liu.FromRGB(E);
+    ls.Pdf = (float)pdf;
+    ls.P = P;
+    sg->Lsamples.push_back(ls);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+static inline float degToRad(float deg) { return deg * kPi / 180.0f; }
+
+// builtin/camera/camera.go:80-98,109-193 (single key: the else branch :154-187 with i=0)
+void Camera::PreRender(float frameAspect) {
+  if (Aspect == 0.0f) Aspect = frameAspect;
+  TanThetaFocal = Tan(degToRad(Fov / 2)) * Focal;
+
+  float time = (float)0 / (float)1;
+  float k = time * (float)(1 - 1);
+  float t = k - Floor(k);
+  Vec3 P = Vec3Lerp(To, To, t);
+  Vec3 W = Vec3Normalize(Vec3Sub(From, P));
+  Vec3 u = Vec3Normalize(Vec3Cross(Up, W));
+  Vec3 v = Vec3Normalize(Vec3Cross(u, W));
+  float roll = (1 - t) * Roll + t * Roll;
+  Vec3 U = Vec3Add(Vec3Scale(Cos(roll), u), Vec3Scale(Sin(roll), v));
+  Vec3 V = Vec3Add(Vec3Scale(-Sin(roll), u), Vec3Scale(Cos(roll), v));
+  Matrix4 mtx = Matrix4Mul(Matrix4Translate(From[0], From[1], From[2]), Matrix4Basis(U, V, W));
+  TransformDecomp decomp = TransformDecompMatrix4(mtx);
+  // camera.go:225-236 with len(decomp)==1: k = Time*0 = 0 for every ray, so M is a constant.
+  TransformDecomp trn = TransformDecompLerp(decomp, decomp, 0.0f);
+  M = TransformDecompToMatrix4(trn);
+}
+
+// builtin/camera/camera.go:221-323 (differentials omitted)
+void Camera::ComputeRay(float Sx, float Sy, double lensU, double lensV, const ShaderContext* sc, Ray* ray) const {
+  float camu = Sx * TanThetaFocal;
+  float camv = Sy * (TanThetaFocal / Aspect);
+  Vec3 U = V3(1, 0, 0), V = V3(0, 1, 0), W = V3(0, 0, 1);
+  Vec3 s = Vec3Sub(Vec3Add(Vec3Scale(camu, U), Vec3Scale(camv, V)), Vec3Scale(Focal, W));
+  Vec3 D, P, d;
+  if (Radius > 0.0f) {
+    float x, y;
+    UniformDisk2D(Radius, (float)lensU, (float)lensV, &x, &y);
+    Vec3 e = Vec3Add(Vec3Scale(x, U), Vec3Scale(y, V));
+    d = Matrix4MulVec(M, Vec3Sub(s, e));
+    D = Vec3Normalize(d);
+    P = Matrix4MulPoint(M, e);
+  } else {
+    d = Matrix4MulVec(M, s);
+    D = Vec3Normalize(d);
+    P = Matrix4MulPoint(M, V3(0, 0, 0));
+  }
+  ray->Init(RayTypeCamera, P, D, kInfPos, 0, sc);
+}
+
+// ---------------------------------------------------------------------------------------------
+ShaderStd* Renderer::findShader(const std::string& name) {
+  for (auto& s : shaders) if (s->Name == name) return s.get();
+  return nullptr;
+}
+
+// core/core.go:36-61: nodes PreRender in creation order (lights append their meshes, which are
+// pre-rendered in the next round), then scene.PreRender.
+void Renderer::PreRender() {
+  if (prerendered) return;
+  framebuffer.assign((size_t)XRes * YRes * 3, 0.0f);
+  camera.PreRender((float)XRes / (float)YRes);
+  int gid = 0;
+  for (auto& m : meshes) {
+    m->PreRender();
+    m->id = gid++;
+    scene.geoms.push_back(m.get());
+  }
+  for (auto& t : tris) {
+    PolyMesh* g = t->createMesh();
+    meshes.emplace_back(g);
+    t->geom = g;
+    scene.lights.push_back(t.get());
+  }
+  for (size_t i = scene.geoms.size(); i < meshes.size(); i++) {
+    meshes[i]->PreRender();
+    meshes[i]->id = gid++;
+    scene.geoms.push_back(meshes[i].get());
+  }
+  scene.initAccel();
+  prerendered = true;
+}
+
+// core/render.go:89-124
+void Renderer::GenerateCameraRay(int iter, int x, int y, ShaderContext* sc, Ray* ray) const {
+  int pixIdx = x + y * XRes;
+  double rasterX, rasterY;
+  RasterXY12((uint32_t)iter, (uint32_t)x, (uint32_t)y, 0, 0, &rasterX, &rasterY);
+  const pixelscramble& scr = framescramble[pixIdx];
+  double time = VanDerCorput((uint64_t)iter, scr.time);
+  double lambda = (720 - 450) * VanDerCorput((uint64_t)iter, scr.lambda) + 450;
+  double lensU = VanDerCorput((uint64_t)iter, scr.lensU);
+  double lensV = Sobol((uint64_t)iter, scr.lensV);
+  int w = XRes, h = YRes;
+  float Sx = (float)(-1.0 + 2.0 * (rasterX / (double)w));
+  float Sy = -(float)(-1.0 + 2.0 * (rasterY / (double)h));
+  sc->Lambda = (float)lambda;
+  sc->Time = (float)time;
+  camera.ComputeRay(Sx, Sy, lensU, lensV, sc, ray);
+  ray->I = iter;
+  ray->Scramble[0] = scr.scramble[0];
+  ray->Scramble[1] = scr.scramble[1];
+}
+
+// core/render.go:66-137,140-218. Worker threads pull 32x32 tiles; the per-pixel running mean
+// (fb*iter + c)/(iter+1) with 1-based iter is kept (quirk d).
+RenderStats Renderer::Render(int iterBegin, int iterEnd, int nthreads) {
+  PreRender();
+  if ((int)framescramble.size() != XRes * YRes) throw std::runtime_error("framescramble not set");
+  RenderStats stats;
+  auto t0 = std::chrono::steady_clock::now();
+  const int tilesX = (XRes + 31) / 32, tilesY = (YRes + 31) / 32;
+  for (int iter0 = iterBegin; iter0 < iterEnd; iter0++) {
+    const int iter = iter0 + 1;
+    std::atomic<int> next(0);
+    std::vector<RenderTask> tasks(nthreads);
+    auto worker = [&](int ti) {
+      RenderTask* task = &tasks[ti];
+      task->scene = &scene;
+      task->trace_last_level = trace_last_level;
+      Ray ray;
+      ray.Task = task;
+      ShaderContext sc;
+      sc.task = task;
+      for (;;) {
+        int tile = next.fetch_add(1);
+        if (tile >= tilesX * tilesY) break;
+        int tx = (tile % tilesX) * 32, ty = (tile / tilesX) * 32;
+        for (int j = 0; j < 32; j++)
+          for (int i = 0; i < 32; i++) {
+            int x = i + tx, y = j + ty;
+            if (x >= XRes || y >= YRes) continue;
+            GenerateCameraRay(iter, x, y, &sc, &ray);
+            TraceSample samp;
+            Trace(&ray, &samp);
+            float* px = &framebuffer[(size_t)(x + y * XRes) * 3];
+            for (int k = 0; k < 3; k++) px[k] = (px[k] * (float)iter + samp.Colour[k]) / (float)(iter + 1);
+          }
+      }
+    };
+    if (nthreads <= 1) {
+      worker(0);
+    } else {
+      std::vector<std::thread> th;
+      for (int i = 0; i < nthreads; i++) th.emplace_back(worker, i);
+      for (auto& t : th) t.join();
+    }
+    for (auto& t : tasks) {
+      stats.rayCount += t.rayCount;
+      stats.shadowRayCount += t.shadowRayCount;
+    }
+  }
+  stats.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return stats;
+}
+
+}  // namespace orc

@@ -1,0 +1,101 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY. Not part of the product path.
+// CPU restatement of the reference's default shader, BSDFs, Fresnel, triangle light, camera and
+// frame loop. parity unpinned (no reference tests; Go stdlib trig is replaced by glibc libm in
+// double, rounded to float exactly where the reference rounds).
+// Follows:
+//   builtin/shader/std.go:77-316              (ShaderStd.Eval / EvalEmission)
+//   builtin/shader/bsdf/orennayar.go:16-73    (OrenNayar)
+//   builtin/shader/bsdf/specular.go:13-101    (Specular mirror)
+//   builtin/shader/fresnel/dielectric.go:16-47 (Dielectric)
+//   math/sample/sample.go:18-30,105-129       (CosineHemisphere, UniformDisk2D)
+//   builtin/light/triangle.go:71-343,376-535  (Tri light: area + spherical-triangle sampling)
+//   builtin/light/disk.go:38-51               (rayPlaneIntersect)
+//   builtin/camera/camera.go:80-98,109-193,221-323 (Camera)
+//   core/render.go:18-23,66-137,166-205       (pixelscramble, render, Render)
+// Out of scope here: GGX glossy lobe (roughness>0 spec lobe contributes direct light only in the
+// reference; not restated yet), Conductor fresnel, Disk/Sphere/Quad lights, pixel filters.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "core.h"
+#include "scene.h"
+
+namespace orc {
+
+struct ShaderStd : Shader {
+  std::string Name;
+  bool hasEmissionColour = false, hasEmissionStrength = false;
+  RGB EmissionColour;
+  float EmissionStrength = 0;
+  bool hasDiffuseColour = false, hasDiffuseStrength = false, hasDiffuseRoughness = false;
+  RGB DiffuseColour;
+  float DiffuseStrength = 0, DiffuseRoughness = 0;
+  bool hasSpec1Colour = false, hasSpec1Strength = false, hasSpec1Roughness = false;
+  RGB Spec1Colour;
+  float Spec1Strength = 0, Spec1Roughness = 0;
+  bool hasIOR = false;
+  float IOR = 0;
+
+  void Eval(ShaderContext* sg) override;
+  RGB EvalEmission(ShaderContext* sg, Vec3 omegaO) override;
+};
+
+struct Tri : Light {
+  std::string Name;
+  Vec3 P0, P1, P2;
+  int Samples = 1;
+  Shader* shader = nullptr;
+  PolyMesh* geom = nullptr;
+
+  PolyMesh* createMesh();
+  void SampleArea(ShaderContext* sg, int n) override;
+  void sampleByArea(ShaderContext* sg, int n);
+  float DiffuseShadeMult() override { return 1; }
+  int NumSamples(ShaderContext*) override { return 1 << (unsigned)Samples; }
+  bool ValidSample(ShaderContext* sg, BSDFSample* sample) override;
+  Geom* GetGeom() override { return geom; }
+};
+
+struct Camera {
+  // LookAt, single motion key (camera motion is out of scope)
+  Vec3 From, To, Up;
+  float Roll = 0;
+  float Aspect = 0, Fov = 90, Focal = 12, Radius = 0;
+  float TanThetaFocal = 0;
+  Matrix4 M;  // LocalToWorld after decompose/recompose (camera.go:188-192, 225-236)
+  void PreRender(float frameAspect);
+  void ComputeRay(float Sx, float Sy, double lensU, double lensV, const ShaderContext* sc, Ray* ray) const;
+};
+
+// core/render.go:18-23
+struct pixelscramble {
+  uint64_t lensU, lensV, time, lambda, scramble[2];
+};
+
+struct RenderStats {
+  uint64_t rayCount = 0, shadowRayCount = 0;
+  double seconds = 0;
+};
+
+struct Renderer {
+  Scene scene;
+  Camera camera;
+  int XRes = 1024, YRes = 1024;
+  std::vector<float> framebuffer;
+  std::vector<pixelscramble> framescramble;
+  std::vector<std::unique_ptr<PolyMesh>> meshes;
+  std::vector<std::unique_ptr<ShaderStd>> shaders;
+  std::vector<std::unique_ptr<Tri>> tris;
+  bool prerendered = false;
+  bool trace_last_level = true;  // false: skip the level-4 mirror ray whose shader returns black (std.go:95)
+
+  ShaderStd* findShader(const std::string& name);
+  void PreRender();
+  // iterations [iterBegin, iterEnd) are the reference's 0-based `iter`; render() receives iter+1.
+  RenderStats Render(int iterBegin, int iterEnd, int nthreads);
+  // one camera sample; used by Render and by tests that want the primary ray
+  void GenerateCameraRay(int iter1, int x, int y, ShaderContext* sc, Ray* ray) const;
+};
+
+}  // namespace orc

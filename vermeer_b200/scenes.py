@@ -1,0 +1,328 @@
+"""Scene descriptions and seeded synthetic scene generators (numpy only, no GPU, no oracle).
+
+A `SceneDesc` is the neutral, in-memory equivalent of a reference `.vnf` file: a list of nodes
+(`Globals`, `Camera`, `ShaderStd`, `PolyMesh`, `TriLight`) with the reference's field names
+(builtin/geom/polymesh/polymesh.go:17-40, builtin/shader/std.go:25-47,
+builtin/light/triangle.go:18-28, builtin/camera/camera.go:48-73, core/globals.go:8-16).  The same
+description is fed to the GPU host library (`vermeer_b200.host`) and, in tests and the CPU baseline,
+to the oracle.
+
+Generators follow SURVEY.md §8(d):
+  C1 `cornell_box`      5 diffuse quads + 2 boxes, light = 2 TriLights (QuadLight panics in the reference)
+  C2 `heightfield_scene` one PolyMesh, 2*nq^2 triangles (nq=708 -> 1 002 528), TriLight pair above
+  C3 `sphere_field_scene` n meshes x 2*slices*(stacks-1) triangles, mirror+diffuse ShaderStd
+  C4 `heightfield_scene(motion=True)` same mesh with Verts.MotionKeys=2
+All geometry is wound so the geometric normal (V1-V0)x(V2-V0) faces outward/up: the reference never
+face-forwards.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+__all__ = [
+    "ShaderStd", "PolyMesh", "TriLight", "Camera", "SceneDesc", "splitmix64_table",
+    "heightfield_mesh", "heightfield_scene", "sphere_field_scene", "cornell_box", "incoherent_rays",
+]
+
+
+@dataclass
+class ShaderStd:
+    Name: str
+    EmissionColour: Optional[tuple] = None
+    EmissionStrength: Optional[float] = None
+    DiffuseColour: Optional[tuple] = None
+    DiffuseStrength: Optional[float] = None
+    DiffuseRoughness: Optional[float] = None
+    Spec1Colour: Optional[tuple] = None
+    Spec1Strength: Optional[float] = None
+    Spec1Roughness: Optional[float] = None
+    IOR: Optional[float] = None
+
+    def packed(self):
+        """(mask, 15 floats) in the slot order shared by the host C-ABI and the oracle."""
+        p = np.zeros(15, np.float32)
+        mask = 0
+        slots = [("EmissionColour", 0, 3), ("EmissionStrength", 3, 1), ("DiffuseColour", 4, 3), ("DiffuseStrength", 7, 1),
+                 ("DiffuseRoughness", 8, 1), ("Spec1Colour", 9, 3), ("Spec1Strength", 12, 1), ("Spec1Roughness", 13, 1), ("IOR", 14, 1)]
+        for bit, (name, off, n) in enumerate(slots):
+            v = getattr(self, name)
+            if v is not None:
+                mask |= 1 << bit
+                p[off:off + n] = np.asarray(v, np.float32).reshape(-1)
+        return mask, p
+
+
+@dataclass
+class PolyMesh:
+    Name: str
+    Verts: np.ndarray                      # (keys, nverts, 3) float32
+    Shader: List[str]
+    PolyCount: Optional[np.ndarray] = None  # int32
+    FaceIdx: Optional[np.ndarray] = None    # int32
+    ShaderIdx: Optional[np.ndarray] = None  # int32, per polygon
+    Normals: Optional[np.ndarray] = None    # (n,3) float32
+    NormalIdx: Optional[np.ndarray] = None
+    RayBias: float = 0.0
+
+    def __post_init__(self):
+        v = np.ascontiguousarray(self.Verts, np.float32)
+        if v.ndim == 2:
+            v = v[None]
+        self.Verts = v
+        for k in ("PolyCount", "FaceIdx", "ShaderIdx", "NormalIdx"):
+            a = getattr(self, k)
+            if a is not None:
+                setattr(self, k, np.ascontiguousarray(a, np.int32))
+        if self.Normals is not None:
+            self.Normals = np.ascontiguousarray(self.Normals, np.float32)
+
+    @property
+    def num_tris(self) -> int:
+        if self.PolyCount is not None:
+            return int((self.PolyCount - 2).sum())
+        if self.FaceIdx is not None:
+            return len(self.FaceIdx) // 3
+        return self.Verts.shape[1] // 3
+
+
+@dataclass
+class TriLight:
+    Name: str
+    P0: tuple
+    P1: tuple
+    P2: tuple
+    Shader: str
+    Samples: int = 1
+
+
+@dataclass
+class Camera:
+    From: tuple
+    To: tuple
+    Up: tuple = (0.0, 1.0, 0.0)
+    Roll: float = 0.0
+    Fov: float = 90.0
+    Focal: float = 12.0
+    Aspect: float = 0.0
+    Radius: float = 0.0
+    Name: str = "camera"
+    Type: str = "LookAt"
+
+
+@dataclass
+class SceneDesc:
+    XRes: int
+    YRes: int
+    camera: Camera
+    shaders: List[ShaderStd] = field(default_factory=list)
+    meshes: List[PolyMesh] = field(default_factory=list)
+    lights: List[TriLight] = field(default_factory=list)
+    MaxIter: int = 16
+    name: str = "scene"
+
+    @property
+    def num_tris(self) -> int:
+        return sum(m.num_tris for m in self.meshes) + len(self.lights)
+
+
+# ------------------------------------------------------------------------------------------------
+def splitmix64_table(seed: int, npix: int) -> np.ndarray:
+    """Per-pixel scramble table, (npix, 6) uint64 = {lensU, lensV, time, lambda, scramble[0], scramble[1]}
+    (core/render.go:18-23).  The reference draws these from unseeded math/rand (render.go:169-174); any
+    u64s are valid, so both sides share this seeded splitmix64 stream."""
+    n = npix * 6
+    with np.errstate(over="ignore"):
+        idx = np.arange(1, n + 1, dtype=np.uint64)
+        z = np.uint64(seed) + idx * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return z.reshape(npix, 6)
+
+
+def _hash01(ix, iz, seed):
+    """Cheap integer hash -> [0,1) float32, vectorised."""
+    with np.errstate(over="ignore"):
+        h = (ix.astype(np.uint32) * np.uint32(73856093)) ^ (iz.astype(np.uint32) * np.uint32(19349663)) ^ np.uint32(seed * 83492791 & 0xFFFFFFFF)
+        h ^= h >> np.uint32(13)
+        h *= np.uint32(0x5bd1e995)
+        h ^= h >> np.uint32(15)
+    return (h & np.uint32(0xFFFFFF)).astype(np.float32) / np.float32(1 << 24)
+
+
+def heightfield_mesh(nq: int = 708, amp: float = 0.08, seed: int = 2, motion: bool = False, name: str = "heightfield",
+                     shader: str = "ground", extent: float = 1.0) -> PolyMesh:
+    """(nq+1)^2-vertex grid over [-extent,extent]^2 in xz, y = amp*sin(fx)*sin(fz) + hash noise; 2*nq^2 triangles
+    given as an indexed triangle list (FaceIdx only), wound so Ng = +Y."""
+    n = nq + 1
+    ii, jj = np.meshgrid(np.arange(n), np.arange(n), indexing="xy")
+    x = (-extent + 2.0 * extent * ii / nq).astype(np.float32)
+    z = (-extent + 2.0 * extent * jj / nq).astype(np.float32)
+    y = (amp * np.sin(7.0 * x) * np.sin(5.0 * z)).astype(np.float32)
+    y += np.float32(0.25 * 2.0 * extent / max(nq, 1)) * (_hash01(ii, jj, seed) - np.float32(0.5))
+    v0 = np.stack([x, y.astype(np.float32), z], -1).reshape(-1, 3).astype(np.float32)
+    keys = [v0]
+    if motion:
+        d = np.zeros_like(v0)
+        d[:, 1] = (0.5 * amp * np.sin(3.0 * v0[:, 0] + 1.0) * np.cos(4.0 * v0[:, 2])).astype(np.float32)
+        d[:, 0] = np.float32(0.01) * np.sin(2.0 * v0[:, 2]).astype(np.float32)
+        keys.append((v0 + d).astype(np.float32))
+    qi, qj = np.meshgrid(np.arange(nq), np.arange(nq), indexing="xy")
+    a = (qj * n + qi).reshape(-1)
+    b = a + 1
+    c = a + n + 1
+    dd = a + n
+    tris = np.stack([a, c, b, a, dd, c], -1).reshape(-1).astype(np.int32)
+    return PolyMesh(Name=name, Verts=np.stack(keys, 0), Shader=[shader], FaceIdx=tris)
+
+
+def _light_pair(y: float, half: float, shader: str, samples: int = 1, cx: float = 0.0, cz: float = 0.0):
+    """Two TriLights forming a 45-degree-rotated square (diamond) at height y whose normal (P1-P0)x(P2-P0) faces -Y
+    (into the scene).  A diamond, not an axis-aligned quad: two triangles sharing an axis-aligned rectangle's
+    diagonal have identical bounding-box centroids, and the reference's scene-level builder (leafMax=1) then
+    recurses forever (qbvh/build.go:35-43 flat-axis case; see DESIGN.md "reference quirks", f)."""
+    pw = (cx - half, y, cz)
+    pe = (cx + half, y, cz)
+    pn = (cx, y, cz + half)
+    ps = (cx, y, cz - half)
+    return [TriLight("lightA", pw, pe, pn, shader, samples), TriLight("lightB", pe, pw, ps, shader, samples)]
+
+
+def heightfield_scene(xres: int = 1920, yres: int = 1080, nq: int = 708, motion: bool = False, seed: int = 2) -> SceneDesc:
+    """Configs C2 / C4: one 2*nq^2-triangle PolyMesh, one TriLight pair above, camera at ~30 deg elevation."""
+    shaders = [
+        ShaderStd("ground", DiffuseColour=(0.7, 0.6, 0.5), DiffuseStrength=1.0),
+        ShaderStd("lightmtl", EmissionColour=(1.0, 0.9, 0.8), EmissionStrength=15.0, DiffuseColour=(0.0, 0.0, 0.0), DiffuseStrength=1.0),
+    ]
+    mesh = heightfield_mesh(nq=nq, seed=seed, motion=motion)
+    cam = Camera(From=(0.0, 1.25, 2.1), To=(0.0, 0.0, 0.0), Fov=50.0, Focal=1.0)
+    return SceneDesc(XRes=xres, YRes=yres, camera=cam, shaders=shaders, meshes=[mesh],
+                     lights=_light_pair(1.5, 0.4, "lightmtl"), MaxIter=64,
+                     name=("C4-motion-heightfield" if motion else "C2-heightfield") + "-%dtri" % mesh.num_tris)
+
+
+def _uv_sphere(slices: int, stacks: int):
+    """Unit UV sphere: 2 + (stacks-1)*slices vertices, 2*slices*(stacks-1) triangles, outward winding."""
+    verts = [(0.0, 1.0, 0.0)]
+    for s in range(1, stacks):
+        th = np.pi * s / stacks
+        for l in range(slices):
+            ph = 2.0 * np.pi * l / slices
+            verts.append((np.sin(th) * np.cos(ph), np.cos(th), np.sin(th) * np.sin(ph)))
+    verts.append((0.0, -1.0, 0.0))
+    v = np.asarray(verts, np.float32)
+    tris = []
+    ring = lambda s, l: 1 + (s - 1) * slices + (l % slices)
+    south = len(verts) - 1
+    for l in range(slices):
+        tris += [0, ring(1, l + 1), ring(1, l)]
+    for s in range(1, stacks - 1):
+        for l in range(slices):
+            a, b, c, d = ring(s, l), ring(s, l + 1), ring(s + 1, l + 1), ring(s + 1, l)
+            tris += [a, b, c, a, c, d]
+    for l in range(slices):
+        tris += [south, ring(stacks - 1, l), ring(stacks - 1, l + 1)]
+    t = np.asarray(tris, np.int32).reshape(-1, 3)
+    # make every triangle face outward
+    p0, p1, p2 = v[t[:, 0]], v[t[:, 1]], v[t[:, 2]]
+    n = np.cross(p1 - p0, p2 - p0)
+    flip = (n * (p0 + p1 + p2)).sum(-1) < 0
+    t[flip] = t[flip][:, [0, 2, 1]]
+    return v, t.reshape(-1)
+
+
+def sphere_field_scene(xres: int = 1920, yres: int = 1080, nmesh: int = 1024, slices: int = 70, stacks: int = 71,
+                       seed: int = 3, mirror: bool = True) -> SceneDesc:
+    """Config C3 / C5: nmesh displaced spheres on a jittered grid over a ground quad; mirror+diffuse shader so
+    Level 0..3 chains (the reference's "4 bounces": builtin/shader/std.go:95,219-261)."""
+    rng = np.random.default_rng(seed)
+    base_v, base_t = _uv_sphere(slices, stacks)
+    g = int(np.ceil(np.sqrt(nmesh)))
+    cell = 2.0 / g
+    shaders = [
+        ShaderStd("ground", DiffuseColour=(0.6, 0.6, 0.6), DiffuseStrength=1.0),
+        ShaderStd("lightmtl", EmissionColour=(1.0, 0.95, 0.9), EmissionStrength=20.0, DiffuseColour=(0.0, 0.0, 0.0), DiffuseStrength=1.0),
+    ]
+    if mirror:
+        shaders.append(ShaderStd("chrome", DiffuseColour=(0.5, 0.45, 0.4), DiffuseStrength=0.3,
+                                 Spec1Colour=(0.9, 0.9, 0.9), Spec1Strength=0.7, Spec1Roughness=0.0))
+    else:
+        shaders.append(ShaderStd("chrome", DiffuseColour=(0.5, 0.45, 0.4), DiffuseStrength=1.0))
+    meshes = []
+    gv = np.asarray([[-1.2, 0, -1.2], [-1.2, 0, 1.2], [1.2, 0, 1.2], [1.2, 0, -1.2]], np.float32)
+    meshes.append(PolyMesh("floor", gv, ["ground"], PolyCount=np.asarray([4]), FaceIdx=np.asarray([0, 1, 2, 3])))
+    for m in range(nmesh):
+        gx, gz = m % g, m // g
+        r = cell * (0.28 + 0.12 * rng.random())
+        cx = -1.0 + cell * (gx + 0.5) + cell * 0.15 * (rng.random() - 0.5)
+        cz = -1.0 + cell * (gz + 0.5) + cell * 0.15 * (rng.random() - 0.5)
+        cy = r * 1.05 + cell * 0.3 * rng.random()
+        disp = 1.0 + 0.06 * np.sin(base_v[:, 0] * 9.0 + m) * np.sin(base_v[:, 1] * 7.0 + 2 * m) * np.sin(base_v[:, 2] * 8.0)
+        v = (base_v * disp[:, None].astype(np.float32) * np.float32(r) + np.asarray([cx, cy, cz], np.float32)).astype(np.float32)
+        meshes.append(PolyMesh("sphere%d" % m, v, ["chrome"], FaceIdx=base_t.copy()))
+    cam = Camera(From=(0.0, 1.4, 2.3), To=(0.0, 0.1, 0.0), Fov=45.0, Focal=1.0)
+    sc = SceneDesc(XRes=xres, YRes=yres, camera=cam, shaders=shaders, meshes=meshes,
+                   lights=_light_pair(1.8, 0.5, "lightmtl"), MaxIter=256)
+    sc.name = "C3-spherefield-%dtri" % sc.num_tris
+    return sc
+
+
+def _quad(name, p, shader):
+    return PolyMesh(name, np.asarray(p, np.float32), [shader], PolyCount=np.asarray([4]), FaceIdx=np.asarray([0, 1, 2, 3]))
+
+
+def _box(name, lo, hi, shader):
+    x0, y0, z0 = lo
+    x1, y1, z1 = hi
+    v = np.asarray([[x0, y0, z0], [x1, y0, z0], [x1, y1, z0], [x0, y1, z0], [x0, y0, z1], [x1, y0, z1], [x1, y1, z1], [x0, y1, z1]], np.float32)
+    faces = [[0, 3, 2, 1], [4, 5, 6, 7], [0, 1, 5, 4], [3, 7, 6, 2], [0, 4, 7, 3], [1, 2, 6, 5]]  # outward
+    return PolyMesh(name, v, [shader], PolyCount=np.full(6, 4), FaceIdx=np.asarray(faces).reshape(-1))
+
+
+def cornell_box(xres: int = 512, yres: int = 512, boxes: bool = True) -> SceneDesc:
+    """Config C1: room [-1,1]x[0,2]x[-1,1], camera on +z looking at -z."""
+    shaders = [
+        ShaderStd("white", DiffuseColour=(0.73, 0.73, 0.73), DiffuseStrength=1.0),
+        ShaderStd("red", DiffuseColour=(0.65, 0.05, 0.05), DiffuseStrength=1.0),
+        ShaderStd("green", DiffuseColour=(0.12, 0.45, 0.15), DiffuseStrength=1.0),
+        ShaderStd("lightmtl", EmissionColour=(1.0, 0.9, 0.8), EmissionStrength=15.0, DiffuseColour=(0.0, 0.0, 0.0), DiffuseStrength=1.0),
+    ]
+    meshes = [
+        _quad("floor", [[-1, 0, -1], [-1, 0, 1], [1, 0, 1], [1, 0, -1]], "white"),      # Ng=+Y
+        _quad("ceiling", [[-1, 2, -1], [1, 2, -1], [1, 2, 1], [-1, 2, 1]], "white"),    # Ng=-Y
+        _quad("back", [[-1, 0, -1], [1, 0, -1], [1, 2, -1], [-1, 2, -1]], "white"),     # Ng=+Z
+        _quad("left", [[-1, 0, -1], [-1, 2, -1], [-1, 2, 1], [-1, 0, 1]], "red"),       # Ng=+X
+        _quad("right", [[1, 0, -1], [1, 0, 1], [1, 2, 1], [1, 2, -1]], "green"),        # Ng=-X
+    ]
+    if boxes:
+        meshes.append(_box("shortbox", (0.1, 0.0, 0.0), (0.7, 0.6, 0.6), "white"))
+        meshes.append(_box("tallbox", (-0.7, 0.0, -0.6), (-0.1, 1.2, 0.0), "white"))
+    lights = _light_pair(1.99, 0.35, "lightmtl")
+    cam = Camera(From=(0.0, 1.0, 3.4), To=(0.0, 1.0, 0.0), Fov=40.0, Focal=1.0)
+    return SceneDesc(XRes=xres, YRes=yres, camera=cam, shaders=shaders, meshes=meshes, lights=lights, MaxIter=16, name="C1-cornell")
+
+
+def incoherent_rays(rays: np.ndarray, hits: np.ndarray, seed: int = 7) -> np.ndarray:
+    """Level-1 "incoherent closest-hit" batch: cosine-hemisphere directions about the
+    direction-facing axis-aligned approximation of the surface normal at the primary hit points.
+    `rays` is the structured VgRay array, `hits` the VgHit array of the primary batch.  Only hit rays spawn
+    a bounce ray.  The normal is estimated from the incoming direction (flipped +Y), which is enough to make the
+    batch incoherent; exact normals are not needed because both sides trace these identical rays."""
+    rng = np.random.default_rng(seed)
+    mask = hits["prim"] >= 0
+    o = rays["o"][mask] + rays["d"][mask] * hits["t"][mask][:, None]
+    n = len(o)
+    u0, u1 = rng.random(n), rng.random(n)
+    r = np.sqrt(1.0 - u0)
+    th = 2.0 * np.pi * u1
+    d = np.stack([r * np.cos(th), np.sqrt(u0), r * np.sin(th)], -1)  # hemisphere about +Y
+    out = np.zeros(n, dtype=rays.dtype)
+    out["o"] = (o + np.asarray([0, 1e-3, 0])).astype(np.float32)
+    dn = d / np.linalg.norm(d, axis=1, keepdims=True)
+    out["d"] = dn.astype(np.float32)
+    out["tmax"] = np.float32(np.inf)
+    out["time"] = rays["time"][mask]
+    return out
