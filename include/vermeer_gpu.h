@@ -1,0 +1,230 @@
+/* vermeer_gpu.h — C ABI of the B200-native ray-traversal and path-integration engine.
+ *
+ * Two groups of entry points, both exported by libvermeer_b200.so:
+ *
+ *   vg_*  DEVICE LAYER.  What the reference-side cgo shim binds.  It consumes exactly the data the
+ *         reference's PreRender produces (qbvh.Node[], MotionQBVH, idxp, Verts, shaderidx, the
+ *         scene-level tree and geom order) and replaces the per-ray / per-frame hot path:
+ *             core.TraceProbe   (core/trace.go:26)      -> vg_trace_batch
+ *             core.Render/render (core/render.go:140,66) -> vg_render
+ *         See INTEGRATION.md for the Go stub.
+ *
+ *   vh_*  HOST LAYER.  A C++ mirror of the reference's node registry and PreRender pipeline
+ *         (nodes.Register nodes/register.go:26; PolyMesh.PreRender polymesh.go:73; qbvh.BuildAccel
+ *         build.go:293; scene.initAccel scene.go:135; Camera.PreRender camera.go:80) for hosts
+ *         without a Go toolchain.  It produces the arrays above and feeds them to vg_*.
+ *
+ * Conventions: every call returns 0 on success and <0 on error (vg_last_error gives the text);
+ * nothing throws or aborts across the ABI; all pointers are borrowed for the duration of the call
+ * (cgo rule) and copied before return; calls on one context are serialised by an internal mutex.
+ * There is NO CPU fallback: compute calls fail with VG_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef VERMEER_GPU_H
+#define VERMEER_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VG_OK 0
+#define VG_ERR_INVALID (-1)    /* bad argument / bad state */
+#define VG_ERR_NO_DEVICE (-2)  /* no usable CUDA device (there is no CPU fallback) */
+#define VG_ERR_CUDA (-3)       /* a CUDA call failed */
+#define VG_ERR_BUILD (-4)      /* host-side tree build failed (e.g. reference quirk f: coincident centroids) */
+#define VG_ERR_UNSUPPORTED (-5)
+
+/* ---- records ------------------------------------------------------------------------------ */
+
+/* One ray of a batch: the public part of core.Ray (core/ray.go:27-34).  Ray.Setup (ray.go:103-148:
+ * Kx/Ky/Kz, S, Dinv with float64 divides) runs on the device. 32 bytes. */
+typedef struct VgRay {
+  float o[3];
+  float d[3];
+  float tmax; /* Ray.Tclosest at Init: +Inf for camera/reflected rays, 1 for shadow rays */
+  float time; /* Ray.Time in [0,1) */
+} VgRay;
+
+/* Result of TraceProbe for one ray. 32 bytes.
+ * prim = ShaderContext.ElemID (leaf-order triangle index, polymesh/trace.go:513; original face index for
+ * motion meshes, trace.go:624) or -1 on a miss; geom = index of the Geom in creation order, -1 on a miss.
+ * t = Ray.Tclosest after the call (tmax on a miss). u,v,w = scaled barycentrics U,V,W of trace.go:186-188.
+ * nodesT = interior-node visits (Ray.NodesT, intersect.go:114), trisT = sum of LeafCount over visited
+ * triangle leaves; both feed the bytes model of the roofline. */
+typedef struct VgHit {
+  float t, u, v, w;
+  int32_t prim;
+  int32_t geom;
+  int32_t nodesT;
+  int32_t trisT;
+} VgHit;
+
+/* qbvh.Node, verbatim (qbvh/qbvh.go:31-36). 128 bytes. Boxes[child + 12*(0=min,1=max) + 4*axis]. */
+typedef struct VgNode {
+  float boxes[24];
+  uint32_t axis0, axis1, axis2;
+  int32_t children[4]; /* >=0 node; <0 leaf: bit31 | first<<4 | count-1; -1 empty (qbvh.go:61-91) */
+  int32_t parent;
+} VgNode;
+
+/* qbvh.MotionNode, verbatim (qbvh/mqbvh.go:24-29). 40 bytes. Boxes come separately as [key][node][24]. */
+typedef struct VgMotionNode {
+  int32_t axis0, axis1, axis2;
+  int32_t children[4];
+  int32_t parent;
+  uint32_t pad[2];
+} VgMotionNode;
+
+/* ShaderStd with every parameter a Constant map (builtin/shader/std.go:25-47, builtin/maps/constant.go).
+ * mask bit i set <=> the corresponding parameter is non-nil in the reference. */
+#define VG_MAT_EMISSION_COLOUR 1u
+#define VG_MAT_EMISSION_STRENGTH 2u
+#define VG_MAT_DIFFUSE_COLOUR 4u
+#define VG_MAT_DIFFUSE_STRENGTH 8u
+#define VG_MAT_DIFFUSE_ROUGHNESS 16u
+#define VG_MAT_SPEC1_COLOUR 32u
+#define VG_MAT_SPEC1_STRENGTH 64u
+#define VG_MAT_SPEC1_ROUGHNESS 128u
+#define VG_MAT_IOR 256u
+typedef struct VgMaterial {
+  uint32_t mask;
+  float emission_colour[3];
+  float emission_strength;
+  float diffuse_colour[3];
+  float diffuse_strength;
+  float diffuse_roughness;
+  float spec1_colour[3];
+  float spec1_strength;
+  float spec1_roughness;
+  float ior;
+} VgMaterial;
+
+/* light.Tri (builtin/light/triangle.go:18-28) after PreRender. */
+typedef struct VgTriLight {
+  float p0[3], p1[3], p2[3];
+  int32_t samples;  /* Samples; NumSamples = 1<<samples (triangle.go:71-73) */
+  int32_t material; /* index into the material table (the light's Shader) */
+  int32_t geom;     /* geom id of the mesh the light created for itself (triangle.go:48-50) */
+} VgTriLight;
+
+/* camera.Camera after PreRender (builtin/camera/camera.go:80-98): single-key LocalToWorld after the
+ * decompose/recompose of camera.go:188-192,225-236 (column major, math/matrix4.go:9-18). */
+typedef struct VgCamera {
+  float local_to_world[16];
+  float tan_theta_focal;
+  float aspect;
+  float focal;
+  float radius;
+} VgCamera;
+
+typedef struct VgStats {
+  uint64_t rays;        /* every TraceProbe equivalent (core/stats.go:26-28) */
+  uint64_t shadow_rays; /* of which RayTypeShadow (stats.go:31-33) */
+  uint64_t nodes_t;     /* sum of interior-node visits */
+  uint64_t tris_t;      /* sum of leaf triangle counts */
+  uint64_t kernel_launches;
+  double render_ms;   /* device time of the last vg_render (CUDA events) */
+  double trace_ms;    /* device time of the last vg_trace_batch* kernel (CUDA events) */
+  double traverse_ms; /* device time spent in traversal kernels during the last vg_render */
+} VgStats;
+
+/* ---- device layer ------------------------------------------------------------------------- */
+
+typedef struct vg_ctx vg_ctx;
+
+int vg_create(vg_ctx** out, int device_ordinal);
+void vg_destroy(vg_ctx* ctx);
+const char* vg_last_error(vg_ctx* ctx); /* ctx may be NULL: error of the last failed vg_create */
+int vg_device_count(void);
+
+/* Scene assembly. geom ids are 0..n_geoms-1 in creation order (core.AddNode order, core/core.go:77-93). */
+int vg_scene_begin(vg_ctx* ctx, int n_geoms);
+/* Static PolyMesh after initAccel (buildqbvh.go:85-129): nodes, leaf-ordered idxp (3*n_tris), Verts (n_verts*3),
+ * optional leaf-ordered shaderidx (n_tris) mapping to material_ids[], optional Normals + leaf-ordered normalidx. */
+int vg_mesh_upload(vg_ctx* ctx, int geom_id, const VgNode* nodes, int n_nodes, const uint32_t* idxp, int n_tris,
+                   const float* verts, int n_verts, const uint8_t* shaderidx, const int32_t* material_ids, int n_materials,
+                   const float* normals, int n_normals, const uint32_t* normalidx, float raybias);
+/* Motion PolyMesh after initAccel (buildqbvh.go:19-56,148-212): topology, boxes[key][node][24], UNreordered idxp,
+ * accel_idx (leaf order -> face), Verts keys*n_verts*3 (key-major, core/param/array.go:26).
+ * ref_compat != 0 reproduces reference quirk (b): leaf slot i tests face i (trace.go:532-537). */
+int vg_mesh_upload_motion(vg_ctx* ctx, int geom_id, const VgMotionNode* topo, int n_nodes, const float* boxes, int keys,
+                          const uint32_t* idxp, const int32_t* accel_idx, int n_tris, const float* verts, int n_verts,
+                          const uint8_t* shaderidx, const int32_t* material_ids, int n_materials, float raybias, int ref_compat);
+/* Scene-level tree (builtin/scene/scene.go:135-203): leafMax=1 nodes over geoms; geom_of_slot[i] = geom id at leaf slot i. */
+int vg_scene_upload(vg_ctx* ctx, const VgNode* nodes, int n_nodes, const int32_t* geom_of_slot, int n_slots);
+int vg_scene_upload_motion(vg_ctx* ctx, const VgMotionNode* topo, int n_nodes, const float* boxes, int keys,
+                           const int32_t* geom_of_slot, int n_slots);
+/* Flatten everything into the device layout (DESIGN.md "data layout in HBM") and copy it to HBM. */
+int vg_scene_commit(vg_ctx* ctx);
+
+int vg_set_materials(vg_ctx* ctx, const VgMaterial* mats, int n);
+int vg_set_lights(vg_ctx* ctx, const VgTriLight* lights, int n);
+int vg_set_camera(vg_ctx* ctx, const VgCamera* cam);
+int vg_set_frame(vg_ctx* ctx, int xres, int yres);
+/* Image partition across processes/GPUs: this context renders the 32x32 tiles (tx,ty) with
+ * (tx + ty*stride_k) % world == rank (core/render.go:196-199 tiles). Default rank 0 of 1. */
+int vg_set_partition(vg_ctx* ctx, int rank, int world);
+/* framescramble (core/render.go:18-23,166-176): npix*6 uint64 {lensU,lensV,time,lambda,scramble0,scramble1}, row-major pixels. */
+int vg_set_scramble(vg_ctx* ctx, const uint64_t* table, int64_t npix);
+/* Options: "trace_last_level" (1 = trace the level-4 mirror ray like the reference, std.go:243; default 1),
+ * "iters_per_batch" (wavefront batch depth, default 4). */
+int vg_set_option(vg_ctx* ctx, const char* name, int value);
+
+/* TraceProbe over a batch (core/trace.go:26). flags: */
+#define VG_TRACE_ANY_HIT 1u /* RayTypeShadow: return at the first leaf that reports a hit (intersect.go:228-236) */
+int vg_trace_batch(vg_ctx* ctx, const VgRay* rays, int64_t n, VgHit* hits, uint32_t flags);               /* host buffers */
+int vg_trace_batch_device(vg_ctx* ctx, const VgRay* d_rays, int64_t n, VgHit* d_hits, uint32_t flags);    /* device buffers */
+
+/* The Render loop (core/render.go:184-205) for 0-based iterations [iter_begin, iter_end) over this context's tiles,
+ * continuing the running mean held on the device. fb_out (xres*yres*3 floats, row-major, may be NULL) receives the
+ * full-frame buffer with non-owned pixels left 0. */
+int vg_render(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out);
+int vg_clear_framebuffer(vg_ctx* ctx);
+/* Device pointer to the row-major xres*yres*3 float framebuffer (for NCCL gathers done by the caller). */
+int vg_framebuffer_device(vg_ctx* ctx, float** d_fb);
+int vg_get_stats(vg_ctx* ctx, VgStats* out);
+int vg_reset_stats(vg_ctx* ctx);
+
+/* ---- host layer ---------------------------------------------------------------------------- */
+
+typedef struct vh_scene vh_scene;
+
+int vh_scene_create(vh_scene** out);
+void vh_scene_destroy(vh_scene* s);
+const char* vh_last_error(vh_scene* s);
+
+/* Registered node types, as in nodes.Register (nodes/register.go:26): returns the number of names and, if
+ * names != NULL, fills up to cap of them. */
+int vh_registered_nodes(const char** names, int cap);
+
+int vh_set_globals(vh_scene* s, int xres, int yres, int max_iter);
+int vh_add_shader_std(vh_scene* s, const char* name, const VgMaterial* params);
+int vh_add_polymesh(vh_scene* s, const char* name, const float* verts, int n_verts, int keys, const int32_t* polycount, int n_poly,
+                    const int32_t* faceidx, int n_faceidx, const char* shaders_nl, const int32_t* shaderidx, int n_shaderidx,
+                    const float* normals, int n_normals, const int32_t* normalidx, int n_normalidx, float raybias);
+int vh_add_trilight(vh_scene* s, const char* name, const float* p0, const float* p1, const float* p2, const char* shader, int samples);
+int vh_set_camera_lookat(vh_scene* s, const float* from, const float* to, const float* up, float roll, float fov, float focal,
+                         float aspect, float radius);
+/* core.PreRender (core/core.go:36-61): triangulate, build per-mesh QBVH/MQBVH, light meshes, scene tree, camera matrix. */
+int vh_prerender(vh_scene* s);
+/* Upload the pre-rendered scene into a device context (calls vg_scene_begin .. vg_scene_commit, vg_set_*). */
+int vh_upload(vh_scene* s, vg_ctx* ctx, int motion_ref_compat);
+
+/* Inspection of the host-built structures (parity tests compare them with the oracle's). */
+int vh_num_geoms(vh_scene* s);
+int vh_scene_info(vh_scene* s, int32_t* out4 /* n_nodes, is_motion, keys, n_slots */);
+int vh_scene_nodes(vh_scene* s, VgNode* out);
+int vh_scene_motion_nodes(vh_scene* s, VgMotionNode* topo, float* boxes);
+int vh_scene_geom_order(vh_scene* s, int32_t* out);
+int vh_mesh_info(vh_scene* s, int geom_id, int32_t* out6 /* n_nodes, n_tris, keys, n_verts, is_motion, has_normals */);
+int vh_mesh_nodes(vh_scene* s, int geom_id, VgNode* out);
+int vh_mesh_motion_nodes(vh_scene* s, int geom_id, VgMotionNode* topo, float* boxes);
+int vh_mesh_idxp(vh_scene* s, int geom_id, uint32_t* idxp, int32_t* accel_idx);
+int vh_camera(vh_scene* s, VgCamera* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VERMEER_GPU_H */

@@ -1,0 +1,113 @@
+"""Parity of the CUDA traversal (vg_trace_batch through the C ABI) against the oracle on identical rays.
+
+Bar (BASELINE.json north_star): primitive id and hit/miss bit-exact, t bit-exact (the traversal arithmetic is
+sub/mul/add/div only, so parity mode is expected to be exact, not just within 1e-5)."""
+import numpy as np
+import pytest
+
+from conftest import assert_hits_equal, random_rays
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(scene, motion_ref_compat=False):
+    from oracle.binding import Oracle
+    from vermeer_b200.host import Device, HostScene
+    ora = Oracle(scene, motion_ref_compat=motion_ref_compat)
+    host = HostScene(scene).prerender()
+    dev = Device(0).upload(host, motion_ref_compat=motion_ref_compat)
+    return ora, dev
+
+
+@pytest.mark.parametrize("any_hit", [False, True])
+def test_cornell_random_rays(built_library, any_hit):
+    from vermeer_b200 import scenes
+    ora, dev = _pair(scenes.cornell_box(64, 64))
+    rays = random_rays(20000, 11, lo=(-0.99, 0.01, -0.99), hi=(0.99, 1.98, 0.99), tmax=(1.5 if any_hit else np.inf))
+    g = dev.trace(rays, any_hit=any_hit)
+    o = ora.trace(rays, any_hit=any_hit)
+    assert_hits_equal(g, o, what="cornell any_hit=%s" % any_hit)
+    assert (g["prim"] >= 0).mean() > 0.3
+
+
+def test_cornell_camera_rays(built_library):
+    from vermeer_b200 import scenes
+    sc = scenes.cornell_box(96, 96)
+    ora, dev = _pair(sc)
+    ora.set_scramble(scenes.splitmix64_table(1, 96 * 96))
+    rays = ora.camera_rays(1)
+    assert_hits_equal(dev.trace(rays), ora.trace(rays), what="cornell camera")
+
+
+@pytest.mark.parametrize("nq", [40, 300])
+def test_heightfield_primary_and_incoherent(built_library, nq):
+    from vermeer_b200 import scenes
+    sc = scenes.heightfield_scene(128, 72, nq=nq)
+    ora, dev = _pair(sc)
+    ora.set_scramble(scenes.splitmix64_table(2, 128 * 72))
+    rays = ora.camera_rays(3)
+    g = dev.trace(rays)
+    o = ora.trace(rays)
+    assert_hits_equal(g, o, what="heightfield primary")
+    assert (g["prim"] >= 0).mean() > 0.5
+    inc = scenes.incoherent_rays(rays, g, seed=5)
+    assert_hits_equal(dev.trace(inc), ora.trace(inc), what="heightfield incoherent")
+    sh = inc.copy()
+    sh["tmax"] = 0.7
+    assert_hits_equal(dev.trace(sh, any_hit=True), ora.trace(sh, any_hit=True), what="heightfield any-hit")
+
+
+def test_sphere_field_two_level(built_library):
+    from vermeer_b200 import scenes
+    sc = scenes.sphere_field_scene(64, 64, nmesh=25, slices=16, stacks=17)
+    ora, dev = _pair(sc)
+    rays = random_rays(30000, 3, lo=(-1.1, 0.0, -1.1), hi=(1.1, 1.5, 1.1))
+    assert_hits_equal(dev.trace(rays), ora.trace(rays), what="sphere field")
+    sh = rays.copy()
+    sh["tmax"] = 0.5
+    assert_hits_equal(dev.trace(sh, any_hit=True), ora.trace(sh, any_hit=True), what="sphere field any-hit")
+
+
+@pytest.mark.parametrize("ref_compat", [False, True])
+def test_motion_heightfield(built_library, ref_compat):
+    from vermeer_b200 import scenes
+    sc = scenes.heightfield_scene(64, 64, nq=60, motion=True)
+    ora, dev = _pair(sc, motion_ref_compat=ref_compat)
+    rays = random_rays(20000, 4, lo=(-1.0, 0.3, -1.0), hi=(1.0, 1.4, 1.0))
+    rays["d"][:, 1] = -np.abs(rays["d"][:, 1])  # look down at the field
+    g = dev.trace(rays)
+    o = ora.trace(rays)
+    assert_hits_equal(g, o, what="motion ref_compat=%s" % ref_compat)
+    assert (g["prim"] >= 0).mean() > 0.2
+
+
+def test_degenerate_rays(built_library):
+    """Axis-parallel directions (Dinv = +-Inf), origins on box planes (0*Inf = NaN in the slab test), zero-length and
+    NaN rays: the x86 MINPS/MAXPS operand semantics decide hit/miss here (qbvh/intersect_amd64.s)."""
+    from vermeer_b200 import scenes
+    from vermeer_b200.host import RAY_DTYPE
+    sc = scenes.cornell_box(32, 32)
+    ora, dev = _pair(sc)
+    rays = []
+    for o in [(0, 1, 0), (0.1, 0.0, 0.0), (-1, 1, -1), (1, 2, 1), (0.7, 0.6, 0.6), (0.1, 0.3, 0.0), (-0.7, 1.2, -0.6), (0.25, 1.99, 0.0)]:
+        for d in [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1), (1, 1, 0), (0, 1, 1), (-1, 0, 1), (1, -1, 1)]:
+            rays.append((o, d, np.inf, 0.0))
+    rays.append(((0, 1, 0), (0, 0, 0), np.inf, 0.0))
+    rays.append(((0, 1, 0), (np.nan, 0, 1), np.inf, 0.0))
+    rays.append(((0, 1, 0), (0, 0, -1), 0.0, 0.0))
+    r = np.zeros(len(rays), RAY_DTYPE)
+    for i, (o, d, tm, ti) in enumerate(rays):
+        r[i] = (o, d, tm, ti)
+    g, o = dev.trace(r), ora.trace(r)
+    # t of a miss is tmax (may be inf/nan-free); compare everything bitwise
+    assert_hits_equal(g, o, what="degenerate")
+
+
+def test_empty_and_ragged_batches(built_library):
+    from vermeer_b200 import scenes
+    sc = scenes.cornell_box(32, 32)
+    ora, dev = _pair(sc)
+    assert len(dev.trace(random_rays(0, 1))) == 0
+    for n in (1, 31, 33, 127, 129, 1000):
+        rays = random_rays(n, n, lo=(-0.9, 0.1, -0.9), hi=(0.9, 1.9, 0.9))
+        assert_hits_equal(dev.trace(rays), ora.trace(rays), what="n=%d" % n)

@@ -1,0 +1,126 @@
+// vg_ctx: owner of all device memory and of the staged (reference-format) scene data.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/vermeer_gpu.h"
+#include "device_scene.h"
+
+namespace vg {
+
+struct MeshStage {
+  bool present = false;
+  bool motion = false;
+  std::vector<VgNode> nodes;
+  std::vector<VgMotionNode> topo;
+  std::vector<float> boxes;  // [keys][n_nodes][24]
+  int keys = 1;
+  std::vector<uint32_t> idxp;
+  std::vector<int32_t> accel_idx;
+  int n_tris = 0;
+  std::vector<float> verts;  // [keys][n_verts][3]
+  int n_verts = 0;
+  std::vector<uint8_t> shaderidx;
+  std::vector<int32_t> material_ids;
+  std::vector<float> normals;
+  std::vector<uint32_t> normalidx;
+  float raybias = 0;
+  int ref_compat = 0;
+};
+
+struct SceneStage {
+  bool present = false;
+  bool motion = false;
+  std::vector<VgNode> nodes;
+  std::vector<VgMotionNode> topo;
+  std::vector<float> boxes;
+  int keys = 1;
+  std::vector<int32_t> geom_of_slot;
+};
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct RenderState;  // render.cu
+
+}  // namespace vg
+
+struct vg_ctx {
+  std::mutex mu;
+  std::string err;
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // staged scene (reference formats)
+  std::vector<vg::MeshStage> meshes;
+  vg::SceneStage scene;
+  bool committed = false;
+
+  // device scene
+  vg::DevScene dev{};
+  vg::DevBuf<vg::DevNode> d_nodes;
+  vg::DevBuf<vg::DevMotionNode> d_mtopo;
+  vg::DevBuf<float4> d_mboxes, d_tris, d_mtris, d_normals;
+  vg::DevBuf<vg::DevGeom> d_geoms;
+  vg::DevBuf<uint8_t> d_prim_material;
+  size_t scene_bytes = 0;
+
+  // batch trace scratch
+  vg::DevBuf<VgRay> d_rays;
+  vg::DevBuf<VgHit> d_hits;
+  vg::DevBuf<unsigned long long> d_counters;  // [0] queue head, [1..] stats
+
+  // shading inputs
+  std::vector<VgMaterial> materials;
+  std::vector<VgTriLight> lights;
+  VgCamera camera{};
+  bool have_camera = false;
+  int xres = 0, yres = 0;
+  int rank = 0, world = 1;
+  std::vector<uint64_t> scramble;  // full frame, npix*6
+  int opt_trace_last_level = 1;
+  int opt_iters_per_batch = 4;
+
+  vg::RenderState* rs = nullptr;
+  VgStats stats{};
+
+  int fail(int code, const std::string& msg) {
+    err = msg;
+    return code;
+  }
+  int cuda_fail(cudaError_t e, const char* what) {
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return VG_ERR_CUDA;
+  }
+};
+
+namespace vg {
+// render.cu
+int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out);
+int render_clear(vg_ctx* ctx);
+int render_fb_device(vg_ctx* ctx, float** d_fb);
+void render_invalidate(vg_ctx* ctx);  // scene / frame / partition changed
+void render_destroy(vg_ctx* ctx);
+}  // namespace vg

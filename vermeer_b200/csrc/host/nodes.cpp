@@ -1,0 +1,490 @@
+// Host mirror of the reference's PreRender pipeline — see nodes.h for the interface map.
+#include "nodes.h"
+
+#include <cmath>
+#include <mutex>
+
+#include "builder.h"
+
+namespace vh {
+
+// ---- registry (nodes/register.go) -------------------------------------------------------------
+namespace {
+std::map<std::string, CreateFn>& registry() {
+  static std::map<std::string, CreateFn> r;
+  return r;
+}
+std::mutex& registry_mu() {
+  static std::mutex m;
+  return m;
+}
+}  // namespace
+
+int Register(const std::string& name, CreateFn create) {
+  std::lock_guard<std::mutex> l(registry_mu());
+  if (registry().count(name)) return -1;  // "node type already registered"
+  registry()[name] = std::move(create);
+  return 0;
+}
+std::unique_ptr<Node> CreateNode(const std::string& name) {
+  std::lock_guard<std::mutex> l(registry_mu());
+  auto it = registry().find(name);
+  if (it == registry().end()) return nullptr;
+  return it->second();
+}
+std::vector<std::string> RegisteredNames() {
+  std::lock_guard<std::mutex> l(registry_mu());
+  std::vector<std::string> v;
+  for (auto& kv : registry()) v.push_back(kv.first);
+  return v;
+}
+
+// the builtin nodes register themselves like the reference's init() functions
+// (polymesh.go:120-122, std.go:318-324, triangle.go:350-356, camera.go:325-335, parser.go:76)
+namespace {
+struct RegisterBuiltins {
+  RegisterBuiltins() {
+    Register("Globals", [] { return std::unique_ptr<Node>(new Globals()); });
+    Register("Camera", [] { return std::unique_ptr<Node>(new Camera()); });
+    Register("PolyMesh", [] { return std::unique_ptr<Node>(new PolyMesh()); });
+    Register("ShaderStd", [] { return std::unique_ptr<Node>(new ShaderStd()); });
+    Register("TriLight", [] { return std::unique_ptr<Node>(new TriLight()); });
+  }
+} g_register_builtins;
+}  // namespace
+
+// ---- matrices -----------------------------------------------------------------------------------
+void m4_cofactors(const float* m, float* inv) {  // math/matrix4.go:113-132, term order kept
+  inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+  inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+  inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+  inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+  inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+  inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+  inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+  inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+  inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+  inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+  inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+  inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+  inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+  inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+  inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+  inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+}
+bool m4_inverse(const M4& a, M4* out) {
+  float inv[16];
+  m4_cofactors(a.m, inv);
+  float det = a.m[0] * inv[0] + a.m[1] * inv[4] + a.m[2] * inv[8] + a.m[3] * inv[12];
+  if (det == 0.0f) return false;
+  det = 1.0f / det;
+  for (int i = 0; i < 16; i++) out->m[i] = inv[i] * det;
+  return true;
+}
+float m4_det(const M4& a) {
+  float inv[16];
+  m4_cofactors(a.m, inv);
+  return a.m[0] * inv[0] + a.m[1] * inv[4] + a.m[2] * inv[8] + a.m[3] * inv[12];
+}
+
+namespace {
+struct Quat { float X, Y, Z, W; };
+
+// math/matrix4.go:345-363 — Higham iteration Q <- (Q + Q^-T)/2, at most 10 rounds, one-sided tolerance test (:331-339)
+bool polar_factor(const M4& m, M4* out) {
+  M4 Q = m;
+  for (int it = 0; it < 10; it++) {
+    M4 Qinv;
+    if (!m4_inverse(Q, &Qinv)) return false;
+    M4 Qn = m4_scale(.5f, m4_add(Q, m4_transpose(Qinv)));
+    bool same = true;
+    for (int i = 0; i < 16; i++)
+      if (Qn.m[i] - Q.m[i] > 0.000001f) { same = false; break; }
+    if (same) { *out = Qn; return true; }
+    Q = Qn;
+  }
+  return false;
+}
+Quat to_quat(const M4& m) {  // math/quat.go:124-154
+  Quat q;
+  const float tr = m.at(0, 0) + m.at(1, 1) + m.at(2, 2);
+  if (tr > 0.0f) {
+    const float S = sqrtf(tr + 1.0f) * 2;
+    q.W = 0.25f * S; q.X = (m.at(2, 1) - m.at(1, 2)) / S; q.Y = (m.at(0, 2) - m.at(2, 0)) / S; q.Z = (m.at(1, 0) - m.at(0, 1)) / S;
+  } else if ((m.at(0, 0) > m.at(1, 1)) && (m.at(0, 0) > m.at(2, 2))) {
+    const float S = sqrtf(1.0f + m.at(0, 0) - m.at(1, 1) - m.at(2, 2)) * 2;
+    q.W = (m.at(2, 1) - m.at(1, 2)) / S; q.X = 0.25f * S; q.Y = (m.at(0, 1) + m.at(1, 0)) / S; q.Z = (m.at(0, 2) + m.at(2, 0)) / S;
+  } else if (m.at(1, 1) > m.at(2, 2)) {
+    const float S = sqrtf(1.0f + m.at(1, 1) - m.at(0, 0) - m.at(2, 2)) * 2;
+    q.W = (m.at(0, 2) - m.at(2, 0)) / S; q.X = (m.at(0, 1) + m.at(1, 0)) / S; q.Y = 0.25f * S; q.Z = (m.at(1, 2) + m.at(2, 1)) / S;
+  } else {
+    const float S = sqrtf(1.0f + m.at(2, 2) - m.at(0, 0) - m.at(1, 1)) * 2;
+    q.W = (m.at(1, 0) - m.at(0, 1)) / S; q.X = (m.at(0, 2) + m.at(2, 0)) / S; q.Y = (m.at(1, 2) + m.at(2, 1)) / S; q.Z = 0.25f * S;
+  }
+  return q;
+}
+M4 from_quat(Quat q) {  // math/quat.go:73-96
+  M4 m{};
+  const float n = 1.0f / sqrtf(q.X * q.X + q.Y * q.Y + q.Z * q.Z + q.W * q.W);
+  const float x = q.X * n, y = q.Y * n, z = q.Z * n, w = q.W * n;
+  m.set(0, 0, 1 - 2 * y * y - 2 * z * z); m.set(0, 1, 2 * x * y - 2 * w * z); m.set(0, 2, 2 * x * z + 2 * w * y);
+  m.set(1, 0, 2 * x * y + 2 * w * z); m.set(1, 1, 1 - 2 * x * x - 2 * z * z); m.set(1, 2, 2 * y * z - 2 * w * x);
+  m.set(2, 0, 2 * x * z - 2 * w * y); m.set(2, 1, 2 * y * z + 2 * w * x); m.set(2, 2, 1 - 2 * x * x - 2 * y * y);
+  m.set(3, 3, 1.0f);
+  return m;
+}
+Quat slerp(Quat a, Quat b, float t) {  // math/quat.go:30-66
+  const float c = a.W * b.W + a.X * b.X + a.Y * b.Y + a.Z * b.Z;
+  if (fabs32(c) >= 1.0f) return a;
+  const float half = (float)std::acos((double)c);
+  const float s = sqrtf(1.0f - c * c);
+  if (fabs32(s) < 0.001f) return Quat{a.X * 0.5f + b.X * 0.5f, a.Y * 0.5f + b.Y * 0.5f, a.Z * 0.5f + b.Z * 0.5f, a.W * 0.5f + b.W * 0.5f};
+  const float ra = (float)std::sin((double)((1 - t) * half)) / s;
+  const float rb = (float)std::sin((double)(t * half)) / s;
+  return Quat{a.X * ra + b.X * rb, a.Y * ra + b.Y * rb, a.Z * ra + b.Z * rb, a.W * ra + b.W * rb};
+}
+}  // namespace
+
+// ---- Camera (builtin/camera/camera.go:80-98,109-193; ComputeRay's matrix :225-236) ----------------
+int Camera::PreRender(Core& core, std::string* err) {
+  if (Type != "LookAt") { *err = "Camera: only Type \"LookAt\" is supported on this path"; return -1; }
+  if (Aspect == 0.0f) Aspect = core.FrameAspect();
+  const float deg = Fov / 2;
+  const float tan_theta_focal = (float)std::tan((double)(deg * kPi32 / 180.0f)) * Focal;
+
+  // single motion key: camera.go:154-187 with i = 0 (time = 0, t = 0)
+  const float t = 0.0f;
+  const V3 P = lerp(To, To, t);
+  const V3 W = normalize(From - P);  // W points away from the target
+  const V3 u = normalize(cross(Up, W));
+  const V3 v = normalize(cross(u, W));
+  const float roll = (1 - t) * Roll + t * Roll;
+  const float cr = (float)std::cos((double)roll), sr = (float)std::sin((double)roll);
+  const V3 U = scale(cr, u) + scale(sr, v);
+  const V3 V = scale(-sr, u) + scale(cr, v);
+  M4 basis{};
+  basis.m[0] = U.x; basis.m[1] = U.y; basis.m[2] = U.z;
+  basis.m[4] = V.x; basis.m[5] = V.y; basis.m[6] = V.z;
+  basis.m[8] = W.x; basis.m[9] = W.y; basis.m[10] = W.z;
+  basis.m[15] = 1.0f;
+  M4 trans = m4_identity();
+  trans.m[12] = From.x; trans.m[13] = From.y; trans.m[14] = From.z;
+  M4 mtx = m4_mul(trans, basis);
+
+  // math/animdecomp.go:21-63: M = T * R * S via polar decomposition, then recomposed per ray with
+  // k = Time*(len(decomp)-1) = 0 (camera.go:225-236) -> constant for a single-key camera.
+  const float sign = m4_det(mtx) >= 0.0f ? 1.0f : -1.0f;
+  V3 T{mtx.at(0, 3), mtx.at(1, 3), mtx.at(2, 3)};
+  mtx.set(0, 3, 0); mtx.set(1, 3, 0); mtx.set(2, 3, 0);
+  if (sign < 0.0f) mtx = m4_mul(m4_scale(-1, m4_identity()), mtx);
+  Quat R{0, 0, 0, 1};
+  M4 S = m4_identity();
+  M4 Q;
+  if (polar_factor(mtx, &Q)) {
+    S = m4_mul(m4_transpose(Q), mtx);
+    R = to_quat(Q);
+    if (sign < 0.0f) { S = m4_mul(m4_scale(-1, m4_identity()), S); S.m[15] = 1; }
+  }
+  const V3 Tl = lerp(T, T, 0.0f);
+  const Quat Rl = slerp(R, R, 0.0f);
+  const M4 Sl = m4_lerp(S, S, 0.0f);
+  M4 tl = m4_identity();
+  tl.m[12] = Tl.x; tl.m[13] = Tl.y; tl.m[14] = Tl.z;
+  const M4 M = m4_mul(tl, m4_mul(from_quat(Rl), Sl));
+
+  std::memcpy(out.local_to_world, M.m, sizeof(M.m));
+  out.tan_theta_focal = tan_theta_focal;
+  out.aspect = Aspect;
+  out.focal = Focal;
+  out.radius = Radius;
+  return 0;
+}
+
+// ---- PolyMesh ------------------------------------------------------------------------------------
+// builtin/geom/polymesh/init.go:12-134: fan-triangulate polygons into idxp (+ normal / shader indices)
+void PolyMesh::triangulate() {
+  const bool hasN = !Normals.Elems.empty();
+  auto emit = [&](uint32_t a, uint32_t b, uint32_t c) {
+    idxp.push_back((uint32_t)FaceIdx[a]); idxp.push_back((uint32_t)FaceIdx[b]); idxp.push_back((uint32_t)FaceIdx[c]);
+    if (hasN) {
+      const std::vector<int32_t>& src = hasNormalIdx ? NormalIdx : FaceIdx;
+      normalidx.push_back((uint32_t)src[a]); normalidx.push_back((uint32_t)src[b]); normalidx.push_back((uint32_t)src[c]);
+    }
+  };
+  if (hasPolyCount) {
+    uint32_t base = 0;
+    for (size_t k = 0; k < PolyCount.size(); k++) {
+      for (int j = 1; j <= PolyCount[k] - 2; j++) {
+        emit(base, base + j, base + j + 1);
+        if (!ShaderIdx.empty()) shaderidx.push_back((uint8_t)ShaderIdx[k]);
+      }
+      base += (uint32_t)PolyCount[k];
+    }
+  } else {
+    if (hasFaceIdx) {
+      for (size_t j = 0; j < FaceIdx.size(); j++) {
+        idxp.push_back((uint32_t)FaceIdx[j]);
+        if (hasN) normalidx.push_back(hasNormalIdx ? (uint32_t)NormalIdx[j] : (uint32_t)FaceIdx[j]);
+      }
+    } else {
+      for (int j = 0; j < Verts.ElemsPerKey; j++) {
+        idxp.push_back((uint32_t)j);
+        if (hasN) normalidx.push_back(hasNormalIdx ? (uint32_t)NormalIdx[j] : (uint32_t)j);
+      }
+    }
+    for (int32_t s : ShaderIdx) shaderidx.push_back((uint8_t)s);
+  }
+  FaceIdx.clear(); PolyCount.clear(); NormalIdx.clear(); ShaderIdx.clear();
+}
+
+// polymesh.go:73-97
+int PolyMesh::PreRender(Core& core, std::string* err) {
+  if (Verts.MotionKeys < 1 || Verts.ElemsPerKey < 1) { *err = "PolyMesh " + NodeName + ": no Verts"; return -1; }
+  triangulate();
+  if (idxp.size() % 3 != 0) { *err = "PolyMesh " + NodeName + ": index count is not a multiple of 3"; return -1; }
+  for (uint32_t i : idxp)
+    if (i >= (uint32_t)Verts.ElemsPerKey) { *err = "PolyMesh " + NodeName + ": vertex index out of range"; return -1; }
+  facecount = (int)idxp.size() / 3;
+  for (const std::string& s : Shader) {
+    Node* n = core.FindNode(s);
+    if (!n) { *err = "Unable to find node (shader " + s + ")"; return -1; }
+    ShaderStd* sh = dynamic_cast<ShaderStd*>(n);
+    if (!sh) { *err = "Unable to find shader " + s; return -1; }
+    shader.push_back(sh);
+  }
+  return initAccel(err);
+}
+
+// builtin/geom/polymesh/buildqbvh.go:14-144
+int PolyMesh::initAccel(std::string* err) {
+  std::vector<Box> boxes(facecount);
+  std::vector<V3> cent(facecount);
+  std::vector<int32_t> idxs(facecount);
+  const int E = Verts.ElemsPerKey;
+
+  if (Verts.MotionKeys > 1) {
+    // topology from the mid-time snapshot (:19-52)
+    const float k = 0.5f * (float)(Verts.MotionKeys - 1);
+    const float time = k - floorf(k);
+    const int key = (int)floorf(k), key2 = (int)ceilf(k);
+    for (int i = 0; i < facecount; i++) {
+      V3 p[3];
+      for (int j = 0; j < 3; j++) p[j] = lerp(Verts.Elems[(int)idxp[i * 3 + j] + E * key], Verts.Elems[(int)idxp[i * 3 + j] + E * key2], time);
+      boxes[i].reset();
+      for (int j = 0; j < 3; j++) boxes[i].grow_point(p[j].x, p[j].y, p[j].z);
+      cent[i] = V3{(p[0].x + p[1].x + p[2].x) / 3, (p[0].y + p[1].y + p[2].y) / 3, (p[0].z + p[1].z + p[2].z) / 3};
+      idxs[i] = i;
+    }
+    if (build_mqbvh(boxes.data(), cent.data(), idxs.data(), facecount, 16, mtopo, err) != 0) return -1;
+    accel_idx = idxs;  // NOTE: idxp is NOT reordered on this path (the function returns at :56) — quirk (b)
+    // per-key boxes (:148-212)
+    mboxes.assign((size_t)Verts.MotionKeys * mtopo.size() * 24, 0.0f);
+    Box full;
+    full.reset();
+    for (int kk = 0; kk < Verts.MotionKeys; kk++) {
+      Box b = initMotionBoxesRec(kk, 0);
+      motionBounds.push_back(b);
+      full.grow_box(b);
+    }
+    bounds = full;
+    return 0;
+  }
+
+  for (int i = 0; i < facecount; i++) {
+    const V3 p0 = Verts.Elems[idxp[i * 3 + 0]], p1 = Verts.Elems[idxp[i * 3 + 1]], p2 = Verts.Elems[idxp[i * 3 + 2]];
+    boxes[i].reset();
+    boxes[i].grow_point(p0.x, p0.y, p0.z);
+    boxes[i].grow_point(p1.x, p1.y, p1.z);
+    boxes[i].grow_point(p2.x, p2.y, p2.z);
+    cent[i] = V3{(p0.x + p1.x + p2.x) / 3, (p0.y + p1.y + p2.y) / 3, (p0.z + p1.z + p2.z) / 3};
+    idxs[i] = i;
+  }
+  if (build_qbvh(boxes.data(), cent.data(), idxs.data(), facecount, 16, qbvh, &bounds, err) != 0) return -1;
+  accel_idx = idxs;
+  // reorder per-face arrays into leaf order (:90-129)
+  std::vector<uint32_t> nidx(idxp.size());
+  for (int i = 0; i < facecount; i++)
+    for (int j = 0; j < 3; j++) nidx[i * 3 + j] = idxp[idxs[i] * 3 + j];
+  idxp.swap(nidx);
+  if (!shaderidx.empty()) {
+    std::vector<uint8_t> ns(shaderidx.size());
+    for (int i = 0; i < facecount; i++) ns[i] = shaderidx[idxs[i]];
+    shaderidx.swap(ns);
+  }
+  if (!normalidx.empty()) {
+    std::vector<uint32_t> nn(normalidx.size());
+    for (int i = 0; i < facecount; i++)
+      for (int j = 0; j < 3; j++) nn[i * 3 + j] = normalidx[idxs[i] * 3 + j];
+    normalidx.swap(nn);
+  }
+  return 0;
+}
+
+static inline int ref_leaf_count(int32_t l) { return (int)((l & 0xf) + 1); }
+static inline int ref_leaf_base(int32_t l) { return (int)((l & 0x7ffffff) >> 4); }  // 23-bit decode, quirk (c)
+static inline void store_box(float* dst24, int k, const Box& b) {
+  for (int a = 0; a < 3; a++) { dst24[k + a * 4] = b.lo[a]; dst24[k + 12 + a * 4] = b.hi[a]; }
+}
+
+// buildqbvh.go:171-212 — leaf boxes bound faces accel_idx[i] at key `key`
+Box PolyMesh::initMotionBoxesRec(int key, int32_t node) {
+  Box nodebox;
+  nodebox.reset();
+  const int E = Verts.ElemsPerKey;
+  float* dst = &mboxes[((size_t)key * mtopo.size() + node) * 24];
+  for (int k = 0; k < 4; k++) {
+    const int32_t ch = mtopo[node].children[k];
+    if (ch == -1) continue;
+    Box b;
+    if (ch < 0) {
+      b.reset();
+      const int base = ref_leaf_base(ch), cnt = ref_leaf_count(ch);
+      for (int i = base; i < base + cnt; i++) {
+        const int f = accel_idx[i];
+        for (int j = 0; j < 3; j++) {
+          const V3 p = Verts.Elems[(int)idxp[f * 3 + j] + E * key];
+          b.grow_point(p.x, p.y, p.z);
+        }
+      }
+    } else {
+      b = initMotionBoxesRec(key, ch);
+    }
+    store_box(dst, k, b);
+    nodebox.grow_box(b);
+  }
+  return nodebox;
+}
+
+// builtin/geom/polymesh/bounds.go:25-53
+Box PolyMesh::Bounds(float time) const {
+  if (!qbvh.empty()) return bounds;
+  const float k = time * (float)((int)motionBounds.size() - 1);
+  const float t = k - floorf(k);
+  return box_lerp(motionBounds[(int)floorf(k)], motionBounds[(int)ceilf(k)], t);
+}
+
+// ---- TriLight (builtin/light/triangle.go:37-58,537-565) -----------------------------------------
+int TriLight::PreRender(Core& core, std::string* err) {
+  Node* n = core.FindNode(Shader);
+  if (!n) { *err = "Unable to find node (shader " + Shader + ")"; return -1; }
+  shader = dynamic_cast<ShaderStd*>(n);
+  if (!shader) { *err = "Unable to find shader " + Shader; return -1; }
+  // createMesh: a one-triangle PolyMesh with three identical vertex normals, added as a new node
+  std::unique_ptr<PolyMesh> m(new PolyMesh());
+  m->NodeName = NodeName + ":<mesh>";
+  m->Shader = {Shader};
+  m->Verts.MotionKeys = 1;
+  m->Verts.ElemsPerKey = 3;
+  m->Verts.Elems = {P0, P1, P2};
+  const V3 N = normalize(cross(P1 - P0, P2 - P0));
+  m->Normals.MotionKeys = 1;
+  m->Normals.ElemsPerKey = 3;
+  m->Normals.Elems = {N, N, N};
+  geom = m.get();
+  core.AddNode(std::move(m));
+  return 0;
+}
+
+// ---- Scene (builtin/scene/scene.go:135-268) -------------------------------------------------------
+int Scene::PreRender(std::string* err) {
+  const int n = (int)geoms.size();
+  if (n == 0) { *err = "scene has no geoms"; return -1; }
+  std::vector<Box> boxes(n);
+  std::vector<V3> cent(n);
+  std::vector<int32_t> idx(n);
+  int maxKeys = 0;
+  for (Geom* g : geoms) if (g->MotionKeys() > maxKeys) maxKeys = g->MotionKeys();
+  const float t = maxKeys == 1 ? 0.0f : 0.5f;
+  for (int i = 0; i < n; i++) {
+    boxes[i] = geoms[i]->Bounds(t);
+    idx[i] = i;
+    cent[i] = boxes[i].centroid();
+  }
+  int rc;
+  if (maxKeys == 1) rc = build_qbvh(boxes.data(), cent.data(), idx.data(), n, 1, qbvh, &bounds, err);
+  else rc = build_mqbvh(boxes.data(), cent.data(), idx.data(), n, 1, mtopo, err);
+  if (rc != 0) return -1;
+  std::vector<Geom*> ng(n);
+  for (int i = 0; i < n; i++) ng[i] = geoms[idx[i]];
+  geoms.swap(ng);
+  keys = maxKeys;
+  if (maxKeys > 1) {
+    mboxes.assign((size_t)maxKeys * mtopo.size() * 24, 0.0f);
+    Box full;
+    full.reset();
+    for (int k = 0; k < maxKeys; k++) full.grow_box(initMotionBoxesRec(k, 0, maxKeys));
+    bounds = full;
+  }
+  return 0;
+}
+
+Box Scene::initMotionBoxesRec(int key, int32_t node, int nkeys) {
+  Box nodebox;
+  nodebox.reset();
+  float* dst = &mboxes[((size_t)key * mtopo.size() + node) * 24];
+  for (int k = 0; k < 4; k++) {
+    const int32_t ch = mtopo[node].children[k];
+    if (ch == -1) continue;
+    Box b;
+    if (ch < 0) {
+      b.reset();
+      const int base = ref_leaf_base(ch), cnt = ref_leaf_count(ch);
+      for (int i = base; i < base + cnt; i++) {
+        const float time = (float)key / (float)(nkeys - 1);
+        b.grow_box(geoms[i]->Bounds(time));
+      }
+    } else {
+      b = initMotionBoxesRec(key, ch, nkeys);
+    }
+    store_box(dst, k, b);
+    nodebox.grow_box(b);
+  }
+  return nodebox;
+}
+
+// ---- Core (core/core.go) --------------------------------------------------------------------------
+Core::Core() {
+  std::unique_ptr<Globals> g(new Globals());
+  globals = g.get();
+  owned.push_back(std::move(g));
+}
+
+void Core::AddNode(std::unique_ptr<Node> node) {
+  Node* n = node.get();
+  owned.push_back(std::move(node));
+  pending.push_back(n);
+  nodeMap[n->Name()] = n;
+  if (PolyMesh* pm = dynamic_cast<PolyMesh*>(n)) {
+    pm->id = next_geom_id++;
+    scene.AddGeom(pm);
+  } else if (TriLight* tl = dynamic_cast<TriLight*>(n)) {
+    scene.AddLight(tl);
+  } else if (ShaderStd* sh = dynamic_cast<ShaderStd*>(n)) {
+    sh->material_id = (int)materials.size();
+    materials.push_back(sh);
+  } else if (Globals* g = dynamic_cast<Globals*>(n)) {
+    globals = g;
+  }
+}
+
+Node* Core::FindNode(const std::string& name) const {
+  auto it = nodeMap.find(name);
+  return it == nodeMap.end() ? nullptr : it->second;
+}
+
+// core.go:36-61: PreRender every node; nodes added during a round are processed in the next one
+int Core::PreRender() {
+  if (prerendered) return 0;
+  while (!pending.empty()) {
+    std::vector<Node*> round;
+    round.swap(pending);
+    all.insert(all.end(), round.begin(), round.end());
+    for (Node* n : round)
+      if (n->PreRender(*this, &err) != 0) return -1;
+  }
+  if (scene.PreRender(&err) != 0) return -1;
+  prerendered = true;
+  return 0;
+}
+
+}  // namespace vh

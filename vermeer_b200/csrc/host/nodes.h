@@ -1,0 +1,155 @@
+// Host mirror of the reference's node registry and PreRender pipeline (the vh_* layer).
+//
+//   nodes.Register / createNode          nodes/register.go:14-33
+//   core.Node                            core/node.go:14-28      (Name, PreRender, PostRender)
+//   core.AddNode / FindNode / PreRender  core/core.go:36-105
+//   core.Geom                            core/geom.go:8-18       (MotionKeys, Bounds; Trace runs on the device)
+//   core.Scene (AddGeom, AddLight, PreRender) core/scene.go:8-24, builtin/scene/scene.go:119-268
+//   PolyMesh, ShaderStd, TriLight, Camera, Globals: see nodes.cpp
+//
+// Same names and argument meaning as the reference; error behaviour: the reference returns `error` from
+// PreRender and panics on invariant violations — here both become an int status + message, never an abort.
+#pragma once
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../../include/vermeer_gpu.h"
+#include "hmath.h"
+
+namespace vh {
+
+struct Core;
+
+struct Node {
+  virtual ~Node() {}
+  virtual std::string Name() const = 0;
+  virtual int PreRender(Core& core, std::string* err) { (void)core; (void)err; return 0; }
+  virtual int PostRender() { return 0; }
+};
+
+using CreateFn = std::function<std::unique_ptr<Node>()>;
+// nodes.Register: error (-1) if `name` is already registered.
+int Register(const std::string& name, CreateFn create);
+std::unique_ptr<Node> CreateNode(const std::string& name);
+std::vector<std::string> RegisteredNames();
+
+struct Geom {
+  virtual ~Geom() {}
+  virtual int MotionKeys() const = 0;
+  virtual Box Bounds(float time) const = 0;
+  int id = -1;  // creation order (core.AddNode order)
+};
+
+struct Globals : Node {
+  int XRes = 1024, YRes = 1024, MaxGoRoutines = 5, MaxIter = 16;  // core/core.go:17-23
+  std::string Camera;
+  std::string Name() const override { return "<globals>"; }
+};
+
+struct ShaderStd : Node {
+  std::string MtlName;
+  VgMaterial params{};
+  int material_id = -1;
+  std::string Name() const override { return MtlName; }
+};
+
+struct PointArray {  // core/param/array.go:19-28
+  int MotionKeys = 0, ElemsPerKey = 0;
+  std::vector<V3> Elems;
+};
+
+struct PolyMesh : Node, Geom {
+  std::string NodeName;
+  float RayBias = 0;
+  PointArray Verts;
+  std::vector<int32_t> PolyCount, FaceIdx, ShaderIdx, NormalIdx;
+  bool hasPolyCount = false, hasFaceIdx = false, hasNormalIdx = false;
+  PointArray Normals;
+  std::vector<std::string> Shader;
+  bool IsVisible = true;
+
+  // products of PreRender (polymesh.go:41-57)
+  int facecount = 0;
+  std::vector<uint32_t> idxp, normalidx;
+  std::vector<uint8_t> shaderidx;
+  std::vector<VgNode> qbvh;
+  std::vector<VgMotionNode> mtopo;
+  std::vector<float> mboxes;  // [key][node][24]
+  std::vector<int32_t> accel_idx;
+  std::vector<ShaderStd*> shader;
+  Box bounds;
+  std::vector<Box> motionBounds;
+
+  std::string Name() const override { return NodeName; }
+  int PreRender(Core& core, std::string* err) override;
+  int MotionKeys() const override { return !qbvh.empty() ? 1 : Verts.MotionKeys; }
+  Box Bounds(float time) const override;
+
+ private:
+  void triangulate();
+  int initAccel(std::string* err);
+  Box initMotionBoxesRec(int key, int32_t node);
+};
+
+struct TriLight : Node {
+  std::string NodeName;
+  V3 P0{}, P1{}, P2{};
+  std::string Shader;
+  int Samples = 1;
+  ShaderStd* shader = nullptr;
+  PolyMesh* geom = nullptr;
+  std::string Name() const override { return NodeName; }
+  int PreRender(Core& core, std::string* err) override;
+};
+
+struct Camera : Node {
+  std::string NodeName = "camera";
+  std::string Type = "LookAt";
+  V3 From{}, To{}, Up{0, 1, 0};
+  float Roll = 0;
+  float Aspect = 0, Fov = 90, Focal = 12, Radius = 0;  // camera.go:325-335 defaults
+  VgCamera out{};
+  std::string Name() const override { return NodeName; }
+  int PreRender(Core& core, std::string* err) override;
+};
+
+// builtin/scene/scene.go
+struct Scene {
+  std::vector<Geom*> geoms;
+  std::vector<TriLight*> lights;
+  std::vector<VgNode> qbvh;
+  std::vector<VgMotionNode> mtopo;
+  std::vector<float> mboxes;
+  int keys = 1;
+  Box bounds;
+  void AddGeom(Geom* g) { geoms.push_back(g); }
+  void AddLight(TriLight* l) { lights.push_back(l); }
+  int PreRender(std::string* err);
+
+ private:
+  Box initMotionBoxesRec(int key, int32_t node, int nkeys);
+};
+
+struct Core {
+  Globals* globals = nullptr;
+  Scene scene;
+  std::vector<std::unique_ptr<Node>> owned;
+  std::vector<Node*> pending;  // nodes added since the last PreRender round (core.go:46-58)
+  std::vector<Node*> all;
+  std::map<std::string, Node*> nodeMap;
+  std::vector<ShaderStd*> materials;
+  int next_geom_id = 0;
+  bool prerendered = false;
+  std::string err;
+
+  Core();
+  void AddNode(std::unique_ptr<Node> node);  // core.go:77-93 type-switch wiring
+  Node* FindNode(const std::string& name) const;
+  int PreRender();
+  float FrameAspect() const { return (float)globals->XRes / (float)globals->YRes; }
+};
+
+}  // namespace vh

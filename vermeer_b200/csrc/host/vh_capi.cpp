@@ -1,0 +1,293 @@
+// Host layer of the C ABI (include/vermeer_gpu.h, vh_*): node creation through the registry, PreRender,
+// upload of the pre-rendered scene into a device context through the vg_* layer.
+#include <cstring>
+#include <string>
+
+#include "nodes.h"
+
+using namespace vh;
+
+struct vh_scene {
+  Core core;
+  std::string err;
+};
+
+namespace {
+std::string g_err;
+int fail(vh_scene* s, int code, const std::string& msg) {
+  if (s) s->err = msg; else g_err = msg;
+  return code;
+}
+V3 v3(const float* p) { return V3{p[0], p[1], p[2]}; }
+template <class T>
+T* make(vh_scene* s, const char* type, std::unique_ptr<Node>* holder) {
+  *holder = CreateNode(type);
+  if (!*holder) { fail(s, VG_ERR_INVALID, std::string("node type not registered: ") + type); return nullptr; }
+  T* t = dynamic_cast<T*>(holder->get());
+  if (!t) fail(s, VG_ERR_INVALID, std::string("registered node has the wrong type: ") + type);
+  return t;
+}
+}  // namespace
+
+extern "C" {
+
+int vh_scene_create(vh_scene** out) {
+  if (!out) return VG_ERR_INVALID;
+  *out = new vh_scene();
+  return VG_OK;
+}
+void vh_scene_destroy(vh_scene* s) { delete s; }
+const char* vh_last_error(vh_scene* s) { return s ? s->err.c_str() : g_err.c_str(); }
+
+int vh_registered_nodes(const char** names, int cap) {
+  static std::vector<std::string> keep;
+  keep = RegisteredNames();
+  if (names)
+    for (int i = 0; i < cap && i < (int)keep.size(); i++) names[i] = keep[i].c_str();
+  return (int)keep.size();
+}
+
+int vh_set_globals(vh_scene* s, int xres, int yres, int max_iter) {
+  if (!s) return VG_ERR_INVALID;
+  std::unique_ptr<Node> h;
+  Globals* g = make<Globals>(s, "Globals", &h);
+  if (!g) return VG_ERR_INVALID;
+  if (xres <= 0 || yres <= 0) return fail(s, VG_ERR_INVALID, "Globals: XRes/YRes must be positive");
+  g->XRes = xres;
+  g->YRes = yres;
+  g->MaxIter = max_iter;
+  s->core.AddNode(std::move(h));
+  return VG_OK;
+}
+
+int vh_add_shader_std(vh_scene* s, const char* name, const VgMaterial* params) {
+  if (!s || !name || !params) return fail(s, VG_ERR_INVALID, "vh_add_shader_std: null argument");
+  std::unique_ptr<Node> h;
+  ShaderStd* sh = make<ShaderStd>(s, "ShaderStd", &h);
+  if (!sh) return VG_ERR_INVALID;
+  sh->MtlName = name;
+  sh->params = *params;
+  s->core.AddNode(std::move(h));
+  return VG_OK;
+}
+
+int vh_add_polymesh(vh_scene* s, const char* name, const float* verts, int n_verts, int keys, const int32_t* polycount, int n_poly,
+                    const int32_t* faceidx, int n_faceidx, const char* shaders_nl, const int32_t* shaderidx, int n_shaderidx,
+                    const float* normals, int n_normals, const int32_t* normalidx, int n_normalidx, float raybias) {
+  if (!s || !name || !verts || n_verts <= 0 || keys <= 0) return fail(s, VG_ERR_INVALID, "vh_add_polymesh: bad argument");
+  std::unique_ptr<Node> h;
+  PolyMesh* m = make<PolyMesh>(s, "PolyMesh", &h);
+  if (!m) return VG_ERR_INVALID;
+  m->NodeName = name;
+  m->RayBias = raybias;
+  m->Verts.MotionKeys = keys;
+  m->Verts.ElemsPerKey = n_verts;
+  m->Verts.Elems.resize((size_t)keys * n_verts);
+  std::memcpy(m->Verts.Elems.data(), verts, sizeof(float) * 3 * (size_t)keys * n_verts);
+  if (polycount) { m->hasPolyCount = true; m->PolyCount.assign(polycount, polycount + n_poly); }
+  if (faceidx) { m->hasFaceIdx = true; m->FaceIdx.assign(faceidx, faceidx + n_faceidx); }
+  if (m->hasPolyCount) {
+    if (!m->hasFaceIdx) return fail(s, VG_ERR_INVALID, "PolyMesh: PolyCount without FaceIdx");
+    int64_t tot = 0;
+    for (int32_t c : m->PolyCount) { if (c < 3) return fail(s, VG_ERR_INVALID, "PolyMesh: polygon with < 3 vertices"); tot += c; }
+    if (tot != n_faceidx) return fail(s, VG_ERR_INVALID, "PolyMesh: sum(PolyCount) != len(FaceIdx)");
+  }
+  if (shaderidx) m->ShaderIdx.assign(shaderidx, shaderidx + n_shaderidx);
+  if (normals) {
+    m->Normals.MotionKeys = 1;
+    m->Normals.ElemsPerKey = n_normals;
+    m->Normals.Elems.resize(n_normals);
+    std::memcpy(m->Normals.Elems.data(), normals, sizeof(float) * 3 * (size_t)n_normals);
+    if (normalidx) { m->hasNormalIdx = true; m->NormalIdx.assign(normalidx, normalidx + n_normalidx); }
+  }
+  std::string sn(shaders_nl ? shaders_nl : "");
+  size_t pos = 0;
+  while (!sn.empty()) {
+    size_t e = sn.find('\n', pos);
+    m->Shader.push_back(sn.substr(pos, e == std::string::npos ? std::string::npos : e - pos));
+    if (e == std::string::npos) break;
+    pos = e + 1;
+  }
+  s->core.AddNode(std::move(h));
+  return VG_OK;
+}
+
+int vh_add_trilight(vh_scene* s, const char* name, const float* p0, const float* p1, const float* p2, const char* shader, int samples) {
+  if (!s || !name || !p0 || !p1 || !p2 || !shader) return fail(s, VG_ERR_INVALID, "vh_add_trilight: null argument");
+  if (samples < 0 || samples > 8) return fail(s, VG_ERR_INVALID, "TriLight: Samples must be in [0,8]");
+  std::unique_ptr<Node> h;
+  TriLight* t = make<TriLight>(s, "TriLight", &h);
+  if (!t) return VG_ERR_INVALID;
+  t->NodeName = name;
+  t->P0 = v3(p0);
+  t->P1 = v3(p1);
+  t->P2 = v3(p2);
+  t->Shader = shader;
+  t->Samples = samples;
+  s->core.AddNode(std::move(h));
+  return VG_OK;
+}
+
+int vh_set_camera_lookat(vh_scene* s, const float* from, const float* to, const float* up, float roll, float fov, float focal, float aspect,
+                         float radius) {
+  if (!s || !from || !to || !up) return fail(s, VG_ERR_INVALID, "vh_set_camera_lookat: null argument");
+  std::unique_ptr<Node> h;
+  Camera* c = make<Camera>(s, "Camera", &h);
+  if (!c) return VG_ERR_INVALID;
+  c->From = v3(from);
+  c->To = v3(to);
+  c->Up = v3(up);
+  c->Roll = roll;
+  c->Fov = fov;
+  c->Focal = focal;
+  c->Aspect = aspect;
+  c->Radius = radius;
+  s->core.AddNode(std::move(h));
+  return VG_OK;
+}
+
+int vh_prerender(vh_scene* s) {
+  if (!s) return VG_ERR_INVALID;
+  if (s->core.PreRender() != 0) return fail(s, VG_ERR_BUILD, s->core.err);
+  return VG_OK;
+}
+
+static PolyMesh* mesh_by_id(vh_scene* s, int id) {
+  for (Geom* g : s->core.scene.geoms)
+    if (g->id == id) return static_cast<PolyMesh*>(g);
+  return nullptr;
+}
+
+int vh_upload(vh_scene* s, vg_ctx* ctx, int motion_ref_compat) {
+  if (!s || !ctx) return fail(s, VG_ERR_INVALID, "vh_upload: null argument");
+  if (!s->core.prerendered) return fail(s, VG_ERR_INVALID, "vh_upload: call vh_prerender first");
+  Core& c = s->core;
+  auto chk = [&](int rc) { if (rc != VG_OK) s->err = std::string("device layer: ") + vg_last_error(ctx); return rc; };
+  int rc;
+  const int G = (int)c.scene.geoms.size();
+  if ((rc = chk(vg_set_frame(ctx, c.globals->XRes, c.globals->YRes))) != VG_OK) return rc;
+  std::vector<VgMaterial> mats;
+  for (ShaderStd* sh : c.materials) mats.push_back(sh->params);
+  if ((rc = chk(vg_set_materials(ctx, mats.data(), (int)mats.size()))) != VG_OK) return rc;
+  if ((rc = chk(vg_scene_begin(ctx, G))) != VG_OK) return rc;
+  for (int id = 0; id < G; id++) {
+    PolyMesh* m = mesh_by_id(s, id);
+    if (!m) return fail(s, VG_ERR_INVALID, "geom ids are not dense");
+    std::vector<int32_t> mids;
+    for (ShaderStd* sh : m->shader) mids.push_back(sh->material_id);
+    if (!m->qbvh.empty()) {
+      rc = vg_mesh_upload(ctx, id, m->qbvh.data(), (int)m->qbvh.size(), m->idxp.data(), m->facecount, &m->Verts.Elems[0].x,
+                          m->Verts.ElemsPerKey, m->shaderidx.empty() ? nullptr : m->shaderidx.data(), mids.data(), (int)mids.size(),
+                          m->Normals.Elems.empty() ? nullptr : &m->Normals.Elems[0].x, (int)m->Normals.Elems.size(),
+                          m->normalidx.empty() ? nullptr : m->normalidx.data(), m->RayBias);
+    } else {
+      rc = vg_mesh_upload_motion(ctx, id, m->mtopo.data(), (int)m->mtopo.size(), m->mboxes.data(), m->Verts.MotionKeys, m->idxp.data(),
+                                 m->accel_idx.data(), m->facecount, &m->Verts.Elems[0].x, m->Verts.ElemsPerKey,
+                                 m->shaderidx.empty() ? nullptr : m->shaderidx.data(), mids.data(), (int)mids.size(), m->RayBias,
+                                 motion_ref_compat);
+    }
+    if (chk(rc) != VG_OK) return rc;
+  }
+  std::vector<int32_t> order;
+  for (Geom* g : c.scene.geoms) order.push_back(g->id);
+  if (c.scene.keys == 1)
+    rc = vg_scene_upload(ctx, c.scene.qbvh.data(), (int)c.scene.qbvh.size(), order.data(), (int)order.size());
+  else
+    rc = vg_scene_upload_motion(ctx, c.scene.mtopo.data(), (int)c.scene.mtopo.size(), c.scene.mboxes.data(), c.scene.keys, order.data(), (int)order.size());
+  if (chk(rc) != VG_OK) return rc;
+  if ((rc = chk(vg_scene_commit(ctx))) != VG_OK) return rc;
+
+  std::vector<VgTriLight> lights;
+  for (TriLight* t : c.scene.lights) {
+    VgTriLight l{};
+    l.p0[0] = t->P0.x; l.p0[1] = t->P0.y; l.p0[2] = t->P0.z;
+    l.p1[0] = t->P1.x; l.p1[1] = t->P1.y; l.p1[2] = t->P1.z;
+    l.p2[0] = t->P2.x; l.p2[1] = t->P2.y; l.p2[2] = t->P2.z;
+    l.samples = t->Samples;
+    l.material = t->shader ? t->shader->material_id : -1;
+    l.geom = t->geom ? t->geom->id : -1;
+    lights.push_back(l);
+  }
+  if ((rc = chk(vg_set_lights(ctx, lights.data(), (int)lights.size()))) != VG_OK) return rc;
+
+  // core.Render finds the node named "camera" unless Globals.Camera overrides it (core/render.go:148-164)
+  std::string camName = c.globals->Camera.empty() ? "camera" : c.globals->Camera;
+  Camera* cam = dynamic_cast<Camera*>(c.FindNode(camName));
+  if (cam) {
+    if ((rc = chk(vg_set_camera(ctx, &cam->out))) != VG_OK) return rc;
+  }
+  return VG_OK;
+}
+
+int vh_num_geoms(vh_scene* s) { return s ? (int)s->core.scene.geoms.size() : 0; }
+
+int vh_scene_info(vh_scene* s, int32_t* out4) {
+  if (!s || !out4) return VG_ERR_INVALID;
+  Scene& sc = s->core.scene;
+  out4[0] = sc.keys == 1 ? (int)sc.qbvh.size() : (int)sc.mtopo.size();
+  out4[1] = sc.keys == 1 ? 0 : 1;
+  out4[2] = sc.keys;
+  out4[3] = (int)sc.geoms.size();
+  return VG_OK;
+}
+int vh_scene_nodes(vh_scene* s, VgNode* out) {
+  if (!s || !out) return VG_ERR_INVALID;
+  std::memcpy(out, s->core.scene.qbvh.data(), s->core.scene.qbvh.size() * sizeof(VgNode));
+  return VG_OK;
+}
+int vh_scene_motion_nodes(vh_scene* s, VgMotionNode* topo, float* boxes) {
+  if (!s || !topo || !boxes) return VG_ERR_INVALID;
+  Scene& sc = s->core.scene;
+  std::memcpy(topo, sc.mtopo.data(), sc.mtopo.size() * sizeof(VgMotionNode));
+  std::memcpy(boxes, sc.mboxes.data(), sc.mboxes.size() * sizeof(float));
+  return VG_OK;
+}
+int vh_scene_geom_order(vh_scene* s, int32_t* out) {
+  if (!s || !out) return VG_ERR_INVALID;
+  int i = 0;
+  for (Geom* g : s->core.scene.geoms) out[i++] = g->id;
+  return VG_OK;
+}
+int vh_mesh_info(vh_scene* s, int geom_id, int32_t* o) {
+  if (!s || !o) return VG_ERR_INVALID;
+  PolyMesh* m = mesh_by_id(s, geom_id);
+  if (!m) return fail(s, VG_ERR_INVALID, "no such geom");
+  o[0] = m->qbvh.empty() ? (int)m->mtopo.size() : (int)m->qbvh.size();
+  o[1] = m->facecount;
+  o[2] = m->Verts.MotionKeys;
+  o[3] = m->Verts.ElemsPerKey;
+  o[4] = m->qbvh.empty() ? 1 : 0;
+  o[5] = m->Normals.Elems.empty() ? 0 : 1;
+  return VG_OK;
+}
+int vh_mesh_nodes(vh_scene* s, int geom_id, VgNode* out) {
+  PolyMesh* m = s ? mesh_by_id(s, geom_id) : nullptr;
+  if (!m || !out) return VG_ERR_INVALID;
+  std::memcpy(out, m->qbvh.data(), m->qbvh.size() * sizeof(VgNode));
+  return VG_OK;
+}
+int vh_mesh_motion_nodes(vh_scene* s, int geom_id, VgMotionNode* topo, float* boxes) {
+  PolyMesh* m = s ? mesh_by_id(s, geom_id) : nullptr;
+  if (!m || !topo || !boxes) return VG_ERR_INVALID;
+  std::memcpy(topo, m->mtopo.data(), m->mtopo.size() * sizeof(VgMotionNode));
+  std::memcpy(boxes, m->mboxes.data(), m->mboxes.size() * sizeof(float));
+  return VG_OK;
+}
+int vh_mesh_idxp(vh_scene* s, int geom_id, uint32_t* idxp, int32_t* accel_idx) {
+  PolyMesh* m = s ? mesh_by_id(s, geom_id) : nullptr;
+  if (!m) return VG_ERR_INVALID;
+  if (idxp) std::memcpy(idxp, m->idxp.data(), m->idxp.size() * 4);
+  if (accel_idx) std::memcpy(accel_idx, m->accel_idx.data(), m->accel_idx.size() * 4);
+  return VG_OK;
+}
+int vh_camera(vh_scene* s, VgCamera* out) {
+  if (!s || !out) return VG_ERR_INVALID;
+  Core& c = s->core;
+  std::string camName = c.globals->Camera.empty() ? "camera" : c.globals->Camera;
+  Camera* cam = dynamic_cast<Camera*>(c.FindNode(camName));
+  if (!cam) return fail(s, VG_ERR_INVALID, "no camera node");
+  *out = cam->out;
+  return VG_OK;
+}
+
+}  // extern "C"

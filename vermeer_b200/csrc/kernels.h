@@ -1,0 +1,18 @@
+// Host-visible launchers of the CUDA kernels (implemented in kernels_*.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vermeer_gpu.h"
+#include "device_scene.h"
+
+namespace vg {
+
+static const int kTraceBlock = 128;
+
+// kernels_trace.cu
+cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d_hits, long long n, bool any_hit,
+                               unsigned long long* d_counter, unsigned long long* d_stats, int grid, cudaStream_t stream);
+int trace_batch_blocks_per_sm();
+
+}  // namespace vg

@@ -1,0 +1,79 @@
+// Batch TraceProbe kernels (core/trace.go:26) — persistent warps over a ray queue.
+//
+// Grid = (SMs x resident CTAs); every warp repeatedly claims the next 32 rays of the queue with one
+// warp-aggregated atomicAdd, so the kernel's tail is bounded by one ray rather than by a wave of CTAs.
+// The 32-byte VgRay / VgHit records are read and written as two 128-bit accesses each; consecutive
+// lanes touch consecutive records, so a warp's fetch is one contiguous 1-KB burst.
+#include "kernels.h"
+#include "traverse.cuh"
+
+namespace vg {
+
+template <bool ANY_HIT>
+__global__ void __launch_bounds__(kTraceBlock) k_trace_batch(const DevScene sc, const VgRay* __restrict__ rays, VgHit* __restrict__ hits,
+                                                             long long n, unsigned long long* __restrict__ counter,
+                                                             unsigned long long* __restrict__ stats) {
+  extern __shared__ uint2 smem_stack[];
+  Stack st;
+  st.smem = smem_stack + threadIdx.x;
+  st.stride = blockDim.x;
+  const int lane = threadIdx.x & 31;
+  unsigned long long nodes_acc = 0, tris_acc = 0;
+
+  while (true) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(counter, 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if ((long long)base >= n) break;
+    const long long i = (long long)base + lane;
+    if (i < n) {
+      const float4* rp = reinterpret_cast<const float4*>(rays + i);
+      const float4 a = __ldg(rp), b = __ldg(rp + 1);
+      RayState r;
+      r.ox = a.x; r.oy = a.y; r.oz = a.z;
+      r.dx = a.w; r.dy = b.x; r.dz = b.y;
+      r.tclosest = b.z;
+      r.time = b.w;
+      ray_setup(r);
+      HitState h;
+      trace_ray<ANY_HIT>(sc, r, h, st);
+      float4 o0 = make_float4(r.tclosest, h.u, h.v, h.w);
+      int4 o1 = make_int4(st.overflow ? -2 : h.prim, h.geom, h.nodesT, h.trisT);
+      float4* hp = reinterpret_cast<float4*>(hits + i);
+      hp[0] = o0;
+      reinterpret_cast<int4*>(hp)[1] = o1;
+      nodes_acc += (unsigned long long)h.nodesT;
+      tris_acc += (unsigned long long)h.trisT;
+    }
+  }
+  // warp-aggregated statistics (core/stats.go keeps global atomics per ray; one atomic per warp here)
+  for (int o = 16; o > 0; o >>= 1) {
+    nodes_acc += __shfl_down_sync(0xffffffffu, nodes_acc, o);
+    tris_acc += __shfl_down_sync(0xffffffffu, tris_acc, o);
+  }
+  if (lane == 0 && stats) {
+    atomicAdd(stats + 0, nodes_acc);
+    atomicAdd(stats + 1, tris_acc);
+  }
+}
+
+cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d_hits, long long n, bool any_hit,
+                               unsigned long long* d_counter, unsigned long long* d_stats, int grid, cudaStream_t stream) {
+  const size_t smem = (size_t)kTraceBlock * VG_SMEM_STACK * sizeof(uint2);
+  cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
+  if (e != cudaSuccess) return e;
+  if (any_hit)
+    k_trace_batch<true><<<grid, kTraceBlock, smem, stream>>>(sc, d_rays, d_hits, n, d_counter, d_stats);
+  else
+    k_trace_batch<false><<<grid, kTraceBlock, smem, stream>>>(sc, d_rays, d_hits, n, d_counter, d_stats);
+  return cudaGetLastError();
+}
+
+int trace_batch_blocks_per_sm() {
+  int nb = 0;
+  const size_t smem = (size_t)kTraceBlock * VG_SMEM_STACK * sizeof(uint2);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_batch<false>, kTraceBlock, smem);
+  return nb > 0 ? nb : 1;
+}
+
+}  // namespace vg

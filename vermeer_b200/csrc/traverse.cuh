@@ -1,0 +1,344 @@
+// Per-ray two-level QBVH / MQBVH traversal for sm_100a. One thread owns one ray.
+//
+// Semantics are those of the reference's stack traversal, so that hit/miss, primitive id and t are
+// bit-identical on identical rays:
+//   core.Ray.Setup                core/ray.go:103-148        -> ray_setup()
+//   intersectBoxes (SSE 4-box)    qbvh/intersect_amd64.s:13-100 -> box4()
+//   qbvh.Trace                    qbvh/intersect.go:91-246   -> trace_ray() static-node branch
+//   qbvh.TraceMotion              qbvh/motionintersect.go:22-127 -> trace_ray() motion-node branch
+//   PolyMesh.TraceElems           builtin/geom/polymesh/trace.go:108-194 -> tri_test<false>()
+//   PolyMesh.TraceMotionElems     builtin/geom/polymesh/trace.go:520-615 -> tri_test<true>()
+//   Scene.Trace / TraceElems      builtin/scene/scene.go:30-78 -> geom-leaf branch (unified stack)
+//
+// This translation unit must be compiled with -fmad=false: Go/amd64 never contracts a*b+c, and every
+// float operation below has to round exactly like the SSE scalar code. Min/max are written as
+// compare-selects in the operand order of the x86 MINPS/MAXPS they replace (second operand wins on NaN).
+//
+// B200 mapping: the 128-B node is fetched with 8 LDG.128 through the read-only path; a leaf's
+// triangles are 3 LDG.128 each from one contiguous run; the traversal stack lives in shared memory
+// (kSmemStack entries per thread, interleaved by lane so a warp's accesses are conflict free) and
+// spills to local memory only beyond that.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_scene.h"
+
+namespace vg {
+
+struct RayState {
+  float ox, oy, oz;
+  float dx, dy, dz;
+  float idx, idy, idz;  // Dinv
+  float s0, s1, s2;     // S
+  float pkx, pky, pkz;  // origin permuted by (Kx,Ky,Kz)
+  int kx, ky, kz;
+  uint32_t signbits;  // bit a set <=> D[a] < 0
+  float tclosest;
+  float time;
+};
+
+struct HitState {
+  float u, v, w;
+  int32_t prim;  // -1 = none
+  int32_t geom;
+  int32_t slot;  // global triangle slot of the hit (key-0 slot for motion meshes)
+  int32_t nodesT, trisT;
+};
+
+__device__ __forceinline__ float sel3(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
+
+// core/ray.go:103-148
+__device__ __forceinline__ void ray_setup(RayState& r) {
+  int kz = 0;
+  if (fabsf(r.dy) > fabsf(r.dz)) {
+    if (fabsf(r.dy) > fabsf(r.dx)) kz = 1;
+  } else {
+    if (fabsf(r.dz) > fabsf(r.dx)) kz = 2;
+  }
+  int kx = kz + 1;
+  if (kx == 3) kx = 0;
+  int ky = kx + 1;
+  if (ky == 3) ky = 0;
+  float dkz = sel3(r.dx, r.dy, r.dz, kz);
+  if (dkz < 0.0f) {
+    int t = kx;
+    kx = ky;
+    ky = t;
+  }
+  double z = (double)dkz;
+  r.s2 = (float)(1.0 / z);
+  r.s0 = (float)((double)sel3(r.dx, r.dy, r.dz, kx) / z);
+  r.s1 = (float)((double)sel3(r.dx, r.dy, r.dz, ky) / z);
+  r.idx = (float)(1.0 / (double)r.dx);
+  r.idy = (float)(1.0 / (double)r.dy);
+  r.idz = (float)(1.0 / (double)r.dz);
+  r.kx = kx;
+  r.ky = ky;
+  r.kz = kz;
+  r.pkx = sel3(r.ox, r.oy, r.oz, kx);
+  r.pky = sel3(r.ox, r.oy, r.oz, ky);
+  r.pkz = sel3(r.ox, r.oy, r.oz, kz);
+  r.signbits = (r.dx < 0.0f ? 1u : 0u) | (r.dy < 0.0f ? 2u : 0u) | (r.dz < 0.0f ? 4u : 0u);
+}
+
+// x86 MINPS dst,src: dst = (dst < src) ? dst : src ; MAXPS: dst = (dst > src) ? dst : src
+__device__ __forceinline__ float x86min(float dst, float src) { return dst < src ? dst : src; }
+__device__ __forceinline__ float x86max(float dst, float src) { return dst > src ? dst : src; }
+
+// One child of intersect_amd64.s:13-100. Returns tNear; *hit = tNear <= tmax.
+__device__ __forceinline__ float box1(const RayState& r, float lx, float ly, float lz, float hx, float hy, float hz, bool* hit) {
+  float t1 = (lx - r.ox) * r.idx;
+  float t2 = (hx - r.ox) * r.idx;
+  float x6 = x86min(t2, t1);
+  float x7 = x86max(t2, t1);
+  t1 = (ly - r.oy) * r.idy;
+  t2 = (hy - r.oy) * r.idy;
+  float x1 = x86min(t2, t1);
+  float x0 = x86max(t2, t1);
+  x6 = x86max(x6, x1);
+  x7 = x86min(x7, x0);
+  t1 = (lz - r.oz) * r.idz;
+  t2 = (hz - r.oz) * r.idz;
+  x1 = x86min(t2, t1);
+  x0 = x86max(t2, t1);
+  x6 = x86max(x6, x1);
+  x7 = x86min(x7, x0);
+  float tn = x86max(0.0f, x6);
+  *hit = tn <= x7;
+  return tn;
+}
+
+// Watertight ray/triangle test, trace.go:127-192 (static: bias `<` with eps+RayBias folded into `bias`)
+// and trace.go:556-622 (motion: `<=` with RayBias). Returns true and updates tclosest,u,v,w on accept.
+template <bool MOTION>
+__device__ __forceinline__ bool tri_test(RayState& r, float3 p0, float3 p1, float3 p2, float bias, float* U, float* V, float* W) {
+  const float AKz = sel3(p0.x, p0.y, p0.z, r.kz) - r.pkz;
+  const float BKz = sel3(p1.x, p1.y, p1.z, r.kz) - r.pkz;
+  const float CKz = sel3(p2.x, p2.y, p2.z, r.kz) - r.pkz;
+  const float Cx = (sel3(p2.x, p2.y, p2.z, r.kx) - r.pkx) - r.s0 * CKz;
+  const float By = (sel3(p1.x, p1.y, p1.z, r.ky) - r.pky) - r.s1 * BKz;
+  const float Cy = (sel3(p2.x, p2.y, p2.z, r.ky) - r.pky) - r.s1 * CKz;
+  const float Bx = (sel3(p1.x, p1.y, p1.z, r.kx) - r.pkx) - r.s0 * BKz;
+  const float Ax = (sel3(p0.x, p0.y, p0.z, r.kx) - r.pkx) - r.s0 * AKz;
+  const float Ay = (sel3(p0.x, p0.y, p0.z, r.ky) - r.pky) - r.s1 * AKz;
+  float fU = Cx * By - Cy * Bx;
+  float fV = Ax * Cy - Ay * Cx;
+  float fW = Bx * Ay - By * Ax;
+  if (fU == 0.0f || fV == 0.0f || fW == 0.0f) {
+    double CxBy = (double)Cx * (double)By;
+    double CyBx = (double)Cy * (double)Bx;
+    fU = (float)(CxBy - CyBx);
+    double AxCy = (double)Ax * (double)Cy;
+    double AyCx = (double)Ay * (double)Cx;
+    fV = (float)(AxCy - AyCx);
+    double BxAy = (double)Bx * (double)Ay;
+    double ByAx = (double)By * (double)Ax;
+    fW = (float)(BxAy - ByAx);
+  }
+  if ((fU < 0.0f || fV < 0.0f || fW < 0.0f) && (fU > 0.0f || fV > 0.0f || fW > 0.0f)) return false;
+  const float det = fU + fV + fW;
+  if (det == 0.0f) return false;
+  const float T = r.s2 * (fU * AKz + fV * BKz + fW * CKz);
+  const uint32_t sgn = __float_as_uint(det) & 0x80000000u;
+  const float Ts = __uint_as_float(__float_as_uint(T) ^ sgn);
+  const float ds = __uint_as_float(__float_as_uint(det) ^ sgn);
+  if (MOTION) {
+    if (Ts <= bias * ds || Ts > r.tclosest * ds) return false;
+  } else {
+    if (Ts < bias * ds || Ts > r.tclosest * ds) return false;
+  }
+  const float rcp = 1.0f / det;
+  *U = fU * rcp;
+  *V = fV * rcp;
+  *W = fW * rcp;
+  r.tclosest = T * rcp;
+  return true;
+}
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// Traversal stack: kSmemStack entries per thread in shared memory, the rest in local memory.
+#ifndef VG_SMEM_STACK
+#define VG_SMEM_STACK 16
+#endif
+#define VG_LOCAL_STACK 80
+
+struct Stack {
+  uint2* smem;  // base for this thread: entry i at smem[i * stride]
+  int stride;
+  uint2 local[VG_LOCAL_STACK];
+  int sp;
+  bool overflow;
+  __device__ __forceinline__ void push(float t, int32_t node) {
+    uint2 e = make_uint2(__float_as_uint(t), (uint32_t)node);
+    if (sp < VG_SMEM_STACK) smem[sp * stride] = e;
+    else if (sp < VG_SMEM_STACK + VG_LOCAL_STACK) local[sp - VG_SMEM_STACK] = e;
+    else { overflow = true; return; }
+    sp++;
+  }
+  __device__ __forceinline__ uint2 pop() {
+    sp--;
+    return sp < VG_SMEM_STACK ? smem[sp * stride] : local[sp - VG_SMEM_STACK];
+  }
+};
+
+// Push order of intersect.go:137-216 / motionintersect.go:55-97, expressed as the pop order (reverse of push).
+// With s0 = D[axis0]<0, s1 = D[axis1]<0, s2 = D[axis2]<0 the push sequence is
+//   s0 ? {pair01, pair23} : {pair23, pair01},  pair01 = s1 ? (0,1) : (1,0),  pair23 = s2 ? (2,3) : (3,2).
+struct Child4 {
+  int32_t c[4];
+  float t[4];
+};
+
+__device__ __forceinline__ void cswap(bool doit, int32_t& ca, float& ta, int32_t& cb, float& tb) {
+  int32_t c0 = doit ? cb : ca, c1 = doit ? ca : cb;
+  float t0 = doit ? tb : ta, t1 = doit ? ta : tb;
+  ca = c0; cb = c1; ta = t0; tb = t1;
+}
+
+template <bool ANY_HIT>
+__device__ __forceinline__ bool trace_ray(const DevScene& sc, RayState& r, HitState& h, Stack& st) {
+  h.prim = -1;
+  h.geom = -1;
+  h.slot = -1;
+  h.u = h.v = h.w = 0.0f;
+  h.nodesT = 0;
+  h.trisT = 0;
+  st.sp = 0;
+  st.overflow = false;
+
+  int32_t node = sc.root;
+  bool have = true;  // `node` holds the next entry to process (already passed the pop-time cull)
+
+  while (true) {
+    if (!have) {
+      if (st.sp == 0) break;
+      uint2 e = st.pop();
+      // intersect.go:106: skip if Tclosest < T (entries are only pushed when hit, children != -1)
+      if (r.tclosest < __uint_as_float(e.x)) continue;
+      node = (int32_t)e.y;
+    }
+    have = false;
+
+    if (node >= 0) {
+      h.nodesT++;
+      int32_t c0, c1, c2, c3;
+      float t0, t1, t2, t3;
+      bool h0, h1, h2, h3;
+      uint32_t a0, a1, a2;
+      if (node < sc.n_static) {
+        const DevNode* nd = sc.nodes + node;
+        const float4 lx = ldg4(&nd->lo_x), ly = ldg4(&nd->lo_y), lz = ldg4(&nd->lo_z);
+        const float4 hx = ldg4(&nd->hi_x), hy = ldg4(&nd->hi_y), hz = ldg4(&nd->hi_z);
+        const uint4 m0 = __ldg(&nd->m0), m1 = __ldg(&nd->m1);
+        t0 = box1(r, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, &h0);
+        t1 = box1(r, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, &h1);
+        t2 = box1(r, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, &h2);
+        t3 = box1(r, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, &h3);
+        a0 = m0.x; a1 = m0.y; a2 = m0.z;
+        c0 = (int32_t)m0.w; c1 = (int32_t)m1.x; c2 = (int32_t)m1.y; c3 = (int32_t)m1.z;
+      } else {
+        // motionintersect.go:44-51: lerp the 24 box floats between the two keys, then the same box test
+        const DevMotionNode mn = *(sc.mtopo + (node - sc.n_static));
+        const int keys = (int)(mn.axes_keys >> 8);
+        const float k = r.time * (float)(keys - 1);  // polymesh/trace.go:79-84, scene.go:49-54
+        const float fk = floorf(k);
+        const float tm = k - fk;
+        const int key = (int)fk, key2 = (int)ceilf(k);
+        const float4* b0 = sc.mboxes + (size_t)(mn.box_base + key * mn.box_key_stride) * 6;
+        const float4* b1 = sc.mboxes + (size_t)(mn.box_base + key2 * mn.box_key_stride) * 6;
+        const float om = 1.0f - tm;
+        float4 bx[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          const float4 p = ldg4(b0 + i), q = ldg4(b1 + i);
+          bx[i].x = om * p.x + tm * q.x;
+          bx[i].y = om * p.y + tm * q.y;
+          bx[i].z = om * p.z + tm * q.z;
+          bx[i].w = om * p.w + tm * q.w;
+        }
+        t0 = box1(r, bx[0].x, bx[1].x, bx[2].x, bx[3].x, bx[4].x, bx[5].x, &h0);
+        t1 = box1(r, bx[0].y, bx[1].y, bx[2].y, bx[3].y, bx[4].y, bx[5].y, &h1);
+        t2 = box1(r, bx[0].z, bx[1].z, bx[2].z, bx[3].z, bx[4].z, bx[5].z, &h2);
+        t3 = box1(r, bx[0].w, bx[1].w, bx[2].w, bx[3].w, bx[4].w, bx[5].w, &h3);
+        a0 = mn.axes_keys & 3u; a1 = (mn.axes_keys >> 2) & 3u; a2 = (mn.axes_keys >> 4) & 3u;
+        c0 = mn.child[0]; c1 = mn.child[1]; c2 = mn.child[2]; c3 = mn.child[3];
+      }
+      // Children that miss, are empty, or already lie beyond Tclosest would be culled at pop time
+      // (intersect.go:106, Tclosest only shrinks): drop them now. NodesT is unaffected.
+      if (!h0 || t0 > r.tclosest) c0 = -1;
+      if (!h1 || t1 > r.tclosest) c1 = -1;
+      if (!h2 || t2 > r.tclosest) c2 = -1;
+      if (!h3 || t3 > r.tclosest) c3 = -1;
+      const bool s0 = (r.signbits >> a0) & 1u, s1 = (r.signbits >> a1) & 1u, s2 = (r.signbits >> a2) & 1u;
+      // arrange (e0,e1,e2,e3) = push sequence
+      cswap(!s1, c0, t0, c1, t1);  // pair01 = s1 ? (0,1) : (1,0)
+      cswap(!s2, c2, t2, c3, t3);  // pair23 = s2 ? (2,3) : (3,2)
+      cswap(!s0, c0, t0, c2, t2);  // s0 ? {pair01,pair23} : {pair23,pair01}
+      cswap(!s0, c1, t1, c3, t3);
+      // The last pushed valid entry would be popped next: keep it in registers instead.
+      if (c0 != -1) st.push(t0, c0);
+      if (c1 != -1) st.push(t1, c1);
+      if (c2 != -1) st.push(t2, c2);
+      if (c3 != -1) st.push(t3, c3);
+    } else if (node != -1) {
+      const uint32_t un = (uint32_t)node;
+      if (un & kGeomBit) {
+        // scene.go:61-78 -> Geom.Trace -> qbvh.Trace pushes the mesh root with T = Tclosest and pops it at once
+        node = (int32_t)(un & 0x3FFFFFFFu);
+        have = true;
+        continue;
+      }
+      const int base = (int)((un >> 4) & kLeafBaseMask);
+      const int count = (int)(un & 15u) + 1;
+      h.trisT += count;
+      bool leafhit = false;
+      if (!(un & kMotionTriBit)) {
+        const float4* tp = sc.tris + (size_t)base * 3;
+        for (int i = 0; i < count; i++, tp += 3) {
+          const float4 v0 = ldg4(tp), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
+          float U, V, W;
+          if (tri_test<false>(r, make_float3(v0.x, v0.y, v0.z), make_float3(v1.x, v1.y, v1.z), make_float3(v2.x, v2.y, v2.z), v2.w, &U, &V, &W)) {
+            h.u = U; h.v = V; h.w = W;
+            h.geom = __float_as_int(v0.w);
+            h.prim = __float_as_int(v1.w);
+            h.slot = base + i;
+            leafhit = true;
+          }
+        }
+      } else {
+        // trace.go:547-554: lerp the three vertices between the keys of this mesh
+        const float4 g0 = ldg4(sc.mtris + (size_t)base * 3);  // key-0 record of the first slot: geom id in w
+        const DevGeom gm = sc.geoms[__float_as_int(g0.w)];
+        const float k = r.time * (float)(gm.keys - 1);
+        const float fk = floorf(k);
+        const float tm = k - fk, om = 1.0f - tm;
+        const int key = (int)fk, key2 = (int)ceilf(k);
+        const float4* ta = sc.mtris + ((size_t)base + (size_t)key * gm.tri_key_stride) * 3;
+        const float4* tb = sc.mtris + ((size_t)base + (size_t)key2 * gm.tri_key_stride) * 3;
+        const float4* tk0 = sc.mtris + (size_t)base * 3;
+        for (int i = 0; i < count; i++, ta += 3, tb += 3, tk0 += 3) {
+          const float4 a0 = ldg4(ta), a1 = ldg4(ta + 1), a2 = ldg4(ta + 2);
+          const float4 b0 = ldg4(tb), b1 = ldg4(tb + 1), b2 = ldg4(tb + 2);
+          const float3 p0 = make_float3(om * a0.x + tm * b0.x, om * a0.y + tm * b0.y, om * a0.z + tm * b0.z);
+          const float3 p1 = make_float3(om * a1.x + tm * b1.x, om * a1.y + tm * b1.y, om * a1.z + tm * b1.z);
+          const float3 p2 = make_float3(om * a2.x + tm * b2.x, om * a2.y + tm * b2.y, om * a2.z + tm * b2.z);
+          const float4 w0 = ldg4(tk0), w1 = ldg4(tk0 + 1), w2 = ldg4(tk0 + 2);
+          float U, V, W;
+          if (tri_test<true>(r, p0, p1, p2, w2.w, &U, &V, &W)) {
+            h.u = U; h.v = V; h.w = W;
+            h.geom = __float_as_int(w0.w);
+            h.prim = __float_as_int(w1.w);
+            h.slot = base + i;
+            leafhit = true;
+          }
+        }
+      }
+      if (ANY_HIT && leafhit) return true;  // intersect.go:231-236
+    }
+  }
+  return h.prim >= 0;
+}
+
+}  // namespace vg

@@ -1,0 +1,285 @@
+"""ctypes harness over libvermeer_b200.so (the C ABI of include/vermeer_gpu.h).
+
+Used by tests/ and bench.py; numpy in, numpy out, no torch types in any signature.  There is no CPU
+fallback here: `Device()` raises when the library or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .scenes import SceneDesc
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libvermeer_b200.so")
+
+RAY_DTYPE = np.dtype([("o", np.float32, 3), ("d", np.float32, 3), ("tmax", np.float32), ("time", np.float32)])
+HIT_DTYPE = np.dtype([("t", np.float32), ("u", np.float32), ("v", np.float32), ("w", np.float32),
+                      ("prim", np.int32), ("geom", np.int32), ("nodesT", np.int32), ("trisT", np.int32)])
+NODE_DTYPE = np.dtype([("Boxes", np.float32, 24), ("Axis0", np.uint32), ("Axis1", np.uint32), ("Axis2", np.uint32),
+                       ("Children", np.int32, 4), ("Parent", np.int32)])
+MNODE_DTYPE = np.dtype([("Axis0", np.int32), ("Axis1", np.int32), ("Axis2", np.int32), ("Children", np.int32, 4),
+                        ("Parent", np.int32), ("pad", np.uint32, 2)])
+
+VG_TRACE_ANY_HIT = 1
+
+# every symbol include/vermeer_gpu.h declares (tests check the library exports all of them)
+DECLARED_SYMBOLS = [
+    "vg_create", "vg_destroy", "vg_last_error", "vg_device_count", "vg_scene_begin", "vg_mesh_upload", "vg_mesh_upload_motion",
+    "vg_scene_upload", "vg_scene_upload_motion", "vg_scene_commit", "vg_set_materials", "vg_set_lights", "vg_set_camera", "vg_set_frame",
+    "vg_set_partition", "vg_set_scramble", "vg_set_option", "vg_trace_batch", "vg_trace_batch_device", "vg_render", "vg_clear_framebuffer",
+    "vg_framebuffer_device", "vg_get_stats", "vg_reset_stats",
+    "vh_scene_create", "vh_scene_destroy", "vh_last_error", "vh_registered_nodes", "vh_set_globals", "vh_add_shader_std", "vh_add_polymesh",
+    "vh_add_trilight", "vh_set_camera_lookat", "vh_prerender", "vh_upload", "vh_num_geoms", "vh_scene_info", "vh_scene_nodes",
+    "vh_scene_motion_nodes", "vh_scene_geom_order", "vh_mesh_info", "vh_mesh_nodes", "vh_mesh_motion_nodes", "vh_mesh_idxp", "vh_camera",
+]
+
+
+class VgMaterial(C.Structure):
+    _fields_ = [("mask", C.c_uint32), ("emission_colour", C.c_float * 3), ("emission_strength", C.c_float),
+                ("diffuse_colour", C.c_float * 3), ("diffuse_strength", C.c_float), ("diffuse_roughness", C.c_float),
+                ("spec1_colour", C.c_float * 3), ("spec1_strength", C.c_float), ("spec1_roughness", C.c_float), ("ior", C.c_float)]
+
+
+class VgCamera(C.Structure):
+    _fields_ = [("local_to_world", C.c_float * 16), ("tan_theta_focal", C.c_float), ("aspect", C.c_float), ("focal", C.c_float), ("radius", C.c_float)]
+
+
+class VgStats(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("nodes_t", C.c_uint64), ("tris_t", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("render_ms", C.c_double), ("trace_ms", C.c_double), ("traverse_ms", C.c_double)]
+
+
+_LIB = None
+
+
+def load_library():
+    """dlopen the in-tree library; raises if it has not been built (python -m vermeer_b200.build)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError("libvermeer_b200.so is missing: run `python -m vermeer_b200.build` (there is no CPU fallback)")
+        L = C.CDLL(SO_PATH)
+        L.vg_last_error.restype = C.c_char_p
+        L.vg_last_error.argtypes = [C.c_void_p]
+        L.vh_last_error.restype = C.c_char_p
+        L.vh_last_error.argtypes = [C.c_void_p]
+        L.vg_destroy.argtypes = [C.c_void_p]
+        L.vg_destroy.restype = None
+        L.vh_scene_destroy.argtypes = [C.c_void_p]
+        L.vh_scene_destroy.restype = None
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+def material_struct(sh) -> VgMaterial:
+    mask, p = sh.packed()
+    m = VgMaterial()
+    m.mask = mask
+    m.emission_colour[:] = p[0:3]
+    m.emission_strength = p[3]
+    m.diffuse_colour[:] = p[4:7]
+    m.diffuse_strength = p[7]
+    m.diffuse_roughness = p[8]
+    m.spec1_colour[:] = p[9:12]
+    m.spec1_strength = p[12]
+    m.spec1_roughness = p[13]
+    m.ior = p[14]
+    return m
+
+
+class HostScene:
+    """vh_* layer: the reference's node registry + PreRender, from a SceneDesc."""
+
+    def __init__(self, scene: SceneDesc):
+        self.L = load_library()
+        self.scene = scene
+        h = C.c_void_p()
+        if self.L.vh_scene_create(C.byref(h)) != 0:
+            raise RuntimeError("vh_scene_create failed")
+        self.h = h
+        L = self.L
+        self._chk(L.vh_set_globals(h, scene.XRes, scene.YRes, scene.MaxIter))
+        for s in scene.shaders:
+            m = material_struct(s)
+            self._chk(L.vh_add_shader_std(h, s.Name.encode(), C.byref(m)))
+        for m in scene.meshes:
+            keys, nverts, _ = m.Verts.shape
+            self._chk(L.vh_add_polymesh(
+                h, m.Name.encode(), _p(m.Verts), nverts, keys,
+                _p(m.PolyCount), 0 if m.PolyCount is None else len(m.PolyCount),
+                _p(m.FaceIdx), 0 if m.FaceIdx is None else len(m.FaceIdx),
+                "\n".join(m.Shader).encode(),
+                _p(m.ShaderIdx), 0 if m.ShaderIdx is None else len(m.ShaderIdx),
+                _p(m.Normals), 0 if m.Normals is None else len(m.Normals),
+                _p(m.NormalIdx), 0 if m.NormalIdx is None else len(m.NormalIdx),
+                C.c_float(m.RayBias)))
+        for l in scene.lights:
+            self._chk(L.vh_add_trilight(h, l.Name.encode(), _f3(l.P0), _f3(l.P1), _f3(l.P2), l.Shader.encode(), l.Samples))
+        c = scene.camera
+        self._chk(L.vh_set_camera_lookat(h, _f3(c.From), _f3(c.To), _f3(c.Up), C.c_float(c.Roll), C.c_float(c.Fov), C.c_float(c.Focal),
+                                         C.c_float(c.Aspect), C.c_float(c.Radius)))
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RuntimeError("vermeer host (%d): %s" % (rc, self.L.vh_last_error(self.h).decode()))
+
+    def prerender(self):
+        self._chk(self.L.vh_prerender(self.h))
+        return self
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vh_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # inspection --------------------------------------------------------------------------------
+    def num_geoms(self):
+        return self.L.vh_num_geoms(self.h)
+
+    def scene_info(self):
+        o = np.zeros(4, np.int32)
+        self._chk(self.L.vh_scene_info(self.h, _p(o)))
+        return dict(nodes=int(o[0]), motion=bool(o[1]), keys=int(o[2]), slots=int(o[3]))
+
+    def scene_nodes(self):
+        info = self.scene_info()
+        if info["motion"]:
+            topo = np.zeros(info["nodes"], MNODE_DTYPE)
+            boxes = np.zeros((info["keys"], info["nodes"], 24), np.float32)
+            self._chk(self.L.vh_scene_motion_nodes(self.h, _p(topo), _p(boxes)))
+            return topo, boxes
+        out = np.zeros(info["nodes"], NODE_DTYPE)
+        self._chk(self.L.vh_scene_nodes(self.h, _p(out)))
+        return out
+
+    def scene_geom_order(self):
+        o = np.zeros(self.num_geoms(), np.int32)
+        self._chk(self.L.vh_scene_geom_order(self.h, _p(o)))
+        return o
+
+    def mesh_info(self, gid):
+        o = np.zeros(6, np.int32)
+        self._chk(self.L.vh_mesh_info(self.h, gid, _p(o)))
+        return dict(nodes=int(o[0]), tris=int(o[1]), keys=int(o[2]), nverts=int(o[3]), motion=bool(o[4]), normals=bool(o[5]))
+
+    def mesh_nodes(self, gid):
+        info = self.mesh_info(gid)
+        if info["motion"]:
+            topo = np.zeros(info["nodes"], MNODE_DTYPE)
+            boxes = np.zeros((info["keys"], info["nodes"], 24), np.float32)
+            self._chk(self.L.vh_mesh_motion_nodes(self.h, gid, _p(topo), _p(boxes)))
+            return topo, boxes
+        out = np.zeros(info["nodes"], NODE_DTYPE)
+        self._chk(self.L.vh_mesh_nodes(self.h, gid, _p(out)))
+        return out
+
+    def mesh_idxp(self, gid):
+        info = self.mesh_info(gid)
+        idxp = np.zeros(info["tris"] * 3, np.uint32)
+        aidx = np.zeros(info["tris"], np.int32)
+        self._chk(self.L.vh_mesh_idxp(self.h, gid, _p(idxp), _p(aidx)))
+        return idxp, aidx
+
+    def camera(self):
+        c = VgCamera()
+        self._chk(self.L.vh_camera(self.h, C.byref(c)))
+        return np.asarray(c.local_to_world[:], np.float32), c.tan_theta_focal, c.aspect
+
+
+class Device:
+    """vg_* layer: one context on one B200."""
+
+    def __init__(self, ordinal: int = 0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.vg_create(C.byref(h), ordinal)
+        if rc != 0:
+            raise RuntimeError("vg_create failed (%d): %s" % (rc, self.L.vg_last_error(None).decode()))
+        self.h = h
+        self.xres = self.yres = 0
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RuntimeError("vermeer device (%d): %s" % (rc, self.L.vg_last_error(self.h).decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, host: HostScene, motion_ref_compat: bool = False):
+        rc = self.L.vh_upload(host.h, self.h, 1 if motion_ref_compat else 0)
+        if rc != 0:
+            raise RuntimeError("vh_upload (%d): %s" % (rc, self.L.vh_last_error(host.h).decode()))
+        self.xres, self.yres = host.scene.XRes, host.scene.YRes
+        return self
+
+    def set_partition(self, rank: int, world: int):
+        self._chk(self.L.vg_set_partition(self.h, rank, world))
+
+    def set_scramble(self, table: np.ndarray):
+        table = np.ascontiguousarray(table, np.uint64)
+        self._chk(self.L.vg_set_scramble(self.h, _p(table), C.c_int64(table.shape[0])))
+
+    def set_option(self, name: str, value: int):
+        self._chk(self.L.vg_set_option(self.h, name.encode(), int(value)))
+
+    def trace(self, rays: np.ndarray, any_hit: bool = False, out: np.ndarray | None = None) -> np.ndarray:
+        """vg_trace_batch with HOST buffers (H2D + kernel + D2H inside the call)."""
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        hits = np.empty(len(rays), HIT_DTYPE) if out is None else out
+        self._chk(self.L.vg_trace_batch(self.h, _p(rays), C.c_int64(len(rays)), _p(hits), C.c_uint32(VG_TRACE_ANY_HIT if any_hit else 0)))
+        return hits
+
+    def trace_device(self, d_rays_ptr: int, n: int, d_hits_ptr: int, any_hit: bool = False):
+        """vg_trace_batch_device: rays/hits already resident in HBM (raw device pointers, e.g. torch .data_ptr())."""
+        self._chk(self.L.vg_trace_batch_device(self.h, C.c_void_p(d_rays_ptr), C.c_int64(n), C.c_void_p(d_hits_ptr),
+                                               C.c_uint32(VG_TRACE_ANY_HIT if any_hit else 0)))
+
+    def render(self, iter_begin: int, iter_end: int, fetch: bool = True):
+        fb = np.zeros((self.yres, self.xres, 3), np.float32) if fetch else None
+        self._chk(self.L.vg_render(self.h, iter_begin, iter_end, _p(fb)))
+        return fb
+
+    def clear(self):
+        self._chk(self.L.vg_clear_framebuffer(self.h))
+
+    def framebuffer_ptr(self) -> int:
+        p = C.c_void_p()
+        self._chk(self.L.vg_framebuffer_device(self.h, C.byref(p)))
+        return p.value
+
+    def stats(self) -> dict:
+        s = VgStats()
+        self._chk(self.L.vg_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in VgStats._fields_}
+
+    def reset_stats(self):
+        self._chk(self.L.vg_reset_stats(self.h))
+
+
+def device_count() -> int:
+    return load_library().vg_device_count()
