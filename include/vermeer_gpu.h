@@ -122,12 +122,17 @@ typedef struct VgCamera {
 typedef struct VgStats {
   uint64_t rays;        /* every TraceProbe equivalent (core/stats.go:26-28) */
   uint64_t shadow_rays; /* of which RayTypeShadow (stats.go:31-33) */
-  uint64_t nodes_t;     /* sum of interior-node visits */
-  uint64_t tris_t;      /* sum of leaf triangle counts */
+  uint64_t nodes_t;     /* interior-node visits, closest-hit rays (vg_trace_batch* and the render's closest-hit kernel) */
+  uint64_t tris_t;      /* leaf triangle counts, closest-hit rays */
+  uint64_t shadow_nodes_t; /* same for the render's any-hit kernel */
+  uint64_t shadow_tris_t;
   uint64_t kernel_launches;
-  double render_ms;   /* device time of the last vg_render (CUDA events) */
-  double trace_ms;    /* device time of the last vg_trace_batch* kernel (CUDA events) */
-  double traverse_ms; /* device time spent in traversal kernels during the last vg_render */
+  uint64_t closest_launches; /* traversal launches inside vg_render, per kind */
+  uint64_t shadow_launches;
+  double render_ms;  /* device time of the last vg_render (CUDA events on the launching stream) */
+  double trace_ms;   /* device time of the last vg_trace_batch* kernel */
+  double closest_ms; /* summed device time of the closest-hit traversal launches of the last vg_render */
+  double shadow_ms;  /* summed device time of the any-hit traversal launches of the last vg_render */
 } VgStats;
 
 /* ---- device layer ------------------------------------------------------------------------- */

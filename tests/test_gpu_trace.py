@@ -78,7 +78,10 @@ def test_motion_heightfield(built_library, ref_compat):
     g = dev.trace(rays)
     o = ora.trace(rays)
     assert_hits_equal(g, o, what="motion ref_compat=%s" % ref_compat)
-    assert (g["prim"] >= 0).mean() > 0.2
+    if not ref_compat:
+        assert (g["prim"] >= 0).mean() > 0.2
+    # ref_compat reproduces reference quirk (b): leaf boxes bound face accel.idx[i] but face i is tested, so almost
+    # every ray misses — parity with the oracle above is what matters there.
 
 
 def test_degenerate_rays(built_library):

@@ -468,9 +468,8 @@ int vg_set_partition(vg_ctx* ctx, int rank, int world) {
 int vg_set_scramble(vg_ctx* ctx, const uint64_t* table, int64_t npix) {
   VG_LOCK(ctx);
   if (!table || npix <= 0) return ctx->fail(VG_ERR_INVALID, "vg_set_scramble: bad input");
-  ctx->scramble.assign(table, table + (size_t)npix * 6);
-  render_invalidate(ctx);
-  return VG_OK;
+  VG_CUDA(ctx, cudaSetDevice(ctx->device));
+  return render_set_scramble(ctx, table, npix);
 }
 
 int vg_set_option(vg_ctx* ctx, const char* name, int value) {
@@ -554,9 +553,9 @@ int vg_get_stats(vg_ctx* ctx, VgStats* out) {
   unsigned long long c[3] = {0, 0, 0};
   cudaSetDevice(ctx->device);
   cudaMemcpy(c, ctx->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost);
-  ctx->stats.nodes_t = c[1];
-  ctx->stats.tris_t = c[2];
   *out = ctx->stats;
+  out->nodes_t += c[1];  // batch-trace kernels accumulate on the device; the render adds its totals on the host
+  out->tris_t += c[2];
   return VG_OK;
 }
 

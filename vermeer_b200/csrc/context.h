@@ -122,5 +122,6 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out);
 int render_clear(vg_ctx* ctx);
 int render_fb_device(vg_ctx* ctx, float** d_fb);
 void render_invalidate(vg_ctx* ctx);  // scene / frame / partition changed
+int render_set_scramble(vg_ctx* ctx, const uint64_t* table, int64_t npix);
 void render_destroy(vg_ctx* ctx);
 }  // namespace vg

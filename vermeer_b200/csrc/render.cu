@@ -1,10 +1,971 @@
-// placeholder until the wavefront pipeline lands
+// Wavefront path integrator: the device replacement of core.Render / render / core.Trace / ShaderStd.Eval /
+// ShaderContext.EvaluateLightSamples (core/render.go:66-218, core/trace.go:40-83, builtin/shader/std.go:77-296,
+// core/shader.go:203-402).
+//
+// One batch = (owned pixels) x (iters_per_batch iterations) paths. Per batch, all on one stream with no host
+// round trip (queue sizes stay in device memory):
+//   k_raygen      QMC sample (RasterXY/VdC/Sobol) -> camera ray                     render.go:89-124, camera.go:221-323
+//   for level 0..3:
+//     k_trace_queue<closest>   persistent warps over the ray queue                  core/trace.go:26 -> traverse.cuh
+//     k_shade     hit record, ShaderStd, light/BSDF samples -> shadow-ray queue (+ mirror extension-ray queue),
+//                 both compacted with warp ballot + prefix popcount + one atomicAdd per warp
+//     k_trace_queue<shadow>    any-hit; an occluded sample zeroes its contribution slot
+//     k_resolve   per light: sum the slots in the reference's order, /total, *DiffuseColour, ... -> L[level]
+//   k_accumulate  fold levels back to front, then fb = (fb*iter + C)/(iter+1) per iteration in order (render.go:127-129)
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
 #include "context.h"
+#include "kernels.h"
+#include "shade.cuh"
+#include "traverse.cuh"
+
 namespace vg {
-struct RenderState {};
-int render_run(vg_ctx* ctx, int, int, float*) { return ctx->fail(VG_ERR_UNSUPPORTED, "vg_render: not built yet"); }
-int render_clear(vg_ctx*) { return VG_OK; }
-int render_fb_device(vg_ctx* ctx, float**) { return ctx->fail(VG_ERR_UNSUPPORTED, "not built yet"); }
-void render_invalidate(vg_ctx*) {}
-void render_destroy(vg_ctx*) {}
+
+struct DevLight {
+  f3 p0, p1, p2;
+  f3 N;            // normalize((P1-P0)x(P2-P0)), triangle.go:302
+  float inv_area;  // 1/triangleArea, triangle.go:234
+  f3 E;            // EvalEmission of the light's shader (std.go:299-316)
+  int nsamples;    // 1 << Samples
+  int geom;
+  int slot_base;
+};
+
+struct DevMat {
+  f3 emission;     // EmissionColour * EmissionStrength (0 if EmissionStrength unset)
+  f3 diff_colour;
+  float diff_weight, spec_weight;  // normalised by their sum (std.go:137-139)
+  float rough2;                    // DiffuseRoughness^2, default .5^2 (std.go:108-115, orennayar.go:25)
+  f3 spec_colour;
+  float spec_rough;
+  float ior;
+  int bad;  // 1: total weight 0 (the reference panics, std.go:141-143); 2: glossy lobe (not built yet)
+};
+
+struct __align__(16) DevHit {
+  float t, u, v, w;
+  int32_t prim, geom, slot, pad;
+};
+
+struct RenderParams {
+  DevScene sc;
+  int xres, yres, nown, P;  // P = paths per batch
+  const int* pix;           // [nown] full-frame pixel index, tile-major
+  const uint64_t* scr;      // [nown*6]
+  VgCamera cam;
+  const DevMat* mats;
+  const DevLight* lights;
+  int nlights, S, levels, trace_last_level;
+  VgRay* rayq[2];
+  int* pathq[2];
+  DevHit* hits;
+  float* lambda;
+  float* time;
+  uint8_t* v_mat;
+  float* v_invtot;  // [P*nlights]
+  float4* contrib;  // [P*S]
+  VgRay* sray;      // [P*S]
+  int* sslot;       // [P*S]
+  float4* L;        // [levels*P] rgb = emission + diffuse
+  float4* T;        // [levels*P] rgb = mirror throughput, w = spec weight
+  int* counts;      // [0],[1] ray queue sizes, [2] shadow queue size, [3] closest fetch head, [4] shadow fetch head, [5] error flags
+  unsigned long long* stats;  // [0] rays [1] shadow rays [2] nodesT [3] trisT (closest) [4] nodesT [5] trisT (shadow)
+  float* fb;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_reset(int* counts, int q0) {
+  counts[0] = q0;
+  counts[1] = 0;
+  counts[2] = 0;
+  counts[3] = 0;
+  counts[4] = 0;
 }
+__global__ void k_next_level(int* counts, int qout) {
+  counts[1 - qout] = 0;  // the queue that was just consumed becomes the next output queue
+  counts[2] = 0;
+  counts[3] = 0;
+  counts[4] = 0;
+}
+
+// core/render.go:89-124 + builtin/camera/camera.go:221-323 (differentials omitted)
+__global__ void __launch_bounds__(256) k_raygen(const RenderParams p, int iter_base, int niters) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.nown * niters) return;
+  const int own = i % p.nown, it = i / p.nown;
+  const int iter = iter_base + it + 1;  // render() receives iter+1 (render.go:192)
+  const int pixel = p.pix[own];
+  const int x = pixel % p.xres, y = pixel / p.xres;
+  const uint64_t* scr = p.scr + (size_t)own * 6;
+  double rasterX, rasterY;
+  raster_xy12((uint32_t)iter, (uint32_t)x, (uint32_t)y, &rasterX, &rasterY);
+  const double time = vdc((uint64_t)iter, scr[2]);
+  const double lambda = (720 - 450) * vdc((uint64_t)iter, scr[3]) + 450;
+  const double lensU = vdc((uint64_t)iter, scr[0]);
+  const double lensV = sobol((uint64_t)iter, scr[1]);
+  const float Sx = (float)(-1.0 + 2.0 * (rasterX / (double)p.xres));
+  const float Sy = -(float)(-1.0 + 2.0 * (rasterY / (double)p.yres));
+
+  const float* M = p.cam.local_to_world;
+  const float camu = Sx * p.cam.tan_theta_focal;
+  const float camv = Sy * (p.cam.tan_theta_focal / p.cam.aspect);
+  // s = camu*U + camv*V - Focal*W with the canonical basis (camera.go:248-252); the products with 0/1 are exact
+  f3 s = mk3(camu, camv, 0.0f - p.cam.focal);
+  f3 e = mk3(0, 0, 0);
+  if (p.cam.radius > 0.0f) {
+    float lx, ly;
+    uniform_disk2d(p.cam.radius, (float)lensU, (float)lensV, &lx, &ly);
+    e = mk3(lx, ly, 0.0f);
+    s = sub3(s, e);
+  }
+  const f3 d = mk3(M[0] * s.x + M[4] * s.y + M[8] * s.z, M[1] * s.x + M[5] * s.y + M[9] * s.z, M[2] * s.x + M[6] * s.y + M[10] * s.z);
+  const f3 D = normalize3(d);
+  const f3 O = mk3(M[0] * e.x + M[4] * e.y + M[8] * e.z + M[12], M[1] * e.x + M[5] * e.y + M[9] * e.z + M[13],
+                   M[2] * e.x + M[6] * e.y + M[10] * e.z + M[14]);
+  float4* rp = reinterpret_cast<float4*>(p.rayq[0] + i);
+  rp[0] = make_float4(O.x, O.y, O.z, D.x);
+  rp[1] = make_float4(D.y, D.z, __int_as_float(0x7f800000), (float)time);
+  p.pathq[0][i] = i;
+  p.lambda[i] = (float)lambda;
+  p.time[i] = (float)time;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Persistent traversal over a device-resident queue. MODE 0: closest hit -> hits[]. MODE 1: shadow rays (any hit);
+// an occluded sample zeroes its contribution slot.
+template <int MODE>
+__global__ void __launch_bounds__(kTraceBlock) k_trace_queue(const RenderParams p, int q) {
+  extern __shared__ uint2 smem_stack[];
+  Stack st;
+  st.smem = smem_stack + threadIdx.x;
+  st.stride = blockDim.x;
+  const int lane = threadIdx.x & 31;
+  const int n = MODE == 0 ? p.counts[q] : p.counts[2];
+  const VgRay* rays = MODE == 0 ? p.rayq[q] : p.sray;
+  int* head = p.counts + (MODE == 0 ? 3 : 4);
+  unsigned long long nodes_acc = 0, tris_acc = 0;
+  while (true) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(head, 32);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n) break;
+    const int i = base + lane;
+    if (i < n) {
+      const float4* rp = reinterpret_cast<const float4*>(rays + i);
+      const float4 a = __ldg(rp), b = __ldg(rp + 1);
+      RayState r;
+      r.ox = a.x; r.oy = a.y; r.oz = a.z;
+      r.dx = a.w; r.dy = b.x; r.dz = b.y;
+      r.tclosest = b.z;
+      r.time = b.w;
+      ray_setup(r);
+      HitState h;
+      const bool hit = trace_ray<MODE == 1>(p.sc, r, h, st);
+      if (st.overflow) atomicOr(p.counts + 5, 4);
+      if (MODE == 0) {
+        DevHit o;
+        o.t = r.tclosest; o.u = h.u; o.v = h.v; o.w = h.w;
+        o.prim = h.prim; o.geom = h.geom; o.slot = h.slot; o.pad = 0;
+        *reinterpret_cast<float4*>(&p.hits[i]) = make_float4(o.t, o.u, o.v, o.w);
+        *(reinterpret_cast<int4*>(&p.hits[i]) + 1) = make_int4(o.prim, o.geom, o.slot, 0);
+      } else {
+        if (hit) p.contrib[p.sslot[i]] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      nodes_acc += (unsigned long long)h.nodesT;
+      tris_acc += (unsigned long long)h.trisT;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    nodes_acc += __shfl_down_sync(0xffffffffu, nodes_acc, o);
+    tris_acc += __shfl_down_sync(0xffffffffu, tris_acc, o);
+  }
+  if (lane == 0) {
+    atomicAdd(p.stats + (MODE == 0 ? 2 : 4), nodes_acc);
+    atomicAdd(p.stats + (MODE == 0 ? 3 : 5), tris_acc);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(p.stats + 0, (unsigned long long)n);  // every TraceProbe counts (core/stats.go:26-33)
+    if (MODE == 1) atomicAdd(p.stats + 1, (unsigned long long)n);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+struct ShadeCtx {
+  f3 P, Poffset, N, Ng, DdPdu, DdPdv;
+};
+
+__device__ __forceinline__ f3 ld3(const float4* p) {
+  const float4 v = __ldg(p);
+  return mk3(v.x, v.y, v.z);
+}
+
+// polymesh/trace.go:276-360,504-515 (static) / :625-667 (motion), then ShaderContext.ApplyTransform (core/shader.go:129-135,
+// identity transform: only the re-normalisations remain).
+__device__ inline void build_context(const RenderParams& p, const DevHit& h, float time, ShadeCtx& c) {
+  const DevGeom g = p.sc.geoms[h.geom];
+  const float U = h.u, V = h.v, W = h.w;
+  f3 E0, E1, E2;
+  const bool motion = g.keys > 1;
+  if (!motion) {
+    const float4* tp = p.sc.tris + (size_t)h.slot * 3;
+    E0 = ld3(tp); E1 = ld3(tp + 1); E2 = ld3(tp + 2);
+  } else {
+    const float k = time * (float)(g.keys - 1);
+    const float fk = floorf(k);
+    const float tm = k - fk, om = 1.0f - tm;
+    const int key = (int)fk, key2 = (int)ceilf(k);
+    const float4* ta = p.sc.mtris + ((size_t)h.slot + (size_t)key * g.tri_key_stride) * 3;
+    const float4* tb = p.sc.mtris + ((size_t)h.slot + (size_t)key2 * g.tri_key_stride) * 3;
+    const f3 a0 = ld3(ta), a1 = ld3(ta + 1), a2 = ld3(ta + 2), b0 = ld3(tb), b1 = ld3(tb + 1), b2 = ld3(tb + 2);
+    E0 = mk3(om * a0.x + tm * b0.x, om * a0.y + tm * b0.y, om * a0.z + tm * b0.z);
+    E1 = mk3(om * a1.x + tm * b1.x, om * a1.y + tm * b1.y, om * a1.z + tm * b1.z);
+    E2 = mk3(om * a2.x + tm * b2.x, om * a2.y + tm * b2.y, om * a2.z + tm * b2.z);
+  }
+  const float xAbs = fabsf(U * E0.x) + fabsf(V * E1.x) + fabsf(W * E2.x);
+  const float yAbs = fabsf(U * E0.y) + fabsf(V * E1.y) + fabsf(W * E2.y);
+  const float zAbs = fabsf(U * E0.z) + fabsf(V * E1.z) + fabsf(W * E2.z);
+  const f3 e0 = sub3(E1, E0), e1 = sub3(E2, E0);
+  f3 Ng = normalize3(cross3(e0, e1));
+  f3 N = Ng;
+  if (!motion && g.normal_base >= 0 && p.sc.tri_normals) {
+    const float4* np = p.sc.tri_normals + (size_t)h.slot * 3;
+    const f3 n0 = ld3(np), n1 = ld3(np + 1), n2 = ld3(np + 2);
+    N = normalize3(mk3(U * n0.x + V * n1.x + W * n2.x, U * n0.y + V * n1.y + W * n2.y, U * n0.z + V * n1.z + W * n2.z));
+  }
+  const float g7 = (7.0f * 5.9604644775390625e-08f) / (1 - 7.0f * 5.9604644775390625e-08f);  // math/ferror.go:22-24, Gamma(7)
+  const float d = g7 * xAbs * fabsf(Ng.x) + g7 * yAbs * fabsf(Ng.y) + g7 * zAbs * fabsf(Ng.z);
+  c.Poffset = scale3(d, Ng);
+  c.P = mk3(U * E0.x + V * E1.x + W * E2.x, U * E0.y + V * E1.y + W * E2.y, U * E0.z + V * E1.z + W * E2.z);
+  if (!motion) {
+    f3 axisu = sub3(mk3(1, 0, 0), scale3(Ng.x, Ng));
+    if (len2_3(axisu) < 0.1f || fabsf(dot3(axisu, Ng)) > 0.3f) axisu = sub3(mk3(0, 0, 1), scale3(Ng.z, Ng));
+    c.DdPdu = normalize3(axisu);
+    c.DdPdv = cross3(Ng, c.DdPdu);
+  } else {
+    c.DdPdu = e0;
+    c.DdPdv = e1;
+  }
+  // ApplyTransform
+  c.N = normalize3(N);
+  c.Ng = normalize3(Ng);
+  c.DdPdu = normalize3(c.DdPdu);
+  c.DdPdv = normalize3(c.DdPdv);
+}
+
+// Warp-aggregated append: every lane of the warp must call this. Returns the slot index (or -1).
+__device__ __forceinline__ int warp_append(int* counter, bool want) {
+  const unsigned mask = __ballot_sync(0xffffffffu, want);
+  if (mask == 0) return -1;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(mask) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(mask));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return want ? base + __popc(mask & ((1u << lane) - 1u)) : -1;
+}
+
+struct LightRec {
+  bool valid;
+  f3 Ld;
+  float Ldist;
+  float pdf;
+};
+struct BsdfRec {
+  bool valid;
+  f3 Ld;
+  float Ldist;
+  double pdf;
+  float pdfLight;
+};
+
+// light.Tri.SampleArea, sample `i` of `n` (builtin/light/triangle.go:232-343)
+__device__ inline LightRec light_sample(const DevLight& L, const ShadeCtx& c, bool by_area, long long I, int n, int i, uint64_t scr0, uint64_t scr1) {
+  LightRec r;
+  const uint64_t idx = (uint64_t)(I * n + i);
+  const double r0 = vdc(idx, scr0);
+  const double r1 = sobol(idx, scr1);
+  f3 Pl;
+  if (by_area) {
+    const double sq = sqrt(1 - r0);
+    const f3 a = scale3((float)(r1 * sq), sub3(L.p1, L.p0)), b = scale3((float)(1 - sq), sub3(L.p2, L.p0));
+    Pl = mk3(L.p0.x + a.x + b.x, L.p0.y + a.y + b.y, L.p0.z + a.z + b.z);
+  } else {
+    double pdf;
+    const f3 x = sample_spherical_triangle(L.p0, L.p1, L.p2, c.P, r0, r1, &pdf);
+    const float t = ray_plane(c.P, x, L.p0, L.N);
+    Pl = mad3(c.P, x, t);
+    r.pdf = (float)pdf;
+  }
+  const f3 D = sub3(Pl, c.P);
+  r.Ldist = length3(D);
+  r.Ld = normalize3(D);
+  r.valid = !(dot3(r.Ld, L.N) > 0 || dot3(r.Ld, c.Ng) < 0);
+  if (by_area) {
+    const float pdfA = (float)(double)L.inv_area;
+    r.pdf = pdfA * (r.Ldist * r.Ldist) / fabsf(dot3(r.Ld, L.N));
+  }
+  return r;
+}
+
+// BSDF sample `i` of `h` through Light.ValidSample (core/shader.go:212-229, triangle.go:136-230)
+__device__ inline BsdfRec bsdf_sample(const DevLight& L, const ShadeCtx& c, const Frame& fr, long long I, int h, int i, uint64_t scr0, uint64_t scr1) {
+  BsdfRec r;
+  r.valid = false;
+  const uint64_t idx = (uint64_t)(I * h + i);
+  const double r0 = vdc(idx, scr0);
+  const double r1 = sobol(idx, scr1);
+  const f3 wo = normalize3(basis_expand(fr.U, fr.V, fr.N, cosine_hemisphere(r0, r1)));
+  r.pdf = oren_pdf(fr, wo);
+  if (r.pdf <= 0) return r;
+  f3 Pl;
+  if (!ray_triangle(c.P, wo, L.p0, L.p1, L.p2, &Pl)) return r;
+  const bool by_area = dot3(c.Ng, sub3(L.p0, Pl)) < 0 || dot3(c.Ng, sub3(L.p1, Pl)) < 0 || dot3(c.Ng, sub3(L.p2, Pl)) < 0;
+  float pdfl;
+  if (by_area) {
+    pdfl = (float)(double)L.inv_area;
+  } else {
+    const f3 pa = normalize3(sub3(L.p0, c.P)), pb = normalize3(sub3(L.p1, c.P)), pc = normalize3(sub3(L.p2, c.P));
+    const float area = spherical_area(pa, pb, pc, nullptr, nullptr);
+    pdfl = (float)(double)(1 / area);
+  }
+  const f3 D = sub3(Pl, c.P);
+  r.Ldist = length3(D);
+  r.Ld = normalize3(D);
+  if (dot3(r.Ld, L.N) > 0 || dot3(r.Ld, c.Ng) < 0) return r;
+  r.pdfLight = by_area ? pdfl * (r.Ldist * r.Ldist) / fabsf(dot3(r.Ld, L.N)) : pdfl;
+  r.valid = true;
+  return r;
+}
+
+__global__ void __launch_bounds__(128) k_shade(const RenderParams p, int level, int qin, int qout, int iter_base) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = p.counts[qin];
+  // whole warps past the end leave together (appends below are warp-collective)
+  if ((i & ~31) >= n) return;
+  bool active = i < n;
+  int path = 0;
+  DevHit h;
+  h.prim = -1;
+  f3 Ro = mk3(0, 0, 0), Rd = mk3(0, 0, 1);
+  if (active) {
+    path = p.pathq[qin][i];
+    const float4 h0 = *reinterpret_cast<const float4*>(&p.hits[i]);
+    const int4 h1 = *(reinterpret_cast<const int4*>(&p.hits[i]) + 1);
+    h.t = h0.x; h.u = h0.y; h.v = h0.z; h.w = h0.w;
+    h.prim = h1.x; h.geom = h1.y; h.slot = h1.z;
+    const float4* rp = reinterpret_cast<const float4*>(p.rayq[qin] + i);
+    const float4 a = rp[0], b = rp[1];
+    Ro = mk3(a.x, a.y, a.z);
+    Rd = mk3(a.w, b.x, b.y);
+  }
+  int matid = 255;
+  if (active && h.prim >= 0) matid = p.sc.prim_material[p.sc.geoms[h.geom].prim_base + h.prim];
+  if (active) {
+    p.v_mat[i] = (uint8_t)matid;
+    for (int s = 0; s < p.S; s++) p.contrib[(size_t)i * p.S + s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int l = 0; l < p.nlights; l++) p.v_invtot[(size_t)i * p.nlights + l] = 0.0f;
+    p.T[(size_t)level * p.P + path] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // miss, or hit without a shader (core/trace.go:63-65): nothing to shade. At Level > 3 Eval returns at once (std.go:95).
+  active = active && matid != 255 && level <= 3;
+
+  DevMat m;
+  ShadeCtx c;
+  Frame fr;
+  f3 omegaI = mk3(0, 0, 1);
+  float lambda = 0, time = 0;
+  long long I = 0;
+  uint64_t scr0 = 0, scr1 = 0;
+  if (active) {
+    m = p.mats[matid];
+    if (m.bad) {
+      atomicOr(p.counts + 5, m.bad);
+      active = false;
+    }
+  }
+  if (active) {
+    lambda = p.lambda[path];
+    time = p.time[path];
+    const int own = path % p.nown;
+    build_context(p, h, time, c);
+    // tangent frame, std.go:98-106
+    f3 V = cross3(c.N, c.DdPdu);
+    if (len2_3(V) < 0.1f) V = cross3(c.N, c.DdPdv);
+    V = normalize3(V);
+    fr.U = normalize3(cross3(c.N, V));
+    fr.V = V;
+    fr.N = c.N;
+    omegaI = basis_project(fr.U, fr.V, fr.N, neg3(Rd));
+    scr0 = p.scr[(size_t)own * 6 + 4];
+    scr1 = p.scr[(size_t)own * 6 + 5];
+  }
+  // sample index I = ray.I = the 1-based iteration (render.go:123); path = it*nown + own
+  if (active) I = (long long)(iter_base + path / p.nown + 1);
+
+  // ---- diffuse lobe: direct light with MIS (std.go:145-163, core/shader.go:203-402) ----
+  const bool diffuse = active && m.diff_weight > 0.0f;
+  for (int l = 0; l < p.nlights; l++) {
+    const DevLight L = p.lights[l];
+    const int NS = level > 0 ? 1 : L.nsamples;  // shader.go:186-191
+    const bool lit = diffuse && L.geom != h.geom;  // scene.go:106-113
+    Spec4 Liu;
+    bool by_area = false;
+    if (lit) {
+      Liu = spec_from_rgb(L.E, lambda);
+      by_area = dot3(c.Ng, sub3(L.p0, c.P)) < 0 || dot3(c.Ng, sub3(L.p1, c.P)) < 0 || dot3(c.Ng, sub3(L.p2, c.P)) < 0;
+    }
+    const int hN = NS > 1 ? NS / 2 : NS;  // samples per strategy
+    // pass 1: which strategies produced at least one sample (shader.go:241-249)
+    int nB = 0, nLs = 0;
+    LightRec lr0;
+    BsdfRec br0;
+    lr0.valid = false;
+    br0.valid = false;
+    if (lit) {
+      if (NS > 1) {
+        for (int s = 0; s < hN; s++) {
+          const BsdfRec br = bsdf_sample(L, c, fr, I, hN, s, scr0, scr1);
+          if (s == 0) br0 = br;
+          if (br.valid) nB = hN;
+        }
+      }
+      for (int s = 0; s < hN; s++) {
+        const LightRec lr = light_sample(L, c, by_area, I, hN, s, scr0, scr1);
+        if (s == 0) lr0 = lr;
+        if (lr.valid) nLs = hN;
+      }
+    }
+    const int total = nB + nLs;
+    if (lit) p.v_invtot[(size_t)i * p.nlights + l] = NS > 1 ? (total > 0 ? 1.0f / (float)total : 0.0f) : 1.0f;
+
+    // pass 2: contributions + shadow rays, light samples first then BSDF samples (shader.go:260-344)
+    for (int s = 0; s < (NS > 1 ? 2 * hN : hN); s++) {
+      const bool is_bsdf = s >= hN;
+      bool want = false;
+      f3 Ld = mk3(0, 0, 1);
+      float Ldist = 0;
+      float4 rgb4 = make_float4(0, 0, 0, 0);
+      if (lit && (NS == 1 || total > 0)) {
+        float p_hat;
+        bool valid;
+        if (!is_bsdf) {
+          const LightRec lr = (s == 0) ? lr0 : light_sample(L, c, by_area, I, hN, s, scr0, scr1);
+          valid = lr.valid;
+          Ld = lr.Ld;
+          Ldist = lr.Ldist;
+          if (NS > 1) {
+            p_hat = (float)nB * (float)oren_pdf(fr, Ld) / (float)total;
+            p_hat += (float)nLs * lr.pdf / (float)total;
+          } else {
+            p_hat = lr.pdf;
+          }
+        } else {
+          const BsdfRec br = (s == hN) ? br0 : bsdf_sample(L, c, fr, I, hN, s - hN, scr0, scr1);
+          valid = br.valid;
+          Ld = br.Ld;
+          Ldist = br.Ldist;
+          p_hat = (float)nB * (float)br.pdf / (float)total;
+          p_hat += (float)nLs * br.pdfLight / (float)total;
+        }
+        if (valid && !(dot3(Ld, c.N) <= 0)) {
+          Spec4 rho = oren_eval(fr, omegaI, m.rough2, lambda, Ld);
+          const float inv = 1.0f / p_hat;
+#pragma unroll
+          for (int k = 0; k < 4; k++) rho.c[k] = (rho.c[k] * Liu.c[k]) * inv;
+          f3 rgb = spec_to_rgb(rho, lambda);
+          if (NS > 1) {  // shader.go:292-296 clamps only in the MIS branch
+            if (rgb.x < 0) rgb.x = 0;
+            if (rgb.y < 0) rgb.y = 0;
+            if (rgb.z < 0) rgb.z = 0;
+          }
+          rgb4 = make_float4(rgb.x, rgb.y, rgb.z, 0.f);
+          want = true;
+        }
+      }
+      const int slot = i * p.S + L.slot_base + s;
+      if (want) p.contrib[slot] = rgb4;
+      const int qi = warp_append(p.counts + 2, want);
+      if (want) {
+        const f3 o = offset_p(c.P, c.Poffset, dot3(Ld, c.Ng) < 0 ? -1 : 1);
+        const f3 d = scale3(Ldist * (1.0f - 0.0001f), Ld);  // core/ray.go:20, shader.go:269-273
+        float4* rp = reinterpret_cast<float4*>(p.sray + qi);
+        rp[0] = make_float4(o.x, o.y, o.z, d.x);
+        rp[1] = make_float4(d.y, d.z, 1.0f, time);
+        p.sslot[qi] = slot;
+      }
+    }
+  }
+
+  // ---- mirror lobe (std.go:194-261, bsdf/specular.go) ----
+  {
+    bool want = false;
+    f3 wo = mk3(0, 0, 1);
+    float4 T4 = make_float4(0, 0, 0, 0);
+    if (active && m.spec_weight > 0.0f) {
+      const f3 refl = reflect_z(omegaI);
+      wo = basis_expand(fr.U, fr.V, fr.N, normalize3(refl));
+      const f3 o = basis_project(fr.U, fr.V, fr.N, wo);
+      const double pdf = dot3(o, refl) < 0.9999f ? 0.0 : 1.0;
+      if (!(dot3(wo, c.Ng) <= 0.0f)) {
+        Spec4 rho;
+        rho.c[0] = rho.c[1] = rho.c[2] = rho.c[3] = 0.f;
+        if (!(dot3(o, refl) < 0.9999f)) {
+          const float kr = dielectric_kr(m.ior, omegaI.z);
+          rho = spec_from_rgb(mk3(kr, kr, kr), lambda);
+          const float az = fabsf(o.z);
+#pragma unroll
+          for (int k = 0; k < 4; k++) rho.c[k] *= az;
+        }
+        const float inv = 1.0f / (float)pdf;
+#pragma unroll
+        for (int k = 0; k < 4; k++) rho.c[k] *= inv;
+        const f3 rgb = spec_to_rgb(rho, lambda);
+        T4 = make_float4(rgb.x * m.spec_colour.x, rgb.y * m.spec_colour.y, rgb.z * m.spec_colour.z, m.spec_weight);
+        // the level-4 ray is traced by the reference although its shader returns black (std.go:95,243)
+        want = (level + 1 <= 3) || p.trace_last_level;
+      }
+    }
+    if (active) p.T[(size_t)level * p.P + path] = T4;
+    const int qi = warp_append(p.counts + qout, want);
+    if (want) {
+      const f3 o = offset_p(c.P, c.Poffset, 1);
+      float4* rp = reinterpret_cast<float4*>(p.rayq[qout] + qi);
+      rp[0] = make_float4(o.x, o.y, o.z, wo.x);
+      rp[1] = make_float4(wo.y, wo.z, __int_as_float(0x7f800000), time);
+      p.pathq[qout][qi] = path;
+    }
+  }
+}
+
+// Sum the slots in the reference's order and finish the diffuse term (core/shader.go:349, std.go:157-163,287-295).
+__global__ void __launch_bounds__(256) k_resolve(const RenderParams p, int level, int qin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.counts[qin]) return;
+  const int path = p.pathq[qin][i];
+  const int matid = p.v_mat[i];
+  float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (matid != 255 && level <= 3) {
+    const DevMat m = p.mats[matid];
+    f3 diff = mk3(0, 0, 0);
+    if (m.diff_weight > 0.0f) {
+      for (int l = 0; l < p.nlights; l++) {
+        const DevLight& L = p.lights[l];
+        const int NS = level > 0 ? 1 : L.nsamples;
+        const float inv = p.v_invtot[(size_t)i * p.nlights + l];
+        if (inv == 0.0f) continue;  // light excluded (own geom) or no samples: EvaluateLightSamples returned RGB{}
+        f3 col = mk3(0, 0, 0);
+        for (int s = 0; s < NS; s++) {
+          const float4 c = p.contrib[(size_t)i * p.S + L.slot_base + s];
+          col.x += c.x; col.y += c.y; col.z += c.z;
+        }
+        if (NS > 1) { col.x *= inv; col.y *= inv; col.z *= inv; }
+        col.x *= m.diff_colour.x; col.y *= m.diff_colour.y; col.z *= m.diff_colour.z;
+        diff.x += col.x; diff.y += col.y; diff.z += col.z;
+      }
+      diff.x *= m.diff_weight; diff.y *= m.diff_weight; diff.z *= m.diff_weight;
+    }
+    out = make_float4(m.emission.x + diff.x, m.emission.y + diff.y, m.emission.z + diff.z, 0.f);
+  }
+  p.L[(size_t)level * p.P + path] = out;
+}
+
+// Fold the levels back to front (std.go:246-266,287-295) and continue the running mean (render.go:127-129).
+__global__ void __launch_bounds__(256) k_accumulate(const RenderParams p, int iter_base, int niters) {
+  const int own = blockIdx.x * blockDim.x + threadIdx.x;
+  if (own >= p.nown) return;
+  float* px = p.fb + (size_t)p.pix[own] * 3;
+  float r = px[0], g = px[1], b = px[2];
+  for (int it = 0; it < niters; it++) {
+    const int path = it * p.nown + own;
+    f3 C = mk3(0, 0, 0);
+    for (int k = p.levels - 1; k >= 0; k--) {
+      const float4 L = p.L[(size_t)k * p.P + path];
+      f3 sp = mk3(0, 0, 0);
+      if (p.levels > 1) {
+        const float4 T = p.T[(size_t)k * p.P + path];
+        sp = mk3(T.x * C.x, T.y * C.y, T.z * C.z);
+        if (sp.x < 0 || isnan(sp.x)) sp.x = 0;
+        if (sp.y < 0 || isnan(sp.y)) sp.y = 0;
+        if (sp.z < 0 || isnan(sp.z)) sp.z = 0;
+        sp = scale3(T.w, sp);
+      }
+      C = mk3(L.x + sp.x, L.y + sp.y, L.z + sp.z);
+    }
+    const float fi = (float)(iter_base + it + 1);
+    r = (r * fi + C.x) / (fi + 1.0f);
+    g = (g * fi + C.y) / (fi + 1.0f);
+    b = (b * fi + C.z) / (fi + 1.0f);
+  }
+  px[0] = r; px[1] = g; px[2] = b;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+struct RenderState {
+  bool ready = false;
+  int nown = 0, P = 0, S = 0, levels = 1, nlights = 0, iters = 0;
+  DevBuf<int> pix;
+  DevBuf<uint64_t> scr;
+  DevBuf<DevMat> mats;
+  DevBuf<DevLight> lights;
+  DevBuf<VgRay> rayq0, rayq1, sray;
+  DevBuf<int> pathq0, pathq1, sslot, counts;
+  DevBuf<DevHit> hits;
+  DevBuf<float> lambda, time, invtot, fb;
+  DevBuf<uint8_t> vmat;
+  DevBuf<float4> contrib, L, T;
+  DevBuf<unsigned long long> stats;
+  int fb_w = 0, fb_h = 0;
+  int trace_grid = 0;
+  std::vector<int> pix_host;
+  uint64_t* scr_pinned = nullptr;
+  size_t scr_pinned_bytes = 0;
+  float* fb_pinned = nullptr;
+  size_t fb_pinned_bytes = 0;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  std::vector<cudaEvent_t> evpool;  // pairs around every traversal launch (per-kernel device time for the roofline)
+  cudaEvent_t ev(size_t i) {
+    while (evpool.size() <= i) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      evpool.push_back(e);
+    }
+    return evpool[i];
+  }
+  void release() {
+    pix.release(); scr.release(); mats.release(); lights.release(); rayq0.release(); rayq1.release(); sray.release();
+    pathq0.release(); pathq1.release(); sslot.release(); counts.release(); hits.release(); lambda.release(); time.release();
+    invtot.release(); vmat.release(); contrib.release(); L.release(); T.release(); stats.release();
+  }
+};
+
+void render_invalidate(vg_ctx* ctx) {
+  if (ctx->rs) ctx->rs->ready = false;
+}
+void render_destroy(vg_ctx* ctx) {
+  if (!ctx->rs) return;
+  ctx->rs->release();
+  ctx->rs->fb.release();
+  if (ctx->rs->e0) cudaEventDestroy(ctx->rs->e0);
+  if (ctx->rs->e1) cudaEventDestroy(ctx->rs->e1);
+  for (cudaEvent_t e : ctx->rs->evpool) cudaEventDestroy(e);
+  if (ctx->rs->scr_pinned) cudaFreeHost(ctx->rs->scr_pinned);
+  if (ctx->rs->fb_pinned) cudaFreeHost(ctx->rs->fb_pinned);
+  delete ctx->rs;
+  ctx->rs = nullptr;
+}
+
+#define RCUDA(call)                                          \
+  do {                                                       \
+    cudaError_t e_ = (call);                                 \
+    if (e_ != cudaSuccess) return ctx->cuda_fail(e_, #call); \
+  } while (0)
+
+static inline f3 h3(const float* p) { f3 r; r.x = p[0]; r.y = p[1]; r.z = p[2]; return r; }
+
+// host-side normalize with the reference's operation order (math/vec3_amd64.s:11-43); the reciprocal square root is
+// correctly rounded here.
+static f3 host_normalize(f3 a) {
+  float x0 = a.x * a.x, x1 = a.y * a.y, x2 = a.z * a.z;
+  x1 = x1 + x0;
+  x1 = x1 + x2;
+  const float r = (float)(1.0 / std::sqrt((double)x1));
+  f3 o; o.x = a.x * r; o.y = a.y * r; o.z = a.z * r;
+  return o;
+}
+
+static int ensure_fb(vg_ctx* ctx) {
+  if (!ctx->rs) {
+    ctx->rs = new RenderState();
+    cudaEventCreate(&ctx->rs->e0);
+    cudaEventCreate(&ctx->rs->e1);
+  }
+  RenderState& rs = *ctx->rs;
+  if (ctx->xres <= 0 || ctx->yres <= 0) return ctx->fail(VG_ERR_INVALID, "frame size not set (vg_set_frame)");
+  if (rs.fb_w != ctx->xres || rs.fb_h != ctx->yres) {
+    RCUDA(rs.fb.reserve((size_t)ctx->xres * ctx->yres * 3));
+    RCUDA(cudaMemsetAsync(rs.fb.p, 0, (size_t)ctx->xres * ctx->yres * 3 * sizeof(float), ctx->stream));
+    rs.fb_w = ctx->xres;
+    rs.fb_h = ctx->yres;
+  }
+  return VG_OK;
+}
+
+// Partition of framescramble (core/render.go:166-176) at upload: only the rows of owned pixels go to the device.
+static int upload_scramble(vg_ctx* ctx, const uint64_t* table) {
+  RenderState& rs = *ctx->rs;
+  if (rs.nown == 0) return VG_OK;
+  const size_t bytes = (size_t)rs.nown * 48;
+  if (rs.scr_pinned_bytes < bytes) {
+    if (rs.scr_pinned) cudaFreeHost(rs.scr_pinned);
+    rs.scr_pinned = nullptr;
+    RCUDA(cudaMallocHost((void**)&rs.scr_pinned, bytes));
+    rs.scr_pinned_bytes = bytes;
+  }
+  const int* pix = rs.pix_host.data();
+  // owned pixels come in runs of up to 32 consecutive pixels (one tile row): copy run by run
+  size_t i = 0;
+  while (i < (size_t)rs.nown) {
+    size_t j = i + 1;
+    while (j < (size_t)rs.nown && pix[j] == pix[j - 1] + 1) j++;
+    std::memcpy(rs.scr_pinned + i * 6, table + (size_t)pix[i] * 6, (j - i) * 48);
+    i = j;
+  }
+  RCUDA(cudaMemcpyAsync(rs.scr.p, rs.scr_pinned, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  RCUDA(cudaStreamSynchronize(ctx->stream));
+  return VG_OK;
+}
+
+static int prepare(vg_ctx* ctx) {
+  int rc = ensure_fb(ctx);
+  if (rc != VG_OK) return rc;
+  RenderState& rs = *ctx->rs;
+  if (rs.ready) return VG_OK;
+  if (!ctx->committed) return ctx->fail(VG_ERR_INVALID, "scene not committed");
+  if (!ctx->have_camera) return ctx->fail(VG_ERR_INVALID, "no camera (core.Render: ErrNoCamera)");
+  const int W = ctx->xres, H = ctx->yres;
+  if ((int64_t)ctx->scramble.size() != (int64_t)W * H * 6) return ctx->fail(VG_ERR_INVALID, "scramble table missing or of the wrong size (vg_set_scramble)");
+
+  // owned pixels: the reference's 32x32 tiles (render.go:196-199), tile (tx,ty) -> rank (tx + ty*k) % world, k odd
+  const int tilesX = (W + 31) / 32, tilesY = (H + 31) / 32;
+  const int k = (tilesX % 2 == 0) ? tilesX + 1 : tilesX;  // row-major tile index when world divides nothing in common
+  std::vector<int> pix;
+  for (int ty = 0; ty < tilesY; ty++)
+    for (int tx = 0; tx < tilesX; tx++) {
+      if ((tx + ty * k) % ctx->world != ctx->rank) continue;
+      for (int j = 0; j < 32; j++)
+        for (int i = 0; i < 32; i++) {
+          const int x = tx * 32 + i, y = ty * 32 + j;
+          if (x < W && y < H) pix.push_back(x + y * W);
+        }
+    }
+  rs.nown = (int)pix.size();
+  rs.pix_host = pix;
+
+  // materials
+  std::vector<DevMat> mats(ctx->materials.size());
+  bool any_mirror = false;
+  for (size_t i = 0; i < mats.size(); i++) {
+    const VgMaterial& s = ctx->materials[i];
+    DevMat& d = mats[i];
+    std::memset(&d, 0, sizeof(d));
+    if (s.mask & VG_MAT_EMISSION_STRENGTH) {
+      const float zero3[3] = {0, 0, 0};
+      f3 c = h3((s.mask & VG_MAT_EMISSION_COLOUR) ? s.emission_colour : zero3);
+      d.emission.x = c.x * s.emission_strength; d.emission.y = c.y * s.emission_strength; d.emission.z = c.z * s.emission_strength;
+    }
+    if (s.mask & VG_MAT_DIFFUSE_COLOUR) d.diff_colour = h3(s.diffuse_colour);
+    float dw = (s.mask & VG_MAT_DIFFUSE_STRENGTH) ? s.diffuse_strength : 0.0f;
+    float sw = (s.mask & VG_MAT_SPEC1_STRENGTH) ? s.spec1_strength : 0.0f;
+    const float tot = dw + sw;
+    d.diff_weight = dw / tot;
+    d.spec_weight = sw / tot;
+    if (tot == 0.0f) { d.bad = 1; d.diff_weight = d.spec_weight = 0; }
+    const float rough = (s.mask & VG_MAT_DIFFUSE_ROUGHNESS) ? s.diffuse_roughness : 0.5f;
+    d.rough2 = rough * rough;
+    if (s.mask & VG_MAT_SPEC1_COLOUR) d.spec_colour = h3(s.spec1_colour);
+    d.spec_rough = (s.mask & VG_MAT_SPEC1_ROUGHNESS) ? s.spec1_roughness : 0.5f;
+    d.ior = (s.mask & VG_MAT_IOR) ? s.ior : 1.7f;
+    if (d.spec_weight > 0.0f) {
+      if (d.spec_rough != 0.0f) d.bad = 2;
+      else any_mirror = true;
+    }
+  }
+  // lights
+  std::vector<DevLight> lights(ctx->lights.size());
+  int S = 0;
+  for (size_t i = 0; i < lights.size(); i++) {
+    const VgTriLight& s = ctx->lights[i];
+    DevLight& d = lights[i];
+    d.p0 = h3(s.p0); d.p1 = h3(s.p1); d.p2 = h3(s.p2);
+    f3 e1; e1.x = d.p1.x - d.p0.x; e1.y = d.p1.y - d.p0.y; e1.z = d.p1.z - d.p0.z;
+    f3 e2; e2.x = d.p2.x - d.p0.x; e2.y = d.p2.y - d.p0.y; e2.z = d.p2.z - d.p0.z;
+    f3 cr; cr.x = e1.y * e2.z - e1.z * e2.y; cr.y = e1.z * e2.x - e1.x * e2.z; cr.z = e1.x * e2.y - e1.y * e2.x;
+    d.N = host_normalize(cr);
+    float x0 = cr.x * cr.x, x1 = cr.y * cr.y, x2 = cr.z * cr.z;
+    x1 = x1 + x0; x1 = x1 + x2;
+    const float area = 0.5f * std::sqrt(x1);
+    d.inv_area = 1 / area;
+    d.E.x = d.E.y = d.E.z = 0;
+    if (s.material >= 0 && s.material < (int)mats.size()) d.E = mats[s.material].emission;
+    if (s.samples < 0 || s.samples > 8) return ctx->fail(VG_ERR_INVALID, "TriLight.Samples outside [0,8]");
+    d.nsamples = 1 << s.samples;
+    d.geom = s.geom;
+    d.slot_base = S;
+    S += d.nsamples;
+  }
+  if (S == 0) S = 1;
+  rs.S = S;
+  rs.nlights = (int)lights.size();
+  rs.levels = any_mirror ? 4 : 1;
+  rs.iters = ctx->opt_iters_per_batch;
+  rs.P = rs.nown * rs.iters;
+  const size_t P = (size_t)rs.P;
+
+  RCUDA(rs.pix.reserve(pix.size()));
+  RCUDA(rs.scr.reserve((size_t)rs.nown * 6));
+  RCUDA(rs.mats.reserve(mats.size()));
+  RCUDA(rs.lights.reserve(lights.size()));
+  if (!pix.empty()) {
+    RCUDA(cudaMemcpyAsync(rs.pix.p, pix.data(), pix.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (!mats.empty()) RCUDA(cudaMemcpyAsync(rs.mats.p, mats.data(), mats.size() * sizeof(DevMat), cudaMemcpyHostToDevice, ctx->stream));
+  if (!lights.empty()) RCUDA(cudaMemcpyAsync(rs.lights.p, lights.data(), lights.size() * sizeof(DevLight), cudaMemcpyHostToDevice, ctx->stream));
+  RCUDA(rs.rayq0.reserve(P)); RCUDA(rs.rayq1.reserve(P)); RCUDA(rs.pathq0.reserve(P)); RCUDA(rs.pathq1.reserve(P));
+  RCUDA(rs.hits.reserve(P)); RCUDA(rs.lambda.reserve(P)); RCUDA(rs.time.reserve(P)); RCUDA(rs.vmat.reserve(P));
+  RCUDA(rs.invtot.reserve(P * std::max(1, rs.nlights)));
+  RCUDA(rs.contrib.reserve(P * S)); RCUDA(rs.sray.reserve(P * S)); RCUDA(rs.sslot.reserve(P * S));
+  RCUDA(rs.L.reserve(P * rs.levels)); RCUDA(rs.T.reserve(P * rs.levels));
+  RCUDA(rs.counts.reserve(16)); RCUDA(rs.stats.reserve(8));
+  RCUDA(cudaMemsetAsync(rs.counts.p, 0, 16 * sizeof(int), ctx->stream));
+  RCUDA(cudaMemsetAsync(rs.stats.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  RCUDA(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+
+  int nb = 0;
+  const size_t smem = (size_t)kTraceBlock * VG_SMEM_STACK * sizeof(uint2);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_queue<0>, kTraceBlock, smem);
+  rs.trace_grid = ctx->sm_count * std::max(1, nb);
+  rs.ready = true;
+  return upload_scramble(ctx, ctx->scramble.data());
+}
+
+int render_set_scramble(vg_ctx* ctx, const uint64_t* table, int64_t npix) {
+  if ((int64_t)ctx->xres * ctx->yres != npix && ctx->xres > 0) return ctx->fail(VG_ERR_INVALID, "vg_set_scramble: table size != XRes*YRes");
+  if (ctx->rs && ctx->rs->ready) {
+    // steady state: gather this context's rows straight from the caller's table into pinned memory and copy
+    if ((int64_t)ctx->scramble.size() != npix * 6) ctx->scramble.assign(table, table + (size_t)npix * 6);
+    return upload_scramble(ctx, table);
+  }
+  ctx->scramble.assign(table, table + (size_t)npix * 6);
+  return VG_OK;
+}
+
+int render_clear(vg_ctx* ctx) {
+  int rc = ensure_fb(ctx);
+  if (rc != VG_OK) return rc;
+  RCUDA(cudaMemsetAsync(ctx->rs->fb.p, 0, (size_t)ctx->xres * ctx->yres * 3 * sizeof(float), ctx->stream));
+  RCUDA(cudaStreamSynchronize(ctx->stream));
+  return VG_OK;
+}
+
+int render_fb_device(vg_ctx* ctx, float** d_fb) {
+  int rc = ensure_fb(ctx);
+  if (rc != VG_OK) return rc;
+  *d_fb = ctx->rs->fb.p;
+  return VG_OK;
+}
+
+int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
+  if (iter_begin < 0 || iter_end < iter_begin) return ctx->fail(VG_ERR_INVALID, "vg_render: bad iteration range");
+  if (iter_end >= (1 << 28)) return ctx->fail(VG_ERR_INVALID, "vg_render: iteration index beyond the 28 frame bits of RasterXY(12,...)");
+  int rc = prepare(ctx);
+  if (rc != VG_OK) return rc;
+  RenderState& rs = *ctx->rs;
+  cudaStream_t st = ctx->stream;
+
+  RenderParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.sc = ctx->dev;
+  p.xres = ctx->xres; p.yres = ctx->yres; p.nown = rs.nown; p.P = rs.P;
+  p.pix = rs.pix.p; p.scr = rs.scr.p; p.cam = ctx->camera; p.mats = rs.mats.p; p.lights = rs.lights.p;
+  p.nlights = rs.nlights; p.S = rs.S; p.levels = rs.levels; p.trace_last_level = ctx->opt_trace_last_level;
+  p.rayq[0] = rs.rayq0.p; p.rayq[1] = rs.rayq1.p; p.pathq[0] = rs.pathq0.p; p.pathq[1] = rs.pathq1.p;
+  p.hits = rs.hits.p; p.lambda = rs.lambda.p; p.time = rs.time.p; p.v_mat = rs.vmat.p; p.v_invtot = rs.invtot.p;
+  p.contrib = rs.contrib.p; p.sray = rs.sray.p; p.sslot = rs.sslot.p; p.L = rs.L.p; p.T = rs.T.p;
+  p.counts = rs.counts.p; p.stats = rs.stats.p; p.fb = rs.fb.p;
+
+  const size_t smem = (size_t)kTraceBlock * VG_SMEM_STACK * sizeof(uint2);
+  uint64_t launches = 0;
+  size_t nev = 0;
+  std::vector<int> kinds;
+  RCUDA(cudaMemsetAsync(rs.stats.p, 0, 8 * sizeof(unsigned long long), st));
+  RCUDA(cudaEventRecord(rs.e0, st));
+  if (rs.nown > 0) {
+    for (int ib = iter_begin; ib < iter_end; ib += rs.iters) {
+      const int niters = std::min(rs.iters, iter_end - ib);
+      const int np = rs.nown * niters;
+      k_reset<<<1, 1, 0, st>>>(rs.counts.p, np);
+      if (rs.levels > 1) {
+        RCUDA(cudaMemsetAsync(rs.L.p, 0, (size_t)rs.P * rs.levels * sizeof(float4), st));
+        RCUDA(cudaMemsetAsync(rs.T.p, 0, (size_t)rs.P * rs.levels * sizeof(float4), st));
+      }
+      k_raygen<<<(np + 255) / 256, 256, 0, st>>>(p, ib, niters);
+      launches += 2;
+      int qin = 0;
+      // levels 0..3 are shaded; with trace_last_level the level-4 rays are traced (and counted) but not shaded
+      const int nlev = rs.levels == 1 ? 1 : (ctx->opt_trace_last_level ? 5 : 4);
+      for (int level = 0; level < nlev; level++) {
+        const int qout = 1 - qin;
+        cudaEventRecord(rs.ev(nev++), st);
+        k_trace_queue<0><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
+        cudaEventRecord(rs.ev(nev++), st);
+        kinds.push_back(0);
+        launches++;
+        if (level <= 3) {
+          k_shade<<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
+          cudaEventRecord(rs.ev(nev++), st);
+          k_trace_queue<1><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
+          cudaEventRecord(rs.ev(nev++), st);
+          kinds.push_back(1);
+          k_resolve<<<(np + 255) / 256, 256, 0, st>>>(p, level, qin);
+          launches += 3;
+        }
+        if (level + 1 < nlev) {
+          k_next_level<<<1, 1, 0, st>>>(rs.counts.p, qout);
+          launches++;
+        }
+        qin = qout;
+      }
+      k_accumulate<<<(rs.nown + 255) / 256, 256, 0, st>>>(p, ib, niters);
+      launches++;
+    }
+  }
+  RCUDA(cudaGetLastError());
+  RCUDA(cudaEventRecord(rs.e1, st));
+  unsigned long long hstats[6] = {0, 0, 0, 0, 0, 0};
+  int flags = 0;
+  RCUDA(cudaMemcpyAsync(hstats, rs.stats.p, sizeof(hstats), cudaMemcpyDeviceToHost, st));
+  RCUDA(cudaMemcpyAsync(&flags, rs.counts.p + 5, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (fb_out) {
+    // device -> pinned staging -> caller's (pageable) buffer
+    const size_t bytes = (size_t)ctx->xres * ctx->yres * 3 * sizeof(float);
+    if (rs.fb_pinned_bytes < bytes) {
+      if (rs.fb_pinned) cudaFreeHost(rs.fb_pinned);
+      rs.fb_pinned = nullptr;
+      RCUDA(cudaMallocHost((void**)&rs.fb_pinned, bytes));
+      rs.fb_pinned_bytes = bytes;
+    }
+    RCUDA(cudaMemcpyAsync(rs.fb_pinned, rs.fb.p, bytes, cudaMemcpyDeviceToHost, st));
+    RCUDA(cudaStreamSynchronize(st));
+    std::memcpy(fb_out, rs.fb_pinned, bytes);
+  }
+  RCUDA(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, rs.e0, rs.e1);
+  ctx->stats.render_ms = ms;
+  ctx->stats.closest_ms = 0;
+  ctx->stats.shadow_ms = 0;
+  for (size_t k = 0; k < kinds.size(); k++) {
+    float t = 0;
+    cudaEventElapsedTime(&t, rs.ev(2 * k), rs.ev(2 * k + 1));
+    if (kinds[k] == 0) { ctx->stats.closest_ms += t; ctx->stats.closest_launches++; }
+    else { ctx->stats.shadow_ms += t; ctx->stats.shadow_launches++; }
+  }
+  ctx->stats.rays += hstats[0];
+  ctx->stats.shadow_rays += hstats[1];
+  ctx->stats.nodes_t += hstats[2];
+  ctx->stats.tris_t += hstats[3];
+  ctx->stats.shadow_nodes_t += hstats[4];
+  ctx->stats.shadow_tris_t += hstats[5];
+  ctx->stats.kernel_launches += launches;
+  if (flags) {
+    cudaMemsetAsync(rs.counts.p + 5, 0, sizeof(int), st);
+    if (flags & 1) return ctx->fail(VG_ERR_INVALID, "a shaded ShaderStd has no weight (DiffuseStrength + Spec1Strength == 0; the reference panics: std.go:141-143)");
+    if (flags & 2) return ctx->fail(VG_ERR_UNSUPPORTED, "glossy GGX lobe (Spec1Roughness > 0) is not built yet");
+    if (flags & 4) return ctx->fail(VG_ERR_INVALID, "traversal stack overflow (the reference's 90-entry stack would panic)");
+  }
+  return VG_OK;
+}
+
+}  // namespace vg

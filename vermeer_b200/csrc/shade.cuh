@@ -1,0 +1,312 @@
+// Device-side shading for the wavefront path integrator: QMC sequences, hero-wavelength colour,
+// Oren-Nayar / mirror BSDFs, dielectric Fresnel, triangle-light sampling and the camera.
+//
+// Reference functions mirrored (evaluation order kept; compiled with -fmad=false):
+//   ldseq.VanDerCorput/Sobol/RasterXY          math/ldseq/ldseq.go:50-96, raster.go:10-57 (m = 12 rows)
+//   colour.Spectrum / Smits'99 / CIE / sRGB    colour/spectrum.go:49-112, spectrum_smits9.go:16-84,
+//                                              cie1931_2deg.go:62-95, space_srgb.go:8-14
+//   sample.CosineHemisphere / UniformDisk2D    math/sample/sample.go:18-27,105-129
+//   bsdf.OrenNayar                             builtin/shader/bsdf/orennayar.go:24-73
+//   bsdf.Specular, fresnel.Dielectric          builtin/shader/bsdf/specular.go:13-101, fresnel/dielectric.go:34-47
+//   light.Tri sampling                         builtin/light/triangle.go:79-343,376-535, disk.go:38-51
+//   camera.ComputeRay                          builtin/camera/camera.go:221-323
+//   ShaderContext.OffsetP                      core/shader.go:139-162
+// float32 trig goes through float64 exactly like math/sincos.go:16-70 (CUDA's double libm instead of Go's).
+// Vec3Normalize (RSQRTSS + Newton, math/vec3_amd64.s:11-43) is hardware-approximate on the CPU and is
+// replaced by a correctly rounded reciprocal square root: everything downstream of a normalize is
+// tolerance-only (SURVEY.md note N).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define VG_TABLE_QUAL __constant__ const
+#include "colour_tables.h"
+
+namespace vg {
+
+struct f3 {
+  float x, y, z;
+};
+__device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ f3 add3(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ f3 sub3(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ f3 scale3(float s, f3 a) { return mk3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ f3 neg3(f3 a) { return mk3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ f3 cross3(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float len2_3(f3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+__device__ __forceinline__ f3 mad3(f3 a, f3 b, float s) { return mk3(a.x + (b.x * s), a.y + (b.y * s), a.z + (b.z * s)); }
+// math/vec3_amd64.s:46-56 (a1^2 + a0^2) + a2^2
+__device__ __forceinline__ float length3(f3 a) {
+  float x0 = a.x * a.x, x1 = a.y * a.y, x2 = a.z * a.z;
+  x1 = x1 + x0;
+  x1 = x1 + x2;
+  return sqrtf(x1);
+}
+__device__ __forceinline__ f3 normalize3(f3 a) {
+  float x0 = a.x * a.x, x1 = a.y * a.y, x2 = a.z * a.z;
+  x1 = x1 + x0;
+  x1 = x1 + x2;
+  const float r = (float)(1.0 / sqrt((double)x1));
+  return mk3(a.x * r, a.y * r, a.z * r);
+}
+__device__ __forceinline__ f3 basis_project(f3 U, f3 V, f3 W, f3 S) { return mk3(dot3(U, S), dot3(V, S), dot3(W, S)); }
+__device__ __forceinline__ f3 basis_expand(f3 U, f3 V, f3 W, f3 S) {
+  return mk3(U.x * S.x + V.x * S.y + W.x * S.z, U.y * S.x + V.y * S.y + W.y * S.z, U.z * S.x + V.z * S.y + W.z * S.z);
+}
+__device__ __forceinline__ float maxf_x86(float x, float y) { return x > y ? x : y; }  // math/dim_amd64.s
+__device__ __forceinline__ float minf_x86(float x, float y) { return x < y ? x : y; }
+
+// float32 trig via float64 (math/sincos.go)
+__device__ __forceinline__ float sin32(float x) { return (float)sin((double)x); }
+__device__ __forceinline__ float cos32(float x) { return (float)cos((double)x); }
+__device__ __forceinline__ float tan32(float x) { return (float)tan((double)x); }
+__device__ __forceinline__ float acos32(float x) { return (float)acos((double)x); }
+__device__ __forceinline__ float atan32(float x) { return (float)atan((double)x); }
+__device__ __forceinline__ float atan2_32(float y, float x) { return (float)atan2((double)y, (double)x); }
+
+#define VG_PI32 3.14159265358f
+#define VG_PI64 3.14159265358979323846
+
+// ---- QMC (integer exact) ----------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t vdc_u(uint64_t i, uint64_t scramble) {
+  // 64-bit bit reversal == the swap network of ldseq.go:55-77
+  return (scramble ^ __brevll(i)) >> (64 - 52);
+}
+__device__ __forceinline__ double vdc(uint64_t i, uint64_t scramble) { return (double)vdc_u(i, scramble) / (double)(1ull << 52); }
+__device__ __forceinline__ uint64_t sobol_u(uint64_t i, uint64_t scramble) {
+  uint64_t r = scramble >> (64 - 52);
+  for (uint64_t v = 1ull << (52 - 1); i != 0; i >>= 1) {
+    if (i & 1) r ^= v;
+    v ^= v >> 1;
+  }
+  return r;
+}
+__device__ __forceinline__ double sobol(uint64_t i, uint64_t scramble) { return (double)sobol_u(i, scramble) / (double)(1ull << 52); }
+
+__constant__ const uint32_t kVdcSobolM12[28] = {0x808, 0xc0c, 0xa0a, 0xf0f, 0x888, 0xccc, 0xaaa, 0xfff, 0x800, 0xc00, 0xa00, 0xf00, 0x880, 0xcc0,
+                                                0xaa0, 0xff0, 0x808, 0xc0c, 0xa0a, 0xf0f, 0x888, 0xccc, 0xaaa, 0xfff, 0x800, 0xc00, 0xa00, 0xf00};
+__constant__ const uint32_t kVdcSobolInvM12[24] = {0xf0f000, 0x505000, 0x303000, 0x101000, 0xff0000, 0x550000, 0x330000, 0x110000,
+                                                   0xf0000,  0x50000,  0x30000,  0x10000,  0x888800, 0x444400, 0x222200, 0x111100,
+                                                   0x800080, 0x400040, 0x200020, 0x100010, 0x80008,  0x40004,  0x20002,  0x10001};
+// raster.go:10-57 with m = 12 and scrambleX = scrambleY = 0 (core/render.go:89)
+__device__ __forceinline__ void raster_xy12(uint32_t frame, uint32_t px, uint32_t py, double* rx, double* ry) {
+  uint64_t index = (uint64_t)frame << 24;
+  uint32_t delta = 0;
+  for (uint32_t c = 0, f = frame; f != 0; f >>= 1, c++)
+    if (f & 1) delta ^= kVdcSobolM12[c];
+  uint32_t b = ((px << 12) | py) ^ delta;
+  for (uint32_t c = 0; b != 0; b >>= 1, c++)
+    if (b & 1) index ^= (uint64_t)kVdcSobolInvM12[c];
+  *rx = (double)vdc_u(index, 0) / (double)(1ull << 40);
+  *ry = (double)sobol_u(index, 0) / (double)(1ull << 40);
+}
+
+// ---- colour -------------------------------------------------------------------------------------------
+struct Spec4 {
+  float c[4];
+};
+__device__ __forceinline__ float wavelength(float lambda, int j) {  // spectrum.go:101-112
+  float v = (lambda - 450.0f + ((float)j / 4.0f) * 300.0f);
+  if (v >= 300.0f) v -= 300.0f;
+  v += 450.0f;
+  return v;
+}
+__device__ __forceinline__ float smits_eval(const float* s, float lambda) {  // spectrum_smits9.go:16-25
+  if (lambda < 380.0f || lambda >= 720.0f) return 0.0f;
+  const int bin = (int)(((lambda - 380.0f) / (720.0f - 380.0f)) * 10.0f);
+  return s[bin];
+}
+__device__ inline float rgb_to_spectrum(float r, float g, float b, float lambda) {  // spectrum_smits9.go:48-84
+  float c = 0.0f;
+  if (r <= g && r <= b) {
+    c += r * smits_eval(kSmitsWhite, lambda);
+    if (g <= b) { c += (g - r) * smits_eval(kSmitsCyan, lambda); c += (b - g) * smits_eval(kSmitsBlue, lambda); }
+    else { c += (b - r) * smits_eval(kSmitsCyan, lambda); c += (g - b) * smits_eval(kSmitsGreen, lambda); }
+  } else if (g <= r && g <= b) {
+    c += g * smits_eval(kSmitsWhite, lambda);
+    if (r <= b) { c += (r - g) * smits_eval(kSmitsMagenta, lambda); c += (b - r) * smits_eval(kSmitsBlue, lambda); }
+    else { c += (b - g) * smits_eval(kSmitsMagenta, lambda); c += (r - b) * smits_eval(kSmitsRed, lambda); }
+  } else {
+    c += b * smits_eval(kSmitsWhite, lambda);
+    if (r <= g) { c += (r - b) * smits_eval(kSmitsYellow, lambda); c += (g - r) * smits_eval(kSmitsGreen, lambda); }
+    else { c += (g - b) * smits_eval(kSmitsYellow, lambda); c += (r - g) * smits_eval(kSmitsRed, lambda); }
+  }
+  return c;
+}
+__device__ __forceinline__ Spec4 spec_from_rgb(f3 rgb, float lambda) {
+  Spec4 s;
+#pragma unroll
+  for (int k = 0; k < 4; k++) s.c[k] = rgb_to_spectrum(rgb.x, rgb.y, rgb.z, wavelength(lambda, k));
+  return s;
+}
+__device__ __forceinline__ float cie_lookup(const float* tab, float lambda) {  // cie1931_2deg.go:62-70
+  if (lambda < 360.0f || lambda >= 830.0f) return -1.0f;
+  const int bin = (int)(((lambda - 360.0f) / (830.0f - 360.0f)) * 95.0f);
+  return tab[bin];
+}
+__device__ __forceinline__ f3 spec_to_rgb(const Spec4& s, float lambda) {  // spectrum.go:57-72
+  float x = 0, y = 0, z = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float wl = wavelength(lambda, i);
+    x += s.c[i] * cie_lookup(kCieX, wl);
+    y += s.c[i] * cie_lookup(kCieY, wl);
+    z += s.c[i] * cie_lookup(kCieZ, wl);
+  }
+  return mk3(x * 3.2404542f + y * -1.5371385f + z * -0.4985314f, x * -0.9692660f + y * 1.8760108f + z * 0.0415560f,
+             x * 0.0556434f + y * -0.2040259f + z * 1.0572252f);
+}
+
+// ---- sampling warps ---------------------------------------------------------------------------------
+__device__ __forceinline__ f3 cosine_hemisphere(double u0, double u1) {  // sample.go:18-27
+  const double r = sqrt(1 - u0);
+  const double theta = 2 * VG_PI64 * u1;
+  return mk3((float)(r * cos(theta)), (float)(r * sin(theta)), (float)sqrt(u0));
+}
+__device__ inline void uniform_disk2d(float radius, float r0, float r1, float* xo, float* yo) {  // sample.go:105-129
+  const float x = -1 + 2 * r0, y = -1 + 2 * r1;
+  float r = 0, theta = 0;
+  if (x > -y && x > y) { r = x; theta = (VG_PI32 / 4) * y / x; }
+  else if (x > -y && x < y) { r = y; theta = (VG_PI32 / 4) * (2 - x / y); }
+  else if (x < y && x < -y) { r = -x; theta = (VG_PI32 / 4) * (4 + y / x); }
+  else if (x > y && x < -y) { r = -y; theta = (VG_PI32 / 4) * (6 - x / y); }
+  *xo = radius * r * cos32(theta);
+  *yo = radius * r * sin32(theta);
+}
+
+// ---- BSDFs ------------------------------------------------------------------------------------------
+struct Frame {
+  f3 U, V, N;
+};
+// orennayar.go:34-39
+__device__ __forceinline__ double oren_pdf(const Frame& f, f3 wo) {
+  const f3 o = basis_project(f.U, f.V, f.N, wo);
+  return (double)maxf_x86(0.0f, o.z) / VG_PI64;
+}
+// orennayar.go:42-73; omegaI is already in the local frame; roughness2 = Roughness^2 (orennayar.go:25)
+__device__ inline Spec4 oren_eval(const Frame& f, f3 omegaI, float roughness2, float lambda, f3 wo) {
+  const f3 o = basis_project(f.U, f.V, f.N, wo);
+  const float sigma = roughness2;
+  const float A = 1 - (0.5f * (sigma * sigma) / ((sigma * sigma) + 0.57f));
+  const float B = 0.45f * (sigma * sigma) / ((sigma * sigma) + 0.09f);
+  const float phiI = atan2_32(omegaI.y, omegaI.x);
+  const float phiO = atan2_32(o.y, o.x);
+  const float thetaI = acos32(omegaI.z);
+  const float thetaO = acos32(o.z);
+  const float alpha = maxf_x86(thetaI, thetaO);
+  const float beta = minf_x86(thetaI, thetaO);
+  const float Cc = sin32(alpha) * tan32(beta);
+  const float gamma = cos32(phiO - phiI);
+  const float sc = o.z * (A + (B * maxf_x86(0.0f, gamma) * Cc));
+  Spec4 rho = spec_from_rgb(mk3(1, 1, 1), lambda);
+  const float k = sc / (float)VG_PI64;
+#pragma unroll
+  for (int i = 0; i < 4; i++) rho.c[i] *= k;
+  return rho;
+}
+// fresnel/dielectric.go:34-47
+__device__ __forceinline__ float dielectric_kr(float eta, float c) {
+  float g = (eta * eta) - 1 + (c * c);
+  if (g < 0.0f) return 1.0f;
+  g = sqrtf(g);
+  const float a = (g - c) / (g + c);
+  const float b = (c * (g + c) - 1) / (c * (g - c) + 1);
+  return 0.5f * (a * a) * (1 + (b * b));
+}
+__device__ __forceinline__ f3 reflect_z(f3 w) {  // specular.go:13-19 with N = (0,0,1)
+  const f3 n = mk3(0, 0, 1);
+  return sub3(scale3(2.0f * dot3(n, w), n), w);
+}
+
+// ---- OffsetP (core/shader.go:139-162) ----------------------------------------------------------------
+__device__ __forceinline__ float next_up(float v) {  // math/ferror.go:27-45
+  if (isinf(v) && v > 0) return v;
+  if (v == -0.0f) v = 0.0f;
+  uint32_t ui = __float_as_uint(v);
+  if (v >= 0.0f) ui++; else ui--;
+  return __uint_as_float(ui);
+}
+__device__ __forceinline__ float next_down(float v) {  // math/ferror.go:48-66
+  if (isinf(v) && v < 0) return v;
+  if (v == -0.0f) v = 0.0f;
+  uint32_t ui = __float_as_uint(v);
+  if (v >= 0.0f) ui--; else ui++;
+  return __uint_as_float(ui);
+}
+__device__ __forceinline__ float offset1(float p, float o) {
+  float r = p + o;
+  if (o > 0) r = next_up(r);
+  else if (o < -0.0f) r = next_down(r);
+  return r;
+}
+__device__ __forceinline__ f3 offset_p(f3 P, f3 Poffset, int dir) {
+  const f3 o = dir < 0 ? neg3(Poffset) : Poffset;
+  return mk3(offset1(P.x, o.x), offset1(P.y, o.y), offset1(P.z, o.z));
+}
+
+// ---- triangle light ---------------------------------------------------------------------------------
+// builtin/light/triangle.go:79-134 (Moller-Trumbore, no culling)
+__device__ inline bool ray_triangle(f3 Ro, f3 Rd, f3 P0, f3 P1, f3 P2, f3* pout) {
+  const f3 e1 = sub3(P1, P0), e2 = sub3(P2, P0);
+  const f3 P = cross3(Rd, e2);
+  const float det = dot3(e1, P);
+  if (det > -1e-6f && det < 1e-6f) return false;
+  const float inv_det = 1 / det;
+  const f3 T = sub3(Ro, P0);
+  const float u = dot3(T, P) * inv_det;
+  if (u < 0 || u > 1) return false;
+  const f3 Q = cross3(T, e1);
+  const float v = dot3(Rd, Q) * inv_det;
+  if (v < 0 || u + v > 1) return false;
+  const float t = dot3(e2, Q) * inv_det;
+  if (t > 1e-6f) {
+    const f3 a = scale3(1 - u - v, P0), b = scale3(u, P1), c = scale3(v, P2);
+    *pout = mk3(a.x + b.x + c.x, a.y + b.y + c.y, a.z + b.z + c.z);
+    return true;
+  }
+  return false;
+}
+// triangle.go:376-417, 430-459: spherical triangle solid angle from the unit vectors to the vertices
+__device__ inline float spherical_area(f3 pa, f3 pb, f3 pc, float* alpha_out, float* c_out) {
+  const float as = acos32(dot3(pb, pc)), bs = acos32(dot3(pc, pa)), cs = acos32(dot3(pa, pb));
+  const float ssu = (as + bs + cs) / 2;
+  const float sa = sin32(ssu - as), sb = sin32(ssu - bs), scs = sin32(ssu - cs), ss = sin32(ssu);
+  const float tanA2 = sqrtf(sb * scs / (ss * sa));
+  const float tanB2 = sqrtf(sa * scs / (ss * sb));
+  const float tanC2 = sqrtf(sa * sb / (ss * scs));
+  const float alpha = 2 * atan32(tanA2), beta = 2 * atan32(tanB2), gamma = 2 * atan32(tanC2);
+  if (alpha_out) *alpha_out = alpha;
+  if (c_out) *c_out = cs;
+  return alpha + beta + gamma - VG_PI32;
+}
+// triangle.go:474-535 (Arvo). Returns the unit direction; *pdf = 1/solid angle.
+__device__ inline f3 sample_spherical_triangle(f3 p0, f3 p1, f3 p2, f3 p, double r0, double r1, double* pdf) {
+  const f3 pa = normalize3(sub3(p0, p)), pb = normalize3(sub3(p1, p)), pc = normalize3(sub3(p2, p));
+  float alpha, c;
+  const float area = spherical_area(pa, pb, pc, &alpha, &c);
+  const float areaHat = (float)r0 * area;
+  const float s = sin32(areaHat - alpha), t = cos32(areaHat - alpha);
+  const float sinAlpha = sin32(alpha), cosAlpha = cos32(alpha);
+  const float u = t - cosAlpha;
+  const float v = s + sinAlpha * cos32(c);
+  float q = ((v * t - u * s) * cosAlpha - v) / ((v * s + u * t) * sinAlpha);
+  q = maxf_x86(-1.0f, minf_x86(q, 1.0f));
+  float w = dot3(pc, pa);
+  f3 v31 = normalize3(mk3(pc.x - w * pa.x, pc.y - w * pa.y, pc.z - w * pa.z));
+  const float sq = sqrtf(1 - q * q);
+  const f3 v4 = mk3(q * pa.x + sq * v31.x, q * pa.y + sq * v31.y, q * pa.z + sq * v31.z);
+  const float z = 1 - (float)r1 * (1 - dot3(v4, pb));
+  w = dot3(v4, pb);
+  const f3 v42 = normalize3(mk3(v4.x - w * pb.x, v4.y - w * pb.y, v4.z - w * pb.z));
+  *pdf = 1 / (double)area;
+  return add3(scale3(z, pb), scale3(sqrtf(1 - z * z), v42));
+}
+// disk.go:38-51
+__device__ __forceinline__ float ray_plane(f3 Ro, f3 Rd, f3 P, f3 N) {
+  const float denom = dot3(N, Rd);
+  if (fabsf(denom) > 1e-6f) return dot3(sub3(P, Ro), N) / denom;
+  return 0.0f;
+}
+
+}  // namespace vg

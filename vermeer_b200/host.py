@@ -49,7 +49,9 @@ class VgCamera(C.Structure):
 
 class VgStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("nodes_t", C.c_uint64), ("tris_t", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("render_ms", C.c_double), ("trace_ms", C.c_double), ("traverse_ms", C.c_double)]
+                ("shadow_nodes_t", C.c_uint64), ("shadow_tris_t", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("closest_launches", C.c_uint64), ("shadow_launches", C.c_uint64),
+                ("render_ms", C.c_double), ("trace_ms", C.c_double), ("closest_ms", C.c_double), ("shadow_ms", C.c_double)]
 
 
 _LIB = None
