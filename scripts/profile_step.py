@@ -1,0 +1,12 @@
+"""One 1080p C2 render of 8 iterations (2 batches) — short target for `ncu --set full`."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vermeer_b200 import scenes
+from vermeer_b200.host import Device, HostScene
+motion = "--motion" in sys.argv
+sc = scenes.heightfield_scene(1920, 1080, nq=708, motion=motion)
+host = HostScene(sc).prerender()
+dev = Device(0).upload(host)
+dev.set_scramble(scenes.splitmix64_table(1, 1920 * 1080))
+dev.render(0, 8, fetch=False)
+print(dev.stats())

@@ -476,6 +476,7 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
   VG_LOCK(ctx);
   if (!name) return ctx->fail(VG_ERR_INVALID, "null option name");
   if (!std::strcmp(name, "trace_last_level")) ctx->opt_trace_last_level = value != 0;
+  else if (!std::strcmp(name, "precise_trig")) ctx->opt_precise_trig = value != 0;
   else if (!std::strcmp(name, "iters_per_batch")) {
     if (value < 1 || value > 64) return ctx->fail(VG_ERR_INVALID, "iters_per_batch must be in [1,64]");
     ctx->opt_iters_per_batch = value;

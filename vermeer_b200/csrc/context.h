@@ -102,6 +102,7 @@ struct vg_ctx {
   std::vector<uint64_t> scramble;  // full frame, npix*6
   int opt_trace_last_level = 1;
   int opt_iters_per_batch = 4;
+  int opt_precise_trig = 0;
 
   vg::RenderState* rs = nullptr;
   VgStats stats{};

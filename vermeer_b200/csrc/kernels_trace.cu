@@ -1,13 +1,36 @@
 // Batch TraceProbe kernels (core/trace.go:26) — persistent warps over a ray queue.
 //
-// Grid = (SMs x resident CTAs); every warp repeatedly claims the next 32 rays of the queue with one
-// warp-aggregated atomicAdd, so the kernel's tail is bounded by one ray rather than by a wave of CTAs.
+// Grid = (SMs x resident CTAs); every warp claims rays from the queue with one warp-aggregated atomicAdd and
+// refills the lanes whose ray has finished (traverse.cuh: trace_persistent), so neither the kernel's tail nor a
+// warp's slowest ray holds the others.
 // The 32-byte VgRay / VgHit records are read and written as two 128-bit accesses each; consecutive
 // lanes touch consecutive records, so a warp's fetch is one contiguous 1-KB burst.
 #include "kernels.h"
 #include "traverse.cuh"
 
 namespace vg {
+
+struct BatchIO {
+  const VgRay* rays;
+  VgHit* hits;
+  long long n;
+  unsigned long long* counter;
+  __device__ __forceinline__ long long fetch(int c) { return (long long)atomicAdd(counter, (unsigned long long)c); }
+  __device__ __forceinline__ long long size() const { return n; }
+  __device__ __forceinline__ void load(long long i, RayState& r) const {
+    const float4* rp = reinterpret_cast<const float4*>(rays + i);
+    const float4 a = __ldg(rp), b = __ldg(rp + 1);
+    r.ox = a.x; r.oy = a.y; r.oz = a.z;
+    r.dx = a.w; r.dy = b.x; r.dz = b.y;
+    r.tclosest = b.z;
+    r.time = b.w;
+  }
+  __device__ __forceinline__ void store(long long i, const RayState& r, const HitState& h, bool overflow) const {
+    float4* hp = reinterpret_cast<float4*>(hits + i);
+    hp[0] = make_float4(r.tclosest, h.u, h.v, h.w);
+    reinterpret_cast<int4*>(hp)[1] = make_int4(overflow ? -2 : h.prim, h.geom, h.nodesT, h.trisT);
+  }
+};
 
 template <bool ANY_HIT>
 __global__ void __launch_bounds__(kTraceBlock) k_trace_batch(const DevScene sc, const VgRay* __restrict__ rays, VgHit* __restrict__ hits,
@@ -19,33 +42,8 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_batch(const DevScene sc, 
   st.stride = blockDim.x;
   const int lane = threadIdx.x & 31;
   unsigned long long nodes_acc = 0, tris_acc = 0;
-
-  while (true) {
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(counter, 32ull);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if ((long long)base >= n) break;
-    const long long i = (long long)base + lane;
-    if (i < n) {
-      const float4* rp = reinterpret_cast<const float4*>(rays + i);
-      const float4 a = __ldg(rp), b = __ldg(rp + 1);
-      RayState r;
-      r.ox = a.x; r.oy = a.y; r.oz = a.z;
-      r.dx = a.w; r.dy = b.x; r.dz = b.y;
-      r.tclosest = b.z;
-      r.time = b.w;
-      ray_setup(r);
-      HitState h;
-      trace_ray<ANY_HIT>(sc, r, h, st);
-      float4 o0 = make_float4(r.tclosest, h.u, h.v, h.w);
-      int4 o1 = make_int4(st.overflow ? -2 : h.prim, h.geom, h.nodesT, h.trisT);
-      float4* hp = reinterpret_cast<float4*>(hits + i);
-      hp[0] = o0;
-      reinterpret_cast<int4*>(hp)[1] = o1;
-      nodes_acc += (unsigned long long)h.nodesT;
-      tris_acc += (unsigned long long)h.trisT;
-    }
-  }
+  BatchIO io{rays, hits, n, counter};
+  trace_persistent<ANY_HIT>(sc, io, st, nodes_acc, tris_acc);
   // warp-aggregated statistics (core/stats.go keeps global atomics per ray; one atomic per warp here)
   for (int o = 16; o > 0; o >>= 1) {
     nodes_acc += __shfl_down_sync(0xffffffffu, nodes_acc, o);

@@ -136,6 +136,33 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderParams p, int iter_b
 // Persistent traversal over a device-resident queue. MODE 0: closest hit -> hits[]. MODE 1: shadow rays (any hit);
 // an occluded sample zeroes its contribution slot.
 template <int MODE>
+struct QueueIO {
+  const RenderParams& p;
+  const VgRay* rays;
+  int n;
+  int* head;
+  __device__ __forceinline__ long long fetch(int c) { return (long long)atomicAdd(head, c); }
+  __device__ __forceinline__ long long size() const { return n; }
+  __device__ __forceinline__ void load(long long i, RayState& r) const {
+    const float4* rp = reinterpret_cast<const float4*>(rays + i);
+    const float4 a = __ldg(rp), b = __ldg(rp + 1);
+    r.ox = a.x; r.oy = a.y; r.oz = a.z;
+    r.dx = a.w; r.dy = b.x; r.dz = b.y;
+    r.tclosest = b.z;
+    r.time = b.w;
+  }
+  __device__ __forceinline__ void store(long long i, const RayState& r, const HitState& h, bool overflow) const {
+    if (overflow) atomicOr(p.counts + 5, 4);
+    if (MODE == 0) {
+      *reinterpret_cast<float4*>(&p.hits[i]) = make_float4(r.tclosest, h.u, h.v, h.w);
+      *(reinterpret_cast<int4*>(&p.hits[i]) + 1) = make_int4(h.prim, h.geom, h.slot, 0);
+    } else {
+      if (h.prim >= 0) p.contrib[p.sslot[i]] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+};
+
+template <int MODE>
 __global__ void __launch_bounds__(kTraceBlock) k_trace_queue(const RenderParams p, int q) {
   extern __shared__ uint2 smem_stack[];
   Stack st;
@@ -143,40 +170,9 @@ __global__ void __launch_bounds__(kTraceBlock) k_trace_queue(const RenderParams 
   st.stride = blockDim.x;
   const int lane = threadIdx.x & 31;
   const int n = MODE == 0 ? p.counts[q] : p.counts[2];
-  const VgRay* rays = MODE == 0 ? p.rayq[q] : p.sray;
-  int* head = p.counts + (MODE == 0 ? 3 : 4);
   unsigned long long nodes_acc = 0, tris_acc = 0;
-  while (true) {
-    int base = 0;
-    if (lane == 0) base = atomicAdd(head, 32);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= n) break;
-    const int i = base + lane;
-    if (i < n) {
-      const float4* rp = reinterpret_cast<const float4*>(rays + i);
-      const float4 a = __ldg(rp), b = __ldg(rp + 1);
-      RayState r;
-      r.ox = a.x; r.oy = a.y; r.oz = a.z;
-      r.dx = a.w; r.dy = b.x; r.dz = b.y;
-      r.tclosest = b.z;
-      r.time = b.w;
-      ray_setup(r);
-      HitState h;
-      const bool hit = trace_ray<MODE == 1>(p.sc, r, h, st);
-      if (st.overflow) atomicOr(p.counts + 5, 4);
-      if (MODE == 0) {
-        DevHit o;
-        o.t = r.tclosest; o.u = h.u; o.v = h.v; o.w = h.w;
-        o.prim = h.prim; o.geom = h.geom; o.slot = h.slot; o.pad = 0;
-        *reinterpret_cast<float4*>(&p.hits[i]) = make_float4(o.t, o.u, o.v, o.w);
-        *(reinterpret_cast<int4*>(&p.hits[i]) + 1) = make_int4(o.prim, o.geom, o.slot, 0);
-      } else {
-        if (hit) p.contrib[p.sslot[i]] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      nodes_acc += (unsigned long long)h.nodesT;
-      tris_acc += (unsigned long long)h.trisT;
-    }
-  }
+  QueueIO<MODE> io{p, MODE == 0 ? p.rayq[q] : p.sray, n, p.counts + (MODE == 0 ? 3 : 4)};
+  trace_persistent<MODE == 1>(p.sc, io, st, nodes_acc, tris_acc);
   for (int o = 16; o > 0; o >>= 1) {
     nodes_acc += __shfl_down_sync(0xffffffffu, nodes_acc, o);
     tris_acc += __shfl_down_sync(0xffffffffu, tris_acc, o);
@@ -281,53 +277,53 @@ struct BsdfRec {
 };
 
 // light.Tri.SampleArea, sample `i` of `n` (builtin/light/triangle.go:232-343)
-__device__ inline LightRec light_sample(const DevLight& L, const ShadeCtx& c, bool by_area, long long I, int n, int i, uint64_t scr0, uint64_t scr1) {
+template <bool FAST>
+__device__ inline LightRec light_sample(const DevLight& L, const ShadeCtx& c, bool by_area, const SphTri& sph, long long I, int n, int i,
+                                        uint64_t scr0, uint64_t scr1) {
   LightRec r;
   const uint64_t idx = (uint64_t)(I * n + i);
   const double r0 = vdc(idx, scr0);
   const double r1 = sobol(idx, scr1);
   f3 Pl;
   if (by_area) {
-    const double sq = sqrt(1 - r0);
+    const double sq = FAST ? (double)sqrtf((float)(1 - r0)) : sqrt(1 - r0);
     const f3 a = scale3((float)(r1 * sq), sub3(L.p1, L.p0)), b = scale3((float)(1 - sq), sub3(L.p2, L.p0));
     Pl = mk3(L.p0.x + a.x + b.x, L.p0.y + a.y + b.y, L.p0.z + a.z + b.z);
   } else {
-    double pdf;
-    const f3 x = sample_spherical_triangle(L.p0, L.p1, L.p2, c.P, r0, r1, &pdf);
+    const f3 x = sample_spherical_triangle<FAST>(sph, r0, r1);
     const float t = ray_plane(c.P, x, L.p0, L.N);
     Pl = mad3(c.P, x, t);
-    r.pdf = (float)pdf;
+    r.pdf = (float)(1 / (double)sph.area);
   }
   const f3 D = sub3(Pl, c.P);
   r.Ldist = length3(D);
   r.Ld = normalize3(D);
   r.valid = !(dot3(r.Ld, L.N) > 0 || dot3(r.Ld, c.Ng) < 0);
-  if (by_area) {
-    const float pdfA = (float)(double)L.inv_area;
-    r.pdf = pdfA * (r.Ldist * r.Ldist) / fabsf(dot3(r.Ld, L.N));
-  }
+  if (by_area) r.pdf = L.inv_area * (r.Ldist * r.Ldist) / fabsf(dot3(r.Ld, L.N));
   return r;
 }
 
 // BSDF sample `i` of `h` through Light.ValidSample (core/shader.go:212-229, triangle.go:136-230)
-__device__ inline BsdfRec bsdf_sample(const DevLight& L, const ShadeCtx& c, const Frame& fr, long long I, int h, int i, uint64_t scr0, uint64_t scr1) {
+template <bool FAST>
+__device__ inline BsdfRec bsdf_sample(const DevLight& L, const ShadeCtx& c, const Frame& fr, bool have_sph, const SphTri& sph, long long I, int h,
+                                      int i, uint64_t scr0, uint64_t scr1) {
   BsdfRec r;
   r.valid = false;
   const uint64_t idx = (uint64_t)(I * h + i);
   const double r0 = vdc(idx, scr0);
   const double r1 = sobol(idx, scr1);
-  const f3 wo = normalize3(basis_expand(fr.U, fr.V, fr.N, cosine_hemisphere(r0, r1)));
+  const f3 wo = normalize3(basis_expand(fr.U, fr.V, fr.N, cosine_hemisphere<FAST>(r0, r1)));
   r.pdf = oren_pdf(fr, wo);
   if (r.pdf <= 0) return r;
   f3 Pl;
   if (!ray_triangle(c.P, wo, L.p0, L.p1, L.p2, &Pl)) return r;
+  // NOTE: the horizon test of ValidSample is taken at the point ON THE LIGHT (triangle.go:145-147), kept as is
   const bool by_area = dot3(c.Ng, sub3(L.p0, Pl)) < 0 || dot3(c.Ng, sub3(L.p1, Pl)) < 0 || dot3(c.Ng, sub3(L.p2, Pl)) < 0;
   float pdfl;
   if (by_area) {
-    pdfl = (float)(double)L.inv_area;
+    pdfl = L.inv_area;
   } else {
-    const f3 pa = normalize3(sub3(L.p0, c.P)), pb = normalize3(sub3(L.p1, c.P)), pc = normalize3(sub3(L.p2, c.P));
-    const float area = spherical_area(pa, pb, pc, nullptr, nullptr);
+    const float area = have_sph ? sph.area : spherical_setup<FAST>(L.p0, L.p1, L.p2, c.P).area;
     pdfl = (float)(double)(1 / area);
   }
   const f3 D = sub3(Pl, c.P);
@@ -339,6 +335,7 @@ __device__ inline BsdfRec bsdf_sample(const DevLight& L, const ShadeCtx& c, cons
   return r;
 }
 
+template <bool FAST>
 __global__ void __launch_bounds__(128) k_shade(const RenderParams p, int level, int qin, int qout, int iter_base) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = p.counts[qin];
@@ -375,6 +372,7 @@ __global__ void __launch_bounds__(128) k_shade(const RenderParams p, int level, 
   ShadeCtx c;
   Frame fr;
   f3 omegaI = mk3(0, 0, 1);
+  OrenVertex ov;
   float lambda = 0, time = 0;
   long long I = 0;
   uint64_t scr0 = 0, scr1 = 0;
@@ -398,6 +396,7 @@ __global__ void __launch_bounds__(128) k_shade(const RenderParams p, int level, 
     fr.V = V;
     fr.N = c.N;
     omegaI = basis_project(fr.U, fr.V, fr.N, neg3(Rd));
+    ov = oren_vertex<FAST>(omegaI, m.rough2, lambda);
     scr0 = p.scr[(size_t)own * 6 + 4];
     scr1 = p.scr[(size_t)own * 6 + 5];
   }
@@ -411,10 +410,12 @@ __global__ void __launch_bounds__(128) k_shade(const RenderParams p, int level, 
     const int NS = level > 0 ? 1 : L.nsamples;  // shader.go:186-191
     const bool lit = diffuse && L.geom != h.geom;  // scene.go:106-113
     Spec4 Liu;
+    SphTri sph;
     bool by_area = false;
     if (lit) {
       Liu = spec_from_rgb(L.E, lambda);
       by_area = dot3(c.Ng, sub3(L.p0, c.P)) < 0 || dot3(c.Ng, sub3(L.p1, c.P)) < 0 || dot3(c.Ng, sub3(L.p2, c.P)) < 0;
+      if (!by_area) sph = spherical_setup<FAST>(L.p0, L.p1, L.p2, c.P);
     }
     const int hN = NS > 1 ? NS / 2 : NS;  // samples per strategy
     // pass 1: which strategies produced at least one sample (shader.go:241-249)
@@ -426,13 +427,13 @@ __global__ void __launch_bounds__(128) k_shade(const RenderParams p, int level, 
     if (lit) {
       if (NS > 1) {
         for (int s = 0; s < hN; s++) {
-          const BsdfRec br = bsdf_sample(L, c, fr, I, hN, s, scr0, scr1);
+          const BsdfRec br = bsdf_sample<FAST>(L, c, fr, !by_area, sph, I, hN, s, scr0, scr1);
           if (s == 0) br0 = br;
           if (br.valid) nB = hN;
         }
       }
       for (int s = 0; s < hN; s++) {
-        const LightRec lr = light_sample(L, c, by_area, I, hN, s, scr0, scr1);
+        const LightRec lr = light_sample<FAST>(L, c, by_area, sph, I, hN, s, scr0, scr1);
         if (s == 0) lr0 = lr;
         if (lr.valid) nLs = hN;
       }
@@ -451,7 +452,7 @@ __global__ void __launch_bounds__(128) k_shade(const RenderParams p, int level, 
         float p_hat;
         bool valid;
         if (!is_bsdf) {
-          const LightRec lr = (s == 0) ? lr0 : light_sample(L, c, by_area, I, hN, s, scr0, scr1);
+          const LightRec lr = (s == 0) ? lr0 : light_sample<FAST>(L, c, by_area, sph, I, hN, s, scr0, scr1);
           valid = lr.valid;
           Ld = lr.Ld;
           Ldist = lr.Ldist;
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(128) k_shade(const RenderParams p, int level, 
             p_hat = lr.pdf;
           }
         } else {
-          const BsdfRec br = (s == hN) ? br0 : bsdf_sample(L, c, fr, I, hN, s - hN, scr0, scr1);
+          const BsdfRec br = (s == hN) ? br0 : bsdf_sample<FAST>(L, c, fr, !by_area, sph, I, hN, s - hN, scr0, scr1);
           valid = br.valid;
           Ld = br.Ld;
           Ldist = br.Ldist;
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(128) k_shade(const RenderParams p, int level, 
           p_hat += (float)nLs * br.pdfLight / (float)total;
         }
         if (valid && !(dot3(Ld, c.N) <= 0)) {
-          Spec4 rho = oren_eval(fr, omegaI, m.rough2, lambda, Ld);
+          Spec4 rho = oren_eval<FAST>(fr, ov, Ld);
           const float inv = 1.0f / p_hat;
 #pragma unroll
           for (int k = 0; k < 4; k++) rho.c[k] = (rho.c[k] * Liu.c[k]) * inv;
@@ -903,7 +904,8 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
         kinds.push_back(0);
         launches++;
         if (level <= 3) {
-          k_shade<<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
+          if (ctx->opt_precise_trig) k_shade<false><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
+          else k_shade<true><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
           cudaEventRecord(rs.ev(nev++), st);
           k_trace_queue<1><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
           cudaEventRecord(rs.ev(nev++), st);

@@ -47,7 +47,7 @@ __device__ __forceinline__ f3 normalize3(f3 a) {
   float x0 = a.x * a.x, x1 = a.y * a.y, x2 = a.z * a.z;
   x1 = x1 + x0;
   x1 = x1 + x2;
-  const float r = (float)(1.0 / sqrt((double)x1));
+  const float r = 1.0f / sqrtf(x1);  // two correctly rounded float ops: within 1 ulp, like the CPU's RSQRTSS + Newton step
   return mk3(a.x * r, a.y * r, a.z * r);
 }
 __device__ __forceinline__ f3 basis_project(f3 U, f3 V, f3 W, f3 S) { return mk3(dot3(U, S), dot3(V, S), dot3(W, S)); }
@@ -57,13 +57,20 @@ __device__ __forceinline__ f3 basis_expand(f3 U, f3 V, f3 W, f3 S) {
 __device__ __forceinline__ float maxf_x86(float x, float y) { return x > y ? x : y; }  // math/dim_amd64.s
 __device__ __forceinline__ float minf_x86(float x, float y) { return x < y ? x : y; }
 
-// float32 trig via float64 (math/sincos.go)
+// float32 trig. PRECISE: through float64 exactly like math/sincos.go:16-70 (CUDA's double libm instead of Go's).
+// FAST (default): CUDA's single-precision libm (<= 2 ulp), about 3x cheaper on the shading kernel and far smaller
+// code; both variants sit inside the image tolerance (everything here is downstream of a normalize anyway).
+template <bool FAST>
+struct Trig {
+  static __device__ __forceinline__ float sin(float x) { return FAST ? ::sinf(x) : (float)::sin((double)x); }
+  static __device__ __forceinline__ float cos(float x) { return FAST ? ::cosf(x) : (float)::cos((double)x); }
+  static __device__ __forceinline__ float tan(float x) { return FAST ? ::tanf(x) : (float)::tan((double)x); }
+  static __device__ __forceinline__ float acos(float x) { return FAST ? ::acosf(x) : (float)::acos((double)x); }
+  static __device__ __forceinline__ float atan(float x) { return FAST ? ::atanf(x) : (float)::atan((double)x); }
+  static __device__ __forceinline__ float atan2(float y, float x) { return FAST ? ::atan2f(y, x) : (float)::atan2((double)y, (double)x); }
+};
 __device__ __forceinline__ float sin32(float x) { return (float)sin((double)x); }
 __device__ __forceinline__ float cos32(float x) { return (float)cos((double)x); }
-__device__ __forceinline__ float tan32(float x) { return (float)tan((double)x); }
-__device__ __forceinline__ float acos32(float x) { return (float)acos((double)x); }
-__device__ __forceinline__ float atan32(float x) { return (float)atan((double)x); }
-__device__ __forceinline__ float atan2_32(float y, float x) { return (float)atan2((double)y, (double)x); }
 
 #define VG_PI32 3.14159265358f
 #define VG_PI64 3.14159265358979323846
@@ -159,7 +166,14 @@ __device__ __forceinline__ f3 spec_to_rgb(const Spec4& s, float lambda) {  // sp
 }
 
 // ---- sampling warps ---------------------------------------------------------------------------------
+template <bool FAST>
 __device__ __forceinline__ f3 cosine_hemisphere(double u0, double u1) {  // sample.go:18-27
+  if (FAST) {
+    const float r = sqrtf((float)(1 - u0));
+    float sn, cs;
+    sincosf((float)(2 * VG_PI64 * u1), &sn, &cs);
+    return mk3(r * cs, r * sn, sqrtf((float)u0));
+  }
   const double r = sqrt(1 - u0);
   const double theta = 2 * VG_PI64 * u1;
   return mk3((float)(r * cos(theta)), (float)(r * sin(theta)), (float)sqrt(u0));
@@ -184,22 +198,37 @@ __device__ __forceinline__ double oren_pdf(const Frame& f, f3 wo) {
   const f3 o = basis_project(f.U, f.V, f.N, wo);
   return (double)maxf_x86(0.0f, o.z) / VG_PI64;
 }
-// orennayar.go:42-73; omegaI is already in the local frame; roughness2 = Roughness^2 (orennayar.go:25)
-__device__ inline Spec4 oren_eval(const Frame& f, f3 omegaI, float roughness2, float lambda, f3 wo) {
-  const f3 o = basis_project(f.U, f.V, f.N, wo);
+// float32(bsdf.PDF(wo)) as EvaluateLightSamples uses it (core/shader.go:284,323)
+__device__ __forceinline__ float oren_pdf32(const Frame& f, f3 wo) { return (float)oren_pdf(f, wo); }
+// orennayar.go:42-73 split into its per-vertex part (depends on omegaI, lambda and the material only) and its
+// per-sample part; the arithmetic and its order are unchanged.
+struct OrenVertex {
+  float A, B;          // from Roughness^2 (orennayar.go:25,47-49)
+  float phiI, thetaI;  // atan2(omegaI.y, omegaI.x), acos(omegaI.z)
+  Spec4 white;         // FromRGB({1,1,1}) at this path's hero wavelength
+};
+template <bool FAST>
+__device__ __forceinline__ OrenVertex oren_vertex(f3 omegaI, float roughness2, float lambda) {
+  OrenVertex v;
   const float sigma = roughness2;
-  const float A = 1 - (0.5f * (sigma * sigma) / ((sigma * sigma) + 0.57f));
-  const float B = 0.45f * (sigma * sigma) / ((sigma * sigma) + 0.09f);
-  const float phiI = atan2_32(omegaI.y, omegaI.x);
-  const float phiO = atan2_32(o.y, o.x);
-  const float thetaI = acos32(omegaI.z);
-  const float thetaO = acos32(o.z);
-  const float alpha = maxf_x86(thetaI, thetaO);
-  const float beta = minf_x86(thetaI, thetaO);
-  const float Cc = sin32(alpha) * tan32(beta);
-  const float gamma = cos32(phiO - phiI);
-  const float sc = o.z * (A + (B * maxf_x86(0.0f, gamma) * Cc));
-  Spec4 rho = spec_from_rgb(mk3(1, 1, 1), lambda);
+  v.A = 1 - (0.5f * (sigma * sigma) / ((sigma * sigma) + 0.57f));
+  v.B = 0.45f * (sigma * sigma) / ((sigma * sigma) + 0.09f);
+  v.phiI = Trig<FAST>::atan2(omegaI.y, omegaI.x);
+  v.thetaI = Trig<FAST>::acos(omegaI.z);
+  v.white = spec_from_rgb(mk3(1, 1, 1), lambda);
+  return v;
+}
+template <bool FAST>
+__device__ __forceinline__ Spec4 oren_eval(const Frame& f, const OrenVertex& ov, f3 wo) {
+  const f3 o = basis_project(f.U, f.V, f.N, wo);
+  const float phiO = Trig<FAST>::atan2(o.y, o.x);
+  const float thetaO = Trig<FAST>::acos(o.z);
+  const float alpha = maxf_x86(ov.thetaI, thetaO);
+  const float beta = minf_x86(ov.thetaI, thetaO);
+  const float Cc = Trig<FAST>::sin(alpha) * Trig<FAST>::tan(beta);
+  const float gamma = Trig<FAST>::cos(phiO - ov.phiI);
+  const float sc = o.z * (ov.A + (ov.B * maxf_x86(0.0f, gamma) * Cc));
+  Spec4 rho = ov.white;
   const float k = sc / (float)VG_PI64;
 #pragma unroll
   for (int i = 0; i < 4; i++) rho.c[i] *= k;
@@ -267,29 +296,41 @@ __device__ inline bool ray_triangle(f3 Ro, f3 Rd, f3 P0, f3 P1, f3 P2, f3* pout)
   }
   return false;
 }
-// triangle.go:376-417, 430-459: spherical triangle solid angle from the unit vectors to the vertices
-__device__ inline float spherical_area(f3 pa, f3 pb, f3 pc, float* alpha_out, float* c_out) {
-  const float as = acos32(dot3(pb, pc)), bs = acos32(dot3(pc, pa)), cs = acos32(dot3(pa, pb));
+// triangle.go:376-417, 430-459, 474-489: the part of Arvo's spherical-triangle sampling that depends only on the
+// shading point and the light (unit vectors to the vertices, side c, angle alpha, solid angle) — computed once per
+// (vertex, light) and shared by SampleArea and ValidSample, which both recompute it in the reference.
+struct SphTri {
+  f3 pa, pb, pc;
+  float alpha, c, area;
+};
+template <bool FAST>
+__device__ inline SphTri spherical_setup(f3 p0, f3 p1, f3 p2, f3 p) {
+  SphTri t;
+  t.pa = normalize3(sub3(p0, p));
+  t.pb = normalize3(sub3(p1, p));
+  t.pc = normalize3(sub3(p2, p));
+  const float as = Trig<FAST>::acos(dot3(t.pb, t.pc)), bs = Trig<FAST>::acos(dot3(t.pc, t.pa)), cs = Trig<FAST>::acos(dot3(t.pa, t.pb));
   const float ssu = (as + bs + cs) / 2;
-  const float sa = sin32(ssu - as), sb = sin32(ssu - bs), scs = sin32(ssu - cs), ss = sin32(ssu);
+  const float sa = Trig<FAST>::sin(ssu - as), sb = Trig<FAST>::sin(ssu - bs), scs = Trig<FAST>::sin(ssu - cs), ss = Trig<FAST>::sin(ssu);
   const float tanA2 = sqrtf(sb * scs / (ss * sa));
   const float tanB2 = sqrtf(sa * scs / (ss * sb));
   const float tanC2 = sqrtf(sa * sb / (ss * scs));
-  const float alpha = 2 * atan32(tanA2), beta = 2 * atan32(tanB2), gamma = 2 * atan32(tanC2);
-  if (alpha_out) *alpha_out = alpha;
-  if (c_out) *c_out = cs;
-  return alpha + beta + gamma - VG_PI32;
+  const float alpha = 2 * Trig<FAST>::atan(tanA2), beta = 2 * Trig<FAST>::atan(tanB2), gamma = 2 * Trig<FAST>::atan(tanC2);
+  t.alpha = alpha;
+  t.c = cs;
+  t.area = alpha + beta + gamma - VG_PI32;
+  return t;
 }
-// triangle.go:474-535 (Arvo). Returns the unit direction; *pdf = 1/solid angle.
-__device__ inline f3 sample_spherical_triangle(f3 p0, f3 p1, f3 p2, f3 p, double r0, double r1, double* pdf) {
-  const f3 pa = normalize3(sub3(p0, p)), pb = normalize3(sub3(p1, p)), pc = normalize3(sub3(p2, p));
-  float alpha, c;
-  const float area = spherical_area(pa, pb, pc, &alpha, &c);
-  const float areaHat = (float)r0 * area;
-  const float s = sin32(areaHat - alpha), t = cos32(areaHat - alpha);
-  const float sinAlpha = sin32(alpha), cosAlpha = cos32(alpha);
+// triangle.go:490-535 (Arvo). Returns the unit direction; pdf = 1/solid angle.
+template <bool FAST>
+__device__ inline f3 sample_spherical_triangle(const SphTri& st, double r0, double r1) {
+  const f3 pa = st.pa, pb = st.pb, pc = st.pc;
+  const float alpha = st.alpha;
+  const float areaHat = (float)r0 * st.area;
+  const float s = Trig<FAST>::sin(areaHat - alpha), t = Trig<FAST>::cos(areaHat - alpha);
+  const float sinAlpha = Trig<FAST>::sin(alpha), cosAlpha = Trig<FAST>::cos(alpha);
   const float u = t - cosAlpha;
-  const float v = s + sinAlpha * cos32(c);
+  const float v = s + sinAlpha * Trig<FAST>::cos(st.c);
   float q = ((v * t - u * s) * cosAlpha - v) / ((v * s + u * t) * sinAlpha);
   q = maxf_x86(-1.0f, minf_x86(q, 1.0f));
   float w = dot3(pc, pa);
@@ -299,7 +340,6 @@ __device__ inline f3 sample_spherical_triangle(f3 p0, f3 p1, f3 p2, f3 p, double
   const float z = 1 - (float)r1 * (1 - dot3(v4, pb));
   w = dot3(v4, pb);
   const f3 v42 = normalize3(mk3(v4.x - w * pb.x, v4.y - w * pb.y, v4.z - w * pb.z));
-  *pdf = 1 / (double)area;
   return add3(scale3(z, pb), scale3(sqrtf(1 - z * z), v42));
 }
 // disk.go:38-51

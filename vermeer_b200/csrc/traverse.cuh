@@ -197,148 +197,244 @@ __device__ __forceinline__ void cswap(bool doit, int32_t& ca, float& ta, int32_t
   ca = c0; cb = c1; ta = t0; tb = t1;
 }
 
-template <bool ANY_HIT>
-__device__ __forceinline__ bool trace_ray(const DevScene& sc, RayState& r, HitState& h, Stack& st) {
-  h.prim = -1;
-  h.geom = -1;
-  h.slot = -1;
-  h.u = h.v = h.w = 0.0f;
-  h.nodesT = 0;
-  h.trisT = 0;
+// Per-lane traversal state that survives across refills of the warp.
+struct TravState {
+  RayState r;
+  HitState h;
+  int32_t cur;  // node to process next; -1 = none (stack empty and nothing pending => the ray is finished)
+};
+
+__device__ __forceinline__ void trav_begin(const DevScene& sc, TravState& t, Stack& st) {
+  t.h.prim = -1;
+  t.h.geom = -1;
+  t.h.slot = -1;
+  t.h.u = t.h.v = t.h.w = 0.0f;
+  t.h.nodesT = 0;
+  t.h.trisT = 0;
   st.sp = 0;
-  st.overflow = false;
+  t.cur = sc.root;  // qbvh.Trace pushes the root with T = Tclosest and pops it at once (intersect.go:93-104)
+}
 
-  int32_t node = sc.root;
-  bool have = true;  // `node` holds the next entry to process (already passed the pop-time cull)
+// Pop until an entry survives the cull of intersect.go:106 (Tclosest < T); -1 when the stack is empty.
+__device__ __forceinline__ int32_t pop_next(const RayState& r, Stack& st) {
+  while (st.sp > 0) {
+    const uint2 e = st.pop();
+    if (!(r.tclosest < __uint_as_float(e.x))) return (int32_t)e.y;
+  }
+  return -1;
+}
 
-  while (true) {
-    if (!have) {
-      if (st.sp == 0) break;
-      uint2 e = st.pop();
-      // intersect.go:106: skip if Tclosest < T (entries are only pushed when hit, children != -1)
-      if (r.tclosest < __uint_as_float(e.x)) continue;
-      node = (int32_t)e.y;
-    }
-    have = false;
-
-    if (node >= 0) {
-      h.nodesT++;
-      int32_t c0, c1, c2, c3;
-      float t0, t1, t2, t3;
-      bool h0, h1, h2, h3;
-      uint32_t a0, a1, a2;
-      if (node < sc.n_static) {
-        const DevNode* nd = sc.nodes + node;
-        const float4 lx = ldg4(&nd->lo_x), ly = ldg4(&nd->lo_y), lz = ldg4(&nd->lo_z);
-        const float4 hx = ldg4(&nd->hi_x), hy = ldg4(&nd->hi_y), hz = ldg4(&nd->hi_z);
-        const uint4 m0 = __ldg(&nd->m0), m1 = __ldg(&nd->m1);
-        t0 = box1(r, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, &h0);
-        t1 = box1(r, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, &h1);
-        t2 = box1(r, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, &h2);
-        t3 = box1(r, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, &h3);
-        a0 = m0.x; a1 = m0.y; a2 = m0.z;
-        c0 = (int32_t)m0.w; c1 = (int32_t)m1.x; c2 = (int32_t)m1.y; c3 = (int32_t)m1.z;
-      } else {
-        // motionintersect.go:44-51: lerp the 24 box floats between the two keys, then the same box test
-        const DevMotionNode mn = *(sc.mtopo + (node - sc.n_static));
-        const int keys = (int)(mn.axes_keys >> 8);
-        const float k = r.time * (float)(keys - 1);  // polymesh/trace.go:79-84, scene.go:49-54
-        const float fk = floorf(k);
-        const float tm = k - fk;
-        const int key = (int)fk, key2 = (int)ceilf(k);
-        const float4* b0 = sc.mboxes + (size_t)(mn.box_base + key * mn.box_key_stride) * 6;
-        const float4* b1 = sc.mboxes + (size_t)(mn.box_base + key2 * mn.box_key_stride) * 6;
-        const float om = 1.0f - tm;
-        float4 bx[6];
+// One interior node (static or motion): 4 box tests, ordered push, next node. intersect.go:113-216, motionintersect.go:44-97
+__device__ __forceinline__ void node_step(const DevScene& sc, TravState& t, Stack& st) {
+  RayState& r = t.r;
+  const int32_t node = t.cur;
+  t.h.nodesT++;
+  int32_t c0, c1, c2, c3;
+  float t0, t1, t2, t3;
+  bool h0, h1, h2, h3;
+  uint32_t a0, a1, a2;
+  if (node < sc.n_static) {
+    const DevNode* nd = sc.nodes + node;
+    const float4 lx = ldg4(&nd->lo_x), ly = ldg4(&nd->lo_y), lz = ldg4(&nd->lo_z);
+    const float4 hx = ldg4(&nd->hi_x), hy = ldg4(&nd->hi_y), hz = ldg4(&nd->hi_z);
+    const uint4 m0 = __ldg(&nd->m0), m1 = __ldg(&nd->m1);
+    t0 = box1(r, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, &h0);
+    t1 = box1(r, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, &h1);
+    t2 = box1(r, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, &h2);
+    t3 = box1(r, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, &h3);
+    a0 = m0.x; a1 = m0.y; a2 = m0.z;
+    c0 = (int32_t)m0.w; c1 = (int32_t)m1.x; c2 = (int32_t)m1.y; c3 = (int32_t)m1.z;
+  } else {
+    // motionintersect.go:44-51: lerp the 24 box floats between the two keys, then the same box test
+    const DevMotionNode mn = *(sc.mtopo + (node - sc.n_static));
+    const int keys = (int)(mn.axes_keys >> 8);
+    const float k = r.time * (float)(keys - 1);  // polymesh/trace.go:79-84, scene.go:49-54
+    const float fk = floorf(k);
+    const float tm = k - fk;
+    const int key = (int)fk, key2 = (int)ceilf(k);
+    const float4* b0 = sc.mboxes + (size_t)(mn.box_base + key * mn.box_key_stride) * 6;
+    const float4* b1 = sc.mboxes + (size_t)(mn.box_base + key2 * mn.box_key_stride) * 6;
+    const float om = 1.0f - tm;
+    float4 bx[6];
 #pragma unroll
-        for (int i = 0; i < 6; i++) {
-          const float4 p = ldg4(b0 + i), q = ldg4(b1 + i);
-          bx[i].x = om * p.x + tm * q.x;
-          bx[i].y = om * p.y + tm * q.y;
-          bx[i].z = om * p.z + tm * q.z;
-          bx[i].w = om * p.w + tm * q.w;
-        }
-        t0 = box1(r, bx[0].x, bx[1].x, bx[2].x, bx[3].x, bx[4].x, bx[5].x, &h0);
-        t1 = box1(r, bx[0].y, bx[1].y, bx[2].y, bx[3].y, bx[4].y, bx[5].y, &h1);
-        t2 = box1(r, bx[0].z, bx[1].z, bx[2].z, bx[3].z, bx[4].z, bx[5].z, &h2);
-        t3 = box1(r, bx[0].w, bx[1].w, bx[2].w, bx[3].w, bx[4].w, bx[5].w, &h3);
-        a0 = mn.axes_keys & 3u; a1 = (mn.axes_keys >> 2) & 3u; a2 = (mn.axes_keys >> 4) & 3u;
-        c0 = mn.child[0]; c1 = mn.child[1]; c2 = mn.child[2]; c3 = mn.child[3];
+    for (int i = 0; i < 6; i++) {
+      const float4 p = ldg4(b0 + i), q = ldg4(b1 + i);
+      bx[i].x = om * p.x + tm * q.x;
+      bx[i].y = om * p.y + tm * q.y;
+      bx[i].z = om * p.z + tm * q.z;
+      bx[i].w = om * p.w + tm * q.w;
+    }
+    t0 = box1(r, bx[0].x, bx[1].x, bx[2].x, bx[3].x, bx[4].x, bx[5].x, &h0);
+    t1 = box1(r, bx[0].y, bx[1].y, bx[2].y, bx[3].y, bx[4].y, bx[5].y, &h1);
+    t2 = box1(r, bx[0].z, bx[1].z, bx[2].z, bx[3].z, bx[4].z, bx[5].z, &h2);
+    t3 = box1(r, bx[0].w, bx[1].w, bx[2].w, bx[3].w, bx[4].w, bx[5].w, &h3);
+    a0 = mn.axes_keys & 3u; a1 = (mn.axes_keys >> 2) & 3u; a2 = (mn.axes_keys >> 4) & 3u;
+    c0 = mn.child[0]; c1 = mn.child[1]; c2 = mn.child[2]; c3 = mn.child[3];
+  }
+  // Children that miss, are empty, or already lie beyond Tclosest would be culled at pop time
+  // (intersect.go:106, Tclosest only shrinks): drop them now. NodesT is unaffected.
+  if (!h0 || t0 > r.tclosest) c0 = -1;
+  if (!h1 || t1 > r.tclosest) c1 = -1;
+  if (!h2 || t2 > r.tclosest) c2 = -1;
+  if (!h3 || t3 > r.tclosest) c3 = -1;
+  const bool s0 = (r.signbits >> a0) & 1u, s1 = (r.signbits >> a1) & 1u, s2 = (r.signbits >> a2) & 1u;
+  // arrange (e0,e1,e2,e3) = push sequence
+  cswap(!s1, c0, t0, c1, t1);  // pair01 = s1 ? (0,1) : (1,0)
+  cswap(!s2, c2, t2, c3, t3);  // pair23 = s2 ? (2,3) : (3,2)
+  cswap(!s0, c0, t0, c2, t2);  // s0 ? {pair01,pair23} : {pair23,pair01}
+  cswap(!s0, c1, t1, c3, t3);
+  // The entry pushed last is the one the reference pops next: keep it in a register, push the others.
+  int32_t next = -1;
+  if (c3 != -1) { next = c3; c3 = -1; }
+  else if (c2 != -1) { next = c2; c2 = -1; }
+  else if (c1 != -1) { next = c1; c1 = -1; }
+  else if (c0 != -1) { next = c0; c0 = -1; }
+  if (c0 != -1) st.push(t0, c0);
+  if (c1 != -1) st.push(t1, c1);
+  if (c2 != -1) st.push(t2, c2);
+  t.cur = next != -1 ? next : pop_next(r, st);
+}
+
+// One triangle leaf. Returns true if any triangle of the leaf was accepted. trace.go:116-194 / :528-667
+__device__ __forceinline__ bool leaf_step(const DevScene& sc, TravState& t, uint32_t un) {
+  RayState& r = t.r;
+  HitState& h = t.h;
+  const int base = (int)((un >> 4) & kLeafBaseMask);
+  const int count = (int)(un & 15u) + 1;
+  h.trisT += count;
+  bool leafhit = false;
+  if (!(un & kMotionTriBit)) {
+    const float4* tp = sc.tris + (size_t)base * 3;
+    for (int i = 0; i < count; i++, tp += 3) {
+      const float4 v0 = ldg4(tp), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
+      float U, V, W;
+      if (tri_test<false>(r, make_float3(v0.x, v0.y, v0.z), make_float3(v1.x, v1.y, v1.z), make_float3(v2.x, v2.y, v2.z), v2.w, &U, &V, &W)) {
+        h.u = U; h.v = V; h.w = W;
+        h.geom = __float_as_int(v0.w);
+        h.prim = __float_as_int(v1.w);
+        h.slot = base + i;
+        leafhit = true;
       }
-      // Children that miss, are empty, or already lie beyond Tclosest would be culled at pop time
-      // (intersect.go:106, Tclosest only shrinks): drop them now. NodesT is unaffected.
-      if (!h0 || t0 > r.tclosest) c0 = -1;
-      if (!h1 || t1 > r.tclosest) c1 = -1;
-      if (!h2 || t2 > r.tclosest) c2 = -1;
-      if (!h3 || t3 > r.tclosest) c3 = -1;
-      const bool s0 = (r.signbits >> a0) & 1u, s1 = (r.signbits >> a1) & 1u, s2 = (r.signbits >> a2) & 1u;
-      // arrange (e0,e1,e2,e3) = push sequence
-      cswap(!s1, c0, t0, c1, t1);  // pair01 = s1 ? (0,1) : (1,0)
-      cswap(!s2, c2, t2, c3, t3);  // pair23 = s2 ? (2,3) : (3,2)
-      cswap(!s0, c0, t0, c2, t2);  // s0 ? {pair01,pair23} : {pair23,pair01}
-      cswap(!s0, c1, t1, c3, t3);
-      // The last pushed valid entry would be popped next: keep it in registers instead.
-      if (c0 != -1) st.push(t0, c0);
-      if (c1 != -1) st.push(t1, c1);
-      if (c2 != -1) st.push(t2, c2);
-      if (c3 != -1) st.push(t3, c3);
-    } else if (node != -1) {
-      const uint32_t un = (uint32_t)node;
-      if (un & kGeomBit) {
-        // scene.go:61-78 -> Geom.Trace -> qbvh.Trace pushes the mesh root with T = Tclosest and pops it at once
-        node = (int32_t)(un & 0x3FFFFFFFu);
-        have = true;
-        continue;
+    }
+  } else {
+    // trace.go:547-554: lerp the three vertices between the keys of this mesh
+    const float4 g0 = ldg4(sc.mtris + (size_t)base * 3);  // key-0 record of the first slot: geom id in w
+    const DevGeom gm = sc.geoms[__float_as_int(g0.w)];
+    const float k = r.time * (float)(gm.keys - 1);
+    const float fk = floorf(k);
+    const float tm = k - fk, om = 1.0f - tm;
+    const int key = (int)fk, key2 = (int)ceilf(k);
+    const float4* ta = sc.mtris + ((size_t)base + (size_t)key * gm.tri_key_stride) * 3;
+    const float4* tb = sc.mtris + ((size_t)base + (size_t)key2 * gm.tri_key_stride) * 3;
+    const float4* tk0 = sc.mtris + (size_t)base * 3;
+    for (int i = 0; i < count; i++, ta += 3, tb += 3, tk0 += 3) {
+      const float4 a0 = ldg4(ta), a1 = ldg4(ta + 1), a2 = ldg4(ta + 2);
+      const float4 b0 = ldg4(tb), b1 = ldg4(tb + 1), b2 = ldg4(tb + 2);
+      const float3 p0 = make_float3(om * a0.x + tm * b0.x, om * a0.y + tm * b0.y, om * a0.z + tm * b0.z);
+      const float3 p1 = make_float3(om * a1.x + tm * b1.x, om * a1.y + tm * b1.y, om * a1.z + tm * b1.z);
+      const float3 p2 = make_float3(om * a2.x + tm * b2.x, om * a2.y + tm * b2.y, om * a2.z + tm * b2.z);
+      const float4 w0 = ldg4(tk0), w1 = ldg4(tk0 + 1), w2 = ldg4(tk0 + 2);
+      float U, V, W;
+      if (tri_test<true>(r, p0, p1, p2, w2.w, &U, &V, &W)) {
+        h.u = U; h.v = V; h.w = W;
+        h.geom = __float_as_int(w0.w);
+        h.prim = __float_as_int(w1.w);
+        h.slot = base + i;
+        leafhit = true;
       }
-      const int base = (int)((un >> 4) & kLeafBaseMask);
-      const int count = (int)(un & 15u) + 1;
-      h.trisT += count;
-      bool leafhit = false;
-      if (!(un & kMotionTriBit)) {
-        const float4* tp = sc.tris + (size_t)base * 3;
-        for (int i = 0; i < count; i++, tp += 3) {
-          const float4 v0 = ldg4(tp), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
-          float U, V, W;
-          if (tri_test<false>(r, make_float3(v0.x, v0.y, v0.z), make_float3(v1.x, v1.y, v1.z), make_float3(v2.x, v2.y, v2.z), v2.w, &U, &V, &W)) {
-            h.u = U; h.v = V; h.w = W;
-            h.geom = __float_as_int(v0.w);
-            h.prim = __float_as_int(v1.w);
-            h.slot = base + i;
-            leafhit = true;
-          }
-        }
-      } else {
-        // trace.go:547-554: lerp the three vertices between the keys of this mesh
-        const float4 g0 = ldg4(sc.mtris + (size_t)base * 3);  // key-0 record of the first slot: geom id in w
-        const DevGeom gm = sc.geoms[__float_as_int(g0.w)];
-        const float k = r.time * (float)(gm.keys - 1);
-        const float fk = floorf(k);
-        const float tm = k - fk, om = 1.0f - tm;
-        const int key = (int)fk, key2 = (int)ceilf(k);
-        const float4* ta = sc.mtris + ((size_t)base + (size_t)key * gm.tri_key_stride) * 3;
-        const float4* tb = sc.mtris + ((size_t)base + (size_t)key2 * gm.tri_key_stride) * 3;
-        const float4* tk0 = sc.mtris + (size_t)base * 3;
-        for (int i = 0; i < count; i++, ta += 3, tb += 3, tk0 += 3) {
-          const float4 a0 = ldg4(ta), a1 = ldg4(ta + 1), a2 = ldg4(ta + 2);
-          const float4 b0 = ldg4(tb), b1 = ldg4(tb + 1), b2 = ldg4(tb + 2);
-          const float3 p0 = make_float3(om * a0.x + tm * b0.x, om * a0.y + tm * b0.y, om * a0.z + tm * b0.z);
-          const float3 p1 = make_float3(om * a1.x + tm * b1.x, om * a1.y + tm * b1.y, om * a1.z + tm * b1.z);
-          const float3 p2 = make_float3(om * a2.x + tm * b2.x, om * a2.y + tm * b2.y, om * a2.z + tm * b2.z);
-          const float4 w0 = ldg4(tk0), w1 = ldg4(tk0 + 1), w2 = ldg4(tk0 + 2);
-          float U, V, W;
-          if (tri_test<true>(r, p0, p1, p2, w2.w, &U, &V, &W)) {
-            h.u = U; h.v = V; h.w = W;
-            h.geom = __float_as_int(w0.w);
-            h.prim = __float_as_int(w1.w);
-            h.slot = base + i;
-            leafhit = true;
-          }
-        }
-      }
-      if (ANY_HIT && leafhit) return true;  // intersect.go:231-236
     }
   }
+  return leafhit;
+}
+
+// while-while traversal of the lane's ray until it finishes or, if `min_active` > 0, until fewer than `min_active`
+// lanes of the warp are still traversing (the caller then refills the idle lanes and comes back).
+// Returns true when this lane's ray is finished.
+template <bool ANY_HIT>
+__device__ __forceinline__ bool trav_run(const DevScene& sc, TravState& t, Stack& st, int min_active) {
+  while (t.cur != -1) {
+    while (t.cur >= 0) node_step(sc, t, st);
+    while (t.cur < -1) {
+      const uint32_t un = (uint32_t)t.cur;
+      if (un & kGeomBit) {
+        // scene.go:61-78 -> Geom.Trace -> qbvh.Trace pushes the mesh root with T = Tclosest and pops it at once
+        t.cur = (int32_t)(un & 0x3FFFFFFFu);
+        break;
+      }
+      const bool leafhit = leaf_step(sc, t, un);
+      if (ANY_HIT && leafhit) {  // intersect.go:231-236: shadow rays return at the first leaf reporting a hit
+        st.sp = 0;
+        t.cur = -1;
+        return true;
+      }
+      t.cur = pop_next(t.r, st);
+    }
+    if (min_active > 0 && __popc(__activemask()) < min_active) break;
+  }
+  return t.cur == -1;
+}
+
+// Convenience: trace one ray to completion.
+template <bool ANY_HIT>
+__device__ __forceinline__ bool trace_ray(const DevScene& sc, RayState& r, HitState& h, Stack& st) {
+  TravState t;
+  t.r = r;
+  st.overflow = false;
+  trav_begin(sc, t, st);
+  trav_run<ANY_HIT>(sc, t, st, 0);
+  r = t.r;
+  h = t.h;
   return h.prim >= 0;
+}
+
+// Persistent warp loop with refill (Aila & Laine style "dynamic fetch"): lanes whose ray finished take new rays from
+// the queue as soon as fewer than kRefillBelow lanes are busy, so a warp is never held by its slowest rays.
+// IO: long long fetch(int count)  — claim `count` consecutive queue slots, returns the first (lane 0 calls it)
+//     long long size()
+//     void load(long long i, RayState& r)
+//     void store(long long i, const RayState& r, const HitState& h, bool overflow)
+#ifndef VG_REFILL_BELOW
+#define VG_REFILL_BELOW 24
+#endif
+template <bool ANY_HIT, class IO>
+__device__ __forceinline__ void trace_persistent(const DevScene& sc, IO& io, Stack& st, unsigned long long& nodes_acc, unsigned long long& tris_acc) {
+  const int lane = threadIdx.x & 31;
+  const long long n = io.size();
+  TravState t;
+  t.cur = -1;
+  long long my = -1;   // queue index of the ray this lane is tracing
+  bool exhausted = false;
+  st.sp = 0;
+  st.overflow = false;
+  while (true) {
+    const unsigned idle = __ballot_sync(0xffffffffu, my < 0);
+    if (idle != 0 && !exhausted) {
+      const int want = __popc(idle);
+      long long base = 0;
+      if (lane == 0) base = io.fetch(want);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base + want >= n) exhausted = true;
+      if (my < 0) {
+        const long long i = base + __popc(idle & ((1u << lane) - 1u));
+        if (i < n) {
+          my = i;
+          io.load(i, t.r);
+          ray_setup(t.r);
+          trav_begin(sc, t, st);
+        }
+      }
+    }
+    if (__ballot_sync(0xffffffffu, my >= 0) == 0) break;
+    if (my >= 0) {
+      if (trav_run<ANY_HIT>(sc, t, st, exhausted ? 0 : VG_REFILL_BELOW)) {
+        io.store(my, t.r, t.h, st.overflow);
+        nodes_acc += (unsigned long long)t.h.nodesT;
+        tris_acc += (unsigned long long)t.h.trisT;
+        st.overflow = false;
+        my = -1;
+      }
+    }
+  }
 }
 
 }  // namespace vg
