@@ -34,6 +34,8 @@ struct RayState {
   float pkx, pky, pkz;  // origin permuted by (Kx,Ky,Kz)
   int kx, ky, kz;
   uint32_t signbits;  // bit a set <=> D[a] < 0
+  uint32_t xsign;     // 0x80000000 if the reference would have swapped Kx/Ky (D[Kz] < 0)
+  bool special;       // non-finite origin/direction/Dinv: NaNs can reach the slab test, use the exact x86 min/max emulation
   float tclosest;
   float time;
 };
@@ -61,11 +63,12 @@ __device__ __forceinline__ void ray_setup(RayState& r) {
   int ky = kx + 1;
   if (ky == 3) ky = 0;
   float dkz = sel3(r.dx, r.dy, r.dz, kz);
-  if (dkz < 0.0f) {
-    int t = kx;
-    kx = ky;
-    ky = t;
-  }
+  // ray.go:132-136 swaps Kx and Ky when D[Kz] < 0. With the swapped axes the reference's edge functions are
+  // fU = Cy*Bx - Cx*By etc. in terms of the UNswapped sheared coordinates, which is what (-Cx)*By - Cy*(-Bx) evaluates
+  // to bit for bit (negation is exact and IEEE addition commutes, signed zeros included). So the device keeps the cyclic
+  // order (kx,ky,kz) = (kz+1, kz+2, kz) mod 3 — which is what makes the compile-time axis specialisation possible — and
+  // flips the sign of the three sheared x coordinates instead (one XOR each).
+  r.xsign = dkz < 0.0f ? 0x80000000u : 0u;
   double z = (double)dkz;
   r.s2 = (float)(1.0 / z);
   r.s0 = (float)((double)sel3(r.dx, r.dy, r.dz, kx) / z);
@@ -80,6 +83,8 @@ __device__ __forceinline__ void ray_setup(RayState& r) {
   r.pky = sel3(r.ox, r.oy, r.oz, ky);
   r.pkz = sel3(r.ox, r.oy, r.oz, kz);
   r.signbits = (r.dx < 0.0f ? 1u : 0u) | (r.dy < 0.0f ? 2u : 0u) | (r.dz < 0.0f ? 4u : 0u);
+  const float chk = (r.ox + r.oy + r.oz) * 0.0f + (r.dx + r.dy + r.dz) * 0.0f + (r.idx + r.idy + r.idz) * 0.0f;  // NaN iff anything is Inf/NaN
+  r.special = !(chk == 0.0f) || !(fabsf(r.idx) <= 3.4028234e38f) || !(fabsf(r.idy) <= 3.4028234e38f) || !(fabsf(r.idz) <= 3.4028234e38f);
 }
 
 // x86 MINPS dst,src: dst = (dst < src) ? dst : src ; MAXPS: dst = (dst > src) ? dst : src
@@ -87,41 +92,68 @@ __device__ __forceinline__ float x86min(float dst, float src) { return dst < src
 __device__ __forceinline__ float x86max(float dst, float src) { return dst > src ? dst : src; }
 
 // One child of intersect_amd64.s:13-100. Returns tNear; *hit = tNear <= tmax.
+// EXACT: compare-selects in the operand order of MINPS/MAXPS (the second operand wins on NaN). !EXACT: FMNMX — identical
+// bits whenever no operand is NaN, which ray_setup() guarantees for rays without Inf/NaN in origin or Dinv (node boxes are
+// finite or +-Inf, never NaN, and Inf * finite-nonzero Dinv is Inf); only the sign of a zero can differ, and no decision or
+// stored value depends on it.
+template <bool EXACT>
 __device__ __forceinline__ float box1(const RayState& r, float lx, float ly, float lz, float hx, float hy, float hz, bool* hit) {
   float t1 = (lx - r.ox) * r.idx;
   float t2 = (hx - r.ox) * r.idx;
-  float x6 = x86min(t2, t1);
-  float x7 = x86max(t2, t1);
+  float x6 = EXACT ? x86min(t2, t1) : fminf(t2, t1);
+  float x7 = EXACT ? x86max(t2, t1) : fmaxf(t2, t1);
   t1 = (ly - r.oy) * r.idy;
   t2 = (hy - r.oy) * r.idy;
-  float x1 = x86min(t2, t1);
-  float x0 = x86max(t2, t1);
-  x6 = x86max(x6, x1);
-  x7 = x86min(x7, x0);
+  float x1 = EXACT ? x86min(t2, t1) : fminf(t2, t1);
+  float x0 = EXACT ? x86max(t2, t1) : fmaxf(t2, t1);
+  x6 = EXACT ? x86max(x6, x1) : fmaxf(x6, x1);
+  x7 = EXACT ? x86min(x7, x0) : fminf(x7, x0);
   t1 = (lz - r.oz) * r.idz;
   t2 = (hz - r.oz) * r.idz;
-  x1 = x86min(t2, t1);
-  x0 = x86max(t2, t1);
-  x6 = x86max(x6, x1);
-  x7 = x86min(x7, x0);
-  float tn = x86max(0.0f, x6);
+  x1 = EXACT ? x86min(t2, t1) : fminf(t2, t1);
+  x0 = EXACT ? x86max(t2, t1) : fmaxf(t2, t1);
+  x6 = EXACT ? x86max(x6, x1) : fmaxf(x6, x1);
+  x7 = EXACT ? x86min(x7, x0) : fminf(x7, x0);
+  float tn = EXACT ? x86max(0.0f, x6) : fmaxf(0.0f, x6);
   *hit = tn <= x7;
   return tn;
+}
+struct Box4Out {
+  float t0, t1, t2, t3;
+  bool h0, h1, h2, h3;
+};
+template <bool EXACT>
+__device__ __forceinline__ void box4(const RayState& r, const float4& lx, const float4& ly, const float4& lz, const float4& hx, const float4& hy,
+                                     const float4& hz, Box4Out& o) {
+  o.t0 = box1<EXACT>(r, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, &o.h0);
+  o.t1 = box1<EXACT>(r, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, &o.h1);
+  o.t2 = box1<EXACT>(r, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, &o.h2);
+  o.t3 = box1<EXACT>(r, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, &o.h3);
 }
 
 // Watertight ray/triangle test, trace.go:127-192 (static: bias `<` with eps+RayBias folded into `bias`)
 // and trace.go:556-622 (motion: `<=` with RayBias). Returns true and updates tclosest,u,v,w on accept.
-template <bool MOTION>
+// KZ = 0,1,2: the ray's dominant axis is known at compile time (warp-uniform fast path, no selects); KZ = -1: per-lane selects.
+template <int KZ>
+__device__ __forceinline__ float pick(float x, float y, float z, int k) {
+  if (KZ < 0) return sel3(x, y, z, k);
+  const int kk = k;  // k is (KZ + const) % 3 at the call sites below; resolved at compile time
+  return kk == 0 ? x : (kk == 1 ? y : z);
+}
+template <bool MOTION, int KZ>
 __device__ __forceinline__ bool tri_test(RayState& r, float3 p0, float3 p1, float3 p2, float bias, float* U, float* V, float* W) {
-  const float AKz = sel3(p0.x, p0.y, p0.z, r.kz) - r.pkz;
-  const float BKz = sel3(p1.x, p1.y, p1.z, r.kz) - r.pkz;
-  const float CKz = sel3(p2.x, p2.y, p2.z, r.kz) - r.pkz;
-  const float Cx = (sel3(p2.x, p2.y, p2.z, r.kx) - r.pkx) - r.s0 * CKz;
-  const float By = (sel3(p1.x, p1.y, p1.z, r.ky) - r.pky) - r.s1 * BKz;
-  const float Cy = (sel3(p2.x, p2.y, p2.z, r.ky) - r.pky) - r.s1 * CKz;
-  const float Bx = (sel3(p1.x, p1.y, p1.z, r.kx) - r.pkx) - r.s0 * BKz;
-  const float Ax = (sel3(p0.x, p0.y, p0.z, r.kx) - r.pkx) - r.s0 * AKz;
-  const float Ay = (sel3(p0.x, p0.y, p0.z, r.ky) - r.pky) - r.s1 * AKz;
+  const int kz = KZ < 0 ? r.kz : KZ;
+  const int kx = KZ < 0 ? r.kx : (KZ + 1) % 3;
+  const int ky = KZ < 0 ? r.ky : (KZ + 2) % 3;
+  const float AKz = pick<KZ>(p0.x, p0.y, p0.z, kz) - r.pkz;
+  const float BKz = pick<KZ>(p1.x, p1.y, p1.z, kz) - r.pkz;
+  const float CKz = pick<KZ>(p2.x, p2.y, p2.z, kz) - r.pkz;
+  const float Cx = __uint_as_float(__float_as_uint((pick<KZ>(p2.x, p2.y, p2.z, kx) - r.pkx) - r.s0 * CKz) ^ r.xsign);
+  const float By = (pick<KZ>(p1.x, p1.y, p1.z, ky) - r.pky) - r.s1 * BKz;
+  const float Cy = (pick<KZ>(p2.x, p2.y, p2.z, ky) - r.pky) - r.s1 * CKz;
+  const float Bx = __uint_as_float(__float_as_uint((pick<KZ>(p1.x, p1.y, p1.z, kx) - r.pkx) - r.s0 * BKz) ^ r.xsign);
+  const float Ax = __uint_as_float(__float_as_uint((pick<KZ>(p0.x, p0.y, p0.z, kx) - r.pkx) - r.s0 * AKz) ^ r.xsign);
+  const float Ay = (pick<KZ>(p0.x, p0.y, p0.z, ky) - r.pky) - r.s1 * AKz;
   float fU = Cx * By - Cy * Bx;
   float fV = Ax * Cy - Ay * Cx;
   float fW = Bx * Ay - By * Ax;
@@ -238,10 +270,11 @@ __device__ __forceinline__ void node_step(const DevScene& sc, TravState& t, Stac
     const float4 lx = ldg4(&nd->lo_x), ly = ldg4(&nd->lo_y), lz = ldg4(&nd->lo_z);
     const float4 hx = ldg4(&nd->hi_x), hy = ldg4(&nd->hi_y), hz = ldg4(&nd->hi_z);
     const uint4 m0 = __ldg(&nd->m0), m1 = __ldg(&nd->m1);
-    t0 = box1(r, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, &h0);
-    t1 = box1(r, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, &h1);
-    t2 = box1(r, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, &h2);
-    t3 = box1(r, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, &h3);
+    Box4Out bo;
+    if (r.special) box4<true>(r, lx, ly, lz, hx, hy, hz, bo);
+    else box4<false>(r, lx, ly, lz, hx, hy, hz, bo);
+    t0 = bo.t0; t1 = bo.t1; t2 = bo.t2; t3 = bo.t3;
+    h0 = bo.h0; h1 = bo.h1; h2 = bo.h2; h3 = bo.h3;
     a0 = m0.x; a1 = m0.y; a2 = m0.z;
     c0 = (int32_t)m0.w; c1 = (int32_t)m1.x; c2 = (int32_t)m1.y; c3 = (int32_t)m1.z;
   } else {
@@ -264,10 +297,11 @@ __device__ __forceinline__ void node_step(const DevScene& sc, TravState& t, Stac
       bx[i].z = om * p.z + tm * q.z;
       bx[i].w = om * p.w + tm * q.w;
     }
-    t0 = box1(r, bx[0].x, bx[1].x, bx[2].x, bx[3].x, bx[4].x, bx[5].x, &h0);
-    t1 = box1(r, bx[0].y, bx[1].y, bx[2].y, bx[3].y, bx[4].y, bx[5].y, &h1);
-    t2 = box1(r, bx[0].z, bx[1].z, bx[2].z, bx[3].z, bx[4].z, bx[5].z, &h2);
-    t3 = box1(r, bx[0].w, bx[1].w, bx[2].w, bx[3].w, bx[4].w, bx[5].w, &h3);
+    Box4Out bo;
+    if (r.special) box4<true>(r, bx[0], bx[1], bx[2], bx[3], bx[4], bx[5], bo);
+    else box4<false>(r, bx[0], bx[1], bx[2], bx[3], bx[4], bx[5], bo);
+    t0 = bo.t0; t1 = bo.t1; t2 = bo.t2; t3 = bo.t3;
+    h0 = bo.h0; h1 = bo.h1; h2 = bo.h2; h3 = bo.h3;
     a0 = mn.axes_keys & 3u; a1 = (mn.axes_keys >> 2) & 3u; a2 = (mn.axes_keys >> 4) & 3u;
     c0 = mn.child[0]; c1 = mn.child[1]; c2 = mn.child[2]; c3 = mn.child[3];
   }
@@ -295,56 +329,80 @@ __device__ __forceinline__ void node_step(const DevScene& sc, TravState& t, Stac
   t.cur = next != -1 ? next : pop_next(r, st);
 }
 
+// Triangle loops of one leaf. The next triangle's 3 x LDG.128 are issued before the current one is tested.
+template <int KZ>
+__device__ __forceinline__ bool leaf_static(const DevScene& sc, RayState& r, HitState& h, int base, int count) {
+  bool leafhit = false;
+  const float4* tp = sc.tris + (size_t)base * 3;
+  float4 n0 = ldg4(tp), n1 = ldg4(tp + 1), n2 = ldg4(tp + 2);
+  for (int i = 0; i < count; i++) {
+    const float4 v0 = n0, v1 = n1, v2 = n2;
+    if (i + 1 < count) {
+      tp += 3;
+      n0 = ldg4(tp); n1 = ldg4(tp + 1); n2 = ldg4(tp + 2);
+    }
+    float U, V, W;
+    if (tri_test<false, KZ>(r, make_float3(v0.x, v0.y, v0.z), make_float3(v1.x, v1.y, v1.z), make_float3(v2.x, v2.y, v2.z), v2.w, &U, &V, &W)) {
+      h.u = U; h.v = V; h.w = W;
+      h.geom = __float_as_int(v0.w);
+      h.prim = __float_as_int(v1.w);
+      h.slot = base + i;
+      leafhit = true;
+    }
+  }
+  return leafhit;
+}
+
+template <int KZ>
+__device__ __forceinline__ bool leaf_motion(const DevScene& sc, RayState& r, HitState& h, int base, int count) {
+  bool leafhit = false;
+  // trace.go:547-554: lerp the three vertices between the keys of this mesh
+  const float4 g0 = ldg4(sc.mtris + (size_t)base * 3);  // key-0 record of the first slot: geom id in w
+  const DevGeom gm = sc.geoms[__float_as_int(g0.w)];
+  const float k = r.time * (float)(gm.keys - 1);
+  const float fk = floorf(k);
+  const float tm = k - fk, om = 1.0f - tm;
+  const int key = (int)fk, key2 = (int)ceilf(k);
+  const float4* ta = sc.mtris + ((size_t)base + (size_t)key * gm.tri_key_stride) * 3;
+  const float4* tb = sc.mtris + ((size_t)base + (size_t)key2 * gm.tri_key_stride) * 3;
+  const float4* tk0 = sc.mtris + (size_t)base * 3;
+  for (int i = 0; i < count; i++, ta += 3, tb += 3, tk0 += 3) {
+    const float4 a0 = ldg4(ta), a1 = ldg4(ta + 1), a2 = ldg4(ta + 2);
+    const float4 b0 = ldg4(tb), b1 = ldg4(tb + 1), b2 = ldg4(tb + 2);
+    const float3 p0 = make_float3(om * a0.x + tm * b0.x, om * a0.y + tm * b0.y, om * a0.z + tm * b0.z);
+    const float3 p1 = make_float3(om * a1.x + tm * b1.x, om * a1.y + tm * b1.y, om * a1.z + tm * b1.z);
+    const float3 p2 = make_float3(om * a2.x + tm * b2.x, om * a2.y + tm * b2.y, om * a2.z + tm * b2.z);
+    const float4 w0 = ldg4(tk0), w1 = ldg4(tk0 + 1), w2 = ldg4(tk0 + 2);
+    float U, V, W;
+    if (tri_test<true, KZ>(r, p0, p1, p2, w2.w, &U, &V, &W)) {
+      h.u = U; h.v = V; h.w = W;
+      h.geom = __float_as_int(w0.w);
+      h.prim = __float_as_int(w1.w);
+      h.slot = base + i;
+      leafhit = true;
+    }
+  }
+  return leafhit;
+}
+
 // One triangle leaf. Returns true if any triangle of the leaf was accepted. trace.go:116-194 / :528-667
+// If every lane that arrived here together has the same dominant axis Kz (coherent camera / shadow rays), the
+// component selection is resolved at compile time; otherwise per-lane selects.
 __device__ __forceinline__ bool leaf_step(const DevScene& sc, TravState& t, uint32_t un) {
   RayState& r = t.r;
   HitState& h = t.h;
   const int base = (int)((un >> 4) & kLeafBaseMask);
   const int count = (int)(un & 15u) + 1;
   h.trisT += count;
-  bool leafhit = false;
-  if (!(un & kMotionTriBit)) {
-    const float4* tp = sc.tris + (size_t)base * 3;
-    for (int i = 0; i < count; i++, tp += 3) {
-      const float4 v0 = ldg4(tp), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
-      float U, V, W;
-      if (tri_test<false>(r, make_float3(v0.x, v0.y, v0.z), make_float3(v1.x, v1.y, v1.z), make_float3(v2.x, v2.y, v2.z), v2.w, &U, &V, &W)) {
-        h.u = U; h.v = V; h.w = W;
-        h.geom = __float_as_int(v0.w);
-        h.prim = __float_as_int(v1.w);
-        h.slot = base + i;
-        leafhit = true;
-      }
-    }
-  } else {
-    // trace.go:547-554: lerp the three vertices between the keys of this mesh
-    const float4 g0 = ldg4(sc.mtris + (size_t)base * 3);  // key-0 record of the first slot: geom id in w
-    const DevGeom gm = sc.geoms[__float_as_int(g0.w)];
-    const float k = r.time * (float)(gm.keys - 1);
-    const float fk = floorf(k);
-    const float tm = k - fk, om = 1.0f - tm;
-    const int key = (int)fk, key2 = (int)ceilf(k);
-    const float4* ta = sc.mtris + ((size_t)base + (size_t)key * gm.tri_key_stride) * 3;
-    const float4* tb = sc.mtris + ((size_t)base + (size_t)key2 * gm.tri_key_stride) * 3;
-    const float4* tk0 = sc.mtris + (size_t)base * 3;
-    for (int i = 0; i < count; i++, ta += 3, tb += 3, tk0 += 3) {
-      const float4 a0 = ldg4(ta), a1 = ldg4(ta + 1), a2 = ldg4(ta + 2);
-      const float4 b0 = ldg4(tb), b1 = ldg4(tb + 1), b2 = ldg4(tb + 2);
-      const float3 p0 = make_float3(om * a0.x + tm * b0.x, om * a0.y + tm * b0.y, om * a0.z + tm * b0.z);
-      const float3 p1 = make_float3(om * a1.x + tm * b1.x, om * a1.y + tm * b1.y, om * a1.z + tm * b1.z);
-      const float3 p2 = make_float3(om * a2.x + tm * b2.x, om * a2.y + tm * b2.y, om * a2.z + tm * b2.z);
-      const float4 w0 = ldg4(tk0), w1 = ldg4(tk0 + 1), w2 = ldg4(tk0 + 2);
-      float U, V, W;
-      if (tri_test<true>(r, p0, p1, p2, w2.w, &U, &V, &W)) {
-        h.u = U; h.v = V; h.w = W;
-        h.geom = __float_as_int(w0.w);
-        h.prim = __float_as_int(w1.w);
-        h.slot = base + i;
-        leafhit = true;
-      }
-    }
+  if (un & kMotionTriBit) return leaf_motion<-1>(sc, r, h, base, count);
+  const unsigned am = __activemask();
+  const int k0 = __shfl_sync(am, r.kz, __ffs(am) - 1);
+  if (__all_sync(am, r.kz == k0)) {
+    if (k0 == 0) return leaf_static<0>(sc, r, h, base, count);
+    if (k0 == 1) return leaf_static<1>(sc, r, h, base, count);
+    return leaf_static<2>(sc, r, h, base, count);
   }
-  return leafhit;
+  return leaf_static<-1>(sc, r, h, base, count);
 }
 
 // while-while traversal of the lane's ray until it finishes or, if `min_active` > 0, until fewer than `min_active`
