@@ -179,16 +179,24 @@ def heightfield_mesh(nq: int = 708, amp: float = 0.08, seed: int = 2, motion: bo
     return PolyMesh(Name=name, Verts=np.stack(keys, 0), Shader=[shader], FaceIdx=tris)
 
 
-def _light_pair(y: float, half: float, shader: str, samples: int = 1, cx: float = 0.0, cz: float = 0.0):
-    """Two TriLights forming a 45-degree-rotated square (diamond) at height y whose normal (P1-P0)x(P2-P0) faces -Y
-    (into the scene).  A diamond, not an axis-aligned quad: two triangles sharing an axis-aligned rectangle's
-    diagonal have identical bounding-box centroids, and the reference's scene-level builder (leafMax=1) then
-    recurses forever (qbvh/build.go:35-43 flat-axis case; see DESIGN.md "reference quirks", f)."""
+def _light_pair(y: float, half: float, shader: str, samples: int = 1, cx: float = 0.0, cz: float = 0.0, dy: float = 0.1):
+    """Two TriLights forming a 45-degree-rotated square (diamond) whose normals (P1-P0)x(P2-P0) face -Y (into the scene),
+    the second one lowered by `dy`.
+
+    * A diamond, not an axis-aligned quad: two triangles sharing an axis-aligned rectangle's diagonal have identical
+      bounding-box centroids, and the reference's scene-level builder (leafMax=1) then recurses forever
+      (qbvh/build.go:35-43 flat-axis case; DESIGN.md "reference quirks", f).
+    * Not coplanar: a ray that hits light A (directly or through a mirror) evaluates light B from the shading point
+      (builtin/scene/scene.go:100-116 only excludes the hit light itself). If B lies in A's plane, B's spherical-triangle
+      sampling runs from inside its own plane and is decided by rounding noise — NaN or finite, black or bright
+      (DESIGN.md "reference quirks", g). The offset keeps the reference's own result well defined."""
     pw = (cx - half, y, cz)
     pe = (cx + half, y, cz)
     pn = (cx, y, cz + half)
-    ps = (cx, y, cz - half)
-    return [TriLight("lightA", pw, pe, pn, shader, samples), TriLight("lightB", pe, pw, ps, shader, samples)]
+    lw = (cx - half, y - dy, cz)
+    le = (cx + half, y - dy, cz)
+    ls = (cx, y - dy, cz - half)
+    return [TriLight("lightA", pw, pe, pn, shader, samples), TriLight("lightB", le, lw, ls, shader, samples)]
 
 
 def heightfield_scene(xres: int = 1920, yres: int = 1080, nq: int = 708, motion: bool = False, seed: int = 2) -> SceneDesc:
@@ -300,7 +308,7 @@ def cornell_box(xres: int = 512, yres: int = 512, boxes: bool = True) -> SceneDe
     if boxes:
         meshes.append(_box("shortbox", (0.1, 0.0, 0.0), (0.7, 0.6, 0.6), "white"))
         meshes.append(_box("tallbox", (-0.7, 0.0, -0.6), (-0.1, 1.2, 0.0), "white"))
-    lights = _light_pair(1.99, 0.35, "lightmtl")
+    lights = _light_pair(1.99, 0.35, "lightmtl", dy=0.03)
     cam = Camera(From=(0.0, 1.0, 3.4), To=(0.0, 1.0, 0.0), Fov=40.0, Focal=1.0)
     return SceneDesc(XRes=xres, YRes=yres, camera=cam, shaders=shaders, meshes=meshes, lights=lights, MaxIter=16, name="C1-cornell")
 
