@@ -41,13 +41,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in _deps()):
         return SO
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("VG_EXTRA_NVCC_FLAGS", "").split()   # tuning experiments only (e.g. -DVG_REFILL_BELOW=20)
+    out = os.environ.get("VG_SO_OUT", SO)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libvermeer_b200.so")
-    return SO
+    return out
 
 
 if __name__ == "__main__":

@@ -8,7 +8,13 @@
 
 namespace vg {
 
-static const int kTraceBlock = 128;
+#ifndef VG_TRACE_BLOCK
+#define VG_TRACE_BLOCK 128
+#endif
+#ifndef VG_TRACE_MIN_BLOCKS
+#define VG_TRACE_MIN_BLOCKS 7
+#endif
+static const int kTraceBlock = VG_TRACE_BLOCK;
 
 // kernels_trace.cu
 cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d_hits, long long n, bool any_hit,

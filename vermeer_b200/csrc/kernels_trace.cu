@@ -33,7 +33,7 @@ struct BatchIO {
 };
 
 template <bool ANY_HIT>
-__global__ void __launch_bounds__(kTraceBlock) k_trace_batch(const DevScene sc, const VgRay* __restrict__ rays, VgHit* __restrict__ hits,
+__global__ void __launch_bounds__(kTraceBlock, VG_TRACE_MIN_BLOCKS) k_trace_batch(const DevScene sc, const VgRay* __restrict__ rays, VgHit* __restrict__ hits,
                                                              long long n, unsigned long long* __restrict__ counter,
                                                              unsigned long long* __restrict__ stats) {
   extern __shared__ uint2 smem_stack[];

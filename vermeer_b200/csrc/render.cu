@@ -163,7 +163,7 @@ struct QueueIO {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kTraceBlock) k_trace_queue(const RenderParams p, int q) {
+__global__ void __launch_bounds__(kTraceBlock, VG_TRACE_MIN_BLOCKS) k_trace_queue(const RenderParams p, int q) {
   extern __shared__ uint2 smem_stack[];
   Stack st;
   st.smem = smem_stack + threadIdx.x;

@@ -13,7 +13,7 @@ import numpy as np
 from .scenes import SceneDesc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libvermeer_b200.so")
+SO_PATH = os.environ.get("VG_SO_PATH", os.path.join(_HERE, "libvermeer_b200.so"))
 
 RAY_DTYPE = np.dtype([("o", np.float32, 3), ("d", np.float32, 3), ("tmax", np.float32), ("time", np.float32)])
 HIT_DTYPE = np.dtype([("t", np.float32), ("u", np.float32), ("v", np.float32), ("w", np.float32),
