@@ -156,7 +156,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    build()
+    if not os.environ.get("VG_SO_PATH"):
+        build()
 
     scene = build_scene()
     table = scenes.splitmix64_table(SCRAMBLE_SEED, XRES * YRES)

@@ -297,7 +297,7 @@ __device__ inline LightRec light_sample(const DevLight& L, const ShadeCtx& c, bo
   }
   const f3 D = sub3(Pl, c.P);
   r.Ldist = length3(D);
-  r.Ld = normalize3(D);
+  r.Ld = normalize3t<FAST>(D);
   r.valid = !(dot3(r.Ld, L.N) > 0 || dot3(r.Ld, c.Ng) < 0);
   if (by_area) r.pdf = L.inv_area * (r.Ldist * r.Ldist) / fabsf(dot3(r.Ld, L.N));
   return r;
@@ -312,7 +312,7 @@ __device__ inline BsdfRec bsdf_sample(const DevLight& L, const ShadeCtx& c, cons
   const uint64_t idx = (uint64_t)(I * h + i);
   const double r0 = vdc(idx, scr0);
   const double r1 = sobol(idx, scr1);
-  const f3 wo = normalize3(basis_expand(fr.U, fr.V, fr.N, cosine_hemisphere<FAST>(r0, r1)));
+  const f3 wo = normalize3t<FAST>(basis_expand(fr.U, fr.V, fr.N, cosine_hemisphere<FAST>(r0, r1)));
   r.pdf = oren_pdf(fr, wo);
   if (r.pdf <= 0) return r;
   f3 Pl;
@@ -328,15 +328,18 @@ __device__ inline BsdfRec bsdf_sample(const DevLight& L, const ShadeCtx& c, cons
   }
   const f3 D = sub3(Pl, c.P);
   r.Ldist = length3(D);
-  r.Ld = normalize3(D);
+  r.Ld = normalize3t<FAST>(D);
   if (dot3(r.Ld, L.N) > 0 || dot3(r.Ld, c.Ng) < 0) return r;
   r.pdfLight = by_area ? pdfl * (r.Ldist * r.Ldist) / fabsf(dot3(r.Ld, L.N)) : pdfl;
   r.valid = true;
   return r;
 }
 
+#ifndef VG_SHADE_MIN_BLOCKS
+#define VG_SHADE_MIN_BLOCKS 6
+#endif
 template <bool FAST>
-__global__ void __launch_bounds__(128) k_shade(const RenderParams p, int level, int qin, int qout, int iter_base) {
+__global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const RenderParams p, int level, int qin, int qout, int iter_base) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = p.counts[qin];
   // whole warps past the end leave together (appends below are warp-collective)
@@ -373,6 +376,7 @@ __global__ void __launch_bounds__(128) k_shade(const RenderParams p, int level, 
   Frame fr;
   f3 omegaI = mk3(0, 0, 1);
   OrenVertex ov;
+  Hero hero;
   float lambda = 0, time = 0;
   long long I = 0;
   uint64_t scr0 = 0, scr1 = 0;
@@ -396,7 +400,8 @@ __global__ void __launch_bounds__(128) k_shade(const RenderParams p, int level, 
     fr.V = V;
     fr.N = c.N;
     omegaI = basis_project(fr.U, fr.V, fr.N, neg3(Rd));
-    ov = oren_vertex<FAST>(omegaI, m.rough2, lambda);
+    hero = hero_setup(lambda);
+    ov = oren_vertex<FAST>(omegaI, m.rough2, hero);
     scr0 = p.scr[(size_t)own * 6 + 4];
     scr1 = p.scr[(size_t)own * 6 + 5];
   }
@@ -413,7 +418,7 @@ __global__ void __launch_bounds__(128) k_shade(const RenderParams p, int level, 
     SphTri sph;
     bool by_area = false;
     if (lit) {
-      Liu = spec_from_rgb(L.E, lambda);
+      Liu = spec_from_rgb(L.E, hero);
       by_area = dot3(c.Ng, sub3(L.p0, c.P)) < 0 || dot3(c.Ng, sub3(L.p1, c.P)) < 0 || dot3(c.Ng, sub3(L.p2, c.P)) < 0;
       if (!by_area) sph = spherical_setup<FAST>(L.p0, L.p1, L.p2, c.P);
     }
@@ -475,7 +480,7 @@ __global__ void __launch_bounds__(128) k_shade(const RenderParams p, int level, 
           const float inv = 1.0f / p_hat;
 #pragma unroll
           for (int k = 0; k < 4; k++) rho.c[k] = (rho.c[k] * Liu.c[k]) * inv;
-          f3 rgb = spec_to_rgb(rho, lambda);
+          f3 rgb = spec_to_rgb(rho, hero);
           if (NS > 1) {  // shader.go:292-296 clamps only in the MIS branch
             if (rgb.x < 0) rgb.x = 0;
             if (rgb.y < 0) rgb.y = 0;
@@ -514,7 +519,7 @@ __global__ void __launch_bounds__(128) k_shade(const RenderParams p, int level, 
         rho.c[0] = rho.c[1] = rho.c[2] = rho.c[3] = 0.f;
         if (!(dot3(o, refl) < 0.9999f)) {
           const float kr = dielectric_kr(m.ior, omegaI.z);
-          rho = spec_from_rgb(mk3(kr, kr, kr), lambda);
+          rho = spec_from_rgb(mk3(kr, kr, kr), hero);
           const float az = fabsf(o.z);
 #pragma unroll
           for (int k = 0; k < 4; k++) rho.c[k] *= az;
@@ -522,7 +527,7 @@ __global__ void __launch_bounds__(128) k_shade(const RenderParams p, int level, 
         const float inv = 1.0f / (float)pdf;
 #pragma unroll
         for (int k = 0; k < 4; k++) rho.c[k] *= inv;
-        const f3 rgb = spec_to_rgb(rho, lambda);
+        const f3 rgb = spec_to_rgb(rho, hero);
         T4 = make_float4(rgb.x * m.spec_colour.x, rgb.y * m.spec_colour.y, rgb.z * m.spec_colour.z, m.spec_weight);
         // the level-4 ray is traced by the reference although its shader returns black (std.go:95,243)
         want = (level + 1 <= 3) || p.trace_last_level;

@@ -50,6 +50,16 @@ __device__ __forceinline__ f3 normalize3(f3 a) {
   const float r = 1.0f / sqrtf(x1);  // two correctly rounded float ops: within 1 ulp, like the CPU's RSQRTSS + Newton step
   return mk3(a.x * r, a.y * r, a.z * r);
 }
+// FAST shading variant: one MUFU.RSQ (<= 2 ulp) instead of sqrt + divide
+template <bool FAST>
+__device__ __forceinline__ f3 normalize3t(f3 a) {
+  if (!FAST) return normalize3(a);
+  float x0 = a.x * a.x, x1 = a.y * a.y, x2 = a.z * a.z;
+  x1 = x1 + x0;
+  x1 = x1 + x2;
+  const float r = rsqrtf(x1);
+  return mk3(a.x * r, a.y * r, a.z * r);
+}
 __device__ __forceinline__ f3 basis_project(f3 U, f3 V, f3 W, f3 S) { return mk3(dot3(U, S), dot3(V, S), dot3(W, S)); }
 __device__ __forceinline__ f3 basis_expand(f3 U, f3 V, f3 W, f3 S) {
   return mk3(U.x * S.x + V.x * S.y + W.x * S.z, U.y * S.x + V.y * S.y + W.y * S.z, U.z * S.x + V.z * S.y + W.z * S.z);
@@ -119,47 +129,59 @@ __device__ __forceinline__ float wavelength(float lambda, int j) {  // spectrum.
   v += 450.0f;
   return v;
 }
-__device__ __forceinline__ float smits_eval(const float* s, float lambda) {  // spectrum_smits9.go:16-25
-  if (lambda < 380.0f || lambda >= 720.0f) return 0.0f;
-  const int bin = (int)(((lambda - 380.0f) / (720.0f - 380.0f)) * 10.0f);
-  return s[bin];
+// The 4 hero wavelengths of a path depend on its Lambda only (spectrum.go:101-112), so the Smits bin
+// (spectrum_smits9.go:16-25: -1 outside [380,720)) and the three nearest-bin CIE observer values (cie1931_2deg.go:62-95:
+// -1 outside [360,830)) are looked up once per path vertex instead of once per FromRGB / ToRGB call.
+struct Hero {
+  int sbin[4];
+  float cx[4], cy[4], cz[4];
+};
+__device__ __forceinline__ Hero hero_setup(float lambda) {
+  Hero h;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const float wl = wavelength(lambda, k);
+    h.sbin[k] = (wl < 380.0f || wl >= 720.0f) ? -1 : (int)(((wl - 380.0f) / (720.0f - 380.0f)) * 10.0f);
+    if (wl < 360.0f || wl >= 830.0f) {
+      h.cx[k] = h.cy[k] = h.cz[k] = -1.0f;
+    } else {
+      const int bin = (int)(((wl - 360.0f) / (830.0f - 360.0f)) * 95.0f);
+      h.cx[k] = kCieX[bin]; h.cy[k] = kCieY[bin]; h.cz[k] = kCieZ[bin];
+    }
+  }
+  return h;
 }
-__device__ inline float rgb_to_spectrum(float r, float g, float b, float lambda) {  // spectrum_smits9.go:48-84
+__device__ __forceinline__ float smits_eval(const float* s, int bin) { return bin < 0 ? 0.0f : s[bin]; }
+__device__ inline float rgb_to_spectrum(float r, float g, float b, int bin) {  // spectrum_smits9.go:48-84
   float c = 0.0f;
   if (r <= g && r <= b) {
-    c += r * smits_eval(kSmitsWhite, lambda);
-    if (g <= b) { c += (g - r) * smits_eval(kSmitsCyan, lambda); c += (b - g) * smits_eval(kSmitsBlue, lambda); }
-    else { c += (b - r) * smits_eval(kSmitsCyan, lambda); c += (g - b) * smits_eval(kSmitsGreen, lambda); }
+    c += r * smits_eval(kSmitsWhite, bin);
+    if (g <= b) { c += (g - r) * smits_eval(kSmitsCyan, bin); c += (b - g) * smits_eval(kSmitsBlue, bin); }
+    else { c += (b - r) * smits_eval(kSmitsCyan, bin); c += (g - b) * smits_eval(kSmitsGreen, bin); }
   } else if (g <= r && g <= b) {
-    c += g * smits_eval(kSmitsWhite, lambda);
-    if (r <= b) { c += (r - g) * smits_eval(kSmitsMagenta, lambda); c += (b - r) * smits_eval(kSmitsBlue, lambda); }
-    else { c += (b - g) * smits_eval(kSmitsMagenta, lambda); c += (r - b) * smits_eval(kSmitsRed, lambda); }
+    c += g * smits_eval(kSmitsWhite, bin);
+    if (r <= b) { c += (r - g) * smits_eval(kSmitsMagenta, bin); c += (b - r) * smits_eval(kSmitsBlue, bin); }
+    else { c += (b - g) * smits_eval(kSmitsMagenta, bin); c += (r - b) * smits_eval(kSmitsRed, bin); }
   } else {
-    c += b * smits_eval(kSmitsWhite, lambda);
-    if (r <= g) { c += (r - b) * smits_eval(kSmitsYellow, lambda); c += (g - r) * smits_eval(kSmitsGreen, lambda); }
-    else { c += (g - b) * smits_eval(kSmitsYellow, lambda); c += (r - g) * smits_eval(kSmitsRed, lambda); }
+    c += b * smits_eval(kSmitsWhite, bin);
+    if (r <= g) { c += (r - b) * smits_eval(kSmitsYellow, bin); c += (g - r) * smits_eval(kSmitsGreen, bin); }
+    else { c += (g - b) * smits_eval(kSmitsYellow, bin); c += (r - g) * smits_eval(kSmitsRed, bin); }
   }
   return c;
 }
-__device__ __forceinline__ Spec4 spec_from_rgb(f3 rgb, float lambda) {
+__device__ __forceinline__ Spec4 spec_from_rgb(f3 rgb, const Hero& h) {  // spectrum.go:49-54
   Spec4 s;
 #pragma unroll
-  for (int k = 0; k < 4; k++) s.c[k] = rgb_to_spectrum(rgb.x, rgb.y, rgb.z, wavelength(lambda, k));
+  for (int k = 0; k < 4; k++) s.c[k] = rgb_to_spectrum(rgb.x, rgb.y, rgb.z, h.sbin[k]);
   return s;
 }
-__device__ __forceinline__ float cie_lookup(const float* tab, float lambda) {  // cie1931_2deg.go:62-70
-  if (lambda < 360.0f || lambda >= 830.0f) return -1.0f;
-  const int bin = (int)(((lambda - 360.0f) / (830.0f - 360.0f)) * 95.0f);
-  return tab[bin];
-}
-__device__ __forceinline__ f3 spec_to_rgb(const Spec4& s, float lambda) {  // spectrum.go:57-72
+__device__ __forceinline__ f3 spec_to_rgb(const Spec4& s, const Hero& h) {  // spectrum.go:57-72
   float x = 0, y = 0, z = 0;
 #pragma unroll
   for (int i = 0; i < 4; i++) {
-    const float wl = wavelength(lambda, i);
-    x += s.c[i] * cie_lookup(kCieX, wl);
-    y += s.c[i] * cie_lookup(kCieY, wl);
-    z += s.c[i] * cie_lookup(kCieZ, wl);
+    x += s.c[i] * h.cx[i];
+    y += s.c[i] * h.cy[i];
+    z += s.c[i] * h.cz[i];
   }
   return mk3(x * 3.2404542f + y * -1.5371385f + z * -0.4985314f, x * -0.9692660f + y * 1.8760108f + z * 0.0415560f,
              x * 0.0556434f + y * -0.2040259f + z * 1.0572252f);
@@ -208,14 +230,14 @@ struct OrenVertex {
   Spec4 white;         // FromRGB({1,1,1}) at this path's hero wavelength
 };
 template <bool FAST>
-__device__ __forceinline__ OrenVertex oren_vertex(f3 omegaI, float roughness2, float lambda) {
+__device__ __forceinline__ OrenVertex oren_vertex(f3 omegaI, float roughness2, const Hero& hero) {
   OrenVertex v;
   const float sigma = roughness2;
   v.A = 1 - (0.5f * (sigma * sigma) / ((sigma * sigma) + 0.57f));
   v.B = 0.45f * (sigma * sigma) / ((sigma * sigma) + 0.09f);
   v.phiI = Trig<FAST>::atan2(omegaI.y, omegaI.x);
   v.thetaI = Trig<FAST>::acos(omegaI.z);
-  v.white = spec_from_rgb(mk3(1, 1, 1), lambda);
+  v.white = spec_from_rgb(mk3(1, 1, 1), hero);
   return v;
 }
 template <bool FAST>
@@ -306,9 +328,9 @@ struct SphTri {
 template <bool FAST>
 __device__ inline SphTri spherical_setup(f3 p0, f3 p1, f3 p2, f3 p) {
   SphTri t;
-  t.pa = normalize3(sub3(p0, p));
-  t.pb = normalize3(sub3(p1, p));
-  t.pc = normalize3(sub3(p2, p));
+  t.pa = normalize3t<FAST>(sub3(p0, p));
+  t.pb = normalize3t<FAST>(sub3(p1, p));
+  t.pc = normalize3t<FAST>(sub3(p2, p));
   const float as = Trig<FAST>::acos(dot3(t.pb, t.pc)), bs = Trig<FAST>::acos(dot3(t.pc, t.pa)), cs = Trig<FAST>::acos(dot3(t.pa, t.pb));
   const float ssu = (as + bs + cs) / 2;
   const float sa = Trig<FAST>::sin(ssu - as), sb = Trig<FAST>::sin(ssu - bs), scs = Trig<FAST>::sin(ssu - cs), ss = Trig<FAST>::sin(ssu);
@@ -334,12 +356,12 @@ __device__ inline f3 sample_spherical_triangle(const SphTri& st, double r0, doub
   float q = ((v * t - u * s) * cosAlpha - v) / ((v * s + u * t) * sinAlpha);
   q = maxf_x86(-1.0f, minf_x86(q, 1.0f));
   float w = dot3(pc, pa);
-  f3 v31 = normalize3(mk3(pc.x - w * pa.x, pc.y - w * pa.y, pc.z - w * pa.z));
+  f3 v31 = normalize3t<FAST>(mk3(pc.x - w * pa.x, pc.y - w * pa.y, pc.z - w * pa.z));
   const float sq = sqrtf(1 - q * q);
   const f3 v4 = mk3(q * pa.x + sq * v31.x, q * pa.y + sq * v31.y, q * pa.z + sq * v31.z);
   const float z = 1 - (float)r1 * (1 - dot3(v4, pb));
   w = dot3(v4, pb);
-  const f3 v42 = normalize3(mk3(v4.x - w * pb.x, v4.y - w * pb.y, v4.z - w * pb.z));
+  const f3 v42 = normalize3t<FAST>(mk3(v4.x - w * pb.x, v4.y - w * pb.y, v4.z - w * pb.z));
   return add3(scale3(z, pb), scale3(sqrtf(1 - z * z), v42));
 }
 // disk.go:38-51
