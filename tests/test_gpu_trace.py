@@ -114,3 +114,18 @@ def test_empty_and_ragged_batches(built_library):
     for n in (1, 31, 33, 127, 129, 1000):
         rays = random_rays(n, n, lo=(-0.9, 0.1, -0.9), hi=(0.9, 1.9, 0.9))
         assert_hits_equal(dev.trace(rays), ora.trace(rays), what="n=%d" % n)
+
+
+def test_tma_staged_queue_variant(built_library):
+    """The cp.async.bulk (TMA) staged ray-queue variant of the persistent kernels gives the same bits as the default."""
+    from vermeer_b200 import scenes
+    sc = scenes.heightfield_scene(128, 72, nq=64)
+    ora, dev = _pair(sc)
+    dev.set_option("tma_stage", 1)
+    for n in (1, 33, 1000, 50001):
+        rays = random_rays(n, n, lo=(-1, 0.2, -1), hi=(1, 1.2, 1))
+        rays["d"][:, 1] = -np.abs(rays["d"][:, 1])
+        assert_hits_equal(dev.trace(rays), ora.trace(rays), what="tma n=%d" % n)
+        sh = rays.copy()
+        sh["tmax"] = 0.6
+        assert_hits_equal(dev.trace(sh, any_hit=True), ora.trace(sh, any_hit=True), what="tma any-hit n=%d" % n)

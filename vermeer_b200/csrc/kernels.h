@@ -15,9 +15,14 @@ namespace vg {
 #define VG_TRACE_MIN_BLOCKS 7
 #endif
 static const int kTraceBlock = VG_TRACE_BLOCK;
+#ifndef VG_SMEM_STACK
+#define VG_SMEM_STACK 16
+#endif
+// dynamic shared memory of the traversal kernels: per-warp TMA ray slots + mbarriers, then the per-thread stacks
+inline size_t trace_smem_bytes() { return (size_t)(kTraceBlock / 32) * (2048 + 16) + (size_t)kTraceBlock * VG_SMEM_STACK * 8; }
 
 // kernels_trace.cu
-cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d_hits, long long n, bool any_hit,
+cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d_hits, long long n, bool any_hit, bool tma,
                                unsigned long long* d_counter, unsigned long long* d_stats, int grid, cudaStream_t stream);
 int trace_batch_blocks_per_sm();
 

@@ -17,6 +17,7 @@ struct BatchIO {
   unsigned long long* counter;
   __device__ __forceinline__ long long fetch(int c) { return (long long)atomicAdd(counter, (unsigned long long)c); }
   __device__ __forceinline__ long long size() const { return n; }
+  __device__ __forceinline__ const VgRay* ray_ptr() const { return rays; }
   __device__ __forceinline__ void load(long long i, RayState& r) const {
     const float4* rp = reinterpret_cast<const float4*>(rays + i);
     const float4 a = __ldg(rp), b = __ldg(rp + 1);
@@ -32,18 +33,23 @@ struct BatchIO {
   }
 };
 
-template <bool ANY_HIT>
+template <bool ANY_HIT, bool TMA>
 __global__ void __launch_bounds__(kTraceBlock, VG_TRACE_MIN_BLOCKS) k_trace_batch(const DevScene sc, const VgRay* __restrict__ rays, VgHit* __restrict__ hits,
                                                              long long n, unsigned long long* __restrict__ counter,
                                                              unsigned long long* __restrict__ stats) {
-  extern __shared__ uint2 smem_stack[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: [warps x (2 x 1 KB ray slots)] [warps x 2 mbarriers] [threads x VG_SMEM_STACK stack entries]
+  const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
+  WarpStage ws;
+  ws.buf = reinterpret_cast<float4*>(smem_raw) + warp * 128;
+  ws.bar = reinterpret_cast<unsigned long long*>(smem_raw + nwarps * 2048) + warp * 2;
   Stack st;
-  st.smem = smem_stack + threadIdx.x;
+  st.smem = reinterpret_cast<uint2*>(smem_raw + nwarps * (2048 + 16)) + threadIdx.x;
   st.stride = blockDim.x;
   const int lane = threadIdx.x & 31;
   unsigned long long nodes_acc = 0, tris_acc = 0;
   BatchIO io{rays, hits, n, counter};
-  trace_persistent<ANY_HIT>(sc, io, st, nodes_acc, tris_acc);
+  trace_persistent<ANY_HIT, TMA>(sc, io, st, ws, nodes_acc, tris_acc);
   // warp-aggregated statistics (core/stats.go keeps global atomics per ray; one atomic per warp here)
   for (int o = 16; o > 0; o >>= 1) {
     nodes_acc += __shfl_down_sync(0xffffffffu, nodes_acc, o);
@@ -55,22 +61,22 @@ __global__ void __launch_bounds__(kTraceBlock, VG_TRACE_MIN_BLOCKS) k_trace_batc
   }
 }
 
-cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d_hits, long long n, bool any_hit,
+cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d_hits, long long n, bool any_hit, bool tma,
                                unsigned long long* d_counter, unsigned long long* d_stats, int grid, cudaStream_t stream) {
-  const size_t smem = (size_t)kTraceBlock * VG_SMEM_STACK * sizeof(uint2);
+  const size_t smem = trace_smem_bytes();
   cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
-  if (any_hit)
-    k_trace_batch<true><<<grid, kTraceBlock, smem, stream>>>(sc, d_rays, d_hits, n, d_counter, d_stats);
-  else
-    k_trace_batch<false><<<grid, kTraceBlock, smem, stream>>>(sc, d_rays, d_hits, n, d_counter, d_stats);
+  if (any_hit && tma) k_trace_batch<true, true><<<grid, kTraceBlock, smem, stream>>>(sc, d_rays, d_hits, n, d_counter, d_stats);
+  else if (any_hit) k_trace_batch<true, false><<<grid, kTraceBlock, smem, stream>>>(sc, d_rays, d_hits, n, d_counter, d_stats);
+  else if (tma) k_trace_batch<false, true><<<grid, kTraceBlock, smem, stream>>>(sc, d_rays, d_hits, n, d_counter, d_stats);
+  else k_trace_batch<false, false><<<grid, kTraceBlock, smem, stream>>>(sc, d_rays, d_hits, n, d_counter, d_stats);
   return cudaGetLastError();
 }
 
 int trace_batch_blocks_per_sm() {
   int nb = 0;
-  const size_t smem = (size_t)kTraceBlock * VG_SMEM_STACK * sizeof(uint2);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_batch<false>, kTraceBlock, smem);
+  const size_t smem = trace_smem_bytes();
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_batch<false, false>, kTraceBlock, smem);
   return nb > 0 ? nb : 1;
 }
 

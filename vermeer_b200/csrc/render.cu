@@ -144,6 +144,7 @@ struct QueueIO {
   int* head;
   __device__ __forceinline__ long long fetch(int c) { return (long long)atomicAdd(head, c); }
   __device__ __forceinline__ long long size() const { return n; }
+  __device__ __forceinline__ const VgRay* ray_ptr() const { return rays; }
   __device__ __forceinline__ void load(long long i, RayState& r) const {
     const float4* rp = reinterpret_cast<const float4*>(rays + i);
     const float4 a = __ldg(rp), b = __ldg(rp + 1);
@@ -163,17 +164,22 @@ struct QueueIO {
   }
 };
 
-template <int MODE>
+template <int MODE, bool TMA>
 __global__ void __launch_bounds__(kTraceBlock, VG_TRACE_MIN_BLOCKS) k_trace_queue(const RenderParams p, int q) {
-  extern __shared__ uint2 smem_stack[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: [warps x (2 x 1 KB ray slots)] [warps x 2 mbarriers] [threads x VG_SMEM_STACK stack entries]
+  const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
+  WarpStage ws;
+  ws.buf = reinterpret_cast<float4*>(smem_raw) + warp * 128;
+  ws.bar = reinterpret_cast<unsigned long long*>(smem_raw + nwarps * 2048) + warp * 2;
   Stack st;
-  st.smem = smem_stack + threadIdx.x;
+  st.smem = reinterpret_cast<uint2*>(smem_raw + nwarps * (2048 + 16)) + threadIdx.x;
   st.stride = blockDim.x;
   const int lane = threadIdx.x & 31;
   const int n = MODE == 0 ? p.counts[q] : p.counts[2];
   unsigned long long nodes_acc = 0, tris_acc = 0;
   QueueIO<MODE> io{p, MODE == 0 ? p.rayq[q] : p.sray, n, p.counts + (MODE == 0 ? 3 : 4)};
-  trace_persistent<MODE == 1>(p.sc, io, st, nodes_acc, tris_acc);
+  trace_persistent<MODE == 1, TMA>(p.sc, io, st, ws, nodes_acc, tris_acc);
   for (int o = 16; o > 0; o >>= 1) {
     nodes_acc += __shfl_down_sync(0xffffffffu, nodes_acc, o);
     tris_acc += __shfl_down_sync(0xffffffffu, tris_acc, o);
@@ -843,8 +849,8 @@ static int prepare(vg_ctx* ctx) {
   RCUDA(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
 
   int nb = 0;
-  const size_t smem = (size_t)kTraceBlock * VG_SMEM_STACK * sizeof(uint2);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_queue<0>, kTraceBlock, smem);
+  const size_t smem = trace_smem_bytes();
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_queue<0, false>, kTraceBlock, smem);
   rs.trace_grid = ctx->sm_count * std::max(1, nb);
   rs.ready = true;
   return upload_scramble(ctx, ctx->scramble.data());
@@ -895,7 +901,7 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
   p.contrib = rs.contrib.p; p.sray = rs.sray.p; p.sslot = rs.sslot.p; p.L = rs.L.p; p.T = rs.T.p;
   p.counts = rs.counts.p; p.stats = rs.stats.p; p.fb = rs.fb.p;
 
-  const size_t smem = (size_t)kTraceBlock * VG_SMEM_STACK * sizeof(uint2);
+  const size_t smem = trace_smem_bytes();
   uint64_t launches = 0;
   size_t nev = 0;
   std::vector<int> kinds;
@@ -918,7 +924,8 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
       for (int level = 0; level < nlev; level++) {
         const int qout = 1 - qin;
         cudaEventRecord(rs.ev(nev++), st);
-        k_trace_queue<0><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
+        if (ctx->opt_tma_stage) k_trace_queue<0, true><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
+        else k_trace_queue<0, false><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
         cudaEventRecord(rs.ev(nev++), st);
         kinds.push_back(0);
         launches++;
@@ -926,7 +933,8 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
           if (ctx->opt_precise_trig) k_shade<false><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
           else k_shade<true><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
           cudaEventRecord(rs.ev(nev++), st);
-          k_trace_queue<1><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
+          if (ctx->opt_tma_stage) k_trace_queue<1, true><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
+          else k_trace_queue<1, false><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
           cudaEventRecord(rs.ev(nev++), st);
           kinds.push_back(1);
           k_resolve<<<(np + 255) / 256, 256, 0, st>>>(p, level, qin);
