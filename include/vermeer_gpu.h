@@ -173,6 +173,10 @@ int vg_set_frame(vg_ctx* ctx, int xres, int yres);
 int vg_set_partition(vg_ctx* ctx, int rank, int world);
 /* framescramble (core/render.go:18-23,166-176): npix*6 uint64 {lensU,lensV,time,lambda,scramble0,scramble1}, row-major pixels. */
 int vg_set_scramble(vg_ctx* ctx, const uint64_t* table, int64_t npix);
+/* core.PixelFilter (core/pixelfilter.go:8) as the tables filter.CreateSampler builds (builtin/filter/filter.go:88-173):
+ * n, width w, marginal CDF cdfV[n] and conditional CDFs cdfVU[n*n] (row uI). The FIS warp of filter.go:40-86 runs on the
+ * device in ray generation (core/render.go:99-107). n = 0 removes the filter. */
+int vg_set_filter(vg_ctx* ctx, int n, double w, const double* cdfV, const double* cdfVU);
 /* Options: "trace_last_level" (1 = trace the level-4 mirror ray like the reference, std.go:243; default 1),
  * "iters_per_batch" (wavefront batch depth, default 4), "precise_trig" (1 = shading trig through float64 exactly like
  * math/sincos.go; 0 = single-precision libm, default; both are within the image tolerance), "tma_stage" (1 = traversal kernels
@@ -211,6 +215,9 @@ int vh_add_shader_std(vh_scene* s, const char* name, const VgMaterial* params);
 int vh_add_polymesh(vh_scene* s, const char* name, const float* verts, int n_verts, int keys, const int32_t* polycount, int n_poly,
                     const int32_t* faceidx, int n_faceidx, const char* shaders_nl, const int32_t* shaderidx, int n_shaderidx,
                     const float* normals, int n_normals, const int32_t* normalidx, int n_normalidx, float raybias);
+/* AiryFilter / GaussianFilter nodes (builtin/filter/airy.go:13, gauss.go:13). width/res/peak <= 0 keep the registered
+ * defaults (Airy: Res 49, Width 6, Peak 4; Gaussian: Res 17, Width 2 — filter.go:14-26). */
+int vh_add_filter(vh_scene* s, const char* type, const char* name, float width, int res, float peak);
 int vh_add_trilight(vh_scene* s, const char* name, const float* p0, const float* p1, const float* p2, const char* shader, int samples);
 int vh_set_camera_lookat(vh_scene* s, const float* from, const float* to, const float* up, float roll, float fov, float focal,
                          float aspect, float radius);

@@ -47,6 +47,10 @@ def lib():
         L.orc_vdc.restype = C.c_double
         L.orc_sobol.restype = C.c_double
         L.orc_raster_xy.restype = C.c_uint64
+        L.orc_bessel_j1.restype = C.c_double
+        L.orc_bessel_j1.argtypes = [C.c_double]
+        L.orc_filter_warp.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.orc_filter_warp.restype = None
         for f in ("orc_vdc_u", "orc_sobol_u", "orc_vdc", "orc_sobol"):
             getattr(L, f).argtypes = [C.c_uint64, C.c_uint64]
         L.orc_raster_xy.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -90,6 +94,10 @@ class Oracle:
         c = scene.camera
         self._chk(L.orc_set_camera(h, _f3(c.From), _f3(c.To), _f3(c.Up), C.c_float(c.Roll), C.c_float(c.Fov), C.c_float(c.Focal),
                                    C.c_float(c.Aspect), C.c_float(c.Radius)))
+        if getattr(scene, "filter", None) is not None:
+            f = scene.filter
+            airy = f.Type == "AiryFilter"
+            L.orc_set_filter(h, 1 if airy else 2, C.c_float(f.Width or (6 if airy else 2)), int(f.Res or (49 if airy else 17)), C.c_float(f.Peak or (4 if airy else 0)))
         L.orc_set_motion_ref_compat(h, 1 if motion_ref_compat else 0)
         self._chk(L.orc_prerender(h))
 

@@ -135,6 +135,32 @@ int orc_set_camera(void* h, const float* from, const float* to, const float* up,
   return 0;
 }
 
+// kind: 1 = AiryFilter (defaults Res 49, Width 6, Peak 4), 2 = GaussianFilter (Res 17, Width 2)  — builtin/filter/filter.go:14-26
+int orc_set_filter(void* h, int kind, float width, int res, float peak) {
+  Handle* H = (Handle*)h;
+  if (kind == 0) { H->r.filter.reset(); return 0; }
+  H->r.filter.reset(new PixelFilter());
+  H->r.filter->kind = kind;
+  H->r.filter->Width = width;
+  H->r.filter->Res = res;
+  H->r.filter->Peak = peak;
+  return 0;
+}
+int orc_filter_tables(void* h, double* cdfV, double* cdfVU) {
+  Handle* H = (Handle*)h;
+  if (!H->r.filter) return -1;
+  const FilterSampler& s = H->r.filter->sampler;
+  for (int i = 0; i < s.n; i++) cdfV[i] = s.cdfV[i];
+  for (int j = 0; j < s.n; j++)
+    for (int i = 0; i < s.n; i++) cdfVU[j * s.n + i] = s.cdfVU[j][i];
+  return 0;
+}
+void orc_filter_warp(void* h, double r0, double r1, double* u, double* v) {
+  Handle* H = (Handle*)h;
+  H->r.filter->sampler.WarpSample(r0, r1, u, v);
+}
+double orc_bessel_j1(double x) { return BesselJ1(x); }
+
 int orc_set_motion_ref_compat(void* h, int on) {
   Handle* H = (Handle*)h;
   for (auto& m : H->r.meshes) m->ref_compat_motion = on != 0;

@@ -473,6 +473,127 @@ void Camera::ComputeRay(float Sx, float Sy, double lensU, double lensV, const Sh
 }
 
 // ---------------------------------------------------------------------------------------------
+// builtin/filter/filter.go:88-173
+void FilterSampler::Create(int n_, double w_, double (*f)(double, double, void*), void* ctx) {
+  n = n_;
+  w = w_;
+  std::vector<double> filter((size_t)n * n);
+  double du = w / (double)(n - 1);
+  double u = -w / 2;
+  double F = 0;
+  for (int j = 0; j < n; j++) {
+    double dv = w / (double)(n - 1);
+    double v = -w / 2;
+    for (int i = 0; i < n; i++) {
+      double fuv = f(u, v, ctx);
+      filter[j + (i * n)] = fuv;
+      F += fuv;
+      v += dv;
+    }
+    u += du;
+  }
+  std::vector<std::vector<double>> pdf(n, std::vector<double>(n));
+  for (int j = 0; j < n; j++)
+    for (int i = 0; i < n; i++) pdf[j][i] = filter[j + (i * n)] / F;
+  std::vector<double> pV(n, 0.0);
+  for (int j = 0; j < n; j++)
+    for (int i = 0; i < n; i++) pV[j] += pdf[j][i];
+  std::vector<std::vector<double>> pVU(n, std::vector<double>(n));
+  for (int j = 0; j < n; j++)
+    for (int i = 0; i < n; i++) pVU[j][i] = pdf[j][i] / pV[j];
+  double p = 0;
+  cdfV.assign(n, 0.0);
+  for (int i = 0; i < n; i++) {
+    p += pV[i];
+    cdfV[i] = p;
+  }
+  cdfVU.assign(n, std::vector<double>(n));
+  for (int j = 0; j < n; j++) {
+    double q = 0;
+    for (int i = 0; i < n; i++) {
+      q += pVU[j][i];
+      cdfVU[j][i] = q;
+    }
+  }
+}
+
+// builtin/filter/filter.go:40-86 (including the `du / w` of the first bin, kept as is)
+void FilterSampler::WarpSample(double r0, double r1, double* uo, double* vo) const {
+  double u = 0, v = 0;
+  int uI = -1;
+  for (int i = 0; i < (int)cdfV.size(); i++) {
+    uI = i;
+    if (r0 < cdfV[i]) {
+      if (i == 0) {
+        double du = r0 / cdfV[i];
+        u = (-w / 2) + (du / w);
+      } else {
+        double du = (r0 - cdfV[i - 1]) / (cdfV[i] - cdfV[i - 1]);
+        u = (-w / 2) + w * ((double)i + du) / (double)(n - 1);
+      }
+      break;
+    }
+  }
+  const std::vector<double>& c = cdfVU[uI];
+  for (int i = 0; i < (int)c.size(); i++) {
+    if (r1 < c[i]) {
+      if (i == 0) {
+        double dv = r1 / c[i];
+        v = (-w / 2) + (dv / w);
+      } else {
+        double dv = (r1 - c[i - 1]) / (c[i] - c[i - 1]);
+        v = (-w / 2) + w * ((double)i + dv) / (double)(n - 1);
+      }
+      *uo = u;
+      *vo = v;
+      return;
+    }
+  }
+  *uo = 0;
+  *vo = 0;
+}
+
+// builtin/filter/airy.go:34-72
+double BesselJ1(double x) {
+  double ax = std::fabs(x);
+  if (ax < 8.0) {
+    double y = x * x;
+    double ans1 = x * (72362614232.0 + y * (-7895059235.0 + y * (242396853.1 + y * (-2972611.439 + y * (15704.48260 + y * (-30.16036606))))));
+    double ans2 = 144725228442.0 + y * (2300535178.0 + y * (18583304.74 + y * (99447.43394 + y * (376.9991397 + y * 1.0))));
+    return ans1 / ans2;
+  }
+  double z = 8.0 / ax;
+  double y = z * z;
+  double xx = ax - 2.356194491;
+  double ans1 = 1.0 + y * (0.183105e-2 + y * (-0.3516396496e-4 + y * (0.2457520174e-5 + y * (-0.240337019e-6))));
+  double ans2 = 0.04687499995 + y * (-0.2002690873e-3 + y * (0.8449199096e-5 + y * (-0.88228987e-6 + y * 0.105787412e-6)));
+  double ans = std::sqrt(0.636619772 / ax) * (std::cos(xx) * ans1 - z * std::sin(xx) * ans2);
+  if (x < 0.0) ans = -ans;
+  return ans;
+}
+
+static double sqrd(double x) { return x * x; }
+// builtin/filter/airy.go:74-101
+static double airyFn(double x, double y, void* ctx) {
+  PixelFilter* f = (PixelFilter*)ctx;
+  double q = std::sqrt(x * x + y * y);
+  if (q > (double)(f->Width / 2)) return 0;
+  double lambda = 550.0;
+  double N = 5.6;
+  double v = (20000 / (double)f->Width) * (M_PI * q) / (lambda * N);
+  return (double)f->Peak * sqrd(2 * BesselJ1(v) / v);
+}
+// builtin/filter/gauss.go:31-50
+static double gaussFn(double x, double y, void* ctx) {
+  PixelFilter* f = (PixelFilter*)ctx;
+  double q = std::sqrt(x * x + y * y);
+  if (q > (double)(f->Width / 2)) return 0;
+  double sigma = (double)(1.0 / std::sqrt((double)f->Width));
+  return (1 / (2 * M_PI * sqrd(sigma))) * std::exp((double)(-(x * x + y * y) / 2 * sqrd(sigma)));
+}
+void PixelFilter::PreRender() { sampler.Create(Res, (double)Width, kind == 1 ? airyFn : gaussFn, this); }
+
+// ---------------------------------------------------------------------------------------------
 ShaderStd* Renderer::findShader(const std::string& name) {
   for (auto& s : shaders) if (s->Name == name) return s.get();
   return nullptr;
@@ -484,6 +605,7 @@ void Renderer::PreRender() {
   if (prerendered) return;
   framebuffer.assign((size_t)XRes * YRes * 3, 0.0f);
   camera.PreRender((float)XRes / (float)YRes);
+  if (filter) filter->PreRender();
   int gid = 0;
   for (auto& m : meshes) {
     m->PreRender();
@@ -515,6 +637,14 @@ void Renderer::GenerateCameraRay(int iter, int x, int y, ShaderContext* sc, Ray*
   double lambda = (720 - 450) * VanDerCorput((uint64_t)iter, scr.lambda) + 450;
   double lensU = VanDerCorput((uint64_t)iter, scr.lensU);
   double lensV = Sobol((uint64_t)iter, scr.lensV);
+  if (filter) {  // core/render.go:99-107
+    double pixu = rasterX - std::floor(rasterX);
+    double pixv = rasterY - std::floor(rasterY);
+    double u, v;
+    filter->sampler.WarpSample(pixu, pixv, &u, &v);
+    rasterX = std::floor(rasterX) + 0.5 + u;
+    rasterY = std::floor(rasterY) + 0.5 + v;
+  }
   int w = XRes, h = YRes;
   float Sx = (float)(-1.0 + 2.0 * (rasterX / (double)w));
   float Sy = -(float)(-1.0 + 2.0 * (rasterY / (double)h));

@@ -68,6 +68,24 @@ struct Camera {
   void ComputeRay(float Sx, float Sy, double lensU, double lensV, const ShaderContext* sc, Ray* ray) const;
 };
 
+// builtin/filter/filter.go:29-173 — filter-importance-sampling tables (marginal + conditional CDFs)
+struct FilterSampler {
+  std::vector<double> cdfV;
+  std::vector<std::vector<double>> cdfVU;
+  int n = 0;
+  double w = 0;
+  void Create(int n, double w, double (*f)(double, double, void*), void* ctx);
+  void WarpSample(double r0, double r1, double* u, double* v) const;
+};
+double BesselJ1(double x);  // builtin/filter/airy.go:34-72
+struct PixelFilter {         // AiryFilter (airy.go:13-101) / GaussianFilter (gauss.go:13-50)
+  int kind = 0;              // 1 = Airy, 2 = Gaussian
+  float Width = 0, Peak = 0;
+  int Res = 0;
+  FilterSampler sampler;
+  void PreRender();
+};
+
 // core/render.go:18-23
 struct pixelscramble {
   uint64_t lensU, lensV, time, lambda, scramble[2];
@@ -88,6 +106,7 @@ struct Renderer {
   std::vector<std::unique_ptr<ShaderStd>> shaders;
   std::vector<std::unique_ptr<Tri>> tris;
   bool prerendered = false;
+  std::unique_ptr<PixelFilter> filter;  // core.filter (core/core.go:15), set by AddNode for a PixelFilter node
   bool trace_last_level = true;  // false: skip the level-4 mirror ray whose shader returns black (std.go:95)
 
   ShaderStd* findShader(const std::string& name);

@@ -164,3 +164,19 @@ def test_error_paths(built_library):
     dev2.set_scramble(scenes.splitmix64_table(1, 32 * 32))
     with pytest.raises(RuntimeError, match="no weight"):
         dev2.render(0, 1)
+
+
+@pytest.mark.parametrize("ftype,res", [("AiryFilter", None), ("AiryFilter", 48), ("GaussianFilter", None)])
+def test_pixel_filter_image(built_library, ftype, res):
+    """core.PixelFilter: the FIS warp (filter.WarpSample) moves the sample position; device and oracle agree, and the
+    filter visibly changes the image compared with the unfiltered render."""
+    from vermeer_b200 import scenes
+    sc = scenes.heightfield_scene(128, 96, nq=48)
+    sc.filter = scenes.PixelFilter(Type=ftype, Res=res)   # Res None = registered default (Airy 49: reference quirk h, NaN tables)
+    fo, so, fg, st, _ = _render_pair(sc, 8)
+    rmse, ok = _rmse(fo, fg)
+    assert ok.all() and rmse <= 1e-3, rmse
+    assert np.median(np.abs(fo - fg)) <= 1e-6
+    sc2 = scenes.heightfield_scene(128, 96, nq=48)
+    _, _, fg2, _, _ = _render_pair(sc2, 8)
+    assert np.sqrt(((fg - fg2) ** 2).mean()) > 1e-3

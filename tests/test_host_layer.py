@@ -34,7 +34,7 @@ def test_registry_mirrors_nodes_register(built_library):
     arr = (C.c_char_p * n)()
     lib.vh_registered_nodes(arr, n)
     names = sorted(a.decode() for a in arr)
-    assert names == ["Camera", "Globals", "PolyMesh", "ShaderStd", "TriLight"]
+    assert names == ["AiryFilter", "Camera", "GaussianFilter", "Globals", "PolyMesh", "ShaderStd", "TriLight"]
 
 
 def _equal_nodes(a, b):

@@ -48,3 +48,38 @@ def test_sequence_is_a_0_2_net_per_pixel(oracle_lib):
         L.orc_raster_xy(f, 7, 9, 0, 0, C.byref(rx), C.byref(ry))
         cells.add((int((rx.value - 7) * 4), int((ry.value - 9) * 4)))
     assert len(cells) == 16
+
+
+def test_pixel_filter_tables(oracle_lib):
+    """FIS pixel filters (builtin/filter): Bessel J1 against published values, and the warp stays inside the filter support
+    and is monotone in r0 within a CDF bin."""
+    from oracle.binding import Oracle
+    from vermeer_b200 import scenes
+    L = oracle_lib
+    assert abs(L.orc_bessel_j1(1.0) - 0.4400505857449335) < 1e-8
+    assert abs(L.orc_bessel_j1(10.0) - 0.04347274616886144) < 1e-8
+    assert abs(L.orc_bessel_j1(-2.5) + 0.4970941024642741) < 1e-8
+    # Reference quirk (h): the default AiryFilter (Res 49, Width 6) tabulates the point (0,0) exactly, where
+    # 2*J1(v)/v is 0/0 = NaN (airy.go:90-92); the NaN poisons the normalisation and every CDF, so WarpSample never finds a
+    # bin and returns (0,0): all samples land on the pixel centre. An even Res avoids the origin and behaves as intended.
+    sc = scenes.cornell_box(16, 16)
+    sc.filter = scenes.PixelFilter(Type="AiryFilter")
+    o = Oracle(sc)
+    u, v = C.c_double(), C.c_double()
+    for r0, r1 in ((0.1, 0.9), (0.5, 0.5), (0.99, 0.01)):
+        L.orc_filter_warp(o.h, r0, r1, C.byref(u), C.byref(v))
+        assert (u.value, v.value) == (0.0, 0.0)
+    for ftype, w, res in (("AiryFilter", 6.0, 48), ("GaussianFilter", 2.0, None)):
+        sc = scenes.cornell_box(16, 16)
+        sc.filter = scenes.PixelFilter(Type=ftype, Res=res)
+        o = Oracle(sc)
+        u, v = C.c_double(), C.c_double()
+        rng = np.random.default_rng(3)
+        us = []
+        for _ in range(2000):
+            r0, r1 = rng.random(), rng.random()
+            L.orc_filter_warp(o.h, r0, r1, C.byref(u), C.byref(v))
+            hi = w / 2 + w / 15 + 1e-9   # bin i maps to -w/2 + w*(i+du)/(n-1), so the last bin reaches w/2 + w/(n-1)
+            assert -w / 2 - 1e-9 <= u.value <= hi and -w / 2 - 1e-9 <= v.value <= hi
+            us.append(u.value)
+        assert np.std(us) > 0.05 * w   # it actually spreads samples

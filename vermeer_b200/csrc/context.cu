@@ -472,6 +472,23 @@ int vg_set_scramble(vg_ctx* ctx, const uint64_t* table, int64_t npix) {
   return render_set_scramble(ctx, table, npix);
 }
 
+int vg_set_filter(vg_ctx* ctx, int n, double w, const double* cdfV, const double* cdfVU) {
+  VG_LOCK(ctx);
+  if (n == 0) {
+    ctx->filter_n = 0;
+    ctx->filter_cdf.clear();
+    render_invalidate(ctx);
+    return VG_OK;
+  }
+  if (n < 2 || n > 1024 || !(w > 0) || !cdfV || !cdfVU) return ctx->fail(VG_ERR_INVALID, "vg_set_filter: bad input");
+  ctx->filter_n = n;
+  ctx->filter_w = w;
+  ctx->filter_cdf.assign(cdfV, cdfV + n);
+  ctx->filter_cdf.insert(ctx->filter_cdf.end(), cdfVU, cdfVU + (size_t)n * n);
+  render_invalidate(ctx);
+  return VG_OK;
+}
+
 int vg_set_option(vg_ctx* ctx, const char* name, int value) {
   VG_LOCK(ctx);
   if (!name) return ctx->fail(VG_ERR_INVALID, "null option name");

@@ -100,6 +100,9 @@ struct vg_ctx {
   int xres = 0, yres = 0;
   int rank = 0, world = 1;
   std::vector<uint64_t> scramble;  // full frame, npix*6
+  int filter_n = 0;
+  double filter_w = 0;
+  std::vector<double> filter_cdf;  // cdfV[n] then cdfVU[n*n]
   int opt_trace_last_level = 1;
   int opt_iters_per_batch = 4;
   int opt_precise_trig = 0;

@@ -49,6 +49,9 @@ struct RegisterBuiltins {
     Register("PolyMesh", [] { return std::unique_ptr<Node>(new PolyMesh()); });
     Register("ShaderStd", [] { return std::unique_ptr<Node>(new ShaderStd()); });
     Register("TriLight", [] { return std::unique_ptr<Node>(new TriLight()); });
+    // builtin/filter/filter.go:14-26
+    Register("AiryFilter", [] { PixelFilter* f = new PixelFilter(); f->kind = 1; f->Res = 49; f->Width = 6; f->Peak = 4; return std::unique_ptr<Node>(f); });
+    Register("GaussianFilter", [] { PixelFilter* f = new PixelFilter(); f->kind = 2; f->Res = 17; f->Width = 2; f->Peak = 0; return std::unique_ptr<Node>(f); });
   }
 } g_register_builtins;
 }  // namespace
@@ -385,6 +388,74 @@ int TriLight::PreRender(Core& core, std::string* err) {
   return 0;
 }
 
+// ---- pixel filters (builtin/filter) -----------------------------------------------------------------
+namespace {
+double bessel_j1(double x) {  // airy.go:34-72 (Numerical-Recipes rational approximations)
+  const double ax = std::fabs(x);
+  if (ax < 8.0) {
+    const double y = x * x;
+    const double a1 = x * (72362614232.0 + y * (-7895059235.0 + y * (242396853.1 + y * (-2972611.439 + y * (15704.48260 + y * (-30.16036606))))));
+    const double a2 = 144725228442.0 + y * (2300535178.0 + y * (18583304.74 + y * (99447.43394 + y * (376.9991397 + y * 1.0))));
+    return a1 / a2;
+  }
+  const double z = 8.0 / ax, y = z * z, xx = ax - 2.356194491;
+  const double a1 = 1.0 + y * (0.183105e-2 + y * (-0.3516396496e-4 + y * (0.2457520174e-5 + y * (-0.240337019e-6))));
+  const double a2 = 0.04687499995 + y * (-0.2002690873e-3 + y * (0.8449199096e-5 + y * (-0.88228987e-6 + y * 0.105787412e-6)));
+  double ans = std::sqrt(0.636619772 / ax) * (std::cos(xx) * a1 - z * std::sin(xx) * a2);
+  return x < 0.0 ? -ans : ans;
+}
+}  // namespace
+
+int PixelFilter::PreRender(Core&, std::string* err) {
+  const int n = Res;
+  if (n < 2 || n > 1024 || !(Width > 0)) { *err = "PixelFilter " + NodeName + ": bad Res/Width"; return -1; }
+  const double w = (double)Width;
+  auto f = [&](double x, double y) -> double {
+    const double q = std::sqrt(x * x + y * y);
+    if (q > (double)(Width / 2)) return 0;  // cut-off
+    if (kind == 1) {                        // airy.go:76-97
+      const double v = (20000 / (double)Width) * (M_PI * q) / (550.0 * 5.6);
+      const double b = 2 * bessel_j1(v) / v;
+      return (double)Peak * (b * b);
+    }
+    const double sigma = (double)(1.0 / std::sqrt((double)Width));  // gauss.go:33-45
+    return (1 / (2 * M_PI * (sigma * sigma))) * std::exp((double)(-(x * x + y * y) / 2 * (sigma * sigma)));
+  };
+  // filter.go:88-173: tabulate (u outer, v inner, both advanced by repeated addition), normalise, marginal and conditional CDFs
+  std::vector<double> tab((size_t)n * n);
+  const double du = w / (double)(n - 1);
+  double u = -w / 2, F = 0;
+  for (int j = 0; j < n; j++) {
+    double v = -w / 2;
+    for (int i = 0; i < n; i++) {
+      const double fuv = f(u, v);
+      tab[j + (size_t)i * n] = fuv;
+      F += fuv;
+      v += du;
+    }
+    u += du;
+  }
+  std::vector<double> pV(n, 0.0), pdf((size_t)n * n);
+  for (int j = 0; j < n; j++)
+    for (int i = 0; i < n; i++) {
+      pdf[(size_t)j * n + i] = tab[j + (size_t)i * n] / F;
+      pV[j] += pdf[(size_t)j * n + i];
+    }
+  cdfV.assign(n, 0.0);
+  cdfVU.assign((size_t)n * n, 0.0);
+  double p = 0;
+  for (int j = 0; j < n; j++) {
+    p += pV[j];
+    cdfV[j] = p;
+    double q = 0;
+    for (int i = 0; i < n; i++) {
+      q += pdf[(size_t)j * n + i] / pV[j];
+      cdfVU[(size_t)j * n + i] = q;
+    }
+  }
+  return 0;
+}
+
 // ---- Scene (builtin/scene/scene.go:135-268) -------------------------------------------------------
 int Scene::PreRender(std::string* err) {
   const int n = (int)geoms.size();
@@ -464,6 +535,8 @@ void Core::AddNode(std::unique_ptr<Node> node) {
     materials.push_back(sh);
   } else if (Globals* g = dynamic_cast<Globals*>(n)) {
     globals = g;
+  } else if (PixelFilter* pf = dynamic_cast<PixelFilter*>(n)) {
+    filter = pf;
   }
 }
 

@@ -116,6 +116,18 @@ struct Camera : Node {
   int PreRender(Core& core, std::string* err) override;
 };
 
+// builtin/filter: core.PixelFilter nodes. PreRender tabulates the filter and builds the FIS CDF tables
+// (filter.CreateSampler, filter.go:88-173); WarpSample itself runs on the device.
+struct PixelFilter : Node {
+  std::string NodeName;
+  int kind = 1;  // 1 Airy, 2 Gaussian
+  float Width = 6, Peak = 4;
+  int Res = 49;
+  std::vector<double> cdfV, cdfVU;  // n, n*n
+  std::string Name() const override { return NodeName; }
+  int PreRender(Core& core, std::string* err) override;
+};
+
 // builtin/scene/scene.go
 struct Scene {
   std::vector<Geom*> geoms;
@@ -141,6 +153,7 @@ struct Core {
   std::vector<Node*> all;
   std::map<std::string, Node*> nodeMap;
   std::vector<ShaderStd*> materials;
+  PixelFilter* filter = nullptr;  // core.filter (core/core.go:15,89)
   int next_geom_id = 0;
   bool prerendered = false;
   std::string err;

@@ -112,6 +112,19 @@ int vh_add_polymesh(vh_scene* s, const char* name, const float* verts, int n_ver
   return VG_OK;
 }
 
+int vh_add_filter(vh_scene* s, const char* type, const char* name, float width, int res, float peak) {
+  if (!s || !type || !name) return fail(s, VG_ERR_INVALID, "vh_add_filter: null argument");
+  std::unique_ptr<Node> h;
+  PixelFilter* f = make<PixelFilter>(s, type, &h);
+  if (!f) return VG_ERR_INVALID;
+  f->NodeName = name;
+  if (width > 0) f->Width = width;
+  if (res > 0) f->Res = res;
+  if (peak > 0) f->Peak = peak;
+  s->core.AddNode(std::move(h));
+  return VG_OK;
+}
+
 int vh_add_trilight(vh_scene* s, const char* name, const float* p0, const float* p1, const float* p2, const char* shader, int samples) {
   if (!s || !name || !p0 || !p1 || !p2 || !shader) return fail(s, VG_ERR_INVALID, "vh_add_trilight: null argument");
   if (samples < 0 || samples > 8) return fail(s, VG_ERR_INVALID, "TriLight: Samples must be in [0,8]");
@@ -209,6 +222,10 @@ int vh_upload(vh_scene* s, vg_ctx* ctx, int motion_ref_compat) {
     lights.push_back(l);
   }
   if ((rc = chk(vg_set_lights(ctx, lights.data(), (int)lights.size()))) != VG_OK) return rc;
+
+  if (c.filter) rc = vg_set_filter(ctx, c.filter->Res, (double)c.filter->Width, c.filter->cdfV.data(), c.filter->cdfVU.data());
+  else rc = vg_set_filter(ctx, 0, 0.0, nullptr, nullptr);
+  if (chk(rc) != VG_OK) return rc;
 
   // core.Render finds the node named "camera" unless Globals.Camera overrides it (core/render.go:148-164)
   std::string camName = c.globals->Camera.empty() ? "camera" : c.globals->Camera;

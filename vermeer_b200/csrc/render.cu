@@ -59,6 +59,9 @@ struct RenderParams {
   const DevMat* mats;
   const DevLight* lights;
   int nlights, S, levels, trace_last_level;
+  const double* filter_cdf;  // cdfV[n] then cdfVU[n*n], or null
+  int filter_n;
+  double filter_w;
   VgRay* rayq[2];
   int* pathq[2];
   DevHit* hits;
@@ -91,6 +94,41 @@ __global__ void k_next_level(int* counts, int qout) {
   counts[4] = 0;
 }
 
+// filter.Sampler.WarpSample (builtin/filter/filter.go:40-86): linear search of the marginal CDF, then of the conditional
+// one; the first bin's `du / w` is the reference's formula, kept as is.
+__device__ inline void warp_sample(const double* cdfV, const double* cdfVU, int n, double w, double r0, double r1, double* uo, double* vo) {
+  double u = 0, v = 0;
+  int uI = -1;
+  for (int i = 0; i < n; i++) {
+    uI = i;
+    const double c = cdfV[i];
+    if (r0 < c) {
+      if (i == 0) u = (-w / 2) + ((r0 / c) / w);
+      else {
+        const double c1 = cdfV[i - 1];
+        u = (-w / 2) + w * ((double)i + (r0 - c1) / (c - c1)) / (double)(n - 1);
+      }
+      break;
+    }
+  }
+  const double* row = cdfVU + (size_t)uI * n;
+  for (int i = 0; i < n; i++) {
+    const double c = row[i];
+    if (r1 < c) {
+      if (i == 0) v = (-w / 2) + ((r1 / c) / w);
+      else {
+        const double c1 = row[i - 1];
+        v = (-w / 2) + w * ((double)i + (r1 - c1) / (c - c1)) / (double)(n - 1);
+      }
+      *uo = u;
+      *vo = v;
+      return;
+    }
+  }
+  *uo = 0;
+  *vo = 0;
+}
+
 // core/render.go:89-124 + builtin/camera/camera.go:221-323 (differentials omitted)
 __global__ void __launch_bounds__(256) k_raygen(const RenderParams p, int iter_base, int niters) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -106,6 +144,13 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderParams p, int iter_b
   const double lambda = (720 - 450) * vdc((uint64_t)iter, scr[3]) + 450;
   const double lensU = vdc((uint64_t)iter, scr[0]);
   const double lensV = sobol((uint64_t)iter, scr[1]);
+  if (p.filter_cdf) {  // core/render.go:99-107
+    const double fx = floor(rasterX), fy = floor(rasterY);
+    double u, v;
+    warp_sample(p.filter_cdf, p.filter_cdf + p.filter_n, p.filter_n, p.filter_w, rasterX - fx, rasterY - fy, &u, &v);
+    rasterX = fx + 0.5 + u;
+    rasterY = fy + 0.5 + v;
+  }
   const float Sx = (float)(-1.0 + 2.0 * (rasterX / (double)p.xres));
   const float Sy = -(float)(-1.0 + 2.0 * (rasterY / (double)p.yres));
 
@@ -626,6 +671,7 @@ struct RenderState {
   DevBuf<int> pathq0, pathq1, sslot, counts;
   DevBuf<DevHit> hits;
   DevBuf<float> lambda, time, invtot, fb;
+  DevBuf<double> filter;
   DevBuf<uint8_t> vmat;
   DevBuf<float4> contrib, L, T;
   DevBuf<unsigned long long> stats;
@@ -649,7 +695,7 @@ struct RenderState {
   void release() {
     pix.release(); scr.release(); mats.release(); lights.release(); rayq0.release(); rayq1.release(); sray.release();
     pathq0.release(); pathq1.release(); sslot.release(); counts.release(); hits.release(); lambda.release(); time.release();
-    invtot.release(); vmat.release(); contrib.release(); L.release(); T.release(); stats.release();
+    invtot.release(); vmat.release(); filter.release(); contrib.release(); L.release(); T.release(); stats.release();
   }
 };
 
@@ -829,6 +875,10 @@ static int prepare(vg_ctx* ctx) {
   rs.P = rs.nown * rs.iters;
   const size_t P = (size_t)rs.P;
 
+  if (ctx->filter_n > 0) {
+    RCUDA(rs.filter.reserve(ctx->filter_cdf.size()));
+    RCUDA(cudaMemcpyAsync(rs.filter.p, ctx->filter_cdf.data(), ctx->filter_cdf.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
   RCUDA(rs.pix.reserve(pix.size()));
   RCUDA(rs.scr.reserve((size_t)rs.nown * 6));
   RCUDA(rs.mats.reserve(mats.size()));
@@ -895,6 +945,7 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
   p.sc = ctx->dev;
   p.xres = ctx->xres; p.yres = ctx->yres; p.nown = rs.nown; p.P = rs.P;
   p.pix = rs.pix.p; p.scr = rs.scr.p; p.cam = ctx->camera; p.mats = rs.mats.p; p.lights = rs.lights.p;
+  p.filter_cdf = ctx->filter_n > 0 ? rs.filter.p : nullptr; p.filter_n = ctx->filter_n; p.filter_w = ctx->filter_w;
   p.nlights = rs.nlights; p.S = rs.S; p.levels = rs.levels; p.trace_last_level = ctx->opt_trace_last_level;
   p.rayq[0] = rs.rayq0.p; p.rayq[1] = rs.rayq1.p; p.pathq[0] = rs.pathq0.p; p.pathq[1] = rs.pathq1.p;
   p.hits = rs.hits.p; p.lambda = rs.lambda.p; p.time = rs.time.p; p.v_mat = rs.vmat.p; p.v_invtot = rs.invtot.p;

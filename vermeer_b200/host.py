@@ -29,10 +29,10 @@ VG_TRACE_ANY_HIT = 1
 DECLARED_SYMBOLS = [
     "vg_create", "vg_destroy", "vg_last_error", "vg_device_count", "vg_scene_begin", "vg_mesh_upload", "vg_mesh_upload_motion",
     "vg_scene_upload", "vg_scene_upload_motion", "vg_scene_commit", "vg_set_materials", "vg_set_lights", "vg_set_camera", "vg_set_frame",
-    "vg_set_partition", "vg_set_scramble", "vg_set_option", "vg_trace_batch", "vg_trace_batch_device", "vg_render", "vg_clear_framebuffer",
+    "vg_set_partition", "vg_set_scramble", "vg_set_filter", "vg_set_option", "vg_trace_batch", "vg_trace_batch_device", "vg_render", "vg_clear_framebuffer",
     "vg_framebuffer_device", "vg_get_stats", "vg_reset_stats",
     "vh_scene_create", "vh_scene_destroy", "vh_last_error", "vh_registered_nodes", "vh_set_globals", "vh_add_shader_std", "vh_add_polymesh",
-    "vh_add_trilight", "vh_set_camera_lookat", "vh_prerender", "vh_upload", "vh_num_geoms", "vh_scene_info", "vh_scene_nodes",
+    "vh_add_filter", "vh_add_trilight", "vh_set_camera_lookat", "vh_prerender", "vh_upload", "vh_num_geoms", "vh_scene_info", "vh_scene_nodes",
     "vh_scene_motion_nodes", "vh_scene_geom_order", "vh_mesh_info", "vh_mesh_nodes", "vh_mesh_motion_nodes", "vh_mesh_idxp", "vh_camera",
 ]
 
@@ -128,6 +128,9 @@ class HostScene:
                 C.c_float(m.RayBias)))
         for l in scene.lights:
             self._chk(L.vh_add_trilight(h, l.Name.encode(), _f3(l.P0), _f3(l.P1), _f3(l.P2), l.Shader.encode(), l.Samples))
+        if scene.filter is not None:
+            f = scene.filter
+            self._chk(L.vh_add_filter(h, f.Type.encode(), f.Name.encode(), C.c_float(f.Width or 0), int(f.Res or 0), C.c_float(f.Peak or 0)))
         c = scene.camera
         self._chk(L.vh_set_camera_lookat(h, _f3(c.From), _f3(c.To), _f3(c.Up), C.c_float(c.Roll), C.c_float(c.Fov), C.c_float(c.Focal),
                                          C.c_float(c.Aspect), C.c_float(c.Radius)))

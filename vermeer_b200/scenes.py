@@ -23,7 +23,7 @@ from typing import List, Optional
 import numpy as np
 
 __all__ = [
-    "ShaderStd", "PolyMesh", "TriLight", "Camera", "SceneDesc", "splitmix64_table",
+    "ShaderStd", "PolyMesh", "TriLight", "Camera", "PixelFilter", "SceneDesc", "splitmix64_table",
     "heightfield_mesh", "heightfield_scene", "sphere_field_scene", "cornell_box", "incoherent_rays",
 ]
 
@@ -113,6 +113,16 @@ class Camera:
 
 
 @dataclass
+class PixelFilter:
+    """AiryFilter / GaussianFilter node (builtin/filter/airy.go:13-22, gauss.go:13-21). None = the registered default."""
+    Type: str = "AiryFilter"
+    Name: str = "filter"
+    Width: Optional[float] = None
+    Res: Optional[int] = None
+    Peak: Optional[float] = None
+
+
+@dataclass
 class SceneDesc:
     XRes: int
     YRes: int
@@ -122,6 +132,7 @@ class SceneDesc:
     lights: List[TriLight] = field(default_factory=list)
     MaxIter: int = 16
     name: str = "scene"
+    filter: Optional[PixelFilter] = None
 
     @property
     def num_tris(self) -> int:
