@@ -33,8 +33,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "C2: 1M-triangle heightfield (1002528 tris), primary+shadow rays, 1920x1080, 64 spp"
-XRES, YRES, SPP, NQ = 1920, 1080, 64, 708
+CONFIGS = {
+    # BASELINE.json configs[1] — the headline (default)
+    "c2": dict(workload="C2: 1M-triangle heightfield (1002528 tris), primary+shadow rays, 1920x1080, 64 spp", spp=64),
+    # configs[2]: 10M-triangle displaced-sphere field, mirror chains Level 0..3 (the reference's "4 bounces"), 256 spp
+    "c3": dict(workload="C3: 10M-triangle displaced-sphere field (1024 meshes x 9800 tris), mirror chains, 1920x1080, 256 spp", spp=256),
+    # configs[3]: motion-blurred mesh (MQBVH, 2 keys)
+    "c4": dict(workload="C4: motion-blurred 1M-triangle heightfield (MQBVH, 2 keys), 1920x1080, 64 spp", spp=64),
+}
+CONFIG = os.environ.get("VG_BENCH_CONFIG", "c2")
+WORKLOAD = CONFIGS[CONFIG]["workload"]
+XRES, YRES, SPP, NQ = 1920, 1080, CONFIGS[CONFIG]["spp"], 708
 SCRAMBLE_SEED = 1
 ITERS_PER_BATCH = 8
 
@@ -95,7 +104,9 @@ class ClockSampler:
 
 def build_scene():
     from vermeer_b200 import scenes
-    return scenes.heightfield_scene(XRES, YRES, nq=NQ)
+    if CONFIG == "c3":
+        return scenes.sphere_field_scene(XRES, YRES)
+    return scenes.heightfield_scene(XRES, YRES, nq=NQ, motion=(CONFIG == "c4"))
 
 
 def cpu_reference_run(scene, table, iters, nthreads):
@@ -140,6 +151,59 @@ def run_reference(args):
         "samples_per_s": XRES * YRES * sample_iters * args.steps / secs,
     }
     print(json.dumps(out))
+
+
+def incoherent_leg(dev, host, scene, torch, cpu_cores):
+    """Mrays/s of closest-hit traversal alone on an incoherent batch: level-1 cosine-hemisphere rays from the primary hit points
+    of the C2 scene, identical rays on both sides. GPU: rays resident in HBM (vg_trace_batch_device) and through host buffers
+    (vg_trace_batch). CPU: the oracle's qbvh.Trace restatement on all host threads, bounded sample of the same batch."""
+    from vermeer_b200 import scenes
+    from vermeer_b200.host import HIT_DTYPE, RAY_DTYPE
+    cam_m, ttf, asp = host.camera()
+    ys, xs = np.meshgrid(np.arange(YRES), np.arange(XRES), indexing="ij")
+    sx = (-1 + 2 * (xs + 0.5) / XRES).astype(np.float32)
+    sy = -(-1 + 2 * (ys + 0.5) / YRES).astype(np.float32)
+    M = cam_m.reshape(4, 4).T
+    d = np.stack([sx * ttf, sy * (ttf / asp), -np.full_like(sx, scene.camera.Focal)], -1).reshape(-1, 3) @ M[:3, :3].T
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    prim = np.zeros(XRES * YRES, RAY_DTYPE)
+    prim["o"] = M[:3, 3]
+    prim["d"] = d.astype(np.float32)
+    prim["tmax"] = np.inf
+    hits = dev.trace(prim)
+    inc = scenes.incoherent_rays(prim, hits, seed=5)
+    inc = inc[np.random.default_rng(1).permutation(len(inc))]      # shuffled: no residual image-space coherence
+    n = len(inc)
+    d_r = torch.from_numpy(inc.view(np.uint8).reshape(n, 32)).cuda()
+    d_h = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
+    best = 1e30
+    for i in range(8):
+        dev.reset_stats()
+        dev.trace_device(d_r.data_ptr(), n, d_h.data_ptr(), False)
+        st = dev.stats()
+        if i >= 3:
+            best = min(best, st["trace_ms"])
+    out_hits = np.empty(n, HIT_DTYPE)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        dev.trace(inc, out=out_hits)
+    e2e_ms = (time.perf_counter() - t0) / 3 * 1e3
+    res = {"rays": n, "value": n / best / 1e3, "unit": "Mrays/s", "e2e": n / e2e_ms / 1e3, "hit_fraction": float((out_hits["prim"] >= 0).mean()),
+           "nodesT_per_ray": st["nodes_t"] / n, "trisT_per_ray": st["tris_t"] / n,
+           "alg_gbs": (64.0 * n + 128.0 * st["nodes_t"] + 48.0 * st["tris_t"]) / best / 1e6}
+    if cpu_cores:
+        from oracle.binding import Oracle
+        ora = Oracle(scene)
+        sample = inc[: min(n, 1 << 20)]
+        ora.trace(sample[:65536], nthreads=cpu_cores)
+        t0 = time.perf_counter()
+        oh = ora.trace(sample, nthreads=cpu_cores)
+        secs = time.perf_counter() - t0
+        same = bool(np.array_equal(oh["prim"], out_hits["prim"][: len(sample)]) and
+                    np.array_equal(oh["t"].view(np.uint32), out_hits["t"][: len(sample)].view(np.uint32)))
+        res["cpu"] = {"value": len(sample) / secs / 1e6, "cores": cpu_cores, "kind": "port", "sample": "%d of the same rays" % len(sample),
+                      "bit_identical_to_gpu": same}
+    return res
 
 
 def run_ours(args):
@@ -262,16 +326,19 @@ def run_ours(args):
     # ---- roofline of the dominant kernel -------------------------------------------------------------
     peaks, peak_src = measured_peaks()
     closest_rays = rays_rank - st["shadow_rays"]
-    alg_bytes_closest = 64.0 * closest_rays + 128.0 * st["nodes_t"] + 48.0 * st["tris_t"]
+    # static 64 + 128*NodesT + 48*TrisT; motion 64 + 232*NodesT + 84*TrisT
+    bn, bt = (232.0, 84.0) if CONFIG == "c4" else (128.0, 48.0)
+    alg_bytes_closest = 64.0 * closest_rays + bn * st["nodes_t"] + bt * st["tris_t"]
     launches = max(1, st["closest_launches"])
     achieved = alg_bytes_closest / (closest_ms * 1e-3) / 1e9 if closest_ms > 0 else 0.0
     roofline = {
-        "bound": "hbm", "kernel": "k_trace_queue<0> (closest-hit QBVH traversal)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        "bound": "hbm", "kernel": "k_trace_queue<0> (closest-hit %s traversal)" % ("MQBVH" if CONFIG == "c4" else "QBVH"), "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
         "bytes_per_launch": alg_bytes_closest / launches, "ms_per_launch": closest_ms / launches,
         "rays_per_launch": closest_rays / launches, "nodesT_per_ray": st["nodes_t"] / max(1, closest_rays), "trisT_per_ray": st["tris_t"] / max(1, closest_rays),
         "share_of_step": closest_ms / dev_ms if dev_ms > 0 else None,
-        "note": "1M-triangle scene (6 MB nodes + 48 MB triangles) is L2-resident: the bytes model is algorithmic, not DRAM traffic",
+        "note": ("10M-triangle scene (0.55 GB) exceeds L2: HBM-bound model" if CONFIG == "c3" else
+                 "1M-triangle scene (6 MB nodes + 48 MB triangles) is L2-resident: the bytes model is algorithmic, not DRAM traffic"),
     }
 
     # ---- CPU baseline: the oracle on a bounded sample (rank 0, N=1 only) ------------------------------
@@ -283,6 +350,11 @@ def run_ours(args):
         v, rays, secs = cpu_reference_run(scene, table, iters, cores) if iters > 1 else (v1, rays1, secs1)
         cpu = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
                "sample": "%d iteration(s) (spp) of the same 1920x1080 workload, all %d host threads: %d rays in %.2f s" % (iters, cores, rays, secs)}
+
+    # ---- closest-hit, incoherent micro-config: cosine-hemisphere bounce rays from the primary hit points -----
+    incoherent = None
+    if world == 1 and CONFIG == "c2":
+        incoherent = incoherent_leg(dev, host, scene, torch, cpu_cores=(os.cpu_count() or 1) if not args.no_cpu else 0)
 
     value = rays_total / (dev_ms_max * 1e-3) / 1e6
     out = {
@@ -301,6 +373,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "incoherent_closest_hit": incoherent,
         "host_prerender_s": t_build,
     }
     print(json.dumps(out))
@@ -315,6 +388,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    # other BASELINE.json configs (c3, c4) are selected with VG_BENCH_CONFIG; the driver's contract runs the default (c2)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
