@@ -248,16 +248,20 @@ def run_ours(args):
     def step_e2e():
         dev.set_scramble(table)       # H2D of this rank's rows of the scramble table, from the caller's host buffer
         dev.clear()
-        return dev.render(0, SPP, fetch=True)  # D2H of the framebuffer into a host buffer
+        # N=1: D2H of the framebuffer into a host buffer. N>1: the frame is gathered on the device first (below) and
+        # rank 0 alone copies the complete frame to the host.
+        return dev.render(0, SPP, fetch=(world == 1))
 
+    # clocks / throttle reasons are sampled from the warm-up through the timed region (a timed region of a few x 10 ms is
+    # shorter than nvidia-smi's sampling period)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_resident()
 
     # ---- timed: K steps, inputs resident in HBM -----------------------------------------------------
-    sampler = ClockSampler(local_rank)
     dev.reset_stats()
     barrier()
-    sampler.start()
     t0 = time.perf_counter()
     dev_ms = 0.0
     closest_ms = shadow_ms = 0.0
@@ -291,6 +295,7 @@ def run_ours(args):
     fb_t = torch.as_tensor(_Ext(fb_ptr, XRES * YRES * 3), device="cuda")
     from vermeer_b200.multigpu import FrameGather
     gather = FrameGather(XRES, YRES, rank, world, torch.device("cuda", local_rank)) if world > 1 else None
+    host_fb = torch.empty((YRES, XRES, 3), dtype=torch.float32, pin_memory=True) if (world > 1 and rank == 0) else None
     for _ in range(2):           # warm-up of the e2e leg, including NCCL's lazy communicator set-up for the all-gather
         step_e2e()
         if gather is not None:
@@ -304,6 +309,8 @@ def run_ours(args):
         if gather is not None:
             # the one exchange of the frame: NCCL all-gather of each rank's owned pixels over NVLink, then a scatter
             full = gather.gather(fb_t)
+            if rank == 0:
+                host_fb.copy_(full, non_blocking=True)   # D2H of the complete frame into pinned host memory
             torch.cuda.synchronize()
     barrier()
     e2e_wall = time.perf_counter() - t0
