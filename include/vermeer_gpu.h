@@ -179,8 +179,10 @@ int vg_set_scramble(vg_ctx* ctx, const uint64_t* table, int64_t npix);
 int vg_set_filter(vg_ctx* ctx, int n, double w, const double* cdfV, const double* cdfVU);
 /* Options: "trace_last_level" (1 = trace the level-4 mirror ray like the reference, std.go:243; default 1),
  * "iters_per_batch" (wavefront batch depth, default 4), "precise_trig" (1 = shading trig through float64 exactly like
- * math/sincos.go; 0 = single-precision libm, default; both are within the image tolerance), "tma_stage" (1 = traversal kernels
- * stage their ray queue into shared memory with cp.async.bulk + mbarrier; 0 = coalesced LDG refill, default, measured faster). */
+ * math/sincos.go; 0 = single-precision libm, default; both are within the image tolerance), "traversal" (persistent-kernel variant:
+ * 2 = warp-cooperative leaf phase, default; 0 = per-lane while-while loop with coalesced LDG refill; 1 = the per-lane loop with
+ * its ray queue staged into shared memory by cp.async.bulk + mbarrier; all three are bit-identical), "tma_stage" (1 = alias of
+ * traversal 1, 0 = default). */
 int vg_set_option(vg_ctx* ctx, const char* name, int value);
 
 /* TraceProbe over a batch (core/trace.go:26). flags: */

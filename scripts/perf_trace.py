@@ -12,6 +12,7 @@ W, H = 1920, 1080
 sc = scenes.heightfield_scene(W, H, nq=nq)
 t = time.time(); host = HostScene(sc).prerender(); print("prerender %.2fs" % (time.time() - t))
 dev = Device(0).upload(host)
+if os.environ.get("VG_TRAVERSAL"): dev.set_option("traversal", int(os.environ["VG_TRAVERSAL"]))
 cam_m, ttf, asp = host.camera()
 
 # primary rays: pinhole through pixel centres (host numpy; not the QMC sampler)

@@ -116,16 +116,23 @@ def test_empty_and_ragged_batches(built_library):
         assert_hits_equal(dev.trace(rays), ora.trace(rays), what="n=%d" % n)
 
 
-def test_tma_staged_queue_variant(built_library):
-    """The cp.async.bulk (TMA) staged ray-queue variant of the persistent kernels gives the same bits as the default."""
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_traversal_variants(built_library, variant):
+    """The three persistent-kernel variants (0 per-lane while-while, 1 the same over the cp.async.bulk/TMA-staged ray queue,
+    2 warp-cooperative leaves = default) give the same bits as the oracle, counters included."""
     from vermeer_b200 import scenes
     sc = scenes.heightfield_scene(128, 72, nq=64)
     ora, dev = _pair(sc)
-    dev.set_option("tma_stage", 1)
+    dev.set_option("traversal", variant)
     for n in (1, 33, 1000, 50001):
         rays = random_rays(n, n, lo=(-1, 0.2, -1), hi=(1, 1.2, 1))
         rays["d"][:, 1] = -np.abs(rays["d"][:, 1])
-        assert_hits_equal(dev.trace(rays), ora.trace(rays), what="tma n=%d" % n)
+        assert_hits_equal(dev.trace(rays), ora.trace(rays), what="variant %d n=%d" % (variant, n))
         sh = rays.copy()
         sh["tmax"] = 0.6
-        assert_hits_equal(dev.trace(sh, any_hit=True), ora.trace(sh, any_hit=True), what="tma any-hit n=%d" % n)
+        assert_hits_equal(dev.trace(sh, any_hit=True), ora.trace(sh, any_hit=True), what="variant %d any-hit n=%d" % (variant, n))
+    sc = scenes.sphere_field_scene(64, 64, nmesh=25, slices=16, stacks=17)
+    ora, dev = _pair(sc)
+    dev.set_option("traversal", variant)
+    rays = random_rays(30000, 3, lo=(-1.1, 0.0, -1.1), hi=(1.1, 1.5, 1.1))
+    assert_hits_equal(dev.trace(rays), ora.trace(rays), what="variant %d sphere field" % variant)

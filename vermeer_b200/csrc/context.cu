@@ -494,7 +494,11 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
   if (!name) return ctx->fail(VG_ERR_INVALID, "null option name");
   if (!std::strcmp(name, "trace_last_level")) ctx->opt_trace_last_level = value != 0;
   else if (!std::strcmp(name, "precise_trig")) ctx->opt_precise_trig = value != 0;
-  else if (!std::strcmp(name, "tma_stage")) ctx->opt_tma_stage = value != 0;
+  else if (!std::strcmp(name, "tma_stage")) ctx->opt_traversal = value != 0 ? 1 : 2;
+  else if (!std::strcmp(name, "traversal")) {
+    if (value < 0 || value > 2) return ctx->fail(VG_ERR_INVALID, "traversal must be 0 (per-lane), 1 (TMA-staged queue) or 2 (cooperative leaves)");
+    ctx->opt_traversal = value;
+  }
   else if (!std::strcmp(name, "iters_per_batch")) {
     if (value < 1 || value > 64) return ctx->fail(VG_ERR_INVALID, "iters_per_batch must be in [1,64]");
     ctx->opt_iters_per_batch = value;
@@ -513,7 +517,7 @@ static int trace_device_locked(vg_ctx* ctx, const VgRay* d_rays, int64_t n, VgHi
   long long grid = (long long)ctx->sm_count * blocks_per_sm;
   if (grid > want) grid = want;
   VG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  VG_CUDA(ctx, launch_trace_batch(ctx->dev, d_rays, d_hits, n, (flags & VG_TRACE_ANY_HIT) != 0, ctx->opt_tma_stage != 0, ctx->d_counters.p, ctx->d_counters.p + 1, (int)grid, ctx->stream));
+  VG_CUDA(ctx, launch_trace_batch(ctx->dev, d_rays, d_hits, n, (flags & VG_TRACE_ANY_HIT) != 0, ctx->opt_traversal, ctx->d_counters.p, ctx->d_counters.p + 1, (int)grid, ctx->stream));
   VG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   float ms = 0;

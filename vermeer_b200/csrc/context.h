@@ -106,7 +106,7 @@ struct vg_ctx {
   int opt_trace_last_level = 1;
   int opt_iters_per_batch = 4;
   int opt_precise_trig = 0;
-  int opt_tma_stage = 0;  // 1: ray queues staged into shared memory by cp.async.bulk (measured slower; see traverse.cuh)
+  int opt_traversal = 2;  // 0: per-lane while-while, 1: the same over a TMA-staged ray queue, 2: warp-cooperative leaves (traverse.cuh)
 
   vg::RenderState* rs = nullptr;
   VgStats stats{};

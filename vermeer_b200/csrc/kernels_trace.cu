@@ -33,23 +33,20 @@ struct BatchIO {
   }
 };
 
-template <bool ANY_HIT, bool TMA>
+template <bool ANY_HIT, int VARIANT>
 __global__ void __launch_bounds__(kTraceBlock, VG_TRACE_MIN_BLOCKS) k_trace_batch(const DevScene sc, const VgRay* __restrict__ rays, VgHit* __restrict__ hits,
                                                              long long n, unsigned long long* __restrict__ counter,
                                                              unsigned long long* __restrict__ stats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: [warps x (2 x 1 KB ray slots)] [warps x 2 mbarriers] [threads x VG_SMEM_STACK stack entries]
+  // layout: [warps x kWarpSmemBytes (TMA ray slots + mbarriers, or cooperative-leaf blocks)] [threads x VG_SMEM_STACK stack entries]
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
-  WarpStage ws;
-  ws.buf = reinterpret_cast<float4*>(smem_raw) + warp * 128;
-  ws.bar = reinterpret_cast<unsigned long long*>(smem_raw + nwarps * 2048) + warp * 2;
   Stack st;
-  st.smem = reinterpret_cast<uint2*>(smem_raw + nwarps * (2048 + 16)) + threadIdx.x;
+  st.smem = reinterpret_cast<uint2*>(smem_raw + nwarps * kWarpSmemBytes) + threadIdx.x;
   st.stride = blockDim.x;
   const int lane = threadIdx.x & 31;
   unsigned long long nodes_acc = 0, tris_acc = 0;
   BatchIO io{rays, hits, n, counter};
-  trace_persistent<ANY_HIT, TMA>(sc, io, st, ws, nodes_acc, tris_acc);
+  trace_persistent<ANY_HIT, VARIANT>(sc, io, st, smem_raw + warp * kWarpSmemBytes, nodes_acc, tris_acc);
   // warp-aggregated statistics (core/stats.go keeps global atomics per ray; one atomic per warp here)
   for (int o = 16; o > 0; o >>= 1) {
     nodes_acc += __shfl_down_sync(0xffffffffu, nodes_acc, o);
@@ -61,22 +58,29 @@ __global__ void __launch_bounds__(kTraceBlock, VG_TRACE_MIN_BLOCKS) k_trace_batc
   }
 }
 
-cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d_hits, long long n, bool any_hit, bool tma,
+cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d_hits, long long n, bool any_hit, int variant,
                                unsigned long long* d_counter, unsigned long long* d_stats, int grid, cudaStream_t stream) {
   const size_t smem = trace_smem_bytes();
   cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
-  if (any_hit && tma) k_trace_batch<true, true><<<grid, kTraceBlock, smem, stream>>>(sc, d_rays, d_hits, n, d_counter, d_stats);
-  else if (any_hit) k_trace_batch<true, false><<<grid, kTraceBlock, smem, stream>>>(sc, d_rays, d_hits, n, d_counter, d_stats);
-  else if (tma) k_trace_batch<false, true><<<grid, kTraceBlock, smem, stream>>>(sc, d_rays, d_hits, n, d_counter, d_stats);
-  else k_trace_batch<false, false><<<grid, kTraceBlock, smem, stream>>>(sc, d_rays, d_hits, n, d_counter, d_stats);
+#define VG_LAUNCH(A, V) k_trace_batch<A, V><<<grid, kTraceBlock, smem, stream>>>(sc, d_rays, d_hits, n, d_counter, d_stats)
+  if (any_hit) {
+    if (variant == 1) VG_LAUNCH(true, 1);
+    else if (variant == 2) VG_LAUNCH(true, 2);
+    else VG_LAUNCH(true, 0);
+  } else {
+    if (variant == 1) VG_LAUNCH(false, 1);
+    else if (variant == 2) VG_LAUNCH(false, 2);
+    else VG_LAUNCH(false, 0);
+  }
+#undef VG_LAUNCH
   return cudaGetLastError();
 }
 
 int trace_batch_blocks_per_sm() {
   int nb = 0;
   const size_t smem = trace_smem_bytes();
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_batch<false, false>, kTraceBlock, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_batch<false, 2>, kTraceBlock, smem);
   return nb > 0 ? nb : 1;
 }
 

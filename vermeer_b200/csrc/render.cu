@@ -209,22 +209,19 @@ struct QueueIO {
   }
 };
 
-template <int MODE, bool TMA>
+template <int MODE, int VARIANT>
 __global__ void __launch_bounds__(kTraceBlock, VG_TRACE_MIN_BLOCKS) k_trace_queue(const RenderParams p, int q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: [warps x (2 x 1 KB ray slots)] [warps x 2 mbarriers] [threads x VG_SMEM_STACK stack entries]
+  // layout: [warps x kWarpSmemBytes scratch] [threads x VG_SMEM_STACK stack entries]
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
-  WarpStage ws;
-  ws.buf = reinterpret_cast<float4*>(smem_raw) + warp * 128;
-  ws.bar = reinterpret_cast<unsigned long long*>(smem_raw + nwarps * 2048) + warp * 2;
   Stack st;
-  st.smem = reinterpret_cast<uint2*>(smem_raw + nwarps * (2048 + 16)) + threadIdx.x;
+  st.smem = reinterpret_cast<uint2*>(smem_raw + nwarps * kWarpSmemBytes) + threadIdx.x;
   st.stride = blockDim.x;
   const int lane = threadIdx.x & 31;
   const int n = MODE == 0 ? p.counts[q] : p.counts[2];
   unsigned long long nodes_acc = 0, tris_acc = 0;
   QueueIO<MODE> io{p, MODE == 0 ? p.rayq[q] : p.sray, n, p.counts + (MODE == 0 ? 3 : 4)};
-  trace_persistent<MODE == 1, TMA>(p.sc, io, st, ws, nodes_acc, tris_acc);
+  trace_persistent<MODE == 1, VARIANT>(p.sc, io, st, smem_raw + warp * kWarpSmemBytes, nodes_acc, tris_acc);
   for (int o = 16; o > 0; o >>= 1) {
     nodes_acc += __shfl_down_sync(0xffffffffu, nodes_acc, o);
     tris_acc += __shfl_down_sync(0xffffffffu, tris_acc, o);
@@ -900,7 +897,7 @@ static int prepare(vg_ctx* ctx) {
 
   int nb = 0;
   const size_t smem = trace_smem_bytes();
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_queue<0, false>, kTraceBlock, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_queue<0, 2>, kTraceBlock, smem);
   rs.trace_grid = ctx->sm_count * std::max(1, nb);
   rs.ready = true;
   return upload_scramble(ctx, ctx->scramble.data());
@@ -953,6 +950,7 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
   p.counts = rs.counts.p; p.stats = rs.stats.p; p.fb = rs.fb.p;
 
   const size_t smem = trace_smem_bytes();
+  const int variant = ctx->opt_traversal;
   uint64_t launches = 0;
   size_t nev = 0;
   std::vector<int> kinds;
@@ -975,8 +973,9 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
       for (int level = 0; level < nlev; level++) {
         const int qout = 1 - qin;
         cudaEventRecord(rs.ev(nev++), st);
-        if (ctx->opt_tma_stage) k_trace_queue<0, true><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
-        else k_trace_queue<0, false><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
+        if (variant == 1) k_trace_queue<0, 1><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
+        else if (variant == 2) k_trace_queue<0, 2><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
+        else k_trace_queue<0, 0><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
         cudaEventRecord(rs.ev(nev++), st);
         kinds.push_back(0);
         launches++;
@@ -984,8 +983,9 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
           if (ctx->opt_precise_trig) k_shade<false><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
           else k_shade<true><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
           cudaEventRecord(rs.ev(nev++), st);
-          if (ctx->opt_tma_stage) k_trace_queue<1, true><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
-          else k_trace_queue<1, false><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
+          if (variant == 1) k_trace_queue<1, 1><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
+          else if (variant == 2) k_trace_queue<1, 2><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
+          else k_trace_queue<1, 0><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
           cudaEventRecord(rs.ev(nev++), st);
           kinds.push_back(1);
           k_resolve<<<(np + 255) / 256, 256, 0, st>>>(p, level, qin);

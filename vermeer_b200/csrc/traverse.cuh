@@ -617,11 +617,274 @@ __device__ __forceinline__ void trace_persistent_ldg(const DevScene& sc, IO& io,
   }
 }
 
-template <bool ANY_HIT, bool TMA, class IO>
-__device__ __forceinline__ void trace_persistent(const DevScene& sc, IO& io, Stack& st, WarpStage ws, unsigned long long& nodes_acc,
+// ---- Warp-cooperative leaves ------------------------------------------------------------------------------------
+// The per-lane while-while loop above leaves most of a warp idle on incoherent rays: lanes sit at leaves of 1..16
+// triangles while others still walk nodes, and inside the leaf phase every lane runs its own trip count (measured
+// 8-15 of 32 lanes active per instruction). Here the node phase stays per lane, but the leaf phase is flattened:
+// all (ray, triangle) pairs pending in the warp are enumerated with a warp prefix sum and tested 32 at a time by ALL
+// lanes (also those that hold no leaf), reading consecutive 48-B triangle records. A lane that needs the node phase
+// is therefore never idle during the leaf phase, and the node phase can stop as soon as fewer than VG_NODE_MIN lanes
+// still want it.
+//
+// Exactness (polymesh/trace.go:116-194 is a sequential loop over the leaf): everything up to the sign/det/bias tests is
+// independent of Tclosest; the only dependent test is `T^sign > Tclosest*|det|`. Since Tclosest only shrinks inside the
+// loop and rounding is monotone, a triangle rejected against the leaf-entry Tclosest is rejected in the sequential
+// loop too. So the parallel pass tests against the entry value and yields "candidates"; the owner lane then replays
+// its candidates in triangle order against its live Tclosest (one shuffle round per candidate, almost always <= 1 per
+// leaf), which reproduces the sequential accept/reject decisions and the final (T,U,V,W,idx) bit for bit.
+#ifndef VG_NODE_MIN
+#define VG_NODE_MIN 8
+#endif
+#ifndef VG_REFILL_IDLE
+#define VG_REFILL_IDLE 8
+#endif
+static const int kCoopBytesPerWarp = 32 * 48;  // 32 ray-parameter blocks of 3 float4
+
+struct TriCand {
+  float fU, fV, fW, det, T;
+};
+
+// Tclosest-independent part of the watertight test + the entry-Tclosest cull. Returns "candidate".
+template <bool MOTION, int KZ>
+__device__ __forceinline__ bool tri_candidate(float pkx, float pky, float pkz, float s0, float s1, float s2, uint32_t xsign, int kzr, float tcl,
+                                              float3 p0, float3 p1, float3 p2, float bias, TriCand& o) {
+  const int kz = KZ < 0 ? kzr : KZ;
+  const int kx = KZ < 0 ? (kzr == 2 ? 0 : kzr + 1) : (KZ + 1) % 3;
+  const int ky = KZ < 0 ? (kx == 2 ? 0 : kx + 1) : (KZ + 2) % 3;
+  const float AKz = pick<KZ>(p0.x, p0.y, p0.z, kz) - pkz;
+  const float BKz = pick<KZ>(p1.x, p1.y, p1.z, kz) - pkz;
+  const float CKz = pick<KZ>(p2.x, p2.y, p2.z, kz) - pkz;
+  const float Cx = __uint_as_float(__float_as_uint((pick<KZ>(p2.x, p2.y, p2.z, kx) - pkx) - s0 * CKz) ^ xsign);
+  const float By = (pick<KZ>(p1.x, p1.y, p1.z, ky) - pky) - s1 * BKz;
+  const float Cy = (pick<KZ>(p2.x, p2.y, p2.z, ky) - pky) - s1 * CKz;
+  const float Bx = __uint_as_float(__float_as_uint((pick<KZ>(p1.x, p1.y, p1.z, kx) - pkx) - s0 * BKz) ^ xsign);
+  const float Ax = __uint_as_float(__float_as_uint((pick<KZ>(p0.x, p0.y, p0.z, kx) - pkx) - s0 * AKz) ^ xsign);
+  const float Ay = (pick<KZ>(p0.x, p0.y, p0.z, ky) - pky) - s1 * AKz;
+  float fU = Cx * By - Cy * Bx;
+  float fV = Ax * Cy - Ay * Cx;
+  float fW = Bx * Ay - By * Ax;
+  if (fU == 0.0f || fV == 0.0f || fW == 0.0f) {
+    double CxBy = (double)Cx * (double)By;
+    double CyBx = (double)Cy * (double)Bx;
+    fU = (float)(CxBy - CyBx);
+    double AxCy = (double)Ax * (double)Cy;
+    double AyCx = (double)Ay * (double)Cx;
+    fV = (float)(AxCy - AyCx);
+    double BxAy = (double)Bx * (double)Ay;
+    double ByAx = (double)By * (double)Ax;
+    fW = (float)(BxAy - ByAx);
+  }
+  if ((fU < 0.0f || fV < 0.0f || fW < 0.0f) && (fU > 0.0f || fV > 0.0f || fW > 0.0f)) return false;
+  const float det = fU + fV + fW;
+  if (det == 0.0f) return false;
+  const float T = s2 * (fU * AKz + fV * BKz + fW * CKz);
+  const uint32_t sgn = __float_as_uint(det) & 0x80000000u;
+  const float Ts = __uint_as_float(__float_as_uint(T) ^ sgn);
+  const float ds = __uint_as_float(__float_as_uint(det) ^ sgn);
+  if (MOTION) {
+    if (Ts <= bias * ds || Ts > tcl * ds) return false;
+  } else {
+    if (Ts < bias * ds || Ts > tcl * ds) return false;
+  }
+  o.fU = fU; o.fV = fV; o.fW = fW; o.det = det; o.T = T;
+  return true;
+}
+
+struct CoopSmem {
+  float4* rp;  // [32][3] ray-parameter blocks of this warp, indexed by the owner's rank among the lanes holding a leaf
+};
+
+// The (ray, triangle) items of one 32-wide window. KZ >= 0: every item's ray has dominant axis KZ (static component access).
+template <int KZ>
+__device__ __forceinline__ bool coop_item(const DevScene& sc, const float4 q0, const float4 q1, const float4 q2, int j, TriCand& tc) {
+  const int i = j - __float_as_int(q2.z);
+  const float4* tp = sc.tris + (size_t)(__float_as_int(q2.y) + i) * 3;
+  const float4 v0 = ldg4(tp), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
+  return tri_candidate<false, KZ>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, __float_as_uint(q1.z), __float_as_int(q2.x), q1.w, make_float3(v0.x, v0.y, v0.z),
+                                  make_float3(v1.x, v1.y, v1.z), make_float3(v2.x, v2.y, v2.z), v2.w, tc);
+}
+
+// One cooperative leaf phase. `isleaf`: this lane's t.cur is a static triangle leaf. Returns leafhit for the lane.
+__device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bool isleaf, const CoopSmem& cs) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
+  RayState& r = t.r;
+  HitState& h = t.h;
+  const uint32_t un = (uint32_t)t.cur;
+  const int count = isleaf ? (int)(un & 15u) + 1 : 0;
+  const int base = (int)((un >> 4) & kLeafBaseMask);
+  int incl = count;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int start = incl - count;
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  const uint32_t leafmask = __ballot_sync(0xffffffffu, isleaf);
+  if (isleaf) {
+    h.trisT += count;
+    float4* b = cs.rp + __popc(leafmask & lt) * 3;
+    b[0] = make_float4(r.pkx, r.pky, r.pkz, r.s0);
+    b[1] = make_float4(r.s1, r.s2, __uint_as_float(r.xsign), r.tclosest);
+    b[2] = make_float4(__int_as_float(r.kz), __int_as_float(base), __int_as_float(start), 0.0f);
+  }
+  const int kz0 = __shfl_sync(0xffffffffu, r.kz, __ffs(leafmask) - 1);
+  const bool kz_uniform = __all_sync(0xffffffffu, !isleaf || r.kz == kz0);
+  __syncwarp();
+  bool leafhit = false;
+  for (int w = 0; w < total; w += 32) {
+    const int j = w + lane;
+    // owner rank of item j = (#segments starting at or before j) - 1: segments that start before this window (warp-uniform)
+    // plus the segment heads inside the window at slots <= lane (one REDUX.OR builds the head bitmask)
+    const int f = start - w;
+    const uint32_t heads = __reduce_or_sync(0xffffffffu, (isleaf && f >= 0 && f < 32) ? (1u << f) : 0u);
+    const int before = __popc(__ballot_sync(0xffffffffu, isleaf && f < 0));
+    bool cand = false;
+    TriCand tc;
+    tc.fU = tc.fV = tc.fW = tc.det = tc.T = 0.0f;
+    if (j < total) {
+      const int R = before + __popc(heads & (lt | (1u << lane))) - 1;
+      const float4* b = cs.rp + R * 3;
+      const float4 q0 = b[0], q1 = b[1], q2 = b[2];
+      if (kz_uniform) {
+        if (kz0 == 0) cand = coop_item<0>(sc, q0, q1, q2, j, tc);
+        else if (kz0 == 1) cand = coop_item<1>(sc, q0, q1, q2, j, tc);
+        else cand = coop_item<2>(sc, q0, q1, q2, j, tc);
+      } else {
+        cand = coop_item<-1>(sc, q0, q1, q2, j, tc);
+      }
+    }
+    const uint32_t cm = __ballot_sync(0xffffffffu, cand);
+    if (cm == 0) continue;
+    // this lane's items inside the window: item slots [start-w, start+count-w) clipped to [0,32)
+    uint32_t mine = 0;
+    if (isleaf) {
+      const int lo = f, hi = f + count;
+      if (hi > 0 && lo < 32) {
+        const uint32_t mlo = lo <= 0 ? 0xffffffffu : (0xffffffffu << lo);
+        const uint32_t mhi = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
+        mine = cm & mlo & mhi;
+      }
+    }
+    while (__any_sync(0xffffffffu, mine != 0)) {
+      const int src = mine ? (__ffs(mine) - 1) : lane;
+      const float fU = __shfl_sync(0xffffffffu, tc.fU, src);
+      const float fV = __shfl_sync(0xffffffffu, tc.fV, src);
+      const float fW = __shfl_sync(0xffffffffu, tc.fW, src);
+      const float det = __shfl_sync(0xffffffffu, tc.det, src);
+      const float T = __shfl_sync(0xffffffffu, tc.T, src);
+      if (mine) {
+        mine &= mine - 1;
+        const uint32_t sgn = __float_as_uint(det) & 0x80000000u;
+        const float Ts = __uint_as_float(__float_as_uint(T) ^ sgn);
+        const float ds = __uint_as_float(__float_as_uint(det) ^ sgn);
+        if (!(Ts > r.tclosest * ds)) {  // trace.go:182, the Tclosest half of the test against the live value
+          const float rcp = 1.0f / det;
+          h.u = fU * rcp;
+          h.v = fV * rcp;
+          h.w = fW * rcp;
+          r.tclosest = T * rcp;
+          h.slot = base + (src - f);
+          h.prim = -2;  // geom / prim ids are read from the triangle record once, when the ray is stored
+          leafhit = true;
+        }
+      }
+    }
+  }
+  __syncwarp();  // the blocks are rewritten by the next leaf phase
+  return leafhit;
+}
+
+template <bool ANY_HIT, class IO>
+__device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io, Stack& st, const CoopSmem& cs, unsigned long long& nodes_acc,
+                                                      unsigned long long& tris_acc) {
+  const int lane = threadIdx.x & 31;
+  const long long n = io.size();
+  TravState t;
+  t.cur = -1;
+  long long my = -1;
+  bool exhausted = false;
+  st.sp = 0;
+  st.overflow = false;
+  while (true) {
+    const unsigned idle = __ballot_sync(0xffffffffu, my < 0);
+    if (!exhausted && __popc(idle) >= VG_REFILL_IDLE) {
+      const int want = __popc(idle);
+      long long base = 0;
+      if (lane == 0) base = io.fetch(want);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base + want >= n) exhausted = true;
+      if (my < 0) {
+        const long long i = base + __popc(idle & ((1u << lane) - 1u));
+        if (i < n) {
+          my = i;
+          io.load(i, t.r);
+          ray_setup(t.r);
+          trav_begin(sc, t, st);
+        }
+      }
+    }
+    if (__ballot_sync(0xffffffffu, my >= 0) == 0) break;
+    // node phase: per lane, until fewer than VG_NODE_MIN lanes want it and at least one leaf is pending
+    while (true) {
+      if (t.cur < -1 && ((uint32_t)t.cur & kGeomBit)) t.cur = (int32_t)((uint32_t)t.cur & 0x3FFFFFFFu);  // scene.go:61-78 -> mesh root next
+      const unsigned nm = __ballot_sync(0xffffffffu, t.cur >= 0);
+      if (nm == 0) break;
+      if (__popc(nm) < VG_NODE_MIN && __any_sync(0xffffffffu, t.cur < -1)) break;
+      if (t.cur >= 0) node_step(sc, t, st);
+    }
+    // leaf phase
+    const bool leaf = t.cur < -1;
+    const bool mleaf = leaf && ((uint32_t)t.cur & kMotionTriBit);
+    if (__any_sync(0xffffffffu, leaf)) {
+      bool leafhit = coop_leaves(sc, t, leaf && !mleaf, cs);
+      if (mleaf) {
+        const uint32_t un = (uint32_t)t.cur;
+        const int count = (int)(un & 15u) + 1;
+        t.h.trisT += count;
+        leafhit = leaf_motion<-1>(sc, t.r, t.h, (int)((un >> 4) & kLeafBaseMask), count);
+      }
+      if (leaf) {
+        if (ANY_HIT && leafhit) {  // intersect.go:231-236
+          st.sp = 0;
+          t.cur = -1;
+        } else {
+          t.cur = pop_next(t.r, st);
+        }
+      }
+    }
+    if (my >= 0 && t.cur == -1) {
+      if (t.h.prim == -2) {
+        const float4* tp = sc.tris + (size_t)t.h.slot * 3;
+        t.h.geom = __float_as_int(ldg4(tp).w);
+        t.h.prim = __float_as_int(ldg4(tp + 1).w);
+      }
+      io.store(my, t.r, t.h, st.overflow);
+      nodes_acc += (unsigned long long)t.h.nodesT;
+      tris_acc += (unsigned long long)t.h.trisT;
+      st.overflow = false;
+      my = -1;
+    }
+  }
+}
+
+// VARIANT: 0 = per-lane while-while with coalesced LDG refill, 1 = the same over the TMA-staged queue, 2 = warp-cooperative leaves.
+template <bool ANY_HIT, int VARIANT, class IO>
+__device__ __forceinline__ void trace_persistent(const DevScene& sc, IO& io, Stack& st, unsigned char* warp_smem, unsigned long long& nodes_acc,
                                                  unsigned long long& tris_acc) {
-  if (TMA) trace_persistent_tma<ANY_HIT>(sc, io, st, ws, nodes_acc, tris_acc);
-  else trace_persistent_ldg<ANY_HIT>(sc, io, st, nodes_acc, tris_acc);
+  if (VARIANT == 1) {
+    WarpStage ws;
+    ws.buf = reinterpret_cast<float4*>(warp_smem);
+    ws.bar = reinterpret_cast<unsigned long long*>(warp_smem + 2048);
+    trace_persistent_tma<ANY_HIT>(sc, io, st, ws, nodes_acc, tris_acc);
+  } else if (VARIANT == 2) {
+    CoopSmem cs;
+    cs.rp = reinterpret_cast<float4*>(warp_smem);
+    trace_persistent_coop<ANY_HIT>(sc, io, st, cs, nodes_acc, tris_acc);
+  } else {
+    trace_persistent_ldg<ANY_HIT>(sc, io, st, nodes_acc, tris_acc);
+  }
 }
 
 }  // namespace vg
