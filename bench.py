@@ -112,7 +112,7 @@ def build_scene():
 def cpu_reference_run(scene, table, iters, nthreads):
     """The oracle (reference-semantics CPU path) on `iters` iterations of the workload. Returns (Mrays/s, rays, seconds)."""
     from oracle.binding import Oracle
-    ora = Oracle(scene)
+    ora = Oracle(scene, motion_ref_compat=False)   # same MQBVH leaf mode as the device default ("fixed", DESIGN.md quirk b)
     ora.set_scramble(table)
     _, st = ora.render(0, iters, nthreads=nthreads)
     return st["rays"] / st["seconds"] / 1e6, st["rays"], st["seconds"]
@@ -129,7 +129,7 @@ def run_reference(args):
     table = scenes.splitmix64_table(SCRAMBLE_SEED, XRES * YRES)
     from oracle.binding import Oracle
     cores = os.cpu_count() or 1
-    ora = Oracle(scene)
+    ora = Oracle(scene, motion_ref_compat=False)   # same MQBVH leaf mode as the device default ("fixed", DESIGN.md quirk b)
     ora.set_scramble(table)
     sample_iters = 4
     for _ in range(args.warmup):
@@ -193,7 +193,7 @@ def incoherent_leg(dev, host, scene, torch, cpu_cores):
            "alg_gbs": (64.0 * n + 128.0 * st["nodes_t"] + 48.0 * st["tris_t"]) / best / 1e6}
     if cpu_cores:
         from oracle.binding import Oracle
-        ora = Oracle(scene)
+        ora = Oracle(scene, motion_ref_compat=False)   # same MQBVH leaf mode as the device default ("fixed", DESIGN.md quirk b)
         sample = inc[: min(n, 1 << 20)]
         ora.trace(sample[:65536], nthreads=cpu_cores)
         t0 = time.perf_counter()
@@ -234,6 +234,8 @@ def run_ours(args):
     dev.set_partition(rank, world)
     dev.set_scramble(table)
     dev.set_option("iters_per_batch", ITERS_PER_BATCH)
+    for k, v in [kv.split("=") for kv in os.environ.get("VG_OPTIONS", "").split(",") if kv]:   # tuning experiments, e.g. VG_OPTIONS=traversal=0
+        dev.set_option(k, int(v))
 
     def barrier():
         torch.cuda.synchronize()
@@ -377,6 +379,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(evec[0]) * 1e3 / max(1, args.steps)},
         "gpu_launches": int(st["kernel_launches"]),
+        "stage_ms_per_step": {"closest_traversal": closest_ms / max(1, args.steps), "shadow_traversal": shadow_ms / max(1, args.steps),
+                              "raygen_shade_resolve_accumulate": (dev_ms - closest_ms - shadow_ms) / max(1, args.steps)},
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,

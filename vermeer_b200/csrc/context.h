@@ -106,6 +106,8 @@ struct vg_ctx {
   int opt_trace_last_level = 1;
   int opt_iters_per_batch = 4;
   int opt_precise_trig = 0;
+  int opt_primary_per_lane = 1;  // with traversal=2: camera rays (level 0) still use the per-lane loop
+  int opt_shadow_unordered = 1;  // integrator shadow queue: skip the sign-ordered push (occlusion is order independent)
   int opt_traversal = 2;  // 0: per-lane while-while, 1: the same over a TMA-staged ray queue, 2: warp-cooperative leaves (traverse.cuh)
 
   vg::RenderState* rs = nullptr;

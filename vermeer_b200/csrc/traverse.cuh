@@ -248,15 +248,21 @@ __device__ __forceinline__ void trav_begin(const DevScene& sc, TravState& t, Sta
 }
 
 // Pop until an entry survives the cull of intersect.go:106 (Tclosest < T); -1 when the stack is empty.
+// !ORDERED (occlusion-only rays): Tclosest never changes before the ray terminates, so nothing is ever culled.
+template <bool ORDERED = true>
 __device__ __forceinline__ int32_t pop_next(const RayState& r, Stack& st) {
   while (st.sp > 0) {
     const uint2 e = st.pop();
-    if (!(r.tclosest < __uint_as_float(e.x))) return (int32_t)e.y;
+    if (!ORDERED || !(r.tclosest < __uint_as_float(e.x))) return (int32_t)e.y;
   }
   return -1;
 }
 
 // One interior node (static or motion): 4 box tests, ordered push, next node. intersect.go:113-216, motionintersect.go:44-97
+// ORDERED = false is for rays whose only result is "occluded or not" (the integrator's shadow queue): every box-hit
+// child is visited whatever the order until the first accepted triangle, so the sign-ordered push sequence is skipped.
+// The set of nodes/leaves visited by an unoccluded ray, hence its NodesT/TrisT, is unchanged.
+template <bool ORDERED = true>
 __device__ __forceinline__ void node_step(const DevScene& sc, TravState& t, Stack& st) {
   RayState& r = t.r;
   const int32_t node = t.cur;
@@ -311,22 +317,31 @@ __device__ __forceinline__ void node_step(const DevScene& sc, TravState& t, Stac
   if (!h1 || t1 > r.tclosest) c1 = -1;
   if (!h2 || t2 > r.tclosest) c2 = -1;
   if (!h3 || t3 > r.tclosest) c3 = -1;
-  const bool s0 = (r.signbits >> a0) & 1u, s1 = (r.signbits >> a1) & 1u, s2 = (r.signbits >> a2) & 1u;
-  // arrange (e0,e1,e2,e3) = push sequence
-  cswap(!s1, c0, t0, c1, t1);  // pair01 = s1 ? (0,1) : (1,0)
-  cswap(!s2, c2, t2, c3, t3);  // pair23 = s2 ? (2,3) : (3,2)
-  cswap(!s0, c0, t0, c2, t2);  // s0 ? {pair01,pair23} : {pair23,pair01}
-  cswap(!s0, c1, t1, c3, t3);
-  // The entry pushed last is the one the reference pops next: keep it in a register, push the others.
-  int32_t next = -1;
-  if (c3 != -1) { next = c3; c3 = -1; }
-  else if (c2 != -1) { next = c2; c2 = -1; }
-  else if (c1 != -1) { next = c1; c1 = -1; }
-  else if (c0 != -1) { next = c0; c0 = -1; }
-  if (c0 != -1) st.push(t0, c0);
-  if (c1 != -1) st.push(t1, c1);
-  if (c2 != -1) st.push(t2, c2);
-  t.cur = next != -1 ? next : pop_next(r, st);
+  if (ORDERED) {
+    const bool s0 = (r.signbits >> a0) & 1u, s1 = (r.signbits >> a1) & 1u, s2 = (r.signbits >> a2) & 1u;
+    // arrange (e0,e1,e2,e3) = push sequence
+    cswap(!s1, c0, t0, c1, t1);  // pair01 = s1 ? (0,1) : (1,0)
+    cswap(!s2, c2, t2, c3, t3);  // pair23 = s2 ? (2,3) : (3,2)
+    cswap(!s0, c0, t0, c2, t2);  // s0 ? {pair01,pair23} : {pair23,pair01}
+    cswap(!s0, c1, t1, c3, t3);
+  }
+  // The entry pushed last is the one the reference pops next: keep it in a register, push the others. Branch-free:
+  // entry i is pushed iff it is valid and a valid entry follows it.
+  const bool v0 = c0 != -1, v1 = c1 != -1, v2 = c2 != -1, v3 = c3 != -1;
+  const int32_t next = v3 ? c3 : (v2 ? c2 : (v1 ? c1 : c0));
+  const bool p0 = v0 && (v1 || v2 || v3), p1 = v1 && (v2 || v3), p2 = v2 && v3;
+  const int sp0 = st.sp, sp1 = sp0 + (p0 ? 1 : 0), sp2 = sp1 + (p1 ? 1 : 0), sp3 = sp2 + (p2 ? 1 : 0);
+  if (sp0 + 3 <= VG_SMEM_STACK) {
+    if (p0) st.smem[sp0 * st.stride] = make_uint2(__float_as_uint(t0), (uint32_t)c0);
+    if (p1) st.smem[sp1 * st.stride] = make_uint2(__float_as_uint(t1), (uint32_t)c1);
+    if (p2) st.smem[sp2 * st.stride] = make_uint2(__float_as_uint(t2), (uint32_t)c2);
+    st.sp = sp3;
+  } else {
+    if (p0) st.push(t0, c0);
+    if (p1) st.push(t1, c1);
+    if (p2) st.push(t2, c2);
+  }
+  t.cur = next != -1 ? next : pop_next<ORDERED>(r, st);
 }
 
 // Triangle loops of one leaf. The next triangle's 3 x LDG.128 are issued before the current one is tested.
@@ -796,7 +811,7 @@ __device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bo
   return leafhit;
 }
 
-template <bool ANY_HIT, class IO>
+template <bool ANY_HIT, bool ORDERED, class IO>
 __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io, Stack& st, const CoopSmem& cs, unsigned long long& nodes_acc,
                                                       unsigned long long& tris_acc) {
   const int lane = threadIdx.x & 31;
@@ -832,7 +847,7 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
       const unsigned nm = __ballot_sync(0xffffffffu, t.cur >= 0);
       if (nm == 0) break;
       if (__popc(nm) < VG_NODE_MIN && __any_sync(0xffffffffu, t.cur < -1)) break;
-      if (t.cur >= 0) node_step(sc, t, st);
+      if (t.cur >= 0) node_step<ORDERED>(sc, t, st);
     }
     // leaf phase
     const bool leaf = t.cur < -1;
@@ -850,7 +865,7 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
           st.sp = 0;
           t.cur = -1;
         } else {
-          t.cur = pop_next(t.r, st);
+          t.cur = pop_next<ORDERED>(t.r, st);
         }
       }
     }
@@ -869,7 +884,8 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
   }
 }
 
-// VARIANT: 0 = per-lane while-while with coalesced LDG refill, 1 = the same over the TMA-staged queue, 2 = warp-cooperative leaves.
+// VARIANT: 0 = per-lane while-while with coalesced LDG refill, 1 = the same over the TMA-staged queue, 2 = warp-cooperative leaves,
+// 3 = cooperative leaves without the ordered push (occlusion-only any-hit rays).
 template <bool ANY_HIT, int VARIANT, class IO>
 __device__ __forceinline__ void trace_persistent(const DevScene& sc, IO& io, Stack& st, unsigned char* warp_smem, unsigned long long& nodes_acc,
                                                  unsigned long long& tris_acc) {
@@ -881,7 +897,11 @@ __device__ __forceinline__ void trace_persistent(const DevScene& sc, IO& io, Sta
   } else if (VARIANT == 2) {
     CoopSmem cs;
     cs.rp = reinterpret_cast<float4*>(warp_smem);
-    trace_persistent_coop<ANY_HIT>(sc, io, st, cs, nodes_acc, tris_acc);
+    trace_persistent_coop<ANY_HIT, true>(sc, io, st, cs, nodes_acc, tris_acc);
+  } else if (VARIANT == 3) {
+    CoopSmem cs;
+    cs.rp = reinterpret_cast<float4*>(warp_smem);
+    trace_persistent_coop<ANY_HIT, false>(sc, io, st, cs, nodes_acc, tris_acc);
   } else {
     trace_persistent_ldg<ANY_HIT>(sc, io, st, nodes_acc, tris_acc);
   }
