@@ -321,7 +321,7 @@ struct BsdfRec {
   bool valid;
   f3 Ld;
   float Ldist;
-  double pdf;
+  float pdf;  // float32(bsdf.PDF(wo)): the reference keeps the float64 but only ever uses it rounded (core/shader.go:323)
   float pdfLight;
 };
 
@@ -358,12 +358,21 @@ __device__ inline BsdfRec bsdf_sample(const DevLight& L, const ShadeCtx& c, cons
                                       int i, uint64_t scr0, uint64_t scr1) {
   BsdfRec r;
   r.valid = false;
+  r.pdfLight = 0.0f;
+  r.Ldist = 0.0f;
+  r.Ld = mk3(0, 0, 1);
   const uint64_t idx = (uint64_t)(I * h + i);
   const double r0 = vdc(idx, scr0);
   const double r1 = sobol(idx, scr1);
   const f3 wo = normalize3t<FAST>(basis_expand(fr.U, fr.V, fr.N, cosine_hemisphere<FAST>(r0, r1)));
-  r.pdf = oren_pdf(fr, wo);
-  if (r.pdf <= 0) return r;
+  if (FAST) {
+    r.pdf = oren_pdf32<true>(fr, wo);
+    if (r.pdf <= 0) return r;
+  } else {
+    const double pd = oren_pdf(fr, wo);  // the reference tests the float64 value (core/shader.go:218)
+    if (pd <= 0) return r;
+    r.pdf = (float)pd;
+  }
   f3 Pl;
   if (!ray_triangle(c.P, wo, L.p0, L.p1, L.p2, &Pl)) return r;
   // NOTE: the horizon test of ValidSample is taken at the point ON THE LIGHT (triangle.go:145-147), kept as is
@@ -511,7 +520,7 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
           Ld = lr.Ld;
           Ldist = lr.Ldist;
           if (NS > 1) {
-            p_hat = (float)nB * (float)oren_pdf(fr, Ld) / (float)total;
+            p_hat = (float)nB * oren_pdf32<FAST>(fr, Ld) / (float)total;
             p_hat += (float)nLs * lr.pdf / (float)total;
           } else {
             p_hat = lr.pdf;
@@ -521,7 +530,7 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
           valid = br.valid;
           Ld = br.Ld;
           Ldist = br.Ldist;
-          p_hat = (float)nB * (float)br.pdf / (float)total;
+          p_hat = (float)nB * br.pdf / (float)total;
           p_hat += (float)nLs * br.pdfLight / (float)total;
         }
         if (valid && !(dot3(Ld, c.N) <= 0)) {

@@ -193,7 +193,7 @@ __device__ __forceinline__ f3 cosine_hemisphere(double u0, double u1) {  // samp
   if (FAST) {
     const float r = sqrtf((float)(1 - u0));
     float sn, cs;
-    sincosf((float)(2 * VG_PI64 * u1), &sn, &cs);
+    sincospif((float)(2 * u1), &sn, &cs);
     return mk3(r * cs, r * sn, sqrtf((float)u0));
   }
   const double r = sqrt(1 - u0);
@@ -220,38 +220,81 @@ __device__ __forceinline__ double oren_pdf(const Frame& f, f3 wo) {
   const f3 o = basis_project(f.U, f.V, f.N, wo);
   return (double)maxf_x86(0.0f, o.z) / VG_PI64;
 }
-// float32(bsdf.PDF(wo)) as EvaluateLightSamples uses it (core/shader.go:284,323)
-__device__ __forceinline__ float oren_pdf32(const Frame& f, f3 wo) { return (float)oren_pdf(f, wo); }
+// float32(bsdf.PDF(wo)) as EvaluateLightSamples uses it (core/shader.go:284,323). FAST: one float multiply by 1/pi instead
+// of the float64 divide (the two differ by at most 1 ulp of float32).
+template <bool FAST>
+__device__ __forceinline__ float oren_pdf32(const Frame& f, f3 wo) {
+  if (!FAST) return (float)oren_pdf(f, wo);
+  return maxf_x86(0.0f, dot3(f.N, wo)) * 0.318309886183790671538f;
+}
 // orennayar.go:42-73 split into its per-vertex part (depends on omegaI, lambda and the material only) and its
 // per-sample part; the arithmetic and its order are unchanged.
 struct OrenVertex {
   float A, B;          // from Roughness^2 (orennayar.go:25,47-49)
-  float phiI, thetaI;  // atan2(omegaI.y, omegaI.x), acos(omegaI.z)
+  float phiI, thetaI;  // atan2(omegaI.y, omegaI.x), acos(omegaI.z)           (precise variant)
+  float cosI, sinI, cphiI, sphiI;  // the same two angles as cosine/sine pairs  (FAST variant, no inverse trig)
   Spec4 white;         // FromRGB({1,1,1}) at this path's hero wavelength
 };
+// (cos, sin) of atan2(y, x) without the angle; atan2(0, 0) = 0 -> (1, 0)
+__device__ __forceinline__ void unit2(float x, float y, float* c, float* s) {
+  const float l2 = x * x + y * y;
+  if (l2 > 0.0f) {
+    const float r = rsqrtf(l2);
+    *c = x * r;
+    *s = y * r;
+  } else {
+    *c = 1.0f;
+    *s = 0.0f;
+  }
+}
 template <bool FAST>
 __device__ __forceinline__ OrenVertex oren_vertex(f3 omegaI, float roughness2, const Hero& hero) {
   OrenVertex v;
   const float sigma = roughness2;
   v.A = 1 - (0.5f * (sigma * sigma) / ((sigma * sigma) + 0.57f));
   v.B = 0.45f * (sigma * sigma) / ((sigma * sigma) + 0.09f);
-  v.phiI = Trig<FAST>::atan2(omegaI.y, omegaI.x);
-  v.thetaI = Trig<FAST>::acos(omegaI.z);
+  if (FAST) {
+    v.cosI = omegaI.z;
+    v.sinI = sqrtf(1.0f - omegaI.z * omegaI.z);  // NaN for |z| > 1, like acos
+    unit2(omegaI.x, omegaI.y, &v.cphiI, &v.sphiI);
+    v.phiI = v.thetaI = 0.0f;
+  } else {
+    v.phiI = Trig<FAST>::atan2(omegaI.y, omegaI.x);
+    v.thetaI = Trig<FAST>::acos(omegaI.z);
+    v.cosI = v.sinI = v.cphiI = v.sphiI = 0.0f;
+  }
   v.white = spec_from_rgb(mk3(1, 1, 1), hero);
   return v;
 }
 template <bool FAST>
 __device__ __forceinline__ Spec4 oren_eval(const Frame& f, const OrenVertex& ov, f3 wo) {
   const f3 o = basis_project(f.U, f.V, f.N, wo);
-  const float phiO = Trig<FAST>::atan2(o.y, o.x);
-  const float thetaO = Trig<FAST>::acos(o.z);
-  const float alpha = maxf_x86(ov.thetaI, thetaO);
-  const float beta = minf_x86(ov.thetaI, thetaO);
-  const float Cc = Trig<FAST>::sin(alpha) * Trig<FAST>::tan(beta);
-  const float gamma = Trig<FAST>::cos(phiO - ov.phiI);
+  float Cc, gamma;
+  if (FAST) {
+    // the same expression without inverse trig: theta = acos(cos) is decreasing, so max/min of the angles are picked by
+    // comparing cosines; sin(alpha) tan(beta) and cos(phiO - phiI) follow from the cosine/sine pairs. NaN cases keep the
+    // reference's x86 max/min semantics (a NaN thetaI is dropped, a NaN thetaO propagates).
+    const float cosO = o.z, sinO = sqrtf(1.0f - o.z * o.z);
+    const bool ok = (ov.sinI == ov.sinI) && (sinO == sinO);
+    const bool aI = ok && ov.cosI < cosO;  // alpha = thetaI
+    const bool bI = ok && ov.cosI > cosO;  // beta = thetaI
+    const float sinA = aI ? ov.sinI : sinO;
+    const float tanB = bI ? ov.sinI / ov.cosI : sinO / cosO;
+    Cc = sinA * tanB;
+    float cphiO, sphiO;
+    unit2(o.x, o.y, &cphiO, &sphiO);
+    gamma = cphiO * ov.cphiI + sphiO * ov.sphiI;
+  } else {
+    const float phiO = Trig<FAST>::atan2(o.y, o.x);
+    const float thetaO = Trig<FAST>::acos(o.z);
+    const float alpha = maxf_x86(ov.thetaI, thetaO);
+    const float beta = minf_x86(ov.thetaI, thetaO);
+    Cc = Trig<FAST>::sin(alpha) * Trig<FAST>::tan(beta);
+    gamma = Trig<FAST>::cos(phiO - ov.phiI);
+  }
   const float sc = o.z * (ov.A + (ov.B * maxf_x86(0.0f, gamma) * Cc));
   Spec4 rho = ov.white;
-  const float k = sc / (float)VG_PI64;
+  const float k = FAST ? sc * 0.318309886183790671538f : sc / (float)VG_PI64;
 #pragma unroll
   for (int i = 0; i < 4; i++) rho.c[i] *= k;
   return rho;
@@ -323,7 +366,8 @@ __device__ inline bool ray_triangle(f3 Ro, f3 Rd, f3 P0, f3 P1, f3 P2, f3* pout)
 // (vertex, light) and shared by SampleArea and ValidSample, which both recompute it in the reference.
 struct SphTri {
   f3 pa, pb, pc;
-  float alpha, c, area;
+  float alpha, c, area;        // precise variant: the angle at A, the side AB, the solid angle
+  float cosAlpha, sinAlpha, cosC;  // FAST variant: the same two angles as cosine/sine values
 };
 template <bool FAST>
 __device__ inline SphTri spherical_setup(f3 p0, f3 p1, f3 p2, f3 p) {
@@ -331,6 +375,21 @@ __device__ inline SphTri spherical_setup(f3 p0, f3 p1, f3 p2, f3 p) {
   t.pa = normalize3t<FAST>(sub3(p0, p));
   t.pb = normalize3t<FAST>(sub3(p1, p));
   t.pc = normalize3t<FAST>(sub3(p2, p));
+  if (FAST) {
+    // Same quantities without the six inverse-trig calls: the vertex angle alpha is the dihedral angle between the planes
+    // (pa,pb) and (pa,pc); the solid angle by Van Oosterom & Strackee, tan(O/2) = |pa.(pb x pc)| / (1 + pa.pb + pb.pc + pc.pa).
+    const f3 n1 = cross3(t.pa, t.pb), n2 = cross3(t.pa, t.pc);
+    const float trip = fabsf(dot3(t.pa, cross3(t.pb, t.pc)));
+    const float rn = rsqrtf(len2_3(n1) * len2_3(n2));
+    t.cosAlpha = dot3(n1, n2) * rn;
+    t.sinAlpha = trip * rn;
+    t.cosC = dot3(t.pa, t.pb);
+    const float denom = 1.0f + t.cosC + dot3(t.pb, t.pc) + dot3(t.pc, t.pa);
+    t.area = 2.0f * atan2f(trip, denom);
+    t.alpha = t.c = 0.0f;
+    return t;
+  }
+  t.cosAlpha = t.sinAlpha = t.cosC = 0.0f;
   const float as = Trig<FAST>::acos(dot3(t.pb, t.pc)), bs = Trig<FAST>::acos(dot3(t.pc, t.pa)), cs = Trig<FAST>::acos(dot3(t.pa, t.pb));
   const float ssu = (as + bs + cs) / 2;
   const float sa = Trig<FAST>::sin(ssu - as), sb = Trig<FAST>::sin(ssu - bs), scs = Trig<FAST>::sin(ssu - cs), ss = Trig<FAST>::sin(ssu);
@@ -349,10 +408,20 @@ __device__ inline f3 sample_spherical_triangle(const SphTri& st, double r0, doub
   const f3 pa = st.pa, pb = st.pb, pc = st.pc;
   const float alpha = st.alpha;
   const float areaHat = (float)r0 * st.area;
-  const float s = Trig<FAST>::sin(areaHat - alpha), t = Trig<FAST>::cos(areaHat - alpha);
-  const float sinAlpha = Trig<FAST>::sin(alpha), cosAlpha = Trig<FAST>::cos(alpha);
+  float s, t, sinAlpha, cosAlpha, cosC;
+  if (FAST) {
+    float sh, ch;
+    sincosf(areaHat, &sh, &ch);
+    sinAlpha = st.sinAlpha; cosAlpha = st.cosAlpha; cosC = st.cosC;
+    s = sh * cosAlpha - ch * sinAlpha;  // sin(areaHat - alpha)
+    t = ch * cosAlpha + sh * sinAlpha;  // cos(areaHat - alpha)
+  } else {
+    s = Trig<FAST>::sin(areaHat - alpha); t = Trig<FAST>::cos(areaHat - alpha);
+    sinAlpha = Trig<FAST>::sin(alpha); cosAlpha = Trig<FAST>::cos(alpha);
+    cosC = Trig<FAST>::cos(st.c);
+  }
   const float u = t - cosAlpha;
-  const float v = s + sinAlpha * Trig<FAST>::cos(st.c);
+  const float v = s + sinAlpha * cosC;
   float q = ((v * t - u * s) * cosAlpha - v) / ((v * s + u * t) * sinAlpha);
   q = maxf_x86(-1.0f, minf_x86(q, 1.0f));
   float w = dot3(pc, pa);
