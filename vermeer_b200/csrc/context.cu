@@ -497,6 +497,10 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
   else if (!std::strcmp(name, "tma_stage")) ctx->opt_traversal = value != 0 ? 1 : 2;
   else if (!std::strcmp(name, "primary_per_lane")) ctx->opt_primary_per_lane = value != 0;
   else if (!std::strcmp(name, "shadow_unordered")) ctx->opt_shadow_unordered = value != 0;
+  else if (!std::strcmp(name, "pixel_block")) {
+    ctx->opt_pixel_block = value != 0;
+    render_invalidate(ctx);
+  }
   else if (!std::strcmp(name, "traversal")) {
     if (value < 0 || value > 2) return ctx->fail(VG_ERR_INVALID, "traversal must be 0 (per-lane), 1 (TMA-staged queue) or 2 (cooperative leaves)");
     ctx->opt_traversal = value;

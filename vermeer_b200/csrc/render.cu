@@ -396,7 +396,10 @@ __device__ inline BsdfRec bsdf_sample(const DevLight& L, const ShadeCtx& c, cons
 #ifndef VG_SHADE_MIN_BLOCKS
 #define VG_SHADE_MIN_BLOCKS 6
 #endif
-template <bool FAST>
+// H1: every light takes at most one sample per strategy (NumSamples <= 2, the `Samples 1` default of the light nodes, and
+// always at level > 0): pass 2 then reuses the pass-1 records and the second inlined copy of the sampling code disappears
+// (the kernel is instruction-cache bound: ncu shows 20 % of its stall samples in no_instructions).
+template <bool FAST, bool H1>
 __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const RenderParams p, int level, int qin, int qout, int iter_base) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = p.counts[qin];
@@ -480,7 +483,7 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
       by_area = dot3(c.Ng, sub3(L.p0, c.P)) < 0 || dot3(c.Ng, sub3(L.p1, c.P)) < 0 || dot3(c.Ng, sub3(L.p2, c.P)) < 0;
       if (!by_area) sph = spherical_setup<FAST>(L.p0, L.p1, L.p2, c.P);
     }
-    const int hN = NS > 1 ? NS / 2 : NS;  // samples per strategy
+    const int hN = H1 ? 1 : (NS > 1 ? NS / 2 : NS);  // samples per strategy
     // pass 1: which strategies produced at least one sample (shader.go:241-249)
     int nB = 0, nLs = 0;
     LightRec lr0;
@@ -515,7 +518,7 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
         float p_hat;
         bool valid;
         if (!is_bsdf) {
-          const LightRec lr = (s == 0) ? lr0 : light_sample<FAST>(L, c, by_area, sph, I, hN, s, scr0, scr1);
+          const LightRec lr = (H1 || s == 0) ? lr0 : light_sample<FAST>(L, c, by_area, sph, I, hN, s, scr0, scr1);
           valid = lr.valid;
           Ld = lr.Ld;
           Ldist = lr.Ldist;
@@ -526,7 +529,7 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
             p_hat = lr.pdf;
           }
         } else {
-          const BsdfRec br = (s == hN) ? br0 : bsdf_sample<FAST>(L, c, fr, !by_area, sph, I, hN, s - hN, scr0, scr1);
+          const BsdfRec br = (H1 || s == hN) ? br0 : bsdf_sample<FAST>(L, c, fr, !by_area, sph, I, hN, s - hN, scr0, scr1);
           valid = br.valid;
           Ld = br.Ld;
           Ldist = br.Ldist;
@@ -683,6 +686,7 @@ struct RenderState {
   DevBuf<unsigned long long> stats;
   int fb_w = 0, fb_h = 0;
   int trace_grid = 0;
+  int max_light_samples = 0;
   std::vector<int> pix_host;
   uint64_t* scr_pinned = nullptr;
   size_t scr_pinned_bytes = 0;
@@ -812,11 +816,22 @@ static int prepare(vg_ctx* ctx) {
   for (int ty = 0; ty < tilesY; ty++)
     for (int tx = 0; tx < tilesX; tx++) {
       if ((tx + ty * k) % ctx->world != ctx->rank) continue;
-      for (int j = 0; j < 32; j++)
-        for (int i = 0; i < 32; i++) {
-          const int x = tx * 32 + i, y = ty * 32 + j;
-          if (x < W && y < H) pix.push_back(x + y * W);
-        }
+      // Path order inside a tile decides which 32 camera rays share a warp. 8x4 pixel blocks keep a warp's rays (and the
+      // shadow rays spawned from their hits) in fewer BVH leaves than a 32x1 row does; results are per pixel and do not
+      // depend on this order.
+      if (ctx->opt_pixel_block) {
+        for (int b = 0; b < 32; b++)
+          for (int l = 0; l < 32; l++) {
+            const int x = tx * 32 + (b & 3) * 8 + (l & 7), y = ty * 32 + (b >> 2) * 4 + (l >> 3);
+            if (x < W && y < H) pix.push_back(x + y * W);
+          }
+      } else {
+        for (int j = 0; j < 32; j++)
+          for (int i = 0; i < 32; i++) {
+            const int x = tx * 32 + i, y = ty * 32 + j;
+            if (x < W && y < H) pix.push_back(x + y * W);
+          }
+      }
     }
   rs.nown = (int)pix.size();
   rs.pix_host = pix;
@@ -853,6 +868,7 @@ static int prepare(vg_ctx* ctx) {
   // lights
   std::vector<DevLight> lights(ctx->lights.size());
   int S = 0;
+  rs.max_light_samples = 0;
   for (size_t i = 0; i < lights.size(); i++) {
     const VgTriLight& s = ctx->lights[i];
     DevLight& d = lights[i];
@@ -869,6 +885,7 @@ static int prepare(vg_ctx* ctx) {
     if (s.material >= 0 && s.material < (int)mats.size()) d.E = mats[s.material].emission;
     if (s.samples < 0 || s.samples > 8) return ctx->fail(VG_ERR_INVALID, "TriLight.Samples outside [0,8]");
     d.nsamples = 1 << s.samples;
+    rs.max_light_samples = std::max(rs.max_light_samples, d.nsamples);
     d.geom = s.geom;
     d.slot_base = S;
     S += d.nsamples;
@@ -991,8 +1008,14 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
         kinds.push_back(0);
         launches++;
         if (level <= 3) {
-          if (ctx->opt_precise_trig) k_shade<false><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
-          else k_shade<true><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
+          const bool h1 = rs.max_light_samples <= 2 || level > 0;
+          if (ctx->opt_precise_trig) {
+            if (h1) k_shade<false, true><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
+            else k_shade<false, false><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
+          } else {
+            if (h1) k_shade<true, true><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
+            else k_shade<true, false><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
+          }
           cudaEventRecord(rs.ev(nev++), st);
           if (variant == 1) k_trace_queue<1, 1><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
           else if (variant == 2 && ctx->opt_shadow_unordered) k_trace_queue<1, 3><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
