@@ -88,6 +88,11 @@ typedef struct VgMotionNode {
 #define VG_MAT_SPEC1_STRENGTH 64u
 #define VG_MAT_SPEC1_ROUGHNESS 128u
 #define VG_MAT_IOR 256u
+#define VG_MAT_SPEC1_FRESNEL_MODEL 512u /* Spec1FresnelModel given ("Dielectric" | "Metal", std.go:65-73) */
+#define VG_MAT_SPEC1_FRESNEL_REFL 1024u
+#define VG_MAT_SPEC1_FRESNEL_EDGE 2048u
+#define VG_FRESNEL_DIELECTRIC 0 /* fresnel.DielectricModel (fresnel/models.go:13-17), also the value when the string is unset */
+#define VG_FRESNEL_CONDUCTOR 1  /* fresnel.ConductorModel ("Metal") */
 typedef struct VgMaterial {
   uint32_t mask;
   float emission_colour[3];
@@ -97,8 +102,11 @@ typedef struct VgMaterial {
   float diffuse_roughness;
   float spec1_colour[3];
   float spec1_strength;
-  float spec1_roughness;
+  float spec1_roughness; /* 0 = mirror lobe (bsdf.Specular), > 0 = GGX glossy lobe (bsdf.MicrofacetGGX, direct light only) */
   float ior;
+  int32_t spec1_fresnel_model; /* VG_FRESNEL_* */
+  float spec1_fresnel_refl[3];
+  float spec1_fresnel_edge[3];
 } VgMaterial;
 
 /* light.Tri (builtin/light/triangle.go:18-28) after PreRender. */
@@ -108,6 +116,24 @@ typedef struct VgTriLight {
   int32_t material; /* index into the material table (the light's Shader) */
   int32_t geom;     /* geom id of the mesh the light created for itself (triangle.go:48-50) */
 } VgTriLight;
+
+/* Any in-scope core.Light after PreRender, in scene order (scene.AddLight order, builtin/scene/scene.go:126-129):
+ *   VG_LIGHT_TRI    light.Tri    (builtin/light/triangle.go:18-28)  p0,p1,p2 = vertices
+ *   VG_LIGHT_DISK   light.Disk   (builtin/light/disk.go:21-34)      p0 = P, p1 = T, p2 = B, n = N (disk.go:90-97), radius
+ *   VG_LIGHT_SPHERE light.Sphere (builtin/light/sphere.go:17-28)    p0 = P, radius; geom = the sphere geom it created
+ * light.Quad is not offered: both of its sampling entry points panic in the reference (quad.go:88,94). */
+#define VG_LIGHT_TRI 0
+#define VG_LIGHT_DISK 1
+#define VG_LIGHT_SPHERE 2
+typedef struct VgLight {
+  int32_t type;
+  int32_t samples;  /* Samples; NumSamples = 1<<samples */
+  int32_t material; /* the light's Shader (EvalEmission) */
+  int32_t geom;     /* geom id of the mesh / sphere the light created for itself */
+  float p0[3], p1[3], p2[3];
+  float n[3];
+  float radius;
+} VgLight;
 
 /* camera.Camera after PreRender (builtin/camera/camera.go:80-98): single-key LocalToWorld after the
  * decompose/recompose of camera.go:188-192,225-236 (column major, math/matrix4.go:9-18). */
@@ -157,6 +183,9 @@ int vg_mesh_upload(vg_ctx* ctx, int geom_id, const VgNode* nodes, int n_nodes, c
 int vg_mesh_upload_motion(vg_ctx* ctx, int geom_id, const VgMotionNode* topo, int n_nodes, const float* boxes, int keys,
                           const uint32_t* idxp, const int32_t* accel_idx, int n_tris, const float* verts, int n_verts,
                           const uint8_t* shaderidx, const int32_t* material_ids, int n_materials, float raybias, int ref_compat);
+/* sphere.Sphere geom (builtin/geom/sphere/sphere.go:15-28; "only used for spherical light sources"): an analytic leaf of the
+ * scene-level tree, intersected like sphere/trace.go:13-109. */
+int vg_sphere_upload(vg_ctx* ctx, int geom_id, const float* centre, float radius, int32_t material_id);
 /* Scene-level tree (builtin/scene/scene.go:135-203): leafMax=1 nodes over geoms; geom_of_slot[i] = geom id at leaf slot i. */
 int vg_scene_upload(vg_ctx* ctx, const VgNode* nodes, int n_nodes, const int32_t* geom_of_slot, int n_slots);
 int vg_scene_upload_motion(vg_ctx* ctx, const VgMotionNode* topo, int n_nodes, const float* boxes, int keys,
@@ -165,7 +194,8 @@ int vg_scene_upload_motion(vg_ctx* ctx, const VgMotionNode* topo, int n_nodes, c
 int vg_scene_commit(vg_ctx* ctx);
 
 int vg_set_materials(vg_ctx* ctx, const VgMaterial* mats, int n);
-int vg_set_lights(vg_ctx* ctx, const VgTriLight* lights, int n);
+int vg_set_lights(vg_ctx* ctx, const VgTriLight* lights, int n);   /* TriLights only (kept for callers that have nothing else) */
+int vg_set_area_lights(vg_ctx* ctx, const VgLight* lights, int n);  /* any mix of light types, scene order */
 int vg_set_camera(vg_ctx* ctx, const VgCamera* cam);
 int vg_set_frame(vg_ctx* ctx, int xres, int yres);
 /* Image partition across processes/GPUs: this context renders the 32x32 tiles (tx,ty) with
@@ -221,6 +251,11 @@ int vh_add_polymesh(vh_scene* s, const char* name, const float* verts, int n_ver
  * defaults (Airy: Res 49, Width 6, Peak 4; Gaussian: Res 17, Width 2 — filter.go:14-26). */
 int vh_add_filter(vh_scene* s, const char* type, const char* name, float width, int res, float peak);
 int vh_add_trilight(vh_scene* s, const char* name, const float* p0, const float* p1, const float* p2, const char* shader, int samples);
+/* DiskLight (builtin/light/disk.go; registered defaults Segments 20, Samples 1) and SphereLight (builtin/light/sphere.go;
+ * defaults Radius 1, Samples 1). Like the reference, PreRender makes each light add its own geom (a fan mesh / a Sphere). */
+int vh_add_disklight(vh_scene* s, const char* name, const float* P, const float* lookat, const float* up, float radius, const char* shader,
+                     int segments, int samples);
+int vh_add_spherelight(vh_scene* s, const char* name, const float* P, float radius, const char* shader, int samples);
 int vh_set_camera_lookat(vh_scene* s, const float* from, const float* to, const float* up, float roll, float fov, float focal,
                          float aspect, float radius);
 /* core.PreRender (core/core.go:36-61): triangulate, build per-mesh QBVH/MQBVH, light meshes, scene tree, camera matrix. */

@@ -90,7 +90,16 @@ class Oracle:
                 _p(m.NormalIdx), 0 if m.NormalIdx is None else len(m.NormalIdx),
                 C.c_float(m.RayBias)))
         for l in scene.lights:
-            self._chk(L.orc_add_trilight(h, l.Name.encode(), _f3(l.P0), _f3(l.P1), _f3(l.P2), l.Shader.encode(), l.Samples))
+            kind = type(l).__name__
+            if kind == "TriLight":
+                self._chk(L.orc_add_trilight(h, l.Name.encode(), _f3(l.P0), _f3(l.P1), _f3(l.P2), l.Shader.encode(), l.Samples))
+            elif kind == "DiskLight":
+                self._chk(L.orc_add_disklight(h, l.Name.encode(), _f3(l.P), _f3(l.LookAt), _f3(l.Up), C.c_float(l.Radius), l.Shader.encode(),
+                                              int(l.Segments), int(l.Samples)))
+            elif kind == "SphereLight":
+                self._chk(L.orc_add_spherelight(h, l.Name.encode(), _f3(l.P), C.c_float(l.Radius), l.Shader.encode(), int(l.Samples)))
+            else:
+                raise ValueError("unknown light node %r" % kind)
         c = scene.camera
         self._chk(L.orc_set_camera(h, _f3(c.From), _f3(c.To), _f3(c.Up), C.c_float(c.Roll), C.c_float(c.Fov), C.c_float(c.Focal),
                                    C.c_float(c.Aspect), C.c_float(c.Radius)))
@@ -171,7 +180,7 @@ class Oracle:
 
     def mesh_info(self, gid):
         o = np.zeros(6, np.int32)
-        self.L.orc_mesh_info(self.h, gid, _p(o))
+        self._chk(self.L.orc_mesh_info(self.h, gid, _p(o)))
         return dict(nodes=int(o[0]), tris=int(o[1]), keys=int(o[2]), nverts=int(o[3]), motion=bool(o[4]), normals=bool(o[5]))
 
     def mesh_nodes(self, gid):

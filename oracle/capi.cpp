@@ -51,6 +51,7 @@ int orc_set_globals(void* h, int xres, int yres) {
 
 // mask bits / p[] slots: 0 EmissionColour(p0..2) 1 EmissionStrength(p3) 2 DiffuseColour(p4..6) 3 DiffuseStrength(p7)
 // 4 DiffuseRoughness(p8) 5 Spec1Colour(p9..11) 6 Spec1Strength(p12) 7 Spec1Roughness(p13) 8 IOR(p14)
+// 9 Spec1FresnelModel(p15: 0 "Dielectric", 1 "Metal") 10 Spec1FresnelRefl(p16..18) 11 Spec1FresnelEdge(p19..21)
 int orc_add_shader(void* h, const char* name, uint32_t mask, const float* p) {
   Handle* H = (Handle*)h;
   auto s = std::make_unique<ShaderStd>();
@@ -64,6 +65,9 @@ int orc_add_shader(void* h, const char* name, uint32_t mask, const float* p) {
   if (mask & 64) { s->hasSpec1Strength = true; s->Spec1Strength = p[12]; }
   if (mask & 128) { s->hasSpec1Roughness = true; s->Spec1Roughness = p[13]; }
   if (mask & 256) { s->hasIOR = true; s->IOR = p[14]; }
+  if (mask & 512) s->spec1FresnelModel = p[15] != 0.0f ? 1 : 0;
+  if (mask & 1024) { s->hasSpec1FresnelRefl = true; s->Spec1FresnelRefl = MakeRGB(p[16], p[17], p[18]); }
+  if (mask & 2048) { s->hasSpec1FresnelEdge = true; s->Spec1FresnelEdge = MakeRGB(p[19], p[20], p[21]); }
   H->r.shaders.push_back(std::move(s));
   return 0;
 }
@@ -118,7 +122,44 @@ int orc_add_trilight(void* h, const char* name, const float* p0, const float* p1
     t->Samples = samples;
     t->shader = H->r.findShader(shader);
     if (!t->shader) throw std::runtime_error(std::string("Unable to find node (shader ") + shader + ")");
+    H->r.lightOrder.push_back(t.get());
     H->r.tris.push_back(std::move(t));
+  });
+}
+
+// DiskLight (builtin/light/disk.go:21-34; registered defaults Segments 20, Samples 1, :263-269)
+int orc_add_disklight(void* h, const char* name, const float* P, const float* lookat, const float* up, float radius, const char* shader,
+                      int segments, int samples) {
+  Handle* H = (Handle*)h;
+  return guard([&] {
+    auto d = std::make_unique<Disk>();
+    d->Name = name;
+    d->P = v3(P);
+    d->LookAt = v3(lookat);
+    d->Up = v3(up);
+    d->Radius = radius;
+    d->Segments = segments;
+    d->Samples = samples;
+    d->shader = H->r.findShader(shader);
+    if (!d->shader) throw std::runtime_error(std::string("Unable to find node (shader ") + shader + ")");
+    H->r.lightOrder.push_back(d.get());
+    H->r.disks.push_back(std::move(d));
+  });
+}
+
+// SphereLight (builtin/light/sphere.go:17-28; registered defaults Radius 1, Samples 1, :297-303)
+int orc_add_spherelight(void* h, const char* name, const float* P, float radius, const char* shader, int samples) {
+  Handle* H = (Handle*)h;
+  return guard([&] {
+    auto d = std::make_unique<SphereLight>();
+    d->Name = name;
+    d->P = v3(P);
+    d->Radius = radius;
+    d->Samples = samples;
+    d->shader = H->r.findShader(shader);
+    if (!d->shader) throw std::runtime_error(std::string("Unable to find node (shader ") + shader + ")");
+    H->r.lightOrder.push_back(d.get());
+    H->r.sphereLights.push_back(std::move(d));
   });
 }
 
@@ -241,8 +282,8 @@ int orc_trace_batch(void* h, const OrcRay* rays, int64_t n, uint32_t flags, int 
         if (flags & 2) {
           hit = false;
           for (Geom* g : H->r.scene.geoms) {
-            PolyMesh* pm = static_cast<PolyMesh*>(g);
-            if (pm->TraceBrute(&ray, &sc)) { hit = true; sc.geom = g; }
+            PolyMesh* pm = dynamic_cast<PolyMesh*>(g);
+            if (pm ? pm->TraceBrute(&ray, &sc) : g->Trace(&ray, &sc)) { hit = true; sc.geom = g; }
           }
         } else {
           hit = TraceProbe(&ray, &sc);

@@ -81,25 +81,65 @@ struct OrenNayar : BSDF {
   }
 };
 
+// core.Fresnel (core/shader.go:16-19)
+struct Fresnel {
+  virtual ~Fresnel() {}
+  virtual RGB Kr(float cosTheta) const = 0;
+};
+
 // builtin/shader/fresnel/dielectric.go:34-47
-static RGB DielectricKr(float eta, float cosTheta) {
-  float c = cosTheta;
-  float g = (eta * eta) - 1 + (c * c);
-  if (g < 0.0f) return MakeRGB(1, 1, 1);
-  g = Sqrt(g);
-  float fr = 0.5f * sqr((g - c) / (g + c)) * (1 + sqr((c * (g + c) - 1) / (c * (g - c) + 1)));
-  return MakeRGB(fr, fr, fr);
-}
+struct Dielectric : Fresnel {
+  float eta;
+  explicit Dielectric(float e) : eta(e) {}
+  RGB Kr(float cosTheta) const override {
+    float c = cosTheta;
+    float g = (eta * eta) - 1 + (c * c);
+    if (g < 0.0f) return MakeRGB(1, 1, 1);
+    g = Sqrt(g);
+    float fr = 0.5f * sqr((g - c) / (g + c)) * (1 + sqr((c * (g + c) - 1) / (c * (g - c) + 1)));
+    return MakeRGB(fr, fr, fr);
+  }
+};
+
+// builtin/shader/fresnel/conductor.go:19-89 ('Artist Friendly Metallic Fresnel', Gulbrandsen)
+struct Conductor : Fresnel {
+  RGB r, g;
+  Conductor(RGB r_, RGB g_) : r(r_), g(g_) {}
+  static float nMin(float r) { return (1 - r) / (1 + r); }
+  static float nMax(float r) { return (1 + Sqrt(r)) / (1 - Sqrt(r)); }
+  static float getN(float r, float g) { return nMin(r) * g + (1 - g) * nMax(r); }
+  static float getK2(float r, float n) {
+    float nr = (n + 1) * (n + 1) * r - (n - 1) * (n - 1);
+    return nr / (1 - r);
+  }
+  static float fresnel(float r, float g, float cosTheta) {
+    float nr = Clamp(r, 0, 0.99f);
+    float n = getN(nr, g);
+    float k2 = getK2(nr, n);
+    float rsNum = n * n + k2 - 2 * n * cosTheta + cosTheta * cosTheta;
+    float rsDen = n * n + k2 + 2 * n * cosTheta + cosTheta * cosTheta;
+    float rs = rsNum / rsDen;
+    float rpNum = (n * n + k2) * cosTheta * cosTheta - 2 * n * cosTheta + 1;
+    float rpDen = (n * n + k2) * cosTheta * cosTheta + 2 * n * cosTheta + 1;
+    float rp = rpNum / rpDen;
+    return 0.5f * (rs + rp);
+  }
+  RGB Kr(float cosTheta) const override {
+    RGB out;
+    for (int k = 0; k < 3; k++) out[k] = fresnel(r[k], g[k], cosTheta);
+    return out;
+  }
+};
 
 // builtin/shader/bsdf/specular.go:13-101
 static Vec3 reflectV(Vec3 omegaR, Vec3 N) { return Vec3Sub(Vec3Scale(2.0f * Vec3Dot(N, omegaR), N), omegaR); }
 struct Specular : BSDF {
   float Lambda;
   Vec3 OmegaR;
-  float eta;
+  const Fresnel* fresnel;
   Vec3 U, V, N;
-  Specular(float lambda, Vec3 omegaI, float eta_, Vec3 U_, Vec3 V_, Vec3 N_)
-      : Lambda(lambda), OmegaR(Vec3BasisProject(U_, V_, N_, omegaI)), eta(eta_), U(U_), V(V_), N(N_) {}
+  Specular(float lambda, Vec3 omegaI, const Fresnel* f, Vec3 U_, Vec3 V_, Vec3 N_)
+      : Lambda(lambda), OmegaR(Vec3BasisProject(U_, V_, N_, omegaI)), fresnel(f), U(U_), V(V_), N(N_) {}
   Vec3 Sample(double, double) override {
     Vec3 omegaO = reflectV(OmegaR, V3(0, 0, 1));
     omegaO = Vec3Normalize(omegaO);
@@ -116,10 +156,65 @@ struct Specular : BSDF {
     Vec3 omegaO = Vec3BasisProject(U, V, N, _omegaO);
     Vec3 omegaORefl = reflectV(OmegaR, V3(0, 0, 1));
     if (Vec3Dot(omegaO, omegaORefl) < 0.9999f) return rho;
-    RGB fresnel = DielectricKr(eta, OmegaR[2]);
+    RGB fr = fresnel->Kr(OmegaR[2]);
     rho.Lambda = Lambda;
-    rho.FromRGB(fresnel);
+    rho.FromRGB(fr);
     rho.Scale(Vec3DotAbs(omegaO, V3(0, 0, 1)));
+    return rho;
+  }
+};
+
+// builtin/shader/bsdf/microfacetggx.go:16-146
+static inline float chi(float x) { return x > 0.0f ? 1.0f : 0.0f; }
+static inline float signGGX(float v) { return v < 0 ? -1.0f : 1.0f; }
+static float ggxSmithG1(Vec3 omega, Vec3 omegaM, float alpha) {
+  float ODotN = Vec3Dot(omega, omegaM);
+  float denom = 1 + Sqrt(1 + (alpha * alpha) * ((1.0f / (omega[2] * omega[2])) - 1));
+  return chi(ODotN / omega[2]) * 2 / denom;
+}
+static float ggxD(Vec3 omegaM, float alpha) {
+  float numer = alpha * alpha * chi(omegaM[2]);
+  if (omegaM[2] == 1.0f) return 1.0f / (kPi * alpha * alpha);
+  float denom = kPi * sqr(omegaM[2] * omegaM[2]) * sqr(alpha * alpha + ((1.0f / (omegaM[2] * omegaM[2])) - 1));
+  return numer / denom;
+}
+struct MicrofacetGGX : BSDF {
+  float Lambda;
+  Vec3 OmegaR;
+  float Roughness;  // roughness^2 (NewMicrofacetGGX, :87); Sample/PDF/Eval square it again (alpha = roughness^4)
+  const Fresnel* fresnel;
+  Vec3 U, V, N;
+  MicrofacetGGX(float lambda, Vec3 omegaI, const Fresnel* f, float roughness, Vec3 U_, Vec3 V_, Vec3 N_)
+      : Lambda(lambda), OmegaR(Vec3BasisProject(U_, V_, N_, omegaI)), Roughness(roughness * roughness), fresnel(f), U(U_), V(V_), N(N_) {}
+  Vec3 Sample(double r0, double r1) override {
+    float alpha = sqr(Roughness);
+    double thetaM = std::atan2((double)alpha * std::sqrt(r0), std::sqrt(1 - r0));
+    double phiM = 2.0 * M_PI * r1;
+    Vec3 omegaM = V3(Sin((float)thetaM) * Cos((float)phiM), Sin((float)thetaM) * Sin((float)phiM), Cos((float)thetaM));
+    Vec3 omegaO = Vec3Sub(Vec3Scale(2.0f * Vec3DotAbs(omegaM, OmegaR), omegaM), OmegaR);
+    return Vec3BasisExpand(U, V, N, Vec3Normalize(omegaO));
+  }
+  double PDF(Vec3 _omegaO) override {
+    Vec3 omegaO = Vec3BasisProject(U, V, N, _omegaO);
+    float alpha = sqr(Roughness);
+    Vec3 omegaM = Vec3Scale(signGGX(OmegaR[2]), Vec3Normalize(Vec3Add(OmegaR, omegaO)));
+    double pdf = (double)(ggxD(omegaM, alpha) * omegaM[2]);
+    if (std::isnan(pdf)) return 0;
+    return pdf;
+  }
+  Spectrum Eval(Vec3 _omegaO) override {
+    Spectrum rho;
+    Vec3 omegaI = Vec3BasisProject(U, V, N, _omegaO);
+    float alpha = sqr(Roughness);
+    Vec3 h = Vec3Scale(signGGX(OmegaR[2]), Vec3Normalize(Vec3Add(OmegaR, omegaI)));
+    RGB fr = fresnel->Kr(Vec3DotAbs(OmegaR, h));
+    float numer = ggxSmithG1(OmegaR, h, alpha) * ggxSmithG1(omegaI, h, alpha) * ggxD(h, alpha);
+    float denom = 4 * Abs(OmegaR[2]) * Abs(omegaI[2]);
+    rho.Lambda = Lambda;
+    rho.FromRGB(fr);
+    rho.Scale(Abs(omegaI[2]) * numer / denom);
+    for (int k = 0; k < 4; k++)
+      if (rho.C[k] < 0 || std::isnan((double)rho.C[k])) rho.C[k] = 0;
     return rho;
   }
 };
@@ -165,19 +260,29 @@ void ShaderStd::Eval(ShaderContext* sg) {
   float ior = 1.7f;
   if (hasIOR) ior = IOR;
 
+  // std.go:172-192
+  Dielectric dielectric(ior);
+  RGB refl = MakeRGB(0.5f, 0.5f, 0.5f), edge = MakeRGB(0.5f, 0.5f, 0.5f);
+  if (hasSpec1FresnelRefl) refl = Spec1FresnelRefl;
+  if (hasSpec1FresnelEdge) refl = Spec1FresnelEdge;  // sic: std.go:187-189 assigns the edge tint to `refl`
+  Conductor conductor(refl, edge);
+  const Fresnel* fresnel = spec1FresnelModel == 1 ? static_cast<const Fresnel*>(&conductor) : static_cast<const Fresnel*>(&dielectric);
+
   RGB spec1Contrib;
   if (spec1Weight > 0.0f) {
     float spec1Roughness = 0.5f;
     if (hasSpec1Roughness) spec1Roughness = Spec1Roughness;
     RGB spec1Colour;
     if (hasSpec1Colour) spec1Colour = Spec1Colour;
-    if (spec1Roughness != 0.0f) throw std::runtime_error("oracle: GGX glossy lobe (Spec1Roughness>0) is not restated yet");
-    Specular spec1BRDF(sg->Lambda, Vec3Neg(sg->Rd), ior, U, V, sg->N);
+    Specular specBRDF(sg->Lambda, Vec3Neg(sg->Rd), fresnel, U, V, sg->N);
+    MicrofacetGGX ggxBRDF(sg->Lambda, Vec3Neg(sg->Rd), fresnel, spec1Roughness, U, V, sg->N);
+    BSDF& spec1BRDF = spec1Roughness == 0.0f ? static_cast<BSDF&>(specBRDF) : static_cast<BSDF&>(ggxBRDF);
 
     TraceSample samp;
     Ray ray;
     ray.Task = sg->task;
-    int spec1Samples = 1;
+    int spec1Samples = 0;
+    if (spec1Roughness == 0.0f) spec1Samples = 1;
     for (int i = 0; i < spec1Samples; i++) {
       uint64_t idx = (uint64_t)(sg->I * spec1Samples + i);
       double r0 = VanDerCorput(idx, sg->Scramble[0]);
@@ -204,6 +309,15 @@ void ShaderStd::Eval(ShaderContext* sg) {
       }
     }
     if (spec1Samples > 0) spec1Contrib.Scale(spec1Weight / (float)spec1Samples);
+
+    if (spec1Roughness > 0.0f) {  // std.go:269-284: glossy lobe = direct light only, NOT scaled by spec1Weight
+      sg->LightsPrepare();
+      while (sg->NextLight()) {
+        RGB col = sg->EvaluateLightSamples(&spec1BRDF);
+        col.Mul(spec1Colour);
+        spec1Contrib.Add(col);
+      }
+    }
   }
 
   RGB contrib;
@@ -426,6 +540,218 @@ void Tri::SampleArea(ShaderContext* sg, int n) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// builtin/light/disk.go:38-68
+static bool rayPlaneIntersectOk(Vec3 Ro, Vec3 Rd, Vec3 P, Vec3 N, float* t) {
+  float denom = Vec3Dot(N, Rd);
+  if (Abs(denom) > 1e-6f) {
+    Vec3 p0l0 = Vec3Sub(P, Ro);
+    *t = Vec3Dot(p0l0, N) / denom;
+    return *t >= 0;
+  }
+  *t = 0;
+  return false;
+}
+static bool rayDiskIntersect(Vec3 Ro, Vec3 Rd, Vec3 P, Vec3 N, float radius, float* t) {
+  if (rayPlaneIntersectOk(Ro, Rd, P, N, t)) {
+    Vec3 p = Vec3Mad(Ro, Rd, *t);
+    Vec3 v = Vec3Sub(p, P);
+    float d2 = Vec3Dot(v, v);
+    return Sqrt(d2) <= radius;
+  }
+  *t = 0;
+  return false;
+}
+
+// builtin/light/disk.go:90-97
+void Disk::PreRender() {
+  N = Vec3Normalize(Vec3Sub(LookAt, P));
+  T = Vec3Normalize(Vec3Cross(N, Up));
+  B = Vec3Cross(N, T);
+}
+
+// builtin/light/disk.go:224-262 (UVs omitted): a fan of `Segments` unindexed triangles
+PolyMesh* Disk::createMesh() {
+  PolyMesh* msh = new PolyMesh();
+  msh->Name = Name + ":<mesh>";
+  msh->shader.push_back(shader);
+  int nv = Segments;
+  float dv = 2 * kPi / (float)nv;
+  float ang = 0;
+  msh->Verts.MotionKeys = 1;
+  msh->Normals.MotionKeys = 1;
+  for (int i = 0; i < nv; i++) {
+    msh->Verts.Elems.push_back(P);
+    msh->Verts.Elems.push_back(Vec3Add(P, Vec3Add(Vec3Scale(Radius * Cos(ang), B), Vec3Scale(Radius * Sin(ang), T))));
+    msh->Verts.Elems.push_back(Vec3Add(P, Vec3Add(Vec3Scale(Radius * Cos(ang + dv), B), Vec3Scale(Radius * Sin(ang + dv), T))));
+    msh->Verts.ElemsPerKey += 3;
+    msh->Normals.Elems.push_back(N);
+    msh->Normals.Elems.push_back(N);
+    msh->Normals.Elems.push_back(N);
+    msh->Normals.ElemsPerKey += 3;
+    ang += dv;
+  }
+  return msh;
+}
+
+// builtin/light/disk.go:123-169
+bool Disk::ValidSample(ShaderContext* sg, BSDFSample* sample) {
+  double pdf = (double)(1.0f / (kPi * Radius * Radius));
+  float t;
+  if (!rayDiskIntersect(sg->P, sample->D, P, N, Radius, &t)) return false;
+  Vec3 p = Vec3Mad(sg->P, sample->D, t);
+  Vec3 V = Vec3Sub(p, sg->P);
+  if (Vec3Dot(V, sg->Ng) <= 0.0f || Vec3Dot(V, N) >= 0.0f) return false;
+  sample->Ldist = Vec3Length(V);
+  sample->Ld = Vec3Normalize(V);
+  sample->Liu.Lambda = sg->Lambda;
+  RGB E = shader->EvalEmission(nullptr, Vec3Neg(sample->Ld));
+  sample->Liu.FromRGB(E);
+  sample->PdfLight = (float)pdf * (sample->Ldist * sample->Ldist) / (Abs(Vec3Dot(sample->Ld, N)));
+  return true;
+}
+
+// builtin/light/disk.go:172-217
+void Disk::SampleArea(ShaderContext* sg, int n) {
+  for (int i = 0; i < n; i++) {
+    uint64_t idx = (uint64_t)(sg->I * n + i);
+    double r0 = VanDerCorput(idx, sg->Scramble[0]);
+    double r1 = Sobol(idx, sg->Scramble[1]);
+    float u = Radius * Sqrt((float)r0) * Cos(2 * kPi * (float)r1);
+    float v = Radius * Sqrt((float)r0) * Sin(2 * kPi * (float)r1);
+    double pdf = (double)(1.0f / (kPi * Radius * Radius));
+    Vec3 Pl = Vec3Add3(P, Vec3Scale(u, B), Vec3Scale(v, T));
+    Vec3 V = Vec3Sub(Pl, sg->P);
+    LightSample ls{};
+    if (Vec3Dot(V, sg->Ng) > 0.0f && Vec3Dot(V, N) < 0.0f) {
+      ls.Ldist = Vec3Length(V);
+      ls.Ld = Vec3Normalize(V);
+      ls.Liu.Lambda = sg->Lambda;
+      RGB E = shader->EvalEmission(nullptr, Vec3Neg(ls.Ld));
+      ls.Liu.FromRGB(E);
+      ls.Pdf = (float)pdf * (ls.Ldist * ls.Ldist) / Abs(Vec3Dot(ls.Ld, N));
+      sg->Lsamples.push_back(ls);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// builtin/geom/sphere/trace.go:53-109 == builtin/light/sphere.go:69-127
+static bool solveQuadratic(float a, float b, float c, float* x0, float* x1) {
+  float discr = b * b - 4 * a * c;
+  if (discr < 0) return false;
+  if (discr == 0) {
+    *x1 = -0.5f * b / a;
+    *x0 = *x1;
+  } else {
+    float q;
+    if (b > 0) q = -0.5f * (b + Sqrt(discr));
+    else q = -0.5f * (b - Sqrt(discr));
+    *x0 = q / a;
+    *x1 = c / q;
+  }
+  if (*x0 > *x1) std::swap(*x0, *x1);
+  return true;
+}
+static bool raySphereIntersect(Vec3 Ro, Vec3 Rd, Vec3 P, float radius, float* t) {
+  Vec3 L = Vec3Sub(Ro, P);
+  float a = Vec3Dot(Rd, Rd);
+  float b = 2 * Vec3Dot(Rd, L);
+  float c = Vec3Dot(L, L) - radius * radius;
+  float t0 = 0, t1 = 0;
+  if (!solveQuadratic(a, b, c, &t0, &t1)) return false;
+  if (t0 > t1) std::swap(t0, t1);
+  if (t0 < 0) {
+    t0 = t1;
+    if (t0 < 0) return false;
+  }
+  *t = t0;
+  return true;
+}
+
+// builtin/geom/sphere/trace.go:13-51 (U,V surface parameters omitted: every in-scope shader parameter is a Constant map)
+bool SphereGeom::Trace(Ray* ray, ShaderContext* sg) {
+  float t;
+  if (raySphereIntersect(ray->P, ray->D, P, Radius, &t)) {
+    if (t < ray->Tclosest) {
+      ray->Tclosest = t;
+      Vec3 Ph = Vec3Mad(ray->P, ray->D, t);
+      Vec3 N = Vec3Normalize(Vec3Sub(Ph, P));
+      sg->Poffset = Vec3Scale(0.001f, N);
+      sg->Ng = N;
+      sg->N = N;
+      sg->Bu = 0;
+      sg->Bv = 0;
+      sg->Bw = 0;
+      sg->P = Ph;
+      sg->Po = sg->P;
+      sg->DdPdu = V3(1, 0, 0);
+      sg->DdPdv = V3(0, 0, 1);
+      sg->shader = shader;
+      sg->ElemID = 0;  // the reference leaves ElemID untouched (stale); the oracle and the device both report 0
+      return true;
+    }
+  }
+  return false;
+}
+// builtin/geom/sphere/sphere.go:66-76
+BoundingBox SphereGeom::Bounds(float) const {
+  BoundingBox b;
+  for (int k = 0; k < 3; k++) {
+    b.b[0][k] = P[k] - Radius;
+    b.b[1][k] = P[k] + Radius;
+  }
+  return b;
+}
+
+// builtin/light/sphere.go:132-183
+bool SphereLight::ValidSample(ShaderContext* sg, BSDFSample* sample) {
+  float t;
+  if (!raySphereIntersect(sg->P, sample->D, P, Radius, &t)) return false;
+  Vec3 x = Vec3Mad(sg->P, sample->D, t);
+  Vec3 D = Vec3Sub(x, sg->P);
+  sample->Ldist = Vec3Length(D);
+  sample->Ld = Vec3Normalize(D);
+  sample->Liu.Lambda = sg->Lambda;
+  RGB E = shader->EvalEmission(nullptr, Vec3Neg(sample->D));
+  sample->Liu.FromRGB(E);
+  Vec3 V = Vec3Sub(P, sg->P);
+  float l = Vec3Length(V);
+  sample->PdfLight = 1 / (2 * kPi * (1 - Sqrt(1 - sqr(Radius / l))));
+  return true;
+}
+
+// builtin/light/sphere.go:186-270 (sg.Sample is never set on this path: 0)
+void SphereLight::SampleArea(ShaderContext* sg, int n) {
+  Vec3 V = Vec3Sub(P, sg->P);
+  float l = Vec3Length(V);
+  Vec3 w = Vec3Normalize(V);
+  Vec3 v = Vec3Normalize(Vec3Cross(w, sg->Ng));
+  Vec3 u = Vec3Cross(w, v);
+  for (int i = 0; i < n; i++) {
+    uint64_t idx = (uint64_t)(sg->I * n + 0 + i);
+    double r0 = VanDerCorput(idx, sg->Scramble[0]);
+    double r1 = Sobol(idx, sg->Scramble[1]);
+    float theta = Acos(1 - (float)r0 + (float)r0 * Sqrt(1 - sqr(Radius / l)));
+    float phi = 2 * kPi * (float)r1;
+    Vec3 a = V3(Cos(phi) * Sin(theta), Sin(phi) * Sin(theta), Cos(theta));
+    Vec3 omega = Vec3BasisExpand(u, v, w, a);
+    if (Vec3Dot(omega, sg->Ng) < 0) continue;
+    float t;
+    if (!raySphereIntersect(sg->P, omega, P, Radius, &t)) continue;
+    Vec3 x = Vec3Mad(sg->P, omega, t);
+    Vec3 D = Vec3Sub(x, sg->P);
+    LightSample ls{};
+    ls.Ldist = Vec3Length(D);
+    ls.Ld = Vec3Normalize(D);
+    ls.Liu.Lambda = sg->Lambda;
+    RGB E = shader->EvalEmission(nullptr, Vec3Neg(omega));
+    ls.Liu.FromRGB(E);
+    ls.Pdf = 1 / (2 * kPi * (1 - Sqrt(1 - sqr(Radius / l))));
+    sg->Lsamples.push_back(ls);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 static inline float degToRad(float deg) { return deg * kPi / 180.0f; }
 
 // builtin/camera/camera.go:80-98,109-193 (single key: the else branch :154-187 with i=0)
@@ -612,16 +938,37 @@ void Renderer::PreRender() {
     m->id = gid++;
     scene.geoms.push_back(m.get());
   }
-  for (auto& t : tris) {
-    PolyMesh* g = t->createMesh();
-    meshes.emplace_back(g);
-    t->geom = g;
-    scene.lights.push_back(t.get());
+  // lights PreRender in creation order; each appends its geom (core.AddNode), which is pre-rendered in the next round
+  const size_t firstLightGeom = meshes.size();
+  std::vector<Geom*> lightGeoms;
+  for (Light* l : lightOrder) {
+    if (Tri* t = dynamic_cast<Tri*>(l)) {
+      PolyMesh* g = t->createMesh();
+      meshes.emplace_back(g);
+      t->geom = g;
+      lightGeoms.push_back(g);
+    } else if (Disk* d = dynamic_cast<Disk*>(l)) {
+      d->PreRender();
+      PolyMesh* g = d->createMesh();
+      meshes.emplace_back(g);
+      d->geom = g;
+      lightGeoms.push_back(g);
+    } else if (SphereLight* sl = dynamic_cast<SphereLight*>(l)) {
+      SphereGeom* g = new SphereGeom();
+      g->Name = sl->Name + ":<sphere>";
+      g->P = sl->P;
+      g->Radius = sl->Radius;
+      g->shader = sl->shader;
+      sphereGeoms.emplace_back(g);
+      sl->geom = g;
+      lightGeoms.push_back(g);
+    }
+    scene.lights.push_back(l);
   }
-  for (size_t i = scene.geoms.size(); i < meshes.size(); i++) {
-    meshes[i]->PreRender();
-    meshes[i]->id = gid++;
-    scene.geoms.push_back(meshes[i].get());
+  for (size_t i = firstLightGeom; i < meshes.size(); i++) meshes[i]->PreRender();
+  for (Geom* g : lightGeoms) {
+    g->id = gid++;
+    scene.geoms.push_back(g);
   }
   scene.initAccel();
   prerendered = true;

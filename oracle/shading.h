@@ -6,14 +6,16 @@
 //   builtin/shader/std.go:77-316              (ShaderStd.Eval / EvalEmission)
 //   builtin/shader/bsdf/orennayar.go:16-73    (OrenNayar)
 //   builtin/shader/bsdf/specular.go:13-101    (Specular mirror)
-//   builtin/shader/fresnel/dielectric.go:16-47 (Dielectric)
+//   builtin/shader/bsdf/microfacetggx.go:16-146 (MicrofacetGGX glossy lobe)
+//   builtin/shader/fresnel/dielectric.go:16-47, conductor.go:19-89, models.go:13-17 (Dielectric, Conductor)
 //   math/sample/sample.go:18-30,105-129       (CosineHemisphere, UniformDisk2D)
 //   builtin/light/triangle.go:71-343,376-535  (Tri light: area + spherical-triangle sampling)
-//   builtin/light/disk.go:38-51               (rayPlaneIntersect)
+//   builtin/light/disk.go:21-270              (Disk light; rayPlaneIntersect / rayDiskIntersect)
+//   builtin/light/sphere.go:17-304            (Sphere light)
+//   builtin/geom/sphere/sphere.go:15-86, trace.go:13-109 (Sphere geom, only used by the sphere light)
 //   builtin/camera/camera.go:80-98,109-193,221-323 (Camera)
 //   core/render.go:18-23,66-137,166-205       (pixelscramble, render, Render)
-// Out of scope here: GGX glossy lobe (roughness>0 spec lobe contributes direct light only in the
-// reference; not restated yet), Conductor fresnel, Disk/Sphere/Quad lights, pixel filters.
+// Out of scope here: Quad light (both sampling entry points panic in the reference, quad.go:88,94).
 #pragma once
 #include <string>
 #include <vector>
@@ -36,6 +38,9 @@ struct ShaderStd : Shader {
   float Spec1Strength = 0, Spec1Roughness = 0;
   bool hasIOR = false;
   float IOR = 0;
+  int spec1FresnelModel = 0;  // fresnel.DielectricModel = 0 (the zero value when Spec1FresnelModel is unset), ConductorModel = 1
+  bool hasSpec1FresnelRefl = false, hasSpec1FresnelEdge = false;
+  RGB Spec1FresnelRefl, Spec1FresnelEdge;
 
   void Eval(ShaderContext* sg) override;
   RGB EvalEmission(ShaderContext* sg, Vec3 omegaO) override;
@@ -51,6 +56,52 @@ struct Tri : Light {
   PolyMesh* createMesh();
   void SampleArea(ShaderContext* sg, int n) override;
   void sampleByArea(ShaderContext* sg, int n);
+  float DiffuseShadeMult() override { return 1; }
+  int NumSamples(ShaderContext*) override { return 1 << (unsigned)Samples; }
+  bool ValidSample(ShaderContext* sg, BSDFSample* sample) override;
+  Geom* GetGeom() override { return geom; }
+};
+
+// builtin/light/disk.go:21-34
+struct Disk : Light {
+  std::string Name;
+  Vec3 P, Up, LookAt;
+  Vec3 T, B, N;
+  float Radius = 0;
+  int Segments = 20, Samples = 1;
+  Shader* shader = nullptr;
+  PolyMesh* geom = nullptr;
+
+  void PreRender();  // disk.go:90-97: N, T, B
+  PolyMesh* createMesh();
+  void SampleArea(ShaderContext* sg, int n) override;
+  float DiffuseShadeMult() override { return 1; }
+  int NumSamples(ShaderContext*) override { return 1 << (unsigned)Samples; }
+  bool ValidSample(ShaderContext* sg, BSDFSample* sample) override;
+  Geom* GetGeom() override { return geom; }
+};
+
+// builtin/geom/sphere/sphere.go:15-86, trace.go:13-109
+struct SphereGeom : Geom {
+  std::string Name;
+  Vec3 P;
+  float Radius = 1;
+  Shader* shader = nullptr;
+  bool Trace(Ray*, ShaderContext*) override;
+  int MotionKeys() const override { return 1; }
+  BoundingBox Bounds(float time) const override;
+};
+
+// builtin/light/sphere.go:17-304
+struct SphereLight : Light {
+  std::string Name;
+  Vec3 P;
+  float Radius = 1;
+  int Samples = 1;
+  Shader* shader = nullptr;
+  SphereGeom* geom = nullptr;
+
+  void SampleArea(ShaderContext* sg, int n) override;
   float DiffuseShadeMult() override { return 1; }
   int NumSamples(ShaderContext*) override { return 1 << (unsigned)Samples; }
   bool ValidSample(ShaderContext* sg, BSDFSample* sample) override;
@@ -105,6 +156,10 @@ struct Renderer {
   std::vector<std::unique_ptr<PolyMesh>> meshes;
   std::vector<std::unique_ptr<ShaderStd>> shaders;
   std::vector<std::unique_ptr<Tri>> tris;
+  std::vector<std::unique_ptr<Disk>> disks;
+  std::vector<std::unique_ptr<SphereLight>> sphereLights;
+  std::vector<std::unique_ptr<SphereGeom>> sphereGeoms;
+  std::vector<Light*> lightOrder;  // every light in node-creation order (core.AddNode -> scene.AddLight, core/core.go:77-93)
   bool prerendered = false;
   std::unique_ptr<PixelFilter> filter;  // core.filter (core/core.go:15), set by AddNode for a PixelFilter node
   bool trace_last_level = true;  // false: skip the level-4 mirror ray whose shader returns black (std.go:95)

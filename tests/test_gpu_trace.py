@@ -136,3 +136,35 @@ def test_traversal_variants(built_library, variant):
     dev.set_option("traversal", variant)
     rays = random_rays(30000, 3, lo=(-1.1, 0.0, -1.1), hi=(1.1, 1.5, 1.1))
     assert_hits_equal(dev.trace(rays), ora.trace(rays), what="variant %d sphere field" % variant)
+
+
+def test_sphere_geom_leaf_is_bit_exact(built_library):
+    """The analytic Sphere geom a SphereLight adds to the scene-level tree (builtin/geom/sphere/trace.go): closest-hit and
+    any-hit batches through every traversal variant agree with the oracle bit for bit, sphere hits included."""
+    from oracle.binding import Oracle
+    from vermeer_b200 import scenes
+    from vermeer_b200.host import Device, HostScene
+    from conftest import assert_hits_equal, random_rays
+    sc = scenes.glossy_box(64, 64)
+    ora = Oracle(sc)
+    ora.set_scramble(scenes.splitmix64_table(1, 64 * 64))
+    host = HostScene(sc).prerender()
+    dev = Device(0).upload(host)
+    rays = np.concatenate([ora.camera_rays(1), random_rays(40000, 11, lo=(-0.9, 0.1, -0.9), hi=(0.9, 1.9, 0.9))])
+    # aim a third of the random rays at the sphere light so that the analytic leaf is hit often
+    n = len(rays)
+    tgt = np.asarray([0.0, 1.3, 0.55], np.float32) + np.random.default_rng(5).normal(scale=0.08, size=(n, 3)).astype(np.float32)
+    aim = np.arange(n) % 3 == 0
+    d = tgt - rays["o"]
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays["d"][aim] = d[aim].astype(np.float32)
+    o = ora.trace(rays)
+    sphere_geom = int(o["geom"][(o["prim"] == 0) & (o["u"] == 0) & (o["v"] == 0) & (o["geom"] >= 0)].max())
+    assert (o["geom"] == sphere_geom).sum() > 1000
+    for variant in (0, 1, 2):
+        dev.set_option("traversal", variant)
+        assert_hits_equal(dev.trace(rays), o, what="sphere scene closest variant %d" % variant)
+        sh = rays.copy()
+        sh["tmax"] = 2.5
+        og, gg = ora.trace(sh, any_hit=True), dev.trace(sh, any_hit=True)
+        assert np.array_equal(og["prim"] >= 0, gg["prim"] >= 0), "any-hit occlusion differs (variant %d)" % variant

@@ -34,7 +34,7 @@ def test_registry_mirrors_nodes_register(built_library):
     arr = (C.c_char_p * n)()
     lib.vh_registered_nodes(arr, n)
     names = sorted(a.decode() for a in arr)
-    assert names == ["AiryFilter", "Camera", "GaussianFilter", "Globals", "PolyMesh", "ShaderStd", "TriLight"]
+    assert names == ["AiryFilter", "Camera", "DiskLight", "GaussianFilter", "Globals", "PolyMesh", "ShaderStd", "Sphere", "SphereLight", "TriLight"]
 
 
 def _equal_nodes(a, b):
@@ -43,7 +43,7 @@ def _equal_nodes(a, b):
     return a.tobytes() == b.tobytes()
 
 
-@pytest.mark.parametrize("name", ["cornell", "heightfield", "motion", "spheres"])
+@pytest.mark.parametrize("name", ["cornell", "heightfield", "motion", "spheres", "glossy"])
 def test_host_prerender_matches_oracle_bit_for_bit(built_library, name):
     from oracle.binding import Oracle
     from vermeer_b200 import scenes
@@ -51,13 +51,21 @@ def test_host_prerender_matches_oracle_bit_for_bit(built_library, name):
     sc = {"cornell": lambda: scenes.cornell_box(64, 48),
           "heightfield": lambda: scenes.heightfield_scene(64, 48, nq=300),   # > 65536 triangles: exercises the parallel builder
           "motion": lambda: scenes.heightfield_scene(64, 48, nq=90, motion=True),
-          "spheres": lambda: scenes.sphere_field_scene(64, 48, nmesh=9, slices=12, stacks=13)}[name]()
+          "spheres": lambda: scenes.sphere_field_scene(64, 48, nmesh=9, slices=12, stacks=13),
+          # TriLight + DiskLight (fan mesh) + SphereLight (analytic Sphere geom in the scene-level tree)
+          "glossy": lambda: scenes.glossy_box(64, 48)}[name]()
     o = Oracle(sc)
     h = HostScene(sc).prerender()
     assert np.array_equal(o.scene_geom_order(), h.scene_geom_order())
     assert _equal_nodes(o.scene_nodes(), h.scene_nodes())
     for g in range(o.num_geoms()):
-        assert o.mesh_info(g) == h.mesh_info(g)
+        try:
+            info = o.mesh_info(g)
+        except RuntimeError:   # an analytic Sphere geom: no mesh on either side
+            with pytest.raises(RuntimeError):
+                h.mesh_info(g)
+            continue
+        assert info == h.mesh_info(g)
         assert _equal_nodes(o.mesh_nodes(g), h.mesh_nodes(g))
         io, ih = o.mesh_idxp(g), h.mesh_idxp(g)
         assert np.array_equal(io[0], ih[0]) and np.array_equal(io[1], ih[1])

@@ -161,6 +161,22 @@ int vg_mesh_upload_motion(vg_ctx* ctx, int geom_id, const VgMotionNode* topo, in
   return VG_OK;
 }
 
+int vg_sphere_upload(vg_ctx* ctx, int geom_id, const float* centre, float radius, int32_t material_id) {
+  VG_LOCK(ctx);
+  if (geom_id < 0 || geom_id >= (int)ctx->meshes.size()) return ctx->fail(VG_ERR_INVALID, "geom_id out of range");
+  if (!centre) return ctx->fail(VG_ERR_INVALID, "vg_sphere_upload: null centre");
+  MeshStage& m = ctx->meshes[geom_id];
+  m = MeshStage();
+  m.present = true;
+  m.sphere = true;
+  m.centre[0] = centre[0]; m.centre[1] = centre[1]; m.centre[2] = centre[2];
+  m.radius = radius;
+  m.n_tris = 1;  // one record in the triangle array, one prim (ElemID 0)
+  m.material_ids.assign(1, material_id);
+  ctx->committed = false;
+  return VG_OK;
+}
+
 int vg_scene_upload(vg_ctx* ctx, const VgNode* nodes, int n_nodes, const int32_t* geom_of_slot, int n_slots) {
   VG_LOCK(ctx);
   if (!nodes || n_nodes <= 0 || !geom_of_slot || n_slots < 0) return ctx->fail(VG_ERR_INVALID, "vg_scene_upload: null/empty input");
@@ -231,7 +247,7 @@ int vg_scene_commit(vg_ctx* ctx) {
   }
   if (n_tris > (int64_t)kLeafBaseMask || n_mtris > (int64_t)kLeafBaseMask)
     return ctx->fail(VG_ERR_UNSUPPORTED, "scene exceeds 2^25 triangle slots");
-  if (n_static + n_motion >= (int64_t)0x3FFFFFFF) return ctx->fail(VG_ERR_UNSUPPORTED, "too many nodes");
+  if (n_static + n_motion >= (int64_t)kGeomRootMask) return ctx->fail(VG_ERR_UNSUPPORTED, "too many nodes");
   auto motion_global = [&](int64_t rel) { return (int32_t)(n_static + rel); };
   auto mesh_root = [&](int g) -> int32_t {
     return ctx->meshes[g].motion ? motion_global(node_base[g]) : (int32_t)node_base[g];
@@ -262,7 +278,14 @@ int vg_scene_commit(vg_ctx* ctx) {
     dg.pad0 = dg.pad1 = 0;
     if (m.material_ids.size() > 255) return ctx->fail(VG_ERR_UNSUPPORTED, "more than 255 shaders on one mesh");
 
-    if (!m.motion) {
+    if (m.sphere) {
+      dg.keys = 0;
+      float4* t = &tris[(size_t)tri_base[g] * 3];
+      t[0] = make_float4(m.centre[0], m.centre[1], m.centre[2], i2f((int32_t)g));
+      t[1] = make_float4(m.radius, 0.f, 0.f, i2f(0));
+      t[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+      prim_material[(size_t)prim_base[g]] = (uint8_t)m.material_ids[0];
+    } else if (!m.motion) {
       for (size_t i = 0; i < m.nodes.size(); i++) {
         const VgNode& s = m.nodes[i];
         int32_t c[4];
@@ -363,7 +386,8 @@ int vg_scene_commit(vg_ctx* ctx) {
       if (count != 1 || first >= (int)S.geom_of_slot.size()) return false;
       const int g = S.geom_of_slot[first];
       if (g < 0 || g >= G) return false;
-      *out = (int32_t)(kLeafBit | kGeomBit | (uint32_t)mesh_root(g));
+      if (ctx->meshes[g].sphere) *out = (int32_t)(kLeafBit | kGeomBit | kSphereBit | (uint32_t)tri_base[g]);
+      else *out = (int32_t)(kLeafBit | kGeomBit | (uint32_t)mesh_root(g));
     }
     return true;
   };
@@ -415,7 +439,8 @@ int vg_scene_commit(vg_ctx* ctx) {
   d.n_static = (int32_t)n_static;
   d.root = S.motion ? motion_global(scene_node_base) : (int32_t)scene_node_base;
   d.n_geoms = G;
-  d.pad = 0;
+  d.n_spheres = 0;
+  for (int g = 0; g < G; g++) d.n_spheres += ctx->meshes[g].sphere ? 1 : 0;
   ctx->committed = true;
   render_invalidate(ctx);
   return VG_OK;
@@ -433,6 +458,27 @@ int vg_set_materials(vg_ctx* ctx, const VgMaterial* mats, int n) {
 int vg_set_lights(vg_ctx* ctx, const VgTriLight* lights, int n) {
   VG_LOCK(ctx);
   if (n < 0 || (n > 0 && !lights)) return ctx->fail(VG_ERR_INVALID, "vg_set_lights: bad input");
+  ctx->lights.clear();
+  for (int i = 0; i < n; i++) {
+    VgLight l{};
+    l.type = VG_LIGHT_TRI;
+    l.samples = lights[i].samples;
+    l.material = lights[i].material;
+    l.geom = lights[i].geom;
+    std::memcpy(l.p0, lights[i].p0, 12);
+    std::memcpy(l.p1, lights[i].p1, 12);
+    std::memcpy(l.p2, lights[i].p2, 12);
+    ctx->lights.push_back(l);
+  }
+  render_invalidate(ctx);
+  return VG_OK;
+}
+
+int vg_set_area_lights(vg_ctx* ctx, const VgLight* lights, int n) {
+  VG_LOCK(ctx);
+  if (n < 0 || (n > 0 && !lights)) return ctx->fail(VG_ERR_INVALID, "vg_set_area_lights: bad input");
+  for (int i = 0; i < n; i++)
+    if (lights[i].type < VG_LIGHT_TRI || lights[i].type > VG_LIGHT_SPHERE) return ctx->fail(VG_ERR_INVALID, "vg_set_area_lights: unknown light type");
   ctx->lights.assign(lights, lights + n);
   render_invalidate(ctx);
   return VG_OK;
@@ -497,6 +543,10 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
   else if (!std::strcmp(name, "tma_stage")) ctx->opt_traversal = value != 0 ? 1 : 2;
   else if (!std::strcmp(name, "primary_per_lane")) ctx->opt_primary_per_lane = value != 0;
   else if (!std::strcmp(name, "shadow_unordered")) ctx->opt_shadow_unordered = value != 0;
+  else if (!std::strcmp(name, "generic_shade")) {
+    ctx->opt_generic_shade = value != 0;
+    render_invalidate(ctx);
+  }
   else if (!std::strcmp(name, "pixel_block")) {
     ctx->opt_pixel_block = value != 0;
     render_invalidate(ctx);

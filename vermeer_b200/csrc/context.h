@@ -14,6 +14,9 @@ namespace vg {
 struct MeshStage {
   bool present = false;
   bool motion = false;
+  bool sphere = false;  // sphere.Sphere geom: centre/radius below, one triangle-slot-sized record, one prim
+  float centre[3] = {0, 0, 0};
+  float radius = 0;
   std::vector<VgNode> nodes;
   std::vector<VgMotionNode> topo;
   std::vector<float> boxes;  // [keys][n_nodes][24]
@@ -94,7 +97,7 @@ struct vg_ctx {
 
   // shading inputs
   std::vector<VgMaterial> materials;
-  std::vector<VgTriLight> lights;
+  std::vector<VgLight> lights;
   VgCamera camera{};
   bool have_camera = false;
   int xres = 0, yres = 0;
@@ -108,6 +111,7 @@ struct vg_ctx {
   int opt_precise_trig = 0;
   int opt_primary_per_lane = 1;  // with traversal=2: camera rays (level 0) still use the per-lane loop
   int opt_shadow_unordered = 1;  // integrator shadow queue: skip the sign-ordered push (occlusion is order independent)
+  int opt_generic_shade = 0;     // 1 = always shade with the general kernel (tests: it must agree with the specialised one)
   int opt_pixel_block = 1;       // paths of one warp cover an 8x4 pixel block of a tile (1) or a 32x1 row (0)
   int opt_traversal = 2;  // 0: per-lane while-while, 1: the same over a TMA-staged ray queue, 2: warp-cooperative leaves (traverse.cuh)
 

@@ -20,10 +20,14 @@ namespace vg {
 //   c >= 0                      interior node, global index (static if c < n_static, else motion node c - n_static)
 //   c == -1                     empty child (qbvh.go:67-79)
 //   bit31=1 bit30=0             triangle leaf: bit29 = motion triangles, base = (c>>4)&0x1FFFFFF, count = (c&15)+1
-//   bit31=1 bit30=1 (c != -1)   geom leaf (scene level, leafMax=1): root node global index = c & 0x3FFFFFFF
+//   bit31=1 bit30=1 (c != -1)   geom leaf (scene level, leafMax=1): bit29 = 0: root node global index = c & 0x1FFFFFFF
+//                               bit29 = 1: analytic sphere geom, record at triangle slot c & 0x1FFFFFF of `tris`
+//                               ({centre.xyz, geom id}, {radius, 0, 0, prim 0}, {0,0,0,0})
 static const uint32_t kLeafBit = 0x80000000u;
 static const uint32_t kGeomBit = 0x40000000u;
 static const uint32_t kMotionTriBit = 0x20000000u;
+static const uint32_t kSphereBit = 0x20000000u;      // with kGeomBit
+static const uint32_t kGeomRootMask = 0x1FFFFFFFu;
 static const uint32_t kLeafBaseMask = 0x1FFFFFFu;  // 25 bits: 33.5 M triangle slots per kind
 
 struct __align__(16) DevNode {  // 128 B
@@ -44,7 +48,7 @@ struct DevGeom {  // per geom (creation order)
   int32_t tri_base;     // global slot of the mesh's first triangle (static or motion space)
   int32_t prim_base;    // into prim_material[]
   int32_t normal_base;  // slot base into tri_normals[] (3 float4 per slot), or -1
-  int32_t keys;         // 1 = static
+  int32_t keys;         // 1 = static mesh, > 1 = motion mesh, 0 = analytic sphere (tri_base = its record)
   int32_t tri_key_stride;
   int32_t n_tris;
   int32_t pad0, pad1;
@@ -62,7 +66,7 @@ struct DevScene {
   int32_t n_static;              // number of static nodes (motion node global index = n_static + i)
   int32_t root;                  // global index of the scene-level root node
   int32_t n_geoms;
-  int32_t pad;
+  int32_t n_spheres;             // analytic sphere geoms in the scene-level tree (selects the kernels that carry their leaf test)
 };
 
 }  // namespace vg

@@ -49,6 +49,9 @@ struct RegisterBuiltins {
     Register("PolyMesh", [] { return std::unique_ptr<Node>(new PolyMesh()); });
     Register("ShaderStd", [] { return std::unique_ptr<Node>(new ShaderStd()); });
     Register("TriLight", [] { return std::unique_ptr<Node>(new TriLight()); });
+    Register("DiskLight", [] { return std::unique_ptr<Node>(new DiskLight()); });      // disk.go:263-269
+    Register("SphereLight", [] { return std::unique_ptr<Node>(new SphereLight()); });  // sphere.go:297-303
+    Register("Sphere", [] { return std::unique_ptr<Node>(new SphereGeom()); });        // geom/sphere/sphere.go:78-86
     // builtin/filter/filter.go:14-26
     Register("AiryFilter", [] { PixelFilter* f = new PixelFilter(); f->kind = 1; f->Res = 49; f->Width = 6; f->Peak = 4; return std::unique_ptr<Node>(f); });
     Register("GaussianFilter", [] { PixelFilter* f = new PixelFilter(); f->kind = 2; f->Res = 17; f->Width = 2; f->Peak = 0; return std::unique_ptr<Node>(f); });
@@ -388,6 +391,99 @@ int TriLight::PreRender(Core& core, std::string* err) {
   return 0;
 }
 
+static void put3(float* d, V3 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
+void TriLight::Describe(VgLight* o) const {
+  std::memset(o, 0, sizeof(*o));
+  o->type = VG_LIGHT_TRI;
+  o->samples = Samples;
+  o->material = shader ? shader->material_id : -1;
+  o->geom = geom ? geom->id : -1;
+  put3(o->p0, P0); put3(o->p1, P1); put3(o->p2, P2);
+}
+
+// ---- DiskLight (builtin/light/disk.go:76-106,224-262) ----------------------------------------------
+static inline float cos32f(float x) { return (float)std::cos((double)x); }  // math/sincos.go: float32 trig goes through float64
+static inline float sin32f(float x) { return (float)std::sin((double)x); }
+int DiskLight::PreRender(Core& core, std::string* err) {
+  Node* n = core.FindNode(Shader);
+  if (!n) { *err = "Unable to find node (shader " + Shader + ")"; return -1; }
+  shader = dynamic_cast<ShaderStd*>(n);
+  if (!shader) { *err = "Unable to find shader " + Shader; return -1; }
+  N = normalize(LookAt - P);
+  T = normalize(cross(N, Up));
+  B = cross(N, T);
+  // createMesh: a fan of `Segments` unindexed triangles with the normal N on every vertex (UVs omitted)
+  std::unique_ptr<PolyMesh> m(new PolyMesh());
+  m->NodeName = NodeName + ":<mesh>";
+  m->Shader = {Shader};
+  m->Verts.MotionKeys = 1;
+  m->Normals.MotionKeys = 1;
+  const int nv = Segments;
+  const float dv = 2 * kPi32 / (float)nv;
+  float ang = 0;
+  for (int i = 0; i < nv; i++) {
+    m->Verts.Elems.push_back(P);
+    m->Verts.Elems.push_back(P + (scale(Radius * cos32f(ang), B) + scale(Radius * sin32f(ang), T)));
+    m->Verts.Elems.push_back(P + (scale(Radius * cos32f(ang + dv), B) + scale(Radius * sin32f(ang + dv), T)));
+    m->Verts.ElemsPerKey += 3;
+    m->Normals.Elems.push_back(N);
+    m->Normals.Elems.push_back(N);
+    m->Normals.Elems.push_back(N);
+    m->Normals.ElemsPerKey += 3;
+    ang += dv;
+  }
+  geom = m.get();
+  core.AddNode(std::move(m));
+  return 0;
+}
+void DiskLight::Describe(VgLight* o) const {
+  std::memset(o, 0, sizeof(*o));
+  o->type = VG_LIGHT_DISK;
+  o->samples = Samples;
+  o->material = shader ? shader->material_id : -1;
+  o->geom = geom ? geom->id : -1;
+  put3(o->p0, P); put3(o->p1, T); put3(o->p2, B); put3(o->n, N);
+  o->radius = Radius;
+}
+
+// ---- Sphere geom + SphereLight (builtin/geom/sphere/sphere.go:41-76, builtin/light/sphere.go:38-61) ----
+int SphereGeom::PreRender(Core& core, std::string* err) {
+  Node* n = core.FindNode(Shader);
+  if (!n) { *err = "Unable to find node (shader " + Shader + ")"; return -1; }
+  shader = dynamic_cast<ShaderStd*>(n);
+  if (!shader) { *err = "Unable to find shader " + Shader; return -1; }
+  return 0;
+}
+Box SphereGeom::Bounds(float) const {
+  Box b;
+  b.lo[0] = P.x - Radius; b.lo[1] = P.y - Radius; b.lo[2] = P.z - Radius;
+  b.hi[0] = P.x + Radius; b.hi[1] = P.y + Radius; b.hi[2] = P.z + Radius;
+  return b;
+}
+int SphereLight::PreRender(Core& core, std::string* err) {
+  Node* n = core.FindNode(Shader);
+  if (!n) { *err = "Unable to find node (shader " + Shader + ")"; return -1; }
+  shader = dynamic_cast<ShaderStd*>(n);
+  if (!shader) { *err = "Unable to find shader " + Shader; return -1; }
+  std::unique_ptr<SphereGeom> g(new SphereGeom());
+  g->NodeName = NodeName + ":<sphere>";  // the reference leaves the geom unnamed; a name keeps the node map unambiguous
+  g->P = P;
+  g->Radius = Radius;
+  g->Shader = Shader;
+  geom = g.get();
+  core.AddNode(std::move(g));
+  return 0;
+}
+void SphereLight::Describe(VgLight* o) const {
+  std::memset(o, 0, sizeof(*o));
+  o->type = VG_LIGHT_SPHERE;
+  o->samples = Samples;
+  o->material = shader ? shader->material_id : -1;
+  o->geom = geom ? geom->id : -1;
+  put3(o->p0, P);
+  o->radius = Radius;
+}
+
 // ---- pixel filters (builtin/filter) -----------------------------------------------------------------
 namespace {
 double bessel_j1(double x) {  // airy.go:34-72 (Numerical-Recipes rational approximations)
@@ -528,8 +624,11 @@ void Core::AddNode(std::unique_ptr<Node> node) {
   if (PolyMesh* pm = dynamic_cast<PolyMesh*>(n)) {
     pm->id = next_geom_id++;
     scene.AddGeom(pm);
-  } else if (TriLight* tl = dynamic_cast<TriLight*>(n)) {
-    scene.AddLight(tl);
+  } else if (SphereGeom* sg = dynamic_cast<SphereGeom*>(n)) {
+    sg->id = next_geom_id++;
+    scene.AddGeom(sg);
+  } else if (Light* lt = dynamic_cast<Light*>(n)) {
+    scene.AddLight(lt);
   } else if (ShaderStd* sh = dynamic_cast<ShaderStd*>(n)) {
     sh->material_id = (int)materials.size();
     materials.push_back(sh);

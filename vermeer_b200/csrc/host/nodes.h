@@ -5,7 +5,7 @@
 //   core.AddNode / FindNode / PreRender  core/core.go:36-105
 //   core.Geom                            core/geom.go:8-18       (MotionKeys, Bounds; Trace runs on the device)
 //   core.Scene (AddGeom, AddLight, PreRender) core/scene.go:8-24, builtin/scene/scene.go:119-268
-//   PolyMesh, ShaderStd, TriLight, Camera, Globals: see nodes.cpp
+//   PolyMesh, Sphere, ShaderStd, TriLight, DiskLight, SphereLight, Camera, Globals: see nodes.cpp
 //
 // Same names and argument meaning as the reference; error behaviour: the reference returns `error` from
 // PreRender and panics on invariant violations — here both become an int status + message, never an abort.
@@ -94,7 +94,28 @@ struct PolyMesh : Node, Geom {
   Box initMotionBoxesRec(int key, int32_t node);
 };
 
-struct TriLight : Node {
+// core.Light (core/light.go:21-42) as far as the host needs it: which geom the light made for itself and the record the
+// device consumes. Sampling (SampleArea / ValidSample) runs on the device.
+struct Light {
+  virtual ~Light() {}
+  virtual Geom* LightGeom() const = 0;
+  virtual void Describe(VgLight* out) const = 0;
+};
+
+// sphere.Sphere (builtin/geom/sphere/sphere.go:15-86): "only used for spherical light sources"
+struct SphereGeom : Node, Geom {
+  std::string NodeName;
+  V3 P{};
+  float Radius = 1;
+  std::string Shader;
+  ShaderStd* shader = nullptr;
+  std::string Name() const override { return NodeName; }
+  int PreRender(Core& core, std::string* err) override;
+  int MotionKeys() const override { return 1; }
+  Box Bounds(float time) const override;
+};
+
+struct TriLight : Node, Light {
   std::string NodeName;
   V3 P0{}, P1{}, P2{};
   std::string Shader;
@@ -103,6 +124,39 @@ struct TriLight : Node {
   PolyMesh* geom = nullptr;
   std::string Name() const override { return NodeName; }
   int PreRender(Core& core, std::string* err) override;
+  Geom* LightGeom() const override { return geom; }
+  void Describe(VgLight* out) const override;
+};
+
+// light.Disk (builtin/light/disk.go:21-34,76-106,224-262)
+struct DiskLight : Node, Light {
+  std::string NodeName;
+  V3 P{}, Up{}, LookAt{};
+  V3 T{}, B{}, N{};
+  float Radius = 0;
+  std::string Shader;
+  int Segments = 20, Samples = 1;  // registered defaults, disk.go:263-269
+  ShaderStd* shader = nullptr;
+  PolyMesh* geom = nullptr;
+  std::string Name() const override { return NodeName; }
+  int PreRender(Core& core, std::string* err) override;
+  Geom* LightGeom() const override { return geom; }
+  void Describe(VgLight* out) const override;
+};
+
+// light.Sphere (builtin/light/sphere.go:17-28,38-61)
+struct SphereLight : Node, Light {
+  std::string NodeName;
+  V3 P{};
+  float Radius = 1;  // registered defaults Radius 1, Samples 1 (sphere.go:297-303)
+  std::string Shader;
+  int Samples = 1;
+  ShaderStd* shader = nullptr;
+  SphereGeom* geom = nullptr;
+  std::string Name() const override { return NodeName; }
+  int PreRender(Core& core, std::string* err) override;
+  Geom* LightGeom() const override { return geom; }
+  void Describe(VgLight* out) const override;
 };
 
 struct Camera : Node {
@@ -131,14 +185,14 @@ struct PixelFilter : Node {
 // builtin/scene/scene.go
 struct Scene {
   std::vector<Geom*> geoms;
-  std::vector<TriLight*> lights;
+  std::vector<Light*> lights;
   std::vector<VgNode> qbvh;
   std::vector<VgMotionNode> mtopo;
   std::vector<float> mboxes;
   int keys = 1;
   Box bounds;
   void AddGeom(Geom* g) { geoms.push_back(g); }
-  void AddLight(TriLight* l) { lights.push_back(l); }
+  void AddLight(Light* l) { lights.push_back(l); }
   int PreRender(std::string* err);
 
  private:

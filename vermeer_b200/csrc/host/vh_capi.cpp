@@ -141,6 +141,41 @@ int vh_add_trilight(vh_scene* s, const char* name, const float* p0, const float*
   return VG_OK;
 }
 
+int vh_add_disklight(vh_scene* s, const char* name, const float* P, const float* lookat, const float* up, float radius, const char* shader,
+                     int segments, int samples) {
+  if (!s || !name || !P || !lookat || !up || !shader) return fail(s, VG_ERR_INVALID, "vh_add_disklight: null argument");
+  if (samples < 0 || samples > 8) return fail(s, VG_ERR_INVALID, "DiskLight: Samples must be in [0,8]");
+  if (segments < 3 || segments > 4096) return fail(s, VG_ERR_INVALID, "DiskLight: Segments must be in [3,4096]");
+  std::unique_ptr<Node> h;
+  DiskLight* d = make<DiskLight>(s, "DiskLight", &h);
+  if (!d) return VG_ERR_INVALID;
+  d->NodeName = name;
+  d->P = v3(P);
+  d->LookAt = v3(lookat);
+  d->Up = v3(up);
+  d->Radius = radius;
+  d->Shader = shader;
+  d->Segments = segments;
+  d->Samples = samples;
+  s->core.AddNode(std::move(h));
+  return VG_OK;
+}
+
+int vh_add_spherelight(vh_scene* s, const char* name, const float* P, float radius, const char* shader, int samples) {
+  if (!s || !name || !P || !shader) return fail(s, VG_ERR_INVALID, "vh_add_spherelight: null argument");
+  if (samples < 0 || samples > 8) return fail(s, VG_ERR_INVALID, "SphereLight: Samples must be in [0,8]");
+  std::unique_ptr<Node> h;
+  SphereLight* d = make<SphereLight>(s, "SphereLight", &h);
+  if (!d) return VG_ERR_INVALID;
+  d->NodeName = name;
+  d->P = v3(P);
+  d->Radius = radius;
+  d->Shader = shader;
+  d->Samples = samples;
+  s->core.AddNode(std::move(h));
+  return VG_OK;
+}
+
 int vh_set_camera_lookat(vh_scene* s, const float* from, const float* to, const float* up, float roll, float fov, float focal, float aspect,
                          float radius) {
   if (!s || !from || !to || !up) return fail(s, VG_ERR_INVALID, "vh_set_camera_lookat: null argument");
@@ -165,11 +200,12 @@ int vh_prerender(vh_scene* s) {
   return VG_OK;
 }
 
-static PolyMesh* mesh_by_id(vh_scene* s, int id) {
+static Geom* geom_by_id(vh_scene* s, int id) {
   for (Geom* g : s->core.scene.geoms)
-    if (g->id == id) return static_cast<PolyMesh*>(g);
+    if (g->id == id) return g;
   return nullptr;
 }
+static PolyMesh* mesh_by_id(vh_scene* s, int id) { return dynamic_cast<PolyMesh*>(geom_by_id(s, id)); }
 
 int vh_upload(vh_scene* s, vg_ctx* ctx, int motion_ref_compat) {
   if (!s || !ctx) return fail(s, VG_ERR_INVALID, "vh_upload: null argument");
@@ -184,8 +220,15 @@ int vh_upload(vh_scene* s, vg_ctx* ctx, int motion_ref_compat) {
   if ((rc = chk(vg_set_materials(ctx, mats.data(), (int)mats.size()))) != VG_OK) return rc;
   if ((rc = chk(vg_scene_begin(ctx, G))) != VG_OK) return rc;
   for (int id = 0; id < G; id++) {
-    PolyMesh* m = mesh_by_id(s, id);
-    if (!m) return fail(s, VG_ERR_INVALID, "geom ids are not dense");
+    Geom* gm = geom_by_id(s, id);
+    if (!gm) return fail(s, VG_ERR_INVALID, "geom ids are not dense");
+    if (SphereGeom* sp = dynamic_cast<SphereGeom*>(gm)) {
+      const float ctr[3] = {sp->P.x, sp->P.y, sp->P.z};
+      if (chk(vg_sphere_upload(ctx, id, ctr, sp->Radius, sp->shader ? sp->shader->material_id : -1)) != VG_OK) return VG_ERR_INVALID;
+      continue;
+    }
+    PolyMesh* m = dynamic_cast<PolyMesh*>(gm);
+    if (!m) return fail(s, VG_ERR_INVALID, "unknown geom type");
     std::vector<int32_t> mids;
     for (ShaderStd* sh : m->shader) mids.push_back(sh->material_id);
     if (!m->qbvh.empty()) {
@@ -210,18 +253,13 @@ int vh_upload(vh_scene* s, vg_ctx* ctx, int motion_ref_compat) {
   if (chk(rc) != VG_OK) return rc;
   if ((rc = chk(vg_scene_commit(ctx))) != VG_OK) return rc;
 
-  std::vector<VgTriLight> lights;
-  for (TriLight* t : c.scene.lights) {
-    VgTriLight l{};
-    l.p0[0] = t->P0.x; l.p0[1] = t->P0.y; l.p0[2] = t->P0.z;
-    l.p1[0] = t->P1.x; l.p1[1] = t->P1.y; l.p1[2] = t->P1.z;
-    l.p2[0] = t->P2.x; l.p2[1] = t->P2.y; l.p2[2] = t->P2.z;
-    l.samples = t->Samples;
-    l.material = t->shader ? t->shader->material_id : -1;
-    l.geom = t->geom ? t->geom->id : -1;
+  std::vector<VgLight> lights;
+  for (Light* t : c.scene.lights) {
+    VgLight l;
+    t->Describe(&l);
     lights.push_back(l);
   }
-  if ((rc = chk(vg_set_lights(ctx, lights.data(), (int)lights.size()))) != VG_OK) return rc;
+  if ((rc = chk(vg_set_area_lights(ctx, lights.data(), (int)lights.size()))) != VG_OK) return rc;
 
   if (c.filter) rc = vg_set_filter(ctx, c.filter->Res, (double)c.filter->Width, c.filter->cdfV.data(), c.filter->cdfVU.data());
   else rc = vg_set_filter(ctx, 0, 0.0, nullptr, nullptr);

@@ -64,7 +64,15 @@ cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d
   cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
 #define VG_LAUNCH(A, V) k_trace_batch<A, V><<<grid, kTraceBlock, smem, stream>>>(sc, d_rays, d_hits, n, d_counter, d_stats)
-  if (any_hit) {
+  if (sc.n_spheres > 0) {  // kernels that carry the analytic sphere leaf (traverse.cuh: VARIANT & 8)
+    if (any_hit) {
+      if (variant == 2) VG_LAUNCH(true, 10);
+      else VG_LAUNCH(true, 8);
+    } else {
+      if (variant == 2) VG_LAUNCH(false, 10);
+      else VG_LAUNCH(false, 8);
+    }
+  } else if (any_hit) {
     if (variant == 1) VG_LAUNCH(true, 1);
     else if (variant == 2) VG_LAUNCH(true, 2);
     else VG_LAUNCH(true, 0);

@@ -25,9 +25,11 @@
 namespace vg {
 
 struct DevLight {
-  f3 p0, p1, p2;
-  f3 N;            // normalize((P1-P0)x(P2-P0)), triangle.go:302
-  float inv_area;  // 1/triangleArea, triangle.go:234
+  f3 p0, p1, p2;   // tri: vertices; disk: P, T, B; sphere: P
+  f3 N;            // tri: normalize((P1-P0)x(P2-P0)), triangle.go:302; disk: N (disk.go:93)
+  float inv_area;  // tri: 1/triangleArea, triangle.go:234; disk: 1/(Pi R^2), disk.go:125,179
+  float radius;    // disk, sphere
+  int type;        // VG_LIGHT_*
   f3 E;            // EvalEmission of the light's shader (std.go:299-316)
   int nsamples;    // 1 << Samples
   int geom;
@@ -42,7 +44,9 @@ struct DevMat {
   f3 spec_colour;
   float spec_rough;
   float ior;
-  int bad;  // 1: total weight 0 (the reference panics, std.go:141-143); 2: glossy lobe (not built yet)
+  int fresnel_model;     // VG_FRESNEL_* (std.go:172-192)
+  f3 fres_refl, fres_edge;  // conductor r, g AFTER the reference's assignment quirk (std.go:187-189 writes the edge tint into refl)
+  int bad;  // 1: total weight 0 (the reference panics, std.go:141-143)
 };
 
 struct __align__(16) DevHit {
@@ -59,6 +63,7 @@ struct RenderParams {
   const DevMat* mats;
   const DevLight* lights;
   int nlights, S, levels, trace_last_level;
+  int nlobes;  // 1: diffuse light slots only (k_shade); 2: + GGX glossy slots (k_shade_generic)
   const double* filter_cdf;  // cdfV[n] then cdfVU[n*n], or null
   int filter_n;
   double filter_w;
@@ -297,6 +302,18 @@ __device__ inline void build_context(const RenderParams& p, const DevHit& h, flo
   c.Ng = normalize3(Ng);
   c.DdPdu = normalize3(c.DdPdu);
   c.DdPdv = normalize3(c.DdPdv);
+}
+
+// sphere.Sphere.Trace hit record (builtin/geom/sphere/trace.go:17-47), then ApplyTransform's re-normalisations
+__device__ inline void build_context_sphere(const RenderParams& p, const DevHit& h, f3 Ro, f3 Rd, ShadeCtx& c) {
+  const f3 centre = ld3(p.sc.tris + (size_t)h.slot * 3);
+  c.P = mad3(Ro, Rd, h.t);
+  const f3 N = normalize3(sub3(c.P, centre));
+  c.Poffset = scale3(0.001f, N);
+  c.N = normalize3(N);
+  c.Ng = normalize3(N);
+  c.DdPdu = normalize3(mk3(1, 0, 0));
+  c.DdPdv = normalize3(mk3(0, 0, 1));
 }
 
 // Warp-aggregated append: every lane of the warp must call this. Returns the slot index (or -1).
@@ -606,34 +623,48 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
   }
 }
 
-// Sum the slots in the reference's order and finish the diffuse term (core/shader.go:349, std.go:157-163,287-295).
+}  // namespace vg
+#include "shade_generic.cuh"
+namespace vg {
+
+// Sum the slots in the reference's order and finish the diffuse / glossy terms (core/shader.go:349, std.go:157-163,269-295).
 __global__ void __launch_bounds__(256) k_resolve(const RenderParams p, int level, int qin) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.counts[qin]) return;
   const int path = p.pathq[qin][i];
   const int matid = p.v_mat[i];
+  const int SL = p.S * p.nlobes;
   float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
   if (matid != 255 && level <= 3) {
     const DevMat m = p.mats[matid];
-    f3 diff = mk3(0, 0, 0);
-    if (m.diff_weight > 0.0f) {
+    f3 sum[2];
+    sum[0] = sum[1] = mk3(0, 0, 0);
+    for (int lobe = 0; lobe < p.nlobes; lobe++) {
+      const bool on = lobe == 0 ? m.diff_weight > 0.0f : (m.spec_weight > 0.0f && m.spec_rough > 0.0f);
+      if (!on) continue;
+      const f3 colour = lobe == 0 ? m.diff_colour : m.spec_colour;
+      f3 acc = mk3(0, 0, 0);
       for (int l = 0; l < p.nlights; l++) {
         const DevLight& L = p.lights[l];
         const int NS = level > 0 ? 1 : L.nsamples;
-        const float inv = p.v_invtot[(size_t)i * p.nlights + l];
+        const float inv = p.v_invtot[((size_t)i * p.nlobes + lobe) * p.nlights + l];
         if (inv == 0.0f) continue;  // light excluded (own geom) or no samples: EvaluateLightSamples returned RGB{}
         f3 col = mk3(0, 0, 0);
         for (int s = 0; s < NS; s++) {
-          const float4 c = p.contrib[(size_t)i * p.S + L.slot_base + s];
+          const float4 c = p.contrib[(size_t)i * SL + lobe * p.S + L.slot_base + s];
           col.x += c.x; col.y += c.y; col.z += c.z;
         }
         if (NS > 1) { col.x *= inv; col.y *= inv; col.z *= inv; }
-        col.x *= m.diff_colour.x; col.y *= m.diff_colour.y; col.z *= m.diff_colour.z;
-        diff.x += col.x; diff.y += col.y; diff.z += col.z;
+        col.x *= colour.x; col.y *= colour.y; col.z *= colour.z;
+        acc.x += col.x; acc.y += col.y; acc.z += col.z;
       }
-      diff.x *= m.diff_weight; diff.y *= m.diff_weight; diff.z *= m.diff_weight;
+      // the diffuse sum is scaled by diffWeight (std.go:162); the glossy direct light is NOT scaled by spec1Weight
+      // (spec1Samples == 0 skips std.go:265-267)
+      if (lobe == 0) { acc.x *= m.diff_weight; acc.y *= m.diff_weight; acc.z *= m.diff_weight; }
+      sum[lobe] = acc;
     }
-    out = make_float4(m.emission.x + diff.x, m.emission.y + diff.y, m.emission.z + diff.z, 0.f);
+    // contrib = emission + diffuse + spec1 (std.go:287-293)
+    out = make_float4((m.emission.x + sum[0].x) + sum[1].x, (m.emission.y + sum[0].y) + sum[1].y, (m.emission.z + sum[0].z) + sum[1].z, 0.f);
   }
   p.L[(size_t)level * p.P + path] = out;
 }
@@ -687,6 +718,8 @@ struct RenderState {
   int fb_w = 0, fb_h = 0;
   int trace_grid = 0;
   int max_light_samples = 0;
+  bool generic = false;  // shade with k_shade_generic (glossy lobe / conductor Fresnel / Disk or Sphere lights / sphere geoms)
+  int nlobes = 1;
   std::vector<int> pix_host;
   uint64_t* scr_pinned = nullptr;
   size_t scr_pinned_bytes = 0;
@@ -838,7 +871,7 @@ static int prepare(vg_ctx* ctx) {
 
   // materials
   std::vector<DevMat> mats(ctx->materials.size());
-  bool any_mirror = false;
+  bool any_mirror = false, any_glossy = false, any_conductor = false, any_other_light = false;
   for (size_t i = 0; i < mats.size(); i++) {
     const VgMaterial& s = ctx->materials[i];
     DevMat& d = mats[i];
@@ -860,9 +893,17 @@ static int prepare(vg_ctx* ctx) {
     if (s.mask & VG_MAT_SPEC1_COLOUR) d.spec_colour = h3(s.spec1_colour);
     d.spec_rough = (s.mask & VG_MAT_SPEC1_ROUGHNESS) ? s.spec1_roughness : 0.5f;
     d.ior = (s.mask & VG_MAT_IOR) ? s.ior : 1.7f;
+    // std.go:172-192: Fresnel model of the spec lobe. NewConductor(0, refl, edge) with both defaulting to .5; the reference
+    // assigns Spec1FresnelEdge to `refl` (std.go:187-189), so the edge tint stays .5 whatever the scene says.
+    d.fresnel_model = (s.mask & VG_MAT_SPEC1_FRESNEL_MODEL) ? s.spec1_fresnel_model : VG_FRESNEL_DIELECTRIC;
+    d.fres_refl.x = d.fres_refl.y = d.fres_refl.z = 0.5f;
+    d.fres_edge = d.fres_refl;
+    if (s.mask & VG_MAT_SPEC1_FRESNEL_REFL) d.fres_refl = h3(s.spec1_fresnel_refl);
+    if (s.mask & VG_MAT_SPEC1_FRESNEL_EDGE) d.fres_refl = h3(s.spec1_fresnel_edge);
     if (d.spec_weight > 0.0f) {
-      if (d.spec_rough != 0.0f) d.bad = 2;
-      else any_mirror = true;
+      if (d.spec_rough == 0.0f) any_mirror = true;
+      else any_glossy = true;
+      if (d.fresnel_model != VG_FRESNEL_DIELECTRIC) any_conductor = true;
     }
   }
   // lights
@@ -870,17 +911,25 @@ static int prepare(vg_ctx* ctx) {
   int S = 0;
   rs.max_light_samples = 0;
   for (size_t i = 0; i < lights.size(); i++) {
-    const VgTriLight& s = ctx->lights[i];
+    const VgLight& s = ctx->lights[i];
     DevLight& d = lights[i];
+    d.type = s.type;
+    d.radius = s.radius;
     d.p0 = h3(s.p0); d.p1 = h3(s.p1); d.p2 = h3(s.p2);
-    f3 e1; e1.x = d.p1.x - d.p0.x; e1.y = d.p1.y - d.p0.y; e1.z = d.p1.z - d.p0.z;
-    f3 e2; e2.x = d.p2.x - d.p0.x; e2.y = d.p2.y - d.p0.y; e2.z = d.p2.z - d.p0.z;
-    f3 cr; cr.x = e1.y * e2.z - e1.z * e2.y; cr.y = e1.z * e2.x - e1.x * e2.z; cr.z = e1.x * e2.y - e1.y * e2.x;
-    d.N = host_normalize(cr);
-    float x0 = cr.x * cr.x, x1 = cr.y * cr.y, x2 = cr.z * cr.z;
-    x1 = x1 + x0; x1 = x1 + x2;
-    const float area = 0.5f * std::sqrt(x1);
-    d.inv_area = 1 / area;
+    if (s.type == VG_LIGHT_TRI) {
+      f3 e1; e1.x = d.p1.x - d.p0.x; e1.y = d.p1.y - d.p0.y; e1.z = d.p1.z - d.p0.z;
+      f3 e2; e2.x = d.p2.x - d.p0.x; e2.y = d.p2.y - d.p0.y; e2.z = d.p2.z - d.p0.z;
+      f3 cr; cr.x = e1.y * e2.z - e1.z * e2.y; cr.y = e1.z * e2.x - e1.x * e2.z; cr.z = e1.x * e2.y - e1.y * e2.x;
+      d.N = host_normalize(cr);
+      float x0 = cr.x * cr.x, x1 = cr.y * cr.y, x2 = cr.z * cr.z;
+      x1 = x1 + x0; x1 = x1 + x2;
+      const float area = 0.5f * std::sqrt(x1);
+      d.inv_area = 1 / area;
+    } else {
+      any_other_light = true;
+      d.N = h3(s.n);
+      d.inv_area = 1.0f / (3.14159265358f * s.radius * s.radius);  // disk.go:125,179 (float32 expression)
+    }
     d.E.x = d.E.y = d.E.z = 0;
     if (s.material >= 0 && s.material < (int)mats.size()) d.E = mats[s.material].emission;
     if (s.samples < 0 || s.samples > 8) return ctx->fail(VG_ERR_INVALID, "TriLight.Samples outside [0,8]");
@@ -892,6 +941,11 @@ static int prepare(vg_ctx* ctx) {
   }
   if (S == 0) S = 1;
   rs.S = S;
+  // sphere geoms need the analytic hit record; glossy lobes, conductor Fresnel and non-Tri lights the general kernel
+  bool any_sphere_geom = false;
+  for (const MeshStage& m : ctx->meshes) any_sphere_geom |= m.sphere;
+  rs.generic = any_glossy || any_conductor || any_other_light || any_sphere_geom || ctx->opt_generic_shade;
+  rs.nlobes = any_glossy ? 2 : 1;
   rs.nlights = (int)lights.size();
   rs.levels = any_mirror ? 4 : 1;
   rs.iters = ctx->opt_iters_per_batch;
@@ -913,8 +967,9 @@ static int prepare(vg_ctx* ctx) {
   if (!lights.empty()) RCUDA(cudaMemcpyAsync(rs.lights.p, lights.data(), lights.size() * sizeof(DevLight), cudaMemcpyHostToDevice, ctx->stream));
   RCUDA(rs.rayq0.reserve(P)); RCUDA(rs.rayq1.reserve(P)); RCUDA(rs.pathq0.reserve(P)); RCUDA(rs.pathq1.reserve(P));
   RCUDA(rs.hits.reserve(P)); RCUDA(rs.lambda.reserve(P)); RCUDA(rs.time.reserve(P)); RCUDA(rs.vmat.reserve(P));
-  RCUDA(rs.invtot.reserve(P * std::max(1, rs.nlights)));
-  RCUDA(rs.contrib.reserve(P * S)); RCUDA(rs.sray.reserve(P * S)); RCUDA(rs.sslot.reserve(P * S));
+  RCUDA(rs.invtot.reserve(P * std::max(1, rs.nlights) * rs.nlobes));
+  const size_t SL = (size_t)S * rs.nlobes;
+  RCUDA(rs.contrib.reserve(P * SL)); RCUDA(rs.sray.reserve(P * SL)); RCUDA(rs.sslot.reserve(P * SL));
   RCUDA(rs.L.reserve(P * rs.levels)); RCUDA(rs.T.reserve(P * rs.levels));
   RCUDA(rs.counts.reserve(16)); RCUDA(rs.stats.reserve(8));
   RCUDA(cudaMemsetAsync(rs.counts.p, 0, 16 * sizeof(int), ctx->stream));
@@ -970,6 +1025,7 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
   p.pix = rs.pix.p; p.scr = rs.scr.p; p.cam = ctx->camera; p.mats = rs.mats.p; p.lights = rs.lights.p;
   p.filter_cdf = ctx->filter_n > 0 ? rs.filter.p : nullptr; p.filter_n = ctx->filter_n; p.filter_w = ctx->filter_w;
   p.nlights = rs.nlights; p.S = rs.S; p.levels = rs.levels; p.trace_last_level = ctx->opt_trace_last_level;
+  p.nlobes = rs.nlobes;
   p.rayq[0] = rs.rayq0.p; p.rayq[1] = rs.rayq1.p; p.pathq[0] = rs.pathq0.p; p.pathq[1] = rs.pathq1.p;
   p.hits = rs.hits.p; p.lambda = rs.lambda.p; p.time = rs.time.p; p.v_mat = rs.vmat.p; p.v_invtot = rs.invtot.p;
   p.contrib = rs.contrib.p; p.sray = rs.sray.p; p.sslot = rs.sslot.p; p.L = rs.L.p; p.T = rs.T.p;
@@ -977,6 +1033,7 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
 
   const size_t smem = trace_smem_bytes();
   const int variant = ctx->opt_traversal;
+  const bool sph = ctx->dev.n_spheres > 0;  // kernels that carry the analytic sphere leaf (traverse.cuh: VARIANT & 8)
   uint64_t launches = 0;
   size_t nev = 0;
   std::vector<int> kinds;
@@ -1001,7 +1058,10 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
         cudaEventRecord(rs.ev(nev++), st);
         // camera rays are coherent: the per-lane loop with its compile-time axis specialisation is faster there (measured
         // 3.81 vs 3.48 Grays/s); every later level is incoherent and takes the cooperative leaf phase
-        if (variant == 1) k_trace_queue<0, 1><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
+        if (sph) {
+          if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 10><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
+          else k_trace_queue<0, 8><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
+        } else if (variant == 1) k_trace_queue<0, 1><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
         else if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 2><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
         else k_trace_queue<0, 0><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
         cudaEventRecord(rs.ev(nev++), st);
@@ -1009,7 +1069,10 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
         launches++;
         if (level <= 3) {
           const bool h1 = rs.max_light_samples <= 2 || level > 0;
-          if (ctx->opt_precise_trig) {
+          if (rs.generic) {
+            if (ctx->opt_precise_trig) k_shade_generic<false><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
+            else k_shade_generic<true><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
+          } else if (ctx->opt_precise_trig) {
             if (h1) k_shade<false, true><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
             else k_shade<false, false><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
           } else {
@@ -1017,7 +1080,11 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
             else k_shade<true, false><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
           }
           cudaEventRecord(rs.ev(nev++), st);
-          if (variant == 1) k_trace_queue<1, 1><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
+          if (sph) {
+            if (variant == 2 && ctx->opt_shadow_unordered) k_trace_queue<1, 11><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
+            else if (variant == 2) k_trace_queue<1, 10><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
+            else k_trace_queue<1, 8><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
+          } else if (variant == 1) k_trace_queue<1, 1><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
           else if (variant == 2 && ctx->opt_shadow_unordered) k_trace_queue<1, 3><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
           else if (variant == 2) k_trace_queue<1, 2><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
           else k_trace_queue<1, 0><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
@@ -1088,7 +1155,6 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
   if (flags) {
     cudaMemsetAsync(rs.counts.p + 5, 0, sizeof(int), st);
     if (flags & 1) return ctx->fail(VG_ERR_INVALID, "a shaded ShaderStd has no weight (DiffuseStrength + Spec1Strength == 0; the reference panics: std.go:141-143)");
-    if (flags & 2) return ctx->fail(VG_ERR_UNSUPPORTED, "glossy GGX lobe (Spec1Roughness > 0) is not built yet");
     if (flags & 4) return ctx->fail(VG_ERR_INVALID, "traversal stack overflow (the reference's 90-entry stack would panic)");
   }
   return VG_OK;

@@ -420,18 +420,69 @@ __device__ __forceinline__ bool leaf_step(const DevScene& sc, TravState& t, uint
   return leaf_static<-1>(sc, r, h, base, count);
 }
 
+// Analytic sphere geom at the scene level (builtin/geom/sphere/trace.go:13-109): solveQuadratic / raySphereIntersect in the
+// reference's float32 operation order (-fmad=false), accepted iff t < Tclosest. Rare (only sphere lights create these), so
+// the arithmetic is kept out of line and takes/returns scalars only: the traversal state stays in registers and the hot
+// loops pay one predicate for it. Returns the accepted t, or -1.
+static __device__ __noinline__ float sphere_hit_t(float4 c0, float radius, float ox, float oy, float oz, float dx, float dy, float dz, float tclosest) {
+  const float Lx = ox - c0.x, Ly = oy - c0.y, Lz = oz - c0.z;
+  const float a = dx * dx + dy * dy + dz * dz;
+  const float b = 2 * (dx * Lx + dy * Ly + dz * Lz);
+  const float c = (Lx * Lx + Ly * Ly + Lz * Lz) - radius * radius;
+  const float discr = b * b - 4 * a * c;
+  if (discr < 0) return -1.0f;
+  float x0, x1;
+  if (discr == 0) {
+    x1 = -0.5f * b / a;
+    x0 = x1;
+  } else {
+    const float q = b > 0 ? -0.5f * (b + sqrtf(discr)) : -0.5f * (b - sqrtf(discr));
+    x0 = q / a;
+    x1 = c / q;
+  }
+  if (x0 > x1) { const float tmp = x0; x0 = x1; x1 = tmp; }
+  if (x0 < 0) {
+    x0 = x1;
+    if (x0 < 0) return -1.0f;
+  }
+  if (!(x0 < tclosest)) return -1.0f;
+  return x0;
+}
+__device__ __forceinline__ bool sphere_leaf(const DevScene& sc, TravState& t, uint32_t un) {
+  const int slot = (int)(un & kLeafBaseMask);
+  const float4 c0 = ldg4(sc.tris + (size_t)slot * 3), c1 = ldg4(sc.tris + (size_t)slot * 3 + 1);
+  const float th = sphere_hit_t(c0, c1.x, t.r.ox, t.r.oy, t.r.oz, t.r.dx, t.r.dy, t.r.dz, t.r.tclosest);
+  if (th < 0.0f) return false;
+  t.r.tclosest = th;
+  t.h.u = t.h.v = t.h.w = 0.0f;
+  t.h.geom = __float_as_int(c0.w);
+  t.h.prim = 0;
+  t.h.slot = slot;
+  return true;
+}
+
 // while-while traversal of the lane's ray until it finishes or, if `min_active` > 0, until fewer than `min_active`
 // lanes of the warp are still traversing (the caller then refills the idle lanes and comes back).
 // Returns true when this lane's ray is finished.
-template <bool ANY_HIT>
+// SPH: the scene holds analytic sphere geoms (kernels for scenes without them do not carry the call).
+template <bool ANY_HIT, bool SPH = false>
 __device__ __forceinline__ bool trav_run(const DevScene& sc, TravState& t, Stack& st, int min_active) {
   while (t.cur != -1) {
     while (t.cur >= 0) node_step(sc, t, st);
     while (t.cur < -1) {
       const uint32_t un = (uint32_t)t.cur;
       if (un & kGeomBit) {
+        if (SPH && (un & kSphereBit)) {  // scene.go:61-78 -> sphere.Trace
+          if (sphere_leaf(sc, t, un) && ANY_HIT) {
+            st.sp = 0;
+            t.cur = -1;
+            return true;
+          }
+          t.cur = pop_next(t.r, st);
+          continue;
+        }
         // scene.go:61-78 -> Geom.Trace -> qbvh.Trace pushes the mesh root with T = Tclosest and pops it at once
-        t.cur = (int32_t)(un & 0x3FFFFFFFu);
+        t.cur = (int32_t)(un & kGeomRootMask);
         break;
       }
       const bool leafhit = leaf_step(sc, t, un);
@@ -591,7 +642,7 @@ __device__ __forceinline__ void trace_persistent_tma(const DevScene& sc, IO& io,
 // coalesced LDG.128 each. Measured faster than the TMA-staged variant on B200 (3.83 vs 3.16 Grays/s on C2 primary rays,
 // profiles/README.md): the fetch is <4 % of a ray's loads and 28 resident warps already hide its latency, while the
 // staging state costs registers under the 72-register cap.
-template <bool ANY_HIT, class IO>
+template <bool ANY_HIT, bool SPH, class IO>
 __device__ __forceinline__ void trace_persistent_ldg(const DevScene& sc, IO& io, Stack& st, unsigned long long& nodes_acc, unsigned long long& tris_acc) {
   const int lane = threadIdx.x & 31;
   const long long n = io.size();
@@ -621,7 +672,7 @@ __device__ __forceinline__ void trace_persistent_ldg(const DevScene& sc, IO& io,
     }
     if (__ballot_sync(0xffffffffu, my >= 0) == 0) break;
     if (my >= 0) {
-      if (trav_run<ANY_HIT>(sc, t, st, exhausted ? 0 : VG_REFILL_BELOW)) {
+      if (trav_run<ANY_HIT, SPH>(sc, t, st, exhausted ? 0 : VG_REFILL_BELOW)) {
         io.store(my, t.r, t.h, st.overflow);
         nodes_acc += (unsigned long long)t.h.nodesT;
         tris_acc += (unsigned long long)t.h.trisT;
@@ -811,7 +862,7 @@ __device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bo
   return leafhit;
 }
 
-template <bool ANY_HIT, bool ORDERED, class IO>
+template <bool ANY_HIT, bool ORDERED, bool SPH, class IO>
 __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io, Stack& st, const CoopSmem& cs, unsigned long long& nodes_acc,
                                                       unsigned long long& tris_acc) {
   const int lane = threadIdx.x & 31;
@@ -843,7 +894,18 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
     if (__ballot_sync(0xffffffffu, my >= 0) == 0) break;
     // node phase: per lane, until fewer than VG_NODE_MIN lanes want it and at least one leaf is pending
     while (true) {
-      if (t.cur < -1 && ((uint32_t)t.cur & kGeomBit)) t.cur = (int32_t)((uint32_t)t.cur & 0x3FFFFFFFu);  // scene.go:61-78 -> mesh root next
+      while (t.cur < -1 && ((uint32_t)t.cur & kGeomBit)) {  // scene.go:61-78
+        if (SPH && ((uint32_t)t.cur & kSphereBit)) {        // -> sphere.Trace
+          if (sphere_leaf(sc, t, (uint32_t)t.cur) && ANY_HIT) {
+            st.sp = 0;
+            t.cur = -1;
+          } else {
+            t.cur = pop_next<ORDERED>(t.r, st);
+          }
+        } else {
+          t.cur = (int32_t)((uint32_t)t.cur & kGeomRootMask);  // -> mesh root next
+        }
+      }
       const unsigned nm = __ballot_sync(0xffffffffu, t.cur >= 0);
       if (nm == 0) break;
       if (__popc(nm) < VG_NODE_MIN && __any_sync(0xffffffffu, t.cur < -1)) break;
@@ -884,26 +946,29 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
   }
 }
 
-// VARIANT: 0 = per-lane while-while with coalesced LDG refill, 1 = the same over the TMA-staged queue, 2 = warp-cooperative leaves,
-// 3 = cooperative leaves without the ordered push (occlusion-only any-hit rays).
+// VARIANT & 7: 0 = per-lane while-while with coalesced LDG refill, 1 = the same over the TMA-staged queue, 2 = warp-cooperative
+// leaves, 3 = cooperative leaves without the ordered push (occlusion-only any-hit rays). VARIANT & 8: the scene holds analytic
+// sphere geoms (variants 0, 2, 3 only; the launchers map variant 1 to 0 for such scenes).
 template <bool ANY_HIT, int VARIANT, class IO>
 __device__ __forceinline__ void trace_persistent(const DevScene& sc, IO& io, Stack& st, unsigned char* warp_smem, unsigned long long& nodes_acc,
                                                  unsigned long long& tris_acc) {
-  if (VARIANT == 1) {
+  constexpr int V = VARIANT & 7;
+  constexpr bool SPH = (VARIANT & 8) != 0;
+  if (V == 1) {
     WarpStage ws;
     ws.buf = reinterpret_cast<float4*>(warp_smem);
     ws.bar = reinterpret_cast<unsigned long long*>(warp_smem + 2048);
     trace_persistent_tma<ANY_HIT>(sc, io, st, ws, nodes_acc, tris_acc);
-  } else if (VARIANT == 2) {
+  } else if (V == 2) {
     CoopSmem cs;
     cs.rp = reinterpret_cast<float4*>(warp_smem);
-    trace_persistent_coop<ANY_HIT, true>(sc, io, st, cs, nodes_acc, tris_acc);
-  } else if (VARIANT == 3) {
+    trace_persistent_coop<ANY_HIT, true, SPH>(sc, io, st, cs, nodes_acc, tris_acc);
+  } else if (V == 3) {
     CoopSmem cs;
     cs.rp = reinterpret_cast<float4*>(warp_smem);
-    trace_persistent_coop<ANY_HIT, false>(sc, io, st, cs, nodes_acc, tris_acc);
+    trace_persistent_coop<ANY_HIT, false, SPH>(sc, io, st, cs, nodes_acc, tris_acc);
   } else {
-    trace_persistent_ldg<ANY_HIT>(sc, io, st, nodes_acc, tris_acc);
+    trace_persistent_ldg<ANY_HIT, SPH>(sc, io, st, nodes_acc, tris_acc);
   }
 }
 

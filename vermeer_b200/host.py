@@ -28,11 +28,11 @@ VG_TRACE_ANY_HIT = 1
 # every symbol include/vermeer_gpu.h declares (tests check the library exports all of them)
 DECLARED_SYMBOLS = [
     "vg_create", "vg_destroy", "vg_last_error", "vg_device_count", "vg_scene_begin", "vg_mesh_upload", "vg_mesh_upload_motion",
-    "vg_scene_upload", "vg_scene_upload_motion", "vg_scene_commit", "vg_set_materials", "vg_set_lights", "vg_set_camera", "vg_set_frame",
+    "vg_sphere_upload", "vg_scene_upload", "vg_scene_upload_motion", "vg_scene_commit", "vg_set_materials", "vg_set_lights", "vg_set_area_lights", "vg_set_camera", "vg_set_frame",
     "vg_set_partition", "vg_set_scramble", "vg_set_filter", "vg_set_option", "vg_trace_batch", "vg_trace_batch_device", "vg_render", "vg_clear_framebuffer",
     "vg_framebuffer_device", "vg_get_stats", "vg_reset_stats",
     "vh_scene_create", "vh_scene_destroy", "vh_last_error", "vh_registered_nodes", "vh_set_globals", "vh_add_shader_std", "vh_add_polymesh",
-    "vh_add_filter", "vh_add_trilight", "vh_set_camera_lookat", "vh_prerender", "vh_upload", "vh_num_geoms", "vh_scene_info", "vh_scene_nodes",
+    "vh_add_filter", "vh_add_trilight", "vh_add_disklight", "vh_add_spherelight", "vh_set_camera_lookat", "vh_prerender", "vh_upload", "vh_num_geoms", "vh_scene_info", "vh_scene_nodes",
     "vh_scene_motion_nodes", "vh_scene_geom_order", "vh_mesh_info", "vh_mesh_nodes", "vh_mesh_motion_nodes", "vh_mesh_idxp", "vh_camera",
 ]
 
@@ -40,7 +40,8 @@ DECLARED_SYMBOLS = [
 class VgMaterial(C.Structure):
     _fields_ = [("mask", C.c_uint32), ("emission_colour", C.c_float * 3), ("emission_strength", C.c_float),
                 ("diffuse_colour", C.c_float * 3), ("diffuse_strength", C.c_float), ("diffuse_roughness", C.c_float),
-                ("spec1_colour", C.c_float * 3), ("spec1_strength", C.c_float), ("spec1_roughness", C.c_float), ("ior", C.c_float)]
+                ("spec1_colour", C.c_float * 3), ("spec1_strength", C.c_float), ("spec1_roughness", C.c_float), ("ior", C.c_float),
+                ("spec1_fresnel_model", C.c_int32), ("spec1_fresnel_refl", C.c_float * 3), ("spec1_fresnel_edge", C.c_float * 3)]
 
 
 class VgCamera(C.Structure):
@@ -97,6 +98,9 @@ def material_struct(sh) -> VgMaterial:
     m.spec1_strength = p[12]
     m.spec1_roughness = p[13]
     m.ior = p[14]
+    m.spec1_fresnel_model = int(p[15])
+    m.spec1_fresnel_refl[:] = p[16:19]
+    m.spec1_fresnel_edge[:] = p[19:22]
     return m
 
 
@@ -127,7 +131,16 @@ class HostScene:
                 _p(m.NormalIdx), 0 if m.NormalIdx is None else len(m.NormalIdx),
                 C.c_float(m.RayBias)))
         for l in scene.lights:
-            self._chk(L.vh_add_trilight(h, l.Name.encode(), _f3(l.P0), _f3(l.P1), _f3(l.P2), l.Shader.encode(), l.Samples))
+            kind = type(l).__name__
+            if kind == "TriLight":
+                self._chk(L.vh_add_trilight(h, l.Name.encode(), _f3(l.P0), _f3(l.P1), _f3(l.P2), l.Shader.encode(), l.Samples))
+            elif kind == "DiskLight":
+                self._chk(L.vh_add_disklight(h, l.Name.encode(), _f3(l.P), _f3(l.LookAt), _f3(l.Up), C.c_float(l.Radius), l.Shader.encode(),
+                                             int(l.Segments), int(l.Samples)))
+            elif kind == "SphereLight":
+                self._chk(L.vh_add_spherelight(h, l.Name.encode(), _f3(l.P), C.c_float(l.Radius), l.Shader.encode(), int(l.Samples)))
+            else:
+                raise ValueError("unknown light node %r" % kind)
         if scene.filter is not None:
             f = scene.filter
             self._chk(L.vh_add_filter(h, f.Type.encode(), f.Name.encode(), C.c_float(f.Width or 0), int(f.Res or 0), C.c_float(f.Peak or 0)))

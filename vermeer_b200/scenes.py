@@ -23,8 +23,8 @@ from typing import List, Optional
 import numpy as np
 
 __all__ = [
-    "ShaderStd", "PolyMesh", "TriLight", "Camera", "PixelFilter", "SceneDesc", "splitmix64_table",
-    "heightfield_mesh", "heightfield_scene", "sphere_field_scene", "cornell_box", "incoherent_rays",
+    "ShaderStd", "PolyMesh", "TriLight", "DiskLight", "SphereLight", "Camera", "PixelFilter", "SceneDesc", "splitmix64_table",
+    "heightfield_mesh", "heightfield_scene", "sphere_field_scene", "cornell_box", "glossy_box", "incoherent_rays",
 ]
 
 
@@ -40,17 +40,23 @@ class ShaderStd:
     Spec1Strength: Optional[float] = None
     Spec1Roughness: Optional[float] = None
     IOR: Optional[float] = None
+    Spec1FresnelModel: Optional[str] = None   # "Dielectric" | "Metal" (std.go:65-73); unset = Dielectric (the zero value)
+    Spec1FresnelRefl: Optional[tuple] = None
+    Spec1FresnelEdge: Optional[tuple] = None
 
     def packed(self):
-        """(mask, 15 floats) in the slot order shared by the host C-ABI and the oracle."""
-        p = np.zeros(15, np.float32)
+        """(mask, 22 floats) in the slot order shared by the host C-ABI and the oracle."""
+        p = np.zeros(22, np.float32)
         mask = 0
         slots = [("EmissionColour", 0, 3), ("EmissionStrength", 3, 1), ("DiffuseColour", 4, 3), ("DiffuseStrength", 7, 1),
-                 ("DiffuseRoughness", 8, 1), ("Spec1Colour", 9, 3), ("Spec1Strength", 12, 1), ("Spec1Roughness", 13, 1), ("IOR", 14, 1)]
+                 ("DiffuseRoughness", 8, 1), ("Spec1Colour", 9, 3), ("Spec1Strength", 12, 1), ("Spec1Roughness", 13, 1), ("IOR", 14, 1),
+                 ("Spec1FresnelModel", 15, 1), ("Spec1FresnelRefl", 16, 3), ("Spec1FresnelEdge", 19, 3)]
         for bit, (name, off, n) in enumerate(slots):
             v = getattr(self, name)
             if v is not None:
                 mask |= 1 << bit
+                if name == "Spec1FresnelModel":
+                    v = {"Dielectric": 0.0, "Metal": 1.0}[v]
                 p[off:off + n] = np.asarray(v, np.float32).reshape(-1)
         return mask, p
 
@@ -99,6 +105,29 @@ class TriLight:
 
 
 @dataclass
+class DiskLight:
+    """builtin/light/disk.go:21-34 (registered defaults Segments 20, Samples 1)."""
+    Name: str
+    P: tuple
+    LookAt: tuple
+    Up: tuple
+    Radius: float
+    Shader: str
+    Segments: int = 20
+    Samples: int = 1
+
+
+@dataclass
+class SphereLight:
+    """builtin/light/sphere.go:17-28 (registered defaults Radius 1, Samples 1)."""
+    Name: str
+    P: tuple
+    Shader: str
+    Radius: float = 1.0
+    Samples: int = 1
+
+
+@dataclass
 class Camera:
     From: tuple
     To: tuple
@@ -129,14 +158,15 @@ class SceneDesc:
     camera: Camera
     shaders: List[ShaderStd] = field(default_factory=list)
     meshes: List[PolyMesh] = field(default_factory=list)
-    lights: List[TriLight] = field(default_factory=list)
+    lights: list = field(default_factory=list)   # TriLight | DiskLight | SphereLight, in node order
     MaxIter: int = 16
     name: str = "scene"
     filter: Optional[PixelFilter] = None
 
     @property
     def num_tris(self) -> int:
-        return sum(m.num_tris for m in self.meshes) + len(self.lights)
+        per_light = {"TriLight": lambda l: 1, "DiskLight": lambda l: l.Segments, "SphereLight": lambda l: 0}
+        return sum(m.num_tris for m in self.meshes) + sum(per_light[type(l).__name__](l) for l in self.lights)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -322,6 +352,45 @@ def cornell_box(xres: int = 512, yres: int = 512, boxes: bool = True) -> SceneDe
     lights = _light_pair(1.99, 0.35, "lightmtl", dy=0.03)
     cam = Camera(From=(0.0, 1.0, 3.4), To=(0.0, 1.0, 0.0), Fov=40.0, Focal=1.0)
     return SceneDesc(XRes=xres, YRes=yres, camera=cam, shaders=shaders, meshes=meshes, lights=lights, MaxIter=16, name="C1-cornell")
+
+
+def glossy_box(xres: int = 256, yres: int = 256, lights: str = "tri,disk,sphere") -> SceneDesc:
+    """SURVEY.md 8(f).1 test scene: the Cornell room with a GGX-glossy dielectric floor, a GGX "Metal" (conductor Fresnel)
+    tall box, a mirror short box, and one light of each in-scope type (TriLight, DiskLight, SphereLight) in node order."""
+    shaders = [
+        ShaderStd("white", DiffuseColour=(0.73, 0.73, 0.73), DiffuseStrength=1.0),
+        ShaderStd("red", DiffuseColour=(0.65, 0.05, 0.05), DiffuseStrength=1.0),
+        ShaderStd("green", DiffuseColour=(0.12, 0.45, 0.15), DiffuseStrength=1.0),
+        ShaderStd("lightmtl", EmissionColour=(1.0, 0.9, 0.8), EmissionStrength=12.0, DiffuseColour=(0.0, 0.0, 0.0), DiffuseStrength=1.0),
+        ShaderStd("glossfloor", DiffuseColour=(0.5, 0.5, 0.55), DiffuseStrength=0.6, Spec1Colour=(1.0, 1.0, 1.0), Spec1Strength=0.4,
+                  Spec1Roughness=0.45, IOR=1.5),
+        ShaderStd("gold", DiffuseColour=(0.3, 0.2, 0.05), DiffuseStrength=0.2, Spec1Colour=(1.0, 0.85, 0.5), Spec1Strength=0.8,
+                  Spec1Roughness=0.6, Spec1FresnelModel="Metal", Spec1FresnelRefl=(0.95, 0.75, 0.35), Spec1FresnelEdge=(0.9, 0.8, 0.6)),
+        ShaderStd("mirror", DiffuseColour=(0.2, 0.2, 0.2), DiffuseStrength=0.2, Spec1Colour=(0.9, 0.9, 0.9), Spec1Strength=0.8,
+                  Spec1Roughness=0.0, Spec1FresnelModel="Metal", Spec1FresnelRefl=(0.8, 0.8, 0.85)),
+    ]
+    meshes = [
+        _quad("floor", [[-1, 0, -1], [-1, 0, 1], [1, 0, 1], [1, 0, -1]], "glossfloor"),
+        _quad("ceiling", [[-1, 2, -1], [1, 2, -1], [1, 2, 1], [-1, 2, 1]], "white"),
+        _quad("back", [[-1, 0, -1], [1, 0, -1], [1, 2, -1], [-1, 2, -1]], "white"),
+        _quad("left", [[-1, 0, -1], [-1, 2, -1], [-1, 2, 1], [-1, 0, 1]], "red"),
+        _quad("right", [[1, 0, -1], [1, 0, 1], [1, 2, 1], [1, 2, -1]], "green"),
+        _box("shortbox", (0.1, 0.0, 0.0), (0.7, 0.6, 0.6), "mirror"),
+        _box("tallbox", (-0.7, 0.0, -0.6), (-0.1, 1.2, 0.0), "gold"),
+    ]
+    ls = []
+    for kind in [k for k in lights.split(",") if k]:
+        if kind == "tri":
+            ls.append(TriLight("lightT", (-0.9, 1.95, -0.2), (-0.3, 1.95, -0.2), (-0.6, 1.95, 0.4), "lightmtl", 1))
+        elif kind == "disk":
+            ls.append(DiskLight("lightD", P=(0.45, 1.97, 0.1), LookAt=(0.45, 0.0, 0.15), Up=(0.0, 0.0, 1.0), Radius=0.3, Shader="lightmtl",
+                                Segments=12, Samples=1))
+        elif kind == "sphere":
+            ls.append(SphereLight("lightS", P=(0.0, 1.3, 0.55), Shader="lightmtl", Radius=0.12, Samples=1))
+        else:
+            raise ValueError(kind)
+    cam = Camera(From=(0.0, 1.0, 3.4), To=(0.0, 1.0, 0.0), Fov=40.0, Focal=1.0)
+    return SceneDesc(XRes=xres, YRes=yres, camera=cam, shaders=shaders, meshes=meshes, lights=ls, MaxIter=16, name="F1-glossy-box")
 
 
 def incoherent_rays(rays: np.ndarray, hits: np.ndarray, seed: int = 7) -> np.ndarray:
