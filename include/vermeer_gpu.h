@@ -258,6 +258,20 @@ int vh_add_disklight(vh_scene* s, const char* name, const float* P, const float*
 int vh_add_spherelight(vh_scene* s, const char* name, const float* P, float radius, const char* shader, int samples);
 int vh_set_camera_lookat(vh_scene* s, const float* from, const float* to, const float* up, float roll, float fov, float focal,
                          float aspect, float radius);
+/* nodes.Parse (nodes/parser.go:110-131): read a .vnf scene description (text in memory, or a file) and add its nodes in file
+ * order, exactly like the vh_add_* calls would. In scope: Globals, Camera (single-key LookAt), ShaderStd (constant maps),
+ * PolyMesh, TriLight, DiskLight, SphereLight, Sphere, AiryFilter, GaussianFilter, OutputFloat, OutputHDR. Returns the number
+ * of parse errors the reference would have printed (0 = clean; nodes that parsed are kept, like the reference keeps them),
+ * or < 0 if the file cannot be read; vh_last_error holds the "<file>:<line>:<col>: message" lines. */
+int vh_parse_vnf(vh_scene* s, const char* text, size_t len, const char* filename);
+int vh_load_vnf(vh_scene* s, const char* path);
+int vh_globals(vh_scene* s, int32_t* out3 /* XRes, YRes, MaxIter */);
+/* core.PostRender (core/core.go:63-73): run the output nodes on the finished frame (xres*yres*3 floats, row-major, top row
+ * first). OutputFloat = little-endian float32 RGB rows top to bottom (builtin/driver/outputfloat.go:30-42); OutputHDR =
+ * Radiance header + flat RGBE scanlines written bottom row first (image/hdr/writer.go:58-91, hdr.go:26-50). */
+int vh_postrender(vh_scene* s, const float* framebuffer, int xres, int yres);
+/* convertRGBToRGBE (image/hdr/hdr.go:26-50) for one pixel: known-answer tests bind this. */
+int vh_rgbe(float r, float g, float b, uint8_t* out4);
 /* core.PreRender (core/core.go:36-61): triangulate, build per-mesh QBVH/MQBVH, light meshes, scene tree, camera matrix. */
 int vh_prerender(vh_scene* s);
 /* Upload the pre-rendered scene into a device context (calls vg_scene_begin .. vg_scene_commit, vg_set_*). */

@@ -18,7 +18,7 @@ SO = os.path.join(HERE, "libvermeer_b200.so")
 
 SOURCES = [
     "context.cu", "kernels_trace.cu", "render.cu",
-    "host/builder.cpp", "host/nodes.cpp", "host/vh_capi.cpp",
+    "host/builder.cpp", "host/nodes.cpp", "host/vh_capi.cpp", "host/vnf.cpp",
 ]
 
 NVCC_FLAGS = [

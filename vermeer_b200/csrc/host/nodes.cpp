@@ -52,6 +52,9 @@ struct RegisterBuiltins {
     Register("DiskLight", [] { return std::unique_ptr<Node>(new DiskLight()); });      // disk.go:263-269
     Register("SphereLight", [] { return std::unique_ptr<Node>(new SphereLight()); });  // sphere.go:297-303
     Register("Sphere", [] { return std::unique_ptr<Node>(new SphereGeom()); });        // geom/sphere/sphere.go:78-86
+    // builtin/driver/outputfloat.go:44-50, outputhdr.go:59-65
+    Register("OutputFloat", [] { OutputNode* o = new OutputNode(); o->Filename = "out.float"; return std::unique_ptr<Node>(o); });
+    Register("OutputHDR", [] { OutputNode* o = new OutputNode(); o->Filename = "out.hdr"; o->hdr = true; return std::unique_ptr<Node>(o); });
     // builtin/filter/filter.go:14-26
     Register("AiryFilter", [] { PixelFilter* f = new PixelFilter(); f->kind = 1; f->Res = 49; f->Width = 6; f->Peak = 4; return std::unique_ptr<Node>(f); });
     Register("GaussianFilter", [] { PixelFilter* f = new PixelFilter(); f->kind = 2; f->Res = 17; f->Width = 2; f->Peak = 0; return std::unique_ptr<Node>(f); });

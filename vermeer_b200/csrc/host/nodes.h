@@ -182,6 +182,18 @@ struct PixelFilter : Node {
   int PreRender(Core& core, std::string* err) override;
 };
 
+// driver.OutputFloat / driver.OutputHDR (builtin/driver/outputfloat.go, outputhdr.go): PostRender writes the finished frame.
+struct OutputNode : Node {
+  std::string Filename;
+  bool hdr = false;
+  std::string Name() const override { return hdr ? "OutputHDR<>" : "OutputFloat<>"; }
+  int Write(const float* fb, int w, int h, std::string* err) const;  // vnf.cpp
+};
+void RgbToRgbe(float r, float g, float b, uint8_t out[4]);  // image/hdr/hdr.go:26-50
+
+// nodes.Parse (nodes/parser.go): adds the file's nodes to `core` in file order; returns the number of parse errors.
+int ParseVnf(Core& core, const char* text, size_t len, const std::string& filename, std::string* messages);
+
 // builtin/scene/scene.go
 struct Scene {
   std::vector<Geom*> geoms;

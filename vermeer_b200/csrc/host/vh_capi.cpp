@@ -1,5 +1,6 @@
 // Host layer of the C ABI (include/vermeer_gpu.h, vh_*): node creation through the registry, PreRender,
 // upload of the pre-rendered scene into a device context through the vg_* layer.
+#include <cstdio>
 #include <cstring>
 #include <string>
 
@@ -191,6 +192,52 @@ int vh_set_camera_lookat(vh_scene* s, const float* from, const float* to, const 
   c->Aspect = aspect;
   c->Radius = radius;
   s->core.AddNode(std::move(h));
+  return VG_OK;
+}
+
+int vh_parse_vnf(vh_scene* s, const char* text, size_t len, const char* filename) {
+  if (!s || (!text && len > 0)) return fail(s, VG_ERR_INVALID, "vh_parse_vnf: null argument");
+  std::string msgs;
+  const int n = ParseVnf(s->core, text ? text : "", len, filename ? filename : "<memory>", &msgs);
+  s->err = msgs;
+  return n;
+}
+
+int vh_load_vnf(vh_scene* s, const char* path) {
+  if (!s || !path) return fail(s, VG_ERR_INVALID, "vh_load_vnf: null argument");
+  FILE* fp = std::fopen(path, "rb");
+  if (!fp) return fail(s, VG_ERR_INVALID, std::string("open ") + path + ": no such file or directory");
+  std::string text;
+  char buf[1 << 16];
+  size_t n;
+  while ((n = std::fread(buf, 1, sizeof(buf), fp)) > 0) text.append(buf, n);
+  std::fclose(fp);
+  return vh_parse_vnf(s, text.data(), text.size(), path);
+}
+
+int vh_globals(vh_scene* s, int32_t* out3) {
+  if (!s || !out3) return VG_ERR_INVALID;
+  out3[0] = s->core.globals->XRes;
+  out3[1] = s->core.globals->YRes;
+  out3[2] = s->core.globals->MaxIter;
+  return VG_OK;
+}
+
+int vh_postrender(vh_scene* s, const float* framebuffer, int xres, int yres) {
+  if (!s || !framebuffer || xres <= 0 || yres <= 0) return fail(s, VG_ERR_INVALID, "vh_postrender: bad argument");
+  // core.PostRender (core/core.go:63-73): every node in creation order; only the output drivers do anything
+  for (Node* n : s->core.all) {
+    if (OutputNode* o = dynamic_cast<OutputNode*>(n)) {
+      std::string err;
+      if (o->Write(framebuffer, xres, yres, &err) != 0) return fail(s, VG_ERR_INVALID, err);
+    }
+  }
+  return VG_OK;
+}
+
+int vh_rgbe(float r, float g, float b, uint8_t* out4) {
+  if (!out4) return VG_ERR_INVALID;
+  RgbToRgbe(r, g, b, out4);
   return VG_OK;
 }
 

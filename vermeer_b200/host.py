@@ -32,7 +32,7 @@ DECLARED_SYMBOLS = [
     "vg_set_partition", "vg_set_scramble", "vg_set_filter", "vg_set_option", "vg_trace_batch", "vg_trace_batch_device", "vg_render", "vg_clear_framebuffer",
     "vg_framebuffer_device", "vg_get_stats", "vg_reset_stats",
     "vh_scene_create", "vh_scene_destroy", "vh_last_error", "vh_registered_nodes", "vh_set_globals", "vh_add_shader_std", "vh_add_polymesh",
-    "vh_add_filter", "vh_add_trilight", "vh_add_disklight", "vh_add_spherelight", "vh_set_camera_lookat", "vh_prerender", "vh_upload", "vh_num_geoms", "vh_scene_info", "vh_scene_nodes",
+    "vh_add_filter", "vh_add_trilight", "vh_add_disklight", "vh_add_spherelight", "vh_parse_vnf", "vh_load_vnf", "vh_globals", "vh_postrender", "vh_rgbe", "vh_set_camera_lookat", "vh_prerender", "vh_upload", "vh_num_geoms", "vh_scene_info", "vh_scene_nodes",
     "vh_scene_motion_nodes", "vh_scene_geom_order", "vh_mesh_info", "vh_mesh_nodes", "vh_mesh_motion_nodes", "vh_mesh_idxp", "vh_camera",
 ]
 
@@ -147,6 +147,36 @@ class HostScene:
         c = scene.camera
         self._chk(L.vh_set_camera_lookat(h, _f3(c.From), _f3(c.To), _f3(c.Up), C.c_float(c.Roll), C.c_float(c.Fov), C.c_float(c.Focal),
                                          C.c_float(c.Aspect), C.c_float(c.Radius)))
+
+    @classmethod
+    def from_vnf(cls, text: str | None = None, path: str | None = None, strict: bool = True):
+        """nodes.Parse: build the scene from a .vnf description (text in memory or a file). With `strict`, any parse error the
+        reference would have printed raises; otherwise the nodes that parsed are kept and `parse_errors`/`parse_log` tell."""
+        from types import SimpleNamespace
+        self = cls.__new__(cls)
+        self.L = load_library()
+        h = C.c_void_p()
+        if self.L.vh_scene_create(C.byref(h)) != 0:
+            raise RuntimeError("vh_scene_create failed")
+        self.h = h
+        if path is not None:
+            n = self.L.vh_load_vnf(h, path.encode())
+        else:
+            b = (text or "").encode()
+            n = self.L.vh_parse_vnf(h, b, C.c_size_t(len(b)), b"<memory>")
+        self.parse_errors = n
+        self.parse_log = self.L.vh_last_error(h).decode()
+        if n < 0 or (strict and n > 0):
+            raise RuntimeError("vnf (%d): %s" % (n, self.parse_log))
+        g = np.zeros(3, np.int32)
+        self._chk(self.L.vh_globals(h, _p(g)))
+        self.scene = SimpleNamespace(XRes=int(g[0]), YRes=int(g[1]), MaxIter=int(g[2]))
+        return self
+
+    def postrender(self, fb: np.ndarray):
+        """core.PostRender: run the scene's OutputFloat / OutputHDR nodes on the finished frame."""
+        fb = np.ascontiguousarray(fb, np.float32)
+        self._chk(self.L.vh_postrender(self.h, _p(fb), int(fb.shape[1]), int(fb.shape[0])))
 
     def _chk(self, rc):
         if rc != 0:

@@ -24,7 +24,7 @@ import numpy as np
 
 __all__ = [
     "ShaderStd", "PolyMesh", "TriLight", "DiskLight", "SphereLight", "Camera", "PixelFilter", "SceneDesc", "splitmix64_table",
-    "heightfield_mesh", "heightfield_scene", "sphere_field_scene", "cornell_box", "glossy_box", "incoherent_rays",
+    "heightfield_mesh", "heightfield_scene", "sphere_field_scene", "cornell_box", "glossy_box", "incoherent_rays", "to_vnf",
 ]
 
 
@@ -170,6 +170,88 @@ class SceneDesc:
 
 
 # ------------------------------------------------------------------------------------------------
+def _num(v) -> str:
+    """Shortest text that nodes.Lex + float32(strconv.ParseFloat(..., 64)) reads back to exactly this float32
+    (nodes/lex.go:168-205 accepts [0-9-.eE] only: no '+' in exponents)."""
+    f = np.float32(v)
+    if float(f).is_integer() and abs(float(f)) < 1e15:
+        return str(int(f))
+    return ("%.9g" % float(f)).replace("e+", "e")
+
+
+def _vec(v) -> str:
+    return " ".join(_num(x) for x in v)
+
+
+def to_vnf(sc: "SceneDesc", outputs=()) -> str:
+    """The scene as reference-valid .vnf text (syntax: nodes/parser.go). `outputs` = [("OutputFloat" |
+    "OutputHDR", filename), ...]. Nodes are written in the order the in-memory path adds them (Globals, shaders, meshes,
+    lights, filter, camera), so both paths build identical scenes."""
+    o = []
+    o.append("Globals { XRes %d YRes %d MaxIter %d }" % (sc.XRes, sc.YRes, sc.MaxIter))
+    for s in sc.shaders:
+        parts = ['Name "%s"' % s.Name]
+        for name in ("EmissionColour", "DiffuseColour", "Spec1Colour", "Spec1FresnelRefl", "Spec1FresnelEdge"):
+            v = getattr(s, name)
+            if v is not None:
+                parts.append("%s rgb %s" % (name, _vec(v)))
+        for name in ("EmissionStrength", "DiffuseStrength", "DiffuseRoughness", "Spec1Strength", "Spec1Roughness", "IOR"):
+            v = getattr(s, name)
+            if v is not None:
+                parts.append("%s float %s" % (name, _num(v)))
+        if s.Spec1FresnelModel is not None:
+            parts.append('Spec1FresnelModel "%s"' % s.Spec1FresnelModel)
+        o.append("ShaderStd { %s }" % " ".join(parts))
+    for m in sc.meshes:
+        keys, nv, _ = m.Verts.shape
+        parts = ['Name "%s"' % m.Name]
+        if m.RayBias:
+            parts.append("RayBias %s" % _num(m.RayBias))
+        parts.append("Verts %d %d point %s" % (keys, nv, _vec(m.Verts.reshape(-1))))
+        if m.PolyCount is not None:
+            parts.append("PolyCount %d int %s" % (len(m.PolyCount), " ".join(str(int(x)) for x in m.PolyCount)))
+        if m.FaceIdx is not None:
+            parts.append("FaceIdx %d int %s" % (len(m.FaceIdx), " ".join(str(int(x)) for x in m.FaceIdx)))
+        parts.append("Shader %d string %s" % (len(m.Shader), " ".join('"%s"' % x for x in m.Shader)))
+        if m.ShaderIdx is not None:
+            parts.append("ShaderIdx %d int %s" % (len(m.ShaderIdx), " ".join(str(int(x)) for x in m.ShaderIdx)))
+        if m.Normals is not None:
+            parts.append("Normals 1 %d vec3 %s" % (len(m.Normals), _vec(m.Normals.reshape(-1))))
+            if m.NormalIdx is not None:
+                parts.append("NormalIdx %d int %s" % (len(m.NormalIdx), " ".join(str(int(x)) for x in m.NormalIdx)))
+        o.append("PolyMesh { %s }" % "\n  ".join(parts))
+    for l in sc.lights:
+        kind = type(l).__name__
+        if kind == "TriLight":
+            o.append('TriLight { Name "%s" Shader "%s" P0 %s P1 %s P2 %s Samples %d }' % (l.Name, l.Shader, _vec(l.P0), _vec(l.P1), _vec(l.P2), l.Samples))
+        elif kind == "DiskLight":
+            o.append('DiskLight { Name "%s" Shader "%s" P %s LookAt %s Up %s Radius %s Segments %d Samples %d }' % (
+                l.Name, l.Shader, _vec(l.P), _vec(l.LookAt), _vec(l.Up), _num(l.Radius), l.Segments, l.Samples))
+        elif kind == "SphereLight":
+            o.append('SphereLight { Name "%s" Shader "%s" P %s Radius %s Samples %d }' % (l.Name, l.Shader, _vec(l.P), _num(l.Radius), l.Samples))
+    if sc.filter is not None:
+        f = sc.filter
+        parts = ['Name "%s"' % f.Name]
+        if f.Width is not None:
+            parts.append("Width %s" % _num(f.Width))
+        if f.Res is not None:
+            parts.append("Res %d" % f.Res)
+        if f.Peak is not None and f.Type == "AiryFilter":
+            parts.append("Peak %s" % _num(f.Peak))
+        o.append("%s { %s }" % (f.Type, " ".join(parts)))
+    c = sc.camera
+    cam = ['Name "%s"' % c.Name, 'Type "%s"' % c.Type, "From 1 1 point %s" % _vec(c.From), "To 1 1 point %s" % _vec(c.To),
+           "Roll 1 1 float %s" % _num(c.Roll), "Up %s" % _vec(c.Up), "Fov %s" % _num(c.Fov), "Focal %s" % _num(c.Focal)]
+    if c.Aspect:
+        cam.append("Aspect %s" % _num(c.Aspect))
+    if c.Radius:
+        cam.append("Radius %s" % _num(c.Radius))
+    o.append("Camera { %s }" % " ".join(cam))
+    for kind, fn in outputs:
+        o.append('%s { Filename "%s" }' % (kind, fn))
+    return "\n".join(o) + "\n"
+
+
 def splitmix64_table(seed: int, npix: int) -> np.ndarray:
     """Per-pixel scramble table, (npix, 6) uint64 = {lensU, lensV, time, lambda, scramble[0], scramble[1]}
     (core/render.go:18-23).  The reference draws these from unseeded math/rand (render.go:169-174); any
