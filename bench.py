@@ -340,9 +340,17 @@ def run_ours(args):
     alg_bytes_closest = 64.0 * closest_rays + bn * st["nodes_t"] + bt * st["tris_t"]
     launches = max(1, st["closest_launches"])
     achieved = alg_bytes_closest / (closest_ms * 1e-3) / 1e9 if closest_ms > 0 else 0.0
+    # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel (C2 scene), scaled to this run's rays
+    # per launch; null for the configs that have no capture
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if CONFIG == "c2" and os.path.exists(tpath):
+        t = json.load(open(tpath)).get("k_trace_queue<0>")
+        if t:
+            traffic = t["dram_bytes"] / t["rays"] * (closest_rays / launches)
     roofline = {
         "bound": "hbm", "kernel": "k_trace_queue<0> (closest-hit %s traversal)" % ("MQBVH" if CONFIG == "c4" else "QBVH"), "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
         "bytes_per_launch": alg_bytes_closest / launches, "ms_per_launch": closest_ms / launches,
         "rays_per_launch": closest_rays / launches, "nodesT_per_ray": st["nodes_t"] / max(1, closest_rays), "trisT_per_ray": st["tris_t"] / max(1, closest_rays),
         "share_of_step": closest_ms / dev_ms if dev_ms > 0 else None,
