@@ -735,6 +735,15 @@ struct RenderState {
     }
     return evpool[i];
   }
+  std::vector<cudaEvent_t> fetchpool;
+  cudaEvent_t fetch_ev(int i) {
+    while ((int)fetchpool.size() <= i) {
+      cudaEvent_t e;
+      cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      fetchpool.push_back(e);
+    }
+    return fetchpool[(size_t)i];
+  }
   void release() {
     pix.release(); scr.release(); mats.release(); lights.release(); rayq0.release(); rayq1.release(); sray.release();
     pathq0.release(); pathq1.release(); sslot.release(); counts.release(); hits.release(); lambda.release(); time.release();
@@ -752,6 +761,7 @@ void render_destroy(vg_ctx* ctx) {
   if (ctx->rs->e0) cudaEventDestroy(ctx->rs->e0);
   if (ctx->rs->e1) cudaEventDestroy(ctx->rs->e1);
   for (cudaEvent_t e : ctx->rs->evpool) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->rs->fetchpool) cudaEventDestroy(e);
   if (ctx->rs->scr_pinned) cudaFreeHost(ctx->rs->scr_pinned);
   if (ctx->rs->fb_pinned) cudaFreeHost(ctx->rs->fb_pinned);
   delete ctx->rs;
@@ -806,28 +816,40 @@ static int upload_scramble(vg_ctx* ctx, const uint64_t* table) {
     rs.scr_pinned_bytes = bytes;
   }
   const int* pix = rs.pix_host.data();
-  // owned pixels come in runs of up to 32 consecutive pixels (one tile row): copy run by run, a few host threads in
-  // parallel (a single core's memcpy, ~10 GB/s, would be slower than the PCIe copy that follows)
-  const int nthreads = 4;
+  // Owned pixels come in runs of 8 (or 32) consecutive pixels of one raster row. A few host threads gather their slice of the
+  // rows run by run into pinned memory, chunk by chunk, and each issues the H2D copy of a chunk as soon as it is gathered, so
+  // the PCIe transfer overlaps the gathering of the next chunks (one core's memcpy, ~10 GB/s, is slower than the link).
   const size_t n = (size_t)rs.nown;
-  auto work = [&](size_t b, size_t e) {
-    size_t i = b;
-    while (i < e) {
-      size_t j = i + 1;
-      while (j < e && pix[j] == pix[j - 1] + 1) j++;
-      std::memcpy(rs.scr_pinned + i * 6, table + (size_t)pix[i] * 6, (j - i) * 48);
-      i = j;
+  const int nthreads = n >= (1u << 16) ? 8 : 1;
+  const size_t chunk = 1u << 15;  // pixels per copy: 1.5 MB
+  uint64_t* dst_dev = rs.scr.p;
+  cudaStream_t stream = ctx->stream;
+  const int device = ctx->device;
+  std::vector<cudaError_t> errs((size_t)nthreads, cudaSuccess);
+  auto work = [&](int t, size_t b, size_t e) {
+    if (t > 0) cudaSetDevice(device);
+    for (size_t c0 = b; c0 < e; c0 += chunk) {
+      const size_t c1 = std::min(e, c0 + chunk);
+      size_t i = c0;
+      while (i < c1) {
+        size_t j = i + 1;
+        while (j < c1 && pix[j] == pix[j - 1] + 1) j++;
+        std::memcpy(rs.scr_pinned + i * 6, table + (size_t)pix[i] * 6, (j - i) * 48);
+        i = j;
+      }
+      const cudaError_t e2 = cudaMemcpyAsync(dst_dev + c0 * 6, rs.scr_pinned + c0 * 6, (c1 - c0) * 48, cudaMemcpyHostToDevice, stream);
+      if (e2 != cudaSuccess) errs[(size_t)t] = e2;
     }
   };
   {
     std::vector<std::thread> th;
     const size_t per = (n + nthreads - 1) / nthreads;
     for (int t = 1; t < nthreads; t++)
-      if ((size_t)t * per < n) th.emplace_back(work, (size_t)t * per, std::min(n, (size_t)(t + 1) * per));
-    work(0, std::min(n, per));
+      if ((size_t)t * per < n) th.emplace_back(work, t, (size_t)t * per, std::min(n, (size_t)(t + 1) * per));
+    work(0, 0, std::min(n, per));
     for (auto& t : th) t.join();
   }
-  RCUDA(cudaMemcpyAsync(rs.scr.p, rs.scr_pinned, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  for (cudaError_t e2 : errs) RCUDA(e2);
   RCUDA(cudaStreamSynchronize(ctx->stream));
   return VG_OK;
 }
@@ -1118,18 +1140,31 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
       RCUDA(cudaMallocHost((void**)&rs.fb_pinned, bytes));
       rs.fb_pinned_bytes = bytes;
     }
-    RCUDA(cudaMemcpyAsync(rs.fb_pinned, rs.fb.p, bytes, cudaMemcpyDeviceToHost, st));
-    RCUDA(cudaStreamSynchronize(st));
+    // D2H in chunks, each followed by an event; host threads copy a chunk from the pinned staging buffer into the caller's
+    // (pageable) buffer as soon as its event has fired, so the host memcpy overlaps the rest of the transfer
+    const int nchunks = 8, nthreads = 4;
+    const size_t per = ((bytes + nchunks - 1) / nchunks + 255) & ~(size_t)255;
+    for (int c = 0; c < nchunks; c++) {
+      const size_t off = (size_t)c * per;
+      if (off < bytes) RCUDA(cudaMemcpyAsync((char*)rs.fb_pinned + off, (const char*)rs.fb.p + off, std::min(per, bytes - off), cudaMemcpyDeviceToHost, st));
+      RCUDA(cudaEventRecord(rs.fetch_ev(c), st));
+    }
     {
-      const int nthreads = 4;
-      const size_t per = (bytes / nthreads + 63) & ~(size_t)63;
       char* dst = (char*)fb_out;
       const char* src = (const char*)rs.fb_pinned;
+      const int device = ctx->device;
+      auto work = [&, dst, src](int t) {
+        if (t > 0) cudaSetDevice(device);
+        for (int c = t; c < nchunks; c += nthreads) {
+          cudaEventSynchronize(rs.fetch_ev(c));
+          const size_t off = (size_t)c * per;
+          if (off < bytes) std::memcpy(dst + off, src + off, std::min(per, bytes - off));
+        }
+      };
+      for (int c = 0; c < nchunks; c++) rs.fetch_ev(c);  // create before the threads start
       std::vector<std::thread> th;
-      for (int t = 1; t < nthreads; t++)
-        if ((size_t)t * per < bytes)
-          th.emplace_back([dst, src, t, per, bytes] { std::memcpy(dst + (size_t)t * per, src + (size_t)t * per, std::min(per, bytes - (size_t)t * per)); });
-      std::memcpy(dst, src, std::min(per, bytes));
+      for (int t = 1; t < nthreads; t++) th.emplace_back(work, t);
+      work(0);
       for (auto& t : th) t.join();
     }
   }

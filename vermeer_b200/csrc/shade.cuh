@@ -19,7 +19,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// The CIE / Smits tables are indexed by a per-lane wavelength bin: in __constant__ memory a warp's lookup is serialised over
+// its distinct addresses (ncu: the largest stall lines of k_shade), in global memory it is one L1-resident LDG.
+#ifdef VG_TABLES_CONSTANT
 #define VG_TABLE_QUAL __constant__ const
+#else
+#define VG_TABLE_QUAL __device__ const
+#endif
 #include "colour_tables.h"
 
 namespace vg {
