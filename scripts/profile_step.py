@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vermeer_b200 import scenes
 from vermeer_b200.host import Device, HostScene
 motion = "--motion" in sys.argv
-sc = scenes.heightfield_scene(1920, 1080, nq=708, motion=motion)
+sc = scenes.sphere_field_scene(1920, 1080) if "--c3" in sys.argv else scenes.heightfield_scene(1920, 1080, nq=708, motion=motion)
 host = HostScene(sc).prerender()
 dev = Device(0).upload(host)
 dev.set_scramble(scenes.splitmix64_table(1, 1920 * 1080))
