@@ -186,6 +186,17 @@ int vg_mesh_upload_motion(vg_ctx* ctx, int geom_id, const VgMotionNode* topo, in
 /* sphere.Sphere geom (builtin/geom/sphere/sphere.go:15-28; "only used for spherical light sources"): an analytic leaf of the
  * scene-level tree, intersected like sphere/trace.go:13-109. */
 int vg_sphere_upload(vg_ctx* ctx, int geom_id, const float* centre, float radius, int32_t material_id);
+/* instance.Instance after PreRender (builtin/geom/instance/instance.go:36-51,117-146): a second placement of an already
+ * uploaded PolyMesh geom. srt = transformSRT, one m.TransformDecomp per Transform key (math/animdecomp.go:12-17: T, R{X,Y,Z,W},
+ * S column major — 23 contiguous floats, the Go struct's own layout); per ray the keys are interpolated at Ray.Time
+ * (TimeKey, instance.go:16-33), recomposed, inverted, and the ray is re-Setup in object space (instance.go:86-93). The
+ * instance's bounds are whatever the scene-level tree was built with (the scene file gives them). */
+typedef struct VgTransformSRT {
+  float T[3];
+  float R[4];
+  float S[16];
+} VgTransformSRT;
+int vg_instance_upload(vg_ctx* ctx, int geom_id, int target_geom_id, const VgTransformSRT* srt, int keys);
 /* Scene-level tree (builtin/scene/scene.go:135-203): leafMax=1 nodes over geoms; geom_of_slot[i] = geom id at leaf slot i. */
 int vg_scene_upload(vg_ctx* ctx, const VgNode* nodes, int n_nodes, const int32_t* geom_of_slot, int n_slots);
 int vg_scene_upload_motion(vg_ctx* ctx, const VgMotionNode* topo, int n_nodes, const float* boxes, int keys,
@@ -256,6 +267,10 @@ int vh_add_trilight(vh_scene* s, const char* name, const float* p0, const float*
 int vh_add_disklight(vh_scene* s, const char* name, const float* P, const float* lookat, const float* up, float radius, const char* shader,
                      int segments, int samples);
 int vh_add_spherelight(vh_scene* s, const char* name, const float* P, float radius, const char* shader, int samples);
+/* GeomInstance (builtin/geom/instance/instance.go): geom = name of an earlier PolyMesh; transforms = keys x 16 floats in
+ * math.Matrix4 storage (column major); bmin/bmax = n_bounds points each (only the first is used, instance.go:66-70). */
+int vh_add_instance(vh_scene* s, const char* name, const char* geom, const float* bmin, const float* bmax, int n_bounds,
+                    const float* transforms, int keys);
 int vh_set_camera_lookat(vh_scene* s, const float* from, const float* to, const float* up, float roll, float fov, float focal,
                          float aspect, float radius);
 /* nodes.Parse (nodes/parser.go:110-131): read a .vnf scene description (text in memory, or a file) and add its nodes in file

@@ -89,6 +89,11 @@ class Oracle:
                 _p(m.Normals), 0 if m.Normals is None else len(m.Normals),
                 _p(m.NormalIdx), 0 if m.NormalIdx is None else len(m.NormalIdx),
                 C.c_float(m.RayBias)))
+        for ins in getattr(scene, "instances", []):
+            bmin = np.ascontiguousarray(ins.BMin, np.float32).reshape(-1, 3)
+            bmax = np.ascontiguousarray(ins.BMax, np.float32).reshape(-1, 3)
+            tr = np.ascontiguousarray(ins.Transform, np.float32).reshape(-1, 16)
+            self._chk(L.orc_add_instance(h, ins.Name.encode(), ins.Geom.encode(), _p(bmin), _p(bmax), len(bmin), _p(tr), len(tr)))
         for l in scene.lights:
             kind = type(l).__name__
             if kind == "TriLight":

@@ -111,6 +111,27 @@ int orc_add_polymesh(void* h, const char* name, const float* verts, int nverts, 
   });
 }
 
+// GeomInstance (builtin/geom/instance/instance.go:36-51): transforms = keys x 16 floats, column major (math.Matrix4 layout,
+// i.e. what the parser stores after its transpose); bmin/bmax = nb points each.
+int orc_add_instance(void* h, const char* name, const char* geom_name, const float* bmin, const float* bmax, int nb, const float* transforms, int keys) {
+  Handle* H = (Handle*)h;
+  return guard([&] {
+    auto in = std::make_unique<Instance>();
+    in->Name = name;
+    for (auto& m : H->r.meshes)
+      if (m->Name == geom_name) in->geom = m.get();
+    if (!in->geom) throw std::runtime_error(std::string("Instance ") + name + ": Unable to find node " + geom_name);
+    for (int i = 0; i < nb; i++) { in->BMin.push_back(v3(bmin + 3 * i)); in->BMax.push_back(v3(bmax + 3 * i)); }
+    for (int k = 0; k < keys; k++) {
+      Matrix4 m;
+      std::memcpy(m.m, transforms + 16 * k, 64);
+      in->Transform.push_back(m);
+    }
+    if (in->Transform.empty() || in->BMin.empty()) throw std::runtime_error("Instance: Transform and BMin/BMax need at least one element");
+    H->r.instances.push_back(std::move(in));
+  });
+}
+
 int orc_add_trilight(void* h, const char* name, const float* p0, const float* p1, const float* p2, const char* shader, int samples) {
   Handle* H = (Handle*)h;
   return guard([&] {

@@ -139,6 +139,8 @@ struct ShaderContext {
   std::vector<LightSample> Lsamples;
   Light* Lp = nullptr;
   RGB OutRGB{};
+  Matrix4 Transform = Matrix4Identity(), InvTransform = Matrix4Identity();  // core/trace.go:57-58
+  bool transformSet = false;  // oracle-only: an Instance overwrote Transform (identity otherwise)
   RenderTask* task = nullptr;
 
   void ApplyTransform();

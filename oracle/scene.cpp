@@ -419,6 +419,54 @@ bool PolyMesh::TraceMotionElems(float time, int key, int key2, Ray* ray, ShaderC
 }
 
 // ---------------------------------------------------------------------------------------------
+// builtin/geom/instance/instance.go
+void Instance::PreRender() {  // :117-146
+  for (const Matrix4& m : Transform) transformSRT.push_back(TransformDecompMatrix4(m));
+  for (size_t i = 0; i < BMin.size(); i++) {
+    BoundingBox box;  // zero value, NOT Reset(): the box always contains the origin (instance.go:124)
+    for (int k = 0; k < 3; k++) box.b[0][k] = box.b[1][k] = 0.0f;
+    box.GrowVec3(BMin[i]);
+    box.GrowVec3(BMax[i]);
+    bounds.push_back(box);
+  }
+}
+TransformDecomp Instance::TimeKey(float time) const {  // :16-33
+  if (transformSRT.size() > 1) {
+    float k = time * (float)((int)transformSRT.size() - 1);
+    float timeFrac = k - Floor(k);
+    int key = (int)Floor(k);
+    int key2 = (int)Ceil(k);
+    return TransformDecompLerp(transformSRT[key], transformSRT[key2], timeFrac);
+  }
+  return transformSRT[0];
+}
+bool Instance::Trace(Ray* ray, ShaderContext* sg) {  // :73-114
+  Vec3 Rp = ray->P, Rd = ray->D, Rdinv = ray->Dinv;
+  float S[3] = {ray->S[0], ray->S[1], ray->S[2]};
+  int32_t Kx = ray->Kx, Ky = ray->Ky, Kz = ray->Kz;
+  Matrix4 transform = TransformDecompToMatrix4(TimeKey(ray->Time));
+  Matrix4 invTransform;
+  Matrix4Inverse(transform, &invTransform);
+  ray->P = Matrix4MulPoint(invTransform, Rp);
+  ray->D = Matrix4MulVec(invTransform, Rd);
+  ray->Setup();
+  bool hit = geom->Trace(ray, sg);
+  ray->P = Rp;
+  ray->D = Rd;
+  ray->Dinv = Rdinv;
+  ray->S[0] = S[0]; ray->S[1] = S[1]; ray->S[2] = S[2];
+  ray->Kx = Kx; ray->Ky = Ky; ray->Kz = Kz;
+  if (hit) {
+    // "we know that this ray has hit this geom as closest point so ok to overwrite" — and nothing ever resets it: a later,
+    // closer hit on an un-instanced geom is still shaded with this transform (kept; DESIGN.md quirk o)
+    sg->Transform = transform;
+    sg->InvTransform = invTransform;
+    sg->transformSet = true;
+  }
+  return hit;
+}
+
+// ---------------------------------------------------------------------------------------------
 // builtin/scene/scene.go:30-59
 bool Scene::Trace(Ray* ray, ShaderContext* sg) {
   if (!qbvh.empty()) return QTrace(qbvh, this, ray, sg);
@@ -568,6 +616,15 @@ bool Trace(Ray* ray, TraceSample* samp) {
 // core/shader.go:129-135 with Transform = InvTransform = identity (object transforms out of scope):
 // the matrix products are exact, the re-normalisations are kept.
 void ShaderContext::ApplyTransform() {
+  if (transformSet) {  // core/shader.go:129-135
+    P = Matrix4MulPoint(Transform, Po);
+    N = Vec3Normalize(Matrix4MulVec(Matrix4Transpose(InvTransform), N));
+    Ng = Vec3Normalize(Matrix4MulVec(Matrix4Transpose(InvTransform), Ng));
+    DdPdu = Vec3Normalize(Matrix4MulVec(Transform, DdPdu));
+    DdPdv = Vec3Normalize(Matrix4MulVec(Transform, DdPdv));
+    return;
+  }
+  // Transform == identity (core/trace.go:57-58): the products with 0/1 are exact, only the re-normalisations remain
   P = Po;
   N = Vec3Normalize(N);
   Ng = Vec3Normalize(Ng);

@@ -8,6 +8,7 @@
 //   builtin/geom/polymesh/trace.go:15-104,108-194,276-360,504-515,520-719 (Trace, TraceElems, TraceMotionElems)
 //   builtin/geom/polymesh/bounds.go:25-53      (Bounds)
 //   builtin/scene/scene.go:15-268              (Scene: Trace, TraceElems, LightsPrepare, initAccel, initMotionBoxes)
+//   builtin/geom/instance/instance.go:16-160   (GeomInstance: SRT-interpolated transform, ray re-Setup, user-given bounds)
 // Out of scope here: object Transform, UVs, ray differentials.
 #pragma once
 #include <memory>
@@ -62,6 +63,22 @@ struct PolyMesh : Geom, Primitive, MotionPrimitive {
   bool TraceMotionElems(float time, int key, int key2, Ray* ray, ShaderContext* sg, int base, int count) override;
   // brute force over all triangles with the same routine (anchor for the BVH)
   bool TraceBrute(Ray* ray, ShaderContext* sg);
+};
+
+// builtin/geom/instance/instance.go:36-160. "Instance duplicates an existing geom but with a new transform."
+struct Instance : Geom {
+  std::string Name;
+  Geom* geom = nullptr;                    // ins.geom (the target keeps being a scene geom of its own)
+  std::vector<Vec3> BMin, BMax;            // param.PointArray elements
+  std::vector<Matrix4> Transform;          // param.MatrixArray elements
+  std::vector<TransformDecomp> transformSRT;
+  std::vector<BoundingBox> bounds;
+
+  void PreRender();                        // instance.go:117-146
+  TransformDecomp TimeKey(float time) const;  // instance.go:16-33
+  bool Trace(Ray*, ShaderContext*) override;
+  int MotionKeys() const override { return geom->MotionKeys(); }
+  BoundingBox Bounds(float) const override { return bounds[0]; }
 };
 
 struct Scene : Primitive, MotionPrimitive {

@@ -938,6 +938,11 @@ void Renderer::PreRender() {
     m->id = gid++;
     scene.geoms.push_back(m.get());
   }
+  for (auto& in : instances) {
+    in->PreRender();
+    in->id = gid++;
+    scene.geoms.push_back(in.get());
+  }
   // lights PreRender in creation order; each appends its geom (core.AddNode), which is pre-rendered in the next round
   const size_t firstLightGeom = meshes.size();
   std::vector<Geom*> lightGeoms;

@@ -154,6 +154,7 @@ struct Renderer {
   std::vector<float> framebuffer;
   std::vector<pixelscramble> framescramble;
   std::vector<std::unique_ptr<PolyMesh>> meshes;
+  std::vector<std::unique_ptr<Instance>> instances;  // GeomInstance nodes, created after the meshes they refer to
   std::vector<std::unique_ptr<ShaderStd>> shaders;
   std::vector<std::unique_ptr<Tri>> tris;
   std::vector<std::unique_ptr<Disk>> disks;

@@ -216,3 +216,16 @@ def test_general_shading_kernel_equals_specialised_one(built_library):
     assert imgs[1] == imgs[3]
     ok = np.isfinite(imgs[0]).all(-1) & np.isfinite(imgs[2]).all(-1)
     assert np.abs(imgs[0] - imgs[2])[ok].max() <= 1e-6
+
+
+# ---- GeomInstance ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["static", "moving", "moving_motion_base"])
+def test_instanced_scene_image(built_library, kind):
+    from vermeer_b200 import scenes
+    sc = scenes.instanced_scene(112, 84, moving=kind != "static", motion_base=kind == "moving_motion_base")
+    fo, so, fg, st, _ = _render_pair(sc, 16)
+    rmse, ok = _rmse(fo, fg)
+    assert ok.all()
+    assert rmse <= 1e-3, rmse
+    assert np.median(np.abs(fo - fg)) <= 2e-6
+    assert abs(st["rays"] - so["rays"]) <= 1e-3 * so["rays"]

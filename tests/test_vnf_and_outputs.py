@@ -35,14 +35,15 @@ def _same_structures(h1, h2):
     assert ca[0].tobytes() == cb[0].tobytes() and ca[1:] == cb[1:]
 
 
-@pytest.mark.parametrize("name", ["cornell", "glossy", "motion", "filter"])
+@pytest.mark.parametrize("name", ["cornell", "glossy", "motion", "filter", "instances"])
 def test_vnf_path_builds_the_same_scene(built_library, name):
     from vermeer_b200 import scenes
     from vermeer_b200.host import HostScene
     sc = {"cornell": lambda: scenes.cornell_box(64, 48),
           "glossy": lambda: scenes.glossy_box(64, 48),
           "motion": lambda: scenes.heightfield_scene(64, 48, nq=24, motion=True),
-          "filter": lambda: scenes.cornell_box(32, 32, boxes=False)}[name]()
+          "filter": lambda: scenes.cornell_box(32, 32, boxes=False),
+          "instances": lambda: scenes.instanced_scene(64, 48, moving=True)}[name]()
     if name == "filter":
         sc.filter = scenes.PixelFilter("AiryFilter", Res=48)
     text = scenes.to_vnf(sc)

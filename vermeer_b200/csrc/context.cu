@@ -84,6 +84,7 @@ void vg_destroy(vg_ctx* ctx) {
   render_destroy(ctx);
   ctx->d_nodes.release(); ctx->d_mtopo.release(); ctx->d_mboxes.release(); ctx->d_tris.release();
   ctx->d_mtris.release(); ctx->d_normals.release(); ctx->d_geoms.release(); ctx->d_prim_material.release();
+  ctx->d_xforms.release(); ctx->d_xf_keys.release(); ctx->d_xf_static.release();
   ctx->d_rays.release(); ctx->d_hits.release(); ctx->d_counters.release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -177,6 +178,23 @@ int vg_sphere_upload(vg_ctx* ctx, int geom_id, const float* centre, float radius
   return VG_OK;
 }
 
+int vg_instance_upload(vg_ctx* ctx, int geom_id, int target_geom_id, const VgTransformSRT* srt, int keys) {
+  VG_LOCK(ctx);
+  if (geom_id < 0 || geom_id >= (int)ctx->meshes.size()) return ctx->fail(VG_ERR_INVALID, "geom_id out of range");
+  if (target_geom_id < 0 || target_geom_id >= (int)ctx->meshes.size() || target_geom_id == geom_id)
+    return ctx->fail(VG_ERR_INVALID, "vg_instance_upload: target geom out of range");
+  if (!srt || keys < 1 || keys > 255) return ctx->fail(VG_ERR_INVALID, "vg_instance_upload: need 1..255 transform keys");
+  MeshStage& m = ctx->meshes[geom_id];
+  m = MeshStage();
+  m.present = true;
+  m.instance = true;
+  m.target = target_geom_id;
+  m.srt.assign(srt, srt + keys);
+  m.n_tris = 0;
+  ctx->committed = false;
+  return VG_OK;
+}
+
 int vg_scene_upload(vg_ctx* ctx, const VgNode* nodes, int n_nodes, const int32_t* geom_of_slot, int n_slots) {
   VG_LOCK(ctx);
   if (!nodes || n_nodes <= 0 || !geom_of_slot || n_slots < 0) return ctx->fail(VG_ERR_INVALID, "vg_scene_upload: null/empty input");
@@ -208,6 +226,13 @@ int vg_scene_commit(vg_ctx* ctx) {
   const int G = (int)ctx->meshes.size();
   for (int g = 0; g < G; g++)
     if (!ctx->meshes[g].present) return ctx->fail(VG_ERR_INVALID, "vg_scene_commit: geom " + std::to_string(g) + " was not uploaded");
+
+  for (int g = 0; g < G; g++) {
+    const MeshStage& m = ctx->meshes[g];
+    if (!m.instance) continue;
+    const MeshStage& tg = ctx->meshes[m.target];
+    if (tg.instance || tg.sphere) return ctx->fail(VG_ERR_UNSUPPORTED, "GeomInstance of an Instance or a Sphere is outside this path (PolyMesh targets only)");
+  }
 
   // ---- index spaces ----
   std::vector<int64_t> node_base(G), tri_base(G), prim_base(G), normal_base(G, -1), mbox_base(G, 0);
@@ -278,6 +303,7 @@ int vg_scene_commit(vg_ctx* ctx) {
     dg.pad0 = dg.pad1 = 0;
     if (m.material_ids.size() > 255) return ctx->fail(VG_ERR_UNSUPPORTED, "more than 255 shaders on one mesh");
 
+    if (m.instance) continue;  // filled from the target below
     if (m.sphere) {
       dg.keys = 0;
       float4* t = &tris[(size_t)tri_base[g] * 3];
@@ -374,6 +400,34 @@ int vg_scene_commit(vg_ctx* ctx) {
     }
   }
 
+  // ---- instances: the hit record of an instance is the target mesh's, under the instance's geom id ----
+  std::vector<DevXform> xforms;
+  std::vector<XfSRT> xf_keys;
+  std::vector<Mat4> xf_static;
+  std::vector<int> xform_of_geom((size_t)G, -1);
+  for (int g = 0; g < G; g++) {
+    const MeshStage& m = ctx->meshes[g];
+    if (!m.instance) continue;
+    geoms[g] = geoms[m.target];
+    DevXform x;
+    x.root = mesh_root(m.target);
+    x.geom = g;
+    x.nkeys = (int32_t)m.srt.size();
+    x.key_base = (int32_t)xf_keys.size();
+    for (const VgTransformSRT& k : m.srt) {
+      XfSRT d;
+      std::memcpy(&d, &k, sizeof(d));
+      xf_keys.push_back(d);
+    }
+    Mat4 M, Minv;
+    xf_matrices(&xf_keys[(size_t)x.key_base], 1, 0.0f, &M, &Minv);  // what every ray computes when there is one key
+    xf_static.push_back(M);
+    xf_static.push_back(Minv);
+    xform_of_geom[g] = (int)xforms.size();
+    xforms.push_back(x);
+  }
+  if (!xforms.empty() && n_static + n_motion >= (int64_t)kXformMask) return ctx->fail(VG_ERR_UNSUPPORTED, "too many nodes for a scene with instances");
+
   // ---- scene level: leaves (leafMax = 1) become links to the mesh roots ----
   auto scene_child = [&](int32_t ch, int nn, int64_t base, bool motion, int32_t* out) -> bool {
     if (ch >= 0) {
@@ -386,7 +440,8 @@ int vg_scene_commit(vg_ctx* ctx) {
       if (count != 1 || first >= (int)S.geom_of_slot.size()) return false;
       const int g = S.geom_of_slot[first];
       if (g < 0 || g >= G) return false;
-      if (ctx->meshes[g].sphere) *out = (int32_t)(kLeafBit | kGeomBit | kSphereBit | (uint32_t)tri_base[g]);
+      if (ctx->meshes[g].instance) *out = (int32_t)(kLeafBit | kGeomBit | kXformBit | (uint32_t)xform_of_geom[g]);
+      else if (ctx->meshes[g].sphere) *out = (int32_t)(kLeafBit | kGeomBit | kSphereBit | (uint32_t)tri_base[g]);
       else *out = (int32_t)(kLeafBit | kGeomBit | (uint32_t)mesh_root(g));
     }
     return true;
@@ -424,6 +479,9 @@ int vg_scene_commit(vg_ctx* ctx) {
   VG_CUDA(ctx, upload(ctx->d_normals, normals, ctx->stream));
   VG_CUDA(ctx, upload(ctx->d_geoms, geoms, ctx->stream));
   VG_CUDA(ctx, upload(ctx->d_prim_material, prim_material, ctx->stream));
+  VG_CUDA(ctx, upload(ctx->d_xforms, xforms, ctx->stream));
+  VG_CUDA(ctx, upload(ctx->d_xf_keys, xf_keys, ctx->stream));
+  VG_CUDA(ctx, upload(ctx->d_xf_static, xf_static, ctx->stream));
   VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->scene_bytes = nodes.size() * sizeof(DevNode) + mtopo.size() * sizeof(DevMotionNode) + (mboxes.size() + tris.size() + mtris.size() + normals.size()) * sizeof(float4);
 
@@ -438,6 +496,10 @@ int vg_scene_commit(vg_ctx* ctx) {
   d.tri_normals = any_normals ? ctx->d_normals.p : nullptr;
   d.n_static = (int32_t)n_static;
   d.root = S.motion ? motion_global(scene_node_base) : (int32_t)scene_node_base;
+  d.xforms = ctx->d_xforms.p;
+  d.xf_keys = ctx->d_xf_keys.p;
+  d.xf_static = ctx->d_xf_static.p;
+  d.n_xforms = (int32_t)xforms.size();
   d.n_geoms = G;
   d.n_spheres = 0;
   for (int g = 0; g < G; g++) d.n_spheres += ctx->meshes[g].sphere ? 1 : 0;

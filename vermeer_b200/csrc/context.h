@@ -17,6 +17,9 @@ struct MeshStage {
   bool sphere = false;  // sphere.Sphere geom: centre/radius below, one triangle-slot-sized record, one prim
   float centre[3] = {0, 0, 0};
   float radius = 0;
+  bool instance = false;  // instance.Instance: a transformed placement of geom `target`
+  int target = -1;
+  std::vector<VgTransformSRT> srt;
   std::vector<VgNode> nodes;
   std::vector<VgMotionNode> topo;
   std::vector<float> boxes;  // [keys][n_nodes][24]
@@ -88,6 +91,9 @@ struct vg_ctx {
   vg::DevBuf<float4> d_mboxes, d_tris, d_mtris, d_normals;
   vg::DevBuf<vg::DevGeom> d_geoms;
   vg::DevBuf<uint8_t> d_prim_material;
+  vg::DevBuf<vg::DevXform> d_xforms;
+  vg::DevBuf<vg::XfSRT> d_xf_keys;
+  vg::DevBuf<vg::Mat4> d_xf_static;
   size_t scene_bytes = 0;
 
   // batch trace scratch

@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "xform_math.h"
+
 namespace vg {
 
 // Child link encoding on the device (host flattening re-encodes the reference's links):
@@ -28,6 +30,17 @@ static const uint32_t kGeomBit = 0x40000000u;
 static const uint32_t kMotionTriBit = 0x20000000u;
 static const uint32_t kSphereBit = 0x20000000u;      // with kGeomBit
 static const uint32_t kGeomRootMask = 0x1FFFFFFFu;
+//                               bit28 = 1 (bit29 = 0): instance geom, payload = index into `xforms` (enter: transform the ray)
+//                               bit28 = 1 and bit29 = 1: the stack sentinel pushed on entering an instance (leave: restore)
+static const uint32_t kXformBit = 0x10000000u;       // with kGeomBit; mesh roots of such scenes must stay below 2^28
+static const uint32_t kXformMask = 0x0FFFFFFFu;
+
+struct DevXform {
+  int32_t root;      // global node index of the target mesh's root
+  int32_t geom;      // geom id of the instance (what a hit reports, scene.go:65)
+  int32_t nkeys;     // transform keys; 1 = static: M / Minv pre-multiplied on the host in xf_static[2*i], [2*i+1]
+  int32_t key_base;  // first XfSRT of this instance in xf_keys
+};
 static const uint32_t kLeafBaseMask = 0x1FFFFFFu;  // 25 bits: 33.5 M triangle slots per kind
 
 struct __align__(16) DevNode {  // 128 B
@@ -66,6 +79,10 @@ struct DevScene {
   int32_t n_static;              // number of static nodes (motion node global index = n_static + i)
   int32_t root;                  // global index of the scene-level root node
   int32_t n_geoms;
+  const DevXform* xforms;
+  const XfSRT* xf_keys;
+  const Mat4* xf_static;
+  int32_t n_xforms;              // instance geoms (selects the kernels that carry the transform enter/leave code)
   int32_t n_spheres;             // analytic sphere geoms in the scene-level tree (selects the kernels that carry their leaf test)
 };
 

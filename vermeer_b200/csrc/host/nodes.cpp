@@ -51,6 +51,7 @@ struct RegisterBuiltins {
     Register("TriLight", [] { return std::unique_ptr<Node>(new TriLight()); });
     Register("DiskLight", [] { return std::unique_ptr<Node>(new DiskLight()); });      // disk.go:263-269
     Register("SphereLight", [] { return std::unique_ptr<Node>(new SphereLight()); });  // sphere.go:297-303
+    Register("GeomInstance", [] { return std::unique_ptr<Node>(new GeomInstance()); });  // instance.go:163-165
     Register("Sphere", [] { return std::unique_ptr<Node>(new SphereGeom()); });        // geom/sphere/sphere.go:78-86
     // builtin/driver/outputfloat.go:44-50, outputhdr.go:59-65
     Register("OutputFloat", [] { OutputNode* o = new OutputNode(); o->Filename = "out.float"; return std::unique_ptr<Node>(o); });
@@ -151,6 +152,25 @@ Quat slerp(Quat a, Quat b, float t) {  // math/quat.go:30-66
   const float ra = (float)std::sin((double)((1 - t) * half)) / s;
   const float rb = (float)std::sin((double)(t * half)) / s;
   return Quat{a.X * ra + b.X * rb, a.Y * ra + b.Y * rb, a.Z * ra + b.Z * rb, a.W * ra + b.W * rb};
+}
+// math/animdecomp.go:21-63: M = T * R * S via polar decomposition
+VgTransformSRT transform_decomp(M4 mtx) {
+  VgTransformSRT d;
+  const float sign = m4_det(mtx) >= 0.0f ? 1.0f : -1.0f;
+  d.T[0] = mtx.at(0, 3); d.T[1] = mtx.at(1, 3); d.T[2] = mtx.at(2, 3);
+  mtx.set(0, 3, 0); mtx.set(1, 3, 0); mtx.set(2, 3, 0);
+  if (sign < 0.0f) mtx = m4_mul(m4_scale(-1, m4_identity()), mtx);
+  Quat R{0, 0, 0, 1};
+  M4 S = m4_identity();
+  M4 Q;
+  if (polar_factor(mtx, &Q)) {
+    S = m4_mul(m4_transpose(Q), mtx);
+    R = to_quat(Q);
+    if (sign < 0.0f) { S = m4_mul(m4_scale(-1, m4_identity()), S); S.m[15] = 1; }
+  }
+  d.R[0] = R.X; d.R[1] = R.Y; d.R[2] = R.Z; d.R[3] = R.W;
+  std::memcpy(d.S, S.m, sizeof(d.S));
+  return d;
 }
 }  // namespace
 
@@ -487,6 +507,25 @@ void SphereLight::Describe(VgLight* o) const {
   o->radius = Radius;
 }
 
+// ---- GeomInstance (builtin/geom/instance/instance.go:117-146) -----------------------------------------
+int GeomInstance::PreRender(Core& core, std::string* err) {
+  for (const M4& m : Transform) transformSRT.push_back(transform_decomp(m));
+  for (size_t i = 0; i < BMin.size(); i++) {
+    Box b;  // the zero value, not Reset(): the bounds always contain the origin (instance.go:124)
+    for (int k = 0; k < 3; k++) b.lo[k] = b.hi[k] = 0.0f;
+    b.grow_point(BMin[i].x, BMin[i].y, BMin[i].z);
+    b.grow_point(BMax[i].x, BMax[i].y, BMax[i].z);
+    bounds.push_back(b);
+  }
+  Node* n = core.FindNode(GeomName);
+  if (!n) { *err = "Instance " + NodeName + ": Unable to find node " + GeomName; return -1; }
+  geom = dynamic_cast<Geom*>(n);
+  if (!geom) { *err = "Instance " + NodeName + ": Unable to find geom " + GeomName; return -1; }
+  if (!dynamic_cast<PolyMesh*>(n)) { *err = "Instance " + NodeName + ": only PolyMesh targets are supported on this path"; return -1; }
+  if (transformSRT.empty() || bounds.empty()) { *err = "Instance " + NodeName + ": Transform and BMin/BMax need at least one element"; return -1; }
+  return 0;
+}
+
 // ---- pixel filters (builtin/filter) -----------------------------------------------------------------
 namespace {
 double bessel_j1(double x) {  // airy.go:34-72 (Numerical-Recipes rational approximations)
@@ -627,6 +666,9 @@ void Core::AddNode(std::unique_ptr<Node> node) {
   if (PolyMesh* pm = dynamic_cast<PolyMesh*>(n)) {
     pm->id = next_geom_id++;
     scene.AddGeom(pm);
+  } else if (GeomInstance* gi = dynamic_cast<GeomInstance*>(n)) {
+    gi->id = next_geom_id++;
+    scene.AddGeom(gi);
   } else if (SphereGeom* sg = dynamic_cast<SphereGeom*>(n)) {
     sg->id = next_geom_id++;
     scene.AddGeom(sg);

@@ -115,6 +115,21 @@ struct SphereGeom : Node, Geom {
   Box Bounds(float time) const override;
 };
 
+// instance.Instance (builtin/geom/instance/instance.go:36-160)
+struct GeomInstance : Node, Geom {
+  std::string NodeName;
+  std::string GeomName;           // `Geom`
+  std::vector<V3> BMin, BMax;     // param.PointArray elements
+  std::vector<M4> Transform;      // param.MatrixArray elements (column major)
+  std::vector<VgTransformSRT> transformSRT;
+  std::vector<Box> bounds;
+  Geom* geom = nullptr;
+  std::string Name() const override { return NodeName; }
+  int PreRender(Core& core, std::string* err) override;
+  int MotionKeys() const override { return geom ? geom->MotionKeys() : 1; }
+  Box Bounds(float) const override { return bounds[0]; }
+};
+
 struct TriLight : Node, Light {
   std::string NodeName;
   V3 P0{}, P1{}, P2{};

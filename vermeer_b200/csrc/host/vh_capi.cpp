@@ -142,6 +142,25 @@ int vh_add_trilight(vh_scene* s, const char* name, const float* p0, const float*
   return VG_OK;
 }
 
+int vh_add_instance(vh_scene* s, const char* name, const char* geom, const float* bmin, const float* bmax, int n_bounds, const float* transforms,
+                    int keys) {
+  if (!s || !name || !geom || !bmin || !bmax || !transforms) return fail(s, VG_ERR_INVALID, "vh_add_instance: null argument");
+  if (n_bounds < 1 || keys < 1 || keys > 255) return fail(s, VG_ERR_INVALID, "GeomInstance: need BMin/BMax and 1..255 Transform keys");
+  std::unique_ptr<Node> h;
+  GeomInstance* g = make<GeomInstance>(s, "GeomInstance", &h);
+  if (!g) return VG_ERR_INVALID;
+  g->NodeName = name;
+  g->GeomName = geom;
+  for (int i = 0; i < n_bounds; i++) { g->BMin.push_back(v3(bmin + 3 * i)); g->BMax.push_back(v3(bmax + 3 * i)); }
+  for (int k = 0; k < keys; k++) {
+    M4 m;
+    std::memcpy(m.m, transforms + 16 * k, sizeof(m.m));
+    g->Transform.push_back(m);
+  }
+  s->core.AddNode(std::move(h));
+  return VG_OK;
+}
+
 int vh_add_disklight(vh_scene* s, const char* name, const float* P, const float* lookat, const float* up, float radius, const char* shader,
                      int segments, int samples) {
   if (!s || !name || !P || !lookat || !up || !shader) return fail(s, VG_ERR_INVALID, "vh_add_disklight: null argument");
@@ -272,6 +291,10 @@ int vh_upload(vh_scene* s, vg_ctx* ctx, int motion_ref_compat) {
     if (SphereGeom* sp = dynamic_cast<SphereGeom*>(gm)) {
       const float ctr[3] = {sp->P.x, sp->P.y, sp->P.z};
       if (chk(vg_sphere_upload(ctx, id, ctr, sp->Radius, sp->shader ? sp->shader->material_id : -1)) != VG_OK) return VG_ERR_INVALID;
+      continue;
+    }
+    if (GeomInstance* gi = dynamic_cast<GeomInstance*>(gm)) {
+      if (chk(vg_instance_upload(ctx, id, gi->geom->id, gi->transformSRT.data(), (int)gi->transformSRT.size())) != VG_OK) return VG_ERR_INVALID;
       continue;
     }
     PolyMesh* m = dynamic_cast<PolyMesh*>(gm);

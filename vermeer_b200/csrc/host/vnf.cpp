@@ -10,7 +10,7 @@
 //                                  image/hdr/writer.go:58-91
 // Error behaviour: the reference prints "<file>:<line>:<col>: message", keeps going and exits after more than 10 errors;
 // here the messages are collected (vh_last_error), the count is returned, and parsing stops after more than 10.
-// Node types that are registered in the reference but out of scope here (QuadLight, Proc, GeomInstance, Include,
+// Node types that are registered in the reference but out of scope here (QuadLight, Proc, Include,
 // DebugShader) are reported like an unregistered type. `rgbtex` maps need the texture subsystem and are reported too.
 #include <cmath>
 #include <cstdio>
@@ -232,6 +232,9 @@ const std::vector<NodeDefn>& node_table() {
       {"SphereLight", {{"Name", KString, true}, {"P", KVec3, true}, {"Radius", KFloat, true}, {"Shader", KString, true}, {"Samples", KInt, false}}, true},
       // builtin/geom/sphere/sphere.go:15-28
       {"Sphere", {{"Name", KString, true}, {"RayBias", KFloat, false}, {"P", KVec3, true}, {"Radius", KFloat, true}, {"Shader", KString, true}}, true},
+      // builtin/geom/instance/instance.go:36-51
+      {"GeomInstance", {{"Name", KString, true}, {"Geom", KString, true}, {"BMin", KPointArray, true}, {"BMax", KPointArray, true},
+                        {"Transform", KMatrixArray, true}}, true},
       // builtin/filter/airy.go:13-22 (GaussianFilter's untagged NodeDef field makes it unparseable in the reference, gauss.go:14;
       // accepted here with its two fields)
       {"AiryFilter", {{"Name", KString, true}, {"Width", KFloat, false}, {"Res", KInt, false}, {"Peak", KFloat, false}}, true},
@@ -240,7 +243,7 @@ const std::vector<NodeDefn>& node_table() {
       {"OutputFloat", {{"Filename", KString, true}}, true},
       {"OutputHDR", {{"Filename", KString, true}}, true},
       // registered in the reference, not on this path
-      {"QuadLight", {}, false}, {"Proc", {}, false}, {"GeomInstance", {}, false}, {"Include", {}, false}, {"DebugShader", {}, false},
+      {"QuadLight", {}, false}, {"Proc", {}, false}, {"Include", {}, false}, {"DebugShader", {}, false},
   };
   return t;
 }
@@ -569,6 +572,19 @@ std::string build_node(Core& core, const std::string& type, std::map<std::string
     g->P = v3of(f["P"].c);
     g->Radius = (float)f["Radius"].f;
     g->Shader = f["Shader"].s;
+  } else if (type == "GeomInstance") {
+    GeomInstance* g = static_cast<GeomInstance*>(h.get());
+    g->NodeName = f["Name"].s;
+    g->GeomName = f["Geom"].s;
+    const Value &bmin = f["BMin"], &bmax = f["BMax"], &tr = f["Transform"];
+    if (bmin.elems.size() < 3 || bmax.elems.size() != bmin.elems.size()) return "GeomInstance: BMin/BMax need the same number (>= 1) of points";
+    for (size_t i = 0; i + 3 <= bmin.elems.size(); i += 3) { g->BMin.push_back(v3of(&bmin.elems[i])); g->BMax.push_back(v3of(&bmax.elems[i])); }
+    if (tr.elems.size() < 16 || tr.elems.size() / 16 > 255) return "GeomInstance: Transform needs 1..255 matrices";
+    for (size_t i = 0; i + 16 <= tr.elems.size(); i += 16) {
+      M4 m;
+      std::memcpy(m.m, &tr.elems[i], sizeof(m.m));
+      g->Transform.push_back(m);
+    }
   } else if (type == "AiryFilter" || type == "GaussianFilter") {
     PixelFilter* p = static_cast<PixelFilter*>(h.get());
     p->NodeName = f["Name"].s;

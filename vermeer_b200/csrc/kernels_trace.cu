@@ -64,7 +64,10 @@ cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d
   cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
 #define VG_LAUNCH(A, V) k_trace_batch<A, V><<<grid, kTraceBlock, smem, stream>>>(sc, d_rays, d_hits, n, d_counter, d_stats)
-  if (sc.n_spheres > 0) {  // kernels that carry the analytic sphere leaf (traverse.cuh: VARIANT & 8)
+  if (sc.n_xforms > 0) {  // instances: cooperative kernels with the transform enter/leave code (traverse.cuh: VARIANT & 16)
+    if (any_hit) VG_LAUNCH(true, 26);
+    else VG_LAUNCH(false, 26);
+  } else if (sc.n_spheres > 0) {  // kernels that carry the analytic sphere leaf (traverse.cuh: VARIANT & 8)
     if (any_hit) {
       if (variant == 2) VG_LAUNCH(true, 10);
       else VG_LAUNCH(true, 8);

@@ -51,7 +51,8 @@ struct DevMat {
 
 struct __align__(16) DevHit {
   float t, u, v, w;
-  int32_t prim, geom, slot, pad;
+  int32_t prim, geom, slot;
+  int32_t xf;  // 1 + index of the last instance that reported a hit along this ray (0 = none): ShaderContext.Transform
 };
 
 struct RenderParams {
@@ -207,7 +208,7 @@ struct QueueIO {
     if (overflow) atomicOr(p.counts + 5, 4);
     if (MODE == 0) {
       *reinterpret_cast<float4*>(&p.hits[i]) = make_float4(r.tclosest, h.u, h.v, h.w);
-      *(reinterpret_cast<int4*>(&p.hits[i]) + 1) = make_int4(h.prim, h.geom, h.slot, 0);
+      *(reinterpret_cast<int4*>(&p.hits[i]) + 1) = make_int4(h.prim, h.geom, h.slot, h.xf_last + 1);
     } else {
       if (h.prim >= 0) p.contrib[p.sslot[i]] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -253,6 +254,8 @@ __device__ __forceinline__ f3 ld3(const float4* p) {
 
 // polymesh/trace.go:276-360,504-515 (static) / :625-667 (motion), then ShaderContext.ApplyTransform (core/shader.go:129-135,
 // identity transform: only the re-normalisations remain).
+// APPLY_IDENTITY = false leaves N, Ng, DdPdu, DdPdv as the geom wrote them, for a caller that applies a real transform.
+template <bool APPLY_IDENTITY = true>
 __device__ inline void build_context(const RenderParams& p, const DevHit& h, float time, ShadeCtx& c) {
   const DevGeom g = p.sc.geoms[h.geom];
   const float U = h.u, V = h.v, W = h.w;
@@ -297,11 +300,41 @@ __device__ inline void build_context(const RenderParams& p, const DevHit& h, flo
     c.DdPdu = e0;
     c.DdPdv = e1;
   }
+  if (!APPLY_IDENTITY) {
+    c.N = N;
+    c.Ng = Ng;
+    return;
+  }
   // ApplyTransform
   c.N = normalize3(N);
   c.Ng = normalize3(Ng);
   c.DdPdu = normalize3(c.DdPdu);
   c.DdPdv = normalize3(c.DdPdv);
+}
+
+// ShaderContext.ApplyTransform (core/shader.go:129-135) with the transform the last hit instance left in the context
+// (instance.go:107-111) at this ray's time. Poffset stays as the geom computed it, in object space, like the reference.
+__device__ inline void apply_instance_transform(const RenderParams& p, int xi, float time, ShadeCtx& c) {
+  const DevXform x = p.sc.xforms[xi];
+  Mat4 M, Minv;
+  if (x.nkeys == 1) {
+    M = p.sc.xf_static[2 * xi];
+    Minv = p.sc.xf_static[2 * xi + 1];
+  } else {
+    xf_matrices(p.sc.xf_keys + x.key_base, x.nkeys, time, &M, &Minv);
+  }
+  const Mat4 MinvT = m4_transpose(Minv);
+  float o[3];
+  m4_mul_point(M, c.P.x, c.P.y, c.P.z, o);
+  c.P = mk3(o[0], o[1], o[2]);
+  m4_mul_vec(MinvT, c.N.x, c.N.y, c.N.z, o);
+  c.N = normalize3(mk3(o[0], o[1], o[2]));
+  m4_mul_vec(MinvT, c.Ng.x, c.Ng.y, c.Ng.z, o);
+  c.Ng = normalize3(mk3(o[0], o[1], o[2]));
+  m4_mul_vec(M, c.DdPdu.x, c.DdPdu.y, c.DdPdu.z, o);
+  c.DdPdu = normalize3(mk3(o[0], o[1], o[2]));
+  m4_mul_vec(M, c.DdPdv.x, c.DdPdv.y, c.DdPdv.z, o);
+  c.DdPdv = normalize3(mk3(o[0], o[1], o[2]));
 }
 
 // sphere.Sphere.Trace hit record (builtin/geom/sphere/trace.go:17-47), then ApplyTransform's re-normalisations
@@ -966,7 +999,7 @@ static int prepare(vg_ctx* ctx) {
   // sphere geoms need the analytic hit record; glossy lobes, conductor Fresnel and non-Tri lights the general kernel
   bool any_sphere_geom = false;
   for (const MeshStage& m : ctx->meshes) any_sphere_geom |= m.sphere;
-  rs.generic = any_glossy || any_conductor || any_other_light || any_sphere_geom || ctx->opt_generic_shade;
+  rs.generic = any_glossy || any_conductor || any_other_light || any_sphere_geom || ctx->dev.n_xforms > 0 || ctx->opt_generic_shade;
   rs.nlobes = any_glossy ? 2 : 1;
   rs.nlights = (int)lights.size();
   rs.levels = any_mirror ? 4 : 1;
@@ -1055,6 +1088,7 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
 
   const size_t smem = trace_smem_bytes();
   const int variant = ctx->opt_traversal;
+  const bool xf = ctx->dev.n_xforms > 0;    // kernels that carry the instance enter/leave code (VARIANT & 16)
   const bool sph = ctx->dev.n_spheres > 0;  // kernels that carry the analytic sphere leaf (traverse.cuh: VARIANT & 8)
   uint64_t launches = 0;
   size_t nev = 0;
@@ -1080,7 +1114,8 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
         cudaEventRecord(rs.ev(nev++), st);
         // camera rays are coherent: the per-lane loop with its compile-time axis specialisation is faster there (measured
         // 3.81 vs 3.48 Grays/s); every later level is incoherent and takes the cooperative leaf phase
-        if (sph) {
+        if (xf) k_trace_queue<0, 26><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
+        else if (sph) {
           if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 10><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
           else k_trace_queue<0, 8><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
         } else if (variant == 1) k_trace_queue<0, 1><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
@@ -1102,7 +1137,10 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
             else k_shade<true, false><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
           }
           cudaEventRecord(rs.ev(nev++), st);
-          if (sph) {
+          if (xf) {
+            if (ctx->opt_shadow_unordered) k_trace_queue<1, 27><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
+            else k_trace_queue<1, 26><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
+          } else if (sph) {
             if (variant == 2 && ctx->opt_shadow_unordered) k_trace_queue<1, 11><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
             else if (variant == 2) k_trace_queue<1, 10><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
             else k_trace_queue<1, 8><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);

@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(128, 4) k_shade_generic(const RenderParams p, 
     const float4 h0 = *reinterpret_cast<const float4*>(&p.hits[i]);
     const int4 h1 = *(reinterpret_cast<const int4*>(&p.hits[i]) + 1);
     h.t = h0.x; h.u = h0.y; h.v = h0.z; h.w = h0.w;
-    h.prim = h1.x; h.geom = h1.y; h.slot = h1.z;
+    h.prim = h1.x; h.geom = h1.y; h.slot = h1.z; h.xf = h1.w;
     const float4* rp = reinterpret_cast<const float4*>(p.rayq[qin] + i);
     const float4 a = rp[0], b = rp[1];
     Ro = mk3(a.x, a.y, a.z);
@@ -309,8 +309,15 @@ __global__ void __launch_bounds__(128, 4) k_shade_generic(const RenderParams p, 
     const float lambda = p.lambda[path];
     time = p.time[path];
     const int own = path % p.nown;
-    if (p.sc.geoms[h.geom].keys == 0) build_context_sphere(p, h, Ro, Rd, c);
-    else build_context(p, h, time, c);
+    if (h.xf > 0) {  // an instance left its transform in the context (instance.go:107-111)
+      if (p.sc.geoms[h.geom].keys == 0) build_context_sphere(p, h, Ro, Rd, c);  // (its own re-normalisations are idempotent)
+      else build_context<false>(p, h, time, c);
+      apply_instance_transform(p, h.xf - 1, time, c);
+    } else if (p.sc.geoms[h.geom].keys == 0) {
+      build_context_sphere(p, h, Ro, Rd, c);
+    } else {
+      build_context(p, h, time, c);
+    }
     f3 V = cross3(c.N, c.DdPdu);
     if (len2_3(V) < 0.1f) V = cross3(c.N, c.DdPdv);
     V = normalize3(V);

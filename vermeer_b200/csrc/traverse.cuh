@@ -46,6 +46,8 @@ struct HitState {
   int32_t geom;
   int32_t slot;  // global triangle slot of the hit (key-0 slot for motion meshes)
   int32_t nodesT, trisT;
+  int32_t xf_hit;   // instance (index into DevScene::xforms) inside which the current closest hit was found, or -1
+  int32_t xf_last;  // last instance that reported a hit: the transform ShaderContext ends up with (instance.go:107-111), or -1
 };
 
 __device__ __forceinline__ float sel3(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
@@ -243,6 +245,8 @@ __device__ __forceinline__ void trav_begin(const DevScene& sc, TravState& t, Sta
   t.h.u = t.h.v = t.h.w = 0.0f;
   t.h.nodesT = 0;
   t.h.trisT = 0;
+  t.h.xf_hit = -1;
+  t.h.xf_last = -1;
   st.sp = 0;
   t.cur = sc.root;  // qbvh.Trace pushes the root with T = Tclosest and pops it at once (intersect.go:93-104)
 }
@@ -683,6 +687,22 @@ __device__ __forceinline__ void trace_persistent_ldg(const DevScene& sc, IO& io,
   }
 }
 
+// ---- Instances (builtin/geom/instance/instance.go:73-114) ------------------------------------------------------------
+// Entering an instance leaf replaces the lane's ray by its object-space image (Matrix4MulPoint / MulVec with the inverse
+// transform at Ray.Time, then Ray.Setup) and pushes a sentinel under the target mesh's root; popping the sentinel restores
+// the world-space ray from the queue record. t is the same parameter in both spaces (D is not re-normalised), so Tclosest
+// and the T keys of the stack entries pushed before entering stay valid. Rare and heavy (a 4x4 inverse, and a slerp when
+// the transform has motion keys): kept out of line, scalars in, six floats out.
+static __device__ __noinline__ void xf_object_ray(const DevScene& sc, int xi, float time, float ox, float oy, float oz, float dx, float dy, float dz,
+                                                 float* out6) {
+  const DevXform x = sc.xforms[xi];
+  Mat4 M, Minv;
+  if (x.nkeys == 1) Minv = sc.xf_static[2 * xi + 1];
+  else xf_matrices(sc.xf_keys + x.key_base, x.nkeys, time, &M, &Minv);
+  m4_mul_point(Minv, ox, oy, oz, out6);
+  m4_mul_vec(Minv, dx, dy, dz, out6 + 3);
+}
+
 // ---- Warp-cooperative leaves ------------------------------------------------------------------------------------
 // The per-lane while-while loop above leaves most of a warp idle on incoherent rays: lanes sit at leaves of 1..16
 // triangles while others still walk nodes, and inside the leaf phase every lane runs its own trip count (measured
@@ -862,7 +882,7 @@ __device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bo
   return leafhit;
 }
 
-template <bool ANY_HIT, bool ORDERED, bool SPH, class IO>
+template <bool ANY_HIT, bool ORDERED, bool SPH, bool XF, class IO>
 __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io, Stack& st, const CoopSmem& cs, unsigned long long& nodes_acc,
                                                       unsigned long long& tris_acc) {
   const int lane = threadIdx.x & 31;
@@ -871,6 +891,7 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
   t.cur = -1;
   long long my = -1;
   bool exhausted = false;
+  int cur_xf = -1;  // XF: instance the lane's ray is currently inside of
   st.sp = 0;
   st.overflow = false;
   while (true) {
@@ -895,8 +916,29 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
     // node phase: per lane, until fewer than VG_NODE_MIN lanes want it and at least one leaf is pending
     while (true) {
       while (t.cur < -1 && ((uint32_t)t.cur & kGeomBit)) {  // scene.go:61-78
-        if (SPH && ((uint32_t)t.cur & kSphereBit)) {        // -> sphere.Trace
-          if (sphere_leaf(sc, t, (uint32_t)t.cur) && ANY_HIT) {
+        if (XF && ((uint32_t)t.cur & kXformBit)) {          // -> instance.Trace
+          if ((uint32_t)t.cur & kSphereBit) {               // the sentinel: leave the instance (instance.go:98-105)
+            const float tcl = t.r.tclosest;
+            io.load(my, t.r);
+            t.r.tclosest = tcl;
+            ray_setup(t.r);
+            cur_xf = -1;
+            t.cur = pop_next<ORDERED>(t.r, st);
+          } else {                                          // enter (instance.go:86-96)
+            const int xi = (int)((uint32_t)t.cur & kXformMask);
+            st.push(__int_as_float(0xff800000), (int32_t)(kLeafBit | kGeomBit | kXformBit | kSphereBit | (uint32_t)xi));  // T = -Inf: never culled
+            float o6[6];
+            xf_object_ray(sc, xi, t.r.time, t.r.ox, t.r.oy, t.r.oz, t.r.dx, t.r.dy, t.r.dz, o6);
+            t.r.ox = o6[0]; t.r.oy = o6[1]; t.r.oz = o6[2];
+            t.r.dx = o6[3]; t.r.dy = o6[4]; t.r.dz = o6[5];
+            ray_setup(t.r);
+            cur_xf = xi;
+            t.cur = sc.xforms[xi].root;
+          }
+        } else if (SPH && ((uint32_t)t.cur & kSphereBit)) {  // -> sphere.Trace
+          const bool sh = sphere_leaf(sc, t, (uint32_t)t.cur);
+          if (XF && sh) t.h.xf_hit = -1;
+          if (sh && ANY_HIT) {
             st.sp = 0;
             t.cur = -1;
           } else {
@@ -923,6 +965,10 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
         leafhit = leaf_motion<-1>(sc, t.r, t.h, (int)((un >> 4) & kLeafBaseMask), count);
       }
       if (leaf) {
+        if (XF && leafhit) {
+          t.h.xf_hit = cur_xf;
+          if (cur_xf >= 0) t.h.xf_last = cur_xf;
+        }
         if (ANY_HIT && leafhit) {  // intersect.go:231-236
           st.sp = 0;
           t.cur = -1;
@@ -937,6 +983,8 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
         t.h.geom = __float_as_int(ldg4(tp).w);
         t.h.prim = __float_as_int(ldg4(tp + 1).w);
       }
+      if (XF && t.h.xf_hit >= 0 && t.h.prim >= 0) t.h.geom = sc.xforms[t.h.xf_hit].geom;  // scene.go:65: sc.Geom = the Instance
+      if (XF) cur_xf = -1;
       io.store(my, t.r, t.h, st.overflow);
       nodes_acc += (unsigned long long)t.h.nodesT;
       tris_acc += (unsigned long long)t.h.trisT;
@@ -948,12 +996,14 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
 
 // VARIANT & 7: 0 = per-lane while-while with coalesced LDG refill, 1 = the same over the TMA-staged queue, 2 = warp-cooperative
 // leaves, 3 = cooperative leaves without the ordered push (occlusion-only any-hit rays). VARIANT & 8: the scene holds analytic
-// sphere geoms (variants 0, 2, 3 only; the launchers map variant 1 to 0 for such scenes).
+// sphere geoms (variants 0, 2, 3 only; the launchers map variant 1 to 0 for such scenes). VARIANT & 16: the scene holds
+// instances (cooperative variants 2 and 3 only, always together with & 8).
 template <bool ANY_HIT, int VARIANT, class IO>
 __device__ __forceinline__ void trace_persistent(const DevScene& sc, IO& io, Stack& st, unsigned char* warp_smem, unsigned long long& nodes_acc,
                                                  unsigned long long& tris_acc) {
   constexpr int V = VARIANT & 7;
   constexpr bool SPH = (VARIANT & 8) != 0;
+  constexpr bool XF = (VARIANT & 16) != 0;
   if (V == 1) {
     WarpStage ws;
     ws.buf = reinterpret_cast<float4*>(warp_smem);
@@ -962,11 +1012,11 @@ __device__ __forceinline__ void trace_persistent(const DevScene& sc, IO& io, Sta
   } else if (V == 2) {
     CoopSmem cs;
     cs.rp = reinterpret_cast<float4*>(warp_smem);
-    trace_persistent_coop<ANY_HIT, true, SPH>(sc, io, st, cs, nodes_acc, tris_acc);
+    trace_persistent_coop<ANY_HIT, true, SPH, XF>(sc, io, st, cs, nodes_acc, tris_acc);
   } else if (V == 3) {
     CoopSmem cs;
     cs.rp = reinterpret_cast<float4*>(warp_smem);
-    trace_persistent_coop<ANY_HIT, false, SPH>(sc, io, st, cs, nodes_acc, tris_acc);
+    trace_persistent_coop<ANY_HIT, false, SPH, XF>(sc, io, st, cs, nodes_acc, tris_acc);
   } else {
     trace_persistent_ldg<ANY_HIT, SPH>(sc, io, st, nodes_acc, tris_acc);
   }

@@ -28,11 +28,11 @@ VG_TRACE_ANY_HIT = 1
 # every symbol include/vermeer_gpu.h declares (tests check the library exports all of them)
 DECLARED_SYMBOLS = [
     "vg_create", "vg_destroy", "vg_last_error", "vg_device_count", "vg_scene_begin", "vg_mesh_upload", "vg_mesh_upload_motion",
-    "vg_sphere_upload", "vg_scene_upload", "vg_scene_upload_motion", "vg_scene_commit", "vg_set_materials", "vg_set_lights", "vg_set_area_lights", "vg_set_camera", "vg_set_frame",
+    "vg_sphere_upload", "vg_instance_upload", "vg_scene_upload", "vg_scene_upload_motion", "vg_scene_commit", "vg_set_materials", "vg_set_lights", "vg_set_area_lights", "vg_set_camera", "vg_set_frame",
     "vg_set_partition", "vg_set_scramble", "vg_set_filter", "vg_set_option", "vg_trace_batch", "vg_trace_batch_device", "vg_render", "vg_clear_framebuffer",
     "vg_framebuffer_device", "vg_get_stats", "vg_reset_stats",
     "vh_scene_create", "vh_scene_destroy", "vh_last_error", "vh_registered_nodes", "vh_set_globals", "vh_add_shader_std", "vh_add_polymesh",
-    "vh_add_filter", "vh_add_trilight", "vh_add_disklight", "vh_add_spherelight", "vh_parse_vnf", "vh_load_vnf", "vh_globals", "vh_postrender", "vh_rgbe", "vh_set_camera_lookat", "vh_prerender", "vh_upload", "vh_num_geoms", "vh_scene_info", "vh_scene_nodes",
+    "vh_add_filter", "vh_add_instance", "vh_add_trilight", "vh_add_disklight", "vh_add_spherelight", "vh_parse_vnf", "vh_load_vnf", "vh_globals", "vh_postrender", "vh_rgbe", "vh_set_camera_lookat", "vh_prerender", "vh_upload", "vh_num_geoms", "vh_scene_info", "vh_scene_nodes",
     "vh_scene_motion_nodes", "vh_scene_geom_order", "vh_mesh_info", "vh_mesh_nodes", "vh_mesh_motion_nodes", "vh_mesh_idxp", "vh_camera",
 ]
 
@@ -130,6 +130,11 @@ class HostScene:
                 _p(m.Normals), 0 if m.Normals is None else len(m.Normals),
                 _p(m.NormalIdx), 0 if m.NormalIdx is None else len(m.NormalIdx),
                 C.c_float(m.RayBias)))
+        for ins in getattr(scene, "instances", []):
+            bmin = np.ascontiguousarray(ins.BMin, np.float32).reshape(-1, 3)
+            bmax = np.ascontiguousarray(ins.BMax, np.float32).reshape(-1, 3)
+            tr = np.ascontiguousarray(ins.Transform, np.float32).reshape(-1, 16)
+            self._chk(L.vh_add_instance(h, ins.Name.encode(), ins.Geom.encode(), _p(bmin), _p(bmax), len(bmin), _p(tr), len(tr)))
         for l in scene.lights:
             kind = type(l).__name__
             if kind == "TriLight":

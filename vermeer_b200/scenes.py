@@ -23,8 +23,8 @@ from typing import List, Optional
 import numpy as np
 
 __all__ = [
-    "ShaderStd", "PolyMesh", "TriLight", "DiskLight", "SphereLight", "Camera", "PixelFilter", "SceneDesc", "splitmix64_table",
-    "heightfield_mesh", "heightfield_scene", "sphere_field_scene", "cornell_box", "glossy_box", "incoherent_rays", "to_vnf",
+    "ShaderStd", "PolyMesh", "GeomInstance", "matrix4", "srt_matrix", "TriLight", "DiskLight", "SphereLight", "Camera", "PixelFilter", "SceneDesc", "splitmix64_table",
+    "heightfield_mesh", "heightfield_scene", "sphere_field_scene", "cornell_box", "glossy_box", "instanced_scene", "incoherent_rays", "to_vnf",
 ]
 
 
@@ -95,6 +95,36 @@ class PolyMesh:
 
 
 @dataclass
+class GeomInstance:
+    """builtin/geom/instance/instance.go:36-51. Transform: (keys, 16) float32 in math.Matrix4 layout (column major: element
+    (row i, col j) at [j*4 + i]); a .vnf file lists each matrix row by row and the parser transposes (nodes/parser.go:487).
+    BMin/BMax: world-space bounds given by the scene author (the reference never derives them; Bounds() also always contains
+    the origin, instance.go:124)."""
+    Name: str
+    Geom: str
+    Transform: np.ndarray
+    BMin: tuple
+    BMax: tuple
+
+    def __post_init__(self):
+        self.Transform = np.ascontiguousarray(self.Transform, np.float32).reshape(-1, 16)
+
+
+def matrix4(rows) -> np.ndarray:
+    """A 4x4 given row by row (as in a .vnf file) -> math.Matrix4 storage (column major), float32."""
+    return np.ascontiguousarray(np.asarray(rows, np.float32).reshape(4, 4).T).reshape(16)
+
+
+def srt_matrix(translate=(0, 0, 0), rotate_y_deg=0.0, scale=1.0) -> np.ndarray:
+    """translate * rotateY * uniform scale as math.Matrix4 storage; every factor rounded to float32 first."""
+    a = np.float32(np.deg2rad(rotate_y_deg))
+    c, s_ = np.float32(np.cos(a)), np.float32(np.sin(a))
+    k = np.float32(scale)
+    rows = [[c * k, 0, s_ * k, translate[0]], [0, k, 0, translate[1]], [-s_ * k, 0, c * k, translate[2]], [0, 0, 0, 1]]
+    return matrix4(rows)
+
+
+@dataclass
 class TriLight:
     Name: str
     P0: tuple
@@ -159,6 +189,7 @@ class SceneDesc:
     shaders: List[ShaderStd] = field(default_factory=list)
     meshes: List[PolyMesh] = field(default_factory=list)
     lights: list = field(default_factory=list)   # TriLight | DiskLight | SphereLight, in node order
+    instances: list = field(default_factory=list)   # GeomInstance nodes (created after the meshes)
     MaxIter: int = 16
     name: str = "scene"
     filter: Optional[PixelFilter] = None
@@ -220,6 +251,11 @@ def to_vnf(sc: "SceneDesc", outputs=()) -> str:
             if m.NormalIdx is not None:
                 parts.append("NormalIdx %d int %s" % (len(m.NormalIdx), " ".join(str(int(x)) for x in m.NormalIdx)))
         o.append("PolyMesh { %s }" % "\n  ".join(parts))
+    for ins in sc.instances:
+        rows = ins.Transform.reshape(-1, 4, 4).transpose(0, 2, 1).reshape(-1)     # file order is row major (parser.go:487)
+        bmin, bmax = np.asarray(ins.BMin, np.float32).reshape(-1), np.asarray(ins.BMax, np.float32).reshape(-1)
+        o.append('GeomInstance { Name "%s" Geom "%s" BMin 1 %d point %s BMax 1 %d point %s Transform %d matrix %s }' % (
+            ins.Name, ins.Geom, len(bmin) // 3, _vec(bmin), len(bmax) // 3, _vec(bmax), len(ins.Transform), _vec(rows)))
     for l in sc.lights:
         kind = type(l).__name__
         if kind == "TriLight":
@@ -473,6 +509,48 @@ def glossy_box(xres: int = 256, yres: int = 256, lights: str = "tri,disk,sphere"
             raise ValueError(kind)
     cam = Camera(From=(0.0, 1.0, 3.4), To=(0.0, 1.0, 0.0), Fov=40.0, Focal=1.0)
     return SceneDesc(XRes=xres, YRes=yres, camera=cam, shaders=shaders, meshes=meshes, lights=ls, MaxIter=16, name="F1-glossy-box")
+
+
+def instanced_scene(xres: int = 128, yres: int = 96, moving: bool = True, motion_base: bool = False) -> SceneDesc:
+    """SURVEY.md 8(f).3 test scene: one displaced-sphere mesh at the origin, three GeomInstances of it (translated, rotated,
+    uniformly scaled; the last one with two transform keys when `moving`), a floor and a TriLight pair. Bounds are the
+    transformed mesh bounds with a margin, over both keys."""
+    base_v, base_t = _uv_sphere(20, 21)
+    disp = 1.0 + 0.15 * np.sin(base_v[:, 0] * 5.0) * np.sin(base_v[:, 1] * 4.0 + 1.0)
+    v0 = (base_v * disp[:, None] * 0.22 + np.asarray([0.0, 0.25, 0.0])).astype(np.float32)
+    verts = v0[None]
+    if motion_base:
+        v1 = (v0 + np.asarray([0.0, 0.05, 0.0], np.float32) * np.sin(v0[:, :1] * 9.0)).astype(np.float32)
+        verts = np.stack([v0, v1], 0)
+    shaders = [
+        ShaderStd("ground", DiffuseColour=(0.6, 0.6, 0.6), DiffuseStrength=1.0),
+        ShaderStd("lightmtl", EmissionColour=(1.0, 0.95, 0.9), EmissionStrength=20.0, DiffuseColour=(0.0, 0.0, 0.0), DiffuseStrength=1.0),
+        ShaderStd("clay", DiffuseColour=(0.7, 0.35, 0.25), DiffuseStrength=1.0),
+    ]
+    gv = np.asarray([[-1.5, 0, -1.5], [-1.5, 0, 1.5], [1.5, 0, 1.5], [1.5, 0, -1.5]], np.float32)
+    meshes = [PolyMesh("floor", gv, ["ground"], PolyCount=np.asarray([4]), FaceIdx=np.asarray([0, 1, 2, 3])),
+              PolyMesh("blob", verts, ["clay"], FaceIdx=base_t.copy())]
+
+    def bounds(mats):
+        lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
+        for m in mats:
+            M = m.reshape(4, 4).T.astype(np.float64)
+            for vv in verts:
+                w = vv.astype(np.float64) @ M[:3, :3].T + M[:3, 3]
+                lo, hi = np.minimum(lo, w.min(0)), np.maximum(hi, w.max(0))
+        return tuple((lo - 0.02).astype(np.float32)), tuple((hi + 0.02).astype(np.float32))
+
+    specs = [[srt_matrix((-0.75, 0.0, 0.2), 30.0, 1.0)],
+             [srt_matrix((0.7, 0.1, -0.3), -50.0, 1.4)],
+             [srt_matrix((0.1, 0.0, 0.8), 10.0, 0.8)] + ([srt_matrix((0.3, 0.15, 0.8), 70.0, 0.8)] if moving else [])]
+    instances = []
+    for i, mats in enumerate(specs):
+        lo, hi = bounds(mats)
+        instances.append(GeomInstance("inst%d" % i, "blob", np.stack(mats, 0), lo, hi))
+    cam = Camera(From=(0.0, 1.3, 2.6), To=(0.0, 0.2, 0.0), Fov=42.0, Focal=1.0)
+    sc = SceneDesc(XRes=xres, YRes=yres, camera=cam, shaders=shaders, meshes=meshes, lights=_light_pair(1.9, 0.5, "lightmtl"),
+                   instances=instances, MaxIter=16, name="F3-instances")
+    return sc
 
 
 def incoherent_rays(rays: np.ndarray, hits: np.ndarray, seed: int = 7) -> np.ndarray:
