@@ -45,7 +45,7 @@ CONFIG = os.environ.get("VG_BENCH_CONFIG", "c2")
 WORKLOAD = CONFIGS[CONFIG]["workload"]
 XRES, YRES, SPP, NQ = 1920, 1080, CONFIGS[CONFIG]["spp"], 708
 SCRAMBLE_SEED = 1
-ITERS_PER_BATCH = 8
+ITERS_PER_BATCH = 16   # wavefront batch depth at N=1; scaled by N (capped at the frame's spp) so that a batch keeps ~33 M paths per GPU
 
 
 def measured_peaks():
@@ -233,7 +233,8 @@ def run_ours(args):
     dev.upload(host)
     dev.set_partition(rank, world)
     dev.set_scramble(table)
-    dev.set_option("iters_per_batch", ITERS_PER_BATCH)
+    iters_per_batch = min(SPP, ITERS_PER_BATCH * world)
+    dev.set_option("iters_per_batch", iters_per_batch)
     for k, v in [kv.split("=") for kv in os.environ.get("VG_OPTIONS", "").split(",") if kv]:   # tuning experiments, e.g. VG_OPTIONS=traversal=0
         dev.set_option(k, int(v))
 
@@ -380,7 +381,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "xres": XRES, "yres": YRES, "spp": SPP, "triangles": scene.num_tris,
                    "partition": "interleaved 32x32 tiles, BVH replicated" if world > 1 else "single GPU",
-                   "l2_policy": "per-step working set (ray/hit/path queues, >1 GB) exceeds the 126 MB L2", "iters_per_batch": ITERS_PER_BATCH},
+                   "l2_policy": "per-step working set (ray/hit/path queues, >1 GB) exceeds the 126 MB L2", "iters_per_batch": iters_per_batch},
         "samples_per_s": XRES * YRES * SPP * args.steps / (dev_ms_max * 1e-3),
         "rays_per_step": rays_total / max(1, args.steps), "shadow_rays_per_step": shadow_total / max(1, args.steps),
         "wall_ms_per_step": wall_ms_max / max(1, args.steps),

@@ -444,7 +444,7 @@ __device__ inline BsdfRec bsdf_sample(const DevLight& L, const ShadeCtx& c, cons
 }
 
 #ifndef VG_SHADE_MIN_BLOCKS
-#define VG_SHADE_MIN_BLOCKS 6
+#define VG_SHADE_MIN_BLOCKS 4
 #endif
 // H1: every light takes at most one sample per strategy (NumSamples <= 2, the `Samples 1` default of the light nodes, and
 // always at level > 0): pass 2 then reuses the pass-1 records and the second inlined copy of the sampling code disappears
