@@ -16,12 +16,15 @@ namespace vg {
 #endif
 static const int kTraceBlock = VG_TRACE_BLOCK;
 #ifndef VG_SMEM_STACK
-#define VG_SMEM_STACK 16
+#define VG_SMEM_STACK 8
 #endif
-// dynamic shared memory of the traversal kernels: a per-warp scratch region (TMA ray slots + mbarriers, or the ray-parameter
-// blocks + owner table of the cooperative leaf phase), then the per-thread stacks
-static const int kWarpSmemBytes = 2048 + 16;
-inline size_t trace_smem_bytes() { return (size_t)(kTraceBlock / 32) * kWarpSmemBytes + (size_t)kTraceBlock * VG_SMEM_STACK * 8; }
+// Dynamic shared memory of the traversal kernels: a per-warp scratch region, then the per-thread stacks. The scratch depends on
+// the kernel variant (VARIANT & 7): none for the per-lane loop, 2 x 1 KB ray slots + 2 mbarriers for the TMA-staged queue,
+// 32 x 48 B ray-parameter blocks for the cooperative leaf phase. Shared memory not taken here stays L1: the scene data these
+// kernels re-read lives there, and the measured optimum is a SHORT shared stack (8 entries/thread: C2 frame 105.6 -> 102.9 ms
+// against 16; 4 and 2 lose again to local-memory spills of the stack).
+__host__ __device__ constexpr int warp_smem_bytes(int variant) { return (variant & 7) == 1 ? 2048 + 16 : ((variant & 7) >= 2 ? 32 * 48 : 0); }
+inline size_t trace_smem_bytes(int variant) { return (size_t)(kTraceBlock / 32) * warp_smem_bytes(variant) + (size_t)kTraceBlock * VG_SMEM_STACK * 8; }
 
 // kernels_trace.cu
 cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d_hits, long long n, bool any_hit, int variant,

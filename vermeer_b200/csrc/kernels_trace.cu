@@ -38,15 +38,15 @@ __global__ void __launch_bounds__(kTraceBlock, VG_TRACE_MIN_BLOCKS) k_trace_batc
                                                              long long n, unsigned long long* __restrict__ counter,
                                                              unsigned long long* __restrict__ stats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: [warps x kWarpSmemBytes (TMA ray slots + mbarriers, or cooperative-leaf blocks)] [threads x VG_SMEM_STACK stack entries]
+  // layout: [warps x warp_smem_bytes(VARIANT) (TMA ray slots + mbarriers, or cooperative-leaf blocks)] [threads x VG_SMEM_STACK stack entries]
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
   Stack st;
-  st.smem = reinterpret_cast<uint2*>(smem_raw + nwarps * kWarpSmemBytes) + threadIdx.x;
+  st.smem = reinterpret_cast<uint2*>(smem_raw + nwarps * warp_smem_bytes(VARIANT)) + threadIdx.x;
   st.stride = blockDim.x;
   const int lane = threadIdx.x & 31;
   unsigned long long nodes_acc = 0, tris_acc = 0;
   BatchIO io{rays, hits, n, counter};
-  trace_persistent<ANY_HIT, VARIANT>(sc, io, st, smem_raw + warp * kWarpSmemBytes, nodes_acc, tris_acc);
+  trace_persistent<ANY_HIT, VARIANT>(sc, io, st, smem_raw + warp * warp_smem_bytes(VARIANT), nodes_acc, tris_acc);
   // warp-aggregated statistics (core/stats.go keeps global atomics per ray; one atomic per warp here)
   for (int o = 16; o > 0; o >>= 1) {
     nodes_acc += __shfl_down_sync(0xffffffffu, nodes_acc, o);
@@ -60,10 +60,9 @@ __global__ void __launch_bounds__(kTraceBlock, VG_TRACE_MIN_BLOCKS) k_trace_batc
 
 cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d_hits, long long n, bool any_hit, int variant,
                                unsigned long long* d_counter, unsigned long long* d_stats, int grid, cudaStream_t stream) {
-  const size_t smem = trace_smem_bytes();
   cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
-#define VG_LAUNCH(A, V) k_trace_batch<A, V><<<grid, kTraceBlock, smem, stream>>>(sc, d_rays, d_hits, n, d_counter, d_stats)
+#define VG_LAUNCH(A, V) k_trace_batch<A, V><<<grid, kTraceBlock, trace_smem_bytes(V), stream>>>(sc, d_rays, d_hits, n, d_counter, d_stats)
   if (sc.n_xforms > 0) {  // instances: cooperative kernels with the transform enter/leave code (traverse.cuh: VARIANT & 16)
     if (any_hit) VG_LAUNCH(true, 26);
     else VG_LAUNCH(false, 26);
@@ -90,8 +89,7 @@ cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d
 
 int trace_batch_blocks_per_sm() {
   int nb = 0;
-  const size_t smem = trace_smem_bytes();
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_batch<false, 2>, kTraceBlock, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_batch<false, 2>, kTraceBlock, trace_smem_bytes(2));
   return nb > 0 ? nb : 1;
 }
 

@@ -218,16 +218,16 @@ struct QueueIO {
 template <int MODE, int VARIANT>
 __global__ void __launch_bounds__(kTraceBlock, VG_TRACE_MIN_BLOCKS) k_trace_queue(const RenderParams p, int q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: [warps x kWarpSmemBytes scratch] [threads x VG_SMEM_STACK stack entries]
+  // layout: [warps x warp_smem_bytes(VARIANT) scratch] [threads x VG_SMEM_STACK stack entries]
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
   Stack st;
-  st.smem = reinterpret_cast<uint2*>(smem_raw + nwarps * kWarpSmemBytes) + threadIdx.x;
+  st.smem = reinterpret_cast<uint2*>(smem_raw + nwarps * warp_smem_bytes(VARIANT)) + threadIdx.x;
   st.stride = blockDim.x;
   const int lane = threadIdx.x & 31;
   const int n = MODE == 0 ? p.counts[q] : p.counts[2];
   unsigned long long nodes_acc = 0, tris_acc = 0;
   QueueIO<MODE> io{p, MODE == 0 ? p.rayq[q] : p.sray, n, p.counts + (MODE == 0 ? 3 : 4)};
-  trace_persistent<MODE == 1, VARIANT>(p.sc, io, st, smem_raw + warp * kWarpSmemBytes, nodes_acc, tris_acc);
+  trace_persistent<MODE == 1, VARIANT>(p.sc, io, st, smem_raw + warp * warp_smem_bytes(VARIANT), nodes_acc, tris_acc);
   for (int o = 16; o > 0; o >>= 1) {
     nodes_acc += __shfl_down_sync(0xffffffffu, nodes_acc, o);
     tris_acc += __shfl_down_sync(0xffffffffu, tris_acc, o);
@@ -1032,8 +1032,7 @@ static int prepare(vg_ctx* ctx) {
   RCUDA(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
 
   int nb = 0;
-  const size_t smem = trace_smem_bytes();
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_queue<0, 2>, kTraceBlock, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_queue<0, 2>, kTraceBlock, trace_smem_bytes(2));
   rs.trace_grid = ctx->sm_count * std::max(1, nb);
   rs.ready = true;
   return upload_scramble(ctx, ctx->scramble.data());
@@ -1086,7 +1085,6 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
   p.contrib = rs.contrib.p; p.sray = rs.sray.p; p.sslot = rs.sslot.p; p.L = rs.L.p; p.T = rs.T.p;
   p.counts = rs.counts.p; p.stats = rs.stats.p; p.fb = rs.fb.p;
 
-  const size_t smem = trace_smem_bytes();
   const int variant = ctx->opt_traversal;
   const bool xf = ctx->dev.n_xforms > 0;    // kernels that carry the instance enter/leave code (VARIANT & 16)
   const bool sph = ctx->dev.n_spheres > 0;  // kernels that carry the analytic sphere leaf (traverse.cuh: VARIANT & 8)
@@ -1114,13 +1112,13 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
         cudaEventRecord(rs.ev(nev++), st);
         // camera rays are coherent: the per-lane loop with its compile-time axis specialisation is faster there (measured
         // 3.81 vs 3.48 Grays/s); every later level is incoherent and takes the cooperative leaf phase
-        if (xf) k_trace_queue<0, 26><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
+        if (xf) k_trace_queue<0, 26><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(26), st>>>(p, qin);
         else if (sph) {
-          if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 10><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
-          else k_trace_queue<0, 8><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
-        } else if (variant == 1) k_trace_queue<0, 1><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
-        else if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 2><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
-        else k_trace_queue<0, 0><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, qin);
+          if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 10><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(10), st>>>(p, qin);
+          else k_trace_queue<0, 8><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(8), st>>>(p, qin);
+        } else if (variant == 1) k_trace_queue<0, 1><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(1), st>>>(p, qin);
+        else if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 2><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(2), st>>>(p, qin);
+        else k_trace_queue<0, 0><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(0), st>>>(p, qin);
         cudaEventRecord(rs.ev(nev++), st);
         kinds.push_back(0);
         launches++;
@@ -1138,16 +1136,16 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
           }
           cudaEventRecord(rs.ev(nev++), st);
           if (xf) {
-            if (ctx->opt_shadow_unordered) k_trace_queue<1, 27><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
-            else k_trace_queue<1, 26><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
+            if (ctx->opt_shadow_unordered) k_trace_queue<1, 27><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(27), st>>>(p, 0);
+            else k_trace_queue<1, 26><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(26), st>>>(p, 0);
           } else if (sph) {
-            if (variant == 2 && ctx->opt_shadow_unordered) k_trace_queue<1, 11><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
-            else if (variant == 2) k_trace_queue<1, 10><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
-            else k_trace_queue<1, 8><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
-          } else if (variant == 1) k_trace_queue<1, 1><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
-          else if (variant == 2 && ctx->opt_shadow_unordered) k_trace_queue<1, 3><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
-          else if (variant == 2) k_trace_queue<1, 2><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
-          else k_trace_queue<1, 0><<<rs.trace_grid, kTraceBlock, smem, st>>>(p, 0);
+            if (variant == 2 && ctx->opt_shadow_unordered) k_trace_queue<1, 11><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(11), st>>>(p, 0);
+            else if (variant == 2) k_trace_queue<1, 10><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(10), st>>>(p, 0);
+            else k_trace_queue<1, 8><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(8), st>>>(p, 0);
+          } else if (variant == 1) k_trace_queue<1, 1><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(1), st>>>(p, 0);
+          else if (variant == 2 && ctx->opt_shadow_unordered) k_trace_queue<1, 3><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(3), st>>>(p, 0);
+          else if (variant == 2) k_trace_queue<1, 2><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(2), st>>>(p, 0);
+          else k_trace_queue<1, 0><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(0), st>>>(p, 0);
           cudaEventRecord(rs.ev(nev++), st);
           kinds.push_back(1);
           k_resolve<<<(np + 255) / 256, 256, 0, st>>>(p, level, qin);

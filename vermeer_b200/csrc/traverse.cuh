@@ -194,7 +194,7 @@ __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
 // Traversal stack: kSmemStack entries per thread in shared memory, the rest in local memory.
 #ifndef VG_SMEM_STACK
-#define VG_SMEM_STACK 16
+#define VG_SMEM_STACK 8
 #endif
 #define VG_LOCAL_STACK 80
 
