@@ -229,3 +229,26 @@ def test_instanced_scene_image(built_library, kind):
     assert rmse <= 1e-3, rmse
     assert np.median(np.abs(fo - fg)) <= 2e-6
     assert abs(st["rays"] - so["rays"]) <= 1e-3 * so["rays"]
+
+
+def test_pinned_host_buffers_take_the_direct_dma_path(built_library):
+    """A page-locked scramble table is copied as it is (the kernels then index it by raster pixel) and a page-locked frame
+    buffer is written by DMA; both must give the image of the pageable path bit for bit."""
+    import torch
+    from vermeer_b200 import scenes
+    from vermeer_b200.host import Device, HostScene
+    sc = scenes.cornell_box(96, 80)
+    tab = scenes.splitmix64_table(4, sc.XRes * sc.YRes)
+    dev = Device(0).upload(HostScene(sc).prerender())
+    dev.set_scramble(tab)
+    ref = dev.render(0, 6)
+    tab_pinned = torch.from_numpy(tab.view(np.int64)).pin_memory().numpy().view(np.uint64)
+    out_pinned = torch.empty((sc.YRes, sc.XRes, 3), dtype=torch.float32, pin_memory=True).numpy()
+    dev.set_scramble(tab_pinned)
+    dev.clear()
+    got = dev.render(0, 6, out=out_pinned)
+    assert got is out_pinned
+    assert got.tobytes() == ref.tobytes()
+    dev.set_scramble(tab)          # and back to the gathered layout
+    dev.clear()
+    assert dev.render(0, 6).tobytes() == ref.tobytes()

@@ -59,7 +59,8 @@ struct RenderParams {
   DevScene sc;
   int xres, yres, nown, P;  // P = paths per batch
   const int* pix;           // [nown] full-frame pixel index, tile-major
-  const uint64_t* scr;      // [nown*6]
+  const uint64_t* scr;      // [nown*6] rows in path order, or (scr_by_pixel) the caller's whole table [xres*yres*6] in raster order
+  int scr_by_pixel;
   VgCamera cam;
   const DevMat* mats;
   const DevLight* lights;
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderParams p, int iter_b
   const int iter = iter_base + it + 1;  // render() receives iter+1 (render.go:192)
   const int pixel = p.pix[own];
   const int x = pixel % p.xres, y = pixel / p.xres;
-  const uint64_t* scr = p.scr + (size_t)own * 6;
+  const uint64_t* scr = p.scr + (size_t)(p.scr_by_pixel ? pixel : own) * 6;
   double rasterX, rasterY;
   raster_xy12((uint32_t)iter, (uint32_t)x, (uint32_t)y, &rasterX, &rasterY);
   const double time = vdc((uint64_t)iter, scr[2]);
@@ -513,8 +514,9 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
     omegaI = basis_project(fr.U, fr.V, fr.N, neg3(Rd));
     hero = hero_setup(lambda);
     ov = oren_vertex<FAST>(omegaI, m.rough2, hero);
-    scr0 = p.scr[(size_t)own * 6 + 4];
-    scr1 = p.scr[(size_t)own * 6 + 5];
+    const size_t srow = p.scr_by_pixel ? (size_t)p.pix[own] : (size_t)own;
+    scr0 = p.scr[srow * 6 + 4];
+    scr1 = p.scr[srow * 6 + 5];
   }
   // sample index I = ray.I = the 1-based iteration (render.go:123); path = it*nown + own
   if (active) I = (long long)(iter_base + path / p.nown + 1);
@@ -751,6 +753,7 @@ struct RenderState {
   int fb_w = 0, fb_h = 0;
   int trace_grid = 0;
   int max_light_samples = 0;
+  bool scr_by_pixel = false;  // the device holds the caller's whole scramble table in raster order (pinned fast path)
   bool generic = false;  // shade with k_shade_generic (glossy lobe / conductor Fresnel / Disk or Sphere lights / sphere geoms)
   int nlobes = 1;
   std::vector<int> pix_host;
@@ -838,9 +841,30 @@ static int ensure_fb(vg_ctx* ctx) {
 }
 
 // Partition of framescramble (core/render.go:166-176) at upload: only the rows of owned pixels go to the device.
+// true if `p` is page-locked host memory the GPU can DMA from/to directly (cudaHostAlloc / cudaHostRegister / torch pin_memory)
+static bool is_pinned_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
 static int upload_scramble(vg_ctx* ctx, const uint64_t* table) {
   RenderState& rs = *ctx->rs;
   if (rs.nown == 0) return VG_OK;
+  rs.scr_by_pixel = false;
+  if (ctx->world == 1 && is_pinned_host(table)) {
+    // The caller's table is page-locked and this context owns every pixel: one DMA of the table as it is, no host pass;
+    // the kernels index it by raster pixel instead of by path order.
+    const size_t all = (size_t)ctx->xres * ctx->yres * 6;
+    RCUDA(rs.scr.reserve(all));
+    RCUDA(cudaMemcpyAsync(rs.scr.p, table, all * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    RCUDA(cudaStreamSynchronize(ctx->stream));
+    rs.scr_by_pixel = true;
+    return VG_OK;
+  }
   const size_t bytes = (size_t)rs.nown * 48;
   if (rs.scr_pinned_bytes < bytes) {
     if (rs.scr_pinned) cudaFreeHost(rs.scr_pinned);
@@ -1012,7 +1036,7 @@ static int prepare(vg_ctx* ctx) {
     RCUDA(cudaMemcpyAsync(rs.filter.p, ctx->filter_cdf.data(), ctx->filter_cdf.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   }
   RCUDA(rs.pix.reserve(pix.size()));
-  RCUDA(rs.scr.reserve((size_t)rs.nown * 6));
+  RCUDA(rs.scr.reserve(ctx->world == 1 ? (size_t)W * H * 6 : (size_t)rs.nown * 6));
   RCUDA(rs.mats.reserve(mats.size()));
   RCUDA(rs.lights.reserve(lights.size()));
   if (!pix.empty()) {
@@ -1076,7 +1100,7 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
   std::memset(&p, 0, sizeof(p));
   p.sc = ctx->dev;
   p.xres = ctx->xres; p.yres = ctx->yres; p.nown = rs.nown; p.P = rs.P;
-  p.pix = rs.pix.p; p.scr = rs.scr.p; p.cam = ctx->camera; p.mats = rs.mats.p; p.lights = rs.lights.p;
+  p.pix = rs.pix.p; p.scr = rs.scr.p; p.scr_by_pixel = rs.scr_by_pixel ? 1 : 0; p.cam = ctx->camera; p.mats = rs.mats.p; p.lights = rs.lights.p;
   p.filter_cdf = ctx->filter_n > 0 ? rs.filter.p : nullptr; p.filter_n = ctx->filter_n; p.filter_w = ctx->filter_w;
   p.nlights = rs.nlights; p.S = rs.S; p.levels = rs.levels; p.trace_last_level = ctx->opt_trace_last_level;
   p.nlobes = rs.nlobes;
@@ -1167,7 +1191,10 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
   int flags = 0;
   RCUDA(cudaMemcpyAsync(hstats, rs.stats.p, sizeof(hstats), cudaMemcpyDeviceToHost, st));
   RCUDA(cudaMemcpyAsync(&flags, rs.counts.p + 5, sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (fb_out) {
+  if (fb_out && is_pinned_host(fb_out)) {
+    // the caller's buffer is page-locked: DMA straight into it
+    RCUDA(cudaMemcpyAsync(fb_out, rs.fb.p, (size_t)ctx->xres * ctx->yres * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  } else if (fb_out) {
     // device -> pinned staging -> caller's (pageable) buffer
     const size_t bytes = (size_t)ctx->xres * ctx->yres * 3 * sizeof(float);
     if (rs.fb_pinned_bytes < bytes) {

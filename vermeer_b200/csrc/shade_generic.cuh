@@ -329,8 +329,9 @@ __global__ void __launch_bounds__(128, 4) k_shade_generic(const RenderParams p, 
     ov = oren_vertex<FAST>(omegaI, m.rough2, hero);
     gv.omegaR = omegaI;
     gv.alpha = sqr32(m.spec_rough * m.spec_rough);
-    scr0 = p.scr[(size_t)own * 6 + 4];
-    scr1 = p.scr[(size_t)own * 6 + 5];
+    const size_t srow = p.scr_by_pixel ? (size_t)p.pix[own] : (size_t)own;
+    scr0 = p.scr[srow * 6 + 4];
+    scr1 = p.scr[srow * 6 + 5];
     I = (long long)(iter_base + path / p.nown + 1);
   }
 

@@ -312,8 +312,14 @@ class Device:
         self._chk(self.L.vg_trace_batch_device(self.h, C.c_void_p(d_rays_ptr), C.c_int64(n), C.c_void_p(d_hits_ptr),
                                                C.c_uint32(VG_TRACE_ANY_HIT if any_hit else 0)))
 
-    def render(self, iter_begin: int, iter_end: int, fetch: bool = True):
-        fb = np.zeros((self.yres, self.xres, 3), np.float32) if fetch else None
+    def render(self, iter_begin: int, iter_end: int, fetch: bool = True, out: np.ndarray | None = None):
+        """vg_render. `out`: a caller-owned (yres, xres, 3) float32 buffer for the frame; if it is page-locked (e.g. a
+        torch pin_memory tensor's numpy view) the library DMAs straight into it."""
+        if out is not None:
+            assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (self.yres, self.xres, 3)
+            fb = out
+        else:
+            fb = np.zeros((self.yres, self.xres, 3), np.float32) if fetch else None
         self._chk(self.L.vg_render(self.h, iter_begin, iter_end, _p(fb)))
         return fb
 
