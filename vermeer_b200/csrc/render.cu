@@ -66,6 +66,7 @@ struct RenderParams {
   const DevLight* lights;
   int nlights, S, levels, trace_last_level;
   int nlobes;  // 1: diffuse light slots only (k_shade); 2: + GGX glossy slots (k_shade_generic)
+  const QmcTables* qmc;      // byte-sliced RasterXY tables
   const double* filter_cdf;  // cdfV[n] then cdfVU[n*n], or null
   int filter_n;
   double filter_w;
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderParams p, int iter_b
   const int x = pixel % p.xres, y = pixel / p.xres;
   const uint64_t* scr = p.scr + (size_t)(p.scr_by_pixel ? pixel : own) * 6;
   double rasterX, rasterY;
-  raster_xy12((uint32_t)iter, (uint32_t)x, (uint32_t)y, &rasterX, &rasterY);
+  raster_xy12_tab(p.qmc, (uint32_t)iter, (uint32_t)x, (uint32_t)y, &rasterX, &rasterY);
   const double time = vdc((uint64_t)iter, scr[2]);
   const double lambda = (720 - 450) * vdc((uint64_t)iter, scr[3]) + 450;
   const double lensU = vdc((uint64_t)iter, scr[0]);
@@ -663,10 +664,7 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
 namespace vg {
 
 // Sum the slots in the reference's order and finish the diffuse / glossy terms (core/shader.go:349, std.go:157-163,269-295).
-__global__ void __launch_bounds__(256) k_resolve(const RenderParams p, int level, int qin) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.counts[qin]) return;
-  const int path = p.pathq[qin][i];
+__device__ __forceinline__ float4 resolve_vertex(const RenderParams& p, int level, int i) {
   const int matid = p.v_mat[i];
   const int SL = p.S * p.nlobes;
   float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -701,7 +699,29 @@ __global__ void __launch_bounds__(256) k_resolve(const RenderParams p, int level
     // contrib = emission + diffuse + spec1 (std.go:287-293)
     out = make_float4((m.emission.x + sum[0].x) + sum[1].x, (m.emission.y + sum[0].y) + sum[1].y, (m.emission.z + sum[0].z) + sum[1].z, 0.f);
   }
-  p.L[(size_t)level * p.P + path] = out;
+  return out;
+}
+__global__ void __launch_bounds__(256) k_resolve(const RenderParams p, int level, int qin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.counts[qin]) return;
+  p.L[(size_t)level * p.P + p.pathq[qin][i]] = resolve_vertex(p, level, i);
+}
+
+// Scenes without a mirror lobe have one level: the level-0 queue is the identity (queue slot == path), so the per-vertex sum and
+// the running mean (render.go:127-129) are one kernel and L never goes to memory.
+__global__ void __launch_bounds__(256) k_resolve_accumulate(const RenderParams p, int iter_base, int niters) {
+  const int own = blockIdx.x * blockDim.x + threadIdx.x;
+  if (own >= p.nown) return;
+  float* px = p.fb + (size_t)p.pix[own] * 3;
+  float r = px[0], g = px[1], b = px[2];
+  for (int it = 0; it < niters; it++) {
+    const float4 C = resolve_vertex(p, 0, it * p.nown + own);
+    const float fi = (float)(iter_base + it + 1);
+    r = (r * fi + C.x) / (fi + 1.0f);
+    g = (g * fi + C.y) / (fi + 1.0f);
+    b = (b * fi + C.z) / (fi + 1.0f);
+  }
+  px[0] = r; px[1] = g; px[2] = b;
 }
 
 // Fold the levels back to front (std.go:246-266,287-295) and continue the running mean (render.go:127-129).
@@ -747,6 +767,7 @@ struct RenderState {
   DevBuf<DevHit> hits;
   DevBuf<float> lambda, time, invtot, fb;
   DevBuf<double> filter;
+  DevBuf<QmcTables> qmc;
   DevBuf<uint8_t> vmat;
   DevBuf<float4> contrib, L, T;
   DevBuf<unsigned long long> stats;
@@ -783,7 +804,7 @@ struct RenderState {
   void release() {
     pix.release(); scr.release(); mats.release(); lights.release(); rayq0.release(); rayq1.release(); sray.release();
     pathq0.release(); pathq1.release(); sslot.release(); counts.release(); hits.release(); lambda.release(); time.release();
-    invtot.release(); vmat.release(); filter.release(); contrib.release(); L.release(); T.release(); stats.release();
+    invtot.release(); vmat.release(); filter.release(); qmc.release(); contrib.release(); L.release(); T.release(); stats.release();
   }
 };
 
@@ -1031,6 +1052,34 @@ static int prepare(vg_ctx* ctx) {
   rs.P = rs.nown * rs.iters;
   const size_t P = (size_t)rs.P;
 
+  {
+    // byte-sliced tables of the two XOR enumerations in RasterXY (shade.cuh: raster_xy12_tab)
+    static const uint32_t inv12[24] = {0xf0f000, 0x505000, 0x303000, 0x101000, 0xff0000, 0x550000, 0x330000, 0x110000,
+                                       0xf0000,  0x50000,  0x30000,  0x10000,  0x888800, 0x444400, 0x222200, 0x111100,
+                                       0x800080, 0x400040, 0x200020, 0x100010, 0x80008,  0x40004,  0x20002,  0x10001};
+    std::vector<QmcTables> tv(1);
+    QmcTables& T = tv[0];
+    uint64_t v[56];
+    v[0] = 1ull << 51;
+    for (int k = 1; k < 56; k++) v[k] = v[k - 1] ^ (v[k - 1] >> 1);
+    for (int byte = 0; byte < 7; byte++)
+      for (int x = 0; x < 256; x++) {
+        uint64_t r = 0;
+        for (int j = 0; j < 8; j++)
+          if (x & (1 << j)) r ^= v[byte * 8 + j];
+        T.sob[byte][x] = r;
+      }
+    for (int byte = 0; byte < 3; byte++)
+      for (int x = 0; x < 256; x++) {
+        uint32_t r = 0;
+        for (int j = 0; j < 8; j++)
+          if (x & (1 << j)) r ^= inv12[byte * 8 + j];
+        T.rinv[byte][x] = r;
+      }
+    RCUDA(rs.qmc.reserve(1));
+    RCUDA(cudaMemcpyAsync(rs.qmc.p, tv.data(), sizeof(QmcTables), cudaMemcpyHostToDevice, ctx->stream));
+    RCUDA(cudaStreamSynchronize(ctx->stream));
+  }
   if (ctx->filter_n > 0) {
     RCUDA(rs.filter.reserve(ctx->filter_cdf.size()));
     RCUDA(cudaMemcpyAsync(rs.filter.p, ctx->filter_cdf.data(), ctx->filter_cdf.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -1100,7 +1149,7 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
   std::memset(&p, 0, sizeof(p));
   p.sc = ctx->dev;
   p.xres = ctx->xres; p.yres = ctx->yres; p.nown = rs.nown; p.P = rs.P;
-  p.pix = rs.pix.p; p.scr = rs.scr.p; p.scr_by_pixel = rs.scr_by_pixel ? 1 : 0; p.cam = ctx->camera; p.mats = rs.mats.p; p.lights = rs.lights.p;
+  p.pix = rs.pix.p; p.qmc = rs.qmc.p; p.scr = rs.scr.p; p.scr_by_pixel = rs.scr_by_pixel ? 1 : 0; p.cam = ctx->camera; p.mats = rs.mats.p; p.lights = rs.lights.p;
   p.filter_cdf = ctx->filter_n > 0 ? rs.filter.p : nullptr; p.filter_n = ctx->filter_n; p.filter_w = ctx->filter_w;
   p.nlights = rs.nlights; p.S = rs.S; p.levels = rs.levels; p.trace_last_level = ctx->opt_trace_last_level;
   p.nlobes = rs.nlobes;
@@ -1172,8 +1221,11 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
           else k_trace_queue<1, 0><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(0), st>>>(p, 0);
           cudaEventRecord(rs.ev(nev++), st);
           kinds.push_back(1);
-          k_resolve<<<(np + 255) / 256, 256, 0, st>>>(p, level, qin);
-          launches += 3;
+          if (rs.levels > 1) {
+            k_resolve<<<(np + 255) / 256, 256, 0, st>>>(p, level, qin);
+            launches++;
+          }
+          launches += 2;
         }
         if (level + 1 < nlev) {
           k_next_level<<<1, 1, 0, st>>>(rs.counts.p, qout);
@@ -1181,7 +1233,8 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
         }
         qin = qout;
       }
-      k_accumulate<<<(rs.nown + 255) / 256, 256, 0, st>>>(p, ib, niters);
+      if (rs.levels > 1) k_accumulate<<<(rs.nown + 255) / 256, 256, 0, st>>>(p, ib, niters);
+      else k_resolve_accumulate<<<(rs.nown + 255) / 256, 256, 0, st>>>(p, ib, niters);
       launches++;
     }
   }

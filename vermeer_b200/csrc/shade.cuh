@@ -125,6 +125,26 @@ __device__ __forceinline__ void raster_xy12(uint32_t frame, uint32_t px, uint32_
   *ry = (double)sobol_u(index, 0) / (double)(1ull << 40);
 }
 
+// Byte-sliced form of the same enumeration: the XOR over the set bits of `b` (24 bits) and of `index` (52 bits) is looked up
+// 8 bits at a time in tables built on the host from the same matrices (RenderState::qmc). Integer exact, so identical.
+struct QmcTables {
+  uint64_t sob[7][256];   // XOR of the Sobol' direction numbers v_k (ldseq.go:83-96) over the set bits of byte k
+  uint32_t rinv[3][256];  // XOR of vdCSobolInvMatrices[12] rows (raster.go:24-36) over the set bits of byte k
+};
+__device__ __forceinline__ void raster_xy12_tab(const QmcTables* __restrict__ T, uint32_t frame, uint32_t px, uint32_t py, double* rx, double* ry) {
+  uint64_t index = (uint64_t)frame << 24;
+  uint32_t delta = 0;
+  for (uint32_t c = 0, f = frame; f != 0; f >>= 1, c++)
+    if (f & 1) delta ^= kVdcSobolM12[c];
+  const uint32_t b = ((px << 12) | py) ^ delta;
+  index ^= (uint64_t)(__ldg(&T->rinv[0][b & 255u]) ^ __ldg(&T->rinv[1][(b >> 8) & 255u]) ^ __ldg(&T->rinv[2][(b >> 16) & 255u]));
+  *rx = (double)vdc_u(index, 0) / (double)(1ull << 40);
+  uint64_t r = 0;
+  int k = 0;
+  for (uint64_t i = index; i != 0; i >>= 8, k++) r ^= __ldg(&T->sob[k][i & 255u]);
+  *ry = (double)r / (double)(1ull << 40);
+}
+
 // ---- colour -------------------------------------------------------------------------------------------
 struct Spec4 {
   float c[4];
