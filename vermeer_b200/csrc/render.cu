@@ -379,12 +379,8 @@ struct BsdfRec {
 
 // light.Tri.SampleArea, sample `i` of `n` (builtin/light/triangle.go:232-343)
 template <bool FAST>
-__device__ inline LightRec light_sample(const DevLight& L, const ShadeCtx& c, bool by_area, const SphTri& sph, long long I, int n, int i,
-                                        uint64_t scr0, uint64_t scr1) {
+__device__ inline LightRec light_sample_r(const DevLight& L, const ShadeCtx& c, bool by_area, const SphTri& sph, double r0, double r1) {
   LightRec r;
-  const uint64_t idx = (uint64_t)(I * n + i);
-  const double r0 = vdc(idx, scr0);
-  const double r1 = sobol(idx, scr1);
   f3 Pl;
   if (by_area) {
     const double sq = FAST ? (double)sqrtf((float)(1 - r0)) : sqrt(1 - r0);
@@ -404,27 +400,36 @@ __device__ inline LightRec light_sample(const DevLight& L, const ShadeCtx& c, bo
   return r;
 }
 
-// BSDF sample `i` of `h` through Light.ValidSample (core/shader.go:212-229, triangle.go:136-230)
 template <bool FAST>
-__device__ inline BsdfRec bsdf_sample(const DevLight& L, const ShadeCtx& c, const Frame& fr, bool have_sph, const SphTri& sph, long long I, int h,
-                                      int i, uint64_t scr0, uint64_t scr1) {
+__device__ inline LightRec light_sample(const DevLight& L, const ShadeCtx& c, bool by_area, const SphTri& sph, long long I, int n, int i,
+                                        uint64_t scr0, uint64_t scr1) {
+  const uint64_t idx = (uint64_t)(I * n + i);
+  return light_sample_r<FAST>(L, c, by_area, sph, vdc(idx, scr0), sobol(idx, scr1));
+}
+
+// BSDF sample `i` of `h` through Light.ValidSample (core/shader.go:212-229, triangle.go:136-230)
+// The direction and pdf of an Oren-Nayar BSDF sample (core/shader.go:212-218): independent of the light.
+template <bool FAST>
+__device__ inline bool bsdf_dir(const Frame& fr, double r0, double r1, f3* wo, float* pdf) {
+  *wo = normalize3t<FAST>(basis_expand(fr.U, fr.V, fr.N, cosine_hemisphere<FAST>(r0, r1)));
+  if (FAST) {
+    *pdf = oren_pdf32<true>(fr, *wo);
+    return *pdf > 0;
+  }
+  const double pd = oren_pdf(fr, *wo);  // the reference tests the float64 value (core/shader.go:218)
+  *pdf = (float)pd;
+  return pd > 0;
+}
+// Light.ValidSample for that direction (triangle.go:136-230)
+template <bool FAST>
+__device__ inline BsdfRec bsdf_hit(const DevLight& L, const ShadeCtx& c, bool have_sph, const SphTri& sph, bool dir_ok, f3 wo, float pdf) {
   BsdfRec r;
   r.valid = false;
   r.pdfLight = 0.0f;
   r.Ldist = 0.0f;
   r.Ld = mk3(0, 0, 1);
-  const uint64_t idx = (uint64_t)(I * h + i);
-  const double r0 = vdc(idx, scr0);
-  const double r1 = sobol(idx, scr1);
-  const f3 wo = normalize3t<FAST>(basis_expand(fr.U, fr.V, fr.N, cosine_hemisphere<FAST>(r0, r1)));
-  if (FAST) {
-    r.pdf = oren_pdf32<true>(fr, wo);
-    if (r.pdf <= 0) return r;
-  } else {
-    const double pd = oren_pdf(fr, wo);  // the reference tests the float64 value (core/shader.go:218)
-    if (pd <= 0) return r;
-    r.pdf = (float)pd;
-  }
+  r.pdf = pdf;
+  if (!dir_ok) return r;
   f3 Pl;
   if (!ray_triangle(c.P, wo, L.p0, L.p1, L.p2, &Pl)) return r;
   // NOTE: the horizon test of ValidSample is taken at the point ON THE LIGHT (triangle.go:145-147), kept as is
@@ -443,6 +448,16 @@ __device__ inline BsdfRec bsdf_sample(const DevLight& L, const ShadeCtx& c, cons
   r.pdfLight = by_area ? pdfl * (r.Ldist * r.Ldist) / fabsf(dot3(r.Ld, L.N)) : pdfl;
   r.valid = true;
   return r;
+}
+// BSDF sample `i` of `h` through Light.ValidSample (core/shader.go:212-229)
+template <bool FAST>
+__device__ inline BsdfRec bsdf_sample(const DevLight& L, const ShadeCtx& c, const Frame& fr, bool have_sph, const SphTri& sph, long long I, int h,
+                                      int i, uint64_t scr0, uint64_t scr1) {
+  const uint64_t idx = (uint64_t)(I * h + i);
+  f3 wo;
+  float pdf;
+  const bool ok = bsdf_dir<FAST>(fr, vdc(idx, scr0), sobol(idx, scr1), &wo, &pdf);
+  return bsdf_hit<FAST>(L, c, have_sph, sph, ok, wo, pdf);
 }
 
 #ifndef VG_SHADE_MIN_BLOCKS
@@ -524,6 +539,17 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
 
   // ---- diffuse lobe: direct light with MIS (std.go:145-163, core/shader.go:203-402) ----
   const bool diffuse = active && m.diff_weight > 0.0f;
+  // H1: sample index I*1+0 for both strategies and every light (shader.go:212-214, triangle.go:295-297): one pair of QMC
+  // numbers and one BSDF direction per vertex
+  double h_r0 = 0, h_r1 = 0;
+  f3 h_wo = mk3(0, 0, 1);
+  float h_pdf = 0;
+  bool h_ok = false;
+  if (H1 && diffuse) {
+    h_r0 = vdc((uint64_t)I, scr0);
+    h_r1 = sobol((uint64_t)I, scr1);
+    if (level == 0) h_ok = bsdf_dir<FAST>(fr, h_r0, h_r1, &h_wo, &h_pdf);  // BSDF samples are taken at level 0 only (NS > 1)
+  }
   for (int l = 0; l < p.nlights; l++) {
     const DevLight L = p.lights[l];
     const int NS = level > 0 ? 1 : L.nsamples;  // shader.go:186-191
@@ -546,13 +572,13 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
     if (lit) {
       if (NS > 1) {
         for (int s = 0; s < hN; s++) {
-          const BsdfRec br = bsdf_sample<FAST>(L, c, fr, !by_area, sph, I, hN, s, scr0, scr1);
+          const BsdfRec br = H1 ? bsdf_hit<FAST>(L, c, !by_area, sph, h_ok, h_wo, h_pdf) : bsdf_sample<FAST>(L, c, fr, !by_area, sph, I, hN, s, scr0, scr1);
           if (s == 0) br0 = br;
           if (br.valid) nB = hN;
         }
       }
       for (int s = 0; s < hN; s++) {
-        const LightRec lr = light_sample<FAST>(L, c, by_area, sph, I, hN, s, scr0, scr1);
+        const LightRec lr = H1 ? light_sample_r<FAST>(L, c, by_area, sph, h_r0, h_r1) : light_sample<FAST>(L, c, by_area, sph, I, hN, s, scr0, scr1);
         if (s == 0) lr0 = lr;
         if (lr.valid) nLs = hN;
       }
