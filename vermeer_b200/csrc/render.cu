@@ -492,8 +492,8 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
   if (active && h.prim >= 0) matid = p.sc.prim_material[p.sc.geoms[h.geom].prim_base + h.prim];
   if (active) {
     p.v_mat[i] = (uint8_t)matid;
-    for (int s = 0; s < p.S; s++) p.contrib[(size_t)i * p.S + s] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int l = 0; l < p.nlights; l++) p.v_invtot[(size_t)i * p.nlights + l] = 0.0f;
+    // contribution slots and 1/total are written exactly once below, for every (light, sample) of a shaded vertex; k_resolve
+    // reads none of them for an unshaded one (matid 255 or level > 3)
     p.T[(size_t)level * p.P + path] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   // miss, or hit without a shader (core/trace.go:63-65): nothing to shade. At Level > 3 Eval returns at once (std.go:95).
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
       }
     }
     const int total = nB + nLs;
-    if (lit) p.v_invtot[(size_t)i * p.nlights + l] = NS > 1 ? (total > 0 ? 1.0f / (float)total : 0.0f) : 1.0f;
+    if (active) p.v_invtot[(size_t)i * p.nlights + l] = !lit ? 0.0f : (NS > 1 ? (total > 0 ? 1.0f / (float)total : 0.0f) : 1.0f);
 
     // pass 2: contributions + shadow rays, light samples first then BSDF samples (shader.go:260-344)
     for (int s = 0; s < (NS > 1 ? 2 * hN : hN); s++) {
@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
         }
       }
       const int slot = i * p.S + L.slot_base + s;
-      if (want) p.contrib[slot] = rgb4;
+      if (active) p.contrib[slot] = rgb4;  // zero unless `want`
       const int qi = warp_append(p.counts + 2, want);
       if (want) {
         const f3 o = offset_p(c.P, c.Poffset, dot3(Ld, c.Ng) < 0 ? -1 : 1);

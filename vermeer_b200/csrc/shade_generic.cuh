@@ -282,8 +282,6 @@ __global__ void __launch_bounds__(128, 4) k_shade_generic(const RenderParams p, 
   if (active && h.prim >= 0) matid = p.sc.prim_material[p.sc.geoms[h.geom].prim_base + h.prim];
   if (active) {
     p.v_mat[i] = (uint8_t)matid;
-    for (int s = 0; s < SL; s++) p.contrib[(size_t)i * SL + s] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int l = 0; l < p.nlights * p.nlobes; l++) p.v_invtot[(size_t)i * p.nlights * p.nlobes + l] = 0.0f;
     p.T[(size_t)level * p.P + path] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   active = active && matid != 255 && level <= 3;
@@ -383,7 +381,7 @@ __global__ void __launch_bounds__(128, 4) k_shade_generic(const RenderParams p, 
           if (light_sample_any<FAST>(L, c, lv, I, hN, s, scr0, scr1).valid) nLs = hN;
       }
       const int total = nB + nLs;
-      if (lit) p.v_invtot[((size_t)i * p.nlobes + lobe) * p.nlights + l] = NS > 1 ? (total > 0 ? 1.0f / (float)total : 0.0f) : 1.0f;
+      if (active) p.v_invtot[((size_t)i * p.nlobes + lobe) * p.nlights + l] = !lit ? 0.0f : (NS > 1 ? (total > 0 ? 1.0f / (float)total : 0.0f) : 1.0f);
 
       for (int s = 0; s < (NS > 1 ? 2 * hN : hN); s++) {
         const bool is_bsdf = s >= hN;
@@ -430,7 +428,7 @@ __global__ void __launch_bounds__(128, 4) k_shade_generic(const RenderParams p, 
           }
         }
         const int slot = i * SL + lobe * p.S + L.slot_base + s;
-        if (want) p.contrib[slot] = rgb4;
+        if (active) p.contrib[slot] = rgb4;  // zero unless `want`
         const int qi = warp_append(p.counts + 2, want);
         if (want) {
           const f3 o = offset_p(c.P, c.Poffset, dot3(Ld, c.Ng) < 0 ? -1 : 1);
