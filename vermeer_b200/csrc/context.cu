@@ -605,7 +605,6 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
   else if (!std::strcmp(name, "tma_stage")) ctx->opt_traversal = value != 0 ? 1 : 2;
   else if (!std::strcmp(name, "primary_per_lane")) ctx->opt_primary_per_lane = value != 0;
   else if (!std::strcmp(name, "shadow_unordered")) ctx->opt_shadow_unordered = value != 0;
-  else if (!std::strcmp(name, "coop_nodes")) ctx->opt_coop_nodes = value & 3;
   else if (!std::strcmp(name, "generic_shade")) {
     ctx->opt_generic_shade = value != 0;
     render_invalidate(ctx);
@@ -636,7 +635,7 @@ static int trace_device_locked(vg_ctx* ctx, const VgRay* d_rays, int64_t n, VgHi
   long long grid = (long long)ctx->sm_count * blocks_per_sm;
   if (grid > want) grid = want;
   VG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  VG_CUDA(ctx, launch_trace_batch(ctx->dev, d_rays, d_hits, n, (flags & VG_TRACE_ANY_HIT) != 0, ctx->opt_traversal, (ctx->opt_coop_nodes & 1) != 0, ctx->d_counters.p, ctx->d_counters.p + 1, (int)grid, ctx->stream));
+  VG_CUDA(ctx, launch_trace_batch(ctx->dev, d_rays, d_hits, n, (flags & VG_TRACE_ANY_HIT) != 0, ctx->opt_traversal, ctx->d_counters.p, ctx->d_counters.p + 1, (int)grid, ctx->stream));
   VG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   float ms = 0;

@@ -117,7 +117,6 @@ struct vg_ctx {
   int opt_precise_trig = 0;
   int opt_primary_per_lane = 1;  // with traversal=2: camera rays (level 0) still use the per-lane loop
   int opt_shadow_unordered = 1;  // integrator shadow queue: skip the sign-ordered push (occlusion is order independent)
-  int opt_coop_nodes = 0;        // cooperative node fetch: bit 0 = closest-hit kernels with cooperative leaves, bit 1 = the shadow queue
   int opt_generic_shade = 0;     // 1 = always shade with the general kernel (tests: it must agree with the specialised one)
   int opt_pixel_block = 1;       // paths of one warp cover an 8x4 pixel block of a tile (1) or a 32x1 row (0)
   int opt_traversal = 2;  // 0: per-lane while-while, 1: the same over a TMA-staged ray queue, 2: warp-cooperative leaves (traverse.cuh)

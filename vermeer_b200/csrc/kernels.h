@@ -23,14 +23,11 @@ static const int kTraceBlock = VG_TRACE_BLOCK;
 // 32 x 48 B ray-parameter blocks for the cooperative leaf phase. Shared memory not taken here stays L1: the scene data these
 // kernels re-read lives there, and the measured optimum is a SHORT shared stack (8 entries/thread: C2 frame 105.6 -> 102.9 ms
 // against 16; 4 and 2 lose again to local-memory spills of the stack).
-// (VARIANT & 32: + the 16 x 144 B node rows of the cooperative node fetch, aliased with the leaf scratch)
-__host__ __device__ constexpr int warp_smem_bytes(int variant) {
-  return (variant & 7) == 1 ? 2048 + 16 : ((variant & 7) >= 2 ? ((variant & 32) ? 16 * 144 : 32 * 48) : 0);
-}
+__host__ __device__ constexpr int warp_smem_bytes(int variant) { return (variant & 7) == 1 ? 2048 + 16 : ((variant & 7) >= 2 ? 32 * 48 : 0); }
 inline size_t trace_smem_bytes(int variant) { return (size_t)(kTraceBlock / 32) * warp_smem_bytes(variant) + (size_t)kTraceBlock * VG_SMEM_STACK * 8; }
 
 // kernels_trace.cu
-cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d_hits, long long n, bool any_hit, int variant, bool coop_nodes,
+cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d_hits, long long n, bool any_hit, int variant,
                                unsigned long long* d_counter, unsigned long long* d_stats, int grid, cudaStream_t stream);
 int trace_batch_blocks_per_sm();
 

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kTraceBlock, VG_TRACE_MIN_BLOCKS) k_trace_batc
   }
 }
 
-cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d_hits, long long n, bool any_hit, int variant, bool coop_nodes,
+cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d_hits, long long n, bool any_hit, int variant,
                                unsigned long long* d_counter, unsigned long long* d_stats, int grid, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
@@ -76,12 +76,10 @@ cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d
     }
   } else if (any_hit) {
     if (variant == 1) VG_LAUNCH(true, 1);
-    else if (variant == 2 && coop_nodes) VG_LAUNCH(true, 34);
     else if (variant == 2) VG_LAUNCH(true, 2);
     else VG_LAUNCH(true, 0);
   } else {
     if (variant == 1) VG_LAUNCH(false, 1);
-    else if (variant == 2 && coop_nodes) VG_LAUNCH(false, 34);
     else if (variant == 2) VG_LAUNCH(false, 2);
     else VG_LAUNCH(false, 0);
   }

@@ -1216,7 +1216,6 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
           if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 10><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(10), st>>>(p, qin);
           else k_trace_queue<0, 8><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(8), st>>>(p, qin);
         } else if (variant == 1) k_trace_queue<0, 1><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(1), st>>>(p, qin);
-        else if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane) && (ctx->opt_coop_nodes & 1)) k_trace_queue<0, 34><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(34), st>>>(p, qin);
         else if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 2><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(2), st>>>(p, qin);
         else k_trace_queue<0, 0><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(0), st>>>(p, qin);
         cudaEventRecord(rs.ev(nev++), st);
@@ -1243,7 +1242,6 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
             else if (variant == 2) k_trace_queue<1, 10><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(10), st>>>(p, 0);
             else k_trace_queue<1, 8><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(8), st>>>(p, 0);
           } else if (variant == 1) k_trace_queue<1, 1><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(1), st>>>(p, 0);
-          else if (variant == 2 && ctx->opt_shadow_unordered && (ctx->opt_coop_nodes & 2)) k_trace_queue<1, 35><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(35), st>>>(p, 0);
           else if (variant == 2 && ctx->opt_shadow_unordered) k_trace_queue<1, 3><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(3), st>>>(p, 0);
           else if (variant == 2) k_trace_queue<1, 2><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(2), st>>>(p, 0);
           else k_trace_queue<1, 0><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(0), st>>>(p, 0);

@@ -262,10 +262,6 @@ __device__ __forceinline__ int32_t pop_next(const RayState& r, Stack& st) {
   return -1;
 }
 
-template <bool ORDERED>
-__device__ __forceinline__ void node_finish(TravState& t, Stack& st, float t0, float t1, float t2, float t3, bool h0, bool h1, bool h2, bool h3,
-                                            uint32_t a0, uint32_t a1, uint32_t a2, int32_t c0, int32_t c1, int32_t c2, int32_t c3);
-
 // One interior node (static or motion): 4 box tests, ordered push, next node. intersect.go:113-216, motionintersect.go:44-97
 // ORDERED = false is for rays whose only result is "occluded or not" (the integrator's shadow queue): every box-hit
 // child is visited whatever the order until the first accepted triangle, so the sign-ordered push sequence is skipped.
@@ -319,14 +315,6 @@ __device__ __forceinline__ void node_step(const DevScene& sc, TravState& t, Stac
     a0 = mn.axes_keys & 3u; a1 = (mn.axes_keys >> 2) & 3u; a2 = (mn.axes_keys >> 4) & 3u;
     c0 = mn.child[0]; c1 = mn.child[1]; c2 = mn.child[2]; c3 = mn.child[3];
   }
-  node_finish<ORDERED>(t, st, t0, t1, t2, t3, h0, h1, h2, h3, a0, a1, a2, c0, c1, c2, c3);
-}
-
-// The part of a node visit after the four box tests: cull, order, push, next (intersect.go:137-216).
-template <bool ORDERED>
-__device__ __forceinline__ void node_finish(TravState& t, Stack& st, float t0, float t1, float t2, float t3, bool h0, bool h1, bool h2, bool h3,
-                                            uint32_t a0, uint32_t a1, uint32_t a2, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
-  RayState& r = t.r;
   // Children that miss, are empty, or already lie beyond Tclosest would be culled at pop time
   // (intersect.go:106, Tclosest only shrinks): drop them now. NodesT is unaffected.
   if (!h0 || t0 > r.tclosest) c0 = -1;
@@ -894,59 +882,7 @@ __device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bo
   return leafhit;
 }
 
-// ---- Warp-cooperative node fetch -------------------------------------------------------------------------------------
-// In an incoherent warp every lane sits in a different 128-B node, so each of the 8 LDG.128 of a per-lane node fetch touches
-// up to 32 lines; the L1TEX queue serialises them at ~2 cycles per line within one instruction (B300_MICROARCH.md, "L1tex
-// wavefront queue"), and ncu shows that data pipe at 89 % on the incoherent batch — the binding unit. Here the warp fetches
-// the nodes TOGETHER: in one round, 8 consecutive lanes load the eight 16-B chunks of ONE node (one line, one wavefront), four
-// nodes per LDG.128; the chunks go through a padded shared-memory row per owner lane (144-B stride: conflict-free for the
-// quarter-warp phases of both the STS.128 and the owner's LDS.128). 16 owner rows per pass, two passes; the buffer aliases the
-// cooperative-leaf scratch (the phases never overlap). Only static nodes; a motion node keeps its per-lane fetch.
-static const int kCoopNodeBytesPerWarp = 16 * 144;
-struct NodeRegs {
-  float4 lx, ly, lz, hx, hy, hz;
-  uint4 m0, m1;
-};
-__device__ __forceinline__ void coop_fetch_nodes(const DevScene& sc, int32_t cur, bool stat, float4* rows, NodeRegs& nr) {
-  const int lane = threadIdx.x & 31;
-  const unsigned sm = __ballot_sync(0xffffffffu, stat);
-  if (sm == 0) return;
-#pragma unroll
-  for (int half = 0; half < 2; half++) {
-    const unsigned hm = (sm >> (16 * half)) & 0xffffu;
-    if (hm == 0) continue;  // warp-uniform
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      if (((hm >> (4 * k)) & 0xfu) == 0) continue;  // warp-uniform: none of this round's four owners has a node
-      const int row = 4 * k + (lane >> 3);
-      const int owner = 16 * half + row;
-      const int32_t node = __shfl_sync(0xffffffffu, cur, owner);
-      if ((sm >> owner) & 1u) rows[row * 9 + (lane & 7)] = ldg4(reinterpret_cast<const float4*>(sc.nodes + node) + (lane & 7));
-    }
-    __syncwarp();
-    if ((lane >> 4) == half && stat) {
-      const float4* rr = rows + (lane & 15) * 9;
-      nr.lx = rr[0]; nr.ly = rr[1]; nr.lz = rr[2]; nr.hx = rr[3]; nr.hy = rr[4]; nr.hz = rr[5];
-      const float4 a = rr[6], b = rr[7];
-      nr.m0 = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
-      nr.m1 = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
-    }
-    __syncwarp();
-  }
-}
-// A static node visit on pre-fetched node data (the arithmetic of node_step's static branch).
-template <bool ORDERED>
-__device__ __forceinline__ void node_step_regs(TravState& t, Stack& st, const NodeRegs& n) {
-  RayState& r = t.r;
-  t.h.nodesT++;
-  Box4Out bo;
-  if (r.special) box4<true>(r, n.lx, n.ly, n.lz, n.hx, n.hy, n.hz, bo);
-  else box4<false>(r, n.lx, n.ly, n.lz, n.hx, n.hy, n.hz, bo);
-  node_finish<ORDERED>(t, st, bo.t0, bo.t1, bo.t2, bo.t3, bo.h0, bo.h1, bo.h2, bo.h3, n.m0.x, n.m0.y, n.m0.z, (int32_t)n.m0.w, (int32_t)n.m1.x,
-                       (int32_t)n.m1.y, (int32_t)n.m1.z);
-}
-
-template <bool ANY_HIT, bool ORDERED, bool SPH, bool XF, bool COOPN, class IO>
+template <bool ANY_HIT, bool ORDERED, bool SPH, bool XF, class IO>
 __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io, Stack& st, const CoopSmem& cs, unsigned long long& nodes_acc,
                                                       unsigned long long& tris_acc) {
   const int lane = threadIdx.x & 31;
@@ -1015,15 +951,7 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
       const unsigned nm = __ballot_sync(0xffffffffu, t.cur >= 0);
       if (nm == 0) break;
       if (__popc(nm) < VG_NODE_MIN && __any_sync(0xffffffffu, t.cur < -1)) break;
-      if (COOPN) {
-        const bool stat = t.cur >= 0 && t.cur < sc.n_static;
-        NodeRegs nr;
-        coop_fetch_nodes(sc, t.cur, stat, cs.rp, nr);
-        if (stat) node_step_regs<ORDERED>(t, st, nr);
-        else if (t.cur >= 0) node_step<ORDERED>(sc, t, st);
-      } else {
-        if (t.cur >= 0) node_step<ORDERED>(sc, t, st);
-      }
+      if (t.cur >= 0) node_step<ORDERED>(sc, t, st);
     }
     // leaf phase
     const bool leaf = t.cur < -1;
@@ -1076,7 +1004,6 @@ __device__ __forceinline__ void trace_persistent(const DevScene& sc, IO& io, Sta
   constexpr int V = VARIANT & 7;
   constexpr bool SPH = (VARIANT & 8) != 0;
   constexpr bool XF = (VARIANT & 16) != 0;
-  constexpr bool COOPN = (VARIANT & 32) != 0;  // cooperative node fetch (variants 2, 3)
   if (V == 1) {
     WarpStage ws;
     ws.buf = reinterpret_cast<float4*>(warp_smem);
@@ -1085,11 +1012,11 @@ __device__ __forceinline__ void trace_persistent(const DevScene& sc, IO& io, Sta
   } else if (V == 2) {
     CoopSmem cs;
     cs.rp = reinterpret_cast<float4*>(warp_smem);
-    trace_persistent_coop<ANY_HIT, true, SPH, XF, COOPN>(sc, io, st, cs, nodes_acc, tris_acc);
+    trace_persistent_coop<ANY_HIT, true, SPH, XF>(sc, io, st, cs, nodes_acc, tris_acc);
   } else if (V == 3) {
     CoopSmem cs;
     cs.rp = reinterpret_cast<float4*>(warp_smem);
-    trace_persistent_coop<ANY_HIT, false, SPH, XF, COOPN>(sc, io, st, cs, nodes_acc, tris_acc);
+    trace_persistent_coop<ANY_HIT, false, SPH, XF>(sc, io, st, cs, nodes_acc, tris_acc);
   } else {
     trace_persistent_ldg<ANY_HIT, SPH>(sc, io, st, nodes_acc, tris_acc);
   }
