@@ -252,3 +252,13 @@ def test_pinned_host_buffers_take_the_direct_dma_path(built_library):
     dev.set_scramble(tab)          # and back to the gathered layout
     dev.clear()
     assert dev.render(0, 6).tobytes() == ref.tobytes()
+    # a rank of a 2-way partition: the owned rows are gathered from the page-locked table by a kernel (zero-copy)
+    dev.set_partition(1, 2)
+    dev.set_scramble(tab)
+    dev.clear()
+    part = dev.render(0, 6)
+    dev.set_scramble(tab_pinned)
+    dev.clear()
+    assert dev.render(0, 6).tobytes() == part.tobytes()
+    own = part.any(-1)
+    assert 0.3 < own.mean() < 0.7 and np.array_equal(part[own], ref[own])

@@ -888,6 +888,14 @@ static int ensure_fb(vg_ctx* ctx) {
 }
 
 // Partition of framescramble (core/render.go:166-176) at upload: only the rows of owned pixels go to the device.
+// rows of the caller's (page-locked, device-visible) scramble table -> path order; thread = one 16-byte third of a row
+__global__ void k_gather_scramble(const uint4* __restrict__ table, const int* __restrict__ pix, int nown, uint4* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)nown * 3) return;
+  const int own = (int)(i / 3), part = (int)(i % 3);
+  out[i] = table[(size_t)pix[own] * 3 + part];
+}
+
 // true if `p` is page-locked host memory the GPU can DMA from/to directly (cudaHostAlloc / cudaHostRegister / torch pin_memory)
 static bool is_pinned_host(const void* p) {
   cudaPointerAttributes a;
@@ -911,6 +919,21 @@ static int upload_scramble(vg_ctx* ctx, const uint64_t* table) {
     RCUDA(cudaStreamSynchronize(ctx->stream));
     rs.scr_by_pixel = true;
     return VG_OK;
+  }
+  if (is_pinned_host(table)) {
+    // Page-locked table, this context owns a subset of the pixels: a kernel gathers the owned rows straight from host memory
+    // over PCIe (zero-copy read of 48-B rows, runs of 8 or 32 rows contiguous), no host pass and no staging copy.
+    void* dview = nullptr;
+    if (cudaHostGetDevicePointer(&dview, const_cast<uint64_t*>(table), 0) == cudaSuccess && dview) {
+      RCUDA(rs.scr.reserve((size_t)rs.nown * 6));
+      const long long n2 = (long long)rs.nown * 3;  // one thread per 16 bytes
+      k_gather_scramble<<<(unsigned)((n2 + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(dview), rs.pix.p, rs.nown,
+                                                                                reinterpret_cast<uint4*>(rs.scr.p));
+      RCUDA(cudaGetLastError());
+      RCUDA(cudaStreamSynchronize(ctx->stream));
+      return VG_OK;
+    }
+    cudaGetLastError();
   }
   const size_t bytes = (size_t)rs.nown * 48;
   if (rs.scr_pinned_bytes < bytes) {
