@@ -718,11 +718,18 @@ static __device__ __noinline__ void xf_object_ray(const DevScene& sc, int xi, fl
 // loop too. So the parallel pass tests against the entry value and yields "candidates"; the owner lane then replays
 // its candidates in triangle order against its live Tclosest (one shuffle round per candidate, almost always <= 1 per
 // leaf), which reproduces the sequential accept/reject decisions and the final (T,U,V,W,idx) bit for bit.
+// Node phase: keep stepping nodes until fewer than VG_NODE_MIN lanes want one (and a leaf is pending). Refill: fetch new rays
+// once that many lanes are idle — occlusion rays (coherent in queue order) do best refilled in big groups, closest-hit bounce
+// rays in smaller ones. Measured on C2 (shadow queue ms per frame / incoherent Mrays/s): NODE_MIN 8,4,2 -> 42.3, 41.8, 40.7(*);
+// REFILL_IDLE 8,16,24,32 -> 42.3, 41.0, 39.9(*), 40.3 / 2110, 2144, 2107, - (* with NODE_MIN 4).
 #ifndef VG_NODE_MIN
-#define VG_NODE_MIN 8
+#define VG_NODE_MIN 4
 #endif
-#ifndef VG_REFILL_IDLE
-#define VG_REFILL_IDLE 8
+#ifndef VG_REFILL_IDLE_ANYHIT
+#define VG_REFILL_IDLE_ANYHIT 24
+#endif
+#ifndef VG_REFILL_IDLE_CLOSEST
+#define VG_REFILL_IDLE_CLOSEST 16
 #endif
 static const int kCoopBytesPerWarp = 32 * 48;  // 32 ray-parameter blocks of 3 float4
 
@@ -896,7 +903,7 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
   st.overflow = false;
   while (true) {
     const unsigned idle = __ballot_sync(0xffffffffu, my < 0);
-    if (!exhausted && __popc(idle) >= VG_REFILL_IDLE) {
+    if (!exhausted && __popc(idle) >= (ANY_HIT ? VG_REFILL_IDLE_ANYHIT : VG_REFILL_IDLE_CLOSEST)) {
       const int want = __popc(idle);
       long long base = 0;
       if (lane == 0) base = io.fetch(want);
