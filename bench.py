@@ -160,18 +160,27 @@ def incoherent_leg(dev, host, scene, torch, cpu_cores):
     from vermeer_b200 import scenes
     from vermeer_b200.host import HIT_DTYPE, RAY_DTYPE
     cam_m, ttf, asp = host.camera()
-    ys, xs = np.meshgrid(np.arange(YRES), np.arange(XRES), indexing="ij")
-    sx = (-1 + 2 * (xs + 0.5) / XRES).astype(np.float32)
-    sy = -(-1 + 2 * (ys + 0.5) / YRES).astype(np.float32)
     M = cam_m.reshape(4, 4).T
-    d = np.stack([sx * ttf, sy * (ttf / asp), -np.full_like(sx, scene.camera.Focal)], -1).reshape(-1, 3) @ M[:3, :3].T
-    d /= np.linalg.norm(d, axis=1, keepdims=True)
-    prim = np.zeros(XRES * YRES, RAY_DTYPE)
-    prim["o"] = M[:3, 3]
-    prim["d"] = d.astype(np.float32)
-    prim["tmax"] = np.inf
-    hits = dev.trace(prim)
-    inc = scenes.incoherent_rays(prim, hits, seed=5)
+
+    def primary(jx, jy):
+        ys, xs = np.meshgrid(np.arange(YRES), np.arange(XRES), indexing="ij")
+        sx = (-1 + 2 * (xs + jx) / XRES).astype(np.float32)
+        sy = -(-1 + 2 * (ys + jy) / YRES).astype(np.float32)
+        d = np.stack([sx * ttf, sy * (ttf / asp), -np.full_like(sx, scene.camera.Focal)], -1).reshape(-1, 3) @ M[:3, :3].T
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        r = np.zeros(XRES * YRES, RAY_DTYPE)
+        r["o"] = M[:3, 3]
+        r["d"] = d.astype(np.float32)
+        r["tmax"] = np.inf
+        return r
+
+    # four jittered primary passes (4 spp) -> ~5.9 M bounce rays: large enough that the persistent kernel's ramp-up and tail
+    # (a 1.5 M-ray batch lasts 0.8 ms) do not dominate the rate
+    parts = []
+    for s, (jx, jy) in enumerate([(0.5, 0.5), (0.25, 0.75), (0.75, 0.25), (0.1, 0.4)]):
+        prim = primary(jx, jy)
+        parts.append(scenes.incoherent_rays(prim, dev.trace(prim), seed=5 + s))
+    inc = np.concatenate(parts)
     inc = inc[np.random.default_rng(1).permutation(len(inc))]      # shuffled: no residual image-space coherence
     n = len(inc)
     d_r = torch.from_numpy(inc.view(np.uint8).reshape(n, 32)).cuda()
@@ -183,10 +192,13 @@ def incoherent_leg(dev, host, scene, torch, cpu_cores):
         st = dev.stats()
         if i >= 3:
             best = min(best, st["trace_ms"])
-    out_hits = np.empty(n, HIT_DTYPE)
+    # e2e of this leg: rays and hits in page-locked host memory, H2D + traversal + D2H inside the timed call
+    inc_pinned = torch.from_numpy(inc.view(np.uint8).reshape(n, 32)).pin_memory().numpy().reshape(-1).view(RAY_DTYPE)
+    out_hits = torch.empty((n, 32), dtype=torch.uint8, pin_memory=True).numpy().reshape(-1).view(HIT_DTYPE)
+    dev.trace(inc_pinned, out=out_hits)
     t0 = time.perf_counter()
     for _ in range(3):
-        dev.trace(inc, out=out_hits)
+        dev.trace(inc_pinned, out=out_hits)
     e2e_ms = (time.perf_counter() - t0) / 3 * 1e3
     res = {"rays": n, "value": n / best / 1e3, "unit": "Mrays/s", "e2e": n / e2e_ms / 1e3, "hit_fraction": float((out_hits["prim"] >= 0).mean()),
            "nodesT_per_ray": st["nodes_t"] / n, "trisT_per_ray": st["tris_t"] / n,

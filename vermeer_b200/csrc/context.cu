@@ -1,6 +1,7 @@
 // Device layer of the C ABI (include/vermeer_gpu.h, vg_*): context, scene flattening, batch TraceProbe.
 #include "context.h"
 
+#include <algorithm>
 #include <cstring>
 
 #include "kernels.h"
@@ -86,6 +87,10 @@ void vg_destroy(vg_ctx* ctx) {
   ctx->d_mtris.release(); ctx->d_normals.release(); ctx->d_geoms.release(); ctx->d_prim_material.release();
   ctx->d_xforms.release(); ctx->d_xf_keys.release(); ctx->d_xf_static.release();
   ctx->d_rays.release(); ctx->d_hits.release(); ctx->d_counters.release();
+  for (int i = 0; i < 3; i++) {
+    if (ctx->pipe_stream[i]) cudaStreamDestroy(ctx->pipe_stream[i]);
+    if (ctx->pipe_done[i]) cudaEventDestroy(ctx->pipe_done[i]);
+  }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -654,13 +659,60 @@ int vg_trace_batch_device(vg_ctx* ctx, const VgRay* d_rays, int64_t n, VgHit* d_
   return trace_device_locked(ctx, d_rays, n, d_hits, flags);
 }
 
+static bool pinned_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
 int vg_trace_batch(vg_ctx* ctx, const VgRay* rays, int64_t n, VgHit* hits, uint32_t flags) {
   VG_LOCK(ctx);
   if (n < 0 || (n > 0 && (!rays || !hits))) return ctx->fail(VG_ERR_INVALID, "vg_trace_batch: bad input");
   if (n == 0) return VG_OK;
   VG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->committed) return ctx->fail(VG_ERR_INVALID, "scene not committed");
   VG_CUDA(ctx, ctx->d_rays.reserve((size_t)n));
   VG_CUDA(ctx, ctx->d_hits.reserve((size_t)n));
+  const int64_t chunk = 1 << 19;  // 16 MB of rays
+  if (n >= 2 * chunk && pinned_host(rays) && pinned_host(hits)) {
+    // Page-locked caller buffers: the batch goes through in chunks on three streams, so the H2D copy of one chunk, the
+    // traversal of the previous one and the D2H copy of the one before overlap (PCIe is full duplex; each direction carries
+    // 32 B per ray, which at ~50 GB/s is slower than the traversal itself).
+    for (int s = 0; s < 3; s++) {
+      if (!ctx->pipe_stream[s]) VG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->pipe_stream[s], cudaStreamNonBlocking));
+      if (!ctx->pipe_done[s]) VG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_done[s], cudaEventDisableTiming));
+    }
+    static int blocks_per_sm = 0;
+    if (!blocks_per_sm) blocks_per_sm = trace_batch_blocks_per_sm();
+    VG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int s = 0; s < 3; s++) VG_CUDA(ctx, cudaStreamWaitEvent(ctx->pipe_stream[s], ctx->ev0, 0));
+    int c = 0;
+    for (int64_t off = 0; off < n; off += chunk, c++) {
+      const int64_t m = std::min(chunk, n - off);
+      cudaStream_t st = ctx->pipe_stream[c % 3];
+      VG_CUDA(ctx, cudaMemcpyAsync(ctx->d_rays.p + off, rays + off, (size_t)m * sizeof(VgRay), cudaMemcpyHostToDevice, st));
+      long long grid = std::min<long long>((long long)ctx->sm_count * blocks_per_sm, (m + kTraceBlock - 1) / kTraceBlock);
+      VG_CUDA(ctx, launch_trace_batch(ctx->dev, ctx->d_rays.p + off, ctx->d_hits.p + off, m, (flags & VG_TRACE_ANY_HIT) != 0, ctx->opt_traversal,
+                                      ctx->d_counters.p + 4 + (c % 3), ctx->d_counters.p + 1, (int)grid, st));
+      VG_CUDA(ctx, cudaMemcpyAsync(hits + off, ctx->d_hits.p + off, (size_t)m * sizeof(VgHit), cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < 3; s++) {
+      VG_CUDA(ctx, cudaEventRecord(ctx->pipe_done[s], ctx->pipe_stream[s]));
+      VG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_done[s], 0));
+    }
+    VG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->stats.trace_ms = ms;  // copies included: the whole pipelined call
+    ctx->stats.rays += (uint64_t)n;
+    if (flags & VG_TRACE_ANY_HIT) ctx->stats.shadow_rays += (uint64_t)n;
+    ctx->stats.kernel_launches += (uint64_t)c;
+    return VG_OK;
+  }
   VG_CUDA(ctx, cudaMemcpyAsync(ctx->d_rays.p, rays, (size_t)n * sizeof(VgRay), cudaMemcpyHostToDevice, ctx->stream));
   int rc = trace_device_locked(ctx, ctx->d_rays.p, n, ctx->d_hits.p, flags);
   if (rc != VG_OK) return rc;

@@ -78,6 +78,8 @@ struct vg_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};  // vg_trace_batch with page-locked buffers: copy/compute overlap
+  cudaEvent_t pipe_done[3] = {nullptr, nullptr, nullptr};
 
   // staged scene (reference formats)
   std::vector<vg::MeshStage> meshes;

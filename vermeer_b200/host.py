@@ -302,7 +302,8 @@ class Device:
 
     def trace(self, rays: np.ndarray, any_hit: bool = False, out: np.ndarray | None = None) -> np.ndarray:
         """vg_trace_batch with HOST buffers (H2D + kernel + D2H inside the call)."""
-        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        if not (isinstance(rays, np.ndarray) and rays.dtype == RAY_DTYPE and rays.flags.c_contiguous):
+            rays = np.ascontiguousarray(rays, RAY_DTYPE)      # (a page-locked array passes through untouched)
         hits = np.empty(len(rays), HIT_DTYPE) if out is None else out
         self._chk(self.L.vg_trace_batch(self.h, _p(rays), C.c_int64(len(rays)), _p(hits), C.c_uint32(VG_TRACE_ANY_HIT if any_hit else 0)))
         return hits
