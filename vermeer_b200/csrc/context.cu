@@ -505,6 +505,7 @@ int vg_scene_commit(vg_ctx* ctx) {
   d.xf_keys = ctx->d_xf_keys.p;
   d.xf_static = ctx->d_xf_static.p;
   d.n_xforms = (int32_t)xforms.size();
+  d.n_mtris = (int32_t)n_mtris;
   d.n_geoms = G;
   d.n_spheres = 0;
   for (int g = 0; g < G; g++) d.n_spheres += ctx->meshes[g].sphere ? 1 : 0;

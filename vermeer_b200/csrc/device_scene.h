@@ -82,6 +82,7 @@ struct DevScene {
   const DevXform* xforms;
   const XfSRT* xf_keys;
   const Mat4* xf_static;
+  int32_t n_mtris;               // motion triangle slots (selects the kernels whose cooperative leaf phase handles them)
   int32_t n_xforms;              // instance geoms (selects the kernels that carry the transform enter/leave code)
   int32_t n_spheres;             // analytic sphere geoms in the scene-level tree (selects the kernels that carry their leaf test)
 };

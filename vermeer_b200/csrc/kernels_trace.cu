@@ -74,6 +74,9 @@ cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d
       if (variant == 2) VG_LAUNCH(false, 10);
       else VG_LAUNCH(false, 8);
     }
+  } else if (sc.n_mtris > 0 && variant == 2) {  // motion triangles in the cooperative leaf phase (VARIANT & 64)
+    if (any_hit) VG_LAUNCH(true, 66);
+    else VG_LAUNCH(false, 66);
   } else if (any_hit) {
     if (variant == 1) VG_LAUNCH(true, 1);
     else if (variant == 2) VG_LAUNCH(true, 2);

@@ -1098,6 +1098,17 @@ static int prepare(vg_ctx* ctx) {
   rs.nlights = (int)lights.size();
   rs.levels = any_mirror ? 4 : 1;
   rs.iters = ctx->opt_iters_per_batch;
+  {
+    // The batch depth is a request: queue slots are 32-bit indices (paths x contribution slots must stay below 2^31) and the
+    // wavefront state (~230 B + 52 B per contribution slot + 32 B per level and path) has to fit the free device memory.
+    const size_t per_path = 230 + (size_t)S * rs.nlobes * 52 + (size_t)rs.levels * 32 + (size_t)std::max(1, (int)lights.size()) * rs.nlobes * 4;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = (size_t)16 << 30;
+    const size_t by_mem = (free_b / 10 * 8) / per_path / (size_t)std::max(1, rs.nown);
+    const size_t by_idx = (((size_t)1 << 31) - 1) / ((size_t)S * rs.nlobes) / (size_t)std::max(1, rs.nown);
+    const size_t cap = std::max<size_t>(1, std::min(by_mem, by_idx));
+    if ((size_t)rs.iters > cap) rs.iters = (int)cap;
+  }
   rs.P = rs.nown * rs.iters;
   const size_t P = (size_t)rs.P;
 
@@ -1209,7 +1220,8 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
 
   const int variant = ctx->opt_traversal;
   const bool xf = ctx->dev.n_xforms > 0;    // kernels that carry the instance enter/leave code (VARIANT & 16)
-  const bool sph = ctx->dev.n_spheres > 0;  // kernels that carry the analytic sphere leaf (traverse.cuh: VARIANT & 8)
+  const bool sph = ctx->dev.n_spheres > 0;
+  const bool mot = ctx->dev.n_mtris > 0;    // kernels whose cooperative leaf phase takes motion triangles (VARIANT & 64)  // kernels that carry the analytic sphere leaf (traverse.cuh: VARIANT & 8)
   uint64_t launches = 0;
   size_t nev = 0;
   std::vector<int> kinds;
@@ -1238,7 +1250,8 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
         else if (sph) {
           if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 10><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(10), st>>>(p, qin);
           else k_trace_queue<0, 8><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(8), st>>>(p, qin);
-        } else if (variant == 1) k_trace_queue<0, 1><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(1), st>>>(p, qin);
+        } else if (mot && variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 66><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(66), st>>>(p, qin);
+        else if (variant == 1) k_trace_queue<0, 1><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(1), st>>>(p, qin);
         else if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 2><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(2), st>>>(p, qin);
         else k_trace_queue<0, 0><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(0), st>>>(p, qin);
         cudaEventRecord(rs.ev(nev++), st);
@@ -1264,6 +1277,9 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
             if (variant == 2 && ctx->opt_shadow_unordered) k_trace_queue<1, 11><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(11), st>>>(p, 0);
             else if (variant == 2) k_trace_queue<1, 10><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(10), st>>>(p, 0);
             else k_trace_queue<1, 8><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(8), st>>>(p, 0);
+          } else if (mot && variant == 2) {
+            if (ctx->opt_shadow_unordered) k_trace_queue<1, 67><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(67), st>>>(p, 0);
+            else k_trace_queue<1, 66><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(66), st>>>(p, 0);
           } else if (variant == 1) k_trace_queue<1, 1><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(1), st>>>(p, 0);
           else if (variant == 2 && ctx->opt_shadow_unordered) k_trace_queue<1, 3><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(3), st>>>(p, 0);
           else if (variant == 2) k_trace_queue<1, 2><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(2), st>>>(p, 0);

@@ -793,11 +793,34 @@ __device__ __forceinline__ bool coop_item(const DevScene& sc, const float4 q0, c
   const int i = j - __float_as_int(q2.z);
   const float4* tp = sc.tris + (size_t)(__float_as_int(q2.y) + i) * 3;
   const float4 v0 = ldg4(tp), v1 = ldg4(tp + 1), v2 = ldg4(tp + 2);
-  return tri_candidate<false, KZ>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, __float_as_uint(q1.z), __float_as_int(q2.x), q1.w, make_float3(v0.x, v0.y, v0.z),
+  return tri_candidate<false, KZ>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, __float_as_uint(q1.z), __float_as_int(q2.x) & 3, q1.w, make_float3(v0.x, v0.y, v0.z),
                                   make_float3(v1.x, v1.y, v1.z), make_float3(v2.x, v2.y, v2.z), v2.w, tc);
 }
 
-// One cooperative leaf phase. `isleaf`: this lane's t.cur is a static triangle leaf. Returns leafhit for the lane.
+// A motion-triangle item (polymesh/trace.go:547-554,556-622): the two keys' vertices are lerped at the ray's time; the key count
+// and key stride come from the item's geom record.
+__device__ __forceinline__ bool coop_item_motion(const DevScene& sc, const float4 q0, const float4 q1, const float4 q2, int j, TriCand& tc) {
+  const int i = j - __float_as_int(q2.z);
+  const size_t slot = (size_t)(__float_as_int(q2.y) + i);
+  const float4* k0 = sc.mtris + slot * 3;  // key-0 record of the slot: geom id in [0].w, RayBias in [2].w
+  const DevGeom gm = sc.geoms[__float_as_int(ldg4(k0).w)];
+  const float k = q2.w * (float)(gm.keys - 1);
+  const float fk = floorf(k);
+  const float tm = k - fk, om = 1.0f - tm;
+  const int key = (int)fk, key2 = (int)ceilf(k);
+  const float4* ta = sc.mtris + (slot + (size_t)key * gm.tri_key_stride) * 3;
+  const float4* tb = sc.mtris + (slot + (size_t)key2 * gm.tri_key_stride) * 3;
+  const float4 a0 = ldg4(ta), a1 = ldg4(ta + 1), a2 = ldg4(ta + 2);
+  const float4 b0 = ldg4(tb), b1 = ldg4(tb + 1), b2 = ldg4(tb + 2);
+  const float3 p0 = make_float3(om * a0.x + tm * b0.x, om * a0.y + tm * b0.y, om * a0.z + tm * b0.z);
+  const float3 p1 = make_float3(om * a1.x + tm * b1.x, om * a1.y + tm * b1.y, om * a1.z + tm * b1.z);
+  const float3 p2 = make_float3(om * a2.x + tm * b2.x, om * a2.y + tm * b2.y, om * a2.z + tm * b2.z);
+  return tri_candidate<true, -1>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, __float_as_uint(q1.z), __float_as_int(q2.x) & 3, q1.w, p0, p1, p2, ldg4(k0 + 2).w, tc);
+}
+
+// One cooperative leaf phase. `isleaf`: this lane's t.cur is a triangle leaf that takes part (static; also motion leaves when
+// MOT). Returns leafhit for the lane.
+template <bool MOT>
 __device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bool isleaf, const CoopSmem& cs) {
   const int lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
@@ -820,10 +843,13 @@ __device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bo
     float4* b = cs.rp + __popc(leafmask & lt) * 3;
     b[0] = make_float4(r.pkx, r.pky, r.pkz, r.s0);
     b[1] = make_float4(r.s1, r.s2, __uint_as_float(r.xsign), r.tclosest);
-    b[2] = make_float4(__int_as_float(r.kz), __int_as_float(base), __int_as_float(start), 0.0f);
+    // kz in bits 0-1, bit 8 = motion-triangle leaf; .w = Ray.Time for the motion items
+    const bool mot = MOT && (un & kMotionTriBit);
+    b[2] = make_float4(__int_as_float(r.kz | (mot ? 256 : 0)), __int_as_float(base), __int_as_float(start), r.time);
   }
   const int kz0 = __shfl_sync(0xffffffffu, r.kz, __ffs(leafmask) - 1);
-  const bool kz_uniform = __all_sync(0xffffffffu, !isleaf || r.kz == kz0);
+  const bool any_mot = MOT && __any_sync(0xffffffffu, isleaf && (un & kMotionTriBit));
+  const bool kz_uniform = !any_mot && __all_sync(0xffffffffu, !isleaf || r.kz == kz0);
   __syncwarp();
   bool leafhit = false;
   for (int w = 0; w < total; w += 32) {
@@ -844,6 +870,8 @@ __device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bo
         if (kz0 == 0) cand = coop_item<0>(sc, q0, q1, q2, j, tc);
         else if (kz0 == 1) cand = coop_item<1>(sc, q0, q1, q2, j, tc);
         else cand = coop_item<2>(sc, q0, q1, q2, j, tc);
+      } else if (MOT && (__float_as_int(q2.x) & 256)) {
+        cand = coop_item_motion(sc, q0, q1, q2, j, tc);
       } else {
         cand = coop_item<-1>(sc, q0, q1, q2, j, tc);
       }
@@ -879,7 +907,7 @@ __device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bo
           h.w = fW * rcp;
           r.tclosest = T * rcp;
           h.slot = base + (src - f);
-          h.prim = -2;  // geom / prim ids are read from the triangle record once, when the ray is stored
+          h.prim = (MOT && (un & kMotionTriBit)) ? -3 : -2;  // geom / prim ids are read from the (motion) triangle record once, when the ray is stored
           leafhit = true;
         }
       }
@@ -889,7 +917,7 @@ __device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bo
   return leafhit;
 }
 
-template <bool ANY_HIT, bool ORDERED, bool SPH, bool XF, class IO>
+template <bool ANY_HIT, bool ORDERED, bool SPH, bool XF, bool MOT, class IO>
 __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io, Stack& st, const CoopSmem& cs, unsigned long long& nodes_acc,
                                                       unsigned long long& tris_acc) {
   const int lane = threadIdx.x & 31;
@@ -964,8 +992,8 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
     const bool leaf = t.cur < -1;
     const bool mleaf = leaf && ((uint32_t)t.cur & kMotionTriBit);
     if (__any_sync(0xffffffffu, leaf)) {
-      bool leafhit = coop_leaves(sc, t, leaf && !mleaf, cs);
-      if (mleaf) {
+      bool leafhit = coop_leaves<MOT>(sc, t, leaf && (MOT || !mleaf), cs);
+      if (!MOT && mleaf) {
         const uint32_t un = (uint32_t)t.cur;
         const int count = (int)(un & 15u) + 1;
         t.h.trisT += count;
@@ -985,7 +1013,11 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
       }
     }
     if (my >= 0 && t.cur == -1) {
-      if (t.h.prim == -2) {
+      if (MOT && t.h.prim == -3) {
+        const float4* tp = sc.mtris + (size_t)t.h.slot * 3;
+        t.h.geom = __float_as_int(ldg4(tp).w);
+        t.h.prim = __float_as_int(ldg4(tp + 1).w);
+      } else if (t.h.prim == -2) {
         const float4* tp = sc.tris + (size_t)t.h.slot * 3;
         t.h.geom = __float_as_int(ldg4(tp).w);
         t.h.prim = __float_as_int(ldg4(tp + 1).w);
@@ -1011,6 +1043,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene& sc, IO& io, Sta
   constexpr int V = VARIANT & 7;
   constexpr bool SPH = (VARIANT & 8) != 0;
   constexpr bool XF = (VARIANT & 16) != 0;
+  constexpr bool MOT = (VARIANT & 64) != 0 || XF;  // motion-triangle leaves take part in the cooperative leaf phase (variants 2, 3)
   if (V == 1) {
     WarpStage ws;
     ws.buf = reinterpret_cast<float4*>(warp_smem);
@@ -1019,11 +1052,11 @@ __device__ __forceinline__ void trace_persistent(const DevScene& sc, IO& io, Sta
   } else if (V == 2) {
     CoopSmem cs;
     cs.rp = reinterpret_cast<float4*>(warp_smem);
-    trace_persistent_coop<ANY_HIT, true, SPH, XF>(sc, io, st, cs, nodes_acc, tris_acc);
+    trace_persistent_coop<ANY_HIT, true, SPH, XF, MOT>(sc, io, st, cs, nodes_acc, tris_acc);
   } else if (V == 3) {
     CoopSmem cs;
     cs.rp = reinterpret_cast<float4*>(warp_smem);
-    trace_persistent_coop<ANY_HIT, false, SPH, XF>(sc, io, st, cs, nodes_acc, tris_acc);
+    trace_persistent_coop<ANY_HIT, false, SPH, XF, MOT>(sc, io, st, cs, nodes_acc, tris_acc);
   } else {
     trace_persistent_ldg<ANY_HIT, SPH>(sc, io, st, nodes_acc, tris_acc);
   }
