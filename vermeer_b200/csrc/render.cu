@@ -1245,12 +1245,14 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
         const int qout = 1 - qin;
         cudaEventRecord(rs.ev(nev++), st);
         // camera rays are coherent: the per-lane loop with its compile-time axis specialisation is faster there (measured
-        // 3.81 vs 3.48 Grays/s); every later level is incoherent and takes the cooperative leaf phase
+        // 3.81 vs 3.48 Grays/s); every later level is incoherent and takes the cooperative leaf phase. Motion meshes are the
+        // exception: their leaves cost 2-3x a static one (two keys to load and lerp), so the cooperative phase wins at level 0
+        // too (C4: 49.6 vs 56.7 ms per frame)
         if (xf) k_trace_queue<0, 26><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(26), st>>>(p, qin);
         else if (sph) {
           if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 10><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(10), st>>>(p, qin);
           else k_trace_queue<0, 8><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(8), st>>>(p, qin);
-        } else if (mot && variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 66><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(66), st>>>(p, qin);
+        } else if (mot && variant == 2) k_trace_queue<0, 66><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(66), st>>>(p, qin);
         else if (variant == 1) k_trace_queue<0, 1><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(1), st>>>(p, qin);
         else if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 2><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(2), st>>>(p, qin);
         else k_trace_queue<0, 0><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(0), st>>>(p, qin);
