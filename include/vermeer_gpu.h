@@ -208,6 +208,9 @@ int vg_set_materials(vg_ctx* ctx, const VgMaterial* mats, int n);
 int vg_set_lights(vg_ctx* ctx, const VgTriLight* lights, int n);   /* TriLights only (kept for callers that have nothing else) */
 int vg_set_area_lights(vg_ctx* ctx, const VgLight* lights, int n);  /* any mix of light types, scene order */
 int vg_set_camera(vg_ctx* ctx, const VgCamera* cam);
+/* A camera with motion keys (builtin/camera/camera.go:225-236): decomp = Camera.decomp, one m.TransformDecomp per LocalToWorld
+ * key; every camera ray lerps/slerps the keys at its Time and recomposes the matrix on the device. keys <= 1 is vg_set_camera. */
+int vg_set_camera_motion(vg_ctx* ctx, const VgCamera* cam, const VgTransformSRT* decomp, int keys);
 int vg_set_frame(vg_ctx* ctx, int xres, int yres);
 /* Image partition across processes/GPUs: this context renders the 32x32 tiles (tx,ty) with
  * (tx + ty*stride_k) % world == rank (core/render.go:196-199 tiles). Default rank 0 of 1. */
@@ -273,8 +276,14 @@ int vh_add_instance(vh_scene* s, const char* name, const char* geom, const float
                     const float* transforms, int keys);
 int vh_set_camera_lookat(vh_scene* s, const float* from, const float* to, const float* up, float roll, float fov, float focal,
                          float aspect, float radius);
+/* The Camera node in full (camera.go:48-73): type "LookAt" with n_from / n_to / n_roll motion keys of From / To / Roll, or type
+ * "Matrix" with n_mat WorldToLocal matrices (column major). */
+int vh_set_camera_keys(vh_scene* s, const char* type, const float* from, int n_from, const float* to, int n_to, const float* roll, int n_roll,
+                       const float* up, const float* world_to_local, int n_mat, float fov, float focal, float aspect, float radius);
+/* Camera.decomp after PreRender: returns the number of keys; out (may be NULL) receives keys records. */
+int vh_camera_decomp(vh_scene* s, VgTransformSRT* out);
 /* nodes.Parse (nodes/parser.go:110-131): read a .vnf scene description (text in memory, or a file) and add its nodes in file
- * order, exactly like the vh_add_* calls would. In scope: Globals, Camera (single-key LookAt), ShaderStd (constant maps),
+ * order, exactly like the vh_add_* calls would. In scope: Globals, Camera (LookAt or Matrix, with motion keys), ShaderStd (constant maps),
  * PolyMesh, TriLight, DiskLight, SphereLight, Sphere, AiryFilter, GaussianFilter, OutputFloat, OutputHDR. Returns the number
  * of parse errors the reference would have printed (0 = clean; nodes that parsed are kept, like the reference keeps them),
  * or < 0 if the file cannot be read; vh_last_error holds the "<file>:<line>:<col>: message" lines. */

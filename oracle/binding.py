@@ -106,8 +106,13 @@ class Oracle:
             else:
                 raise ValueError("unknown light node %r" % kind)
         c = scene.camera
-        self._chk(L.orc_set_camera(h, _f3(c.From), _f3(c.To), _f3(c.Up), C.c_float(c.Roll), C.c_float(c.Fov), C.c_float(c.Focal),
-                                   C.c_float(c.Aspect), C.c_float(c.Radius)))
+        if getattr(c, "has_keys", False):
+            fr, to, ro, w2l = c.keys()
+            self._chk(L.orc_set_camera_keys(h, c.Type.encode(), _p(fr), len(fr), _p(to), len(to), _p(ro), len(ro), _f3(c.Up), _p(w2l), len(w2l),
+                                            C.c_float(c.Fov), C.c_float(c.Focal), C.c_float(c.Aspect), C.c_float(c.Radius)))
+        else:
+            self._chk(L.orc_set_camera(h, _f3(c.From), _f3(c.To), _f3(c.Up), C.c_float(c.Roll), C.c_float(c.Fov), C.c_float(c.Focal),
+                                       C.c_float(c.Aspect), C.c_float(c.Radius)))
         if getattr(scene, "filter", None) is not None:
             f = scene.filter
             airy = f.Type == "AiryFilter"
@@ -205,6 +210,12 @@ class Oracle:
         aidx = np.zeros(info["tris"], np.int32)
         self.L.orc_mesh_idxp(self.h, gid, _p(idxp), _p(aidx))
         return idxp, aidx
+
+    def camera_decomp(self):
+        """Camera.decomp: [keys, 23] float32."""
+        out = np.zeros((256, 23), np.float32)
+        n = self.L.orc_camera_decomp(self.h, _p(out))
+        return out[:n].copy()
 
     def camera_matrix(self):
         m = np.zeros(16, np.float32)

@@ -197,6 +197,36 @@ int orc_set_camera(void* h, const float* from, const float* to, const float* up,
   return 0;
 }
 
+// Camera with motion keys (camera.go:48-73): from/to = n points each, roll = n floats (nroll 0 = Roll unset), or
+// world_to_local = nmat column-major matrices for Type "Matrix".
+int orc_set_camera_keys(void* h, const char* type, const float* from, int nfrom, const float* to, int nto, const float* roll, int nroll,
+                        const float* up, const float* world_to_local, int nmat, float fov, float focal, float aspect, float radius) {
+  Handle* H = (Handle*)h;
+  Camera& c = H->r.camera;
+  c.Type = type;
+  c.FromKeys.clear(); c.ToKeys.clear(); c.RollKeys.clear(); c.WorldToLocal.clear();
+  for (int i = 0; i < nfrom; i++) c.FromKeys.push_back(v3(from + 3 * i));
+  for (int i = 0; i < nto; i++) c.ToKeys.push_back(v3(to + 3 * i));
+  for (int i = 0; i < nroll; i++) c.RollKeys.push_back(roll[i]);
+  for (int i = 0; i < nmat; i++) { Matrix4 m; std::memcpy(m.m, world_to_local + 16 * i, 64); c.WorldToLocal.push_back(m); }
+  if (nfrom > 0) c.From = c.FromKeys[0];
+  if (nto > 0) c.To = c.ToKeys[0];
+  c.Up = v3(up);
+  c.Fov = fov; c.Focal = focal; c.Aspect = aspect; c.Radius = radius;
+  return 0;
+}
+int orc_camera_decomp(void* h, float* out23 /* keys x 23 */) {
+  Handle* H = (Handle*)h;
+  const Camera& c = H->r.camera;
+  for (size_t i = 0; i < c.decomp.size(); i++) {
+    float* o = out23 + 23 * i;
+    for (int k = 0; k < 3; k++) o[k] = c.decomp[i].T[k];
+    o[3] = c.decomp[i].R.X; o[4] = c.decomp[i].R.Y; o[5] = c.decomp[i].R.Z; o[6] = c.decomp[i].R.W;
+    std::memcpy(o + 7, c.decomp[i].S.m, 64);
+  }
+  return (int)c.decomp.size();
+}
+
 // kind: 1 = AiryFilter (defaults Res 49, Width 6, Peak 4), 2 = GaussianFilter (Res 17, Width 2)  — builtin/filter/filter.go:14-26
 int orc_set_filter(void* h, int kind, float width, int res, float peak) {
   Handle* H = (Handle*)h;

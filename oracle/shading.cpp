@@ -758,22 +758,61 @@ static inline float degToRad(float deg) { return deg * kPi / 180.0f; }
 void Camera::PreRender(float frameAspect) {
   if (Aspect == 0.0f) Aspect = frameAspect;
   TanThetaFocal = Tan(degToRad(Fov / 2)) * Focal;
+  if (FromKeys.empty()) FromKeys.push_back(From);
+  if (ToKeys.empty()) ToKeys.push_back(To);
+  if (RollKeys.empty()) RollKeys.push_back(Roll);
+  LocalToWorld.clear();
+  decomp.clear();
+  if (Type == "LookAt") {
+    // camera.go:109-193 (calcLookatMatrices): one matrix per key of whichever of From / To has more keys; the other one and
+    // Roll are interpolated at time = i / keys (NOT i / (keys-1): kept)
+    const int nF = (int)FromKeys.size(), nT = (int)ToKeys.size(), nR = (int)RollKeys.size();
+    const bool byTarget = nT > nF;
+    const int n = byTarget ? nT : nF;
+    for (int i = 0; i < n; i++) {
+      float time = (float)i / (float)n;
+      Vec3 eye, tgt;
+      {
+        const std::vector<Vec3>& other = byTarget ? FromKeys : ToKeys;
+        float k = time * (float)((int)other.size() - 1);
+        float t = k - Floor(k);
+        int key = (int)Floor(k), key2 = (int)Ceil(k);
+        Vec3 P = Vec3Lerp(other[key], other[key2], t);
+        if (byTarget) { eye = P; tgt = ToKeys[i]; } else { eye = FromKeys[i]; tgt = P; }
+      }
+      Vec3 W = Vec3Normalize(Vec3Sub(eye, tgt));  // W points away from the target
+      Vec3 u = Vec3Normalize(Vec3Cross(Up, W));
+      Vec3 v = Vec3Normalize(Vec3Cross(u, W));
+      float roll = 0;
+      {
+        float k = time * (float)(nR - 1);
+        float t = k - Floor(k);
+        int key = (int)Floor(k), key2 = (int)Ceil(k);
+        roll = (1 - t) * RollKeys[key] + t * RollKeys[key2];
+      }
+      Vec3 U = Vec3Add(Vec3Scale(Cos(roll), u), Vec3Scale(Sin(roll), v));
+      Vec3 V = Vec3Add(Vec3Scale(-Sin(roll), u), Vec3Scale(Cos(roll), v));
+      LocalToWorld.push_back(Matrix4Mul(Matrix4Translate(eye[0], eye[1], eye[2]), Matrix4Basis(U, V, W)));
+    }
+  } else {
+    // camera.go:205-216 (matrixCalc)
+    for (const Matrix4& w2l : WorldToLocal) {
+      Matrix4 inv;
+      Matrix4Inverse(w2l, &inv);
+      LocalToWorld.push_back(inv);
+    }
+  }
+  for (const Matrix4& m : LocalToWorld) decomp.push_back(TransformDecompMatrix4(m));
+  M = MatrixAt(0.0f);
+}
 
-  float time = (float)0 / (float)1;
-  float k = time * (float)(1 - 1);
+// camera.go:225-236
+Matrix4 Camera::MatrixAt(float time) const {
+  if (decomp.empty()) return Matrix4Identity();
+  float k = time * (float)((int)decomp.size() - 1);
   float t = k - Floor(k);
-  Vec3 P = Vec3Lerp(To, To, t);
-  Vec3 W = Vec3Normalize(Vec3Sub(From, P));
-  Vec3 u = Vec3Normalize(Vec3Cross(Up, W));
-  Vec3 v = Vec3Normalize(Vec3Cross(u, W));
-  float roll = (1 - t) * Roll + t * Roll;
-  Vec3 U = Vec3Add(Vec3Scale(Cos(roll), u), Vec3Scale(Sin(roll), v));
-  Vec3 V = Vec3Add(Vec3Scale(-Sin(roll), u), Vec3Scale(Cos(roll), v));
-  Matrix4 mtx = Matrix4Mul(Matrix4Translate(From[0], From[1], From[2]), Matrix4Basis(U, V, W));
-  TransformDecomp decomp = TransformDecompMatrix4(mtx);
-  // camera.go:225-236 with len(decomp)==1: k = Time*0 = 0 for every ray, so M is a constant.
-  TransformDecomp trn = TransformDecompLerp(decomp, decomp, 0.0f);
-  M = TransformDecompToMatrix4(trn);
+  int key = (int)Floor(k), key2 = (int)Ceil(k);
+  return TransformDecompToMatrix4(TransformDecompLerp(decomp[key], decomp[key2], t));
 }
 
 // builtin/camera/camera.go:221-323 (differentials omitted)
@@ -783,6 +822,7 @@ void Camera::ComputeRay(float Sx, float Sy, double lensU, double lensV, const Sh
   Vec3 U = V3(1, 0, 0), V = V3(0, 1, 0), W = V3(0, 0, 1);
   Vec3 s = Vec3Sub(Vec3Add(Vec3Scale(camu, U), Vec3Scale(camv, V)), Vec3Scale(Focal, W));
   Vec3 D, P, d;
+  const Matrix4 M = decomp.size() > 1 ? MatrixAt(sc->Time) : this->M;
   if (Radius > 0.0f) {
     float x, y;
     UniformDisk2D(Radius, (float)lensU, (float)lensV, &x, &y);

@@ -109,13 +109,23 @@ struct SphereLight : Light {
 };
 
 struct Camera {
-  // LookAt, single motion key (camera motion is out of scope)
-  Vec3 From, To, Up;
-  float Roll = 0;
+  // Type "LookAt": From/To/Roll with any number of motion keys (param.PointArray / Float32Array); Type "Matrix":
+  // WorldToLocal matrices (camera.go:48-73,109-216)
+  std::string Type = "LookAt";
+  std::vector<Vec3> FromKeys, ToKeys;
+  std::vector<float> RollKeys;  // empty = Roll.Elems == nil
+  std::vector<Matrix4> WorldToLocal;
+  Vec3 Up;
   float Aspect = 0, Fov = 90, Focal = 12, Radius = 0;
   float TanThetaFocal = 0;
-  Matrix4 M;  // LocalToWorld after decompose/recompose (camera.go:188-192, 225-236)
+  std::vector<Matrix4> LocalToWorld;
+  std::vector<TransformDecomp> decomp;
+  // convenience for single-key LookAt cameras
+  Vec3 From, To;
+  float Roll = 0;
+  Matrix4 M;  // LocalToWorld at Time 0 after decompose/recompose (what every ray of a single-key camera uses)
   void PreRender(float frameAspect);
+  Matrix4 MatrixAt(float time) const;  // camera.go:225-236
   void ComputeRay(float Sx, float Sy, double lensU, double lensV, const ShaderContext* sc, Ray* ray) const;
 };
 

@@ -262,3 +262,26 @@ def test_pinned_host_buffers_take_the_direct_dma_path(built_library):
     assert dev.render(0, 6).tobytes() == part.tobytes()
     own = part.any(-1)
     assert 0.3 < own.mean() < 0.7 and np.array_equal(part[own], ref[own])
+
+
+# ---- Camera motion keys (camera.go:109-236): every camera ray recomposes LocalToWorld at its own Time ----------------------
+@pytest.mark.parametrize("variant", ["from3", "to4_from2", "roll", "matrix2"])
+def test_camera_motion_image(built_library, variant):
+    from vermeer_b200 import scenes
+    from vermeer_b200.host import Device, HostScene
+    sc = scenes.heightfield_scene(128, 96, nq=60)
+    static_cam = sc.camera
+    sc.camera = scenes.camera_motion_variants()[variant]
+    fo, so, fg, st, dev = _render_pair(sc, 16)
+    rmse, ok = _rmse(fo, fg)
+    assert ok.all()
+    # the per-ray quaternion slerp goes through another libm's acos/sin (like instance transform motion): tolerance, not bits
+    assert rmse <= 1e-3, rmse
+    assert np.median(np.abs(fo - fg)) <= 2e-6
+    assert abs(st["rays"] - so["rays"]) <= 1e-3 * so["rays"]
+    if variant != "roll":
+        # and the motion is really there: the same scene through the key-0 camera alone is a different image
+        sc.camera = static_cam
+        dev2 = Device(0).upload(HostScene(sc).prerender())
+        dev2.set_scramble(scenes.splitmix64_table(1, sc.XRes * sc.YRes))
+        assert _rmse(fo, dev2.render(0, 16))[0] > 10 * max(rmse, 1e-4)

@@ -102,3 +102,42 @@ def test_tile_partition_is_a_partition():
                 sizes.append(len(p))
             assert np.all(seen == 1)
             assert max(sizes) - min(sizes) <= 2 * 32 * 32 * (1 if world > 1 else 0) + 0 or world == 1
+
+
+@pytest.mark.parametrize("variant", ["from3", "to4_from2", "roll", "matrix2"])
+def test_camera_motion_keys_decompose_like_the_oracle(built_library, variant):
+    """Camera.PreRender with motion keys (camera.go:109-216): the host's LocalToWorld decompositions are bit-identical to the
+    oracle's, through the vh_* calls and through the .vnf reader."""
+    from oracle.binding import Oracle
+    from vermeer_b200 import scenes
+    from vermeer_b200.host import HostScene
+    sc = scenes.heightfield_scene(48, 32, nq=8)
+    sc.camera = scenes.camera_motion_variants()[variant]
+    want_keys = {"from3": 3, "to4_from2": 4, "roll": 1, "matrix2": 2}[variant]
+    o = Oracle(sc)
+    h = HostScene(sc).prerender()
+    do, dh = o.camera_decomp(), h.camera_decomp()
+    assert do.shape == (want_keys, 23) and np.isfinite(do).all()
+    assert do.tobytes() == dh.tobytes()
+    mo, ttf, asp = o.camera_matrix()
+    mh, ttf2, asp2 = h.camera()
+    assert mo.tobytes() == mh.tobytes() and ttf == ttf2 and asp == asp2
+    h2 = HostScene.from_vnf(scenes.to_vnf(sc)).prerender()
+    assert h2.camera_decomp().tobytes() == dh.tobytes()
+    assert h2.camera()[0].tobytes() == mh.tobytes()
+    if want_keys > 1:   # the keys differ: the camera really moves
+        assert not np.array_equal(do[0], do[-1])
+
+
+def test_matrix_camera_without_keys_is_the_identity(built_library):
+    """A non-LookAt camera with no WorldToLocal: c.decomp is nil and ComputeRay keeps Matrix4Identity (camera.go:223-236)."""
+    from oracle.binding import Oracle
+    from vermeer_b200 import scenes
+    from vermeer_b200.host import HostScene
+    sc = scenes.heightfield_scene(48, 32, nq=8)
+    sc.camera = scenes.Camera(From=(0, 0, 0), To=(0, 0, -1), Type="Matrix", Fov=50.0, Focal=1.0)
+    h = HostScene(sc).prerender()
+    o = Oracle(sc)
+    assert h.camera_decomp().shape[0] == 0 and o.camera_decomp().shape[0] == 0
+    assert np.array_equal(h.camera()[0], np.eye(4, dtype=np.float32).reshape(-1))
+    assert np.array_equal(o.camera_matrix()[0], np.eye(4, dtype=np.float32).reshape(-1))

@@ -86,7 +86,7 @@ void vg_destroy(vg_ctx* ctx) {
   ctx->d_nodes.release(); ctx->d_mtopo.release(); ctx->d_mboxes.release(); ctx->d_tris.release();
   ctx->d_mtris.release(); ctx->d_normals.release(); ctx->d_geoms.release(); ctx->d_prim_material.release();
   ctx->d_xforms.release(); ctx->d_xf_keys.release(); ctx->d_xf_static.release();
-  ctx->d_rays.release(); ctx->d_hits.release(); ctx->d_counters.release();
+  ctx->d_rays.release(); ctx->d_hits.release(); ctx->d_counters.release(); ctx->d_cam_keys.release();
   for (int i = 0; i < 3; i++) {
     if (ctx->pipe_stream[i]) cudaStreamDestroy(ctx->pipe_stream[i]);
     if (ctx->pipe_done[i]) cudaEventDestroy(ctx->pipe_done[i]);
@@ -557,6 +557,24 @@ int vg_set_camera(vg_ctx* ctx, const VgCamera* cam) {
   if (!cam) return ctx->fail(VG_ERR_INVALID, "vg_set_camera: null");
   ctx->camera = *cam;
   ctx->have_camera = true;
+  ctx->cam_nkeys = 0;
+  return VG_OK;
+}
+
+int vg_set_camera_motion(vg_ctx* ctx, const VgCamera* cam, const VgTransformSRT* decomp, int keys) {
+  VG_LOCK(ctx);
+  if (!cam) return ctx->fail(VG_ERR_INVALID, "vg_set_camera_motion: null");
+  if (keys < 0 || keys > 255 || (keys > 0 && !decomp)) return ctx->fail(VG_ERR_INVALID, "vg_set_camera_motion: bad keys");
+  static_assert(sizeof(VgTransformSRT) == sizeof(vg::XfSRT), "VgTransformSRT is m.TransformDecomp's 23 floats");
+  ctx->camera = *cam;
+  ctx->have_camera = true;
+  ctx->cam_nkeys = keys > 1 ? keys : 0;
+  if (keys > 1) {
+    VG_CUDA(ctx, cudaSetDevice(ctx->device));
+    VG_CUDA(ctx, ctx->d_cam_keys.reserve((size_t)keys));
+    VG_CUDA(ctx, cudaMemcpyAsync(ctx->d_cam_keys.p, decomp, (size_t)keys * sizeof(vg::XfSRT), cudaMemcpyHostToDevice, ctx->stream));
+    VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   return VG_OK;
 }
 

@@ -108,6 +108,8 @@ struct vg_ctx {
   std::vector<VgLight> lights;
   VgCamera camera{};
   bool have_camera = false;
+  vg::DevBuf<vg::XfSRT> d_cam_keys;  // Camera.decomp when the camera has motion keys (vg_set_camera_motion)
+  int cam_nkeys = 0;
   int xres = 0, yres = 0;
   int rank = 0, world = 1;
   std::vector<uint64_t> scramble;  // full frame, npix*6

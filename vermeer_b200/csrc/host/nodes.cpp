@@ -176,50 +176,72 @@ VgTransformSRT transform_decomp(M4 mtx) {
 
 // ---- Camera (builtin/camera/camera.go:80-98,109-193; ComputeRay's matrix :225-236) ----------------
 int Camera::PreRender(Core& core, std::string* err) {
-  if (Type != "LookAt") { *err = "Camera: only Type \"LookAt\" is supported on this path"; return -1; }
   if (Aspect == 0.0f) Aspect = core.FrameAspect();
   const float deg = Fov / 2;
   const float tan_theta_focal = (float)std::tan((double)(deg * kPi32 / 180.0f)) * Focal;
-
-  // single motion key: camera.go:154-187 with i = 0 (time = 0, t = 0)
-  const float t = 0.0f;
-  const V3 P = lerp(To, To, t);
-  const V3 W = normalize(From - P);  // W points away from the target
-  const V3 u = normalize(cross(Up, W));
-  const V3 v = normalize(cross(u, W));
-  const float roll = (1 - t) * Roll + t * Roll;
-  const float cr = (float)std::cos((double)roll), sr = (float)std::sin((double)roll);
-  const V3 U = scale(cr, u) + scale(sr, v);
-  const V3 V = scale(-sr, u) + scale(cr, v);
-  M4 basis{};
-  basis.m[0] = U.x; basis.m[1] = U.y; basis.m[2] = U.z;
-  basis.m[4] = V.x; basis.m[5] = V.y; basis.m[6] = V.z;
-  basis.m[8] = W.x; basis.m[9] = W.y; basis.m[10] = W.z;
-  basis.m[15] = 1.0f;
-  M4 trans = m4_identity();
-  trans.m[12] = From.x; trans.m[13] = From.y; trans.m[14] = From.z;
-  M4 mtx = m4_mul(trans, basis);
-
-  // math/animdecomp.go:21-63: M = T * R * S via polar decomposition, then recomposed per ray with
-  // k = Time*(len(decomp)-1) = 0 (camera.go:225-236) -> constant for a single-key camera.
-  const float sign = m4_det(mtx) >= 0.0f ? 1.0f : -1.0f;
-  V3 T{mtx.at(0, 3), mtx.at(1, 3), mtx.at(2, 3)};
-  mtx.set(0, 3, 0); mtx.set(1, 3, 0); mtx.set(2, 3, 0);
-  if (sign < 0.0f) mtx = m4_mul(m4_scale(-1, m4_identity()), mtx);
-  Quat R{0, 0, 0, 1};
-  M4 S = m4_identity();
-  M4 Q;
-  if (polar_factor(mtx, &Q)) {
-    S = m4_mul(m4_transpose(Q), mtx);
-    R = to_quat(Q);
-    if (sign < 0.0f) { S = m4_mul(m4_scale(-1, m4_identity()), S); S.m[15] = 1; }
+  if (FromKeys.empty()) FromKeys.push_back(From);
+  if (ToKeys.empty()) ToKeys.push_back(To);
+  if (RollKeys.empty()) RollKeys.push_back(Roll);
+  std::vector<M4> l2w;
+  if (Type == "LookAt") {
+    // calcLookatMatrices (camera.go:109-193): one matrix per key of whichever of From / To has more keys; the other one and Roll
+    // are interpolated at time = i / keys
+    const int nF = (int)FromKeys.size(), nT = (int)ToKeys.size(), nR = (int)RollKeys.size();
+    const bool byTarget = nT > nF;
+    const int n = byTarget ? nT : nF;
+    for (int i = 0; i < n; i++) {
+      const float time = (float)i / (float)n;
+      const std::vector<V3>& other = byTarget ? FromKeys : ToKeys;
+      const float k = time * (float)((int)other.size() - 1);
+      const float t = k - floorf(k);
+      const V3 P = lerp(other[(int)floorf(k)], other[(int)ceilf(k)], t);
+      const V3 eye = byTarget ? P : FromKeys[i], tgt = byTarget ? ToKeys[i] : P;
+      const V3 W = normalize(eye - tgt);  // W points away from the target
+      const V3 u = normalize(cross(Up, W));
+      const V3 v = normalize(cross(u, W));
+      const float kr = time * (float)(nR - 1);
+      const float tr = kr - floorf(kr);
+      const float roll = (1 - tr) * RollKeys[(int)floorf(kr)] + tr * RollKeys[(int)ceilf(kr)];
+      const float cr = (float)std::cos((double)roll), sr = (float)std::sin((double)roll);
+      const V3 U = scale(cr, u) + scale(sr, v);
+      const V3 V = scale(-sr, u) + scale(cr, v);
+      M4 basis{};
+      basis.m[0] = U.x; basis.m[1] = U.y; basis.m[2] = U.z;
+      basis.m[4] = V.x; basis.m[5] = V.y; basis.m[6] = V.z;
+      basis.m[8] = W.x; basis.m[9] = W.y; basis.m[10] = W.z;
+      basis.m[15] = 1.0f;
+      M4 trans = m4_identity();
+      trans.m[12] = eye.x; trans.m[13] = eye.y; trans.m[14] = eye.z;
+      l2w.push_back(m4_mul(trans, basis));
+    }
+  } else {
+    // matrixCalc (camera.go:205-216): every Type other than "LookAt" is a matrix camera (camera.go:91-95); a singular
+    // WorldToLocal inverts to the null matrix (matrix4.go:134-147)
+    for (const M4& w2l : WorldToLocal) {
+      M4 inv{};
+      m4_inverse(w2l, &inv);
+      l2w.push_back(inv);
+    }
   }
-  const V3 Tl = lerp(T, T, 0.0f);
-  const Quat Rl = slerp(R, R, 0.0f);
-  const M4 Sl = m4_lerp(S, S, 0.0f);
-  M4 tl = m4_identity();
-  tl.m[12] = Tl.x; tl.m[13] = Tl.y; tl.m[14] = Tl.z;
-  const M4 M = m4_mul(tl, m4_mul(from_quat(Rl), Sl));
+  if (l2w.size() > 255) { *err = "Camera: more than 255 motion keys"; return -1; }
+  decomp.clear();
+  for (const M4& m : l2w) decomp.push_back(transform_decomp(m));
+
+  // ComputeRay's matrix (camera.go:225-236) at Time 0 — what every ray of a single-key camera uses: Lerp(d0, d0, 0) recomposed;
+  // no keys at all (a matrix camera without WorldToLocal): c.decomp == nil and M stays the identity
+  M4 M = m4_identity();
+  if (!decomp.empty()) {
+    const VgTransformSRT& d0 = decomp[0];
+    const V3 Tl = lerp(V3{d0.T[0], d0.T[1], d0.T[2]}, V3{d0.T[0], d0.T[1], d0.T[2]}, 0.0f);
+    const Quat R0{d0.R[0], d0.R[1], d0.R[2], d0.R[3]};
+    const Quat Rl = slerp(R0, R0, 0.0f);
+    M4 S0;
+    std::memcpy(S0.m, d0.S, sizeof(S0.m));
+    const M4 Sl = m4_lerp(S0, S0, 0.0f);
+    M4 tl = m4_identity();
+    tl.m[12] = Tl.x; tl.m[13] = Tl.y; tl.m[14] = Tl.z;
+    M = m4_mul(tl, m4_mul(from_quat(Rl), Sl));
+  }
 
   std::memcpy(out.local_to_world, M.m, sizeof(M.m));
   out.tan_theta_focal = tan_theta_focal;

@@ -179,8 +179,12 @@ struct Camera : Node {
   std::string Type = "LookAt";
   V3 From{}, To{}, Up{0, 1, 0};
   float Roll = 0;
+  std::vector<V3> FromKeys, ToKeys;   // motion keys of From / To (empty: the single From / To above)
+  std::vector<float> RollKeys;
+  std::vector<M4> WorldToLocal;       // Type "Matrix"
   float Aspect = 0, Fov = 90, Focal = 12, Radius = 0;  // camera.go:325-335 defaults
-  VgCamera out{};
+  VgCamera out{};                     // single-key matrix (Time 0)
+  std::vector<VgTransformSRT> decomp; // c.decomp: one per LocalToWorld key (camera.go:188-192)
   std::string Name() const override { return NodeName; }
   int PreRender(Core& core, std::string* err) override;
 };

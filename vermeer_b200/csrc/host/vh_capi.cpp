@@ -214,6 +214,36 @@ int vh_set_camera_lookat(vh_scene* s, const float* from, const float* to, const 
   return VG_OK;
 }
 
+int vh_set_camera_keys(vh_scene* s, const char* type, const float* from, int n_from, const float* to, int n_to, const float* roll, int n_roll,
+                       const float* up, const float* world_to_local, int n_mat, float fov, float focal, float aspect, float radius) {
+  if (!s || !type || !up) return fail(s, VG_ERR_INVALID, "vh_set_camera_keys: null argument");
+  if (n_from < 0 || n_to < 0 || n_roll < 0 || n_mat < 0 || (n_from > 0 && !from) || (n_to > 0 && !to) || (n_roll > 0 && !roll) ||
+      (n_mat > 0 && !world_to_local))
+    return fail(s, VG_ERR_INVALID, "vh_set_camera_keys: bad key arrays");
+  if (std::string(type) == "LookAt" && (n_from < 1 || n_to < 1)) return fail(s, VG_ERR_INVALID, "vh_set_camera_keys: a LookAt camera needs From and To");
+  std::unique_ptr<Node> h;
+  Camera* c = make<Camera>(s, "Camera", &h);
+  if (!c) return VG_ERR_INVALID;
+  c->Type = type;
+  for (int i = 0; i < n_from; i++) c->FromKeys.push_back(v3(from + 3 * i));
+  for (int i = 0; i < n_to; i++) c->ToKeys.push_back(v3(to + 3 * i));
+  for (int i = 0; i < n_roll; i++) c->RollKeys.push_back(roll[i]);
+  for (int i = 0; i < n_mat; i++) {
+    M4 m;
+    std::memcpy(m.m, world_to_local + 16 * i, sizeof(m.m));
+    c->WorldToLocal.push_back(m);
+  }
+  if (n_from > 0) c->From = c->FromKeys[0];
+  if (n_to > 0) c->To = c->ToKeys[0];
+  c->Up = v3(up);
+  c->Fov = fov;
+  c->Focal = focal;
+  c->Aspect = aspect;
+  c->Radius = radius;
+  s->core.AddNode(std::move(h));
+  return VG_OK;
+}
+
 int vh_parse_vnf(vh_scene* s, const char* text, size_t len, const char* filename) {
   if (!s || (!text && len > 0)) return fail(s, VG_ERR_INVALID, "vh_parse_vnf: null argument");
   std::string msgs;
@@ -339,7 +369,7 @@ int vh_upload(vh_scene* s, vg_ctx* ctx, int motion_ref_compat) {
   std::string camName = c.globals->Camera.empty() ? "camera" : c.globals->Camera;
   Camera* cam = dynamic_cast<Camera*>(c.FindNode(camName));
   if (cam) {
-    if ((rc = chk(vg_set_camera(ctx, &cam->out))) != VG_OK) return rc;
+    if ((rc = chk(vg_set_camera_motion(ctx, &cam->out, cam->decomp.data(), (int)cam->decomp.size()))) != VG_OK) return rc;
   }
   return VG_OK;
 }
@@ -413,6 +443,15 @@ int vh_camera(vh_scene* s, VgCamera* out) {
   if (!cam) return fail(s, VG_ERR_INVALID, "no camera node");
   *out = cam->out;
   return VG_OK;
+}
+int vh_camera_decomp(vh_scene* s, VgTransformSRT* out) {
+  if (!s) return VG_ERR_INVALID;
+  Core& c = s->core;
+  std::string camName = c.globals->Camera.empty() ? "camera" : c.globals->Camera;
+  Camera* cam = dynamic_cast<Camera*>(c.FindNode(camName));
+  if (!cam) return fail(s, VG_ERR_INVALID, "no camera node");
+  if (out) std::memcpy(out, cam->decomp.data(), cam->decomp.size() * sizeof(VgTransformSRT));
+  return (int)cam->decomp.size();
 }
 
 }  // extern "C"

@@ -473,12 +473,26 @@ std::string build_node(Core& core, const std::string& type, std::map<std::string
     Camera* c = static_cast<Camera*>(h.get());
     c->NodeName = f["Name"].s;
     c->Type = f["Type"].s;
+    // From / To / Roll keep their motion keys; calcLookatMatrices indexes Elems[key] (camera.go:109-193), i.e. one element per key
     const Value &from = f["From"], &to = f["To"], &roll = f["Roll"];
-    if (from.MotionKeys > 1 || to.MotionKeys > 1 || roll.MotionKeys > 1) return "Camera: motion keys are outside this path (single-key LookAt cameras only)";
-    if (from.elems.size() < 3 || to.elems.size() < 3) return "Camera: From/To need one point";
-    c->From = v3of(from.elems.data());
-    c->To = v3of(to.elems.data());
-    c->Roll = roll.elems.empty() ? 0.0f : roll.elems[0];
+    const int nF = from.MotionKeys == 0 ? 1 : from.MotionKeys, nT = to.MotionKeys == 0 ? 1 : to.MotionKeys;
+    const int nR = roll.MotionKeys == 0 ? 1 : roll.MotionKeys;
+    if (c->Type == "LookAt" && (from.elems.size() < (size_t)3 * nF || to.elems.size() < (size_t)3 * nT)) return "Camera: From/To need one point per motion key";
+    for (int i = 0; i < nF && (size_t)3 * (i + 1) <= from.elems.size(); i++) c->FromKeys.push_back(v3of(from.elems.data() + 3 * i));
+    for (int i = 0; i < nT && (size_t)3 * (i + 1) <= to.elems.size(); i++) c->ToKeys.push_back(v3of(to.elems.data() + 3 * i));
+    for (int i = 0; i < nR && (size_t)(i + 1) <= roll.elems.size(); i++) c->RollKeys.push_back(roll.elems[i]);
+    if (!c->FromKeys.empty()) c->From = c->FromKeys[0];
+    if (!c->ToKeys.empty()) c->To = c->ToKeys[0];
+    c->Roll = c->RollKeys.empty() ? 0.0f : c->RollKeys[0];
+    if (has("WorldToLocal")) {
+      const Value& w = f["WorldToLocal"];
+      for (size_t m = 0; m + 16 <= w.elems.size(); m += 16) {
+        M4 mm;
+        std::memcpy(mm.m, &w.elems[m], sizeof(mm.m));
+        c->WorldToLocal.push_back(mm);
+      }
+    }
+    if (has("LocalToWorld")) return "Camera: a LocalToWorld given in the file (PreRender appends to it) is outside this path";
     c->Up = v3of(f["Up"].c);
     if (has("Aspect")) c->Aspect = (float)f["Aspect"].f;
     if (has("Fov")) c->Fov = (float)f["Fov"].f;

@@ -62,6 +62,8 @@ struct RenderParams {
   const uint64_t* scr;      // [nown*6] rows in path order, or (scr_by_pixel) the caller's whole table [xres*yres*6] in raster order
   int scr_by_pixel;
   VgCamera cam;
+  const vg::XfSRT* cam_keys;  // Camera.decomp, one per LocalToWorld motion key (camera.go:188-192); cam_nkeys <= 1: cam.local_to_world
+  int cam_nkeys;
   const DevMat* mats;
   const DevLight* lights;
   int nlights, S, levels, trace_last_level;
@@ -138,6 +140,8 @@ __device__ inline void warp_sample(const double* cdfV, const double* cdfVU, int 
 }
 
 // core/render.go:89-124 + builtin/camera/camera.go:221-323 (differentials omitted)
+// MOTION: the camera has several motion keys and every ray recomposes its LocalToWorld at its own Time (camera.go:225-236).
+template <bool MOTION>
 __global__ void __launch_bounds__(256) k_raygen(const RenderParams p, int iter_base, int niters) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.nown * niters) return;
@@ -163,6 +167,13 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderParams p, int iter_b
   const float Sy = -(float)(-1.0 + 2.0 * (rasterY / (double)p.yres));
 
   const float* M = p.cam.local_to_world;
+  vg::Mat4 Mt;
+  if (MOTION) {
+    const float k = (float)time * (float)(p.cam_nkeys - 1);
+    const float fk = floorf(k);
+    Mt = vg::srt_to_m4(vg::srt_lerp(p.cam_keys[(int)fk], p.cam_keys[(int)ceilf(k)], k - fk));
+    M = Mt.m;
+  }
   const float camu = Sx * p.cam.tan_theta_focal;
   const float camv = Sy * (p.cam.tan_theta_focal / p.cam.aspect);
   // s = camu*U + camv*V - Focal*W with the canonical basis (camera.go:248-252); the products with 0/1 are exact
@@ -1209,7 +1220,7 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
   std::memset(&p, 0, sizeof(p));
   p.sc = ctx->dev;
   p.xres = ctx->xres; p.yres = ctx->yres; p.nown = rs.nown; p.P = rs.P;
-  p.pix = rs.pix.p; p.qmc = rs.qmc.p; p.scr = rs.scr.p; p.scr_by_pixel = rs.scr_by_pixel ? 1 : 0; p.cam = ctx->camera; p.mats = rs.mats.p; p.lights = rs.lights.p;
+  p.pix = rs.pix.p; p.qmc = rs.qmc.p; p.scr = rs.scr.p; p.scr_by_pixel = rs.scr_by_pixel ? 1 : 0; p.cam = ctx->camera; p.cam_keys = ctx->d_cam_keys.p; p.cam_nkeys = ctx->cam_nkeys; p.mats = rs.mats.p; p.lights = rs.lights.p;
   p.filter_cdf = ctx->filter_n > 0 ? rs.filter.p : nullptr; p.filter_n = ctx->filter_n; p.filter_w = ctx->filter_w;
   p.nlights = rs.nlights; p.S = rs.S; p.levels = rs.levels; p.trace_last_level = ctx->opt_trace_last_level;
   p.nlobes = rs.nlobes;
@@ -1236,7 +1247,8 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
         RCUDA(cudaMemsetAsync(rs.L.p, 0, (size_t)rs.P * rs.levels * sizeof(float4), st));
         RCUDA(cudaMemsetAsync(rs.T.p, 0, (size_t)rs.P * rs.levels * sizeof(float4), st));
       }
-      k_raygen<<<(np + 255) / 256, 256, 0, st>>>(p, ib, niters);
+      if (p.cam_nkeys > 1) k_raygen<true><<<(np + 255) / 256, 256, 0, st>>>(p, ib, niters);
+      else k_raygen<false><<<(np + 255) / 256, 256, 0, st>>>(p, ib, niters);
       launches += 2;
       int qin = 0;
       // levels 0..3 are shaded; with trace_last_level the level-4 rays are traced (and counted) but not shaded

@@ -28,11 +28,11 @@ VG_TRACE_ANY_HIT = 1
 # every symbol include/vermeer_gpu.h declares (tests check the library exports all of them)
 DECLARED_SYMBOLS = [
     "vg_create", "vg_destroy", "vg_last_error", "vg_device_count", "vg_scene_begin", "vg_mesh_upload", "vg_mesh_upload_motion",
-    "vg_sphere_upload", "vg_instance_upload", "vg_scene_upload", "vg_scene_upload_motion", "vg_scene_commit", "vg_set_materials", "vg_set_lights", "vg_set_area_lights", "vg_set_camera", "vg_set_frame",
+    "vg_sphere_upload", "vg_instance_upload", "vg_scene_upload", "vg_scene_upload_motion", "vg_scene_commit", "vg_set_materials", "vg_set_lights", "vg_set_area_lights", "vg_set_camera", "vg_set_camera_motion", "vg_set_frame",
     "vg_set_partition", "vg_set_scramble", "vg_set_filter", "vg_set_option", "vg_trace_batch", "vg_trace_batch_device", "vg_render", "vg_clear_framebuffer",
     "vg_framebuffer_device", "vg_get_stats", "vg_reset_stats",
     "vh_scene_create", "vh_scene_destroy", "vh_last_error", "vh_registered_nodes", "vh_set_globals", "vh_add_shader_std", "vh_add_polymesh",
-    "vh_add_filter", "vh_add_instance", "vh_add_trilight", "vh_add_disklight", "vh_add_spherelight", "vh_parse_vnf", "vh_load_vnf", "vh_globals", "vh_postrender", "vh_rgbe", "vh_set_camera_lookat", "vh_prerender", "vh_upload", "vh_num_geoms", "vh_scene_info", "vh_scene_nodes",
+    "vh_add_filter", "vh_add_instance", "vh_add_trilight", "vh_add_disklight", "vh_add_spherelight", "vh_parse_vnf", "vh_load_vnf", "vh_globals", "vh_postrender", "vh_rgbe", "vh_set_camera_lookat", "vh_set_camera_keys", "vh_camera_decomp", "vh_prerender", "vh_upload", "vh_num_geoms", "vh_scene_info", "vh_scene_nodes",
     "vh_scene_motion_nodes", "vh_scene_geom_order", "vh_mesh_info", "vh_mesh_nodes", "vh_mesh_motion_nodes", "vh_mesh_idxp", "vh_camera",
 ]
 
@@ -150,8 +150,13 @@ class HostScene:
             f = scene.filter
             self._chk(L.vh_add_filter(h, f.Type.encode(), f.Name.encode(), C.c_float(f.Width or 0), int(f.Res or 0), C.c_float(f.Peak or 0)))
         c = scene.camera
-        self._chk(L.vh_set_camera_lookat(h, _f3(c.From), _f3(c.To), _f3(c.Up), C.c_float(c.Roll), C.c_float(c.Fov), C.c_float(c.Focal),
-                                         C.c_float(c.Aspect), C.c_float(c.Radius)))
+        if getattr(c, "has_keys", False):
+            fr, to, ro, w2l = c.keys()
+            self._chk(L.vh_set_camera_keys(h, c.Type.encode(), _p(fr), len(fr), _p(to), len(to), _p(ro), len(ro), _f3(c.Up), _p(w2l), len(w2l),
+                                           C.c_float(c.Fov), C.c_float(c.Focal), C.c_float(c.Aspect), C.c_float(c.Radius)))
+        else:
+            self._chk(L.vh_set_camera_lookat(h, _f3(c.From), _f3(c.To), _f3(c.Up), C.c_float(c.Roll), C.c_float(c.Fov), C.c_float(c.Focal),
+                                             C.c_float(c.Aspect), C.c_float(c.Radius)))
 
     @classmethod
     def from_vnf(cls, text: str | None = None, path: str | None = None, strict: bool = True):
@@ -254,6 +259,16 @@ class HostScene:
         c = VgCamera()
         self._chk(self.L.vh_camera(self.h, C.byref(c)))
         return np.asarray(c.local_to_world[:], np.float32), c.tan_theta_focal, c.aspect
+
+    def camera_decomp(self):
+        """Camera.decomp after PreRender: [keys, 23] float32 (T, R{X,Y,Z,W}, S column major)."""
+        n = self.L.vh_camera_decomp(self.h, None)
+        if n < 0:
+            raise RuntimeError("vh_camera_decomp: %s" % self.L.vh_last_error(self.h).decode())
+        out = np.zeros((n, 23), np.float32)
+        if n:
+            self.L.vh_camera_decomp(self.h, _p(out))
+        return out
 
 
 class Device:

@@ -23,7 +23,7 @@ from typing import List, Optional
 import numpy as np
 
 __all__ = [
-    "ShaderStd", "PolyMesh", "GeomInstance", "matrix4", "srt_matrix", "TriLight", "DiskLight", "SphereLight", "Camera", "PixelFilter", "SceneDesc", "splitmix64_table",
+    "ShaderStd", "PolyMesh", "GeomInstance", "matrix4", "srt_matrix", "TriLight", "DiskLight", "SphereLight", "Camera", "PixelFilter", "SceneDesc", "splitmix64_table", "camera_motion_variants",
     "heightfield_mesh", "heightfield_scene", "sphere_field_scene", "cornell_box", "glossy_box", "instanced_scene", "incoherent_rays", "to_vnf",
 ]
 
@@ -169,6 +169,23 @@ class Camera:
     Radius: float = 0.0
     Name: str = "camera"
     Type: str = "LookAt"
+    # motion keys (camera.go:48-73): lists of points / floats / 4x4 column-major matrices; None = the single From / To / Roll above
+    FromKeys: Optional[list] = None
+    ToKeys: Optional[list] = None
+    RollKeys: Optional[list] = None
+    WorldToLocal: Optional[list] = None   # Type "Matrix"
+
+    def keys(self):
+        """(from points, to points, rolls, matrices) as float32 arrays, one row per motion key."""
+        fr = np.asarray(self.FromKeys if self.FromKeys else [self.From], np.float32).reshape(-1, 3)
+        to = np.asarray(self.ToKeys if self.ToKeys else [self.To], np.float32).reshape(-1, 3)
+        ro = np.asarray(self.RollKeys if self.RollKeys else [self.Roll], np.float32).reshape(-1)
+        w2l = np.asarray(self.WorldToLocal if self.WorldToLocal else [], np.float32).reshape(-1, 16)
+        return fr, to, ro, w2l
+
+    @property
+    def has_keys(self):
+        return bool(self.FromKeys or self.ToKeys or self.RollKeys or self.WorldToLocal) or self.Type != "LookAt"
 
 
 @dataclass
@@ -276,8 +293,13 @@ def to_vnf(sc: "SceneDesc", outputs=()) -> str:
             parts.append("Peak %s" % _num(f.Peak))
         o.append("%s { %s }" % (f.Type, " ".join(parts)))
     c = sc.camera
-    cam = ['Name "%s"' % c.Name, 'Type "%s"' % c.Type, "From 1 1 point %s" % _vec(c.From), "To 1 1 point %s" % _vec(c.To),
-           "Roll 1 1 float %s" % _num(c.Roll), "Up %s" % _vec(c.Up), "Fov %s" % _num(c.Fov), "Focal %s" % _num(c.Focal)]
+    fr, to, ro, w2l = c.keys()
+    cam = ['Name "%s"' % c.Name, 'Type "%s"' % c.Type, "From %d 1 point %s" % (len(fr), " ".join(_vec(v) for v in fr)),
+           "To %d 1 point %s" % (len(to), " ".join(_vec(v) for v in to)), "Roll %d 1 float %s" % (len(ro), " ".join(_num(v) for v in ro)),
+           "Up %s" % _vec(c.Up), "Fov %s" % _num(c.Fov), "Focal %s" % _num(c.Focal)]
+    if len(w2l):
+        # the file holds matrices row major (parser.go:487 transposes on read)
+        cam.append("WorldToLocal %d matrix %s" % (len(w2l), _vec(w2l.reshape(-1, 4, 4).transpose(0, 2, 1).reshape(-1))))
     if c.Aspect:
         cam.append("Aspect %s" % _num(c.Aspect))
     if c.Radius:
@@ -573,4 +595,31 @@ def incoherent_rays(rays: np.ndarray, hits: np.ndarray, seed: int = 7) -> np.nda
     out["d"] = dn.astype(np.float32)
     out["tmax"] = np.float32(np.inf)
     out["time"] = rays["time"][mask]
+    return out
+
+
+def camera_motion_variants():
+    """Camera nodes with motion keys (camera.go:48-73) for the heightfield / Cornell framing: name -> Camera.
+    'from3': three From keys, fixed target; 'to4_from2': more To keys than From keys (the other calcLookatMatrices branch, where the
+    eye is the interpolated From); 'roll': two Roll keys and a lens radius; 'matrix2': Type "Matrix" with two WorldToLocal keys."""
+    base = dict(Fov=50.0, Focal=1.0)
+    out = {
+        "from3": Camera(From=(0.0, 1.25, 2.1), To=(0.0, 0.0, 0.0), FromKeys=[(-0.25, 1.25, 2.1), (0.0, 1.3, 2.0), (0.3, 1.2, 2.15)], **base),
+        "to4_from2": Camera(From=(0.0, 1.25, 2.1), To=(0.0, 0.0, 0.0), FromKeys=[(-0.1, 1.25, 2.1), (0.1, 1.25, 2.1)],
+                            ToKeys=[(0.0, 0.0, 0.0), (0.05, 0.02, 0.0), (0.1, 0.0, 0.05), (0.12, 0.0, 0.1)], **base),
+        "roll": Camera(From=(0.0, 1.25, 2.1), To=(0.0, 0.0, 0.0), RollKeys=[-0.1, 0.15], Radius=0.01, **base),
+    }
+    # two rigid world-to-camera matrices: local-to-world = T(eye) * Ry(yaw) * Rx(-pitch) (the camera looks down its local -z),
+    # yaw -4 and +4 degrees; WorldToLocal is the inverse, rounded to float32
+    pitch = np.arctan2(1.25, 2.1)
+    cp, sp = np.cos(-pitch), np.sin(-pitch)
+    rx = np.array([[1, 0, 0, 0], [0, cp, -sp, 0], [0, sp, cp, 0], [0, 0, 0, 1]], np.float64)
+    t = np.eye(4)
+    t[:3, 3] = (0.0, 1.25, 2.1)
+    mats = []
+    for deg in (-4.0, 4.0):
+        a = np.deg2rad(deg)
+        ry = np.array([[np.cos(a), 0, np.sin(a), 0], [0, 1, 0, 0], [-np.sin(a), 0, np.cos(a), 0], [0, 0, 0, 1]], np.float64)
+        mats.append(matrix4(np.linalg.inv(t @ ry @ rx)))
+    out["matrix2"] = Camera(From=(0.0, 0.0, 0.0), To=(0.0, 0.0, -1.0), Type="Matrix", WorldToLocal=mats, **base)
     return out
