@@ -40,10 +40,12 @@ CONFIGS = {
     "c3": dict(workload="C3: 10M-triangle displaced-sphere field (1024 meshes x 9800 tris), mirror chains, 1920x1080, 256 spp", spp=256),
     # configs[3]: motion-blurred mesh (MQBVH, 2 keys)
     "c4": dict(workload="C4: motion-blurred 1M-triangle heightfield (MQBVH, 2 keys), 1920x1080, 64 spp", spp=64),
+    # configs[4]: the C3 scene at 4K, 1024 spp, meant for 8 GPUs (tile-partitioned, NCCL framebuffer gather)
+    "c5": dict(workload="C5: 10M-triangle displaced-sphere field, mirror chains, 3840x2160, 1024 spp", spp=1024, xres=3840, yres=2160),
 }
 CONFIG = os.environ.get("VG_BENCH_CONFIG", "c2")
 WORKLOAD = CONFIGS[CONFIG]["workload"]
-XRES, YRES, SPP, NQ = 1920, 1080, CONFIGS[CONFIG]["spp"], 708
+XRES, YRES, SPP, NQ = CONFIGS[CONFIG].get("xres", 1920), CONFIGS[CONFIG].get("yres", 1080), CONFIGS[CONFIG]["spp"], 708
 SCRAMBLE_SEED = 1
 ITERS_PER_BATCH = 16   # wavefront batch depth at N=1; scaled by N (capped at the frame's spp) so that a batch keeps ~33 M paths per GPU
 
@@ -104,7 +106,7 @@ class ClockSampler:
 
 def build_scene():
     from vermeer_b200 import scenes
-    if CONFIG == "c3":
+    if CONFIG in ("c3", "c5"):
         return scenes.sphere_field_scene(XRES, YRES)
     return scenes.heightfield_scene(XRES, YRES, nq=NQ, motion=(CONFIG == "c4"))
 
@@ -250,7 +252,8 @@ def run_ours(args):
     dev.upload(host)
     dev.set_partition(rank, world)
     dev.set_scramble(table)
-    iters_per_batch = min(SPP, ITERS_PER_BATCH * world)
+    # ~33 M paths per GPU and batch whatever the frame size and world
+    iters_per_batch = min(SPP, max(1, round(ITERS_PER_BATCH * world * (1920 * 1080) / (XRES * YRES))))
     dev.set_option("iters_per_batch", iters_per_batch)
     for k, v in [kv.split("=") for kv in os.environ.get("VG_OPTIONS", "").split(",") if kv]:   # tuning experiments, e.g. VG_OPTIONS=traversal=0
         dev.set_option(k, int(v))
@@ -372,7 +375,7 @@ def run_ours(args):
         "bytes_per_launch": alg_bytes_closest / launches, "ms_per_launch": closest_ms / launches,
         "rays_per_launch": closest_rays / launches, "nodesT_per_ray": st["nodes_t"] / max(1, closest_rays), "trisT_per_ray": st["tris_t"] / max(1, closest_rays),
         "share_of_step": closest_ms / dev_ms if dev_ms > 0 else None,
-        "note": ("10M-triangle scene (0.55 GB) exceeds L2: HBM-bound model" if CONFIG == "c3" else
+        "note": ("10M-triangle scene (0.55 GB) exceeds L2: HBM-bound model" if CONFIG in ("c3", "c5") else
                  "1M-triangle scene (6 MB nodes + 48 MB triangles) is L2-resident: the bytes model is algorithmic, not DRAM traffic"),
     }
 
@@ -425,7 +428,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    # other BASELINE.json configs (c3, c4) are selected with VG_BENCH_CONFIG; the driver's contract runs the default (c2)
+    # other BASELINE.json configs (c3, c4, c5) are selected with VG_BENCH_CONFIG; the driver's contract runs the default (c2)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -91,6 +91,9 @@ typedef struct VgMotionNode {
 #define VG_MAT_SPEC1_FRESNEL_MODEL 512u /* Spec1FresnelModel given ("Dielectric" | "Metal", std.go:65-73) */
 #define VG_MAT_SPEC1_FRESNEL_REFL 1024u
 #define VG_MAT_SPEC1_FRESNEL_EDGE 2048u
+/* shader.Debug (builtin/shader/debug.go:15-49, node "DebugShader"): Eval sets OutRGB = Colour and nothing else — no lights, no
+ * rays, no Level check — and EvalEmission returns black. Colour travels in diffuse_colour; every other field is ignored. */
+#define VG_MAT_DEBUG 4096u
 #define VG_FRESNEL_DIELECTRIC 0 /* fresnel.DielectricModel (fresnel/models.go:13-17), also the value when the string is unset */
 #define VG_FRESNEL_CONDUCTOR 1  /* fresnel.ConductorModel ("Metal") */
 typedef struct VgMaterial {
@@ -258,6 +261,8 @@ int vh_registered_nodes(const char** names, int cap);
 
 int vh_set_globals(vh_scene* s, int xres, int yres, int max_iter);
 int vh_add_shader_std(vh_scene* s, const char* name, const VgMaterial* params);
+/* DebugShader node (builtin/shader/debug.go:51-57): Colour is a constant rgb map */
+int vh_add_shader_debug(vh_scene* s, const char* name, const float* colour);
 int vh_add_polymesh(vh_scene* s, const char* name, const float* verts, int n_verts, int keys, const int32_t* polycount, int n_poly,
                     const int32_t* faceidx, int n_faceidx, const char* shaders_nl, const int32_t* shaderidx, int n_shaderidx,
                     const float* normals, int n_normals, const int32_t* normalidx, int n_normalidx, float raybias);

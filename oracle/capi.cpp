@@ -54,6 +54,13 @@ int orc_set_globals(void* h, int xres, int yres) {
 // 9 Spec1FresnelModel(p15: 0 "Dielectric", 1 "Metal") 10 Spec1FresnelRefl(p16..18) 11 Spec1FresnelEdge(p19..21)
 int orc_add_shader(void* h, const char* name, uint32_t mask, const float* p) {
   Handle* H = (Handle*)h;
+  if (mask & 4096) {  // DebugShader: Colour in the DiffuseColour slot
+    auto d = std::make_unique<DebugShader>();
+    d->Name = name;
+    d->Colour = MakeRGB(p[4], p[5], p[6]);
+    H->r.shaders.push_back(std::move(d));
+    return 0;
+  }
   auto s = std::make_unique<ShaderStd>();
   s->Name = name;
   if (mask & 1) { s->hasEmissionColour = true; s->EmissionColour = MakeRGB(p[0], p[1], p[2]); }

@@ -221,6 +221,10 @@ struct MicrofacetGGX : BSDF {
 
 // ---------------------------------------------------------------------------------------------
 // builtin/shader/std.go:77-296
+// builtin/shader/debug.go:42-49
+void DebugShader::Eval(ShaderContext* sg) { sg->OutRGB = Colour; }
+RGB DebugShader::EvalEmission(ShaderContext*, Vec3) { return RGB{}; }
+
 void ShaderStd::Eval(ShaderContext* sg) {
   if (sg->Level > 3) return;
 

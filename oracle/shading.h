@@ -46,6 +46,14 @@ struct ShaderStd : Shader {
   RGB EvalEmission(ShaderContext* sg, Vec3 omegaO) override;
 };
 
+// builtin/shader/debug.go:15-49 (node "DebugShader"): OutRGB = Colour, no emission. Derived from ShaderStd only so that the
+// renderer's shader list keeps one element type; nothing of ShaderStd is used.
+struct DebugShader : ShaderStd {
+  RGB Colour;
+  void Eval(ShaderContext* sg) override;
+  RGB EvalEmission(ShaderContext* sg, Vec3 omegaO) override;
+};
+
 struct Tri : Light {
   std::string Name;
   Vec3 P0, P1, P2;

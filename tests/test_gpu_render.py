@@ -285,3 +285,19 @@ def test_camera_motion_image(built_library, variant):
         dev2 = Device(0).upload(HostScene(sc).prerender())
         dev2.set_scramble(scenes.splitmix64_table(1, sc.XRes * sc.YRes))
         assert _rmse(fo, dev2.render(0, 16))[0] > 10 * max(rmse, 1e-4)
+
+
+# ---- DebugShader (builtin/shader/debug.go): OutRGB = Colour, no lights, no rays, no Level check -----------------------------
+@pytest.mark.parametrize("mirrors", [False, True])
+def test_debug_shader_image(built_library, mirrors):
+    from vermeer_b200 import scenes
+    sc = scenes.debug_shader_box(128, 128, mirrors=mirrors)
+    fo, so, fg, st, _ = _render_pair(sc, 16)
+    rmse, ok = _rmse(fo, fg)
+    assert rmse <= 1e-3, rmse
+    assert np.median(np.abs(fo - fg)[ok]) <= 1e-5
+    assert abs(st["rays"] - so["rays"]) <= 1e-3 * so["rays"]
+    # a pixel that looks straight at the left wall holds the wall's colour times N/(N+1) (reference quirk d), exactly
+    want = np.float32([0.2, 0.6, 0.9])
+    px = fg[64, 2]
+    assert np.allclose(px, want * (16.0 / 17.0), rtol=1e-5), px

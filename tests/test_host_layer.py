@@ -34,7 +34,7 @@ def test_registry_mirrors_nodes_register(built_library):
     arr = (C.c_char_p * n)()
     lib.vh_registered_nodes(arr, n)
     names = sorted(a.decode() for a in arr)
-    assert names == ["AiryFilter", "Camera", "DiskLight", "GaussianFilter", "GeomInstance", "Globals", "OutputFloat", "OutputHDR", "PolyMesh", "ShaderStd", "Sphere", "SphereLight", "TriLight"]
+    assert names == ["AiryFilter", "Camera", "DebugShader", "DiskLight", "GaussianFilter", "GeomInstance", "Globals", "OutputFloat", "OutputHDR", "PolyMesh", "ShaderStd", "Sphere", "SphereLight", "TriLight"]
 
 
 def _equal_nodes(a, b):
@@ -43,7 +43,7 @@ def _equal_nodes(a, b):
     return a.tobytes() == b.tobytes()
 
 
-@pytest.mark.parametrize("name", ["cornell", "heightfield", "motion", "spheres", "glossy", "instances"])
+@pytest.mark.parametrize("name", ["cornell", "heightfield", "motion", "spheres", "glossy", "instances", "debug"])
 def test_host_prerender_matches_oracle_bit_for_bit(built_library, name):
     from oracle.binding import Oracle
     from vermeer_b200 import scenes
@@ -55,7 +55,8 @@ def test_host_prerender_matches_oracle_bit_for_bit(built_library, name):
           # TriLight + DiskLight (fan mesh) + SphereLight (analytic Sphere geom in the scene-level tree)
           "glossy": lambda: scenes.glossy_box(64, 48),
           # GeomInstances (one with two transform keys) of a two-key motion mesh: scene-level MQBVH over user-given bounds
-          "instances": lambda: scenes.instanced_scene(64, 48, moving=True, motion_base=True)}[name]()
+          "instances": lambda: scenes.instanced_scene(64, 48, moving=True, motion_base=True),
+          "debug": lambda: scenes.debug_shader_box(64, 48)}[name]()
     o = Oracle(sc)
     h = HostScene(sc).prerender()
     assert np.array_equal(o.scene_geom_order(), h.scene_geom_order())

@@ -35,7 +35,7 @@ def _same_structures(h1, h2):
     assert ca[0].tobytes() == cb[0].tobytes() and ca[1:] == cb[1:]
 
 
-@pytest.mark.parametrize("name", ["cornell", "glossy", "motion", "filter", "instances"])
+@pytest.mark.parametrize("name", ["cornell", "glossy", "motion", "filter", "instances", "debug"])
 def test_vnf_path_builds_the_same_scene(built_library, name):
     from vermeer_b200 import scenes
     from vermeer_b200.host import HostScene
@@ -43,7 +43,8 @@ def test_vnf_path_builds_the_same_scene(built_library, name):
           "glossy": lambda: scenes.glossy_box(64, 48),
           "motion": lambda: scenes.heightfield_scene(64, 48, nq=24, motion=True),
           "filter": lambda: scenes.cornell_box(32, 32, boxes=False),
-          "instances": lambda: scenes.instanced_scene(64, 48, moving=True)}[name]()
+          "instances": lambda: scenes.instanced_scene(64, 48, moving=True),
+          "debug": lambda: scenes.debug_shader_box(64, 48)}[name]()
     if name == "filter":
         sc.filter = scenes.PixelFilter("AiryFilter", Res=48)
     text = scenes.to_vnf(sc)

@@ -56,6 +56,10 @@ struct ShaderStd : Node {
   std::string Name() const override { return MtlName; }
 };
 
+// builtin/shader/debug.go:15-22 ("DebugShader"): a core.Shader whose Eval is OutRGB = Colour. It shares ShaderStd's slot in the
+// material table; params.mask = VG_MAT_DEBUG | VG_MAT_DIFFUSE_COLOUR, Colour in params.diffuse_colour.
+struct DebugShader : ShaderStd {};
+
 struct PointArray {  // core/param/array.go:19-28
   int MotionKeys = 0, ElemsPerKey = 0;
   std::vector<V3> Elems;

@@ -72,6 +72,19 @@ int vh_add_shader_std(vh_scene* s, const char* name, const VgMaterial* params) {
   return VG_OK;
 }
 
+int vh_add_shader_debug(vh_scene* s, const char* name, const float* colour) {
+  if (!s || !name || !colour) return fail(s, VG_ERR_INVALID, "vh_add_shader_debug: null argument");
+  std::unique_ptr<Node> h;
+  DebugShader* sh = make<DebugShader>(s, "DebugShader", &h);
+  if (!sh) return VG_ERR_INVALID;
+  sh->MtlName = name;
+  std::memset(&sh->params, 0, sizeof(sh->params));
+  sh->params.mask = VG_MAT_DEBUG | VG_MAT_DIFFUSE_COLOUR;
+  for (int i = 0; i < 3; i++) sh->params.diffuse_colour[i] = colour[i];
+  s->core.AddNode(std::move(h));
+  return VG_OK;
+}
+
 int vh_add_polymesh(vh_scene* s, const char* name, const float* verts, int n_verts, int keys, const int32_t* polycount, int n_poly,
                     const int32_t* faceidx, int n_faceidx, const char* shaders_nl, const int32_t* shaderidx, int n_shaderidx,
                     const float* normals, int n_normals, const int32_t* normalidx, int n_normalidx, float raybias) {

@@ -219,6 +219,8 @@ const std::vector<NodeDefn>& node_table() {
                      {"Spec1Colour", KMap, false}, {"Spec1Strength", KMap, false}, {"Spec1Roughness", KMap, false},
                      {"Spec1FresnelModel", KString, false}, {"Spec1FresnelRefl", KMap, false}, {"Spec1FresnelEdge", KMap, false},
                      {"IOR", KMap, false}}, true},
+      // builtin/shader/debug.go:15-22
+      {"DebugShader", {{"Name", KString, true}, {"Sides", KInt, false}, {"Colour", KMap, true}}, true},
       // builtin/geom/polymesh/polymesh.go:17-40
       {"PolyMesh", {{"Name", KString, true}, {"RayBias", KFloat, false}, {"Verts", KPointArray, true}, {"PolyCount", KInt32Slice, false},
                     {"FaceIdx", KInt32Slice, false}, {"Shader", KStringSlice, true}, {"ShaderIdx", KInt32Slice, false},
@@ -243,7 +245,7 @@ const std::vector<NodeDefn>& node_table() {
       {"OutputFloat", {{"Filename", KString, true}}, true},
       {"OutputHDR", {{"Filename", KString, true}}, true},
       // registered in the reference, not on this path
-      {"QuadLight", {}, false}, {"Proc", {}, false}, {"Include", {}, false}, {"DebugShader", {}, false},
+      {"QuadLight", {}, false}, {"Proc", {}, false}, {"Include", {}, false},
   };
   return t;
 }
@@ -518,6 +520,13 @@ std::string build_node(Core& core, const std::string& type, std::map<std::string
       m.mask |= VG_MAT_SPEC1_FRESNEL_MODEL;
       m.spec1_fresnel_model = f["Spec1FresnelModel"].s == "Metal" ? VG_FRESNEL_CONDUCTOR : VG_FRESNEL_DIELECTRIC;
     }
+  } else if (type == "DebugShader") {
+    DebugShader* s = static_cast<DebugShader*>(h.get());
+    s->MtlName = f["Name"].s;
+    VgMaterial& m = s->params;
+    std::memset(&m, 0, sizeof(m));
+    m.mask = VG_MAT_DEBUG;
+    set_map(m, VG_MAT_DIFFUSE_COLOUR, f["Colour"], m.diffuse_colour, nullptr);
   } else if (type == "PolyMesh") {
     PolyMesh* m = static_cast<PolyMesh*>(h.get());
     m->NodeName = f["Name"].s;

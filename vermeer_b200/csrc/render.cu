@@ -47,6 +47,7 @@ struct DevMat {
   int fresnel_model;     // VG_FRESNEL_* (std.go:172-192)
   f3 fres_refl, fres_edge;  // conductor r, g AFTER the reference's assignment quirk (std.go:187-189 writes the edge tint into refl)
   int bad;  // 1: total weight 0 (the reference panics, std.go:141-143)
+  int debug;  // shader.Debug (debug.go:42-49): `emission` holds its Colour, both weights are 0 and no Level check applies
 };
 
 struct __align__(16) DevHit {
@@ -744,6 +745,19 @@ __global__ void __launch_bounds__(256) k_resolve(const RenderParams p, int level
   p.L[(size_t)level * p.P + p.pathq[qin][i]] = resolve_vertex(p, level, i);
 }
 
+// Level 4 of a mirror chain (scenes that hold a DebugShader next to a mirror lobe): ShaderStd.Eval returns at once there
+// (std.go:95) but Debug.Eval still sets OutRGB = Colour (debug.go:42-44), which the Level-3 mirror lobe then picks up.
+__global__ void __launch_bounds__(256) k_debug_last(const RenderParams p, int level, int qin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.counts[qin]) return;
+  const DevHit h = p.hits[i];
+  if (h.prim < 0) return;
+  const int matid = p.sc.prim_material[p.sc.geoms[h.geom].prim_base + h.prim];
+  if (matid == 255) return;
+  const DevMat& m = p.mats[matid];
+  if (m.debug) p.L[(size_t)level * p.P + p.pathq[qin][i]] = make_float4(m.emission.x, m.emission.y, m.emission.z, 0.f);
+}
+
 // Scenes without a mirror lobe have one level: the level-0 queue is the identity (queue slot == path), so the per-vertex sum and
 // the running mean (render.go:127-129) are one kernel and L never goes to memory.
 __global__ void __launch_bounds__(256) k_resolve_accumulate(const RenderParams p, int iter_base, int niters) {
@@ -1031,11 +1045,18 @@ static int prepare(vg_ctx* ctx) {
 
   // materials
   std::vector<DevMat> mats(ctx->materials.size());
-  bool any_mirror = false, any_glossy = false, any_conductor = false, any_other_light = false;
+  bool any_mirror = false, any_glossy = false, any_conductor = false, any_other_light = false, any_debug = false;
   for (size_t i = 0; i < mats.size(); i++) {
     const VgMaterial& s = ctx->materials[i];
     DevMat& d = mats[i];
     std::memset(&d, 0, sizeof(d));
+    if (s.mask & VG_MAT_DEBUG) {
+      // Eval: OutRGB = Colour (resolve_vertex's emission + 0 + 0); no lights, no lobes
+      d.debug = 1;
+      if (s.mask & VG_MAT_DIFFUSE_COLOUR) d.emission = h3(s.diffuse_colour);
+      any_debug = true;
+      continue;
+    }
     if (s.mask & VG_MAT_EMISSION_STRENGTH) {
       const float zero3[3] = {0, 0, 0};
       f3 c = h3((s.mask & VG_MAT_EMISSION_COLOUR) ? s.emission_colour : zero3);
@@ -1091,7 +1112,8 @@ static int prepare(vg_ctx* ctx) {
       d.inv_area = 1.0f / (3.14159265358f * s.radius * s.radius);  // disk.go:125,179 (float32 expression)
     }
     d.E.x = d.E.y = d.E.z = 0;
-    if (s.material >= 0 && s.material < (int)mats.size()) d.E = mats[s.material].emission;
+    // Debug.EvalEmission returns black (debug.go:49)
+    if (s.material >= 0 && s.material < (int)mats.size() && !mats[s.material].debug) d.E = mats[s.material].emission;
     if (s.samples < 0 || s.samples > 8) return ctx->fail(VG_ERR_INVALID, "TriLight.Samples outside [0,8]");
     d.nsamples = 1 << s.samples;
     rs.max_light_samples = std::max(rs.max_light_samples, d.nsamples);
@@ -1107,7 +1129,9 @@ static int prepare(vg_ctx* ctx) {
   rs.generic = any_glossy || any_conductor || any_other_light || any_sphere_geom || ctx->dev.n_xforms > 0 || ctx->opt_generic_shade;
   rs.nlobes = any_glossy ? 2 : 1;
   rs.nlights = (int)lights.size();
-  rs.levels = any_mirror ? 4 : 1;
+  // a mirror chain's Level-4 ray is shaded by nothing but a DebugShader (ShaderStd.Eval returns at Level > 3, std.go:95; Debug.Eval
+  // has no such test): scenes that hold both keep a fifth level for that colour
+  rs.levels = any_mirror ? (any_debug ? 5 : 4) : 1;
   rs.iters = ctx->opt_iters_per_batch;
   {
     // The batch depth is a request: queue slots are 32-bit indices (paths x contribution slots must stay below 2^31) and the
@@ -1222,7 +1246,7 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
   p.xres = ctx->xres; p.yres = ctx->yres; p.nown = rs.nown; p.P = rs.P;
   p.pix = rs.pix.p; p.qmc = rs.qmc.p; p.scr = rs.scr.p; p.scr_by_pixel = rs.scr_by_pixel ? 1 : 0; p.cam = ctx->camera; p.cam_keys = ctx->d_cam_keys.p; p.cam_nkeys = ctx->cam_nkeys; p.mats = rs.mats.p; p.lights = rs.lights.p;
   p.filter_cdf = ctx->filter_n > 0 ? rs.filter.p : nullptr; p.filter_n = ctx->filter_n; p.filter_w = ctx->filter_w;
-  p.nlights = rs.nlights; p.S = rs.S; p.levels = rs.levels; p.trace_last_level = ctx->opt_trace_last_level;
+  p.nlights = rs.nlights; p.S = rs.S; p.levels = rs.levels; p.trace_last_level = (ctx->opt_trace_last_level || rs.levels == 5) ? 1 : 0;
   p.nlobes = rs.nlobes;
   p.rayq[0] = rs.rayq0.p; p.rayq[1] = rs.rayq1.p; p.pathq[0] = rs.pathq0.p; p.pathq[1] = rs.pathq1.p;
   p.hits = rs.hits.p; p.lambda = rs.lambda.p; p.time = rs.time.p; p.v_mat = rs.vmat.p; p.v_invtot = rs.invtot.p;
@@ -1252,7 +1276,7 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
       launches += 2;
       int qin = 0;
       // levels 0..3 are shaded; with trace_last_level the level-4 rays are traced (and counted) but not shaded
-      const int nlev = rs.levels == 1 ? 1 : (ctx->opt_trace_last_level ? 5 : 4);
+      const int nlev = rs.levels == 1 ? 1 : (p.trace_last_level ? 5 : 4);
       for (int level = 0; level < nlev; level++) {
         const int qout = 1 - qin;
         cudaEventRecord(rs.ev(nev++), st);
@@ -1305,6 +1329,10 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
             launches++;
           }
           launches += 2;
+        }
+        if (level == 4 && rs.levels == 5) {
+          k_debug_last<<<(np + 255) / 256, 256, 0, st>>>(p, level, qin);
+          launches++;
         }
         if (level + 1 < nlev) {
           k_next_level<<<1, 1, 0, st>>>(rs.counts.p, qout);

@@ -31,7 +31,7 @@ DECLARED_SYMBOLS = [
     "vg_sphere_upload", "vg_instance_upload", "vg_scene_upload", "vg_scene_upload_motion", "vg_scene_commit", "vg_set_materials", "vg_set_lights", "vg_set_area_lights", "vg_set_camera", "vg_set_camera_motion", "vg_set_frame",
     "vg_set_partition", "vg_set_scramble", "vg_set_filter", "vg_set_option", "vg_trace_batch", "vg_trace_batch_device", "vg_render", "vg_clear_framebuffer",
     "vg_framebuffer_device", "vg_get_stats", "vg_reset_stats",
-    "vh_scene_create", "vh_scene_destroy", "vh_last_error", "vh_registered_nodes", "vh_set_globals", "vh_add_shader_std", "vh_add_polymesh",
+    "vh_scene_create", "vh_scene_destroy", "vh_last_error", "vh_registered_nodes", "vh_set_globals", "vh_add_shader_std", "vh_add_shader_debug", "vh_add_polymesh",
     "vh_add_filter", "vh_add_instance", "vh_add_trilight", "vh_add_disklight", "vh_add_spherelight", "vh_parse_vnf", "vh_load_vnf", "vh_globals", "vh_postrender", "vh_rgbe", "vh_set_camera_lookat", "vh_set_camera_keys", "vh_camera_decomp", "vh_prerender", "vh_upload", "vh_num_geoms", "vh_scene_info", "vh_scene_nodes",
     "vh_scene_motion_nodes", "vh_scene_geom_order", "vh_mesh_info", "vh_mesh_nodes", "vh_mesh_motion_nodes", "vh_mesh_idxp", "vh_camera",
 ]
@@ -117,6 +117,9 @@ class HostScene:
         L = self.L
         self._chk(L.vh_set_globals(h, scene.XRes, scene.YRes, scene.MaxIter))
         for s in scene.shaders:
+            if hasattr(s, "Colour"):   # scenes.DebugShader
+                self._chk(L.vh_add_shader_debug(h, s.Name.encode(), _f3(s.Colour)))
+                continue
             m = material_struct(s)
             self._chk(L.vh_add_shader_std(h, s.Name.encode(), C.byref(m)))
         for m in scene.meshes:

@@ -23,7 +23,7 @@ from typing import List, Optional
 import numpy as np
 
 __all__ = [
-    "ShaderStd", "PolyMesh", "GeomInstance", "matrix4", "srt_matrix", "TriLight", "DiskLight", "SphereLight", "Camera", "PixelFilter", "SceneDesc", "splitmix64_table", "camera_motion_variants",
+    "ShaderStd", "DebugShader", "PolyMesh", "GeomInstance", "matrix4", "srt_matrix", "TriLight", "DiskLight", "SphereLight", "Camera", "PixelFilter", "SceneDesc", "splitmix64_table", "camera_motion_variants", "debug_shader_box",
     "heightfield_mesh", "heightfield_scene", "sphere_field_scene", "cornell_box", "glossy_box", "instanced_scene", "incoherent_rays", "to_vnf",
 ]
 
@@ -59,6 +59,18 @@ class ShaderStd:
                     v = {"Dielectric": 0.0, "Metal": 1.0}[v]
                 p[off:off + n] = np.asarray(v, np.float32).reshape(-1)
         return mask, p
+
+
+@dataclass
+class DebugShader:
+    """builtin/shader/debug.go:15-22: OutRGB = Colour."""
+    Name: str
+    Colour: tuple = (0.0, 0.0, 0.0)
+
+    def packed(self):
+        p = np.zeros(22, np.float32)
+        p[4:7] = np.asarray(self.Colour, np.float32)
+        return 4096 | 4, p
 
 
 @dataclass
@@ -238,6 +250,9 @@ def to_vnf(sc: "SceneDesc", outputs=()) -> str:
     o = []
     o.append("Globals { XRes %d YRes %d MaxIter %d }" % (sc.XRes, sc.YRes, sc.MaxIter))
     for s in sc.shaders:
+        if isinstance(s, DebugShader):
+            o.append('DebugShader { Name "%s" Colour rgb %s }' % (s.Name, _vec(s.Colour)))
+            continue
         parts = ['Name "%s"' % s.Name]
         for name in ("EmissionColour", "DiffuseColour", "Spec1Colour", "Spec1FresnelRefl", "Spec1FresnelEdge"):
             v = getattr(s, name)
@@ -492,6 +507,27 @@ def cornell_box(xres: int = 512, yres: int = 512, boxes: bool = True) -> SceneDe
     lights = _light_pair(1.99, 0.35, "lightmtl", dy=0.03)
     cam = Camera(From=(0.0, 1.0, 3.4), To=(0.0, 1.0, 0.0), Fov=40.0, Focal=1.0)
     return SceneDesc(XRes=xres, YRes=yres, camera=cam, shaders=shaders, meshes=meshes, lights=lights, MaxIter=16, name="C1-cornell")
+
+
+def debug_shader_box(xres: int = 128, yres: int = 128, mirrors: bool = True) -> SceneDesc:
+    """The Cornell room with DebugShader walls (builtin/shader/debug.go: OutRGB = Colour). With `mirrors` the floor and the ceiling
+    are facing mirrors, so chains run to Level 4, where a DebugShader still answers while ShaderStd does not (std.go:95)."""
+    sc = cornell_box(xres, yres)
+    sc.shaders.append(DebugShader("dbg_blue", Colour=(0.2, 0.6, 0.9)))
+    sc.shaders.append(DebugShader("dbg_orange", Colour=(0.9, 0.5, 0.1)))
+    sc.meshes[3].Shader = ["dbg_blue"]      # left wall
+    sc.meshes[2].Shader = ["dbg_orange"]    # back wall
+    if mirrors:
+        sc.shaders.append(ShaderStd("mirror", DiffuseColour=(0.5, 0.5, 0.5), DiffuseStrength=0.3,
+                                    Spec1Colour=(0.9, 0.9, 0.9), Spec1Strength=0.7, Spec1Roughness=0.0))
+        sc.meshes[0].Shader = ["mirror"]    # floor
+        sc.meshes[1].Shader = ["mirror"]    # ceiling
+    # off the room's axis: from (0, 1, z) the wall/ceiling edges project exactly onto the image diagonals, and the one sample per
+    # diagonal pixel that sits on the sub-pixel diagonal then runs precisely along the crack between two meshes, where the last bit
+    # of the direction's normalize (RSQRTSS in the reference) decides between a constant colour and a lit wall
+    sc.camera = Camera(From=(0.03, 1.02, 3.4), To=(0.0, 1.0, 0.0), Fov=40.0, Focal=1.0)
+    sc.name = "debug-shader-box"
+    return sc
 
 
 def glossy_box(xres: int = 256, yres: int = 256, lights: str = "tri,disk,sphere") -> SceneDesc:
