@@ -289,7 +289,9 @@ int vh_set_camera_keys(vh_scene* s, const char* type, const float* from, int n_f
 int vh_camera_decomp(vh_scene* s, VgTransformSRT* out);
 /* nodes.Parse (nodes/parser.go:110-131): read a .vnf scene description (text in memory, or a file) and add its nodes in file
  * order, exactly like the vh_add_* calls would. In scope: Globals, Camera (LookAt or Matrix, with motion keys), ShaderStd (constant maps),
- * PolyMesh, TriLight, DiskLight, SphereLight, Sphere, AiryFilter, GaussianFilter, OutputFloat, OutputHDR. Returns the number
+ * DebugShader, PolyMesh, GeomInstance, TriLight, DiskLight, SphereLight, Sphere, AiryFilter, GaussianFilter, OutputFloat, OutputHDR,
+ * Include (its file is read by vh_prerender, like misc.Include.PreRender; parse messages of such files are left in
+ * vh_last_error after a successful vh_prerender, a file that cannot be opened fails it). Returns the number
  * of parse errors the reference would have printed (0 = clean; nodes that parsed are kept, like the reference keeps them),
  * or < 0 if the file cannot be read; vh_last_error holds the "<file>:<line>:<col>: message" lines. */
 int vh_parse_vnf(vh_scene* s, const char* text, size_t len, const char* filename);

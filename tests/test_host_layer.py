@@ -34,7 +34,7 @@ def test_registry_mirrors_nodes_register(built_library):
     arr = (C.c_char_p * n)()
     lib.vh_registered_nodes(arr, n)
     names = sorted(a.decode() for a in arr)
-    assert names == ["AiryFilter", "Camera", "DebugShader", "DiskLight", "GaussianFilter", "GeomInstance", "Globals", "OutputFloat", "OutputHDR", "PolyMesh", "ShaderStd", "Sphere", "SphereLight", "TriLight"]
+    assert names == ["AiryFilter", "Camera", "DebugShader", "DiskLight", "GaussianFilter", "GeomInstance", "Globals", "Include", "OutputFloat", "OutputHDR", "PolyMesh", "ShaderStd", "Sphere", "SphereLight", "TriLight"]
 
 
 def _equal_nodes(a, b):

@@ -168,3 +168,28 @@ def test_render_from_vnf_equals_in_memory_path(built_library, tmp_path):
     assert imgs[0].tobytes() == imgs[1].tobytes()
     last.postrender(imgs[1])
     assert np.fromfile(out, "<f4").tobytes() == imgs[1].tobytes()
+
+
+def test_include_node_reads_the_other_file_at_prerender(built_library, tmp_path, monkeypatch):
+    """misc.Include (builtin/misc/include.go): PreRender = nodes.Parse(Filename), relative to the working directory; the nodes it adds
+    are pre-rendered in the next round. Globals + Include of everything else builds the single-file scene bit for bit."""
+    from vermeer_b200 import scenes
+    from vermeer_b200.host import HostScene
+    sc = scenes.debug_shader_box(64, 48)
+    text = scenes.to_vnf(sc)
+    head, rest = text.split("\n", 1)
+    assert head.startswith("Globals")
+    (tmp_path / "rest.vnf").write_text(rest)
+    monkeypatch.chdir(tmp_path)
+    h1 = HostScene.from_vnf(text).prerender()
+    h2 = HostScene.from_vnf(head + '\nInclude { Filename "rest.vnf" }\n').prerender()
+    _same_structures(h1, h2)
+    # a file that cannot be opened is PreRender's error (include.go:24-26 returns os.Open's)
+    h3 = HostScene.from_vnf(head + '\nInclude { Name "inc" Filename "nonexistent.vnf" }\n')
+    with pytest.raises(RuntimeError, match="nonexistent.vnf"):
+        h3.prerender()
+    # parse errors inside the included file are printed, not returned (parser.go:862-899): the nodes that parsed are kept
+    (tmp_path / "bad.vnf").write_text(rest + "\nNoSuchNode { }\n")
+    h4 = HostScene.from_vnf(head + '\nInclude { Filename "bad.vnf" }\n').prerender()
+    _same_structures(h1, h4)
+    assert "NoSuchNode" in h4.L.vh_last_error(h4.h).decode()

@@ -48,6 +48,7 @@ struct RegisterBuiltins {
     Register("Camera", [] { return std::unique_ptr<Node>(new Camera()); });
     Register("PolyMesh", [] { return std::unique_ptr<Node>(new PolyMesh()); });
     Register("ShaderStd", [] { return std::unique_ptr<Node>(new ShaderStd()); });
+    Register("Include", [] { return std::unique_ptr<Node>(new Include()); });  // misc/include.go:30-36
     Register("DebugShader", [] { return std::unique_ptr<Node>(new DebugShader()); });  // debug.go:51-57
     Register("TriLight", [] { return std::unique_ptr<Node>(new TriLight()); });
     Register("DiskLight", [] { return std::unique_ptr<Node>(new DiskLight()); });      // disk.go:263-269

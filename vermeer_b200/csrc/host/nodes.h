@@ -214,6 +214,15 @@ struct OutputNode : Node {
 };
 void RgbToRgbe(float r, float g, float b, uint8_t out[4]);  // image/hdr/hdr.go:26-50
 
+// misc.Include (builtin/misc/include.go:9-36): PreRender parses another .vnf file into the core; the nodes it adds are
+// pre-rendered in the next round of core.PreRender (core/core.go:46-57). Only a file that cannot be opened is an error
+// (nodes.Parse returns nil after printing its parse errors, parser.go:862-899); those land in Core::include_log.
+struct Include : Node {
+  std::string NodeName, Filename;
+  std::string Name() const override { return NodeName; }
+  int PreRender(Core& core, std::string* err) override;  // vnf.cpp
+};
+
 // nodes.Parse (nodes/parser.go): adds the file's nodes to `core` in file order; returns the number of parse errors.
 int ParseVnf(Core& core, const char* text, size_t len, const std::string& filename, std::string* messages);
 
@@ -246,6 +255,8 @@ struct Core {
   int next_geom_id = 0;
   bool prerendered = false;
   std::string err;
+  std::string include_log;  // parse messages of files read by Include nodes
+  int include_errors = 0;
 
   Core();
   void AddNode(std::unique_ptr<Node> node);  // core.go:77-93 type-switch wiring

@@ -306,6 +306,7 @@ int vh_rgbe(float r, float g, float b, uint8_t* out4) {
 int vh_prerender(vh_scene* s) {
   if (!s) return VG_ERR_INVALID;
   if (s->core.PreRender() != 0) return fail(s, VG_ERR_BUILD, s->core.err);
+  if (!s->core.include_log.empty()) s->err = s->core.include_log;  // what nodes.Parse printed for the Include'd files
   return VG_OK;
 }
 

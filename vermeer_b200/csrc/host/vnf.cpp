@@ -245,7 +245,9 @@ const std::vector<NodeDefn>& node_table() {
       {"OutputFloat", {{"Filename", KString, true}}, true},
       {"OutputHDR", {{"Filename", KString, true}}, true},
       // registered in the reference, not on this path
-      {"QuadLight", {}, false}, {"Proc", {}, false}, {"Include", {}, false},
+      // builtin/misc/include.go:9-13
+      {"Include", {{"Name", KString, false}, {"Filename", KString, true}}, true},
+      {"QuadLight", {}, false}, {"Proc", {}, false},
   };
   return t;
 }
@@ -520,6 +522,10 @@ std::string build_node(Core& core, const std::string& type, std::map<std::string
       m.mask |= VG_MAT_SPEC1_FRESNEL_MODEL;
       m.spec1_fresnel_model = f["Spec1FresnelModel"].s == "Metal" ? VG_FRESNEL_CONDUCTOR : VG_FRESNEL_DIELECTRIC;
     }
+  } else if (type == "Include") {
+    Include* inc = static_cast<Include*>(h.get());
+    if (has("Name")) inc->NodeName = f["Name"].s;
+    inc->Filename = f["Filename"].s;
   } else if (type == "DebugShader") {
     DebugShader* s = static_cast<DebugShader*>(h.get());
     s->MtlName = f["Name"].s;
@@ -657,6 +663,21 @@ int ParseVnf(Core& core, const char* text, size_t len, const std::string& filena
   }
   if (messages) *messages = p.log.str();
   return p.nerrors;
+}
+
+// misc.Include.PreRender (include.go:24-26) = nodes.Parse(Filename): os.Open resolves the name against the working directory
+int Include::PreRender(Core& core, std::string* err) {
+  FILE* fp = std::fopen(Filename.c_str(), "rb");
+  if (!fp) { *err = "open " + Filename + ": no such file or directory"; return -1; }
+  std::string text;
+  char buf[1 << 16];
+  size_t n;
+  while ((n = std::fread(buf, 1, sizeof(buf), fp)) > 0) text.append(buf, n);
+  std::fclose(fp);
+  std::string msgs;
+  core.include_errors += ParseVnf(core, text.data(), text.size(), Filename, &msgs);
+  core.include_log += msgs;
+  return 0;
 }
 
 // ---- output drivers ----------------------------------------------------------------------------------
