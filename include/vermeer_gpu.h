@@ -208,6 +208,34 @@ int vg_scene_upload_motion(vg_ctx* ctx, const VgMotionNode* topo, int n_nodes, c
 int vg_scene_commit(vg_ctx* ctx);
 
 int vg_set_materials(vg_ctx* ctx, const VgMaterial* mats, int n);
+
+/* ---- texture maps ------------------------------------------------------------------------------------
+ * The reference's texture store (texture/texture.go:36-47) and the maps that read it (builtin/maps/texture.go:17-83).
+ * vg_texture_upload: one texture.Texture after loadTexture (texture.go:118-160): RGB8, w*h*3 bytes, row 0 = BOTTOM row of
+ * the image (loadTexture flips while copying, :139). The mip pyramid of stdfilter (texture/mipmap.go:122-315) is built on the
+ * device, byte-identical to the reference's. Image decoding (png/jpeg/tiff/tga) stays with the caller. *tex_id receives the
+ * store index. A 1x1 image is refused (the reference panics on it, mipmap.go:127). Textures outlive vg_scene_begin. */
+int vg_texture_upload(vg_ctx* ctx, const uint8_t* rgb8, int w, int h, int* tex_id);
+int vg_textures_clear(vg_ctx* ctx);
+/* Pyramid inspection: number of levels = ceil(log2(max(w,h))); one level as RGB8 rows (bottom-up). rgb8_out may be NULL. */
+int vg_texture_levels(vg_ctx* ctx, int tex_id, int* n_levels);
+int vg_texture_read_level(vg_ctx* ctx, int tex_id, int level, int* w, int* h, uint8_t* rgb8_out);
+/* filter: the map type CreateRGBTextureMap / CreateFloat32TextureMap picks from the "?filter=" query (maps/texture.go:48-83) */
+#define VG_TEXFILTER_FELINE 0    /* maps.Texture: texture.SampleFeline (texture/feline.go:25-151), the default */
+#define VG_TEXFILTER_TRILINEAR 1 /* maps.TextureTrilinear: texture.SampleRGB (texture/texture.go:219-311) */
+/* Parameter `slot` of material `material` becomes a texture map: slot = bit index of the VG_MAT_* flag of that parameter
+ * (0 EmissionColour .. 8 IOR, 10 Spec1FresnelRefl, 11 Spec1FresnelEdge); chan = the channel a float parameter reads
+ * ("?ch=N"). Sets the parameter's VG_MAT_* bit. vg_set_materials drops all bindings. Textured scenes hold static PolyMeshes
+ * only (the reference's motion path leaves the footprint 0 and Feline then divides 0/0, trace.go:677-684, feline.go:57-61);
+ * a texture on the emission of a LIGHT's shader is refused (lights evaluate it with their own lsg). */
+int vg_material_set_texture(vg_ctx* ctx, int material, int slot, int tex_id, int chan, int filter);
+/* PolyMesh.UV (polymesh.go:36) and the triangulated, leaf-ordered UV indices (uvtriidx after init.go:38-106 and
+ * buildqbvh.go:106-116): uv = n_uv pairs, uvtriidx = 3 per triangle in the order of idxp. After vg_mesh_upload, before commit.
+ * Meshes without UVs use the barycentrics (trace.go:355-358,495-501). */
+int vg_mesh_set_uv(vg_ctx* ctx, int geom_id, const float* uv, int n_uv, const uint32_t* uvtriidx);
+/* The two filters over a batch of lookups (host buffers): coords = n x 8 floats {U, V, Dduvdx[2], Dduvdy[2], PixelDelta[2]}
+ * (core/shader.go:78-86, core/render.go:32-35), out = n x 3 floats. */
+int vg_texture_sample_batch(vg_ctx* ctx, int tex_id, int filter, const float* coords, int64_t n, float* out);
 int vg_set_lights(vg_ctx* ctx, const VgTriLight* lights, int n);   /* TriLights only (kept for callers that have nothing else) */
 int vg_set_area_lights(vg_ctx* ctx, const VgLight* lights, int n);  /* any mix of light types, scene order */
 int vg_set_camera(vg_ctx* ctx, const VgCamera* cam);
@@ -261,6 +289,15 @@ int vh_registered_nodes(const char** names, int cap);
 
 int vh_set_globals(vh_scene* s, int xres, int yres, int max_iter);
 int vh_add_shader_std(vh_scene* s, const char* name, const VgMaterial* params);
+/* Texture maps (builtin/maps/texture.go, texture/texture.go). vh_add_texture: one decoded image file under the name the
+ * shaders use (rgb8 rows bottom-up, see vg_texture_upload); the first registration of a name wins, like the reference's cache.
+ * vh_shader_set_texture: parameter `slot` (see vg_material_set_texture) of ShaderStd `shader` reads the file named by `value`,
+ * a reference texture URL: "path[?filter=trilinear][&ch=N]" (CreateRGBTextureMap / CreateFloat32TextureMap, maps/texture.go:48-83).
+ * The .vnf form is `Param rgbtex "value"` (nodes/parser.go:247-268). vh_polymesh_set_uv: PolyMesh.UV / UVIdx (polymesh.go:36-37),
+ * before vh_prerender. vh_upload fails for a map whose file was never registered (the reference substitutes a checker image). */
+int vh_add_texture(vh_scene* s, const char* name, int w, int h, const uint8_t* rgb8_bottom_up);
+int vh_shader_set_texture(vh_scene* s, const char* shader, int slot, const char* value);
+int vh_polymesh_set_uv(vh_scene* s, const char* mesh, const float* uv, int n_uv, const int32_t* uvidx, int n_uvidx);
 /* DebugShader node (builtin/shader/debug.go:51-57): Colour is a constant rgb map */
 int vh_add_shader_debug(vh_scene* s, const char* name, const float* colour);
 int vh_add_polymesh(vh_scene* s, const char* name, const float* verts, int n_verts, int keys, const int32_t* polycount, int n_poly,

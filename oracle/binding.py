@@ -78,6 +78,12 @@ class Oracle:
         for s in scene.shaders:
             mask, p = s.packed()
             self._chk(L.orc_add_shader(h, s.Name.encode(), C.c_uint32(mask), _p(p)))
+        for t in getattr(scene, "textures", []):
+            px = t.rows_bottom_up()
+            self._chk(L.orc_add_texture(h, t.Name.encode(), px.shape[1], px.shape[0], _p(px)))
+        for s in scene.shaders:
+            for slot, path, chan, tri in (s.texture_bindings() if hasattr(s, "texture_bindings") else []):
+                self._chk(L.orc_shader_set_texture(h, s.Name.encode(), slot, path.encode(), chan, 1 if tri else 0))
         for m in scene.meshes:
             keys, nverts, _ = m.Verts.shape
             self._chk(L.orc_add_polymesh(
@@ -89,6 +95,8 @@ class Oracle:
                 _p(m.Normals), 0 if m.Normals is None else len(m.Normals),
                 _p(m.NormalIdx), 0 if m.NormalIdx is None else len(m.NormalIdx),
                 C.c_float(m.RayBias)))
+            if getattr(m, "UV", None) is not None:
+                self._chk(L.orc_mesh_set_uv(h, m.Name.encode(), _p(m.UV), len(m.UV), _p(m.UVIdx), 0 if m.UVIdx is None else len(m.UVIdx)))
         for ins in getattr(scene, "instances", []):
             bmin = np.ascontiguousarray(ins.BMin, np.float32).reshape(-1, 3)
             bmax = np.ascontiguousarray(ins.BMax, np.float32).reshape(-1, 3)
@@ -165,6 +173,33 @@ class Oracle:
         flags = (1 if any_hit else 0) | (2 if brute else 0)
         self._chk(self.L.orc_trace_batch(self.h, _p(rays), C.c_int64(len(rays)), C.c_uint32(flags), nthreads, _p(hits)))
         return hits
+
+    # -- textures ------------------------------------------------------------------------------------
+    def texture_levels(self, name: str):
+        """The mip pyramid stdfilter built: list of (h, w, 3) uint8 arrays, rows bottom-up."""
+        out = []
+        for l in range(self.L.orc_texture_num_levels(self.h, name.encode())):
+            w, hh = C.c_int(), C.c_int()
+            self._chk(self.L.orc_texture_level(self.h, name.encode(), l, C.byref(w), C.byref(hh), None))
+            a = np.zeros((hh.value, w.value, 3), np.uint8)
+            self._chk(self.L.orc_texture_level(self.h, name.encode(), l, C.byref(w), C.byref(hh), _p(a)))
+            out.append(a)
+        return out
+
+    def texture_sample(self, name: str, coords: np.ndarray, trilinear: bool = False) -> np.ndarray:
+        """coords: (n, 8) float32 {U, V, Dduvdx[2], Dduvdy[2], PixelDelta[2]} -> (n, 3)."""
+        coords = np.ascontiguousarray(coords, np.float32).reshape(-1, 8)
+        out = np.zeros((len(coords), 3), np.float32)
+        self._chk(self.L.orc_texture_sample(self.h, name.encode(), 1 if trilinear else 0, C.c_int64(len(coords)), _p(coords), _p(out)))
+        return out
+
+    def camera_texcoords(self, iter1: int, x0=0, y0=0, w=None, h=None) -> np.ndarray:
+        """(n, 8): what a texture map sees at the first hit of each camera sample (NaN rows for misses)."""
+        w = self.scene.XRes if w is None else w
+        h = self.scene.YRes if h is None else h
+        out = np.zeros((w * h, 8), np.float32)
+        self._chk(self.L.orc_camera_texcoords(self.h, iter1, x0, y0, w, h, _p(out)))
+        return out
 
     # -- structure export --------------------------------------------------------------------------
     def num_geoms(self):

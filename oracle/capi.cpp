@@ -299,6 +299,130 @@ int orc_render(void* h, int iter_begin, int iter_end, int nthreads, int trace_la
   });
 }
 
+// ---- textures (texture/texture.go, mipmap.go, feline.go; builtin/maps/texture.go) --------------------------------------
+// rgb8: w*h*3 bytes, row 0 = BOTTOM row of the image (loadTexture flips while copying, texture.go:139).
+int orc_add_texture(void* h, const char* name, int w, int hgt, const uint8_t* rgb8) {
+  Handle* H = (Handle*)h;
+  return guard([&] {
+    auto t = std::make_unique<Texture>();
+    t->url = name;
+    t->w = w;
+    t->h = hgt;
+    t->data.assign(rgb8, rgb8 + (size_t)w * hgt * 3);
+    t->mipmap = stdfilter(w, hgt, t->data, 3);
+    if (t->mipmap.mipmap.empty()) throw std::runtime_error("texture " + t->url + ": a 1x1 image has no mip level (the reference panics, mipmap.go:127)");
+    H->r.textures.push_back(std::move(t));
+  });
+}
+static Texture* find_texture(Handle* H, const char* name) {
+  for (auto& t : H->r.textures) if (t->url == name) return t.get();
+  throw std::runtime_error(std::string("texture not loaded: ") + name);
+}
+// slot: ShaderStd::k* (node order). filter 1 = "?filter=trilinear" (maps.TextureTrilinear), 0 = Feline (maps.Texture).
+int orc_shader_set_texture(void* h, const char* shader, int slot, const char* texname, int chan, int trilinear) {
+  Handle* H = (Handle*)h;
+  return guard([&] {
+    ShaderStd* sh = H->r.findShader(shader);
+    if (!sh) throw std::runtime_error(std::string("Unable to find node (shader ") + shader + ")");
+    if (slot < 0 || slot >= ShaderStd::kNumSlots || slot == ShaderStd::kSpec1FresnelModel) throw std::runtime_error("bad parameter slot");
+    sh->tex[slot].tex = find_texture(H, texname);
+    sh->tex[slot].Chan = chan;
+    sh->tex[slot].trilinear = trilinear != 0;
+    switch (slot) {  // the parameter is present (a non-nil map)
+      case ShaderStd::kEmissionColour: sh->hasEmissionColour = true; break;
+      case ShaderStd::kEmissionStrength: sh->hasEmissionStrength = true; break;
+      case ShaderStd::kDiffuseColour: sh->hasDiffuseColour = true; break;
+      case ShaderStd::kDiffuseStrength: sh->hasDiffuseStrength = true; break;
+      case ShaderStd::kDiffuseRoughness: sh->hasDiffuseRoughness = true; break;
+      case ShaderStd::kSpec1Colour: sh->hasSpec1Colour = true; break;
+      case ShaderStd::kSpec1Strength: sh->hasSpec1Strength = true; break;
+      case ShaderStd::kSpec1Roughness: sh->hasSpec1Roughness = true; break;
+      case ShaderStd::kIOR: sh->hasIOR = true; break;
+      case ShaderStd::kSpec1FresnelRefl: sh->hasSpec1FresnelRefl = true; break;
+      case ShaderStd::kSpec1FresnelEdge: sh->hasSpec1FresnelEdge = true; break;
+    }
+  });
+}
+// PolyMesh.UV / UVIdx (polymesh.go:36-37); before prerender.
+int orc_mesh_set_uv(void* h, const char* mesh, const float* uv, int nuv, const int32_t* uvidx, int nuvidx) {
+  Handle* H = (Handle*)h;
+  return guard([&] {
+    for (auto& m : H->r.meshes)
+      if (m->Name == mesh) {
+        m->UV.resize(nuv);
+        std::memcpy(m->UV.data(), uv, sizeof(float) * 2 * (size_t)nuv);
+        if (uvidx) { m->hasUVIdx = true; m->UVIdx.assign(uvidx, uvidx + nuvidx); }
+        return;
+      }
+    throw std::runtime_error(std::string("Unable to find node (mesh ") + mesh + ")");
+  });
+}
+int orc_texture_num_levels(void* h, const char* name) {
+  Handle* H = (Handle*)h;
+  int n = -1;
+  guard([&] { n = (int)find_texture(H, name)->mipmap.mipmap.size(); });
+  return n;
+}
+int orc_texture_level(void* h, const char* name, int level, int* w, int* hgt, uint8_t* out) {
+  Handle* H = (Handle*)h;
+  return guard([&] {
+    const MipLevel& L = find_texture(H, name)->mipmap.mipmap.at(level);
+    *w = L.w;
+    *hgt = L.h;
+    if (out) std::memcpy(out, L.mipmap.data(), L.mipmap.size());
+  });
+}
+// coords: n x 8 floats {U, V, Dduvdx[2], Dduvdy[2], PixelDelta[2]}; out: n x 3
+int orc_texture_sample(void* h, const char* name, int trilinear, int64_t n, const float* coords, float* out) {
+  Handle* H = (Handle*)h;
+  return guard([&] {
+    TextureMap m;
+    m.tex = find_texture(H, name);
+    m.trilinear = trilinear != 0;
+    for (int64_t i = 0; i < n; i++) {
+      const float* c = coords + i * 8;
+      TexCoord t;
+      t.U = c[0]; t.V = c[1];
+      t.Dduvdx[0] = c[2]; t.Dduvdx[1] = c[3];
+      t.Dduvdy[0] = c[4]; t.Dduvdy[1] = c[5];
+      t.PixelDelta[0] = c[6]; t.PixelDelta[1] = c[7];
+      m.Sample(t, out + i * 3);
+    }
+  });
+}
+// What the texture maps see at the first hit of camera sample (iter1, x, y): out n x 8 like orc_texture_sample's coords
+// (NaN rows for misses), through GenerateCameraRay -> TraceProbe -> DifferentialTransfer (core/trace.go:61-67).
+int orc_camera_texcoords(void* h, int iter1, int x0, int y0, int w, int hh, float* out) {
+  Handle* H = (Handle*)h;
+  return guard([&] {
+    H->r.PreRender();
+    RenderTask task;
+    task.scene = &H->r.scene;
+    float pd[2];
+    H->r.camera.PixelDelta(H->r.XRes, H->r.YRes, pd);
+    Ray ray;
+    ray.Task = &task;
+    size_t n = 0;
+    for (int y = y0; y < y0 + hh; y++)
+      for (int x = x0; x < x0 + w; x++) {
+        ShaderContext sc;
+        sc.task = &task;
+        H->r.GenerateCameraRay(iter1, x, y, &sc, &ray);
+        ShaderContext sg;
+        sg.task = &task;
+        sg.Time = ray.Time;
+        float* o = out + (n++) * 8;
+        if (TraceProbe(&ray, &sg)) {
+          ray.DifferentialTransfer(&sg);
+          o[0] = sg.U; o[1] = sg.V; o[2] = sg.Dduvdx[0]; o[3] = sg.Dduvdx[1]; o[4] = sg.Dduvdy[0]; o[5] = sg.Dduvdy[1];
+          o[6] = pd[0]; o[7] = pd[1];
+        } else {
+          for (int k = 0; k < 8; k++) o[k] = NAN;
+        }
+      }
+  });
+}
+
 // camera rays of iteration `iter1` (1-based, as render() receives it) for the pixel rectangle
 int orc_camera_rays(void* h, int iter1, int x0, int y0, int w, int hh, OrcRay* out) {
   Handle* H = (Handle*)h;

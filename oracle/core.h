@@ -6,8 +6,7 @@
 //   core/shader.go:53-102,129-162                    (ShaderContext, ApplyTransform, OffsetP)
 //   core/geom.go:8-18, core/light.go:13-42, core/shader.go:16-49 (Geom/Light/BSDF/Shader interfaces)
 //   qbvh/qbvh.go:18-20, qbvh/mqbvh.go:13-15          (Primitive / MotionPrimitive)
-// Ray differentials (core/ray.go:72-87,95-99) are omitted: they only feed texture LOD and every
-// in-scope shader parameter is a constant map.
+// Ray differentials (core/ray.go:40-44,72-87,95-99) are carried: they feed the texture footprint of texture.h.
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -45,6 +44,7 @@ struct alignas(16) RenderTask {
   uint64_t rayCount = 0;         // core/stats.go:26-33 (kept per task, summed at the end)
   uint64_t shadowRayCount = 0;
   bool trace_last_level = true;  // trace the level-4 mirror ray like the reference does (std.go:243)
+  float PixelDelta[2] = {0, 0};  // core.Image.PixelDelta: a package global in the reference (render.go:47, camera.go:316-317)
   RenderTask() { Traversal.StackTop = 0; }
 };
 
@@ -62,6 +62,8 @@ struct Ray {
   int64_t NodesT, LeafsT;
   int64_t TrisT;  // oracle-only counter: sum of LeafCount over visited triangle leaves (bytes model)
   RenderTask* Task;
+  Vec3 DdPdx{}, DdPdy{}, DdDdx{}, DdDdy{};  // core/ray.go:40-44
+  void DifferentialTransfer(ShaderContext* sc) const;  // core/ray.go:95-104
 
   void Setup();
   void Init(uint32_t ty, Vec3 P, Vec3 D, float maxdist, uint8_t level, const ShaderContext* sc);
@@ -133,6 +135,10 @@ struct ShaderContext {
   Vec3 Po{}, P{}, Poffset{};
   Vec3 N{}, Ng{};
   Vec3 DdPdu{}, DdPdv{};
+  float U = 0, V = 0;                           // surface parameters (texture coordinates), core/shader.go:78-79
+  Vec3 DdPdx{}, DdPdy{}, DdDdx{}, DdDdy{}, DdNdx{}, DdNdy{};  // core/shader.go:81-86
+  float Dduvdx[2] = {0, 0}, Dduvdy[2] = {0, 0};
+  float PixelDelta[2] = {0, 0};                 // core.Image.PixelDelta (render.go:32-35): a process-wide constant of the camera
   float Bu = 0, Bv = 0, Bw = 0;  // Bw is oracle-only (W is a local in trace.go:113)
   std::vector<Light*> Lights;
   int Lidx = 0;

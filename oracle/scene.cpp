@@ -34,7 +34,7 @@ void Ray::Setup() {
   Dinv[2] = (float)(1.0 / (double)D[2]);
 }
 
-// core/ray.go:56-93 (differentials omitted)
+// core/ray.go:56-93
 void Ray::Init(uint32_t ty, Vec3 P_, Vec3 D_, float maxdist, uint8_t level, const ShaderContext* sc) {
   P = P_;
   D = D_;
@@ -50,12 +50,32 @@ void Ray::Init(uint32_t ty, Vec3 P_, Vec3 D_, float maxdist, uint8_t level, cons
   Scramble[0] = sc->Scramble[0];
   Scramble[1] = sc->Scramble[1];
   I = sc->I;
+  // Compute ray differentials for reflection (ray.go:72-87)
+  if (ty & RayTypeReflected) {
+    DdPdx = sc->DdPdx;
+    DdPdy = sc->DdPdy;
+    const float DdotNdx = Vec3Dot(sc->DdDdx, sc->N) + Vec3Dot(sc->Rd, sc->DdNdx);
+    const float DdotNdy = Vec3Dot(sc->DdDdy, sc->N) + Vec3Dot(sc->Rd, sc->DdNdy);
+    DdDdx = Vec3Mad(sc->DdDdx, Vec3Add(Vec3Scale(Vec3Dot(sc->Rd, sc->N), sc->DdNdx), Vec3Scale(DdotNdx, sc->N)), -2);
+    DdDdy = Vec3Mad(sc->DdDdy, Vec3Add(Vec3Scale(Vec3Dot(sc->Rd, sc->N), sc->DdNdy), Vec3Scale(DdotNdy, sc->N)), -2);
+  }
+}
+
+// core/ray.go:95-104
+void Ray::DifferentialTransfer(ShaderContext* sc) const {
+  const float dtdx = -Vec3Dot(Vec3Mad(DdPdx, DdDdx, Tclosest), sc->Ng) / Vec3Dot(D, sc->Ng);
+  const float dtdy = -Vec3Dot(Vec3Mad(DdPdy, DdDdy, Tclosest), sc->Ng) / Vec3Dot(D, sc->Ng);
+  sc->DdPdx = Vec3Add(Vec3Mad(DdPdx, DdDdx, Tclosest), Vec3Scale(dtdx, D));
+  sc->DdPdy = Vec3Add(Vec3Mad(DdPdy, DdDdy, Tclosest), Vec3Scale(dtdy, D));
+  sc->DdDdx = DdDdx;
+  sc->DdDdy = DdDdy;
 }
 
 // ---------------------------------------------------------------------------------------------
 // builtin/geom/polymesh/init.go:12-134
 void PolyMesh::init() {
   const bool hasNormals = !Normals.Elems.empty();
+  const bool hasUV = !UV.empty();  // init.go:38-48,77-83,100-106
   if (hasPolyCount) {
     uint32_t basei = 0;
     for (size_t k = 0; k < PolyCount.size(); k++) {
@@ -71,6 +91,12 @@ void PolyMesh::init() {
           normalidx.push_back((uint32_t)src[basei + i]);
           normalidx.push_back((uint32_t)src[basei + i + 1]);
         }
+        if (hasUV) {
+          const std::vector<int32_t>& src = hasUVIdx ? UVIdx : FaceIdx;
+          uvtriidx.push_back((uint32_t)src[basei]);
+          uvtriidx.push_back((uint32_t)src[basei + i]);
+          uvtriidx.push_back((uint32_t)src[basei + i + 1]);
+        }
         if (!ShaderIdx.empty()) shaderidx.push_back((uint8_t)ShaderIdx[k]);
       }
       basei += (uint32_t)PolyCount[k];
@@ -80,11 +106,13 @@ void PolyMesh::init() {
       for (size_t j = 0; j < FaceIdx.size(); j++) {
         idxp.push_back((uint32_t)FaceIdx[j]);
         if (hasNormals) normalidx.push_back(hasNormalIdx ? (uint32_t)NormalIdx[j] : (uint32_t)FaceIdx[j]);
+        if (hasUV) uvtriidx.push_back(hasUVIdx ? (uint32_t)UVIdx[j] : (uint32_t)FaceIdx[j]);
       }
     } else {
       for (int j = 0; j < Verts.ElemsPerKey; j++) {
         idxp.push_back((uint32_t)j);
         if (hasNormals) normalidx.push_back(hasNormalIdx ? (uint32_t)NormalIdx[j] : (uint32_t)j);
+        if (hasUV) uvtriidx.push_back(hasUVIdx ? (uint32_t)UVIdx[j] : (uint32_t)j);
       }
     }
     for (int32_t idx : ShaderIdx) shaderidx.push_back((uint8_t)idx);
@@ -93,6 +121,7 @@ void PolyMesh::init() {
   PolyCount.clear();
   NormalIdx.clear();
   ShaderIdx.clear();
+  UVIdx.clear();
 }
 
 // builtin/geom/polymesh/buildqbvh.go:14-144
@@ -157,6 +186,15 @@ void PolyMesh::initAccel() {
       nn[i * 3 + 2] = normalidx[idxs[i] * 3 + 2];
     }
     normalidx = nn;
+  }
+  if (!uvtriidx.empty()) {  // buildqbvh.go:106-116
+    std::vector<uint32_t> uu(uvtriidx.size());
+    for (size_t i = 0; i < idxs.size(); i++) {
+      uu[i * 3 + 0] = uvtriidx[idxs[i] * 3 + 0];
+      uu[i * 3 + 1] = uvtriidx[idxs[i] * 3 + 1];
+      uu[i * 3 + 2] = uvtriidx[idxs[i] * 3 + 2];
+    }
+    uvtriidx = uu;
   }
   idxp = nidxp;
 }
@@ -312,11 +350,14 @@ bool PolyMesh::TraceElems(Ray* ray, ShaderContext* sg, int base, int count) {
   sg->Ng[2] = e00 * e11 - e01 * e10;
   sg->Ng = Vec3Normalize(sg->Ng);
 
+  Vec3 N;  // the interpolated normal BEFORE normalisation (trace.go:326-336), used by the normal differentials
   if (!Normals.Elems.empty()) {
     for (int k = 0; k < 3; k++)
       sg->N[k] = U * Normals.Elems[normalidx[(idx * 3) + 0]][k] + V * Normals.Elems[normalidx[(idx * 3) + 1]][k] + W * Normals.Elems[normalidx[(idx * 3) + 2]][k];
+    N = sg->N;
     sg->N = Vec3Normalize(sg->N);
   } else {
+    N = sg->Ng;
     sg->N = sg->Ng;
   }
 
@@ -327,6 +368,89 @@ bool PolyMesh::TraceElems(Ray* ray, ShaderContext* sg, int base, int count) {
   sg->Bw = W;
   for (int k = 0; k < 3; k++) sg->P[k] = U * E0[k] + V * E1[k] + W * E2[k];
   sg->Po = sg->P;
+
+  // trace.go:350-358
+  if (!UV.empty()) {
+    const float* t0 = UV[uvtriidx[(idx * 3) + 0]].v;
+    const float* t1 = UV[uvtriidx[(idx * 3) + 1]].v;
+    const float* t2 = UV[uvtriidx[(idx * 3) + 2]].v;
+    sg->U = U * t0[0] + V * t1[0] + W * t2[0];
+    sg->V = U * t0[1] + V * t1[1] + W * t2[1];
+  } else {
+    sg->U = U;
+    sg->V = V;
+  }
+  ray->DifferentialTransfer(sg);  // trace.go:360
+
+  // trace.go:362-502: barycentric planes -> d(alpha,beta,gamma)/dx,dy -> normal and texture-coordinate differentials
+  {
+    auto sq = [](float x) { return x * x; };
+    const Vec3& Ng = sg->Ng;
+    float nalphax = Ng[1] * (E2[2] - E1[2]) - Ng[2] * (E2[1] - E1[1]);
+    float nalphay = Ng[2] * (E2[0] - E1[0]) - Ng[0] * (E2[2] - E1[2]);
+    float nalphaz = Ng[0] * (E2[1] - E1[1]) - Ng[1] * (E2[0] - E1[0]);
+    float q = Sqrt(sq(nalphax) + sq(nalphay) + sq(nalphaz));
+    nalphax /= q; nalphay /= q; nalphaz /= q;
+    float nalphad = -E1[0] * nalphax - E1[1] * nalphay - E1[2] * nalphaz;
+    float l = E0[0] * nalphax + E0[1] * nalphay + E0[2] * nalphaz + nalphad;
+    nalphax /= l; nalphay /= l; nalphaz /= l; nalphad /= l;
+
+    float nbetax = Ng[1] * (E2[2] - E0[2]) - Ng[2] * (E2[1] - E0[1]);
+    float nbetay = Ng[2] * (E2[0] - E0[0]) - Ng[0] * (E2[2] - E0[2]);
+    float nbetaz = Ng[0] * (E2[1] - E0[1]) - Ng[1] * (E2[0] - E0[0]);
+    q = Sqrt(sq(nbetax) + sq(nbetay) + sq(nbetaz));
+    nbetax /= q; nbetay /= q; nbetaz /= q;
+    float nbetad = -E0[0] * nbetax - E0[1] * nbetay - E0[2] * nbetaz;
+    l = nbetax * E1[0] + nbetay * E1[1] + nbetaz * E1[2] + nbetad;
+    nbetax /= l; nbetay /= l; nbetaz /= l; nbetad /= l;
+
+    float ngammax = Ng[1] * (E1[2] - E0[2]) - Ng[2] * (E1[1] - E0[1]);
+    float ngammay = Ng[2] * (E1[0] - E0[0]) - Ng[0] * (E1[2] - E0[2]);
+    float ngammaz = Ng[0] * (E1[1] - E0[1]) - Ng[1] * (E1[0] - E0[0]);
+    q = Sqrt(sq(ngammax) + sq(ngammay) + sq(ngammaz));
+    ngammax /= q; ngammay /= q; ngammaz /= q;
+    float ngammad = -E0[0] * ngammax - E0[1] * ngammay - E0[2] * ngammaz;
+    l = ngammax * E2[0] + ngammay * E2[1] + ngammaz * E2[2] + ngammad;
+    ngammax /= l; ngammay /= l; ngammaz /= l; ngammad /= l;
+    (void)nalphad; (void)nbetad; (void)ngammad;
+
+    const float alphax = nalphax * sg->DdPdx[0] + nalphay * sg->DdPdx[1] + nalphaz * sg->DdPdx[2];
+    const float betax = nbetax * sg->DdPdx[0] + nbetay * sg->DdPdx[1] + nbetaz * sg->DdPdx[2];
+    const float gammax = ngammax * sg->DdPdx[0] + ngammay * sg->DdPdx[1] + ngammaz * sg->DdPdx[2];
+    const float alphay = nalphax * sg->DdPdy[0] + nalphay * sg->DdPdy[1] + nalphaz * sg->DdPdy[2];
+    const float betay = nbetax * sg->DdPdy[0] + nbetay * sg->DdPdy[1] + nbetaz * sg->DdPdy[2];
+    const float gammay = ngammax * sg->DdPdy[0] + ngammay * sg->DdPdy[1] + ngammaz * sg->DdPdy[2];
+
+    Vec3 dndx = V3(0, 0, 0), dndy = V3(0, 0, 0);
+    if (!Normals.Elems.empty()) {
+      const Vec3& n0 = Normals.Elems[normalidx[(idx * 3) + 0]];
+      const Vec3& n1 = Normals.Elems[normalidx[(idx * 3) + 1]];
+      const Vec3& n2 = Normals.Elems[normalidx[(idx * 3) + 2]];
+      for (int k = 0; k < 3; k++) {
+        dndx[k] = alphax * n0[k] + betax * n1[k] + gammax * n2[k];
+        dndy[k] = alphay * n0[k] + betay * n1[k] + gammay * n2[k];
+      }
+    }
+    sg->DdNdx = Vec3Sub(Vec3Scale(Vec3Dot(N, N), dndx), Vec3Scale(Vec3Dot(N, dndx), N));
+    sg->DdNdx = Vec3Scale(1 / (Vec3Dot(N, N) * Sqrt(Vec3Dot(N, N))), sg->DdNdx);
+    sg->DdNdy = Vec3Sub(Vec3Scale(Vec3Dot(N, N), dndy), Vec3Scale(Vec3Dot(N, dndy), N));
+    sg->DdNdy = Vec3Scale(1 / (Vec3Dot(N, N) * Sqrt(Vec3Dot(N, N))), sg->DdNdy);
+
+    if (!UV.empty()) {
+      const float* t0 = UV[uvtriidx[(idx * 3) + 0]].v;
+      const float* t1 = UV[uvtriidx[(idx * 3) + 1]].v;
+      const float* t2 = UV[uvtriidx[(idx * 3) + 2]].v;
+      for (int k = 0; k < 2; k++) {
+        sg->Dduvdx[k] = alphax * t0[k] + betax * t1[k] + gammax * t2[k];
+        sg->Dduvdy[k] = alphay * t0[k] + betay * t1[k] + gammay * t2[k];
+      }
+    } else {  // trace.go:495-501, as written (U above is the FIRST barycentric, these follow the second and third)
+      sg->Dduvdx[0] = alphax * 0 + betax * 1 + gammax * 0;
+      sg->Dduvdx[1] = alphax * 0 + betax * 0 + gammax * 1;
+      sg->Dduvdy[0] = alphay * 0 + betay * 1 + gammay * 0;
+      sg->Dduvdy[1] = alphay * 0 + betay * 0 + gammay * 1;
+    }
+  }
 
   // trace.go:504-511
   Vec3 axisu = Vec3Sub(V3(1, 0, 0), Vec3Scale(Vec3Dot(V3(1, 0, 0), sg->Ng), sg->Ng));
@@ -404,6 +528,18 @@ bool PolyMesh::TraceMotionElems(float time, int key, int key2, Ray* ray, ShaderC
   if (!shaderidx.empty()) shaderIdx = shaderidx[idx];
   sg->shader = shader.empty() ? nullptr : shader[shaderIdx];
   sg->P = sg->Po;
+
+  // trace.go:677-684: surface parameters only; the motion path transfers no differentials (Dduvdx/y stay 0)
+  if (!UV.empty()) {
+    const float* t0 = UV[uvtriidx[(idx * 3) + 0]].v;
+    const float* t1 = UV[uvtriidx[(idx * 3) + 1]].v;
+    const float* t2 = UV[uvtriidx[(idx * 3) + 2]].v;
+    sg->U = U * t0[0] + V * t1[0] + W * t2[0];
+    sg->V = U * t0[1] + V * t1[1] + W * t2[1];
+  } else {
+    sg->U = U;
+    sg->V = V;
+  }
 
   if (!Normals.Elems.empty() && Normals.MotionKeys == Verts.MotionKeys) {
     Vec3 N0 = Vec3Lerp(Normals.Elems[(int)((idx * 3) + 0) + Normals.ElemsPerKey * key], Normals.Elems[(int)((idx * 3) + 0) + Normals.ElemsPerKey * key2], time);
@@ -597,9 +733,14 @@ bool Trace(Ray* ray, TraceSample* samp) {
   sg.task = ray->Task;
   sg.Scramble[0] = ray->Scramble[0];
   sg.Scramble[1] = ray->Scramble[1];
+  if (ray->Task) {  // Image: image (trace.go:55) — the package-level constants the camera wrote (camera.go:316-317)
+    sg.PixelDelta[0] = ray->Task->PixelDelta[0];
+    sg.PixelDelta[1] = ray->Task->PixelDelta[1];
+  }
 
   if (TraceProbe(ray, &sg)) {
     if (sg.shader == nullptr) return false;
+    ray->DifferentialTransfer(&sg);  // trace.go:67 (a second time for meshes: same inputs, same result)
     sg.ApplyTransform();
     sg.shader->Eval(&sg);
     if (samp != nullptr) {

@@ -9,7 +9,8 @@
 //   builtin/geom/polymesh/bounds.go:25-53      (Bounds)
 //   builtin/scene/scene.go:15-268              (Scene: Trace, TraceElems, LightsPrepare, initAccel, initMotionBoxes)
 //   builtin/geom/instance/instance.go:16-160   (GeomInstance: SRT-interpolated transform, ray re-Setup, user-given bounds)
-// Out of scope here: object Transform, UVs, ray differentials.
+// UVs and ray differentials (trace.go:350-502) are computed for static meshes, like the reference (TraceMotionElems sets
+// U,V but leaves every differential 0, trace.go:677-684). Out of scope: the mesh's own Transform (quirk q).
 #pragma once
 #include <memory>
 #include <string>
@@ -34,7 +35,11 @@ struct PolyMesh : Geom, Primitive, MotionPrimitive {
   std::vector<int32_t> ShaderIdx;
   PointArray Normals;
   std::vector<int32_t> NormalIdx;
-  bool hasPolyCount = false, hasFaceIdx = false, hasNormalIdx = false;
+  bool hasPolyCount = false, hasFaceIdx = false, hasNormalIdx = false, hasUVIdx = false;
+  struct Vec2 { float v[2]; };
+  std::vector<Vec2> UV;           // param.Vec2Array, one key (polymesh.go:36)
+  std::vector<int32_t> UVIdx;     // polymesh.go:37
+  std::vector<uint32_t> uvtriidx;  // triangulated UV indexes (polymesh.go:45)
 
   int facecount = 0;
   std::vector<uint32_t> idxp;

@@ -225,6 +225,31 @@ struct MicrofacetGGX : BSDF {
 void DebugShader::Eval(ShaderContext* sg) { sg->OutRGB = Colour; }
 RGB DebugShader::EvalEmission(ShaderContext*, Vec3) { return RGB{}; }
 
+// param.RGBUniform / Float32Uniform (core/param/param.go): a constant map, or builtin/maps/texture.go:22-46 when the .vnf
+// value was a file name
+static TexCoord tex_coord(const ShaderContext* sg) {
+  TexCoord t;
+  t.U = sg->U; t.V = sg->V;
+  t.Dduvdx[0] = sg->Dduvdx[0]; t.Dduvdx[1] = sg->Dduvdx[1];
+  t.Dduvdy[0] = sg->Dduvdy[0]; t.Dduvdy[1] = sg->Dduvdy[1];
+  t.PixelDelta[0] = sg->PixelDelta[0]; t.PixelDelta[1] = sg->PixelDelta[1];
+  return t;
+}
+RGB ShaderStd::rgb(int slot, const RGB& constant, const ShaderContext* sg) const {
+  if (!tex[slot].tex) return constant;
+  if (!sg) throw std::runtime_error("Shader " + Name + ": a texture map on a light's emission is out of scope (the light passes its own lsg)");
+  float c[3];
+  tex[slot].Sample(tex_coord(sg), c);
+  return MakeRGB(c[0], c[1], c[2]);
+}
+float ShaderStd::f32(int slot, float constant, const ShaderContext* sg) const {
+  if (!tex[slot].tex) return constant;
+  if (!sg) throw std::runtime_error("Shader " + Name + ": a texture map on a light's emission is out of scope (the light passes its own lsg)");
+  float c[3];
+  tex[slot].Sample(tex_coord(sg), c);
+  return c[tex[slot].Chan];
+}
+
 void ShaderStd::Eval(ShaderContext* sg) {
   if (sg->Level > 3) return;
 
@@ -234,16 +259,16 @@ void ShaderStd::Eval(ShaderContext* sg) {
   Vec3 U = Vec3Normalize(Vec3Cross(sg->N, V));
 
   float diffRoughness = 0.5f;
-  if (hasDiffuseRoughness) diffRoughness = DiffuseRoughness;
+  if (hasDiffuseRoughness) diffRoughness = f32(kDiffuseRoughness, DiffuseRoughness, sg);
   OrenNayar diffBrdf(sg->Lambda, Vec3Neg(sg->Rd), diffRoughness, U, V, sg->N);
 
   RGB diffContrib;
   RGB diffColour;
-  if (hasDiffuseColour) diffColour = DiffuseColour;
+  if (hasDiffuseColour) diffColour = rgb(kDiffuseColour, DiffuseColour, sg);
 
   float diffWeight = 0, spec1Weight = 0;
-  if (hasDiffuseStrength) diffWeight = DiffuseStrength;
-  if (hasSpec1Strength) spec1Weight = Spec1Strength;
+  if (hasDiffuseStrength) diffWeight = f32(kDiffuseStrength, DiffuseStrength, sg);
+  if (hasSpec1Strength) spec1Weight = f32(kSpec1Strength, Spec1Strength, sg);
   float totalWeight = diffWeight + spec1Weight;
   diffWeight /= totalWeight;
   spec1Weight /= totalWeight;
@@ -262,22 +287,22 @@ void ShaderStd::Eval(ShaderContext* sg) {
   }
 
   float ior = 1.7f;
-  if (hasIOR) ior = IOR;
+  if (hasIOR) ior = f32(kIOR, IOR, sg);
 
   // std.go:172-192
   Dielectric dielectric(ior);
   RGB refl = MakeRGB(0.5f, 0.5f, 0.5f), edge = MakeRGB(0.5f, 0.5f, 0.5f);
-  if (hasSpec1FresnelRefl) refl = Spec1FresnelRefl;
-  if (hasSpec1FresnelEdge) refl = Spec1FresnelEdge;  // sic: std.go:187-189 assigns the edge tint to `refl`
+  if (hasSpec1FresnelRefl) refl = rgb(kSpec1FresnelRefl, Spec1FresnelRefl, sg);
+  if (hasSpec1FresnelEdge) refl = rgb(kSpec1FresnelEdge, Spec1FresnelEdge, sg);  // sic: std.go:187-189 assigns the edge tint to `refl`
   Conductor conductor(refl, edge);
   const Fresnel* fresnel = spec1FresnelModel == 1 ? static_cast<const Fresnel*>(&conductor) : static_cast<const Fresnel*>(&dielectric);
 
   RGB spec1Contrib;
   if (spec1Weight > 0.0f) {
     float spec1Roughness = 0.5f;
-    if (hasSpec1Roughness) spec1Roughness = Spec1Roughness;
+    if (hasSpec1Roughness) spec1Roughness = f32(kSpec1Roughness, Spec1Roughness, sg);
     RGB spec1Colour;
-    if (hasSpec1Colour) spec1Colour = Spec1Colour;
+    if (hasSpec1Colour) spec1Colour = rgb(kSpec1Colour, Spec1Colour, sg);
     Specular specBRDF(sg->Lambda, Vec3Neg(sg->Rd), fresnel, U, V, sg->N);
     MicrofacetGGX ggxBRDF(sg->Lambda, Vec3Neg(sg->Rd), fresnel, spec1Roughness, U, V, sg->N);
     BSDF& spec1BRDF = spec1Roughness == 0.0f ? static_cast<BSDF&>(specBRDF) : static_cast<BSDF&>(ggxBRDF);
@@ -333,11 +358,11 @@ void ShaderStd::Eval(ShaderContext* sg) {
 }
 
 // builtin/shader/std.go:299-316
-RGB ShaderStd::EvalEmission(ShaderContext*, Vec3) {
+RGB ShaderStd::EvalEmission(ShaderContext* sg, Vec3) {
   RGB emissColour;
   float emissStrength = 0;
-  if (hasEmissionColour) emissColour = EmissionColour;
-  if (hasEmissionStrength) emissStrength = EmissionStrength;
+  if (hasEmissionColour) emissColour = rgb(kEmissionColour, EmissionColour, sg);
+  if (hasEmissionStrength) emissStrength = f32(kEmissionStrength, EmissionStrength, sg);
   else return RGB{};
   emissColour.Scale(emissStrength);
   return emissColour;
@@ -819,7 +844,7 @@ Matrix4 Camera::MatrixAt(float time) const {
   return TransformDecompToMatrix4(TransformDecompLerp(decomp[key], decomp[key2], t));
 }
 
-// builtin/camera/camera.go:221-323 (differentials omitted)
+// builtin/camera/camera.go:221-323
 void Camera::ComputeRay(float Sx, float Sy, double lensU, double lensV, const ShaderContext* sc, Ray* ray) const {
   float camu = Sx * TanThetaFocal;
   float camv = Sy * (TanThetaFocal / Aspect);
@@ -839,7 +864,20 @@ void Camera::ComputeRay(float Sx, float Sy, double lensU, double lensV, const Sh
     D = Vec3Normalize(d);
     P = Matrix4MulPoint(M, V3(0, 0, 0));
   }
+  // camera.go:300-306 (the finite-difference dx, dy of :268-295 are computed and then discarded by the reference)
+  const Vec3 right = V3(M.m[0], M.m[1], M.m[2]);
+  const Vec3 up = V3(M.m[4], M.m[5], M.m[6]);
+  ray->DdPdx = V3(0, 0, 0);
+  ray->DdPdy = V3(0, 0, 0);
+  ray->DdDdx = Vec3Scale(1 / (Vec3Dot(d, d) * Sqrt(Vec3Dot(d, d))), Vec3Sub(Vec3Scale(Vec3Dot(d, d), right), Vec3Scale(Vec3Dot(d, right), d)));
+  ray->DdDdy = Vec3Scale(1 / (Vec3Dot(d, d) * Sqrt(Vec3Dot(d, d))), Vec3Sub(Vec3Scale(Vec3Dot(d, d), up), Vec3Scale(Vec3Dot(d, up), d)));
   ray->Init(RayTypeCamera, P, D, kInfPos, 0, sc);
+}
+
+// camera.go:316-317: sc.Image.PixelDelta, the same two numbers on every call
+void Camera::PixelDelta(int w, int h, float out[2]) const {
+  out[0] = 2 * TanThetaFocal / (float)w;
+  out[1] = 2 * TanThetaFocal / (Aspect * (float)h);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1068,6 +1106,7 @@ RenderStats Renderer::Render(int iterBegin, int iterEnd, int nthreads) {
       RenderTask* task = &tasks[ti];
       task->scene = &scene;
       task->trace_last_level = trace_last_level;
+      camera.PixelDelta(XRes, YRes, task->PixelDelta);
       Ray ray;
       ray.Task = task;
       ShaderContext sc;

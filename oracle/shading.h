@@ -22,6 +22,7 @@
 
 #include "core.h"
 #include "scene.h"
+#include "texture.h"
 
 namespace orc {
 
@@ -41,6 +42,12 @@ struct ShaderStd : Shader {
   int spec1FresnelModel = 0;  // fresnel.DielectricModel = 0 (the zero value when Spec1FresnelModel is unset), ConductorModel = 1
   bool hasSpec1FresnelRefl = false, hasSpec1FresnelEdge = false;
   RGB Spec1FresnelRefl, Spec1FresnelEdge;
+  // parameter slots in node order (std.go:28-46); a slot with a texture bound is a maps.Texture / TextureTrilinear
+  enum { kEmissionColour = 0, kEmissionStrength, kDiffuseColour, kDiffuseStrength, kDiffuseRoughness, kSpec1Colour, kSpec1Strength,
+         kSpec1Roughness, kIOR, kSpec1FresnelModel, kSpec1FresnelRefl, kSpec1FresnelEdge, kNumSlots };
+  TextureMap tex[kNumSlots];
+  RGB rgb(int slot, const RGB& constant, const ShaderContext* sg) const;
+  float f32(int slot, float constant, const ShaderContext* sg) const;
 
   void Eval(ShaderContext* sg) override;
   RGB EvalEmission(ShaderContext* sg, Vec3 omegaO) override;
@@ -135,6 +142,7 @@ struct Camera {
   void PreRender(float frameAspect);
   Matrix4 MatrixAt(float time) const;  // camera.go:225-236
   void ComputeRay(float Sx, float Sy, double lensU, double lensV, const ShaderContext* sc, Ray* ray) const;
+  void PixelDelta(int w, int h, float out[2]) const;
 };
 
 // builtin/filter/filter.go:29-173 — filter-importance-sampling tables (marginal + conditional CDFs)
@@ -174,6 +182,7 @@ struct Renderer {
   std::vector<std::unique_ptr<PolyMesh>> meshes;
   std::vector<std::unique_ptr<Instance>> instances;  // GeomInstance nodes, created after the meshes they refer to
   std::vector<std::unique_ptr<ShaderStd>> shaders;
+  std::vector<std::unique_ptr<Texture>> textures;  // texture.TexStore (texture/texture.go:45-47), filled before PreRender
   std::vector<std::unique_ptr<Tri>> tris;
   std::vector<std::unique_ptr<Disk>> disks;
   std::vector<std::unique_ptr<SphereLight>> sphereLights;

@@ -58,6 +58,9 @@ static inline float Tan(float x) { return (float)std::tan((double)x); }
 static inline float Acos(float x) { return (float)std::acos((double)x); }
 static inline float Atan(float x) { return (float)std::atan((double)x); }
 static inline float Atan2(float y, float x) { return (float)std::atan2((double)y, (double)x); }
+// math/pow.go:11-19
+static inline float Log2(float x) { return (float)std::log2((double)x); }
+static inline float Exp(float x) { return (float)std::exp((double)x); }
 
 // math/inf.go:24-26
 static inline bool IsInf(float v) { return v > std::numeric_limits<float>::max() || v < -std::numeric_limits<float>::max(); }

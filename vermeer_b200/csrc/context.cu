@@ -85,6 +85,7 @@ void vg_destroy(vg_ctx* ctx) {
   render_destroy(ctx);
   ctx->d_nodes.release(); ctx->d_mtopo.release(); ctx->d_mboxes.release(); ctx->d_tris.release();
   ctx->d_mtris.release(); ctx->d_normals.release(); ctx->d_geoms.release(); ctx->d_prim_material.release();
+  ctx->d_tri_uv.release(); ctx->d_texels.release(); ctx->d_tex_levels.release(); ctx->d_textures.release();
   ctx->d_xforms.release(); ctx->d_xf_keys.release(); ctx->d_xf_static.release();
   ctx->d_rays.release(); ctx->d_hits.release(); ctx->d_counters.release(); ctx->d_cam_keys.release();
   for (int i = 0; i < 3; i++) {
@@ -287,6 +288,9 @@ int vg_scene_commit(vg_ctx* ctx) {
   std::vector<DevMotionNode> mtopo((size_t)n_motion);
   std::vector<float4> mboxes((size_t)n_mboxes * 6);
   std::vector<float4> tris((size_t)n_tris * 3), mtris((size_t)n_mtris * 3), normals((size_t)n_normal_slots * 3);
+  bool any_uv = false;
+  for (int g = 0; g < G; g++) any_uv |= (!ctx->meshes[g].motion && !ctx->meshes[g].uvtriidx.empty());
+  std::vector<float2> tri_uv(any_uv ? (size_t)n_tris * 3 : 0);
   std::vector<DevGeom> geoms((size_t)G);
   std::vector<uint8_t> prim_material((size_t)n_prims, 255);
 
@@ -305,7 +309,8 @@ int vg_scene_commit(vg_ctx* ctx) {
     dg.keys = m.motion ? m.keys : 1;
     dg.tri_key_stride = m.n_tris;
     dg.n_tris = m.n_tris;
-    dg.pad0 = dg.pad1 = 0;
+    dg.uv_base = -1;
+    dg.pad1 = 0;
     if (m.material_ids.size() > 255) return ctx->fail(VG_ERR_UNSUPPORTED, "more than 255 shaders on one mesh");
 
     if (m.instance) continue;  // filled from the target below
@@ -357,6 +362,14 @@ int vg_scene_commit(vg_ctx* ctx) {
           for (int j = 0; j < 3; j++) {
             const float* v = &m.normals[(size_t)m.normalidx[(size_t)i * 3 + j] * 3];
             normals[(size_t)(tri_base[g] + i) * 3 + j] = make_float4(v[0], v[1], v[2], 0.f);
+          }
+      }
+      if (!m.uvtriidx.empty()) {
+        dg.uv_base = (int32_t)tri_base[g];
+        for (int i = 0; i < m.n_tris; i++)
+          for (int j = 0; j < 3; j++) {
+            const float* v = &m.uv[(size_t)m.uvtriidx[(size_t)i * 3 + j] * 2];
+            tri_uv[(size_t)(tri_base[g] + i) * 3 + j] = make_float2(v[0], v[1]);
           }
       }
     } else {
@@ -482,6 +495,7 @@ int vg_scene_commit(vg_ctx* ctx) {
   VG_CUDA(ctx, upload(ctx->d_tris, tris, ctx->stream));
   VG_CUDA(ctx, upload(ctx->d_mtris, mtris, ctx->stream));
   VG_CUDA(ctx, upload(ctx->d_normals, normals, ctx->stream));
+  VG_CUDA(ctx, upload(ctx->d_tri_uv, tri_uv, ctx->stream));
   VG_CUDA(ctx, upload(ctx->d_geoms, geoms, ctx->stream));
   VG_CUDA(ctx, upload(ctx->d_prim_material, prim_material, ctx->stream));
   VG_CUDA(ctx, upload(ctx->d_xforms, xforms, ctx->stream));
@@ -499,6 +513,7 @@ int vg_scene_commit(vg_ctx* ctx) {
   d.geoms = ctx->d_geoms.p;
   d.prim_material = ctx->d_prim_material.p;
   d.tri_normals = any_normals ? ctx->d_normals.p : nullptr;
+  d.tri_uv = any_uv ? ctx->d_tri_uv.p : nullptr;
   d.n_static = (int32_t)n_static;
   d.root = S.motion ? motion_global(scene_node_base) : (int32_t)scene_node_base;
   d.xforms = ctx->d_xforms.p;
@@ -519,7 +534,155 @@ int vg_set_materials(vg_ctx* ctx, const VgMaterial* mats, int n) {
   if (n < 0 || (n > 0 && !mats)) return ctx->fail(VG_ERR_INVALID, "vg_set_materials: bad input");
   if (n > 254) return ctx->fail(VG_ERR_UNSUPPORTED, "more than 254 materials");
   ctx->materials.assign(mats, mats + n);
+  ctx->mat_tex.assign((size_t)n, MatTex());
   render_invalidate(ctx);
+  return VG_OK;
+}
+
+// ---- texture store ----------------------------------------------------------------------------------------------------
+int vg_texture_upload(vg_ctx* ctx, const uint8_t* rgb8, int w, int h, int* tex_id) {
+  VG_LOCK(ctx);
+  if (!rgb8 || w <= 0 || h <= 0 || !tex_id) return ctx->fail(VG_ERR_INVALID, "vg_texture_upload: null/empty input");
+  if (w > 32768 || h > 32768) return ctx->fail(VG_ERR_UNSUPPORTED, "vg_texture_upload: image larger than 32768 texels on a side");
+  // maxlevel := int(Ceil(Log2(Max(w, h)))) (mipmap.go:123): exact for integers
+  int maxlevel = 0;
+  while ((1 << maxlevel) < std::max(w, h)) maxlevel++;
+  if (maxlevel <= 0) return ctx->fail(VG_ERR_INVALID, "vg_texture_upload: a 1x1 image has no mip level (the reference panics, mipmap.go:127)");
+  VG_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevTexture T;
+  T.w = w; T.h = h;
+  T.first_level = (int32_t)ctx->tex_levels.size();
+  T.n_levels = maxlevel;
+  std::vector<DevTexLevel> lv((size_t)maxlevel);
+  size_t off = ctx->n_texels;
+  int cw = w, ch = h;
+  for (int l = 0; l < maxlevel; l++) {
+    if (l > 0) {  // nwidth := int(Max(1, Ceil(width / 2))) (mipmap.go:138-139)
+      // a level filtered FROM a 1-texel-high level reads row 1 (y2 := mini(2y+1, maxi(1, height-1)), mipmap.go:205,245; the x
+      // axis has a wrap rule, :179-182, the y axis has none): the reference panics with an index out of range, i.e. it cannot
+      // load images that are 4x or more wider than high (roughly: ceil(log2 w) - ceil(log2 h) >= 2)
+      if (ch == 1)
+        return ctx->fail(VG_ERR_INVALID, "vg_texture_upload: image much wider than high (the reference's stdfilter indexes row 1 of a 1-row level, mipmap.go:205,245)");
+      cw = std::max(1, (cw + 1) / 2);
+      ch = std::max(1, (ch + 1) / 2);
+    }
+    lv[(size_t)l] = DevTexLevel{(uint32_t)off, cw, ch, 0};
+    off += (size_t)cw * ch;
+  }
+  if (off > 0xffffffffull) return ctx->fail(VG_ERR_UNSUPPORTED, "texture store exceeds 2^32 texels");
+  // grow the shared texel array (device-to-device copy of what is there)
+  if (off > ctx->d_texels.cap) {
+    uchar4* np = nullptr;
+    const size_t ncap = std::max(off, ctx->d_texels.cap * 2);
+    VG_CUDA(ctx, cudaMalloc((void**)&np, ncap * sizeof(uchar4)));
+    if (ctx->n_texels) VG_CUDA(ctx, cudaMemcpyAsync(np, ctx->d_texels.p, ctx->n_texels * sizeof(uchar4), cudaMemcpyDeviceToDevice, ctx->stream));
+    VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_texels.p) cudaFree(ctx->d_texels.p);
+    ctx->d_texels.p = np;
+    ctx->d_texels.cap = ncap;
+  }
+  std::vector<uchar4> l0((size_t)w * h);
+  for (size_t i = 0; i < l0.size(); i++) l0[i] = make_uchar4(rgb8[i * 3], rgb8[i * 3 + 1], rgb8[i * 3 + 2], 0);
+  VG_CUDA(ctx, cudaMemcpyAsync(ctx->d_texels.p + lv[0].off, l0.data(), l0.size() * sizeof(uchar4), cudaMemcpyHostToDevice, ctx->stream));
+  for (int l = 1; l < maxlevel; l++) VG_CUDA(ctx, launch_mip_level(ctx->d_texels.p, lv[(size_t)l - 1], lv[(size_t)l], ctx->stream));
+  VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stats.kernel_launches += (uint64_t)(maxlevel - 1);
+  ctx->n_texels = off;
+  ctx->tex_levels.insert(ctx->tex_levels.end(), lv.begin(), lv.end());
+  ctx->textures.push_back(T);
+  VG_CUDA(ctx, upload(ctx->d_tex_levels, ctx->tex_levels, ctx->stream));
+  VG_CUDA(ctx, upload(ctx->d_textures, ctx->textures, ctx->stream));
+  VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *tex_id = (int)ctx->textures.size() - 1;
+  render_invalidate(ctx);
+  return VG_OK;
+}
+
+int vg_textures_clear(vg_ctx* ctx) {
+  VG_LOCK(ctx);
+  ctx->textures.clear();
+  ctx->tex_levels.clear();
+  ctx->n_texels = 0;
+  for (MatTex& m : ctx->mat_tex) m = MatTex();
+  render_invalidate(ctx);
+  return VG_OK;
+}
+
+int vg_texture_levels(vg_ctx* ctx, int tex_id, int* n_levels) {
+  VG_LOCK(ctx);
+  if (tex_id < 0 || tex_id >= (int)ctx->textures.size() || !n_levels) return ctx->fail(VG_ERR_INVALID, "vg_texture_levels: bad texture id");
+  *n_levels = ctx->textures[(size_t)tex_id].n_levels;
+  return VG_OK;
+}
+
+int vg_texture_read_level(vg_ctx* ctx, int tex_id, int level, int* w, int* h, uint8_t* rgb8_out) {
+  VG_LOCK(ctx);
+  if (tex_id < 0 || tex_id >= (int)ctx->textures.size()) return ctx->fail(VG_ERR_INVALID, "vg_texture_read_level: bad texture id");
+  const DevTexture& T = ctx->textures[(size_t)tex_id];
+  if (level < 0 || level >= T.n_levels) return ctx->fail(VG_ERR_INVALID, "vg_texture_read_level: bad level");
+  const DevTexLevel& L = ctx->tex_levels[(size_t)T.first_level + level];
+  if (w) *w = L.w;
+  if (h) *h = L.h;
+  if (!rgb8_out) return VG_OK;
+  VG_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<uchar4> tmp((size_t)L.w * L.h);
+  VG_CUDA(ctx, cudaMemcpyAsync(tmp.data(), ctx->d_texels.p + L.off, tmp.size() * sizeof(uchar4), cudaMemcpyDeviceToHost, ctx->stream));
+  VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < tmp.size(); i++) {
+    rgb8_out[i * 3] = tmp[i].x;
+    rgb8_out[i * 3 + 1] = tmp[i].y;
+    rgb8_out[i * 3 + 2] = tmp[i].z;
+  }
+  return VG_OK;
+}
+
+int vg_material_set_texture(vg_ctx* ctx, int material, int slot, int tex_id, int chan, int filter) {
+  VG_LOCK(ctx);
+  if (material < 0 || material >= (int)ctx->materials.size()) return ctx->fail(VG_ERR_INVALID, "vg_material_set_texture: bad material index");
+  if (slot < 0 || slot > 11 || slot == 9) return ctx->fail(VG_ERR_INVALID, "vg_material_set_texture: bad parameter slot");
+  if (tex_id < 0 || tex_id >= (int)ctx->textures.size()) return ctx->fail(VG_ERR_INVALID, "vg_material_set_texture: bad texture id");
+  if (chan < 0 || chan > 2) return ctx->fail(VG_ERR_INVALID, "vg_material_set_texture: channel outside [0,2] (the reference would index out of range)");
+  if (filter != VG_TEXFILTER_FELINE && filter != VG_TEXFILTER_TRILINEAR) return ctx->fail(VG_ERR_INVALID, "vg_material_set_texture: bad filter");
+  if (ctx->materials[(size_t)material].mask & VG_MAT_DEBUG) return ctx->fail(VG_ERR_UNSUPPORTED, "vg_material_set_texture: DebugShader.Colour as a texture map");
+  ctx->mat_tex.resize(ctx->materials.size());
+  TexBind& b = ctx->mat_tex[(size_t)material].slot[slot];
+  b.tex = tex_id; b.chan = chan; b.filter = filter;
+  ctx->materials[(size_t)material].mask |= (1u << slot);
+  render_invalidate(ctx);
+  return VG_OK;
+}
+
+int vg_mesh_set_uv(vg_ctx* ctx, int geom_id, const float* uv, int n_uv, const uint32_t* uvtriidx) {
+  VG_LOCK(ctx);
+  if (geom_id < 0 || geom_id >= (int)ctx->meshes.size()) return ctx->fail(VG_ERR_INVALID, "geom_id out of range");
+  MeshStage& m = ctx->meshes[(size_t)geom_id];
+  if (!m.present || m.sphere || m.instance) return ctx->fail(VG_ERR_INVALID, "vg_mesh_set_uv: upload the mesh first");
+  if (!uv || n_uv <= 0 || !uvtriidx) return ctx->fail(VG_ERR_INVALID, "vg_mesh_set_uv: null/empty input");
+  m.uv.assign(uv, uv + (size_t)n_uv * 2);
+  m.uvtriidx.assign(uvtriidx, uvtriidx + (size_t)m.n_tris * 3);
+  for (uint32_t i : m.uvtriidx)
+    if (i >= (uint32_t)n_uv) return ctx->fail(VG_ERR_INVALID, "vg_mesh_set_uv: UV index out of range");
+  ctx->committed = false;
+  return VG_OK;
+}
+
+int vg_texture_sample_batch(vg_ctx* ctx, int tex_id, int filter, const float* coords, int64_t n, float* out) {
+  VG_LOCK(ctx);
+  if (tex_id < 0 || tex_id >= (int)ctx->textures.size()) return ctx->fail(VG_ERR_INVALID, "vg_texture_sample_batch: bad texture id");
+  if (n < 0 || (n > 0 && (!coords || !out))) return ctx->fail(VG_ERR_INVALID, "vg_texture_sample_batch: bad input");
+  if (n == 0) return VG_OK;
+  VG_CUDA(ctx, cudaSetDevice(ctx->device));
+  float *d_in = nullptr, *d_out = nullptr;
+  VG_CUDA(ctx, cudaMalloc((void**)&d_in, (size_t)n * 8 * sizeof(float)));
+  cudaError_t e = cudaMalloc((void**)&d_out, (size_t)n * 3 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, coords, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = launch_texture_sample(ctx->tex_store(), tex_id, filter, d_in, n, d_out, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_in);
+  if (d_out) cudaFree(d_out);
+  if (e != cudaSuccess) return ctx->cuda_fail(e, "vg_texture_sample_batch");
+  ctx->stats.kernel_launches += 1;
   return VG_OK;
 }
 

@@ -8,6 +8,7 @@
 
 #include "../../include/vermeer_gpu.h"
 #include "device_scene.h"
+#include "texture.cuh"
 
 namespace vg {
 
@@ -35,6 +36,20 @@ struct MeshStage {
   std::vector<uint32_t> normalidx;
   float raybias = 0;
   int ref_compat = 0;
+  std::vector<float> uv;           // PolyMesh.UV pairs
+  std::vector<uint32_t> uvtriidx;  // 3 per triangle, leaf order
+};
+
+struct TexBind {  // one ShaderStd parameter read through maps.Texture / maps.TextureTrilinear
+  int32_t tex = -1, chan = 0, filter = 0;
+};
+struct MatTex {
+  TexBind slot[12];
+  bool any() const {
+    for (const TexBind& b : slot)
+      if (b.tex >= 0) return true;
+    return false;
+  }
 };
 
 struct SceneStage {
@@ -102,6 +117,17 @@ struct vg_ctx {
   vg::DevBuf<VgRay> d_rays;
   vg::DevBuf<VgHit> d_hits;
   vg::DevBuf<unsigned long long> d_counters;  // [0] queue head, [1..] stats
+
+  // texture store: every level of every texture in one texel array
+  std::vector<vg::DevTexture> textures;
+  std::vector<vg::DevTexLevel> tex_levels;
+  size_t n_texels = 0;
+  vg::DevBuf<uchar4> d_texels;
+  vg::DevBuf<vg::DevTexLevel> d_tex_levels;
+  vg::DevBuf<vg::DevTexture> d_textures;
+  vg::DevBuf<float2> d_tri_uv;
+  std::vector<vg::MatTex> mat_tex;  // parallel to `materials`
+  vg::DevTexStore tex_store() const { return vg::DevTexStore{d_texels.p, d_tex_levels.p, d_textures.p, (int32_t)textures.size()}; }
 
   // shading inputs
   std::vector<VgMaterial> materials;

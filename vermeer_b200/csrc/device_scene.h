@@ -64,7 +64,8 @@ struct DevGeom {  // per geom (creation order)
   int32_t keys;         // 1 = static mesh, > 1 = motion mesh, 0 = analytic sphere (tri_base = its record)
   int32_t tri_key_stride;
   int32_t n_tris;
-  int32_t pad0, pad1;
+  int32_t uv_base;      // slot base into tri_uv[] (3 float2 per slot), or -1: the mesh has no UVs
+  int32_t pad1;
 };
 
 struct DevScene {
@@ -76,6 +77,7 @@ struct DevScene {
   const DevGeom* geoms;
   const uint8_t* prim_material;  // global material id per (geom, prim)
   const float4* tri_normals;     // optional per-slot vertex normals (static meshes only)
+  const float2* tri_uv;          // optional per-slot texture coordinates (static meshes only), 3 per slot
   int32_t n_static;              // number of static nodes (motion node global index = n_static + i)
   int32_t root;                  // global index of the scene-level root node
   int32_t n_geoms;

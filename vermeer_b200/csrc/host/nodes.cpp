@@ -255,10 +255,46 @@ int Camera::PreRender(Core& core, std::string* err) {
 
 // ---- PolyMesh ------------------------------------------------------------------------------------
 // builtin/geom/polymesh/init.go:12-134: fan-triangulate polygons into idxp (+ normal / shader indices)
+// builtin/maps/texture.go:48-83 (net/url.Parse: path up to '?', then '&'-separated key=value pairs; first value wins)
+TextureMap TextureMap::Parse(const std::string& value, bool read_channel) {
+  TextureMap m;
+  m.set = true;
+  const size_t q = value.find('?');
+  m.path = value.substr(0, q);
+  if (q == std::string::npos) return m;
+  const size_t frag = value.find('#', q);
+  std::string query = value.substr(q + 1, frag == std::string::npos ? std::string::npos : frag - q - 1);
+  bool got_ch = false, got_filter = false;
+  size_t pos = 0;
+  while (pos <= query.size()) {
+    size_t e = query.find('&', pos);
+    if (e == std::string::npos) e = query.size();
+    const std::string kv = query.substr(pos, e - pos);
+    const size_t eq = kv.find('=');
+    const std::string k = kv.substr(0, eq), v = eq == std::string::npos ? "" : kv.substr(eq + 1);
+    if (k == "ch" && !got_ch) {
+      got_ch = true;
+      char* end = nullptr;
+      const long c = std::strtol(v.c_str(), &end, 10);
+      if (read_channel && end && *end == 0 && !v.empty()) m.chan = (int)c;  // strconv.Atoi; its error is dropped (texture.go:57)
+    } else if (k == "filter" && !got_filter) {
+      got_filter = true;
+      if (v == "trilinear") m.filter = VG_TEXFILTER_TRILINEAR;
+    }
+    pos = e + 1;
+  }
+  return m;
+}
+
 void PolyMesh::triangulate() {
   const bool hasN = !Normals.Elems.empty();
+  const bool hasUV = !UV.empty();  // init.go:38-48,77-83,100-106
   auto emit = [&](uint32_t a, uint32_t b, uint32_t c) {
     idxp.push_back((uint32_t)FaceIdx[a]); idxp.push_back((uint32_t)FaceIdx[b]); idxp.push_back((uint32_t)FaceIdx[c]);
+    if (hasUV) {
+      const std::vector<int32_t>& src = hasUVIdx ? UVIdx : FaceIdx;
+      uvtriidx.push_back((uint32_t)src[a]); uvtriidx.push_back((uint32_t)src[b]); uvtriidx.push_back((uint32_t)src[c]);
+    }
     if (hasN) {
       const std::vector<int32_t>& src = hasNormalIdx ? NormalIdx : FaceIdx;
       normalidx.push_back((uint32_t)src[a]); normalidx.push_back((uint32_t)src[b]); normalidx.push_back((uint32_t)src[c]);
@@ -278,16 +314,18 @@ void PolyMesh::triangulate() {
       for (size_t j = 0; j < FaceIdx.size(); j++) {
         idxp.push_back((uint32_t)FaceIdx[j]);
         if (hasN) normalidx.push_back(hasNormalIdx ? (uint32_t)NormalIdx[j] : (uint32_t)FaceIdx[j]);
+        if (hasUV) uvtriidx.push_back(hasUVIdx ? (uint32_t)UVIdx[j] : (uint32_t)FaceIdx[j]);
       }
     } else {
       for (int j = 0; j < Verts.ElemsPerKey; j++) {
         idxp.push_back((uint32_t)j);
         if (hasN) normalidx.push_back(hasNormalIdx ? (uint32_t)NormalIdx[j] : (uint32_t)j);
+        if (hasUV) uvtriidx.push_back(hasUVIdx ? (uint32_t)UVIdx[j] : (uint32_t)j);
       }
     }
     for (int32_t s : ShaderIdx) shaderidx.push_back((uint8_t)s);
   }
-  FaceIdx.clear(); PolyCount.clear(); NormalIdx.clear(); ShaderIdx.clear();
+  FaceIdx.clear(); PolyCount.clear(); NormalIdx.clear(); ShaderIdx.clear(); UVIdx.clear();
 }
 
 // polymesh.go:73-97
@@ -297,6 +335,9 @@ int PolyMesh::PreRender(Core& core, std::string* err) {
   if (idxp.size() % 3 != 0) { *err = "PolyMesh " + NodeName + ": index count is not a multiple of 3"; return -1; }
   for (uint32_t i : idxp)
     if (i >= (uint32_t)Verts.ElemsPerKey) { *err = "PolyMesh " + NodeName + ": vertex index out of range"; return -1; }
+  if (uvtriidx.size() != 0 && uvtriidx.size() != idxp.size()) { *err = "PolyMesh " + NodeName + ": UVIdx does not match FaceIdx"; return -1; }
+  for (uint32_t i : uvtriidx)
+    if ((size_t)i * 2 + 1 >= UV.size()) { *err = "PolyMesh " + NodeName + ": UV index out of range"; return -1; }
   facecount = (int)idxp.size() / 3;
   for (const std::string& s : Shader) {
     Node* n = core.FindNode(s);
@@ -369,6 +410,12 @@ int PolyMesh::initAccel(std::string* err) {
     for (int i = 0; i < facecount; i++)
       for (int j = 0; j < 3; j++) nn[i * 3 + j] = normalidx[idxs[i] * 3 + j];
     normalidx.swap(nn);
+  }
+  if (!uvtriidx.empty()) {  // buildqbvh.go:106-116
+    std::vector<uint32_t> uu(uvtriidx.size());
+    for (int i = 0; i < facecount; i++)
+      for (int j = 0; j < 3; j++) uu[i * 3 + j] = uvtriidx[idxs[i] * 3 + j];
+    uvtriidx.swap(uu);
   }
   return 0;
 }

@@ -49,9 +49,22 @@ struct Globals : Node {
   std::string Name() const override { return "<globals>"; }
 };
 
+// builtin/maps/texture.go:17-83: a shader parameter read from a texture file. `Parse` is CreateRGBTextureMap /
+// CreateFloat32TextureMap: url.Parse the value, path = EscapedPath, "?filter=trilinear" picks TextureTrilinear, "ch=N" the
+// channel of a float parameter (only CreateFloat32TextureMap reads it; the .vnf `rgbtex` form always goes through
+// CreateRGBTextureMap, nodes/parser.go:259, so its channel is 0).
+struct TextureMap {
+  bool set = false;
+  std::string path;
+  int chan = 0;
+  int filter = VG_TEXFILTER_FELINE;
+  static TextureMap Parse(const std::string& value, bool read_channel);
+};
+
 struct ShaderStd : Node {
   std::string MtlName;
   VgMaterial params{};
+  TextureMap texmaps[12];  // by parameter slot (bit index of the VG_MAT_* flag)
   int material_id = -1;
   std::string Name() const override { return MtlName; }
 };
@@ -72,6 +85,10 @@ struct PolyMesh : Node, Geom {
   std::vector<int32_t> PolyCount, FaceIdx, ShaderIdx, NormalIdx;
   bool hasPolyCount = false, hasFaceIdx = false, hasNormalIdx = false;
   PointArray Normals;
+  std::vector<float> UV;         // param.Vec2Array, one key (polymesh.go:36)
+  std::vector<int32_t> UVIdx;    // polymesh.go:37
+  bool hasUVIdx = false;
+  std::vector<uint32_t> uvtriidx;  // triangulated UV indexes (polymesh.go:45), leaf order after initAccel
   std::vector<std::string> Shader;
   bool IsVisible = true;
 
@@ -243,7 +260,17 @@ struct Scene {
   Box initMotionBoxesRec(int key, int32_t node, int nkeys);
 };
 
+// One entry of texture.TexStore (texture/texture.go:36-47): the decoded image, rows bottom-up (loadTexture flips, :139).
+// Image decoding is the caller's (vh_add_texture); a map whose file was never registered is an error at vh_upload, where the
+// reference would substitute its embedded checker image (texture.go:103-106,187-190).
+struct TextureImage {
+  std::string name;
+  int w = 0, h = 0;
+  std::vector<uint8_t> rgb;
+};
+
 struct Core {
+  std::vector<TextureImage> textures;
   Globals* globals = nullptr;
   Scene scene;
   std::vector<std::unique_ptr<Node>> owned;

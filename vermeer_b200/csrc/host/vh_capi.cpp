@@ -2,6 +2,7 @@
 // upload of the pre-rendered scene into a device context through the vg_* layer.
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 
 #include "nodes.h"
@@ -69,6 +70,42 @@ int vh_add_shader_std(vh_scene* s, const char* name, const VgMaterial* params) {
   sh->MtlName = name;
   sh->params = *params;
   s->core.AddNode(std::move(h));
+  return VG_OK;
+}
+
+int vh_add_texture(vh_scene* s, const char* name, int w, int h, const uint8_t* rgb8_bottom_up) {
+  if (!s || !name || !rgb8_bottom_up || w <= 0 || h <= 0) return fail(s, VG_ERR_INVALID, "vh_add_texture: null/empty argument");
+  for (TextureImage& t : s->core.textures)
+    if (t.name == name) return VG_OK;  // cacheMiss: the first load of a file name wins (texture.go:178-186)
+  TextureImage t;
+  t.name = name;
+  t.w = w;
+  t.h = h;
+  t.rgb.assign(rgb8_bottom_up, rgb8_bottom_up + (size_t)w * h * 3);
+  s->core.textures.push_back(std::move(t));
+  return VG_OK;
+}
+
+int vh_shader_set_texture(vh_scene* s, const char* shader, int slot, const char* value) {
+  if (!s || !shader || !value) return fail(s, VG_ERR_INVALID, "vh_shader_set_texture: null argument");
+  if (slot < 0 || slot > 11 || slot == 9) return fail(s, VG_ERR_INVALID, "vh_shader_set_texture: bad parameter slot");
+  ShaderStd* sh = dynamic_cast<ShaderStd*>(s->core.FindNode(shader));
+  if (!sh || (sh->params.mask & VG_MAT_DEBUG)) return fail(s, VG_ERR_INVALID, std::string("Unable to find node (shader ") + shader + ")");
+  // float parameters go through CreateFloat32TextureMap (reads "ch"), colours through CreateRGBTextureMap (channel 0)
+  const bool is_float = slot == 1 || slot == 3 || slot == 4 || slot == 6 || slot == 7 || slot == 8;
+  sh->texmaps[slot] = TextureMap::Parse(value, is_float);
+  sh->params.mask |= (1u << slot);
+  return VG_OK;
+}
+
+int vh_polymesh_set_uv(vh_scene* s, const char* mesh, const float* uv, int n_uv, const int32_t* uvidx, int n_uvidx) {
+  if (!s || !mesh || !uv || n_uv <= 0) return fail(s, VG_ERR_INVALID, "vh_polymesh_set_uv: null/empty argument");
+  if (s->core.prerendered) return fail(s, VG_ERR_INVALID, "vh_polymesh_set_uv: after vh_prerender");
+  PolyMesh* m = dynamic_cast<PolyMesh*>(s->core.FindNode(mesh));
+  if (!m) return fail(s, VG_ERR_INVALID, std::string("Unable to find node (mesh ") + mesh + ")");
+  m->UV.assign(uv, uv + (size_t)n_uv * 2);
+  m->hasUVIdx = uvidx != nullptr;
+  if (uvidx) m->UVIdx.assign(uvidx, uvidx + n_uvidx);
   return VG_OK;
 }
 
@@ -357,6 +394,31 @@ int vh_upload(vh_scene* s, vg_ctx* ctx, int motion_ref_compat) {
                                  motion_ref_compat);
     }
     if (chk(rc) != VG_OK) return rc;
+    if (!m->uvtriidx.empty() && !m->qbvh.empty())
+      if ((rc = chk(vg_mesh_set_uv(ctx, id, m->UV.data(), (int)(m->UV.size() / 2), m->uvtriidx.data()))) != VG_OK) return rc;
+  }
+  // texture maps: the files the shaders name, each uploaded once (texture.TexStore), then the parameter bindings
+  {
+    if ((rc = chk(vg_textures_clear(ctx))) != VG_OK) return rc;
+    std::map<std::string, int> ids;
+    for (size_t mi = 0; mi < c.materials.size(); mi++)
+      for (int slot = 0; slot < 12; slot++) {
+        const TextureMap& tm = c.materials[mi]->texmaps[slot];
+        if (!tm.set) continue;
+        auto it = ids.find(tm.path);
+        if (it == ids.end()) {
+          const TextureImage* img = nullptr;
+          for (const TextureImage& t : c.textures)
+            if (t.name == tm.path) img = &t;
+          if (!img)
+            return fail(s, VG_ERR_INVALID, "texture \"" + tm.path + "\" (shader " + c.materials[mi]->MtlName +
+                                               ") was not registered: decode the file and pass it to vh_add_texture before vh_upload");
+          int id = -1;
+          if ((rc = chk(vg_texture_upload(ctx, img->rgb.data(), img->w, img->h, &id))) != VG_OK) return rc;
+          it = ids.emplace(tm.path, id).first;
+        }
+        if ((rc = chk(vg_material_set_texture(ctx, (int)mi, slot, it->second, tm.chan, tm.filter))) != VG_OK) return rc;
+      }
   }
   std::vector<int32_t> order;
   for (Geom* g : c.scene.geoms) order.push_back(g->id);

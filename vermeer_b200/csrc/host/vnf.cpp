@@ -11,7 +11,7 @@
 // Error behaviour: the reference prints "<file>:<line>:<col>: message", keeps going and exits after more than 10 errors;
 // here the messages are collected (vh_last_error), the count is returned, and parsing stops after more than 10.
 // Node types that are registered in the reference but out of scope here (QuadLight, Proc, Include,
-// DebugShader) are reported like an unregistered type. `rgbtex` maps need the texture subsystem and are reported too.
+// DebugShader) are reported like an unregistered type. `rgbtex "file?filter=trilinear"` maps are kept as TextureMap bindings.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -188,6 +188,7 @@ struct Value {
   std::vector<std::string> strs;
   float c[3] = {0, 0, 0};          // constant map / vec3
   bool is_float_map = false;
+  bool is_texture = false;         // rgbtex "file?query": v.s
   int MotionKeys = 0, ElemsPerKey = 0;
   std::vector<float> elems;        // arrays, flattened
   bool set = false;
@@ -364,9 +365,12 @@ struct Parser {
           v.is_float_map = true;
         } else if (s.str == "rgbtex") {
           lex.lex(&s);
-          lex.lex(&s);
-          v.set = false;
-          errorf("nodes.rgbtex: texture maps are outside this path (constant maps only)");
+          if (lex.lex(&s) != TString) {  // parser.go:255-257; the error value is dropped by parseParam (:646)
+            v.set = false;
+            return nullptr;
+          }
+          v.s = s.str;
+          v.is_texture = true;
         } else {
           v.set = false;  // the reference leaves the interface nil and the stray token is reported as an unknown field
         }
@@ -452,9 +456,16 @@ struct Parser {
 
 V3 v3of(const float* c) { return V3{c[0], c[1], c[2]}; }
 
-void set_map(VgMaterial& m, uint32_t bit, const Value& v, float* dst3, float* dst1) {
+void set_map(VgMaterial& m, uint32_t bit, const Value& v, float* dst3, float* dst1, TextureMap* texmaps = nullptr) {
   if (!v.set) return;
   m.mask |= bit;
+  if (v.is_texture && texmaps) {
+    // parser.rgbtex always builds the map with CreateRGBTextureMap (parser.go:259): channel 0 even on a float parameter
+    int slot = 0;
+    while ((1u << slot) != bit) slot++;
+    texmaps[slot] = TextureMap::Parse(v.s, false);
+    return;
+  }
   if (dst3) { dst3[0] = v.c[0]; dst3[1] = v.c[1]; dst3[2] = v.c[2]; }
   if (dst1) *dst1 = v.c[0];  // param.Float32Uniform of a Constant map returns C[0] (builtin/maps/constant.go)
 }
@@ -507,17 +518,17 @@ std::string build_node(Core& core, const std::string& type, std::map<std::string
     s->MtlName = f["Name"].s;
     VgMaterial& m = s->params;
     std::memset(&m, 0, sizeof(m));
-    set_map(m, VG_MAT_EMISSION_COLOUR, f["EmissionColour"], m.emission_colour, nullptr);
-    set_map(m, VG_MAT_EMISSION_STRENGTH, f["EmissionStrength"], nullptr, &m.emission_strength);
-    set_map(m, VG_MAT_DIFFUSE_COLOUR, f["DiffuseColour"], m.diffuse_colour, nullptr);
-    set_map(m, VG_MAT_DIFFUSE_STRENGTH, f["DiffuseStrength"], nullptr, &m.diffuse_strength);
-    set_map(m, VG_MAT_DIFFUSE_ROUGHNESS, f["DiffuseRoughness"], nullptr, &m.diffuse_roughness);
-    set_map(m, VG_MAT_SPEC1_COLOUR, f["Spec1Colour"], m.spec1_colour, nullptr);
-    set_map(m, VG_MAT_SPEC1_STRENGTH, f["Spec1Strength"], nullptr, &m.spec1_strength);
-    set_map(m, VG_MAT_SPEC1_ROUGHNESS, f["Spec1Roughness"], nullptr, &m.spec1_roughness);
-    set_map(m, VG_MAT_IOR, f["IOR"], nullptr, &m.ior);
-    set_map(m, VG_MAT_SPEC1_FRESNEL_REFL, f["Spec1FresnelRefl"], m.spec1_fresnel_refl, nullptr);
-    set_map(m, VG_MAT_SPEC1_FRESNEL_EDGE, f["Spec1FresnelEdge"], m.spec1_fresnel_edge, nullptr);
+    set_map(m, VG_MAT_EMISSION_COLOUR, f["EmissionColour"], m.emission_colour, nullptr, s->texmaps);
+    set_map(m, VG_MAT_EMISSION_STRENGTH, f["EmissionStrength"], nullptr, &m.emission_strength, s->texmaps);
+    set_map(m, VG_MAT_DIFFUSE_COLOUR, f["DiffuseColour"], m.diffuse_colour, nullptr, s->texmaps);
+    set_map(m, VG_MAT_DIFFUSE_STRENGTH, f["DiffuseStrength"], nullptr, &m.diffuse_strength, s->texmaps);
+    set_map(m, VG_MAT_DIFFUSE_ROUGHNESS, f["DiffuseRoughness"], nullptr, &m.diffuse_roughness, s->texmaps);
+    set_map(m, VG_MAT_SPEC1_COLOUR, f["Spec1Colour"], m.spec1_colour, nullptr, s->texmaps);
+    set_map(m, VG_MAT_SPEC1_STRENGTH, f["Spec1Strength"], nullptr, &m.spec1_strength, s->texmaps);
+    set_map(m, VG_MAT_SPEC1_ROUGHNESS, f["Spec1Roughness"], nullptr, &m.spec1_roughness, s->texmaps);
+    set_map(m, VG_MAT_IOR, f["IOR"], nullptr, &m.ior, s->texmaps);
+    set_map(m, VG_MAT_SPEC1_FRESNEL_REFL, f["Spec1FresnelRefl"], m.spec1_fresnel_refl, nullptr, s->texmaps);
+    set_map(m, VG_MAT_SPEC1_FRESNEL_EDGE, f["Spec1FresnelEdge"], m.spec1_fresnel_edge, nullptr, s->texmaps);
     if (has("Spec1FresnelModel")) {  // std.go:65-73: anything but "Metal" leaves the zero value (Dielectric)
       m.mask |= VG_MAT_SPEC1_FRESNEL_MODEL;
       m.spec1_fresnel_model = f["Spec1FresnelModel"].s == "Metal" ? VG_FRESNEL_CONDUCTOR : VG_FRESNEL_DIELECTRIC;
@@ -569,7 +580,13 @@ std::string build_node(Core& core, const std::string& type, std::map<std::string
       if (t.MotionKeys > 1 || t.elems.size() != 16 || std::memcmp(t.elems.data(), ident, sizeof(ident)) != 0)
         return "PolyMesh: Transform other than a single identity matrix is outside this path";
     }
-    // UV / UVIdx feed textures only; CalcNormals and IsVisible are never read by the reference
+    if (has("UV")) {  // polymesh.go:36-37
+      const Value& uv = f["UV"];
+      if (uv.MotionKeys > 1) return "PolyMesh: UV with motion keys is outside this path";
+      m->UV = uv.elems;
+      if (has("UVIdx")) { m->hasUVIdx = true; m->UVIdx = f["UVIdx"].ints; }
+    }
+    // CalcNormals and IsVisible are never read by the reference
   } else if (type == "TriLight") {
     TriLight* t = static_cast<TriLight*>(h.get());
     t->NodeName = f["Name"].s;

@@ -50,6 +50,49 @@ struct DevMat {
   int debug;  // shader.Debug (debug.go:42-49): `emission` holds its Colour, both weights are 0 and no Level check applies
 };
 
+// ShaderStd's parameters -> the constants the kernels use (std.go:108-143,165-192,299-316). Shared by the host (constant maps,
+// once per material) and the device (materials with texture maps, once per shaded vertex: k_surface).
+__host__ __device__ inline DevMat derive_mat(const VgMaterial& s) {
+  DevMat d;
+  d.emission.x = d.emission.y = d.emission.z = 0;
+  d.diff_colour = d.emission; d.spec_colour = d.emission;
+  d.diff_weight = d.spec_weight = 0; d.rough2 = 0; d.spec_rough = 0; d.ior = 0; d.fresnel_model = 0;
+  d.fres_refl = d.emission; d.fres_edge = d.emission;
+  d.bad = 0; d.debug = 0;
+  if (s.mask & VG_MAT_DEBUG) {
+    // Eval: OutRGB = Colour (resolve_vertex's emission + 0 + 0); no lights, no lobes
+    d.debug = 1;
+    if (s.mask & VG_MAT_DIFFUSE_COLOUR) { d.emission.x = s.diffuse_colour[0]; d.emission.y = s.diffuse_colour[1]; d.emission.z = s.diffuse_colour[2]; }
+    return d;
+  }
+  if (s.mask & VG_MAT_EMISSION_STRENGTH) {
+    const bool hc = (s.mask & VG_MAT_EMISSION_COLOUR) != 0;
+    d.emission.x = (hc ? s.emission_colour[0] : 0.0f) * s.emission_strength;
+    d.emission.y = (hc ? s.emission_colour[1] : 0.0f) * s.emission_strength;
+    d.emission.z = (hc ? s.emission_colour[2] : 0.0f) * s.emission_strength;
+  }
+  if (s.mask & VG_MAT_DIFFUSE_COLOUR) { d.diff_colour.x = s.diffuse_colour[0]; d.diff_colour.y = s.diffuse_colour[1]; d.diff_colour.z = s.diffuse_colour[2]; }
+  const float dw = (s.mask & VG_MAT_DIFFUSE_STRENGTH) ? s.diffuse_strength : 0.0f;
+  const float sw = (s.mask & VG_MAT_SPEC1_STRENGTH) ? s.spec1_strength : 0.0f;
+  const float tot = dw + sw;
+  d.diff_weight = dw / tot;
+  d.spec_weight = sw / tot;
+  if (tot == 0.0f) { d.bad = 1; d.diff_weight = d.spec_weight = 0; }
+  const float rough = (s.mask & VG_MAT_DIFFUSE_ROUGHNESS) ? s.diffuse_roughness : 0.5f;
+  d.rough2 = rough * rough;
+  if (s.mask & VG_MAT_SPEC1_COLOUR) { d.spec_colour.x = s.spec1_colour[0]; d.spec_colour.y = s.spec1_colour[1]; d.spec_colour.z = s.spec1_colour[2]; }
+  d.spec_rough = (s.mask & VG_MAT_SPEC1_ROUGHNESS) ? s.spec1_roughness : 0.5f;
+  d.ior = (s.mask & VG_MAT_IOR) ? s.ior : 1.7f;
+  // std.go:172-192: Fresnel model of the spec lobe. NewConductor(0, refl, edge) with both defaulting to .5; the reference
+  // assigns Spec1FresnelEdge to `refl` (std.go:187-189), so the edge tint stays .5 whatever the scene says.
+  d.fresnel_model = (s.mask & VG_MAT_SPEC1_FRESNEL_MODEL) ? s.spec1_fresnel_model : VG_FRESNEL_DIELECTRIC;
+  d.fres_refl.x = d.fres_refl.y = d.fres_refl.z = 0.5f;
+  d.fres_edge = d.fres_refl;
+  if (s.mask & VG_MAT_SPEC1_FRESNEL_REFL) { d.fres_refl.x = s.spec1_fresnel_refl[0]; d.fres_refl.y = s.spec1_fresnel_refl[1]; d.fres_refl.z = s.spec1_fresnel_refl[2]; }
+  if (s.mask & VG_MAT_SPEC1_FRESNEL_EDGE) { d.fres_refl.x = s.spec1_fresnel_edge[0]; d.fres_refl.y = s.spec1_fresnel_edge[1]; d.fres_refl.z = s.spec1_fresnel_edge[2]; }
+  return d;
+}
+
 struct __align__(16) DevHit {
   float t, u, v, w;
   int32_t prim, geom, slot;
@@ -66,6 +109,13 @@ struct RenderParams {
   const vg::XfSRT* cam_keys;  // Camera.decomp, one per LocalToWorld motion key (camera.go:188-192); cam_nkeys <= 1: cam.local_to_world
   int cam_nkeys;
   const DevMat* mats;
+  // texture maps (null / 0 in scenes without them)
+  DevTexStore tex;
+  const VgMaterial* rawmats;  // the materials as the caller gave them: a textured one is re-derived per vertex
+  const MatTex* mat_tex;      // [materials] parameter -> texture bindings
+  DevMat* vmats;              // [P] per-vertex materials, indexed like hits[] (queue slot)
+  float* diff;                // [12][P] ray differentials per path: DdPdx, DdPdy, DdDdx, DdDdy (core/ray.go:40-44)
+  float pd0, pd1;             // core.Image.PixelDelta (camera.go:316-317)
   const DevLight* lights;
   int nlights, S, levels, trace_last_level;
   int nlobes;  // 1: diffuse light slots only (k_shade); 2: + GGX glossy slots (k_shade_generic)
@@ -140,7 +190,7 @@ __device__ inline void warp_sample(const double* cdfV, const double* cdfVU, int 
   *vo = 0;
 }
 
-// core/render.go:89-124 + builtin/camera/camera.go:221-323 (differentials omitted)
+// core/render.go:89-124 + builtin/camera/camera.go:221-323 (ray differentials only in scenes with texture maps)
 // MOTION: the camera has several motion keys and every ray recomposes its LocalToWorld at its own Time (camera.go:225-236).
 template <bool MOTION>
 __global__ void __launch_bounds__(256) k_raygen(const RenderParams p, int iter_base, int niters) {
@@ -196,6 +246,18 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderParams p, int iter_b
   p.pathq[0][i] = i;
   p.lambda[i] = (float)lambda;
   p.time[i] = (float)time;
+  if (p.diff) {
+    // camera.go:300-306: DdPdx = DdPdy = 0; DdDdx/y = d(normalize d)/d(right|up) with the UNnormalised direction d
+    const f3 right = mk3(M[0], M[1], M[2]), up = mk3(M[4], M[5], M[6]);
+    const float dd = dot3(d, d);
+    const float k = 1 / (dd * sqrtf(dd));
+    const f3 ddx = scale3(k, sub3(scale3(dd, right), scale3(dot3(d, right), d)));
+    const f3 ddy = scale3(k, sub3(scale3(dd, up), scale3(dot3(d, up), d)));
+    float* q = p.diff + i;
+    const size_t P = (size_t)p.P;
+    q[0] = 0.f; q[P] = 0.f; q[2 * P] = 0.f; q[3 * P] = 0.f; q[4 * P] = 0.f; q[5 * P] = 0.f;
+    q[6 * P] = ddx.x; q[7 * P] = ddx.y; q[8 * P] = ddx.z; q[9 * P] = ddy.x; q[10 * P] = ddy.y; q[11 * P] = ddy.z;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -260,6 +322,11 @@ __global__ void __launch_bounds__(kTraceBlock, VG_TRACE_MIN_BLOCKS) k_trace_queu
 struct ShadeCtx {
   f3 P, Poffset, N, Ng, DdPdu, DdPdv;
 };
+struct Plane4 {
+  f3 n;
+  float d;
+};
+__device__ __forceinline__ Plane4 mk4(f3 n, float d, f3) { Plane4 r; r.n = n; r.d = d; return r; }
 
 __device__ __forceinline__ f3 ld3(const float4* p) {
   const float4 v = __ldg(p);
@@ -324,6 +391,157 @@ __device__ inline void build_context(const RenderParams& p, const DevHit& h, flo
   c.Ng = normalize3(Ng);
   c.DdPdu = normalize3(c.DdPdu);
   c.DdPdv = normalize3(c.DdPdv);
+}
+
+// Scenes with texture maps: one pass over the hit queue between traversal and shading.
+//   * texture coordinates and their screen-space derivatives at the hit: Ray.DifferentialTransfer (core/ray.go:95-104), the
+//     barycentric-plane construction of polymesh/trace.go:350-502 (U, V, DdNdx/y, Dduvdx/y);
+//   * every parameter of the hit material that is a maps.Texture / maps.TextureTrilinear is looked up (texture.cuh) and the
+//     material constants are re-derived for this vertex (derive_mat) into vmats[queue slot];
+//   * the path's ray differentials are replaced, in place, by those of the mirror ray Ray.Init(RayTypeReflected) would
+//     build from this context (core/ray.go:72-87), whether or not the shader goes on to spawn it.
+// Static meshes only (prepare() refuses textured scenes with other geoms).
+__global__ void __launch_bounds__(128) k_surface(const RenderParams p, int level, int qin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.counts[qin]) return;
+  const int4 h1 = *(reinterpret_cast<const int4*>(&p.hits[i]) + 1);
+  const int prim = h1.x, geom = h1.y, slot = h1.z;
+  if (prim < 0) return;
+  const float4 h0 = *reinterpret_cast<const float4*>(&p.hits[i]);
+  const float T = h0.x, U = h0.y, V = h0.z, W = h0.w;
+  const DevGeom g = p.sc.geoms[geom];
+  const int matid = p.sc.prim_material[g.prim_base + prim];
+  if (matid == 255) return;
+  const int path = p.pathq[qin][i];
+  const float4* rp = reinterpret_cast<const float4*>(p.rayq[qin] + i);
+  const float4 ra = rp[0], rb = rp[1];
+  const f3 D = mk3(ra.w, rb.x, rb.y);
+
+  const float4* tp = p.sc.tris + (size_t)slot * 3;
+  const f3 E0 = ld3(tp), E1 = ld3(tp + 1), E2 = ld3(tp + 2);
+  const f3 Ng = normalize3(cross3(sub3(E1, E0), sub3(E2, E0)));
+  f3 n0 = mk3(0, 0, 0), n1 = n0, n2 = n0;
+  const bool has_n = g.normal_base >= 0 && p.sc.tri_normals;
+  f3 N = Ng;  // the interpolated normal BEFORE normalisation (trace.go:326-336)
+  if (has_n) {
+    const float4* np = p.sc.tri_normals + (size_t)slot * 3;
+    n0 = ld3(np); n1 = ld3(np + 1); n2 = ld3(np + 2);
+    N = mk3(U * n0.x + V * n1.x + W * n2.x, U * n0.y + V * n1.y + W * n2.y, U * n0.z + V * n1.z + W * n2.z);
+  }
+  float2 t0 = make_float2(0, 0), t1 = t0, t2 = t0;
+  const bool has_uv = g.uv_base >= 0 && p.sc.tri_uv;
+  TexCoord tc;
+  if (has_uv) {
+    const float2* up = p.sc.tri_uv + (size_t)slot * 3;
+    t0 = __ldg(up); t1 = __ldg(up + 1); t2 = __ldg(up + 2);
+    tc.U = U * t0.x + V * t1.x + W * t2.x;
+    tc.V = U * t0.y + V * t1.y + W * t2.y;
+  } else {
+    tc.U = U;
+    tc.V = V;
+  }
+
+  // incoming ray differentials
+  float* q = p.diff + path;
+  const size_t P = (size_t)p.P;
+  const f3 rPx = mk3(q[0], q[P], q[2 * P]), rPy = mk3(q[3 * P], q[4 * P], q[5 * P]);
+  const f3 rDx = mk3(q[6 * P], q[7 * P], q[8 * P]), rDy = mk3(q[9 * P], q[10 * P], q[11 * P]);
+  // DifferentialTransfer (core/ray.go:95-104)
+  const float DNg = dot3(D, Ng);
+  const f3 ax = mad3(rPx, rDx, T), ay = mad3(rPy, rDy, T);
+  const float dtdx = -dot3(ax, Ng) / DNg;
+  const float dtdy = -dot3(ay, Ng) / DNg;
+  const f3 dPdx = add3(ax, scale3(dtdx, D));
+  const f3 dPdy = add3(ay, scale3(dtdy, D));
+
+  // barycentric planes (trace.go:362-436): n = Ng x edge, normalised, then scaled so that the opposite vertex evaluates to 1
+  auto plane = [&](f3 a, f3 b, f3 on, f3 opp) {
+    f3 n = mk3(Ng.y * (a.z - b.z) - Ng.z * (a.y - b.y), Ng.z * (a.x - b.x) - Ng.x * (a.z - b.z), Ng.x * (a.y - b.y) - Ng.y * (a.x - b.x));
+    const float qn = sqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
+    n.x /= qn; n.y /= qn; n.z /= qn;
+    const float d = -on.x * n.x - on.y * n.y - on.z * n.z;
+    return mk4(n, d, opp);
+  };
+  // alpha: edge E2-E1 through E1, opposite E0 (evaluated as E0.n + d); beta: E2-E0 through E0, opposite E1 (n.E1 + d);
+  // gamma: E1-E0 through E0, opposite E2 (n.E2 + d) -- the operand order of each `l` is the reference's
+  f3 na, nb, ng;
+  {
+    const Plane4 A = plane(E2, E1, E1, E0);
+    const float l = E0.x * A.n.x + E0.y * A.n.y + E0.z * A.n.z + A.d;
+    na = mk3(A.n.x / l, A.n.y / l, A.n.z / l);
+    const Plane4 B = plane(E2, E0, E0, E1);
+    const float lb = B.n.x * E1.x + B.n.y * E1.y + B.n.z * E1.z + B.d;
+    nb = mk3(B.n.x / lb, B.n.y / lb, B.n.z / lb);
+    const Plane4 G = plane(E1, E0, E0, E2);
+    const float lg = G.n.x * E2.x + G.n.y * E2.y + G.n.z * E2.z + G.d;
+    ng = mk3(G.n.x / lg, G.n.y / lg, G.n.z / lg);
+  }
+  const float alphax = na.x * dPdx.x + na.y * dPdx.y + na.z * dPdx.z;
+  const float betax = nb.x * dPdx.x + nb.y * dPdx.y + nb.z * dPdx.z;
+  const float gammax = ng.x * dPdx.x + ng.y * dPdx.y + ng.z * dPdx.z;
+  const float alphay = na.x * dPdy.x + na.y * dPdy.y + na.z * dPdy.z;
+  const float betay = nb.x * dPdy.x + nb.y * dPdy.y + nb.z * dPdy.z;
+  const float gammay = ng.x * dPdy.x + ng.y * dPdy.y + ng.z * dPdy.z;
+
+  f3 dndx = mk3(0, 0, 0), dndy = mk3(0, 0, 0);
+  if (has_n) {
+    dndx = mk3(alphax * n0.x + betax * n1.x + gammax * n2.x, alphax * n0.y + betax * n1.y + gammax * n2.y, alphax * n0.z + betax * n1.z + gammax * n2.z);
+    dndy = mk3(alphay * n0.x + betay * n1.x + gammay * n2.x, alphay * n0.y + betay * n1.y + gammay * n2.y, alphay * n0.z + betay * n1.z + gammay * n2.z);
+  }
+  const float NN = dot3(N, N);
+  const float kN = 1 / (NN * sqrtf(NN));
+  const f3 DdNdx = scale3(kN, sub3(scale3(NN, dndx), scale3(dot3(N, dndx), N)));
+  const f3 DdNdy = scale3(kN, sub3(scale3(NN, dndy), scale3(dot3(N, dndy), N)));
+  if (has_uv) {
+    tc.dudx = alphax * t0.x + betax * t1.x + gammax * t2.x;
+    tc.dvdx = alphax * t0.y + betax * t1.y + gammax * t2.y;
+    tc.dudy = alphay * t0.x + betay * t1.x + gammay * t2.x;
+    tc.dvdy = alphay * t0.y + betay * t1.y + gammay * t2.y;
+  } else {  // trace.go:495-501 as written
+    tc.dudx = alphax * 0 + betax * 1 + gammax * 0;
+    tc.dvdx = alphax * 0 + betax * 0 + gammax * 1;
+    tc.dudy = alphay * 0 + betay * 1 + gammay * 0;
+    tc.dvdy = alphay * 0 + betay * 0 + gammay * 1;
+  }
+  tc.pd0 = p.pd0;
+  tc.pd1 = p.pd1;
+
+  // the material at this vertex
+  const MatTex mt = p.mat_tex[matid];
+  bool any = false;
+#pragma unroll
+  for (int k = 0; k < 12; k++) any |= mt.slot[k].tex >= 0;
+  if (!any) {
+    p.vmats[i] = p.mats[matid];
+  } else {
+    VgMaterial s = p.rawmats[matid];
+    auto rgb = [&](int k, float* dst) {
+      if (mt.slot[k].tex < 0) return;
+      tex_sample(p.tex, mt.slot[k].tex, mt.slot[k].filter, tc, dst);
+    };
+    auto f32 = [&](int k, float* dst) {
+      if (mt.slot[k].tex < 0) return;
+      float c[3];
+      tex_sample(p.tex, mt.slot[k].tex, mt.slot[k].filter, tc, c);
+      *dst = mt.slot[k].chan == 0 ? c[0] : (mt.slot[k].chan == 1 ? c[1] : c[2]);
+    };
+    rgb(0, s.emission_colour); f32(1, &s.emission_strength);
+    rgb(2, s.diffuse_colour); f32(3, &s.diffuse_strength); f32(4, &s.diffuse_roughness);
+    rgb(5, s.spec1_colour); f32(6, &s.spec1_strength); f32(7, &s.spec1_roughness); f32(8, &s.ior);
+    rgb(10, s.spec1_fresnel_refl); rgb(11, s.spec1_fresnel_edge);
+    p.vmats[i] = derive_mat(s);
+  }
+
+  // differentials of the mirror ray (core/ray.go:72-87); sc.N is the shading normal after ApplyTransform (normalised twice,
+  // like build_context), sc.DdDdx/y are the incoming ray's
+  const f3 Ns = has_n ? normalize3(normalize3(N)) : normalize3(Ng);
+  const float RdN = dot3(D, Ns);
+  const float DdotNdx = dot3(rDx, Ns) + dot3(D, DdNdx);
+  const float DdotNdy = dot3(rDy, Ns) + dot3(D, DdNdy);
+  const f3 oDx = mad3(rDx, add3(scale3(RdN, DdNdx), scale3(DdotNdx, Ns)), -2.0f);
+  const f3 oDy = mad3(rDy, add3(scale3(RdN, DdNdy), scale3(DdotNdy, Ns)), -2.0f);
+  q[0] = dPdx.x; q[P] = dPdx.y; q[2 * P] = dPdx.z; q[3 * P] = dPdy.x; q[4 * P] = dPdy.y; q[5 * P] = dPdy.z;
+  q[6 * P] = oDx.x; q[7 * P] = oDx.y; q[8 * P] = oDx.z; q[9 * P] = oDy.x; q[10 * P] = oDy.y; q[11 * P] = oDy.z;
 }
 
 // ShaderContext.ApplyTransform (core/shader.go:129-135) with the transform the last hit instance left in the context
@@ -521,7 +739,7 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
   long long I = 0;
   uint64_t scr0 = 0, scr1 = 0;
   if (active) {
-    m = p.mats[matid];
+    m = p.vmats ? p.vmats[i] : p.mats[matid];
     if (m.bad) {
       atomicOr(p.counts + 5, m.bad);
       active = false;
@@ -707,7 +925,7 @@ __device__ __forceinline__ float4 resolve_vertex(const RenderParams& p, int leve
   const int SL = p.S * p.nlobes;
   float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
   if (matid != 255 && level <= 3) {
-    const DevMat m = p.mats[matid];
+    const DevMat m = p.vmats ? p.vmats[i] : p.mats[matid];
     f3 sum[2];
     sum[0] = sum[1] = mk3(0, 0, 0);
     for (int lobe = 0; lobe < p.nlobes; lobe++) {
@@ -812,6 +1030,11 @@ struct RenderState {
   DevBuf<int> pix;
   DevBuf<uint64_t> scr;
   DevBuf<DevMat> mats;
+  DevBuf<DevMat> vmats;          // textured scenes only
+  DevBuf<VgMaterial> rawmats;
+  DevBuf<MatTex> mat_tex;
+  DevBuf<float> diff;
+  bool textured = false;
   DevBuf<DevLight> lights;
   DevBuf<VgRay> rayq0, rayq1, sray;
   DevBuf<int> pathq0, pathq1, sslot, counts;
@@ -853,7 +1076,7 @@ struct RenderState {
     return fetchpool[(size_t)i];
   }
   void release() {
-    pix.release(); scr.release(); mats.release(); lights.release(); rayq0.release(); rayq1.release(); sray.release();
+    pix.release(); scr.release(); mats.release(); vmats.release(); rawmats.release(); mat_tex.release(); diff.release(); lights.release(); rayq0.release(); rayq1.release(); sray.release();
     pathq0.release(); pathq1.release(); sslot.release(); counts.release(); hits.release(); lambda.release(); time.release();
     invtot.release(); vmat.release(); filter.release(); qmc.release(); contrib.release(); L.release(); T.release(); stats.release();
   }
@@ -1046,47 +1269,37 @@ static int prepare(vg_ctx* ctx) {
   // materials
   std::vector<DevMat> mats(ctx->materials.size());
   bool any_mirror = false, any_glossy = false, any_conductor = false, any_other_light = false, any_debug = false;
+  bool textured = false;
   for (size_t i = 0; i < mats.size(); i++) {
     const VgMaterial& s = ctx->materials[i];
     DevMat& d = mats[i];
-    std::memset(&d, 0, sizeof(d));
-    if (s.mask & VG_MAT_DEBUG) {
-      // Eval: OutRGB = Colour (resolve_vertex's emission + 0 + 0); no lights, no lobes
-      d.debug = 1;
-      if (s.mask & VG_MAT_DIFFUSE_COLOUR) d.emission = h3(s.diffuse_colour);
+    d = derive_mat(s);
+    if (d.debug) {
       any_debug = true;
       continue;
     }
-    if (s.mask & VG_MAT_EMISSION_STRENGTH) {
-      const float zero3[3] = {0, 0, 0};
-      f3 c = h3((s.mask & VG_MAT_EMISSION_COLOUR) ? s.emission_colour : zero3);
-      d.emission.x = c.x * s.emission_strength; d.emission.y = c.y * s.emission_strength; d.emission.z = c.z * s.emission_strength;
-    }
-    if (s.mask & VG_MAT_DIFFUSE_COLOUR) d.diff_colour = h3(s.diffuse_colour);
-    float dw = (s.mask & VG_MAT_DIFFUSE_STRENGTH) ? s.diffuse_strength : 0.0f;
-    float sw = (s.mask & VG_MAT_SPEC1_STRENGTH) ? s.spec1_strength : 0.0f;
-    const float tot = dw + sw;
-    d.diff_weight = dw / tot;
-    d.spec_weight = sw / tot;
-    if (tot == 0.0f) { d.bad = 1; d.diff_weight = d.spec_weight = 0; }
-    const float rough = (s.mask & VG_MAT_DIFFUSE_ROUGHNESS) ? s.diffuse_roughness : 0.5f;
-    d.rough2 = rough * rough;
-    if (s.mask & VG_MAT_SPEC1_COLOUR) d.spec_colour = h3(s.spec1_colour);
-    d.spec_rough = (s.mask & VG_MAT_SPEC1_ROUGHNESS) ? s.spec1_roughness : 0.5f;
-    d.ior = (s.mask & VG_MAT_IOR) ? s.ior : 1.7f;
-    // std.go:172-192: Fresnel model of the spec lobe. NewConductor(0, refl, edge) with both defaulting to .5; the reference
-    // assigns Spec1FresnelEdge to `refl` (std.go:187-189), so the edge tint stays .5 whatever the scene says.
-    d.fresnel_model = (s.mask & VG_MAT_SPEC1_FRESNEL_MODEL) ? s.spec1_fresnel_model : VG_FRESNEL_DIELECTRIC;
-    d.fres_refl.x = d.fres_refl.y = d.fres_refl.z = 0.5f;
-    d.fres_edge = d.fres_refl;
-    if (s.mask & VG_MAT_SPEC1_FRESNEL_REFL) d.fres_refl = h3(s.spec1_fresnel_refl);
-    if (s.mask & VG_MAT_SPEC1_FRESNEL_EDGE) d.fres_refl = h3(s.spec1_fresnel_edge);
-    if (d.spec_weight > 0.0f) {
-      if (d.spec_rough == 0.0f) any_mirror = true;
-      else any_glossy = true;
+    const MatTex* mt = i < ctx->mat_tex.size() && ctx->mat_tex[i].any() ? &ctx->mat_tex[i] : nullptr;
+    textured |= mt != nullptr;
+    // a textured strength / roughness can take any value at a vertex: keep every kernel path it may reach
+    const bool spec_maybe = d.spec_weight > 0.0f || (mt && (mt->slot[6].tex >= 0 || mt->slot[3].tex >= 0));
+    if (mt && mt->slot[6].tex >= 0 && d.bad) d.bad = 0;
+    if (spec_maybe) {
+      const bool rough_tex = mt && mt->slot[7].tex >= 0;
+      if (d.spec_rough == 0.0f || rough_tex) any_mirror = true;
+      if (d.spec_rough != 0.0f || rough_tex) any_glossy = true;
       if (d.fresnel_model != VG_FRESNEL_DIELECTRIC) any_conductor = true;
     }
   }
+  if (textured) {
+    for (const MeshStage& m : ctx->meshes)
+      if (m.present && (m.motion || m.sphere || m.instance))
+        return ctx->fail(VG_ERR_UNSUPPORTED, "texture maps need a scene of static PolyMeshes (the reference's motion path leaves the texture "
+                                             "footprint 0: trace.go:677-684, feline.go:57-61); sphere and instance geoms carry no UV differentials here");
+    for (const VgLight& l : ctx->lights)
+      if (l.material >= 0 && l.material < (int)ctx->mat_tex.size() && (ctx->mat_tex[(size_t)l.material].slot[0].tex >= 0 || ctx->mat_tex[(size_t)l.material].slot[1].tex >= 0))
+        return ctx->fail(VG_ERR_UNSUPPORTED, "a texture map on the emission of a light's shader (the light evaluates it with its own lsg)");
+  }
+  rs.textured = textured;
   // lights
   std::vector<DevLight> lights(ctx->lights.size());
   int S = 0;
@@ -1136,7 +1349,7 @@ static int prepare(vg_ctx* ctx) {
   {
     // The batch depth is a request: queue slots are 32-bit indices (paths x contribution slots must stay below 2^31) and the
     // wavefront state (~230 B + 52 B per contribution slot + 32 B per level and path) has to fit the free device memory.
-    const size_t per_path = 230 + (size_t)S * rs.nlobes * 52 + (size_t)rs.levels * 32 + (size_t)std::max(1, (int)lights.size()) * rs.nlobes * 4;
+    const size_t per_path = 230 + (textured ? sizeof(DevMat) + 48 : 0) + (size_t)S * rs.nlobes * 52 + (size_t)rs.levels * 32 + (size_t)std::max(1, (int)lights.size()) * rs.nlobes * 4;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = (size_t)16 << 30;
     const size_t by_mem = (free_b / 10 * 8) / per_path / (size_t)std::max(1, rs.nown);
@@ -1194,6 +1407,15 @@ static int prepare(vg_ctx* ctx) {
   const size_t SL = (size_t)S * rs.nlobes;
   RCUDA(rs.contrib.reserve(P * SL)); RCUDA(rs.sray.reserve(P * SL)); RCUDA(rs.sslot.reserve(P * SL));
   RCUDA(rs.L.reserve(P * rs.levels)); RCUDA(rs.T.reserve(P * rs.levels));
+  if (rs.textured) {
+    RCUDA(rs.vmats.reserve(P)); RCUDA(rs.diff.reserve(P * 12));
+    RCUDA(rs.rawmats.reserve(ctx->materials.size())); RCUDA(rs.mat_tex.reserve(ctx->materials.size()));
+    std::vector<MatTex> mt(ctx->materials.size());
+    for (size_t i = 0; i < mt.size() && i < ctx->mat_tex.size(); i++) mt[i] = ctx->mat_tex[i];
+    RCUDA(cudaMemcpyAsync(rs.rawmats.p, ctx->materials.data(), ctx->materials.size() * sizeof(VgMaterial), cudaMemcpyHostToDevice, ctx->stream));
+    RCUDA(cudaMemcpyAsync(rs.mat_tex.p, mt.data(), mt.size() * sizeof(MatTex), cudaMemcpyHostToDevice, ctx->stream));
+    RCUDA(cudaStreamSynchronize(ctx->stream));
+  }
   RCUDA(rs.counts.reserve(16)); RCUDA(rs.stats.reserve(8));
   RCUDA(cudaMemsetAsync(rs.counts.p, 0, 16 * sizeof(int), ctx->stream));
   RCUDA(cudaMemsetAsync(rs.stats.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -1252,6 +1474,13 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
   p.hits = rs.hits.p; p.lambda = rs.lambda.p; p.time = rs.time.p; p.v_mat = rs.vmat.p; p.v_invtot = rs.invtot.p;
   p.contrib = rs.contrib.p; p.sray = rs.sray.p; p.sslot = rs.sslot.p; p.L = rs.L.p; p.T = rs.T.p;
   p.counts = rs.counts.p; p.stats = rs.stats.p; p.fb = rs.fb.p;
+  if (rs.textured) {
+    p.tex = ctx->tex_store();
+    p.rawmats = rs.rawmats.p; p.mat_tex = rs.mat_tex.p; p.vmats = rs.vmats.p; p.diff = rs.diff.p;
+    // sc.Image.PixelDelta (camera.go:316-317)
+    p.pd0 = 2 * ctx->camera.tan_theta_focal / (float)ctx->xres;
+    p.pd1 = 2 * ctx->camera.tan_theta_focal / (ctx->camera.aspect * (float)ctx->yres);
+  }
 
   const int variant = ctx->opt_traversal;
   const bool xf = ctx->dev.n_xforms > 0;    // kernels that carry the instance enter/leave code (VARIANT & 16)
@@ -1296,6 +1525,10 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
         kinds.push_back(0);
         launches++;
         if (level <= 3) {
+          if (rs.textured) {
+            k_surface<<<(np + 127) / 128, 128, 0, st>>>(p, level, qin);
+            launches++;
+          }
           const bool h1 = rs.max_light_samples <= 2 || level > 0;
           if (rs.generic) {
             if (ctx->opt_precise_trig) k_shade_generic<false><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);

@@ -31,6 +31,8 @@ DECLARED_SYMBOLS = [
     "vg_sphere_upload", "vg_instance_upload", "vg_scene_upload", "vg_scene_upload_motion", "vg_scene_commit", "vg_set_materials", "vg_set_lights", "vg_set_area_lights", "vg_set_camera", "vg_set_camera_motion", "vg_set_frame",
     "vg_set_partition", "vg_set_scramble", "vg_set_filter", "vg_set_option", "vg_trace_batch", "vg_trace_batch_device", "vg_render", "vg_clear_framebuffer",
     "vg_framebuffer_device", "vg_get_stats", "vg_reset_stats",
+    "vg_texture_upload", "vg_textures_clear", "vg_texture_levels", "vg_texture_read_level", "vg_material_set_texture", "vg_mesh_set_uv", "vg_texture_sample_batch",
+    "vh_add_texture", "vh_shader_set_texture", "vh_polymesh_set_uv",
     "vh_scene_create", "vh_scene_destroy", "vh_last_error", "vh_registered_nodes", "vh_set_globals", "vh_add_shader_std", "vh_add_shader_debug", "vh_add_polymesh",
     "vh_add_filter", "vh_add_instance", "vh_add_trilight", "vh_add_disklight", "vh_add_spherelight", "vh_parse_vnf", "vh_load_vnf", "vh_globals", "vh_postrender", "vh_rgbe", "vh_set_camera_lookat", "vh_set_camera_keys", "vh_camera_decomp", "vh_prerender", "vh_upload", "vh_num_geoms", "vh_scene_info", "vh_scene_nodes",
     "vh_scene_motion_nodes", "vh_scene_geom_order", "vh_mesh_info", "vh_mesh_nodes", "vh_mesh_motion_nodes", "vh_mesh_idxp", "vh_camera",
@@ -122,6 +124,13 @@ class HostScene:
                 continue
             m = material_struct(s)
             self._chk(L.vh_add_shader_std(h, s.Name.encode(), C.byref(m)))
+            from .scenes import SHADER_SLOTS
+            for slot, (name, _, _) in enumerate(SHADER_SLOTS):
+                v = getattr(s, name)
+                if isinstance(v, str) and name != "Spec1FresnelModel":
+                    self._chk(L.vh_shader_set_texture(h, s.Name.encode(), slot, v.encode()))
+        for t in getattr(scene, "textures", []):
+            self.add_texture(t)
         for m in scene.meshes:
             keys, nverts, _ = m.Verts.shape
             self._chk(L.vh_add_polymesh(
@@ -133,6 +142,8 @@ class HostScene:
                 _p(m.Normals), 0 if m.Normals is None else len(m.Normals),
                 _p(m.NormalIdx), 0 if m.NormalIdx is None else len(m.NormalIdx),
                 C.c_float(m.RayBias)))
+            if getattr(m, "UV", None) is not None:
+                self._chk(L.vh_polymesh_set_uv(h, m.Name.encode(), _p(m.UV), len(m.UV), _p(m.UVIdx), 0 if m.UVIdx is None else len(m.UVIdx)))
         for ins in getattr(scene, "instances", []):
             bmin = np.ascontiguousarray(ins.BMin, np.float32).reshape(-1, 3)
             bmax = np.ascontiguousarray(ins.BMax, np.float32).reshape(-1, 3)
@@ -185,6 +196,11 @@ class HostScene:
         self._chk(self.L.vh_globals(h, _p(g)))
         self.scene = SimpleNamespace(XRes=int(g[0]), YRes=int(g[1]), MaxIter=int(g[2]))
         return self
+
+    def add_texture(self, tex):
+        """Register a decoded image (scenes.Texture) under the file name the shaders' texture maps use."""
+        px = tex.rows_bottom_up()
+        self._chk(self.L.vh_add_texture(self.h, tex.Name.encode(), int(px.shape[1]), int(px.shape[0]), _p(px)))
 
     def postrender(self, fb: np.ndarray):
         """core.PostRender: run the scene's OutputFloat / OutputHDR nodes on the finished frame."""
@@ -349,6 +365,34 @@ class Device:
         p = C.c_void_p()
         self._chk(self.L.vg_framebuffer_device(self.h, C.byref(p)))
         return p.value
+
+    # -- texture store (vg_texture_*) ---------------------------------------------------------------
+    def texture_upload(self, pixels_bottom_up: np.ndarray) -> int:
+        px = np.ascontiguousarray(pixels_bottom_up, np.uint8)
+        assert px.ndim == 3 and px.shape[2] == 3
+        tid = C.c_int(-1)
+        self._chk(self.L.vg_texture_upload(self.h, _p(px), int(px.shape[1]), int(px.shape[0]), C.byref(tid)))
+        return tid.value
+
+    def texture_levels(self, tex_id: int):
+        """The pyramid the device built: list of (h, w, 3) uint8 arrays, rows bottom-up."""
+        n = C.c_int()
+        self._chk(self.L.vg_texture_levels(self.h, tex_id, C.byref(n)))
+        out = []
+        for l in range(n.value):
+            w, h = C.c_int(), C.c_int()
+            self._chk(self.L.vg_texture_read_level(self.h, tex_id, l, C.byref(w), C.byref(h), None))
+            a = np.zeros((h.value, w.value, 3), np.uint8)
+            self._chk(self.L.vg_texture_read_level(self.h, tex_id, l, C.byref(w), C.byref(h), _p(a)))
+            out.append(a)
+        return out
+
+    def texture_sample(self, tex_id: int, coords: np.ndarray, trilinear: bool = False) -> np.ndarray:
+        """vg_texture_sample_batch: coords (n, 8) {U, V, Dduvdx[2], Dduvdy[2], PixelDelta[2]} -> (n, 3)."""
+        coords = np.ascontiguousarray(coords, np.float32).reshape(-1, 8)
+        out = np.zeros((len(coords), 3), np.float32)
+        self._chk(self.L.vg_texture_sample_batch(self.h, tex_id, 1 if trilinear else 0, _p(coords), C.c_int64(len(coords)), _p(out)))
+        return out
 
     def stats(self) -> dict:
         s = VgStats()

@@ -23,13 +23,50 @@ from typing import List, Optional
 import numpy as np
 
 __all__ = [
-    "ShaderStd", "DebugShader", "PolyMesh", "GeomInstance", "matrix4", "srt_matrix", "TriLight", "DiskLight", "SphereLight", "Camera", "PixelFilter", "SceneDesc", "splitmix64_table", "camera_motion_variants", "debug_shader_box",
+    "ShaderStd", "DebugShader", "Texture", "parse_texture_url", "SHADER_SLOTS", "textured_room", "PolyMesh", "GeomInstance", "matrix4", "srt_matrix", "TriLight", "DiskLight", "SphereLight", "Camera", "PixelFilter", "SceneDesc", "splitmix64_table", "camera_motion_variants", "debug_shader_box",
     "heightfield_mesh", "heightfield_scene", "sphere_field_scene", "cornell_box", "glossy_box", "instanced_scene", "incoherent_rays", "to_vnf",
 ]
 
 
 @dataclass
+class Texture:
+    """One entry of the reference's texture store (texture/texture.go:36-47), keyed by the file name the shader parameters
+    use.  Pixels: (h, w, 3) uint8 in IMAGE order (row 0 = top), i.e. what image.Decode hands to loadTexture; `rows_bottom_up()`
+    is the texture's own storage order (texture.go:139 flips while copying).  Image decoding is outside the path."""
+    Name: str
+    Pixels: np.ndarray
+
+    def __post_init__(self):
+        self.Pixels = np.ascontiguousarray(self.Pixels, np.uint8)
+        assert self.Pixels.ndim == 3 and self.Pixels.shape[2] == 3
+
+    def rows_bottom_up(self) -> np.ndarray:
+        return np.ascontiguousarray(self.Pixels[::-1])
+
+
+def parse_texture_url(value: str):
+    """builtin/maps/texture.go:48-83: `path?filter=trilinear&ch=N` -> (path, chan, trilinear)."""
+    from urllib.parse import urlsplit, parse_qs
+    u = urlsplit(value)
+    q = parse_qs(u.query)
+    ch = q.get("ch", ["0"])[0]
+    try:
+        chan = int(ch)
+    except ValueError:
+        chan = 0                      # strconv.Atoi error is dropped (texture.go:57)
+    return u.path, chan, q.get("filter", [""])[0] == "trilinear"
+
+
+# ShaderStd parameter slots in node order (std.go:28-46): (name, offset in the packed float block, floats)
+SHADER_SLOTS = [("EmissionColour", 0, 3), ("EmissionStrength", 3, 1), ("DiffuseColour", 4, 3), ("DiffuseStrength", 7, 1),
+                ("DiffuseRoughness", 8, 1), ("Spec1Colour", 9, 3), ("Spec1Strength", 12, 1), ("Spec1Roughness", 13, 1), ("IOR", 14, 1),
+                ("Spec1FresnelModel", 15, 1), ("Spec1FresnelRefl", 16, 3), ("Spec1FresnelEdge", 19, 3)]
+
+
+@dataclass
 class ShaderStd:
+    """A parameter given as a `str` is a texture map (the .vnf `rgbtex "file?filter=trilinear"` form, nodes/parser.go:247-268;
+    the `ch` query selects the channel of a float parameter, builtin/maps/texture.go:48-67)."""
     Name: str
     EmissionColour: Optional[tuple] = None
     EmissionStrength: Optional[float] = None
@@ -48,17 +85,25 @@ class ShaderStd:
         """(mask, 22 floats) in the slot order shared by the host C-ABI and the oracle."""
         p = np.zeros(22, np.float32)
         mask = 0
-        slots = [("EmissionColour", 0, 3), ("EmissionStrength", 3, 1), ("DiffuseColour", 4, 3), ("DiffuseStrength", 7, 1),
-                 ("DiffuseRoughness", 8, 1), ("Spec1Colour", 9, 3), ("Spec1Strength", 12, 1), ("Spec1Roughness", 13, 1), ("IOR", 14, 1),
-                 ("Spec1FresnelModel", 15, 1), ("Spec1FresnelRefl", 16, 3), ("Spec1FresnelEdge", 19, 3)]
-        for bit, (name, off, n) in enumerate(slots):
+        for bit, (name, off, n) in enumerate(SHADER_SLOTS):
             v = getattr(self, name)
+            if isinstance(v, str) and name != "Spec1FresnelModel":
+                continue   # texture map: bound separately (texture_bindings)
             if v is not None:
                 mask |= 1 << bit
                 if name == "Spec1FresnelModel":
                     v = {"Dielectric": 0.0, "Metal": 1.0}[v]
                 p[off:off + n] = np.asarray(v, np.float32).reshape(-1)
         return mask, p
+
+    def texture_bindings(self):
+        """[(slot, path, chan, trilinear)] for the parameters that are texture maps."""
+        out = []
+        for slot, (name, _, _) in enumerate(SHADER_SLOTS):
+            v = getattr(self, name)
+            if isinstance(v, str) and name != "Spec1FresnelModel":
+                out.append((slot,) + parse_texture_url(v))
+        return out
 
 
 @dataclass
@@ -84,13 +129,17 @@ class PolyMesh:
     Normals: Optional[np.ndarray] = None    # (n,3) float32
     NormalIdx: Optional[np.ndarray] = None
     RayBias: float = 0.0
+    UV: Optional[np.ndarray] = None         # (n,2) float32 (param.Vec2Array, one key)
+    UVIdx: Optional[np.ndarray] = None
 
     def __post_init__(self):
         v = np.ascontiguousarray(self.Verts, np.float32)
         if v.ndim == 2:
             v = v[None]
         self.Verts = v
-        for k in ("PolyCount", "FaceIdx", "ShaderIdx", "NormalIdx"):
+        if self.UV is not None:
+            self.UV = np.ascontiguousarray(self.UV, np.float32).reshape(-1, 2)
+        for k in ("PolyCount", "FaceIdx", "ShaderIdx", "NormalIdx", "UVIdx"):
             a = getattr(self, k)
             if a is not None:
                 setattr(self, k, np.ascontiguousarray(a, np.int32))
@@ -222,6 +271,7 @@ class SceneDesc:
     MaxIter: int = 16
     name: str = "scene"
     filter: Optional[PixelFilter] = None
+    textures: list = field(default_factory=list)   # Texture entries: the decoded files the shaders' texture maps name
 
     @property
     def num_tris(self) -> int:
@@ -256,11 +306,16 @@ def to_vnf(sc: "SceneDesc", outputs=()) -> str:
         parts = ['Name "%s"' % s.Name]
         for name in ("EmissionColour", "DiffuseColour", "Spec1Colour", "Spec1FresnelRefl", "Spec1FresnelEdge"):
             v = getattr(s, name)
-            if v is not None:
+            if isinstance(v, str):
+                parts.append('%s rgbtex "%s"' % (name, v))      # nodes/parser.go:247-268
+            elif v is not None:
                 parts.append("%s rgb %s" % (name, _vec(v)))
         for name in ("EmissionStrength", "DiffuseStrength", "DiffuseRoughness", "Spec1Strength", "Spec1Roughness", "IOR"):
             v = getattr(s, name)
-            if v is not None:
+            if isinstance(v, str):
+                # the only texture form the parser has; it builds an RGB map, so a float parameter reads channel 0
+                parts.append('%s rgbtex "%s"' % (name, v))
+            elif v is not None:
                 parts.append("%s float %s" % (name, _num(v)))
         if s.Spec1FresnelModel is not None:
             parts.append('Spec1FresnelModel "%s"' % s.Spec1FresnelModel)
@@ -282,6 +337,10 @@ def to_vnf(sc: "SceneDesc", outputs=()) -> str:
             parts.append("Normals 1 %d vec3 %s" % (len(m.Normals), _vec(m.Normals.reshape(-1))))
             if m.NormalIdx is not None:
                 parts.append("NormalIdx %d int %s" % (len(m.NormalIdx), " ".join(str(int(x)) for x in m.NormalIdx)))
+        if m.UV is not None:
+            parts.append("UV 1 %d vec2 %s" % (len(m.UV), _vec(m.UV.reshape(-1))))
+            if m.UVIdx is not None:
+                parts.append("UVIdx %d int %s" % (len(m.UVIdx), " ".join(str(int(x)) for x in m.UVIdx)))
         o.append("PolyMesh { %s }" % "\n  ".join(parts))
     for ins in sc.instances:
         rows = ins.Transform.reshape(-1, 4, 4).transpose(0, 2, 1).reshape(-1)     # file order is row major (parser.go:487)
@@ -507,6 +566,68 @@ def cornell_box(xres: int = 512, yres: int = 512, boxes: bool = True) -> SceneDe
     lights = _light_pair(1.99, 0.35, "lightmtl", dy=0.03)
     cam = Camera(From=(0.0, 1.0, 3.4), To=(0.0, 1.0, 0.0), Fov=40.0, Focal=1.0)
     return SceneDesc(XRes=xres, YRes=yres, camera=cam, shaders=shaders, meshes=meshes, lights=lights, MaxIter=16, name="C1-cornell")
+
+
+def _test_texture(w: int, h: int, seed: int) -> np.ndarray:
+    """A seeded image with structure at every scale (checker + stripes + noise), (h, w, 3) uint8, row 0 = top."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:h, 0:w]
+    chk = (((x * 8) // w + (y * 8) // h) & 1).astype(np.float32)
+    img = np.zeros((h, w, 3), np.float32)
+    img[..., 0] = 40 + 180 * chk
+    img[..., 1] = 30 + 200 * (0.5 + 0.5 * np.sin(x * (2 * np.pi * 5 / w)))
+    img[..., 2] = 50 + 150 * (0.5 + 0.5 * np.cos(y * (2 * np.pi * 3 / h)))
+    img += rng.integers(-25, 26, size=(h, w, 3))
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def textured_room(xres: int = 160, yres: int = 120, mirror: bool = True, smooth: bool = True, float_maps: bool = False) -> SceneDesc:
+    """SURVEY.md 8(f).4 test scene: the Cornell room with texture maps (builtin/maps/texture.go) on ShaderStd parameters.
+      floor     DiffuseColour = Feline map, UVs tiled 3x -> grazing, strongly anisotropic footprints (many probes)
+      back      EmissionColour = trilinear map on a black diffuse wall: the image shows the filtered texture itself
+      left      DiffuseColour = Feline map on a mesh WITHOUT UVs (the barycentric fallback of trace.go:355-358,495-501)
+      right     odd-sized (37x23) texture: the NP2 branches of the pyramid
+      shortbox  mirror (mirror=True): the floor texture seen through Ray.Init's reflected differentials
+      ball      a smooth-shaded sphere mesh (smooth=True) with a mirror lobe: DdNdx/DdNdy of interpolated normals
+      tallbox   float_maps=True: DiffuseStrength / DiffuseRoughness read from texture channels
+    """
+    sc = cornell_box(xres, yres)
+    sc.textures = [Texture("floor.png", _test_texture(64, 64, 11)), Texture("picture.png", _test_texture(128, 64, 12)),
+                   Texture("wall.png", _test_texture(32, 32, 13)), Texture("odd.png", _test_texture(37, 23, 14))]
+    sh = {s.Name: s for s in sc.shaders}
+    sc.shaders.append(ShaderStd("floor_tex", DiffuseColour="floor.png", DiffuseStrength=1.0))
+    sc.shaders.append(ShaderStd("picture", EmissionColour="picture.png?filter=trilinear", EmissionStrength=0.8,
+                                DiffuseColour=(0.0, 0.0, 0.0), DiffuseStrength=1.0))
+    sc.shaders.append(ShaderStd("wall_tex", DiffuseColour="wall.png", DiffuseStrength=1.0))
+    sc.shaders.append(ShaderStd("odd_tex", DiffuseColour="odd.png?filter=trilinear", DiffuseStrength=1.0))
+    by = {m.Name: m for m in sc.meshes}
+    by["floor"].Shader = ["floor_tex"]
+    by["floor"].UV = np.asarray([[0, 0], [0, 3], [3, 3], [3, 0]], np.float32)
+    by["back"].Shader = ["picture"]
+    by["back"].UV = np.asarray([[0.1, 0.2], [1.7, 0.2], [1.7, 1.3], [0.1, 1.3]], np.float32)
+    by["back"].UVIdx = np.asarray([0, 1, 2, 3], np.int32)
+    by["left"].Shader = ["wall_tex"]
+    by["right"].Shader = ["odd_tex"]
+    by["right"].UV = np.asarray([[0, 0], [2, 0], [2, 2], [0, 2]], np.float32)
+    if mirror:
+        sc.shaders.append(ShaderStd("mirror", DiffuseColour=(0.4, 0.4, 0.4), DiffuseStrength=0.3,
+                                    Spec1Colour=(0.9, 0.9, 0.9), Spec1Strength=0.7, Spec1Roughness=0.0))
+        by["shortbox"].Shader = ["mirror"]
+    if smooth:
+        v, t = _uv_sphere(12, 8)
+        if not mirror:
+            sc.shaders.append(ShaderStd("mirror", DiffuseColour=(0.4, 0.4, 0.4), DiffuseStrength=0.3,
+                                        Spec1Colour=(0.9, 0.9, 0.9), Spec1Strength=0.7, Spec1Roughness=0.0))
+        pos = (v * np.float32(0.28) + np.asarray([0.45, 0.95, 0.25], np.float32)).astype(np.float32)
+        sc.meshes.append(PolyMesh("ball", pos, ["mirror"], FaceIdx=t.copy(), Normals=v.copy()))
+    if float_maps:
+        sc.shaders.append(ShaderStd("tall_tex", DiffuseColour=(0.7, 0.7, 0.6), DiffuseStrength="wall.png?ch=1", DiffuseRoughness="floor.png?ch=2&filter=trilinear",
+                                    Spec1Colour=(0.9, 0.9, 0.9), Spec1Strength=0.25, Spec1Roughness=0.0))
+        by["tallbox"].Shader = ["tall_tex"]
+    # looking down into the room: the floor is seen at a grazing angle (long, thin texture footprints)
+    sc.camera = Camera(From=(0.03, 1.6, 3.4), To=(0.0, 0.4, 0.0), Fov=50.0, Focal=1.0)
+    sc.name = "textured-room"
+    return sc
 
 
 def debug_shader_box(xres: int = 128, yres: int = 128, mirrors: bool = True) -> SceneDesc:
