@@ -40,6 +40,8 @@ CONFIGS = {
     "c3": dict(workload="C3: 10M-triangle displaced-sphere field (1024 meshes x 9800 tris), mirror chains, 1920x1080, 256 spp", spp=256),
     # configs[3]: motion-blurred mesh (MQBVH, 2 keys)
     "c4": dict(workload="C4: motion-blurred 1M-triangle heightfield (MQBVH, 2 keys), 1920x1080, 64 spp", spp=64),
+    # C2 with a Feline texture map on the ground's DiffuseColour: what the texture path costs on the headline scene
+    "c2t": dict(workload="C2T: C2 with a 1024x1024 Feline texture map on the ground (UV = 8 tiles over the mesh), 1920x1080, 64 spp", spp=64),
     # configs[4]: the C3 scene at 4K, 1024 spp, meant for 8 GPUs (tile-partitioned, NCCL framebuffer gather)
     "c5": dict(workload="C5: 10M-triangle displaced-sphere field, mirror chains, 3840x2160, 1024 spp", spp=1024, xres=3840, yres=2160),
 }
@@ -108,7 +110,14 @@ def build_scene():
     from vermeer_b200 import scenes
     if CONFIG in ("c3", "c5"):
         return scenes.sphere_field_scene(XRES, YRES)
-    return scenes.heightfield_scene(XRES, YRES, nq=NQ, motion=(CONFIG == "c4"))
+    sc = scenes.heightfield_scene(XRES, YRES, nq=NQ, motion=(CONFIG == "c4"))
+    if CONFIG == "c2t":
+        m = sc.meshes[0]
+        xz = m.Verts[0][:, [0, 2]]
+        m.UV = ((xz - xz.min(0)) / (xz.max(0) - xz.min(0)) * 8.0).astype(np.float32)
+        sc.textures = [scenes.Texture("ground.png", scenes._test_texture(1024, 1024, 21))]
+        [s for s in sc.shaders if s.Name == m.Shader[0]][0].DiffuseColour = "ground.png"
+    return sc
 
 
 def cpu_reference_run(scene, table, iters, nthreads):

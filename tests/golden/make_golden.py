@@ -58,6 +58,42 @@ def main():
     np.savez_compressed(os.path.join(HERE, "cornell48_v1.npz"), rays=rays, closest=closest, shadow_rays=sh, anyhit=anyhit,
                         image=fb, ray_count=np.asarray([st["rays"], st["shadow_rays"]]))
     print("wrote qmc_kat.json, cornell48_v1.npz (%d rays)" % len(rays))
+    make_texture_golden()
+
+
+def texture_golden_inputs():
+    """Seeded inputs of texture_v1.npz: two images (one odd-sized) and a batch of lookups."""
+    rng = np.random.default_rng(77)
+    imgs = {"sq": rng.integers(0, 256, (32, 32, 3), dtype=np.uint8), "odd": rng.integers(0, 256, (13, 21, 3), dtype=np.uint8)}
+    n = 512
+    co = np.zeros((n, 8), np.float32)
+    co[:, 0:2] = rng.uniform(-1, 2, (n, 2))
+    r = 10.0 ** rng.uniform(-3, 0, n)
+    ratio = 10.0 ** rng.uniform(0, 1.5, n)
+    ang = rng.uniform(0, 2 * np.pi, n)
+    co[:, 2] = np.cos(ang) * r
+    co[:, 3] = np.sin(ang) * r
+    co[:, 4] = -np.sin(ang) * r / ratio
+    co[:, 5] = np.cos(ang) * r / ratio
+    co[:, 6:8] = 1.0
+    return imgs, co
+
+
+def make_texture_golden():
+    """3. the texture subsystem: mip pyramids (bytes) and both filters on a seeded batch of lookups."""
+    from vermeer_b200 import scenes
+    imgs, co = texture_golden_inputs()
+    sc = scenes.cornell_box(8, 8, boxes=False)
+    sc.textures = [scenes.Texture(k, v) for k, v in imgs.items()]
+    ora = Oracle(sc)
+    out = {"coords": co}
+    for k in imgs:
+        for l, a in enumerate(ora.texture_levels(k)):
+            out["%s_level%d" % (k, l)] = a
+        out["%s_feline" % k] = ora.texture_sample(k, co, trilinear=False)
+        out["%s_trilinear" % k] = ora.texture_sample(k, co, trilinear=True)
+    np.savez_compressed(os.path.join(HERE, "texture_v1.npz"), **out)
+    print("wrote texture_v1.npz")
 
 
 if __name__ == "__main__":

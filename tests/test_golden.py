@@ -61,3 +61,40 @@ def test_gpu_reproduces_golden_image(built_library):
     assert np.sqrt(((fo[ok] - fg[ok]) ** 2).mean()) <= 1e-3
     st = dev.stats()
     assert abs(int(st["rays"]) - int(g["ray_count"][0])) <= 1e-3 * int(g["ray_count"][0])
+
+
+def _texture_golden():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    return mg.texture_golden_inputs(), np.load(os.path.join(GOLD, "texture_v1.npz"))
+
+
+def test_oracle_reproduces_golden_textures(oracle_lib):
+    from oracle.binding import Oracle
+    from vermeer_b200 import scenes
+    (imgs, co), g = _texture_golden()
+    assert np.array_equal(co, g["coords"])
+    sc = scenes.cornell_box(8, 8, boxes=False)
+    sc.textures = [scenes.Texture(k, v) for k, v in imgs.items()]
+    ora = Oracle(sc)
+    for k in imgs:
+        for l, a in enumerate(ora.texture_levels(k)):
+            assert np.array_equal(a, g["%s_level%d" % (k, l)])
+        assert np.array_equal(ora.texture_sample(k, co, trilinear=False).view(np.uint32), g["%s_feline" % k].view(np.uint32))
+        assert np.array_equal(ora.texture_sample(k, co, trilinear=True).view(np.uint32), g["%s_trilinear" % k].view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_golden_textures(built_library):
+    from vermeer_b200.host import Device
+    (imgs, co), g = _texture_golden()
+    dev = Device(0)
+    for k, img in imgs.items():
+        tid = dev.texture_upload(img[::-1])
+        for l, a in enumerate(dev.texture_levels(tid)):
+            assert np.array_equal(a, g["%s_level%d" % (k, l)]), (k, l)
+        for name, tri in (("feline", False), ("trilinear", True)):
+            d = np.abs(dev.texture_sample(tid, co, trilinear=tri) - g["%s_%s" % (k, name)])
+            assert d.max() <= 2e-5, (k, name, d.max())

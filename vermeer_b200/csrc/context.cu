@@ -792,6 +792,7 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
   else if (!std::strcmp(name, "tma_stage")) ctx->opt_traversal = value != 0 ? 1 : 2;
   else if (!std::strcmp(name, "primary_per_lane")) ctx->opt_primary_per_lane = value != 0;
   else if (!std::strcmp(name, "shadow_unordered")) ctx->opt_shadow_unordered = value != 0;
+  else if (!std::strcmp(name, "texture_coop")) ctx->opt_texture_coop = value != 0;
   else if (!std::strcmp(name, "generic_shade")) {
     ctx->opt_generic_shade = value != 0;
     render_invalidate(ctx);

@@ -326,7 +326,7 @@ struct Plane4 {
   f3 n;
   float d;
 };
-__device__ __forceinline__ Plane4 mk4(f3 n, float d, f3) { Plane4 r; r.n = n; r.d = d; return r; }
+__device__ __forceinline__ Plane4 mk4(f3 n, float d) { Plane4 r; r.n = n; r.d = d; return r; }
 
 __device__ __forceinline__ f3 ld3(const float4* p) {
   const float4 v = __ldg(p);
@@ -401,147 +401,200 @@ __device__ inline void build_context(const RenderParams& p, const DevHit& h, flo
 //   * the path's ray differentials are replaced, in place, by those of the mirror ray Ray.Init(RayTypeReflected) would
 //     build from this context (core/ray.go:72-87), whether or not the shader goes on to spawn it.
 // Static meshes only (prepare() refuses textured scenes with other geoms).
-__global__ void __launch_bounds__(128) k_surface(const RenderParams p, int level, int qin) {
+// parameter slot k of a VgMaterial (bit index of its VG_MAT_* flag) <- the colour a texture map returned
+__device__ __forceinline__ void set_param(VgMaterial& s, int k, const float c[3], int chan) {
+  const float f = chan == 0 ? c[0] : (chan == 1 ? c[1] : c[2]);
+  switch (k) {
+    case 0: s.emission_colour[0] = c[0]; s.emission_colour[1] = c[1]; s.emission_colour[2] = c[2]; break;
+    case 1: s.emission_strength = f; break;
+    case 2: s.diffuse_colour[0] = c[0]; s.diffuse_colour[1] = c[1]; s.diffuse_colour[2] = c[2]; break;
+    case 3: s.diffuse_strength = f; break;
+    case 4: s.diffuse_roughness = f; break;
+    case 5: s.spec1_colour[0] = c[0]; s.spec1_colour[1] = c[1]; s.spec1_colour[2] = c[2]; break;
+    case 6: s.spec1_strength = f; break;
+    case 7: s.spec1_roughness = f; break;
+    case 8: s.ior = f; break;
+    case 10: s.spec1_fresnel_refl[0] = c[0]; s.spec1_fresnel_refl[1] = c[1]; s.spec1_fresnel_refl[2] = c[2]; break;
+    case 11: s.spec1_fresnel_edge[0] = c[0]; s.spec1_fresnel_edge[1] = c[1]; s.spec1_fresnel_edge[2] = c[2]; break;
+    default: break;
+  }
+}
+
+// COOP: the probes of a warp's texture lookups are shared evenly between its lanes (texture.cuh: tex_sample_warp); false = one
+// lane per lookup (bit-identical; kept for the A/B measurement and as the cross-check in the tests).
+#ifndef VG_SURFACE_MIN_BLOCKS
+#define VG_SURFACE_MIN_BLOCKS 5
+#endif
+template <bool COOP>
+__global__ void __launch_bounds__(128, VG_SURFACE_MIN_BLOCKS) k_surface(const RenderParams p, int level, int qin, int fast) {
+  __shared__ TexWarpScratch scratch[COOP ? 4 : 1];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.counts[qin]) return;
-  const int4 h1 = *(reinterpret_cast<const int4*>(&p.hits[i]) + 1);
-  const int prim = h1.x, geom = h1.y, slot = h1.z;
-  if (prim < 0) return;
-  const float4 h0 = *reinterpret_cast<const float4*>(&p.hits[i]);
-  const float T = h0.x, U = h0.y, V = h0.z, W = h0.w;
-  const DevGeom g = p.sc.geoms[geom];
-  const int matid = p.sc.prim_material[g.prim_base + prim];
-  if (matid == 255) return;
-  const int path = p.pathq[qin][i];
-  const float4* rp = reinterpret_cast<const float4*>(p.rayq[qin] + i);
-  const float4 ra = rp[0], rb = rp[1];
-  const f3 D = mk3(ra.w, rb.x, rb.y);
-
-  const float4* tp = p.sc.tris + (size_t)slot * 3;
-  const f3 E0 = ld3(tp), E1 = ld3(tp + 1), E2 = ld3(tp + 2);
-  const f3 Ng = normalize3(cross3(sub3(E1, E0), sub3(E2, E0)));
-  f3 n0 = mk3(0, 0, 0), n1 = n0, n2 = n0;
-  const bool has_n = g.normal_base >= 0 && p.sc.tri_normals;
-  f3 N = Ng;  // the interpolated normal BEFORE normalisation (trace.go:326-336)
-  if (has_n) {
-    const float4* np = p.sc.tri_normals + (size_t)slot * 3;
-    n0 = ld3(np); n1 = ld3(np + 1); n2 = ld3(np + 2);
-    N = mk3(U * n0.x + V * n1.x + W * n2.x, U * n0.y + V * n1.y + W * n2.y, U * n0.z + V * n1.z + W * n2.z);
+  const int nq = p.counts[qin];
+  if ((i & ~31) >= nq) return;  // whole warps leave together: the texture phase below is warp-collective
+  int prim = -1, geom = 0, slot = 0, matid = 255;
+  float T = 0, U = 0, V = 0, W = 0;
+  if (i < nq) {
+    const int4 h1 = *(reinterpret_cast<const int4*>(&p.hits[i]) + 1);
+    prim = h1.x; geom = h1.y; slot = h1.z;
   }
-  float2 t0 = make_float2(0, 0), t1 = t0, t2 = t0;
-  const bool has_uv = g.uv_base >= 0 && p.sc.tri_uv;
+  DevGeom g;
+  g.normal_base = -1; g.uv_base = -1; g.prim_base = 0;
+  if (prim >= 0) {
+    const float4 h0 = *reinterpret_cast<const float4*>(&p.hits[i]);
+    T = h0.x; U = h0.y; V = h0.z; W = h0.w;
+    g = p.sc.geoms[geom];
+    matid = p.sc.prim_material[g.prim_base + prim];
+  }
+  const bool active = matid != 255;
+  int path = 0;
+  f3 D = mk3(0, 0, 1);
   TexCoord tc;
-  if (has_uv) {
-    const float2* up = p.sc.tri_uv + (size_t)slot * 3;
-    t0 = __ldg(up); t1 = __ldg(up + 1); t2 = __ldg(up + 2);
-    tc.U = U * t0.x + V * t1.x + W * t2.x;
-    tc.V = U * t0.y + V * t1.y + W * t2.y;
-  } else {
-    tc.U = U;
-    tc.V = V;
-  }
-
-  // incoming ray differentials
-  float* q = p.diff + path;
-  const size_t P = (size_t)p.P;
-  const f3 rPx = mk3(q[0], q[P], q[2 * P]), rPy = mk3(q[3 * P], q[4 * P], q[5 * P]);
-  const f3 rDx = mk3(q[6 * P], q[7 * P], q[8 * P]), rDy = mk3(q[9 * P], q[10 * P], q[11 * P]);
-  // DifferentialTransfer (core/ray.go:95-104)
-  const float DNg = dot3(D, Ng);
-  const f3 ax = mad3(rPx, rDx, T), ay = mad3(rPy, rDy, T);
-  const float dtdx = -dot3(ax, Ng) / DNg;
-  const float dtdy = -dot3(ay, Ng) / DNg;
-  const f3 dPdx = add3(ax, scale3(dtdx, D));
-  const f3 dPdy = add3(ay, scale3(dtdy, D));
-
-  // barycentric planes (trace.go:362-436): n = Ng x edge, normalised, then scaled so that the opposite vertex evaluates to 1
-  auto plane = [&](f3 a, f3 b, f3 on, f3 opp) {
-    f3 n = mk3(Ng.y * (a.z - b.z) - Ng.z * (a.y - b.y), Ng.z * (a.x - b.x) - Ng.x * (a.z - b.z), Ng.x * (a.y - b.y) - Ng.y * (a.x - b.x));
-    const float qn = sqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
-    n.x /= qn; n.y /= qn; n.z /= qn;
-    const float d = -on.x * n.x - on.y * n.y - on.z * n.z;
-    return mk4(n, d, opp);
-  };
-  // alpha: edge E2-E1 through E1, opposite E0 (evaluated as E0.n + d); beta: E2-E0 through E0, opposite E1 (n.E1 + d);
-  // gamma: E1-E0 through E0, opposite E2 (n.E2 + d) -- the operand order of each `l` is the reference's
-  f3 na, nb, ng;
-  {
-    const Plane4 A = plane(E2, E1, E1, E0);
-    const float l = E0.x * A.n.x + E0.y * A.n.y + E0.z * A.n.z + A.d;
-    na = mk3(A.n.x / l, A.n.y / l, A.n.z / l);
-    const Plane4 B = plane(E2, E0, E0, E1);
-    const float lb = B.n.x * E1.x + B.n.y * E1.y + B.n.z * E1.z + B.d;
-    nb = mk3(B.n.x / lb, B.n.y / lb, B.n.z / lb);
-    const Plane4 G = plane(E1, E0, E0, E2);
-    const float lg = G.n.x * E2.x + G.n.y * E2.y + G.n.z * E2.z + G.d;
-    ng = mk3(G.n.x / lg, G.n.y / lg, G.n.z / lg);
-  }
-  const float alphax = na.x * dPdx.x + na.y * dPdx.y + na.z * dPdx.z;
-  const float betax = nb.x * dPdx.x + nb.y * dPdx.y + nb.z * dPdx.z;
-  const float gammax = ng.x * dPdx.x + ng.y * dPdx.y + ng.z * dPdx.z;
-  const float alphay = na.x * dPdy.x + na.y * dPdy.y + na.z * dPdy.z;
-  const float betay = nb.x * dPdy.x + nb.y * dPdy.y + nb.z * dPdy.z;
-  const float gammay = ng.x * dPdy.x + ng.y * dPdy.y + ng.z * dPdy.z;
-
-  f3 dndx = mk3(0, 0, 0), dndy = mk3(0, 0, 0);
-  if (has_n) {
-    dndx = mk3(alphax * n0.x + betax * n1.x + gammax * n2.x, alphax * n0.y + betax * n1.y + gammax * n2.y, alphax * n0.z + betax * n1.z + gammax * n2.z);
-    dndy = mk3(alphay * n0.x + betay * n1.x + gammay * n2.x, alphay * n0.y + betay * n1.y + gammay * n2.y, alphay * n0.z + betay * n1.z + gammay * n2.z);
-  }
-  const float NN = dot3(N, N);
-  const float kN = 1 / (NN * sqrtf(NN));
-  const f3 DdNdx = scale3(kN, sub3(scale3(NN, dndx), scale3(dot3(N, dndx), N)));
-  const f3 DdNdy = scale3(kN, sub3(scale3(NN, dndy), scale3(dot3(N, dndy), N)));
-  if (has_uv) {
-    tc.dudx = alphax * t0.x + betax * t1.x + gammax * t2.x;
-    tc.dvdx = alphax * t0.y + betax * t1.y + gammax * t2.y;
-    tc.dudy = alphay * t0.x + betay * t1.x + gammay * t2.x;
-    tc.dvdy = alphay * t0.y + betay * t1.y + gammay * t2.y;
-  } else {  // trace.go:495-501 as written
-    tc.dudx = alphax * 0 + betax * 1 + gammax * 0;
-    tc.dvdx = alphax * 0 + betax * 0 + gammax * 1;
-    tc.dudy = alphay * 0 + betay * 1 + gammay * 0;
-    tc.dvdy = alphay * 0 + betay * 0 + gammay * 1;
-  }
+  tc.U = tc.V = tc.dudx = tc.dvdx = tc.dudy = tc.dvdy = 0.f;
   tc.pd0 = p.pd0;
   tc.pd1 = p.pd1;
+  f3 dPdx = mk3(0, 0, 0), dPdy = dPdx, oDx = dPdx, oDy = dPdx;
+  if (active) {
+    path = p.pathq[qin][i];
+    const float4* rp = reinterpret_cast<const float4*>(p.rayq[qin] + i);
+    const float4 ra = rp[0], rb = rp[1];
+    D = mk3(ra.w, rb.x, rb.y);
 
-  // the material at this vertex
-  const MatTex mt = p.mat_tex[matid];
-  bool any = false;
-#pragma unroll
-  for (int k = 0; k < 12; k++) any |= mt.slot[k].tex >= 0;
-  if (!any) {
-    p.vmats[i] = p.mats[matid];
-  } else {
-    VgMaterial s = p.rawmats[matid];
-    auto rgb = [&](int k, float* dst) {
-      if (mt.slot[k].tex < 0) return;
-      tex_sample(p.tex, mt.slot[k].tex, mt.slot[k].filter, tc, dst);
+    const float4* tp = p.sc.tris + (size_t)slot * 3;
+    const f3 E0 = ld3(tp), E1 = ld3(tp + 1), E2 = ld3(tp + 2);
+    const f3 Ng = normalize3(cross3(sub3(E1, E0), sub3(E2, E0)));
+    f3 n0 = mk3(0, 0, 0), n1 = n0, n2 = n0;
+    const bool has_n = g.normal_base >= 0 && p.sc.tri_normals;
+    f3 N = Ng;  // the interpolated normal BEFORE normalisation (trace.go:326-336)
+    if (has_n) {
+      const float4* np = p.sc.tri_normals + (size_t)slot * 3;
+      n0 = ld3(np); n1 = ld3(np + 1); n2 = ld3(np + 2);
+      N = mk3(U * n0.x + V * n1.x + W * n2.x, U * n0.y + V * n1.y + W * n2.y, U * n0.z + V * n1.z + W * n2.z);
+    }
+    float2 t0 = make_float2(0, 0), t1 = t0, t2 = t0;
+    const bool has_uv = g.uv_base >= 0 && p.sc.tri_uv;
+    if (has_uv) {
+      const float2* up = p.sc.tri_uv + (size_t)slot * 3;
+      t0 = __ldg(up); t1 = __ldg(up + 1); t2 = __ldg(up + 2);
+      tc.U = U * t0.x + V * t1.x + W * t2.x;
+      tc.V = U * t0.y + V * t1.y + W * t2.y;
+    } else {
+      tc.U = U;
+      tc.V = V;
+    }
+
+    // incoming ray differentials
+    const float* q = p.diff + path;
+    const size_t P = (size_t)p.P;
+    const f3 rPx = mk3(q[0], q[P], q[2 * P]), rPy = mk3(q[3 * P], q[4 * P], q[5 * P]);
+    const f3 rDx = mk3(q[6 * P], q[7 * P], q[8 * P]), rDy = mk3(q[9 * P], q[10 * P], q[11 * P]);
+    // DifferentialTransfer (core/ray.go:95-104)
+    const float DNg = dot3(D, Ng);
+    const f3 ax = mad3(rPx, rDx, T), ay = mad3(rPy, rDy, T);
+    const float dtdx = -dot3(ax, Ng) / DNg;
+    const float dtdy = -dot3(ay, Ng) / DNg;
+    dPdx = add3(ax, scale3(dtdx, D));
+    dPdy = add3(ay, scale3(dtdy, D));
+
+    // barycentric planes (trace.go:362-436): n = Ng x edge, normalised, then scaled so that the opposite vertex evaluates to 1
+    auto plane = [&](f3 a, f3 b, f3 on) {
+      f3 n = mk3(Ng.y * (a.z - b.z) - Ng.z * (a.y - b.y), Ng.z * (a.x - b.x) - Ng.x * (a.z - b.z), Ng.x * (a.y - b.y) - Ng.y * (a.x - b.x));
+      const float qn = sqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
+      n.x /= qn; n.y /= qn; n.z /= qn;
+      const float d = -on.x * n.x - on.y * n.y - on.z * n.z;
+      return mk4(n, d);
     };
-    auto f32 = [&](int k, float* dst) {
-      if (mt.slot[k].tex < 0) return;
-      float c[3];
-      tex_sample(p.tex, mt.slot[k].tex, mt.slot[k].filter, tc, c);
-      *dst = mt.slot[k].chan == 0 ? c[0] : (mt.slot[k].chan == 1 ? c[1] : c[2]);
-    };
-    rgb(0, s.emission_colour); f32(1, &s.emission_strength);
-    rgb(2, s.diffuse_colour); f32(3, &s.diffuse_strength); f32(4, &s.diffuse_roughness);
-    rgb(5, s.spec1_colour); f32(6, &s.spec1_strength); f32(7, &s.spec1_roughness); f32(8, &s.ior);
-    rgb(10, s.spec1_fresnel_refl); rgb(11, s.spec1_fresnel_edge);
-    p.vmats[i] = derive_mat(s);
+    // alpha: edge E2-E1 through E1, opposite E0 (evaluated as E0.n + d); beta: E2-E0 through E0, opposite E1 (n.E1 + d);
+    // gamma: E1-E0 through E0, opposite E2 (n.E2 + d) -- the operand order of each `l` is the reference's
+    f3 na, nb, ng;
+    {
+      const Plane4 A = plane(E2, E1, E1);
+      const float l = E0.x * A.n.x + E0.y * A.n.y + E0.z * A.n.z + A.d;
+      na = mk3(A.n.x / l, A.n.y / l, A.n.z / l);
+      const Plane4 B = plane(E2, E0, E0);
+      const float lb = B.n.x * E1.x + B.n.y * E1.y + B.n.z * E1.z + B.d;
+      nb = mk3(B.n.x / lb, B.n.y / lb, B.n.z / lb);
+      const Plane4 G = plane(E1, E0, E0);
+      const float lg = G.n.x * E2.x + G.n.y * E2.y + G.n.z * E2.z + G.d;
+      ng = mk3(G.n.x / lg, G.n.y / lg, G.n.z / lg);
+    }
+    const float alphax = na.x * dPdx.x + na.y * dPdx.y + na.z * dPdx.z;
+    const float betax = nb.x * dPdx.x + nb.y * dPdx.y + nb.z * dPdx.z;
+    const float gammax = ng.x * dPdx.x + ng.y * dPdx.y + ng.z * dPdx.z;
+    const float alphay = na.x * dPdy.x + na.y * dPdy.y + na.z * dPdy.z;
+    const float betay = nb.x * dPdy.x + nb.y * dPdy.y + nb.z * dPdy.z;
+    const float gammay = ng.x * dPdy.x + ng.y * dPdy.y + ng.z * dPdy.z;
+
+    f3 dndx = mk3(0, 0, 0), dndy = mk3(0, 0, 0);
+    if (has_n) {
+      dndx = mk3(alphax * n0.x + betax * n1.x + gammax * n2.x, alphax * n0.y + betax * n1.y + gammax * n2.y, alphax * n0.z + betax * n1.z + gammax * n2.z);
+      dndy = mk3(alphay * n0.x + betay * n1.x + gammay * n2.x, alphay * n0.y + betay * n1.y + gammay * n2.y, alphay * n0.z + betay * n1.z + gammay * n2.z);
+    }
+    const float NN = dot3(N, N);
+    const float kN = 1 / (NN * sqrtf(NN));
+    const f3 DdNdx = scale3(kN, sub3(scale3(NN, dndx), scale3(dot3(N, dndx), N)));
+    const f3 DdNdy = scale3(kN, sub3(scale3(NN, dndy), scale3(dot3(N, dndy), N)));
+    if (has_uv) {
+      tc.dudx = alphax * t0.x + betax * t1.x + gammax * t2.x;
+      tc.dvdx = alphax * t0.y + betax * t1.y + gammax * t2.y;
+      tc.dudy = alphay * t0.x + betay * t1.x + gammay * t2.x;
+      tc.dvdy = alphay * t0.y + betay * t1.y + gammay * t2.y;
+    } else {  // trace.go:495-501 as written
+      tc.dudx = alphax * 0 + betax * 1 + gammax * 0;
+      tc.dvdx = alphax * 0 + betax * 0 + gammax * 1;
+      tc.dudy = alphay * 0 + betay * 1 + gammay * 0;
+      tc.dvdy = alphay * 0 + betay * 0 + gammay * 1;
+    }
+
+    // differentials of the mirror ray (core/ray.go:72-87); sc.N is the shading normal after ApplyTransform (normalised once more,
+    // like build_context), sc.DdDdx/y are the incoming ray's
+    const f3 Ns = has_n ? normalize3(normalize3(N)) : normalize3(Ng);
+    const float RdN = dot3(D, Ns);
+    const float DdotNdx = dot3(rDx, Ns) + dot3(D, DdNdx);
+    const float DdotNdy = dot3(rDy, Ns) + dot3(D, DdNdy);
+    oDx = mad3(rDx, add3(scale3(RdN, DdNdx), scale3(DdotNdx, Ns)), -2.0f);
+    oDy = mad3(rDy, add3(scale3(RdN, DdNdy), scale3(DdotNdy, Ns)), -2.0f);
   }
 
-  // differentials of the mirror ray (core/ray.go:72-87); sc.N is the shading normal after ApplyTransform (normalised twice,
-  // like build_context), sc.DdDdx/y are the incoming ray's
-  const f3 Ns = has_n ? normalize3(normalize3(N)) : normalize3(Ng);
-  const float RdN = dot3(D, Ns);
-  const float DdotNdx = dot3(rDx, Ns) + dot3(D, DdNdx);
-  const float DdotNdy = dot3(rDy, Ns) + dot3(D, DdNdy);
-  const f3 oDx = mad3(rDx, add3(scale3(RdN, DdNdx), scale3(DdotNdx, Ns)), -2.0f);
-  const f3 oDy = mad3(rDy, add3(scale3(RdN, DdNdy), scale3(DdotNdy, Ns)), -2.0f);
-  q[0] = dPdx.x; q[P] = dPdx.y; q[2 * P] = dPdx.z; q[3 * P] = dPdy.x; q[4 * P] = dPdy.y; q[5 * P] = dPdy.z;
-  q[6 * P] = oDx.x; q[7 * P] = oDx.y; q[8 * P] = oDx.z; q[9 * P] = oDy.x; q[10 * P] = oDy.y; q[11 * P] = oDy.z;
+  // the material at this vertex: every parameter that is a texture map is looked up, then the constants are re-derived.
+  // One copy of the lookup code, looped over the slots some lane of the warp needs (the unrolled form was instruction-cache bound)
+  const MatTex* mt = active ? p.mat_tex + matid : nullptr;
+  const unsigned mask = active ? mt->mask : 0u;
+  const bool any = mask != 0u;
+  unsigned wm = __reduce_or_sync(0xffffffffu, mask);
+  if (wm) {
+    VgMaterial s;
+    if (any) s = p.rawmats[matid];
+#pragma unroll 1
+    while (wm) {
+      const int k = __ffs(wm) - 1;
+      wm &= wm - 1;
+      const int tex = (mask >> k) & 1u ? mt->slot[k].tex : -1;
+      float c[3] = {0.f, 0.f, 0.f};
+      if (COOP) {
+        TexProbeSetup su;
+        su.tex = -1; su.nprobes = 0; su.feline = 0;
+        su.U = su.V = su.dU = su.dV = su.lod = su.mr2 = su.n0 = 0.f;
+        if (tex >= 0) su = tex_setup(p.tex, tex, mt->slot[k].filter, tc, fast != 0);
+        tex_sample_warp(p.tex, su, &scratch[(threadIdx.x >> 5) & 3], c);
+      } else if (tex >= 0) {
+        const TexProbeSetup su = tex_setup(p.tex, tex, mt->slot[k].filter, tc, fast != 0);
+        TexAccum acc;
+        acc.init();
+        for (int j = 0; j < su.nprobes; j++) acc.add(su, tex_probe(p.tex, su, j));
+        acc.finish(su, c);
+      }
+      if (tex >= 0) set_param(s, k, c, mt->slot[k].chan);
+    }
+    if (any) p.vmats[i] = derive_mat(s);
+  }
+  if (active && !any) p.vmats[i] = p.mats[matid];
+
+  if (active) {
+    float* q = p.diff + path;
+    const size_t P = (size_t)p.P;
+    q[0] = dPdx.x; q[P] = dPdx.y; q[2 * P] = dPdx.z; q[3 * P] = dPdy.x; q[4 * P] = dPdy.y; q[5 * P] = dPdy.z;
+    q[6 * P] = oDx.x; q[7 * P] = oDx.y; q[8 * P] = oDx.z; q[9 * P] = oDy.x; q[10 * P] = oDy.y; q[11 * P] = oDy.z;
+  }
 }
 
 // ShaderContext.ApplyTransform (core/shader.go:129-135) with the transform the last hit instance left in the context
@@ -1411,7 +1464,12 @@ static int prepare(vg_ctx* ctx) {
     RCUDA(rs.vmats.reserve(P)); RCUDA(rs.diff.reserve(P * 12));
     RCUDA(rs.rawmats.reserve(ctx->materials.size())); RCUDA(rs.mat_tex.reserve(ctx->materials.size()));
     std::vector<MatTex> mt(ctx->materials.size());
-    for (size_t i = 0; i < mt.size() && i < ctx->mat_tex.size(); i++) mt[i] = ctx->mat_tex[i];
+    for (size_t i = 0; i < mt.size() && i < ctx->mat_tex.size(); i++) {
+      mt[i] = ctx->mat_tex[i];
+      mt[i].mask = 0;
+      for (int k = 0; k < 12; k++)
+        if (mt[i].slot[k].tex >= 0) mt[i].mask |= 1u << k;
+    }
     RCUDA(cudaMemcpyAsync(rs.rawmats.p, ctx->materials.data(), ctx->materials.size() * sizeof(VgMaterial), cudaMemcpyHostToDevice, ctx->stream));
     RCUDA(cudaMemcpyAsync(rs.mat_tex.p, mt.data(), mt.size() * sizeof(MatTex), cudaMemcpyHostToDevice, ctx->stream));
     RCUDA(cudaStreamSynchronize(ctx->stream));
@@ -1526,7 +1584,9 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
         launches++;
         if (level <= 3) {
           if (rs.textured) {
-            k_surface<<<(np + 127) / 128, 128, 0, st>>>(p, level, qin);
+            const int fast = ctx->opt_precise_trig ? 0 : 1;
+            if (ctx->opt_texture_coop) k_surface<true><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, fast);
+            else k_surface<false><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, fast);
             launches++;
           }
           const bool h1 = rs.max_light_samples <= 2 || level > 0;

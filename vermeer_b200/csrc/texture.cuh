@@ -41,8 +41,19 @@ struct TexCoord {
   float pd0, pd1;
 };
 
-__device__ __forceinline__ float tex_log2(float x) { return (float)log2((double)x); }  // math/pow.go:12-14
-__device__ __forceinline__ float tex_exp(float x) { return (float)exp((double)x); }
+// math/pow.go:12-19, sincos.go:16-64: float32 -> float64 stdlib -> float32. `fast` = the single-precision libm (1-2 ulp), the same
+// switch as the shading kernels' trig ("precise_trig" option); both are far inside the image tolerance.
+__device__ __forceinline__ float tex_log2(float x, bool fast) { return fast ? log2f(x) : (float)log2((double)x); }
+__device__ __forceinline__ float tex_exp(float x, bool fast) { return fast ? expf(x) : (float)exp((double)x); }
+__device__ __forceinline__ float tex_atan(float x, bool fast) { return fast ? atanf(x) : (float)atan((double)x); }
+__device__ __forceinline__ void tex_sincos(float x, bool fast, float* sn, float* cs) {
+  if (fast) {
+    sincosf(x, sn, cs);
+  } else {
+    *sn = (float)sin((double)x);
+    *cs = (float)cos((double)x);
+  }
+}
 
 // mipmap.go:15-58
 __device__ inline void tex_bilinear(const DevTexStore& ts, const DevTexLevel& L, float s, float t, float c[3]) {
@@ -55,12 +66,13 @@ __device__ inline void tex_bilinear(const DevTexStore& ts, const DevTexLevel& L,
   int y0 = (int)floorf(mt * fh);
   int y1 = (int)ceilf(mt * fh);
   const float dy = mt * fh - floorf(mt * fh);
-  x0 %= L.w; x1 %= L.w;
-  if (x0 < 0) x0 += L.w;
-  if (x1 < 0) x1 += L.w;
-  y0 %= L.h; y1 %= L.h;
-  if (y0 < 0) y0 += L.h;
-  if (y1 < 0) y1 += L.h;
+  // x0 %= w etc. (mipmap.go:30-47): ms is in [0,1), so the texel coordinates are in [0, w] and the modulo only ever folds w
+  // onto 0 (ms*w can round up to w; ceil reaches w on the last texel) — a compare instead of an integer division. NaN
+  // coordinates convert to 0 here where amd64's CVTTSS2SQ gives the "integer indefinite"; the colour is NaN either way.
+  x0 = (x0 >= L.w || x0 < 0) ? 0 : x0;
+  x1 = (x1 >= L.w || x1 < 0) ? 0 : x1;
+  y0 = (y0 >= L.h || y0 < 0) ? 0 : y0;
+  y1 = (y1 >= L.h || y1 < 0) ? 0 : y1;
   const uchar4* base = ts.texels + L.off;
   const uchar4 t00 = __ldg(base + x0 + y0 * L.w), t10 = __ldg(base + x1 + y0 * L.w);
   const uchar4 t01 = __ldg(base + x0 + y1 * L.w), t11 = __ldg(base + x1 + y1 * L.w);
@@ -94,8 +106,19 @@ __device__ inline void tex_trilinear(const DevTexStore& ts, const DevTexture& T,
   for (int k = 0; k < 3; k++) c[k] = dl * c0[k] + (1 - dl) * c1[k];
 }
 
-// texture.go:219-311
-__device__ inline void tex_sample_rgb(const DevTexStore& ts, const DevTexture& T, const TexCoord& sg, float out[3]) {
+// One lookup = a set-up (the footprint analysis, once) and 1..16 probes (a trilinear tap and its weight each). The split is what
+// lets a warp share the probes of its 32 lookups evenly (tex_sample_warp): Feline's probe count follows the anisotropy of the
+// footprint, so lane-per-lookup execution leaves most of a warp idle (ncu: 6.6 of 32 threads active in the taps).
+struct TexProbeSetup {
+  int32_t tex;      // texture id; < 0: no lookup
+  int32_t nprobes;  // 1 for the trilinear filter
+  int32_t feline;   // bit 0: Feline lookup; bit 1: single-precision exp for the probe weights
+  float U, V;       // feline: w*U, h*V (texel units); trilinear: U, V
+  float dU, dV, lod, mr2, n0;
+};
+
+// texture.go:219-311 up to the tap (SampleRGB)
+__device__ inline TexProbeSetup tex_setup_rgb(const DevTexture& T, int tex, const TexCoord& sg, bool fast) {
   float tx0 = sg.dudx * sg.pd0, tx1 = sg.dvdx * sg.pd0;
   float ty0 = sg.dudy * sg.pd1, ty1 = sg.dvdy * sg.pd1;
   tx0 = tx0 * (float)T.w;
@@ -104,18 +127,18 @@ __device__ inline void tex_sample_rgb(const DevTexStore& ts, const DevTexture& T
   ty1 = ty1 * (float)T.h;
   const float ds = sqrtf(tx0 * tx0 + tx1 * tx1);
   const float dt = sqrtf(ty0 * ty0 + ty1 * ty1);
-  float lod = tex_log2(ds > dt ? ds : dt);  // m.Max = MAXSS: the second operand when unordered
+  float lod = tex_log2(ds > dt ? ds : dt, fast);  // m.Max = MAXSS: the second operand when unordered
   const float maxlod = (float)(T.n_levels - 1);
   if (lod > maxlod) lod = maxlod;
   if (lod < 0) lod = 0;
-  tex_trilinear(ts, T, sg.U, sg.V, lod, out);
-  out[0] /= 255.0f;
-  out[1] /= 255.0f;
-  out[2] /= 255.0f;
+  TexProbeSetup s;
+  s.tex = tex; s.nprobes = 1; s.feline = 0;
+  s.U = sg.U; s.V = sg.V; s.dU = 0; s.dV = 0; s.lod = lod; s.mr2 = 1; s.n0 = 0;
+  return s;
 }
 
-// feline.go:25-151
-__device__ inline void tex_sample_feline(const DevTexStore& ts, const DevTexture& T, const TexCoord& sc, float c[3]) {
+// feline.go:25-116 (SampleFeline up to the probe loop)
+__device__ inline TexProbeSetup tex_setup_feline(const DevTexture& T, int tex, const TexCoord& sc, bool fast) {
   float ux = sc.dudx * sc.pd0, vx = sc.dvdx * sc.pd0;
   float uy = sc.dudy * sc.pd1, vy = sc.dvdy * sc.pd1;
   const float fw = (float)T.w, fh = (float)T.h;
@@ -136,7 +159,7 @@ __device__ inline void tex_sample_feline(const DevTexStore& ts, const DevTexture
   const float Cprm = (A + C + root) / 2;
   float majorRadius = sqrtf(1 / Aprm);
   float minorRadius = sqrtf(1 / Cprm);
-  float theta = (float)atan((double)(B / amc)) / 2;
+  float theta = tex_atan(B / amc, fast) / 2;
   if (A > C) theta = theta + 3.14159265358f / 2;
   minorRadius = minorRadius > 1.0f ? minorRadius : 1.0f;
   majorRadius = majorRadius > 1.0f ? majorRadius : 1.0f;
@@ -144,7 +167,7 @@ __device__ inline void tex_sample_feline(const DevTexStore& ts, const DevTexture
   float iProbes = floorf(fProbes + 0.5f);
   iProbes = iProbes < 16.0f ? iProbes : 16.0f;
   if (iProbes < fProbes) minorRadius = 2 * majorRadius / (iProbes + 1);
-  float lod = tex_log2(minorRadius);
+  float lod = tex_log2(minorRadius, fast);
   const float maxlod = (float)(T.n_levels - 1);
   if (lod > maxlod) {
     lod = maxlod;
@@ -152,39 +175,130 @@ __device__ inline void tex_sample_feline(const DevTexStore& ts, const DevTexture
   }
   if (lod < 0) lod = 0;
   const float lineLength = 2 * (majorRadius - minorRadius);
-  float dU = (float)cos((double)theta) * lineLength / (iProbes - 1);
-  float dV = (float)sin((double)theta) * lineLength / (iProbes - 1);
-  const int nProbes = (int)iProbes;
+  float sn, cs;
+  tex_sincos(theta, fast, &sn, &cs);
+  float dU = cs * lineLength / (iProbes - 1);
+  float dV = sn * lineLength / (iProbes - 1);
+  // int(iProbes): a NaN footprint (parallel derivatives: F = 0) reaches here as NaN, which amd64 converts to the most negative
+  // integer, i.e. no probe and 0/0 = NaN for the colour; `0 probes` gives the same NaN
+  const int nProbes = iProbes == iProbes ? (int)iProbes : 0;
   if (nProbes == 1) {
     dU = 0;
     dV = 0;
   }
-  float n = (float)(-(nProbes - 1));
-  const float alpha = 0.6f;
-  float accum[3] = {0, 0, 0};
-  float accumWeight = 0;
-  const float mr2 = majorRadius * majorRadius;
-  for (int i = 0; i < nProbes; i++) {
-    const float u = fw * sc.U + (n / 2) * dU;
-    const float v = fh * sc.V + (n / 2) * dV;
-    const float d2 = ((n * n) / 4) * (dU * dU + dV * dV) / mr2;
-    const float relativeWeight = tex_exp(-alpha * d2);
-    float sample[3];
-    tex_trilinear(ts, T, u / fw, v / fh, lod, sample);
-#pragma unroll
-    for (int k = 0; k < 3; k++) accum[k] += (sample[k] / 255.0f) * relativeWeight;
-    accumWeight += relativeWeight;
-    n += 2;
-  }
-#pragma unroll
-  for (int k = 0; k < 3; k++) c[k] = accum[k] / accumWeight;
+  TexProbeSetup s;
+  s.tex = tex; s.nprobes = nProbes; s.feline = fast ? 3 : 1;
+  s.U = fw * sc.U; s.V = fh * sc.V; s.dU = dU; s.dV = dV; s.lod = lod; s.mr2 = majorRadius * majorRadius;
+  s.n0 = (float)(-(nProbes - 1));
+  return s;
 }
 
-#define VG_TEXFILTER_FELINE_ 0
-__device__ inline void tex_sample(const DevTexStore& ts, int tex, int filter, const TexCoord& tc, float out[3]) {
+__device__ inline TexProbeSetup tex_setup(const DevTexStore& ts, int tex, int filter, const TexCoord& tc, bool fast = false) {
   const DevTexture T = ts.textures[tex];
-  if (filter == 1) tex_sample_rgb(ts, T, tc, out);
-  else tex_sample_feline(ts, T, tc, out);
+  return filter == 1 ? tex_setup_rgb(T, tex, tc, fast) : tex_setup_feline(T, tex, tc, fast);
+}
+
+// probe i of a lookup: Feline: (sample / 255) * weight in .xyz and the weight in .w (feline.go:118-137); trilinear: sample / 255
+// (texture.go:305-308). The divisions sit here, with the taps, so that the owner's in-order pass is additions only.
+__device__ inline float4 tex_probe(const DevTexStore& ts, const TexProbeSetup& s, int i) {
+  const DevTexture T = ts.textures[s.tex];
+  float sample[3];
+  float w = 1.0f;
+  if (s.feline) {
+    const float fw = (float)T.w, fh = (float)T.h;
+    const float n = s.n0 + (float)(2 * i);  // the reference's running n += 2: small integers, exact either way
+    const float u = s.U + (n / 2) * s.dU;
+    const float v = s.V + (n / 2) * s.dV;
+    const float d2 = ((n * n) / 4) * (s.dU * s.dU + s.dV * s.dV) / s.mr2;
+    w = tex_exp(-0.6f * d2, (s.feline & 2) != 0);
+    tex_trilinear(ts, T, u / fw, v / fh, s.lod, sample);
+    return make_float4((sample[0] / 255.0f) * w, (sample[1] / 255.0f) * w, (sample[2] / 255.0f) * w, w);
+  }
+  tex_trilinear(ts, T, s.U, s.V, s.lod, sample);
+  return make_float4(sample[0] / 255.0f, sample[1] / 255.0f, sample[2] / 255.0f, w);
+}
+
+// the owner's side: probes in order (feline.go:133-147), or the single tap / 255 (texture.go:305-308)
+struct TexAccum {
+  float a0, a1, a2, w;
+  __device__ __forceinline__ void init() { a0 = a1 = a2 = w = 0.0f; }
+  __device__ __forceinline__ void add(const TexProbeSetup& s, const float4 r) {
+    if (s.feline) {
+      a0 += r.x;
+      a1 += r.y;
+      a2 += r.z;
+      w += r.w;
+    } else {
+      a0 = r.x;
+      a1 = r.y;
+      a2 = r.z;
+    }
+  }
+  __device__ __forceinline__ void finish(const TexProbeSetup& s, float out[3]) const {
+    if (s.feline) {
+      out[0] = a0 / w;
+      out[1] = a1 / w;
+      out[2] = a2 / w;
+    } else {
+      out[0] = a0; out[1] = a1; out[2] = a2;
+    }
+  }
+};
+
+// one lane, one lookup (the batch entry point and the reference for the cooperative form)
+__device__ inline void tex_sample(const DevTexStore& ts, int tex, int filter, const TexCoord& tc, float out[3]) {
+  const TexProbeSetup s = tex_setup(ts, tex, filter, tc);
+  TexAccum acc;
+  acc.init();
+  for (int i = 0; i < s.nprobes; i++) acc.add(s, tex_probe(ts, s, i));
+  acc.finish(s, out);
+}
+
+// Warp-cooperative form: all 32 lanes call it; lanes with `mine.tex >= 0` own a lookup. The probes of the warp's lookups are
+// numbered consecutively (exclusive prefix sum of the probe counts) and taken 32 at a time, one per lane; each owner then adds
+// the results of its own probes in probe order, so the sums are bit-identical to tex_sample's.
+struct TexWarpScratch {  // per warp, shared memory
+  TexProbeSetup setup[32];
+  int incl[32];
+  float4 res[32];
+};
+__device__ inline void tex_sample_warp(const DevTexStore& ts, const TexProbeSetup& mine, TexWarpScratch* sh, float out[3]) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int n = mine.tex >= 0 ? mine.nprobes : 0;
+  int incl = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(full, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(full, incl, 31);
+  sh->setup[lane] = mine;
+  sh->incl[lane] = incl;
+  __syncwarp();
+  const int begin = incl - n;
+  TexAccum acc;
+  acc.init();
+  for (int base = 0; base < total; base += 32) {
+    const int j = base + lane;
+    if (j < total) {
+      int lo = 0, hi = 31;  // owner = first lane whose inclusive count exceeds j
+#pragma unroll
+      for (int step = 0; step < 5; step++) {
+        const int mid = (lo + hi) >> 1;
+        if (sh->incl[mid] > j) hi = mid;
+        else lo = mid + 1;
+      }
+      const TexProbeSetup& s = sh->setup[lo];
+      sh->res[lane] = tex_probe(ts, s, j - (sh->incl[lo] - s.nprobes));
+    }
+    __syncwarp();
+    const int a = begin > base ? begin : base;
+    const int b = begin + n < base + 32 ? begin + n : base + 32;
+    for (int q = a; q < b; q++) acc.add(mine, sh->res[q - base]);
+    __syncwarp();
+  }
+  if (n > 0 || mine.tex >= 0) acc.finish(mine, out);
 }
 
 // ---- kernels (texture.cu) --------------------------------------------------------------------------------------------
