@@ -207,6 +207,18 @@ int vg_scene_upload_motion(vg_ctx* ctx, const VgMotionNode* topo, int n_nodes, c
 /* Flatten everything into the device layout (DESIGN.md "data layout in HBM") and copy it to HBM. */
 int vg_scene_commit(vg_ctx* ctx);
 
+/* qbvh.BuildAccel (qbvh/build.go:293-307) on the device: the reference's top-down binned-SAH build (8 bins on the longest axis
+ * of the centroid bounds, cost = area * count, three binary splits per 4-wide node, leafMax clamped to [1,16]) run
+ * level-synchronously over all open ranges. boxes = n x {min xyz, max xyz}, centroids = n x 3 (build.go:293: the caller's
+ * arrays); idx_out receives the leaf-order permutation (what the reference leaves in `idxs`), bounds6 the root box. The nodes
+ * stay in the context until vg_build_qbvh_nodes copies them out (*n_nodes says how many), in the reference's preorder
+ * numbering and link encoding. Every split decision is a function of the SET of primitives in a range (min/max, integer
+ * counts, a fixed-order float32 cost loop), so nodes, boxes and leaf sets are bit-identical to the reference's; the order of
+ * the <= 16 primitives inside one leaf differs (stable partition here, two-pointer swap there), which can only re-order ties
+ * between equal-t hits within a leaf. VG_ERR_BUILD for the inputs the reference cannot build (quirk f, non-finite centroids). */
+int vg_build_qbvh(vg_ctx* ctx, const float* boxes, const float* centroids, int n, int leaf_max, int32_t* idx_out, float* bounds6, int* n_nodes);
+int vg_build_qbvh_nodes(vg_ctx* ctx, VgNode* nodes_out, int nodes_cap);
+
 int vg_set_materials(vg_ctx* ctx, const VgMaterial* mats, int n);
 
 /* ---- texture maps ------------------------------------------------------------------------------------
@@ -342,6 +354,9 @@ int vh_postrender(vh_scene* s, const float* framebuffer, int xres, int yres);
 int vh_rgbe(float r, float g, float b, uint8_t* out4);
 /* core.PreRender (core/core.go:36-61): triangulate, build per-mesh QBVH/MQBVH, light meshes, scene tree, camera matrix. */
 int vh_prerender(vh_scene* s);
+/* The same, with the QBVH of every static PolyMesh of 32768+ triangles built on the device of `ctx` (vg_build_qbvh): identical
+ * nodes, boxes and leaf sets; the order of the triangles inside a leaf differs (see vg_build_qbvh). */
+int vh_prerender_device(vh_scene* s, vg_ctx* ctx);
 /* Upload the pre-rendered scene into a device context (calls vg_scene_begin .. vg_scene_commit, vg_set_*). */
 int vh_upload(vh_scene* s, vg_ctx* ctx, int motion_ref_compat);
 

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libvermeer_b200.so")
 
 SOURCES = [
-    "context.cu", "kernels_trace.cu", "render.cu", "texture.cu",
+    "context.cu", "kernels_trace.cu", "render.cu", "texture.cu", "build_bvh.cu",
     "host/builder.cpp", "host/nodes.cpp", "host/vh_capi.cpp", "host/vnf.cpp",
 ]
 

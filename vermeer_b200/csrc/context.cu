@@ -83,6 +83,7 @@ void vg_destroy(vg_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   render_destroy(ctx);
+  build_scratch_destroy(ctx);
   ctx->d_nodes.release(); ctx->d_mtopo.release(); ctx->d_mboxes.release(); ctx->d_tris.release();
   ctx->d_mtris.release(); ctx->d_normals.release(); ctx->d_geoms.release(); ctx->d_prim_material.release();
   ctx->d_tri_uv.release(); ctx->d_texels.release(); ctx->d_tex_levels.release(); ctx->d_textures.release();

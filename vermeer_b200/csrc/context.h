@@ -84,6 +84,7 @@ struct DevBuf {
 };
 
 struct RenderState;  // render.cu
+struct BuildScratch;  // build_bvh.cu
 
 }  // namespace vg
 
@@ -130,6 +131,9 @@ struct vg_ctx {
   std::vector<vg::MatTex> mat_tex;  // parallel to `materials`
   vg::DevTexStore tex_store() const { return vg::DevTexStore{d_texels.p, d_tex_levels.p, d_textures.p, (int32_t)textures.size()}; }
 
+  vg::BuildScratch* build_scratch = nullptr;
+  std::vector<VgNode> built_nodes;  // result of the last vg_build_qbvh, until vg_build_qbvh_nodes fetches it
+
   // shading inputs
   std::vector<VgMaterial> materials;
   std::vector<VgLight> lights;
@@ -174,4 +178,5 @@ int render_fb_device(vg_ctx* ctx, float** d_fb);
 void render_invalidate(vg_ctx* ctx);  // scene / frame / partition changed
 int render_set_scramble(vg_ctx* ctx, const uint64_t* table, int64_t npix);
 void render_destroy(vg_ctx* ctx);
+void build_scratch_destroy(vg_ctx* ctx);  // build_bvh.cu
 }  // namespace vg

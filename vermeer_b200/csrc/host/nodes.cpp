@@ -346,11 +346,15 @@ int PolyMesh::PreRender(Core& core, std::string* err) {
     if (!sh) { *err = "Unable to find shader " + s; return -1; }
     shader.push_back(sh);
   }
-  return initAccel(err);
+  return initAccel(err, core.build_ctx);
 }
 
 // builtin/geom/polymesh/buildqbvh.go:14-144
-int PolyMesh::initAccel(std::string* err) {
+// below this a mesh is built faster by the host builder (a device build is ~16 rounds of 13 launches and one sync each,
+// ~1 ms however small the mesh; scenes of many small meshes also keep the host's threads busy in parallel)
+static const int kDeviceBuildMinFaces = 32768;
+
+int PolyMesh::initAccel(std::string* err, vg_ctx* build_ctx) {
   std::vector<Box> boxes(facecount);
   std::vector<V3> cent(facecount);
   std::vector<int32_t> idxs(facecount);
@@ -393,7 +397,25 @@ int PolyMesh::initAccel(std::string* err) {
     cent[i] = V3{(p0.x + p1.x + p2.x) / 3, (p0.y + p1.y + p2.y) / 3, (p0.z + p1.z + p2.z) / 3};
     idxs[i] = i;
   }
-  if (build_qbvh(boxes.data(), cent.data(), idxs.data(), facecount, 16, qbvh, &bounds, err) != 0) return -1;
+  // the same tree from either builder (node for node, box for box; only the order inside a leaf differs): on the device
+  // (build_bvh.cu) for meshes large enough to pay for the round trips, else on the host
+  if (build_ctx && facecount >= kDeviceBuildMinFaces) {
+    static_assert(sizeof(Box) == 6 * sizeof(float) && sizeof(V3) == 3 * sizeof(float), "Box / V3 are passed as flat floats");
+    int n_nodes = 0;
+    float b6[6];
+    if (vg_build_qbvh(build_ctx, &boxes[0].lo[0], &cent[0].x, facecount, 16, idxs.data(), b6, &n_nodes) != VG_OK) {
+      *err = std::string("device QBVH build: ") + vg_last_error(build_ctx);
+      return -1;
+    }
+    qbvh.resize((size_t)n_nodes);
+    if (vg_build_qbvh_nodes(build_ctx, qbvh.data(), n_nodes) != VG_OK) {
+      *err = std::string("device QBVH build: ") + vg_last_error(build_ctx);
+      return -1;
+    }
+    for (int a = 0; a < 3; a++) { bounds.lo[a] = b6[a]; bounds.hi[a] = b6[3 + a]; }
+  } else if (build_qbvh(boxes.data(), cent.data(), idxs.data(), facecount, 16, qbvh, &bounds, err) != 0) {
+    return -1;
+  }
   accel_idx = idxs;
   // reorder per-face arrays into leaf order (:90-129)
   std::vector<uint32_t> nidx(idxp.size());

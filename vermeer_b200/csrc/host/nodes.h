@@ -111,7 +111,7 @@ struct PolyMesh : Node, Geom {
 
  private:
   void triangulate();
-  int initAccel(std::string* err);
+  int initAccel(std::string* err, vg_ctx* build_ctx);
   Box initMotionBoxesRec(int key, int32_t node);
 };
 
@@ -270,6 +270,7 @@ struct TextureImage {
 };
 
 struct Core {
+  vg_ctx* build_ctx = nullptr;  // vh_prerender_device: static-mesh QBVHs are built on this device (vg_build_qbvh)
   std::vector<TextureImage> textures;
   Globals* globals = nullptr;
   Scene scene;

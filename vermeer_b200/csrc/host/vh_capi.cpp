@@ -347,6 +347,14 @@ int vh_prerender(vh_scene* s) {
   return VG_OK;
 }
 
+int vh_prerender_device(vh_scene* s, vg_ctx* ctx) {
+  if (!s || !ctx) return VG_ERR_INVALID;
+  s->core.build_ctx = ctx;
+  const int rc = vh_prerender(s);
+  s->core.build_ctx = nullptr;
+  return rc;
+}
+
 static Geom* geom_by_id(vh_scene* s, int id) {
   for (Geom* g : s->core.scene.geoms)
     if (g->id == id) return g;

@@ -32,7 +32,7 @@ DECLARED_SYMBOLS = [
     "vg_set_partition", "vg_set_scramble", "vg_set_filter", "vg_set_option", "vg_trace_batch", "vg_trace_batch_device", "vg_render", "vg_clear_framebuffer",
     "vg_framebuffer_device", "vg_get_stats", "vg_reset_stats",
     "vg_texture_upload", "vg_textures_clear", "vg_texture_levels", "vg_texture_read_level", "vg_material_set_texture", "vg_mesh_set_uv", "vg_texture_sample_batch",
-    "vh_add_texture", "vh_shader_set_texture", "vh_polymesh_set_uv",
+    "vh_add_texture", "vh_shader_set_texture", "vh_polymesh_set_uv", "vg_build_qbvh", "vg_build_qbvh_nodes", "vh_prerender_device",
     "vh_scene_create", "vh_scene_destroy", "vh_last_error", "vh_registered_nodes", "vh_set_globals", "vh_add_shader_std", "vh_add_shader_debug", "vh_add_polymesh",
     "vh_add_filter", "vh_add_instance", "vh_add_trilight", "vh_add_disklight", "vh_add_spherelight", "vh_parse_vnf", "vh_load_vnf", "vh_globals", "vh_postrender", "vh_rgbe", "vh_set_camera_lookat", "vh_set_camera_keys", "vh_camera_decomp", "vh_prerender", "vh_upload", "vh_num_geoms", "vh_scene_info", "vh_scene_nodes",
     "vh_scene_motion_nodes", "vh_scene_geom_order", "vh_mesh_info", "vh_mesh_nodes", "vh_mesh_motion_nodes", "vh_mesh_idxp", "vh_camera",
@@ -211,8 +211,12 @@ class HostScene:
         if rc != 0:
             raise RuntimeError("vermeer host (%d): %s" % (rc, self.L.vh_last_error(self.h).decode()))
 
-    def prerender(self):
-        self._chk(self.L.vh_prerender(self.h))
+    def prerender(self, device=None):
+        """core.PreRender. `device` (a host.Device): build the static meshes' QBVHs on that GPU (vh_prerender_device)."""
+        if device is not None:
+            self._chk(self.L.vh_prerender_device(self.h, device.h))
+        else:
+            self._chk(self.L.vh_prerender(self.h))
         return self
 
     def close(self):
@@ -365,6 +369,19 @@ class Device:
         p = C.c_void_p()
         self._chk(self.L.vg_framebuffer_device(self.h, C.byref(p)))
         return p.value
+
+    def build_qbvh(self, boxes: np.ndarray, centroids: np.ndarray, leaf_max: int = 16):
+        """vg_build_qbvh: (n,6) boxes {min,max}, (n,3) centroids -> (nodes NODE_DTYPE[], idx int32[n], bounds float32[6])."""
+        boxes = np.ascontiguousarray(boxes, np.float32).reshape(-1, 6)
+        centroids = np.ascontiguousarray(centroids, np.float32).reshape(-1, 3)
+        n = len(boxes)
+        idx = np.zeros(n, np.int32)
+        b6 = np.zeros(6, np.float32)
+        nn = C.c_int()
+        self._chk(self.L.vg_build_qbvh(self.h, _p(boxes), _p(centroids), n, leaf_max, _p(idx), _p(b6), C.byref(nn)))
+        nodes = np.zeros(nn.value, NODE_DTYPE)
+        self._chk(self.L.vg_build_qbvh_nodes(self.h, _p(nodes), nn.value))
+        return nodes, idx, b6
 
     # -- texture store (vg_texture_*) ---------------------------------------------------------------
     def texture_upload(self, pixels_bottom_up: np.ndarray) -> int:
