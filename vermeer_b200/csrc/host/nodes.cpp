@@ -1,6 +1,9 @@
 // Host mirror of the reference's PreRender pipeline — see nodes.h for the interface map.
 #include "nodes.h"
 
+#include <atomic>
+#include <thread>
+
 #include <cmath>
 #include <mutex>
 
@@ -789,8 +792,39 @@ int Core::PreRender() {
     std::vector<Node*> round;
     round.swap(pending);
     all.insert(all.end(), round.begin(), round.end());
+    // PolyMesh.PreRender only reads the core (FindNode) and writes its own mesh, so the meshes of a round are pre-rendered
+    // concurrently (the reference does them one after the other in this loop: C3's 1024 meshes took 0.94 s that way); every other
+    // node type runs in order below, and a mesh's error is still reported at its place in that order.
+    std::vector<PolyMesh*> meshes;
     for (Node* n : round)
+      if (PolyMesh* pm = dynamic_cast<PolyMesh*>(n)) meshes.push_back(pm);
+    std::vector<int> mesh_rc(meshes.size(), 0);
+    std::vector<std::string> mesh_err(meshes.size());
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nthreads = (int)std::min<size_t>(std::min<unsigned>(hw ? hw : 1, 16), meshes.size());
+    if (nthreads >= 2) {
+      std::atomic<size_t> next(0);
+      auto work = [&] {
+        for (;;) {
+          const size_t i = next.fetch_add(1);
+          if (i >= meshes.size()) return;
+          mesh_rc[i] = meshes[i]->PreRender(*this, &mesh_err[i]);
+        }
+      };
+      std::vector<std::thread> th;
+      for (int t = 1; t < nthreads; t++) th.emplace_back(work);
+      work();
+      for (auto& t : th) t.join();
+    }
+    size_t mi = 0;
+    for (Node* n : round) {
+      if (nthreads >= 2 && dynamic_cast<PolyMesh*>(n)) {
+        const size_t i = mi++;
+        if (mesh_rc[i] != 0) { err = mesh_err[i]; return -1; }
+        continue;
+      }
       if (n->PreRender(*this, &err) != 0) return -1;
+    }
   }
   if (scene.PreRender(&err) != 0) return -1;
   prerendered = true;

@@ -36,7 +36,7 @@ struct DevLight {
   int slot_base;
 };
 
-struct DevMat {
+struct __align__(16) DevMat {  // 96 B: six 128-bit loads / stores (the per-vertex copies of textured scenes go through memory)
   f3 emission;     // EmissionColour * EmissionStrength (0 if EmissionStrength unset)
   f3 diff_colour;
   float diff_weight, spec_weight;  // normalised by their sum (std.go:137-139)
@@ -48,7 +48,9 @@ struct DevMat {
   f3 fres_refl, fres_edge;  // conductor r, g AFTER the reference's assignment quirk (std.go:187-189 writes the edge tint into refl)
   int bad;  // 1: total weight 0 (the reference panics, std.go:141-143)
   int debug;  // shader.Debug (debug.go:42-49): `emission` holds its Colour, both weights are 0 and no Level check applies
+  int pad_;
 };
+static_assert(sizeof(DevMat) == 96, "DevMat is stored per vertex as six float4");
 
 // ShaderStd's parameters -> the constants the kernels use (std.go:108-143,165-192,299-316). Shared by the host (constant maps,
 // once per material) and the device (materials with texture maps, once per shaded vertex: k_surface).
@@ -58,7 +60,7 @@ __host__ __device__ inline DevMat derive_mat(const VgMaterial& s) {
   d.diff_colour = d.emission; d.spec_colour = d.emission;
   d.diff_weight = d.spec_weight = 0; d.rough2 = 0; d.spec_rough = 0; d.ior = 0; d.fresnel_model = 0;
   d.fres_refl = d.emission; d.fres_edge = d.emission;
-  d.bad = 0; d.debug = 0;
+  d.bad = 0; d.debug = 0; d.pad_ = 0;
   if (s.mask & VG_MAT_DEBUG) {
     // Eval: OutRGB = Colour (resolve_vertex's emission + 0 + 0); no lights, no lobes
     d.debug = 1;
@@ -113,7 +115,7 @@ struct RenderParams {
   DevTexStore tex;
   const VgMaterial* rawmats;  // the materials as the caller gave them: a textured one is re-derived per vertex
   const MatTex* mat_tex;      // [materials] parameter -> texture bindings
-  DevMat* vmats;              // [P] per-vertex materials, indexed like hits[] (queue slot)
+  DevMat* vmats;              // [P] per-vertex materials of TEXTURED materials (mat_tex[matid].mask != 0), indexed like hits[] (queue slot)
   float* diff;                // [12][P] ray differentials per path: DdPdx, DdPdy, DdDdx, DdDdy (core/ray.go:40-44)
   float pd0, pd1;             // core.Image.PixelDelta (camera.go:316-317)
   const DevLight* lights;
@@ -587,7 +589,6 @@ __global__ void __launch_bounds__(128, VG_SURFACE_MIN_BLOCKS) k_surface(const Re
     }
     if (any) p.vmats[i] = derive_mat(s);
   }
-  if (active && !any) p.vmats[i] = p.mats[matid];
 
   if (active) {
     float* q = p.diff + path;
@@ -792,7 +793,7 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
   long long I = 0;
   uint64_t scr0 = 0, scr1 = 0;
   if (active) {
-    m = p.vmats ? p.vmats[i] : p.mats[matid];
+    m = (p.vmats && p.mat_tex[matid].mask) ? p.vmats[i] : p.mats[matid];
     if (m.bad) {
       atomicOr(p.counts + 5, m.bad);
       active = false;
@@ -978,7 +979,7 @@ __device__ __forceinline__ float4 resolve_vertex(const RenderParams& p, int leve
   const int SL = p.S * p.nlobes;
   float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
   if (matid != 255 && level <= 3) {
-    const DevMat m = p.vmats ? p.vmats[i] : p.mats[matid];
+    const DevMat m = (p.vmats && p.mat_tex[matid].mask) ? p.vmats[i] : p.mats[matid];
     f3 sum[2];
     sum[0] = sum[1] = mk3(0, 0, 0);
     for (int lobe = 0; lobe < p.nlobes; lobe++) {
