@@ -1,7 +1,7 @@
 """C3-scale sanity: 1024 displaced spheres x 9800 tris (10.04 M triangles) under the scene-level QBVH, mirror chains.
 Checks host PreRender time, device memory, traversal parity against the oracle on a sample of camera rays, and throughput."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from vermeer_b200 import scenes
 from vermeer_b200.host import Device, HostScene

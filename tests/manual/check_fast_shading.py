@@ -1,7 +1,7 @@
 """FAST (algebraic, single precision) vs precise (float64 trig, literal transcription) shading against the oracle:
 RMSE, median |diff|, max |diff| and ray counts on the parity scenes."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle.binding import Oracle
 from vermeer_b200 import scenes

@@ -1,6 +1,6 @@
 """GPU vs oracle image comparison on small configs (debug helper; the pytest versions live in tests/)."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle.binding import Oracle
 from vermeer_b200 import scenes
