@@ -406,6 +406,9 @@ int PolyMesh::initAccel(std::string* err, vg_ctx* build_ctx) {
     static_assert(sizeof(Box) == 6 * sizeof(float) && sizeof(V3) == 3 * sizeof(float), "Box / V3 are passed as flat floats");
     int n_nodes = 0;
     float b6[6];
+    // build + fetch is a two-call protocol on the context; the meshes of a round are pre-rendered concurrently
+    static std::mutex device_build_mu;
+    std::lock_guard<std::mutex> build_lock(device_build_mu);
     if (vg_build_qbvh(build_ctx, &boxes[0].lo[0], &cent[0].x, facecount, 16, idxs.data(), b6, &n_nodes) != VG_OK) {
       *err = std::string("device QBVH build: ") + vg_last_error(build_ctx);
       return -1;

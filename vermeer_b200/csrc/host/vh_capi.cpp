@@ -2,6 +2,9 @@
 // upload of the pre-rendered scene into a device context through the vg_* layer.
 #include <cstdio>
 #include <cstring>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <string>
 
@@ -374,6 +377,8 @@ int vh_upload(vh_scene* s, vg_ctx* ctx, int motion_ref_compat) {
   for (ShaderStd* sh : c.materials) mats.push_back(sh->params);
   if ((rc = chk(vg_set_materials(ctx, mats.data(), (int)mats.size()))) != VG_OK) return rc;
   if ((rc = chk(vg_scene_begin(ctx, G))) != VG_OK) return rc;
+  const bool timing = std::getenv("VG_TIMING") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
   for (int id = 0; id < G; id++) {
     Geom* gm = geom_by_id(s, id);
     if (!gm) return fail(s, VG_ERR_INVALID, "geom ids are not dense");
@@ -405,6 +410,7 @@ int vh_upload(vh_scene* s, vg_ctx* ctx, int motion_ref_compat) {
     if (!m->uvtriidx.empty() && !m->qbvh.empty())
       if ((rc = chk(vg_mesh_set_uv(ctx, id, m->UV.data(), (int)(m->UV.size() / 2), m->uvtriidx.data()))) != VG_OK) return rc;
   }
+  if (timing) std::fprintf(stderr, "[vh_upload] mesh staging           %8.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
   // texture maps: the files the shaders name, each uploaded once (texture.TexStore), then the parameter bindings
   {
     if ((rc = chk(vg_textures_clear(ctx))) != VG_OK) return rc;
