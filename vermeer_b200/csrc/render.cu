@@ -447,7 +447,10 @@ __global__ void __launch_bounds__(128, VG_SURFACE_MIN_BLOCKS) k_surface(const Re
     g = p.sc.geoms[geom];
     matid = p.sc.prim_material[g.prim_base + prim];
   }
-  const bool active = matid != 255;
+  // a vertex needs this pass if its material has a texture map, or if it may spawn the mirror ray whose differentials are
+  // produced here; an untextured, purely diffuse/glossy vertex ends its path's use of the differentials
+  bool active = matid != 255;
+  if (active) active = p.mat_tex[matid].mask != 0u || p.mats[matid].spec_weight > 0.0f;
   int path = 0;
   f3 D = mk3(0, 0, 1);
   TexCoord tc;
