@@ -376,7 +376,33 @@ int PolyMesh::initAccel(std::string* err, vg_ctx* build_ctx) {
       cent[i] = V3{(p[0].x + p[1].x + p[2].x) / 3, (p[0].y + p[1].y + p[2].y) / 3, (p[0].z + p[1].z + p[2].z) / 3};
       idxs[i] = i;
     }
-    if (build_mqbvh(boxes.data(), cent.data(), idxs.data(), facecount, 16, mtopo, err) != 0) return -1;
+    if (build_ctx && facecount >= kDeviceBuildMinFaces) {
+      // BuildAccelMotion (motionbuild.go:108-122) is BuildAccel's recursion on the mid-time snapshot without the boxes: the
+      // device builder's topology (axes, child links, leaf ranges) is copied, the per-key boxes are filled below as before
+      int n_nodes = 0;
+      float b6[6];
+      static std::mutex device_build_mu;
+      std::lock_guard<std::mutex> build_lock(device_build_mu);
+      std::vector<VgNode> tmp;
+      if (vg_build_qbvh(build_ctx, &boxes[0].lo[0], &cent[0].x, facecount, 16, idxs.data(), b6, &n_nodes) != VG_OK) {
+        *err = std::string("device MQBVH build: ") + vg_last_error(build_ctx);
+        return -1;
+      }
+      tmp.resize((size_t)n_nodes);
+      if (vg_build_qbvh_nodes(build_ctx, tmp.data(), n_nodes) != VG_OK) {
+        *err = std::string("device MQBVH build: ") + vg_last_error(build_ctx);
+        return -1;
+      }
+      mtopo.assign((size_t)n_nodes, VgMotionNode{});
+      for (int i = 0; i < n_nodes; i++) {
+        mtopo[(size_t)i].axis0 = (int32_t)tmp[(size_t)i].axis0;
+        mtopo[(size_t)i].axis1 = (int32_t)tmp[(size_t)i].axis1;
+        mtopo[(size_t)i].axis2 = (int32_t)tmp[(size_t)i].axis2;
+        for (int k = 0; k < 4; k++) mtopo[(size_t)i].children[k] = tmp[(size_t)i].children[k];
+      }
+    } else if (build_mqbvh(boxes.data(), cent.data(), idxs.data(), facecount, 16, mtopo, err) != 0) {
+      return -1;
+    }
     accel_idx = idxs;  // NOTE: idxp is NOT reordered on this path (the function returns at :56) — quirk (b)
     // per-key boxes (:148-212)
     mboxes.assign((size_t)Verts.MotionKeys * mtopo.size() * 24, 0.0f);
