@@ -258,6 +258,8 @@ def run_ours(args):
     host = HostScene(scene).prerender()
     t_build = time.time() - t0
     dev = Device(local_rank)
+    for k, v in [kv.split("=") for kv in os.environ.get("VG_OPTIONS", "").split(",") if kv]:   # options that act at upload (node_order)
+        dev.set_option(k, int(v))
     # the same PreRender with the static meshes' QBVHs built on the GPU (vg_build_qbvh: the same tree), reported only
     t_build_dev = None
     if rank == 0 and os.environ.get("VG_BENCH_DEVICE_BUILD", "1") != "0":

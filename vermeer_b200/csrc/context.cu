@@ -427,6 +427,27 @@ int vg_scene_commit(vg_ctx* ctx) {
       t[2] = make_float4(0.f, 0.f, 0.f, 0.f);
       prim_material[(size_t)prim_base[g]] = (uint8_t)m.material_ids[0];
     } else if (!m.motion) {
+      // Device node order. The reference numbers nodes in depth-first preorder (child 0 next to its parent, children 1-3 a
+      // subtree away). Option node_order=1 renumbers each mesh breadth-first, so the four children of a node are neighbours
+      // and the top of the tree is one compact block; links are re-encoded anyway, results and NodesT do not depend on it.
+      std::vector<int32_t> place;  // reference index -> position inside this mesh's block (identity when empty)
+      if (ctx->opt_node_order == 1 && m.nodes.size() > 1) {
+        place.assign(m.nodes.size(), -1);
+        std::vector<int32_t> order;
+        order.reserve(m.nodes.size());
+        order.push_back(0);
+        place[0] = 0;
+        for (size_t q = 0; q < order.size(); q++)
+          for (int k = 0; k < 4; k++) {
+            const int32_t ch = m.nodes[(size_t)order[q]].children[k];
+            if (ch >= 0 && ch < (int32_t)m.nodes.size() && place[(size_t)ch] < 0) {
+              place[(size_t)ch] = (int32_t)order.size();
+              order.push_back(ch);
+            }
+          }
+        if (order.size() != m.nodes.size()) place.clear();  // unreachable nodes: keep the reference order
+      }
+      auto pos = [&](size_t i) { return place.empty() ? (int64_t)i : (int64_t)place[i]; };
       for (size_t i = 0; i < m.nodes.size(); i++) {
         const VgNode& s = m.nodes[i];
         int32_t c[4];
@@ -434,7 +455,7 @@ int vg_scene_commit(vg_ctx* ctx) {
           const int32_t ch = s.children[k];
           if (ch >= 0) {
             if (ch >= (int32_t)m.nodes.size()) return FlatErr{VG_ERR_INVALID, "child index out of range"};
-            c[k] = (int32_t)(node_base[g] + ch);
+            c[k] = (int32_t)(node_base[g] + pos((size_t)ch));
           } else if (ch == -1) {
             c[k] = -1;
           } else {
@@ -443,7 +464,7 @@ int vg_scene_commit(vg_ctx* ctx) {
             c[k] = (int32_t)(kLeafBit | ((uint32_t)(tri_base[g] + first) << 4) | (uint32_t)(count - 1));
           }
         }
-        put_static_node(nodes[(size_t)node_base[g] + i], s, c);
+        put_static_node(nodes[(size_t)node_base[g] + (size_t)pos(i)], s, c);
       }
       // polymesh/trace.go:182: bias term (EpsilonFloat32 + RayBias), one float32 add
       const float bias = 1.19209290E-07f + m.raybias;
@@ -925,6 +946,9 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
   else if (!std::strcmp(name, "primary_per_lane")) ctx->opt_primary_per_lane = value != 0;
   else if (!std::strcmp(name, "shadow_unordered")) ctx->opt_shadow_unordered = value != 0;
   else if (!std::strcmp(name, "texture_coop")) ctx->opt_texture_coop = value != 0;
+  else if (!std::strcmp(name, "node_order")) {  // takes effect at the next vg_scene_commit
+    ctx->opt_node_order = value;
+  }
   else if (!std::strcmp(name, "generic_shade")) {
     ctx->opt_generic_shade = value != 0;
     render_invalidate(ctx);
