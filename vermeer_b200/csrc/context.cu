@@ -387,7 +387,7 @@ int vg_scene_commit(vg_ctx* ctx) {
   HostArr<DevNode> nodes((size_t)n_static);
   HostArr<DevMotionNode> mtopo((size_t)n_motion);
   HostArr<float4> mboxes((size_t)n_mboxes * 6);
-  HostArr<float4> tris((size_t)n_tris * 3), mtris((size_t)n_mtris * 3), normals((size_t)n_normal_slots * 3);
+  HostArr<float4> tris((size_t)n_tris * kTriStride), mtris((size_t)n_mtris * 3), normals((size_t)n_normal_slots * 3);
   bool any_uv = false;
   for (int g = 0; g < G; g++) any_uv |= (!ctx->meshes[g].motion && !ctx->meshes[g].uvtriidx.empty());
   HostArr<float2> tri_uv(any_uv ? (size_t)n_tris * 3 : 0);
@@ -421,7 +421,7 @@ int vg_scene_commit(vg_ctx* ctx) {
     if (m.instance) return FlatErr{VG_OK, nullptr};  // filled from the target below
     if (m.sphere) {
       dg.keys = 0;
-      float4* t = &tris[(size_t)tri_base[g] * 3];
+      float4* t = &tris[(size_t)tri_base[g] * kTriStride];
       t[0] = make_float4(m.centre[0], m.centre[1], m.centre[2], i2f((int32_t)g));
       t[1] = make_float4(m.radius, 0.f, 0.f, i2f(0));
       t[2] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -469,7 +469,7 @@ int vg_scene_commit(vg_ctx* ctx) {
       // polymesh/trace.go:182: bias term (EpsilonFloat32 + RayBias), one float32 add
       const float bias = 1.19209290E-07f + m.raybias;
       for (int i = 0; i < m.n_tris; i++) {
-        float4* t = &tris[(size_t)(tri_base[g] + i) * 3];
+        float4* t = &tris[(size_t)(tri_base[g] + i) * kTriStride];
         for (int j = 0; j < 3; j++) {
           const float* v = &m.verts[(size_t)m.idxp[(size_t)i * 3 + j] * 3];
           t[j] = make_float4(v[0], v[1], v[2], 0.f);

@@ -345,7 +345,7 @@ __device__ inline void build_context(const RenderParams& p, const DevHit& h, flo
   f3 E0, E1, E2;
   const bool motion = g.keys > 1;
   if (!motion) {
-    const float4* tp = p.sc.tris + (size_t)h.slot * 3;
+    const float4* tp = p.sc.tris + (size_t)h.slot * kTriStride;
     E0 = ld3(tp); E1 = ld3(tp + 1); E2 = ld3(tp + 2);
   } else {
     const float k = time * (float)(g.keys - 1);
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(128, VG_SURFACE_MIN_BLOCKS) k_surface(const Re
     const float4 ra = rp[0], rb = rp[1];
     D = mk3(ra.w, rb.x, rb.y);
 
-    const float4* tp = p.sc.tris + (size_t)slot * 3;
+    const float4* tp = p.sc.tris + (size_t)slot * kTriStride;
     const f3 E0 = ld3(tp), E1 = ld3(tp + 1), E2 = ld3(tp + 2);
     const f3 Ng = normalize3(cross3(sub3(E1, E0), sub3(E2, E0)));
     f3 n0 = mk3(0, 0, 0), n1 = n0, n2 = n0;
@@ -628,7 +628,7 @@ __device__ inline void apply_instance_transform(const RenderParams& p, int xi, f
 
 // sphere.Sphere.Trace hit record (builtin/geom/sphere/trace.go:17-47), then ApplyTransform's re-normalisations
 __device__ inline void build_context_sphere(const RenderParams& p, const DevHit& h, f3 Ro, f3 Rd, ShadeCtx& c) {
-  const f3 centre = ld3(p.sc.tris + (size_t)h.slot * 3);
+  const f3 centre = ld3(p.sc.tris + (size_t)h.slot * kTriStride);
   c.P = mad3(Ro, Rd, h.t);
   const f3 N = normalize3(sub3(c.P, centre));
   c.Poffset = scale3(0.001f, N);
