@@ -199,7 +199,10 @@ __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 #endif
 __device__ __forceinline__ void ldg8(const void* p, float4& a, float4& b) {
 #if VG_LDG256
-  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#ifndef VG_NODE_HINT
+#define VG_NODE_HINT ""
+#endif
+  asm volatile("ld.global.nc" VG_NODE_HINT ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                : "l"(p));
 #else
