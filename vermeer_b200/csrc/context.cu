@@ -946,6 +946,11 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
   else if (!std::strcmp(name, "primary_per_lane")) ctx->opt_primary_per_lane = value != 0;
   else if (!std::strcmp(name, "shadow_unordered")) ctx->opt_shadow_unordered = value != 0;
   else if (!std::strcmp(name, "texture_coop")) ctx->opt_texture_coop = value != 0;
+  else if (!std::strcmp(name, "zero_copy_batch")) ctx->opt_zero_copy_batch = value != 0;
+  else if (!std::strcmp(name, "batch_chunk_log2")) {
+    if (value < 14 || value > 24) return ctx->fail(VG_ERR_INVALID, "batch_chunk_log2 outside [14,24]");
+    ctx->opt_batch_chunk_log2 = value;
+  }
   else if (!std::strcmp(name, "node_order")) {  // takes effect at the next vg_scene_commit
     ctx->opt_node_order = value;
   }
@@ -1015,7 +1020,19 @@ int vg_trace_batch(vg_ctx* ctx, const VgRay* rays, int64_t n, VgHit* hits, uint3
   if (!ctx->committed) return ctx->fail(VG_ERR_INVALID, "scene not committed");
   VG_CUDA(ctx, ctx->d_rays.reserve((size_t)n));
   VG_CUDA(ctx, ctx->d_hits.reserve((size_t)n));
-  const int64_t chunk = 1 << 19;  // 16 MB of rays
+  const int64_t chunk = (int64_t)1 << ctx->opt_batch_chunk_log2;  // rays per pipeline stage (default 2^19 = 16 MB of rays)
+  if (ctx->opt_zero_copy_batch && n >= 2 * chunk && pinned_host(rays) && pinned_host(hits)) {
+    // Page-locked caller buffers, option zero_copy_batch: ONE launch whose warps read the rays from host memory and write the hits
+    // back over PCIe themselves (coalesced 1-KB reads and writes per warp); no staging copies, no chunking.
+    void *dr = nullptr, *dh = nullptr;
+    if (cudaHostGetDevicePointer(&dr, const_cast<VgRay*>(rays), 0) == cudaSuccess && cudaHostGetDevicePointer(&dh, hits, 0) == cudaSuccess && dr && dh) {
+      const int rc = trace_device_locked(ctx, reinterpret_cast<const VgRay*>(dr), n, reinterpret_cast<VgHit*>(dh), flags);
+      if (rc != VG_OK) return rc;
+      VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      return VG_OK;
+    }
+    cudaGetLastError();
+  }
   if (n >= 2 * chunk && pinned_host(rays) && pinned_host(hits)) {
     // Page-locked caller buffers: the batch goes through in chunks on three streams, so the H2D copy of one chunk, the
     // traversal of the previous one and the D2H copy of the one before overlap (PCIe is full duplex; each direction carries
