@@ -193,3 +193,41 @@ def test_include_node_reads_the_other_file_at_prerender(built_library, tmp_path,
     h4 = HostScene.from_vnf(head + '\nInclude { Filename "bad.vnf" }\n').prerender()
     _same_structures(h1, h4)
     assert "NoSuchNode" in h4.L.vh_last_error(h4.h).decode()
+
+
+def test_vnf_texture_maps_and_uvs(built_library):
+    """`Param rgbtex "file?query"` (nodes/parser.go:247-268), PolyMesh UV / UVIdx (polymesh.go:36-37): parsed, pre-rendered, and a
+    mesh whose UVIdx does not match its FaceIdx is refused by PreRender."""
+    from vermeer_b200 import scenes
+    from vermeer_b200.host import HostScene
+    sc = scenes.textured_room(48, 36, float_maps=True)
+    text = scenes.to_vnf(sc)
+    assert 'DiffuseColour rgbtex "floor.png"' in text and 'EmissionColour rgbtex "picture.png?filter=trilinear"' in text
+    assert "UV 1 4 vec2" in text and "UVIdx 4 int" in text
+    h = HostScene.from_vnf(text)
+    assert h.parse_errors == 0
+    for t in sc.textures:
+        h.add_texture(t)
+    h.prerender()
+    assert h.num_geoms() == HostScene(sc).prerender().num_geoms()
+    # rgbtex without a file name: the reference's parser drops the value (parser.go:255-257) and goes on
+    bad = text.replace('DiffuseColour rgbtex "floor.png"', "DiffuseColour rgbtex 5")
+    hb = HostScene.from_vnf(bad, strict=False)
+    assert hb.parse_errors >= 0
+    # a UV index beyond the UV array
+    sc2 = scenes.textured_room(48, 36)
+    [m for m in sc2.meshes if m.Name == "back"][0].UVIdx = np.asarray([0, 1, 2, 9], np.int32)
+    with pytest.raises(RuntimeError, match="UV index out of range"):
+        HostScene(sc2).prerender()
+
+
+def test_prerender_reports_the_first_failing_node_in_order(built_library):
+    """The meshes of a PreRender round are pre-rendered concurrently; the error reported is still the first failing node's in
+    node order, like the reference's sequential loop (core/core.go:46-57)."""
+    from vermeer_b200 import scenes
+    from vermeer_b200.host import HostScene
+    sc = scenes.sphere_field_scene(32, 24, nmesh=12, slices=8, stacks=8)
+    sc.meshes[3].Shader = ["no_such_shader_3"]
+    sc.meshes[9].Shader = ["no_such_shader_9"]
+    with pytest.raises(RuntimeError, match="no_such_shader_3"):
+        HostScene(sc).prerender()

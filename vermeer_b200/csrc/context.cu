@@ -677,6 +677,25 @@ int vg_scene_commit(vg_ctx* ctx) {
   d.n_geoms = G;
   d.n_spheres = 0;
   for (int g = 0; g < G; g++) d.n_spheres += ctx->meshes[g].sphere ? 1 : 0;
+  // Option l2_persist_nodes: pin the static node array in the persisting part of L2 (access-policy window on the stream the
+  // render kernels run on), so that triangle records streaming through cannot evict the tree of a scene larger than L2.
+  if (ctx->opt_l2_persist_nodes && n_static > 0) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+      const size_t bytes = (size_t)n_static * sizeof(DevNode);
+      const size_t carve = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, bytes);
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+      cudaStreamAttrValue attr;
+      std::memset(&attr, 0, sizeof(attr));
+      attr.accessPolicyWindow.base_ptr = (void*)ctx->d_nodes.p;
+      attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+      attr.accessPolicyWindow.hitRatio = bytes <= carve ? 1.0f : (float)((double)carve / (double)bytes);
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+      cudaGetLastError();
+    }
+  }
   ctx->committed = true;
   render_invalidate(ctx);
   return VG_OK;
@@ -947,6 +966,7 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
   else if (!std::strcmp(name, "shadow_unordered")) ctx->opt_shadow_unordered = value != 0;
   else if (!std::strcmp(name, "texture_coop")) ctx->opt_texture_coop = value != 0;
   else if (!std::strcmp(name, "zero_copy_batch")) ctx->opt_zero_copy_batch = value != 0;
+  else if (!std::strcmp(name, "l2_persist_nodes")) ctx->opt_l2_persist_nodes = value != 0;  // takes effect at the next vg_scene_commit
   else if (!std::strcmp(name, "batch_chunk_log2")) {
     if (value < 14 || value > 24) return ctx->fail(VG_ERR_INVALID, "batch_chunk_log2 outside [14,24]");
     ctx->opt_batch_chunk_log2 = value;

@@ -155,6 +155,7 @@ struct vg_ctx {
   int opt_generic_shade = 0;     // 1 = always shade with the general kernel (tests: it must agree with the specialised one)
   int opt_pixel_block = 1;       // paths of one warp cover an 8x4 pixel block of a tile (1) or a 32x1 row (0)
   int opt_batch_chunk_log2 = 19; // vg_trace_batch copy pipeline: rays per stage
+  int opt_l2_persist_nodes = 0;  // persisting-L2 access-policy window over the static node array
   int opt_zero_copy_batch = 0;   // vg_trace_batch with page-locked buffers: kernel reads rays / writes hits over PCIe itself (1) or 3-stream copy pipeline (0)
   int opt_node_order = 0;        // device order of a mesh's nodes: 0 = the reference's preorder, 1 = breadth-first (siblings adjacent)
   int opt_texture_coop = 1;      // k_surface: probes of a warp's texture lookups shared between its lanes (1) or one lane per lookup (0)
