@@ -796,7 +796,7 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
   long long I = 0;
   uint64_t scr0 = 0, scr1 = 0;
   if (active) {
-    m = (p.vmats && p.mat_tex[matid].mask) ? p.vmats[i] : p.mats[matid];
+    m = *((p.vmats && p.mat_tex[matid].mask) ? p.vmats + i : p.mats + matid);  // one load site: only the fields used are fetched
     if (m.bad) {
       atomicOr(p.counts + 5, m.bad);
       active = false;
@@ -982,7 +982,7 @@ __device__ __forceinline__ float4 resolve_vertex(const RenderParams& p, int leve
   const int SL = p.S * p.nlobes;
   float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
   if (matid != 255 && level <= 3) {
-    const DevMat m = (p.vmats && p.mat_tex[matid].mask) ? p.vmats[i] : p.mats[matid];
+    const DevMat m = *((p.vmats && p.mat_tex[matid].mask) ? p.vmats + i : p.mats + matid);  // one load site: only the fields used are fetched
     f3 sum[2];
     sum[0] = sum[1] = mk3(0, 0, 0);
     for (int lobe = 0; lobe < p.nlobes; lobe++) {

@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(128, 4) k_shade_generic(const RenderParams p, 
   long long I = 0;
   uint64_t scr0 = 0, scr1 = 0;
   if (active) {
-    m = (p.vmats && p.mat_tex[matid].mask) ? p.vmats[i] : p.mats[matid];
+    m = *((p.vmats && p.mat_tex[matid].mask) ? p.vmats + i : p.mats + matid);  // one load site: only the fields used are fetched
     if (m.bad) {
       atomicOr(p.counts + 5, m.bad);
       active = false;
