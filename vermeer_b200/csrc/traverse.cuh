@@ -448,7 +448,7 @@ __device__ __forceinline__ bool leaf_motion(const DevScene& sc, RayState& r, Hit
     const float3 p0 = make_float3(om * a0.x + tm * b0.x, om * a0.y + tm * b0.y, om * a0.z + tm * b0.z);
     const float3 p1 = make_float3(om * a1.x + tm * b1.x, om * a1.y + tm * b1.y, om * a1.z + tm * b1.z);
     const float3 p2 = make_float3(om * a2.x + tm * b2.x, om * a2.y + tm * b2.y, om * a2.z + tm * b2.z);
-    const float4 w0 = ldg4(tk0), w1 = ldg4(tk0 + 1), w2 = ldg4(tk0 + 2);
+    const float4 w0 = a0, w1 = a1, w2 = a2;  // geom id / face / RayBias in .w are the same in every key's record
     float U, V, W;
     if (tri_test<true, KZ>(r, p0, p1, p2, w2.w, &U, &V, &W)) {
       h.u = U; h.v = V; h.w = W;
@@ -873,7 +873,7 @@ __device__ __forceinline__ bool coop_item_motion(const DevScene& sc, const float
   const float3 p0 = make_float3(om * a0.x + tm * b0.x, om * a0.y + tm * b0.y, om * a0.z + tm * b0.z);
   const float3 p1 = make_float3(om * a1.x + tm * b1.x, om * a1.y + tm * b1.y, om * a1.z + tm * b1.z);
   const float3 p2 = make_float3(om * a2.x + tm * b2.x, om * a2.y + tm * b2.y, om * a2.z + tm * b2.z);
-  return tri_candidate<true, -1>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, __float_as_uint(q1.z), __float_as_int(q2.x) & 3, q1.w, p0, p1, p2, ldg4(k0 + 2).w, tc);
+  return tri_candidate<true, -1>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, __float_as_uint(q1.z), __float_as_int(q2.x) & 3, q1.w, p0, p1, p2, a2.w, tc);  // the w fields (geom id, face, RayBias) are the same in every key's record
 }
 
 // One cooperative leaf phase. `isleaf`: this lane's t.cur is a triangle leaf that takes part (static; also motion leaves when
