@@ -495,8 +495,9 @@ __global__ void __launch_bounds__(128, VG_SURFACE_MIN_BLOCKS) k_surface(const Re
     // DifferentialTransfer (core/ray.go:95-104)
     const float DNg = dot3(D, Ng);
     const f3 ax = mad3(rPx, rDx, T), ay = mad3(rPy, rDy, T);
-    const float dtdx = -dot3(ax, Ng) / DNg;
-    const float dtdy = -dot3(ay, Ng) / DNg;
+    const bool fdv = fast != 0;  // approximate reciprocals on the FAST path (tolerance-only quantities, see texture.cuh)
+    const float dtdx = tex_div(-dot3(ax, Ng), DNg, fdv);
+    const float dtdy = tex_div(-dot3(ay, Ng), DNg, fdv);
     dPdx = add3(ax, scale3(dtdx, D));
     dPdy = add3(ay, scale3(dtdy, D));
 
@@ -504,7 +505,12 @@ __global__ void __launch_bounds__(128, VG_SURFACE_MIN_BLOCKS) k_surface(const Re
     auto plane = [&](f3 a, f3 b, f3 on) {
       f3 n = mk3(Ng.y * (a.z - b.z) - Ng.z * (a.y - b.y), Ng.z * (a.x - b.x) - Ng.x * (a.z - b.z), Ng.x * (a.y - b.y) - Ng.y * (a.x - b.x));
       const float qn = sqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
-      n.x /= qn; n.y /= qn; n.z /= qn;
+      if (fast) {
+        const float rq = __fdividef(1.0f, qn);
+        n.x *= rq; n.y *= rq; n.z *= rq;
+      } else {
+        n.x /= qn; n.y /= qn; n.z /= qn;
+      }
       const float d = -on.x * n.x - on.y * n.y - on.z * n.z;
       return mk4(n, d);
     };
@@ -514,13 +520,13 @@ __global__ void __launch_bounds__(128, VG_SURFACE_MIN_BLOCKS) k_surface(const Re
     {
       const Plane4 A = plane(E2, E1, E1);
       const float l = E0.x * A.n.x + E0.y * A.n.y + E0.z * A.n.z + A.d;
-      na = mk3(A.n.x / l, A.n.y / l, A.n.z / l);
+      na = fast ? scale3(__fdividef(1.0f, l), A.n) : mk3(A.n.x / l, A.n.y / l, A.n.z / l);
       const Plane4 B = plane(E2, E0, E0);
       const float lb = B.n.x * E1.x + B.n.y * E1.y + B.n.z * E1.z + B.d;
-      nb = mk3(B.n.x / lb, B.n.y / lb, B.n.z / lb);
+      nb = fast ? scale3(__fdividef(1.0f, lb), B.n) : mk3(B.n.x / lb, B.n.y / lb, B.n.z / lb);
       const Plane4 G = plane(E1, E0, E0);
       const float lg = G.n.x * E2.x + G.n.y * E2.y + G.n.z * E2.z + G.d;
-      ng = mk3(G.n.x / lg, G.n.y / lg, G.n.z / lg);
+      ng = fast ? scale3(__fdividef(1.0f, lg), G.n) : mk3(G.n.x / lg, G.n.y / lg, G.n.z / lg);
     }
     const float alphax = na.x * dPdx.x + na.y * dPdx.y + na.z * dPdx.z;
     const float betax = nb.x * dPdx.x + nb.y * dPdx.y + nb.z * dPdx.z;
@@ -535,7 +541,7 @@ __global__ void __launch_bounds__(128, VG_SURFACE_MIN_BLOCKS) k_surface(const Re
       dndy = mk3(alphay * n0.x + betay * n1.x + gammay * n2.x, alphay * n0.y + betay * n1.y + gammay * n2.y, alphay * n0.z + betay * n1.z + gammay * n2.z);
     }
     const float NN = dot3(N, N);
-    const float kN = 1 / (NN * sqrtf(NN));
+    const float kN = tex_div(1.0f, NN * sqrtf(NN), fdv);
     const f3 DdNdx = scale3(kN, sub3(scale3(NN, dndx), scale3(dot3(N, dndx), N)));
     const f3 DdNdy = scale3(kN, sub3(scale3(NN, dndy), scale3(dot3(N, dndy), N)));
     if (has_uv) {

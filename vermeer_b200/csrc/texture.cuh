@@ -43,6 +43,10 @@ struct TexCoord {
 
 // math/pow.go:12-19, sincos.go:16-64: float32 -> float64 stdlib -> float32. `fast` = the single-precision libm (1-2 ulp), the same
 // switch as the shading kernels' trig ("precise_trig" option); both are far inside the image tolerance.
+// `fast` also replaces the correctly rounded divisions of the footprint analysis and of the probes by the approximate
+// reciprocal (2 ulp): everything here is downstream of a normalize, i.e. tolerance-only either way, and a correctly rounded
+// float division is ~10 instructions against 2.
+__device__ __forceinline__ float tex_div(float a, float b, bool fast) { return fast ? __fdividef(a, b) : a / b; }
 __device__ __forceinline__ float tex_log2(float x, bool fast) { return fast ? log2f(x) : (float)log2((double)x); }
 __device__ __forceinline__ float tex_exp(float x, bool fast) { return fast ? expf(x) : (float)exp((double)x); }
 __device__ __forceinline__ float tex_atan(float x, bool fast) { return fast ? atanf(x) : (float)atan((double)x); }
@@ -112,7 +116,7 @@ __device__ inline void tex_trilinear(const DevTexStore& ts, const DevTexture& T,
 struct TexProbeSetup {
   int32_t tex;      // texture id; < 0: no lookup
   int32_t nprobes;  // 1 for the trilinear filter
-  int32_t feline;   // bit 0: Feline lookup; bit 1: single-precision exp for the probe weights
+  int32_t feline;   // bit 0: Feline lookup; bits 1 / 2: fast arithmetic (Feline / trilinear lookup)
   float U, V;       // feline: w*U, h*V (texel units); trilinear: U, V
   float dU, dV, lod, mr2, n0;
 };
@@ -132,7 +136,7 @@ __device__ inline TexProbeSetup tex_setup_rgb(const DevTexture& T, int tex, cons
   if (lod > maxlod) lod = maxlod;
   if (lod < 0) lod = 0;
   TexProbeSetup s;
-  s.tex = tex; s.nprobes = 1; s.feline = 0;
+  s.tex = tex; s.nprobes = 1; s.feline = fast ? 4 : 0;  // bit 2: fast arithmetic for a trilinear lookup (bit 0 stays clear)
   s.U = sg.U; s.V = sg.V; s.dU = 0; s.dV = 0; s.lod = lod; s.mr2 = 1; s.n0 = 0;
   return s;
 }
@@ -150,23 +154,23 @@ __device__ inline TexProbeSetup tex_setup_feline(const DevTexture& T, int tex, c
   const float Bnn = -2 * (ux * vx + uy * vy);
   const float Cnn = ux * ux + uy * uy;
   const float F = Ann * Cnn - (Bnn * Bnn / 4);
-  const float A = Ann / F;
-  const float B = Bnn / F;
-  const float C = Cnn / F;
+  const float A = tex_div(Ann, F, fast);
+  const float B = tex_div(Bnn, F, fast);
+  const float C = tex_div(Cnn, F, fast);
   const float amc = A - C;
   const float root = sqrtf(amc * amc + B * B);
   const float Aprm = (A + C - root) / 2;
   const float Cprm = (A + C + root) / 2;
-  float majorRadius = sqrtf(1 / Aprm);
-  float minorRadius = sqrtf(1 / Cprm);
-  float theta = tex_atan(B / amc, fast) / 2;
+  float majorRadius = sqrtf(tex_div(1, Aprm, fast));
+  float minorRadius = sqrtf(tex_div(1, Cprm, fast));
+  float theta = tex_atan(tex_div(B, amc, fast), fast) / 2;
   if (A > C) theta = theta + 3.14159265358f / 2;
   minorRadius = minorRadius > 1.0f ? minorRadius : 1.0f;
   majorRadius = majorRadius > 1.0f ? majorRadius : 1.0f;
-  const float fProbes = 2 * (majorRadius / minorRadius) - 1;
+  const float fProbes = 2 * tex_div(majorRadius, minorRadius, fast) - 1;
   float iProbes = floorf(fProbes + 0.5f);
   iProbes = iProbes < 16.0f ? iProbes : 16.0f;
-  if (iProbes < fProbes) minorRadius = 2 * majorRadius / (iProbes + 1);
+  if (iProbes < fProbes) minorRadius = tex_div(2 * majorRadius, iProbes + 1, fast);
   float lod = tex_log2(minorRadius, fast);
   const float maxlod = (float)(T.n_levels - 1);
   if (lod > maxlod) {
@@ -177,8 +181,8 @@ __device__ inline TexProbeSetup tex_setup_feline(const DevTexture& T, int tex, c
   const float lineLength = 2 * (majorRadius - minorRadius);
   float sn, cs;
   tex_sincos(theta, fast, &sn, &cs);
-  float dU = cs * lineLength / (iProbes - 1);
-  float dV = sn * lineLength / (iProbes - 1);
+  float dU = tex_div(cs * lineLength, iProbes - 1, fast);
+  float dV = tex_div(sn * lineLength, iProbes - 1, fast);
   // int(iProbes): a NaN footprint (parallel derivatives: F = 0) reaches here as NaN, which amd64 converts to the most negative
   // integer, i.e. no probe and 0/0 = NaN for the colour; `0 probes` gives the same NaN
   const int nProbes = iProbes == iProbes ? (int)iProbes : 0;
@@ -204,17 +208,23 @@ __device__ inline float4 tex_probe(const DevTexStore& ts, const TexProbeSetup& s
   const DevTexture T = ts.textures[s.tex];
   float sample[3];
   float w = 1.0f;
-  if (s.feline) {
+  if (s.feline & 1) {
     const float fw = (float)T.w, fh = (float)T.h;
     const float n = s.n0 + (float)(2 * i);  // the reference's running n += 2: small integers, exact either way
     const float u = s.U + (n / 2) * s.dU;
     const float v = s.V + (n / 2) * s.dV;
-    const float d2 = ((n * n) / 4) * (s.dU * s.dU + s.dV * s.dV) / s.mr2;
-    w = tex_exp(-0.6f * d2, (s.feline & 2) != 0);
-    tex_trilinear(ts, T, u / fw, v / fh, s.lod, sample);
+    const bool fast = (s.feline & 2) != 0;
+    const float d2 = tex_div(((n * n) / 4) * (s.dU * s.dU + s.dV * s.dV), s.mr2, fast);
+    w = tex_exp(-0.6f * d2, fast);
+    tex_trilinear(ts, T, tex_div(u, fw, fast), tex_div(v, fh, fast), s.lod, sample);
+    if (fast) {
+      const float k = w * (1.0f / 255.0f);
+      return make_float4(sample[0] * k, sample[1] * k, sample[2] * k, w);
+    }
     return make_float4((sample[0] / 255.0f) * w, (sample[1] / 255.0f) * w, (sample[2] / 255.0f) * w, w);
   }
   tex_trilinear(ts, T, s.U, s.V, s.lod, sample);
+  if (s.feline & 4) return make_float4(sample[0] * (1.0f / 255.0f), sample[1] * (1.0f / 255.0f), sample[2] * (1.0f / 255.0f), w);
   return make_float4(sample[0] / 255.0f, sample[1] / 255.0f, sample[2] / 255.0f, w);
 }
 
@@ -223,7 +233,7 @@ struct TexAccum {
   float a0, a1, a2, w;
   __device__ __forceinline__ void init() { a0 = a1 = a2 = w = 0.0f; }
   __device__ __forceinline__ void add(const TexProbeSetup& s, const float4 r) {
-    if (s.feline) {
+    if (s.feline & 1) {
       a0 += r.x;
       a1 += r.y;
       a2 += r.z;
@@ -235,7 +245,12 @@ struct TexAccum {
     }
   }
   __device__ __forceinline__ void finish(const TexProbeSetup& s, float out[3]) const {
-    if (s.feline) {
+    if (s.feline & 2) {
+      const float r = __fdividef(1.0f, w);
+      out[0] = a0 * r;
+      out[1] = a1 * r;
+      out[2] = a2 * r;
+    } else if (s.feline & 1) {
       out[0] = a0 / w;
       out[1] = a1 / w;
       out[2] = a2 / w;
