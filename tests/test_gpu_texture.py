@@ -199,3 +199,23 @@ def test_cooperative_lookups_are_bit_identical(built_library):
         dev.set_option("texture_coop", coop)
         imgs.append(dev.render(0, 4))
     assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32))
+
+
+def test_tile_partitions_of_a_textured_scene_tile_the_frame(built_library):
+    """Two contexts rendering the interleaved tiles of ranks 0 and 1 (what two GPUs do) reproduce the single-context frame bit
+    for bit: texture lookups and ray differentials do not depend on which pixels a context owns."""
+    from vermeer_b200 import scenes
+    from vermeer_b200.host import Device, HostScene
+    sc = scenes.textured_room(160, 128, float_maps=True)
+    tab = scenes.splitmix64_table(5, sc.XRes * sc.YRes)
+    host = HostScene(sc).prerender()
+    one = Device(0).upload(host)
+    one.set_scramble(tab)
+    full = one.render(0, 3)
+    acc = np.zeros_like(full)
+    for rank in range(2):
+        d = Device(0).upload(host)
+        d.set_partition(rank, 2)
+        d.set_scramble(tab)
+        acc += d.render(0, 3)
+    assert np.array_equal(np.nan_to_num(acc).view(np.uint32), np.nan_to_num(full).view(np.uint32))
