@@ -395,6 +395,11 @@ def run_ours(args):
         "share_of_step": closest_ms / dev_ms if dev_ms > 0 else None,
         "note": ("10M-triangle scene (0.55 GB) exceeds L2: HBM-bound model" if CONFIG in ("c3", "c5") else
                  "1M-triangle scene (6 MB nodes + 48 MB triangles) is L2-resident: the bytes model is algorithmic, not DRAM traffic"),
+        # what ncu says binds the kernel (static text: the captures live under profiles/, see profiles/README.md)
+        "binding": ("L1TEX tag throughput / L2 latency (DRAM 7-15 % of peak, long_scoreboard ~49 % of stall samples): profiles/ncu_full_r01d_c3_summary.txt"
+                    if CONFIG in ("c3", "c5") else
+                    "instruction issue x SIMD efficiency (75 % issue slots active, 16.4 of 32 lanes per instruction, DRAM 4.7 % of peak): "
+                    "profiles/ncu_full_r01f_summary.txt; a frac above 1 means the algorithmic bytes are served from L1/L2, not from HBM"),
     }
 
     # ---- CPU baseline: the oracle on a bounded sample (rank 0, N=1 only) ------------------------------
