@@ -1,0 +1,25 @@
+#!/bin/bash
+# compute-sanitizer passes over the hot path (run on the GPU box: `gpurun -- bash scripts/sanitize.sh`).
+# memcheck / racecheck / synccheck / initcheck over smoke() (traversal batch + a small wavefront frame), then memcheck over
+# the traversal, build and render parity tests.  Logs go to gpurun_out/sanitize_*.log; the script prints one summary line
+# per pass ("ERROR SUMMARY: n errors" as compute-sanitizer reports it).  Each pass is bounded by its own timeout.
+set -u
+OUT=gpurun_out
+mkdir -p $OUT
+CS=/usr/local/cuda/bin/compute-sanitizer
+SMOKE='import __graft_entry__ as g; g.smoke()'
+
+run() {  # name, timeout, tool options..., -- command
+  local name=$1 tmo=$2; shift 2
+  local log=$OUT/sanitize_$name.log
+  timeout "$tmo" $CS "$@" > "$log" 2>&1
+  local rc=$?
+  echo "$name rc=$rc $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' "$log" | tail -1) $(grep -E 'smoke ok|passed|failed' "$log" | tail -1)"
+}
+
+run memcheck_smoke 300 --tool memcheck --leak-check no --error-exitcode 1 python -c "$SMOKE"
+run racecheck_smoke 400 --tool racecheck --racecheck-report all --error-exitcode 1 python -c "$SMOKE"
+run synccheck_smoke 300 --tool synccheck --error-exitcode 1 python -c "$SMOKE"
+run initcheck_smoke 300 --tool initcheck --error-exitcode 1 python -c "$SMOKE"
+run memcheck_trace 600 --tool memcheck --leak-check no --error-exitcode 1 python -m pytest tests/test_gpu_trace.py tests/test_gpu_build.py -m gpu -x -q
+run memcheck_render 600 --tool memcheck --leak-check no --error-exitcode 1 python -m pytest tests/test_gpu_render.py tests/test_gpu_texture.py -m gpu -x -q
