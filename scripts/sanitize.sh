@@ -23,3 +23,9 @@ run synccheck_smoke 300 --tool synccheck --error-exitcode 1 python -c "$SMOKE"
 run initcheck_smoke 300 --tool initcheck --error-exitcode 1 python -c "$SMOKE"
 run memcheck_trace 600 --tool memcheck --leak-check no --error-exitcode 1 python -m pytest tests/test_gpu_trace.py tests/test_gpu_build.py -m gpu -x -q
 run memcheck_render 600 --tool memcheck --leak-check no --error-exitcode 1 python -m pytest tests/test_gpu_render.py tests/test_gpu_texture.py -m gpu -x -q
+
+# negative control: the same tool invocations must flag a deliberately broken kernel loaded the same way (ctypes)
+nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -shared -Xcompiler -fPIC -o $OUT/libsanitize_control.so scripts/sanitize_control.cu
+run control_memcheck 120 --tool memcheck --leak-check no --error-exitcode 1 python -c "import ctypes; ctypes.CDLL('$OUT/libsanitize_control.so').control_oob()"
+run control_racecheck 120 --tool racecheck --racecheck-report all --error-exitcode 1 python -c "import ctypes; ctypes.CDLL('$OUT/libsanitize_control.so').control_race()"
+rm -f $OUT/libsanitize_control.so
