@@ -155,8 +155,9 @@ def run_reference(args):
     sample = "%d iteration(s) (spp) of the 1920x1080 frame per step = %d rays/step" % (sample_iters, rays // max(1, args.steps))
     out = {
         "impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": secs / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "ms_per_step": secs / max(1, args.steps) * 1e3, "higher_is_better": True,
+        "scaling": "strong" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else "weak",   # the same label as the GPU arm at this N
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "samples_per_s": XRES * YRES * sample_iters * args.steps / secs,
