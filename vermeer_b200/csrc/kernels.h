@@ -14,6 +14,13 @@ namespace vg {
 #ifndef VG_TRACE_MIN_BLOCKS
 #define VG_TRACE_MIN_BLOCKS 7
 #endif
+// resident CTAs per SM the shadow (any-hit) queue kernels are compiled for; its own switch so that the two can be tuned apart
+#ifndef VG_TRACE_MIN_BLOCKS_SHADOW
+#define VG_TRACE_MIN_BLOCKS_SHADOW 8
+#endif
+#ifndef VG_TRACE_MIN_BLOCKS_SHADOW_MOTION
+#define VG_TRACE_MIN_BLOCKS_SHADOW_MOTION VG_TRACE_MIN_BLOCKS_SHADOW
+#endif
 static const int kTraceBlock = VG_TRACE_BLOCK;
 #ifndef VG_SMEM_STACK
 #define VG_SMEM_STACK 8

@@ -294,7 +294,7 @@ struct QueueIO {
 };
 
 template <int MODE, int VARIANT>
-__global__ void __launch_bounds__(kTraceBlock, VG_TRACE_MIN_BLOCKS) k_trace_queue(const RenderParams p, int q) {
+__global__ void __launch_bounds__(kTraceBlock, MODE == 1 ? ((VARIANT & 64) ? VG_TRACE_MIN_BLOCKS_SHADOW_MOTION : VG_TRACE_MIN_BLOCKS_SHADOW) : VG_TRACE_MIN_BLOCKS) k_trace_queue(const RenderParams p, int q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [warps x warp_smem_bytes(VARIANT) scratch] [threads x VG_SMEM_STACK stack entries]
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
@@ -1110,6 +1110,7 @@ struct RenderState {
   DevBuf<unsigned long long> stats;
   int fb_w = 0, fb_h = 0;
   int trace_grid = 0;
+  int shadow_grid = 0, shadow_grid_mot = 0;  // the any-hit kernels may be compiled for another residency (VG_TRACE_MIN_BLOCKS_SHADOW)
   int max_light_samples = 0;
   bool scr_by_pixel = false;  // the device holds the caller's whole scramble table in raster order (pinned fast path)
   bool generic = false;  // shade with k_shade_generic (glossy lobe / conductor Fresnel / Disk or Sphere lights / sphere geoms)
@@ -1492,6 +1493,10 @@ static int prepare(vg_ctx* ctx) {
   int nb = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_queue<0, 2>, kTraceBlock, trace_smem_bytes(2));
   rs.trace_grid = ctx->sm_count * std::max(1, nb);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_queue<1, 3>, kTraceBlock, trace_smem_bytes(3));
+  rs.shadow_grid = ctx->sm_count * std::max(1, nb);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_queue<1, 67>, kTraceBlock, trace_smem_bytes(67));
+  rs.shadow_grid_mot = ctx->sm_count * std::max(1, nb);
   rs.ready = true;
   return upload_scramble(ctx, ctx->scramble.data());
 }
@@ -1612,19 +1617,19 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
           }
           cudaEventRecord(rs.ev(nev++), st);
           if (xf) {
-            if (ctx->opt_shadow_unordered) k_trace_queue<1, 27><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(27), st>>>(p, 0);
-            else k_trace_queue<1, 26><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(26), st>>>(p, 0);
+            if (ctx->opt_shadow_unordered) k_trace_queue<1, 27><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(27), st>>>(p, 0);
+            else k_trace_queue<1, 26><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(26), st>>>(p, 0);
           } else if (sph) {
-            if (variant == 2 && ctx->opt_shadow_unordered) k_trace_queue<1, 11><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(11), st>>>(p, 0);
-            else if (variant == 2) k_trace_queue<1, 10><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(10), st>>>(p, 0);
-            else k_trace_queue<1, 8><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(8), st>>>(p, 0);
+            if (variant == 2 && ctx->opt_shadow_unordered) k_trace_queue<1, 11><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(11), st>>>(p, 0);
+            else if (variant == 2) k_trace_queue<1, 10><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(10), st>>>(p, 0);
+            else k_trace_queue<1, 8><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(8), st>>>(p, 0);
           } else if (mot && variant == 2) {
-            if (ctx->opt_shadow_unordered) k_trace_queue<1, 67><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(67), st>>>(p, 0);
-            else k_trace_queue<1, 66><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(66), st>>>(p, 0);
-          } else if (variant == 1) k_trace_queue<1, 1><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(1), st>>>(p, 0);
-          else if (variant == 2 && ctx->opt_shadow_unordered) k_trace_queue<1, 3><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(3), st>>>(p, 0);
-          else if (variant == 2) k_trace_queue<1, 2><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(2), st>>>(p, 0);
-          else k_trace_queue<1, 0><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(0), st>>>(p, 0);
+            if (ctx->opt_shadow_unordered) k_trace_queue<1, 67><<<rs.shadow_grid_mot, kTraceBlock, trace_smem_bytes(67), st>>>(p, 0);
+            else k_trace_queue<1, 66><<<rs.shadow_grid_mot, kTraceBlock, trace_smem_bytes(66), st>>>(p, 0);
+          } else if (variant == 1) k_trace_queue<1, 1><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(1), st>>>(p, 0);
+          else if (variant == 2 && ctx->opt_shadow_unordered) k_trace_queue<1, 3><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(3), st>>>(p, 0);
+          else if (variant == 2) k_trace_queue<1, 2><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(2), st>>>(p, 0);
+          else k_trace_queue<1, 0><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(0), st>>>(p, 0);
           cudaEventRecord(rs.ev(nev++), st);
           kinds.push_back(1);
           if (rs.levels > 1) {
