@@ -294,7 +294,7 @@ struct QueueIO {
 };
 
 template <int MODE, int VARIANT>
-__global__ void __launch_bounds__(kTraceBlock, MODE == 1 ? ((VARIANT & 64) ? VG_TRACE_MIN_BLOCKS_SHADOW_MOTION : VG_TRACE_MIN_BLOCKS_SHADOW) : VG_TRACE_MIN_BLOCKS) k_trace_queue(const RenderParams p, int q) {
+__global__ void __launch_bounds__(kTraceBlock, MODE == 1 ? ((VARIANT & 64) ? VG_TRACE_MIN_BLOCKS_SHADOW_MOTION : VG_TRACE_MIN_BLOCKS_SHADOW) : ((VARIANT & 2) ? ((VARIANT & 64) ? VG_TRACE_MIN_BLOCKS_COOP_MOTION : VG_TRACE_MIN_BLOCKS_COOP) : VG_TRACE_MIN_BLOCKS)) k_trace_queue(const RenderParams p, int q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [warps x warp_smem_bytes(VARIANT) scratch] [threads x VG_SMEM_STACK stack entries]
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
@@ -1110,6 +1110,7 @@ struct RenderState {
   DevBuf<unsigned long long> stats;
   int fb_w = 0, fb_h = 0;
   int trace_grid = 0;
+  int coop_grid = 0, coop_grid_mot = 0;    // closest-hit kernels with cooperative leaves (VG_TRACE_MIN_BLOCKS_COOP)
   int shadow_grid = 0, shadow_grid_mot = 0;  // the any-hit kernels may be compiled for another residency (VG_TRACE_MIN_BLOCKS_SHADOW)
   int max_light_samples = 0;
   bool scr_by_pixel = false;  // the device holds the caller's whole scramble table in raster order (pinned fast path)
@@ -1491,8 +1492,12 @@ static int prepare(vg_ctx* ctx) {
   RCUDA(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
 
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_queue<0, 2>, kTraceBlock, trace_smem_bytes(2));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_queue<0, 0>, kTraceBlock, trace_smem_bytes(0));
   rs.trace_grid = ctx->sm_count * std::max(1, nb);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_queue<0, 2>, kTraceBlock, trace_smem_bytes(2));
+  rs.coop_grid = ctx->sm_count * std::max(1, nb);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_queue<0, 66>, kTraceBlock, trace_smem_bytes(66));
+  rs.coop_grid_mot = ctx->sm_count * std::max(1, nb);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_queue<1, 3>, kTraceBlock, trace_smem_bytes(3));
   rs.shadow_grid = ctx->sm_count * std::max(1, nb);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_queue<1, 67>, kTraceBlock, trace_smem_bytes(67));
@@ -1586,13 +1591,13 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
         // 3.81 vs 3.48 Grays/s); every later level is incoherent and takes the cooperative leaf phase. Motion meshes are the
         // exception: their leaves cost 2-3x a static one (two keys to load and lerp), so the cooperative phase wins at level 0
         // too (C4: 49.6 vs 56.7 ms per frame)
-        if (xf) k_trace_queue<0, 26><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(26), st>>>(p, qin);
+        if (xf) k_trace_queue<0, 26><<<rs.coop_grid, kTraceBlock, trace_smem_bytes(26), st>>>(p, qin);
         else if (sph) {
-          if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 10><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(10), st>>>(p, qin);
+          if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 10><<<rs.coop_grid, kTraceBlock, trace_smem_bytes(10), st>>>(p, qin);
           else k_trace_queue<0, 8><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(8), st>>>(p, qin);
-        } else if (mot && variant == 2) k_trace_queue<0, 66><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(66), st>>>(p, qin);
+        } else if (mot && variant == 2) k_trace_queue<0, 66><<<rs.coop_grid_mot, kTraceBlock, trace_smem_bytes(66), st>>>(p, qin);
         else if (variant == 1) k_trace_queue<0, 1><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(1), st>>>(p, qin);
-        else if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 2><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(2), st>>>(p, qin);
+        else if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 2><<<rs.coop_grid, kTraceBlock, trace_smem_bytes(2), st>>>(p, qin);
         else k_trace_queue<0, 0><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(0), st>>>(p, qin);
         cudaEventRecord(rs.ev(nev++), st);
         kinds.push_back(0);
