@@ -26,6 +26,9 @@ namespace vg {
 #ifndef VG_TRACE_MIN_BLOCKS_COOP_MOTION
 #define VG_TRACE_MIN_BLOCKS_COOP_MOTION VG_TRACE_MIN_BLOCKS
 #endif
+#ifndef VG_TRACE_MIN_BLOCKS_BATCH_COOP
+#define VG_TRACE_MIN_BLOCKS_BATCH_COOP 8
+#endif
 #ifndef VG_TRACE_MIN_BLOCKS_SHADOW_MOTION
 #define VG_TRACE_MIN_BLOCKS_SHADOW_MOTION VG_TRACE_MIN_BLOCKS_SHADOW
 #endif

@@ -34,7 +34,9 @@ struct BatchIO {
 };
 
 template <bool ANY_HIT, int VARIANT>
-__global__ void __launch_bounds__(kTraceBlock, VG_TRACE_MIN_BLOCKS) k_trace_batch(const DevScene sc, const VgRay* __restrict__ rays, VgHit* __restrict__ hits,
+// residency per kernel family as for the queue kernels (kernels.h); the grid is sized for the static cooperative variant, the
+// default of vg_trace_batch: a persistent kernel that fits fewer CTAs just leaves the surplus ones to find the counter exhausted
+__global__ void __launch_bounds__(kTraceBlock, ((VARIANT & 2) && !(VARIANT & 64)) ? VG_TRACE_MIN_BLOCKS_BATCH_COOP : VG_TRACE_MIN_BLOCKS) k_trace_batch(const DevScene sc, const VgRay* __restrict__ rays, VgHit* __restrict__ hits,
                                                              long long n, unsigned long long* __restrict__ counter,
                                                              unsigned long long* __restrict__ stats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
