@@ -400,7 +400,7 @@ def run_ours(args):
         "binding": ("L1TEX tag throughput / L2 latency (DRAM 7-15 % of peak, long_scoreboard ~49 % of stall samples): profiles/ncu_full_r01d_c3_summary.txt"
                     if CONFIG in ("c3", "c5") else
                     "instruction issue x SIMD efficiency (75 % issue slots active, 16.4 of 32 lanes per instruction, DRAM 4.7 % of peak): "
-                    "profiles/ncu_full_r01f_summary.txt; a frac above 1 means the algorithmic bytes are served from L1/L2, not from HBM"),
+                    "profiles/ncu_full_r01i_final_summary.txt; a frac above 1 means the algorithmic bytes are served from L1/L2, not from HBM"),
     }
 
     if CONFIG in ("c2", "c2t", "c4"):
