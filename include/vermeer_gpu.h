@@ -35,6 +35,7 @@ extern "C" {
 #define VG_ERR_CUDA (-3)       /* a CUDA call failed */
 #define VG_ERR_BUILD (-4)      /* host-side tree build failed (e.g. reference quirk f: coincident centroids) */
 #define VG_ERR_UNSUPPORTED (-5)
+#define VG_ERR_COMM (-6)        /* NCCL missing or an NCCL call failed (vg_comm_*, vg_gather_frame) */
 
 /* ---- records ------------------------------------------------------------------------------ */
 
@@ -162,6 +163,8 @@ typedef struct VgStats {
   double trace_ms;   /* device time of the last vg_trace_batch* kernel */
   double closest_ms; /* summed device time of the closest-hit traversal launches of the last vg_render */
   double shadow_ms;  /* summed device time of the any-hit traversal launches of the last vg_render */
+  double shade_ms;   /* summed device time of the shading launches (k_surface + k_shade*) of the last vg_render */
+  double gather_ms;  /* device time of the last vg_gather_frame exchange (pack + NCCL + scatter), without the D2H copy */
 } VgStats;
 
 /* ---- device layer ------------------------------------------------------------------------- */
@@ -265,7 +268,8 @@ int vg_set_scramble(vg_ctx* ctx, const uint64_t* table, int64_t npix);
  * device in ray generation (core/render.go:99-107). n = 0 removes the filter. */
 int vg_set_filter(vg_ctx* ctx, int n, double w, const double* cdfV, const double* cdfVU);
 /* Options: "trace_last_level" (1 = trace the level-4 mirror ray like the reference, std.go:243; default 1),
- * "iters_per_batch" (wavefront batch depth, default 4), "precise_trig" (1 = shading trig through float64 exactly like
+ * "iters_per_batch" (wavefront batch depth, default 4), "iter_group" (a warp's 32 paths = 32/iter_group neighbouring pixels x
+ * iter_group consecutive iterations of the batch; power of two, default 4; results do not depend on it), "precise_trig" (1 = shading trig through float64 exactly like
  * math/sincos.go; 0 = single-precision libm, default; both are within the image tolerance), "traversal" (persistent-kernel variant:
  * 2 = warp-cooperative leaf phase, default; 0 = per-lane while-while loop with coalesced LDG refill; 1 = the per-lane loop with
  * its ray queue staged into shared memory by cp.async.bulk + mbarrier; all three are bit-identical), "tma_stage" (1 = alias of
@@ -274,18 +278,71 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value);
 
 /* TraceProbe over a batch (core/trace.go:26). flags: */
 #define VG_TRACE_ANY_HIT 1u /* RayTypeShadow: return at the first leaf that reports a hit (intersect.go:228-236) */
+/* `hits` is an array of 16-byte VgHitCompact records instead of VgHit: half the device->host bytes of a batch whose cost is the
+ * PCIe transfer. slot = the hit triangle's global leaf-order slot (vg_slot_table maps it to ElemID and geom), -1 on a miss;
+ * w is not returned (the caller recomputes what it needs from u, v). Scenes of static PolyMeshes only (VG_ERR_UNSUPPORTED
+ * otherwise). t, u, v and the hit triangle are the same bits as in the full record. */
+#define VG_TRACE_COMPACT_HITS 2u
+typedef struct VgHitCompact {
+  float t, u, v;
+  int32_t slot;
+} VgHitCompact;
 int vg_trace_batch(vg_ctx* ctx, const VgRay* rays, int64_t n, VgHit* hits, uint32_t flags);               /* host buffers */
 int vg_trace_batch_device(vg_ctx* ctx, const VgRay* d_rays, int64_t n, VgHit* d_hits, uint32_t flags);    /* device buffers */
+/* ElemID (VgHit.prim) and geom of every static triangle slot; returns the slot count (buffers may be NULL to ask for it). */
+int vg_slot_table(vg_ctx* ctx, int32_t* prim_of_slot, int32_t* geom_of_slot, int64_t cap);
 
 /* The Render loop (core/render.go:184-205) for 0-based iterations [iter_begin, iter_end) over this context's tiles,
  * continuing the running mean held on the device. fb_out (xres*yres*3 floats, row-major, may be NULL) receives the
  * full-frame buffer with non-owned pixels left 0. */
 int vg_render(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out);
 int vg_clear_framebuffer(vg_ctx* ctx);
+/* Benchmarking aid: with option "capture_levels" = bitmask of path levels (bit 1 = the first mirror bounce ...), vg_render keeps a
+ * host copy of the closest-hit ray queue of those levels (core.Trace's reflected rays, builtin/shader/std.go:219-261), appended
+ * batch after batch. vg_captured_rays returns their number (out == NULL) or copies them out and clears the store. This is how
+ * bench.py obtains a genuinely incoherent closest-hit batch "from the wavefront itself". */
+int64_t vg_captured_rays(vg_ctx* ctx, VgRay* out, int64_t cap);
 /* Device pointer to the row-major xres*yres*3 float framebuffer (for NCCL gathers done by the caller). */
 int vg_framebuffer_device(vg_ctx* ctx, float** d_fb);
 int vg_get_stats(vg_ctx* ctx, VgStats* out);
 int vg_reset_stats(vg_ctx* ctx);
+
+/* ---- multi-GPU: one process (or thread) per GPU, one context each -----------------------------------------
+ * The reference renders its 32x32 tiles on <= 10 goroutines of one process (core/render.go:186-203) and has no exchange step;
+ * here the tiles are dealt over `world` contexts and the owned pixels are brought to rank 0 once per frame.
+ *   vg_comm_unique_id   rank 0 creates the NCCL id (VG_COMM_ID_BYTES bytes); the HOST distributes it to the other ranks by
+ *                       whatever means it has (the Go shim: a channel between its per-GPU goroutines; bench.py: a broadcast).
+ *   vg_comm_init        every rank: ncclCommInitRank on the context's device, then the image partition of
+ *                       vg_set_partition(rank, world). Collective. world == 1 needs no NCCL and no id.
+ *   vg_gather_frame     collective, after vg_render: every rank packs its owned pixels (own kernel), ranks > 0 ncclSend them
+ *                       to rank 0, which ncclRecvs into a staging buffer and scatters them into its row-major frame (own
+ *                       kernel; disjoint ownership, nothing is summed: the result is bit-identical to a 1-GPU render), then
+ *                       copies the complete frame into fb_out (xres*yres*3 floats; rank 0 only, may be NULL: the frame stays
+ *                       in the buffer vg_framebuffer_device returns). fb_out is ignored on the other ranks.
+ * NCCL is bound at run time (dlopen libnccl.so.2, or the path in $VG_NCCL_LIB); without it these calls fail with VG_ERR_COMM
+ * and everything else keeps working. */
+#define VG_COMM_ID_BYTES 128
+int vg_comm_unique_id(vg_ctx* ctx, void* id_out);
+int vg_comm_init(vg_ctx* ctx, int rank, int world, const void* id);
+int vg_comm_destroy(vg_ctx* ctx);
+int vg_gather_frame(vg_ctx* ctx, float* fb_out);
+int vg_nccl_version(void); /* ncclGetVersion of the library that was bound, 0 if none */
+/* The tile-major list of the full-frame pixel indices `rank` of `world` owns (host only, no device needed): returns the count,
+ * fills pix_out (may be NULL) if it holds at least that many. pixel_block = the "pixel_block" option (default 1). */
+int vg_owned_pixels(int xres, int yres, int rank, int world, int pixel_block, int32_t* pix_out, int64_t cap);
+
+/* ---- measured ceilings ---------------------------------------------------------------------------------------------------
+ * Read bandwidth of HBM, L2 and L1 on this context's GPU, measured with streaming kernels (csrc/peaks.cu): the denominators
+ * of the roofline fractions bench.py reports for the L2-/L1-resident configs. No reference counterpart. */
+typedef struct VgPeaks {
+  double hbm_read_gbs;     /* read-only stream over hbm_buffer_bytes (>> L2), ld.global.cg */
+  double l2_read_gbs;      /* the same over l2_buffer_bytes (fits L2), re-read many times */
+  double l1_read_gbs;      /* every SM re-reads its own l1_window_bytes, ld.global.ca */
+  double hbm_buffer_bytes, l2_buffer_bytes, l1_window_bytes;
+  int32_t sm_count;
+  int32_t pad_;
+} VgPeaks;
+int vg_measure_peaks(vg_ctx* ctx, VgPeaks* out);
 
 /* ---- host layer ---------------------------------------------------------------------------- */
 

@@ -154,7 +154,8 @@ class Oracle:
         self.L.orc_clear_framebuffer(self.h)
 
     def render(self, iter_begin: int, iter_end: int, nthreads: int = 1, trace_last_level: bool = True):
-        """Returns (framebuffer (H,W,3) float32, dict(rays, shadow_rays, seconds))."""
+        """Returns (framebuffer (H,W,3) float32, dict(rays, shadow_rays, seconds)). nthreads < 0 = the reference's own worker
+        policy: min(-nthreads, 10) workers (core/render.go:190) and global atomic ray counters (core/stats.go:26-33)."""
         fb = np.zeros((self.scene.YRes, self.scene.XRes, 3), np.float32)
         st = np.zeros(3, np.uint64)
         self._chk(self.L.orc_render(self.h, iter_begin, iter_end, nthreads, 1 if trace_last_level else 0, _p(fb), _p(st)))

@@ -8,6 +8,7 @@
 //   qbvh/qbvh.go:18-20, qbvh/mqbvh.go:13-15          (Primitive / MotionPrimitive)
 // Ray differentials (core/ray.go:40-44,72-87,95-99) are carried: they feed the texture footprint of texture.h.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <vector>
 
@@ -43,6 +44,11 @@ struct alignas(16) RenderTask {
   Scene* scene = nullptr;        // the reference uses a package global (core/core.go:11)
   uint64_t rayCount = 0;         // core/stats.go:26-33 (kept per task, summed at the end)
   uint64_t shadowRayCount = 0;
+  // reference-faithful statistics: the reference bumps two process-global counters with atomic.AddUint64 on EVERY ray
+  // (core/stats.go:26-33, core/trace.go:28-32). When set, TraceProbe does the same on these shared counters instead of
+  // the per-task ones: the contended cache line is a real cost of the reference on many cores (bench.py's "faithful" CPU leg).
+  std::atomic<uint64_t>* sharedRayCount = nullptr;
+  std::atomic<uint64_t>* sharedShadowRayCount = nullptr;
   bool trace_last_level = true;  // trace the level-4 mirror ray like the reference does (std.go:243)
   float PixelDelta[2] = {0, 0};  // core.Image.PixelDelta: a package global in the reference (render.go:47, camera.go:316-317)
   RenderTask() { Traversal.StackTop = 0; }

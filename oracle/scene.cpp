@@ -716,8 +716,13 @@ BoundingBox Scene::initMotionBoxesRec(int key, int32_t node) {
 // ---------------------------------------------------------------------------------------------
 // core/trace.go:26-35
 bool TraceProbe(Ray* ray, ShaderContext* sg) {
-  ray->Task->rayCount++;
-  if (ray->Type & RayTypeShadow) ray->Task->shadowRayCount++;
+  if (ray->Task->sharedRayCount) {  // stats.incRayCount / incShadowRayCount: global atomics (core/stats.go:26-33)
+    ray->Task->sharedRayCount->fetch_add(1);
+    if (ray->Type & RayTypeShadow) ray->Task->sharedShadowRayCount->fetch_add(1);
+  } else {
+    ray->Task->rayCount++;
+    if (ray->Type & RayTypeShadow) ray->Task->shadowRayCount++;
+  }
   return ray->Task->scene->Trace(ray, sg);
 }
 

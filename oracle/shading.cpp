@@ -1096,6 +1096,11 @@ RenderStats Renderer::Render(int iterBegin, int iterEnd, int nthreads) {
   PreRender();
   if ((int)framescramble.size() != XRes * YRes) throw std::runtime_error("framescramble not set");
   RenderStats stats;
+  // nthreads < 0: the reference's own worker policy — min(MaxGoRoutines, 10) goroutines (core/render.go:190; MaxGoRoutines is
+  // given as -nthreads) and the two global atomic ray counters (core/stats.go:26-33)
+  const bool faithful = nthreads < 0;
+  if (faithful) nthreads = std::min(-nthreads, 10);
+  std::atomic<uint64_t> sharedRays(0), sharedShadow(0);
   auto t0 = std::chrono::steady_clock::now();
   const int tilesX = (XRes + 31) / 32, tilesY = (YRes + 31) / 32;
   for (int iter0 = iterBegin; iter0 < iterEnd; iter0++) {
@@ -1106,6 +1111,10 @@ RenderStats Renderer::Render(int iterBegin, int iterEnd, int nthreads) {
       RenderTask* task = &tasks[ti];
       task->scene = &scene;
       task->trace_last_level = trace_last_level;
+      if (faithful) {
+        task->sharedRayCount = &sharedRays;
+        task->sharedShadowRayCount = &sharedShadow;
+      }
       camera.PixelDelta(XRes, YRes, task->PixelDelta);
       Ray ray;
       ray.Task = task;
@@ -1139,6 +1148,8 @@ RenderStats Renderer::Render(int iterBegin, int iterEnd, int nthreads) {
       stats.shadowRayCount += t.shadowRayCount;
     }
   }
+  stats.rayCount += sharedRays.load();
+  stats.shadowRayCount += sharedShadow.load();
   stats.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return stats;
 }

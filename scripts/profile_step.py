@@ -15,5 +15,12 @@ if "--tex" in sys.argv:   # the C2T bench scene: a 1024x1024 Feline map on the g
 host = HostScene(sc).prerender()
 dev = Device(0).upload(host)
 dev.set_scramble(scenes.splitmix64_table(1, 1920 * 1080))
-dev.render(0, 8, fetch=False)
+iters = 8
+for a in sys.argv:
+    if a.startswith("--iters="):
+        iters = int(a.split("=")[1])
+    if a.startswith("--opt="):   # --opt=name=value
+        _, k, v = a.split("=")
+        dev.set_option(k, int(v))
+dev.render(0, iters, fetch=False)
 print(dev.stats())

@@ -172,6 +172,7 @@ int vg_create(vg_ctx** out, int device_ordinal) {
 void vg_destroy(vg_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  comm_destroy(ctx);
   render_destroy(ctx);
   build_scratch_destroy(ctx);
   ctx->d_nodes.release(); ctx->d_mtopo.release(); ctx->d_mboxes.release(); ctx->d_tris.release();
@@ -674,6 +675,7 @@ int vg_scene_commit(vg_ctx* ctx) {
   d.xf_static = ctx->d_xf_static.p;
   d.n_xforms = (int32_t)xforms.size();
   d.n_mtris = (int32_t)n_mtris;
+  ctx->n_tri_slots = n_tris;
   d.n_geoms = G;
   d.n_spheres = 0;
   for (int g = 0; g < G; g++) d.n_spheres += ctx->meshes[g].sphere ? 1 : 0;
@@ -964,6 +966,11 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
   else if (!std::strcmp(name, "tma_stage")) ctx->opt_traversal = value != 0 ? 1 : 2;
   else if (!std::strcmp(name, "primary_per_lane")) ctx->opt_primary_per_lane = value != 0;
   else if (!std::strcmp(name, "shadow_unordered")) ctx->opt_shadow_unordered = value != 0;
+  else if (!std::strcmp(name, "shadow_per_lane")) ctx->opt_shadow_per_lane = value != 0;
+  else if (!std::strcmp(name, "capture_levels")) {
+    ctx->opt_capture_levels = value & 31;
+    ctx->captured.clear();
+  }
   else if (!std::strcmp(name, "texture_coop")) ctx->opt_texture_coop = value != 0;
   else if (!std::strcmp(name, "zero_copy_batch")) ctx->opt_zero_copy_batch = value != 0;
   else if (!std::strcmp(name, "l2_persist_nodes")) ctx->opt_l2_persist_nodes = value != 0;  // takes effect at the next vg_scene_commit
@@ -982,6 +989,10 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
     ctx->opt_pixel_block = value != 0;
     render_invalidate(ctx);
   }
+  else if (!std::strcmp(name, "iter_group")) {
+    if (value < 1 || value > 32 || (value & (value - 1))) return ctx->fail(VG_ERR_INVALID, "iter_group must be a power of two in [1,32]");
+    ctx->opt_iter_group = value;
+  }
   else if (!std::strcmp(name, "traversal")) {
     if (value < 0 || value > 2) return ctx->fail(VG_ERR_INVALID, "traversal must be 0 (per-lane), 1 (TMA-staged queue) or 2 (cooperative leaves)");
     ctx->opt_traversal = value;
@@ -998,13 +1009,15 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
 static int trace_device_locked(vg_ctx* ctx, const VgRay* d_rays, int64_t n, VgHit* d_hits, uint32_t flags) {
   if (!ctx->committed) return ctx->fail(VG_ERR_INVALID, "scene not committed");
   if (n == 0) return VG_OK;
+  if ((flags & VG_TRACE_COMPACT_HITS) && (ctx->dev.n_mtris > 0 || ctx->dev.n_spheres > 0 || ctx->dev.n_xforms > 0))
+    return ctx->fail(VG_ERR_UNSUPPORTED, "VG_TRACE_COMPACT_HITS: the 16-byte record identifies a hit by its static triangle slot; scenes with motion meshes, sphere geoms or instances need the full VgHit");
   static int blocks_per_sm = 0;
   if (!blocks_per_sm) blocks_per_sm = trace_batch_blocks_per_sm();
   long long want = (n + kTraceBlock - 1) / kTraceBlock;
   long long grid = (long long)ctx->sm_count * blocks_per_sm;
   if (grid > want) grid = want;
   VG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  VG_CUDA(ctx, launch_trace_batch(ctx->dev, d_rays, d_hits, n, (flags & VG_TRACE_ANY_HIT) != 0, ctx->opt_traversal, ctx->d_counters.p, ctx->d_counters.p + 1, (int)grid, ctx->stream));
+  VG_CUDA(ctx, launch_trace_batch(ctx->dev, d_rays, d_hits, n, (flags & VG_TRACE_ANY_HIT) != 0, ctx->opt_traversal, ctx->d_counters.p, ctx->d_counters.p + 1, (int)grid, ctx->stream, (flags & VG_TRACE_COMPACT_HITS) != 0));
   VG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   float ms = 0;
@@ -1040,6 +1053,12 @@ int vg_trace_batch(vg_ctx* ctx, const VgRay* rays, int64_t n, VgHit* hits, uint3
   if (!ctx->committed) return ctx->fail(VG_ERR_INVALID, "scene not committed");
   VG_CUDA(ctx, ctx->d_rays.reserve((size_t)n));
   VG_CUDA(ctx, ctx->d_hits.reserve((size_t)n));
+  const bool compact = (flags & VG_TRACE_COMPACT_HITS) != 0;
+  if (compact && (ctx->dev.n_mtris > 0 || ctx->dev.n_spheres > 0 || ctx->dev.n_xforms > 0))
+    return ctx->fail(VG_ERR_UNSUPPORTED, "VG_TRACE_COMPACT_HITS: the 16-byte record identifies a hit by its static triangle slot; scenes with motion meshes, sphere geoms or instances need the full VgHit");
+  const size_t hit_bytes = compact ? sizeof(VgHitCompact) : sizeof(VgHit);
+  char* const hits_b = reinterpret_cast<char*>(hits);
+  char* const d_hits_b = reinterpret_cast<char*>(ctx->d_hits.p);
   const int64_t chunk = (int64_t)1 << ctx->opt_batch_chunk_log2;  // rays per pipeline stage (default 2^19 = 16 MB of rays)
   if (ctx->opt_zero_copy_batch && n >= 2 * chunk && pinned_host(rays) && pinned_host(hits)) {
     // Page-locked caller buffers, option zero_copy_batch: ONE launch whose warps read the rays from host memory and write the hits
@@ -1071,9 +1090,9 @@ int vg_trace_batch(vg_ctx* ctx, const VgRay* rays, int64_t n, VgHit* hits, uint3
       cudaStream_t st = ctx->pipe_stream[c % 3];
       VG_CUDA(ctx, cudaMemcpyAsync(ctx->d_rays.p + off, rays + off, (size_t)m * sizeof(VgRay), cudaMemcpyHostToDevice, st));
       long long grid = std::min<long long>((long long)ctx->sm_count * blocks_per_sm, (m + kTraceBlock - 1) / kTraceBlock);
-      VG_CUDA(ctx, launch_trace_batch(ctx->dev, ctx->d_rays.p + off, ctx->d_hits.p + off, m, (flags & VG_TRACE_ANY_HIT) != 0, ctx->opt_traversal,
-                                      ctx->d_counters.p + 4 + (c % 3), ctx->d_counters.p + 1, (int)grid, st));
-      VG_CUDA(ctx, cudaMemcpyAsync(hits + off, ctx->d_hits.p + off, (size_t)m * sizeof(VgHit), cudaMemcpyDeviceToHost, st));
+      VG_CUDA(ctx, launch_trace_batch(ctx->dev, ctx->d_rays.p + off, reinterpret_cast<VgHit*>(d_hits_b + (size_t)off * hit_bytes), m, (flags & VG_TRACE_ANY_HIT) != 0, ctx->opt_traversal,
+                                      ctx->d_counters.p + 4 + (c % 3), ctx->d_counters.p + 1, (int)grid, st, compact));
+      VG_CUDA(ctx, cudaMemcpyAsync(hits_b + (size_t)off * hit_bytes, d_hits_b + (size_t)off * hit_bytes, (size_t)m * hit_bytes, cudaMemcpyDeviceToHost, st));
     }
     for (int s = 0; s < 3; s++) {
       VG_CUDA(ctx, cudaEventRecord(ctx->pipe_done[s], ctx->pipe_stream[s]));
@@ -1092,9 +1111,40 @@ int vg_trace_batch(vg_ctx* ctx, const VgRay* rays, int64_t n, VgHit* hits, uint3
   VG_CUDA(ctx, cudaMemcpyAsync(ctx->d_rays.p, rays, (size_t)n * sizeof(VgRay), cudaMemcpyHostToDevice, ctx->stream));
   int rc = trace_device_locked(ctx, ctx->d_rays.p, n, ctx->d_hits.p, flags);
   if (rc != VG_OK) return rc;
-  VG_CUDA(ctx, cudaMemcpyAsync(hits, ctx->d_hits.p, (size_t)n * sizeof(VgHit), cudaMemcpyDeviceToHost, ctx->stream));
+  VG_CUDA(ctx, cudaMemcpyAsync(hits, ctx->d_hits.p, (size_t)n * hit_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return VG_OK;
+}
+
+// slot -> (ElemID, geom) of every static triangle slot: what a VG_TRACE_COMPACT_HITS record's `slot` stands for
+int vg_slot_table(vg_ctx* ctx, int32_t* prim_of_slot, int32_t* geom_of_slot, int64_t cap) {
+  VG_LOCK(ctx);
+  if (!ctx->committed) return ctx->fail(VG_ERR_INVALID, "scene not committed");
+  const int64_t n = ctx->n_tri_slots;
+  if (!prim_of_slot && !geom_of_slot) return (int)n;
+  if (cap < n) return ctx->fail(VG_ERR_INVALID, "vg_slot_table: buffers too small");
+  VG_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<float4> t((size_t)n * kTriStride);
+  VG_CUDA(ctx, cudaMemcpy(t.data(), ctx->d_tris.p, t.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n; i++) {
+    int32_t g, pr;
+    std::memcpy(&g, &t[(size_t)i * kTriStride].w, 4);
+    std::memcpy(&pr, &t[(size_t)i * kTriStride + 1].w, 4);
+    if (geom_of_slot) geom_of_slot[i] = g;
+    if (prim_of_slot) prim_of_slot[i] = pr;
+  }
+  return (int)n;
+}
+
+int64_t vg_captured_rays(vg_ctx* ctx, VgRay* out, int64_t cap) {
+  VG_LOCK(ctx);
+  const int64_t n = (int64_t)ctx->captured.size();
+  if (!out) return n;
+  if (cap < n) return ctx->fail(VG_ERR_INVALID, "vg_captured_rays: buffer too small");
+  if (n > 0) std::memcpy(out, ctx->captured.data(), (size_t)n * sizeof(VgRay));
+  ctx->captured.clear();
+  ctx->captured.shrink_to_fit();
+  return n;
 }
 
 int vg_render(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {

@@ -84,6 +84,7 @@ struct DevBuf {
 };
 
 struct RenderState;  // render.cu
+struct CommState;    // comm.cu
 struct BuildScratch;  // build_bvh.cu
 
 }  // namespace vg
@@ -114,6 +115,7 @@ struct vg_ctx {
   vg::DevBuf<vg::XfSRT> d_xf_keys;
   vg::DevBuf<vg::Mat4> d_xf_static;
   size_t scene_bytes = 0;
+  int64_t n_tri_slots = 0;  // static triangle slots of the committed scene (d_tris holds kTriStride float4 each)
 
   // batch trace scratch
   vg::DevBuf<VgRay> d_rays;
@@ -144,6 +146,7 @@ struct vg_ctx {
   int xres = 0, yres = 0;
   int rank = 0, world = 1;
   std::vector<uint64_t> scramble;  // full frame, npix*6
+  bool scramble_stale = false;     // a later vg_set_scramble went straight to the device (render.cu: render_set_scramble)
   int filter_n = 0;
   double filter_w = 0;
   std::vector<double> filter_cdf;  // cdfV[n] then cdfVU[n*n]
@@ -153,6 +156,10 @@ struct vg_ctx {
   int opt_primary_per_lane = 1;  // with traversal=2: camera rays (level 0) still use the per-lane loop
   int opt_shadow_unordered = 1;  // integrator shadow queue: skip the sign-ordered push (occlusion is order independent)
   int opt_generic_shade = 0;     // 1 = always shade with the general kernel (tests: it must agree with the specialised one)
+  int opt_capture_levels = 0;    // bit L: vg_render keeps a host copy of the level-L closest-hit ray queue (vg_captured_rays)
+  std::vector<VgRay> captured;
+  int opt_shadow_per_lane = 0;   // integrator shadow queue through the per-lane while-while kernel instead of the cooperative one
+  int opt_iter_group = 32;       // a warp's 32 paths = (32/iter_group) pixels x iter_group iterations of the batch (render.cu: path_index)
   int opt_pixel_block = 1;       // paths of one warp cover an 8x4 pixel block of a tile (1) or a 32x1 row (0)
   int opt_batch_chunk_log2 = 19; // vg_trace_batch copy pipeline: rays per stage
   int opt_l2_persist_nodes = 0;  // persisting-L2 access-policy window over the static node array
@@ -162,6 +169,7 @@ struct vg_ctx {
   int opt_traversal = 2;  // 0: per-lane while-while, 1: the same over a TMA-staged ray queue, 2: warp-cooperative leaves (traverse.cuh)
 
   vg::RenderState* rs = nullptr;
+  vg::CommState* comm = nullptr;  // vg_comm_init: NCCL communicator + gather staging (comm.cu)
   VgStats stats{};
 
   int fail(int code, const std::string& msg) {
@@ -183,4 +191,8 @@ void render_invalidate(vg_ctx* ctx);  // scene / frame / partition changed
 int render_set_scramble(vg_ctx* ctx, const uint64_t* table, int64_t npix);
 void render_destroy(vg_ctx* ctx);
 void build_scratch_destroy(vg_ctx* ctx);  // build_bvh.cu
+// comm.cu
+void comm_destroy(vg_ctx* ctx);
+int partition_stride(int tilesX, int world);
+void owned_pixels(int W, int H, int rank, int world, bool pixel_block, std::vector<int>& pix);  // tile-major pixel list of `rank`
 }  // namespace vg

@@ -334,6 +334,23 @@ void PolyMesh::triangulate() {
 // polymesh.go:73-97
 int PolyMesh::PreRender(Core& core, std::string* err) {
   if (Verts.MotionKeys < 1 || Verts.ElemsPerKey < 1) { *err = "PolyMesh " + NodeName + ": no Verts"; return -1; }
+  {
+    // init.go:12-134 indexes NormalIdx / UVIdx by FaceIdx position and ShaderIdx by polygon; Go panics on a short slice
+    // (bounds check), here the mesh is refused before anything is indexed
+    size_t nidx = hasFaceIdx ? FaceIdx.size() : (size_t)Verts.ElemsPerKey;
+    if (hasPolyCount) {
+      size_t sum = 0;
+      for (int32_t c : PolyCount) {
+        if (c < 0) { *err = "PolyMesh " + NodeName + ": negative PolyCount"; return -1; }
+        sum += (size_t)c;
+      }
+      if (!hasFaceIdx || sum > FaceIdx.size()) { *err = "PolyMesh " + NodeName + ": PolyCount sums to more indices than FaceIdx holds"; return -1; }
+      if (!ShaderIdx.empty() && ShaderIdx.size() < PolyCount.size()) { *err = "PolyMesh " + NodeName + ": ShaderIdx is shorter than PolyCount"; return -1; }
+      nidx = sum;
+    }
+    if (!Normals.Elems.empty() && hasNormalIdx && NormalIdx.size() < nidx) { *err = "PolyMesh " + NodeName + ": NormalIdx is shorter than FaceIdx"; return -1; }
+    if (!UV.empty() && hasUVIdx && UVIdx.size() < nidx) { *err = "PolyMesh " + NodeName + ": UVIdx is shorter than FaceIdx"; return -1; }
+  }
   triangulate();
   if (idxp.size() % 3 != 0) { *err = "PolyMesh " + NodeName + ": index count is not a multiple of 3"; return -1; }
   for (uint32_t i : idxp)
@@ -342,6 +359,12 @@ int PolyMesh::PreRender(Core& core, std::string* err) {
   for (uint32_t i : uvtriidx)
     if ((size_t)i * 2 + 1 >= UV.size()) { *err = "PolyMesh " + NodeName + ": UV index out of range"; return -1; }
   facecount = (int)idxp.size() / 3;
+  if (!normalidx.empty() && normalidx.size() != idxp.size()) { *err = "PolyMesh " + NodeName + ": NormalIdx does not match FaceIdx"; return -1; }
+  for (uint32_t i : normalidx)
+    if ((size_t)i >= Normals.Elems.size()) { *err = "PolyMesh " + NodeName + ": normal index out of range"; return -1; }
+  if (!shaderidx.empty() && shaderidx.size() != (size_t)facecount) { *err = "PolyMesh " + NodeName + ": ShaderIdx does not give one shader per face"; return -1; }
+  for (uint8_t i : shaderidx)
+    if ((size_t)i >= Shader.size()) { *err = "PolyMesh " + NodeName + ": ShaderIdx value beyond the Shader list"; return -1; }
   for (const std::string& s : Shader) {
     Node* n = core.FindNode(s);
     if (!n) { *err = "Unable to find node (shader " + s + ")"; return -1; }

@@ -46,7 +46,7 @@ inline size_t trace_smem_bytes(int variant) { return (size_t)(kTraceBlock / 32) 
 
 // kernels_trace.cu
 cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d_hits, long long n, bool any_hit, int variant,
-                               unsigned long long* d_counter, unsigned long long* d_stats, int grid, cudaStream_t stream);
+                               unsigned long long* d_counter, unsigned long long* d_stats, int grid, cudaStream_t stream, bool compact = false);
 int trace_batch_blocks_per_sm();
 
 }  // namespace vg

@@ -15,6 +15,7 @@ struct BatchIO {
   VgHit* hits;
   long long n;
   unsigned long long* counter;
+  int compact;  // VG_TRACE_COMPACT_HITS: 16-byte records {t, u, v, slot}
   __device__ __forceinline__ long long fetch(int c) { return (long long)atomicAdd(counter, (unsigned long long)c); }
   __device__ __forceinline__ long long size() const { return n; }
   __device__ __forceinline__ const VgRay* ray_ptr() const { return rays; }
@@ -27,6 +28,10 @@ struct BatchIO {
     r.time = b.w;
   }
   __device__ __forceinline__ void store(long long i, const RayState& r, const HitState& h, bool overflow) const {
+    if (compact) {
+      reinterpret_cast<float4*>(hits)[i] = make_float4(r.tclosest, h.u, h.v, __int_as_float(overflow ? -2 : (h.prim == -1 ? -1 : h.slot)));
+      return;
+    }
     float4* hp = reinterpret_cast<float4*>(hits + i);
     hp[0] = make_float4(r.tclosest, h.u, h.v, h.w);
     reinterpret_cast<int4*>(hp)[1] = make_int4(overflow ? -2 : h.prim, h.geom, h.nodesT, h.trisT);
@@ -38,7 +43,7 @@ template <bool ANY_HIT, int VARIANT>
 // default of vg_trace_batch: a persistent kernel that fits fewer CTAs just leaves the surplus ones to find the counter exhausted
 __global__ void __launch_bounds__(kTraceBlock, ((VARIANT & 2) && !(VARIANT & 64)) ? VG_TRACE_MIN_BLOCKS_BATCH_COOP : VG_TRACE_MIN_BLOCKS) k_trace_batch(const DevScene sc, const VgRay* __restrict__ rays, VgHit* __restrict__ hits,
                                                              long long n, unsigned long long* __restrict__ counter,
-                                                             unsigned long long* __restrict__ stats) {
+                                                             unsigned long long* __restrict__ stats, int compact) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [warps x warp_smem_bytes(VARIANT) (TMA ray slots + mbarriers, or cooperative-leaf blocks)] [threads x VG_SMEM_STACK stack entries]
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
@@ -47,7 +52,7 @@ __global__ void __launch_bounds__(kTraceBlock, ((VARIANT & 2) && !(VARIANT & 64)
   st.stride = blockDim.x;
   const int lane = threadIdx.x & 31;
   unsigned long long nodes_acc = 0, tris_acc = 0;
-  BatchIO io{rays, hits, n, counter};
+  BatchIO io{rays, hits, n, counter, compact};
   trace_persistent<ANY_HIT, VARIANT>(sc, io, st, smem_raw + warp * warp_smem_bytes(VARIANT), nodes_acc, tris_acc);
   // warp-aggregated statistics (core/stats.go keeps global atomics per ray; one atomic per warp here)
   for (int o = 16; o > 0; o >>= 1) {
@@ -61,10 +66,10 @@ __global__ void __launch_bounds__(kTraceBlock, ((VARIANT & 2) && !(VARIANT & 64)
 }
 
 cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d_hits, long long n, bool any_hit, int variant,
-                               unsigned long long* d_counter, unsigned long long* d_stats, int grid, cudaStream_t stream) {
+                               unsigned long long* d_counter, unsigned long long* d_stats, int grid, cudaStream_t stream, bool compact) {
   cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
-#define VG_LAUNCH(A, V) k_trace_batch<A, V><<<grid, kTraceBlock, trace_smem_bytes(V), stream>>>(sc, d_rays, d_hits, n, d_counter, d_stats)
+#define VG_LAUNCH(A, V) k_trace_batch<A, V><<<grid, kTraceBlock, trace_smem_bytes(V), stream>>>(sc, d_rays, d_hits, n, d_counter, d_stats, compact ? 1 : 0)
   if (sc.n_xforms > 0) {  // instances: cooperative kernels with the transform enter/leave code (traverse.cuh: VARIANT & 16)
     if (any_hit) VG_LAUNCH(true, 26);
     else VG_LAUNCH(false, 26);

@@ -104,6 +104,8 @@ struct __align__(16) DevHit {
 struct RenderParams {
   DevScene sc;
   int xres, yres, nown, P;  // P = paths per batch
+  // path index <-> (owned pixel, iteration of the batch): see path_index()
+  int pm_B, pm_G, pm_nownB, pm_nitG, pm_A, pm_rem, niters;
   const int* pix;           // [nown] full-frame pixel index, tile-major
   const uint64_t* scr;      // [nown*6] rows in path order, or (scr_by_pixel) the caller's whole table [xres*yres*6] in raster order
   int scr_by_pixel;
@@ -141,6 +143,36 @@ struct RenderParams {
   unsigned long long* stats;  // [0] rays [1] shadow rays [2] nodesT [3] trisT (closest) [4] nodesT [5] trisT (shadow)
   float* fb;
 };
+
+// Path order inside a batch. A warp's 32 consecutive paths are B pixels x G iterations (B*G = 32): the samples of one pixel
+// at different iterations lie within one pixel of each other, so a 4x2-pixel x 4-iteration warp spans a quarter of the image
+// area an 8x4-pixel x 1-iteration warp does, stays in fewer BVH leaves, and so do the shadow rays spawned from its hits
+// (results are per (pixel, iteration) and do not depend on the order). `pix` enumerates a tile's pixels in Morton order
+// inside 8x4 blocks, so any B = 32, 16, 8, 4, 2 consecutive owned pixels form a compact block.
+// Region A: full pixel groups x full iteration groups, warp-sized cells; the remainders (nown % B pixels, niters % G
+// iterations) follow densely in iteration-major order, so queue slot == path stays a bijection on [0, nown*niters).
+__device__ __forceinline__ int path_index(const RenderParams& p, int own, int it) {
+  if (own < p.pm_nownB && it < p.pm_nitG) return (((it / p.pm_G) * (p.pm_nownB / p.pm_B) + own / p.pm_B) << 5) + (it % p.pm_G) * p.pm_B + own % p.pm_B;
+  if (it < p.pm_nitG) return p.pm_A + it * p.pm_rem + (own - p.pm_nownB);
+  return p.pm_A + p.pm_nitG * p.pm_rem + (it - p.pm_nitG) * p.nown + own;
+}
+__device__ __forceinline__ void path_decode(const RenderParams& p, int path, int& own, int& it) {
+  if (path < p.pm_A) {
+    const int cell = path >> 5, r = path & 31, nblk = p.pm_nownB / p.pm_B;
+    own = (cell % nblk) * p.pm_B + r % p.pm_B;
+    it = (cell / nblk) * p.pm_G + r / p.pm_B;
+    return;
+  }
+  int q = path - p.pm_A;
+  if (q < p.pm_nitG * p.pm_rem) {
+    it = q / p.pm_rem;
+    own = p.pm_nownB + q % p.pm_rem;
+    return;
+  }
+  q -= p.pm_nitG * p.pm_rem;
+  it = p.pm_nitG + q / p.nown;
+  own = q % p.nown;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_reset(int* counts, int q0) {
@@ -198,7 +230,8 @@ template <bool MOTION>
 __global__ void __launch_bounds__(256) k_raygen(const RenderParams p, int iter_base, int niters) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.nown * niters) return;
-  const int own = i % p.nown, it = i / p.nown;
+  int own, it;
+  path_decode(p, i, own, it);
   const int iter = iter_base + it + 1;  // render() receives iter+1 (render.go:192)
   const int pixel = p.pix[own];
   const int x = pixel % p.xres, y = pixel / p.xres;
@@ -811,7 +844,9 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
   if (active) {
     lambda = p.lambda[path];
     time = p.time[path];
-    const int own = path % p.nown;
+    int own, it;
+    path_decode(p, path, own, it);
+    I = (long long)(iter_base + it + 1);  // sample index I = ray.I = the 1-based iteration (render.go:123)
     build_context(p, h, time, c);
     // tangent frame, std.go:98-106
     f3 V = cross3(c.N, c.DdPdu);
@@ -827,8 +862,6 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
     scr0 = p.scr[srow * 6 + 4];
     scr1 = p.scr[srow * 6 + 5];
   }
-  // sample index I = ray.I = the 1-based iteration (render.go:123); path = it*nown + own
-  if (active) I = (long long)(iter_base + path / p.nown + 1);
 
   // ---- diffuse lobe: direct light with MIS (std.go:145-163, core/shader.go:203-402) ----
   const bool diffuse = active && m.diff_weight > 0.0f;
@@ -1047,7 +1080,7 @@ __global__ void __launch_bounds__(256) k_resolve_accumulate(const RenderParams p
   float* px = p.fb + (size_t)p.pix[own] * 3;
   float r = px[0], g = px[1], b = px[2];
   for (int it = 0; it < niters; it++) {
-    const float4 C = resolve_vertex(p, 0, it * p.nown + own);
+    const float4 C = resolve_vertex(p, 0, path_index(p, own, it));
     const float fi = (float)(iter_base + it + 1);
     r = (r * fi + C.x) / (fi + 1.0f);
     g = (g * fi + C.y) / (fi + 1.0f);
@@ -1063,7 +1096,7 @@ __global__ void __launch_bounds__(256) k_accumulate(const RenderParams p, int it
   float* px = p.fb + (size_t)p.pix[own] * 3;
   float r = px[0], g = px[1], b = px[2];
   for (int it = 0; it < niters; it++) {
-    const int path = it * p.nown + own;
+    const int path = path_index(p, own, it);
     f3 C = mk3(0, 0, 0);
     for (int k = p.levels - 1; k >= 0; k--) {
       const float4 L = p.L[(size_t)k * p.P + path];
@@ -1114,6 +1147,9 @@ struct RenderState {
   int shadow_grid = 0, shadow_grid_mot = 0;  // the any-hit kernels may be compiled for another residency (VG_TRACE_MIN_BLOCKS_SHADOW)
   int max_light_samples = 0;
   bool scr_by_pixel = false;  // the device holds the caller's whole scramble table in raster order (pinned fast path)
+  // which rows rs.scr holds: valid only for this (frame, partition, pixel order); scr_valid is cleared when rs.scr is dropped
+  bool scr_valid = false;
+  int scr_w = 0, scr_h = 0, scr_rank = 0, scr_world = 0, scr_pixel_block = 0;
   bool generic = false;  // shade with k_shade_generic (glossy lobe / conductor Fresnel / Disk or Sphere lights / sphere geoms)
   int nlobes = 1;
   std::vector<int> pix_host;
@@ -1122,7 +1158,10 @@ struct RenderState {
   float* fb_pinned = nullptr;
   size_t fb_pinned_bytes = 0;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  std::vector<cudaEvent_t> evpool;  // pairs around every traversal launch (per-kernel device time for the roofline)
+  // Events around the traversal and shading launches (per-stage device time for the roofline). A fixed pool: a call that
+  // launches more than kMaxTimed stages leaves the later ones untimed (VgStats says how many were timed).
+  static const size_t kMaxTimedEvents = 4096;
+  std::vector<cudaEvent_t> evpool;
   cudaEvent_t ev(size_t i) {
     while (evpool.size() <= i) {
       cudaEvent_t e;
@@ -1219,7 +1258,18 @@ static bool is_pinned_host(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
+static int upload_scramble_rows(vg_ctx* ctx, const uint64_t* table);
 static int upload_scramble(vg_ctx* ctx, const uint64_t* table) {
+  RenderState& rs = *ctx->rs;
+  rs.scr_valid = false;
+  const int rc = upload_scramble_rows(ctx, table);
+  if (rc == VG_OK) {
+    rs.scr_valid = true;
+    rs.scr_w = ctx->xres; rs.scr_h = ctx->yres; rs.scr_rank = ctx->rank; rs.scr_world = ctx->world; rs.scr_pixel_block = ctx->opt_pixel_block;
+  }
+  return rc;
+}
+static int upload_scramble_rows(vg_ctx* ctx, const uint64_t* table) {
   RenderState& rs = *ctx->rs;
   if (rs.nown == 0) return VG_OK;
   rs.scr_by_pixel = false;
@@ -1304,30 +1354,9 @@ static int prepare(vg_ctx* ctx) {
   const int W = ctx->xres, H = ctx->yres;
   if ((int64_t)ctx->scramble.size() != (int64_t)W * H * 6) return ctx->fail(VG_ERR_INVALID, "scramble table missing or of the wrong size (vg_set_scramble)");
 
-  // owned pixels: the reference's 32x32 tiles (render.go:196-199), tile (tx,ty) -> rank (tx + ty*k) % world, k odd
-  const int tilesX = (W + 31) / 32, tilesY = (H + 31) / 32;
-  const int k = (tilesX % 2 == 0) ? tilesX + 1 : tilesX;  // row-major tile index when world divides nothing in common
+  // owned pixels: the reference's 32x32 tiles (render.go:196-199) dealt round-robin over the ranks (comm.cu: owned_pixels)
   std::vector<int> pix;
-  for (int ty = 0; ty < tilesY; ty++)
-    for (int tx = 0; tx < tilesX; tx++) {
-      if ((tx + ty * k) % ctx->world != ctx->rank) continue;
-      // Path order inside a tile decides which 32 camera rays share a warp. 8x4 pixel blocks keep a warp's rays (and the
-      // shadow rays spawned from their hits) in fewer BVH leaves than a 32x1 row does; results are per pixel and do not
-      // depend on this order.
-      if (ctx->opt_pixel_block) {
-        for (int b = 0; b < 32; b++)
-          for (int l = 0; l < 32; l++) {
-            const int x = tx * 32 + (b & 3) * 8 + (l & 7), y = ty * 32 + (b >> 2) * 4 + (l >> 3);
-            if (x < W && y < H) pix.push_back(x + y * W);
-          }
-      } else {
-        for (int j = 0; j < 32; j++)
-          for (int i = 0; i < 32; i++) {
-            const int x = tx * 32 + i, y = ty * 32 + j;
-            if (x < W && y < H) pix.push_back(x + y * W);
-          }
-      }
-    }
+  owned_pixels(W, H, ctx->rank, ctx->world, ctx->opt_pixel_block != 0, pix);
   rs.nown = (int)pix.size();
   rs.pix_host = pix;
 
@@ -1417,6 +1446,10 @@ static int prepare(vg_ctx* ctx) {
     const size_t per_path = 230 + (textured ? sizeof(DevMat) + 48 : 0) + (size_t)S * rs.nlobes * 52 + (size_t)rs.levels * 32 + (size_t)std::max(1, (int)lights.size()) * rs.nlobes * 4;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = (size_t)16 << 30;
+    // the wavefront buffers of an earlier prepare() are re-used (DevBuf::reserve keeps what is large enough): they count as free
+    free_b += rs.rayq0.cap * sizeof(VgRay) * 2 + rs.sray.cap * sizeof(VgRay) + (rs.pathq0.cap * 2 + rs.sslot.cap) * sizeof(int) +
+              rs.hits.cap * sizeof(DevHit) + (rs.invtot.cap + rs.diff.cap) * sizeof(float) + rs.vmat.cap +
+              (rs.contrib.cap + rs.L.cap + rs.T.cap) * sizeof(float4) + rs.vmats.cap * sizeof(DevMat);
     const size_t by_mem = (free_b / 10 * 8) / per_path / (size_t)std::max(1, rs.nown);
     const size_t by_idx = (((size_t)1 << 31) - 1) / ((size_t)S * rs.nlobes) / (size_t)std::max(1, rs.nown);
     const size_t cap = std::max<size_t>(1, std::min(by_mem, by_idx));
@@ -1458,7 +1491,11 @@ static int prepare(vg_ctx* ctx) {
     RCUDA(cudaMemcpyAsync(rs.filter.p, ctx->filter_cdf.data(), ctx->filter_cdf.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   }
   RCUDA(rs.pix.reserve(pix.size()));
-  RCUDA(rs.scr.reserve(ctx->world == 1 ? (size_t)W * H * 6 : (size_t)rs.nown * 6));
+  {
+    const size_t need = ctx->world == 1 ? (size_t)W * H * 6 : (size_t)rs.nown * 6;
+    if (need > rs.scr.cap) rs.scr_valid = false;  // reserve() reallocates: the rows on the device are gone
+    RCUDA(rs.scr.reserve(need));
+  }
   RCUDA(rs.mats.reserve(mats.size()));
   RCUDA(rs.lights.reserve(lights.size()));
   if (!pix.empty()) {
@@ -1502,18 +1539,46 @@ static int prepare(vg_ctx* ctx) {
   rs.shadow_grid = ctx->sm_count * std::max(1, nb);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_queue<1, 67>, kTraceBlock, trace_smem_bytes(67));
   rs.shadow_grid_mot = ctx->sm_count * std::max(1, nb);
+  // The scramble rows. The steady-state vg_set_scramble uploads straight from the caller's table and does not refresh the host
+  // copy (a 100 MB memcpy per frame); if the device still holds the rows of exactly this frame / partition / pixel order they
+  // are the latest ones and stay. Otherwise they are re-gathered from the host copy, which must then be current.
+  const bool resident = rs.scr_valid && rs.scr_w == W && rs.scr_h == H && rs.scr_rank == ctx->rank && rs.scr_world == ctx->world &&
+                        (rs.scr_by_pixel || rs.scr_pixel_block == ctx->opt_pixel_block);
+  if (!resident) {
+    if (ctx->scramble_stale) {
+      if (rs.scr_valid && rs.scr_by_pixel && rs.scr_w == W && rs.scr_h == H) {
+        // the device holds the caller's latest whole table: bring the host copy up to date from it
+        RCUDA(cudaMemcpyAsync(ctx->scramble.data(), rs.scr.p, (size_t)W * H * 48, cudaMemcpyDeviceToHost, ctx->stream));
+        RCUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->scramble_stale = false;
+      } else {
+        return ctx->fail(VG_ERR_INVALID, "the image partition or pixel order changed after a vg_set_scramble that went straight to the device: "
+                                         "call vg_set_scramble again");
+      }
+    }
+    rc = upload_scramble(ctx, ctx->scramble.data());
+    if (rc != VG_OK) return rc;
+  }
   rs.ready = true;
-  return upload_scramble(ctx, ctx->scramble.data());
+  return VG_OK;
 }
 
 int render_set_scramble(vg_ctx* ctx, const uint64_t* table, int64_t npix) {
   if ((int64_t)ctx->xres * ctx->yres != npix && ctx->xres > 0) return ctx->fail(VG_ERR_INVALID, "vg_set_scramble: table size != XRes*YRes");
   if (ctx->rs && ctx->rs->ready) {
-    // steady state: gather this context's rows straight from the caller's table into pinned memory and copy
-    if ((int64_t)ctx->scramble.size() != npix * 6) ctx->scramble.assign(table, table + (size_t)npix * 6);
+    // steady state: this context's rows go straight from the caller's table to the device. The host copy is NOT refreshed
+    // (100 MB per frame at 1080p); it is marked stale and prepare() either keeps the device rows or refuses to fall back on it.
+    if ((int64_t)ctx->scramble.size() != npix * 6) {
+      ctx->scramble.assign(table, table + (size_t)npix * 6);
+      ctx->scramble_stale = false;
+    } else {
+      ctx->scramble_stale = true;
+    }
     return upload_scramble(ctx, table);
   }
   ctx->scramble.assign(table, table + (size_t)npix * 6);
+  ctx->scramble_stale = false;
+  if (ctx->rs) ctx->rs->scr_valid = false;
   return VG_OK;
 }
 
@@ -1566,13 +1631,35 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
   const bool mot = ctx->dev.n_mtris > 0;    // kernels whose cooperative leaf phase takes motion triangles (VARIANT & 64)  // kernels that carry the analytic sphere leaf (traverse.cuh: VARIANT & 8)
   uint64_t launches = 0;
   size_t nev = 0;
-  std::vector<int> kinds;
+  struct Timed { int kind; size_t e0, e1; };  // kind 0 closest-hit traversal, 1 any-hit traversal, 2 shading (k_surface + k_shade*)
+  std::vector<Timed> timed;
+  bool untimed = false;
+  // one event between consecutive stages: the end of one stage is the start of the next
+  auto mark = [&]() -> size_t {
+    if (nev >= RenderState::kMaxTimedEvents) { untimed = true; return (size_t)-1; }
+    cudaEventRecord(rs.ev(nev), st);
+    return nev++;
+  };
+  auto stage = [&](int kind, size_t a, size_t b) {
+    if (a != (size_t)-1 && b != (size_t)-1) timed.push_back(Timed{kind, a, b});
+  };
   RCUDA(cudaMemsetAsync(rs.stats.p, 0, 8 * sizeof(unsigned long long), st));
   RCUDA(cudaEventRecord(rs.e0, st));
   if (rs.nown > 0) {
     for (int ib = iter_begin; ib < iter_end; ib += rs.iters) {
       const int niters = std::min(rs.iters, iter_end - ib);
       const int np = rs.nown * niters;
+      {
+        int G = 1;  // the largest power of two within the option, the warp size and this batch's iteration count
+        while (G * 2 <= ctx->opt_iter_group && G * 2 <= 32 && G * 2 <= niters) G *= 2;
+        p.pm_G = G;
+        p.pm_B = 32 / G;
+        p.pm_nownB = rs.nown - rs.nown % p.pm_B;
+        p.pm_nitG = niters - niters % G;
+        p.pm_A = p.pm_nownB * p.pm_nitG;
+        p.pm_rem = rs.nown - p.pm_nownB;
+        p.niters = niters;
+      }
       k_reset<<<1, 1, 0, st>>>(rs.counts.p, np);
       if (rs.levels > 1) {
         RCUDA(cudaMemsetAsync(rs.L.p, 0, (size_t)rs.P * rs.levels * sizeof(float4), st));
@@ -1586,7 +1673,16 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
       const int nlev = rs.levels == 1 ? 1 : (p.trace_last_level ? 5 : 4);
       for (int level = 0; level < nlev; level++) {
         const int qout = 1 - qin;
-        cudaEventRecord(rs.ev(nev++), st);
+        if (ctx->opt_capture_levels & (1 << level)) {
+          // debug / benchmarking aid: keep a host copy of this level's closest-hit input queue (vg_captured_rays)
+          int cnt = 0;
+          RCUDA(cudaMemcpyAsync(&cnt, rs.counts.p + qin, sizeof(int), cudaMemcpyDeviceToHost, st));
+          RCUDA(cudaStreamSynchronize(st));
+          const size_t old = ctx->captured.size();
+          ctx->captured.resize(old + (size_t)cnt);
+          if (cnt > 0) RCUDA(cudaMemcpy(ctx->captured.data() + old, p.rayq[qin], (size_t)cnt * sizeof(VgRay), cudaMemcpyDeviceToHost));
+        }
+        const size_t ev_a = mark();
         // camera rays are coherent: the per-lane loop with its compile-time axis specialisation is faster there (measured
         // 3.81 vs 3.48 Grays/s); every later level is incoherent and takes the cooperative leaf phase. Motion meshes are the
         // exception: their leaves cost 2-3x a static one (two keys to load and lerp), so the cooperative phase wins at level 0
@@ -1599,8 +1695,8 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
         else if (variant == 1) k_trace_queue<0, 1><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(1), st>>>(p, qin);
         else if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 2><<<rs.coop_grid, kTraceBlock, trace_smem_bytes(2), st>>>(p, qin);
         else k_trace_queue<0, 0><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(0), st>>>(p, qin);
-        cudaEventRecord(rs.ev(nev++), st);
-        kinds.push_back(0);
+        const size_t ev_b = mark();
+        stage(0, ev_a, ev_b);
         launches++;
         if (level <= 3) {
           if (rs.textured) {
@@ -1620,7 +1716,8 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
             if (h1) k_shade<true, true><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
             else k_shade<true, false><<<(np + 127) / 128, 128, 0, st>>>(p, level, qin, qout, ib);
           }
-          cudaEventRecord(rs.ev(nev++), st);
+          const size_t ev_c = mark();
+          stage(2, ev_b, ev_c);
           if (xf) {
             if (ctx->opt_shadow_unordered) k_trace_queue<1, 27><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(27), st>>>(p, 0);
             else k_trace_queue<1, 26><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(26), st>>>(p, 0);
@@ -1632,11 +1729,11 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
             if (ctx->opt_shadow_unordered) k_trace_queue<1, 67><<<rs.shadow_grid_mot, kTraceBlock, trace_smem_bytes(67), st>>>(p, 0);
             else k_trace_queue<1, 66><<<rs.shadow_grid_mot, kTraceBlock, trace_smem_bytes(66), st>>>(p, 0);
           } else if (variant == 1) k_trace_queue<1, 1><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(1), st>>>(p, 0);
+          else if (variant == 2 && ctx->opt_shadow_per_lane) k_trace_queue<1, 0><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(0), st>>>(p, 0);
           else if (variant == 2 && ctx->opt_shadow_unordered) k_trace_queue<1, 3><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(3), st>>>(p, 0);
           else if (variant == 2) k_trace_queue<1, 2><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(2), st>>>(p, 0);
           else k_trace_queue<1, 0><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(0), st>>>(p, 0);
-          cudaEventRecord(rs.ev(nev++), st);
-          kinds.push_back(1);
+          stage(1, ev_c, mark());
           if (rs.levels > 1) {
             k_resolve<<<(np + 255) / 256, 256, 0, st>>>(p, level, qin);
             launches++;
@@ -1708,14 +1805,17 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
   float ms = 0;
   cudaEventElapsedTime(&ms, rs.e0, rs.e1);
   ctx->stats.render_ms = ms;
-  ctx->stats.closest_ms = 0;
-  ctx->stats.shadow_ms = 0;
-  for (size_t k = 0; k < kinds.size(); k++) {
+  // per-stage times and launch counts of THIS call (stages beyond the event pool are not timed; `untimed` says so)
+  ctx->stats.closest_ms = ctx->stats.shadow_ms = ctx->stats.shade_ms = 0;
+  ctx->stats.closest_launches = ctx->stats.shadow_launches = 0;
+  for (const Timed& k : timed) {
     float t = 0;
-    cudaEventElapsedTime(&t, rs.ev(2 * k), rs.ev(2 * k + 1));
-    if (kinds[k] == 0) { ctx->stats.closest_ms += t; ctx->stats.closest_launches++; }
-    else { ctx->stats.shadow_ms += t; ctx->stats.shadow_launches++; }
+    cudaEventElapsedTime(&t, rs.ev(k.e0), rs.ev(k.e1));
+    if (k.kind == 0) { ctx->stats.closest_ms += t; ctx->stats.closest_launches++; }
+    else if (k.kind == 1) { ctx->stats.shadow_ms += t; ctx->stats.shadow_launches++; }
+    else ctx->stats.shade_ms += t;
   }
+  (void)untimed;
   ctx->stats.rays += hstats[0];
   ctx->stats.shadow_rays += hstats[1];
   ctx->stats.nodes_t += hstats[2];

@@ -306,7 +306,8 @@ __global__ void __launch_bounds__(128, 4) k_shade_generic(const RenderParams p, 
   if (active) {
     const float lambda = p.lambda[path];
     time = p.time[path];
-    const int own = path % p.nown;
+    int own, it;
+    path_decode(p, path, own, it);
     if (h.xf > 0) {  // an instance left its transform in the context (instance.go:107-111)
       if (p.sc.geoms[h.geom].keys == 0) build_context_sphere(p, h, Ro, Rd, c);  // (its own re-normalisations are idempotent)
       else build_context<false>(p, h, time, c);
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(128, 4) k_shade_generic(const RenderParams p, 
     const size_t srow = p.scr_by_pixel ? (size_t)p.pix[own] : (size_t)own;
     scr0 = p.scr[srow * 6 + 4];
     scr1 = p.scr[srow * 6 + 5];
-    I = (long long)(iter_base + path / p.nown + 1);
+    I = (long long)(iter_base + it + 1);
   }
 
   for (int lobe = 0; lobe < p.nlobes; lobe++) {

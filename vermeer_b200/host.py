@@ -24,6 +24,8 @@ MNODE_DTYPE = np.dtype([("Axis0", np.int32), ("Axis1", np.int32), ("Axis2", np.i
                         ("Parent", np.int32), ("pad", np.uint32, 2)])
 
 VG_TRACE_ANY_HIT = 1
+VG_TRACE_COMPACT_HITS = 2
+HITC_DTYPE = np.dtype([("t", np.float32), ("u", np.float32), ("v", np.float32), ("slot", np.int32)])
 
 # every symbol include/vermeer_gpu.h declares (tests check the library exports all of them)
 DECLARED_SYMBOLS = [
@@ -31,6 +33,7 @@ DECLARED_SYMBOLS = [
     "vg_sphere_upload", "vg_instance_upload", "vg_scene_upload", "vg_scene_upload_motion", "vg_scene_commit", "vg_set_materials", "vg_set_lights", "vg_set_area_lights", "vg_set_camera", "vg_set_camera_motion", "vg_set_frame",
     "vg_set_partition", "vg_set_scramble", "vg_set_filter", "vg_set_option", "vg_trace_batch", "vg_trace_batch_device", "vg_render", "vg_clear_framebuffer",
     "vg_framebuffer_device", "vg_get_stats", "vg_reset_stats",
+    "vg_comm_unique_id", "vg_comm_init", "vg_comm_destroy", "vg_gather_frame", "vg_nccl_version", "vg_owned_pixels", "vg_measure_peaks", "vg_slot_table", "vg_captured_rays",
     "vg_texture_upload", "vg_textures_clear", "vg_texture_levels", "vg_texture_read_level", "vg_material_set_texture", "vg_mesh_set_uv", "vg_texture_sample_batch",
     "vh_add_texture", "vh_shader_set_texture", "vh_polymesh_set_uv", "vg_build_qbvh", "vg_build_qbvh_nodes", "vh_prerender_device",
     "vh_scene_create", "vh_scene_destroy", "vh_last_error", "vh_registered_nodes", "vh_set_globals", "vh_add_shader_std", "vh_add_shader_debug", "vh_add_polymesh",
@@ -54,7 +57,17 @@ class VgStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("nodes_t", C.c_uint64), ("tris_t", C.c_uint64),
                 ("shadow_nodes_t", C.c_uint64), ("shadow_tris_t", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("closest_launches", C.c_uint64), ("shadow_launches", C.c_uint64),
-                ("render_ms", C.c_double), ("trace_ms", C.c_double), ("closest_ms", C.c_double), ("shadow_ms", C.c_double)]
+                ("render_ms", C.c_double), ("trace_ms", C.c_double), ("closest_ms", C.c_double), ("shadow_ms", C.c_double),
+                ("shade_ms", C.c_double), ("gather_ms", C.c_double)]
+
+
+class VgPeaks(C.Structure):
+    _fields_ = [("hbm_read_gbs", C.c_double), ("l2_read_gbs", C.c_double), ("l1_read_gbs", C.c_double),
+                ("hbm_buffer_bytes", C.c_double), ("l2_buffer_bytes", C.c_double), ("l1_window_bytes", C.c_double),
+                ("sm_count", C.c_int32), ("pad_", C.c_int32)]
+
+
+VG_COMM_ID_BYTES = 128
 
 
 _LIB = None
@@ -338,13 +351,35 @@ class Device:
     def set_option(self, name: str, value: int):
         self._chk(self.L.vg_set_option(self.h, name.encode(), int(value)))
 
-    def trace(self, rays: np.ndarray, any_hit: bool = False, out: np.ndarray | None = None) -> np.ndarray:
-        """vg_trace_batch with HOST buffers (H2D + kernel + D2H inside the call)."""
+    def trace(self, rays: np.ndarray, any_hit: bool = False, out: np.ndarray | None = None, compact: bool = False) -> np.ndarray:
+        """vg_trace_batch with HOST buffers (H2D + kernel + D2H inside the call). compact: 16-byte VgHitCompact records."""
         if not (isinstance(rays, np.ndarray) and rays.dtype == RAY_DTYPE and rays.flags.c_contiguous):
             rays = np.ascontiguousarray(rays, RAY_DTYPE)      # (a page-locked array passes through untouched)
-        hits = np.empty(len(rays), HIT_DTYPE) if out is None else out
-        self._chk(self.L.vg_trace_batch(self.h, _p(rays), C.c_int64(len(rays)), _p(hits), C.c_uint32(VG_TRACE_ANY_HIT if any_hit else 0)))
+        hits = np.empty(len(rays), HITC_DTYPE if compact else HIT_DTYPE) if out is None else out
+        flags = (VG_TRACE_ANY_HIT if any_hit else 0) | (VG_TRACE_COMPACT_HITS if compact else 0)
+        self._chk(self.L.vg_trace_batch(self.h, _p(rays), C.c_int64(len(rays)), _p(hits), C.c_uint32(flags)))
         return hits
+
+    def slot_table(self):
+        """vg_slot_table: (prim_of_slot, geom_of_slot) for the static triangle slots compact hits refer to."""
+        self.L.vg_slot_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        n = self.L.vg_slot_table(self.h, None, None, 0)
+        if n < 0:
+            self._chk(n)
+        prim, geom = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        if self.L.vg_slot_table(self.h, _p(prim), _p(geom), n) < 0:
+            self._chk(-1)
+        return prim, geom
+
+    def captured_rays(self) -> np.ndarray:
+        """vg_captured_rays: the ray queues kept by the "capture_levels" option, as a VgRay array."""
+        self.L.vg_captured_rays.restype = C.c_int64
+        self.L.vg_captured_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        n = self.L.vg_captured_rays(self.h, None, 0)
+        out = np.zeros(n, RAY_DTYPE)
+        if n:
+            self.L.vg_captured_rays(self.h, _p(out), n)
+        return out
 
     def trace_device(self, d_rays_ptr: int, n: int, d_hits_ptr: int, any_hit: bool = False):
         """vg_trace_batch_device: rays/hits already resident in HBM (raw device pointers, e.g. torch .data_ptr())."""
@@ -411,6 +446,32 @@ class Device:
         self._chk(self.L.vg_texture_sample_batch(self.h, tex_id, 1 if trilinear else 0, _p(coords), C.c_int64(len(coords)), _p(out)))
         return out
 
+    # -- multi-GPU (vg_comm_*, vg_gather_frame) -----------------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        """Rank 0: the NCCL id every rank passes to comm_init (the caller distributes it)."""
+        buf = C.create_string_buffer(VG_COMM_ID_BYTES)
+        self._chk(self.L.vg_comm_unique_id(self.h, buf))
+        return buf.raw
+
+    def comm_init(self, rank: int, world: int, uid: bytes | None):
+        """Collective: NCCL communicator on this context's GPU + the image partition of set_partition(rank, world)."""
+        buf = C.create_string_buffer(uid, VG_COMM_ID_BYTES) if uid is not None else None
+        self._chk(self.L.vg_comm_init(self.h, rank, world, buf))
+
+    def gather_frame(self, out: np.ndarray | None = None):
+        """Collective: owned pixels -> rank 0 (NCCL send/recv + the library's own pack/scatter kernels); rank 0 receives the
+        complete frame in `out` (yres, xres, 3) float32."""
+        if out is not None:
+            assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (self.yres, self.xres, 3)
+        self._chk(self.L.vg_gather_frame(self.h, _p(out)))
+        return out
+
+    def measure_peaks(self) -> dict:
+        """Streaming-read bandwidth of HBM, L2 and L1 on this GPU (csrc/peaks.cu)."""
+        pk = VgPeaks()
+        self._chk(self.L.vg_measure_peaks(self.h, C.byref(pk)))
+        return {k: getattr(pk, k) for k, _ in VgPeaks._fields_ if k != "pad_"}
+
     def stats(self) -> dict:
         s = VgStats()
         self._chk(self.L.vg_get_stats(self.h, C.byref(s)))
@@ -422,3 +483,15 @@ class Device:
 
 def device_count() -> int:
     return load_library().vg_device_count()
+
+
+def owned_pixels(xres: int, yres: int, rank: int, world: int, pixel_block: bool = True) -> np.ndarray:
+    """vg_owned_pixels: the library's own tile-major pixel list of `rank` (host code, no GPU needed)."""
+    L = load_library()
+    L.vg_owned_pixels.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64]
+    n = L.vg_owned_pixels(xres, yres, rank, world, 1 if pixel_block else 0, None, 0)
+    if n < 0:
+        raise ValueError("vg_owned_pixels: bad arguments")
+    out = np.zeros(n, np.int32)
+    L.vg_owned_pixels(xres, yres, rank, world, 1 if pixel_block else 0, _p(out), n)
+    return out
