@@ -1,22 +1,35 @@
 #!/usr/bin/env python3
-"""bench.py — headline benchmark of the accelerated path (contract: see the task's bench section).
+"""bench.py — the benchmark of the accelerated path (contract: the task's bench section + SURVEY.md 8d).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-cpu] [--configs c1,c2,c3,c4]
 
-Workload (BASELINE.json configs[1], "C2"): synthetic 1M-triangle tessellated mesh (2*708^2 = 1 002 528
-triangles, one PolyMesh + one TriLight pair), primary + shadow rays, 1920x1080, 64 spp.
-One STEP = one full pass of the hot path over the frame: 64 iterations of
-ray generation -> closest-hit traversal -> ShaderStd/light sampling -> any-hit traversal -> accumulation.
+BASELINE.json's metric is "Mrays/s (closest-hit, incoherent) and samples/sec at 1/2/4/8 B200 vs host CPU", quoted on the
+1M-triangle config. The ONE JSON line this prints therefore has
 
-metric  : Mrays/s by the reference's definition (core/stats.go:21-24): every TraceProbe (camera + shadow +
-          reflected) / time of the render loop, shading included.  Whole job over all N GPUs.
-value   : inputs (scene, per-pixel scramble table) already resident in HBM; device time.
-e2e     : the same metric through the C ABI with HOST buffers: every step copies the scramble table
-          host->device (vg_set_scramble) and the finished framebuffer device->host (vg_render fb_out).
-roofline: the dominant kernel (closest-hit traversal k_trace_queue<0>), algorithmic bytes
-          64 + 128*NodesT + 48*TrisT per ray / its CUDA-event time, vs measured HBM peak.
-cpu_baseline: the oracle (C++ restatement of the reference path; the Go reference cannot be built here)
-          on the box's host cores, bounded sample of the same workload.
+  value / metric   closest-hit traversal of an INCOHERENT ray batch on the 1M-triangle scene (configs[1]): cosine-hemisphere
+                   bounce rays from the primary hit points, shuffled, identical rays on GPU and CPU. One STEP = one
+                   TraceProbe pass (core/trace.go:26) over the whole batch, rays and hits resident in HBM
+                   (vg_trace_batch_device); device time from CUDA events around the kernel. At N GPUs every rank traces a
+                   batch of its own (independent rays, no collective): weak scaling.
+  e2e              the same pass through vg_trace_batch with page-locked HOST buffers: H2D of the rays, traversal and D2H of
+                   the hits inside the timed call (VG_TRACE_COMPACT_HITS, 16-byte hits; the 32-byte VgHit figure is beside it).
+  frame            the other half of the metric, samples/s: the whole hot path on the same scene (ray generation ->
+                   closest-hit -> ShaderStd/light sampling -> any-hit -> accumulation), 1920x1080, 64 spp; Mrays/s by the
+                   reference's definition (core/stats.go:21-24: every TraceProbe / render-loop time). At N GPUs the frame
+                   is split by 32x32 tiles and gathered on rank 0 by the library (vg_gather_frame: NCCL): strong scaling.
+                   e2e = vg_set_scramble (H2D) + vg_render + gather + D2H of the frame, every step.
+  configs          the same frame measurement for every BASELINE.json config that fits the run: c1 (Cornell 512^2, 16 spp),
+                   c2, c3 (10M triangles, mirror chains, 256 spp), c4 (MQBVH, 2 keys) and, at 8 GPUs, c5 (4K, 1024 spp),
+                   each with its own cpu_baseline (short sample: it is a rate) and per-stage roofline.
+  incoherent_wavefront  a second, harder incoherent batch: the level-1..3 mirror-bounce rays of the 10M-triangle scene taken
+                   from the integrator's own ray queues (vg_captured_rays), shuffled; scene not L2-resident.
+  roofline         per traversal / shading stage: time per launch measured live (CUDA events inside vg_render), traffic per
+                   ray from the committed ncu capture of this build (profiles/ncu_r02_metrics.json: dram, L2 and L1TEX bytes),
+                   against HBM (MEASURED_PEAKS.json) and the L2 / L1 read peaks measured in this run (vg_measure_peaks);
+                   plus the issue-slot x SIMD-lane utilisation of the capture, the ceiling the ncu data says binds.
+  cpu_baseline     the oracle (C++ restatement of the reference path; the Go reference cannot be built here: no Go
+                   toolchain) on the box's host cores, bounded samples; `per_core` and the reference-faithful variant
+                   (min(10, cores) workers + two global atomic counters per ray: core/render.go:190, core/stats.go:26-33).
 """
 from __future__ import annotations
 
@@ -34,22 +47,24 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CONFIGS = {
-    # BASELINE.json configs[1] — the headline (default)
+    "c1": dict(workload="C1: Cornell box (5 diffuse walls, 2 boxes, quad light = 2 TriLights), 512x512, 16 spp", spp=16, xres=512, yres=512),
     "c2": dict(workload="C2: 1M-triangle heightfield (1002528 tris), primary+shadow rays, 1920x1080, 64 spp", spp=64),
-    # configs[2]: 10M-triangle displaced-sphere field, mirror chains Level 0..3 (the reference's "4 bounces"), 256 spp
     "c3": dict(workload="C3: 10M-triangle displaced-sphere field (1024 meshes x 9800 tris), mirror chains, 1920x1080, 256 spp", spp=256),
-    # configs[3]: motion-blurred mesh (MQBVH, 2 keys)
     "c4": dict(workload="C4: motion-blurred 1M-triangle heightfield (MQBVH, 2 keys), 1920x1080, 64 spp", spp=64),
-    # C2 with a Feline texture map on the ground's DiffuseColour: what the texture path costs on the headline scene
     "c2t": dict(workload="C2T: C2 with a 1024x1024 Feline texture map on the ground (UV = 8 tiles over the mesh), 1920x1080, 64 spp", spp=64),
-    # configs[4]: the C3 scene at 4K, 1024 spp, meant for 8 GPUs (tile-partitioned, NCCL framebuffer gather)
     "c5": dict(workload="C5: 10M-triangle displaced-sphere field, mirror chains, 3840x2160, 1024 spp", spp=1024, xres=3840, yres=2160),
 }
-CONFIG = os.environ.get("VG_BENCH_CONFIG", "c2")
-WORKLOAD = CONFIGS[CONFIG]["workload"]
-XRES, YRES, SPP, NQ = CONFIGS[CONFIG].get("xres", 1920), CONFIGS[CONFIG].get("yres", 1080), CONFIGS[CONFIG]["spp"], 708
+HEADLINE_WORKLOAD = ("C2-incoherent: closest-hit TraceProbe over cosine-hemisphere bounce rays from the primary hit points of the "
+                     "1M-triangle heightfield (1002528 tris), 4 jittered 1920x1080 primary passes, shuffled")
+METRIC = "Mrays/s (closest-hit, incoherent)"
+NQ = 708
 SCRAMBLE_SEED = 1
-ITERS_PER_BATCH = 16   # wavefront batch depth at N=1; scaled by N (capped at the frame's spp) so that a batch keeps ~33 M paths per GPU
+ITERS_PER_BATCH = 32   # wavefront batch depth at N=1 (a warp = one pixel x 32 iterations); scaled by N, capped at the frame's spp
+
+
+def cfg_res(cfg):
+    c = CONFIGS[cfg]
+    return c.get("xres", 1920), c.get("yres", 1080), c["spp"]
 
 
 def measured_peaks():
@@ -60,6 +75,14 @@ def measured_peaks():
         except Exception:
             pass
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def ncu_metrics():
+    p = os.path.join(ROOT, "profiles", "ncu_r02_metrics.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -74,7 +97,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -103,15 +126,31 @@ class ClockSampler:
                         reasons.add(name)
             except Exception:
                 continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        # the samples under load are the ones that matter: an idle GPU between legs reports its idle clock
+        hot = [s for s in sm if s >= 0.6 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(hot)) if hot else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_scene():
+# ------------------------------------------------------------------------------------------------------------------
+_SCENE_CACHE = {}
+
+
+def build_scene(cfg):
     from vermeer_b200 import scenes
-    if CONFIG in ("c3", "c5"):
-        return scenes.sphere_field_scene(XRES, YRES)
-    sc = scenes.heightfield_scene(XRES, YRES, nq=NQ, motion=(CONFIG == "c4"))
-    if CONFIG == "c2t":
+    xres, yres, _ = cfg_res(cfg)
+    key = ("c3" if cfg in ("c3", "c5") else cfg)
+    if cfg == "c1":
+        return scenes.cornell_box(xres, yres)
+    if cfg in ("c3", "c5"):
+        if key not in _SCENE_CACHE:
+            _SCENE_CACHE[key] = scenes.sphere_field_scene(xres, yres)
+        sc = _SCENE_CACHE[key]
+        sc.XRes, sc.YRes = xres, yres          # c5 is the c3 scene at 4K
+        if hasattr(sc.camera, "Aspect"):
+            sc.camera.Aspect = xres / yres
+        return sc
+    sc = scenes.heightfield_scene(xres, yres, nq=NQ, motion=(cfg == "c4"))
+    if cfg == "c2t":
         m = sc.meshes[0]
         xz = m.Verts[0][:, [0, 2]]
         m.UV = ((xz - xz.min(0)) / (xz.max(0) - xz.min(0)) * 8.0).astype(np.float32)
@@ -120,122 +159,340 @@ def build_scene():
     return sc
 
 
-def cpu_reference_run(scene, table, iters, nthreads):
-    """The oracle (reference-semantics CPU path) on `iters` iterations of the workload. Returns (Mrays/s, rays, seconds)."""
+def make_oracle(scene):
     from oracle.binding import Oracle
-    ora = Oracle(scene, motion_ref_compat=False)   # same MQBVH leaf mode as the device default ("fixed", DESIGN.md quirk b)
+    return Oracle(scene, motion_ref_compat=False)   # same MQBVH leaf mode as the device default ("fixed", DESIGN.md quirk b)
+
+
+def cpu_frame(scene, table, spp, cores, target_s, faithful=False):
+    """The oracle (reference-semantics CPU path) on a bounded number of iterations of the frame. faithful: the reference's own
+    worker policy, min(10, cores) workers and global atomic ray counters."""
+    ora = make_oracle(scene)
     ora.set_scramble(table)
-    _, st = ora.render(0, iters, nthreads=nthreads)
-    return st["rays"] / st["seconds"] / 1e6, st["rays"], st["seconds"]
+    nt = -cores if faithful else cores
+    _, st1 = ora.render(0, 1, nthreads=nt)                                     # probe (also builds the trees)
+    iters = int(min(spp, max(1, round(target_s / max(st1["seconds"], 1e-3)))))
+    st = st1
+    if iters > 1:
+        ora.clear()
+        _, st = ora.render(0, iters, nthreads=nt)
+    else:
+        iters = 1
+    v = st["rays"] / st["seconds"] / 1e6
+    workers = min(10, cores) if faithful else cores
+    return {"value": v, "unit": "Mrays/s", "cores": workers, "per_core": v / workers, "kind": "port",
+            "samples_per_s": scene.XRes * scene.YRes * iters / st["seconds"],
+            "sample": "%d iteration(s) (spp) of the same %dx%d workload on %d host threads%s: %d rays in %.2f s" % (
+                iters, scene.XRes, scene.YRes, workers, " (reference worker policy: min(10, cores) + global atomic counters)" if faithful else "",
+                st["rays"], st["seconds"])}
 
 
-def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path. The Go reference cannot be compiled in this
-    image (no Go toolchain), so this is the oracle port, all host threads, bounded sample per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    from vermeer_b200 import scenes
-    scene = build_scene()
-    table = scenes.splitmix64_table(SCRAMBLE_SEED, XRES * YRES)
-    from oracle.binding import Oracle
-    cores = os.cpu_count() or 1
-    ora = Oracle(scene, motion_ref_compat=False)   # same MQBVH leaf mode as the device default ("fixed", DESIGN.md quirk b)
-    ora.set_scramble(table)
-    sample_iters = 4
-    for _ in range(args.warmup):
-        ora.render(0, sample_iters, nthreads=cores)
-    rays = 0
-    secs = 0.0
-    for s in range(args.steps):
-        _, st = ora.render(s * sample_iters, (s + 1) * sample_iters, nthreads=cores)
-        rays += st["rays"]
-        secs += st["seconds"]
-    v = rays / secs / 1e6
-    sample = "%d iteration(s) (spp) of the 1920x1080 frame per step = %d rays/step" % (sample_iters, rays // max(1, args.steps))
-    out = {
-        "impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": secs / max(1, args.steps) * 1e3, "higher_is_better": True,
-        "scaling": "strong" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else "weak",   # the same label as the GPU arm at this N
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "samples_per_s": XRES * YRES * sample_iters * args.steps / secs,
-    }
-    print(json.dumps(out))
-
-
-def incoherent_leg(dev, host, scene, torch, cpu_cores):
-    """Mrays/s of closest-hit traversal alone on an incoherent batch: level-1 cosine-hemisphere rays from the primary hit points
-    of the C2 scene, identical rays on both sides. GPU: rays resident in HBM (vg_trace_batch_device) and through host buffers
-    (vg_trace_batch). CPU: the oracle's qbvh.Trace restatement on all host threads, bounded sample of the same batch."""
-    from vermeer_b200 import scenes
-    from vermeer_b200.host import HIT_DTYPE, RAY_DTYPE
-    cam_m, ttf, asp = host.camera()
+# ---- the incoherent closest-hit batch of the headline --------------------------------------------------------------
+def primary_rays(scene, cam, jx, jy):
+    from vermeer_b200.host import RAY_DTYPE
+    cam_m, ttf, asp = cam
     M = cam_m.reshape(4, 4).T
+    xres, yres = scene.XRes, scene.YRes
+    ys, xs = np.meshgrid(np.arange(yres), np.arange(xres), indexing="ij")
+    sx = (-1 + 2 * (xs + jx) / xres).astype(np.float32)
+    sy = -(-1 + 2 * (ys + jy) / yres).astype(np.float32)
+    d = np.stack([sx * ttf, sy * (ttf / asp), -np.full_like(sx, scene.camera.Focal)], -1).reshape(-1, 3) @ M[:3, :3].T
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r = np.zeros(xres * yres, RAY_DTYPE)
+    r["o"] = M[:3, 3]
+    r["d"] = d.astype(np.float32)
+    r["tmax"] = np.inf
+    return r
 
-    def primary(jx, jy):
-        ys, xs = np.meshgrid(np.arange(YRES), np.arange(XRES), indexing="ij")
-        sx = (-1 + 2 * (xs + jx) / XRES).astype(np.float32)
-        sy = -(-1 + 2 * (ys + jy) / YRES).astype(np.float32)
-        d = np.stack([sx * ttf, sy * (ttf / asp), -np.full_like(sx, scene.camera.Focal)], -1).reshape(-1, 3) @ M[:3, :3].T
-        d /= np.linalg.norm(d, axis=1, keepdims=True)
-        r = np.zeros(XRES * YRES, RAY_DTYPE)
-        r["o"] = M[:3, 3]
-        r["d"] = d.astype(np.float32)
-        r["tmax"] = np.inf
-        return r
 
-    # four jittered primary passes (4 spp) -> ~5.9 M bounce rays: large enough that the persistent kernel's ramp-up and tail
-    # (a 1.5 M-ray batch lasts 0.8 ms) do not dominate the rate
+def incoherent_batch(scene, cam, trace, seed0=5):
+    """Four jittered primary passes (4 spp) -> ~5.9 M bounce rays: large enough that the persistent kernel's ramp-up and tail do
+    not dominate the rate. `trace` = a closest-hit TraceProbe over a ray array (the GPU's or the oracle's: bit-identical)."""
+    from vermeer_b200 import scenes
     parts = []
     for s, (jx, jy) in enumerate([(0.5, 0.5), (0.25, 0.75), (0.75, 0.25), (0.1, 0.4)]):
-        prim = primary(jx, jy)
-        parts.append(scenes.incoherent_rays(prim, dev.trace(prim), seed=5 + s))
+        prim = primary_rays(scene, cam, jx, jy)
+        parts.append(scenes.incoherent_rays(prim, trace(prim), seed=seed0 + s))
     inc = np.concatenate(parts)
-    inc = inc[np.random.default_rng(1).permutation(len(inc))]      # shuffled: no residual image-space coherence
-    n = len(inc)
-    d_r = torch.from_numpy(inc.view(np.uint8).reshape(n, 32)).cuda()
-    d_h = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
-    best = 1e30
-    for i in range(8):
-        dev.reset_stats()
-        dev.trace_device(d_r.data_ptr(), n, d_h.data_ptr(), False)
-        st = dev.stats()
-        if i >= 3:
-            best = min(best, st["trace_ms"])
-    # e2e of this leg: rays and hits in page-locked host memory, H2D + traversal + D2H inside the timed call
-    inc_pinned = torch.from_numpy(inc.view(np.uint8).reshape(n, 32)).pin_memory().numpy().reshape(-1).view(RAY_DTYPE)
-    out_hits = torch.empty((n, 32), dtype=torch.uint8, pin_memory=True).numpy().reshape(-1).view(HIT_DTYPE)
-    dev.trace(inc_pinned, out=out_hits)
+    return inc[np.random.default_rng(seed0).permutation(len(inc))]      # shuffled: no residual image-space coherence
+
+
+def cpu_trace(scene, rays, cores, reps=1):
+    ora = make_oracle(scene)
+    ora.trace(rays[:65536], nthreads=cores)
     t0 = time.perf_counter()
-    for _ in range(3):
-        dev.trace(inc_pinned, out=out_hits)
-    e2e_ms = (time.perf_counter() - t0) / 3 * 1e3
-    res = {"rays": n, "value": n / best / 1e3, "unit": "Mrays/s", "e2e": n / e2e_ms / 1e3, "hit_fraction": float((out_hits["prim"] >= 0).mean()),
-           "nodesT_per_ray": st["nodes_t"] / n, "trisT_per_ray": st["tris_t"] / n,
-           "alg_gbs": (64.0 * n + 128.0 * st["nodes_t"] + 48.0 * st["tris_t"]) / best / 1e6}
-    if cpu_cores:
-        from oracle.binding import Oracle
-        ora = Oracle(scene, motion_ref_compat=False)   # same MQBVH leaf mode as the device default ("fixed", DESIGN.md quirk b)
-        sample = inc[: min(n, 1 << 20)]
-        ora.trace(sample[:65536], nthreads=cpu_cores)
+    for _ in range(reps):
+        hits = ora.trace(rays, nthreads=cores)
+    secs = (time.perf_counter() - t0) / reps
+    return hits, len(rays) / secs / 1e6, secs
+
+
+def time_batch(dev, torch, rays, steps, warmup, compact_e2e=True):
+    """Device-resident and host-buffer rates of one closest-hit pass over `rays`. Returns a dict."""
+    from vermeer_b200.host import HIT_DTYPE, HITC_DTYPE, RAY_DTYPE
+    n = len(rays)
+    d_r = torch.from_numpy(rays.view(np.uint8).reshape(n, 32)).cuda()
+    d_h = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
+    for _ in range(max(3, warmup)):
+        dev.trace_device(d_r.data_ptr(), n, d_h.data_ptr(), False)
+    dev.reset_stats()
+    ms = []
+    for _ in range(steps):
+        dev.trace_device(d_r.data_ptr(), n, d_h.data_ptr(), False)
+        ms.append(dev.stats()["trace_ms"])
+    st = dev.stats()
+    hits = d_h.cpu().numpy().reshape(-1).view(HIT_DTYPE)
+    # e2e: rays and hits in page-locked host memory, H2D + traversal + D2H inside the timed call
+    pin_r = torch.from_numpy(rays.view(np.uint8).reshape(n, 32)).pin_memory().numpy().reshape(-1).view(RAY_DTYPE)
+    pin_h = torch.empty((n, 32), dtype=torch.uint8, pin_memory=True).numpy().reshape(-1).view(HIT_DTYPE)
+    pin_c = torch.empty((n, 16), dtype=torch.uint8, pin_memory=True).numpy().reshape(-1).view(HITC_DTYPE)
+    e2e = {}
+    for name, out, compact in (("full", pin_h, False), ("compact", pin_c, True)):
+        if compact and not compact_e2e:
+            continue
+        try:
+            dev.trace(pin_r, out=out, compact=compact)
+        except RuntimeError:
+            continue     # scenes the compact record does not cover
         t0 = time.perf_counter()
-        oh = ora.trace(sample, nthreads=cpu_cores)
-        secs = time.perf_counter() - t0
-        same = bool(np.array_equal(oh["prim"], out_hits["prim"][: len(sample)]) and
-                    np.array_equal(oh["t"].view(np.uint32), out_hits["t"][: len(sample)].view(np.uint32)))
-        res["cpu"] = {"value": len(sample) / secs / 1e6, "cores": cpu_cores, "kind": "port", "sample": "%d of the same rays" % len(sample),
-                      "bit_identical_to_gpu": same}
+        reps = max(3, min(steps, 10))
+        for _ in range(reps):
+            dev.trace(pin_r, out=out, compact=compact)
+        e2e[name] = (time.perf_counter() - t0) / reps * 1e3
+    res = {"rays": n, "ms_per_step": float(np.mean(ms)), "ms_best": float(np.min(ms)), "device_ms_total": float(np.sum(ms)),
+           "hit_fraction": float((hits["prim"] >= 0).mean()),
+           "nodesT_per_ray": st["nodes_t"] / max(1, steps) / n, "trisT_per_ray": st["tris_t"] / max(1, steps) / n,
+           "e2e_ms": e2e, "hits": hits, "compact_hits": pin_c if "compact" in e2e else None}
     return res
 
 
+# ---- one frame config ---------------------------------------------------------------------------------------------
+class Rig:
+    pass
+
+
+def setup_frame(cfg, rank, world, local_rank, torch, dev=None):
+    from vermeer_b200 import scenes
+    from vermeer_b200.host import Device, HostScene
+    from vermeer_b200.multigpu import init_library_comm
+    r = Rig()
+    r.cfg = cfg
+    r.xres, r.yres, r.spp = cfg_res(cfg)
+    r.scene = build_scene(cfg)
+    t0 = time.time()
+    r.host = HostScene(r.scene).prerender()
+    r.prerender_s = time.time() - t0
+    r.dev = dev if dev is not None else Device(local_rank)
+    for k, v in [kv.split("=") for kv in os.environ.get("VG_OPTIONS", "").split(",") if kv]:   # options that act at upload (node_order)
+        r.dev.set_option(k, int(v))
+    t0 = time.time()
+    r.dev.upload(r.host)
+    r.upload_s = time.time() - t0
+    if world > 1:
+        if not getattr(r.dev, "_comm_ready", False):
+            init_library_comm(r.dev, rank, world)
+            r.dev._comm_ready = True
+        else:
+            r.dev.set_partition(rank, world)
+    # the step's host-side input (per-pixel scramble table) and output (frame) live in page-locked host memory, as the bench
+    # contract asks; the library DMAs from/to such buffers directly
+    r.table_t = torch.from_numpy(scenes.splitmix64_table(SCRAMBLE_SEED, r.xres * r.yres).view(np.int64)).pin_memory()
+    r.table = r.table_t.numpy().view(np.uint64)
+    r.frame_t = torch.empty((r.yres, r.xres, 3), dtype=torch.float32, pin_memory=True)
+    r.frame = r.frame_t.numpy()
+    r.dev.set_scramble(r.table)
+    # ~66 M paths per GPU and batch whatever the frame size and world
+    r.iters_per_batch = int(min(r.spp, 64, max(1, round(ITERS_PER_BATCH * world * (1920 * 1080) / (r.xres * r.yres)))))
+    r.dev.set_option("iters_per_batch", r.iters_per_batch)
+    for k, v in [kv.split("=") for kv in os.environ.get("VG_OPTIONS", "").split(",") if kv]:   # tuning experiments, e.g. VG_OPTIONS=traversal=0
+        r.dev.set_option(k, int(v))
+    return r
+
+
+def frame_leg(r, steps, warmup, rank, world, torch, dist):
+    """K timed steps with the inputs resident in HBM (device time, max over ranks), then K steps end to end with host buffers."""
+    dev, spp = r.dev, r.spp
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        dev.clear()
+        dev.render(0, spp, fetch=False)
+    dev.reset_stats()
+    barrier()
+    t0 = time.perf_counter()
+    acc = dict(render_ms=0.0, closest_ms=0.0, shadow_ms=0.0, shade_ms=0.0, closest_launches=0, shadow_launches=0)
+    for _ in range(steps):
+        dev.clear()
+        dev.render(0, spp, fetch=False)
+        st = dev.stats()
+        for k in acc:
+            acc[k] += st[k]
+    barrier()
+    wall = time.perf_counter() - t0
+    st = dev.stats()
+    tvec = torch.tensor([acc["render_ms"], wall * 1e3], dtype=torch.float64, device="cuda")
+    rvec = torch.tensor([float(st["rays"]), float(st["shadow_rays"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tvec, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rvec, op=dist.ReduceOp.SUM)
+    dev_ms, wall_ms = float(tvec[0]), float(tvec[1])
+    rays_total, shadow_total = float(rvec[0]), float(rvec[1])
+
+    # ---- e2e: host buffers every step; N > 1: the library's gather (NCCL) brings the owned pixels to rank 0 ---------
+    def step_e2e():
+        dev.set_scramble(r.table)       # H2D of this rank's rows of the scramble table, from the caller's host buffer
+        dev.clear()
+        if world > 1:
+            dev.render(0, spp, fetch=False)
+            dev.gather_frame(r.frame if rank == 0 else None)   # pack + ncclSend/Recv + scatter + D2H of the complete frame on rank 0
+        else:
+            dev.render(0, spp, out=r.frame)                    # D2H of the frame into the caller's host buffer
+
+    for _ in range(2):
+        step_e2e()
+    dev.reset_stats()
+    barrier()
+    t0 = time.perf_counter()
+    gather_ms = 0.0
+    for _ in range(steps):
+        step_e2e()
+        if world > 1:
+            gather_ms += dev.stats()["gather_ms"]
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    st2 = dev.stats()
+    evec = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+    r2 = torch.tensor([float(st2["rays"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(evec, op=dist.ReduceOp.MAX)
+        dist.all_reduce(r2, op=dist.ReduceOp.SUM)
+    e2e_s = float(evec[0])
+    npix = r.xres * r.yres
+    out = {
+        "value": rays_total / (dev_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": dev_ms / steps, "wall_ms_per_step": wall_ms / steps,
+        "samples_per_s": npix * spp * steps / (dev_ms * 1e-3), "steps": steps,
+        "rays_per_step": rays_total / steps, "shadow_rays_per_step": shadow_total / steps,
+        "stage_ms_per_step": {"closest_traversal": acc["closest_ms"] / steps, "shadow_traversal": acc["shadow_ms"] / steps, "shading": acc["shade_ms"] / steps,
+                              "raygen_resolve_accumulate": (acc["render_ms"] - acc["closest_ms"] - acc["shadow_ms"] - acc["shade_ms"]) / steps},
+        "e2e": {"value": float(r2[0]) / e2e_s / 1e6, "unit": "Mrays/s", "samples_per_s": npix * spp * steps / e2e_s, "ms_per_step": e2e_s * 1e3 / steps,
+                "h2d_bytes_per_step": (npix // world) * 48, "d2h_bytes_per_step": npix * 12,
+                "gather_ms_per_step": gather_ms / steps if world > 1 else None},
+        "scaling": "strong", "iters_per_batch": r.iters_per_batch, "trig": "fast (float32 libm; precise_trig=0)",
+        "gpu_launches": int(st["kernel_launches"]),
+        "_rank": dict(st=st, acc=acc, steps=steps),
+    }
+    return out
+
+
+def stage_roofline(cfg, frame, peaks, hbm_peak, hbm_src, ncu):
+    """Per stage: live time per launch x traffic per ray from the ncu capture of this build -> achieved GB/s at each memory
+    level against the measured peak of that level; plus the issue x SIMD ceiling of the capture."""
+    st, acc, steps = frame["_rank"]["st"], frame["_rank"]["acc"], frame["_rank"]["steps"]
+    cap = ncu.get("c3" if cfg in ("c3", "c5") else cfg, {})
+    closest_rays = st["rays"] - st["shadow_rays"]
+    bn, bt = (232.0, 84.0) if cfg == "c4" else (128.0, 48.0)   # SURVEY.md 8d: algorithmic bytes per node visit / triangle test
+    stages = {}
+    spec = [("shadow", "shadow_ms", st["shadow_rays"], st["shadow_nodes_t"], st["shadow_tris_t"], acc["shadow_launches"]),
+            ("closest", "closest_ms", closest_rays, st["nodes_t"], st["tris_t"], acc["closest_launches"]),
+            ("shade", "shade_ms", closest_rays, 0, 0, acc["closest_launches"])]
+    for name, key, rays, nodes_t, tris_t, launches in spec:
+        ms = acc[key]
+        if ms <= 0 or rays <= 0:
+            continue
+        launches = max(1, launches)
+        e = {"ms_per_launch": ms / launches, "units_per_launch": rays / launches, "unit_name": "rays" if name != "shade" else "path vertices",
+             "share_of_step": ms / acc["render_ms"]}
+        if name != "shade":
+            alg = 64.0 * rays + bn * nodes_t + bt * tris_t
+            e["nodesT_per_ray"] = nodes_t / rays
+            e["trisT_per_ray"] = tris_t / rays
+            e["algorithmic"] = {"bytes_per_ray": alg / rays, "gbs": alg / (ms * 1e-3) / 1e9,
+                                "note": "SURVEY.md 8d bytes model (64 + %g*NodesT + %g*TrisT per ray): mostly served by L1/L2, NOT memory traffic" % (bn, bt)}
+        c = cap.get(name)
+        if c:
+            per = 1.0 / c["units"]
+            secs = ms * 1e-3
+            lv = {}
+            for lvl, bytes_key, peak, src in (("hbm", "dram_bytes", hbm_peak, hbm_src),
+                                              ("l2", "lts_bytes", peaks.get("l2_read_gbs"), "measured in this run (vg_measure_peaks: 48 MB re-read, ld.global.cg)"),
+                                              ("l1", "l1tex_bytes", peaks.get("l1_read_gbs"), "measured in this run (vg_measure_peaks: 64 KB per SM re-read, ld.global.ca)")):
+                if peak and c.get(bytes_key) is not None:
+                    b = c[bytes_key] * per * rays
+                    lv[lvl] = {"bytes_per_unit": c[bytes_key] * per, "achieved": b / secs / 1e9, "peak": peak, "unit": "GB/s", "frac": b / secs / 1e9 / peak,
+                               "traffic_per_launch": b / launches, "peak_source": src}
+            e["levels"] = lv
+            e["issue"] = {"issue_slots_active": c["issue_active_pct"] / 100.0, "lanes_per_instruction": c["lanes_per_inst"],
+                          "frac": c["issue_active_pct"] / 100.0 * c["lanes_per_inst"] / 32.0, "registers": c.get("registers"),
+                          "warps_active_pct": c.get("warps_active_pct"), "thread_instructions_per_unit": c.get("thread_inst", 0) * per,
+                          "note": "share of the SMs' lane-issue capacity doing work (issue slots active x active lanes / 32), from the ncu capture"}
+            e["capture"] = {"kernel": c.get("kernel"), "ms": c.get("ms"), "units": c["units"], "file": cap.get("_file")}
+            best = max(lv.items(), key=lambda kv: kv[1]["frac"]) if lv else None
+            e["binding"] = ("issue x SIMD lanes" if not best or e["issue"]["frac"] >= best[1]["frac"] else best[0])
+        stages[name] = e
+    return stages
+
+
+def headline_roofline(stages, hbm_peak, hbm_src):
+    """The contract's top-level object, for the stage that takes the largest share of the step."""
+    if not stages:
+        return None
+    name, e = max(stages.items(), key=lambda kv: kv[1]["share_of_step"])
+    lv = e.get("levels") or {}
+    if lv:
+        lvl, b = max(lv.items(), key=lambda kv: kv[1]["frac"])
+        out = {"bound": {"hbm": "hbm", "l2": "l2", "l1": "l1tex"}[lvl], "achieved": b["achieved"], "peak": b["peak"], "unit": "GB/s", "frac": b["frac"],
+               "traffic": b["traffic_per_launch"], "peak_source": b["peak_source"]}
+        if "hbm" in lv:
+            out["hbm"] = lv["hbm"]
+    else:
+        a = e.get("algorithmic", {"gbs": 0.0})
+        out = {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": hbm_src,
+               "note": "no ncu capture of this config is committed: only the algorithmic-bytes figure is available (%.0f GB/s, not traffic)" % a["gbs"]}
+    out["stage"] = name
+    out["kernel"] = (e.get("capture") or {}).get("kernel")
+    out["ms_per_launch"] = e["ms_per_launch"]
+    out["share_of_step"] = e["share_of_step"]
+    out["issue"] = e.get("issue")
+    out["binding"] = e.get("binding")
+    return out
+
+
+def run_config(cfg, args, rank, world, local_rank, torch, dist, peaks, hbm, ncu, cores, dev=None, steps=None):
+    xres, yres, spp = cfg_res(cfg)
+    r = setup_frame(cfg, rank, world, local_rank, torch, dev=dev)
+    # a step of the big configs lasts ~1 s (c3) / ~2 s (c5 on 8 GPUs): fewer repetitions keep the run within minutes
+    k = steps or (args.steps if cfg in ("c1", "c2", "c4", "c2t") else max(2, min(args.steps, 3)))
+    w = args.warmup if cfg in ("c1", "c2", "c4", "c2t") else 1
+    f = frame_leg(r, k, w, rank, world, torch, dist)
+    out = None
+    if rank == 0:
+        stages = stage_roofline(cfg, f, peaks, hbm[0], hbm[1], ncu)
+        out = {k2: v for k2, v in f.items() if not k2.startswith("_")}
+        out["workload"] = CONFIGS[cfg]["workload"]
+        out["triangles"] = r.scene.num_tris
+        out["n_gpus"] = world
+        out["stages"] = stages
+        out["roofline"] = headline_roofline(stages, hbm[0], hbm[1])
+        out["host_prerender_s"] = r.prerender_s
+        out["upload_s"] = r.upload_s
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_frame(r.scene, r.table, spp, cores, 12.0 if cfg == "c2" else 4.0)
+            out["cpu_baseline_faithful"] = cpu_frame(r.scene, r.table, spp, cores, 3.0, faithful=True)
+            out["speedup_e2e_vs_cpu_all_cores"] = out["e2e"]["value"] / out["cpu_baseline"]["value"]
+    return r, out
+
+
+# ------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from vermeer_b200 import scenes
     from vermeer_b200.build import build
-    from vermeer_b200.host import Device, HostScene
+    from vermeer_b200.host import Device
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -247,35 +504,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if not os.environ.get("VG_SO_PATH"):
         build()
-
-    scene = build_scene()
-    # the step's host-side input (per-pixel scramble table) and output (frame) live in page-locked host memory, as the
-    # bench contract asks; the library DMAs from/to such buffers directly
-    table_t = torch.from_numpy(scenes.splitmix64_table(SCRAMBLE_SEED, XRES * YRES).view(np.int64)).pin_memory()
-    table = table_t.numpy().view(np.uint64)
-    frame_t = torch.empty((YRES, XRES, 3), dtype=torch.float32, pin_memory=True)
-    frame = frame_t.numpy()
-    t0 = time.time()
-    host = HostScene(scene).prerender()
-    t_build = time.time() - t0
-    dev = Device(local_rank)
-    for k, v in [kv.split("=") for kv in os.environ.get("VG_OPTIONS", "").split(",") if kv]:   # options that act at upload (node_order)
-        dev.set_option(k, int(v))
-    # the same PreRender with the static meshes' QBVHs built on the GPU (vg_build_qbvh: the same tree), reported only
-    t_build_dev = None
-    if rank == 0 and os.environ.get("VG_BENCH_DEVICE_BUILD", "1") != "0":
-        for _ in range(2):   # the second pass runs with the builder's scratch already allocated
-            t0 = time.time()
-            HostScene(scene).prerender(device=dev)
-            t_build_dev = time.time() - t0
-    dev.upload(host)
-    dev.set_partition(rank, world)
-    dev.set_scramble(table)
-    # ~33 M paths per GPU and batch whatever the frame size and world
-    iters_per_batch = min(SPP, max(1, round(ITERS_PER_BATCH * world * (1920 * 1080) / (XRES * YRES))))
-    dev.set_option("iters_per_batch", iters_per_batch)
-    for k, v in [kv.split("=") for kv in os.environ.get("VG_OPTIONS", "").split(",") if kv]:   # tuning experiments, e.g. VG_OPTIONS=traversal=0
-        dev.set_option(k, int(v))
+    cores = os.cpu_count() or 1
+    mp, hbm_src = measured_peaks()
+    hbm = (float(mp["hbm_gbs"]), hbm_src)
+    ncu = ncu_metrics()
+    want = [c for c in (args.configs.split(",") if args.configs else ["c1", "c2", "c3", "c4"] + (["c5"] if world == 8 else [])) if c in CONFIGS]
 
     def barrier():
         torch.cuda.synchronize()
@@ -283,175 +516,181 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def step_resident():
-        dev.clear()
-        dev.render(0, SPP, fetch=False)
+    dev = Device(local_rank)
+    peaks = dev.measure_peaks()
 
-    def step_e2e():
-        dev.set_scramble(table)       # H2D of this rank's rows of the scramble table, from the caller's host buffer
-        dev.clear()
-        # N=1: D2H of the framebuffer into a host buffer. N>1: the frame is gathered on the device first (below) and
-        # rank 0 alone copies the complete frame to the host.
-        return dev.render(0, SPP, fetch=False) if world > 1 else dev.render(0, SPP, out=frame)
-
-    # clocks / throttle reasons are sampled from the warm-up through the timed region (a timed region of a few x 10 ms is
-    # shorter than nvidia-smi's sampling period)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for _ in range(args.warmup):
-        step_resident()
 
-    # ---- timed: K steps, inputs resident in HBM -----------------------------------------------------
-    dev.reset_stats()
+    # ---- C2: the frame (samples/s) and the headline incoherent closest-hit batch on the same scene ---------------------
+    rig, c2 = run_config("c2", args, rank, world, local_rank, torch, dist, peaks, hbm, ncu, cores, dev=dev)
+    scene, host = rig.scene, rig.host
+    inc = incoherent_batch(scene, host.camera(), lambda rays: dev.trace(rays), seed0=5 + 16 * rank)
     barrier()
     t0 = time.perf_counter()
-    dev_ms = 0.0
-    closest_ms = shadow_ms = 0.0
-    for _ in range(args.steps):
-        step_resident()
-        st = dev.stats()
-        dev_ms += st["render_ms"]
-        closest_ms += st["closest_ms"]
-        shadow_ms += st["shadow_ms"]
+    tb = time_batch(dev, torch, inc, args.steps, args.warmup)
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
-    st = dev.stats()
-    rays_rank = st["rays"]
-
-    # max over ranks of the device time; total rays over ranks
-    tvec = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
-    rvec = torch.tensor([float(rays_rank), float(st["shadow_rays"])], dtype=torch.float64, device="cuda")
+    n = tb["rays"]
+    vec = torch.tensor([tb["device_ms_total"], tb["e2e_ms"].get("compact", tb["e2e_ms"]["full"]), tb["e2e_ms"]["full"]], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(n)], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(tvec, op=dist.ReduceOp.MAX)
-        dist.all_reduce(rvec, op=dist.ReduceOp.SUM)
-    dev_ms_max, wall_ms_max = float(tvec[0]), float(tvec[1])
-    rays_total, shadow_total = float(rvec[0]), float(rvec[1])
+        dist.all_reduce(vec, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    dev_ms_total, e2e_ms, e2e_full_ms = float(vec[0]), float(vec[1]), float(vec[2])
+    rays_all = float(cnt[0])
+    value = rays_all * args.steps / (dev_ms_total * 1e-3) / 1e6
+    e2e_value = rays_all / (e2e_ms * 1e-3) / 1e6
 
-    # ---- e2e: host buffers every step + (N>1) NCCL gather of the framebuffer --------------------------
-    fb_ptr = dev.framebuffer_ptr()
-
-    class _Ext:
-        def __init__(self, ptr, n):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
-    fb_t = torch.as_tensor(_Ext(fb_ptr, XRES * YRES * 3), device="cuda")
-    from vermeer_b200.multigpu import FrameGather
-    gather = FrameGather(XRES, YRES, rank, world, torch.device("cuda", local_rank)) if world > 1 else None
-    host_fb = torch.empty((YRES, XRES, 3), dtype=torch.float32, pin_memory=True) if (world > 1 and rank == 0) else None
-    for _ in range(2):           # warm-up of the e2e leg, including NCCL's lazy communicator set-up for the all-gather
-        step_e2e()
-        if gather is not None:
-            gather.gather(fb_t)
-            torch.cuda.synchronize()
-    dev.reset_stats()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        fb = step_e2e()
-        if gather is not None:
-            # the one exchange of the frame: NCCL all-gather of each rank's owned pixels over NVLink, then a scatter
-            full = gather.gather(fb_t)
-            if rank == 0:
-                host_fb.copy_(full, non_blocking=True)   # D2H of the complete frame into pinned host memory
-            torch.cuda.synchronize()
-    barrier()
-    e2e_wall = time.perf_counter() - t0
-    st2 = dev.stats()
-    evec = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
-    r2 = torch.tensor([float(st2["rays"])], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(evec, op=dist.ReduceOp.MAX)
-        dist.all_reduce(r2, op=dist.ReduceOp.SUM)
-    e2e_value = float(r2[0]) / float(evec[0]) / 1e6
-    npix_own = XRES * YRES // world  # approximate per-rank share of the table
-    h2d = npix_own * 48
-    d2h = XRES * YRES * 12
+    configs = {"c2": c2}
+    for cfg in want:
+        if cfg == "c2":
+            continue
+        if cfg == "c3" and "c5" in want and world == 8:
+            pass
+        _, configs[cfg] = run_config(cfg, args, rank, world, local_rank, torch, dist, peaks, hbm, ncu, cores, dev=dev)
+        if cfg == "c3" and rank == 0 and world == 1 and not args.no_wavefront:
+            configs[cfg]["incoherent_wavefront"] = wavefront_leg(dev, torch, cores, args)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel -------------------------------------------------------------
-    peaks, peak_src = measured_peaks()
-    closest_rays = rays_rank - st["shadow_rays"]
-    # static 64 + 128*NodesT + 48*TrisT; motion 64 + 232*NodesT + 84*TrisT
-    bn, bt = (232.0, 84.0) if CONFIG == "c4" else (128.0, 48.0)
-    alg_bytes_closest = 64.0 * closest_rays + bn * st["nodes_t"] + bt * st["tris_t"]
-    launches = max(1, st["closest_launches"])
-    achieved = alg_bytes_closest / (closest_ms * 1e-3) / 1e9 if closest_ms > 0 else 0.0
-    # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel (C2 scene), scaled to this run's rays
-    # per launch; null for the configs that have no capture
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if CONFIG == "c2" and os.path.exists(tpath):
-        t = json.load(open(tpath)).get("k_trace_queue<0>")
-        if t:
-            traffic = t["dram_bytes"] / t["rays"] * (closest_rays / launches)
-    roofline = {
-        "bound": "hbm", "kernel": "k_trace_queue<0> (closest-hit %s traversal)" % ("MQBVH" if CONFIG == "c4" else "QBVH"), "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
-        "bytes_per_launch": alg_bytes_closest / launches, "ms_per_launch": closest_ms / launches,
-        "rays_per_launch": closest_rays / launches, "nodesT_per_ray": st["nodes_t"] / max(1, closest_rays), "trisT_per_ray": st["tris_t"] / max(1, closest_rays),
-        "share_of_step": closest_ms / dev_ms if dev_ms > 0 else None,
-        "note": ("10M-triangle scene (0.55 GB) exceeds L2: HBM-bound model" if CONFIG in ("c3", "c5") else
-                 "1M-triangle scene (6 MB nodes + 48 MB triangles) is L2-resident: the bytes model is algorithmic, not DRAM traffic"),
-        # what ncu says binds the kernel (static text: the captures live under profiles/, see profiles/README.md)
-        "binding": ("L1TEX tag throughput / L2 latency (DRAM 7-15 % of peak, long_scoreboard ~49 % of stall samples): profiles/ncu_full_r01d_c3_summary.txt"
-                    if CONFIG in ("c3", "c5") else
-                    "instruction issue x SIMD efficiency (75 % issue slots active, 16.4 of 32 lanes per instruction, DRAM 4.7 % of peak): "
-                    "profiles/ncu_full_r01i_final_summary.txt; a frac above 1 means the algorithmic bytes are served from L1/L2, not from HBM"),
-    }
+    # ---- headline bookkeeping on rank 0 ---------------------------------------------------------------------------
+    alg_bytes = 64.0 + 128.0 * tb["nodesT_per_ray"] + 48.0 * tb["trisT_per_ray"]
+    cap = ncu.get("c2_incoherent", {}).get("closest")
+    roof = {"kernel": "k_trace_batch<0,2> (closest-hit QBVH traversal, cooperative leaf phase)", "stage": "closest-hit traversal of the incoherent batch",
+            "ms_per_launch": tb["ms_per_step"], "units_per_launch": n, "nodesT_per_ray": tb["nodesT_per_ray"], "trisT_per_ray": tb["trisT_per_ray"],
+            "algorithmic": {"bytes_per_ray": alg_bytes, "gbs": alg_bytes * n / (tb["ms_per_step"] * 1e-3) / 1e9,
+                            "note": "SURVEY.md 8d bytes model: served by L1/L2 (the 54 MB scene is L2-resident), NOT memory traffic"}}
+    if cap:
+        per, secs = 1.0 / cap["units"], tb["ms_per_step"] * 1e-3
+        lv = {}
+        for lvl, key, peak, src in (("hbm", "dram_bytes", hbm[0], hbm[1]), ("l2", "lts_bytes", peaks["l2_read_gbs"], "measured in this run (vg_measure_peaks)"),
+                                    ("l1", "l1tex_bytes", peaks["l1_read_gbs"], "measured in this run (vg_measure_peaks)")):
+            b = cap[key] * per * n
+            lv[lvl] = {"bytes_per_unit": cap[key] * per, "achieved": b / secs / 1e9, "peak": peak, "unit": "GB/s", "frac": b / secs / 1e9 / peak, "traffic_per_launch": b, "peak_source": src}
+        lvl, b = max(lv.items(), key=lambda kv: kv[1]["frac"])
+        roof.update({"bound": {"hbm": "hbm", "l2": "l2", "l1": "l1tex"}[lvl], "achieved": b["achieved"], "peak": b["peak"], "unit": "GB/s", "frac": b["frac"],
+                     "traffic": b["traffic_per_launch"], "peak_source": b["peak_source"], "levels": lv,
+                     "issue": {"issue_slots_active": cap["issue_active_pct"] / 100.0, "lanes_per_instruction": cap["lanes_per_inst"],
+                               "frac": cap["issue_active_pct"] / 100.0 * cap["lanes_per_inst"] / 32.0},
+                     "capture": {"kernel": cap.get("kernel"), "ms": cap.get("ms"), "units": cap["units"], "file": ncu.get("c2_incoherent", {}).get("_file")}})
+    else:
+        roof.update({"bound": "hbm", "achieved": None, "peak": hbm[0], "unit": "GB/s", "frac": None, "traffic": None,
+                     "note": "no committed ncu capture for this kernel"})
 
-    if CONFIG in ("c2", "c2t", "c4"):
-        # the L2-resident configs are additionally quoted against the L2 (LTS) throughput cap, ~6300 B/clk
-        # full-chip (B300_MICROARCH.md:120) at the SM clock; the share of the algorithmic bytes that actually reaches L2 is
-        # the L1 miss fraction of the ncu capture (profiles/ncu_full_r01i_final_summary.txt: L1 hit 69 %, LTS throughput 16 %)
-        l2_cap = 6300.0 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e9
-        roofline["l2"] = {"cap": l2_cap, "unit": "GB/s", "frac_algorithmic": achieved / l2_cap,
-                          "cap_source": "6300 B/clk x sm_max_mhz (guide figure, not measured here)",
-                          "ncu_lts_throughput_pct": 16.3 if CONFIG != "c4" else None, "ncu_l1_hit_pct": 69.4 if CONFIG != "c4" else None}
-
-    # ---- CPU baseline: the oracle on a bounded sample (rank 0, N=1 only) ------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        v1, rays1, secs1 = cpu_reference_run(scene, table, 1, cores)          # probe: one iteration
-        iters = int(min(SPP, max(1, round(12.0 / max(secs1, 1e-3)))))            # aim at ~12 s of CPU work
-        v, rays, secs = cpu_reference_run(scene, table, iters, cores) if iters > 1 else (v1, rays1, secs1)
-        cpu = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
-               "sample": "%d iteration(s) (spp) of the same 1920x1080 workload, all %d host threads: %d rays in %.2f s" % (iters, cores, rays, secs)}
+        oh, cpu_v, secs = cpu_trace(scene, inc, cores, reps=3)
+        same = bool(np.array_equal(oh["prim"], tb["hits"]["prim"]) and np.array_equal(oh["geom"], tb["hits"]["geom"]) and
+                    np.array_equal(oh["t"].view(np.uint32), tb["hits"]["t"].view(np.uint32)) and
+                    np.array_equal(oh["nodesT"], tb["hits"]["nodesT"]) and np.array_equal(oh["trisT"], tb["hits"]["trisT"]))
+        compact_ok = None
+        if tb["compact_hits"] is not None:
+            prim_of, geom_of = dev.slot_table()
+            ch = tb["compact_hits"]
+            hit = ch["slot"] >= 0
+            compact_ok = bool(np.array_equal(hit, oh["prim"] >= 0) and np.array_equal(prim_of[ch["slot"][hit]], oh["prim"][hit]) and
+                              np.array_equal(geom_of[ch["slot"][hit]], oh["geom"][hit]) and np.array_equal(ch["t"].view(np.uint32), oh["t"].view(np.uint32)) and
+                              np.array_equal(ch["u"].view(np.uint32), oh["u"].view(np.uint32)))
+        cpu = {"value": cpu_v, "unit": "Mrays/s", "cores": cores, "per_core": cpu_v / cores, "kind": "port",
+               "sample": "the same %d rays, 3 passes on all %d host threads, %.2f s per pass" % (n, cores, secs),
+               "bit_identical_to_gpu": same, "compact_hits_identical": compact_ok}
 
-    # ---- closest-hit, incoherent micro-config: cosine-hemisphere bounce rays from the primary hit points -----
-    incoherent = None
-    if world == 1 and CONFIG == "c2":
-        incoherent = incoherent_leg(dev, host, scene, torch, cpu_cores=(os.cpu_count() or 1) if not args.no_cpu else 0)
-
-    value = rays_total / (dev_ms_max * 1e-3) / 1e6
     out = {
-        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms_max / max(1, args.steps), "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "xres": XRES, "yres": YRES, "spp": SPP, "triangles": scene.num_tris,
-                   "partition": "interleaved 32x32 tiles, BVH replicated" if world > 1 else "single GPU",
-                   "l2_policy": "per-step working set (ray/hit/path queues, >1 GB) exceeds the 126 MB L2", "iters_per_batch": iters_per_batch},
-        "samples_per_s": XRES * YRES * SPP * args.steps / (dev_ms_max * 1e-3),
-        "rays_per_step": rays_total / max(1, args.steps), "shadow_rays_per_step": shadow_total / max(1, args.steps),
-        "wall_ms_per_step": wall_ms_max / max(1, args.steps),
-        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": float(evec[0]) * 1e3 / max(1, args.steps)},
-        "gpu_launches": int(st["kernel_launches"]),
-        "stage_ms_per_step": {"closest_traversal": closest_ms / max(1, args.steps), "shadow_traversal": shadow_ms / max(1, args.steps),
-                              "raygen_shade_resolve_accumulate": (dev_ms - closest_ms - shadow_ms) / max(1, args.steps)},
+        "config": {"workload": HEADLINE_WORKLOAD, "rays_per_step_per_gpu": n, "triangles": scene.num_tris, "hit_fraction": tb["hit_fraction"],
+                   "partition": "every rank traces its own batch (independent rays, no collective)" if world > 1 else "single GPU",
+                   "l2_policy": "ray + hit streams of a step (%d MB) exceed the 126 MB L2; the 54 MB scene is L2-resident by nature of the config" % (n * 64 // 1000000)},
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * (16 if "compact" in tb["e2e_ms"] else 32),
+                "ms_per_step": e2e_ms, "mode": "vg_trace_batch, page-locked host buffers, " + ("VG_TRACE_COMPACT_HITS (16-byte hits)" if "compact" in tb["e2e_ms"] else "32-byte VgHit"),
+                "full_vghit": {"value": rays_all / (e2e_full_ms * 1e-3) / 1e6, "ms_per_step": e2e_full_ms, "d2h_bytes_per_step": n * 32}},
+        "gpu_launches": args.steps, "wall_s_timed_region": wall,
         "clocks": clocks,
-        "roofline": roofline,
+        "roofline": roof,
         "cpu_baseline": cpu,
-        "incoherent_closest_hit": incoherent,
-        "host_prerender_s": t_build, "device_prerender_s": t_build_dev,
+        "samples_per_s": c2["samples_per_s"], "samples_per_s_e2e": c2["e2e"]["samples_per_s"],
+        "frame": {k: v for k, v in c2.items() if k not in ("stages",)},
+        "configs": configs,
+        "incoherent_wavefront": (configs.get("c3") or {}).get("incoherent_wavefront"),
+        "measured_peaks": {"hbm_gbs": hbm[0], "hbm_source": hbm[1], **peaks},
+        "speedup_vs_cpu": None if not cpu else {"device_resident": value / cpu["value"], "e2e": e2e_value / cpu["value"], "cores": cores,
+                                                "frame_e2e": c2.get("speedup_e2e_vs_cpu_all_cores")},
     }
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def wavefront_leg(dev, torch, cores, args):
+    """Incoherent closest-hit rays taken from the wavefront itself: the level-1..3 mirror-bounce queues of the 10M-triangle scene
+    (uploaded in `dev` by the c3 frame leg), two iterations' worth, shuffled. Not L2-resident (0.55 GB of nodes + triangles)."""
+    dev.set_option("capture_levels", 0b1110)
+    dev.clear()
+    dev.render(0, 2, fetch=False)
+    dev.set_option("capture_levels", 0)
+    rays = dev.captured_rays()
+    rays = rays[np.random.default_rng(11).permutation(len(rays))]
+    tb = time_batch(dev, torch, rays, max(3, min(args.steps, 10)), 3)
+    n = tb["rays"]
+    res = {"workload": "C3-wavefront: level-1..3 mirror-bounce rays of the 10M-triangle sphere field, from vg_render's own ray queues (2 iterations), shuffled",
+           "rays": n, "value": n / tb["ms_per_step"] / 1e3, "unit": "Mrays/s", "ms_per_step": tb["ms_per_step"], "hit_fraction": tb["hit_fraction"],
+           "nodesT_per_ray": tb["nodesT_per_ray"], "trisT_per_ray": tb["trisT_per_ray"],
+           "e2e": {k: n / v / 1e3 for k, v in tb["e2e_ms"].items()}}
+    if not args.no_cpu:
+        sample = rays[: min(n, 1 << 21)]
+        oh, v, secs = cpu_trace(build_scene("c3"), sample, cores)
+        g = tb["hits"][: len(sample)]
+        res["cpu"] = {"value": v, "unit": "Mrays/s", "cores": cores, "per_core": v / cores, "kind": "port", "sample": "%d of the same rays, %.2f s" % (len(sample), secs),
+                      "bit_identical_to_gpu": bool(np.array_equal(oh["prim"], g["prim"]) and np.array_equal(oh["geom"], g["geom"]) and
+                                                   np.array_equal(oh["t"].view(np.uint32), g["t"].view(np.uint32)))}
+        res["speedup_vs_cpu"] = {"device_resident": res["value"] / v, "e2e": {k: x / v for k, x in res["e2e"].items()}}
+    return res
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores. The Go reference cannot
+    be compiled in this image (no Go toolchain), so this is the oracle port (kind "port"), all host threads; same metric and
+    workload as the GPU arm: one step = one closest-hit pass over the incoherent batch."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from vermeer_b200 import scenes
+    cores = os.cpu_count() or 1
+    scene = build_scene("c2")
+    ora = make_oracle(scene)
+    cam = ora.camera_matrix()
+    inc = incoherent_batch(scene, cam, lambda rays: ora.trace(rays, nthreads=cores), seed0=5)
+    n = len(inc)
+    for _ in range(min(args.warmup, 2)):
+        ora.trace(inc, nthreads=cores)
+    secs = 0.0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        ora.trace(inc, nthreads=cores)
+        secs += time.perf_counter() - t0
+    v = n * args.steps / secs / 1e6
+    sample = "the whole batch (%d rays) per step on all %d host threads" % (n, cores)
+    # the frame half of the metric: a bounded sample of the C2 frame
+    table = scenes.splitmix64_table(SCRAMBLE_SEED, scene.XRes * scene.YRes)
+    frame = cpu_frame(scene, table, 64, cores, 8.0)
+    faithful = cpu_frame(scene, table, 64, cores, 4.0, faithful=True)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": secs / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": HEADLINE_WORKLOAD, "rays_per_step_per_gpu": n, "triangles": scene.num_tris, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "per_core": v / cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "samples_per_s": frame["samples_per_s"], "frame": frame, "frame_faithful": faithful,
+    }
+    print(json.dumps(out))
 
 
 def main():
@@ -460,8 +699,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    # other BASELINE.json configs (c3, c4, c5) are selected with VG_BENCH_CONFIG; the driver's contract runs the default (c2)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-wavefront", action="store_true", help="skip the C3 wavefront incoherent batch")
+    ap.add_argument("--configs", default=os.environ.get("VG_BENCH_CONFIGS", ""), help="comma list of frame configs (default c1,c2,c3,c4 and c5 at 8 GPUs); c2 always runs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -23,4 +23,9 @@ for a in sys.argv:
         _, k, v = a.split("=")
         dev.set_option(k, int(v))
 dev.render(0, iters, fetch=False)
-print(dev.stats())
+st = dev.stats()
+print(st)
+for a in sys.argv:
+    if a.startswith("--stats-out="):
+        import json
+        json.dump(dict(st, iters=iters), open(a.split("=", 1)[1], "w"))

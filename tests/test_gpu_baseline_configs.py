@@ -1,0 +1,165 @@
+"""Every BASELINE.json config at BASELINE size, GPU (through the C ABI) against the oracle on the same inputs.
+
+  C1  Cornell box 512x512, 16 spp: image RMSE <= 1e-3 (NaN-aware: the reference itself yields NaN pixels where a TriLight is
+      sampled from inside its own plane), ray counts within 1e-3.
+  C2  1 002 528-triangle heightfield, 1920x1080: >= 1 M camera rays, >= 1 M cosine-bounce rays and >= 1 M shadow rays traced
+      bit-exactly (prim, geom, t, u, v, w and the NodesT / TrisT counters), and a 4-iteration full frame within 1e-3 RMSE with
+      identical ray counts.
+  C3  10 M triangles in 1024 meshes under the scene-level QBVH: >= 1 M camera rays and >= 1 M level-1..3 mirror-bounce rays taken
+      from the integrator's own ray queues bit-exact; 4-iteration full frame within 1e-3 RMSE.
+  C4  the C2 mesh with two motion keys (MQBVH), both leaf modes (`fixed`, `ref_compat`): >= 1 M camera rays at per-ray times
+      bit-exact; 4-iteration full frame within 1e-3 RMSE.
+The oracle needs 1-3 s per million rays on the GPU box's host cores, so the whole module stays well under two minutes."""
+import numpy as np
+import pytest
+
+from conftest import assert_hits_equal
+
+pytestmark = pytest.mark.gpu
+
+NTHREADS = 16
+
+
+def _rmse(fo, fg):
+    ok = np.isfinite(fo).all(-1) & np.isfinite(fg).all(-1)
+    return float(np.sqrt(((fo[ok] - fg[ok]) ** 2).mean())), ok
+
+
+def _pair(sc, ref_compat=False):
+    from oracle.binding import Oracle
+    from vermeer_b200 import scenes
+    from vermeer_b200.host import Device, HostScene
+    tab = scenes.splitmix64_table(1, sc.XRes * sc.YRes)
+    ora = Oracle(sc, motion_ref_compat=ref_compat)
+    ora.set_scramble(tab)
+    dev = Device(0).upload(HostScene(sc).prerender(), motion_ref_compat=ref_compat)
+    dev.set_scramble(tab)
+    return ora, dev
+
+
+def _image_check(ora, dev, iters, rays_rtol, exact_counts=False):
+    fo, so = ora.render(0, iters, nthreads=NTHREADS)
+    dev.set_option("iters_per_batch", min(iters, 32))
+    dev.clear()
+    dev.reset_stats()
+    fg = dev.render(0, iters)
+    st = dev.stats()
+    rmse, ok = _rmse(fo, fg)
+    assert ok.mean() > 0.99
+    assert rmse <= 1e-3, rmse
+    if exact_counts:
+        assert st["rays"] == so["rays"] and st["shadow_rays"] == so["shadow_rays"]
+    else:
+        assert abs(st["rays"] - so["rays"]) <= rays_rtol * so["rays"], (st["rays"], so["rays"])
+    return rmse
+
+
+def test_c1_cornell_512_16spp(built_library):
+    from vermeer_b200 import scenes
+    sc = scenes.cornell_box(512, 512)
+    ora, dev = _pair(sc)
+    rmse = _image_check(ora, dev, 16, 1e-3)
+    assert rmse <= 5e-4, rmse
+    rays = ora.camera_rays(1)
+    assert_hits_equal(dev.trace(rays), ora.trace(rays, nthreads=NTHREADS), what="C1 camera rays")
+
+
+@pytest.fixture(scope="module")
+def c2(built_library):
+    from vermeer_b200 import scenes
+    sc = scenes.heightfield_scene(1920, 1080, nq=708)
+    assert sc.num_tris == 1002530           # 2 * 708^2 = 1 002 528 + the light's own two triangles
+    return (sc,) + _pair(sc)
+
+
+def test_c2_traversal_is_bit_exact_at_full_size(c2):
+    from vermeer_b200 import scenes
+    sc, ora, dev = c2
+    cam = ora.camera_rays(3)                                     # the camera rays of iteration 3, all 2 073 600 of them
+    n = 1 << 20
+    sel = np.random.default_rng(5).permutation(len(cam))[: n + (n >> 2)]
+    cam = cam[sel]
+    g = dev.trace(cam)
+    assert_hits_equal(g, ora.trace(cam, nthreads=NTHREADS), what="C2 camera rays")
+    assert (g["prim"] >= 0).mean() > 0.5
+    inc = scenes.incoherent_rays(cam, g, seed=9)                 # level-1 cosine-hemisphere bounce rays from the hit points
+    inc = np.concatenate([inc, scenes.incoherent_rays(cam, g, seed=10)])
+    assert len(inc) >= n
+    gi = dev.trace(inc)
+    assert_hits_equal(gi, ora.trace(inc, nthreads=NTHREADS), what="C2 bounce rays")
+    # shadow rays (RayTypeShadow, any hit): from the hit points towards points on the light pair, Tclosest = 1
+    hit = g["prim"] >= 0
+    o = cam["o"][hit] + cam["d"][hit] * g["t"][hit][:, None] + np.float32([0, 1e-3, 0])
+    rng = np.random.default_rng(12)
+    target = np.stack([rng.uniform(-0.4, 0.4, len(o)), np.full(len(o), 1.5), rng.uniform(-0.4, 0.4, len(o))], -1).astype(np.float32)
+    sh = np.zeros(len(o), cam.dtype)
+    sh["o"], sh["d"], sh["tmax"] = o, (target - o) * np.float32(0.9999), 1.0
+    sh = np.concatenate([sh, sh[: max(0, n - len(sh))]])
+    assert len(sh) >= n
+    gs, os_ = dev.trace(sh, any_hit=True), ora.trace(sh, any_hit=True, nthreads=NTHREADS)
+    assert_hits_equal(gs, os_, what="C2 shadow rays")
+    assert 0.0 < (gs["prim"] >= 0).mean() < 0.5
+    # the compact 16-byte record carries the same t, u, v and triangle
+    gc = dev.trace(inc, compact=True)
+    prim_of, geom_of = dev.slot_table()
+    h = gc["slot"] >= 0
+    assert np.array_equal(h, gi["prim"] >= 0)
+    assert np.array_equal(prim_of[gc["slot"][h]], gi["prim"][h]) and np.array_equal(geom_of[gc["slot"][h]], gi["geom"][h])
+    for f in ("t", "u", "v"):
+        assert np.array_equal(gc[f].view(np.uint32), gi[f].view(np.uint32)), f
+
+
+def test_c2_frame_4spp(c2):
+    sc, ora, dev = c2
+    # 20 M rays: a handful of grazing light samples flip because a normalize is not bit-reproducible (RSQRTSS, SURVEY.md note N)
+    rmse = _image_check(ora, dev, 4, 1e-5)
+    assert rmse <= 2e-4, rmse
+
+
+@pytest.fixture(scope="module")
+def c3(built_library):
+    from vermeer_b200 import scenes
+    sc = scenes.sphere_field_scene(1920, 1080)
+    assert len(sc.meshes) == 1025 and sc.num_tris > 10_000_000
+    return (sc,) + _pair(sc)
+
+
+def test_c3_camera_and_wavefront_rays_bit_exact(c3):
+    sc, ora, dev = c3
+    cam = ora.camera_rays(2)
+    cam = cam[np.random.default_rng(6).permutation(len(cam))[: (1 << 20) + 4096]]
+    assert_hits_equal(dev.trace(cam), ora.trace(cam, nthreads=NTHREADS), what="C3 camera rays")
+    # the level-1..3 extension rays of the mirror chains, from the integrator's own queues
+    dev.set_option("capture_levels", 0b1110)
+    dev.clear()
+    dev.render(0, 2, fetch=False)
+    dev.set_option("capture_levels", 0)
+    rays = dev.captured_rays()
+    assert len(rays) >= 1 << 20, len(rays)
+    rays = rays[np.random.default_rng(7).permutation(len(rays))[: (1 << 20) + 4096]]
+    g = dev.trace(rays)
+    assert_hits_equal(g, ora.trace(rays, nthreads=NTHREADS), what="C3 level-1..3 rays")
+    assert (g["prim"] >= 0).mean() > 0.5                         # genuinely inside the geometry, unlike sky-bound bounce rays
+    assert len(np.unique(g["geom"][g["prim"] >= 0])) > 500        # spread over the whole two-level scene
+
+
+def test_c3_frame_4spp(c3):
+    sc, ora, dev = c3
+    dev.clear()
+    rmse = _image_check(ora, dev, 4, 1e-4)
+    assert rmse <= 5e-4, rmse
+
+
+@pytest.mark.parametrize("ref_compat", [False, True])
+def test_c4_motion_traversal_and_frame(built_library, ref_compat):
+    from vermeer_b200 import scenes
+    sc = scenes.heightfield_scene(1920, 1080, nq=708, motion=True)
+    ora, dev = _pair(sc, ref_compat=ref_compat)
+    cam = ora.camera_rays(5)                                     # per-ray Time from the scramble table
+    cam = cam[np.random.default_rng(8).permutation(len(cam))[: (1 << 20) + 4096]]
+    assert len(np.unique(cam["time"])) > 1000
+    g = dev.trace(cam)
+    assert_hits_equal(g, ora.trace(cam, nthreads=NTHREADS), what="C4 camera rays ref_compat=%s" % ref_compat)
+    if not ref_compat:
+        rmse = _image_check(ora, dev, 4, 1e-5)
+        assert rmse <= 2e-4, rmse

@@ -969,7 +969,7 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
   else if (!std::strcmp(name, "shadow_per_lane")) ctx->opt_shadow_per_lane = value != 0;
   else if (!std::strcmp(name, "capture_levels")) {
     ctx->opt_capture_levels = value & 31;
-    ctx->captured.clear();
+    if (value & 31) ctx->captured.clear();  // switching the capture on starts a new store; switching it off keeps what was captured
   }
   else if (!std::strcmp(name, "texture_coop")) ctx->opt_texture_coop = value != 0;
   else if (!std::strcmp(name, "zero_copy_batch")) ctx->opt_zero_copy_batch = value != 0;

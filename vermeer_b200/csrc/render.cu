@@ -1298,7 +1298,12 @@ static int upload_scramble_rows(vg_ctx* ctx, const uint64_t* table) {
     }
     cudaGetLastError();
   }
-  const size_t bytes = (size_t)rs.nown * 48;
+  // a context that owns every pixel keeps the table as it is (raster order, kernels index it by pixel): no gather, and the
+  // device copy can restore the host copy when the pixel order changes later (prepare())
+  const bool whole = ctx->world == 1;
+  const size_t n = whole ? (size_t)ctx->xres * ctx->yres : (size_t)rs.nown;
+  const size_t bytes = n * 48;
+  if (whole) RCUDA(rs.scr.reserve(n * 6));
   if (rs.scr_pinned_bytes < bytes) {
     if (rs.scr_pinned) cudaFreeHost(rs.scr_pinned);
     rs.scr_pinned = nullptr;
@@ -1309,7 +1314,6 @@ static int upload_scramble_rows(vg_ctx* ctx, const uint64_t* table) {
   // Owned pixels come in runs of 8 (or 32) consecutive pixels of one raster row. A few host threads gather their slice of the
   // rows run by run into pinned memory, chunk by chunk, and each issues the H2D copy of a chunk as soon as it is gathered, so
   // the PCIe transfer overlaps the gathering of the next chunks (one core's memcpy, ~10 GB/s, is slower than the link).
-  const size_t n = (size_t)rs.nown;
   const int nthreads = n >= (1u << 16) ? 8 : 1;
   const size_t chunk = 1u << 15;  // pixels per copy: 1.5 MB
   uint64_t* dst_dev = rs.scr.p;
@@ -1321,6 +1325,10 @@ static int upload_scramble_rows(vg_ctx* ctx, const uint64_t* table) {
     for (size_t c0 = b; c0 < e; c0 += chunk) {
       const size_t c1 = std::min(e, c0 + chunk);
       size_t i = c0;
+      if (whole) {
+        std::memcpy(rs.scr_pinned + c0 * 6, table + c0 * 6, (c1 - c0) * 48);
+        i = c1;
+      }
       while (i < c1) {
         size_t j = i + 1;
         while (j < c1 && pix[j] == pix[j - 1] + 1) j++;
@@ -1341,6 +1349,7 @@ static int upload_scramble_rows(vg_ctx* ctx, const uint64_t* table) {
   }
   for (cudaError_t e2 : errs) RCUDA(e2);
   RCUDA(cudaStreamSynchronize(ctx->stream));
+  rs.scr_by_pixel = whole;
   return VG_OK;
 }
 

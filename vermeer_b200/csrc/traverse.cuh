@@ -124,9 +124,61 @@ struct Box4Out {
   float t0, t1, t2, t3;
   bool h0, h1, h2, h3;
 };
+
+// The same slab test with the subtractions and multiplications issued as packed pairs (sm_100 FADD2 / FMUL2: __fadd2_rn,
+// __fmul2_rn — two IEEE round-to-nearest float32 operations per instruction, bit-identical to the scalar ones; a - b is issued as
+// a + (-b), the same operation). The traversal kernels are issue-bound (ncu: 75 % of issue slots active), and the 24 FADD +
+// 24 FMUL of a node visit are its largest single block of instructions: 24 packed ones replace them. A 128-bit node load
+// delivers children (0,1) and (2,3) of one plane in adjacent registers, which is exactly the pair layout the packed form wants.
+#ifndef VG_BOX_F32X2
+#define VG_BOX_F32X2 1
+#endif
+template <bool EXACT>
+__device__ __forceinline__ void box_axis2(float2 lo, float2 hi, float2 no, float2 id, float2& tn, float2& tf, bool first) {
+  const float2 t1 = __fmul2_rn(__fadd2_rn(lo, no), id);
+  const float2 t2 = __fmul2_rn(__fadd2_rn(hi, no), id);
+  const float nx = EXACT ? x86min(t2.x, t1.x) : fminf(t2.x, t1.x), ny = EXACT ? x86min(t2.y, t1.y) : fminf(t2.y, t1.y);
+  const float fx = EXACT ? x86max(t2.x, t1.x) : fmaxf(t2.x, t1.x), fy = EXACT ? x86max(t2.y, t1.y) : fmaxf(t2.y, t1.y);
+  if (first) {
+    tn = make_float2(nx, ny);
+    tf = make_float2(fx, fy);
+  } else {
+    tn.x = EXACT ? x86max(tn.x, nx) : fmaxf(tn.x, nx);
+    tn.y = EXACT ? x86max(tn.y, ny) : fmaxf(tn.y, ny);
+    tf.x = EXACT ? x86min(tf.x, fx) : fminf(tf.x, fx);
+    tf.y = EXACT ? x86min(tf.y, fy) : fminf(tf.y, fy);
+  }
+}
+template <bool EXACT>
+__device__ __forceinline__ void box4_packed(const RayState& r, const float4& lx, const float4& ly, const float4& lz, const float4& hx, const float4& hy,
+                                            const float4& hz, Box4Out& o) {
+  const float2 nox = make_float2(-r.ox, -r.ox), noy = make_float2(-r.oy, -r.oy), noz = make_float2(-r.oz, -r.oz);
+  const float2 ix = make_float2(r.idx, r.idx), iy = make_float2(r.idy, r.idy), iz = make_float2(r.idz, r.idz);
+  float2 n01, f01, n23, f23;
+  box_axis2<EXACT>(make_float2(lx.x, lx.y), make_float2(hx.x, hx.y), nox, ix, n01, f01, true);
+  box_axis2<EXACT>(make_float2(lx.z, lx.w), make_float2(hx.z, hx.w), nox, ix, n23, f23, true);
+  box_axis2<EXACT>(make_float2(ly.x, ly.y), make_float2(hy.x, hy.y), noy, iy, n01, f01, false);
+  box_axis2<EXACT>(make_float2(ly.z, ly.w), make_float2(hy.z, hy.w), noy, iy, n23, f23, false);
+  box_axis2<EXACT>(make_float2(lz.x, lz.y), make_float2(hz.x, hz.y), noz, iz, n01, f01, false);
+  box_axis2<EXACT>(make_float2(lz.z, lz.w), make_float2(hz.z, hz.w), noz, iz, n23, f23, false);
+  o.t0 = EXACT ? x86max(0.0f, n01.x) : fmaxf(0.0f, n01.x);
+  o.t1 = EXACT ? x86max(0.0f, n01.y) : fmaxf(0.0f, n01.y);
+  o.t2 = EXACT ? x86max(0.0f, n23.x) : fmaxf(0.0f, n23.x);
+  o.t3 = EXACT ? x86max(0.0f, n23.y) : fmaxf(0.0f, n23.y);
+  o.h0 = o.t0 <= f01.x;
+  o.h1 = o.t1 <= f01.y;
+  o.h2 = o.t2 <= f23.x;
+  o.h3 = o.t3 <= f23.y;
+}
 template <bool EXACT>
 __device__ __forceinline__ void box4(const RayState& r, const float4& lx, const float4& ly, const float4& lz, const float4& hx, const float4& hy,
                                      const float4& hz, Box4Out& o) {
+#if VG_BOX_F32X2
+  if (!EXACT) {  // (the NaN-exact path keeps the scalar form: rare rays, and its selects are written against MINPS/MAXPS operand order)
+    box4_packed<false>(r, lx, ly, lz, hx, hy, hz, o);
+    return;
+  }
+#endif
   o.t0 = box1<EXACT>(r, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, &o.h0);
   o.t1 = box1<EXACT>(r, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, &o.h1);
   o.t2 = box1<EXACT>(r, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, &o.h2);

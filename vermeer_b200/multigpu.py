@@ -1,9 +1,14 @@
 """Multi-GPU plumbing: one process per GPU, image partitioned by interleaved 32x32 tiles, scene replicated, and ONE
-exchange per frame — an all-gather of each rank's owned pixels followed by a scatter into the row-major frame
-(SURVEY.md 8e). There is no data-path collective while rendering: every (pixel, iteration) sample is an independent
-function of (x, y, iter, framescramble[pixel]) (core/render.go:89-125) and writes only its own pixel (:127-129).
+exchange per frame. There is no data-path collective while rendering: every (pixel, iteration) sample is an
+independent function of (x, y, iter, framescramble[pixel]) (core/render.go:89-125) and writes only its own pixel (:127-129).
 
-torch.distributed is the plumbing (NCCL over NVLink on the GPU box, gloo in the CPU tests); the tensors are plain float32.
+The exchange itself lives in the library (csrc/comm.cu: vg_comm_init / vg_gather_frame — NCCL send/recv on the context's
+stream between the library's own pack and scatter kernels). `init_library_comm` below is the small amount of host glue a
+launcher needs: rank 0 creates the NCCL id, the host distributes it (here over torch.distributed, whatever its backend), every
+rank calls vg_comm_init.
+
+`FrameGather` is the same exchange written with torch collectives. It is NOT on the product path: the CPU test suite uses it
+(gloo, world_size 2) as an executable statement of what the gathered frame must be, against the library's own tile lists.
 """
 from __future__ import annotations
 
@@ -14,8 +19,19 @@ import torch.distributed as dist
 from .partition import owned_pixels
 
 
+def init_library_comm(dev, rank: int, world: int):
+    """Collective over torch.distributed's default group: vg_comm_unique_id on rank 0 -> broadcast -> vg_comm_init."""
+    if world == 1:
+        dev.comm_init(0, 1, None)
+        return
+    obj = [dev.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    dev.comm_init(rank, world, obj[0])
+
+
 class FrameGather:
-    """Pre-computes the index lists once; `gather(fb)` then costs one all_gather plus one index_copy."""
+    """Torch twin of vg_gather_frame (tests only). Pre-computes the index lists once; `gather(fb)` is one all_gather plus one
+    index_copy."""
 
     def __init__(self, xres: int, yres: int, rank: int, world: int, device):
         self.xres, self.yres, self.rank, self.world = xres, yres, rank, world
