@@ -389,6 +389,28 @@ def frame_leg(r, steps, warmup, rank, world, torch, dist):
     return out
 
 
+def gathered_frame_check(r, rank, world, local_rank, iters=4):
+    """N > 1: the frame the library gathers on rank 0 (vg_gather_frame) must be the single-GPU render of the same iterations, bit for
+    bit (ownership is disjoint, nothing is summed). Rank 0 renders the reference frame in a second, unpartitioned context."""
+    from vermeer_b200.host import Device
+    dev = r.dev
+    dev.clear()
+    dev.render(0, iters, fetch=False)
+    dev.gather_frame(r.frame if rank == 0 else None)
+    if rank != 0:
+        return None
+    got = r.frame.copy()
+    solo = Device(local_rank).upload(r.host)
+    solo.set_scramble(r.table)
+    solo.set_option("iters_per_batch", iters)
+    want = solo.render(0, iters)
+    solo.close()
+    same = bool(np.array_equal(got.view(np.uint32), want.view(np.uint32)))
+    if not same:
+        raise SystemExit("bench.py: the NCCL-gathered %d-GPU frame differs from the single-GPU frame (%d pixels)" % (world, int((got != want).any(-1).sum())))
+    return same
+
+
 def stage_roofline(cfg, frame, peaks, hbm_peak, hbm_src, ncu):
     """Per stage: live time per launch x traffic per ray from the ncu capture of this build -> achieved GB/s at each memory
     level against the measured peak of that level; plus the issue x SIMD ceiling of the capture."""
@@ -469,6 +491,7 @@ def run_config(cfg, args, rank, world, local_rank, torch, dist, peaks, hbm, ncu,
     k = steps or (args.steps if cfg in ("c1", "c2", "c4", "c2t") else max(2, min(args.steps, 3)))
     w = args.warmup if cfg in ("c1", "c2", "c4", "c2t") else 1
     f = frame_leg(r, k, w, rank, world, torch, dist)
+    check = gathered_frame_check(r, rank, world, local_rank) if (world > 1 and cfg in ("c1", "c2")) else None
     out = None
     if rank == 0:
         stages = stage_roofline(cfg, f, peaks, hbm[0], hbm[1], ncu)
@@ -479,6 +502,8 @@ def run_config(cfg, args, rank, world, local_rank, torch, dist, peaks, hbm, ncu,
         out["stages"] = stages
         out["roofline"] = headline_roofline(stages, hbm[0], hbm[1])
         out["host_prerender_s"] = r.prerender_s
+        if check is not None:
+            out["gathered_frame_bit_identical_to_single_gpu"] = check
         out["upload_s"] = r.upload_s
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_frame(r.scene, r.table, spp, cores, 12.0 if cfg == "c2" else 4.0)
@@ -543,6 +568,26 @@ def run_ours(args):
     value = rays_all * args.steps / (dev_ms_total * 1e-3) / 1e6
     e2e_value = rays_all / (e2e_ms * 1e-3) / 1e6
 
+    # CPU on the same rays + bit-identity, while the C2 scene is still the one uploaded (the slot table belongs to it)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        oh, cpu_v, secs = cpu_trace(scene, inc, cores, reps=3)
+        same = bool(np.array_equal(oh["prim"], tb["hits"]["prim"]) and np.array_equal(oh["geom"], tb["hits"]["geom"]) and
+                    np.array_equal(oh["t"].view(np.uint32), tb["hits"]["t"].view(np.uint32)) and
+                    np.array_equal(oh["nodesT"], tb["hits"]["nodesT"]) and np.array_equal(oh["trisT"], tb["hits"]["trisT"]))
+        compact_ok = None
+        if tb["compact_hits"] is not None:
+            prim_of, geom_of = dev.slot_table()
+            ch = tb["compact_hits"]
+            hit = ch["slot"] >= 0
+            compact_ok = bool(np.array_equal(hit, oh["prim"] >= 0) and np.array_equal(prim_of[ch["slot"][hit]], oh["prim"][hit]) and
+                              np.array_equal(geom_of[ch["slot"][hit]], oh["geom"][hit]) and np.array_equal(ch["t"].view(np.uint32), oh["t"].view(np.uint32)) and
+                              np.array_equal(ch["u"].view(np.uint32), oh["u"].view(np.uint32)))
+        cpu = {"value": cpu_v, "unit": "Mrays/s", "cores": cores, "per_core": cpu_v / cores, "kind": "port",
+               "sample": "the same %d rays, 3 passes on all %d host threads, %.2f s per pass" % (n, cores, secs),
+               "bit_identical_to_gpu": same, "compact_hits_identical": compact_ok}
+
+
     configs = {"c2": c2}
     for cfg in want:
         if cfg == "c2":
@@ -581,24 +626,6 @@ def run_ours(args):
     else:
         roof.update({"bound": "hbm", "achieved": None, "peak": hbm[0], "unit": "GB/s", "frac": None, "traffic": None,
                      "note": "no committed ncu capture for this kernel"})
-
-    cpu = None
-    if world == 1 and not args.no_cpu:
-        oh, cpu_v, secs = cpu_trace(scene, inc, cores, reps=3)
-        same = bool(np.array_equal(oh["prim"], tb["hits"]["prim"]) and np.array_equal(oh["geom"], tb["hits"]["geom"]) and
-                    np.array_equal(oh["t"].view(np.uint32), tb["hits"]["t"].view(np.uint32)) and
-                    np.array_equal(oh["nodesT"], tb["hits"]["nodesT"]) and np.array_equal(oh["trisT"], tb["hits"]["trisT"]))
-        compact_ok = None
-        if tb["compact_hits"] is not None:
-            prim_of, geom_of = dev.slot_table()
-            ch = tb["compact_hits"]
-            hit = ch["slot"] >= 0
-            compact_ok = bool(np.array_equal(hit, oh["prim"] >= 0) and np.array_equal(prim_of[ch["slot"][hit]], oh["prim"][hit]) and
-                              np.array_equal(geom_of[ch["slot"][hit]], oh["geom"][hit]) and np.array_equal(ch["t"].view(np.uint32), oh["t"].view(np.uint32)) and
-                              np.array_equal(ch["u"].view(np.uint32), oh["u"].view(np.uint32)))
-        cpu = {"value": cpu_v, "unit": "Mrays/s", "cores": cores, "per_core": cpu_v / cores, "kind": "port",
-               "sample": "the same %d rays, 3 passes on all %d host threads, %.2f s per pass" % (n, cores, secs),
-               "bit_identical_to_gpu": same, "compact_hits_identical": compact_ok}
 
     out = {
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -357,6 +357,12 @@ const char* vh_last_error(vh_scene* s);
 int vh_registered_nodes(const char** names, int cap);
 
 int vh_set_globals(vh_scene* s, int xres, int yres, int max_iter);
+/* Host-layer options, before vh_prerender. "leaf_max" (default 16 = the reference's value, buildqbvh.go:85): leafMax of the per-mesh
+ * QBVH / MQBVH builds. Any other value is the OPT-IN NON-PARITY MODE: the reference's own builder run with smaller
+ * leaves gives another tree over the same triangles; the intersection routine and therefore every hit's t, u, v and face are the
+ * same (up to which of two equal-t triangles wins), but NodesT / TrisT, the leaf-order ElemID numbering and the work per ray are
+ * not the reference's. Parity tests and the headline numbers use 16; bench.py reports the mode beside them. */
+int vh_set_option(vh_scene* s, const char* name, int value);
 int vh_add_shader_std(vh_scene* s, const char* name, const VgMaterial* params);
 /* Texture maps (builtin/maps/texture.go, texture/texture.go). vh_add_texture: one decoded image file under the name the
  * shaders use (rgb8 rows bottom-up, see vg_texture_upload); the first registration of a name wins, like the reference's cache.

@@ -587,6 +587,24 @@ void orc_box_test(const float* P, const float* D, const float* boxes, int which,
   std::memcpy(hits, hh, 16);
   std::memcpy(t, tt, 16);
 }
+// the three box tests of qbvh/intersect.go side by side for one ray with a given Tclosest: which = 0 asm (intersect_amd64.s),
+// 1 intersectBoxesSlow2 (:52), 2 intersectBoxesSlow (:17, the Tclosest-clamped one)
+void orc_box_test3(const float* P, const float* D, float tclosest, const float* boxes, int which, int32_t* hits, float* t) {
+  Ray ray;
+  ray.P = v3(P);
+  ray.D = v3(D);
+  ray.Setup();
+  ray.Tclosest = tclosest;
+  alignas(16) float b[24];
+  alignas(16) float tt[4];
+  alignas(16) int32_t hh[4];
+  std::memcpy(b, boxes, 96);
+  if (which == 0) intersectBoxes(&ray, b, hh, tt);
+  else if (which == 1) intersectBoxesSlow2(&ray, b, hh, tt);
+  else intersectBoxesSlow(&ray, b, hh, tt);
+  std::memcpy(hits, hh, 16);
+  std::memcpy(t, tt, 16);
+}
 void orc_ray_setup(const float* P, const float* D, float* out /* Dinv3 S3 */, int32_t* k /*Kx Ky Kz*/) {
   Ray ray;
   ray.P = v3(P);

@@ -245,6 +245,27 @@ void intersectBoxes(const Ray* ray, const float* boxes, int32_t* hits, float* t)
   _mm_store_si128((__m128i*)hits, _mm_castps_si128(X0));
 }
 
+// qbvh/intersect.go:17-50 — the reference's OTHER scalar version: planes picked by the sign of Dinv instead of min/max, and
+// tFar additionally clamped by Tclosest (:39). The reference's commented-out self-check (:116-133) compares the asm's hits with
+// this one; tests/test_oracle_traversal.py restates that check and pins where the two may differ.
+void intersectBoxesSlow(const Ray* ray, const float* boxes, int32_t* hits, float* t) {
+  uint8_t sign[3] = {0, 0, 0};
+  for (int k = 0; k < 3; k++)
+    if (ray->Dinv[k] < 0.0f) sign[k] = 1;
+  for (int idx = 0; idx < 4; idx++) {
+    float tmin = (boxes[idx + (sign[0] * 12) + 0] - ray->P[0]) * ray->Dinv[0];
+    float tmax = (boxes[idx + ((1 - sign[0]) * 12) + 0] - ray->P[0]) * ray->Dinv[0];
+    float tymin = (boxes[idx + (sign[1] * 12) + 4] - ray->P[1]) * ray->Dinv[1];
+    float tymax = (boxes[idx + ((1 - sign[1]) * 12) + 4] - ray->P[1]) * ray->Dinv[1];
+    float tzmin = (boxes[idx + (sign[2] * 12) + 8] - ray->P[2]) * ray->Dinv[2];
+    float tzmax = (boxes[idx + ((1 - sign[2]) * 12) + 8] - ray->P[2]) * ray->Dinv[2];
+    float tNear = Max(Max(tmin, tymin), Max(0.0f, tzmin));
+    float tFar = Min(Min(tmax, tymax), Min(ray->Tclosest, tzmax));
+    t[idx] = tNear;
+    hits[idx] = (tNear <= tFar) ? -1 : 0;
+  }
+}
+
 // qbvh/intersect.go:52-87 — the reference's scalar twin of the asm.
 void intersectBoxesSlow2(const Ray* ray, const float* boxes, int32_t* hits, float* t) {
   for (int idx = 0; idx < 4; idx++) {

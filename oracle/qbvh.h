@@ -76,6 +76,7 @@ std::vector<MotionNode> BuildAccelMotion(BoundingBox* boxes, Vec3* centroids, in
 
 void intersectBoxes(const Ray* ray, const float* boxes, int32_t* hits, float* t);
 void intersectBoxesSlow2(const Ray* ray, const float* boxes, int32_t* hits, float* t);
+void intersectBoxesSlow(const Ray* ray, const float* boxes, int32_t* hits, float* t);  // intersect.go:17-50
 
 bool QTrace(const std::vector<Node>& qbvh, Primitive* prim, Ray* ray, ShaderContext* sg);
 bool QTraceMotion(const MotionQBVH& qbvh, float time, int key, int key2, MotionPrimitive* prim, Ray* ray, ShaderContext* sg);

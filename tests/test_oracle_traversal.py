@@ -116,3 +116,59 @@ def test_builder_reports_reference_quirk_f():
         Oracle(sc)
     with pytest.raises(RuntimeError, match="unbounded recursion"):
         HostScene(sc).prerender()
+
+
+def _box3(L, P, D, tclosest, boxes, which):
+    hits = (C.c_int32 * 4)()
+    t = (C.c_float * 4)()
+    L.orc_box_test3.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_box_test3((C.c_float * 3)(*P), (C.c_float * 3)(*D), C.c_float(tclosest), (C.c_float * 24)(*boxes), which, hits, t)
+    return np.asarray(list(hits), np.int32), np.asarray(list(t), np.float32)
+
+
+def test_reference_self_check_asm_vs_slow_vs_slow2(oracle_lib):
+    """The reference's own (commented-out) cross-check, qbvh/intersect.go:116-133: the asm box test against intersectBoxesSlow
+    (:17-50) and intersectBoxesSlow2 (:52-87), here on the nodes of a real tree plus random boxes, and WHERE they may differ:
+      * asm == Slow2 everywhere on finite inputs (hits and t bit for bit): Slow2 is the asm's twin;
+      * Slow clamps tFar by Tclosest (:39), the asm does not: with Tclosest = +Inf the three agree; with a finite Tclosest the
+        asm's extra hits are exactly the children whose tNear lies beyond Tclosest — the ones Trace discards at pop time
+        (:106, Tclosest < Stack.T), which is why the reference can push them unclamped;
+      * tNear itself is the same number in all three (the near plane picked by the sign of Dinv is the min of the two products).
+    Rays with a zero direction component are left to test_box_test_nan_semantics: there Slow's sign-based plane choice and the
+    MINPS/MAXPS operand order genuinely part ways."""
+    from oracle.binding import Oracle
+    from vermeer_b200 import scenes
+    sc = scenes.heightfield_scene(32, 32, nq=40)
+    ora = Oracle(sc)
+    nodes = ora.mesh_nodes(0)
+    rng = np.random.default_rng(3)
+    n_extra = 0
+    for i in range(4000):
+        if i % 2 == 0:
+            nd = nodes[rng.integers(len(nodes))]
+            boxes = nd["Boxes"].copy()
+            boxes[~np.isfinite(boxes)] = 0.0       # empty children hold +-Inf boxes; the finite-input claim is about real boxes
+            P = np.float32([rng.uniform(-1, 1), rng.uniform(0.2, 1.5), rng.uniform(-1, 1)])
+            D = np.float32([rng.normal() * 0.5, -abs(rng.normal()) - 0.05, rng.normal() * 0.5])
+        else:
+            lo = rng.uniform(-2, 2, (3, 4)).astype(np.float32)
+            hi = lo + rng.uniform(0, 1.5, (3, 4)).astype(np.float32)
+            boxes = np.concatenate([lo.reshape(-1), hi.reshape(-1)])
+            P = rng.uniform(-3, 3, 3).astype(np.float32)
+            D = rng.normal(size=3).astype(np.float32)
+        D[D == 0] = np.float32(0.25)
+        for tcl in (np.inf, float(rng.uniform(0.05, 1.0))):
+            ha, ta = _box3(oracle_lib, P, D, tcl, boxes, 0)
+            h2, t2 = _box3(oracle_lib, P, D, tcl, boxes, 1)
+            hs, ts = _box3(oracle_lib, P, D, tcl, boxes, 2)
+            assert np.array_equal(ha, h2) and np.array_equal(ta.view(np.uint32), t2.view(np.uint32))
+            assert np.array_equal(ta, ts)                          # the same tNear (== : the sign of a zero may differ)
+            if np.isinf(tcl):
+                assert np.array_equal(ha, hs)
+            else:
+                assert np.all(hs[ha == 0] == 0)                    # Slow never reports a box the asm misses
+                extra = (ha != 0) & (hs == 0)
+                assert np.all(ta[extra] > tcl)                     # ... and misses only children beyond Tclosest
+                assert np.all(hs[(ha != 0) & (ta <= tcl)] != 0)
+                n_extra += int(extra.sum())
+    assert n_extra > 50                                            # the difference is exercised, not vacuous

@@ -372,7 +372,7 @@ int PolyMesh::PreRender(Core& core, std::string* err) {
     if (!sh) { *err = "Unable to find shader " + s; return -1; }
     shader.push_back(sh);
   }
-  return initAccel(err, core.build_ctx);
+  return initAccel(err, core.build_ctx, core.leaf_max);
 }
 
 // builtin/geom/polymesh/buildqbvh.go:14-144
@@ -380,7 +380,7 @@ int PolyMesh::PreRender(Core& core, std::string* err) {
 // ~1 ms however small the mesh; scenes of many small meshes also keep the host's threads busy in parallel)
 static const int kDeviceBuildMinFaces = 32768;
 
-int PolyMesh::initAccel(std::string* err, vg_ctx* build_ctx) {
+int PolyMesh::initAccel(std::string* err, vg_ctx* build_ctx, int leaf_max) {
   std::vector<Box> boxes(facecount);
   std::vector<V3> cent(facecount);
   std::vector<int32_t> idxs(facecount);
@@ -407,7 +407,7 @@ int PolyMesh::initAccel(std::string* err, vg_ctx* build_ctx) {
       static std::mutex device_build_mu;
       std::lock_guard<std::mutex> build_lock(device_build_mu);
       std::vector<VgNode> tmp;
-      if (vg_build_qbvh(build_ctx, &boxes[0].lo[0], &cent[0].x, facecount, 16, idxs.data(), b6, &n_nodes) != VG_OK) {
+      if (vg_build_qbvh(build_ctx, &boxes[0].lo[0], &cent[0].x, facecount, leaf_max, idxs.data(), b6, &n_nodes) != VG_OK) {
         *err = std::string("device MQBVH build: ") + vg_last_error(build_ctx);
         return -1;
       }
@@ -423,7 +423,7 @@ int PolyMesh::initAccel(std::string* err, vg_ctx* build_ctx) {
         mtopo[(size_t)i].axis2 = (int32_t)tmp[(size_t)i].axis2;
         for (int k = 0; k < 4; k++) mtopo[(size_t)i].children[k] = tmp[(size_t)i].children[k];
       }
-    } else if (build_mqbvh(boxes.data(), cent.data(), idxs.data(), facecount, 16, mtopo, err) != 0) {
+    } else if (build_mqbvh(boxes.data(), cent.data(), idxs.data(), facecount, leaf_max, mtopo, err) != 0) {
       return -1;
     }
     accel_idx = idxs;  // NOTE: idxp is NOT reordered on this path (the function returns at :56) — quirk (b)
@@ -458,7 +458,7 @@ int PolyMesh::initAccel(std::string* err, vg_ctx* build_ctx) {
     // build + fetch is a two-call protocol on the context; the meshes of a round are pre-rendered concurrently
     static std::mutex device_build_mu;
     std::lock_guard<std::mutex> build_lock(device_build_mu);
-    if (vg_build_qbvh(build_ctx, &boxes[0].lo[0], &cent[0].x, facecount, 16, idxs.data(), b6, &n_nodes) != VG_OK) {
+    if (vg_build_qbvh(build_ctx, &boxes[0].lo[0], &cent[0].x, facecount, leaf_max, idxs.data(), b6, &n_nodes) != VG_OK) {
       *err = std::string("device QBVH build: ") + vg_last_error(build_ctx);
       return -1;
     }
@@ -468,7 +468,7 @@ int PolyMesh::initAccel(std::string* err, vg_ctx* build_ctx) {
       return -1;
     }
     for (int a = 0; a < 3; a++) { bounds.lo[a] = b6[a]; bounds.hi[a] = b6[3 + a]; }
-  } else if (build_qbvh(boxes.data(), cent.data(), idxs.data(), facecount, 16, qbvh, &bounds, err) != 0) {
+  } else if (build_qbvh(boxes.data(), cent.data(), idxs.data(), facecount, leaf_max, qbvh, &bounds, err) != 0) {
     return -1;
   }
   accel_idx = idxs;

@@ -111,7 +111,7 @@ struct PolyMesh : Node, Geom {
 
  private:
   void triangulate();
-  int initAccel(std::string* err, vg_ctx* build_ctx);
+  int initAccel(std::string* err, vg_ctx* build_ctx, int leaf_max = 16);
   Box initMotionBoxesRec(int key, int32_t node);
 };
 
@@ -271,6 +271,9 @@ struct TextureImage {
 
 struct Core {
   vg_ctx* build_ctx = nullptr;  // vh_prerender_device: static-mesh QBVHs are built on this device (vg_build_qbvh)
+  // leafMax of the per-mesh builds. 16 is what the reference passes (buildqbvh.go:85, motionbuild.go callers); any other value is the
+  // opt-in NON-PARITY mode of vh_set_option("leaf_max"): another tree, same triangles, same intersection routine.
+  int leaf_max = 16;
   std::vector<TextureImage> textures;
   Globals* globals = nullptr;
   Scene scene;

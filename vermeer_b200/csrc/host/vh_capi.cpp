@@ -52,6 +52,16 @@ int vh_registered_nodes(const char** names, int cap) {
   return (int)keep.size();
 }
 
+int vh_set_option(vh_scene* s, const char* name, int value) {
+  if (!s || !name) return VG_ERR_INVALID;
+  if (!std::strcmp(name, "leaf_max")) {
+    if (value < 1 || value > 16) return fail(s, VG_ERR_INVALID, "leaf_max must be in [1,16] (qbvh/build.go:296-302 clamps to the same range)");
+    s->core.leaf_max = value;
+    return VG_OK;
+  }
+  return fail(s, VG_ERR_INVALID, std::string("unknown option ") + name);
+}
+
 int vh_set_globals(vh_scene* s, int xres, int yres, int max_iter) {
   if (!s) return VG_ERR_INVALID;
   std::unique_ptr<Node> h;

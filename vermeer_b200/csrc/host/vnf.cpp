@@ -668,9 +668,11 @@ int ParseVnf(Core& core, const char* text, size_t len, const std::string& filena
       }
       continue;
     }
-    if (!defn) why = "node type \"" + type + "\" not registered";
+    // createNode's error text (nodes/register.go:23) for an unknown type; a node that p.node() dropped comes back as (nil, nil)
+    // and Go's %v prints that error as "<nil>" (parser.go:889)
+    if (!defn) why = "Node type " + type + " not registered.";
     else if (!defn->in_scope) why = "node type \"" + type + "\" is outside this path (SURVEY.md 8, out of scope)";
-    p.errorf("Node is nil: " + why);
+    p.errorf("Node is nil: " + (why.empty() ? std::string("<nil>") : why));
     // parser.go:893-899: skip to the next '}' — for a node dropped at its own '}' this swallows the FOLLOWING node, as in
     // the reference
     for (;;) {

@@ -130,8 +130,12 @@ struct Box4Out {
 // a + (-b), the same operation). The traversal kernels are issue-bound (ncu: 75 % of issue slots active), and the 24 FADD +
 // 24 FMUL of a node visit are its largest single block of instructions: 24 packed ones replace them. A 128-bit node load
 // delivers children (0,1) and (2,3) of one plane in adjacent registers, which is exactly the pair layout the packed form wants.
+// MEASURED on B200 (round 2) and left OFF: C2 closest / shadow 19.23 / 32.93 ms with it, 19.16 / 33.04 ms without, C3 308.3 / 281.1
+// vs 311.0 / 279.2 ms — no difference beyond noise. The packed instructions evidently occupy the FP32 pipe for two issue cycles, so
+// the issue slots they free cannot be used by the dependent min/max chain, and the duplicated (-O, Dinv) pairs cost 6 registers
+// under the 64/72-register caps (+8..32 B of spills). Kept as a build switch (bit-identical, parity-tested once).
 #ifndef VG_BOX_F32X2
-#define VG_BOX_F32X2 1
+#define VG_BOX_F32X2 0
 #endif
 template <bool EXACT>
 __device__ __forceinline__ void box_axis2(float2 lo, float2 hi, float2 no, float2 id, float2& tn, float2& tf, bool first) {

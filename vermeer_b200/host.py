@@ -36,7 +36,7 @@ DECLARED_SYMBOLS = [
     "vg_comm_unique_id", "vg_comm_init", "vg_comm_destroy", "vg_gather_frame", "vg_nccl_version", "vg_owned_pixels", "vg_measure_peaks", "vg_slot_table", "vg_captured_rays",
     "vg_texture_upload", "vg_textures_clear", "vg_texture_levels", "vg_texture_read_level", "vg_material_set_texture", "vg_mesh_set_uv", "vg_texture_sample_batch",
     "vh_add_texture", "vh_shader_set_texture", "vh_polymesh_set_uv", "vg_build_qbvh", "vg_build_qbvh_nodes", "vh_prerender_device",
-    "vh_scene_create", "vh_scene_destroy", "vh_last_error", "vh_registered_nodes", "vh_set_globals", "vh_add_shader_std", "vh_add_shader_debug", "vh_add_polymesh",
+    "vh_set_option", "vh_scene_create", "vh_scene_destroy", "vh_last_error", "vh_registered_nodes", "vh_set_globals", "vh_add_shader_std", "vh_add_shader_debug", "vh_add_polymesh",
     "vh_add_filter", "vh_add_instance", "vh_add_trilight", "vh_add_disklight", "vh_add_spherelight", "vh_parse_vnf", "vh_load_vnf", "vh_globals", "vh_postrender", "vh_rgbe", "vh_set_camera_lookat", "vh_set_camera_keys", "vh_camera_decomp", "vh_prerender", "vh_upload", "vh_num_geoms", "vh_scene_info", "vh_scene_nodes",
     "vh_scene_motion_nodes", "vh_scene_geom_order", "vh_mesh_info", "vh_mesh_nodes", "vh_mesh_motion_nodes", "vh_mesh_idxp", "vh_camera",
 ]
@@ -122,7 +122,7 @@ def material_struct(sh) -> VgMaterial:
 class HostScene:
     """vh_* layer: the reference's node registry + PreRender, from a SceneDesc."""
 
-    def __init__(self, scene: SceneDesc):
+    def __init__(self, scene: SceneDesc, leaf_max: int | None = None):
         self.L = load_library()
         self.scene = scene
         h = C.c_void_p()
@@ -130,6 +130,8 @@ class HostScene:
             raise RuntimeError("vh_scene_create failed")
         self.h = h
         L = self.L
+        if leaf_max is not None:   # opt-in non-parity mode: the reference's builder with another leafMax (vh_set_option)
+            self._chk(L.vh_set_option(h, b"leaf_max", int(leaf_max)))
         self._chk(L.vh_set_globals(h, scene.XRes, scene.YRes, scene.MaxIter))
         for s in scene.shaders:
             if hasattr(s, "Colour"):   # scenes.DebugShader
