@@ -588,6 +588,14 @@ def run_ours(args):
                "bit_identical_to_gpu": same, "compact_hits_identical": compact_ok}
 
 
+    # parity-mode hits of the headline batch by original face, for the non-parity leg's check (the C2 scene is still uploaded)
+    nonparity = None
+    if rank == 0 and world == 1 and not args.no_nonparity:
+        _, aidx16 = host.mesh_idxp(0)
+        h16 = tb["hits"]
+        face16 = np.where((h16["prim"] >= 0) & (h16["geom"] == 0), aidx16[np.maximum(h16["prim"], 0) % len(aidx16)], -1 - h16["geom"])
+        nonparity = nonparity_leg(scene, inc, h16, face16, torch, local_rank)
+
     configs = {"c2": c2}
     for cfg in want:
         if cfg == "c2":
@@ -645,6 +653,7 @@ def run_ours(args):
         "frame": {k: v for k, v in c2.items() if k not in ("stages",)},
         "configs": configs,
         "incoherent_wavefront": (configs.get("c3") or {}).get("incoherent_wavefront"),
+        "nonparity": nonparity,
         "measured_peaks": {"hbm_gbs": hbm[0], "hbm_source": hbm[1], **peaks},
         "speedup_vs_cpu": None if not cpu else {"device_resident": value / cpu["value"], "e2e": e2e_value / cpu["value"], "cores": cores,
                                                 "frame_e2e": c2.get("speedup_e2e_vs_cpu_all_cores")},
@@ -652,6 +661,42 @@ def run_ours(args):
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def nonparity_leg(scene, inc, ref_hits, ref_face, torch, local_rank, leaf_max=4):
+    """Opt-in NON-PARITY mode (vh_set_option "leaf_max"): the reference's own builder run with leafMax 4 instead of
+    16 — another tree over the same triangles, same intersection routine. Reported beside the parity numbers, never instead of
+    them. Same frame (C2, 64 spp) and same incoherent batch; the hits must be the same t and the same face."""
+    from vermeer_b200 import scenes
+    from vermeer_b200.host import Device, HostScene
+    host = HostScene(scene, leaf_max=leaf_max).prerender()
+    dev = Device(local_rank).upload(host)
+    dev.set_scramble(scenes.splitmix64_table(SCRAMBLE_SEED, scene.XRes * scene.YRes))
+    dev.set_option("iters_per_batch", ITERS_PER_BATCH)
+    ms = []
+    for i in range(4):
+        dev.clear()
+        dev.render(0, 64, fetch=False)
+        st = dev.stats()
+        if i >= 1:
+            ms.append((st["render_ms"], st["closest_ms"], st["shadow_ms"], st["shade_ms"]))
+    m = np.mean(np.asarray(ms), 0)
+    dev.reset_stats()
+    dev.clear()
+    dev.render(0, 64, fetch=False)
+    rays = dev.stats()["rays"]
+    tb = time_batch(dev, torch, inc, 5, 3, compact_e2e=False)
+    _, aidx = host.mesh_idxp(0)
+    h = tb["hits"]
+    face = np.where((h["prim"] >= 0) & (h["geom"] == 0), aidx[np.maximum(h["prim"], 0) % len(aidx)], -1 - h["geom"])
+    out = {"mode": "leaf_max=%d (reference builder, smaller leaves; NOT the reference's tree)" % leaf_max, "nodes": host.mesh_info(0)["nodes"],
+           "frame": {"value": rays / m[0] / 1e3, "unit": "Mrays/s", "ms_per_step": float(m[0]),
+                     "stage_ms_per_step": {"closest_traversal": float(m[1]), "shadow_traversal": float(m[2]), "shading": float(m[3])}},
+           "incoherent": {"value": tb["rays"] / tb["ms_per_step"] / 1e3, "unit": "Mrays/s", "nodesT_per_ray": tb["nodesT_per_ray"], "trisT_per_ray": tb["trisT_per_ray"]},
+           "same_t_as_parity_mode": float((h["t"].view(np.uint32) == ref_hits["t"].view(np.uint32)).mean()),
+           "same_face_as_parity_mode": float((face == ref_face).mean())}
+    dev.close()
+    return out
 
 
 def wavefront_leg(dev, torch, cores, args):
@@ -728,6 +773,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-wavefront", action="store_true", help="skip the C3 wavefront incoherent batch")
+    ap.add_argument("--no-nonparity", action="store_true", help="skip the opt-in non-parity (leaf_max=4) leg")
     ap.add_argument("--configs", default=os.environ.get("VG_BENCH_CONFIGS", ""), help="comma list of frame configs (default c1,c2,c3,c4 and c5 at 8 GPUs); c2 always runs")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -106,6 +106,7 @@ struct RenderParams {
   int xres, yres, nown, P;  // P = paths per batch
   // path index <-> (owned pixel, iteration of the batch): see path_index()
   int pm_B, pm_G, pm_nownB, pm_nitG, pm_A, pm_rem, niters;
+  int pm_lB, pm_lG;  // log2 of pm_B, pm_G (both powers of two)
   const int* pix;           // [nown] full-frame pixel index, tile-major
   const uint64_t* scr;      // [nown*6] rows in path order, or (scr_by_pixel) the caller's whole table [xres*yres*6] in raster order
   int scr_by_pixel;
@@ -152,15 +153,17 @@ struct RenderParams {
 // Region A: full pixel groups x full iteration groups, warp-sized cells; the remainders (nown % B pixels, niters % G
 // iterations) follow densely in iteration-major order, so queue slot == path stays a bijection on [0, nown*niters).
 __device__ __forceinline__ int path_index(const RenderParams& p, int own, int it) {
-  if (own < p.pm_nownB && it < p.pm_nitG) return (((it / p.pm_G) * (p.pm_nownB / p.pm_B) + own / p.pm_B) << 5) + (it % p.pm_G) * p.pm_B + own % p.pm_B;
+  if (own < p.pm_nownB && it < p.pm_nitG)
+    return ((((it >> p.pm_lG) * (p.pm_nownB >> p.pm_lB)) + (own >> p.pm_lB)) << 5) + ((it & (p.pm_G - 1)) << p.pm_lB) + (own & (p.pm_B - 1));
   if (it < p.pm_nitG) return p.pm_A + it * p.pm_rem + (own - p.pm_nownB);
   return p.pm_A + p.pm_nitG * p.pm_rem + (it - p.pm_nitG) * p.nown + own;
 }
 __device__ __forceinline__ void path_decode(const RenderParams& p, int path, int& own, int& it) {
   if (path < p.pm_A) {
-    const int cell = path >> 5, r = path & 31, nblk = p.pm_nownB / p.pm_B;
-    own = (cell % nblk) * p.pm_B + r % p.pm_B;
-    it = (cell / nblk) * p.pm_G + r / p.pm_B;
+    const int cell = path >> 5, r = path & 31, nblk = p.pm_nownB >> p.pm_lB;
+    const int cq = cell / nblk;
+    own = ((cell - cq * nblk) << p.pm_lB) + (r & (p.pm_B - 1));
+    it = (cq << p.pm_lG) + (r >> p.pm_lB);
     return;
   }
   int q = path - p.pm_A;
@@ -371,7 +374,9 @@ __device__ __forceinline__ f3 ld3(const float4* p) {
 // polymesh/trace.go:276-360,504-515 (static) / :625-667 (motion), then ShaderContext.ApplyTransform (core/shader.go:129-135,
 // identity transform: only the re-normalisations remain).
 // APPLY_IDENTITY = false leaves N, Ng, DdPdu, DdPdv as the geom wrote them, for a caller that applies a real transform.
-template <bool APPLY_IDENTITY = true>
+// FAST: the normalisations through MUFU.RSQ (shade.cuh: normalize3t) instead of a correctly rounded sqrt + divide; the
+// reference's own Vec3Normalize is RSQRTSS + one Newton step, so neither form is bit-comparable with it.
+template <bool APPLY_IDENTITY = true, bool FAST = false>
 __device__ inline void build_context(const RenderParams& p, const DevHit& h, float time, ShadeCtx& c) {
   const DevGeom g = p.sc.geoms[h.geom];
   const float U = h.u, V = h.v, W = h.w;
@@ -396,12 +401,12 @@ __device__ inline void build_context(const RenderParams& p, const DevHit& h, flo
   const float yAbs = fabsf(U * E0.y) + fabsf(V * E1.y) + fabsf(W * E2.y);
   const float zAbs = fabsf(U * E0.z) + fabsf(V * E1.z) + fabsf(W * E2.z);
   const f3 e0 = sub3(E1, E0), e1 = sub3(E2, E0);
-  f3 Ng = normalize3(cross3(e0, e1));
+  f3 Ng = normalize3t<FAST>(cross3(e0, e1));
   f3 N = Ng;
   if (!motion && g.normal_base >= 0 && p.sc.tri_normals) {
     const float4* np = p.sc.tri_normals + (size_t)h.slot * 3;
     const f3 n0 = ld3(np), n1 = ld3(np + 1), n2 = ld3(np + 2);
-    N = normalize3(mk3(U * n0.x + V * n1.x + W * n2.x, U * n0.y + V * n1.y + W * n2.y, U * n0.z + V * n1.z + W * n2.z));
+    N = normalize3t<FAST>(mk3(U * n0.x + V * n1.x + W * n2.x, U * n0.y + V * n1.y + W * n2.y, U * n0.z + V * n1.z + W * n2.z));
   }
   const float g7 = (7.0f * 5.9604644775390625e-08f) / (1 - 7.0f * 5.9604644775390625e-08f);  // math/ferror.go:22-24, Gamma(7)
   const float d = g7 * xAbs * fabsf(Ng.x) + g7 * yAbs * fabsf(Ng.y) + g7 * zAbs * fabsf(Ng.z);
@@ -410,7 +415,7 @@ __device__ inline void build_context(const RenderParams& p, const DevHit& h, flo
   if (!motion) {
     f3 axisu = sub3(mk3(1, 0, 0), scale3(Ng.x, Ng));
     if (len2_3(axisu) < 0.1f || fabsf(dot3(axisu, Ng)) > 0.3f) axisu = sub3(mk3(0, 0, 1), scale3(Ng.z, Ng));
-    c.DdPdu = normalize3(axisu);
+    c.DdPdu = normalize3t<FAST>(axisu);
     c.DdPdv = cross3(Ng, c.DdPdu);
   } else {
     c.DdPdu = e0;
@@ -422,10 +427,10 @@ __device__ inline void build_context(const RenderParams& p, const DevHit& h, flo
     return;
   }
   // ApplyTransform
-  c.N = normalize3(N);
-  c.Ng = normalize3(Ng);
-  c.DdPdu = normalize3(c.DdPdu);
-  c.DdPdv = normalize3(c.DdPdv);
+  c.N = normalize3t<FAST>(N);
+  c.Ng = normalize3t<FAST>(Ng);
+  c.DdPdu = normalize3t<FAST>(c.DdPdu);
+  c.DdPdv = normalize3t<FAST>(c.DdPdv);
 }
 
 // Scenes with texture maps: one pass over the hit queue between traversal and shading.
@@ -714,15 +719,15 @@ __device__ inline LightRec light_sample_r(const DevLight& L, const ShadeCtx& c, 
     Pl = mk3(L.p0.x + a.x + b.x, L.p0.y + a.y + b.y, L.p0.z + a.z + b.z);
   } else {
     const f3 x = sample_spherical_triangle<FAST>(sph, r0, r1);
-    const float t = ray_plane(c.P, x, L.p0, L.N);
+    const float t = ray_plane<FAST>(c.P, x, L.p0, L.N);
     Pl = mad3(c.P, x, t);
-    r.pdf = (float)(1 / (double)sph.area);
+    r.pdf = FAST ? __fdividef(1.0f, sph.area) : (float)(1 / (double)sph.area);
   }
   const f3 D = sub3(Pl, c.P);
-  r.Ldist = length3(D);
+  r.Ldist = length3t<FAST>(D);
   r.Ld = normalize3t<FAST>(D);
   r.valid = !(dot3(r.Ld, L.N) > 0 || dot3(r.Ld, c.Ng) < 0);
-  if (by_area) r.pdf = L.inv_area * (r.Ldist * r.Ldist) / fabsf(dot3(r.Ld, L.N));
+  if (by_area) r.pdf = divt<FAST>(L.inv_area * (r.Ldist * r.Ldist), fabsf(dot3(r.Ld, L.N)));
   return r;
 }
 
@@ -757,7 +762,7 @@ __device__ inline BsdfRec bsdf_hit(const DevLight& L, const ShadeCtx& c, bool ha
   r.pdf = pdf;
   if (!dir_ok) return r;
   f3 Pl;
-  if (!ray_triangle(c.P, wo, L.p0, L.p1, L.p2, &Pl)) return r;
+  if (!ray_triangle<FAST>(c.P, wo, L.p0, L.p1, L.p2, &Pl)) return r;
   // NOTE: the horizon test of ValidSample is taken at the point ON THE LIGHT (triangle.go:145-147), kept as is
   const bool by_area = dot3(c.Ng, sub3(L.p0, Pl)) < 0 || dot3(c.Ng, sub3(L.p1, Pl)) < 0 || dot3(c.Ng, sub3(L.p2, Pl)) < 0;
   float pdfl;
@@ -765,13 +770,13 @@ __device__ inline BsdfRec bsdf_hit(const DevLight& L, const ShadeCtx& c, bool ha
     pdfl = L.inv_area;
   } else {
     const float area = have_sph ? sph.area : spherical_setup<FAST>(L.p0, L.p1, L.p2, c.P).area;
-    pdfl = (float)(double)(1 / area);
+    pdfl = FAST ? __fdividef(1.0f, area) : (float)(double)(1 / area);
   }
   const f3 D = sub3(Pl, c.P);
-  r.Ldist = length3(D);
+  r.Ldist = length3t<FAST>(D);
   r.Ld = normalize3t<FAST>(D);
   if (dot3(r.Ld, L.N) > 0 || dot3(r.Ld, c.Ng) < 0) return r;
-  r.pdfLight = by_area ? pdfl * (r.Ldist * r.Ldist) / fabsf(dot3(r.Ld, L.N)) : pdfl;
+  r.pdfLight = by_area ? divt<FAST>(pdfl * (r.Ldist * r.Ldist), fabsf(dot3(r.Ld, L.N))) : pdfl;
   r.valid = true;
   return r;
 }
@@ -847,12 +852,12 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
     int own, it;
     path_decode(p, path, own, it);
     I = (long long)(iter_base + it + 1);  // sample index I = ray.I = the 1-based iteration (render.go:123)
-    build_context(p, h, time, c);
+    build_context<true, FAST>(p, h, time, c);
     // tangent frame, std.go:98-106
     f3 V = cross3(c.N, c.DdPdu);
     if (len2_3(V) < 0.1f) V = cross3(c.N, c.DdPdv);
-    V = normalize3(V);
-    fr.U = normalize3(cross3(c.N, V));
+    V = normalize3t<FAST>(V);
+    fr.U = normalize3t<FAST>(cross3(c.N, V));
     fr.V = V;
     fr.N = c.N;
     omegaI = basis_project(fr.U, fr.V, fr.N, neg3(Rd));
@@ -928,8 +933,8 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
           Ld = lr.Ld;
           Ldist = lr.Ldist;
           if (NS > 1) {
-            p_hat = (float)nB * oren_pdf32<FAST>(fr, Ld) / (float)total;
-            p_hat += (float)nLs * lr.pdf / (float)total;
+            p_hat = divt<FAST>((float)nB * oren_pdf32<FAST>(fr, Ld), (float)total);
+            p_hat += divt<FAST>((float)nLs * lr.pdf, (float)total);
           } else {
             p_hat = lr.pdf;
           }
@@ -938,12 +943,12 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
           valid = br.valid;
           Ld = br.Ld;
           Ldist = br.Ldist;
-          p_hat = (float)nB * br.pdf / (float)total;
-          p_hat += (float)nLs * br.pdfLight / (float)total;
+          p_hat = divt<FAST>((float)nB * br.pdf, (float)total);
+          p_hat += divt<FAST>((float)nLs * br.pdfLight, (float)total);
         }
         if (valid && !(dot3(Ld, c.N) <= 0)) {
           Spec4 rho = oren_eval<FAST>(fr, ov, Ld);
-          const float inv = 1.0f / p_hat;
+          const float inv = divt<FAST>(1.0f, p_hat);
 #pragma unroll
           for (int k = 0; k < 4; k++) rho.c[k] = (rho.c[k] * Liu.c[k]) * inv;
           f3 rgb = spec_to_rgb(rho, hero);
@@ -1673,6 +1678,9 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
         while (G * 2 <= ctx->opt_iter_group && G * 2 <= 32 && G * 2 <= niters) G *= 2;
         p.pm_G = G;
         p.pm_B = 32 / G;
+        p.pm_lG = 0;
+        while ((1 << p.pm_lG) < G) p.pm_lG++;
+        p.pm_lB = 5 - p.pm_lG;
         p.pm_nownB = rs.nown - rs.nown % p.pm_B;
         p.pm_nitG = niters - niters % G;
         p.pm_A = p.pm_nownB * p.pm_nitG;

@@ -66,6 +66,26 @@ __device__ __forceinline__ f3 normalize3t(f3 a) {
   const float r = rsqrtf(x1);
   return mk3(a.x * r, a.y * r, a.z * r);
 }
+// FAST shading variant of the scalar helpers: approximate division (MUFU.RCP + multiply, <= 2 ulp) and square root
+// (MUFU.SQRT, <= 1 ulp; 0 -> 0, negative -> NaN like sqrtf) instead of the correctly rounded multi-instruction sequences
+// -prec-div / -prec-sqrt produce. The traversal needs those flags (its arithmetic is bit-exact); the shading quantities that go
+// through here are all downstream of a normalize, i.e. tolerance-only (SURVEY.md note N), and the precise path keeps IEEE.
+template <bool FAST>
+__device__ __forceinline__ float divt(float a, float b) { return FAST ? __fdividef(a, b) : a / b; }
+template <bool FAST>
+__device__ __forceinline__ float sqrtt(float x) {
+  if (!FAST) return sqrtf(x);
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+template <bool FAST>
+__device__ __forceinline__ float length3t(f3 a) {
+  float x0 = a.x * a.x, x1 = a.y * a.y, x2 = a.z * a.z;
+  x1 = x1 + x0;
+  x1 = x1 + x2;
+  return sqrtt<FAST>(x1);
+}
 __device__ __forceinline__ f3 basis_project(f3 U, f3 V, f3 W, f3 S) { return mk3(dot3(U, S), dot3(V, S), dot3(W, S)); }
 __device__ __forceinline__ f3 basis_expand(f3 U, f3 V, f3 W, f3 S) {
   return mk3(U.x * S.x + V.x * S.y + W.x * S.z, U.y * S.x + V.y * S.y + W.y * S.z, U.z * S.x + V.z * S.y + W.z * S.z);
@@ -217,10 +237,10 @@ __device__ __forceinline__ f3 spec_to_rgb(const Spec4& s, const Hero& h) {  // s
 template <bool FAST>
 __device__ __forceinline__ f3 cosine_hemisphere(double u0, double u1) {  // sample.go:18-27
   if (FAST) {
-    const float r = sqrtf((float)(1 - u0));
+    const float r = sqrtt<true>((float)(1 - u0));
     float sn, cs;
     sincospif((float)(2 * u1), &sn, &cs);
-    return mk3(r * cs, r * sn, sqrtf((float)u0));
+    return mk3(r * cs, r * sn, sqrtt<true>((float)u0));
   }
   const double r = sqrt(1 - u0);
   const double theta = 2 * VG_PI64 * u1;
@@ -281,7 +301,7 @@ __device__ __forceinline__ OrenVertex oren_vertex(f3 omegaI, float roughness2, c
   v.B = 0.45f * (sigma * sigma) / ((sigma * sigma) + 0.09f);
   if (FAST) {
     v.cosI = omegaI.z;
-    v.sinI = sqrtf(1.0f - omegaI.z * omegaI.z);  // NaN for |z| > 1, like acos
+    v.sinI = sqrtt<true>(1.0f - omegaI.z * omegaI.z);  // NaN for |z| > 1, like acos
     unit2(omegaI.x, omegaI.y, &v.cphiI, &v.sphiI);
     v.phiI = v.thetaI = 0.0f;
   } else {
@@ -300,12 +320,12 @@ __device__ __forceinline__ Spec4 oren_eval(const Frame& f, const OrenVertex& ov,
     // the same expression without inverse trig: theta = acos(cos) is decreasing, so max/min of the angles are picked by
     // comparing cosines; sin(alpha) tan(beta) and cos(phiO - phiI) follow from the cosine/sine pairs. NaN cases keep the
     // reference's x86 max/min semantics (a NaN thetaI is dropped, a NaN thetaO propagates).
-    const float cosO = o.z, sinO = sqrtf(1.0f - o.z * o.z);
+    const float cosO = o.z, sinO = sqrtt<true>(1.0f - o.z * o.z);
     const bool ok = (ov.sinI == ov.sinI) && (sinO == sinO);
     const bool aI = ok && ov.cosI < cosO;  // alpha = thetaI
     const bool bI = ok && ov.cosI > cosO;  // beta = thetaI
     const float sinA = aI ? ov.sinI : sinO;
-    const float tanB = bI ? ov.sinI / ov.cosI : sinO / cosO;
+    const float tanB = bI ? __fdividef(ov.sinI, ov.cosI) : __fdividef(sinO, cosO);
     Cc = sinA * tanB;
     float cphiO, sphiO;
     unit2(o.x, o.y, &cphiO, &sphiO);
@@ -367,12 +387,13 @@ __device__ __forceinline__ f3 offset_p(f3 P, f3 Poffset, int dir) {
 
 // ---- triangle light ---------------------------------------------------------------------------------
 // builtin/light/triangle.go:79-134 (Moller-Trumbore, no culling)
+template <bool FAST = false>
 __device__ inline bool ray_triangle(f3 Ro, f3 Rd, f3 P0, f3 P1, f3 P2, f3* pout) {
   const f3 e1 = sub3(P1, P0), e2 = sub3(P2, P0);
   const f3 P = cross3(Rd, e2);
   const float det = dot3(e1, P);
   if (det > -1e-6f && det < 1e-6f) return false;
-  const float inv_det = 1 / det;
+  const float inv_det = divt<FAST>(1.0f, det);
   const f3 T = sub3(Ro, P0);
   const float u = dot3(T, P) * inv_det;
   if (u < 0 || u > 1) return false;
@@ -448,21 +469,22 @@ __device__ inline f3 sample_spherical_triangle(const SphTri& st, double r0, doub
   }
   const float u = t - cosAlpha;
   const float v = s + sinAlpha * cosC;
-  float q = ((v * t - u * s) * cosAlpha - v) / ((v * s + u * t) * sinAlpha);
+  float q = divt<FAST>((v * t - u * s) * cosAlpha - v, (v * s + u * t) * sinAlpha);
   q = maxf_x86(-1.0f, minf_x86(q, 1.0f));
   float w = dot3(pc, pa);
   f3 v31 = normalize3t<FAST>(mk3(pc.x - w * pa.x, pc.y - w * pa.y, pc.z - w * pa.z));
-  const float sq = sqrtf(1 - q * q);
+  const float sq = sqrtt<FAST>(1 - q * q);
   const f3 v4 = mk3(q * pa.x + sq * v31.x, q * pa.y + sq * v31.y, q * pa.z + sq * v31.z);
   const float z = 1 - (float)r1 * (1 - dot3(v4, pb));
   w = dot3(v4, pb);
   const f3 v42 = normalize3t<FAST>(mk3(v4.x - w * pb.x, v4.y - w * pb.y, v4.z - w * pb.z));
-  return add3(scale3(z, pb), scale3(sqrtf(1 - z * z), v42));
+  return add3(scale3(z, pb), scale3(sqrtt<FAST>(1 - z * z), v42));
 }
 // disk.go:38-51
+template <bool FAST = false>
 __device__ __forceinline__ float ray_plane(f3 Ro, f3 Rd, f3 P, f3 N) {
   const float denom = dot3(N, Rd);
-  if (fabsf(denom) > 1e-6f) return dot3(sub3(P, Ro), N) / denom;
+  if (fabsf(denom) > 1e-6f) return divt<FAST>(dot3(sub3(P, Ro), N), denom);
   return 0.0f;
 }
 

@@ -176,9 +176,9 @@ __device__ inline LightRec light_sample_any(const DevLight& L, const ShadeCtx& c
     const f3 Pl = mk3(L.p0.x + a.x + b.x, L.p0.y + a.y + b.y, L.p0.z + a.z + b.z);
     const f3 V = sub3(Pl, c.P);
     if (dot3(V, c.Ng) > 0.0f && dot3(V, L.N) < 0.0f) {
-      r.Ldist = length3(V);
+      r.Ldist = length3t<FAST>(V);
       r.Ld = normalize3t<FAST>(V);
-      r.pdf = L.inv_area * (r.Ldist * r.Ldist) / fabsf(dot3(r.Ld, L.N));
+      r.pdf = divt<FAST>(L.inv_area * (r.Ldist * r.Ldist), fabsf(dot3(r.Ld, L.N)));
       r.valid = true;
     }
   } else {  // sphere.go:186-270
@@ -192,7 +192,7 @@ __device__ inline LightRec light_sample_any(const DevLight& L, const ShadeCtx& c
     if (!(dot3(omega, c.Ng) < 0) && ray_sphere(c.P, omega, L.p0, L.radius, &t)) {
       const f3 x = mad3(c.P, omega, t);
       const f3 D = sub3(x, c.P);
-      r.Ldist = length3(D);
+      r.Ldist = length3t<FAST>(D);
       r.Ld = normalize3t<FAST>(D);
       r.pdf = lv.pdf_cone;
       r.valid = true;
@@ -212,20 +212,20 @@ __device__ inline BsdfRec light_valid_sample(const DevLight& L, const ShadeCtx& 
   r.Ld = mk3(0, 0, 1);
   if (L.type == VG_LIGHT_TRI) {  // triangle.go:136-230
     f3 Pl;
-    if (!ray_triangle(c.P, wo, L.p0, L.p1, L.p2, &Pl)) return r;
+    if (!ray_triangle<FAST>(c.P, wo, L.p0, L.p1, L.p2, &Pl)) return r;
     const bool by_area = dot3(c.Ng, sub3(L.p0, Pl)) < 0 || dot3(c.Ng, sub3(L.p1, Pl)) < 0 || dot3(c.Ng, sub3(L.p2, Pl)) < 0;
     float pdfl;
     if (by_area) {
       pdfl = L.inv_area;
     } else {
       const float area = !lv.by_area ? lv.sph.area : spherical_setup<FAST>(L.p0, L.p1, L.p2, c.P).area;
-      pdfl = (float)(double)(1 / area);
+      pdfl = FAST ? __fdividef(1.0f, area) : (float)(double)(1 / area);
     }
     const f3 D = sub3(Pl, c.P);
-    r.Ldist = length3(D);
+    r.Ldist = length3t<FAST>(D);
     r.Ld = normalize3t<FAST>(D);
     if (dot3(r.Ld, L.N) > 0 || dot3(r.Ld, c.Ng) < 0) return r;
-    r.pdfLight = by_area ? pdfl * (r.Ldist * r.Ldist) / fabsf(dot3(r.Ld, L.N)) : pdfl;
+    r.pdfLight = by_area ? divt<FAST>(pdfl * (r.Ldist * r.Ldist), fabsf(dot3(r.Ld, L.N))) : pdfl;
     r.valid = true;
   } else if (L.type == VG_LIGHT_DISK) {  // disk.go:38-68,123-169
     const float denom = dot3(L.N, wo);
@@ -237,16 +237,16 @@ __device__ inline BsdfRec light_valid_sample(const DevLight& L, const ShadeCtx& 
     if (!(sqrtf(dot3(dv, dv)) <= L.radius)) return r;
     const f3 V = sub3(p, c.P);
     if (dot3(V, c.Ng) <= 0.0f || dot3(V, L.N) >= 0.0f) return r;
-    r.Ldist = length3(V);
+    r.Ldist = length3t<FAST>(V);
     r.Ld = normalize3t<FAST>(V);
-    r.pdfLight = L.inv_area * (r.Ldist * r.Ldist) / fabsf(dot3(r.Ld, L.N));
+    r.pdfLight = divt<FAST>(L.inv_area * (r.Ldist * r.Ldist), fabsf(dot3(r.Ld, L.N)));
     r.valid = true;
   } else {  // sphere.go:132-183
     float t;
     if (!ray_sphere(c.P, wo, L.p0, L.radius, &t)) return r;
     const f3 x = mad3(c.P, wo, t);
     const f3 D = sub3(x, c.P);
-    r.Ldist = length3(D);
+    r.Ldist = length3t<FAST>(D);
     r.Ld = normalize3t<FAST>(D);
     r.pdfLight = lv.pdf_cone;
     r.valid = true;
@@ -310,17 +310,17 @@ __global__ void __launch_bounds__(128, 4) k_shade_generic(const RenderParams p, 
     path_decode(p, path, own, it);
     if (h.xf > 0) {  // an instance left its transform in the context (instance.go:107-111)
       if (p.sc.geoms[h.geom].keys == 0) build_context_sphere(p, h, Ro, Rd, c);  // (its own re-normalisations are idempotent)
-      else build_context<false>(p, h, time, c);
+      else build_context<false, FAST>(p, h, time, c);
       apply_instance_transform(p, h.xf - 1, time, c);
     } else if (p.sc.geoms[h.geom].keys == 0) {
       build_context_sphere(p, h, Ro, Rd, c);
     } else {
-      build_context(p, h, time, c);
+      build_context<true, FAST>(p, h, time, c);
     }
     f3 V = cross3(c.N, c.DdPdu);
     if (len2_3(V) < 0.1f) V = cross3(c.N, c.DdPdv);
-    V = normalize3(V);
-    fr.U = normalize3(cross3(c.N, V));
+    V = normalize3t<FAST>(V);
+    fr.U = normalize3t<FAST>(cross3(c.N, V));
     fr.V = V;
     fr.N = c.N;
     omegaI = basis_project(fr.U, fr.V, fr.N, neg3(Rd));
@@ -400,8 +400,8 @@ __global__ void __launch_bounds__(128, 4) k_shade_generic(const RenderParams p, 
             Ldist = lr.Ldist;
             if (NS > 1) {
               const float bp = lobe == 0 ? oren_pdf32<FAST>(fr, Ld) : ggx_pdf32<FAST>(fr, gv, Ld);
-              p_hat = (float)nB * bp / (float)total;
-              p_hat += (float)nLs * lr.pdf / (float)total;
+              p_hat = divt<FAST>((float)nB * bp, (float)total);
+              p_hat += divt<FAST>((float)nLs * lr.pdf, (float)total);
             } else {
               p_hat = lr.pdf;
             }
@@ -410,12 +410,12 @@ __global__ void __launch_bounds__(128, 4) k_shade_generic(const RenderParams p, 
             valid = br.valid;
             Ld = br.Ld;
             Ldist = br.Ldist;
-            p_hat = (float)nB * br.pdf / (float)total;
-            p_hat += (float)nLs * br.pdfLight / (float)total;
+            p_hat = divt<FAST>((float)nB * br.pdf, (float)total);
+            p_hat += divt<FAST>((float)nLs * br.pdfLight, (float)total);
           }
           if (valid && !(dot3(Ld, c.N) <= 0)) {
             Spec4 rho = lobe == 0 ? oren_eval<FAST>(fr, ov, Ld) : ggx_eval<FAST>(fr, gv, m, hero, Ld);
-            const float inv = 1.0f / p_hat;
+            const float inv = divt<FAST>(1.0f, p_hat);
 #pragma unroll
             for (int k = 0; k < 4; k++) rho.c[k] = (rho.c[k] * Liu.c[k]) * inv;
             f3 rgb = spec_to_rgb(rho, hero);
