@@ -144,6 +144,12 @@ class Oracle:
             pass
 
     # -- rendering -------------------------------------------------------------------------------
+    def mesh_set_transform(self, mesh_name: str, matrices):
+        """PolyMesh.Transform (polymesh.go:32): keys x 16 floats in math.Matrix4 storage. Call before the first trace / render.
+        Exists to document reference quirk q (tests/test_oracle_mesh_transform.py); the GPU path refuses such meshes."""
+        m = np.ascontiguousarray(matrices, np.float32).reshape(-1, 16)
+        self._chk(self.L.orc_mesh_set_transform(self.h, mesh_name.encode(), _p(m), len(m)))
+
     def set_scramble(self, table: np.ndarray):
         table = np.ascontiguousarray(table, np.uint64)
         assert table.shape == (self.scene.XRes * self.scene.YRes, 6)

@@ -118,6 +118,27 @@ int orc_add_polymesh(void* h, const char* name, const float* verts, int nverts, 
   });
 }
 
+// PolyMesh.Transform (polymesh.go:32; init.go:14-18 decomposes every key): keys x 16 floats, column major. Documentation of
+// reference quirk q only — the GPU path has no counterpart.
+int orc_mesh_set_transform(void* h, const char* mesh_name, const float* transforms, int keys) {
+  Handle* H = (Handle*)h;
+  return guard([&] {
+    for (auto& m : H->r.meshes)
+      if (m->Name == mesh_name) {
+        m->Transform.clear();
+        m->transformSRT.clear();
+        for (int k = 0; k < keys; k++) {
+          Matrix4 mm;
+          std::memcpy(&mm, transforms + (size_t)k * 16, sizeof(float) * 16);
+          m->Transform.push_back(mm);
+          m->transformSRT.push_back(TransformDecompMatrix4(mm));
+        }
+        return;
+      }
+    throw std::runtime_error(std::string("orc_mesh_set_transform: no mesh ") + mesh_name);
+  });
+}
+
 // GeomInstance (builtin/geom/instance/instance.go:36-51): transforms = keys x 16 floats, column major (math.Matrix4 layout,
 // i.e. what the parser stores after its transpose); bmin/bmax = nb points each.
 int orc_add_instance(void* h, const char* name, const char* geom_name, const float* bmin, const float* bmax, int nb, const float* transforms, int keys) {
@@ -127,6 +148,8 @@ int orc_add_instance(void* h, const char* name, const char* geom_name, const flo
     in->Name = name;
     for (auto& m : H->r.meshes)
       if (m->Name == geom_name) in->geom = m.get();
+    for (auto& o : H->r.instances)  // core.FindNode finds any Geom: an Instance may duplicate another Instance (instance.go:131-143)
+      if (o->Name == geom_name) in->geom = o.get();
     if (!in->geom) throw std::runtime_error(std::string("Instance ") + name + ": Unable to find node " + geom_name);
     for (int i = 0; i < nb; i++) { in->BMin.push_back(v3(bmin + 3 * i)); in->BMax.push_back(v3(bmax + 3 * i)); }
     for (int k = 0; k < keys; k++) {

@@ -253,14 +253,54 @@ BoundingBox PolyMesh::Bounds(float time) const {
   return BoundingBoxLerp(motionBounds[key], motionBounds[key2], t);
 }
 
-// builtin/geom/polymesh/trace.go:15-104 (object Transform path out of scope)
+// builtin/geom/polymesh/trace.go:15-104, the object Transform path included exactly as written: the ray goes to object space
+// (:22-55), and AFTER the traversal — hit or miss — the context's Transform / InvTransform are overwritten and sg.P, sg.N are
+// re-derived from whatever sg.Po / sg.N currently hold (:62-74, :88-101). Bounds() ignores the transform (bounds.go:26,
+// `if false && ...`), so the scene tree culls the mesh by its UNtransformed box. DESIGN.md quirk q.
 bool PolyMesh::Trace(Ray* ray, ShaderContext* sg) {
-  if (!accel.qbvh.empty()) return QTrace(accel.qbvh, this, ray, sg);
-  float k = ray->Time * (float)(Verts.MotionKeys - 1);
-  float time = k - Floor(k);
-  int key = (int)Floor(k);
-  int key2 = (int)Ceil(k);
-  return QTraceMotion(accel.mqbvh, time, key, key2, this, ray, sg);
+  Vec3 Rp, Rd, Rdinv;
+  float S[3] = {0, 0, 0};
+  int32_t Kx = 0, Ky = 0, Kz = 0;
+  Matrix4 transform, invTransform;
+  const bool xf = !Transform.empty();
+  if (xf) {
+    Rp = ray->P; Rd = ray->D; Rdinv = ray->Dinv;
+    S[0] = ray->S[0]; S[1] = ray->S[1]; S[2] = ray->S[2];
+    Kx = ray->Kx; Ky = ray->Ky; Kz = ray->Kz;
+    if (Transform.size() > 1) {
+      float k = ray->Time * (float)((int)Transform.size() - 1);
+      float time = k - Floor(k);
+      int key = (int)Floor(k), key2 = (int)Ceil(k);
+      transform = TransformDecompToMatrix4(TransformDecompLerp(transformSRT[key], transformSRT[key2], time));
+    } else {
+      transform = Transform[0];
+    }
+    Matrix4Inverse(transform, &invTransform);
+    ray->P = Matrix4MulPoint(invTransform, Rp);
+    ray->D = Matrix4MulVec(invTransform, Rd);
+    ray->Setup();
+  }
+  bool hit;
+  if (!accel.qbvh.empty()) {
+    hit = QTrace(accel.qbvh, this, ray, sg);
+  } else {
+    float k = ray->Time * (float)(Verts.MotionKeys - 1);
+    float time = k - Floor(k);
+    int key = (int)Floor(k);
+    int key2 = (int)Ceil(k);
+    hit = QTraceMotion(accel.mqbvh, time, key, key2, this, ray, sg);
+  }
+  if (xf) {
+    ray->P = Rp; ray->D = Rd; ray->Dinv = Rdinv;
+    ray->S[0] = S[0]; ray->S[1] = S[1]; ray->S[2] = S[2];
+    ray->Kx = Kx; ray->Ky = Ky; ray->Kz = Kz;
+    sg->Transform = transform;       // hit or not (trace.go:70-73)
+    sg->InvTransform = invTransform;
+    sg->transformSet = true;
+    sg->P = Matrix4MulPoint(transform, sg->Po);
+    sg->N = Matrix4MulVec(Matrix4Transpose(invTransform), sg->N);
+  }
+  return hit;
 }
 
 // The watertight edge functions of trace.go:127-155 for one triangle; returns false if rejected.

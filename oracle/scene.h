@@ -10,7 +10,7 @@
 //   builtin/scene/scene.go:15-268              (Scene: Trace, TraceElems, LightsPrepare, initAccel, initMotionBoxes)
 //   builtin/geom/instance/instance.go:16-160   (GeomInstance: SRT-interpolated transform, ray re-Setup, user-given bounds)
 // UVs and ray differentials (trace.go:350-502) are computed for static meshes, like the reference (TraceMotionElems sets
-// U,V but leaves every differential 0, trace.go:677-684). Out of scope: the mesh's own Transform (quirk q).
+// U,V but leaves every differential 0, trace.go:677-684). The mesh's own Transform (quirk q) is restated for documentation only.
 #pragma once
 #include <memory>
 #include <string>
@@ -61,6 +61,10 @@ struct PolyMesh : Geom, Primitive, MotionPrimitive {
   BoundingBox initMotionBoxesRec(int key, int32_t node);
   void PreRender() { init(); facecount = (int)idxp.size() / 3; initAccel(); }
 
+  // PolyMesh.Transform (polymesh.go:32-33, init.go:14-18): restated ONLY to document what the reference does with it (quirk q);
+  // the GPU path refuses non-identity mesh transforms and tests/test_oracle_mesh_transform.py shows why.
+  std::vector<Matrix4> Transform;
+  std::vector<TransformDecomp> transformSRT;
   bool Trace(Ray*, ShaderContext*) override;
   int MotionKeys() const override { return accel.qbvh.empty() ? (int)accel.mqbvh.Boxes.size() : 1; }
   BoundingBox Bounds(float time) const override;

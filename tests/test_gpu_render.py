@@ -231,6 +231,19 @@ def test_instanced_scene_image(built_library, kind):
     assert abs(st["rays"] - so["rays"]) <= 1e-3 * so["rays"]
 
 
+def test_nested_instances_image(built_library):
+    """Instances of instances shaded: the context keeps the OUTER instance's transform only (each Instance.Trace overwrites
+    sg.Transform on its way out, instance.go:107-111), which both sides reproduce."""
+    from vermeer_b200 import scenes
+    sc = scenes.instanced_scene(112, 84, moving=False, nested=True)
+    fo, so, fg, st, _ = _render_pair(sc, 16)
+    rmse, ok = _rmse(fo, fg)
+    assert ok.all()
+    assert rmse <= 1e-3, rmse
+    assert np.median(np.abs(fo - fg)) <= 2e-6
+    assert abs(st["rays"] - so["rays"]) <= 1e-3 * so["rays"]
+
+
 def test_pinned_host_buffers_take_the_direct_dma_path(built_library):
     """A page-locked scramble table is copied as it is (the kernels then index it by raster pixel) and a page-locked frame
     buffer is written by DMA; both must give the image of the pageable path bit for bit."""

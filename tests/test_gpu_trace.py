@@ -170,6 +170,28 @@ def test_sphere_geom_leaf_is_bit_exact(built_library):
         assert np.array_equal(og["prim"] >= 0, gg["prim"] >= 0), "any-hit occlusion differs (variant %d)" % variant
 
 
+def test_nested_instances_trace_parity(built_library):
+    """An instance of an instance (and one three transforms deep): Instance.Trace calls ins.geom.Trace, whatever Geom that is
+    (instance.go:95), so the inverses are applied one after the other and the hit reports the OUTERMOST instance's geom id (the
+    scene-level leaf, scene.go:65). Static transforms: bit-exact incl. the counters."""
+    from oracle.binding import Oracle
+    from vermeer_b200 import scenes
+    from vermeer_b200.host import Device, HostScene
+    from conftest import assert_hits_equal, random_rays
+    sc = scenes.instanced_scene(96, 72, moving=False, nested=True)
+    ora = Oracle(sc, motion_ref_compat=False)
+    ora.set_scramble(scenes.splitmix64_table(1, 96 * 72))
+    dev = Device(0).upload(HostScene(sc).prerender())
+    rays = np.concatenate([ora.camera_rays(1), random_rays(40000, 5, lo=(-2.0, 0.05, -1.5), hi=(1.6, 1.2, 1.6))])
+    o = ora.trace(rays)
+    nest1, nest2 = 2 + 3, 2 + 4                      # geoms: floor, blob, inst0..2, nest1, nest2 (+ the lights' meshes after)
+    assert (o["geom"] == nest1).sum() > 300 and (o["geom"] == nest2).sum() > 300
+    assert_hits_equal(dev.trace(rays), o, what="nested instances")
+    sh = rays.copy()
+    sh["tmax"] = 3.0
+    assert np.array_equal(ora.trace(sh, any_hit=True)["prim"] >= 0, dev.trace(sh, any_hit=True)["prim"] >= 0)
+
+
 @pytest.mark.parametrize("kind", ["static", "moving", "moving_motion_base"])
 def test_instances_trace_parity(built_library, kind):
     """GeomInstance (builtin/geom/instance/instance.go): the ray is taken into object space with the inverse of the

@@ -43,7 +43,7 @@ def _equal_nodes(a, b):
     return a.tobytes() == b.tobytes()
 
 
-@pytest.mark.parametrize("name", ["cornell", "heightfield", "motion", "spheres", "glossy", "instances", "debug"])
+@pytest.mark.parametrize("name", ["cornell", "heightfield", "motion", "spheres", "glossy", "instances", "nested", "debug"])
 def test_host_prerender_matches_oracle_bit_for_bit(built_library, name):
     from oracle.binding import Oracle
     from vermeer_b200 import scenes
@@ -56,6 +56,7 @@ def test_host_prerender_matches_oracle_bit_for_bit(built_library, name):
           "glossy": lambda: scenes.glossy_box(64, 48),
           # GeomInstances (one with two transform keys) of a two-key motion mesh: scene-level MQBVH over user-given bounds
           "instances": lambda: scenes.instanced_scene(64, 48, moving=True, motion_base=True),
+          "nested": lambda: scenes.instanced_scene(64, 48, moving=False, nested=True),   # instances of instances
           "debug": lambda: scenes.debug_shader_box(64, 48)}[name]()
     o = Oracle(sc)
     h = HostScene(sc).prerender()

@@ -338,7 +338,13 @@ int vg_scene_commit(vg_ctx* ctx) {
     const MeshStage& m = ctx->meshes[g];
     if (!m.instance) continue;
     const MeshStage& tg = ctx->meshes[m.target];
-    if (tg.instance || tg.sphere) return ctx->fail(VG_ERR_UNSUPPORTED, "GeomInstance of an Instance or a Sphere is outside this path (PolyMesh targets only)");
+    if (tg.sphere) return ctx->fail(VG_ERR_UNSUPPORTED, "GeomInstance of a Sphere is outside this path (PolyMesh and GeomInstance targets only)");
+    {  // an instance of an instance of ...: the chain must end at a mesh
+      int t = m.target, hops = 0;
+      while (t >= 0 && t < G && ctx->meshes[t].present && ctx->meshes[t].instance && hops <= G) { t = ctx->meshes[t].target; hops++; }
+      if (t < 0 || t >= G || !ctx->meshes[t].present || ctx->meshes[t].instance || ctx->meshes[t].sphere)
+        return ctx->fail(VG_ERR_INVALID, "GeomInstance: the chain of instance targets does not end at a PolyMesh");
+    }
   }
 
   // ---- index spaces ----
@@ -578,10 +584,14 @@ int vg_scene_commit(vg_ctx* ctx) {
   for (int g = 0; g < G; g++) {
     const MeshStage& m = ctx->meshes[g];
     if (!m.instance) continue;
-    geoms[g] = geoms[m.target];
+    int final_target = m.target;  // the mesh at the end of the chain
+    while (ctx->meshes[final_target].instance) final_target = ctx->meshes[final_target].target;
+    geoms[g] = geoms[final_target];
     DevXform x;
-    x.root = mesh_root(m.target);
+    x.root = mesh_root(final_target);
     x.geom = g;
+    x.inner = -1;
+    x.pad_[0] = x.pad_[1] = x.pad_[2] = 0;
     x.nkeys = (int32_t)m.srt.size();
     x.key_base = (int32_t)xf_keys.size();
     for (const VgTransformSRT& k : m.srt) {
@@ -595,6 +605,10 @@ int vg_scene_commit(vg_ctx* ctx) {
     xf_static.push_back(Minv);
     xform_of_geom[g] = (int)xforms.size();
     xforms.push_back(x);
+  }
+  for (int g = 0; g < G; g++) {  // chains: the xform applied after this one is the target instance's
+    const MeshStage& m = ctx->meshes[g];
+    if (m.instance && ctx->meshes[m.target].instance) xforms[(size_t)xform_of_geom[g]].inner = xform_of_geom[m.target];
   }
   if (!xforms.empty() && n_static + n_motion >= (int64_t)kXformMask) return ctx->fail(VG_ERR_UNSUPPORTED, "too many nodes for a scene with instances");
 

@@ -40,6 +40,8 @@ struct DevXform {
   int32_t geom;      // geom id of the instance (what a hit reports, scene.go:65)
   int32_t nkeys;     // transform keys; 1 = static: M / Minv pre-multiplied on the host in xf_static[2*i], [2*i+1]
   int32_t key_base;  // first XfSRT of this instance in xf_keys
+  int32_t inner;     // instance of an instance: the xform applied next on the way to the mesh (instance.go:95), or -1
+  int32_t pad_[3];
 };
 static const uint32_t kLeafBaseMask = 0x1FFFFFFu;
 // float4s per static triangle record: 3 = the packed 48-B record; 4 = padded to 64 B so that a record is two aligned 256-bit loads

@@ -669,7 +669,9 @@ int GeomInstance::PreRender(Core& core, std::string* err) {
   if (!n) { *err = "Instance " + NodeName + ": Unable to find node " + GeomName; return -1; }
   geom = dynamic_cast<Geom*>(n);
   if (!geom) { *err = "Instance " + NodeName + ": Unable to find geom " + GeomName; return -1; }
-  if (!dynamic_cast<PolyMesh*>(n)) { *err = "Instance " + NodeName + ": only PolyMesh targets are supported on this path"; return -1; }
+  // a PolyMesh, or another GeomInstance (Instance.Trace simply calls ins.geom.Trace, instance.go:95: the transforms chain)
+  if (!dynamic_cast<PolyMesh*>(n) && !dynamic_cast<GeomInstance*>(n)) { *err = "Instance " + NodeName + ": only PolyMesh and GeomInstance targets are supported on this path"; return -1; }
+  if (n == this) { *err = "Instance " + NodeName + ": an instance of itself"; return -1; }
   if (transformSRT.empty() || bounds.empty()) { *err = "Instance " + NodeName + ": Transform and BMin/BMax need at least one element"; return -1; }
   return 0;
 }

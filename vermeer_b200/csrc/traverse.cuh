@@ -808,12 +808,22 @@ __device__ __forceinline__ void trace_persistent_ldg(const DevScene& sc, IO& io,
 // the transform has motion keys): kept out of line, scalars in, six floats out.
 static __device__ __noinline__ void xf_object_ray(const DevScene& sc, int xi, float time, float ox, float oy, float oz, float dx, float dy, float dz,
                                                  float* out6) {
-  const DevXform x = sc.xforms[xi];
-  Mat4 M, Minv;
-  if (x.nkeys == 1) Minv = sc.xf_static[2 * xi + 1];
-  else xf_matrices(sc.xf_keys + x.key_base, x.nkeys, time, &M, &Minv);
-  m4_mul_point(Minv, ox, oy, oz, out6);
-  m4_mul_vec(Minv, dx, dy, dz, out6 + 3);
+  out6[0] = ox; out6[1] = oy; out6[2] = oz;
+  out6[3] = dx; out6[4] = dy; out6[5] = dz;
+  // an instance of an instance applies the outer inverse, then the inner one, each on the result of the last — exactly the nested
+  // Instance.Trace calls (instance.go:86-95); the Ray.Setup between them has no effect on P and D
+  for (int hops = 0; xi >= 0 && hops < 8; hops++) {
+    const DevXform x = sc.xforms[xi];
+    Mat4 M, Minv;
+    if (x.nkeys == 1) Minv = sc.xf_static[2 * xi + 1];
+    else xf_matrices(sc.xf_keys + x.key_base, x.nkeys, time, &M, &Minv);
+    float p[3], d[3];
+    m4_mul_point(Minv, out6[0], out6[1], out6[2], p);
+    m4_mul_vec(Minv, out6[3], out6[4], out6[5], d);
+    out6[0] = p[0]; out6[1] = p[1]; out6[2] = p[2];
+    out6[3] = d[0]; out6[4] = d[1]; out6[5] = d[2];
+    xi = x.inner;
+  }
 }
 
 // ---- Warp-cooperative leaves ------------------------------------------------------------------------------------

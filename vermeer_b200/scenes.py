@@ -690,7 +690,7 @@ def glossy_box(xres: int = 256, yres: int = 256, lights: str = "tri,disk,sphere"
     return SceneDesc(XRes=xres, YRes=yres, camera=cam, shaders=shaders, meshes=meshes, lights=ls, MaxIter=16, name="F1-glossy-box")
 
 
-def instanced_scene(xres: int = 128, yres: int = 96, moving: bool = True, motion_base: bool = False) -> SceneDesc:
+def instanced_scene(xres: int = 128, yres: int = 96, moving: bool = True, motion_base: bool = False, nested: bool = False) -> SceneDesc:
     """SURVEY.md 8(f).3 test scene: one displaced-sphere mesh at the origin, three GeomInstances of it (translated, rotated,
     uniformly scaled; the last one with two transform keys when `moving`), a floor and a TriLight pair. Bounds are the
     transformed mesh bounds with a margin, over both keys."""
@@ -726,6 +726,17 @@ def instanced_scene(xres: int = 128, yres: int = 96, moving: bool = True, motion
     for i, mats in enumerate(specs):
         lo, hi = bounds(mats)
         instances.append(GeomInstance("inst%d" % i, "blob", np.stack(mats, 0), lo, hi))
+    if nested:
+        # an instance of an INSTANCE (Instance.Trace just calls ins.geom.Trace, instance.go:95): "inst0" placed once more, the
+        # outer transform applied on top of inst0's own; and an instance of that one (three transforms deep)
+        def compose(outer, inner):
+            return matrix4((outer.reshape(4, 4).T.astype(np.float64) @ inner.reshape(4, 4).T.astype(np.float64)))
+        outer = srt_matrix((0.9, 0.35, 0.9), 20.0, 0.7)
+        lo, hi = bounds([compose(outer, specs[0][0])])
+        instances.append(GeomInstance("nest1", "inst0", np.stack([outer], 0), lo, hi))
+        outer2 = srt_matrix((-1.6, 0.0, -0.2), -35.0, 1.0)
+        lo, hi = bounds([compose(outer2, compose(outer, specs[0][0]))])
+        instances.append(GeomInstance("nest2", "nest1", np.stack([outer2], 0), lo, hi))
     cam = Camera(From=(0.0, 1.3, 2.6), To=(0.0, 0.2, 0.0), Fov=42.0, Focal=1.0)
     sc = SceneDesc(XRes=xres, YRes=yres, camera=cam, shaders=shaders, meshes=meshes, lights=_light_pair(1.9, 0.5, "lightmtl"),
                    instances=instances, MaxIter=16, name="F3-instances")
