@@ -219,3 +219,75 @@ def test_tile_partitions_of_a_textured_scene_tile_the_frame(built_library):
         d.set_scramble(tab)
         acc += d.render(0, 3)
     assert np.array_equal(np.nan_to_num(acc).view(np.uint32), np.nan_to_num(full).view(np.uint32))
+
+
+def _instanced_cards(xres=160, yres=120, emissive=True, moving=False):
+    """A textured card (quad with UVs) and a textured, smooth-shaded mirror ball, each placed twice more through GeomInstances
+    (rotated / scaled; one instance of an instance), over the textured floor of the room."""
+    from vermeer_b200 import scenes
+    sc = scenes.textured_room(xres, yres, mirror=False, smooth=False)
+    sc.meshes = [m for m in sc.meshes if m.Name in ("floor", "back", "left", "right", "ceiling")]
+    card = scenes._quad("card", [[-0.25, 0.05, 0.0], [0.25, 0.05, 0.0], [0.25, 0.55, 0.0], [-0.25, 0.55, 0.0]], "odd_tex")
+    card.UV = np.asarray([[0, 0], [2, 0], [2, 2], [0, 2]], np.float32)
+    sc.meshes.append(card)
+    v, t = scenes._uv_sphere(12, 8)
+    sc.shaders.append(scenes.ShaderStd("ballmtl", DiffuseColour="wall.png", DiffuseStrength=0.5, Spec1Colour=(0.9, 0.9, 0.9), Spec1Strength=0.5, Spec1Roughness=0.0))
+    ball = scenes.PolyMesh("ball", (v * np.float32(0.16) + np.asarray([0.0, 0.2, 0.0], np.float32)).astype(np.float32), ["ballmtl"], FaceIdx=t.copy(), Normals=v.copy())
+    sc.meshes.append(ball)
+
+    def inst(name, geom, mats, verts):
+        lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
+        for m in mats:
+            M = m.reshape(4, 4).T.astype(np.float64)
+            w = verts.astype(np.float64) @ M[:3, :3].T + M[:3, 3]
+            lo, hi = np.minimum(lo, w.min(0)), np.maximum(hi, w.max(0))
+        return scenes.GeomInstance(name, geom, np.stack(mats, 0), tuple((lo - 0.02).astype(np.float32)), tuple((hi + 0.02).astype(np.float32)))
+    cv, bv = card.Verts[0], ball.Verts[0]
+    m1 = [scenes.srt_matrix((-0.55, 0.1, 0.3), 40.0, 1.3)] + ([scenes.srt_matrix((-0.45, 0.2, 0.3), 75.0, 1.3)] if moving else [])
+    m2 = [scenes.srt_matrix((0.55, 0.0, 0.45), -30.0, 0.8)]
+    m3 = [scenes.srt_matrix((0.5, 0.05, -0.35), 15.0, 1.5)]
+    outer = scenes.srt_matrix((-0.1, 0.45, 0.1), 25.0, 0.9)
+    comp = scenes.matrix4(outer.reshape(4, 4).T.astype(np.float64) @ m2[0].reshape(4, 4).T.astype(np.float64))
+    sc.instances = [inst("card1", "card", m1, cv), inst("card2", "card", m2, cv), inst("ball1", "ball", m3, bv),
+                    inst("card3", "card2", [outer], (cv.astype(np.float64) @ m2[0].reshape(4, 4).T[:3, :3].T.astype(np.float64) + m2[0].reshape(4, 4).T[:3, 3]).astype(np.float32))]
+    del comp
+    if emissive:
+        for s in sc.shaders:
+            if isinstance(s.DiffuseColour, str) and s.Name != "ballmtl":
+                s.EmissionColour, s.EmissionStrength, s.DiffuseColour = s.DiffuseColour, 1.0, (0.0, 0.0, 0.0)
+        sc.lights = []
+        sc.meshes = [m for m in sc.meshes if m.Name != "ball"]
+        sc.instances = [i for i in sc.instances if i.Geom != "ball"]
+    return sc
+
+
+def test_texture_footprints_through_instances(built_library):
+    """a textured mesh seen through GeomInstances. PolyMesh.TraceElems runs with the ray in OBJECT space
+    (instance.go:86-95) and transfers the untouched world-space ray differentials with the object-space direction
+    (trace.go:360); k_surface mirrors that. All-emissive: a pixel is the filter's output, so U, V and the footprint are
+    compared with no light sampling in between."""
+    sc = _instanced_cards(emissive=True)
+    fo, so, fg, st, _ = _render_pair(sc, 3)
+    rmse, ok = _rmse(fo, fg)
+    assert ok.all() and fo.max() > 0.3
+    assert rmse <= 1e-4, rmse
+    assert np.quantile(np.abs(fo - fg), 0.99) <= 5e-6
+    # the instanced cards are in the picture: the frame differs from the same room without them
+    sc0 = _instanced_cards(emissive=True)
+    sc0.instances = []
+    f0 = _render_pair(sc0, 3)[2]
+    assert (np.abs(f0 - fg).max(-1) > 0.05).mean() > 0.03
+
+
+@pytest.mark.parametrize("moving", [False, True])
+def test_textured_instances_lit_with_mirror_ball(built_library, moving):
+    """The same placements lit by the TriLights, with an instanced smooth-shaded mirror ball: the reflected ray's differentials
+    (Ray.Init, core/ray.go:72-87) use the context's normal AFTER ApplyTransform with the instance's matrix, and the texture the
+    mirror shows is filtered with them."""
+    sc = _instanced_cards(emissive=False, moving=moving)
+    fo, so, fg, st, _ = _render_pair(sc, 6)
+    rmse, ok = _rmse(fo, fg)
+    assert ok.mean() > 0.99
+    assert rmse <= 1e-3, rmse
+    assert np.median(np.abs(fo - fg)[ok]) <= 2e-6
+    assert abs(st["rays"] - so["rays"]) <= 2e-3 * so["rays"]

@@ -185,7 +185,7 @@ def test_nested_instances_trace_parity(built_library):
     rays = np.concatenate([ora.camera_rays(1), random_rays(40000, 5, lo=(-2.0, 0.05, -1.5), hi=(1.6, 1.2, 1.6))])
     o = ora.trace(rays)
     nest1, nest2 = 2 + 3, 2 + 4                      # geoms: floor, blob, inst0..2, nest1, nest2 (+ the lights' meshes after)
-    assert (o["geom"] == nest1).sum() > 300 and (o["geom"] == nest2).sum() > 300
+    assert (o["geom"] == nest1).sum() > 300 and (o["geom"] == nest2).sum() > 100
     assert_hits_equal(dev.trace(rays), o, what="nested instances")
     sh = rays.copy()
     sh["tmax"] = 3.0

@@ -421,7 +421,7 @@ int vg_scene_commit(vg_ctx* ctx) {
     dg.tri_key_stride = m.n_tris;
     dg.n_tris = m.n_tris;
     dg.uv_base = -1;
-    dg.pad1 = 0;
+    dg.xform = -1;
     if (m.material_ids.size() > 255) return FlatErr{VG_ERR_UNSUPPORTED, "more than 255 shaders on one mesh"};
     if (!m.instance) std::memset(prim_material.data() + prim_base[g], 255, (size_t)(m.sphere ? 1 : m.n_tris));
 
@@ -604,6 +604,7 @@ int vg_scene_commit(vg_ctx* ctx) {
     xf_static.push_back(M);
     xf_static.push_back(Minv);
     xform_of_geom[g] = (int)xforms.size();
+    geoms[g].xform = (int32_t)xforms.size();
     xforms.push_back(x);
   }
   for (int g = 0; g < G; g++) {  // chains: the xform applied after this one is the target instance's

@@ -73,7 +73,7 @@ struct DevGeom {  // per geom (creation order)
   int32_t tri_key_stride;
   int32_t n_tris;
   int32_t uv_base;      // slot base into tri_uv[] (3 float2 per slot), or -1: the mesh has no UVs
-  int32_t pad1;
+  int32_t xform;        // GeomInstance: index into DevScene::xforms of this geom's transform chain; -1 otherwise
 };
 
 struct DevScene {

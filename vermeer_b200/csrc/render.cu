@@ -478,7 +478,9 @@ __global__ void __launch_bounds__(128, VG_SURFACE_MIN_BLOCKS) k_surface(const Re
     prim = h1.x; geom = h1.y; slot = h1.z;
   }
   DevGeom g;
-  g.normal_base = -1; g.uv_base = -1; g.prim_base = 0;
+  g.normal_base = -1; g.uv_base = -1; g.prim_base = 0; g.xform = -1;
+  int hxf = 0;  // 1 + the instance whose transform the context ends up with (DevHit::xf, quirk o)
+  if (i < nq) hxf = (*(reinterpret_cast<const int4*>(&p.hits[i]) + 1)).w;
   if (prim >= 0) {
     const float4 h0 = *reinterpret_cast<const float4*>(&p.hits[i]);
     T = h0.x; U = h0.y; V = h0.z; W = h0.w;
@@ -501,6 +503,16 @@ __global__ void __launch_bounds__(128, VG_SURFACE_MIN_BLOCKS) k_surface(const Re
     const float4* rp = reinterpret_cast<const float4*>(p.rayq[qin] + i);
     const float4 ra = rp[0], rb = rp[1];
     D = mk3(ra.w, rb.x, rb.y);
+    // A hit inside a GeomInstance: PolyMesh.TraceElems runs while the ray is in OBJECT space (Instance.Trace, instance.go:86-95)
+    // and calls Ray.DifferentialTransfer there with the object-space direction but the untouched world-space differentials
+    // (trace.go:360); core.Trace then repeats the transfer with the restored world ray (core/trace.go:67). Both are mirrored:
+    // Dobj feeds the texture footprint, D what the path keeps.
+    f3 Dobj = D;
+    if (g.xform >= 0) {
+      float o6[6];
+      xf_object_ray(p.sc, g.xform, rb.w, ra.x, ra.y, ra.z, D.x, D.y, D.z, o6);
+      Dobj = mk3(o6[3], o6[4], o6[5]);
+    }
 
     const float4* tp = p.sc.tris + (size_t)slot * kTriStride;
     const f3 E0 = ld3(tp), E1 = ld3(tp + 1), E2 = ld3(tp + 2);
@@ -531,13 +543,13 @@ __global__ void __launch_bounds__(128, VG_SURFACE_MIN_BLOCKS) k_surface(const Re
     const f3 rPx = mk3(q[0], q[P], q[2 * P]), rPy = mk3(q[3 * P], q[4 * P], q[5 * P]);
     const f3 rDx = mk3(q[6 * P], q[7 * P], q[8 * P]), rDy = mk3(q[9 * P], q[10 * P], q[11 * P]);
     // DifferentialTransfer (core/ray.go:95-104)
-    const float DNg = dot3(D, Ng);
+    const float DNg = dot3(Dobj, Ng);
     const f3 ax = mad3(rPx, rDx, T), ay = mad3(rPy, rDy, T);
     const bool fdv = fast != 0;  // approximate reciprocals on the FAST path (tolerance-only quantities, see texture.cuh)
     const float dtdx = tex_div(-dot3(ax, Ng), DNg, fdv);
     const float dtdy = tex_div(-dot3(ay, Ng), DNg, fdv);
-    dPdx = add3(ax, scale3(dtdx, D));
-    dPdy = add3(ay, scale3(dtdy, D));
+    dPdx = add3(ax, scale3(dtdx, Dobj));
+    dPdy = add3(ay, scale3(dtdy, Dobj));
 
     // barycentric planes (trace.go:362-436): n = Ng x edge, normalised, then scaled so that the opposite vertex evaluates to 1
     auto plane = [&](f3 a, f3 b, f3 on) {
@@ -596,7 +608,25 @@ __global__ void __launch_bounds__(128, VG_SURFACE_MIN_BLOCKS) k_surface(const Re
 
     // differentials of the mirror ray (core/ray.go:72-87); sc.N is the shading normal after ApplyTransform (normalised once more,
     // like build_context), sc.DdDdx/y are the incoming ray's
-    const f3 Ns = has_n ? normalize3(normalize3(N)) : normalize3(Ng);
+    f3 Ns = has_n ? normalize3(normalize3(N)) : normalize3(Ng);
+    if (g.xform >= 0 || hxf > 0) {
+      // the second DifferentialTransfer (core/trace.go:67): world ray, the geom's own (object-space) Ng
+      const float DNgW = dot3(D, Ng);
+      dPdx = add3(ax, scale3(tex_div(-dot3(ax, Ng), DNgW, fdv), D));
+      dPdy = add3(ay, scale3(tex_div(-dot3(ay, Ng), DNgW, fdv), D));
+      // sc.N after ApplyTransform (core/shader.go:129-135) with the transform the context ends up with
+      if (hxf > 0) {
+        const DevXform x = p.sc.xforms[hxf - 1];
+        Mat4 M, Minv;
+        if (x.nkeys == 1) Minv = p.sc.xf_static[2 * (hxf - 1) + 1];
+        else xf_matrices(p.sc.xf_keys + x.key_base, x.nkeys, rb.w, &M, &Minv);
+        const Mat4 MinvT = m4_transpose(Minv);
+        const f3 n0w = has_n ? normalize3(N) : Ng;
+        float o[3];
+        m4_mul_vec(MinvT, n0w.x, n0w.y, n0w.z, o);
+        Ns = normalize3(mk3(o[0], o[1], o[2]));
+      }
+    }
     const float RdN = dot3(D, Ns);
     const float DdotNdx = dot3(rDx, Ns) + dot3(D, DdNdx);
     const float DdotNdy = dot3(rDy, Ns) + dot3(D, DdNdy);
@@ -1410,9 +1440,15 @@ static int prepare(vg_ctx* ctx) {
   }
   if (textured) {
     for (const MeshStage& m : ctx->meshes)
-      if (m.present && (m.motion || m.sphere || m.instance))
-        return ctx->fail(VG_ERR_UNSUPPORTED, "texture maps need a scene of static PolyMeshes (the reference's motion path leaves the texture "
-                                             "footprint 0: trace.go:677-684, feline.go:57-61); sphere and instance geoms carry no UV differentials here");
+      if (m.present && (m.motion || m.sphere))
+        return ctx->fail(VG_ERR_UNSUPPORTED, "texture maps need a scene of static PolyMeshes and GeomInstances of them (the reference's motion path leaves "
+                                             "the texture footprint 0: trace.go:677-684, feline.go:57-61; a Sphere geom keeps whatever footprint the last mesh leaf left)");
+    for (const MeshStage& m : ctx->meshes) {
+      if (!m.present || !m.instance) continue;
+      int t = m.target;
+      while (ctx->meshes[(size_t)t].instance) t = ctx->meshes[(size_t)t].target;
+      if (ctx->meshes[(size_t)t].motion) return ctx->fail(VG_ERR_UNSUPPORTED, "texture maps: a GeomInstance of a motion mesh (see above)");
+    }
     for (const VgLight& l : ctx->lights)
       if (l.material >= 0 && l.material < (int)ctx->mat_tex.size() && (ctx->mat_tex[(size_t)l.material].slot[0].tex >= 0 || ctx->mat_tex[(size_t)l.material].slot[1].tex >= 0))
         return ctx->fail(VG_ERR_UNSUPPORTED, "a texture map on the emission of a light's shader (the light evaluates it with its own lsg)");
