@@ -345,13 +345,19 @@ def frame_leg(r, steps, warmup, rank, world, torch, dist):
 
     # ---- e2e: host buffers every step; N > 1: the library's gather (NCCL) brings the owned pixels to rank 0 ---------
     def step_e2e():
-        dev.set_scramble(r.table)       # H2D of this rank's rows of the scramble table, from the caller's host buffer
-        dev.clear()
-        if world > 1:
-            dev.render(0, spp, fetch=False)
-            dev.gather_frame(r.frame if rank == 0 else None)   # pack + ncclSend/Recv + scatter + D2H of the complete frame on rank 0
+        # vg_render_frame: H2D of this rank's rows of the scramble table from the caller's host buffer, clear, the render loop, the
+        # library's exchange (N > 1: pack + ncclSend/Recv + scatter) and the D2H of the complete frame into the host buffer on rank 0,
+        # pipelined in slices of tile rows (the copies and the exchange of one slice overlap the rendering of the next)
+        if os.environ.get("VG_BENCH_E2E_PLAIN"):               # the three separate calls, for the A/B
+            dev.set_scramble(r.table)
+            dev.clear()
+            if world > 1:
+                dev.render(0, spp, fetch=False)
+                dev.gather_frame(r.frame if rank == 0 else None)
+            else:
+                dev.render(0, spp, out=r.frame)
         else:
-            dev.render(0, spp, out=r.frame)                    # D2H of the frame into the caller's host buffer
+            dev.render_frame(r.table, 0, spp, out=r.frame if rank == 0 else None, clear=True)
 
     for _ in range(2):
         step_e2e()

@@ -268,7 +268,7 @@ int vg_set_scramble(vg_ctx* ctx, const uint64_t* table, int64_t npix);
  * device in ray generation (core/render.go:99-107). n = 0 removes the filter. */
 int vg_set_filter(vg_ctx* ctx, int n, double w, const double* cdfV, const double* cdfVU);
 /* Options: "trace_last_level" (1 = trace the level-4 mirror ray like the reference, std.go:243; default 1),
- * "iters_per_batch" (wavefront batch depth, default 4), "iter_group" (a warp's 32 paths = 32/iter_group neighbouring pixels x
+ * "frame_slices" (vg_render_frame's pipeline depth), "iters_per_batch" (wavefront batch depth, default 4), "iter_group" (a warp's 32 paths = 32/iter_group neighbouring pixels x
  * iter_group consecutive iterations of the batch; power of two, default 4; results do not depend on it), "precise_trig" (1 = shading trig through float64 exactly like
  * math/sincos.go; 0 = single-precision libm, default; both are within the image tolerance), "traversal" (persistent-kernel variant:
  * 2 = warp-cooperative leaf phase, default; 0 = per-lane while-while loop with coalesced LDG refill; 1 = the per-lane loop with
@@ -327,6 +327,14 @@ int vg_comm_init(vg_ctx* ctx, int rank, int world, const void* id);
 int vg_comm_destroy(vg_ctx* ctx);
 int vg_gather_frame(vg_ctx* ctx, float* fb_out);
 int vg_nccl_version(void); /* ncclGetVersion of the library that was bound, 0 if none */
+/* The whole frame step as ONE call: vg_set_scramble(table) [+ vg_clear_framebuffer] + vg_render(iter_begin, iter_end) + vg_gather_frame
+ * (when a communicator exists; collective then) + the copy of the frame into fb_out (rank 0 / single GPU; may be NULL) — pipelined.
+ * The image is cut into "frame_slices" (option, default 4) runs of tile rows; while slice s renders, the scramble rows of slice s+1
+ * are on their way up and the finished pixels of slice s-1 on their way back (NCCL exchange + D2H of those image rows), each on its
+ * own stream. This is the reference's frame loop (core/render.go:184-205) with its inputs and outputs in HOST memory, which is what
+ * a Go caller has; results are bit-identical to the three separate calls. The overlap needs page-locked `table` and `fb_out`
+ * (cudaHostAlloc / cudaHostRegister); with pageable buffers, or on the first call after a scene change, the plain sequence runs. */
+int vg_render_frame(vg_ctx* ctx, const uint64_t* table, int64_t npix, int iter_begin, int iter_end, int clear_first, float* fb_out);
 /* The tile-major list of the full-frame pixel indices `rank` of `world` owns (host only, no device needed): returns the count,
  * fills pix_out (may be NULL) if it holds at least that many. pixel_block = the "pixel_block" option (default 1). */
 int vg_owned_pixels(int xres, int yres, int rank, int world, int pixel_block, int32_t* pix_out, int64_t cap);

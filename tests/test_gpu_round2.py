@@ -98,6 +98,47 @@ def test_single_rank_communicator_is_a_plain_copy(built_library):
     assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
 
 
+@pytest.mark.parametrize("scene_kind", ["heightfield", "mirror"])
+def test_render_frame_is_the_three_calls_pipelined(built_library, scene_kind):
+    """vg_render_frame = vg_set_scramble + vg_clear_framebuffer + vg_render (+ gather) + frame download, cut into slices of tile rows
+    whose copies overlap the next slice's rendering: bit-identical frames for any slice count, page-locked or pageable buffers,
+    with or without a (single-rank) communicator, and a progressive continuation."""
+    import torch
+    from vermeer_b200 import scenes
+    sc = _scene(200, 140) if scene_kind == "heightfield" else scenes.sphere_field_scene(100, 140, nmesh=9, slices=12, stacks=13)
+    tab1, tab2 = scenes.splitmix64_table(1, sc.XRes * sc.YRes), scenes.splitmix64_table(2, sc.XRes * sc.YRes)
+    want = {}
+    for k, tab in ((1, tab1), (2, tab2)):
+        d = _device(sc, tab)
+        d.set_option("iters_per_batch", 4)
+        want[k] = d.render(0, 6)
+    pin = lambda a: torch.from_numpy(a.view(np.int64).copy()).pin_memory().numpy().view(np.uint64)
+    out_pinned = torch.empty((sc.YRes, sc.XRes, 3), dtype=torch.float32, pin_memory=True).numpy()
+    dev = _device(sc, tab1)
+    dev.set_option("iters_per_batch", 4)
+    dev.render(0, 1)                                            # prepared: the next frames take the pipelined path
+    for slices, tab, key, out in [(4, pin(tab2), 2, out_pinned), (1, pin(tab1), 1, out_pinned), (7, pin(tab2), 2, out_pinned),
+                                  (3, tab1, 1, np.zeros_like(out_pinned)), (5, pin(tab1), 1, np.zeros_like(out_pinned))]:
+        dev.set_option("frame_slices", slices)
+        out[:] = -1.0
+        dev.render_frame(tab, 0, 6, out=out)
+        assert np.array_equal(out.view(np.uint32), want[key].view(np.uint32)), (slices, key)
+    # progressive: [0,3) cleared, then [3,6) continuing the running mean
+    dev.set_option("frame_slices", 4)
+    dev.render_frame(pin(tab2), 0, 3, out=out_pinned)
+    dev.render_frame(pin(tab2), 3, 6, out=out_pinned, clear=False)
+    assert np.array_equal(out_pinned.view(np.uint32), want[2].view(np.uint32))
+    # a single-rank communicator goes through the exchange code path (no NCCL needed)
+    dev.comm_init(0, 1, None)
+    out_pinned[:] = -1.0
+    dev.render_frame(pin(tab1), 0, 6, out=out_pinned)
+    assert np.array_equal(out_pinned.view(np.uint32), want[1].view(np.uint32))
+    # and a later plain render sees the table the pipelined call uploaded (residency bookkeeping)
+    dev.set_option("iters_per_batch", 2)
+    dev.clear()
+    assert np.array_equal(dev.render(0, 6).view(np.uint32), want[1].view(np.uint32))
+
+
 def _gather_worker(rank, world, uid_q, res_q, xres, yres, iters):
     try:
         import numpy as np
@@ -119,6 +160,15 @@ def _gather_worker(rank, world, uid_q, res_q, xres, yres, iters):
         dev.gather_frame(out)
         dev.render(iters, 2 * iters, fetch=False)      # a second frame through the same communicator (progressive)
         dev.gather_frame(out)
+        # the same two steps through the pipelined single call, page-locked buffers, slices exchanged while the next one renders
+        import torch
+        tab = torch.from_numpy(scenes.splitmix64_table(1, xres * yres).view(np.int64)).pin_memory().numpy().view(np.uint64)
+        out2 = torch.empty((yres, xres, 3), dtype=torch.float32, pin_memory=True).numpy() if rank == 0 else None
+        dev.set_option("frame_slices", 3)
+        dev.render_frame(tab, 0, iters, out=out2)
+        dev.render_frame(tab, iters, 2 * iters, out=out2, clear=False)
+        if rank == 0:
+            out = np.stack([out, out2.copy()])
         res_q.put((rank, out, dev.stats()["gather_ms"]))
     except Exception as e:  # noqa: BLE001
         res_q.put((rank, "error: %r" % (e,), 0.0))
@@ -147,7 +197,8 @@ def test_nccl_gathered_frame_equals_the_single_gpu_frame(built_library):
     want = _device(_scene(xres, yres))
     want.set_option("iters_per_batch", 4)
     ref = want.render(0, 2 * iters)
-    assert np.array_equal(got[0].view(np.uint32), ref.view(np.uint32))
+    assert np.array_equal(got[0][0].view(np.uint32), ref.view(np.uint32))      # vg_render + vg_gather_frame
+    assert np.array_equal(got[0][1].view(np.uint32), ref.view(np.uint32))      # vg_render_frame (pipelined slices)
 
 
 def test_measured_peaks_are_plausible(built_library):

@@ -130,6 +130,7 @@ struct CommState {
   int W = 0, H = 0, pixel_block = -1;
   std::vector<int> count;   // owned pixels per rank
   std::vector<int> offset;  // first staging pixel of rank r (ranks 1.., rank 0's pixels are already in place)
+  std::vector<std::vector<int>> row_start;  // [rank][tilesY + 1] first owned-list index of every tile row (slices of the frame)
   DevBuf<int> pix_own;      // this rank's pixel list
   DevBuf<int> pix_others;   // rank 0: concatenated lists of ranks 1..N-1, in staging order
   DevBuf<float> send;       // packed owned pixels
@@ -247,9 +248,17 @@ static int comm_layout(vg_ctx* ctx, CommState* cs) {
   std::vector<int> pix, others;
   cs->count.assign((size_t)cs->world, 0);
   cs->offset.assign((size_t)cs->world, 0);
+  cs->row_start.assign((size_t)cs->world, std::vector<int>());
   for (int r = 0; r < cs->world; r++) {
     owned_pixels(W, H, r, cs->world, pb != 0, pix);
     cs->count[(size_t)r] = (int)pix.size();
+    {
+      const int tilesY = (H + 31) / 32;
+      std::vector<int>& rsr = cs->row_start[(size_t)r];
+      rsr.assign((size_t)tilesY + 1, (int)pix.size());
+      for (int i = (int)pix.size() - 1; i >= 0; i--) rsr[(size_t)((pix[(size_t)i] / W) / 32)] = i;
+      for (int ty = tilesY - 1; ty >= 0; ty--) rsr[(size_t)ty] = std::min(rsr[(size_t)ty], rsr[(size_t)ty + 1]);
+    }
     if (r == cs->rank) {
       CCUDA(cs->pix_own.reserve(pix.size()));
       if (!pix.empty()) CCUDA(cudaMemcpyAsync(cs->pix_own.p, pix.data(), pix.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -272,50 +281,83 @@ static int comm_layout(vg_ctx* ctx, CommState* cs) {
   return VG_OK;
 }
 
+static int comm_layout(vg_ctx* ctx, vg::CommState* cs);
+namespace vg {
+// The exchange for the tile rows [ty0, ty1) on `st` (the whole frame: 0 .. tilesY): pack, send / receive, scatter, and on rank 0 the
+// D2H of those image rows into fb_out. `sync`: wait for it. The caller holds the context lock.
+int comm_gather_rows(vg_ctx* ctx, cudaStream_t st, int ty0, int ty1, float* fb_out, bool sync) {
+  CommState* cs = ctx->comm;
+  if (!cs) return ctx->fail(VG_ERR_INVALID, "vg_gather_frame: no communicator (vg_comm_init)");
+  if (cs->rank != ctx->rank || cs->world != ctx->world) return ctx->fail(VG_ERR_INVALID, "vg_gather_frame: vg_set_partition changed the partition after vg_comm_init");
+  float* fb = nullptr;
+  int rc = render_fb_device(ctx, &fb);
+  if (rc != VG_OK) return rc;
+  if (cs->world > 1) {
+    rc = comm_layout(ctx, cs);
+    if (rc != VG_OK) return rc;
+    const std::vector<int>& mine = cs->row_start[(size_t)cs->rank];
+    const int o0 = mine[(size_t)ty0], nown = mine[(size_t)ty1] - mine[(size_t)ty0];
+    if (cs->rank != 0) {
+      if (nown > 0) {
+        k_pack_owned<<<(nown * 3 + 255) / 256, 256, 0, st>>>(fb, cs->pix_own.p + o0, nown, cs->send.p + (size_t)o0 * 3);
+        CCUDA(cudaGetLastError());
+        CNCCL(g_nccl.Send(cs->send.p + (size_t)o0 * 3, (size_t)nown * 3, kNcclFloat32, 0, cs->comm, st));
+      }
+    } else {
+      CNCCL(g_nccl.GroupStart());
+      for (int r = 1; r < cs->world; r++) {
+        const std::vector<int>& rr = cs->row_start[(size_t)r];
+        const int q0 = rr[(size_t)ty0], n = rr[(size_t)ty1] - rr[(size_t)ty0];
+        if (n <= 0) continue;
+        const int e = g_nccl.Recv(cs->stage.p + ((size_t)cs->offset[(size_t)r] + (size_t)q0) * 3, (size_t)n * 3, kNcclFloat32, r, cs->comm, st);
+        if (e != 0) {
+          g_nccl.GroupEnd();
+          return ctx->fail(VG_ERR_COMM, std::string("ncclRecv: ") + g_nccl.GetErrorString(e));
+        }
+      }
+      CNCCL(g_nccl.GroupEnd());
+      for (int r = 1; r < cs->world; r++) {  // one scatter per rank: that rank's slice is one run of the staging buffer
+        const std::vector<int>& rr = cs->row_start[(size_t)r];
+        const int q0 = rr[(size_t)ty0], n = rr[(size_t)ty1] - rr[(size_t)ty0];
+        if (n <= 0) continue;
+        const size_t at = (size_t)cs->offset[(size_t)r] + (size_t)q0;
+        k_scatter_owned<<<(n * 3 + 255) / 256, 256, 0, st>>>(cs->stage.p + at * 3, cs->pix_others.p + at, n, fb);
+      }
+      CCUDA(cudaGetLastError());
+    }
+  }
+  if (cs->rank == 0 && fb_out) {
+    const size_t r0 = (size_t)std::min(ctx->yres, ty0 * 32) * ctx->xres * 3, r1 = (size_t)std::min(ctx->yres, ty1 * 32) * ctx->xres * 3;
+    if (r1 > r0) CCUDA(cudaMemcpyAsync(fb_out + r0, fb + r0, (r1 - r0) * sizeof(float), cudaMemcpyDeviceToHost, st));  // a pageable destination is staged by the driver
+  }
+  if (sync) CCUDA(cudaStreamSynchronize(st));
+  return VG_OK;
+}
+}  // namespace vg
+
+static int comm_gather_rows_d2h_only(vg_ctx* ctx, cudaStream_t st, float* fb_out) {
+  CommState* cs = ctx->comm;
+  if (cs->rank != 0 || !fb_out) return VG_OK;
+  float* fb = nullptr;
+  int rc = render_fb_device(ctx, &fb);
+  if (rc != VG_OK) return rc;
+  CCUDA(cudaMemcpyAsync(fb_out, fb, (size_t)ctx->xres * ctx->yres * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  return VG_OK;
+}
+
 extern "C" int vg_gather_frame(vg_ctx* ctx, float* fb_out) {
   if (!ctx) return VG_ERR_INVALID;
   std::lock_guard<std::mutex> lock(ctx->mu);
   CommState* cs = ctx->comm;
   if (!cs) return ctx->fail(VG_ERR_INVALID, "vg_gather_frame: no communicator (vg_comm_init)");
-  if (cs->rank != ctx->rank || cs->world != ctx->world) return ctx->fail(VG_ERR_INVALID, "vg_gather_frame: vg_set_partition changed the partition after vg_comm_init");
   CCUDA(cudaSetDevice(ctx->device));
-  float* fb = nullptr;
-  int rc = render_fb_device(ctx, &fb);
-  if (rc != VG_OK) return rc;
   cudaStream_t st = ctx->stream;
   cudaEventRecord(cs->e0, st);
-  if (cs->world > 1) {
-    rc = comm_layout(ctx, cs);
-    if (rc != VG_OK) return rc;
-    const int nown = cs->count[(size_t)cs->rank];
-    if (cs->rank != 0) {
-      if (nown > 0) {
-        k_pack_owned<<<(nown * 3 + 255) / 256, 256, 0, st>>>(fb, cs->pix_own.p, nown, cs->send.p);
-        CCUDA(cudaGetLastError());
-        CNCCL(g_nccl.Send(cs->send.p, (size_t)nown * 3, kNcclFloat32, 0, cs->comm, st));
-      }
-    } else {
-      CNCCL(g_nccl.GroupStart());
-      for (int r = 1; r < cs->world; r++)
-        if (cs->count[(size_t)r] > 0) {
-          const int rr = g_nccl.Recv(cs->stage.p + (size_t)cs->offset[(size_t)r] * 3, (size_t)cs->count[(size_t)r] * 3, kNcclFloat32, r, cs->comm, st);
-          if (rr != 0) {
-            g_nccl.GroupEnd();
-            return ctx->fail(VG_ERR_COMM, std::string("ncclRecv: ") + g_nccl.GetErrorString(rr));
-          }
-        }
-      CNCCL(g_nccl.GroupEnd());
-      if (cs->n_others > 0) {
-        k_scatter_owned<<<(cs->n_others * 3 + 255) / 256, 256, 0, st>>>(cs->stage.p, cs->pix_others.p, cs->n_others, fb);
-        CCUDA(cudaGetLastError());
-      }
-    }
-  }
+  int rc = comm_gather_rows(ctx, st, 0, (ctx->yres + 31) / 32, nullptr, false);
+  if (rc != VG_OK) return rc;
   cudaEventRecord(cs->e1, st);
-  if (cs->rank == 0 && fb_out) {
-    const size_t bytes = (size_t)ctx->xres * ctx->yres * 3 * sizeof(float);
-    CCUDA(cudaMemcpyAsync(fb_out, fb, bytes, cudaMemcpyDeviceToHost, st));  // a pageable destination is staged by the driver
-  }
+  rc = comm_gather_rows_d2h_only(ctx, st, fb_out);
+  if (rc != VG_OK) return rc;
   CCUDA(cudaStreamSynchronize(st));
   float ms = 0;
   cudaEventElapsedTime(&ms, cs->e0, cs->e1);
@@ -324,4 +366,11 @@ extern "C" int vg_gather_frame(vg_ctx* ctx, float* fb_out) {
   ctx->stats.kernel_launches += cs->world > 1 ? 1 : 0;
   ctx->stats.gather_ms = ms;
   return VG_OK;
+}
+
+extern "C" int vg_render_frame(vg_ctx* ctx, const uint64_t* table, int64_t npix, int iter_begin, int iter_end, int clear_first, float* fb_out) {
+  if (!ctx) return VG_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  CCUDA(cudaSetDevice(ctx->device));
+  return render_frame(ctx, table, npix, iter_begin, iter_end, clear_first, fb_out);
 }

@@ -982,6 +982,10 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
   else if (!std::strcmp(name, "primary_per_lane")) ctx->opt_primary_per_lane = value != 0;
   else if (!std::strcmp(name, "shadow_unordered")) ctx->opt_shadow_unordered = value != 0;
   else if (!std::strcmp(name, "shadow_per_lane")) ctx->opt_shadow_per_lane = value != 0;
+  else if (!std::strcmp(name, "frame_slices")) {
+    if (value < 1 || value > 64) return ctx->fail(VG_ERR_INVALID, "frame_slices must be in [1,64]");
+    ctx->opt_frame_slices = value;
+  }
   else if (!std::strcmp(name, "capture_levels")) {
     ctx->opt_capture_levels = value & 31;
     if (value & 31) ctx->captured.clear();  // switching the capture on starts a new store; switching it off keeps what was captured

@@ -156,6 +156,7 @@ struct vg_ctx {
   int opt_primary_per_lane = 1;  // with traversal=2: camera rays (level 0) still use the per-lane loop
   int opt_shadow_unordered = 1;  // integrator shadow queue: skip the sign-ordered push (occlusion is order independent)
   int opt_generic_shade = 0;     // 1 = always shade with the general kernel (tests: it must agree with the specialised one)
+  int opt_frame_slices = 4;      // vg_render_frame: slices of tile rows whose copies / exchange overlap the next slice's rendering
   int opt_capture_levels = 0;    // bit L: vg_render keeps a host copy of the level-L closest-hit ray queue (vg_captured_rays)
   std::vector<VgRay> captured;
   int opt_shadow_per_lane = 0;   // integrator shadow queue through the per-lane while-while kernel instead of the cooperative one
@@ -185,6 +186,7 @@ struct vg_ctx {
 namespace vg {
 // render.cu
 int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out);
+int render_frame(vg_ctx* ctx, const uint64_t* table, int64_t npix, int iter_begin, int iter_end, int clear_first, float* fb_out);
 int render_clear(vg_ctx* ctx);
 int render_fb_device(vg_ctx* ctx, float** d_fb);
 void render_invalidate(vg_ctx* ctx);  // scene / frame / partition changed
@@ -193,6 +195,7 @@ void render_destroy(vg_ctx* ctx);
 void build_scratch_destroy(vg_ctx* ctx);  // build_bvh.cu
 // comm.cu
 void comm_destroy(vg_ctx* ctx);
+int comm_gather_rows(vg_ctx* ctx, cudaStream_t st, int ty0, int ty1, float* fb_out, bool sync);
 int partition_stride(int tilesX, int world);
 void owned_pixels(int W, int H, int rank, int world, bool pixel_block, std::vector<int>& pix);  // tile-major pixel list of `rank`
 }  // namespace vg

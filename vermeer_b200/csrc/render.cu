@@ -1198,6 +1198,16 @@ struct RenderState {
   bool generic = false;  // shade with k_shade_generic (glossy lobe / conductor Fresnel / Disk or Sphere lights / sphere geoms)
   int nlobes = 1;
   std::vector<int> pix_host;
+  std::vector<int> row_start;  // [tilesY + 1] index into pix of the first owned pixel of every tile row (slices of vg_render_frame)
+  std::vector<cudaEvent_t> pipe_ev;  // untimed events of the frame pipeline
+  cudaEvent_t pev(size_t i) {
+    while (pipe_ev.size() <= i) {
+      cudaEvent_t e;
+      cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      pipe_ev.push_back(e);
+    }
+    return pipe_ev[i];
+  }
   uint64_t* scr_pinned = nullptr;
   size_t scr_pinned_bytes = 0;
   float* fb_pinned = nullptr;
@@ -1242,6 +1252,7 @@ void render_destroy(vg_ctx* ctx) {
   if (ctx->rs->e1) cudaEventDestroy(ctx->rs->e1);
   for (cudaEvent_t e : ctx->rs->evpool) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->rs->fetchpool) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->rs->pipe_ev) cudaEventDestroy(e);
   if (ctx->rs->scr_pinned) cudaFreeHost(ctx->rs->scr_pinned);
   if (ctx->rs->fb_pinned) cudaFreeHost(ctx->rs->fb_pinned);
   delete ctx->rs;
@@ -1413,6 +1424,12 @@ static int prepare(vg_ctx* ctx) {
   owned_pixels(W, H, ctx->rank, ctx->world, ctx->opt_pixel_block != 0, pix);
   rs.nown = (int)pix.size();
   rs.pix_host = pix;
+  {
+    const int tilesY = (H + 31) / 32;
+    rs.row_start.assign((size_t)tilesY + 1, (int)pix.size());
+    for (int i = (int)pix.size() - 1; i >= 0; i--) rs.row_start[(size_t)((pix[(size_t)i] / W) / 32)] = i;
+    for (int ty = tilesY - 1; ty >= 0; ty--) rs.row_start[(size_t)ty] = std::min(rs.row_start[(size_t)ty], rs.row_start[(size_t)ty + 1]);
+  }
 
   // materials
   std::vector<DevMat> mats(ctx->materials.size());
@@ -1657,13 +1674,56 @@ int render_fb_device(vg_ctx* ctx, float** d_fb) {
   return VG_OK;
 }
 
-int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
+// vg_render_frame: the frame step as ONE pipelined call. The image is cut into slices of tile rows; the scramble rows of slice
+// s+1 go up (copy stream) and the finished pixels of slice s-1 come back — multi-GPU exchange (comm.cu) and D2H of the slice's
+// image rows (out stream) — while slice s renders on the main stream. Every (pixel, iteration) sample is what vg_render
+// computes, so the frame is bit-identical to vg_set_scramble + vg_render + vg_gather_frame.
+struct FramePipe {
+  const uint64_t* table;  // the caller's framescramble table (page-locked for the overlapped upload)
+  bool clear;
+  int slices;
+};
+static int render_run_impl(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out, const FramePipe* fp);
+int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) { return render_run_impl(ctx, iter_begin, iter_end, fb_out, nullptr); }
+
+int render_frame(vg_ctx* ctx, const uint64_t* table, int64_t npix, int iter_begin, int iter_end, int clear_first, float* fb_out) {
+  if (!table || (int64_t)ctx->xres * ctx->yres != npix) return ctx->fail(VG_ERR_INVALID, "vg_render_frame: table size != XRes*YRes");
+  int rc = ensure_fb(ctx);
+  if (rc != VG_OK) return rc;
+  RenderState& rs = *ctx->rs;
+  const bool pipelined = rs.ready && is_pinned_host(table) && (!fb_out || is_pinned_host(fb_out)) && rs.nown > 0;
+  if (!pipelined) {
+    // first call (nothing prepared yet) or pageable buffers: the plain sequence, same result
+    rc = render_set_scramble(ctx, table, npix);
+    if (rc != VG_OK) return rc;
+    if (clear_first && (rc = render_clear(ctx)) != VG_OK) return rc;
+    if (ctx->comm) {
+      rc = render_run_impl(ctx, iter_begin, iter_end, nullptr, nullptr);
+      return rc != VG_OK ? rc : comm_gather_rows(ctx, ctx->stream, 0, (ctx->yres + 31) / 32, fb_out, true);
+    }
+    return render_run_impl(ctx, iter_begin, iter_end, fb_out, nullptr);
+  }
+  FramePipe fp{table, clear_first != 0, std::max(1, ctx->opt_frame_slices)};
+  return render_run_impl(ctx, iter_begin, iter_end, fb_out, &fp);
+}
+
+static int render_run_impl(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out, const FramePipe* fp) {
   if (iter_begin < 0 || iter_end < iter_begin) return ctx->fail(VG_ERR_INVALID, "vg_render: bad iteration range");
   if (iter_end >= (1 << 28)) return ctx->fail(VG_ERR_INVALID, "vg_render: iteration index beyond the 28 frame bits of RasterXY(12,...)");
   int rc = prepare(ctx);
   if (rc != VG_OK) return rc;
   RenderState& rs = *ctx->rs;
   cudaStream_t st = ctx->stream;
+  const int tilesY = (ctx->yres + 31) / 32;
+  const int S = fp ? std::min(fp->slices, tilesY) : 1;
+  cudaStream_t st_in = nullptr, st_out = nullptr;
+  if (fp) {
+    for (int k = 0; k < 2; k++) {
+      if (!ctx->pipe_stream[k]) RCUDA(cudaStreamCreateWithFlags(&ctx->pipe_stream[k], cudaStreamNonBlocking));
+    }
+    st_in = ctx->pipe_stream[0];
+    st_out = ctx->pipe_stream[1];
+  }
 
   RenderParams p;
   std::memset(&p, 0, sizeof(p));
@@ -1705,10 +1765,54 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
   };
   RCUDA(cudaMemsetAsync(rs.stats.p, 0, 8 * sizeof(unsigned long long), st));
   RCUDA(cudaEventRecord(rs.e0, st));
-  if (rs.nown > 0) {
-    for (int ib = iter_begin; ib < iter_end; ib += rs.iters) {
+  auto slice_rows = [&](int sl, int* ty0, int* ty1) {
+    *ty0 = (int)((long long)tilesY * sl / S);
+    *ty1 = (int)((long long)tilesY * (sl + 1) / S);
+  };
+  if (fp) {
+    // the copy stream starts where the main stream is (earlier work on the buffers is done), then takes the slices' rows in order
+    RCUDA(cudaEventRecord(rs.pev(0), st));
+    RCUDA(cudaStreamWaitEvent(st_in, rs.pev(0), 0));
+    RCUDA(cudaStreamWaitEvent(st_out, rs.pev(0), 0));
+    if (fp->clear) RCUDA(cudaMemsetAsync(rs.fb.p, 0, (size_t)ctx->xres * ctx->yres * 3 * sizeof(float), st));
+    void* dview = nullptr;
+    if (ctx->world > 1 && (cudaHostGetDevicePointer(&dview, const_cast<uint64_t*>(fp->table), 0) != cudaSuccess || !dview)) {
+      cudaGetLastError();
+      return ctx->fail(VG_ERR_CUDA, "vg_render_frame: the page-locked table has no device mapping");
+    }
+    for (int sl = 0; sl < S; sl++) {
+      int ty0, ty1;
+      slice_rows(sl, &ty0, &ty1);
+      if (ctx->world == 1) {  // whole table, raster order: the slice is a run of image rows
+        const size_t r0 = (size_t)std::min(ctx->yres, ty0 * 32) * ctx->xres, r1 = (size_t)std::min(ctx->yres, ty1 * 32) * ctx->xres;
+        if (r1 > r0) RCUDA(cudaMemcpyAsync(rs.scr.p + r0 * 6, fp->table + r0 * 6, (r1 - r0) * 48, cudaMemcpyHostToDevice, st_in));
+      } else {                // owned rows only, gathered straight from host memory by a kernel
+        const int o0 = rs.row_start[(size_t)ty0], o1 = rs.row_start[(size_t)ty1];
+        const long long n2 = (long long)(o1 - o0) * 3;
+        if (n2 > 0) k_gather_scramble<<<(unsigned)((n2 + 255) / 256), 256, 0, st_in>>>(reinterpret_cast<const uint4*>(dview), rs.pix.p + o0, o1 - o0,
+                                                                                         reinterpret_cast<uint4*>(rs.scr.p) + (size_t)o0 * 3);
+      }
+      RCUDA(cudaEventRecord(rs.pev(1 + (size_t)sl), st_in));
+    }
+    RCUDA(cudaGetLastError());
+    rs.scr_by_pixel = ctx->world == 1;
+    rs.scr_valid = true;
+    rs.scr_w = ctx->xres; rs.scr_h = ctx->yres; rs.scr_rank = ctx->rank; rs.scr_world = ctx->world; rs.scr_pixel_block = ctx->opt_pixel_block;
+    ctx->scramble_stale = true;
+    p.scr_by_pixel = rs.scr_by_pixel ? 1 : 0;
+  }
+  for (int sl = 0; sl < S; sl++) {
+    int ty0 = 0, ty1 = tilesY;
+    slice_rows(sl, &ty0, &ty1);
+    const int o0 = rs.row_start[(size_t)ty0], o1 = rs.row_start[(size_t)ty1];
+    const int sn = o1 - o0;  // owned pixels of this slice
+    p.pix = rs.pix.p + o0;
+    p.scr = rs.scr_by_pixel ? rs.scr.p : rs.scr.p + (size_t)o0 * 6;
+    p.nown = sn;
+    if (fp) RCUDA(cudaStreamWaitEvent(st, rs.pev(1 + (size_t)sl), 0));
+    for (int ib = iter_begin; ib < iter_end && sn > 0; ib += rs.iters) {
       const int niters = std::min(rs.iters, iter_end - ib);
-      const int np = rs.nown * niters;
+      const int np = sn * niters;
       {
         int G = 1;  // the largest power of two within the option, the warp size and this batch's iteration count
         while (G * 2 <= ctx->opt_iter_group && G * 2 <= 32 && G * 2 <= niters) G *= 2;
@@ -1717,10 +1821,10 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
         p.pm_lG = 0;
         while ((1 << p.pm_lG) < G) p.pm_lG++;
         p.pm_lB = 5 - p.pm_lG;
-        p.pm_nownB = rs.nown - rs.nown % p.pm_B;
+        p.pm_nownB = sn - sn % p.pm_B;
         p.pm_nitG = niters - niters % G;
         p.pm_A = p.pm_nownB * p.pm_nitG;
-        p.pm_rem = rs.nown - p.pm_nownB;
+        p.pm_rem = sn - p.pm_nownB;
         p.niters = niters;
       }
       k_reset<<<1, 1, 0, st>>>(rs.counts.p, np);
@@ -1818,9 +1922,21 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
         }
         qin = qout;
       }
-      if (rs.levels > 1) k_accumulate<<<(rs.nown + 255) / 256, 256, 0, st>>>(p, ib, niters);
-      else k_resolve_accumulate<<<(rs.nown + 255) / 256, 256, 0, st>>>(p, ib, niters);
+      if (rs.levels > 1) k_accumulate<<<(sn + 255) / 256, 256, 0, st>>>(p, ib, niters);
+      else k_resolve_accumulate<<<(sn + 255) / 256, 256, 0, st>>>(p, ib, niters);
       launches++;
+    }
+    if (fp) {
+      // this slice's pixels are final: send them on their way while the next slice renders
+      RCUDA(cudaEventRecord(rs.pev(1 + (size_t)S + (size_t)sl), st));
+      RCUDA(cudaStreamWaitEvent(st_out, rs.pev(1 + (size_t)S + (size_t)sl), 0));
+      if (ctx->comm) {
+        rc = comm_gather_rows(ctx, st_out, ty0, ty1, fb_out, false);
+        if (rc != VG_OK) return rc;
+      } else if (fb_out) {
+        const size_t r0 = (size_t)std::min(ctx->yres, ty0 * 32) * ctx->xres * 3, r1 = (size_t)std::min(ctx->yres, ty1 * 32) * ctx->xres * 3;
+        if (r1 > r0) RCUDA(cudaMemcpyAsync(fb_out + r0, rs.fb.p + r0, (r1 - r0) * sizeof(float), cudaMemcpyDeviceToHost, st_out));
+      }
     }
   }
   RCUDA(cudaGetLastError());
@@ -1829,7 +1945,10 @@ int render_run(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_out) {
   int flags = 0;
   RCUDA(cudaMemcpyAsync(hstats, rs.stats.p, sizeof(hstats), cudaMemcpyDeviceToHost, st));
   RCUDA(cudaMemcpyAsync(&flags, rs.counts.p + 5, sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (fb_out && is_pinned_host(fb_out)) {
+  if (fp) {
+    RCUDA(cudaStreamSynchronize(st_out));
+    RCUDA(cudaStreamSynchronize(st_in));
+  } else if (fb_out && is_pinned_host(fb_out)) {
     // the caller's buffer is page-locked: DMA straight into it
     RCUDA(cudaMemcpyAsync(fb_out, rs.fb.p, (size_t)ctx->xres * ctx->yres * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
   } else if (fb_out) {

@@ -33,7 +33,7 @@ DECLARED_SYMBOLS = [
     "vg_sphere_upload", "vg_instance_upload", "vg_scene_upload", "vg_scene_upload_motion", "vg_scene_commit", "vg_set_materials", "vg_set_lights", "vg_set_area_lights", "vg_set_camera", "vg_set_camera_motion", "vg_set_frame",
     "vg_set_partition", "vg_set_scramble", "vg_set_filter", "vg_set_option", "vg_trace_batch", "vg_trace_batch_device", "vg_render", "vg_clear_framebuffer",
     "vg_framebuffer_device", "vg_get_stats", "vg_reset_stats",
-    "vg_comm_unique_id", "vg_comm_init", "vg_comm_destroy", "vg_gather_frame", "vg_nccl_version", "vg_owned_pixels", "vg_measure_peaks", "vg_slot_table", "vg_captured_rays",
+    "vg_comm_unique_id", "vg_comm_init", "vg_comm_destroy", "vg_gather_frame", "vg_render_frame", "vg_nccl_version", "vg_owned_pixels", "vg_measure_peaks", "vg_slot_table", "vg_captured_rays",
     "vg_texture_upload", "vg_textures_clear", "vg_texture_levels", "vg_texture_read_level", "vg_material_set_texture", "vg_mesh_set_uv", "vg_texture_sample_batch",
     "vh_add_texture", "vh_shader_set_texture", "vh_polymesh_set_uv", "vg_build_qbvh", "vg_build_qbvh_nodes", "vh_prerender_device",
     "vh_set_option", "vh_scene_create", "vh_scene_destroy", "vh_last_error", "vh_registered_nodes", "vh_set_globals", "vh_add_shader_std", "vh_add_shader_debug", "vh_add_polymesh",
@@ -466,6 +466,14 @@ class Device:
         if out is not None:
             assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (self.yres, self.xres, 3)
         self._chk(self.L.vg_gather_frame(self.h, _p(out)))
+        return out
+
+    def render_frame(self, table: np.ndarray, iter_begin: int, iter_end: int, out: np.ndarray | None = None, clear: bool = True):
+        """vg_render_frame: scramble upload + (clear) + render + (multi-GPU gather) + frame download as one pipelined call."""
+        table = np.ascontiguousarray(table, np.uint64)
+        if out is not None:
+            assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (self.yres, self.xres, 3)
+        self._chk(self.L.vg_render_frame(self.h, _p(table), C.c_int64(table.shape[0]), iter_begin, iter_end, 1 if clear else 0, _p(out)))
         return out
 
     def measure_peaks(self) -> dict:
