@@ -117,6 +117,7 @@ def test_render_frame_is_the_three_calls_pipelined(built_library, scene_kind):
     dev = _device(sc, tab1)
     dev.set_option("iters_per_batch", 4)
     dev.render(0, 1)                                            # prepared: the next frames take the pipelined path
+    dev.set_option("frame_slices_min_paths_off", 1)             # slice even this small frame
     for slices, tab, key, out in [(4, pin(tab2), 2, out_pinned), (1, pin(tab1), 1, out_pinned), (7, pin(tab2), 2, out_pinned),
                                   (3, tab1, 1, np.zeros_like(out_pinned)), (5, pin(tab1), 1, np.zeros_like(out_pinned))]:
         dev.set_option("frame_slices", slices)
@@ -141,6 +142,7 @@ def test_render_frame_is_the_three_calls_pipelined(built_library, scene_kind):
 
 def _gather_worker(rank, world, uid_q, res_q, xres, yres, iters):
     try:
+        import torch  # noqa: F401  (first: a process that uses PyTorch must let it load ITS NCCL before the library binds libnccl.so.2)
         import numpy as np
         from vermeer_b200 import scenes
         from vermeer_b200.host import Device, HostScene
@@ -165,6 +167,8 @@ def _gather_worker(rank, world, uid_q, res_q, xres, yres, iters):
         tab = torch.from_numpy(scenes.splitmix64_table(1, xres * yres).view(np.int64)).pin_memory().numpy().view(np.uint64)
         out2 = torch.empty((yres, xres, 3), dtype=torch.float32, pin_memory=True).numpy() if rank == 0 else None
         dev.set_option("frame_slices", 3)
+        dev.set_option("frame_slices_multi", 1)          # the sliced exchange (off by default for N > 1: measured no gain)
+        dev.set_option("frame_slices_min_paths_off", 1)
         dev.render_frame(tab, 0, iters, out=out2)
         dev.render_frame(tab, iters, 2 * iters, out=out2, clear=False)
         if rank == 0:

@@ -1703,7 +1703,16 @@ int render_frame(vg_ctx* ctx, const uint64_t* table, int64_t npix, int iter_begi
     }
     return render_run_impl(ctx, iter_begin, iter_end, fb_out, nullptr);
   }
-  FramePipe fp{table, clear_first != 0, std::max(1, ctx->opt_frame_slices)};
+  // Slices pay when a slice is still a large batch: each one adds a set of kernel launches with their ramp-up and tail.
+  // Measured on B200 (C2, 64 spp): one GPU 77.81 -> 77.19 ms per frame step with 4 slices (device time 75.4 ms; the exposed copies
+  // shrink from 2.4 to 1.6 ms); two GPUs 39.52 vs 39.65 ms, i.e. no gain once the per-rank slice is a quarter of half a frame and
+  // every slice carries its own NCCL exchange; a 512x512 16-spp frame (0.75 ms of rendering) loses 0.1 ms. Hence: at most
+  // "frame_slices" slices, none smaller than 16 M paths, and the multi-GPU case keeps the whole frame as one slice.
+  const long long paths = (long long)rs.nown * std::max(0, iter_end - iter_begin);
+  int slices = (int)std::min<long long>(std::max(1, ctx->opt_frame_slices), std::max<long long>(1, paths / (16ll << 20)));
+  if (ctx->opt_frame_slices_force) slices = std::max(1, ctx->opt_frame_slices);
+  if (ctx->world > 1 && !ctx->opt_frame_slices_multi) slices = 1;
+  FramePipe fp{table, clear_first != 0, slices};
   return render_run_impl(ctx, iter_begin, iter_end, fb_out, &fp);
 }
 

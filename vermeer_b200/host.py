@@ -451,12 +451,15 @@ class Device:
     # -- multi-GPU (vg_comm_*, vg_gather_frame) -----------------------------------------------------
     def comm_unique_id(self) -> bytes:
         """Rank 0: the NCCL id every rank passes to comm_init (the caller distributes it)."""
+        _torch_nccl_first()
         buf = C.create_string_buffer(VG_COMM_ID_BYTES)
         self._chk(self.L.vg_comm_unique_id(self.h, buf))
         return buf.raw
 
     def comm_init(self, rank: int, world: int, uid: bytes | None):
         """Collective: NCCL communicator on this context's GPU + the image partition of set_partition(rank, world)."""
+        if world > 1:
+            _torch_nccl_first()
         buf = C.create_string_buffer(uid, VG_COMM_ID_BYTES) if uid is not None else None
         self._chk(self.L.vg_comm_init(self.h, rank, world, buf))
 
@@ -489,6 +492,16 @@ class Device:
 
     def reset_stats(self):
         self._chk(self.L.vg_reset_stats(self.h))
+
+
+def _torch_nccl_first():
+    """The library binds NCCL by soname (dlopen "libnccl.so.2") when the first communicator is made. PyTorch ships its own,
+    newer copy under the same soname; the dynamic linker keeps whichever was loaded first for both. If this process is going to
+    import torch at all, it has to do so BEFORE the library binds the system copy, or libtorch_cuda fails to resolve its symbols."""
+    import importlib.util
+    import sys
+    if "torch" not in sys.modules and importlib.util.find_spec("torch") is not None:
+        import torch  # noqa: F401
 
 
 def device_count() -> int:
