@@ -453,6 +453,12 @@ def stage_roofline(cfg, frame, peaks, hbm_peak, hbm_src, ncu):
                     b = c[bytes_key] * per * rays
                     lv[lvl] = {"bytes_per_unit": c[bytes_key] * per, "achieved": b / secs / 1e9, "peak": peak, "unit": "GB/s", "frac": b / secs / 1e9 / peak,
                                "traffic_per_launch": b / launches, "peak_source": src}
+            if c.get("l1tex_wavefronts_pct"):
+                # the L1TEX data pipe counts wavefronts (one per 128-B line a warp's load touches), not bytes: a divergent warp
+                # needs 32 of them for 32 x 32 B. Utilisation of that unit from the capture, scaled by live vs captured time per unit
+                wf = c["l1tex_wavefronts_pct"] / 100.0 * (c["ms"] / c["units"]) / (ms / rays)
+                lv["l1tex_wavefronts"] = {"frac": wf, "unit": "fraction of the L1TEX data pipe's sustained wavefront rate",
+                                          "capture_pct": c["l1tex_wavefronts_pct"], "peak_source": "ncu: l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed"}
             e["levels"] = lv
             e["issue"] = {"issue_slots_active": c["issue_active_pct"] / 100.0, "lanes_per_instruction": c["lanes_per_inst"],
                           "frac": c["issue_active_pct"] / 100.0 * c["lanes_per_inst"] / 32.0, "registers": c.get("registers"),
@@ -460,6 +466,7 @@ def stage_roofline(cfg, frame, peaks, hbm_peak, hbm_src, ncu):
                           "note": "share of the SMs' lane-issue capacity doing work (issue slots active x active lanes / 32), from the ncu capture"}
             e["capture"] = {"kernel": c.get("kernel"), "ms": c.get("ms"), "units": c["units"], "file": cap.get("_file")}
             best = max(lv.items(), key=lambda kv: kv[1]["frac"]) if lv else None
+            e["frac"] = max(best[1]["frac"] if best else 0.0, e["issue"]["frac"])
             e["binding"] = ("issue x SIMD lanes" if not best or e["issue"]["frac"] >= best[1]["frac"] else best[0])
         stages[name] = e
     return stages
@@ -473,8 +480,16 @@ def headline_roofline(stages, hbm_peak, hbm_src):
     lv = e.get("levels") or {}
     if lv:
         lvl, b = max(lv.items(), key=lambda kv: kv[1]["frac"])
-        out = {"bound": {"hbm": "hbm", "l2": "l2", "l1": "l1tex"}[lvl], "achieved": b["achieved"], "peak": b["peak"], "unit": "GB/s", "frac": b["frac"],
-               "traffic": b["traffic_per_launch"], "peak_source": b["peak_source"]}
+        if lvl == "l1tex_wavefronts":   # the binding unit counts wavefronts; quote the byte figures of the L1 level beside the fraction
+            l1 = lv.get("l1", {})
+            out = {"bound": "l1tex (wavefronts)", "achieved": l1.get("achieved"), "peak": l1.get("peak"), "unit": "GB/s", "frac": b["frac"],
+                   "traffic": l1.get("traffic_per_launch"), "peak_source": b["peak_source"],
+                   "note": "frac = utilisation of the L1TEX data pipe (wavefronts/clk), the busiest unit; achieved/peak are the L1 BYTE rates "
+                           "(measured peak for fully coalesced 128-bit loads), whose ratio is lower because divergent lanes use 32 B of every 128-B wavefront"}
+        else:
+            out = {"bound": {"hbm": "hbm", "l2": "l2", "l1": "l1tex"}[lvl], "achieved": b["achieved"], "peak": b["peak"], "unit": "GB/s", "frac": b["frac"],
+                   "traffic": b["traffic_per_launch"], "peak_source": b["peak_source"]}
+        out["levels"] = {k: v["frac"] for k, v in lv.items()}
         if "hbm" in lv:
             out["hbm"] = lv["hbm"]
     else:
@@ -632,6 +647,15 @@ def run_ours(args):
             b = cap[key] * per * n
             lv[lvl] = {"bytes_per_unit": cap[key] * per, "achieved": b / secs / 1e9, "peak": peak, "unit": "GB/s", "frac": b / secs / 1e9 / peak, "traffic_per_launch": b, "peak_source": src}
         lvl, b = max(lv.items(), key=lambda kv: kv[1]["frac"])
+        wf = cap.get("l1tex_wavefronts_pct")
+        if wf:
+            wfrac = wf / 100.0 * (cap["ms"] / cap["units"]) / (tb["ms_per_step"] / n)
+            lv["l1tex_wavefronts"] = {"frac": wfrac, "capture_pct": wf, "unit": "fraction of the L1TEX data pipe's sustained wavefront rate",
+                                      "peak_source": "ncu: l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed"}
+            if wfrac > b["frac"]:
+                lvl, b = "l1", dict(lv["l1"], frac=wfrac, peak_source=lv["l1tex_wavefronts"]["peak_source"])
+                roof["note"] = ("frac = utilisation of the L1TEX data pipe (wavefronts/clk), the busiest unit of this kernel; achieved/peak are the L1 byte "
+                                "rates, whose ratio (levels.l1.frac) is lower because a divergent warp uses 32 B of every 128-B wavefront")
         roof.update({"bound": {"hbm": "hbm", "l2": "l2", "l1": "l1tex"}[lvl], "achieved": b["achieved"], "peak": b["peak"], "unit": "GB/s", "frac": b["frac"],
                      "traffic": b["traffic_per_launch"], "peak_source": b["peak_source"], "levels": lv,
                      "issue": {"issue_slots_active": cap["issue_active_pct"] / 100.0, "lanes_per_instruction": cap["lanes_per_inst"],

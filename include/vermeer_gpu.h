@@ -165,6 +165,8 @@ typedef struct VgStats {
   double shadow_ms;  /* summed device time of the any-hit traversal launches of the last vg_render */
   double shade_ms;   /* summed device time of the shading launches (k_surface + k_shade*) of the last vg_render */
   double gather_ms;  /* device time of the last vg_gather_frame exchange (pack + NCCL + scatter), without the D2H copy */
+  uint64_t max_stack_depth; /* deepest traversal stack (entries) any ray of vg_render needed since vg_reset_stats; 0 unless the library is
+                               a measurement build (-DVG_STACK_STATS). The reference reserves 90 entries (core/ray.go:158). */
 } VgStats;
 
 /* ---- device layer ------------------------------------------------------------------------- */

@@ -350,6 +350,13 @@ __global__ void __launch_bounds__(kTraceBlock, MODE == 1 ? ((VARIANT & 64) ? VG_
     atomicAdd(p.stats + (MODE == 0 ? 2 : 4), nodes_acc);
     atomicAdd(p.stats + (MODE == 0 ? 3 : 5), tris_acc);
   }
+#ifdef VG_STACK_STATS
+  {
+    int m = st.maxsp;
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+    if (lane == 0) atomicMax(p.stats + 6, (unsigned long long)m);
+  }
+#endif
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     atomicAdd(p.stats + 0, (unsigned long long)n);  // every TraceProbe counts (core/stats.go:26-33)
     if (MODE == 1) atomicAdd(p.stats + 1, (unsigned long long)n);
@@ -1950,7 +1957,7 @@ static int render_run_impl(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_
   }
   RCUDA(cudaGetLastError());
   RCUDA(cudaEventRecord(rs.e1, st));
-  unsigned long long hstats[6] = {0, 0, 0, 0, 0, 0};
+  unsigned long long hstats[7] = {0, 0, 0, 0, 0, 0, 0};
   int flags = 0;
   RCUDA(cudaMemcpyAsync(hstats, rs.stats.p, sizeof(hstats), cudaMemcpyDeviceToHost, st));
   RCUDA(cudaMemcpyAsync(&flags, rs.counts.p + 5, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -2018,6 +2025,7 @@ static int render_run_impl(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_
   ctx->stats.tris_t += hstats[3];
   ctx->stats.shadow_nodes_t += hstats[4];
   ctx->stats.shadow_tris_t += hstats[5];
+  ctx->stats.max_stack_depth = std::max<uint64_t>(ctx->stats.max_stack_depth, hstats[6]);
   ctx->stats.kernel_launches += launches;
   if (flags) {
     cudaMemsetAsync(rs.counts.p + 5, 0, sizeof(int), st);

@@ -281,7 +281,12 @@ __device__ __forceinline__ void ld_tri(const float4* tp, float4& v0, float4& v1,
 #ifndef VG_SMEM_STACK
 #define VG_SMEM_STACK 8
 #endif
-#define VG_LOCAL_STACK 80
+// Measured with a -DVG_STACK_STATS build (scripts/stack_depth.py, B200, 8 iterations of each config): the deepest stack any ray
+// needed is 3 entries on C1, 11 on C2, 10 on C4 and 15 on the two-level 10 M-triangle C3 / C5 scene. 8 shared + 40 local entries
+// leave a 3x margin over that (the reference reserves 90 and panics beyond, core/ray.go:158; here an overflow raises the error flag).
+#ifndef VG_LOCAL_STACK
+#define VG_LOCAL_STACK 40
+#endif
 
 struct Stack {
   uint2* smem;  // base for this thread: entry i at smem[i * stride]
@@ -289,12 +294,18 @@ struct Stack {
   uint2 local[VG_LOCAL_STACK];
   int sp;
   bool overflow;
+#ifdef VG_STACK_STATS
+  int maxsp = 0;  // measurement build only: deepest stack this thread has seen (VgStats.max_stack_depth)
+#endif
   __device__ __forceinline__ void push(float t, int32_t node) {
     uint2 e = make_uint2(__float_as_uint(t), (uint32_t)node);
     if (sp < VG_SMEM_STACK) smem[sp * stride] = e;
     else if (sp < VG_SMEM_STACK + VG_LOCAL_STACK) local[sp - VG_SMEM_STACK] = e;
     else { overflow = true; return; }
     sp++;
+#ifdef VG_STACK_STATS
+    if (sp > maxsp) maxsp = sp;
+#endif
   }
   __device__ __forceinline__ uint2 pop() {
     sp--;
@@ -452,6 +463,9 @@ __device__ __forceinline__ void node_step(const DevScene& sc, TravState& t, Stac
     if (p1) st.smem[sp1 * st.stride] = make_uint2(__float_as_uint(t1), (uint32_t)c1);
     if (p2) st.smem[sp2 * st.stride] = make_uint2(__float_as_uint(t2), (uint32_t)c2);
     st.sp = sp3;
+#ifdef VG_STACK_STATS
+    if (sp3 > st.maxsp) st.maxsp = sp3;
+#endif
   } else {
     if (p0) st.push(t0, c0);
     if (p1) st.push(t1, c1);
@@ -666,8 +680,9 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
 // IO: long long fetch(int count)  — claim `count` consecutive queue slots, returns the first (lane 0 calls it)
 //     long long size();  const VgRay* ray_ptr()
 //     void store(long long i, const RayState& r, const HitState& h, bool overflow)
+// round 2, pixel-coherent warps (path_index): 16 / 24 / 30 -> C2 closest 19.08 / 19.16 / 19.43 ms, C3 closest 305.7 / 311.1 / 329.4 ms
 #ifndef VG_REFILL_BELOW
-#define VG_REFILL_BELOW 24
+#define VG_REFILL_BELOW 16
 #endif
 template <bool ANY_HIT, class IO>
 __device__ __forceinline__ void trace_persistent_tma(const DevScene& sc, IO& io, Stack& st, WarpStage ws, unsigned long long& nodes_acc,
@@ -845,8 +860,11 @@ static __device__ __noinline__ void xf_object_ray(const DevScene& sc, int xi, fl
 // once that many lanes are idle — occlusion rays (coherent in queue order) do best refilled in big groups, closest-hit bounce
 // rays in smaller ones. Measured on C2 (shadow queue ms per frame / incoherent Mrays/s): NODE_MIN 8,4,2 -> 42.3, 41.8, 40.7(*);
 // REFILL_IDLE 8,16,24,32 -> 42.3, 41.0, 39.9(*), 40.3 / 2110, 2144, 2107, - (* with NODE_MIN 4).
+// Re-measured in round 2 with pixel-coherent warps: NODE_MIN 2 / 4 / 8 / 16 -> incoherent batch 2290 / 2360 / 2375 / 2289 Mrays/s, C3 closest
+// 318.2 / 311.1 / 306.1 / 307.0 ms, C2 shadow 33.14 / 33.06 / 33.25 / 33.79 ms; REFILL_IDLE_ANYHIT 8 / 16 / 24 / 32 -> C2 shadow 35.28 / 33.80 /
+// 33.06 / 33.94 ms, C3 shadow 311.9 / 288.6 / 279.7 / 302.8 ms.
 #ifndef VG_NODE_MIN
-#define VG_NODE_MIN 4
+#define VG_NODE_MIN 8
 #endif
 #ifndef VG_REFILL_IDLE_ANYHIT
 #define VG_REFILL_IDLE_ANYHIT 24
