@@ -234,3 +234,67 @@ def test_compact_hits_refused_outside_static_polymesh_scenes(built_library):
     dev = _device(scenes.heightfield_scene(64, 64, nq=40, motion=True))
     with pytest.raises(RuntimeError):
         dev.trace(random_rays(1000, 1), compact=True)
+
+
+def test_traversal_stack_overflow_is_reported_not_silent(built_library):
+    """core.RenderTask holds a 90-entry stack and Go panics beyond it (core/ray.go:158). The device stack is 8 shared + 40 local
+    entries (sized from the measured depth of the BASELINE scenes: <= 15); a tree that needs more must raise the overflow marker,
+    never corrupt memory or return a wrong hit. The tree here is hand-made through the device layer (vg_mesh_upload), as a Go
+    caller would hand over its own PreRender products: a 30-level chain whose every node has three leaf children the ray hits
+    FARTHER along than the interior child, so three entries stay on the stack per level."""
+    import ctypes as C
+    from vermeer_b200.host import Device, NODE_DTYPE, RAY_DTYPE, VgCamera, _p
+    levels = 30
+    nodes = np.zeros(levels, NODE_DTYPE)
+    verts, idx = [], []
+    for lv in range(levels):
+        b = nodes[lv]["Boxes"]          # Boxes[child + 12*(0 = min, 1 = max) + 4*axis]
+        z0 = 1.0 + lv                   # the ray runs along +z from z = 0
+        # child 0 = the next level, children 1..3 = leaves. With every axis 2 and D.z > 0 the push order is 3, 2, 1, 0
+        # (intersect.go:137-216): the three leaves are pushed first and STAY on the stack while child 0 is descended into.
+        for ch in range(4):
+            lo = (-1.0, -1.0, z0 + (0.6 if ch > 0 else 0.0))
+            hi = (1.0, 1.0, z0 + (0.9 if ch > 0 else 0.5))
+            for a in range(3):
+                b[ch + 4 * a] = lo[a]
+                b[ch + 12 + 4 * a] = hi[a]
+        nodes[lv]["Axis0"], nodes[lv]["Axis1"], nodes[lv]["Axis2"] = 2, 2, 2
+        for ch in (1, 2, 3):            # one triangle per leaf, far off the ray: every leaf is visited, nothing is hit
+            t = len(idx) // 3
+            verts += [(5.0, 5.0, z0 + 0.7), (6.0, 5.0, z0 + 0.7), (5.0, 6.0, z0 + 0.7)]
+            idx += [3 * t, 3 * t + 1, 3 * t + 2]
+            nodes[lv]["Children"][ch] = np.int32(-(1 << 31) | (t << 4) | 0)
+        nodes[lv]["Children"][0] = lv + 1 if lv + 1 < levels else -1
+    verts = np.asarray(verts, np.float32)
+    idx = np.asarray(idx, np.uint32)
+    top = np.zeros(1, NODE_DTYPE)       # scene level: one leaf holding geom 0
+    tb = top[0]["Boxes"]
+    for a, (lo, hi) in enumerate([(-1, 1), (-1, 1), (0.5, levels + 2.0)]):
+        tb[0 + 4 * a], tb[12 + 4 * a] = lo, hi
+        for ch in (1, 2, 3):
+            tb[ch + 4 * a], tb[ch + 12 + 4 * a] = np.inf, np.inf
+    top[0]["Children"][:] = [np.int32(-(1 << 31) | 0), -1, -1, -1]
+    dev = Device(0)
+    L, h = dev.L, dev.h
+    dev._chk(L.vg_scene_begin(h, 1))
+    mats = np.asarray([0], np.int32)
+    dev._chk(L.vg_mesh_upload(h, 0, _p(nodes), levels, _p(idx), len(idx) // 3, _p(verts), len(verts), None, _p(mats), 1, None, 0, None, C.c_float(0.0)))
+    dev._chk(L.vg_scene_upload(h, _p(top), 1, _p(np.asarray([0], np.int32)), 1))
+    dev._chk(L.vg_scene_commit(h))
+    rays = np.zeros(64, RAY_DTYPE)
+    rays["d"][:, 2] = 1.0
+    rays["tmax"] = np.inf
+    rays["o"][32:, 0] = 50.0            # the second half misses the whole tree: no overflow there
+    hits = dev.trace(rays)
+    assert (hits["prim"][:32] == -2).all()          # the overflow marker of vg_trace_batch (BatchIO::store)
+    assert (hits["prim"][32:] == -1).all()
+    # the same tree cut to 10 levels fits (30 pushes) and reports the plain miss with all 10 interior visits counted
+    dev2 = Device(0)
+    nodes10 = nodes[:10].copy()
+    nodes10[9]["Children"][0] = -1
+    dev2._chk(L.vg_scene_begin(dev2.h, 1))
+    dev2._chk(L.vg_mesh_upload(dev2.h, 0, _p(nodes10), 10, _p(idx[:90]), 30, _p(verts[:90]), 90, None, _p(mats), 1, None, 0, None, C.c_float(0.0)))
+    dev2._chk(L.vg_scene_upload(dev2.h, _p(top), 1, _p(np.asarray([0], np.int32)), 1))
+    dev2._chk(L.vg_scene_commit(dev2.h))
+    h10 = dev2.trace(rays[:4])
+    assert (h10["prim"] == -1).all() and (h10["nodesT"] == 11).all() and (h10["trisT"] == 30).all()
