@@ -34,6 +34,7 @@ struct DevLight {
   int nsamples;    // 1 << Samples
   int geom;
   int slot_base;
+  float spec[12];  // Spectrum.FromRGB(E) per Smits bin, [bin + 1] (k_spectrum_tables); a light sample's Liu is four loads
 };
 
 struct __align__(16) DevMat {  // 96 B: six 128-bit loads / stores (the per-vertex copies of textured scenes go through memory)
@@ -175,6 +176,16 @@ __device__ __forceinline__ void path_decode(const RenderParams& p, int path, int
   q -= p.pm_nitG * p.pm_rem;
   it = p.pm_nitG + q / p.nown;
   own = q % p.nown;
+}
+
+// One thread per (light or white, bin): the 11 values RGBToSpectrumSmits99 can take for a constant colour (shade.cuh).
+__global__ void k_spectrum_tables(DevLight* lights, int nlights, QmcTables* qmc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int which = i / 12, k = i % 12;
+  if (which > nlights) return;
+  const int bin = k - 1;  // -1 .. 10; slot 11 is never indexed
+  if (which == nlights) qmc->white_spec[k] = k <= 10 ? rgb_to_spectrum(1.0f, 1.0f, 1.0f, bin) : 0.0f;
+  else lights[which].spec[k] = k <= 10 ? rgb_to_spectrum(lights[which].E.x, lights[which].E.y, lights[which].E.z, bin) : 0.0f;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -899,7 +910,7 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
     fr.N = c.N;
     omegaI = basis_project(fr.U, fr.V, fr.N, neg3(Rd));
     hero = hero_setup(lambda);
-    ov = oren_vertex<FAST>(omegaI, m.rough2, hero);
+    ov = oren_vertex<FAST>(omegaI, m.rough2, hero, p.qmc->white_spec);
     const size_t srow = p.scr_by_pixel ? (size_t)p.pix[own] : (size_t)own;
     scr0 = p.scr[srow * 6 + 4];
     scr1 = p.scr[srow * 6 + 5];
@@ -926,7 +937,7 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
     SphTri sph;
     bool by_area = false;
     if (lit) {
-      Liu = spec_from_rgb(L.E, hero);
+      Liu = spec_from_table(p.lights[l].spec, hero);
       by_area = dot3(c.Ng, sub3(L.p0, c.P)) < 0 || dot3(c.Ng, sub3(L.p1, c.P)) < 0 || dot3(c.Ng, sub3(L.p2, c.P)) < 0;
       if (!by_area) sph = spherical_setup<FAST>(L.p0, L.p1, L.p2, c.P);
     }
@@ -1587,6 +1598,11 @@ static int prepare(vg_ctx* ctx) {
   }
   if (!mats.empty()) RCUDA(cudaMemcpyAsync(rs.mats.p, mats.data(), mats.size() * sizeof(DevMat), cudaMemcpyHostToDevice, ctx->stream));
   if (!lights.empty()) RCUDA(cudaMemcpyAsync(rs.lights.p, lights.data(), lights.size() * sizeof(DevLight), cudaMemcpyHostToDevice, ctx->stream));
+  {
+    const int nt = ((int)lights.size() + 1) * 12;
+    k_spectrum_tables<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(rs.lights.p, (int)lights.size(), rs.qmc.p);
+    RCUDA(cudaGetLastError());
+  }
   RCUDA(rs.rayq0.reserve(P)); RCUDA(rs.rayq1.reserve(P)); RCUDA(rs.pathq0.reserve(P)); RCUDA(rs.pathq1.reserve(P));
   RCUDA(rs.hits.reserve(P)); RCUDA(rs.lambda.reserve(P)); RCUDA(rs.time.reserve(P)); RCUDA(rs.vmat.reserve(P));
   RCUDA(rs.invtot.reserve(P * std::max(1, rs.nlights) * rs.nlobes));

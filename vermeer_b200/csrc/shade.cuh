@@ -150,6 +150,10 @@ __device__ __forceinline__ void raster_xy12(uint32_t frame, uint32_t px, uint32_
 struct QmcTables {
   uint64_t sob[7][256];   // XOR of the Sobol' direction numbers v_k (ldseq.go:83-96) over the set bits of byte k
   uint32_t rinv[3][256];  // XOR of vdCSobolInvMatrices[12] rows (raster.go:24-36) over the set bits of byte k
+  // Spectrum.FromRGB of white (the Oren-Nayar reflectance's spectrum, orennayar.go:66-69) per Smits bin: [bin + 1], bin = -1..9.
+  // RGBToSpectrumSmits99 depends on the colour and the wavelength's bin only (spectrum_smits9.go:16-25,48-84), so a constant colour
+  // has 11 possible values; k_spectrum_tables evaluates them once with the same device function the per-vertex path used.
+  float white_spec[12];
 };
 __device__ __forceinline__ void raster_xy12_tab(const QmcTables* __restrict__ T, uint32_t frame, uint32_t px, uint32_t py, double* rx, double* ry) {
   uint64_t index = (uint64_t)frame << 24;
@@ -219,6 +223,13 @@ __device__ __forceinline__ Spec4 spec_from_rgb(f3 rgb, const Hero& h) {  // spec
   Spec4 s;
 #pragma unroll
   for (int k = 0; k < 4; k++) s.c[k] = rgb_to_spectrum(rgb.x, rgb.y, rgb.z, h.sbin[k]);
+  return s;
+}
+// the same for a colour whose 11 per-bin values were tabulated (light emissions, white): four loads instead of four Smits evaluations
+__device__ __forceinline__ Spec4 spec_from_table(const float* __restrict__ tab, const Hero& h) {
+  Spec4 s;
+#pragma unroll
+  for (int k = 0; k < 4; k++) s.c[k] = __ldg(tab + h.sbin[k] + 1);
   return s;
 }
 __device__ __forceinline__ f3 spec_to_rgb(const Spec4& s, const Hero& h) {  // spectrum.go:57-72
@@ -294,7 +305,7 @@ __device__ __forceinline__ void unit2(float x, float y, float* c, float* s) {
   }
 }
 template <bool FAST>
-__device__ __forceinline__ OrenVertex oren_vertex(f3 omegaI, float roughness2, const Hero& hero) {
+__device__ __forceinline__ OrenVertex oren_vertex(f3 omegaI, float roughness2, const Hero& hero, const float* __restrict__ white_tab = nullptr) {
   OrenVertex v;
   const float sigma = roughness2;
   v.A = 1 - (0.5f * (sigma * sigma) / ((sigma * sigma) + 0.57f));
@@ -309,7 +320,7 @@ __device__ __forceinline__ OrenVertex oren_vertex(f3 omegaI, float roughness2, c
     v.thetaI = Trig<FAST>::acos(omegaI.z);
     v.cosI = v.sinI = v.cphiI = v.sphiI = 0.0f;
   }
-  v.white = spec_from_rgb(mk3(1, 1, 1), hero);
+  v.white = white_tab ? spec_from_table(white_tab, hero) : spec_from_rgb(mk3(1, 1, 1), hero);
   return v;
 }
 template <bool FAST>

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(128, 4) k_shade_generic(const RenderParams p, 
     fr.N = c.N;
     omegaI = basis_project(fr.U, fr.V, fr.N, neg3(Rd));
     hero = hero_setup(lambda);
-    ov = oren_vertex<FAST>(omegaI, m.rough2, hero);
+    ov = oren_vertex<FAST>(omegaI, m.rough2, hero, p.qmc->white_spec);
     gv.omegaR = omegaI;
     gv.alpha = sqr32(m.spec_rough * m.spec_rough);
     const size_t srow = p.scr_by_pixel ? (size_t)p.pix[own] : (size_t)own;
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(128, 4) k_shade_generic(const RenderParams p, 
       Spec4 Liu;
       LightVertex lv;
       if (lit) {
-        Liu = spec_from_rgb(L.E, hero);
+        Liu = spec_from_table(p.lights[l].spec, hero);
         lv = light_vertex<FAST>(L, c);
       }
       auto bsdf_rec = [&](int s) -> BsdfRec {

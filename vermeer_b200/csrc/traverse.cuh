@@ -599,7 +599,12 @@ __device__ __forceinline__ bool sphere_leaf(const DevScene& sc, TravState& t, ui
 template <bool ANY_HIT, bool SPH = false>
 __device__ __forceinline__ bool trav_run(const DevScene& sc, TravState& t, Stack& st, int min_active) {
   while (t.cur != -1) {
-    while (t.cur >= 0) node_step(sc, t, st);
+    // 256-bit node loads in the per-lane kernel too: re-measured with pixel-coherent warps, C2 closest 19.09 vs 19.15 ms, C3 299.6 vs
+    // 300.5 ms — within noise, so it keeps the 128-bit loads (round 1: 28.59 vs 28.32 ms).
+#ifndef VG_PERLANE_WIDE
+#define VG_PERLANE_WIDE 0
+#endif
+    while (t.cur >= 0) node_step<true, VG_PERLANE_WIDE != 0>(sc, t, st);
     while (t.cur < -1) {
       const uint32_t un = (uint32_t)t.cur;
       if (un & kGeomBit) {
@@ -1134,7 +1139,25 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
     const bool leaf = t.cur < -1;
     const bool mleaf = leaf && ((uint32_t)t.cur & kMotionTriBit);
     if (__any_sync(0xffffffffu, leaf)) {
-      bool leafhit = coop_leaves<MOT>(sc, t, leaf && (MOT || !mleaf), cs);
+      bool leafhit = false;
+#ifndef VG_COOP_UNIFORM
+#define VG_COOP_UNIFORM 0
+#endif
+#if VG_COOP_UNIFORM
+      // Pixel-coherent warps (render.cu: path_index) often arrive with most lanes in the SAME static leaf. Then the plain per-lane
+      // loop over that leaf's triangles (every lane its own ray, the triangle record a broadcast load) does the same tests without
+      // the cooperative phase's bookkeeping; below VG_COOP_UNIFORM lanes the cooperative enumeration is the cheaper one.
+      // MEASURED (round 2, B200) and left OFF: thresholds 16 / 24 / 28 all lose — C2 shadow 34.25 / 34.24 / 34.28 vs 33.33 ms, C3
+      // shadow 290.8 vs 280.3 ms, incoherent batch 2331 vs 2361 Mrays/s: the second inlined leaf loop costs more (code size, registers
+      // across the vote) than the bookkeeping it saves.
+      const uint32_t lm = __ballot_sync(0xffffffffu, leaf && !mleaf);
+      const uint32_t un0 = __shfl_sync(0xffffffffu, (uint32_t)t.cur, lm ? __ffs(lm) - 1 : 0);
+      const bool uni = __popc(lm) >= VG_COOP_UNIFORM && __all_sync(0xffffffffu, !leaf || (!mleaf && (uint32_t)t.cur == un0));
+      if (uni) {
+        if (leaf) leafhit = leaf_step(sc, t, (uint32_t)t.cur);
+      } else
+#endif
+      leafhit = coop_leaves<MOT>(sc, t, leaf && (MOT || !mleaf), cs);
       if (!MOT && mleaf) {
         const uint32_t un = (uint32_t)t.cur;
         const int count = (int)(un & 15u) + 1;
