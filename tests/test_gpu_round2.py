@@ -298,3 +298,22 @@ def test_traversal_stack_overflow_is_reported_not_silent(built_library):
     dev2._chk(L.vg_scene_commit(dev2.h))
     h10 = dev2.trace(rays[:4])
     assert (h10["prim"] == -1).all() and (h10["nodesT"] == 11).all() and (h10["trisT"] == 30).all()
+
+
+def test_tiled_accumulate_is_bit_identical(built_library):
+    """Single-level scenes with one pixel x 32 iterations per warp resolve and accumulate through a shared-memory tile
+    (k_resolve_accumulate_t): the same per-pixel arithmetic in the same order as the plain kernel, for full and ragged pixel counts,
+    one and two iteration groups per batch, progressive continuation."""
+    sc = _scene(200, 140)            # 28 000 pixels: not a multiple of 32 per tile row
+    ref = None
+    for tiled, ipb in [(0, 32), (1, 32), (1, 64), (0, 64)]:
+        dev = _device(sc)
+        dev.set_option("accumulate_tiled", tiled)
+        dev.set_option("iters_per_batch", ipb)
+        fb = dev.render(0, 64).copy()
+        dev.render(64, 96)           # continues the running mean with another 32-iteration batch
+        fb2 = dev.render(96, 100)    # and a ragged tail (4 iterations: the plain kernel)
+        if ref is None:
+            ref = (fb, fb2.copy())
+        assert np.array_equal(fb.view(np.uint32), ref[0].view(np.uint32)), (tiled, ipb)
+        assert np.array_equal(fb2.view(np.uint32), ref[1].view(np.uint32)), (tiled, ipb)

@@ -982,6 +982,7 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
   else if (!std::strcmp(name, "primary_per_lane")) ctx->opt_primary_per_lane = value != 0;
   else if (!std::strcmp(name, "shadow_unordered")) ctx->opt_shadow_unordered = value != 0;
   else if (!std::strcmp(name, "shadow_per_lane")) ctx->opt_shadow_per_lane = value != 0;
+  else if (!std::strcmp(name, "accumulate_tiled")) ctx->opt_accumulate_tiled = value != 0;
   else if (!std::strcmp(name, "frame_slices_multi")) ctx->opt_frame_slices_multi = value != 0;
   else if (!std::strcmp(name, "frame_slices_min_paths_off")) ctx->opt_frame_slices_force = value != 0;
   else if (!std::strcmp(name, "frame_slices")) {

@@ -156,6 +156,7 @@ struct vg_ctx {
   int opt_primary_per_lane = 1;  // with traversal=2: camera rays (level 0) still use the per-lane loop
   int opt_shadow_unordered = 1;  // integrator shadow queue: skip the sign-ordered push (occlusion is order independent)
   int opt_generic_shade = 0;     // 1 = always shade with the general kernel (tests: it must agree with the specialised one)
+  int opt_accumulate_tiled = 0;    // 1 = k_resolve_accumulate_t (shared-memory tile); measured slower: C2 raygen+accumulate 5.76 vs 4.74 ms per frame
   int opt_frame_slices_force = 0;  // tests: ignore the 16 M-path minimum slice size
   int opt_frame_slices_multi = 0; // 1 = slice the frame also when a multi-GPU communicator exists (measured: no gain)
   int opt_frame_slices = 4;      // vg_render_frame: slices of tile rows whose copies / exchange overlap the next slice's rendering

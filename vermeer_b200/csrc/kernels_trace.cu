@@ -34,7 +34,7 @@ struct BatchIO {
     }
     float4* hp = reinterpret_cast<float4*>(hits + i);
     hp[0] = make_float4(r.tclosest, h.u, h.v, h.w);
-    reinterpret_cast<int4*>(hp)[1] = make_int4(overflow ? -2 : h.prim, h.geom, h.nodesT, h.trisT);
+    reinterpret_cast<int4*>(hp)[1] = make_int4(overflow ? -2 : h.prim, h.geom, (int)(h.cnt & 0xffffu), (int)(h.cnt >> 16));
   }
 };
 
@@ -51,9 +51,11 @@ __global__ void __launch_bounds__(kTraceBlock, ((VARIANT & 2) && !(VARIANT & 64)
   st.smem = reinterpret_cast<uint2*>(smem_raw + nwarps * warp_smem_bytes(VARIANT)) + threadIdx.x;
   st.stride = blockDim.x;
   const int lane = threadIdx.x & 31;
-  unsigned long long nodes_acc = 0, tris_acc = 0;
+  // per-thread sums of the packed per-ray counters (a persistent thread sees n / (SMs x CTAs x 128) rays: 32 bits are ample)
+  unsigned nodes_acc32 = 0, tris_acc32 = 0;
   BatchIO io{rays, hits, n, counter, compact};
-  trace_persistent<ANY_HIT, VARIANT>(sc, io, st, smem_raw + warp * warp_smem_bytes(VARIANT), nodes_acc, tris_acc);
+  trace_persistent<ANY_HIT, VARIANT>(sc, io, st, smem_raw + warp * warp_smem_bytes(VARIANT), nodes_acc32, tris_acc32);
+  unsigned long long nodes_acc = nodes_acc32, tris_acc = tris_acc32;
   // warp-aggregated statistics (core/stats.go keeps global atomics per ray; one atomic per warp here)
   for (int o = 16; o > 0; o >>= 1) {
     nodes_acc += __shfl_down_sync(0xffffffffu, nodes_acc, o);

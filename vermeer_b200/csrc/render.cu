@@ -254,8 +254,12 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderParams p, int iter_b
   raster_xy12_tab(p.qmc, (uint32_t)iter, (uint32_t)x, (uint32_t)y, &rasterX, &rasterY);
   const double time = vdc((uint64_t)iter, scr[2]);
   const double lambda = (720 - 450) * vdc((uint64_t)iter, scr[3]) + 450;
-  const double lensU = vdc((uint64_t)iter, scr[0]);
-  const double lensV = sobol((uint64_t)iter, scr[1]);
+  // the lens sample (render.go:96-97) is only consumed by a thin-lens camera (camera.go:254-262): a pinhole skips the two radical inverses
+  double lensU = 0.0, lensV = 0.0;
+  if (p.cam.radius > 0.0f) {
+    lensU = vdc((uint64_t)iter, scr[0]);
+    lensV = sobol((uint64_t)iter, scr[1]);
+  }
   if (p.filter_cdf) {  // core/render.go:99-107
     const double fx = floor(rasterX), fy = floor(rasterY);
     double u, v;
@@ -350,9 +354,11 @@ __global__ void __launch_bounds__(kTraceBlock, MODE == 1 ? ((VARIANT & 64) ? VG_
   st.stride = blockDim.x;
   const int lane = threadIdx.x & 31;
   const int n = MODE == 0 ? p.counts[q] : p.counts[2];
-  unsigned long long nodes_acc = 0, tris_acc = 0;
+  // per-thread sums of the packed per-ray counters (a persistent thread sees n / (SMs x CTAs x 128) rays: 32 bits are ample)
+  unsigned nodes_acc32 = 0, tris_acc32 = 0;
   QueueIO<MODE> io{p, MODE == 0 ? p.rayq[q] : p.sray, n, p.counts + (MODE == 0 ? 3 : 4)};
-  trace_persistent<MODE == 1, VARIANT>(p.sc, io, st, smem_raw + warp * warp_smem_bytes(VARIANT), nodes_acc, tris_acc);
+  trace_persistent<MODE == 1, VARIANT>(p.sc, io, st, smem_raw + warp * warp_smem_bytes(VARIANT), nodes_acc32, tris_acc32);
+  unsigned long long nodes_acc = nodes_acc32, tris_acc = tris_acc32;
   for (int o = 16; o > 0; o >>= 1) {
     nodes_acc += __shfl_down_sync(0xffffffffu, nodes_acc, o);
     tris_acc += __shfl_down_sync(0xffffffffu, tris_acc, o);
@@ -1140,6 +1146,48 @@ __global__ void __launch_bounds__(256) k_resolve_accumulate(const RenderParams p
     b = (b * fi + C.z) / (fi + 1.0f);
   }
   px[0] = r; px[1] = g; px[2] = b;
+}
+
+// The same for the default path order (a warp's 32 paths = ONE pixel x 32 iterations): a thread per pixel would stream through 32 x
+// 64 B of contribution slots on its own, every 16-B load of the warp touching 32 different lines (ncu: L1TEX 89 % busy, the kernel's
+// bound). Here a warp takes 32 pixels: for each of them all 32 lanes resolve the pixel's 32 iterations with coalesced loads
+// (lane = iteration) into a padded shared-memory tile, then every lane runs the sequential running mean of ITS pixel out of the
+// tile (lane = pixel). Same arithmetic in the same order per pixel: bit-identical (tested).
+// MEASURED (round 2) and left OFF (option "accumulate_tiled"): raygen + accumulate 5.76 ms per C2 frame against 4.74 ms for the plain
+// kernel — the 32 serial rounds per warp and 16 resident warps/SM (25 KB of tile per 64 threads) cost more than the coalescing gains;
+// the plain kernel's per-thread streams are served well enough by L1.
+__global__ void __launch_bounds__(64) k_resolve_accumulate_t(const RenderParams p, int iter_base, int niters) {
+  __shared__ float tile[2][3][32 * 33];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int w = blockIdx.x * 2 + wib;  // this warp's group of 32 owned pixels
+  const int own0 = w * 32;
+  if (own0 >= p.nown) return;
+  const int own = own0 + lane;
+  float r = 0, g = 0, b = 0;
+  float* px = nullptr;
+  if (own < p.nown) {
+    px = p.fb + (size_t)p.pix[own] * 3;
+    r = px[0]; g = px[1]; b = px[2];
+  }
+  float(*t)[32 * 33] = tile[wib];
+  for (int itg = 0; itg < (niters >> 5); itg++) {
+    const int npx = min(32, p.nown - own0);
+    for (int k = 0; k < npx; k++) {
+      const float4 C = resolve_vertex(p, 0, ((itg * p.nown + own0 + k) << 5) + lane);  // path_index() for B = 1, G = 32
+      t[0][k * 33 + lane] = C.x; t[1][k * 33 + lane] = C.y; t[2][k * 33 + lane] = C.z;
+    }
+    __syncwarp();
+    if (own < p.nown) {
+      for (int it = 0; it < 32; it++) {
+        const float fi = (float)(iter_base + (itg << 5) + it + 1);
+        r = (r * fi + t[0][lane * 33 + it]) / (fi + 1.0f);
+        g = (g * fi + t[1][lane * 33 + it]) / (fi + 1.0f);
+        b = (b * fi + t[2][lane * 33 + it]) / (fi + 1.0f);
+      }
+    }
+    __syncwarp();
+  }
+  if (own < p.nown) { px[0] = r; px[1] = g; px[2] = b; }
 }
 
 // Fold the levels back to front (std.go:246-266,287-295) and continue the running mean (render.go:127-129).
@@ -1955,6 +2003,7 @@ static int render_run_impl(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_
         qin = qout;
       }
       if (rs.levels > 1) k_accumulate<<<(sn + 255) / 256, 256, 0, st>>>(p, ib, niters);
+      else if (p.pm_G == 32 && (niters & 31) == 0 && ctx->opt_accumulate_tiled) k_resolve_accumulate_t<<<(sn + 63) / 64, 64, 0, st>>>(p, ib, niters);
       else k_resolve_accumulate<<<(sn + 255) / 256, 256, 0, st>>>(p, ib, niters);
       launches++;
     }

@@ -45,7 +45,7 @@ struct HitState {
   int32_t prim;  // -1 = none
   int32_t geom;
   int32_t slot;  // global triangle slot of the hit (key-0 slot for motion meshes)
-  int32_t nodesT, trisT;
+  uint32_t cnt;  // per-ray counters packed into one register: NodesT (interior-node visits) in bits 0-15, TrisT (leaf triangle counts) in bits 16-31
   int32_t xf_hit;   // instance (index into DevScene::xforms) inside which the current closest hit was found, or -1
   int32_t xf_last;  // last instance that reported a hit: the transform ShaderContext ends up with (instance.go:107-111), or -1
 };
@@ -339,8 +339,7 @@ __device__ __forceinline__ void trav_begin(const DevScene& sc, TravState& t, Sta
   t.h.geom = -1;
   t.h.slot = -1;
   t.h.u = t.h.v = t.h.w = 0.0f;
-  t.h.nodesT = 0;
-  t.h.trisT = 0;
+  t.h.cnt = 0;
   t.h.xf_hit = -1;
   t.h.xf_last = -1;
   st.sp = 0;
@@ -369,7 +368,7 @@ template <bool ORDERED = true, bool WIDE = false>
 __device__ __forceinline__ void node_step(const DevScene& sc, TravState& t, Stack& st) {
   RayState& r = t.r;
   const int32_t node = t.cur;
-  t.h.nodesT++;
+  t.h.cnt++;
   int32_t c0, c1, c2, c3;
   float t0, t1, t2, t3;
   bool h0, h1, h2, h3;
@@ -539,7 +538,7 @@ __device__ __forceinline__ bool leaf_step(const DevScene& sc, TravState& t, uint
   HitState& h = t.h;
   const int base = (int)((un >> 4) & kLeafBaseMask);
   const int count = (int)(un & 15u) + 1;
-  h.trisT += count;
+  h.cnt += (uint32_t)count << 16;
   if (un & kMotionTriBit) return leaf_motion<-1>(sc, r, h, base, count);
   const unsigned am = __activemask();
   const int k0 = __shfl_sync(am, r.kz, __ffs(am) - 1);
@@ -690,8 +689,8 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
 #define VG_REFILL_BELOW 16
 #endif
 template <bool ANY_HIT, class IO>
-__device__ __forceinline__ void trace_persistent_tma(const DevScene& sc, IO& io, Stack& st, WarpStage ws, unsigned long long& nodes_acc,
-                                                     unsigned long long& tris_acc) {
+__device__ __forceinline__ void trace_persistent_tma(const DevScene& sc, IO& io, Stack& st, WarpStage ws, unsigned& nodes_acc,
+                                                     unsigned& tris_acc) {
   const int lane = threadIdx.x & 31;
   const long long n = io.size();
   const char* rays = reinterpret_cast<const char*>(io.ray_ptr());
@@ -766,8 +765,8 @@ __device__ __forceinline__ void trace_persistent_tma(const DevScene& sc, IO& io,
     if (my >= 0) {
       if (trav_run<ANY_HIT>(sc, t, st, (cur ? cnt1 : cnt0) == 0 ? 0 : VG_REFILL_BELOW)) {
         io.store(my, t.r, t.h, st.overflow);
-        nodes_acc += (unsigned long long)t.h.nodesT;
-        tris_acc += (unsigned long long)t.h.trisT;
+        nodes_acc += t.h.cnt & 0xffffu;
+        tris_acc += t.h.cnt >> 16;
         st.overflow = false;
         my = -1;
       }
@@ -780,7 +779,7 @@ __device__ __forceinline__ void trace_persistent_tma(const DevScene& sc, IO& io,
 // profiles/README.md): the fetch is <4 % of a ray's loads and 28 resident warps already hide its latency, while the
 // staging state costs registers under the 72-register cap.
 template <bool ANY_HIT, bool SPH, class IO>
-__device__ __forceinline__ void trace_persistent_ldg(const DevScene& sc, IO& io, Stack& st, unsigned long long& nodes_acc, unsigned long long& tris_acc) {
+__device__ __forceinline__ void trace_persistent_ldg(const DevScene& sc, IO& io, Stack& st, unsigned& nodes_acc, unsigned& tris_acc) {
   const int lane = threadIdx.x & 31;
   const long long n = io.size();
   TravState t;
@@ -811,8 +810,8 @@ __device__ __forceinline__ void trace_persistent_ldg(const DevScene& sc, IO& io,
     if (my >= 0) {
       if (trav_run<ANY_HIT, SPH>(sc, t, st, exhausted ? 0 : VG_REFILL_BELOW)) {
         io.store(my, t.r, t.h, st.overflow);
-        nodes_acc += (unsigned long long)t.h.nodesT;
-        tris_acc += (unsigned long long)t.h.trisT;
+        nodes_acc += t.h.cnt & 0xffffu;
+        tris_acc += t.h.cnt >> 16;
         st.overflow = false;
         my = -1;
       }
@@ -986,7 +985,7 @@ __device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bo
   const int total = __shfl_sync(0xffffffffu, incl, 31);
   const uint32_t leafmask = __ballot_sync(0xffffffffu, isleaf);
   if (isleaf) {
-    h.trisT += count;
+    h.cnt += (uint32_t)count << 16;
     float4* b = cs.rp + __popc(leafmask & lt) * 3;
     b[0] = make_float4(r.pkx, r.pky, r.pkz, r.s0);
     b[1] = make_float4(r.s1, r.s2, __uint_as_float(r.xsign), r.tclosest);
@@ -1065,8 +1064,8 @@ __device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bo
 }
 
 template <bool ANY_HIT, bool ORDERED, bool SPH, bool XF, bool MOT, class IO>
-__device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io, Stack& st, const CoopSmem& cs, unsigned long long& nodes_acc,
-                                                      unsigned long long& tris_acc) {
+__device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io, Stack& st, const CoopSmem& cs, unsigned& nodes_acc,
+                                                      unsigned& tris_acc) {
   const int lane = threadIdx.x & 31;
   const long long n = io.size();
   TravState t;
@@ -1161,7 +1160,7 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
       if (!MOT && mleaf) {
         const uint32_t un = (uint32_t)t.cur;
         const int count = (int)(un & 15u) + 1;
-        t.h.trisT += count;
+        t.h.cnt += (uint32_t)count << 16;
         leafhit = leaf_motion<-1>(sc, t.r, t.h, (int)((un >> 4) & kLeafBaseMask), count);
       }
       if (leaf) {
@@ -1190,8 +1189,8 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
       if (XF && t.h.xf_hit >= 0 && t.h.prim >= 0) t.h.geom = sc.xforms[t.h.xf_hit].geom;  // scene.go:65: sc.Geom = the Instance
       if (XF) cur_xf = -1;
       io.store(my, t.r, t.h, st.overflow);
-      nodes_acc += (unsigned long long)t.h.nodesT;
-      tris_acc += (unsigned long long)t.h.trisT;
+      nodes_acc += t.h.cnt & 0xffffu;
+      tris_acc += t.h.cnt >> 16;
       st.overflow = false;
       my = -1;
     }
@@ -1203,8 +1202,8 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
 // sphere geoms (variants 0, 2, 3 only; the launchers map variant 1 to 0 for such scenes). VARIANT & 16: the scene holds
 // instances (cooperative variants 2 and 3 only, always together with & 8).
 template <bool ANY_HIT, int VARIANT, class IO>
-__device__ __forceinline__ void trace_persistent(const DevScene& sc, IO& io, Stack& st, unsigned char* warp_smem, unsigned long long& nodes_acc,
-                                                 unsigned long long& tris_acc) {
+__device__ __forceinline__ void trace_persistent(const DevScene& sc, IO& io, Stack& st, unsigned char* warp_smem, unsigned& nodes_acc,
+                                                 unsigned& tris_acc) {
   constexpr int V = VARIANT & 7;
   constexpr bool SPH = (VARIANT & 8) != 0;
   constexpr bool XF = (VARIANT & 16) != 0;
