@@ -159,6 +159,56 @@ def build_scene(cfg):
     return sc
 
 
+# ---- host placement: page-locked buffers on the GPU's own NUMA node ---------------------------------------------------
+_ALL_CPUS = None
+_GPU_CPUS = None
+
+
+def bind_to_gpu_numa(index):
+    """Run this process on the CPUs of the NUMA node the GPU hangs off (sysfs: /sys/bus/pci/devices/<bdf>/numa_node), so that the
+    page-locked ray / hit / frame buffers (first touch) and the thread that drives the copies are local to the GPU's PCIe root.
+    Eight ranks each moving ~70 GB/s through one socket's memory is what capped the 8-GPU host-buffer rate. Returns a dict for
+    the JSON line; does nothing when the topology cannot be read or the node's CPUs are outside this process's affinity mask."""
+    global _ALL_CPUS, _GPU_CPUS
+    info = {"numa_node": None, "bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()
+        if len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        _ALL_CPUS = os.sched_getaffinity(0)
+        local = cpus & _ALL_CPUS
+        if local and local != _ALL_CPUS:
+            os.sched_setaffinity(0, local)
+            _GPU_CPUS = local
+            info.update(bound=True, cpus=len(local))
+    except Exception as e:   # no NVML / sysfs view in this container: stay where we are
+        info["note"] = "not bound: %s" % type(e).__name__
+    return info
+
+
+class all_host_cpus:
+    """The CPU legs (oracle on every host thread) run with the process's full affinity mask."""
+    def __enter__(self):
+        if _GPU_CPUS:
+            os.sched_setaffinity(0, _ALL_CPUS)
+
+    def __exit__(self, *a):
+        if _GPU_CPUS:
+            os.sched_setaffinity(0, _GPU_CPUS)
+
+
 def make_oracle(scene):
     from oracle.binding import Oracle
     return Oracle(scene, motion_ref_compat=False)   # same MQBVH leaf mode as the device default ("fixed", DESIGN.md quirk b)
@@ -167,17 +217,18 @@ def make_oracle(scene):
 def cpu_frame(scene, table, spp, cores, target_s, faithful=False):
     """The oracle (reference-semantics CPU path) on a bounded number of iterations of the frame. faithful: the reference's own
     worker policy, min(10, cores) workers and global atomic ray counters."""
-    ora = make_oracle(scene)
-    ora.set_scramble(table)
-    nt = -cores if faithful else cores
-    _, st1 = ora.render(0, 1, nthreads=nt)                                     # probe (also builds the trees)
-    iters = int(min(spp, max(1, round(target_s / max(st1["seconds"], 1e-3)))))
-    st = st1
-    if iters > 1:
-        ora.clear()
-        _, st = ora.render(0, iters, nthreads=nt)
-    else:
-        iters = 1
+    with all_host_cpus():
+        ora = make_oracle(scene)
+        ora.set_scramble(table)
+        nt = -cores if faithful else cores
+        _, st1 = ora.render(0, 1, nthreads=nt)                                     # probe (also builds the trees)
+        iters = int(min(spp, max(1, round(target_s / max(st1["seconds"], 1e-3)))))
+        st = st1
+        if iters > 1:
+            ora.clear()
+            _, st = ora.render(0, iters, nthreads=nt)
+        else:
+            iters = 1
     v = st["rays"] / st["seconds"] / 1e6
     workers = min(10, cores) if faithful else cores
     return {"value": v, "unit": "Mrays/s", "cores": workers, "per_core": v / workers, "kind": "port",
@@ -218,18 +269,19 @@ def incoherent_batch(scene, cam, trace, seed0=5):
 
 
 def cpu_trace(scene, rays, cores, reps=1):
-    ora = make_oracle(scene)
-    ora.trace(rays[:65536], nthreads=cores)
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        hits = ora.trace(rays, nthreads=cores)
-    secs = (time.perf_counter() - t0) / reps
+    with all_host_cpus():
+        ora = make_oracle(scene)
+        ora.trace(rays[:65536], nthreads=cores)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            hits = ora.trace(rays, nthreads=cores)
+        secs = (time.perf_counter() - t0) / reps
     return hits, len(rays) / secs / 1e6, secs
 
 
 def time_batch(dev, torch, rays, steps, warmup, compact_e2e=True):
     """Device-resident and host-buffer rates of one closest-hit pass over `rays`. Returns a dict."""
-    from vermeer_b200.host import HIT_DTYPE, HITC_DTYPE, RAY_DTYPE
+    from vermeer_b200.host import HIT_DTYPE, HITC_DTYPE, RAY_DTYPE, RAYPD_DTYPE
     n = len(rays)
     d_r = torch.from_numpy(rays.view(np.uint8).reshape(n, 32)).cuda()
     d_h = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
@@ -246,19 +298,37 @@ def time_batch(dev, torch, rays, steps, warmup, compact_e2e=True):
     pin_r = torch.from_numpy(rays.view(np.uint8).reshape(n, 32)).pin_memory().numpy().reshape(-1).view(RAY_DTYPE)
     pin_h = torch.empty((n, 32), dtype=torch.uint8, pin_memory=True).numpy().reshape(-1).view(HIT_DTYPE)
     pin_c = torch.empty((n, 16), dtype=torch.uint8, pin_memory=True).numpy().reshape(-1).view(HITC_DTYPE)
+    # 24-byte {P, D} records (VG_TRACE_RAYS_PD) when every ray of the batch is Ray.Init(P, D, +Inf) at Time 0: the same hits (checked below)
+    pd_ok = bool(np.isposinf(rays["tmax"]).all() and (rays["time"] == 0).all())
+    pin_pd = None
+    if pd_ok:
+        pd = np.zeros(n, RAYPD_DTYPE)
+        pd["o"], pd["d"] = rays["o"], rays["d"]
+        pin_pd = torch.from_numpy(pd.view(np.uint8).reshape(n, 24)).pin_memory().numpy().reshape(-1).view(RAYPD_DTYPE)
     e2e = {}
-    for name, out, compact in (("full", pin_h, False), ("compact", pin_c, True)):
-        if compact and not compact_e2e:
+    pin_cpd = torch.empty((n, 16), dtype=torch.uint8, pin_memory=True).numpy().reshape(-1).view(HITC_DTYPE) if pd_ok else None
+    for name, inp, out, compact in (("full", pin_r, pin_h, False), ("compact", pin_r, pin_c, True), ("pd_compact", pin_pd, pin_cpd, True)):
+        if (compact and not compact_e2e) or inp is None:
             continue
         try:
-            dev.trace(pin_r, out=out, compact=compact)
+            dev.trace(inp, out=out, compact=compact)
         except RuntimeError:
             continue     # scenes the compact record does not cover
         t0 = time.perf_counter()
         reps = max(3, min(steps, 10))
         for _ in range(reps):
-            dev.trace(pin_r, out=out, compact=compact)
+            dev.trace(inp, out=out, compact=compact)
         e2e[name] = (time.perf_counter() - t0) / reps * 1e3
+    if "pd_compact" in e2e:     # the same call as ONE persistent launch over the arriving ray array (option stream_batch 1; measured slower)
+        dev.set_option("stream_batch", 1)
+        dev.trace(pin_pd, out=pin_cpd, compact=True)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            dev.trace(pin_pd, out=pin_cpd, compact=True)
+        e2e["pd_compact_streamed_launch"] = (time.perf_counter() - t0) / reps * 1e3
+        dev.set_option("stream_batch", 0)
+    if "pd_compact" in e2e and pin_cpd.tobytes() != pin_c.tobytes():
+        raise SystemExit("bench: VG_TRACE_RAYS_PD hits differ from the VgRay hits")
     res = {"rays": n, "ms_per_step": float(np.mean(ms)), "ms_best": float(np.min(ms)), "device_ms_total": float(np.sum(ms)),
            "hit_fraction": float((hits["prim"] >= 0).mean()),
            "nodesT_per_ray": st["nodes_t"] / max(1, steps) / n, "trisT_per_ray": st["tris_t"] / max(1, steps) / n,
@@ -562,6 +632,7 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    placement = bind_to_gpu_numa(local_rank)
     dev = Device(local_rank)
     peaks = dev.measure_peaks()
 
@@ -579,12 +650,13 @@ def run_ours(args):
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     n = tb["rays"]
-    vec = torch.tensor([tb["device_ms_total"], tb["e2e_ms"].get("compact", tb["e2e_ms"]["full"]), tb["e2e_ms"]["full"]], dtype=torch.float64, device="cuda")
+    e2e_mode = "pd_compact" if "pd_compact" in tb["e2e_ms"] else ("compact" if "compact" in tb["e2e_ms"] else "full")
+    vec = torch.tensor([tb["device_ms_total"], tb["e2e_ms"][e2e_mode], tb["e2e_ms"]["full"], tb["e2e_ms"].get("compact", tb["e2e_ms"]["full"])], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([float(n)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(vec, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    dev_ms_total, e2e_ms, e2e_full_ms = float(vec[0]), float(vec[1]), float(vec[2])
+    dev_ms_total, e2e_ms, e2e_full_ms, e2e_compact_ms = float(vec[0]), float(vec[1]), float(vec[2]), float(vec[3])
     rays_all = float(cnt[0])
     value = rays_all * args.steps / (dev_ms_total * 1e-3) / 1e6
     e2e_value = rays_all / (e2e_ms * 1e-3) / 1e6
@@ -672,10 +744,14 @@ def run_ours(args):
         "config": {"workload": HEADLINE_WORKLOAD, "rays_per_step_per_gpu": n, "triangles": scene.num_tris, "hit_fraction": tb["hit_fraction"],
                    "partition": "every rank traces its own batch (independent rays, no collective)" if world > 1 else "single GPU",
                    "l2_policy": "ray + hit streams of a step (%d MB) exceed the 126 MB L2; the 54 MB scene is L2-resident by nature of the config" % (n * 64 // 1000000)},
-        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * (16 if "compact" in tb["e2e_ms"] else 32),
-                "ms_per_step": e2e_ms, "mode": "vg_trace_batch, page-locked host buffers, " + ("VG_TRACE_COMPACT_HITS (16-byte hits)" if "compact" in tb["e2e_ms"] else "32-byte VgHit"),
-                "full_vghit": {"value": rays_all / (e2e_full_ms * 1e-3) / 1e6, "ms_per_step": e2e_full_ms, "d2h_bytes_per_step": n * 32}},
-        "gpu_launches": args.steps, "wall_s_timed_region": wall,
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": n * (24 if e2e_mode == "pd_compact" else 32), "d2h_bytes_per_step": n * (32 if e2e_mode == "full" else 16),
+                "ms_per_step": e2e_ms, "mode": "vg_trace_batch, page-locked host buffers, " +
+                {"pd_compact": "VG_TRACE_RAYS_PD (24-byte {P, D} rays = Ray.Init(P, D, +Inf)) | VG_TRACE_COMPACT_HITS (16-byte hits); hits byte-identical to the VgRay call's",
+                 "compact": "32-byte VgRay, VG_TRACE_COMPACT_HITS (16-byte hits)", "full": "32-byte VgRay, 32-byte VgHit"}[e2e_mode],
+                "all_modes_ms_rank0": tb["e2e_ms"],
+                "vgray_compact": {"value": rays_all / (e2e_compact_ms * 1e-3) / 1e6, "ms_per_step": e2e_compact_ms, "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 16},
+                "full_vghit": {"value": rays_all / (e2e_full_ms * 1e-3) / 1e6, "ms_per_step": e2e_full_ms, "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 32}},
+        "gpu_launches": args.steps, "wall_s_timed_region": wall, "host_placement": placement,
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,

@@ -289,6 +289,14 @@ typedef struct VgHitCompact {
   float t, u, v;
   int32_t slot;
 } VgHitCompact;
+/* `rays` is an array of 24-byte VgRayPD records {P, D} instead of VgRay: what Ray.Init(ty, P, D, maxdist = +Inf, ...) takes for a
+ * camera / reflected ray (core/ray.go:56-61) at Ray.Time 0 — three quarters of the host->device bytes of a batch whose cost is the
+ * PCIe transfer. Hits are the same bits as for the VgRay {P, D, +Inf, 0}. Cast the pointer to const VgRay*. */
+#define VG_TRACE_RAYS_PD 4u
+typedef struct VgRayPD {
+  float o[3];
+  float d[3];
+} VgRayPD;
 int vg_trace_batch(vg_ctx* ctx, const VgRay* rays, int64_t n, VgHit* hits, uint32_t flags);               /* host buffers */
 int vg_trace_batch_device(vg_ctx* ctx, const VgRay* d_rays, int64_t n, VgHit* d_hits, uint32_t flags);    /* device buffers */
 /* ElemID (VgHit.prim) and geom of every static triangle slot; returns the slot count (buffers may be NULL to ask for it). */

@@ -317,3 +317,57 @@ def test_tiled_accumulate_is_bit_identical(built_library):
             ref = (fb, fb2.copy())
         assert np.array_equal(fb.view(np.uint32), ref[0].view(np.uint32)), (tiled, ipb)
         assert np.array_equal(fb2.view(np.uint32), ref[1].view(np.uint32)), (tiled, ipb)
+
+
+@pytest.mark.parametrize("traversal", [0, 1, 2])
+def test_pd_ray_records_give_the_same_hits(built_library, traversal):
+    """VG_TRACE_RAYS_PD: 24-byte {P, D} records are Ray.Init(ty, P, D, +Inf, ...) at Time 0 (core/ray.go:56-65) — the hits are the
+    bits of the 32-byte record {P, D, +Inf, 0}, through the host path (single copy and the chunked 3-stream pipeline) and with the
+    compact 16-byte hits, for every traversal variant (the TMA-staged queue falls back to the LDG refill for these records)."""
+    import torch
+    from conftest import random_rays
+    from vermeer_b200.host import RAYPD_DTYPE, HIT_DTYPE, HITC_DTYPE
+    sc = _scene(64, 48)
+    dev = _device(sc)
+    dev.set_option("traversal", traversal)
+    dev.set_option("batch_chunk_log2", 14)
+    rays = random_rays(100_003, 11)
+    rays["tmax"] = np.inf
+    rays["time"] = 0
+    pd = np.zeros(len(rays), RAYPD_DTYPE)
+    pd["o"], pd["d"] = rays["o"], rays["d"]
+    want = dev.trace(rays)
+    assert (want["prim"] >= 0).any() and (want["prim"] < 0).any()
+    got = dev.trace(pd)
+    assert got.tobytes() == want.tobytes()
+    gc = dev.trace(pd, compact=True)
+    assert np.array_equal(gc["t"].view(np.uint32), want["t"].view(np.uint32)) and np.array_equal(gc["u"], want["u"])
+    assert np.array_equal(gc["slot"] >= 0, want["prim"] >= 0)
+    # page-locked buffers: the streamed persistent launch (stream_batch 1: chunks of 2^12 rays arriving while the kernel runs) and the
+    # chunked three-stream pipeline (stream_batch 0: n >= 2 chunks of 2^14), both record layouts
+    n = len(pd)
+    dev.set_option("stream_chunk_log2", 12)
+    pin_r = torch.from_numpy(pd.view(np.uint8).reshape(n, 24)).pin_memory().numpy().reshape(-1).view(RAYPD_DTYPE)
+    pin_r32 = torch.from_numpy(rays.view(np.uint8).reshape(n, 32)).pin_memory().numpy().reshape(-1).view(rays.dtype)
+    pin_h = torch.empty((n, 32), dtype=torch.uint8, pin_memory=True).numpy().reshape(-1).view(HIT_DTYPE)
+    pin_c = torch.empty((n, 16), dtype=torch.uint8, pin_memory=True).numpy().reshape(-1).view(HITC_DTYPE)
+    for streamed in (1, 0, 1):
+        dev.set_option("stream_batch", streamed)
+        for src in (pin_r, pin_r32):
+            pin_h[:] = 0
+            dev.trace(src, out=pin_h)
+            assert pin_h.tobytes() == want.tobytes(), (streamed, src.dtype.itemsize)
+            pin_c[:] = 0
+            dev.trace(src, out=pin_c, compact=True)
+            assert pin_c.tobytes() == gc.tobytes(), (streamed, src.dtype.itemsize)
+        pin_h[:] = 0
+        dev.trace(pin_r32, out=pin_h, any_hit=True)
+        assert np.array_equal(pin_h["prim"] >= 0, want["prim"] >= 0)
+    # device-resident records
+    d_r = torch.from_numpy(pd.view(np.uint8).reshape(n, 24)).cuda()
+    d_h = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
+    dev.trace_device(d_r.data_ptr(), n, d_h.data_ptr(), pd=True)
+    assert d_h.cpu().numpy().tobytes() == want.tobytes()
+    # shadow rays (any-hit) keep Tclosest = +Inf in this record
+    occ = dev.trace(pd, any_hit=True)
+    assert np.array_equal(occ["prim"] >= 0, want["prim"] >= 0)

@@ -25,6 +25,8 @@ MNODE_DTYPE = np.dtype([("Axis0", np.int32), ("Axis1", np.int32), ("Axis2", np.i
 
 VG_TRACE_ANY_HIT = 1
 VG_TRACE_COMPACT_HITS = 2
+VG_TRACE_RAYS_PD = 4
+RAYPD_DTYPE = np.dtype([("o", np.float32, 3), ("d", np.float32, 3)])   # VgRayPD: tmax = +Inf, time = 0
 HITC_DTYPE = np.dtype([("t", np.float32), ("u", np.float32), ("v", np.float32), ("slot", np.int32)])
 
 # every symbol include/vermeer_gpu.h declares (tests check the library exports all of them)
@@ -354,11 +356,13 @@ class Device:
         self._chk(self.L.vg_set_option(self.h, name.encode(), int(value)))
 
     def trace(self, rays: np.ndarray, any_hit: bool = False, out: np.ndarray | None = None, compact: bool = False) -> np.ndarray:
-        """vg_trace_batch with HOST buffers (H2D + kernel + D2H inside the call). compact: 16-byte VgHitCompact records."""
-        if not (isinstance(rays, np.ndarray) and rays.dtype == RAY_DTYPE and rays.flags.c_contiguous):
-            rays = np.ascontiguousarray(rays, RAY_DTYPE)      # (a page-locked array passes through untouched)
+        """vg_trace_batch with HOST buffers (H2D + kernel + D2H inside the call). compact: 16-byte VgHitCompact records.
+        A RAYPD_DTYPE array (24-byte {P, D} records: tmax = +Inf, time = 0) goes through as VG_TRACE_RAYS_PD."""
+        pd = isinstance(rays, np.ndarray) and rays.dtype == RAYPD_DTYPE
+        if not (isinstance(rays, np.ndarray) and rays.dtype in (RAY_DTYPE, RAYPD_DTYPE) and rays.flags.c_contiguous):
+            rays = np.ascontiguousarray(rays, RAYPD_DTYPE if pd else RAY_DTYPE)      # (a page-locked array passes through untouched)
         hits = np.empty(len(rays), HITC_DTYPE if compact else HIT_DTYPE) if out is None else out
-        flags = (VG_TRACE_ANY_HIT if any_hit else 0) | (VG_TRACE_COMPACT_HITS if compact else 0)
+        flags = (VG_TRACE_ANY_HIT if any_hit else 0) | (VG_TRACE_COMPACT_HITS if compact else 0) | (VG_TRACE_RAYS_PD if pd else 0)
         self._chk(self.L.vg_trace_batch(self.h, _p(rays), C.c_int64(len(rays)), _p(hits), C.c_uint32(flags)))
         return hits
 
@@ -383,10 +387,10 @@ class Device:
             self.L.vg_captured_rays(self.h, _p(out), n)
         return out
 
-    def trace_device(self, d_rays_ptr: int, n: int, d_hits_ptr: int, any_hit: bool = False):
+    def trace_device(self, d_rays_ptr: int, n: int, d_hits_ptr: int, any_hit: bool = False, pd: bool = False, compact: bool = False):
         """vg_trace_batch_device: rays/hits already resident in HBM (raw device pointers, e.g. torch .data_ptr())."""
-        self._chk(self.L.vg_trace_batch_device(self.h, C.c_void_p(d_rays_ptr), C.c_int64(n), C.c_void_p(d_hits_ptr),
-                                               C.c_uint32(VG_TRACE_ANY_HIT if any_hit else 0)))
+        flags = (VG_TRACE_ANY_HIT if any_hit else 0) | (VG_TRACE_COMPACT_HITS if compact else 0) | (VG_TRACE_RAYS_PD if pd else 0)
+        self._chk(self.L.vg_trace_batch_device(self.h, C.c_void_p(d_rays_ptr), C.c_int64(n), C.c_void_p(d_hits_ptr), C.c_uint32(flags)))
 
     def render(self, iter_begin: int, iter_end: int, fetch: bool = True, out: np.ndarray | None = None):
         """vg_render. `out`: a caller-owned (yres, xres, 3) float32 buffer for the frame; if it is page-locked (e.g. a
