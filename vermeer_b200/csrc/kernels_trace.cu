@@ -137,8 +137,7 @@ __global__ void __launch_bounds__(kTraceBlock, ((VARIANT & 2) && !(VARIANT & 64)
   // layout: [warps x warp_smem_bytes(VARIANT) (TMA ray slots + mbarriers, or cooperative-leaf blocks)] [threads x VG_SMEM_STACK stack entries]
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
   Stack st;
-  st.smem = reinterpret_cast<uint2*>(smem_raw + nwarps * warp_smem_bytes(VARIANT)) + threadIdx.x;
-  st.stride = blockDim.x;
+  st.bind(smem_raw + nwarps * warp_smem_bytes(VARIANT));
   const int lane = threadIdx.x & 31;
   // per-thread sums of the packed per-ray counters (a persistent thread sees n / (SMs x CTAs x 128) rays: 32 bits are ample)
   unsigned nodes_acc32 = 0, tris_acc32 = 0;
@@ -165,8 +164,7 @@ __global__ void __launch_bounds__(kTraceBlock, (VARIANT & 2) ? VG_TRACE_MIN_BLOC
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
   Stack st;
-  st.smem = reinterpret_cast<uint2*>(smem_raw + nwarps * warp_smem_bytes(VARIANT)) + threadIdx.x;
-  st.stride = blockDim.x;
+  st.bind(smem_raw + nwarps * warp_smem_bytes(VARIANT));
   const int lane = threadIdx.x & 31;
   unsigned nodes_acc32 = 0, tris_acc32 = 0;
   BatchIO<true> io{rays, hits, n, counter, compact, ss};

@@ -350,8 +350,7 @@ __global__ void __launch_bounds__(kTraceBlock, MODE == 1 ? ((VARIANT & 64) ? VG_
   // layout: [warps x warp_smem_bytes(VARIANT) scratch] [threads x VG_SMEM_STACK stack entries]
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
   Stack st;
-  st.smem = reinterpret_cast<uint2*>(smem_raw + nwarps * warp_smem_bytes(VARIANT)) + threadIdx.x;
-  st.stride = blockDim.x;
+  st.bind(smem_raw + nwarps * warp_smem_bytes(VARIANT));
   const int lane = threadIdx.x & 31;
   const int n = MODE == 0 ? p.counts[q] : p.counts[2];
   // per-thread sums of the packed per-ray counters (a persistent thread sees n / (SMs x CTAs x 128) rays: 32 bits are ample)

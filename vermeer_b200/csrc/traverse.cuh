@@ -288,28 +288,57 @@ __device__ __forceinline__ void ld_tri(const float4* tp, float4& v0, float4& v1,
 #define VG_LOCAL_STACK 40
 #endif
 
+// The shared part is addressed as a 32-bit shared-state-space byte address with a compile-time stride (every traversal kernel runs
+// VG_TRACE_BLOCK threads per CTA): round 2's SASS showed the generic 64-bit base pointer and the runtime stride spilled to local
+// memory and re-read (LDL + LDL.64) for every push of every node step of these L1TEX-wavefront-bound kernels.
+#ifndef VG_TRACE_BLOCK
+#define VG_TRACE_BLOCK 128
+#endif
+static const uint32_t kStackStrideBytes = VG_TRACE_BLOCK * 8;
+__device__ __forceinline__ void sts_u2(uint32_t addr, uint2 v) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+// ONE register holds the stack: `top` = the shared-space address the next push of this thread would write, i.e.
+// region + threadIdx.x * 8 + depth * kStackStrideBytes. The stride is 1024 B and a thread's offset inside an entry row is < 1024,
+// so depth = (top - region) >> 10 with `region` CTA-uniform (the compiler keeps it in a uniform register / rematerialises it).
+// The depth counter and the base address it used to be paired with were both spilled in the 64-register kernels.
 struct Stack {
-  uint2* smem;  // base for this thread: entry i at smem[i * stride]
-  int stride;
+  uint32_t top;
+  uint32_t region;  // CTA-uniform: shared-space address of the stack area
   uint2 local[VG_LOCAL_STACK];
-  int sp;
   bool overflow;
 #ifdef VG_STACK_STATS
   int maxsp = 0;  // measurement build only: deepest stack this thread has seen (VgStats.max_stack_depth)
 #endif
+  static_assert(kStackStrideBytes == 1024, "depth() assumes a 1024-byte entry row (128 threads x 8 B)");
+  // `stack_region`: the CTA's stack area in dynamic shared memory (VG_TRACE_BLOCK x VG_SMEM_STACK entries)
+  __device__ __forceinline__ void bind(const void* stack_region) {
+    region = (uint32_t)__cvta_generic_to_shared(stack_region);
+    top = region + threadIdx.x * 8u;
+  }
+  __device__ __forceinline__ int depth() const { return (int)((top - region) >> 10); }
+  __device__ __forceinline__ bool empty() const { return top - region < kStackStrideBytes; }
+  __device__ __forceinline__ void reset() { top = region + ((top - region) & (kStackStrideBytes - 1u)); }
   __device__ __forceinline__ void push(float t, int32_t node) {
     uint2 e = make_uint2(__float_as_uint(t), (uint32_t)node);
-    if (sp < VG_SMEM_STACK) smem[sp * stride] = e;
-    else if (sp < VG_SMEM_STACK + VG_LOCAL_STACK) local[sp - VG_SMEM_STACK] = e;
+    const uint32_t off = top - region;
+    if (off < VG_SMEM_STACK * kStackStrideBytes) sts_u2(top, e);
+    else if (off < (VG_SMEM_STACK + VG_LOCAL_STACK) * kStackStrideBytes) local[(int)(off >> 10) - VG_SMEM_STACK] = e;
     else { overflow = true; return; }
-    sp++;
+    top += kStackStrideBytes;
 #ifdef VG_STACK_STATS
-    if (sp > maxsp) maxsp = sp;
+    if (depth() > maxsp) maxsp = depth();
 #endif
   }
   __device__ __forceinline__ uint2 pop() {
-    sp--;
-    return sp < VG_SMEM_STACK ? smem[sp * stride] : local[sp - VG_SMEM_STACK];
+    top -= kStackStrideBytes;
+    const uint32_t off = top - region;
+    return off < VG_SMEM_STACK * kStackStrideBytes ? lds_u2(top) : local[(int)(off >> 10) - VG_SMEM_STACK];
   }
 };
 
@@ -342,7 +371,7 @@ __device__ __forceinline__ void trav_begin(const DevScene& sc, TravState& t, Sta
   t.h.cnt = 0;
   t.h.xf_hit = -1;
   t.h.xf_last = -1;
-  st.sp = 0;
+  st.reset();
   t.cur = sc.root;  // qbvh.Trace pushes the root with T = Tclosest and pops it at once (intersect.go:93-104)
 }
 
@@ -350,7 +379,7 @@ __device__ __forceinline__ void trav_begin(const DevScene& sc, TravState& t, Sta
 // !ORDERED (occlusion-only rays): Tclosest never changes before the ray terminates, so nothing is ever culled.
 template <bool ORDERED = true>
 __device__ __forceinline__ int32_t pop_next(const RayState& r, Stack& st) {
-  while (st.sp > 0) {
+  while (!st.empty()) {
     const uint2 e = st.pop();
     if (!ORDERED || !(r.tclosest < __uint_as_float(e.x))) return (int32_t)e.y;
   }
@@ -456,14 +485,14 @@ __device__ __forceinline__ void node_step(const DevScene& sc, TravState& t, Stac
   const bool v0 = c0 != -1, v1 = c1 != -1, v2 = c2 != -1, v3 = c3 != -1;
   const int32_t next = v3 ? c3 : (v2 ? c2 : (v1 ? c1 : c0));
   const bool p0 = v0 && (v1 || v2 || v3), p1 = v1 && (v2 || v3), p2 = v2 && v3;
-  const int sp0 = st.sp, sp1 = sp0 + (p0 ? 1 : 0), sp2 = sp1 + (p1 ? 1 : 0), sp3 = sp2 + (p2 ? 1 : 0);
-  if (sp0 + 3 <= VG_SMEM_STACK) {
-    if (p0) st.smem[sp0 * st.stride] = make_uint2(__float_as_uint(t0), (uint32_t)c0);
-    if (p1) st.smem[sp1 * st.stride] = make_uint2(__float_as_uint(t1), (uint32_t)c1);
-    if (p2) st.smem[sp2 * st.stride] = make_uint2(__float_as_uint(t2), (uint32_t)c2);
-    st.sp = sp3;
+  if (st.top - st.region < (VG_SMEM_STACK - 2) * kStackStrideBytes) {  // depth + 3 <= VG_SMEM_STACK: all three in shared memory
+    const uint32_t a0 = st.top, a1 = a0 + (p0 ? kStackStrideBytes : 0u), a2 = a1 + (p1 ? kStackStrideBytes : 0u);
+    if (p0) sts_u2(a0, make_uint2(__float_as_uint(t0), (uint32_t)c0));
+    if (p1) sts_u2(a1, make_uint2(__float_as_uint(t1), (uint32_t)c1));
+    if (p2) sts_u2(a2, make_uint2(__float_as_uint(t2), (uint32_t)c2));
+    st.top = a2 + (p2 ? kStackStrideBytes : 0u);
 #ifdef VG_STACK_STATS
-    if (sp3 > st.maxsp) st.maxsp = sp3;
+    if (st.depth() > st.maxsp) st.maxsp = st.depth();
 #endif
   } else {
     if (p0) st.push(t0, c0);
@@ -609,7 +638,7 @@ __device__ __forceinline__ bool trav_run(const DevScene& sc, TravState& t, Stack
       if (un & kGeomBit) {
         if (SPH && (un & kSphereBit)) {  // scene.go:61-78 -> sphere.Trace
           if (sphere_leaf(sc, t, un) && ANY_HIT) {
-            st.sp = 0;
+            st.reset();
             t.cur = -1;
             return true;
           }
@@ -622,7 +651,7 @@ __device__ __forceinline__ bool trav_run(const DevScene& sc, TravState& t, Stack
       }
       const bool leafhit = leaf_step(sc, t, un);
       if (ANY_HIT && leafhit) {  // intersect.go:231-236: shadow rays return at the first leaf reporting a hit
-        st.sp = 0;
+        st.reset();
         t.cur = -1;
         return true;
       }
@@ -697,7 +726,7 @@ __device__ __forceinline__ void trace_persistent_tma(const DevScene& sc, IO& io,
   TravState t;
   t.cur = -1;
   long long my = -1;  // queue index of the ray this lane is tracing
-  st.sp = 0;
+  st.reset();
   st.overflow = false;
 
   // warp-uniform staging state, kept in scalars (indexing small arrays by `cur` would push them to local memory)
@@ -786,7 +815,7 @@ __device__ __forceinline__ void trace_persistent_ldg(const DevScene& sc, IO& io,
   t.cur = -1;
   long long my = -1;   // queue index of the ray this lane is tracing
   bool exhausted = false;
-  st.sp = 0;
+  st.reset();
   st.overflow = false;
   while (true) {
     const unsigned idle = __ballot_sync(0xffffffffu, my < 0);
@@ -928,9 +957,20 @@ __device__ __forceinline__ bool tri_candidate(float pkx, float pky, float pkz, f
   return true;
 }
 
+// Per warp: 32 per-LANE blocks of two float4 — the leaf-phase parameters of the lane's current ray {pkx, pky, pkz, s0} {s1, s2, xsign,
+// Tclosest}, written ONCE when the ray is set up (coop_publish) — then 32 per-RANK records {kz | motion << 8 | owner lane << 16, leaf base,
+// item start, Ray.Time} written by the lanes that hold a leaf in the current phase. Round 2 (first half) rewrote all three float4 per
+// leaf visit from registers the 64-register kernels had spilled (5 LDL + 3 STS.128 per lane and phase in the SASS); now the eight
+// parameters leave the register file for good after Ray.Setup and a leaf visit costs one STS.128 (+ one STS.32 for the live Tclosest
+// of a closest-hit ray).
 struct CoopSmem {
-  float4* rp;  // [32][3] ray-parameter blocks of this warp, indexed by the owner's rank among the lanes holding a leaf
+  float4* rp;
 };
+__device__ __forceinline__ void coop_publish(const CoopSmem& cs, const RayState& r) {
+  float4* b = cs.rp + (threadIdx.x & 31) * 2;
+  b[0] = make_float4(r.pkx, r.pky, r.pkz, r.s0);
+  b[1] = make_float4(r.s1, r.s2, __uint_as_float(r.xsign), r.tclosest);
+}
 
 // The (ray, triangle) items of one 32-wide window. KZ >= 0: every item's ray has dominant axis KZ (static component access).
 template <int KZ>
@@ -966,7 +1006,7 @@ __device__ __forceinline__ bool coop_item_motion(const DevScene& sc, const float
 
 // One cooperative leaf phase. `isleaf`: this lane's t.cur is a triangle leaf that takes part (static; also motion leaves when
 // MOT). Returns leafhit for the lane.
-template <bool MOT>
+template <bool MOT, bool LIVE_T>
 __device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bool isleaf, const CoopSmem& cs) {
   const int lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
@@ -986,12 +1026,10 @@ __device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bo
   const uint32_t leafmask = __ballot_sync(0xffffffffu, isleaf);
   if (isleaf) {
     h.cnt += (uint32_t)count << 16;
-    float4* b = cs.rp + __popc(leafmask & lt) * 3;
-    b[0] = make_float4(r.pkx, r.pky, r.pkz, r.s0);
-    b[1] = make_float4(r.s1, r.s2, __uint_as_float(r.xsign), r.tclosest);
-    // kz in bits 0-1, bit 8 = motion-triangle leaf; .w = Ray.Time for the motion items
+    if (LIVE_T) reinterpret_cast<float*>(cs.rp + lane * 2 + 1)[3] = r.tclosest;  // (occlusion rays: Tclosest never changes before the ray ends)
+    // kz in bits 0-1, bit 8 = motion-triangle leaf, bits 16-20 = the owner lane; .w = Ray.Time for the motion items
     const bool mot = MOT && (un & kMotionTriBit);
-    b[2] = make_float4(__int_as_float(r.kz | (mot ? 256 : 0)), __int_as_float(base), __int_as_float(start), r.time);
+    cs.rp[64 + __popc(leafmask & lt)] = make_float4(__int_as_float(r.kz | (mot ? 256 : 0) | (lane << 16)), __int_as_float(base), __int_as_float(start), r.time);
   }
   const int kz0 = __shfl_sync(0xffffffffu, r.kz, __ffs(leafmask) - 1);
   const bool any_mot = MOT && __any_sync(0xffffffffu, isleaf && (un & kMotionTriBit));
@@ -1010,8 +1048,9 @@ __device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bo
     tc.fU = tc.fV = tc.fW = tc.det = tc.T = 0.0f;
     if (j < total) {
       const int R = before + __popc(heads & (lt | (1u << lane))) - 1;
-      const float4* b = cs.rp + R * 3;
-      const float4 q0 = b[0], q1 = b[1], q2 = b[2];
+      const float4 q2 = cs.rp[64 + R];
+      const float4* b = cs.rp + ((__float_as_int(q2.x) >> 16) & 31) * 2;
+      const float4 q0 = b[0], q1 = b[1];
       if (kz_uniform) {
         if (kz0 == 0) cand = coop_item<0>(sc, q0, q1, q2, j, tc);
         else if (kz0 == 1) cand = coop_item<1>(sc, q0, q1, q2, j, tc);
@@ -1059,7 +1098,7 @@ __device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bo
       }
     }
   }
-  __syncwarp();  // the blocks are rewritten by the next leaf phase
+  __syncwarp();  // the records are rewritten by the next leaf phase, the blocks by the next refill
   return leafhit;
 }
 
@@ -1073,7 +1112,7 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
   long long my = -1;
   bool exhausted = false;
   int cur_xf = -1;  // XF: instance the lane's ray is currently inside of
-  st.sp = 0;
+  st.reset();
   st.overflow = false;
   while (true) {
     const unsigned idle = __ballot_sync(0xffffffffu, my < 0);
@@ -1089,6 +1128,7 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
           my = i;
           io.load(i, t.r);
           ray_setup(t.r);
+          coop_publish(cs, t.r);
           trav_begin(sc, t, st);
         }
       }
@@ -1103,6 +1143,7 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
             io.load(my, t.r);
             t.r.tclosest = tcl;
             ray_setup(t.r);
+            coop_publish(cs, t.r);
             cur_xf = -1;
             t.cur = pop_next<ORDERED>(t.r, st);
           } else {                                          // enter (instance.go:86-96)
@@ -1113,6 +1154,7 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
             t.r.ox = o6[0]; t.r.oy = o6[1]; t.r.oz = o6[2];
             t.r.dx = o6[3]; t.r.dy = o6[4]; t.r.dz = o6[5];
             ray_setup(t.r);
+            coop_publish(cs, t.r);
             cur_xf = xi;
             t.cur = sc.xforms[xi].root;
           }
@@ -1120,7 +1162,7 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
           const bool sh = sphere_leaf(sc, t, (uint32_t)t.cur);
           if (XF && sh) t.h.xf_hit = -1;
           if (sh && ANY_HIT) {
-            st.sp = 0;
+            st.reset();
             t.cur = -1;
           } else {
             t.cur = pop_next<ORDERED>(t.r, st);
@@ -1156,12 +1198,19 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
         if (leaf) leafhit = leaf_step(sc, t, (uint32_t)t.cur);
       } else
 #endif
-      leafhit = coop_leaves<MOT>(sc, t, leaf && (MOT || !mleaf), cs);
-      if (!MOT && mleaf) {
+      leafhit = coop_leaves<MOT, !ANY_HIT>(sc, t, leaf && (MOT || !mleaf), cs);
+      if (!MOT && mleaf) {  // (kernels without the motion items in the cooperative phase: per lane, from the lane's published block)
         const uint32_t un = (uint32_t)t.cur;
         const int count = (int)(un & 15u) + 1;
         t.h.cnt += (uint32_t)count << 16;
-        leafhit = leaf_motion<-1>(sc, t.r, t.h, (int)((un >> 4) & kLeafBaseMask), count);
+        RayState rr = t.r;
+        const float4 q0 = cs.rp[lane * 2], q1 = cs.rp[lane * 2 + 1];
+        rr.pkx = q0.x; rr.pky = q0.y; rr.pkz = q0.z; rr.s0 = q0.w;
+        rr.s1 = q1.x; rr.s2 = q1.y; rr.xsign = __float_as_uint(q1.z);
+        rr.kx = rr.kz == 2 ? 0 : rr.kz + 1;
+        rr.ky = rr.kx == 2 ? 0 : rr.kx + 1;
+        leafhit = leaf_motion<-1>(sc, rr, t.h, (int)((un >> 4) & kLeafBaseMask), count);
+        t.r.tclosest = rr.tclosest;
       }
       if (leaf) {
         if (XF && leafhit) {
@@ -1169,7 +1218,7 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
           if (cur_xf >= 0) t.h.xf_last = cur_xf;
         }
         if (ANY_HIT && leafhit) {  // intersect.go:231-236
-          st.sp = 0;
+          st.reset();
           t.cur = -1;
         } else {
           t.cur = pop_next<ORDERED>(t.r, st);
