@@ -167,6 +167,8 @@ typedef struct VgStats {
   double gather_ms;  /* device time of the last vg_gather_frame exchange (pack + NCCL + scatter), without the D2H copy */
   uint64_t max_stack_depth; /* deepest traversal stack (entries) any ray of vg_render needed since vg_reset_stats; 0 unless the library is
                                a measurement build (-DVG_STACK_STATS). The reference reserves 90 entries (core/ray.go:158). */
+  int64_t shadow_level0_kernel; /* any-hit kernel the last vg_render used for the level-0 shadow queue: 0 cooperative, 1 per-lane loop
+                                   (option "shadow_level0_per_lane": 2 = measured on the first calls), -1 not applicable */
 } VgStats;
 
 /* ---- device layer ------------------------------------------------------------------------- */

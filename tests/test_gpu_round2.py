@@ -371,3 +371,24 @@ def test_pd_ray_records_give_the_same_hits(built_library, traversal):
     # shadow rays (any-hit) keep Tclosest = +Inf in this record
     occ = dev.trace(pd, any_hit=True)
     assert np.array_equal(occ["prim"] >= 0, want["prim"] >= 0)
+
+
+@pytest.mark.parametrize("motion", [False, True])
+def test_level0_shadow_queue_per_lane_is_bit_identical(built_library, motion):
+    """The level-0 shadow queue goes through the per-lane loop without the ordered push (k_trace_queue<1,4>), deeper levels through the
+    cooperative kernel: occlusion does not depend on the visiting order, so the frame and the ray counts are the same bits either way
+    (static and MQBVH scenes)."""
+    from vermeer_b200 import scenes
+    sc = scenes.heightfield_scene(160, 120, nq=80, motion=motion)
+    ref = None
+    for opt in (1, 0):
+        dev = _device(sc)
+        dev.set_option("shadow_level0_per_lane", opt)
+        fb = dev.render(0, 8)
+        st = dev.stats()
+        assert st["shadow_rays"] > 0
+        if ref is None:
+            ref = (fb.copy(), st["rays"], st["shadow_rays"])
+        else:
+            assert np.array_equal(fb.view(np.uint32), ref[0].view(np.uint32))
+            assert (st["rays"], st["shadow_rays"]) == ref[1:]

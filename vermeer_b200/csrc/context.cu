@@ -986,6 +986,10 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
   else if (!std::strcmp(name, "primary_per_lane")) ctx->opt_primary_per_lane = value != 0;
   else if (!std::strcmp(name, "shadow_unordered")) ctx->opt_shadow_unordered = value != 0;
   else if (!std::strcmp(name, "shadow_per_lane")) ctx->opt_shadow_per_lane = value != 0;
+  else if (!std::strcmp(name, "shadow_level0_per_lane")) {
+    if (value < 0 || value > 2) return ctx->fail(VG_ERR_INVALID, "shadow_level0_per_lane must be 0 (cooperative kernel), 1 (per-lane loop) or 2 (measured)");
+    ctx->opt_shadow_level0_per_lane = value;
+  }
   else if (!std::strcmp(name, "accumulate_tiled")) ctx->opt_accumulate_tiled = value != 0;
   else if (!std::strcmp(name, "stream_batch")) ctx->opt_stream_batch = value != 0;
   else if (!std::strcmp(name, "stream_chunk_log2")) {

@@ -165,6 +165,10 @@ struct vg_ctx {
   int opt_frame_slices = 4;      // vg_render_frame: slices of tile rows whose copies / exchange overlap the next slice's rendering
   int opt_capture_levels = 0;    // bit L: vg_render keeps a host copy of the level-L closest-hit ray queue (vg_captured_rays)
   std::vector<VgRay> captured;
+  // level-0 shadow queue (coherent rays) through the per-lane loop without the ordered push (k_trace_queue<1,4>): 1 = always, 0 = never
+  // (the cooperative kernel), 2 = whichever the first three vg_render calls measured faster on this scene. Measured: C2 shadow 31.08 ->
+  // 30.12 ms and C1 0.33 -> 0.30 ms with it, but C3 248 -> 292 ms and C4 (MQBVH) 55.3 -> 70.2 ms: scene dependent, hence the measurement.
+  int opt_shadow_level0_per_lane = 2;
   int opt_shadow_per_lane = 0;   // integrator shadow queue through the per-lane while-while kernel instead of the cooperative one
   int opt_iter_group = 32;       // a warp's 32 paths = (32/iter_group) pixels x iter_group iterations of the batch (render.cu: path_index)
   int opt_pixel_block = 1;       // paths of one warp cover an 8x4 pixel block of a tile (1) or a 32x1 row (0)

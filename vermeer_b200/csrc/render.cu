@@ -1260,6 +1260,10 @@ struct RenderState {
   // which rows rs.scr holds: valid only for this (frame, partition, pixel order); scr_valid is cleared when rs.scr is dropped
   bool scr_valid = false;
   int scr_w = 0, scr_h = 0, scr_rank = 0, scr_world = 0, scr_pixel_block = 0;
+  // level-0 shadow queue: per-lane loop (1) or cooperative kernel (0), whichever the first calls measured faster on this scene
+  // (bit-identical results: occlusion does not depend on the order). Trial order 0, 1, 0; reset when the render state is rebuilt.
+  int l0_choice = -1, l0_trials[2] = {0, 0};
+  float l0_ms_per_iter[2] = {0.f, 0.f};
   bool generic = false;  // shade with k_shade_generic (glossy lobe / conductor Fresnel / Disk or Sphere lights / sphere geoms)
   int nlobes = 1;
   std::vector<int> pix_host;
@@ -1307,7 +1311,10 @@ struct RenderState {
 };
 
 void render_invalidate(vg_ctx* ctx) {
-  if (ctx->rs) ctx->rs->ready = false;
+  if (!ctx->rs) return;
+  ctx->rs->ready = false;
+  ctx->rs->l0_choice = -1;
+  ctx->rs->l0_trials[0] = ctx->rs->l0_trials[1] = 0;
 }
 void render_destroy(vg_ctx* ctx) {
   if (!ctx->rs) return;
@@ -1830,7 +1837,11 @@ static int render_run_impl(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_
   const bool mot = ctx->dev.n_mtris > 0;    // kernels whose cooperative leaf phase takes motion triangles (VARIANT & 64)  // kernels that carry the analytic sphere leaf (traverse.cuh: VARIANT & 8)
   uint64_t launches = 0;
   size_t nev = 0;
-  struct Timed { int kind; size_t e0, e1; };  // kind 0 closest-hit traversal, 1 any-hit traversal, 2 shading (k_surface + k_shade*)
+  struct Timed { int kind; size_t e0, e1; };  // kind 0 closest-hit traversal, 1 any-hit traversal, 2 shading (k_surface + k_shade*), 3 any-hit traversal of level 0
+  // level-0 shadow queue kernel of THIS call: option 0 / 1 = fixed, 2 = measured (RenderState::l0_choice)
+  const bool l0_candidate = variant == 2 && !xf && !sph && ctx->opt_shadow_unordered;
+  const bool l0_tuning = l0_candidate && ctx->opt_shadow_level0_per_lane == 2 && rs.l0_choice < 0;
+  const int l0_kernel = !l0_candidate ? 0 : (ctx->opt_shadow_level0_per_lane != 2 ? ctx->opt_shadow_level0_per_lane : (rs.l0_choice >= 0 ? rs.l0_choice : (rs.l0_trials[0] == rs.l0_trials[1] + 1 ? 1 : 0)));
   std::vector<Timed> timed;
   bool untimed = false;
   // one event between consecutive stages: the end of one stage is the start of the next
@@ -1976,6 +1987,10 @@ static int render_run_impl(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_
             if (variant == 2 && ctx->opt_shadow_unordered) k_trace_queue<1, 11><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(11), st>>>(p, 0);
             else if (variant == 2) k_trace_queue<1, 10><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(10), st>>>(p, 0);
             else k_trace_queue<1, 8><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(8), st>>>(p, 0);
+          } else if (level == 0 && l0_kernel == 1) {
+            // the shadow rays of camera hits are as coherent as the camera rays (a warp = one pixel x 32 iterations towards one light):
+            // the per-lane loop, here without the ordered push
+            k_trace_queue<1, 4><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(4), st>>>(p, 0);
           } else if (mot && variant == 2) {
             if (ctx->opt_shadow_unordered) k_trace_queue<1, 67><<<rs.shadow_grid_mot, kTraceBlock, trace_smem_bytes(67), st>>>(p, 0);
             else k_trace_queue<1, 66><<<rs.shadow_grid_mot, kTraceBlock, trace_smem_bytes(66), st>>>(p, 0);
@@ -1984,7 +1999,7 @@ static int render_run_impl(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_
           else if (variant == 2 && ctx->opt_shadow_unordered) k_trace_queue<1, 3><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(3), st>>>(p, 0);
           else if (variant == 2) k_trace_queue<1, 2><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(2), st>>>(p, 0);
           else k_trace_queue<1, 0><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(0), st>>>(p, 0);
-          stage(1, ev_c, mark());
+          stage(level == 0 ? 3 : 1, ev_c, mark());
           if (rs.levels > 1) {
             k_resolve<<<(np + 255) / 256, 256, 0, st>>>(p, level, qin);
             launches++;
@@ -2075,13 +2090,22 @@ static int render_run_impl(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_
   // per-stage times and launch counts of THIS call (stages beyond the event pool are not timed; `untimed` says so)
   ctx->stats.closest_ms = ctx->stats.shadow_ms = ctx->stats.shade_ms = 0;
   ctx->stats.closest_launches = ctx->stats.shadow_launches = 0;
+  float l0_ms = 0.f;
   for (const Timed& k : timed) {
     float t = 0;
     cudaEventElapsedTime(&t, rs.ev(k.e0), rs.ev(k.e1));
     if (k.kind == 0) { ctx->stats.closest_ms += t; ctx->stats.closest_launches++; }
-    else if (k.kind == 1) { ctx->stats.shadow_ms += t; ctx->stats.shadow_launches++; }
+    else if (k.kind == 1 || k.kind == 3) { ctx->stats.shadow_ms += t; ctx->stats.shadow_launches++; if (k.kind == 3) l0_ms += t; }
     else ctx->stats.shade_ms += t;
   }
+  if (l0_tuning && !untimed && l0_ms > 0.f && iter_end > iter_begin) {
+    const float per = l0_ms / (float)(iter_end - iter_begin);
+    float& best = rs.l0_ms_per_iter[l0_kernel];
+    best = rs.l0_trials[l0_kernel] == 0 ? per : std::min(best, per);
+    rs.l0_trials[l0_kernel]++;
+    if (rs.l0_trials[0] >= 2 && rs.l0_trials[1] >= 1) rs.l0_choice = rs.l0_ms_per_iter[1] < rs.l0_ms_per_iter[0] ? 1 : 0;
+  }
+  ctx->stats.shadow_level0_kernel = l0_candidate ? l0_kernel : -1;
   (void)untimed;
   ctx->stats.rays += hstats[0];
   ctx->stats.shadow_rays += hstats[1];

@@ -624,7 +624,7 @@ __device__ __forceinline__ bool sphere_leaf(const DevScene& sc, TravState& t, ui
 // lanes of the warp are still traversing (the caller then refills the idle lanes and comes back).
 // Returns true when this lane's ray is finished.
 // SPH: the scene holds analytic sphere geoms (kernels for scenes without them do not carry the call).
-template <bool ANY_HIT, bool SPH = false>
+template <bool ANY_HIT, bool SPH = false, bool ORDERED = true>
 __device__ __forceinline__ bool trav_run(const DevScene& sc, TravState& t, Stack& st, int min_active) {
   while (t.cur != -1) {
     // 256-bit node loads in the per-lane kernel too: re-measured with pixel-coherent warps, C2 closest 19.09 vs 19.15 ms, C3 299.6 vs
@@ -632,7 +632,7 @@ __device__ __forceinline__ bool trav_run(const DevScene& sc, TravState& t, Stack
 #ifndef VG_PERLANE_WIDE
 #define VG_PERLANE_WIDE 0
 #endif
-    while (t.cur >= 0) node_step<true, VG_PERLANE_WIDE != 0>(sc, t, st);
+    while (t.cur >= 0) node_step<ORDERED, VG_PERLANE_WIDE != 0>(sc, t, st);
     while (t.cur < -1) {
       const uint32_t un = (uint32_t)t.cur;
       if (un & kGeomBit) {
@@ -642,7 +642,7 @@ __device__ __forceinline__ bool trav_run(const DevScene& sc, TravState& t, Stack
             t.cur = -1;
             return true;
           }
-          t.cur = pop_next(t.r, st);
+          t.cur = pop_next<ORDERED>(t.r, st);
           continue;
         }
         // scene.go:61-78 -> Geom.Trace -> qbvh.Trace pushes the mesh root with T = Tclosest and pops it at once
@@ -655,7 +655,7 @@ __device__ __forceinline__ bool trav_run(const DevScene& sc, TravState& t, Stack
         t.cur = -1;
         return true;
       }
-      t.cur = pop_next(t.r, st);
+      t.cur = pop_next<ORDERED>(t.r, st);
     }
     if (min_active > 0 && __popc(__activemask()) < min_active) break;
   }
@@ -807,7 +807,7 @@ __device__ __forceinline__ void trace_persistent_tma(const DevScene& sc, IO& io,
 // coalesced LDG.128 each. Measured faster than the TMA-staged variant on B200 (3.83 vs 3.16 Grays/s on C2 primary rays,
 // profiles/README.md): the fetch is <4 % of a ray's loads and 28 resident warps already hide its latency, while the
 // staging state costs registers under the 72-register cap.
-template <bool ANY_HIT, bool SPH, class IO>
+template <bool ANY_HIT, bool SPH, bool ORDERED, class IO>
 __device__ __forceinline__ void trace_persistent_ldg(const DevScene& sc, IO& io, Stack& st, unsigned& nodes_acc, unsigned& tris_acc) {
   const int lane = threadIdx.x & 31;
   const long long n = io.size();
@@ -837,7 +837,7 @@ __device__ __forceinline__ void trace_persistent_ldg(const DevScene& sc, IO& io,
     }
     if (__ballot_sync(0xffffffffu, my >= 0) == 0) break;
     if (my >= 0) {
-      if (trav_run<ANY_HIT, SPH>(sc, t, st, exhausted ? 0 : VG_REFILL_BELOW)) {
+      if (trav_run<ANY_HIT, SPH, ORDERED>(sc, t, st, exhausted ? 0 : VG_REFILL_BELOW)) {
         io.store(my, t.r, t.h, st.overflow);
         nodes_acc += t.h.cnt & 0xffffu;
         tris_acc += t.h.cnt >> 16;
@@ -1247,7 +1247,7 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
 }
 
 // VARIANT & 7: 0 = per-lane while-while with coalesced LDG refill, 1 = the same over the TMA-staged queue, 2 = warp-cooperative
-// leaves, 3 = cooperative leaves without the ordered push (occlusion-only any-hit rays). VARIANT & 8: the scene holds analytic
+// leaves, 3 = cooperative leaves without the ordered push (occlusion-only any-hit rays), 4 = the per-lane loop without the ordered push. VARIANT & 8: the scene holds analytic
 // sphere geoms (variants 0, 2, 3 only; the launchers map variant 1 to 0 for such scenes). VARIANT & 16: the scene holds
 // instances (cooperative variants 2 and 3 only, always together with & 8).
 template <bool ANY_HIT, int VARIANT, class IO>
@@ -1270,8 +1270,11 @@ __device__ __forceinline__ void trace_persistent(const DevScene& sc, IO& io, Sta
     CoopSmem cs;
     cs.rp = reinterpret_cast<float4*>(warp_smem);
     trace_persistent_coop<ANY_HIT, false, SPH, XF, MOT>(sc, io, st, cs, nodes_acc, tris_acc);
+  } else if (V == 4) {  // per-lane loop without the ordered push: occlusion-only rays that are coherent (the integrator's level-0 shadow queue)
+    static_assert(V != 4 || ANY_HIT, "the unordered per-lane loop is for occlusion-only rays");
+    trace_persistent_ldg<ANY_HIT, SPH, false>(sc, io, st, nodes_acc, tris_acc);
   } else {
-    trace_persistent_ldg<ANY_HIT, SPH>(sc, io, st, nodes_acc, tris_acc);
+    trace_persistent_ldg<ANY_HIT, SPH, true>(sc, io, st, nodes_acc, tris_acc);
   }
 }
 

@@ -60,7 +60,7 @@ class VgStats(C.Structure):
                 ("shadow_nodes_t", C.c_uint64), ("shadow_tris_t", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("closest_launches", C.c_uint64), ("shadow_launches", C.c_uint64),
                 ("render_ms", C.c_double), ("trace_ms", C.c_double), ("closest_ms", C.c_double), ("shadow_ms", C.c_double),
-                ("shade_ms", C.c_double), ("gather_ms", C.c_double), ("max_stack_depth", C.c_uint64)]
+                ("shade_ms", C.c_double), ("gather_ms", C.c_double), ("max_stack_depth", C.c_uint64), ("shadow_level0_kernel", C.c_int64)]
 
 
 class VgPeaks(C.Structure):
