@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -q --tb=short -rf -x 2>&1 | tail -6
+run() { if [ -n "$1" ]; then export VG_SO_PATH=$1; else unset VG_SO_PATH; fi; VG_BENCH_DEVICE_BUILD=0 timeout 300 python bench.py --steps 4 --warmup 3 --no-cpu --no-wavefront --no-nonparity --configs c2,c4,c3,c1 2>/dev/null | python scripts/bench_brief.py /dev/stdin "$2"; }
+run "" base

@@ -41,7 +41,12 @@ static const int kTraceBlock = VG_TRACE_BLOCK;
 // 32 x 48 B ray-parameter blocks for the cooperative leaf phase. Shared memory not taken here stays L1: the scene data these
 // kernels re-read lives there, and the measured optimum is a SHORT shared stack (8 entries/thread: C2 frame 105.6 -> 102.9 ms
 // against 16; 4 and 2 lose again to local-memory spills of the stack).
-__host__ __device__ constexpr int warp_smem_bytes(int variant) { return (variant & 7) == 1 ? 2048 + 16 : (((variant & 7) == 2 || (variant & 7) == 3) ? 32 * 48 : 0); }
+// Per warp: nothing for the per-lane loop (0); 2 x 1 KB ray slots + 2 mbarriers for the TMA-staged queue (1); 32 x 32 B per-lane
+// leaf-parameter blocks (traverse.cuh: coop_publish) for the occlusion-only per-lane loop (4), + 32 x 16 B per-rank leaf records for
+// the cooperative leaf phase (2, 3).
+__host__ __device__ constexpr int warp_smem_bytes(int variant) {
+  return (variant & 7) == 1 ? 2048 + 16 : (((variant & 7) == 2 || (variant & 7) == 3) ? 1024 + 32 * 16 : ((variant & 7) == 4 ? 1024 : 0));
+}
 inline size_t trace_smem_bytes(int variant) { return (size_t)(kTraceBlock / 32) * warp_smem_bytes(variant) + (size_t)kTraceBlock * VG_SMEM_STACK * 8; }
 
 // kernels_trace.cu

@@ -38,6 +38,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 
 template <bool STREAMED = false>
 struct BatchIO {
+  static constexpr bool kHitRecord = true;
   const VgRay* rays;
   VgHit* hits;
   long long n;

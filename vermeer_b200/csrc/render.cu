@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderParams p, int iter_b
 // an occluded sample zeroes its contribution slot.
 template <int MODE>
 struct QueueIO {
+  static constexpr bool kHitRecord = MODE == 0;  // the shadow queue only wants "occluded or not": no U, V, W / ids of the hit
   const RenderParams& p;
   const VgRay* rays;
   int n;
@@ -339,7 +340,7 @@ struct QueueIO {
       *reinterpret_cast<float4*>(&p.hits[i]) = make_float4(r.tclosest, h.u, h.v, h.w);
       *(reinterpret_cast<int4*>(&p.hits[i]) + 1) = make_int4(h.prim, h.geom, h.slot, h.xf_last + 1);
     } else {
-      if (h.prim >= 0) p.contrib[p.sslot[i]] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (h.prim != -1) p.contrib[p.sslot[i]] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
 };
@@ -1261,8 +1262,10 @@ struct RenderState {
   bool scr_valid = false;
   int scr_w = 0, scr_h = 0, scr_rank = 0, scr_world = 0, scr_pixel_block = 0;
   // level-0 shadow queue: per-lane loop (1) or cooperative kernel (0), whichever the first calls measured faster on this scene
-  // (bit-identical results: occlusion does not depend on the order). Trial order 0, 1, 0; reset when the render state is rebuilt.
+  // (bit-identical results: occlusion does not depend on the order). While undecided the batches alternate; two samples of each
+  // kernel decide (minimum per iteration). Reset when the render state is rebuilt.
   int l0_choice = -1, l0_trials[2] = {0, 0};
+  unsigned l0_seq = 0;
   float l0_ms_per_iter[2] = {0.f, 0.f};
   bool generic = false;  // shade with k_shade_generic (glossy lobe / conductor Fresnel / Disk or Sphere lights / sphere geoms)
   int nlobes = 1;
@@ -1315,6 +1318,7 @@ void render_invalidate(vg_ctx* ctx) {
   ctx->rs->ready = false;
   ctx->rs->l0_choice = -1;
   ctx->rs->l0_trials[0] = ctx->rs->l0_trials[1] = 0;
+  ctx->rs->l0_seq = 0;
 }
 void render_destroy(vg_ctx* ctx) {
   if (!ctx->rs) return;
@@ -1837,11 +1841,12 @@ static int render_run_impl(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_
   const bool mot = ctx->dev.n_mtris > 0;    // kernels whose cooperative leaf phase takes motion triangles (VARIANT & 64)  // kernels that carry the analytic sphere leaf (traverse.cuh: VARIANT & 8)
   uint64_t launches = 0;
   size_t nev = 0;
-  struct Timed { int kind; size_t e0, e1; };  // kind 0 closest-hit traversal, 1 any-hit traversal, 2 shading (k_surface + k_shade*), 3 any-hit traversal of level 0
-  // level-0 shadow queue kernel of THIS call: option 0 / 1 = fixed, 2 = measured (RenderState::l0_choice)
+  struct Timed { int kind; size_t e0, e1; int iters; };  // kind 0 closest-hit traversal, 1 any-hit traversal, 2 shading (k_surface + k_shade*), 3 / 4 any-hit traversal of level 0 with the cooperative / per-lane kernel
+  // level-0 shadow queue kernel, per batch: option 0 / 1 = fixed, 2 = measured — while undecided the batches alternate between the
+  // two kernels and their times per iteration are compared after the call (RenderState::l0_choice)
   const bool l0_candidate = variant == 2 && !xf && !sph && ctx->opt_shadow_unordered;
   const bool l0_tuning = l0_candidate && ctx->opt_shadow_level0_per_lane == 2 && rs.l0_choice < 0;
-  const int l0_kernel = !l0_candidate ? 0 : (ctx->opt_shadow_level0_per_lane != 2 ? ctx->opt_shadow_level0_per_lane : (rs.l0_choice >= 0 ? rs.l0_choice : (rs.l0_trials[0] == rs.l0_trials[1] + 1 ? 1 : 0)));
+  int l0_kernel = !l0_candidate ? 0 : (ctx->opt_shadow_level0_per_lane != 2 ? ctx->opt_shadow_level0_per_lane : std::max(rs.l0_choice, 0));
   std::vector<Timed> timed;
   bool untimed = false;
   // one event between consecutive stages: the end of one stage is the start of the next
@@ -1850,8 +1855,8 @@ static int render_run_impl(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_
     cudaEventRecord(rs.ev(nev), st);
     return nev++;
   };
-  auto stage = [&](int kind, size_t a, size_t b) {
-    if (a != (size_t)-1 && b != (size_t)-1) timed.push_back(Timed{kind, a, b});
+  auto stage = [&](int kind, size_t a, size_t b, int iters = 0) {
+    if (a != (size_t)-1 && b != (size_t)-1) timed.push_back(Timed{kind, a, b, iters});
   };
   RCUDA(cudaMemsetAsync(rs.stats.p, 0, 8 * sizeof(unsigned long long), st));
   RCUDA(cudaEventRecord(rs.e0, st));
@@ -1902,6 +1907,7 @@ static int render_run_impl(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_
     if (fp) RCUDA(cudaStreamWaitEvent(st, rs.pev(1 + (size_t)sl), 0));
     for (int ib = iter_begin; ib < iter_end && sn > 0; ib += rs.iters) {
       const int niters = std::min(rs.iters, iter_end - ib);
+      if (l0_tuning) l0_kernel = (rs.l0_seq++) & 1;
       const int np = sn * niters;
       {
         int G = 1;  // the largest power of two within the option, the warp size and this batch's iteration count
@@ -1999,7 +2005,7 @@ static int render_run_impl(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_
           else if (variant == 2 && ctx->opt_shadow_unordered) k_trace_queue<1, 3><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(3), st>>>(p, 0);
           else if (variant == 2) k_trace_queue<1, 2><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(2), st>>>(p, 0);
           else k_trace_queue<1, 0><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(0), st>>>(p, 0);
-          stage(level == 0 ? 3 : 1, ev_c, mark());
+          stage(level == 0 ? 3 + l0_kernel : 1, ev_c, mark(), np);  // (np paths in this batch: slices of a frame differ in size)
           if (rs.levels > 1) {
             k_resolve<<<(np + 255) / 256, 256, 0, st>>>(p, level, qin);
             launches++;
@@ -2090,21 +2096,23 @@ static int render_run_impl(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_
   // per-stage times and launch counts of THIS call (stages beyond the event pool are not timed; `untimed` says so)
   ctx->stats.closest_ms = ctx->stats.shadow_ms = ctx->stats.shade_ms = 0;
   ctx->stats.closest_launches = ctx->stats.shadow_launches = 0;
-  float l0_ms = 0.f;
   for (const Timed& k : timed) {
     float t = 0;
     cudaEventElapsedTime(&t, rs.ev(k.e0), rs.ev(k.e1));
     if (k.kind == 0) { ctx->stats.closest_ms += t; ctx->stats.closest_launches++; }
-    else if (k.kind == 1 || k.kind == 3) { ctx->stats.shadow_ms += t; ctx->stats.shadow_launches++; if (k.kind == 3) l0_ms += t; }
+    else if (k.kind == 1 || k.kind == 3 || k.kind == 4) {
+      ctx->stats.shadow_ms += t;
+      ctx->stats.shadow_launches++;
+      if (l0_tuning && k.kind >= 3 && k.iters > 0) {  // the first sample of a kernel carries its module load: keep the minimum
+        const int kk = k.kind - 3;
+        const float per = t / (float)k.iters;
+        rs.l0_ms_per_iter[kk] = rs.l0_trials[kk] == 0 ? per : std::min(rs.l0_ms_per_iter[kk], per);
+        rs.l0_trials[kk]++;
+      }
+    }
     else ctx->stats.shade_ms += t;
   }
-  if (l0_tuning && !untimed && l0_ms > 0.f && iter_end > iter_begin) {
-    const float per = l0_ms / (float)(iter_end - iter_begin);
-    float& best = rs.l0_ms_per_iter[l0_kernel];
-    best = rs.l0_trials[l0_kernel] == 0 ? per : std::min(best, per);
-    rs.l0_trials[l0_kernel]++;
-    if (rs.l0_trials[0] >= 2 && rs.l0_trials[1] >= 1) rs.l0_choice = rs.l0_ms_per_iter[1] < rs.l0_ms_per_iter[0] ? 1 : 0;
-  }
+  if (l0_tuning && rs.l0_trials[0] >= 2 && rs.l0_trials[1] >= 2) rs.l0_choice = rs.l0_ms_per_iter[1] < rs.l0_ms_per_iter[0] ? 1 : 0;
   ctx->stats.shadow_level0_kernel = l0_candidate ? l0_kernel : -1;
   (void)untimed;
   ctx->stats.rays += hstats[0];

@@ -198,8 +198,15 @@ __device__ __forceinline__ float pick(float x, float y, float z, int k) {
   const int kk = k;  // k is (KZ + const) % 3 at the call sites below; resolved at compile time
   return kk == 0 ? x : (kk == 1 ? y : z);
 }
+// The leaf-phase view of a ray: what the triangle tests read. The persistent kernels publish it to shared memory once per ray
+// (coop_publish) and load it back at a leaf, so the eight values do not occupy registers (or local memory) during the node loop.
+struct LeafRay {
+  float pkx, pky, pkz, s0, s1, s2;
+  uint32_t xsign;
+  int kx, ky, kz;
+};
 template <bool MOTION, int KZ>
-__device__ __forceinline__ bool tri_test(RayState& r, float3 p0, float3 p1, float3 p2, float bias, float* U, float* V, float* W) {
+__device__ __forceinline__ bool tri_test(const LeafRay& r, float& tclosest, float3 p0, float3 p1, float3 p2, float bias, float* U, float* V, float* W) {
   const int kz = KZ < 0 ? r.kz : KZ;
   const int kx = KZ < 0 ? r.kx : (KZ + 1) % 3;
   const int ky = KZ < 0 ? r.ky : (KZ + 2) % 3;
@@ -234,15 +241,15 @@ __device__ __forceinline__ bool tri_test(RayState& r, float3 p0, float3 p1, floa
   const float Ts = __uint_as_float(__float_as_uint(T) ^ sgn);
   const float ds = __uint_as_float(__float_as_uint(det) ^ sgn);
   if (MOTION) {
-    if (Ts <= bias * ds || Ts > r.tclosest * ds) return false;
+    if (Ts <= bias * ds || Ts > tclosest * ds) return false;
   } else {
-    if (Ts < bias * ds || Ts > r.tclosest * ds) return false;
+    if (Ts < bias * ds || Ts > tclosest * ds) return false;
   }
   const float rcp = 1.0f / det;
   *U = fU * rcp;
   *V = fV * rcp;
   *W = fW * rcp;
-  r.tclosest = T * rcp;
+  tclosest = T * rcp;
   return true;
 }
 
@@ -502,9 +509,36 @@ __device__ __forceinline__ void node_step(const DevScene& sc, TravState& t, Stac
   t.cur = next != -1 ? next : pop_next<ORDERED>(r, st);
 }
 
-// Triangle loops of one leaf. The next triangle's 3 x LDG.128 are issued before the current one is tested.
-template <int KZ>
-__device__ __forceinline__ bool leaf_static(const DevScene& sc, RayState& r, HitState& h, int base, int count) {
+// Per warp (every persistent kernel): 32 per-LANE blocks of two float4 — the leaf-phase parameters of the lane's current ray
+// {pkx, pky, pkz, s0} {s1, s2, xsign, Tclosest}, written ONCE when the ray is set up (coop_publish). The cooperative kernels add 32
+// per-RANK records {kz | motion << 8 | owner lane << 16, leaf base, item start, Ray.Time} written by the lanes that hold a leaf in the
+// current phase. Round 2 (first half) kept these values in RayState for the whole traversal: the 64/72-register kernels spilled
+// them and re-read them (5 LDL + 3 STS.128 per lane and leaf phase in the SASS of the cooperative kernels).
+struct CoopSmem {
+  float4* rp;
+};
+__device__ __forceinline__ void coop_publish(const CoopSmem& cs, const RayState& r) {
+  float4* b = cs.rp + (threadIdx.x & 31) * 2;
+  b[0] = make_float4(r.pkx, r.pky, r.pkz, r.s0);
+  b[1] = make_float4(r.s1, r.s2, __uint_as_float(r.xsign), r.tclosest);
+}
+__device__ __forceinline__ LeafRay leaf_ray(const CoopSmem& cs, int kz) {
+  const float4* b = cs.rp + (threadIdx.x & 31) * 2;
+  const float4 q0 = b[0], q1 = b[1];
+  LeafRay lr;
+  lr.pkx = q0.x; lr.pky = q0.y; lr.pkz = q0.z; lr.s0 = q0.w;
+  lr.s1 = q1.x; lr.s2 = q1.y; lr.xsign = __float_as_uint(q1.z);
+  lr.kz = kz;
+  lr.kx = kz == 2 ? 0 : kz + 1;
+  lr.ky = lr.kx == 2 ? 0 : lr.kx + 1;
+  return lr;
+}
+
+// Triangle loops of one leaf. The next triangle's loads are issued before the current one is tested. An accepted triangle only
+// records its slot (h.prim = -2 static / -3 motion): U, V, W and the ids are recomputed from the slot when the ray is stored
+// (finalize_hit), so they are not carried through the traversal loops.
+template <int KZ, bool DEFER>
+__device__ __forceinline__ bool leaf_static(const DevScene& sc, const LeafRay& lr, float& tclosest, HitState& h, int base, int count) {
   bool leafhit = false;
   const float4* tp = sc.tris + (size_t)base * kTriStride;
   float4 n0, n1, n2;
@@ -516,43 +550,67 @@ __device__ __forceinline__ bool leaf_static(const DevScene& sc, RayState& r, Hit
       ld_tri(tp, n0, n1, n2);
     }
     float U, V, W;
-    if (tri_test<false, KZ>(r, make_float3(v0.x, v0.y, v0.z), make_float3(v1.x, v1.y, v1.z), make_float3(v2.x, v2.y, v2.z), v2.w, &U, &V, &W)) {
-      h.u = U; h.v = V; h.w = W;
-      h.geom = __float_as_int(v0.w);
-      h.prim = __float_as_int(v1.w);
+    if (tri_test<false, KZ>(lr, tclosest, make_float3(v0.x, v0.y, v0.z), make_float3(v1.x, v1.y, v1.z), make_float3(v2.x, v2.y, v2.z), v2.w, &U, &V, &W)) {
       h.slot = base + i;
+      if (DEFER) {
+        h.prim = -2;
+      } else {
+        h.u = U; h.v = V; h.w = W;
+        h.geom = __float_as_int(v0.w);
+        h.prim = __float_as_int(v1.w);
+      }
       leafhit = true;
     }
   }
   return leafhit;
 }
 
-template <int KZ>
-__device__ __forceinline__ bool leaf_motion(const DevScene& sc, RayState& r, HitState& h, int base, int count) {
+// trace.go:547-554: the three vertices of motion slot `slot` lerped between the keys of its mesh at `time`; *bias = the record's RayBias
+__device__ __forceinline__ void motion_tri(const DevScene& sc, size_t slot, float time, float3& p0, float3& p1, float3& p2, float* bias) {
+  const float4* k0 = sc.mtris + slot * 3;  // key-0 record of the slot: geom id in [0].w, RayBias in [2].w
+  const DevGeom gm = sc.geoms[__float_as_int(ldg4(k0).w)];
+  const float k = time * (float)(gm.keys - 1);
+  const float fk = floorf(k);
+  const float tm = k - fk, om = 1.0f - tm;
+  const int key = (int)fk, key2 = (int)ceilf(k);
+  const float4* ta = sc.mtris + (slot + (size_t)key * gm.tri_key_stride) * 3;
+  const float4* tb = sc.mtris + (slot + (size_t)key2 * gm.tri_key_stride) * 3;
+  const float4 a0 = ldg4(ta), a1 = ldg4(ta + 1), a2 = ldg4(ta + 2);
+  const float4 b0 = ldg4(tb), b1 = ldg4(tb + 1), b2 = ldg4(tb + 2);
+  p0 = make_float3(om * a0.x + tm * b0.x, om * a0.y + tm * b0.y, om * a0.z + tm * b0.z);
+  p1 = make_float3(om * a1.x + tm * b1.x, om * a1.y + tm * b1.y, om * a1.z + tm * b1.z);
+  p2 = make_float3(om * a2.x + tm * b2.x, om * a2.y + tm * b2.y, om * a2.z + tm * b2.z);
+  *bias = a2.w;  // the w fields (geom id, face, RayBias) are the same in every key's record
+}
+
+template <int KZ, bool DEFER>
+__device__ __forceinline__ bool leaf_motion(const DevScene& sc, const LeafRay& lr, float time, float& tclosest, HitState& h, int base, int count) {
   bool leafhit = false;
   // trace.go:547-554: lerp the three vertices between the keys of this mesh
   const float4 g0 = ldg4(sc.mtris + (size_t)base * 3);  // key-0 record of the first slot: geom id in w
   const DevGeom gm = sc.geoms[__float_as_int(g0.w)];
-  const float k = r.time * (float)(gm.keys - 1);
+  const float k = time * (float)(gm.keys - 1);
   const float fk = floorf(k);
   const float tm = k - fk, om = 1.0f - tm;
   const int key = (int)fk, key2 = (int)ceilf(k);
   const float4* ta = sc.mtris + ((size_t)base + (size_t)key * gm.tri_key_stride) * 3;
   const float4* tb = sc.mtris + ((size_t)base + (size_t)key2 * gm.tri_key_stride) * 3;
-  const float4* tk0 = sc.mtris + (size_t)base * 3;
-  for (int i = 0; i < count; i++, ta += 3, tb += 3, tk0 += 3) {
+  for (int i = 0; i < count; i++, ta += 3, tb += 3) {
     const float4 a0 = ldg4(ta), a1 = ldg4(ta + 1), a2 = ldg4(ta + 2);
     const float4 b0 = ldg4(tb), b1 = ldg4(tb + 1), b2 = ldg4(tb + 2);
     const float3 p0 = make_float3(om * a0.x + tm * b0.x, om * a0.y + tm * b0.y, om * a0.z + tm * b0.z);
     const float3 p1 = make_float3(om * a1.x + tm * b1.x, om * a1.y + tm * b1.y, om * a1.z + tm * b1.z);
     const float3 p2 = make_float3(om * a2.x + tm * b2.x, om * a2.y + tm * b2.y, om * a2.z + tm * b2.z);
-    const float4 w0 = a0, w1 = a1, w2 = a2;  // geom id / face / RayBias in .w are the same in every key's record
     float U, V, W;
-    if (tri_test<true, KZ>(r, p0, p1, p2, w2.w, &U, &V, &W)) {
-      h.u = U; h.v = V; h.w = W;
-      h.geom = __float_as_int(w0.w);
-      h.prim = __float_as_int(w1.w);
+    if (tri_test<true, KZ>(lr, tclosest, p0, p1, p2, a2.w, &U, &V, &W)) {  // (geom id, face and RayBias in .w are the same in every key's record)
       h.slot = base + i;
+      if (DEFER) {
+        h.prim = -3;
+      } else {
+        h.u = U; h.v = V; h.w = W;
+        h.geom = __float_as_int(a0.w);
+        h.prim = __float_as_int(a1.w);
+      }
       leafhit = true;
     }
   }
@@ -562,21 +620,59 @@ __device__ __forceinline__ bool leaf_motion(const DevScene& sc, RayState& r, Hit
 // One triangle leaf. Returns true if any triangle of the leaf was accepted. trace.go:116-194 / :528-667
 // If every lane that arrived here together has the same dominant axis Kz (coherent camera / shadow rays), the
 // component selection is resolved at compile time; otherwise per-lane selects.
-__device__ __forceinline__ bool leaf_step(const DevScene& sc, TravState& t, uint32_t un) {
+// SMEM: the leaf parameters come from the lane's published block and an accepted triangle only records its slot (the occlusion
+// kernel V = 4, compiled for 64 registers); otherwise they stay in RayState and the hit record is written at accept time (the
+// closest-hit per-lane kernels at 72 registers: MEASURED, the published-block form cost them 17.85 -> 19.57 ms on the C2 camera rays —
+// 4 KB more shared memory per CTA moves the carve-out from 64 to 100 KB, and a coherent warp re-reads its blocks at every leaf).
+template <bool SMEM>
+__device__ __forceinline__ bool leaf_step(const DevScene& sc, TravState& t, uint32_t un, const CoopSmem& cs) {
   RayState& r = t.r;
   HitState& h = t.h;
   const int base = (int)((un >> 4) & kLeafBaseMask);
   const int count = (int)(un & 15u) + 1;
   h.cnt += (uint32_t)count << 16;
-  if (un & kMotionTriBit) return leaf_motion<-1>(sc, r, h, base, count);
+  LeafRay lr;
+  if (SMEM) {
+    lr = leaf_ray(cs, r.kz);
+  } else {
+    lr.pkx = r.pkx; lr.pky = r.pky; lr.pkz = r.pkz; lr.s0 = r.s0; lr.s1 = r.s1; lr.s2 = r.s2; lr.xsign = r.xsign; lr.kx = r.kx; lr.ky = r.ky; lr.kz = r.kz;
+  }
+  if (un & kMotionTriBit) return leaf_motion<-1, SMEM>(sc, lr, r.time, r.tclosest, h, base, count);
   const unsigned am = __activemask();
   const int k0 = __shfl_sync(am, r.kz, __ffs(am) - 1);
   if (__all_sync(am, r.kz == k0)) {
-    if (k0 == 0) return leaf_static<0>(sc, r, h, base, count);
-    if (k0 == 1) return leaf_static<1>(sc, r, h, base, count);
-    return leaf_static<2>(sc, r, h, base, count);
+    if (k0 == 0) return leaf_static<0, SMEM>(sc, lr, r.tclosest, h, base, count);
+    if (k0 == 1) return leaf_static<1, SMEM>(sc, lr, r.tclosest, h, base, count);
+    return leaf_static<2, SMEM>(sc, lr, r.tclosest, h, base, count);
   }
-  return leaf_static<-1>(sc, r, h, base, count);
+  return leaf_static<-1, SMEM>(sc, lr, r.tclosest, h, base, count);
+}
+
+// U, V, W of the accepted triangle recomputed from its slot (the same arithmetic on the same inputs as at accept time: the same bits),
+// and the ids of its record. Called once per ray that hit, when the ray is stored.
+__device__ __forceinline__ void hit_uvw_static(const DevScene& sc, const LeafRay& lr, HitState& h) {
+  float4 v0, v1, v2;
+  ld_tri(sc.tris + (size_t)h.slot * kTriStride, v0, v1, v2);
+  float tc = __int_as_float(0x7f800000);
+  tri_test<false, -1>(lr, tc, make_float3(v0.x, v0.y, v0.z), make_float3(v1.x, v1.y, v1.z), make_float3(v2.x, v2.y, v2.z), v2.w, &h.u, &h.v, &h.w);
+  h.geom = __float_as_int(v0.w);
+  h.prim = __float_as_int(v1.w);
+}
+__device__ __forceinline__ void hit_uvw_motion(const DevScene& sc, const LeafRay& lr, float time, HitState& h, bool ids) {
+  float3 p0, p1, p2;
+  float bias;
+  motion_tri(sc, (size_t)h.slot, time, p0, p1, p2, &bias);
+  float tc = __int_as_float(0x7f800000);
+  tri_test<true, -1>(lr, tc, p0, p1, p2, bias, &h.u, &h.v, &h.w);
+  if (ids) {
+    const float4* tp = sc.mtris + (size_t)h.slot * 3;
+    h.geom = __float_as_int(ldg4(tp).w);
+    h.prim = __float_as_int(ldg4(tp + 1).w);
+  }
+}
+__device__ __forceinline__ void finalize_hit(const DevScene& sc, const CoopSmem& cs, TravState& t) {
+  if (t.h.prim == -2) hit_uvw_static(sc, leaf_ray(cs, t.r.kz), t.h);
+  else if (t.h.prim == -3) hit_uvw_motion(sc, leaf_ray(cs, t.r.kz), t.r.time, t.h, true);
 }
 
 // Analytic sphere geom at the scene level (builtin/geom/sphere/trace.go:13-109): solveQuadratic / raySphereIntersect in the
@@ -624,8 +720,8 @@ __device__ __forceinline__ bool sphere_leaf(const DevScene& sc, TravState& t, ui
 // lanes of the warp are still traversing (the caller then refills the idle lanes and comes back).
 // Returns true when this lane's ray is finished.
 // SPH: the scene holds analytic sphere geoms (kernels for scenes without them do not carry the call).
-template <bool ANY_HIT, bool SPH = false, bool ORDERED = true>
-__device__ __forceinline__ bool trav_run(const DevScene& sc, TravState& t, Stack& st, int min_active) {
+template <bool ANY_HIT, bool SPH = false, bool ORDERED = true, bool SMEM = false>
+__device__ __forceinline__ bool trav_run(const DevScene& sc, TravState& t, Stack& st, const CoopSmem& cs, int min_active) {
   while (t.cur != -1) {
     // 256-bit node loads in the per-lane kernel too: re-measured with pixel-coherent warps, C2 closest 19.09 vs 19.15 ms, C3 299.6 vs
     // 300.5 ms — within noise, so it keeps the 128-bit loads (round 1: 28.59 vs 28.32 ms).
@@ -649,7 +745,7 @@ __device__ __forceinline__ bool trav_run(const DevScene& sc, TravState& t, Stack
         t.cur = (int32_t)(un & kGeomRootMask);
         break;
       }
-      const bool leafhit = leaf_step(sc, t, un);
+      const bool leafhit = leaf_step<SMEM>(sc, t, un, cs);
       if (ANY_HIT && leafhit) {  // intersect.go:231-236: shadow rays return at the first leaf reporting a hit
         st.reset();
         t.cur = -1;
@@ -660,19 +756,6 @@ __device__ __forceinline__ bool trav_run(const DevScene& sc, TravState& t, Stack
     if (min_active > 0 && __popc(__activemask()) < min_active) break;
   }
   return t.cur == -1;
-}
-
-// Convenience: trace one ray to completion.
-template <bool ANY_HIT>
-__device__ __forceinline__ bool trace_ray(const DevScene& sc, RayState& r, HitState& h, Stack& st) {
-  TravState t;
-  t.r = r;
-  st.overflow = false;
-  trav_begin(sc, t, st);
-  trav_run<ANY_HIT>(sc, t, st, 0);
-  r = t.r;
-  h = t.h;
-  return h.prim >= 0;
 }
 
 // ---- TMA-staged ray queue ------------------------------------------------------------------------------------
@@ -718,7 +801,7 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
 #define VG_REFILL_BELOW 16
 #endif
 template <bool ANY_HIT, class IO>
-__device__ __forceinline__ void trace_persistent_tma(const DevScene& sc, IO& io, Stack& st, WarpStage ws, unsigned& nodes_acc,
+__device__ __forceinline__ void trace_persistent_tma(const DevScene& sc, IO& io, Stack& st, WarpStage ws, const CoopSmem& cs, unsigned& nodes_acc,
                                                      unsigned& tris_acc) {
   const int lane = threadIdx.x & 31;
   const long long n = io.size();
@@ -792,7 +875,7 @@ __device__ __forceinline__ void trace_persistent_tma(const DevScene& sc, IO& io,
     }
     if (__ballot_sync(0xffffffffu, my >= 0) == 0) break;  // nothing in flight and the queue is drained
     if (my >= 0) {
-      if (trav_run<ANY_HIT>(sc, t, st, (cur ? cnt1 : cnt0) == 0 ? 0 : VG_REFILL_BELOW)) {
+      if (trav_run<ANY_HIT>(sc, t, st, cs, (cur ? cnt1 : cnt0) == 0 ? 0 : VG_REFILL_BELOW)) {
         io.store(my, t.r, t.h, st.overflow);
         nodes_acc += t.h.cnt & 0xffffu;
         tris_acc += t.h.cnt >> 16;
@@ -807,8 +890,8 @@ __device__ __forceinline__ void trace_persistent_tma(const DevScene& sc, IO& io,
 // coalesced LDG.128 each. Measured faster than the TMA-staged variant on B200 (3.83 vs 3.16 Grays/s on C2 primary rays,
 // profiles/README.md): the fetch is <4 % of a ray's loads and 28 resident warps already hide its latency, while the
 // staging state costs registers under the 72-register cap.
-template <bool ANY_HIT, bool SPH, bool ORDERED, class IO>
-__device__ __forceinline__ void trace_persistent_ldg(const DevScene& sc, IO& io, Stack& st, unsigned& nodes_acc, unsigned& tris_acc) {
+template <bool ANY_HIT, bool SPH, bool ORDERED, bool SMEM, class IO>
+__device__ __forceinline__ void trace_persistent_ldg(const DevScene& sc, IO& io, Stack& st, const CoopSmem& cs, unsigned& nodes_acc, unsigned& tris_acc) {
   const int lane = threadIdx.x & 31;
   const long long n = io.size();
   TravState t;
@@ -831,13 +914,15 @@ __device__ __forceinline__ void trace_persistent_ldg(const DevScene& sc, IO& io,
           my = i;
           io.load(i, t.r);
           ray_setup(t.r);
+          if (SMEM) coop_publish(cs, t.r);
           trav_begin(sc, t, st);
         }
       }
     }
     if (__ballot_sync(0xffffffffu, my >= 0) == 0) break;
     if (my >= 0) {
-      if (trav_run<ANY_HIT, SPH, ORDERED>(sc, t, st, exhausted ? 0 : VG_REFILL_BELOW)) {
+      if (trav_run<ANY_HIT, SPH, ORDERED, SMEM>(sc, t, st, cs, exhausted ? 0 : VG_REFILL_BELOW)) {
+        if (SMEM && IO::kHitRecord) finalize_hit(sc, cs, t);
         io.store(my, t.r, t.h, st.overflow);
         nodes_acc += t.h.cnt & 0xffffu;
         tris_acc += t.h.cnt >> 16;
@@ -955,21 +1040,6 @@ __device__ __forceinline__ bool tri_candidate(float pkx, float pky, float pkz, f
   }
   o.fU = fU; o.fV = fV; o.fW = fW; o.det = det; o.T = T;
   return true;
-}
-
-// Per warp: 32 per-LANE blocks of two float4 — the leaf-phase parameters of the lane's current ray {pkx, pky, pkz, s0} {s1, s2, xsign,
-// Tclosest}, written ONCE when the ray is set up (coop_publish) — then 32 per-RANK records {kz | motion << 8 | owner lane << 16, leaf base,
-// item start, Ray.Time} written by the lanes that hold a leaf in the current phase. Round 2 (first half) rewrote all three float4 per
-// leaf visit from registers the 64-register kernels had spilled (5 LDL + 3 STS.128 per lane and phase in the SASS); now the eight
-// parameters leave the register file for good after Ray.Setup and a leaf visit costs one STS.128 (+ one STS.32 for the live Tclosest
-// of a closest-hit ray).
-struct CoopSmem {
-  float4* rp;
-};
-__device__ __forceinline__ void coop_publish(const CoopSmem& cs, const RayState& r) {
-  float4* b = cs.rp + (threadIdx.x & 31) * 2;
-  b[0] = make_float4(r.pkx, r.pky, r.pkz, r.s0);
-  b[1] = make_float4(r.s1, r.s2, __uint_as_float(r.xsign), r.tclosest);
 }
 
 // The (ray, triangle) items of one 32-wide window. KZ >= 0: every item's ray has dominant axis KZ (static component access).
@@ -1181,36 +1251,16 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
     const bool mleaf = leaf && ((uint32_t)t.cur & kMotionTriBit);
     if (__any_sync(0xffffffffu, leaf)) {
       bool leafhit = false;
-#ifndef VG_COOP_UNIFORM
-#define VG_COOP_UNIFORM 0
-#endif
-#if VG_COOP_UNIFORM
-      // Pixel-coherent warps (render.cu: path_index) often arrive with most lanes in the SAME static leaf. Then the plain per-lane
-      // loop over that leaf's triangles (every lane its own ray, the triangle record a broadcast load) does the same tests without
-      // the cooperative phase's bookkeeping; below VG_COOP_UNIFORM lanes the cooperative enumeration is the cheaper one.
-      // MEASURED (round 2, B200) and left OFF: thresholds 16 / 24 / 28 all lose — C2 shadow 34.25 / 34.24 / 34.28 vs 33.33 ms, C3
-      // shadow 290.8 vs 280.3 ms, incoherent batch 2331 vs 2361 Mrays/s: the second inlined leaf loop costs more (code size, registers
-      // across the vote) than the bookkeeping it saves.
-      const uint32_t lm = __ballot_sync(0xffffffffu, leaf && !mleaf);
-      const uint32_t un0 = __shfl_sync(0xffffffffu, (uint32_t)t.cur, lm ? __ffs(lm) - 1 : 0);
-      const bool uni = __popc(lm) >= VG_COOP_UNIFORM && __all_sync(0xffffffffu, !leaf || (!mleaf && (uint32_t)t.cur == un0));
-      if (uni) {
-        if (leaf) leafhit = leaf_step(sc, t, (uint32_t)t.cur);
-      } else
-#endif
+// (A hybrid that ran the plain per-lane loop when >= 16 / 24 / 28 lanes of the warp sat in the SAME static leaf was MEASURED in
+      // round 2 and removed: C2 shadow 34.25 / 34.24 / 34.28 vs 33.33 ms, C3 shadow 290.8 vs 280.3 ms, incoherent batch 2331 vs 2361 Mrays/s —
+      // the second inlined leaf loop cost more in code size and registers across the vote than the bookkeeping it saved.)
       leafhit = coop_leaves<MOT, !ANY_HIT>(sc, t, leaf && (MOT || !mleaf), cs);
       if (!MOT && mleaf) {  // (kernels without the motion items in the cooperative phase: per lane, from the lane's published block)
         const uint32_t un = (uint32_t)t.cur;
         const int count = (int)(un & 15u) + 1;
         t.h.cnt += (uint32_t)count << 16;
-        RayState rr = t.r;
-        const float4 q0 = cs.rp[lane * 2], q1 = cs.rp[lane * 2 + 1];
-        rr.pkx = q0.x; rr.pky = q0.y; rr.pkz = q0.z; rr.s0 = q0.w;
-        rr.s1 = q1.x; rr.s2 = q1.y; rr.xsign = __float_as_uint(q1.z);
-        rr.kx = rr.kz == 2 ? 0 : rr.kz + 1;
-        rr.ky = rr.kx == 2 ? 0 : rr.kx + 1;
-        leafhit = leaf_motion<-1>(sc, rr, t.h, (int)((un >> 4) & kLeafBaseMask), count);
-        t.r.tclosest = rr.tclosest;
+        const LeafRay lr = leaf_ray(cs, t.r.kz);
+        leafhit = leaf_motion<-1, false>(sc, lr, t.r.time, t.r.tclosest, t.h, (int)((un >> 4) & kLeafBaseMask), count);
       }
       if (leaf) {
         if (XF && leafhit) {
@@ -1257,24 +1307,22 @@ __device__ __forceinline__ void trace_persistent(const DevScene& sc, IO& io, Sta
   constexpr bool SPH = (VARIANT & 8) != 0;
   constexpr bool XF = (VARIANT & 16) != 0;
   constexpr bool MOT = (VARIANT & 64) != 0 || XF;  // motion-triangle leaves take part in the cooperative leaf phase (variants 2, 3)
+  CoopSmem cs;
+  cs.rp = reinterpret_cast<float4*>(warp_smem);  // variants 2, 3, 4: the per-lane leaf-parameter blocks at [0, 1024)
   if (V == 1) {
     WarpStage ws;
     ws.buf = reinterpret_cast<float4*>(warp_smem);
     ws.bar = reinterpret_cast<unsigned long long*>(warp_smem + 2048);
-    trace_persistent_tma<ANY_HIT>(sc, io, st, ws, nodes_acc, tris_acc);
+    trace_persistent_tma<ANY_HIT>(sc, io, st, ws, cs, nodes_acc, tris_acc);
   } else if (V == 2) {
-    CoopSmem cs;
-    cs.rp = reinterpret_cast<float4*>(warp_smem);
     trace_persistent_coop<ANY_HIT, true, SPH, XF, MOT>(sc, io, st, cs, nodes_acc, tris_acc);
   } else if (V == 3) {
-    CoopSmem cs;
-    cs.rp = reinterpret_cast<float4*>(warp_smem);
     trace_persistent_coop<ANY_HIT, false, SPH, XF, MOT>(sc, io, st, cs, nodes_acc, tris_acc);
   } else if (V == 4) {  // per-lane loop without the ordered push: occlusion-only rays that are coherent (the integrator's level-0 shadow queue)
     static_assert(V != 4 || ANY_HIT, "the unordered per-lane loop is for occlusion-only rays");
-    trace_persistent_ldg<ANY_HIT, SPH, false>(sc, io, st, nodes_acc, tris_acc);
+    trace_persistent_ldg<ANY_HIT, SPH, false, true>(sc, io, st, cs, nodes_acc, tris_acc);
   } else {
-    trace_persistent_ldg<ANY_HIT, SPH, true>(sc, io, st, nodes_acc, tris_acc);
+    trace_persistent_ldg<ANY_HIT, SPH, true, false>(sc, io, st, cs, nodes_acc, tris_acc);
   }
 }
 
