@@ -200,6 +200,13 @@ __device__ __forceinline__ float pick(float x, float y, float z, int k) {
 }
 // The leaf-phase view of a ray: what the triangle tests read. The persistent kernels publish it to shared memory once per ray
 // (coop_publish) and load it back at a leaf, so the eight values do not occupy registers (or local memory) during the node loop.
+// The occlusion-only per-lane kernel leaves a leaf at its first accepted triangle (the reference finishes the leaf and then returns,
+// intersect.go:231-236: the same "occluded"). Measured: C2 shadow 29.12 -> 28.49 ms. Also measured on that kernel and left as they
+// were: refill below 8 / 16 / 24 / 28 active lanes 29.09 / 29.12 / 29.32 / 30.51 ms, 256-bit node loads 29.31 ms, 9 CTAs per SM
+// (56 registers) 30.44 ms.
+#ifndef VG_OCCL_LEAF_EXIT
+#define VG_OCCL_LEAF_EXIT 1
+#endif
 struct LeafRay {
   float pkx, pky, pkz, s0, s1, s2;
   uint32_t xsign;
@@ -560,6 +567,9 @@ __device__ __forceinline__ bool leaf_static(const DevScene& sc, const LeafRay& l
         h.prim = __float_as_int(v1.w);
       }
       leafhit = true;
+#if VG_OCCL_LEAF_EXIT
+      if (DEFER) break;
+#endif
     }
   }
   return leafhit;
@@ -728,7 +738,10 @@ __device__ __forceinline__ bool trav_run(const DevScene& sc, TravState& t, Stack
 #ifndef VG_PERLANE_WIDE
 #define VG_PERLANE_WIDE 0
 #endif
-    while (t.cur >= 0) node_step<ORDERED, VG_PERLANE_WIDE != 0>(sc, t, st);
+#ifndef VG_OCCL_WIDE
+#define VG_OCCL_WIDE VG_PERLANE_WIDE
+#endif
+    while (t.cur >= 0) node_step<ORDERED, (SMEM ? VG_OCCL_WIDE : VG_PERLANE_WIDE) != 0>(sc, t, st);
     while (t.cur < -1) {
       const uint32_t un = (uint32_t)t.cur;
       if (un & kGeomBit) {
@@ -921,7 +934,10 @@ __device__ __forceinline__ void trace_persistent_ldg(const DevScene& sc, IO& io,
     }
     if (__ballot_sync(0xffffffffu, my >= 0) == 0) break;
     if (my >= 0) {
-      if (trav_run<ANY_HIT, SPH, ORDERED, SMEM>(sc, t, st, cs, exhausted ? 0 : VG_REFILL_BELOW)) {
+#ifndef VG_REFILL_BELOW_OCCL
+#define VG_REFILL_BELOW_OCCL VG_REFILL_BELOW
+#endif
+      if (trav_run<ANY_HIT, SPH, ORDERED, SMEM>(sc, t, st, cs, exhausted ? 0 : (SMEM ? VG_REFILL_BELOW_OCCL : VG_REFILL_BELOW))) {
         if (SMEM && IO::kHitRecord) finalize_hit(sc, cs, t);
         io.store(my, t.r, t.h, st.overflow);
         nodes_acc += t.h.cnt & 0xffffu;
