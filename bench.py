@@ -319,14 +319,6 @@ def time_batch(dev, torch, rays, steps, warmup, compact_e2e=True):
         for _ in range(reps):
             dev.trace(inp, out=out, compact=compact)
         e2e[name] = (time.perf_counter() - t0) / reps * 1e3
-    if "pd_compact" in e2e:     # the same call as ONE persistent launch over the arriving ray array (option stream_batch 1; measured slower)
-        dev.set_option("stream_batch", 1)
-        dev.trace(pin_pd, out=pin_cpd, compact=True)
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            dev.trace(pin_pd, out=pin_cpd, compact=True)
-        e2e["pd_compact_streamed_launch"] = (time.perf_counter() - t0) / reps * 1e3
-        dev.set_option("stream_batch", 0)
     if "pd_compact" in e2e and pin_cpd.tobytes() != pin_c.tobytes():
         raise SystemExit("bench: VG_TRACE_RAYS_PD hits differ from the VgRay hits")
     res = {"rays": n, "ms_per_step": float(np.mean(ms)), "ms_best": float(np.min(ms)), "device_ms_total": float(np.sum(ms)),

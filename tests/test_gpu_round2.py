@@ -343,26 +343,22 @@ def test_pd_ray_records_give_the_same_hits(built_library, traversal):
     gc = dev.trace(pd, compact=True)
     assert np.array_equal(gc["t"].view(np.uint32), want["t"].view(np.uint32)) and np.array_equal(gc["u"], want["u"])
     assert np.array_equal(gc["slot"] >= 0, want["prim"] >= 0)
-    # page-locked buffers: the streamed persistent launch (stream_batch 1: chunks of 2^12 rays arriving while the kernel runs) and the
-    # chunked three-stream pipeline (stream_batch 0: n >= 2 chunks of 2^14), both record layouts
+    # page-locked buffers take the chunked three-stream pipeline (n >= 2 chunks of 2^14), both record layouts
     n = len(pd)
-    dev.set_option("stream_chunk_log2", 12)
     pin_r = torch.from_numpy(pd.view(np.uint8).reshape(n, 24)).pin_memory().numpy().reshape(-1).view(RAYPD_DTYPE)
     pin_r32 = torch.from_numpy(rays.view(np.uint8).reshape(n, 32)).pin_memory().numpy().reshape(-1).view(rays.dtype)
     pin_h = torch.empty((n, 32), dtype=torch.uint8, pin_memory=True).numpy().reshape(-1).view(HIT_DTYPE)
     pin_c = torch.empty((n, 16), dtype=torch.uint8, pin_memory=True).numpy().reshape(-1).view(HITC_DTYPE)
-    for streamed in (1, 0, 1):
-        dev.set_option("stream_batch", streamed)
-        for src in (pin_r, pin_r32):
-            pin_h[:] = 0
-            dev.trace(src, out=pin_h)
-            assert pin_h.tobytes() == want.tobytes(), (streamed, src.dtype.itemsize)
-            pin_c[:] = 0
-            dev.trace(src, out=pin_c, compact=True)
-            assert pin_c.tobytes() == gc.tobytes(), (streamed, src.dtype.itemsize)
+    for src in (pin_r, pin_r32):
         pin_h[:] = 0
-        dev.trace(pin_r32, out=pin_h, any_hit=True)
-        assert np.array_equal(pin_h["prim"] >= 0, want["prim"] >= 0)
+        dev.trace(src, out=pin_h)
+        assert pin_h.tobytes() == want.tobytes(), src.dtype.itemsize
+        pin_c[:] = 0
+        dev.trace(src, out=pin_c, compact=True)
+        assert pin_c.tobytes() == gc.tobytes(), src.dtype.itemsize
+    pin_h[:] = 0
+    dev.trace(pin_r32, out=pin_h, any_hit=True)
+    assert np.array_equal(pin_h["prim"] >= 0, want["prim"] >= 0)
     # device-resident records
     d_r = torch.from_numpy(pd.view(np.uint8).reshape(n, 24)).cuda()
     d_h = torch.empty((n, 32), dtype=torch.uint8, device="cuda")

@@ -179,14 +179,10 @@ void vg_destroy(vg_ctx* ctx) {
   ctx->d_mtris.release(); ctx->d_normals.release(); ctx->d_geoms.release(); ctx->d_prim_material.release();
   ctx->d_tri_uv.release(); ctx->d_texels.release(); ctx->d_tex_levels.release(); ctx->d_textures.release();
   ctx->d_xforms.release(); ctx->d_xf_keys.release(); ctx->d_xf_static.release();
-  ctx->d_rays.release(); ctx->d_hits.release(); ctx->d_counters.release(); ctx->d_stream_sync.release(); ctx->d_cam_keys.release();
+  ctx->d_rays.release(); ctx->d_hits.release(); ctx->d_counters.release(); ctx->d_cam_keys.release();
   for (int i = 0; i < 3; i++) {
     if (ctx->pipe_stream[i]) cudaStreamDestroy(ctx->pipe_stream[i]);
     if (ctx->pipe_done[i]) cudaEventDestroy(ctx->pipe_done[i]);
-  }
-  for (int i = 0; i < 4; i++) {
-    if (ctx->stream_pipe[i]) cudaStreamDestroy(ctx->stream_pipe[i]);
-    if (ctx->stream_pipe_done[i]) cudaEventDestroy(ctx->stream_pipe_done[i]);
   }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -991,11 +987,6 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
     ctx->opt_shadow_level0_per_lane = value;
   }
   else if (!std::strcmp(name, "accumulate_tiled")) ctx->opt_accumulate_tiled = value != 0;
-  else if (!std::strcmp(name, "stream_batch")) ctx->opt_stream_batch = value != 0;
-  else if (!std::strcmp(name, "stream_chunk_log2")) {
-    if (value < 12 || value > 24) return ctx->fail(VG_ERR_INVALID, "stream_chunk_log2 outside [12,24]");
-    ctx->opt_stream_chunk_log2 = value;
-  }
   else if (!std::strcmp(name, "frame_slices_multi")) ctx->opt_frame_slices_multi = value != 0;
   else if (!std::strcmp(name, "frame_slices_min_paths_off")) ctx->opt_frame_slices_force = value != 0;
   else if (!std::strcmp(name, "frame_slices")) {
@@ -1071,32 +1062,6 @@ int vg_trace_batch_device(vg_ctx* ctx, const VgRay* d_rays, int64_t n, VgHit* d_
   return trace_device_locked(ctx, d_rays, n, d_hits, flags);
 }
 
-// Stream memory operations (cuStreamWriteValue32 / cuStreamWaitValue32) through the runtime's driver entry-point query: no link-time
-// dependency on libcuda. Null when the driver does not export them.
-struct StreamMemOps {
-  int (*write32)(cudaStream_t, unsigned long long, unsigned, unsigned);
-  int (*wait32)(cudaStream_t, unsigned long long, unsigned, unsigned);
-};
-static const StreamMemOps* stream_memops() {
-  static StreamMemOps ops{nullptr, nullptr};
-  static int state = 0;  // 0 = not tried, 1 = available, -1 = not
-  if (state == 0) {
-    void *w = nullptr, *q = nullptr;
-    cudaDriverEntryPointQueryResult r1, r2;
-    const bool ok = cudaGetDriverEntryPoint("cuStreamWriteValue32", &w, cudaEnableDefault, &r1) == cudaSuccess && r1 == cudaDriverEntryPointSuccess && w &&
-                    cudaGetDriverEntryPoint("cuStreamWaitValue32", &q, cudaEnableDefault, &r2) == cudaSuccess && r2 == cudaDriverEntryPointSuccess && q;
-    if (ok) {
-      ops.write32 = reinterpret_cast<int (*)(cudaStream_t, unsigned long long, unsigned, unsigned)>(w);
-      ops.wait32 = reinterpret_cast<int (*)(cudaStream_t, unsigned long long, unsigned, unsigned)>(q);
-      state = 1;
-    } else {
-      cudaGetLastError();
-      state = -1;
-    }
-  }
-  return state == 1 ? &ops : nullptr;
-}
-
 static bool pinned_host(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -1139,77 +1104,6 @@ int vg_trace_batch(vg_ctx* ctx, const VgRay* rays, int64_t n, VgHit* hits, uint3
     cudaGetLastError();
   }
   const bool both_pinned = n >= 2 * chunk && pinned_host(rays) && pinned_host(hits);
-  const int64_t schunk = (int64_t)1 << ctx->opt_stream_chunk_log2;
-  if (both_pinned && ctx->opt_stream_batch && n >= 4 * schunk && ctx->dev.n_mtris == 0 && ctx->dev.n_spheres == 0 && ctx->dev.n_xforms == 0 && stream_memops()) {
-    // Page-locked caller buffers, static PolyMesh scene: ONE persistent launch over the whole batch while the rays are still arriving
-    // (kernels_trace.cu: BatchIO<true>). The upload stream raises the "chunks resident" word after every chunk with a stream
-    // memory operation; the kernel's lanes wait at that frontier; the download stream waits (cuStreamWaitValue32) for a chunk's
-    // finished-ray count before it copies the chunk's hits back. Against the three-stream pipeline of per-chunk launches below this
-    // removes the ramp and tail of every chunk kernel (a 2^19-ray chunk is 3.5 rays per resident thread).
-    const StreamMemOps* mo = stream_memops();
-    const int64_t nch = (n + schunk - 1) / schunk;
-    VG_CUDA(ctx, ctx->d_stream_sync.reserve((size_t)(32 + 2 * nch)));
-    // two upload and two download streams take alternate chunks: a stream memory operation is a serialisation point of its stream
-    // (measured ~14 us per chunk with one stream each way), the other stream's copy fills it
-    for (int s = 0; s < 4; s++)
-      if (!ctx->stream_pipe[s]) VG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream_pipe[s], cudaStreamNonBlocking));
-    for (int s = 0; s < 4; s++)
-      if (!ctx->stream_pipe_done[s]) VG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stream_pipe_done[s], cudaEventDisableTiming));
-    static int blocks_per_sm = 0;
-    if (!blocks_per_sm) blocks_per_sm = trace_batch_blocks_per_sm();
-    unsigned* const sync = ctx->d_stream_sync.p;  // [1] error flag, [32 + c] rays of chunk c finished, [32 + nch + c] chunk c resident
-    unsigned* const done = sync + 32;
-    unsigned* const ready = sync + 32 + nch;
-    VG_CUDA(ctx, cudaMemsetAsync(sync, 0, (size_t)(32 + 2 * nch) * sizeof(unsigned), ctx->stream));
-    VG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    for (int s = 0; s < 4; s++) VG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_pipe[s], ctx->ev0, 0));
-    const long long grid = std::min<long long>((long long)ctx->sm_count * blocks_per_sm, (n + kTraceBlock - 1) / kTraceBlock);
-    VG_CUDA(ctx, launch_trace_batch_streamed(ctx->dev, ctx->d_rays.p, ctx->d_hits.p, n, (flags & VG_TRACE_ANY_HIT) != 0, ctx->opt_traversal == 2 ? 2 : 0,
-                                             ctx->d_counters.p, ctx->d_counters.p + 1, (int)grid, ctx->stream, mode, ready, done, sync + 1, ctx->opt_stream_chunk_log2));
-    int rc_up = 0;
-    for (int64_t c = 0; c < nch && !rc_up; c++) {
-      const int64_t off = c * schunk, m = std::min(schunk, n - off);
-      cudaStream_t up = ctx->stream_pipe[c & 1];
-      if (cudaMemcpyAsync(d_rays_b + (size_t)off * ray_bytes, rays_b + (size_t)off * ray_bytes, (size_t)m * ray_bytes, cudaMemcpyHostToDevice, up) != cudaSuccess) rc_up = 1;
-      else if (mo->write32(up, (unsigned long long)(uintptr_t)(ready + c), 1u, 0) != 0) rc_up = 1;
-    }
-    if (rc_up) {  // release the kernel (it would otherwise wait out its timeout), then report
-      cudaGetLastError();
-      cudaStreamSynchronize(ctx->stream_pipe[0]);
-      cudaStreamSynchronize(ctx->stream_pipe[1]);
-      cudaMemset(ready, 1, (size_t)nch * sizeof(unsigned));
-      cudaStreamSynchronize(ctx->stream);
-      return ctx->fail(VG_ERR_CUDA, "vg_trace_batch: streamed upload failed");
-    }
-    for (int64_t c = 0; c < nch; c++) {
-      const int64_t off = c * schunk, m = std::min(schunk, n - off);
-      cudaStream_t down = ctx->stream_pipe[2 + (c & 1)];
-      if (mo->wait32(down, (unsigned long long)(uintptr_t)(done + c), (unsigned)m, 0 /* CU_STREAM_WAIT_VALUE_GEQ */) != 0) {
-        cudaStreamSynchronize(ctx->stream);  // the kernel finishes on its own (all chunks were uploaded); then copy the rest in order
-        cudaStreamSynchronize(ctx->stream_pipe[2]);
-        cudaStreamSynchronize(ctx->stream_pipe[3]);
-        VG_CUDA(ctx, cudaMemcpy(hits_b + (size_t)off * hit_bytes, d_hits_b + (size_t)off * hit_bytes, (size_t)(n - off) * hit_bytes, cudaMemcpyDeviceToHost));
-        break;
-      }
-      VG_CUDA(ctx, cudaMemcpyAsync(hits_b + (size_t)off * hit_bytes, d_hits_b + (size_t)off * hit_bytes, (size_t)m * hit_bytes, cudaMemcpyDeviceToHost, down));
-    }
-    for (int s = 0; s < 4; s++) {
-      VG_CUDA(ctx, cudaEventRecord(ctx->stream_pipe_done[s], ctx->stream_pipe[s]));
-      VG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->stream_pipe_done[s], 0));
-    }
-    VG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    VG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    unsigned flag = 0;
-    VG_CUDA(ctx, cudaMemcpy(&flag, sync + 1, sizeof(flag), cudaMemcpyDeviceToHost));
-    if (flag) return ctx->fail(VG_ERR_CUDA, "vg_trace_batch: the streamed kernel timed out waiting for its rays");
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-    ctx->stats.trace_ms = ms;  // copies included: the whole streamed call
-    ctx->stats.rays += (uint64_t)n;
-    if (flags & VG_TRACE_ANY_HIT) ctx->stats.shadow_rays += (uint64_t)n;
-    ctx->stats.kernel_launches += 1;
-    return VG_OK;
-  }
   if (both_pinned) {
     // Page-locked caller buffers: the batch goes through in chunks on three streams, so the H2D copy of one chunk, the
     // traversal of the previous one and the D2H copy of the one before overlap (PCIe is full duplex; each direction carries

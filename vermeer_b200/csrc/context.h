@@ -98,8 +98,6 @@ struct vg_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};  // vg_trace_batch with page-locked buffers: copy/compute overlap
   cudaEvent_t pipe_done[3] = {nullptr, nullptr, nullptr};
-  cudaStream_t stream_pipe[4] = {nullptr, nullptr, nullptr, nullptr};  // streamed vg_trace_batch: two upload, two download streams
-  cudaEvent_t stream_pipe_done[4] = {nullptr, nullptr, nullptr, nullptr};
 
   // staged scene (reference formats)
   std::vector<vg::MeshStage> meshes;
@@ -123,7 +121,6 @@ struct vg_ctx {
   vg::DevBuf<VgRay> d_rays;
   vg::DevBuf<VgHit> d_hits;
   vg::DevBuf<unsigned long long> d_counters;  // [0] queue head, [1..] stats
-  vg::DevBuf<unsigned> d_stream_sync;         // streamed vg_trace_batch: [1] error, [32 + c] finished rays of chunk c, [32 + nch + c] chunk c resident
 
   // texture store: every level of every texture in one texel array
   std::vector<vg::DevTexture> textures;
@@ -173,13 +170,6 @@ struct vg_ctx {
   int opt_iter_group = 32;       // a warp's 32 paths = (32/iter_group) pixels x iter_group iterations of the batch (render.cu: path_index)
   int opt_pixel_block = 1;       // paths of one warp cover an 8x4 pixel block of a tile (1) or a 32x1 row (0)
   int opt_batch_chunk_log2 = 19; // vg_trace_batch copy pipeline: rays per stage
-  // vg_trace_batch with page-locked buffers on static scenes: 1 = one persistent launch over the arriving ray array, 0 = the chunked
-  // three-stream pipeline. MEASURED (round 2, 5.94 M-ray batch, 24-byte rays / 16-byte hits) and left OFF: 4.42 ms per call at the best
-  // chunk size (2^18; 5.0 / 4.7 / 4.8 ms at 2^16 / 2^17 / 2^19) against 3.93 ms for the pipeline on the same box — the stream memory
-  // operations serialise with the copies of their stream (~14 us per chunk with one stream each way) and the pipeline already sits
-  // within ~10 % of what the PCIe link carries in both directions at once.
-  int opt_stream_batch = 0;
-  int opt_stream_chunk_log2 = 18; // rays per upload / download chunk of the streamed call
   int opt_l2_persist_nodes = 0;  // persisting-L2 access-policy window over the static node array
   int opt_zero_copy_batch = 0;   // vg_trace_batch with page-locked buffers: kernel reads rays / writes hits over PCIe itself (1) or 3-stream copy pipeline (0)
   int opt_node_order = 0;        // device order of a mesh's nodes: 0 = the reference's preorder, 1 = breadth-first (siblings adjacent)

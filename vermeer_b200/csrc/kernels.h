@@ -52,10 +52,6 @@ inline size_t trace_smem_bytes(int variant) { return (size_t)(kTraceBlock / 32) 
 // kernels_trace.cu
 cudaError_t launch_trace_batch(const DevScene& sc, const VgRay* d_rays, VgHit* d_hits, long long n, bool any_hit, int variant,
                                unsigned long long* d_counter, unsigned long long* d_stats, int grid, cudaStream_t stream, int mode = 0);  // mode: bit 0 = 16-byte compact hits, bit 1 = 24-byte {P, D} ray records
-// the same over a ray array that is still arriving (static PolyMesh scenes; variant 0 or 2): see BatchIO<true> in kernels_trace.cu
-cudaError_t launch_trace_batch_streamed(const DevScene& sc, const VgRay* d_rays, VgHit* d_hits, long long n, bool any_hit, int variant,
-                                        unsigned long long* d_counter, unsigned long long* d_stats, int grid, cudaStream_t stream, int mode,
-                                        const unsigned* d_ready, unsigned* d_done, unsigned* d_err, int chunk_log2);
 int trace_batch_blocks_per_sm();
 
 }  // namespace vg
