@@ -544,18 +544,24 @@ __device__ __forceinline__ LeafRay leaf_ray(const CoopSmem& cs, int kz) {
 // Triangle loops of one leaf. The next triangle's loads are issued before the current one is tested. An accepted triangle only
 // records its slot (h.prim = -2 static / -3 motion): U, V, W and the ids are recomputed from the slot when the ray is stored
 // (finalize_hit), so they are not carried through the traversal loops.
+// How the next triangle of a leaf is fetched ahead (VG_LEAF_PIPE): 1 = into a second register set that is copied into the current one
+// every iteration (12 MOV per triangle: `if (i + 1 < count)` is the largest line of the ncu source page, 6.5 %), 2 = a
+// prefetch.global.L1 of the next record and plain loads (no second set, no copies), 0 = nothing. An unroll by two over two
+// alternating register sets was MEASURED out at compile time: under the 64/72-register caps it spills both sets (stack frame
+// 368 -> 576 B, LDL/STL inside the triangle loop).
+// MEASURED (C2, closest / shadow ms): 1 -> 17.85 / 30.48, 0 -> 18.22 / 28.33, 2 -> 18.12 / 29.04: the closest-hit per-lane kernels
+// keep the second register set, the occlusion-only kernel (64 registers) fetches nothing ahead.
+#ifndef VG_LEAF_PIPE
+#define VG_LEAF_PIPE 1
+#endif
+#ifndef VG_LEAF_PIPE_OCCL
+#define VG_LEAF_PIPE_OCCL 0
+#endif
 template <int KZ, bool DEFER>
 __device__ __forceinline__ bool leaf_static(const DevScene& sc, const LeafRay& lr, float& tclosest, HitState& h, int base, int count) {
   bool leafhit = false;
   const float4* tp = sc.tris + (size_t)base * kTriStride;
-  float4 n0, n1, n2;
-  ld_tri(tp, n0, n1, n2);
-  for (int i = 0; i < count; i++) {
-    const float4 v0 = n0, v1 = n1, v2 = n2;
-    if (i + 1 < count) {
-      tp += kTriStride;
-      ld_tri(tp, n0, n1, n2);
-    }
+  auto test = [&](const float4& v0, const float4& v1, const float4& v2, int i) -> bool {
     float U, V, W;
     if (tri_test<false, KZ>(lr, tclosest, make_float3(v0.x, v0.y, v0.z), make_float3(v1.x, v1.y, v1.z), make_float3(v2.x, v2.y, v2.z), v2.w, &U, &V, &W)) {
       h.slot = base + i;
@@ -567,10 +573,31 @@ __device__ __forceinline__ bool leaf_static(const DevScene& sc, const LeafRay& l
         h.prim = __float_as_int(v1.w);
       }
       leafhit = true;
-#if VG_OCCL_LEAF_EXIT
-      if (DEFER) break;
-#endif
+      return true;
     }
+    return false;
+  };
+  constexpr int PIPE = DEFER ? VG_LEAF_PIPE_OCCL : VG_LEAF_PIPE;
+  if (PIPE != 1) {
+    for (int i = 0; i < count; i++, tp += kTriStride) {
+      float4 v0, v1, v2;
+      ld_tri(tp, v0, v1, v2);
+      if (PIPE == 2 && i + 1 < count) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + kTriStride));
+      const bool hit = test(v0, v1, v2, i);
+      if (VG_OCCL_LEAF_EXIT && DEFER && hit) break;
+    }
+    return leafhit;
+  }
+  float4 n0, n1, n2;
+  ld_tri(tp, n0, n1, n2);
+  for (int i = 0; i < count; i++) {
+    const float4 v0 = n0, v1 = n1, v2 = n2;
+    if (i + 1 < count) {
+      tp += kTriStride;
+      ld_tri(tp, n0, n1, n2);
+    }
+    const bool hit = test(v0, v1, v2, i);
+    if (VG_OCCL_LEAF_EXIT && DEFER && hit) break;
   }
   return leafhit;
 }
