@@ -1287,6 +1287,9 @@ __device__ __forceinline__ void trace_persistent_coop(const DevScene& sc, IO& io
       const unsigned nm = __ballot_sync(0xffffffffu, t.cur >= 0);
       if (nm == 0) break;
       if (__popc(nm) < VG_NODE_MIN && __any_sync(0xffffffffu, t.cur < -1)) break;
+      // (MEASURED and removed, round 2: an occlusion-only lane that holds a triangle leaf while the node phase goes on trading it for the
+      // interior node on top of its stack instead of idling — C2 shadow (cooperative kernel) 31.02 -> 32.04 ms, C3 248.2 -> 262.9 ms, C4 55.3 ->
+      // 56.5 ms: the deferred leaves arrive in thinner leaf phases and occluded rays find their occluder later.)
       if (t.cur >= 0) node_step<ORDERED, VG_LDG256 != 0>(sc, t, st);
     }
     // leaf phase
