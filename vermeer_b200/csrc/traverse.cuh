@@ -1038,6 +1038,15 @@ static const int kCoopBytesPerWarp = 32 * 48;  // 32 ray-parameter blocks of 3 f
 struct TriCand {
   float fU, fV, fW, det, T;
 };
+// The per-rank leaf record of a cooperative leaf phase: x = kz (bits 0-1) | motion leaf (bit 2) | owner lane (bits 3-7) | key count of
+// the leaf's mesh (bits 8-15, motion leaves) | first item of the leaf in the phase's enumeration (bits 16-25); y = first triangle slot;
+// z = the mesh's key stride in slots (motion leaves); w = Ray.Time. The leaf's lane looks the mesh up ONCE; round 2 (first half) had
+// every (ray, triangle) item of a motion leaf repeat the two dependent loads (slot record -> geom record) before its own six.
+__device__ __forceinline__ int rec_kz(int x) { return x & 3; }
+__device__ __forceinline__ bool rec_motion(int x) { return (x & 4) != 0; }
+__device__ __forceinline__ int rec_owner(int x) { return (x >> 3) & 31; }
+__device__ __forceinline__ int rec_keys(int x) { return (x >> 8) & 255; }
+__device__ __forceinline__ int rec_start(int x) { return (x >> 16) & 1023; }
 
 // Tclosest-independent part of the watertight test + the entry-Tclosest cull. Returns "candidate".
 template <bool MOTION, int KZ>
@@ -1088,33 +1097,33 @@ __device__ __forceinline__ bool tri_candidate(float pkx, float pky, float pkz, f
 // The (ray, triangle) items of one 32-wide window. KZ >= 0: every item's ray has dominant axis KZ (static component access).
 template <int KZ>
 __device__ __forceinline__ bool coop_item(const DevScene& sc, const float4 q0, const float4 q1, const float4 q2, int j, TriCand& tc) {
-  const int i = j - __float_as_int(q2.z);
+  const int i = j - rec_start(__float_as_int(q2.x));
   const float4* tp = sc.tris + (size_t)(__float_as_int(q2.y) + i) * kTriStride;
   float4 v0, v1, v2;
   ld_tri(tp, v0, v1, v2);
-  return tri_candidate<false, KZ>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, __float_as_uint(q1.z), __float_as_int(q2.x) & 3, q1.w, make_float3(v0.x, v0.y, v0.z),
+  return tri_candidate<false, KZ>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, __float_as_uint(q1.z), rec_kz(__float_as_int(q2.x)), q1.w, make_float3(v0.x, v0.y, v0.z),
                                   make_float3(v1.x, v1.y, v1.z), make_float3(v2.x, v2.y, v2.z), v2.w, tc);
 }
 
 // A motion-triangle item (polymesh/trace.go:547-554,556-622): the two keys' vertices are lerped at the ray's time; the key count
 // and key stride come from the item's geom record.
 __device__ __forceinline__ bool coop_item_motion(const DevScene& sc, const float4 q0, const float4 q1, const float4 q2, int j, TriCand& tc) {
-  const int i = j - __float_as_int(q2.z);
+  const int x = __float_as_int(q2.x);
+  const int i = j - rec_start(x);
   const size_t slot = (size_t)(__float_as_int(q2.y) + i);
-  const float4* k0 = sc.mtris + slot * 3;  // key-0 record of the slot: geom id in [0].w, RayBias in [2].w
-  const DevGeom gm = sc.geoms[__float_as_int(ldg4(k0).w)];
-  const float k = q2.w * (float)(gm.keys - 1);
+  const size_t stride = (size_t)__float_as_int(q2.z);
+  const float k = q2.w * (float)(rec_keys(x) - 1);
   const float fk = floorf(k);
   const float tm = k - fk, om = 1.0f - tm;
   const int key = (int)fk, key2 = (int)ceilf(k);
-  const float4* ta = sc.mtris + (slot + (size_t)key * gm.tri_key_stride) * 3;
-  const float4* tb = sc.mtris + (slot + (size_t)key2 * gm.tri_key_stride) * 3;
+  const float4* ta = sc.mtris + (slot + (size_t)key * stride) * 3;
+  const float4* tb = sc.mtris + (slot + (size_t)key2 * stride) * 3;
   const float4 a0 = ldg4(ta), a1 = ldg4(ta + 1), a2 = ldg4(ta + 2);
   const float4 b0 = ldg4(tb), b1 = ldg4(tb + 1), b2 = ldg4(tb + 2);
   const float3 p0 = make_float3(om * a0.x + tm * b0.x, om * a0.y + tm * b0.y, om * a0.z + tm * b0.z);
   const float3 p1 = make_float3(om * a1.x + tm * b1.x, om * a1.y + tm * b1.y, om * a1.z + tm * b1.z);
   const float3 p2 = make_float3(om * a2.x + tm * b2.x, om * a2.y + tm * b2.y, om * a2.z + tm * b2.z);
-  return tri_candidate<true, -1>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, __float_as_uint(q1.z), __float_as_int(q2.x) & 3, q1.w, p0, p1, p2, a2.w, tc);  // the w fields (geom id, face, RayBias) are the same in every key's record
+  return tri_candidate<true, -1>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, __float_as_uint(q1.z), rec_kz(x), q1.w, p0, p1, p2, a2.w, tc);  // the w fields (geom id, face, RayBias) are the same in every key's record
 }
 
 // One cooperative leaf phase. `isleaf`: this lane's t.cur is a triangle leaf that takes part (static; also motion leaves when
@@ -1140,9 +1149,14 @@ __device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bo
   if (isleaf) {
     h.cnt += (uint32_t)count << 16;
     if (LIVE_T) reinterpret_cast<float*>(cs.rp + lane * 2 + 1)[3] = r.tclosest;  // (occlusion rays: Tclosest never changes before the ray ends)
-    // kz in bits 0-1, bit 8 = motion-triangle leaf, bits 16-20 = the owner lane; .w = Ray.Time for the motion items
     const bool mot = MOT && (un & kMotionTriBit);
-    cs.rp[64 + __popc(leafmask & lt)] = make_float4(__int_as_float(r.kz | (mot ? 256 : 0) | (lane << 16)), __int_as_float(base), __int_as_float(start), r.time);
+    int keys = 0, stride = 0;
+    if (mot) {  // polymesh/trace.go:79-84: the key count and key stride of the leaf's mesh, looked up once per leaf
+      const DevGeom gm = sc.geoms[__float_as_int(ldg4(sc.mtris + (size_t)base * 3).w)];
+      keys = gm.keys;
+      stride = gm.tri_key_stride;
+    }
+    cs.rp[64 + __popc(leafmask & lt)] = make_float4(__int_as_float(r.kz | (mot ? 4 : 0) | (lane << 3) | (keys << 8) | (start << 16)), __int_as_float(base), __int_as_float(stride), r.time);
   }
   const int kz0 = __shfl_sync(0xffffffffu, r.kz, __ffs(leafmask) - 1);
   const bool any_mot = MOT && __any_sync(0xffffffffu, isleaf && (un & kMotionTriBit));
@@ -1162,13 +1176,13 @@ __device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bo
     if (j < total) {
       const int R = before + __popc(heads & (lt | (1u << lane))) - 1;
       const float4 q2 = cs.rp[64 + R];
-      const float4* b = cs.rp + ((__float_as_int(q2.x) >> 16) & 31) * 2;
+      const float4* b = cs.rp + rec_owner(__float_as_int(q2.x)) * 2;
       const float4 q0 = b[0], q1 = b[1];
       if (kz_uniform) {
         if (kz0 == 0) cand = coop_item<0>(sc, q0, q1, q2, j, tc);
         else if (kz0 == 1) cand = coop_item<1>(sc, q0, q1, q2, j, tc);
         else cand = coop_item<2>(sc, q0, q1, q2, j, tc);
-      } else if (MOT && (__float_as_int(q2.x) & 256)) {
+      } else if (MOT && rec_motion(__float_as_int(q2.x))) {
         cand = coop_item_motion(sc, q0, q1, q2, j, tc);
       } else {
         cand = coop_item<-1>(sc, q0, q1, q2, j, tc);
