@@ -980,6 +980,7 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
   else if (!std::strcmp(name, "precise_trig")) ctx->opt_precise_trig = value != 0;
   else if (!std::strcmp(name, "tma_stage")) ctx->opt_traversal = value != 0 ? 1 : 2;
   else if (!std::strcmp(name, "primary_per_lane")) ctx->opt_primary_per_lane = value != 0;
+  else if (!std::strcmp(name, "primary_per_lane_motion")) ctx->opt_primary_per_lane_motion = value != 0;
   else if (!std::strcmp(name, "shadow_unordered")) ctx->opt_shadow_unordered = value != 0;
   else if (!std::strcmp(name, "shadow_per_lane")) ctx->opt_shadow_per_lane = value != 0;
   else if (!std::strcmp(name, "shadow_level0_per_lane")) {

@@ -154,6 +154,7 @@ struct vg_ctx {
   int opt_iters_per_batch = 4;
   int opt_precise_trig = 0;
   int opt_primary_per_lane = 1;  // with traversal=2: camera rays (level 0) still use the per-lane loop
+  int opt_primary_per_lane_motion = 0;  // camera rays of scenes with motion meshes through the per-lane loop too
   int opt_shadow_unordered = 1;  // integrator shadow queue: skip the sign-ordered push (occlusion is order independent)
   int opt_generic_shade = 0;     // 1 = always shade with the general kernel (tests: it must agree with the specialised one)
   int opt_accumulate_tiled = 0;    // 1 = k_resolve_accumulate_t (shared-memory tile); measured slower: C2 raygen+accumulate 5.76 vs 4.74 ms per frame

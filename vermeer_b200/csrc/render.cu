@@ -1959,7 +1959,7 @@ static int render_run_impl(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_
         else if (sph) {
           if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 10><<<rs.coop_grid, kTraceBlock, trace_smem_bytes(10), st>>>(p, qin);
           else k_trace_queue<0, 8><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(8), st>>>(p, qin);
-        } else if (mot && variant == 2) k_trace_queue<0, 66><<<rs.coop_grid_mot, kTraceBlock, trace_smem_bytes(66), st>>>(p, qin);
+        } else if (mot && variant == 2 && (level > 0 || !ctx->opt_primary_per_lane_motion)) k_trace_queue<0, 66><<<rs.coop_grid_mot, kTraceBlock, trace_smem_bytes(66), st>>>(p, qin);
         else if (variant == 1) k_trace_queue<0, 1><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(1), st>>>(p, qin);
         else if (variant == 2 && (level > 0 || !ctx->opt_primary_per_lane)) k_trace_queue<0, 2><<<rs.coop_grid, kTraceBlock, trace_smem_bytes(2), st>>>(p, qin);
         else k_trace_queue<0, 0><<<rs.trace_grid, kTraceBlock, trace_smem_bytes(0), st>>>(p, qin);

@@ -1107,6 +1107,7 @@ __device__ __forceinline__ bool coop_item(const DevScene& sc, const float4 q0, c
 
 // A motion-triangle item (polymesh/trace.go:547-554,556-622): the two keys' vertices are lerped at the ray's time; the key count
 // and key stride come from the item's geom record.
+template <int KZ>
 __device__ __forceinline__ bool coop_item_motion(const DevScene& sc, const float4 q0, const float4 q1, const float4 q2, int j, TriCand& tc) {
   const int x = __float_as_int(q2.x);
   const int i = j - rec_start(x);
@@ -1123,7 +1124,7 @@ __device__ __forceinline__ bool coop_item_motion(const DevScene& sc, const float
   const float3 p0 = make_float3(om * a0.x + tm * b0.x, om * a0.y + tm * b0.y, om * a0.z + tm * b0.z);
   const float3 p1 = make_float3(om * a1.x + tm * b1.x, om * a1.y + tm * b1.y, om * a1.z + tm * b1.z);
   const float3 p2 = make_float3(om * a2.x + tm * b2.x, om * a2.y + tm * b2.y, om * a2.z + tm * b2.z);
-  return tri_candidate<true, -1>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, __float_as_uint(q1.z), rec_kz(x), q1.w, p0, p1, p2, a2.w, tc);  // the w fields (geom id, face, RayBias) are the same in every key's record
+  return tri_candidate<true, KZ>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, __float_as_uint(q1.z), rec_kz(x), q1.w, p0, p1, p2, a2.w, tc);  // the w fields (geom id, face, RayBias) are the same in every key's record
 }
 
 // One cooperative leaf phase. `isleaf`: this lane's t.cur is a triangle leaf that takes part (static; also motion leaves when
@@ -1159,8 +1160,12 @@ __device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bo
     cs.rp[64 + __popc(leafmask & lt)] = make_float4(__int_as_float(r.kz | (mot ? 4 : 0) | (lane << 3) | (keys << 8) | (start << 16)), __int_as_float(base), __int_as_float(stride), r.time);
   }
   const int kz0 = __shfl_sync(0xffffffffu, r.kz, __ffs(leafmask) - 1);
+  // all leaves of this phase static / all motion and one dominant axis: the item test is a template instance with static component
+  // access (a phase that mixes static and motion leaves, or axes, takes the per-lane selects)
   const bool any_mot = MOT && __any_sync(0xffffffffu, isleaf && (un & kMotionTriBit));
   const bool kz_uniform = !any_mot && __all_sync(0xffffffffu, !isleaf || r.kz == kz0);
+  bool kz_uniform_mot = false;
+  if (MOT) kz_uniform_mot = __all_sync(0xffffffffu, !isleaf || ((un & kMotionTriBit) && r.kz == kz0));
   __syncwarp();
   bool leafhit = false;
   for (int w = 0; w < total; w += 32) {
@@ -1182,8 +1187,12 @@ __device__ __forceinline__ bool coop_leaves(const DevScene& sc, TravState& t, bo
         if (kz0 == 0) cand = coop_item<0>(sc, q0, q1, q2, j, tc);
         else if (kz0 == 1) cand = coop_item<1>(sc, q0, q1, q2, j, tc);
         else cand = coop_item<2>(sc, q0, q1, q2, j, tc);
+      } else if (MOT && kz_uniform_mot) {
+        if (kz0 == 0) cand = coop_item_motion<0>(sc, q0, q1, q2, j, tc);
+        else if (kz0 == 1) cand = coop_item_motion<1>(sc, q0, q1, q2, j, tc);
+        else cand = coop_item_motion<2>(sc, q0, q1, q2, j, tc);
       } else if (MOT && rec_motion(__float_as_int(q2.x))) {
-        cand = coop_item_motion(sc, q0, q1, q2, j, tc);
+        cand = coop_item_motion<-1>(sc, q0, q1, q2, j, tc);
       } else {
         cand = coop_item<-1>(sc, q0, q1, q2, j, tc);
       }
