@@ -1996,7 +1996,8 @@ static int render_run_impl(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_
           } else if (level == 0 && l0_kernel == 1) {
             // the shadow rays of camera hits are as coherent as the camera rays (a warp = one pixel x 32 iterations towards one light):
             // the per-lane loop, here without the ordered push
-            k_trace_queue<1, 4><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(4), st>>>(p, 0);
+            if (mot) k_trace_queue<1, 68><<<rs.shadow_grid_mot, kTraceBlock, trace_smem_bytes(68), st>>>(p, 0);
+            else k_trace_queue<1, 4><<<rs.shadow_grid, kTraceBlock, trace_smem_bytes(4), st>>>(p, 0);
           } else if (mot && variant == 2) {
             if (ctx->opt_shadow_unordered) k_trace_queue<1, 67><<<rs.shadow_grid_mot, kTraceBlock, trace_smem_bytes(67), st>>>(p, 0);
             else k_trace_queue<1, 66><<<rs.shadow_grid_mot, kTraceBlock, trace_smem_bytes(66), st>>>(p, 0);

@@ -661,7 +661,7 @@ __device__ __forceinline__ bool leaf_motion(const DevScene& sc, const LeafRay& l
 // kernel V = 4, compiled for 64 registers); otherwise they stay in RayState and the hit record is written at accept time (the
 // closest-hit per-lane kernels at 72 registers: MEASURED, the published-block form cost them 17.85 -> 19.57 ms on the C2 camera rays —
 // 4 KB more shared memory per CTA moves the carve-out from 64 to 100 KB, and a coherent warp re-reads its blocks at every leaf).
-template <bool SMEM>
+template <bool SMEM, bool MOTK = false>
 __device__ __forceinline__ bool leaf_step(const DevScene& sc, TravState& t, uint32_t un, const CoopSmem& cs) {
   RayState& r = t.r;
   HitState& h = t.h;
@@ -674,9 +674,19 @@ __device__ __forceinline__ bool leaf_step(const DevScene& sc, TravState& t, uint
   } else {
     lr.pkx = r.pkx; lr.pky = r.pky; lr.pkz = r.pkz; lr.s0 = r.s0; lr.s1 = r.s1; lr.s2 = r.s2; lr.xsign = r.xsign; lr.kx = r.kx; lr.ky = r.ky; lr.kz = r.kz;
   }
-  if (un & kMotionTriBit) return leaf_motion<-1, SMEM>(sc, lr, r.time, r.tclosest, h, base, count);
+  if (!MOTK && (un & kMotionTriBit)) return leaf_motion<-1, SMEM>(sc, lr, r.time, r.tclosest, h, base, count);
   const unsigned am = __activemask();
   const int k0 = __shfl_sync(am, r.kz, __ffs(am) - 1);
+  if (MOTK) {  // kernels launched for scenes with motion meshes (VARIANT & 64): the motion leaf loop gets the compile-time axis too
+    const bool mo = (un & kMotionTriBit) != 0;
+    if (__all_sync(am, mo && r.kz == k0)) {
+      if (k0 == 0) return leaf_motion<0, SMEM>(sc, lr, r.time, r.tclosest, h, base, count);
+      if (k0 == 1) return leaf_motion<1, SMEM>(sc, lr, r.time, r.tclosest, h, base, count);
+      return leaf_motion<2, SMEM>(sc, lr, r.time, r.tclosest, h, base, count);
+    }
+    if (mo) return leaf_motion<-1, SMEM>(sc, lr, r.time, r.tclosest, h, base, count);
+    return leaf_static<-1, SMEM>(sc, lr, r.tclosest, h, base, count);
+  }
   if (__all_sync(am, r.kz == k0)) {
     if (k0 == 0) return leaf_static<0, SMEM>(sc, lr, r.tclosest, h, base, count);
     if (k0 == 1) return leaf_static<1, SMEM>(sc, lr, r.tclosest, h, base, count);
@@ -757,7 +767,7 @@ __device__ __forceinline__ bool sphere_leaf(const DevScene& sc, TravState& t, ui
 // lanes of the warp are still traversing (the caller then refills the idle lanes and comes back).
 // Returns true when this lane's ray is finished.
 // SPH: the scene holds analytic sphere geoms (kernels for scenes without them do not carry the call).
-template <bool ANY_HIT, bool SPH = false, bool ORDERED = true, bool SMEM = false>
+template <bool ANY_HIT, bool SPH = false, bool ORDERED = true, bool SMEM = false, bool MOTK = false>
 __device__ __forceinline__ bool trav_run(const DevScene& sc, TravState& t, Stack& st, const CoopSmem& cs, int min_active) {
   while (t.cur != -1) {
     // 256-bit node loads in the per-lane kernel too: re-measured with pixel-coherent warps, C2 closest 19.09 vs 19.15 ms, C3 299.6 vs
@@ -785,7 +795,7 @@ __device__ __forceinline__ bool trav_run(const DevScene& sc, TravState& t, Stack
         t.cur = (int32_t)(un & kGeomRootMask);
         break;
       }
-      const bool leafhit = leaf_step<SMEM>(sc, t, un, cs);
+      const bool leafhit = leaf_step<SMEM, MOTK>(sc, t, un, cs);
       if (ANY_HIT && leafhit) {  // intersect.go:231-236: shadow rays return at the first leaf reporting a hit
         st.reset();
         t.cur = -1;
@@ -930,7 +940,7 @@ __device__ __forceinline__ void trace_persistent_tma(const DevScene& sc, IO& io,
 // coalesced LDG.128 each. Measured faster than the TMA-staged variant on B200 (3.83 vs 3.16 Grays/s on C2 primary rays,
 // profiles/README.md): the fetch is <4 % of a ray's loads and 28 resident warps already hide its latency, while the
 // staging state costs registers under the 72-register cap.
-template <bool ANY_HIT, bool SPH, bool ORDERED, bool SMEM, class IO>
+template <bool ANY_HIT, bool SPH, bool ORDERED, bool SMEM, bool MOTK, class IO>
 __device__ __forceinline__ void trace_persistent_ldg(const DevScene& sc, IO& io, Stack& st, const CoopSmem& cs, unsigned& nodes_acc, unsigned& tris_acc) {
   const int lane = threadIdx.x & 31;
   const long long n = io.size();
@@ -964,7 +974,7 @@ __device__ __forceinline__ void trace_persistent_ldg(const DevScene& sc, IO& io,
 #ifndef VG_REFILL_BELOW_OCCL
 #define VG_REFILL_BELOW_OCCL VG_REFILL_BELOW
 #endif
-      if (trav_run<ANY_HIT, SPH, ORDERED, SMEM>(sc, t, st, cs, exhausted ? 0 : (SMEM ? VG_REFILL_BELOW_OCCL : VG_REFILL_BELOW))) {
+      if (trav_run<ANY_HIT, SPH, ORDERED, SMEM, MOTK>(sc, t, st, cs, exhausted ? 0 : (SMEM ? VG_REFILL_BELOW_OCCL : VG_REFILL_BELOW))) {
         if (SMEM && IO::kHitRecord) finalize_hit(sc, cs, t);
         io.store(my, t.r, t.h, st.overflow);
         nodes_acc += t.h.cnt & 0xffffu;
@@ -1389,9 +1399,9 @@ __device__ __forceinline__ void trace_persistent(const DevScene& sc, IO& io, Sta
     trace_persistent_coop<ANY_HIT, false, SPH, XF, MOT>(sc, io, st, cs, nodes_acc, tris_acc);
   } else if (V == 4) {  // per-lane loop without the ordered push: occlusion-only rays that are coherent (the integrator's level-0 shadow queue)
     static_assert(V != 4 || ANY_HIT, "the unordered per-lane loop is for occlusion-only rays");
-    trace_persistent_ldg<ANY_HIT, SPH, false, true>(sc, io, st, cs, nodes_acc, tris_acc);
+    trace_persistent_ldg<ANY_HIT, SPH, false, true, (VARIANT & 64) != 0>(sc, io, st, cs, nodes_acc, tris_acc);
   } else {
-    trace_persistent_ldg<ANY_HIT, SPH, true, false>(sc, io, st, cs, nodes_acc, tris_acc);
+    trace_persistent_ldg<ANY_HIT, SPH, true, false, false>(sc, io, st, cs, nodes_acc, tris_acc);
   }
 }
 
