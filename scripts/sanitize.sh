@@ -21,6 +21,9 @@ run memcheck_smoke 300 --tool memcheck --leak-check no --error-exitcode 1 python
 run racecheck_smoke 400 --tool racecheck --racecheck-report all --error-exitcode 1 python -c "$SMOKE"
 run synccheck_smoke 300 --tool synccheck --error-exitcode 1 python -c "$SMOKE"
 run initcheck_smoke 300 --tool initcheck --error-exitcode 1 python -c "$SMOKE"
+# round 2: the per-lane occlusion kernel (published shared blocks, one-register stack) and the {P, D} ray records
+run racecheck_round2 600 --tool racecheck --racecheck-report all --error-exitcode 1 python -m pytest tests/test_gpu_round2.py -m gpu -x -q -k "level0 or pd_ray"
+run memcheck_round2 600 --tool memcheck --leak-check no --error-exitcode 1 python -m pytest tests/test_gpu_round2.py -m gpu -x -q -k "level0 or pd_ray or path_order or stack_overflow"
 run memcheck_trace 600 --tool memcheck --leak-check no --error-exitcode 1 python -m pytest tests/test_gpu_trace.py tests/test_gpu_build.py -m gpu -x -q
 run memcheck_render 600 --tool memcheck --leak-check no --error-exitcode 1 python -m pytest tests/test_gpu_render.py tests/test_gpu_texture.py -m gpu -x -q
 
