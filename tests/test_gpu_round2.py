@@ -306,9 +306,10 @@ def test_tiled_accumulate_is_bit_identical(built_library):
     one and two iteration groups per batch, progressive continuation."""
     sc = _scene(200, 140)            # 28 000 pixels: not a multiple of 32 per tile row
     ref = None
-    for tiled, ipb in [(0, 32), (1, 32), (1, 64), (0, 64)]:
+    for tiled, ipb in [(0, 32), (1, 32), (1, 64), (0, 64), (2, 32), (2, 7)]:   # 2: the plain kernel without the 256-bit slot loads
         dev = _device(sc)
-        dev.set_option("accumulate_tiled", tiled)
+        dev.set_option("accumulate_tiled", tiled & 1)
+        dev.set_option("accumulate_wide", 0 if tiled == 2 else 1)
         dev.set_option("iters_per_batch", ipb)
         fb = dev.render(0, 64).copy()
         dev.render(64, 96)           # continues the running mean with another 32-iteration batch

@@ -987,6 +987,7 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
     if (value < 0 || value > 2) return ctx->fail(VG_ERR_INVALID, "shadow_level0_per_lane must be 0 (cooperative kernel), 1 (per-lane loop) or 2 (measured)");
     ctx->opt_shadow_level0_per_lane = value;
   }
+  else if (!std::strcmp(name, "accumulate_wide")) ctx->opt_accumulate_wide = value != 0;
   else if (!std::strcmp(name, "accumulate_tiled")) ctx->opt_accumulate_tiled = value != 0;
   else if (!std::strcmp(name, "frame_slices_multi")) ctx->opt_frame_slices_multi = value != 0;
   else if (!std::strcmp(name, "frame_slices_min_paths_off")) ctx->opt_frame_slices_force = value != 0;

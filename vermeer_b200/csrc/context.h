@@ -157,6 +157,7 @@ struct vg_ctx {
   int opt_primary_per_lane_motion = 0;  // camera rays of scenes with motion meshes through the per-lane loop too
   int opt_shadow_unordered = 1;  // integrator shadow queue: skip the sign-ordered push (occlusion is order independent)
   int opt_generic_shade = 0;     // 1 = always shade with the general kernel (tests: it must agree with the specialised one)
+  int opt_accumulate_wide = 1;     // k_resolve_accumulate<true>: a vertex's four slots as two 256-bit loads (one lobe, S = 4, two lights)
   int opt_accumulate_tiled = 0;    // 1 = k_resolve_accumulate_t (shared-memory tile); measured slower: C2 raygen+accumulate 5.76 vs 4.74 ms per frame
   int opt_frame_slices_force = 0;  // tests: ignore the 16 M-path minimum slice size
   int opt_frame_slices_multi = 0; // 1 = slice the frame also when a multi-GPU communicator exists (measured: no gain)

@@ -1075,6 +1075,14 @@ __global__ void __launch_bounds__(128, VG_SHADE_MIN_BLOCKS) k_shade(const Render
 namespace vg {
 
 // Sum the slots in the reference's order and finish the diffuse / glossy terms (core/shader.go:349, std.go:157-163,269-295).
+// WIDE4 (one lobe, four slots, two lights per vertex — the default light nodes of every BASELINE scene): the vertex's 64 bytes of
+// slots come in as two 256-bit loads and its two 1/total factors as one 64-bit load, and the loops pick from registers. The same
+// additions in the same order; what changes is the number of L1TEX wavefronts a thread-per-pixel warp spends per vertex (7 -> 4), the
+// unit that bounds k_resolve_accumulate (ncu: 92 % busy).
+__device__ __forceinline__ float4 pick4(const float4& a, const float4& b, const float4& c, const float4& d, int k) {
+  return k == 0 ? a : (k == 1 ? b : (k == 2 ? c : d));
+}
+template <bool WIDE4 = false>
 __device__ __forceinline__ float4 resolve_vertex(const RenderParams& p, int level, int i) {
   const int matid = p.v_mat[i];
   const int SL = p.S * p.nlobes;
@@ -1083,19 +1091,29 @@ __device__ __forceinline__ float4 resolve_vertex(const RenderParams& p, int leve
     const DevMat m = *((p.vmats && p.mat_tex[matid].mask) ? p.vmats + i : p.mats + matid);  // one load site: only the fields used are fetched
     f3 sum[2];
     sum[0] = sum[1] = mk3(0, 0, 0);
-    for (int lobe = 0; lobe < p.nlobes; lobe++) {
+    float4 w0, w1, w2, w3;
+    float2 inv2 = make_float2(0.f, 0.f);
+    if (WIDE4) {
+      const float4* cp = p.contrib + (size_t)i * 4;
+      asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=f"(w0.x), "=f"(w0.y), "=f"(w0.z), "=f"(w0.w), "=f"(w1.x), "=f"(w1.y), "=f"(w1.z), "=f"(w1.w) : "l"(cp));
+      asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=f"(w2.x), "=f"(w2.y), "=f"(w2.z), "=f"(w2.w), "=f"(w3.x), "=f"(w3.y), "=f"(w3.z), "=f"(w3.w) : "l"(cp + 2));
+      inv2 = *reinterpret_cast<const float2*>(p.v_invtot + (size_t)i * 2);
+    }
+    for (int lobe = 0; lobe < (WIDE4 ? 1 : p.nlobes); lobe++) {
       const bool on = lobe == 0 ? m.diff_weight > 0.0f : (m.spec_weight > 0.0f && m.spec_rough > 0.0f);
       if (!on) continue;
       const f3 colour = lobe == 0 ? m.diff_colour : m.spec_colour;
       f3 acc = mk3(0, 0, 0);
-      for (int l = 0; l < p.nlights; l++) {
+      for (int l = 0; l < (WIDE4 ? 2 : p.nlights); l++) {
         const DevLight& L = p.lights[l];
         const int NS = level > 0 ? 1 : L.nsamples;
-        const float inv = p.v_invtot[((size_t)i * p.nlobes + lobe) * p.nlights + l];
+        const float inv = WIDE4 ? (l == 0 ? inv2.x : inv2.y) : p.v_invtot[((size_t)i * p.nlobes + lobe) * p.nlights + l];
         if (inv == 0.0f) continue;  // light excluded (own geom) or no samples: EvaluateLightSamples returned RGB{}
         f3 col = mk3(0, 0, 0);
         for (int s = 0; s < NS; s++) {
-          const float4 c = p.contrib[(size_t)i * SL + lobe * p.S + L.slot_base + s];
+          const float4 c = WIDE4 ? pick4(w0, w1, w2, w3, L.slot_base + s) : p.contrib[(size_t)i * SL + lobe * p.S + L.slot_base + s];
           col.x += c.x; col.y += c.y; col.z += c.z;
         }
         if (NS > 1) { col.x *= inv; col.y *= inv; col.z *= inv; }
@@ -1133,13 +1151,14 @@ __global__ void __launch_bounds__(256) k_debug_last(const RenderParams p, int le
 
 // Scenes without a mirror lobe have one level: the level-0 queue is the identity (queue slot == path), so the per-vertex sum and
 // the running mean (render.go:127-129) are one kernel and L never goes to memory.
+template <bool WIDE4>
 __global__ void __launch_bounds__(256) k_resolve_accumulate(const RenderParams p, int iter_base, int niters) {
   const int own = blockIdx.x * blockDim.x + threadIdx.x;
   if (own >= p.nown) return;
   float* px = p.fb + (size_t)p.pix[own] * 3;
   float r = px[0], g = px[1], b = px[2];
   for (int it = 0; it < niters; it++) {
-    const float4 C = resolve_vertex(p, 0, path_index(p, own, it));
+    const float4 C = resolve_vertex<WIDE4>(p, 0, path_index(p, own, it));
     const float fi = (float)(iter_base + it + 1);
     r = (r * fi + C.x) / (fi + 1.0f);
     g = (g * fi + C.y) / (fi + 1.0f);
@@ -2025,7 +2044,8 @@ static int render_run_impl(vg_ctx* ctx, int iter_begin, int iter_end, float* fb_
       }
       if (rs.levels > 1) k_accumulate<<<(sn + 255) / 256, 256, 0, st>>>(p, ib, niters);
       else if (p.pm_G == 32 && (niters & 31) == 0 && ctx->opt_accumulate_tiled) k_resolve_accumulate_t<<<(sn + 63) / 64, 64, 0, st>>>(p, ib, niters);
-      else k_resolve_accumulate<<<(sn + 255) / 256, 256, 0, st>>>(p, ib, niters);
+      else if (p.nlobes == 1 && p.S == 4 && p.nlights == 2 && ctx->opt_accumulate_wide) k_resolve_accumulate<true><<<(sn + 255) / 256, 256, 0, st>>>(p, ib, niters);
+      else k_resolve_accumulate<false><<<(sn + 255) / 256, 256, 0, st>>>(p, ib, niters);
       launches++;
     }
     if (fp) {
