@@ -987,6 +987,7 @@ int vg_set_option(vg_ctx* ctx, const char* name, int value) {
     if (value < 0 || value > 2) return ctx->fail(VG_ERR_INVALID, "shadow_level0_per_lane must be 0 (cooperative kernel), 1 (per-lane loop) or 2 (measured)");
     ctx->opt_shadow_level0_per_lane = value;
   }
+  else if (!std::strcmp(name, "batch_taper")) ctx->opt_batch_taper = value != 0;
   else if (!std::strcmp(name, "accumulate_wide")) ctx->opt_accumulate_wide = value != 0;
   else if (!std::strcmp(name, "accumulate_tiled")) ctx->opt_accumulate_tiled = value != 0;
   else if (!std::strcmp(name, "frame_slices_multi")) ctx->opt_frame_slices_multi = value != 0;
@@ -1118,9 +1119,31 @@ int vg_trace_batch(vg_ctx* ctx, const VgRay* rays, int64_t n, VgHit* hits, uint3
     if (!blocks_per_sm) blocks_per_sm = trace_batch_blocks_per_sm();
     VG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     for (int s = 0; s < 3; s++) VG_CUDA(ctx, cudaStreamWaitEvent(ctx->pipe_stream[s], ctx->ev0, 0));
+    // Stage sizes: full chunks in the middle; the first two and the last two stages are a quarter and a half chunk, so that the
+    // pipeline's fill (the first upload, which nothing overlaps) and drain (the last traversal and download) are short.
+    std::vector<int64_t> stages;
+    {
+      int64_t rem = n;
+      const bool taper = ctx->opt_batch_taper && n >= 4 * chunk;
+      if (taper) {
+        stages.push_back(chunk / 4);
+        stages.push_back(chunk / 2);
+        rem -= chunk / 4 + chunk / 2;
+        rem -= chunk / 2 + chunk / 4;  // kept for the tail
+      }
+      while (rem > 0) {
+        stages.push_back(std::min(chunk, rem));
+        rem -= stages.back();
+      }
+      if (taper) {
+        stages.push_back(chunk / 2);
+        stages.push_back(chunk / 4);
+      }
+    }
     int c = 0;
-    for (int64_t off = 0; off < n; off += chunk, c++) {
-      const int64_t m = std::min(chunk, n - off);
+    int64_t off = 0;
+    for (; c < (int)stages.size(); off += stages[c], c++) {
+      const int64_t m = stages[c];
       cudaStream_t st = ctx->pipe_stream[c % 3];
       VG_CUDA(ctx, cudaMemcpyAsync(d_rays_b + (size_t)off * ray_bytes, rays_b + (size_t)off * ray_bytes, (size_t)m * ray_bytes, cudaMemcpyHostToDevice, st));
       long long grid = std::min<long long>((long long)ctx->sm_count * blocks_per_sm, (m + kTraceBlock - 1) / kTraceBlock);

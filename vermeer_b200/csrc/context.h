@@ -172,6 +172,7 @@ struct vg_ctx {
   int opt_iter_group = 32;       // a warp's 32 paths = (32/iter_group) pixels x iter_group iterations of the batch (render.cu: path_index)
   int opt_pixel_block = 1;       // paths of one warp cover an 8x4 pixel block of a tile (1) or a 32x1 row (0)
   int opt_batch_chunk_log2 = 19; // vg_trace_batch copy pipeline: rays per stage
+  int opt_batch_taper = 1;       // ... with quarter / half stages at both ends (shorter pipeline fill and drain)
   int opt_l2_persist_nodes = 0;  // persisting-L2 access-policy window over the static node array
   int opt_zero_copy_batch = 0;   // vg_trace_batch with page-locked buffers: kernel reads rays / writes hits over PCIe itself (1) or 3-stream copy pipeline (0)
   int opt_node_order = 0;        // device order of a mesh's nodes: 0 = the reference's preorder, 1 = breadth-first (siblings adjacent)
