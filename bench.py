@@ -12,7 +12,8 @@ BASELINE.json's metric is "Mrays/s (closest-hit, incoherent) and samples/sec at 
                    (vg_trace_batch_device); device time from CUDA events around the kernel. At N GPUs every rank traces a
                    batch of its own (independent rays, no collective): weak scaling.
   e2e              the same pass through vg_trace_batch with page-locked HOST buffers: H2D of the rays, traversal and D2H of
-                   the hits inside the timed call (VG_TRACE_COMPACT_HITS, 16-byte hits; the 32-byte VgHit figure is beside it).
+                   the hits inside the timed call (VG_TRACE_RAYS_PD 24-byte {P, D} rays up, VG_TRACE_COMPACT_HITS 16-byte hits
+                   down; the 32-byte VgRay / VgHit figures are beside it, the hits are byte-identical in every mode).
   frame            the other half of the metric, samples/s: the whole hot path on the same scene (ray generation ->
                    closest-hit -> ShaderStd/light sampling -> any-hit -> accumulation), 1920x1080, 64 spp; Mrays/s by the
                    reference's definition (core/stats.go:21-24: every TraceProbe / render-loop time). At N GPUs the frame
@@ -23,6 +24,8 @@ BASELINE.json's metric is "Mrays/s (closest-hit, incoherent) and samples/sec at 
                    each with its own cpu_baseline (short sample: it is a rate) and per-stage roofline.
   incoherent_wavefront  a second, harder incoherent batch: the level-1..3 mirror-bounce rays of the 10M-triangle scene taken
                    from the integrator's own ray queues (vg_captured_rays), shuffled; scene not L2-resident.
+  incoherent_diffuse    BASELINE.json's third config by name: bounces 1-4 of cosine-hemisphere DIFFUSE paths on the same scene
+                   (one camera pass; scenes.diffuse_bounce_rays), per bounce and together, CPU on the same rays, bit-identity.
   roofline         per traversal / shading stage: time per launch measured live (CUDA events inside vg_render), traffic per
                    ray from the committed ncu capture of this build (profiles/ncu_r02_metrics.json: dram, L2 and L1TEX bytes),
                    against HBM (MEASURED_PEAKS.json) and the L2 / L1 read peaks measured in this run (vg_measure_peaks);
@@ -700,9 +703,10 @@ def run_ours(args):
             continue
         if cfg == "c3" and "c5" in want and world == 8:
             pass
-        _, configs[cfg] = run_config(cfg, args, rank, world, local_rank, torch, dist, peaks, hbm, ncu, cores, dev=dev)
+        rig_c, configs[cfg] = run_config(cfg, args, rank, world, local_rank, torch, dist, peaks, hbm, ncu, cores, dev=dev)
         if cfg == "c3" and rank == 0 and world == 1 and not args.no_wavefront:
             configs[cfg]["incoherent_wavefront"] = wavefront_leg(dev, torch, cores, args)
+            configs[cfg]["incoherent_diffuse"] = diffuse_leg(dev, rig_c, torch, cores, args)
 
     if rank != 0:
         if world > 1:
@@ -764,6 +768,7 @@ def run_ours(args):
         "frame": {k: v for k, v in c2.items() if k not in ("stages",)},
         "configs": configs,
         "incoherent_wavefront": (configs.get("c3") or {}).get("incoherent_wavefront"),
+        "incoherent_diffuse": (configs.get("c3") or {}).get("incoherent_diffuse"),
         "nonparity": nonparity,
         "measured_peaks": {"hbm_gbs": hbm[0], "hbm_source": hbm[1], **peaks},
         "speedup_vs_cpu": None if not cpu else {"device_resident": value / cpu["value"], "e2e": e2e_value / cpu["value"], "cores": cores,
@@ -832,6 +837,45 @@ def wavefront_leg(dev, torch, cores, args):
         res["cpu"] = {"value": v, "unit": "Mrays/s", "cores": cores, "per_core": v / cores, "kind": "port", "sample": "%d of the same rays, %.2f s" % (len(sample), secs),
                       "bit_identical_to_gpu": bool(np.array_equal(oh["prim"], g["prim"]) and np.array_equal(oh["geom"], g["geom"]) and
                                                    np.array_equal(oh["t"].view(np.uint32), g["t"].view(np.uint32)))}
+        res["speedup_vs_cpu"] = {"device_resident": res["value"] / v, "e2e": {k: x / v for k, x in res["e2e"].items()}}
+    return res
+
+
+def diffuse_leg(dev, rig, torch, cores, args):
+    """BASELINE.json's third config by name: 4-bounce incoherent DIFFUSE paths on the 10M-triangle scene, as a traversal workload (the
+    reference's shader has no diffuse indirect — DESIGN.md quirk e — so the frame config C3 follows mirror chains; this leg traces what
+    a diffuse path tracer would): one 1080p camera pass, then four cosine-hemisphere bounces off the hit points
+    (scenes.diffuse_bounce_rays), every bounce's rays shuffled. Device-resident rate per bounce and for the four together; CPU on the
+    same rays with bit-identity."""
+    from vermeer_b200 import scenes
+    scene, host = rig.scene, rig.host
+    cur = primary_rays(scene, host.camera(), 0.5, 0.5)
+    hits = dev.trace(cur)
+    per, allr = [], []
+    for b in range(1, 5):
+        cur = scenes.diffuse_bounce_rays(scene, cur, hits, seed=40 + b)
+        cur = cur[np.random.default_rng(50 + b).permutation(len(cur))]
+        tb = time_batch(dev, torch, cur, 3, 3, compact_e2e=False)
+        hits = tb["hits"]
+        per.append({"bounce": b, "rays": len(cur), "value": len(cur) / tb["ms_per_step"] / 1e3, "hit_fraction": tb["hit_fraction"],
+                    "nodesT_per_ray": tb["nodesT_per_ray"], "trisT_per_ray": tb["trisT_per_ray"]})
+        allr.append(cur)
+    rays = np.concatenate(allr)
+    rays = rays[np.random.default_rng(60).permutation(len(rays))]
+    tb = time_batch(dev, torch, rays, max(3, min(args.steps, 10)), 3)
+    n = tb["rays"]
+    res = {"workload": "C3-diffuse: bounces 1-4 of cosine-hemisphere diffuse paths on the 10M-triangle sphere field (one 1080p camera pass), shuffled",
+           "rays": n, "value": n / tb["ms_per_step"] / 1e3, "unit": "Mrays/s", "ms_per_step": tb["ms_per_step"], "hit_fraction": tb["hit_fraction"],
+           "nodesT_per_ray": tb["nodesT_per_ray"], "trisT_per_ray": tb["trisT_per_ray"], "per_bounce": per,
+           "e2e": {k: n / v / 1e3 for k, v in tb["e2e_ms"].items()}}
+    if not args.no_cpu:
+        sample = rays[: min(n, 1 << 21)]
+        oh, v, secs = cpu_trace(scene, sample, cores)
+        g = tb["hits"][: len(sample)]
+        res["cpu"] = {"value": v, "unit": "Mrays/s", "cores": cores, "per_core": v / cores, "kind": "port", "sample": "%d of the same rays, %.2f s" % (len(sample), secs),
+                      "bit_identical_to_gpu": bool(np.array_equal(oh["prim"], g["prim"]) and np.array_equal(oh["geom"], g["geom"]) and
+                                                   np.array_equal(oh["t"].view(np.uint32), g["t"].view(np.uint32)) and
+                                                   np.array_equal(oh["nodesT"], g["nodesT"]) and np.array_equal(oh["trisT"], g["trisT"]))}
         res["speedup_vs_cpu"] = {"device_resident": res["value"] / v, "e2e": {k: x / v for k, x in res["e2e"].items()}}
     return res
 

@@ -16,3 +16,7 @@ for k, c in (d.get("configs") or {}).items():
 w = d.get("incoherent_wavefront")
 if w:
     print("  wavefront: %.1f Mrays/s, hit %.2f, nodesT %.1f trisT %.1f, e2e %s, cpu %s" % (w["value"], w["hit_fraction"], w["nodesT_per_ray"], w["trisT_per_ray"], w["e2e"], (w.get("cpu") or {}).get("value")))
+w = d.get("incoherent_diffuse")
+if w:
+    print("  diffuse 4-bounce (C3): %.1f Mrays/s, hit %.2f, nodesT %.1f trisT %.1f, e2e %s, cpu %s | per bounce %s" % (w["value"], w["hit_fraction"], w["nodesT_per_ray"], w["trisT_per_ray"], w["e2e"], (w.get("cpu") or {}).get("value"),
+          [(b["bounce"], b["rays"], round(b["value"]), round(b["hit_fraction"], 2)) for b in w["per_bounce"]]))

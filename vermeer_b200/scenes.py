@@ -766,6 +766,41 @@ def incoherent_rays(rays: np.ndarray, hits: np.ndarray, seed: int = 7) -> np.nda
     return out
 
 
+def diffuse_bounce_rays(scene: SceneDesc, rays: np.ndarray, hits: np.ndarray, seed: int = 7) -> np.ndarray:
+    """One diffuse bounce off the sphere field (bench.py: the 4-bounce incoherent wavefront of the 10 M-triangle scene, the workload
+    BASELINE.json's third config names): from every hit point a cosine-hemisphere direction about the surface normal, taken as the
+    direction from the hit mesh's centroid (the displaced spheres) or +Y (floor, lights), flipped to face the incoming ray. Both sides
+    trace these identical rays, so the normal only has to make the batch look like a diffuse bounce, not match the shading normal."""
+    rng = np.random.default_rng(seed)
+    mask = hits["prim"] >= 0
+    o = rays["o"][mask].astype(np.float64) + rays["d"][mask].astype(np.float64) * hits["t"][mask][:, None].astype(np.float64)
+    geom = hits["geom"][mask]
+    cent = np.zeros((len(scene.meshes), 3))
+    is_sphere = np.zeros(len(scene.meshes), bool)
+    for gi, m in enumerate(scene.meshes):
+        cent[gi] = np.asarray(m.Verts[0], np.float64).mean(0)   # Verts is (keys, nverts, 3)
+        is_sphere[gi] = m.Name.startswith("sphere")
+    gi = np.clip(geom, 0, len(scene.meshes) - 1)
+    nrm = np.where((is_sphere[gi] & (geom < len(scene.meshes)))[:, None], o - cent[gi], np.asarray([0.0, 1.0, 0.0]))
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-20)
+    nrm = np.where((nrm * rays["d"][mask]).sum(1, keepdims=True) > 0, -nrm, nrm)
+    n = len(o)
+    u0, u1 = rng.random(n), rng.random(n)
+    r, th = np.sqrt(1.0 - u0), 2.0 * np.pi * u1
+    a = np.where(np.abs(nrm[:, :1]) > 0.9, np.asarray([0.0, 1.0, 0.0]), np.asarray([1.0, 0.0, 0.0]))
+    t1 = np.cross(nrm, a)
+    t1 /= np.linalg.norm(t1, axis=1, keepdims=True)
+    t2 = np.cross(nrm, t1)
+    d = t1 * (r * np.cos(th))[:, None] + t2 * (r * np.sin(th))[:, None] + nrm * np.sqrt(u0)[:, None]
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    out = np.zeros(n, dtype=rays.dtype)
+    out["o"] = (o + nrm * 1e-4).astype(np.float32)
+    out["d"] = d.astype(np.float32)
+    out["tmax"] = np.float32(np.inf)
+    out["time"] = rays["time"][mask]
+    return out
+
+
 def camera_motion_variants():
     """Camera nodes with motion keys (camera.go:48-73) for the heightfield / Cornell framing: name -> Camera.
     'from3': three From keys, fixed target; 'to4_from2': more To keys than From keys (the other calcLookatMatrices branch, where the
