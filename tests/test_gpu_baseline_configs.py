@@ -144,6 +144,32 @@ def test_c3_camera_and_wavefront_rays_bit_exact(c3):
     assert len(np.unique(g["geom"][g["prim"] >= 0])) > 500        # spread over the whole two-level scene
 
 
+def test_c3_four_diffuse_bounces_bit_exact(c3):
+    """BASELINE.json's third config by name ("4-bounce incoherent diffuse paths" on the 10M-triangle scene) as a traversal workload:
+    four cosine-hemisphere bounces off the hit points of a camera pass (scenes.diffuse_bounce_rays; the reference's own shader has
+    no diffuse indirect, DESIGN.md quirk e). Every bounce bit-exact against the oracle incl. NodesT/TrisT, {P, D} records included."""
+    from vermeer_b200 import scenes
+    from vermeer_b200.host import RAYPD_DTYPE
+    sc, ora, dev = c3
+    cur = ora.camera_rays(3)
+    cur = cur[np.random.default_rng(9).permutation(len(cur))[: 1 << 20]]
+    cur["time"] = 0
+    hits = dev.trace(cur)
+    total = 0
+    for b in range(1, 5):
+        cur = scenes.diffuse_bounce_rays(sc, cur, hits, seed=70 + b)
+        cur = cur[np.random.default_rng(80 + b).permutation(len(cur))]
+        hits = dev.trace(cur)
+        assert_hits_equal(hits, ora.trace(cur, nthreads=NTHREADS), what="C3 diffuse bounce %d" % b)
+        total += len(cur)
+        if b == 1:
+            assert 0.3 < (hits["prim"] >= 0).mean() < 0.7 and len(np.unique(hits["geom"][hits["prim"] >= 0])) > 500
+            pd = np.zeros(len(cur), RAYPD_DTYPE)
+            pd["o"], pd["d"] = cur["o"], cur["d"]
+            assert dev.trace(pd).tobytes() == hits.tobytes()
+    assert total > 1_000_000
+
+
 def test_c3_frame_4spp(c3):
     sc, ora, dev = c3
     dev.clear()
