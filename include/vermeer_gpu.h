@@ -277,7 +277,11 @@ int vg_set_filter(vg_ctx* ctx, int n, double w, const double* cdfV, const double
  * math/sincos.go; 0 = single-precision libm, default; both are within the image tolerance), "traversal" (persistent-kernel variant:
  * 2 = warp-cooperative leaf phase, default; 0 = per-lane while-while loop with coalesced LDG refill; 1 = the per-lane loop with
  * its ray queue staged into shared memory by cp.async.bulk + mbarrier; all three are bit-identical), "tma_stage" (1 = alias of
- * traversal 1, 0 = default). */
+ * traversal 1, 0 = default), "shadow_level0_per_lane" (any-hit kernel of the level-0 shadow queue: 0 = cooperative leaf phase,
+ * 1 = per-lane loop for coherent rays, 2 = whichever the first batches measure faster on this scene, default; the frames are the
+ * same bits either way — VgStats.shadow_level0_kernel reports the choice), "batch_chunk_log2" / "batch_taper" (vg_trace_batch's
+ * copy pipeline with page-locked buffers: rays per stage, shorter stages at both ends), "accumulate_wide" (256-bit slot loads in
+ * the resolve + accumulate kernel; same bits). Measurement switches, none of them changes a result. */
 int vg_set_option(vg_ctx* ctx, const char* name, int value);
 
 /* TraceProbe over a batch (core/trace.go:26). flags: */
