@@ -389,3 +389,31 @@ def test_level0_shadow_queue_per_lane_is_bit_identical(built_library, motion):
         else:
             assert np.array_equal(fb.view(np.uint32), ref[0].view(np.uint32))
             assert (st["rays"], st["shadow_rays"]) == ref[1:]
+
+
+def test_measured_shadow_kernel_choice_settles_and_never_changes_a_frame(built_library):
+    """Option shadow_level0_per_lane = 2 (default): while undecided the level-0 shadow launches of consecutive batches alternate
+    between the two kernels; after two samples of each one is kept. Every frame on the way is the same bits, and
+    VgStats.shadow_level0_kernel names the kernel of the last batch (0 cooperative, 1 per-lane)."""
+    sc = _scene(160, 120)
+    dev = _device(sc)
+    dev.set_option("iters_per_batch", 4)
+    ref = None
+    seen = []
+    for call in range(6):
+        dev.clear()
+        fb = dev.render(0, 8)                      # two batches per call
+        seen.append(int(dev.stats()["shadow_level0_kernel"]))
+        if ref is None:
+            ref = fb.copy()
+        assert np.array_equal(fb.view(np.uint32), ref.view(np.uint32)), call
+    assert set(seen) <= {0, 1}
+    assert seen[-1] == seen[-2] == seen[-3], seen   # settled after the first two calls (4 batches = 2 samples of each kernel)
+    dev.set_option("shadow_level0_per_lane", 1)
+    dev.clear()
+    dev.render(0, 4)
+    assert int(dev.stats()["shadow_level0_kernel"]) == 1
+    dev.set_option("shadow_level0_per_lane", 0)
+    dev.clear()
+    dev.render(0, 4)
+    assert int(dev.stats()["shadow_level0_kernel"]) == 0
