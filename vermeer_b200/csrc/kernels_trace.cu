@@ -12,6 +12,7 @@ namespace vg {
 
 struct BatchIO {
   static constexpr bool kHitRecord = true;
+  static constexpr int kRefillIdleClosest = VG_REFILL_IDLE_CLOSEST;
   const VgRay* rays;
   VgHit* hits;
   long long n;

@@ -318,7 +318,8 @@ __global__ void __launch_bounds__(256) k_raygen(const RenderParams p, int iter_b
 // an occluded sample zeroes its contribution slot.
 template <int MODE>
 struct QueueIO {
-  static constexpr bool kHitRecord = MODE == 0;  // the shadow queue only wants "occluded or not": no U, V, W / ids of the hit
+  static constexpr bool kHitRecord = MODE == 0;
+  static constexpr int kRefillIdleClosest = VG_REFILL_IDLE_CLOSEST_QUEUE;  // the shadow queue only wants "occluded or not": no U, V, W / ids of the hit
   const RenderParams& p;
   const VgRay* rays;
   int n;
