@@ -817,7 +817,6 @@ struct WarpStage {
   float4* buf;         // 2 slots x 32 rays x 2 float4
   unsigned long long* bar;  // 2 mbarriers
 };
-static const int kStageBytesPerWarp = 2 * 32 * 32 + 2 * 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
@@ -1048,7 +1047,6 @@ static __device__ __noinline__ void xf_object_ray(const DevScene& sc, int xi, fl
 #ifndef VG_REFILL_IDLE_CLOSEST_QUEUE
 #define VG_REFILL_IDLE_CLOSEST_QUEUE 24
 #endif
-static const int kCoopBytesPerWarp = 32 * 48;  // 32 ray-parameter blocks of 3 float4
 
 struct TriCand {
   float fU, fV, fW, det, T;
