@@ -53,7 +53,8 @@ typedef struct VgRay {
  * motion meshes, trace.go:624) or -1 on a miss; geom = index of the Geom in creation order, -1 on a miss.
  * t = Ray.Tclosest after the call (tmax on a miss). u,v,w = scaled barycentrics U,V,W of trace.go:186-188.
  * nodesT = interior-node visits (Ray.NodesT, intersect.go:114), trisT = sum of LeafCount over visited
- * triangle leaves; both feed the bytes model of the roofline. */
+ * triangle leaves; both feed the bytes model of the roofline. The device keeps the two counters of a ray in one
+ * register, 16 bits each: exact up to 65 535 node visits / leaf triangles per ray (the BASELINE scenes need < 200). */
 typedef struct VgHit {
   float t, u, v, w;
   int32_t prim;
